@@ -1,0 +1,883 @@
+/* TEST INFRASTRUCTURE -- reference-side oracle harness (never shipped, never linked into the product).
+ *
+ * Builds the *unmodified* reference (arunsethuraman/ima2p, /root/reference/src) into one binary with
+ * its own main() renamed, so that the parity fixtures under tests/golden/ and the CPU baseline of
+ * bench.py come from the reference's own code:  `#include "ima_main_mpi.cpp"` pulls the reference
+ * driver in where it lies (nothing is copied).  The route follows SURVEY.md Appendix B.
+ *
+ *   ref_harness MODE OUT [key=value ...] -- <IMa2p command line>
+ *
+ *   state    burn=N                      full model tables + every chain x locus genealogy + values
+ *                                        recomputed from scratch the way init_p() does
+ *                                        (mcmcfile.cpp:130-193)
+ *   updates  burn=N n=M                  accepted updategenealogy() proposals: tree before/after and
+ *                                        the forward/reverse getmprob() values (update_gtree.cpp:654-663)
+ *   kat                                  tables of the numerics (utilities.cpp, update_gtree_common.cpp:108-304)
+ *   lmode    burn=N rows=G every=K       sampled .ti rows (savegsampinf) and marginp/margincalc/jointp values
+ *   bench    burn=N iters=K full=0|1     times the updategenealogy() loop (or whole qupdate steps)
+ *   lbench   rows=G evals=E              times margincalc / jointp over G synthetic-from-run rows
+ */
+#define main ima2p_reference_main
+#include "ima_main_mpi.cpp"
+#undef main
+#include "update_gtree_common.hpp"      /* getmprob :850, calcmrate :462 */
+
+#include <chrono>
+#include <vector>
+#include <string>
+#include <map>
+
+/* exported by shims.cpp */
+double harness_integrate_coalescent_term (int cc, double fc, double hcc, double max, double min);
+double harness_integrate_migration_term (int cm, double fm, double max, double min);
+double harness_integrate_migration_term_expo_prior (int cm, double fm, double exmean);
+double harness_swapweight (int ci, int cj);
+double harness_swapweight_bwprocesses (double sumi, double sumj, double betai, double betaj);
+double harness_marginp (int param, int firsttree, int lasttree, double x);
+void harness_jointp_setup (void);
+double harness_get_sumlogk (int li);
+double jointp (double *x, int calc_ess, double *effective_n);
+extern struct edgemiginfo oldedgemig, oldsismig, newedgemig, newsismig;
+void harness_init_p (void);                             /* mcmcfile.cpp:130, file-static */
+extern int rootmove;
+
+static FILE *jo;
+static std::map<std::string, std::string> kv;
+
+static long
+kvl (const char *k, long dflt)
+{
+  auto it = kv.find (k);
+  return it == kv.end ()? dflt : atol (it->second.c_str ());
+}
+
+static double
+nowsec ()
+{
+  return std::chrono::duration<double> (std::chrono::steady_clock::now ().time_since_epoch ()).count ();
+}
+
+static void
+jd (double v)
+{
+  if (v != v)
+    fprintf (jo, "\"nan\"");
+  else if (v > DBL_MAX)
+    fprintf (jo, "\"inf\"");
+  else if (v < -DBL_MAX)
+    fprintf (jo, "\"-inf\"");
+  else
+    fprintf (jo, "%.17g", v);
+}
+
+static void
+jdarr (const char *name, const double *a, int n, const char *tail)
+{
+  fprintf (jo, "\"%s\":[", name);
+  for (int i = 0; i < n; i++)
+  {
+    if (i)
+      fputc (',', jo);
+    jd (a[i]);
+  }
+  fprintf (jo, "]%s", tail);
+}
+
+static void
+jiarr (const char *name, const int *a, int n, const char *tail)
+{
+  fprintf (jo, "\"%s\":[", name);
+  for (int i = 0; i < n; i++)
+    fprintf (jo, "%s%d", i ? "," : "", a[i]);
+  fprintf (jo, "]%s", tail);
+}
+
+/* gweight flattened: cc/fc/hcc[k][i] for k=0..numsplittimes, i<npops-k ; mc/fm[k][i][j] k<lastperiodnumber */
+static void
+dump_gweight (const char *name, struct genealogy_weights *gw, const char *tail)
+{
+  int k, i, j, first;
+  fprintf (jo, "\"%s\":{\"cc\":[", name);
+  for (first = 1, k = 0; k <= numsplittimes; k++)
+    for (i = 0; i < npops - k; i++, first = 0)
+      fprintf (jo, "%s%d", first ? "" : ",", gw->cc[k][i]);
+  fprintf (jo, "],\"fc\":[");
+  for (first = 1, k = 0; k <= numsplittimes; k++)
+    for (i = 0; i < npops - k; i++, first = 0)
+    {
+      if (!first)
+        fputc (',', jo);
+      jd (gw->fc[k][i]);
+    }
+  fprintf (jo, "],\"hcc\":[");
+  for (first = 1, k = 0; k <= numsplittimes; k++)
+    for (i = 0; i < npops - k; i++, first = 0)
+    {
+      if (!first)
+        fputc (',', jo);
+      jd (gw->hcc[k][i]);
+    }
+  fprintf (jo, "],\"mc\":[");
+  if (!modeloptions[NOMIGRATION])
+    for (first = 1, k = 0; k < lastperiodnumber; k++)
+      for (i = 0; i < npops - k; i++)
+        for (j = 0; j < npops - k; j++, first = 0)
+          fprintf (jo, "%s%d", first ? "" : ",", gw->mc[k][i][j]);
+  fprintf (jo, "],\"fm\":[");
+  if (!modeloptions[NOMIGRATION])
+    for (first = 1, k = 0; k < lastperiodnumber; k++)
+      for (i = 0; i < npops - k; i++)
+        for (j = 0; j < npops - k; j++, first = 0)
+        {
+          if (!first)
+            fputc (',', jo);
+          jd (gw->fm[k][i][j]);
+        }
+  fprintf (jo, "]}%s", tail);
+}
+
+static void
+dump_tree (int ci, int li, const char *tail)
+{
+  struct genealogy *G = &C[ci]->G[li];
+  struct edge *gt = G->gtree;
+  int nl = L[li].numlines, i, j, ai;
+  fprintf (jo, "{\"root\":%d,\"roottime\":", G->root);
+  jd (G->roottime);
+  fprintf (jo, ",\"up0\":[");
+  for (i = 0; i < nl; i++)
+    fprintf (jo, "%s%d", i ? "," : "", gt[i].up[0]);
+  fprintf (jo, "],\"up1\":[");
+  for (i = 0; i < nl; i++)
+    fprintf (jo, "%s%d", i ? "," : "", gt[i].up[1]);
+  fprintf (jo, "],\"down\":[");
+  for (i = 0; i < nl; i++)
+    fprintf (jo, "%s%d", i ? "," : "", gt[i].down);
+  fprintf (jo, "],\"pop\":[");
+  for (i = 0; i < nl; i++)
+    fprintf (jo, "%s%d", i ? "," : "", gt[i].pop);
+  fprintf (jo, "],\"time\":[");
+  for (i = 0; i < nl; i++)
+  {
+    if (i)
+      fputc (',', jo);
+    jd (gt[i].time);
+  }
+  fprintf (jo, "],\"mig\":[");
+  for (i = 0; i < nl; i++)
+  {
+    fprintf (jo, "%s[", i ? "," : "");
+    for (j = 0; gt[i].mig[j].mt > -0.5; j++)
+    {
+      if (j)
+        fputc (',', jo);
+      jd (gt[i].mig[j].mt);
+      fprintf (jo, ",%d", gt[i].mig[j].mp);
+    }
+    fputc (']', jo);
+  }
+  fprintf (jo, "]");
+  if (L[li].model == STEPWISE || L[li].model == JOINT_IS_SW)
+  {
+    fprintf (jo, ",\"A\":[");
+    for (ai = 0; ai < L[li].nlinked; ai++)
+    {
+      fprintf (jo, "%s[", ai ? "," : "");
+      for (i = 0; i < nl; i++)
+        fprintf (jo, "%s%d", i ? "," : "", (ai == 0 && L[li].model == JOINT_IS_SW) ? 0 : gt[i].A[ai]);
+      fputc (']', jo);
+    }
+    fprintf (jo, "],\"dlikeA\":[");
+    for (ai = 0; ai < L[li].nlinked; ai++)
+    {
+      fprintf (jo, "%s[", ai ? "," : "");
+      for (i = 0; i < nl; i++)
+      {
+        if (i)
+          fputc (',', jo);
+        jd ((ai == 0 && L[li].model == JOINT_IS_SW) ? 0.0 : gt[i].dlikeA[ai]);
+      }
+      fputc (']', jo);
+    }
+    fprintf (jo, "]");
+  }
+  fprintf (jo, "}%s", tail);
+}
+
+static void
+dump_model (void)
+{
+  int i, k, li, j;
+  fprintf (jo, "\"model\":{\"npops\":%d,\"numtreepops\":%d,\"numsplittimes\":%d,\"numpopsizeparams\":%d,"
+           "\"nummigrateparams\":%d,\"nomigration\":%d,\"expomigrationprior\":%d,\"gsampinflength\":%d,\"gbeta\":",
+           npops, numtreepops, numsplittimes, numpopsizeparams, nummigrateparams,
+           modeloptions[NOMIGRATION], modeloptions[EXPOMIGRATIONPRIOR], calc_gsampinf_length ());
+  jd (gbeta);
+  fprintf (jo, ",\"calcmarginallikelihood\":%d,\"rootpop\":%d,", calcoptions[CALCMARGINALLIKELIHOOD], C[0]->rootpop);
+  fprintf (jo, "\"plist\":[");
+  for (k = 0; k < npops; k++)
+  {
+    fprintf (jo, "%s[", k ? "," : "");
+    for (i = 0; i < npops - k; i++)
+      fprintf (jo, "%s%d", i ? "," : "", C[0]->plist[k][i]);
+    fputc (']', jo);
+  }
+  fprintf (jo, "],\"addpop\":[");
+  for (k = 0; k <= numsplittimes; k++)
+    fprintf (jo, "%s%d", k ? "," : "", k == 0 ? -1 : C[0]->addpop[k]);
+  fprintf (jo, "],\"droppops\":[");
+  for (k = 0; k <= numsplittimes; k++)
+    fprintf (jo, "%s[%d,%d]", k ? "," : "", k == 0 ? -1 : C[0]->droppops[k][0], k == 0 ? -1 : C[0]->droppops[k][1]);
+  fprintf (jo, "],\"poptree\":[");
+  for (i = 0; i < numtreepops; i++)
+    fprintf (jo, "%s{\"b\":%d,\"e\":%d,\"down\":%d}", i ? "," : "", C[0]->poptree[i].b, C[0]->poptree[i].e,
+             C[0]->poptree[i].down);
+  fprintf (jo, "],\"itheta\":[");
+  for (i = 0; i < numpopsizeparams; i++)
+  {
+    fprintf (jo, "%s{\"max\":", i ? "," : "");
+    jd (itheta[i].pr.max);
+    fprintf (jo, ",\"min\":");
+    jd (itheta[i].pr.min);
+    fputc (',', jo);
+    jiarr ("p", itheta[i].wp.p, itheta[i].wp.n, ",");
+    jiarr ("r", itheta[i].wp.r, itheta[i].wp.n, "}");
+  }
+  fprintf (jo, "],\"imig\":[");
+  for (i = 0; i < nummigrateparams; i++)
+  {
+    fprintf (jo, "%s{\"max\":", i ? "," : "");
+    jd (imig[i].pr.max);
+    fprintf (jo, ",\"min\":");
+    jd (imig[i].pr.min);
+    fprintf (jo, ",\"mean\":");
+    jd (modeloptions[EXPOMIGRATIONPRIOR] ? imig[i].pr.mean : 0.0);
+    fputc (',', jo);
+    jiarr ("p", imig[i].wp.p, imig[i].wp.n, ",");
+    jiarr ("r", imig[i].wp.r, imig[i].wp.n, ",");
+    jiarr ("c", imig[i].wp.c, imig[i].wp.n, "}");
+  }
+  fprintf (jo, "],\"nomigrationchecklist\":{");
+  jiarr ("p", nomigrationchecklist.p, nomigrationchecklist.n, ",");
+  jiarr ("r", nomigrationchecklist.r, nomigrationchecklist.n, ",");
+  jiarr ("c", nomigrationchecklist.c, nomigrationchecklist.n, "}},\n");
+  fprintf (jo, "\"loci\":[");
+  for (li = 0; li < nloci; li++)
+  {
+    fprintf (jo, "%s{\"model\":%d,\"numgenes\":%d,\"numlines\":%d,\"numsites\":%d,\"totsites\":%d,\"numbases\":%d,\"nlinked\":%d,\"hval\":",
+             li ? ",\n" : "", L[li].model, L[li].numgenes, L[li].numlines, L[li].numsites, L[li].totsites,
+             L[li].numbases, L[li].nlinked);
+    jd (L[li].hval);
+    fprintf (jo, ",\"sumlogk\":");
+    jd (harness_get_sumlogk (li));
+    fputc (',', jo);
+    jiarr ("samppop", L[li].samppop, npops, ",");
+    jiarr ("umodel", L[li].umodel, L[li].nlinked, ",");
+    jiarr ("minA", L[li].minA, L[li].nlinked, ",");
+    jiarr ("maxA", L[li].maxA, L[li].nlinked, ",");
+    if (L[li].model == HKY)
+      jiarr ("mult", L[li].mult, L[li].numsites, ",");
+    fprintf (jo, "\"seq\":[");
+    if (L[li].model == HKY || L[li].model == INFINITESITES || L[li].model == JOINT_IS_SW)
+      for (j = 0; j < L[li].numgenes; j++)
+      {
+        fprintf (jo, "%s[", j ? "," : "");
+        for (i = 0; i < L[li].numsites; i++)
+          fprintf (jo, "%s%d", i ? "," : "", L[li].seq[j][i]);
+        fputc (']', jo);
+      }
+    fprintf (jo, "]}");
+  }
+  fprintf (jo, "],\n");
+}
+
+/* from-scratch evaluation of every chain, as init_p() (mcmcfile.cpp:130-193) does after a reload */
+static void
+recompute_all (void)
+{
+  harness_init_p ();
+}
+
+static void
+dump_state (void)
+{
+  int ci, li;
+  fprintf (jo, "{");
+  dump_model ();
+  fprintf (jo, "\"chains\":[");
+  for (ci = 0; ci < numchains; ci++)
+  {
+    fprintf (jo, "%s{\"beta\":", ci ? ",\n" : "");
+    jd (beta[ci]);
+    fputc (',', jo);
+    jdarr ("tvals", C[ci]->tvals, numsplittimes, ",");
+    dump_gweight ("allgweight", &C[ci]->allgweight, ",");
+    jdarr ("qintegrate", C[ci]->allpcalc.qintegrate, numpopsizeparams, ",");
+    jdarr ("mintegrate", C[ci]->allpcalc.mintegrate, nummigrateparams, ",");
+    fprintf (jo, "\"probg\":");
+    jd (C[ci]->allpcalc.probg);
+    fprintf (jo, ",\"pdg\":");
+    jd (C[ci]->allpcalc.pdg);
+    fprintf (jo, ",\"G\":[");
+    for (li = 0; li < nloci; li++)
+    {
+      struct genealogy *G = &C[ci]->G[li];
+      fprintf (jo, "%s{", li ? ",\n" : "");
+      jdarr ("uvals", G->uvals, L[li].nlinked, ",");
+      fprintf (jo, "\"kappa\":");
+      jd (L[li].model == HKY ? G->kappaval : 0.0);
+      fputc (',', jo);
+      jdarr ("pi", G->pi, 4, ",");
+      fprintf (jo, "\"pdg\":");
+      jd (G->pdg);
+      fputc (',', jo);
+      jdarr ("pdg_a", G->pdg_a, L[li].nlinked, ",");
+      fprintf (jo, "\"length\":");
+      jd (G->length);
+      fprintf (jo, ",\"tlength\":");
+      jd (G->tlength);
+      fprintf (jo, ",\"mignum\":%d,", G->mignum);
+      dump_gweight ("gweight", &G->gweight, ",");
+      fprintf (jo, "\"tree\":");
+      dump_tree (ci, li, "}");
+    }
+    fprintf (jo, "]}");
+  }
+  fprintf (jo, "]}\n");
+}
+
+static void
+do_burn (long burn)
+{
+  for (long s = 0; s < burn; s++)
+  {
+    qupdate (0, 0, 1);
+    step++;
+  }
+}
+
+static void
+dump_emi (const char *name, struct edgemiginfo *em, const char *tail)
+{
+  int j;
+  fprintf (jo, "\"%s\":{\"edgeid\":%d,\"pop\":%d,\"fpop\":%d,\"b\":%d,\"e\":%d,\"mpall\":%d,\"upt\":", name,
+           em->edgeid, em->pop, em->fpop, em->b, em->e, em->mpall);
+  jd (em->upt);
+  fprintf (jo, ",\"dnt\":");
+  jd (em->dnt);
+  fprintf (jo, ",\"mtall\":");
+  jd (em->mtall);
+  fputc (',', jo);
+  jdarr ("mtimeavail", em->mtimeavail, npops, ",");
+  jiarr ("mp", em->mp, npops, ",");
+  fprintf (jo, "\"mig\":[");
+  for (j = 0; em->mig[j].mt > -0.5; j++)
+  {
+    if (j)
+      fputc (',', jo);
+    jd (em->mig[j].mt);
+    fprintf (jo, ",%d", em->mig[j].mp);
+  }
+  fprintf (jo, "]}%s", tail);
+}
+
+static void
+mode_updates (long burn, long n)
+{
+  int ci, li, topol, tmrca, acc, first = 1;
+  long done = 0, tries = 0;
+  do_burn (burn);
+  recompute_all ();
+  fprintf (jo, "{");
+  dump_model ();
+  fprintf (jo, "\"tvals\":[");
+  for (ci = 0; ci < numchains; ci++)
+  {
+    fprintf (jo, "%s[", ci ? "," : "");
+    for (int k = 0; k < numsplittimes; k++)
+    {
+      if (k)
+        fputc (',', jo);
+      jd (C[ci]->tvals[k]);
+    }
+    fputc (']', jo);
+  }
+  fprintf (jo, "],\n\"updates\":[");
+  while (done < n && tries < 200 * n)
+  {
+    for (ci = 0; ci < numchains && done < n; ci++)
+      for (li = 0; li < nloci && done < n; li++)
+      {
+        /* the "before" tree must be written before the call; keep it in a memory stream */
+        char *buf = NULL;
+        size_t blen = 0;
+        FILE *keep = jo;
+        jo = open_memstream (&buf, &blen);
+        dump_tree (ci, li, "");
+        fclose (jo);
+        jo = keep;
+        double oldpdg = C[ci]->G[li].pdg, oldprobg = C[ci]->allpcalc.probg;
+        acc = updategenealogy (ci, li, &topol, &tmrca);
+        tries++;
+        if (acc)
+        {
+          double fwd = getmprob (ci, &newedgemig, &newsismig, &oldedgemig, &oldsismig);
+          double rev = getmprob (ci, &oldedgemig, &oldsismig, &newedgemig, &newsismig);
+          fprintf (jo, "%s{\"ci\":%d,\"li\":%d,\"topolchange\":%d,\"tmrcachange\":%d,\"rootmove\":%d,\"fwd\":", first ? "" : ",\n", ci,
+                   li, topol, tmrca, rootmove);
+          first = 0;
+          jd (fwd);
+          fprintf (jo, ",\"rev\":");
+          jd (rev);
+          fprintf (jo, ",\"oldpdg\":");
+          jd (oldpdg);
+          fprintf (jo, ",\"newpdg\":");
+          jd (C[ci]->G[li].pdg);
+          fprintf (jo, ",\"oldprobg\":");
+          jd (oldprobg);
+          fprintf (jo, ",\"newprobg\":");
+          jd (C[ci]->allpcalc.probg);
+          fputc (',', jo);
+          dump_emi ("oldedgemig", &oldedgemig, ",");
+          dump_emi ("oldsismig", &oldsismig, ",");
+          dump_emi ("newedgemig", &newedgemig, ",");
+          dump_emi ("newsismig", &newsismig, ",");
+          dump_gweight ("newgweight", &C[ci]->G[li].gweight, ",");
+          fprintf (jo, "\"before\":%s,\"after\":", buf);
+          dump_tree (ci, li, "}");
+          done++;
+        }
+        free (buf);
+      }
+  }
+  fprintf (jo, "],\"tries\":%ld}\n", tries);
+}
+
+static void
+mode_kat (void)
+{
+  int a, i, first;
+  double x;
+  /* incomplete gamma on a grid that straddles the x < a+1 switch (utilities.cpp:1053-1122) */
+  static const double xs[] = { 1e-6, 1e-3, 0.01, 0.1, 0.5, 0.9, 1.0, 1.5, 2.0, 3.2, 5.0, 7.5, 10.0, 17.0, 33.0, 64.0,
+    100.0, 250.0, 500.0, 999.0, 1001.0, 1500.0, 2500.0, 4000.0, 1e4
+  };
+  static const int as[] = { 0, 1, 2, 3, 4, 5, 7, 10, 16, 29, 50, 99, 100, 250, 500, 999, 1000, 1450, 2000, 3000 };
+  const int nx = sizeof (xs) / sizeof (xs[0]), na = sizeof (as) / sizeof (as[0]);
+  fprintf (jo, "{\"uppergamma\":[");
+  for (first = 1, a = 0; a < na; a++)
+    for (i = 0; i < nx + 4; i++, first = 0)
+    {
+      /* extra points hugging x = a+1 */
+      x = i < nx ? xs[i] : (as[a] + 1.0) * (i == nx ? 0.999 : i == nx + 1 ? 1.0 : i == nx + 2 ? 1.001 : 0.5);
+      if (as[a] == 0 && x <= 0)
+        continue;
+      fprintf (jo, "%s[%d,", first ? "" : ",", as[a]);
+      jd (x);
+      fputc (',', jo);
+      jd (uppergamma (as[a], x));
+      fputc (']', jo);
+    }
+  fprintf (jo, "],\n\"lowergamma\":[");
+  for (first = 1, a = 1; a < na; a++)
+    for (i = 0; i < nx + 4; i++, first = 0)
+    {
+      x = i < nx ? xs[i] : (as[a] + 1.0) * (i == nx ? 0.999 : i == nx + 1 ? 1.0 : i == nx + 2 ? 1.001 : 0.5);
+      fprintf (jo, "%s[%d,", first ? "" : ",", as[a]);
+      jd (x);
+      fputc (',', jo);
+      jd (lowergamma (as[a], x));
+      fputc (']', jo);
+    }
+  fprintf (jo, "],\n\"bessi\":[");
+  {
+    static const double bx[] = { 0.0, 1e-8, 1e-3, 0.1, 0.5, 1.0, 2.5, 3.74, 3.75, 3.76, 5.0, 10.0, 25.0, 60.0, 150.0, 400.0, 699.0,
+      700.0, 701.0
+    };
+    for (first = 1, a = 0; a <= 40; a += (a < 6 ? 1 : 5))
+      for (i = 0; i < (int) (sizeof (bx) / sizeof (bx[0])); i++, first = 0)
+      {
+        fprintf (jo, "%s[%d,", first ? "" : ",", a);
+        jd (bx[i]);
+        fputc (',', jo);
+        jd (bessi (a, bx[i]));
+        fputc (']', jo);
+      }
+  }
+  fprintf (jo, "],\n\"eexp\":[");
+  {
+    static const double ex[] = { -1e4, -745.2, -700.0, -312.7, -100.0, -23.5, -10.0, -2.302585092994046, -1.0, -0.5, -1e-9, 0.0, 1e-9,
+      0.3, 0.6931471805599453, 1.0, 2.302585092994046, 7.7, 42.0, 100.0, 333.3, 700.0, 709.0, 1e4
+    };
+    for (i = 0; i < (int) (sizeof (ex) / sizeof (ex[0])); i++)
+    {
+      double m;
+      int z;
+      eexp (ex[i], &m, &z);
+      fprintf (jo, "%s[", i ? "," : "");
+      jd (ex[i]);
+      fputc (',', jo);
+      jd (m);
+      fprintf (jo, ",%d]", z);
+    }
+  }
+  fprintf (jo, "],\n\"logfact\":[");
+  for (i = 0; i < 64; i++)
+  {
+    if (i)
+      fputc (',', jo);
+    jd (logfact[i * i]);
+  }
+  /* integrate_coalescent_term / integrate_migration_term: all branches (update_gtree_common.cpp:108-296) */
+  fprintf (jo, "],\n\"integrate_coalescent_term\":[");
+  {
+    static const int ccs[] = { 0, 1, 2, 3, 10, 29, 95, 400, 1450, 2900 };
+    static const double fcs[] = { 0.0, 1e-9, 1e-3, 0.37, 2.0, 9.9, 30.8, 343.7, 1500.0, 9000.0, 60000.0 };
+    static const double maxs[] = { 1.0, 10.0, 50.0 };
+    for (first = 1, a = 0; a < 10; a++)
+      for (i = 0; i < 11; i++)
+        for (int m = 0; m < 3; m++)
+        {
+          if (ccs[a] > 0 && fcs[i] <= 0)
+            continue;
+          double hcc = (m == 1) ? 0.0 : ccs[a] * log (0.75);
+          fprintf (jo, "%s[%d,", first ? "" : ",", ccs[a]);
+          first = 0;
+          jd (fcs[i]);
+          fputc (',', jo);
+          jd (hcc);
+          fputc (',', jo);
+          jd (maxs[m]);
+          fputc (',', jo);
+          jd (harness_integrate_coalescent_term (ccs[a], fcs[i], hcc, maxs[m], 0.0));
+          fputc (']', jo);
+        }
+  }
+  fprintf (jo, "],\n\"integrate_migration_term\":[");
+  {
+    static const int cms[] = { 0, 1, 2, 3, 7, 20, 64, 300, 1000 };
+    static const double fms[] = { 0.0, 5e-7, 2e-6, 1e-3, 0.4, 6.4, 7.07, 55.0, 700.0, 5000.0, 40000.0 };
+    static const double maxs[] = { 1e-6, 0.1, 1.0, 5.0 };
+    for (first = 1, a = 0; a < 9; a++)
+      for (i = 0; i < 11; i++)
+        for (int m = 0; m < 4; m++)
+        {
+          if (cms[a] > 0 && fms[i] <= 0)
+            continue;
+          fprintf (jo, "%s[%d,", first ? "" : ",", cms[a]);
+          first = 0;
+          jd (fms[i]);
+          fputc (',', jo);
+          jd (maxs[m]);
+          fputc (',', jo);
+          jd (harness_integrate_migration_term (cms[a], fms[i], maxs[m], 0.0));
+          fputc (',', jo);
+          jd (harness_integrate_migration_term_expo_prior (cms[a], fms[i], maxs[m]));
+          fputc (']', jo);
+        }
+  }
+  fprintf (jo, "],\n\"calcmrate\":[");
+  {
+    static const int mcs[] = { 0, 1, 4 };
+    static const double mts[] = { -1.0, 0.0, 0.3, 1.0, 2.5 };
+    for (first = 1, a = 0; a < 3; a++)
+      for (i = 0; i < 5; i++, first = 0)
+      {
+        fprintf (jo, "%s[%d,", first ? "" : ",", mcs[a]);
+        jd (mts[i]);
+        fputc (',', jo);
+        jd (calcmrate (mcs[a], mts[i]));
+        fputc (']', jo);
+      }
+  }
+  fprintf (jo, "],\n\"swapweight_bw\":[");
+  {
+    static const double s[] = { -1234.5, -1230.25, -99.0, 10.5 };
+    static const double b[] = { 1.0, 0.96, 0.5, 0.02 };
+    for (first = 1, a = 0; a < 4; a++)
+      for (i = 0; i < 4; i++)
+        for (int c = 0; c < 4; c++)
+          for (int d = 0; d < 4; d++, first = 0)
+          {
+            fprintf (jo, "%s[", first ? "" : ",");
+            jd (s[a]);
+            fputc (',', jo);
+            jd (s[i]);
+            fputc (',', jo);
+            jd (b[c]);
+            fputc (',', jo);
+            jd (b[d]);
+            fputc (',', jo);
+            jd (harness_swapweight_bwprocesses (s[a], s[i], b[c], b[d]));
+            fputc (']', jo);
+          }
+  }
+  /* swapweight on the loaded chains (swapchains.cpp:12-34) */
+  fprintf (jo, "],\n\"swapweight\":[");
+  for (first = 1, a = 0; a < numchains; a++)
+    for (i = 0; i < numchains; i++)
+      if (a != i)
+      {
+        fprintf (jo, "%s[%d,%d,", first ? "" : ",", a, i);
+        first = 0;
+        jd (harness_swapweight (a, i));
+        fputc (']', jo);
+      }
+  fprintf (jo, "],\"betas\":[");
+  for (a = 0; a < numchains; a++)
+  {
+    if (a)
+      fputc (',', jo);
+    jd (beta[a]);
+  }
+  fprintf (jo, "],\"chainsum\":[");
+  for (a = 0; a < numchains; a++)
+  {
+    double s = 0;
+    for (i = 0; i < nloci; i++)
+      s += C[a]->G[i].pdg;
+    s += C[a]->allpcalc.probg;
+    if (a)
+      fputc (',', jo);
+    jd (s);
+  }
+  fprintf (jo, "]}\n");
+}
+
+/* Collect G rows of the cold chain the way savegenealogyinfo() does (ima_main_mpi.cpp:3035-3211 ->
+ * ginfo.cpp:318-377), directly into the reference's global gsampinf. */
+static void
+collect_rows (long rows, long every)
+{
+  long g, s;
+  gsampinflength = calc_gsampinf_length ();
+  gsampinf = static_cast<float **> (malloc (rows * sizeof (float *)));
+  for (g = 0; g < rows; g++)
+  {
+    gsampinf[g] = static_cast<float *> (malloc (gsampinflength * sizeof (float)));
+    for (s = 0; s < every; s++)
+    {
+      qupdate (0, 0, 1);
+      step++;
+    }
+    savegsampinf (gsampinf[g], whichiscoldchain ());
+  }
+  genealogiessaved = (int) rows;
+}
+
+static void
+mode_lmode (long burn, long rows, long every)
+{
+  long g;
+  int p, i, first, np;
+  do_burn (burn);
+  collect_rows (rows, every);
+  np = numpopsizeparams + nummigrateparams;
+  fprintf (jo, "{");
+  dump_model ();
+  fprintf (jo, "\"rows\":[");
+  for (g = 0; g < rows; g++)
+  {
+    fprintf (jo, "%s[", g ? ",\n" : "");
+    for (i = 0; i < gsampinflength; i++)
+      fprintf (jo, "%s%.9g", i ? "," : "", (double) gsampinf[g][i]);
+    fputc (']', jo);
+  }
+  fprintf (jo, "],\n\"margincalc\":[");
+  for (first = 1, p = 0; p < np; p++)
+  {
+    double mx = p < numpopsizeparams ? itheta[p].pr.max : imig[p - numpopsizeparams].pr.max;
+    for (i = 0; i < 40; i++, first = 0)
+    {
+      /* GRIDSIZE-style mid-bin points (histograms.cpp:81-99) thinned to 40, plus points near 0 and max */
+      double x = mx * (i + 0.5) / 40.0;
+      if (i == 0)
+        x = mx * 0.5 / GRIDSIZE;
+      if (i == 39)
+        x = mx * (GRIDSIZE - 0.5) / GRIDSIZE;
+      fprintf (jo, "%s[%d,", first ? "" : ",", p);
+      jd (x);
+      fputc (',', jo);
+      jd (margincalc (x, 0.0, p, 0));
+      fputc (',', jo);
+      jd (margincalc (x, 0.25, p, 1));
+      fputc (',', jo);
+      jd (harness_marginp (p, 0, (int) rows, x));
+      fputc (',', jo);
+      jd (harness_marginp (p, (int) (rows / 3), (int) (2 * rows / 3), x));
+      fputc (']', jo);
+    }
+  }
+  fprintf (jo, "],\n\"jointp\":[");
+  harness_jointp_setup ();
+  {
+    unsigned long long lcg = 88172645463325252ULL;
+    for (i = 0; i < 48; i++)
+    {
+      double xv[32], ess = 0;
+      for (p = 0; p < np; p++)
+      {
+        double mx = p < numpopsizeparams ? itheta[p].pr.max : imig[p - numpopsizeparams].pr.max;
+        lcg ^= lcg << 13;
+        lcg ^= lcg >> 7;
+        lcg ^= lcg << 17;
+        double u = (double) (lcg >> 11) / 9007199254740992.0;
+        /* concentrate half of the points near the bulk of the posterior so that many terms are kept */
+        xv[p] = (i & 1) ? mx * (0.02 + 0.3 * u) : mx * (1e-3 + 0.998 * u);
+      }
+      double q = jointp (xv, 1, &ess);
+      fprintf (jo, "%s{", i ? ",\n" : "");
+      jdarr ("x", xv, np, ",");
+      fprintf (jo, "\"q\":");
+      jd (q);
+      fprintf (jo, ",\"ess\":");
+      jd (ess);
+      fputc ('}', jo);
+    }
+  }
+  fprintf (jo, "]}\n");
+}
+
+static void
+mode_bench (long burn, long iters, long full)
+{
+  long it, acc = 0, tries = 0;
+  int ci, li, a, b;
+  do_burn (burn);
+  double t0 = nowsec ();
+  for (it = 0; it < iters; it++)
+  {
+    if (full)
+    {
+      qupdate (0, 0, 1);
+      step++;
+      tries += (long) numchains *nloci;
+    }
+    else
+      for (ci = 0; ci < numchains; ci++)
+        for (li = 0; li < nloci; li++)
+        {
+          acc += updategenealogy (ci, li, &a, &b);
+          tries++;
+        }
+  }
+  double t1 = nowsec ();
+  fprintf (jo, "{\"mode\":\"%s\",\"chains\":%d,\"loci\":%d,\"iters\":%ld,\"updates\":%ld,\"accepted\":%ld,\"seconds\":%.6f,"
+           "\"updates_per_sec\":%.3f}\n", full ? "qupdate" : "updategenealogy", numchains, nloci, iters, tries, acc, t1 - t0,
+           tries / (t1 - t0));
+}
+
+static void
+mode_lbench (long burn, long rows, long evals)
+{
+  long g, e;
+  int i, np;
+  /* a few hundred real rows, then bootstrap them up to `rows` */
+  long base = rows < 256 ? rows : 256;
+  do_burn (burn);
+  collect_rows (base, 2);
+  gsampinf = static_cast<float **> (realloc (gsampinf, rows * sizeof (float *)));
+  for (g = base; g < rows; g++)
+    gsampinf[g] = gsampinf[(g * 2654435761UL) % base];
+  genealogiessaved = (int) rows;
+  np = numpopsizeparams + nummigrateparams;
+  double acc = 0, t0 = nowsec ();
+  for (e = 0; e < evals; e++)
+  {
+    i = (int) (e % np);
+    double mx = i < numpopsizeparams ? itheta[i].pr.max : imig[i - numpopsizeparams].pr.max;
+    acc += margincalc (mx * (0.5 + (e % 997)) / 1000.0, 0.0, i, 0);
+  }
+  double t1 = nowsec ();
+  harness_jointp_setup ();
+  long jevals = evals / 8 > 0 ? evals / 8 : 1;
+  double t2 = nowsec ();
+  for (e = 0; e < jevals; e++)
+  {
+    double xv[32], ess;
+    for (i = 0; i < np; i++)
+    {
+      double mx = i < numpopsizeparams ? itheta[i].pr.max : imig[i - numpopsizeparams].pr.max;
+      xv[i] = mx * (0.05 + 0.0007 * ((e * 31 + i * 17) % 997));
+    }
+    acc += jointp (xv, 0, &ess);
+  }
+  double t3 = nowsec ();
+  fprintf (jo, "{\"rows\":%ld,\"margincalc_evals\":%ld,\"margincalc_seconds\":%.6f,\"margincalc_geneval_per_sec\":%.3f,"
+           "\"jointp_evals\":%ld,\"jointp_seconds\":%.6f,\"jointp_geneval_per_sec\":%.3f,\"checksum\":%.17g}\n", rows, evals, t1 - t0,
+           (double) evals * rows / (t1 - t0), jevals, t3 - t2, (double) jevals * rows / (t3 - t2), acc);
+}
+
+int
+main (int argc, char *argv[])
+{
+  int i, split = -1;
+  if (argc < 4)
+  {
+    fprintf (stderr, "usage: ref_harness MODE OUT [key=value ...] -- <IMa2p args>\n");
+    return 2;
+  }
+  for (i = 3; i < argc; i++)
+  {
+    if (!strcmp (argv[i], "--"))
+    {
+      split = i;
+      break;
+    }
+    char *eq = strchr (argv[i], '=');
+    if (eq)
+      kv[std::string (argv[i], eq - argv[i])] = std::string (eq + 1);
+  }
+  if (split < 0)
+  {
+    fprintf (stderr, "missing -- before the IMa2p command line\n");
+    return 2;
+  }
+  std::string mode = argv[1];
+  jo = fopen (argv[2], "w");
+  if (!jo)
+  {
+    perror (argv[2]);
+    return 2;
+  }
+  std::vector<char *>av;
+  av.push_back (argv[0]);
+  for (i = split + 1; i < argc; i++)
+    av.push_back (argv[i]);
+  numprocesses = 1;
+  init_IMA ();
+  start ((int) av.size (), av.data (), 0);
+  if (kvl ("seed", -1) >= 0)
+    setseeds ((int) kvl ("seed", 0));     /* -s is ineffective in the serial build */
+  init_after_start_IMA ();
+  step = 0;
+  recordstep = 0;
+  long burn = kvl ("burn", 0);
+  if (mode == "state")
+  {
+    do_burn (burn);
+    recompute_all ();
+    dump_state ();
+  }
+  else if (mode == "updates")
+    mode_updates (burn, kvl ("n", 100));
+  else if (mode == "kat")
+  {
+    do_burn (burn);
+    recompute_all ();
+    mode_kat ();
+  }
+  else if (mode == "lmode")
+    mode_lmode (burn, kvl ("rows", 500), kvl ("every", 5));
+  else if (mode == "bench")
+    mode_bench (burn, kvl ("iters", 10), kvl ("full", 0));
+  else if (mode == "lbench")
+    mode_lbench (burn, kvl ("rows", 100000), kvl ("evals", 50));
+  else
+  {
+    fprintf (stderr, "unknown mode %s\n", mode.c_str ());
+    return 2;
+  }
+  fclose (jo);
+  return 0;
+}

@@ -1,0 +1,58 @@
+/* TEST INFRASTRUCTURE -- reference-side harness shim (never shipped, never linked into the product).
+ *
+ * Each shim translation unit #includes exactly ONE reference source file *where it lies* under
+ * /root/reference/src (nothing is copied into this repo) and appends exported wrappers for the
+ * file-static functions / variables the parity fixtures need.  Which file is included is selected
+ * with -DSHIM_<NAME> by oracle/build_ref.sh; the unmodified reference file of the same name is then
+ * left out of the link.
+ */
+#if defined(SHIM_GTREE_COMMON)
+#include "update_gtree_common.cpp"
+/* update_gtree_common.cpp:108,205,298 are file-static */
+double harness_integrate_coalescent_term (int cc, double fc, double hcc, double max, double min)
+{ return integrate_coalescent_term (cc, fc, hcc, max, min); }
+double harness_integrate_migration_term (int cm, double fm, double max, double min)
+{ return integrate_migration_term (cm, fm, max, min); }
+double harness_integrate_migration_term_expo_prior (int cm, double fm, double exmean)
+{ return integrate_migration_term_expo_prior (cm, fm, exmean); }
+
+#elif defined(SHIM_SWAPCHAINS)
+#include "swapchains.cpp"
+/* swapchains.cpp:12,57 are file-static */
+double harness_swapweight (int ci, int cj) { return swapweight (ci, cj); }
+double harness_swapweight_bwprocesses (double sumi, double sumj, double betai, double betaj)
+{ return swapweight_bwprocesses (sumi, sumj, betai, betaj); }
+double harness_calcpartialswapweight (int c) { return calcpartialswapweight (c); }
+
+#elif defined(SHIM_SURFACE)
+#include "surface_call_functions.cpp"
+/* surface_call_functions.cpp:25 is file-static */
+double harness_marginp (int param, int firsttree, int lasttree, double x)
+{ return marginp (param, firsttree, lasttree, x, 0); }
+
+#elif defined(SHIM_JOINTFIND)
+#include "jointfind.cpp"
+/* jointfind.cpp:159,183,184 are file-static; findjointpeaks() :1074-1115 does this set-up before
+ * the first jointp() call, ima_main_mpi.cpp allocates eexpsum in L mode. */
+void harness_jointp_setup (void)
+{
+  nparams = numpopsizeparams + nummigrateparams;
+  setuplist ();
+  nparamrange[0] = 0;
+  nparamrange[1] = nparams;
+  nowmodeltype = 0;
+  eexpsum = (struct extendnum *) malloc ((genealogiessaved + 1) * sizeof (struct extendnum));
+}
+
+#elif defined(SHIM_CALC_PROB_DATA)
+#include "calc_prob_data.cpp"
+/* calc_prob_data.cpp:8 is file-static */
+double harness_get_sumlogk (int li) { return sumlogk[li] ? *sumlogk[li] : 0.0; }
+
+#elif defined(SHIM_MCMCFILE)
+#include "mcmcfile.cpp"
+/* mcmcfile.cpp:130 is file-static */
+void harness_init_p (void) { init_p (); }
+#else
+#error "select a shim"
+#endif

@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Regenerate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference and `make -C oracle ref`):
+
+    python tests/golden/generate.py
+
+Every fixture is the output of oracle/_ref/ref_harness (the reference's own code, see
+oracle/ref_harness/harness_main.cpp) on the reference's own Simulations/*.u inputs or on inputs
+derived from them by the rules of SURVEY.md section 8c/8d (HKY by relabelling the model letter,
+synthetic stepwise alleles, a 3-population split of the same samples).  Nothing under tests/,
+bench.py or smoke() reads /root/reference at run time -- they read these files.
+"""
+import gzip
+import os
+import random
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("IMA2P_REFERENCE", "/root/reference")
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+TMP = "/tmp/ima2p_golden"
+
+PRIORS = ["-q", "10", "-m", "1", "-t", "3"]
+HEAT = ["-hfg", "-ha", "0.96", "-hb", "0.9"]       # geometric needs >= 4 chains (ima_main_mpi.cpp:1187)
+HEAT_LINEAR = ["-hfl", "-ha", "0.05"]
+COMMON = ["-b", "100", "-l", "100", "-p01", "-z", "100000000"]
+
+
+def run(mode, name, ufile, hn, kv, extra=()):
+    out = os.path.join(TMP, name + ".json")
+    cmd = [HARNESS, mode, out] + ["%s=%s" % p for p in kv.items()] + ["--", "-i", ufile, "-o",
+          os.path.join(TMP, name + ".out")] + PRIORS + COMMON + ["-hn", str(hn)] + (HEAT if hn >= 4 else HEAT_LINEAR if hn > 1 else []) + list(extra)
+    with open(os.path.join(TMP, name + ".log"), "w") as log:
+        subprocess.run(cmd, check=True, stdout=log, stderr=subprocess.STDOUT, cwd=TMP)
+    with open(out, "rb") as f, gzip.GzipFile(os.path.join(HERE, name + ".json.gz"), "wb", mtime=0) as g:
+        shutil.copyfileobj(f, g)
+    print("wrote", name + ".json.gz", os.path.getsize(os.path.join(HERE, name + ".json.gz")), "bytes")
+
+
+def relabel(src, dst, fn):
+    """Copy a .u file, passing each locus header line through fn(fields) -> fields."""
+    lines = open(src).read().split("\n")
+    out, i = [], 0
+    out.append(lines[0]); i = 1
+    while lines[i].startswith("#"):
+        out.append(lines[i]); i += 1
+    npops = int(lines[i].split()[0]); out.append(lines[i]); i += 1
+    out.append(lines[i]); i += 1          # population names
+    out.append(lines[i]); i += 1          # tree string
+    nloci = int(lines[i].split()[0]); out.append(lines[i]); i += 1
+    for _ in range(nloci):
+        f = lines[i].split(); i += 1
+        n = sum(int(x) for x in f[1:1 + npops])
+        rows = lines[i:i + n]; i += n
+        f, rows = fn(f, rows, npops)
+        out.append(" ".join(f)); out.extend(rows)
+    open(dst, "w").write("\n".join(out) + "\n")
+
+
+def to_hky(f, rows, npops):
+    f = list(f); f[2 + npops] = "H"; return f, rows
+
+
+def to_sw(f, rows, npops, rng=random.Random(1)):
+    # synthetic S1 locus: one allele column, uniform int in [10,16] (> MINSTRLENGTH 3, imamp.hpp:144)
+    f = list(f); f[1 + npops] = "1"; f[2 + npops] = "S1"
+    rows = ["%-10s%d" % (r[:10].strip(), rng.randint(10, 16)) for r in rows]
+    return f, rows
+
+
+def three_pops(src, dst):
+    """Same samples as `src`, re-divided into 3 populations with tree ((0,1):3,2):4."""
+    lines = open(src).read().split("\n")
+    out, i = [lines[0]], 1
+    while lines[i].startswith("#"):
+        out.append(lines[i]); i += 1
+    i += 3
+    out += ["3", "pop1 pop2 pop3", "((0,1):3,2):4"]
+    nloci = int(lines[i].split()[0]); out.append(lines[i]); i += 1
+    for _ in range(nloci):
+        f = lines[i].split(); i += 1
+        n0, n1 = int(f[1]), int(f[2])
+        rows = lines[i:i + n0 + n1]; i += n0 + n1
+        a = n0 // 2
+        out.append(" ".join([f[0], str(a), str(n0 - a), str(n1)] + f[3:]))
+        out.extend(rows)
+    open(dst, "w").write("\n".join(out) + "\n")
+
+
+def main():
+    if not os.path.exists(HARNESS):
+        sys.exit("build the reference harness first: make -C oracle ref")
+    os.makedirs(TMP, exist_ok=True)
+    sims = os.path.join(REF, "Simulations")
+    s5, s50, s300 = (os.path.join(sims, "Sim1_%dloci.u" % k) for k in (5, 50, 300))
+    s2, s3 = os.path.join(sims, "Sim2.u"), os.path.join(sims, "Sim3.u")
+    hky5 = os.path.join(TMP, "Sim1_5loci_HKY.u"); relabel(s5, hky5, to_hky)
+    sw3 = os.path.join(TMP, "Sim3_SW.u"); relabel(s3, sw3, to_sw)
+    p3 = os.path.join(TMP, "Sim1_5loci_3pop.u"); three_pops(s5, p3)
+
+    # static-evaluation fixtures (a5, a6, a7, a8, a9, a13): states after a short burn-in
+    run("state", "state_sim5_hn4", s5, 4, {"burn": 200})                 # BASELINE config 1
+    run("state", "state_sim50_hn3", s50, 3, {"burn": 40})                # config 2 shape, 3 chains
+    run("state", "state_sim300_hn1", s300, 1, {"burn": 10})              # config 3 shape, 1 chain
+    run("state", "state_sim2_hn2", s2, 2, {"burn": 60})                  # n = 100 genes
+    run("state", "state_sim3_hn3", s3, 3, {"burn": 300})
+    run("state", "state_sim5_3pop_hn2", p3, 2, {"burn": 150})
+    run("state", "state_sim5_expo_hn2", s5, 2, {"burn": 100}, extra=["-j7"])   # exponential m prior
+    run("state", "state_sim5_hky_hn2", hky5, 2, {"burn": 60})
+    run("state", "state_sim3_sw_hn2", sw3, 2, {"burn": 100})
+    # proposal known-answer fixtures (a2-a4): accepted updategenealogy() calls
+    run("updates", "updates_sim5_hn2", s5, 2, {"burn": 50, "n": 250})
+    run("updates", "updates_sim3_hn2", s3, 2, {"burn": 50, "n": 250})
+    run("updates", "updates_sim5_3pop_hn2", p3, 2, {"burn": 50, "n": 250})
+    # numerics tables (a10, a13) and L mode (a14, a15)
+    run("kat", "kat_sim5_hn4", s5, 4, {"burn": 100})
+    run("lmode", "lmode_sim5_hn2", s5, 2, {"burn": 200, "rows": 600, "every": 3})
+    run("lmode", "lmode_sim5_expo_hn2", s5, 2, {"burn": 200, "rows": 300, "every": 3}, extra=["-j7"])
+
+
+if __name__ == "__main__":
+    main()
