@@ -1,0 +1,183 @@
+"""Pin the CPU oracle (oracle/ima_oracle.c) against fixtures produced by the unmodified reference.
+
+The reference ships no tests or golden vectors; every expected value below was
+written by oracle/_ref/ref_harness, i.e. by the reference's own functions (tests/golden/generate.py).
+Tolerances: integers bit-exact; doubles 1e-12 relative (same recurrences, same operation order, both
+sides FMA-free gcc builds) unless noted.
+"""
+import numpy as np
+import pytest
+
+from support import (FlatModel, FlatTree, OracleModel, _num, f64, fp, dp, i32, ip, load_golden, oracle, rel_close,
+                     weights_from_json)
+
+STATE_FIXTURES = ["state_sim5_hn4", "state_sim50_hn3", "state_sim300_hn1", "state_sim2_hn2", "state_sim3_hn3",
+                  "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim5_hky_hn2", "state_sim3_sw_hn2"]
+IS, HKY, SW = 0, 1, 2           # imamp.hpp mutation model enum order (INFINITESITES, HKY, STEPWISE)
+
+
+@pytest.mark.parametrize("name", STATE_FIXTURES)
+def test_treeweight_matches_reference(name):
+    d = load_golden(name)
+    om = OracleModel(FlatModel(d["model"]))
+    for ch in d["chains"]:
+        for li, g in enumerate(ch["G"]):
+            loc, tree, exp = d["loci"][li], FlatTree(g["tree"]), g["gweight"]
+            w = om.treeweight(ch["tvals"], loc, tree)
+            assert w["mignum"] == g["mignum"]
+            assert np.array_equal(w["cc"], exp["cc"]) and np.array_equal(w["mc"], exp["mc"])
+            assert rel_close(w["fc"], exp["fc"], 1e-13) and rel_close(w["fm"], exp["fm"], 1e-13)
+            assert rel_close(w["hcc"], exp["hcc"], 1e-13)
+            assert rel_close(w["length"], g["length"], 1e-13) and rel_close(w["tlength"], g["tlength"], 1e-13)
+
+
+@pytest.mark.parametrize("name", STATE_FIXTURES)
+def test_data_likelihood_matches_reference(name):
+    d = load_golden(name)
+    om = OracleModel(FlatModel(d["model"]))
+    for ch in d["chains"]:
+        for li, g in enumerate(ch["G"]):
+            loc, tree = d["loci"][li], FlatTree(g["tree"])
+            if loc["model"] == IS:
+                p = om.likelihood_is(loc, tree, g["length"], g["uvals"][0])
+            elif loc["model"] == HKY:
+                p = om.likelihood_hky(loc, tree, g["pi"], g["uvals"][0], g["kappa"])
+            elif loc["model"] == SW:
+                p, dl = om.likelihood_sw(tree, 0, g["uvals"][0])
+                assert rel_close(dl, tree.dlikeA[0], 1e-12, 1e-300)
+            else:
+                pytest.skip("joint model not in fixtures")
+            assert rel_close(p, g["pdg"], 1e-12), (li, p, g["pdg"])
+
+
+@pytest.mark.parametrize("name", STATE_FIXTURES)
+def test_integrated_prior_matches_reference(name):
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    om = OracleModel(fm)
+    for ch in d["chains"]:
+        # all-locus weights are the sum over loci (sum_treeinfo, init_p mcmcfile.cpp:188)
+        w = weights_from_json(ch["allgweight"])
+        acc = dict(cc=np.zeros(fm.ncc, np.int64), mc=np.zeros(fm.nmc, np.int64))
+        for g in ch["G"]:
+            acc["cc"] += i32(g["gweight"]["cc"])
+            acc["mc"] += i32(g["gweight"]["mc"])
+        assert np.array_equal(acc["cc"], w["cc"]) and np.array_equal(acc["mc"], w["mc"])
+        probg, qint, mint = om.init_integrate(w)
+        assert rel_close(qint, ch["qintegrate"], 1e-12)
+        assert rel_close(mint, ch["mintegrate"], 1e-12)
+        assert rel_close(probg, ch["probg"], 1e-12)
+
+
+def test_sumlogk_rule():
+    # calc_sumlogk is evaluated on the first genealogy the reference sees (chain 0's initial tree), which the
+    # fixtures do not hold; check the rule's defining property instead: a compatible genealogy gives a finite
+    # non-negative constant, and the likelihood shifts by exactly that constant.
+    d = load_golden("state_sim5_hn4")
+    om = OracleModel(FlatModel(d["model"]))
+    lib = oracle()
+    g, loc = d["chains"][0]["G"][0], d["loci"][0]
+    t = FlatTree(g["tree"])
+    s = lib.ora_calc_sumlogk(t.numgenes, loc["numsites"], ip(i32(loc["seq"])), ip(t.up0), ip(t.up1), ip(t.down))
+    assert s >= 0 and np.isfinite(s)
+    p0 = om.likelihood_is(loc, t, g["length"], g["uvals"][0], sumlogk=0.0)
+    p1 = om.likelihood_is(loc, t, g["length"], g["uvals"][0], sumlogk=s)
+    assert abs((p0 - p1) - s) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["updates_sim5_hn2", "updates_sim3_hn2", "updates_sim5_3pop_hn2"])
+def test_migration_proposal_probabilities_match_reference(name):
+    d = load_golden(name)
+    om = OracleModel(FlatModel(d["model"]))
+    nroot = 0
+    for u in d["updates"]:
+        before, after = FlatTree(u["before"]), FlatTree(u["after"])
+        edge = u["oldedgemig"]["edgeid"]
+        fwd, rev = om.migration_logprobs(d["tvals"][u["ci"]], before, after, edge)
+        assert rel_close(fwd, u["fwd"], 1e-12, 1e-13), (fwd, u["fwd"])
+        assert rel_close(rev, u["rev"], 1e-12, 1e-13), (rev, u["rev"])
+        nroot += u["newsismig"]["edgeid"] >= 0 or u["oldsismig"]["edgeid"] >= 0
+        # the accepted state's weights are reproduced from the "after" tree alone
+        w = om.treeweight(d["tvals"][u["ci"]], d["loci"][u["li"]], after)
+        assert np.array_equal(w["cc"], u["newgweight"]["cc"]) and np.array_equal(w["mc"], u["newgweight"]["mc"])
+        assert rel_close(w["fc"], u["newgweight"]["fc"], 1e-13)
+    assert nroot > 0, "fixture must exercise the two-edge (root) branch of getmprob"
+
+
+def test_numeric_tables_match_reference():
+    k = load_golden("kat_sim5_hn4")
+    lib = oracle()
+    for a, x, v in k["uppergamma"]:
+        assert rel_close(lib.ora_uppergamma(a, x), _num(v), 1e-13), ("uppergamma", a, x)
+    for a, x, v in k["lowergamma"]:
+        assert rel_close(lib.ora_lowergamma(a, x), _num(v), 1e-13), ("lowergamma", a, x)
+    for n, x, v in k["bessi"]:
+        assert rel_close(lib.ora_bessi(n, x), _num(v), 1e-13), ("bessi", n, x)
+    import ctypes as C
+    for x, m, z in k["eexp"]:
+        mm, zz = C.c_double(), C.c_int()
+        lib.ora_eexp(x, C.byref(mm), C.byref(zz))
+        assert zz.value == z and rel_close(mm.value, m, 1e-14), ("eexp", x)
+    for i, v in enumerate(k["logfact"]):
+        assert lib.ora_logfact(i * i) == v
+    for cc, fc, hcc, mx, v in k["integrate_coalescent_term"]:
+        assert rel_close(lib.ora_integrate_coalescent_term(cc, fc, hcc, mx, 0.0), _num(v), 1e-12), (cc, fc, mx)
+    for cm, fmv, mx, v, ve in k["integrate_migration_term"]:
+        assert rel_close(lib.ora_integrate_migration_term(cm, fmv, mx, 0.0), _num(v), 1e-12), (cm, fmv, mx)
+        assert rel_close(lib.ora_integrate_migration_term_expo_prior(cm, fmv, mx), _num(ve), 1e-12)
+    for mc, mt, v in k["calcmrate"]:
+        assert lib.ora_calcmrate(mc, mt) == v
+    for si, sj, bi, bj, v in k["swapweight_bw"]:
+        assert rel_close(lib.ora_swapweight(si, sj, bi, bj), _num(v), 1e-13)
+    # swapweight(ci, cj) on the loaded chains = exp((beta_i - beta_j)(S_j - S_i)) (swapchains.cpp:12-34)
+    S, b = k["chainsum"], k["betas"]
+    for ci, cj, v in k["swapweight"]:
+        assert rel_close(lib.ora_swapweight(S[ci], S[cj], b[ci], b[cj]), _num(v), 1e-10)
+
+
+def test_setheat_matches_reference_betas():
+    # the kat fixture ran -hfg -ha 0.96 -hb 0.9 with 4 chains; swaps only permute the betas
+    k = load_golden("kat_sim5_hn4")
+    out = np.zeros(4)
+    oracle().ora_setheat(1, 0.96, 0.9, 4, dp(out))
+    assert rel_close(sorted(out), sorted(k["betas"]), 1e-15)
+
+
+@pytest.mark.parametrize("name", ["lmode_sim5_hn2", "lmode_sim5_expo_hn2"])
+def test_lmode_matches_reference(name):
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    om = OracleModel(fm)
+    lib = oracle()
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    G, rl = rows.shape
+    assert rl == fm.rowlen
+    for p, x, mc0, mclog, mp_all, mp_mid in d["margincalc"]:
+        assert rel_close(lib.ora_margincalc(om.h, fp(rows), rl, G, x, 0.0, p, 0), _num(mc0), 1e-12, 1e-300)
+        assert rel_close(lib.ora_margincalc(om.h, fp(rows), rl, G, x, 0.25, p, 1), _num(mclog), 1e-12)
+        assert rel_close(lib.ora_marginp(om.h, fp(rows), rl, p, 0, G, x), _num(mp_all), 1e-12, 1e-300)
+        assert rel_close(lib.ora_marginp(om.h, fp(rows), rl, p, G // 3, 2 * G // 3, x), _num(mp_mid), 1e-12, 1e-300)
+    import ctypes as C
+    for j in d["jointp"]:
+        ess = C.c_double()
+        q = lib.ora_jointp(om.h, fp(rows), rl, G, dp(f64(j["x"])), 1, C.byref(ess))
+        assert rel_close(q, j["q"], 1e-12), (q, j["q"])
+        assert rel_close(ess.value, j["ess"], 1e-10)
+
+
+def test_ti_row_packer_matches_reference_rows():
+    # savegsampinf (ginfo.cpp:318-377): the fixture's state dump and the row layout must agree on a chain
+    d = load_golden("state_sim5_hn4")
+    fm = FlatModel(d["model"])
+    om = OracleModel(fm)
+    ch = d["chains"][0]
+    w = weights_from_json(ch["allgweight"])
+    row = np.zeros(fm.rowlen, np.float32)
+    oracle().ora_savegsampinf(om.h, ip(w["cc"]), dp(w["fc"]), dp(w["hcc"]), ip(w["mc"]), dp(w["fm"]),
+                              dp(f64(ch["qintegrate"])), dp(f64(ch["mintegrate"])), ch["pdg"], ch["probg"],
+                              dp(f64(ch["tvals"])), fp(row))
+    nq, nm = fm.nq, fm.nm
+    assert np.array_equal(row[:nq], np.float32([8, 5, 82]))          # cc0 cc1 cc2 of this fixture
+    assert row[3 * nq + 2 * nm + nq + nm] == np.float32(ch["pdg"])
+    assert row[-1] == np.float32(ch["tvals"][0])
+    assert row[nq:2 * nq].tolist() == [np.float32(v) for v in w["fc"]]
