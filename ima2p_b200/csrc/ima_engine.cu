@@ -1,0 +1,783 @@
+// Host side of the M-mode engine and its C ABI (include/ima2p_b200.h).
+//
+// All chains' genealogies live in HBM in two pair-major buffers (current / proposed).  A step is three
+// kernel launches (propose over pairs, accept over chains, swap) captured once into a CUDA graph and
+// replayed; the step counter that feeds the counter-based RNG lives on the device so the graph needs no
+// parameter updates.
+#include "ima_kernels.h"
+#include "../../include/ima2p_b200.h"
+#include <string>
+#include <vector>
+#include <new>
+
+namespace ima {
+
+#if !IMA_CUDA
+thread_local EmuCtx g_emu;
+#endif
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+
+struct HostLocus {
+  DevLocus d;
+  std::vector<uint32_t> sitemask;
+  std::vector<unsigned char> seq;
+  std::vector<int> mult;
+  bool set = false;
+};
+
+struct Engine {
+  int device = 0;
+  EngineDims d{};
+  DevModel model{};
+  bool model_set = false, finalized = false, graph_ready = false;
+  int graph_swaptries = -1;
+  unsigned long long seed = 0;
+  std::vector<HostLocus> loci;
+  // host staging (engine layout)
+  std::vector<short4_t> h_topo;
+  std::vector<double> h_time, h_mig_t, h_sd, h_uvals, h_kappa, h_pi, h_tvals, h_beta_table;
+  std::vector<ushort2_t> h_mseg;
+  std::vector<short> h_mig_p, h_A;
+  std::vector<int> h_si, h_rank_of_chain, h_chain_of_rank;
+  // device
+  EngineView v{};
+  SwapView sv{};
+  std::vector<void *> allocs;
+  double *d_logfact = nullptr;
+  int *d_err = nullptr;
+  DevLocus *d_loci = nullptr;
+  double *d_beta_table = nullptr;
+  unsigned long long *d_swap_counts = nullptr;
+#if IMA_CUDA
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t own_stream = nullptr;
+#endif
+  size_t pair_smem = 0, chain_smem = 0;
+
+  template <class T> T *alloc(size_t n) {
+    T *p = (T *)dev_alloc(n * sizeof(T));
+    if (p) allocs.push_back(p);
+    return p;
+  }
+  ~Engine() {
+#if IMA_CUDA
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (own_stream) cudaStreamDestroy(own_stream);
+#endif
+    for (void *p : allocs) dev_free(p);
+  }
+};
+
+static bool use_device(Engine *e) {
+#if IMA_CUDA
+  return IMA_CUDA_OK(cudaSetDevice(e->device));
+#else
+  (void)e;
+  return true;
+#endif
+}
+
+static stream_t pick_stream(Engine *e, void *s) {
+#if IMA_CUDA
+  return s ? (cudaStream_t)s : e->own_stream;
+#else
+  (void)e; (void)s;
+  return nullptr;
+#endif
+}
+
+static int check_device_error(Engine *e, stream_t s) {
+  int code = 0;
+  if (!d2h(&code, e->d_err, sizeof(int), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "device sync failed");
+  if (code != 0) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "device error word %d raised by a kernel (14 = LogDiff a<=b, 15 = incomplete gamma, 16 = logfact range)", code);
+    return fail(IMA2P_E_DEVICE, buf);
+  }
+  return IMA2P_OK;
+}
+
+static int launch_eval(Engine *e, stream_t s) {
+  const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  IMA_LAUNCH(k_eval_pairs, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v);
+  IMA_LAUNCH(k_eval_chains, gc, kWarpsPerBlock, e->chain_smem * kWarpsPerBlock, s, e->v);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (eval)");
+#endif
+  return IMA2P_OK;
+}
+
+static void launch_update(Engine *e, stream_t s) {
+  const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v);
+  IMA_LAUNCH(k_accept, gc, kWarpsPerBlock, e->chain_smem * kWarpsPerBlock, s, e->v);
+}
+
+static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries) {
+  SwapView sv = e->sv;
+  sv.S_global = S_global;
+  sv.swaptries = swaptries;
+  sv.advance_step = 1;
+  IMA_LAUNCH(k_swap, 1, 1, 0, s, e->v, sv);
+}
+
+}  // namespace ima
+
+using namespace ima;
+
+struct ima2p_engine { Engine eng; };
+
+extern "C" {
+
+const char *ima2p_version(void) { return "ima2p_b200 0.1 (sm_100a)"; }
+const char *ima2p_last_error(void) { return g_last_error.c_str(); }
+void ima2p_internal_set_error(const char *msg) { g_last_error = msg ? msg : ""; }
+
+int ima2p_engine_create(ima2p_engine **out, int device, int nchains_local, int nchains_global, int chain0, int nloci,
+                        int mig_capacity, uint64_t seed) {
+  if (!out || nchains_local < 1 || nloci < 1 || nchains_global < nchains_local || chain0 < 0 ||
+      chain0 + nchains_local > nchains_global || mig_capacity < 8 || mig_capacity > 8000)
+    return fail(IMA2P_E_ARG, "ima2p_engine_create: bad argument");
+#if IMA_CUDA
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(IMA2P_E_CUDA, "no CUDA device: ima2p_b200 has no CPU path");
+  if (device < 0 || device >= ndev) return fail(IMA2P_E_ARG, "device index out of range");
+#endif
+  ima2p_engine *h = new (std::nothrow) ima2p_engine();
+  if (!h) return fail(IMA2P_E_ARG, "out of host memory");
+  Engine &e = h->eng;
+  e.device = device;
+  e.d.nchains = nchains_local; e.d.nchains_global = nchains_global; e.d.chain0 = chain0;
+  e.d.nloci = nloci; e.d.P = nchains_local * nloci; e.d.CAP = mig_capacity;
+  e.seed = seed;
+  e.loci.resize(nloci);
+  if (!use_device(&e)) { delete h; return fail(IMA2P_E_CUDA, "cudaSetDevice failed"); }
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaStreamCreateWithFlags(&e.own_stream, cudaStreamNonBlocking))) { delete h; return fail(IMA2P_E_CUDA, "stream create failed"); }
+#endif
+  *out = h;
+  return IMA2P_OK;
+}
+
+void ima2p_engine_destroy(ima2p_engine *h) {
+  if (!h) return;
+  use_device(&h->eng);
+  delete h;
+}
+
+int ima2p_engine_set_model(ima2p_engine *h, int npops, int nsplit, const int *plist, const int *addpop, const int *droppops,
+                           const int *pt_e, const int *pt_down, int rootpop, int nq, const int *q_off, const int *q_p,
+                           const int *q_r, const double *q_max, const double *q_min, int nm, const int *m_off,
+                           const int *m_p, const int *m_r, const int *m_c, const double *m_max, const double *m_min,
+                           const double *m_mean, int nomig_n, const int *nomig_p, const int *nomig_r, const int *nomig_c,
+                           int nomigration, int expoprior, int thermo, double gbeta) {
+  if (!h) return fail(IMA2P_E_ARG, "null engine");
+  Engine &e = h->eng;
+  if (e.finalized) return fail(IMA2P_E_ARG, "set_model after finalize");
+  if (npops < 1 || npops > kMaxPops || nsplit < 0 || nsplit > npops - 1 + (npops == 1) || nq < 1 || nq > kMaxParams || nm < 0 ||
+      nm > kMaxParams || nomig_n < 0 || nomig_n > kMaxParams)
+    return fail(IMA2P_E_ARG, "set_model: sizes out of range");
+  DevModel &M = e.model;
+  memset(&M, 0, sizeof M);
+  M.npops = npops; M.nsplit = nsplit; M.ntreepops = 2 * npops - 1; M.rootpop = rootpop;
+  M.nq = nq; M.nm = nm; M.nomigration = nomigration; M.expoprior = expoprior; M.thermo = thermo; M.gbeta = gbeta;
+  for (int k = 0; k < npops; k++) for (int i = 0; i < npops; i++) M.plist[k][i] = (signed char)plist[k * npops + i];
+  for (int k = 0; k <= nsplit; k++) {
+    M.addpop[k] = (signed char)addpop[k];
+    M.droppops[k][0] = (signed char)droppops[2 * k]; M.droppops[k][1] = (signed char)droppops[2 * k + 1];
+  }
+  for (int i = 0; i < M.ntreepops; i++) { M.pt_e[i] = (signed char)pt_e[i]; M.pt_down[i] = (signed char)pt_down[i]; }
+  M.cc_off[0] = M.mc_off[0] = 0;
+  for (int k = 0; k <= nsplit; k++) {
+    M.cc_off[k + 1] = (short)(M.cc_off[k] + (npops - k));
+    M.mc_off[k + 1] = (short)(M.mc_off[k] + (npops - k) * (npops - k));
+  }
+  M.ncc = M.cc_off[nsplit + 1];
+  M.nmc = M.mc_off[nsplit];
+  for (int i = 0; i < nq; i++) {
+    const int n = q_off[i + 1] - q_off[i];
+    if (n < 0 || n > kMaxWp) return fail(IMA2P_E_ARG, "set_model: too many weight positions for a parameter");
+    M.q_n[i] = (signed char)n;
+    for (int j = 0; j < n; j++) M.q_idx[i][j] = (short)(M.cc_off[q_p[q_off[i] + j]] + q_r[q_off[i] + j]);
+    M.q_max[i] = q_max[i]; M.q_min[i] = q_min[i];
+  }
+  for (int i = 0; i < nm; i++) {
+    const int n = m_off[i + 1] - m_off[i];
+    if (n < 0 || n > kMaxWp) return fail(IMA2P_E_ARG, "set_model: too many weight positions for a parameter");
+    M.m_n[i] = (signed char)n;
+    for (int j = 0; j < n; j++) {
+      const int k = m_p[m_off[i] + j];
+      M.m_idx[i][j] = (short)(M.mc_off[k] + m_r[m_off[i] + j] * (npops - k) + m_c[m_off[i] + j]);
+    }
+    M.m_max[i] = m_max[i]; M.m_min[i] = m_min[i]; M.m_mean[i] = m_mean ? m_mean[i] : 0.0;
+  }
+  M.nomig_n = nomig_n;
+  for (int i = 0; i < nomig_n; i++) M.nomig_idx[i] = (short)(M.mc_off[nomig_p[i]] + nomig_r[i] * (npops - nomig_p[i]) + nomig_c[i]);
+  e.d.NI = M.ncc + M.nmc;
+  e.d.ND = 2 * M.ncc + M.nmc;
+  e.model_set = true;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_set_locus(ima2p_engine *h, int li, int model, int numgenes, int numsites, int totsites, double hval,
+                           const int *samppop, const int *seq, const int *mult, int nlinked, const int *minA,
+                           const int *maxA, double sumlogk) {
+  if (!h) return fail(IMA2P_E_ARG, "null engine");
+  Engine &e = h->eng;
+  if (!e.model_set || e.finalized) return fail(IMA2P_E_ARG, "set_locus: call after set_model and before finalize");
+  if (li < 0 || li >= e.d.nloci || numgenes < 2 || numgenes > 16000 || numsites < 0 || nlinked < 1 || nlinked > kMaxLinked)
+    return fail(IMA2P_E_ARG, "set_locus: bad argument");
+  if (model != kInfiniteSites && model != kHKY && model != kStepwise) return fail(IMA2P_E_UNSUPPORTED, "set_locus: mutation model not supported");
+  HostLocus &L = e.loci[li];
+  memset(&L.d, 0, sizeof L.d);
+  L.d.model = model; L.d.ng = numgenes; L.d.nl = 2 * numgenes - 1; L.d.nsites = numsites; L.d.totsites = totsites;
+  L.d.nwords = (numgenes + 31) / 32; L.d.nlinked = nlinked; L.d.hval = hval; L.d.sumlogk = sumlogk;
+  int tot = 0;
+  for (int i = 0; i < e.model.npops; i++) { L.d.samppop[i] = samppop[i]; tot += samppop[i]; }
+  if (tot != numgenes) return fail(IMA2P_E_ARG, "set_locus: samppop does not sum to numgenes");
+  for (int i = 0; i < nlinked; i++) { L.d.minA[i] = minA ? minA[i] : 0; L.d.maxA[i] = maxA ? maxA[i] : 0; }
+  L.sitemask.clear(); L.seq.clear(); L.mult.clear();
+  if (model == kInfiniteSites) {
+    if (numsites > 0 && !seq) return fail(IMA2P_E_ARG, "set_locus: seq required");
+    L.sitemask.assign((size_t)numsites * L.d.nwords, 0u);
+    for (int s = 0; s < numsites; s++) {
+      int carriers = 0;
+      for (int j = 0; j < numgenes; j++) {
+        const int b = seq[(size_t)j * numsites + s];
+        if (b != 0 && b != 1) return fail(IMA2P_E_ARG, "set_locus: infinite-sites data must be 0/1");
+        if (b) { L.sitemask[(size_t)s * L.d.nwords + (j >> 5)] |= 1u << (j & 31); carriers++; }
+      }
+      // a monomorphic column is IMERR_INFINITESITESFAIL in the reference (calc_prob_data.cpp:823-826)
+      if (carriers == 0 || carriers == numgenes) return fail(IMA2P_E_ARG, "set_locus: non-segregating infinite-sites column");
+    }
+  } else if (model == kHKY) {
+    if (!seq || !mult) return fail(IMA2P_E_ARG, "set_locus: seq and mult required for HKY");
+    L.seq.resize((size_t)numgenes * numsites);
+    for (size_t i = 0; i < L.seq.size(); i++) L.seq[i] = (unsigned char)seq[i];
+    L.mult.assign(mult, mult + numsites);
+  }
+  L.set = true;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_finalize(ima2p_engine *h) {
+  if (!h) return fail(IMA2P_E_ARG, "null engine");
+  Engine &e = h->eng;
+  if (!e.model_set || e.finalized) return fail(IMA2P_E_ARG, "finalize: model not set or already finalized");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  EngineDims &d = e.d;
+  d.NL = 0; d.W = 1; d.S = 0; d.any_sw = 0; d.any_hky = 0;
+  int maxng = 0;
+  std::vector<uint32_t> sm; std::vector<unsigned char> sq; std::vector<int> mu; std::vector<DevLocus> dl(d.nloci);
+  for (int li = 0; li < d.nloci; li++) {
+    HostLocus &L = e.loci[li];
+    if (!L.set) return fail(IMA2P_E_ARG, "finalize: a locus was not set");
+    if (L.d.nl > d.NL) d.NL = L.d.nl;
+    if (L.d.nwords > d.W) d.W = L.d.nwords;
+    if (L.d.nsites > d.S) d.S = L.d.nsites;
+    if (L.d.ng > maxng) maxng = L.d.ng;
+    if (L.d.model == kStepwise) d.any_sw = 1;
+    if (L.d.model == kHKY) d.any_hky = 1;
+    L.d.sitemask_off = (long long)sm.size(); sm.insert(sm.end(), L.sitemask.begin(), L.sitemask.end());
+    L.d.seq_off = (long long)sq.size(); sq.insert(sq.end(), L.seq.begin(), L.seq.end());
+    L.d.mult_off = (long long)mu.size(); mu.insert(mu.end(), L.mult.begin(), L.mult.end());
+    dl[li] = L.d;
+  }
+  if (d.NL > 32000) return fail(IMA2P_E_ARG, "finalize: sample too large for 16-bit edge indices");
+  int ev = (maxng - 1) + d.CAP + e.model.nsplit;
+  d.EVP = 1; while (d.EVP < ev) d.EVP <<= 1;
+  e.pair_smem = pair_smem_bytes(d);
+  e.chain_smem = chain_smem_bytes(d);
+#if IMA_CUDA
+  if (e.pair_smem * kWarpsPerBlock > 227 * 1024) return fail(IMA2P_E_ARG, "finalize: pair does not fit in shared memory; lower mig_capacity");
+  if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))))
+    return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
+  if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");
+#else
+  c_model = e.model;
+#endif
+  const size_t P = d.P, NL = d.NL, CAP = d.CAP, C = d.nchains, G = d.nchains_global;
+  // logfact table: same running sum as setlogfact (utilities.cpp:1405-1414)
+  const int nlf = 100 * 5000 + 1;
+  std::vector<double> lf(nlf);
+  lf[0] = 0;
+  for (int i = 1; i < nlf; i++) lf[i] = lf[i - 1] + log((double)i);
+  e.d_logfact = e.alloc<double>(nlf);
+  e.d_err = e.alloc<int>(1);
+  e.d_loci = e.alloc<DevLocus>(d.nloci);
+  uint32_t *d_sm = e.alloc<uint32_t>(sm.size() + 1);
+  unsigned char *d_sq = e.alloc<unsigned char>(sq.size() + 1);
+  int *d_mu = e.alloc<int>(mu.size() + 1);
+  EngineView &v = e.v;
+  v.d = d;
+  for (int b = 0; b < 2; b++) {
+    PairBuf &B = v.buf[b];
+    B.topo = e.alloc<short4_t>(P * NL); B.time = e.alloc<double>(P * NL); B.mseg = e.alloc<ushort2_t>(P * NL);
+    B.mig_t = e.alloc<double>(P * CAP); B.mig_p = e.alloc<short>(P * CAP);
+    B.sd = e.alloc<double>(P * 4); B.si = e.alloc<int>(P * 2);
+    B.gwi = e.alloc<int>(P * d.NI); B.gwd = e.alloc<double>(P * d.ND);
+    if (d.any_sw) { B.A = e.alloc<short>(P * kMaxLinked * NL); B.dlikeA = e.alloc<double>(P * kMaxLinked * NL); B.pdg_a = e.alloc<double>(P * kMaxLinked); }
+    else { B.A = nullptr; B.dlikeA = nullptr; B.pdg_a = nullptr; }
+  }
+  v.cur = e.alloc<unsigned char>(P);
+  v.uvals = e.alloc<double>(P * kMaxLinked); v.kappa = e.alloc<double>(P); v.pi = e.alloc<double>(P * 4);
+  v.tvals = e.alloc<double>(C * kMaxPeriods); v.beta = e.alloc<double>(C);
+  v.all_i = e.alloc<int>(C * d.NI); v.all_d = e.alloc<double>(C * d.ND);
+  v.qint = e.alloc<double>(C * kMaxParams); v.mint = e.alloc<double>(C * kMaxParams);
+  v.probg = e.alloc<double>(C); v.pdgsum = e.alloc<double>(C); v.swapsum = e.alloc<double>(C);
+  v.prop_extra = e.alloc<double>(P); v.prop_flags = e.alloc<uint32_t>(P); v.prop_dbg = e.alloc<double>(P * 4);
+  v.acc = e.alloc<unsigned int>(P * 3);
+  v.nsteps = e.alloc<unsigned long long>(1); v.overflow = e.alloc<unsigned long long>(1);
+  v.seed = e.seed;
+  v.loci = e.d_loci; v.sitemask = d_sm; v.seq = d_sq; v.mult = d_mu;
+  v.mc.logfact = e.d_logfact; v.mc.logfact_n = nlf; v.mc.err = e.d_err;
+  e.sv.rank_of_chain = e.alloc<int>(G); e.sv.chain_of_rank = e.alloc<int>(G);
+  e.d_beta_table = e.alloc<double>(G); e.sv.beta_table = e.d_beta_table;
+  e.d_swap_counts = e.alloc<unsigned long long>(2); e.sv.swap_counts = e.d_swap_counts;
+  if (!v.acc || !v.buf[1].gwd || !e.d_swap_counts || !v.overflow) return fail(IMA2P_E_CUDA, "device allocation failed");
+  stream_t s = pick_stream(&e, nullptr);
+  bool ok = h2d(e.d_logfact, lf.data(), nlf * sizeof(double), s) && h2d(e.d_loci, dl.data(), dl.size() * sizeof(DevLocus), s);
+  if (!sm.empty()) ok = ok && h2d(d_sm, sm.data(), sm.size() * sizeof(uint32_t), s);
+  if (!sq.empty()) ok = ok && h2d(d_sq, sq.data(), sq.size(), s);
+  if (!mu.empty()) ok = ok && h2d(d_mu, mu.data(), mu.size() * sizeof(int), s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "table upload failed");
+  // host staging
+  e.h_topo.assign(P * NL, short4_t{-1, -1, -1, -1});
+  e.h_time.assign(P * NL, 0.0); e.h_mseg.assign(P * NL, ushort2_t{0, 0});
+  e.h_mig_t.assign(P * CAP, 0.0); e.h_mig_p.assign(P * CAP, 0);
+  e.h_sd.assign(P * 4, 0.0); e.h_si.assign(P * 2, 0);
+  e.h_uvals.assign(P * kMaxLinked, 1.0); e.h_kappa.assign(P, 2.0); e.h_pi.assign(P * 4, 0.25);
+  e.h_tvals.assign(C * kMaxPeriods, kTimeMax);
+  if (d.any_sw) e.h_A.assign(P * kMaxLinked * NL, 0);
+  e.h_beta_table.assign(G, 1.0);
+  e.h_rank_of_chain.resize(G); e.h_chain_of_rank.resize(G);
+  for (size_t i = 0; i < G; i++) e.h_rank_of_chain[i] = e.h_chain_of_rank[i] = (int)i;
+  e.finalized = true;
+  return ima2p_engine_set_betas(h, e.h_beta_table.data());
+}
+
+int ima2p_engine_set_betas(ima2p_engine *h, const double *betas_global) {
+  if (!h || !h->eng.finalized || !betas_global) return fail(IMA2P_E_ARG, "set_betas: bad argument / not finalized");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  const int G = e.d.nchains_global;
+  // beta_table[r] = r-th largest beta; chain i starts at the rank of its own beta (setheat: slot i <-> index i)
+  std::vector<int> order(G);
+  for (int i = 0; i < G; i++) order[i] = i;
+  for (int i = 1; i < G; i++) { int k = order[i], j = i; while (j > 0 && betas_global[order[j - 1]] < betas_global[k]) { order[j] = order[j - 1]; j--; } order[j] = k; }
+  for (int r = 0; r < G; r++) { e.h_beta_table[r] = betas_global[order[r]]; e.h_chain_of_rank[r] = order[r]; e.h_rank_of_chain[order[r]] = r; }
+  std::vector<double> local(e.d.nchains);
+  for (int c = 0; c < e.d.nchains; c++) local[c] = betas_global[e.d.chain0 + c];
+  stream_t s = pick_stream(&e, nullptr);
+  bool ok = h2d(e.d_beta_table, e.h_beta_table.data(), G * sizeof(double), s) &&
+            h2d(e.sv.rank_of_chain, e.h_rank_of_chain.data(), G * sizeof(int), s) &&
+            h2d(e.sv.chain_of_rank, e.h_chain_of_rank.data(), G * sizeof(int), s) &&
+            h2d(e.v.beta, local.data(), local.size() * sizeof(double), s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "beta upload failed");
+  return IMA2P_OK;
+}
+
+int ima2p_engine_set_heating(ima2p_engine *h, int heatmode, double hval1, double hval2) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "set_heating: not finalized");
+  const int G = h->eng.d.nchains_global;
+  std::vector<double> b(G, 1.0);
+  // beta[] of setheat (swapchains.cpp:119-163), N = chains over all ranks, one table for everything
+  // (the reference's allbetas[] inconsistencies are not copied)
+  if (G > 1)
+    for (int ci = 0; ci < G; ci++) {
+      if (heatmode == 0) { const double h1 = hval1 < 0.05 ? 0.05 : hval1; b[ci] = 1.0 / (1.0 + h1 * ci); }
+      else if (heatmode == 1) b[ci] = 1 - (1 - hval2) * (ci)*pow(hval1, (double)(G - 1 - (ci))) / (double)(G - 1);
+      else if (heatmode == 2) b[ci] = 1.0 - ci * (1.0 / (G - 1));
+      else return fail(IMA2P_E_ARG, "set_heating: heatmode must be 0, 1 or 2");
+      const bool bad = h->eng.model.thermo ? (b[ci] < 0.0 || b[ci] > 1.0) : (b[ci] <= 0.0 || b[ci] > 1.0);
+      if (bad) return fail(IMA2P_E_ARG, "set_heating: heating terms give a beta out of range (IMERR_COMMANDLINEHEATINGTERMS)");
+    }
+  return ima2p_engine_set_betas(h, b.data());
+}
+
+int ima2p_engine_set_chain(ima2p_engine *h, int ci, const double *tvals) {
+  if (!h || !h->eng.finalized || ci < 0 || ci >= h->eng.d.nchains || !tvals) return fail(IMA2P_E_ARG, "set_chain: bad argument");
+  Engine &e = h->eng;
+  for (int k = 0; k < kMaxPeriods; k++) e.h_tvals[(size_t)ci * kMaxPeriods + k] = k < e.model.nsplit ? tvals[k] : kTimeMax;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_set_genealogy(ima2p_engine *h, int ci, int li, const int *up0, const int *up1, const int *down, const int *pop,
+                               const double *time, const int *mig_off, const double *mig_t, const int *mig_p, int root,
+                               double roottime, const double *uvals, double kappa, const double *pi, const int *A) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "set_genealogy: not finalized");
+  Engine &e = h->eng;
+  if (ci < 0 || ci >= e.d.nchains || li < 0 || li >= e.d.nloci) return fail(IMA2P_E_ARG, "set_genealogy: index out of range");
+  const DevLocus &L = e.loci[li].d;
+  const size_t p = (size_t)ci * e.d.nloci + li, NL = e.d.NL, CAP = e.d.CAP;
+  const int total = mig_off[L.nl] - mig_off[0];
+  if (total > e.d.CAP) return fail(IMA2P_E_CAPACITY, "set_genealogy: more migration events than mig_capacity");
+  if (root < 0 || root >= L.nl || down[root] != -1) return fail(IMA2P_E_ARG, "set_genealogy: bad root");
+  for (int i = 0; i < L.nl; i++) {
+    e.h_topo[p * NL + i] = short4_t{(short)up0[i], (short)up1[i], (short)down[i], (short)pop[i]};
+    e.h_time[p * NL + i] = time[i];
+    e.h_mseg[p * NL + i] = ushort2_t{(unsigned short)(mig_off[i] - mig_off[0]), (unsigned short)(mig_off[i + 1] - mig_off[i])};
+  }
+  for (int j = 0; j < total; j++) { e.h_mig_t[p * CAP + j] = mig_t[mig_off[0] + j]; e.h_mig_p[p * CAP + j] = (short)mig_p[mig_off[0] + j]; }
+  e.h_si[p * 2] = root; e.h_si[p * 2 + 1] = total;
+  e.h_sd[p * 4] = roottime;
+  for (int a = 0; a < L.nlinked; a++) e.h_uvals[p * kMaxLinked + a] = uvals ? uvals[a] : 1.0;
+  e.h_kappa[p] = kappa;
+  if (pi) for (int k = 0; k < 4; k++) e.h_pi[p * 4 + k] = pi[k];
+  if (A && e.d.any_sw) for (int a = 0; a < L.nlinked; a++) for (int i = 0; i < L.nl; i++) e.h_A[(p * kMaxLinked + a) * NL + i] = (short)A[(size_t)a * L.nl + i];
+  return IMA2P_OK;
+}
+
+static int upload_all(Engine &e, stream_t s) {
+  const size_t P = e.d.P, NL = e.d.NL, CAP = e.d.CAP;
+  PairBuf &B = e.v.buf[0];
+  bool ok = h2d(B.topo, e.h_topo.data(), P * NL * sizeof(short4_t), s) && h2d(B.time, e.h_time.data(), P * NL * sizeof(double), s) &&
+            h2d(B.mseg, e.h_mseg.data(), P * NL * sizeof(ushort2_t), s) && h2d(B.mig_t, e.h_mig_t.data(), P * CAP * sizeof(double), s) &&
+            h2d(B.mig_p, e.h_mig_p.data(), P * CAP * sizeof(short), s) && h2d(B.sd, e.h_sd.data(), P * 4 * sizeof(double), s) &&
+            h2d(B.si, e.h_si.data(), P * 2 * sizeof(int), s) && h2d(e.v.uvals, e.h_uvals.data(), P * kMaxLinked * sizeof(double), s) &&
+            h2d(e.v.kappa, e.h_kappa.data(), P * sizeof(double), s) && h2d(e.v.pi, e.h_pi.data(), P * 4 * sizeof(double), s) &&
+            h2d(e.v.tvals, e.h_tvals.data(), e.h_tvals.size() * sizeof(double), s);
+  if (e.d.any_sw) ok = ok && h2d(B.A, e.h_A.data(), e.h_A.size() * sizeof(short), s) && h2d(e.v.buf[1].A, e.h_A.data(), e.h_A.size() * sizeof(short), s);
+#if IMA_CUDA
+  ok = ok && IMA_CUDA_OK(cudaMemsetAsync(e.v.cur, 0, P, s));
+#else
+  memset(e.v.cur, 0, P);
+#endif
+  return ok ? IMA2P_OK : fail(IMA2P_E_CUDA, "state upload failed");
+}
+
+int ima2p_engine_upload(ima2p_engine *h) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "upload: not finalized");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  int rc = upload_all(e, s);
+  if (rc) return rc;
+  return dev_sync(s) ? IMA2P_OK : fail(IMA2P_E_CUDA, "sync failed");
+}
+
+int ima2p_engine_eval(ima2p_engine *h) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "eval: not finalized");
+  Engine &e = h->eng;
+  if (e.d.any_hky) return fail(IMA2P_E_UNSUPPORTED, "eval: HKY loci are not on the device path yet");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  int rc = launch_eval(&e, s);
+  if (rc) return rc;
+  rc = check_device_error(&e, s);
+  if (rc) return rc;
+  // a state the kernels could not evaluate is an input error, not a soft failure
+  std::vector<uint32_t> fl(e.d.P);
+  if (!d2h(fl.data(), e.v.prop_flags, fl.size() * sizeof(uint32_t), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "flag download failed");
+  for (size_t p = 0; p < fl.size(); p++) {
+    if (fl[p] & kFlagBadTree) return fail(IMA2P_E_ARG, "eval: inconsistent genealogy (lineage counts do not close)");
+    if (fl[p] & kFlagOverflow) return fail(IMA2P_E_CAPACITY, "eval: event table capacity exceeded");
+  }
+  return IMA2P_OK;
+}
+
+int ima2p_engine_dims(ima2p_engine *h, int *out) {
+  if (!h || !h->eng.model_set || !out) return fail(IMA2P_E_ARG, "dims: bad argument");
+  Engine &e = h->eng;
+  out[0] = e.d.NI; out[1] = e.d.ND; out[2] = e.d.NL; out[3] = e.d.CAP;
+  out[4] = 4 * e.model.nq + (e.model.nomigration ? 0 : 3 * e.model.nm) + e.model.nsplit + 2;   // calc_gsampinf_length ginfo.cpp:306-316
+  return IMA2P_OK;
+}
+
+int ima2p_engine_get_pair(ima2p_engine *h, int ci, int li, int *wi, double *wd, double *out_d, int *out_i) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "get_pair: not finalized");
+  Engine &e = h->eng;
+  if (ci < 0 || ci >= e.d.nchains || li < 0 || li >= e.d.nloci) return fail(IMA2P_E_ARG, "get_pair: index out of range");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const size_t p = (size_t)ci * e.d.nloci + li;
+  unsigned char cur = 0;
+  if (!d2h(&cur, e.v.cur + p, 1, s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  const PairBuf &B = e.v.buf[cur];
+  double sd[4]; int si[2];
+  bool ok = d2h(sd, B.sd + p * 4, sizeof sd, s) && d2h(si, B.si + p * 2, sizeof si, s);
+  if (wi) ok = ok && d2h(wi, B.gwi + p * e.d.NI, e.d.NI * sizeof(int), s);
+  if (wd) ok = ok && d2h(wd, B.gwd + p * e.d.ND, e.d.ND * sizeof(double), s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  if (out_d) { out_d[0] = sd[3]; out_d[1] = sd[1]; out_d[2] = sd[2]; out_d[3] = sd[0]; }
+  if (out_i) { out_i[0] = si[1]; out_i[1] = si[0]; }
+  return IMA2P_OK;
+}
+
+int ima2p_engine_get_chain(ima2p_engine *h, int ci, int *all_wi, double *all_wd, double *qintegrate, double *mintegrate, double *out_d) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "get_chain: not finalized");
+  Engine &e = h->eng;
+  if (ci < 0 || ci >= e.d.nchains) return fail(IMA2P_E_ARG, "get_chain: index out of range");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  bool ok = true;
+  if (all_wi) ok = ok && d2h(all_wi, e.v.all_i + (size_t)ci * e.d.NI, e.d.NI * sizeof(int), s);
+  if (all_wd) ok = ok && d2h(all_wd, e.v.all_d + (size_t)ci * e.d.ND, e.d.ND * sizeof(double), s);
+  if (qintegrate) ok = ok && d2h(qintegrate, e.v.qint + (size_t)ci * kMaxParams, e.model.nq * sizeof(double), s);
+  if (mintegrate && e.model.nm) ok = ok && d2h(mintegrate, e.v.mint + (size_t)ci * kMaxParams, e.model.nm * sizeof(double), s);
+  if (out_d) ok = ok && d2h(out_d, e.v.probg + ci, sizeof(double), s) && d2h(out_d + 1, e.v.pdgsum + ci, sizeof(double), s) && d2h(out_d + 2, e.v.beta + ci, sizeof(double), s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  return IMA2P_OK;
+}
+
+int ima2p_engine_get_genealogy(ima2p_engine *h, int ci, int li, int which, int *up0, int *up1, int *down, int *pop, double *time, int *mig_off,
+                               double *mig_t, int *mig_p, int mig_room, int *root, double *roottime) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "get_genealogy: not finalized");
+  Engine &e = h->eng;
+  if (ci < 0 || ci >= e.d.nchains || li < 0 || li >= e.d.nloci) return fail(IMA2P_E_ARG, "get_genealogy: index out of range");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const DevLocus &L = e.loci[li].d;
+  const size_t p = (size_t)ci * e.d.nloci + li, NL = e.d.NL, CAP = e.d.CAP;
+  unsigned char cur = 0;
+  if (!d2h(&cur, e.v.cur + p, 1, s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  const PairBuf &B = e.v.buf[which ? (cur ^ 1) : cur];
+  std::vector<short4_t> topo(L.nl); std::vector<ushort2_t> ms(L.nl); std::vector<double> mt(CAP); std::vector<short> mp(CAP);
+  int si[2]; double sd[4];
+  bool ok = d2h(topo.data(), B.topo + p * NL, L.nl * sizeof(short4_t), s) && d2h(time, B.time + p * NL, L.nl * sizeof(double), s) &&
+            d2h(ms.data(), B.mseg + p * NL, L.nl * sizeof(ushort2_t), s) && d2h(mt.data(), B.mig_t + p * CAP, CAP * sizeof(double), s) &&
+            d2h(mp.data(), B.mig_p + p * CAP, CAP * sizeof(short), s) && d2h(si, B.si + p * 2, sizeof si, s) && d2h(sd, B.sd + p * 4, sizeof sd, s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  if (si[1] > mig_room) return fail(IMA2P_E_ARG, "get_genealogy: mig_room too small");
+  int o = 0;
+  for (int i = 0; i < L.nl; i++) {
+    up0[i] = topo[i].x; up1[i] = topo[i].y; down[i] = topo[i].z; pop[i] = topo[i].w;
+    mig_off[i] = o;
+    for (int j = 0; j < ms[i].y; j++) { mig_t[o] = mt[ms[i].x + j]; mig_p[o] = mp[ms[i].x + j]; o++; }
+  }
+  mig_off[L.nl] = o;
+  *root = si[0]; *roottime = sd[0];
+  return IMA2P_OK;
+}
+
+static int ensure_steppable(Engine &e) {
+  if (!e.finalized) return fail(IMA2P_E_ARG, "engine not finalized");
+  if (e.d.any_hky || e.d.any_sw) return fail(IMA2P_E_UNSUPPORTED, "M-mode stepping: only infinite-sites loci are on the device path in this build");
+  if (e.model.nomigration) return fail(IMA2P_E_UNSUPPORTED, "M-mode stepping: the no-migration slider is not on the device path in this build");
+  return IMA2P_OK;
+}
+
+int ima2p_engine_run(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stream) {
+  if (!h || nsteps < 0 || swaptries < 0) return fail(IMA2P_E_ARG, "run: bad argument");
+  Engine &e = h->eng;
+  int rc = ensure_steppable(e);
+  if (rc) return rc;
+  if (e.d.nchains != e.d.nchains_global) return fail(IMA2P_E_ARG, "run: engine holds a shard; use update_genealogies + swap_replay");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+#if IMA_CUDA
+  if (!e.graph_ready || e.graph_swaptries != swaptries) {
+    if (e.graph_exec) { cudaGraphExecDestroy(e.graph_exec); e.graph_exec = nullptr; }
+    if (e.graph) { cudaGraphDestroy(e.graph); e.graph = nullptr; }
+    if (!IMA_CUDA_OK(cudaStreamBeginCapture(e.own_stream, cudaStreamCaptureModeThreadLocal))) return fail(IMA2P_E_CUDA, "graph capture failed");
+    launch_update(&e, e.own_stream);
+    launch_swap(&e, e.own_stream, e.v.swapsum, swaptries);
+    if (!IMA_CUDA_OK(cudaStreamEndCapture(e.own_stream, &e.graph)) || !IMA_CUDA_OK(cudaGraphInstantiate(&e.graph_exec, e.graph, 0)))
+      return fail(IMA2P_E_CUDA, "graph instantiate failed");
+    e.graph_ready = true; e.graph_swaptries = swaptries;
+  }
+  for (int i = 0; i < nsteps; i++)
+    if (!IMA_CUDA_OK(cudaGraphLaunch(e.graph_exec, s))) return fail(IMA2P_E_CUDA, "graph launch failed");
+#else
+  for (int i = 0; i < nsteps; i++) { launch_update(&e, s); launch_swap(&e, s, e.v.swapsum, swaptries); }
+#endif
+  return IMA2P_OK;
+}
+
+int ima2p_engine_update_genealogies(ima2p_engine *h, double *dev_S_local, void *cuda_stream) {
+  if (!h) return fail(IMA2P_E_ARG, "null engine");
+  Engine &e = h->eng;
+  int rc = ensure_steppable(e);
+  if (rc) return rc;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  launch_update(&e, s);
+  if (dev_S_local) IMA_LAUNCH(k_copy_swapsum, (e.d.nchains + kWarpsPerBlock * IMA_WARP - 1) / (kWarpsPerBlock * IMA_WARP), kWarpsPerBlock, 0, s, e.v, dev_S_local);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (update)");
+#endif
+  return IMA2P_OK;
+}
+
+int ima2p_engine_swap_replay(ima2p_engine *h, const double *dev_S_global, int swaptries, void *cuda_stream) {
+  if (!h || !h->eng.finalized || !dev_S_global || swaptries < 0) return fail(IMA2P_E_ARG, "swap_replay: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  launch_swap(&e, s, dev_S_global, swaptries);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (swap)");
+#endif
+  return IMA2P_OK;
+}
+
+int ima2p_engine_get_proposal(ima2p_engine *h, int ci, int li, double *out4, unsigned int *flags, int *is_current) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "get_proposal: not finalized");
+  Engine &e = h->eng;
+  if (ci < 0 || ci >= e.d.nchains || li < 0 || li >= e.d.nloci) return fail(IMA2P_E_ARG, "get_proposal: index out of range");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const size_t p = (size_t)ci * e.d.nloci + li;
+  unsigned char cur = 0;
+  uint32_t fl = 0;
+  bool ok = d2h(out4, e.v.prop_dbg + p * 4, 4 * sizeof(double), s) && d2h(&fl, e.v.prop_flags + p, sizeof fl, s) && d2h(&cur, e.v.cur + p, 1, s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  if (flags) *flags = fl;
+  if (is_current) *is_current = cur;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_sync(ima2p_engine *h) {
+  if (!h) return fail(IMA2P_E_ARG, "null engine");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaDeviceSynchronize())) return fail(IMA2P_E_CUDA, "device synchronize failed");
+#endif
+  return e.finalized ? check_device_error(&e, pick_stream(&e, nullptr)) : IMA2P_OK;
+}
+
+int ima2p_engine_counters(ima2p_engine *h, uint64_t *out8) {
+  if (!h || !h->eng.finalized || !out8) return fail(IMA2P_E_ARG, "counters: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  std::vector<unsigned int> acc((size_t)e.d.P * 3);
+  unsigned long long steps = 0, ovf = 0, sw[2] = {0, 0};
+  bool ok = d2h(acc.data(), e.v.acc, acc.size() * sizeof(unsigned int), s) && d2h(&steps, e.v.nsteps, 8, s) && d2h(&ovf, e.v.overflow, 8, s) &&
+            d2h(sw, e.d_swap_counts, 16, s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  uint64_t a = 0, t = 0, m = 0;
+  for (size_t p = 0; p < (size_t)e.d.P; p++) { a += acc[p * 3]; t += acc[p * 3 + 1]; m += acc[p * 3 + 2]; }
+  out8[0] = steps; out8[1] = steps * (uint64_t)e.d.P; out8[2] = a; out8[3] = t; out8[4] = m; out8[5] = sw[0]; out8[6] = sw[1]; out8[7] = ovf;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_get_betas(ima2p_engine *h, double *betas_global) {
+  if (!h || !h->eng.finalized || !betas_global) return fail(IMA2P_E_ARG, "get_betas: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const int G = e.d.nchains_global;
+  std::vector<int> roc(G);
+  if (!d2h(roc.data(), e.sv.rank_of_chain, G * sizeof(int), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  for (int c = 0; c < G; c++) betas_global[c] = e.h_beta_table[roc[c]];
+  return IMA2P_OK;
+}
+
+int ima2p_engine_cold_row(ima2p_engine *h, float *row, int *present) {
+  if (!h || !h->eng.finalized || !row || !present) return fail(IMA2P_E_ARG, "cold_row: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const DevModel &M = e.model;
+  int cold = -1;
+  if (!d2h(&cold, e.sv.chain_of_rank, sizeof(int), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  const int c = cold - e.d.chain0;
+  *present = (c >= 0 && c < e.d.nchains);
+  if (!*present) return IMA2P_OK;
+  std::vector<int> wi(e.d.NI); std::vector<double> wd(e.d.ND), q(kMaxParams), m(kMaxParams), tv(kMaxPeriods);
+  double pg[2];
+  bool ok = d2h(wi.data(), e.v.all_i + (size_t)c * e.d.NI, e.d.NI * sizeof(int), s) && d2h(wd.data(), e.v.all_d + (size_t)c * e.d.ND, e.d.ND * sizeof(double), s) &&
+            d2h(q.data(), e.v.qint + (size_t)c * kMaxParams, kMaxParams * sizeof(double), s) && d2h(m.data(), e.v.mint + (size_t)c * kMaxParams, kMaxParams * sizeof(double), s) &&
+            d2h(tv.data(), e.v.tvals + (size_t)c * kMaxPeriods, kMaxPeriods * sizeof(double), s) && d2h(pg, e.v.probg + c, 8, s) && d2h(pg + 1, e.v.pdgsum + c, 8, s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  // savegsampinf ginfo.cpp:318-377 (sums accumulated in float, as there)
+  const int nq = M.nq, nm = M.nomigration ? 0 : M.nm;
+  const int fcp = nq, hccp = 2 * nq, mcp = 3 * nq, fmp = mcp + nm, qip = fmp + nm, mip = qip + nq, pdgp = mip + nm;
+  for (int i = 0; i < nq; i++) {
+    int cc = 0; float f = 0.f, hc = 0.f;
+    for (int j = 0; j < M.q_n[i]; j++) { const int x = M.q_idx[i][j]; cc += wi[x]; f += (float)wd[x]; hc += (float)wd[M.ncc + x]; }
+    row[i] = (float)cc; row[fcp + i] = f; row[hccp + i] = hc; row[qip + i] = (float)q[i];
+  }
+  for (int i = 0; i < nm; i++) {
+    int cm = 0; float f = 0.f;
+    for (int j = 0; j < M.m_n[i]; j++) { const int x = M.m_idx[i][j]; cm += wi[M.ncc + x]; f += (float)wd[2 * M.ncc + x]; }
+    row[mcp + i] = (float)cm; row[fmp + i] = f; row[mip + i] = (float)m[i];
+  }
+  row[pdgp] = (float)pg[1]; row[pdgp + 1] = (float)pg[0];
+  for (int i = 0; i < M.nsplit; i++) row[pdgp + 2 + i] = (float)tv[i];
+  return IMA2P_OK;
+}
+
+int ima2p_engine_state_bytes(ima2p_engine *h, uint64_t *out8) {
+  if (!h || !h->eng.finalized || !out8) return fail(IMA2P_E_ARG, "state_bytes: bad argument");
+  const EngineDims &d = h->eng.d;
+  const uint64_t P = d.P, NL = d.NL, CAP = d.CAP;
+  out8[0] = P * NL * sizeof(short4_t); out8[1] = P * NL * sizeof(double); out8[2] = P * NL * sizeof(ushort2_t);
+  out8[3] = P * CAP * sizeof(double); out8[4] = P * CAP * sizeof(short); out8[5] = P * 2 * sizeof(int);
+  out8[6] = P * 4 * sizeof(double); out8[7] = P * kMaxLinked * sizeof(double);
+  return IMA2P_OK;
+}
+
+int ima2p_engine_put_state(ima2p_engine *h, const void *topo, const void *time, const void *mseg, const void *mig_t, const void *mig_p,
+                           const void *scal_i, const void *scal_d, const void *uvals, const double *tvals, void *cuda_stream) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "put_state: not finalized");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  uint64_t b[8];
+  ima2p_engine_state_bytes(h, b);
+  PairBuf &B = e.v.buf[0];
+  bool ok = h2d(B.topo, topo, b[0], s) && h2d(B.time, time, b[1], s) && h2d(B.mseg, mseg, b[2], s) && h2d(B.mig_t, mig_t, b[3], s) &&
+            h2d(B.mig_p, mig_p, b[4], s) && h2d(B.si, scal_i, b[5], s) && h2d(B.sd, scal_d, b[6], s) && h2d(e.v.uvals, uvals, b[7], s);
+  if (tvals) {
+    for (int c = 0; c < e.d.nchains; c++) for (int k = 0; k < kMaxPeriods; k++) e.h_tvals[(size_t)c * kMaxPeriods + k] = k < e.model.nsplit ? tvals[(size_t)c * e.model.nsplit + k] : kTimeMax;
+    ok = ok && h2d(e.v.tvals, e.h_tvals.data(), e.h_tvals.size() * sizeof(double), s);
+  }
+#if IMA_CUDA
+  ok = ok && IMA_CUDA_OK(cudaMemsetAsync(e.v.cur, 0, e.d.P, s));
+#else
+  memset(e.v.cur, 0, e.d.P);
+#endif
+  if (!ok) return fail(IMA2P_E_CUDA, "put_state failed");
+  return launch_eval(&e, s);
+}
+
+// gathers the CURRENT buffer of every pair (pairs flip independently) into host memory
+int ima2p_engine_fetch_state(ima2p_engine *h, void *topo, void *time, void *mseg, void *mig_t, void *mig_p, void *scal_i, void *scal_d,
+                             void *cuda_stream) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "fetch_state: not finalized");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  const size_t P = e.d.P, NL = e.d.NL, CAP = e.d.CAP;
+  std::vector<unsigned char> cur(P);
+  if (!d2h(cur.data(), e.v.cur, P, s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  bool ok = true;
+  // runs of pairs living in the same buffer are copied together
+  for (size_t p0 = 0; p0 < P && ok;) {
+    size_t p1 = p0 + 1;
+    while (p1 < P && cur[p1] == cur[p0]) p1++;
+    const PairBuf &B = e.v.buf[cur[p0]];
+    const size_t n = p1 - p0;
+    ok = d2h((short4_t *)topo + p0 * NL, B.topo + p0 * NL, n * NL * sizeof(short4_t), s) && d2h((double *)time + p0 * NL, B.time + p0 * NL, n * NL * sizeof(double), s) &&
+         d2h((ushort2_t *)mseg + p0 * NL, B.mseg + p0 * NL, n * NL * sizeof(ushort2_t), s) && d2h((double *)mig_t + p0 * CAP, B.mig_t + p0 * CAP, n * CAP * sizeof(double), s) &&
+         d2h((short *)mig_p + p0 * CAP, B.mig_p + p0 * CAP, n * CAP * sizeof(short), s) && d2h((int *)scal_i + p0 * 2, B.si + p0 * 2, n * 2 * sizeof(int), s) &&
+         d2h((double *)scal_d + p0 * 4, B.sd + p0 * 4, n * 4 * sizeof(double), s);
+    p0 = p1;
+  }
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  return check_device_error(&e, s);
+}
+
+int ima2p_engine_fetch_chain_summary(ima2p_engine *h, double *out4, void *cuda_stream) {
+  if (!h || !h->eng.finalized || !out4) return fail(IMA2P_E_ARG, "fetch_chain_summary: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  const int C = e.d.nchains;
+  std::vector<double> b(C), g(C), p(C), w(C);
+  bool ok = d2h(b.data(), e.v.beta, C * 8, s) && d2h(g.data(), e.v.probg, C * 8, s) && d2h(p.data(), e.v.pdgsum, C * 8, s) && d2h(w.data(), e.v.swapsum, C * 8, s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  for (int c = 0; c < C; c++) { out4[c * 4] = b[c]; out4[c * 4 + 1] = g[c]; out4[c * 4 + 2] = p[c]; out4[c * 4 + 3] = w[c]; }
+  return check_device_error(&e, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,828 @@
+// Per-(chain, locus) device work: one warp, the genealogy staged in shared memory.
+//
+//   stage_pair       coalesced load of the pair's edge arrays and migration pool into shared memory
+//   propose_move     the updategenealogy proposal (update_gtree.cpp:723-827): pick an edge, detach,
+//                    slide with reflection, re-attach, simulate the migration path, Hastings terms
+//   eval_weights     treeweight (update_gtree_common.cpp:1679-1931): event build, bitonic sort by
+//                    time, sweep; also produces the subtree tip masks used by the IS likelihood
+//   likelihood_is    infinite sites (calc_prob_data.cpp:731-836) as a bit-mask equality search
+//   store_pair       coalesced write of the proposed state into the pair's other buffer
+//
+// Lane-parallel loops are written `for (i = lane; i < n; i += IMA_WARP)`; strictly sequential parts
+// (tree surgery, event sweep) run on lane 0 between Warp::sync() calls.
+#pragma once
+#include "ima_model.h"
+
+namespace ima {
+
+// shared-memory view of one pair (pointers into the warp's slice of dynamic shared memory)
+struct PairSm {
+  double *time;            // [NL]
+  short *up0, *up1, *down, *pop;   // [NL]
+  unsigned short *ms, *mcn;        // [NL] migration segment start / count (into pt/pp)
+  double *pt;              // [4*CAP] pool: [0,CAP) current lists, [CAP,2CAP) join scratch, [2CAP,3CAP) new edge, [3CAP,4CAP) new sister
+  short *pp;               // [4*CAP]
+  double *evt;             // [EVP] event times (sort keys)
+  int *evi;                // [EVP] packed event info
+  uint32_t *mask;          // [NL*W] subtree tip masks
+  int *moff;               // [NL+1] exclusive prefix of mcn
+  int *gwi;                // [NI]
+  double *gwd;             // [ND]
+  double *ctl_d;           // [8]  roottime, length, tlength, migweight, slideweight, pdg, Aterm, slide distance
+  int *ctl_i;              // [8]  root, mignum, flags, nev, edge, freed, oldsis, newsis
+};
+
+enum { kCdRoottime = 0, kCdLength, kCdTlength, kCdMigw, kCdSlidew, kCdPdg, kCdAterm, kCdSlideDist };
+enum { kCiRoot = 0, kCiMignum, kCiFlags, kCiNev, kCiEdge, kCiFreed, kCiOldsis, kCiNewsis };
+
+IMA_HD size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+// bytes of shared memory one warp needs
+IMA_HD size_t pair_smem_bytes(const EngineDims &d) {
+  size_t b = 0;
+  b += align8(sizeof(double) * d.NL);
+  b += align8(sizeof(short) * d.NL) * 4;
+  b += align8(sizeof(unsigned short) * d.NL) * 2;
+  b += align8(sizeof(double) * 4 * d.CAP);
+  b += align8(sizeof(short) * 4 * d.CAP);
+  b += align8(sizeof(double) * d.EVP);
+  b += align8(sizeof(int) * d.EVP);
+  b += align8(sizeof(uint32_t) * d.NL * d.W);
+  b += align8(sizeof(int) * (d.NL + 1));
+  b += align8(sizeof(int) * d.NI);
+  b += align8(sizeof(double) * d.ND);
+  b += align8(sizeof(double) * 8);
+  b += align8(sizeof(int) * 8);
+  return b;
+}
+
+IMA_DEV PairSm carve_pair_smem(unsigned char *base, const EngineDims &d) {
+  PairSm s;
+  unsigned char *p = base;
+  auto take = [&](size_t bytes) { unsigned char *q = p; p += align8(bytes); return q; };
+  s.time = (double *)take(sizeof(double) * d.NL);
+  s.pt = (double *)take(sizeof(double) * 4 * d.CAP);
+  s.evt = (double *)take(sizeof(double) * d.EVP);
+  s.gwd = (double *)take(sizeof(double) * d.ND);
+  s.ctl_d = (double *)take(sizeof(double) * 8);
+  s.up0 = (short *)take(sizeof(short) * d.NL);
+  s.up1 = (short *)take(sizeof(short) * d.NL);
+  s.down = (short *)take(sizeof(short) * d.NL);
+  s.pop = (short *)take(sizeof(short) * d.NL);
+  s.ms = (unsigned short *)take(sizeof(unsigned short) * d.NL);
+  s.mcn = (unsigned short *)take(sizeof(unsigned short) * d.NL);
+  s.pp = (short *)take(sizeof(short) * 4 * d.CAP);
+  s.evi = (int *)take(sizeof(int) * d.EVP);
+  s.mask = (uint32_t *)take(sizeof(uint32_t) * d.NL * d.W);
+  s.moff = (int *)take(sizeof(int) * (d.NL + 1));
+  s.gwi = (int *)take(sizeof(int) * d.NI);
+  s.ctl_i = (int *)take(sizeof(int) * 8);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// staging
+// ------------------------------------------------------------------------------------------------
+IMA_DEV void stage_pair(const EngineView &E, const PairBuf &B, int p, int nl, PairSm &S) {
+  const int lane = Warp::lane();
+  const short4_t *topo = B.topo + (size_t)p * E.d.NL;
+  const double *time = B.time + (size_t)p * E.d.NL;
+  const ushort2_t *mseg = B.mseg + (size_t)p * E.d.NL;
+  for (int i = lane; i < nl; i += IMA_WARP) {
+    short4_t t = topo[i];
+    S.up0[i] = t.x; S.up1[i] = t.y; S.down[i] = t.z; S.pop[i] = t.w;
+    S.time[i] = time[i];
+    ushort2_t m = mseg[i];
+    S.ms[i] = m.x; S.mcn[i] = m.y;
+  }
+  const int mignum = B.si[(size_t)p * 2 + 1];
+  const double *mt = B.mig_t + (size_t)p * E.d.CAP;
+  const short *mp = B.mig_p + (size_t)p * E.d.CAP;
+  for (int i = lane; i < mignum; i += IMA_WARP) { S.pt[i] = mt[i]; S.pp[i] = mp[i]; }
+  if (lane == 0) {
+    S.ctl_i[kCiRoot] = B.si[(size_t)p * 2];
+    S.ctl_i[kCiMignum] = mignum;
+    S.ctl_i[kCiFlags] = 0;
+    S.ctl_d[kCdRoottime] = B.sd[(size_t)p * 4];
+    S.ctl_d[kCdMigw] = 0.0; S.ctl_d[kCdSlidew] = 0.0; S.ctl_d[kCdAterm] = 0.0;
+  }
+  Warp::sync();
+}
+
+// exclusive prefix sum of the per-edge migration counts -> S.moff[0..nl]; returns total
+IMA_DEV int scan_mig_counts(int nl, PairSm &S) {
+  const int lane = Warp::lane();
+  int carry = 0;
+  for (int base = 0; base < nl; base += IMA_WARP) {
+    int i = base + lane;
+    int v = (i < nl) ? (int)S.mcn[i] : 0;
+    int inc = Warp::scan(v);
+    if (i < nl) S.moff[i] = carry + inc - v;
+    carry += Warp::bcast(inc, IMA_WARP - 1);
+  }
+  if (lane == 0) S.moff[nl] = carry;
+  Warp::sync();
+  return carry;
+}
+
+IMA_DEV void store_pair(const EngineView &E, const PairBuf &B, int p, int nl, const PairSm &S, int total_mig) {
+  const int lane = Warp::lane();
+  short4_t *topo = B.topo + (size_t)p * E.d.NL;
+  double *time = B.time + (size_t)p * E.d.NL;
+  ushort2_t *mseg = B.mseg + (size_t)p * E.d.NL;
+  double *mt = B.mig_t + (size_t)p * E.d.CAP;
+  short *mp = B.mig_p + (size_t)p * E.d.CAP;
+  for (int i = lane; i < nl; i += IMA_WARP) {
+    short4_t t; t.x = S.up0[i]; t.y = S.up1[i]; t.z = S.down[i]; t.w = S.pop[i];
+    topo[i] = t;
+    time[i] = S.time[i];
+    ushort2_t m; m.x = (unsigned short)S.moff[i]; m.y = S.mcn[i];
+    mseg[i] = m;
+    const int src = S.ms[i], dst = S.moff[i], n = S.mcn[i];
+    for (int j = 0; j < n; j++) { mt[dst + j] = S.pt[src + j]; mp[dst + j] = S.pp[src + j]; }   // compaction
+  }
+  for (int i = lane; i < E.d.NI; i += IMA_WARP) B.gwi[(size_t)p * E.d.NI + i] = S.gwi[i];
+  for (int i = lane; i < E.d.ND; i += IMA_WARP) B.gwd[(size_t)p * E.d.ND + i] = S.gwd[i];
+  if (lane == 0) {
+    B.si[(size_t)p * 2] = S.ctl_i[kCiRoot];
+    B.si[(size_t)p * 2 + 1] = total_mig;
+    B.sd[(size_t)p * 4 + 0] = S.ctl_d[kCdRoottime];
+    B.sd[(size_t)p * 4 + 1] = S.ctl_d[kCdLength];
+    B.sd[(size_t)p * 4 + 2] = S.ctl_d[kCdTlength];
+    B.sd[(size_t)p * 4 + 3] = S.ctl_d[kCdPdg];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+// findperiod update_gtree_common.cpp:1625-1633 (tv carries the TIMEMAX sentinel at [nsplit])
+IMA_DEV int findperiod(const DevModel &M, const double *tv, double t) {
+  int k = 0;
+  while (k < M.nsplit && tv[k] <= t) k++;
+  return k;
+}
+// follow a lineage's population down the population tree until it exists in `period`
+IMA_DEV int pop_in_period(const DevModel &M, int pop, int period) {
+  while (M.pt_e[pop] <= period && M.pt_e[pop] != -1) pop = M.pt_down[pop];
+  return pop;
+}
+IMA_DEV double edge_top_time(const PairSm &S, int ng, int e) { return e < ng ? 0.0 : S.time[S.up0[e]]; }
+
+// ------------------------------------------------------------------------------------------------
+// migration-path proposal: struct edgemiginfo (imamp.hpp:627-647) with the list held in the pool
+// ------------------------------------------------------------------------------------------------
+struct Emi {
+  int edgeid, pop, temppop, fpop, b, e, mpall;
+  double upt, dnt, mtall;
+  double mtimeavail[kMaxPeriods];
+  int mp[kMaxPeriods];
+  int seg, nmig;      // migration list: pool[seg .. seg+nmig)
+};
+
+// IMA_reset_edgemiginfo update_gtree_common.cpp:493-514
+IMA_DEV void emi_reset(Emi &em) {
+  em.edgeid = -1; em.pop = em.temppop = em.fpop = -1; em.b = em.e = -1; em.mpall = 0;
+  em.upt = em.dnt = -1.0; em.mtall = 0.0;
+  for (int i = 0; i < kMaxPeriods; i++) { em.mtimeavail[i] = 0.0; em.mp[i] = 0; }
+  em.seg = 0; em.nmig = 0;
+}
+
+// fillmiginfoperiods update_gtree_common.cpp:1100-1162
+IMA_DEV void emi_periods(const DevModel &M, const double *tv, Emi &em) {
+  const int last = M.nsplit;
+  em.b = 0;
+  while (em.upt > tv[em.b]) em.b++;
+  em.e = em.b;
+  while (em.dnt > tv[em.e]) em.e++;
+  if (em.e == em.b) {
+    em.mtimeavail[em.b] = (em.b == last) ? 0.0 : em.dnt - em.upt;
+  } else {
+    em.mtimeavail[em.b] = tv[em.b] - em.upt;
+    em.mtimeavail[em.e] = (em.e == last) ? 0.0 : em.dnt - tv[em.e - 1];
+    for (int i = em.b + 1; i < em.e; i++) em.mtimeavail[i] = tv[i] - tv[i - 1];
+  }
+  em.mtall = (em.b < last) ? ((tv[last - 1] < em.dnt ? tv[last - 1] : em.dnt) - em.upt) : 0.0;
+}
+
+// fillmiginfo for one edge, update_gtree_common.cpp:1169-1246
+IMA_DEV void emi_fill_old(const DevModel &M, const double *tv, const PairSm &S, int ng, int edge, Emi &em) {
+  emi_reset(em);
+  em.edgeid = edge;
+  em.upt = edge_top_time(S, ng, edge);
+  em.pop = em.temppop = S.pop[edge];
+  em.dnt = S.time[edge];
+  em.fpop = S.pop[S.down[edge]];
+  emi_periods(M, tv, em);
+  em.seg = S.ms[edge];
+  em.nmig = S.mcn[edge];
+  int j = em.b;
+  for (int i = 0; i < em.nmig; i++) {
+    while (S.pt[em.seg + i] > tv[j]) j++;
+    em.mp[j]++;
+    em.mpall++;
+  }
+}
+
+// poisson utilities.cpp:516-603 (conditioned draws; normal approximation above 100; ADDMIGMAX cap)
+IMA_DEV int poisson_cond(Philox &rng, double param, int condition) {
+  int i;
+  if (param < 0.25 && condition == 1) {
+    double u = rng.uniform();
+    double sh = sinh(param);
+    if (u < param / sh) return 1;
+    return (u < param * (6 + param * param) / (6 * sh)) ? 3 : 5;
+  }
+  if (param < 0.25 && condition == 2) {
+    double raised = exp(-param);
+    double rcheck = raised = param * raised / (1 - raised);
+    double u = rng.uniform();
+    i = 1;
+    while (u > rcheck && i < kAddMigMax) {
+      raised *= param / (i + 1);
+      rcheck += raised;
+      i++;
+    }
+    return i;
+  }
+  bool stop;
+  do {
+    if (param >= 100.0) {
+      double v = rng.normal(param, param) + 0.5;       // POSROUND of normdev(param, param)
+      long r = (long)v;
+      i = r > 0 ? (r > 1000000 ? 1000000 : (int)r) : 0;
+    } else {
+      double raised = exp(-param);
+      double u = rng.uniform();
+      for (i = 0; u > raised; i++) u *= rng.uniform();
+    }
+    switch (condition) {
+      case 0: stop = !(i & 1); break;
+      case 1: stop = (i & 1); break;
+      case 2: stop = (i != 0); break;
+      case 3: stop = (i != 1); break;
+      default: stop = true; break;
+    }
+  } while (!stop);
+  if (i > kAddMigMax) i = (condition == 1) ? kAddMigMax - 1 : kAddMigMax;
+  return i;
+}
+
+// picktopop / picktopop2 update_gtree_common.cpp:1320-1348
+IMA_DEV int picktopop(const DevModel &M, Philox &rng, int nowpop, int period, int notother) {
+  const int numpops = M.npops - period;
+  int t;
+  do { t = M.plist[period][rng.randint(numpops)]; } while (t == nowpop || t == notother);
+  return t;
+}
+
+// simmpath update_gtree_common.cpp:329-398: numm migration times uniform on the period's stretch of
+// the edge, sorted, re-drawn on an exact tie; destinations random, the last two constrained when the
+// edge must end in `constrainpop`.  Appends to the list of `em` in the pool; false on pool overflow.
+IMA_DEV bool simmpath(const DevModel &M, Philox &rng, PairSm &S, Emi &em, int cap_end, int period, int numm,
+                      double timein, double upt, int pop, int constrainpop) {
+  const int start = em.seg + em.nmig;
+  if (start + numm > cap_end) return false;
+  bool dup;
+  do {
+    for (int i = 0; i < numm; i++) {                   // insertion sort while drawing (hpsortmig :625)
+      double t = upt + rng.uniform() * timein;
+      int j = start + i;
+      while (j > start && S.pt[j - 1] > t) { S.pt[j] = S.pt[j - 1]; j--; }
+      S.pt[j] = t;
+    }
+    dup = false;
+    for (int i = start; i + 1 < start + numm; i++) if (S.pt[i] == S.pt[i + 1]) { dup = true; break; }
+  } while (dup);
+  int lastpop = pop;
+  const int lastm = start + numm - 1;
+  for (int i = start; i <= lastm; i++) {
+    int to;
+    if (constrainpop >= 0 && i >= lastm - 1) to = (i == lastm - 1) ? picktopop(M, rng, lastpop, period, constrainpop) : constrainpop;
+    else to = picktopop(M, rng, lastpop, period, -1);
+    S.pp[i] = (short)to;
+    lastpop = to;
+  }
+  em.nmig += numm;
+  return true;
+}
+
+// one period of one edge, shared by mwork_single_edge (:1353-1427) and mwork_two_edges (:1430-1575)
+// mode: 0 = free period (any count), 1 = last period of the edge (count conditioned on ending in fpop)
+IMA_DEV bool mwork_period(const DevModel &M, Philox &rng, PairSm &S, Emi &em, const Emi &oldem, int cap_end, int periodi,
+                          int mode, double timestart) {
+  const double r = calcmrate(oldem.mp[periodi], oldem.mtimeavail[periodi]) * em.mtimeavail[periodi];
+  int cond = -1, constrain = -1;
+  if (mode == 1) {
+    if (M.npops - periodi == 2) cond = (em.temppop == em.fpop) ? 0 : 1;
+    else { cond = (em.temppop == em.fpop) ? 3 : 2; constrain = em.fpop; }
+  }
+  const int k = poisson_cond(rng, r, cond);
+  em.mp[periodi] = k;
+  if (k > 0) {
+    if (!simmpath(M, rng, S, em, cap_end, periodi, k, em.mtimeavail[periodi], timestart, em.temppop, constrain)) return false;
+    em.mpall += k;
+    em.temppop = S.pp[em.seg + em.nmig - 1];
+  }
+  return true;
+}
+
+// mwork_single_edge update_gtree_common.cpp:1353-1427
+IMA_DEV bool mwork_single_edge(const DevModel &M, const double *tv, Philox &rng, PairSm &S, Emi &em, const Emi &oldem,
+                               int cap_end, int lastmigperiod) {
+  if (lastmigperiod < em.b) return true;
+  double timestart = em.upt;
+  int periodi;
+  for (periodi = em.b; periodi <= lastmigperiod; periodi++) {
+    em.temppop = pop_in_period(M, em.temppop, periodi);
+    if (!mwork_period(M, rng, S, em, oldem, cap_end, periodi, periodi < em.e ? 0 : 1, timestart)) return false;
+    timestart = tv[periodi];
+  }
+  if (em.mtimeavail[periodi] > 0 && M.pt_e[em.temppop] == periodi) em.temppop = M.pt_down[em.temppop];
+  return true;
+}
+
+// mwork_two_edges update_gtree_common.cpp:1430-1575
+IMA_DEV bool mwork_two_edges(const DevModel &M, const double *tv, Philox &rng, PairSm &S, Emi &ee, Emi &se, const Emi &oe,
+                             const Emi &os, int cap_e, int cap_s, int lastmigperiod) {
+  double tstart[2] = { ee.upt, se.upt };
+  const int b = ee.b < se.b ? ee.b : se.b;
+  const int lastperiodi = (ee.e == M.nsplit) ? lastmigperiod : lastmigperiod - 1;
+  int periodi;
+  for (periodi = b; periodi <= lastperiodi; periodi++)
+    for (int ii = 0; ii < 2; ii++) {
+      Emi &mm = ii == 0 ? ee : se;
+      const Emi &oldmm = ii == 0 ? oe : os;
+      if (mm.b <= periodi) {
+        mm.temppop = pop_in_period(M, mm.temppop, periodi);
+        if (!mwork_period(M, rng, S, mm, oldmm, ii == 0 ? cap_e : cap_s, periodi, 0, tstart[ii])) return false;
+        tstart[ii] = tv[periodi];
+      }
+    }
+  if (periodi == M.nsplit) {
+    ee.fpop = se.fpop = M.rootpop;
+    return true;
+  }
+  // both edges end in this period: choose the population in which they join (:1486-1524)
+  if (M.pt_e[ee.temppop] == periodi) ee.temppop = M.pt_down[ee.temppop];
+  if (M.pt_e[se.temppop] == periodi) se.temppop = M.pt_down[se.temppop];
+  int f;
+  if (ee.temppop == se.temppop) {
+    f = (rng.uniform() < kMigCloseFrac) ? ee.temppop : picktopop(M, rng, ee.temppop, periodi, -1);
+  } else if (M.npops - periodi == 2) {
+    f = (rng.uniform() < 0.5) ? ee.temppop : se.temppop;
+  } else if (rng.uniform() < kMigCloseFrac) {
+    f = (rng.uniform() < 0.5) ? ee.temppop : se.temppop;
+  } else {
+    f = picktopop(M, rng, ee.temppop, periodi, se.temppop);
+  }
+  ee.fpop = se.fpop = f;
+  for (int ii = 0; ii < 2; ii++) {
+    Emi &mm = ii == 0 ? ee : se;
+    const Emi &oldmm = ii == 0 ? oe : os;
+    if (!mwork_period(M, rng, S, mm, oldmm, ii == 0 ? cap_e : cap_s, periodi, 1, tstart[ii])) return false;
+    if (mm.mtimeavail[periodi] > 0 && M.pt_e[mm.temppop] == periodi) mm.temppop = M.pt_down[mm.temppop];
+  }
+  return true;
+}
+
+// last-period term of getmprob (update_gtree_common.cpp:879-939 and :1007-1065)
+IMA_DEV double getmprob_last(const DevModel &M, const PairSm &S, const Emi &mm, const Emi &oldmm, int cm) {
+  const int e = mm.e;
+  const double r = calcmrate(oldmm.mp[e], oldmm.mtimeavail[e]) * mm.mtimeavail[e];
+  const int k = mm.mp[e];
+  if (e == M.nsplit - 1)
+    return k * log(r / mm.mtimeavail[e]) - ((k & 1) ? mylogsinh(r) : mylogcosh(r));
+  int pop = (cm == 0) ? mm.pop : (int)S.pp[mm.seg + cm - 1];
+  while (M.pt_e[pop] <= e) pop = M.pt_down[pop];
+  const int topop = mm.fpop, popc = M.npops - e - 1;
+  const double d = (pop == topop) ? log(1 - r * exp(-r)) : log(1 - exp(-r));
+  double n;
+  if (k == 0) n = -r;
+  else if (k == 1) n = log(r / mm.mtimeavail[e]) - r;
+  else {
+    const int lastm_2_pop = (k == 2) ? pop : (int)S.pp[mm.seg + mm.mpall - 3];
+    const double pathc = (lastm_2_pop == topop) ? -log((double)popc) : -log((double)popc - 1);
+    n = k * log(r / mm.mtimeavail[e]) - r + (2 - k) * log((double)popc) + pathc;
+  }
+  return n - d;
+}
+
+// getmprob update_gtree_common.cpp:850-1071: log probability of having simulated the lists of
+// (edgem, sisem) given the migration counts of (oldedgem, oldsisem)
+IMA_DEV double getmprob(const DevModel &M, const double *tv, const PairSm &S, const Emi &edgem, const Emi &sisem,
+                        const Emi &oldedgem, const Emi &oldsisem) {
+  double tempp = 0.0;
+  const int last = M.nsplit, npops = M.npops;
+  const int lastmigrationperiod = edgem.e < last - 1 ? edgem.e : last - 1;
+  if (sisem.mtall <= 0) {
+    int cm = 0;
+    for (int p = edgem.b; p <= edgem.e; p++)
+      if (p < lastmigrationperiod || (p == lastmigrationperiod && edgem.e == last)) {
+        const double r = calcmrate(oldedgem.mp[p], oldedgem.mtimeavail[p]) * edgem.mtimeavail[p];
+        tempp += edgem.mp[p] * log(r / (edgem.mtimeavail[p] * (npops - (p + 1)))) - r;
+        cm += edgem.mp[p];
+      }
+    if (edgem.e < last) tempp += getmprob_last(M, S, edgem, oldedgem, cm);
+    return tempp;
+  }
+  if (edgem.mtall > 0 && sisem.mtall > 0 && edgem.e < last) {
+    int pop[2];
+    for (int ii = 0; ii < 2; ii++) {                   // population of each edge where they join (:945-964)
+      const Emi &mm = ii == 0 ? edgem : sisem;
+      pop[ii] = mm.pop;
+      if (mm.mpall > 0 && mm.e > 0) {
+        const double t = tv[mm.e - 1];
+        int k = -1;
+        while (k + 1 < mm.nmig && S.pt[mm.seg + k + 1] < t) k++;
+        if (k >= 0) pop[ii] = S.pp[mm.seg + k];
+      }
+      if (mm.e > 0) while (M.pt_e[pop[ii]] <= mm.e) pop[ii] = M.pt_down[pop[ii]];
+    }
+    if (pop[0] == pop[1])
+      tempp = (pop[0] == edgem.fpop) ? log(kMigCloseFrac) : log((1.0 - kMigCloseFrac) / (double)(npops - edgem.e - 1));
+    else if (npops - edgem.e == 2)
+      tempp = log(0.5);
+    else if (edgem.fpop == pop[0] || edgem.fpop == pop[1])
+      tempp = log(0.5 * kMigCloseFrac);
+    else
+      tempp = log((1.0 - kMigCloseFrac) / (double)(npops - edgem.e - 2));
+  }
+  for (int ii = 0; ii < 2; ii++) {
+    const Emi &mm = ii == 0 ? edgem : sisem;
+    const Emi &oldmm = ii == 0 ? oldedgem : oldsisem;
+    if (mm.mtall > 0) {
+      int cm = 0;
+      for (int p = mm.b; p <= mm.e; p++)
+        if (p < lastmigrationperiod || (p == lastmigrationperiod && mm.e == last)) {
+          const double r = calcmrate(oldmm.mp[p], oldmm.mtimeavail[p]) * mm.mtimeavail[p];
+          tempp += mm.mp[p] * log(r / (mm.mtimeavail[p] * (npops - (p + 1)))) - r;
+          cm += mm.mp[p];
+        }
+      if (mm.e < last) tempp += getmprob_last(M, S, mm, oldmm, cm);
+    }
+  }
+  return tempp;
+}
+
+// normprob utilities.cpp:463-468
+IMA_DEV double log_normprob(double stdev, double val) {
+  const double z = val / stdev;
+  return log(0.3989422803 * exp(-(z * z) / 2) / stdev);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the proposal (lane 0): update_gtree.cpp:755-825
+// ------------------------------------------------------------------------------------------------
+IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *tv, int ng, int nl, Philox &rng, PairSm &S) {
+  const int CAP = d.CAP;
+  int root = S.ctl_i[kCiRoot];
+  double roottime = S.ctl_d[kCdRoottime];
+  uint32_t flags = 0;
+  int edge;
+  do { edge = rng.randint(nl); } while (S.down[edge] == -1);                       // :756-759
+  const int freed = S.down[edge];
+  const int oldsis = (S.up0[freed] == edge) ? S.up1[freed] : S.up0[freed];
+  Emi oe, os, ne, ns;
+  emi_fill_old(M, tv, S, ng, edge, oe);                                             // :765-772
+  if (freed == root) emi_fill_old(M, tv, S, ng, oldsis, os); else emi_reset(os);
+  S.mcn[edge] = 0;                                                                  // :777
+  const double slidestdv = fmin(kSlideStdvMax, roottime / 3);                      // :782-783
+  const double holdslidedist = rng.normal(0.0, slidestdv);
+  double slidedist = holdslidedist;
+
+  // joinsisdown :374-454 -- sister swallows the freed edge (lists concatenated in the join scratch)
+  int rootmove, tmrca = 0;
+  {
+    const int n1 = S.mcn[oldsis], n2 = S.mcn[freed];
+    if (n1 > 0 && n2 > 0) {
+      if (n1 + n2 > CAP) flags |= kFlagOverflow;
+      else {
+        for (int i = 0; i < n1; i++) { S.pt[CAP + i] = S.pt[S.ms[oldsis] + i]; S.pp[CAP + i] = S.pp[S.ms[oldsis] + i]; }
+        for (int i = 0; i < n2; i++) { S.pt[CAP + n1 + i] = S.pt[S.ms[freed] + i]; S.pp[CAP + n1 + i] = S.pp[S.ms[freed] + i]; }
+        S.ms[oldsis] = (unsigned short)CAP;
+        S.mcn[oldsis] = (unsigned short)(n1 + n2);
+      }
+    } else if (n2 > 0) { S.ms[oldsis] = S.ms[freed]; S.mcn[oldsis] = (unsigned short)n2; }
+    S.time[oldsis] = S.time[freed];
+    const int dd = S.down[freed];
+    S.down[oldsis] = (short)dd;
+    if (dd != -1) {
+      rootmove = 0;
+      if (S.up0[dd] == freed) S.up0[dd] = (short)oldsis; else S.up1[dd] = (short)oldsis;
+    } else {
+      rootmove = 1; tmrca++;
+      root = oldsis;
+      S.time[oldsis] = kTimeMax;
+      S.mcn[oldsis] = 0;
+      roottime = edge_top_time(S, ng, oldsis);
+    }
+  }
+  // slider :255-372 as a loop (the reference recurses)
+  int newsis = oldsis;
+  double tp = S.time[edge];
+  for (int iter = 0;; iter++) {
+    if (iter > 100000) { flags |= kFlagOverflow; break; }
+    if (slidedist < 0) {
+      slidedist = -slidedist;
+      const double uplimit = edge_top_time(S, ng, edge);
+      const int su = S.up0[newsis];
+      if (su == -1 || uplimit >= S.time[su]) {
+        if (slidedist < tp - uplimit) { tp -= slidedist; break; }
+        slidedist -= tp - uplimit; tp = uplimit;                                     // reflect, continue downwards
+      } else {
+        const double sistop = S.time[su];
+        if (slidedist < tp - sistop) { tp -= slidedist; break; }
+        slidedist -= tp - sistop; tp = sistop;
+        newsis = rng.bit() ? S.up0[newsis] : S.up1[newsis];
+        slidedist = -slidedist;                                                      // keep going up
+      }
+    } else {
+      if (S.down[newsis] == -1 || tp + slidedist < S.time[newsis]) {
+        tp += slidedist;
+        if (tp >= kTimeMax) tp = kTimeMax;
+        break;
+      }
+      slidedist -= S.time[newsis] - tp; tp = S.time[newsis];
+      if (rng.bit()) newsis = S.down[newsis];
+      else {
+        const int dn = S.down[newsis];
+        newsis = (S.up0[dn] == newsis) ? S.up1[dn] : S.up0[dn];
+        slidedist = -slidedist;
+      }
+    }
+  }
+  S.time[edge] = tp;
+  const int topol = (oldsis != newsis);
+  // splitsisdown :456-528
+  {
+    const double curt = tp;
+    S.time[freed] = S.time[newsis];
+    S.time[newsis] = curt;
+    const int dd = S.down[newsis];
+    if (dd != -1) {
+      if (S.up0[dd] == newsis) S.up0[dd] = (short)freed; else S.up1[dd] = (short)freed;
+    } else {
+      root = freed; roottime = curt; rootmove = 1;
+    }
+    S.down[freed] = (short)dd;
+    int i = 0;
+    const int n = S.mcn[newsis], s0 = S.ms[newsis];
+    while (i < n && S.pt[s0 + i] < curt) i++;
+    int nowpop = (i > 0) ? (int)S.pp[s0 + i - 1] : (int)S.pop[newsis];
+    nowpop = pop_in_period(M, nowpop, findperiod(M, tv, curt));
+    S.pop[freed] = (short)nowpop;
+    if (dd != -1) { S.ms[freed] = (unsigned short)(s0 + i); S.mcn[freed] = (unsigned short)(n - i); }
+    else S.mcn[freed] = 0;
+    S.mcn[newsis] = (unsigned short)i;
+    S.down[newsis] = S.down[edge] = (short)freed;
+    S.up0[freed] = (short)newsis; S.up1[freed] = (short)edge;
+  }
+  double slideweight = 0.0;                                                         // :803-812
+  if (rootmove) slideweight = -log_normprob(slidestdv, holdslidedist) + log_normprob(fmin(kSlideStdvMax, roottime / 3), holdslidedist);
+
+  // addmigration :588-665
+  double migweight = 0.0;
+  if (!(flags & kFlagOverflow)) {
+    emi_reset(ne); emi_reset(ns);
+    ne.edgeid = edge;
+    ne.upt = edge_top_time(S, ng, edge);
+    ne.fpop = S.pop[freed];
+    ne.pop = ne.temppop = S.pop[edge];
+    ne.dnt = S.time[edge];
+    ne.seg = 2 * CAP; ne.nmig = 0;
+    emi_periods(M, tv, ne);
+    bool ok = true;
+    const int lastmigperiod = ne.e < M.nsplit - 1 ? ne.e : M.nsplit - 1;
+    if (freed == root) {
+      ne.fpop = -1;
+      ns.edgeid = newsis;
+      ns.upt = edge_top_time(S, ng, newsis);
+      ns.fpop = -1;
+      ns.pop = ns.temppop = S.pop[newsis];
+      ns.dnt = S.time[newsis];
+      ns.seg = 3 * CAP; ns.nmig = 0;
+      emi_periods(M, tv, ns);
+      // getm :536-568
+      if (ne.mtall <= 0) ok = mwork_single_edge(M, tv, rng, S, ns, os, 4 * CAP, lastmigperiod);
+      else ok = mwork_two_edges(M, tv, rng, S, ne, ns, oe, os, 3 * CAP, 4 * CAP, lastmigperiod);
+    } else {
+      ns.seg = 3 * CAP;
+      ok = mwork_single_edge(M, tv, rng, S, ne, oe, 3 * CAP, lastmigperiod);
+    }
+    if (!ok) flags |= kFlagOverflow;
+    else {
+      const double fwd = getmprob(M, tv, S, ne, ns, oe, os);
+      const double rev = getmprob(M, tv, S, oe, os, ne, ns);
+      migweight = rev - fwd;                                                         // :654-664
+      // copynewmig_to_gtree update_gtree_common.cpp:1250-1289
+      S.ms[edge] = (unsigned short)ne.seg; S.mcn[edge] = (unsigned short)ne.nmig;
+      if (ns.edgeid >= 0) {
+        S.ms[newsis] = (unsigned short)ns.seg; S.mcn[newsis] = (unsigned short)ns.nmig;
+        int pop = ns.nmig > 0 ? (int)S.pp[ns.seg + ns.nmig - 1] : (int)S.pop[newsis];
+        pop = pop_in_period(M, pop, findperiod(M, tv, S.time[newsis]));
+        S.pop[S.down[newsis]] = (short)pop;
+      }
+    }
+  }
+  if (topol) flags |= kFlagTopol;
+  if (tmrca) flags |= kFlagTmrca;
+  S.ctl_i[kCiRoot] = root;
+  S.ctl_i[kCiFlags] = (int)flags;
+  S.ctl_i[kCiEdge] = edge; S.ctl_i[kCiFreed] = freed; S.ctl_i[kCiOldsis] = oldsis; S.ctl_i[kCiNewsis] = newsis;
+  S.ctl_d[kCdRoottime] = roottime;
+  S.ctl_d[kCdMigw] = migweight;
+  S.ctl_d[kCdSlidew] = slideweight;
+  S.ctl_d[kCdSlideDist] = holdslidedist;
+}
+
+// ------------------------------------------------------------------------------------------------
+// treeweight: update_gtree_common.cpp:1679-1931
+// ------------------------------------------------------------------------------------------------
+// packed event: bits 0-1 kind (0 coalescence, 1 migration, 2 population split), 2-6 pop, 7-11 topop, 12.. node
+IMA_DEV int pack_event(int kind, int pop, int topop, int node) { return kind | (pop << 2) | (topop << 7) | (node << 12); }
+
+// returns false when the event table does not fit (flagged as overflow by the caller)
+IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus &L, const double *tv, PairSm &S) {
+  const int lane = Warp::lane();
+  const int ng = L.ng, nl = L.nl, W = L.nwords;
+  const int mignum = scan_mig_counts(nl, S);
+  const double roottime = S.ctl_d[kCdRoottime];
+  const int nsplitev = findperiod(M, tv, roottime);
+  const int nev = (ng - 1) + mignum + nsplitev;
+  if (nev > d.EVP) return false;
+  // event build (:1741-1799): lane per edge
+  for (int i = lane; i < nl; i += IMA_WARP) {
+    int nowpop = S.pop[i];
+    if (i >= ng) {
+      S.evt[i - ng] = S.time[S.up0[i]];
+      S.evi[i - ng] = pack_event(0, nowpop, 0, i);
+    }
+    const int n = S.mcn[i], s0 = S.ms[i], o = (ng - 1) + S.moff[i];
+    for (int j = 0; j < n; j++) {
+      const double t = S.pt[s0 + j];
+      nowpop = pop_in_period(M, nowpop, findperiod(M, tv, t));
+      const int topop = S.pp[s0 + j];
+      S.evt[o + j] = t;
+      S.evi[o + j] = pack_event(1, nowpop, topop, 0);
+      nowpop = topop;
+    }
+  }
+  for (int i = lane; i < nsplitev; i += IMA_WARP) {
+    S.evt[(ng - 1) + mignum + i] = tv[i];
+    S.evi[(ng - 1) + mignum + i] = pack_event(2, 0, 0, i);
+  }
+  int np2 = 1;
+  while (np2 < nev) np2 <<= 1;
+  for (int i = nev + lane; i < np2; i += IMA_WARP) { S.evt[i] = DBL_MAX; S.evi[i] = 0x7fffffff; }
+  Warp::sync();
+  // bitonic sort by (time, info) in shared memory (the reference: indexx quicksort, utilities.cpp:709-793)
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < np2; i += IMA_WARP) {
+        const int x = i ^ j;
+        if (x > i) {
+          const double a = S.evt[i], b = S.evt[x];
+          const int ia = S.evi[i], ib = S.evi[x];
+          const bool gt = (a > b) || (a == b && ia > ib);
+          if (gt == ((i & k) == 0)) { S.evt[i] = b; S.evt[x] = a; S.evi[i] = ib; S.evi[x] = ia; }
+        }
+      }
+      Warp::sync();
+    }
+  // tip masks
+  for (int i = lane; i < ng * W; i += IMA_WARP) {
+    const int tip = i / W, w = i - tip * W;
+    S.mask[i] = ((tip >> 5) == w) ? (1u << (tip & 31)) : 0u;
+  }
+  for (int i = lane; i < d.NI; i += IMA_WARP) S.gwi[i] = 0;
+  for (int i = lane; i < d.ND; i += IMA_WARP) S.gwd[i] = 0.0;
+  Warp::sync();
+  // sweep (:1805-1921), lane 0; subtree masks are filled in coalescence-time order on the way
+  if (lane == 0) {
+    int n[kMaxTreePops];
+    const int npops = M.npops;
+    for (int i = 0; i < npops; i++) n[i] = L.samppop[i];
+    for (int i = npops; i < 2 * npops - 1; i++) n[i] = 0;
+    int nsum = ng, k = 0, bad = 0;
+    double lasttime = 0.0, length = 0.0, tlength = 0.0;
+    const double h2term = 1 / (2 * L.hval);
+    const double lastsplitt = M.nsplit > 0 ? tv[M.nsplit - 1] : kTimeMax;
+    for (int j = 0; j < nev; j++) {
+      const double t = S.evt[j];
+      const int info = S.evi[j];
+      const double dt = t - lasttime;
+      const double timeadd = nsum * dt;
+      length += timeadd;
+      if (t < lastsplitt) tlength += timeadd;
+      else if (lasttime < lastsplitt) tlength += nsum * (lastsplitt - lasttime);
+      lasttime = t;
+      const int np = npops - k;
+      for (int ii = 0; ii < np; ii++) {
+        const int ip = M.plist[k][ii];
+        S.gwd[wd_fc(M, k, ii)] += ((double)n[ip] * ((double)n[ip] - 1)) * dt * h2term;
+        if (!M.nomigration && k < M.nsplit) {
+          const double fmtemp = n[ip] * dt;
+          for (int jj = 0; jj < np; jj++) if (jj != ii) S.gwd[wd_fm(M, k, ii, jj)] += fmtemp;
+        }
+      }
+      const int kind = info & 3, ip = (info >> 2) & 31, jp = (info >> 7) & 31;
+      if (kind == 0) {
+        int ii = 0;
+        while (ii < np && M.plist[k][ii] != ip) ii++;
+        if (ii >= np || n[ip] < 2) { bad = 1; break; }
+        S.gwi[wi_cc(M, k, ii)]++;
+        n[ip]--; nsum--;
+        const int node = info >> 12, a = S.up0[node], b = S.up1[node];
+        for (int w = 0; w < W; w++) S.mask[node * W + w] = S.mask[a * W + w] | S.mask[b * W + w];
+      } else if (kind == 1) {
+        int ii = 0, jj = 0;
+        while (ii < np && M.plist[k][ii] != ip) ii++;
+        while (jj < np && M.plist[k][jj] != jp) jj++;
+        if (ii >= np || jj >= np || n[ip] < 1 || k >= M.nsplit) { bad = 1; break; }
+        S.gwi[wi_mc(M, k, ii, jj)]++;
+        n[ip]--; n[jp]++;
+      } else {
+        k++;
+        n[M.addpop[k]] = n[M.droppops[k][0]] + n[M.droppops[k][1]];
+        n[M.droppops[k][0]] = n[M.droppops[k][1]] = 0;
+      }
+    }
+    const double hlog = log(L.hval);
+    if (hlog != 0.0)
+      for (int kk = 0; kk <= M.nsplit; kk++)
+        for (int i = 0; i < npops - kk; i++) S.gwd[wd_hcc(M, kk, i)] += hlog * S.gwi[wi_cc(M, kk, i)];
+    if (nsum != 1) bad = 1;
+    if (bad) S.ctl_i[kCiFlags] |= (int)kFlagBadTree;
+    S.ctl_d[kCdLength] = length;
+    S.ctl_d[kCdTlength] = tlength;
+    S.ctl_i[kCiMignum] = mignum;
+    S.ctl_i[kCiNev] = nev;
+  }
+  Warp::sync();
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// infinite sites: calc_prob_data.cpp:731-836.  A site is compatible iff exactly one branch carries
+// its mutation, i.e. iff some non-root edge's subtree tip set equals the site's carrier set or its
+// complement (same accept/reject and same branch as labelgtree's Fitch pass).
+// Every lane returns the likelihood (or kRejectIS).
+// ------------------------------------------------------------------------------------------------
+IMA_DEV double likelihood_is(const EngineView &E, const DevLocus &L, const PairSm &S, double mutrate) {
+  const int lane = Warp::lane();
+  const int ng = L.ng, nl = L.nl, W = L.nwords, root = S.ctl_i[kCiRoot];
+  const uint32_t *sm = E.sitemask + L.sitemask_off;
+  double acc = 0.0;
+  bool reject = false;
+  for (int s = lane; s < L.nsites; s += IMA_WARP) {
+    int found = -1;
+    for (int b = 0; b < nl && found < 0; b++) {
+      if (b == root) continue;
+      bool eq = true, ceq = true;
+      for (int w = 0; w < W; w++) {
+        const uint32_t full = (w == W - 1 && (ng & 31)) ? ((1u << (ng & 31)) - 1u) : 0xffffffffu;
+        const uint32_t m = S.mask[b * W + w], v = sm[(size_t)s * W + w];
+        eq = eq && (m == v);
+        ceq = ceq && (m == (~v & full));
+      }
+      if (eq || ceq) found = b;
+    }
+    if (found < 0) { reject = true; continue; }
+    double ptime = S.time[found] - edge_top_time(S, ng, found);
+    const int dn = S.down[found];
+    if (dn == root) {                                  // mutation on either root branch: both lengths (:791-801)
+      const int a = S.up0[dn], b = S.up1[dn];
+      ptime = (S.time[a] - edge_top_time(S, ng, a)) + (S.time[b] - edge_top_time(S, ng, b));
+    }
+    acc += log(ptime * mutrate);
+  }
+  reject = Warp::any(reject);
+  acc = Warp::sum(acc);
+  if (reject) return kRejectIS;
+  return -S.ctl_d[kCdLength] * mutrate + acc - L.sumlogk;
+}
+
+// stepwise: calc_prob_data.cpp:841-909 (full evaluation of one linked portion); A/dlikeA in global memory
+IMA_DEV double likelihood_sw(const DevLocus &L, const PairSm &S, const short *A, double *dlikeA, double u) {
+  const int lane = Warp::lane();
+  double like = 0.0;
+  bool zero = false;
+  for (int i = lane; i < L.nl; i += IMA_WARP) {
+    double dl = 0.0;
+    if (S.down[i] != -1) {
+      const int dd = A[i] - A[S.down[i]];
+      const double t = S.time[i] - edge_top_time(S, L.ng, i);
+      const double bv = bessi(dd, t * u);
+      if (!(bv > 0.0)) { zero = true; dl = -1e+100; }
+      else dl = -(t * u) + log(bv);
+      like += dl;
+    }
+    dlikeA[i] = dl;
+  }
+  zero = Warp::any(zero);
+  like = Warp::sum(like);
+  return zero ? -DBL_MAX : like;
+}
+
+}  // namespace ima

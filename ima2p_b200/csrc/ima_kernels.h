@@ -1,0 +1,358 @@
+// Kernels of the M-mode engine.  One warp per (chain, locus) pair for the genealogy work, one warp per
+// chain for the prior sweep; a single thread replays the MC3 swap attempts (latency-only work).
+//
+//   k_eval_pairs     static evaluation of the current state (treeweight + P(D|G))
+//   k_eval_chains    per chain: sum the weights over loci, integrate the prior from scratch
+//   k_propose        updategenealogy steps 2-11: proposal + weights + likelihood,
+//                    written to the pair's OTHER buffer (rejection is then free)
+//   k_accept         per chain, loci in order: all-locus sums, integrated prior, MH accept (steps 12-14);
+//                    the loci of one chain are coupled through the prior
+//   k_swap           replicated replay of the step's swap attempts on (beta, S) of all chains
+#pragma once
+#include "ima_genealogy.h"
+#include "ima_devapi.h"
+
+namespace ima {
+
+// the model tables live in __constant__ memory; this header is included by exactly one translation
+// unit (ima_engine.cu), which therefore owns the definition
+IMA_CONSTANT DevModel c_model;
+#define IMA_MODEL c_model
+
+constexpr int kWarpsPerBlock = 4;
+
+IMA_DEV void rng_for(Philox &rng, const EngineView &E, uint32_t stream_id, uint32_t purpose) {
+  const unsigned long long step = *E.nsteps;
+  rng.init(E.seed, stream_id, (uint32_t)step, purpose | ((uint32_t)(step >> 32) << 8));
+}
+
+// P(D|G) of the staged genealogy for the locus's mutation model; every lane returns the value
+IMA_DEV double pair_likelihood(const EngineView &E, const DevLocus &L, const PairBuf &B, int p, PairSm &S, double *pdg_a_out) {
+  const double *u = E.uvals + (size_t)p * kMaxLinked;
+  if (L.model == kInfiniteSites) {
+    const double v = likelihood_is(E, L, S, u[0]);
+    pdg_a_out[0] = v;
+    return v;
+  }
+  if (L.model == kStepwise) {
+    double tot = 0.0;
+    for (int ai = 0; ai < L.nlinked; ai++) {
+      const short *A = B.A + ((size_t)p * kMaxLinked + ai) * E.d.NL;
+      double *dl = B.dlikeA + ((size_t)p * kMaxLinked + ai) * E.d.NL;
+      const double v = likelihood_sw(L, S, A, dl, u[ai]);
+      pdg_a_out[ai] = v;
+      tot += v;
+    }
+    return tot;
+  }
+  pdg_a_out[0] = 0.0;
+  return 0.0;
+}
+
+IMA_KERNEL void k_eval_pairs(EngineView E) {
+  IMA_SMEM_DECL
+  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (p >= E.d.P) return;
+  const DevModel &M = IMA_MODEL;
+  const int c = p / E.d.nloci, li = p - c * E.d.nloci;
+  const DevLocus &L = E.loci[li];
+  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
+  const PairBuf &B = E.buf[E.cur[p]];
+  const double *tv = E.tvals + (size_t)c * kMaxPeriods;
+  stage_pair(E, B, p, L.nl, S);
+  const bool ok = eval_weights(M, E.d, L, tv, S);
+  double pdga[kMaxLinked];
+  const double pdg = ok ? pair_likelihood(E, L, B, p, S, pdga) : 0.0;
+  const int lane = Warp::lane();
+  for (int i = lane; i < E.d.NI; i += IMA_WARP) B.gwi[(size_t)p * E.d.NI + i] = S.gwi[i];
+  for (int i = lane; i < E.d.ND; i += IMA_WARP) B.gwd[(size_t)p * E.d.ND + i] = S.gwd[i];
+  if (lane == 0) {
+    B.sd[(size_t)p * 4 + 1] = S.ctl_d[kCdLength];
+    B.sd[(size_t)p * 4 + 2] = S.ctl_d[kCdTlength];
+    B.sd[(size_t)p * 4 + 3] = pdg;
+    if (B.pdg_a) for (int ai = 0; ai < L.nlinked; ai++) B.pdg_a[(size_t)p * kMaxLinked + ai] = pdga[ai];
+    E.prop_flags[p] = ok ? (uint32_t)S.ctl_i[kCiFlags] : (uint32_t)kFlagOverflow;
+  }
+}
+
+// gather (c, f, hc) of one parameter from a weight record (update_gtree_common.cpp:1985-1994, 2018-2030)
+IMA_DEV void gather_q(const DevModel &M, int t, const int *wi, const double *wd, int &c, double &f, double &hc) {
+  c = 0; f = 0.0; hc = 0.0;
+  for (int j = 0; j < M.q_n[t]; j++) { const int x = M.q_idx[t][j]; c += wi[x]; f += wd[x]; hc += wd[M.ncc + x]; }
+}
+IMA_DEV void gather_m(const DevModel &M, int t, const int *wi, const double *wd, int &c, double &f) {
+  c = 0; f = 0.0;
+  for (int j = 0; j < M.m_n[t]; j++) { const int x = M.m_idx[t][j]; c += wi[M.ncc + x]; f += wd[2 * M.ncc + x]; }
+}
+IMA_DEV bool migration_allowed(const DevModel &M, const int *wi) {
+  if (M.nomigration == 0)
+    for (int i = 0; i < M.nomig_n; i++) if (wi[M.ncc + M.nomig_idx[i]] != 0) return false;
+  return true;
+}
+IMA_DEV double mig_term(const DevModel &M, const MathCtx &mc, int t, int c, double f) {
+  return M.expoprior ? integrate_migration_term_expo(mc, c, f, M.m_mean[t]) : integrate_migration_term(mc, c, f, M.m_max[t], M.m_min[t]);
+}
+
+// shared-memory scratch of the per-chain kernels
+struct ChainSm { int *ai, *ci; double *ad, *cd, *q, *cq; };
+IMA_HD size_t chain_smem_bytes(const EngineDims &d) {
+  return 2 * align8(sizeof(int) * d.NI) + 2 * align8(sizeof(double) * d.ND) + 2 * align8(sizeof(double) * 2 * kMaxParams);
+}
+IMA_DEV ChainSm carve_chain_smem(unsigned char *base, const EngineDims &d) {
+  ChainSm s; unsigned char *p = base;
+  s.ad = (double *)p; p += align8(sizeof(double) * d.ND);
+  s.cd = (double *)p; p += align8(sizeof(double) * d.ND);
+  s.q = (double *)p; p += align8(sizeof(double) * 2 * kMaxParams);
+  s.cq = (double *)p; p += align8(sizeof(double) * 2 * kMaxParams);
+  s.ai = (int *)p; p += align8(sizeof(int) * d.NI);
+  s.ci = (int *)p;
+  return s;
+}
+
+// S of swapweight (swapchains.cpp:12-34): sum over loci of pdg, plus probg unless thermodynamic mode
+IMA_DEV double chain_swapsum(const EngineView &E, const DevModel &M, int c, double probg) {
+  double s = 0.0;
+  for (int li = Warp::lane(); li < E.d.nloci; li += IMA_WARP) {
+    const int p = c * E.d.nloci + li;
+    s += E.buf[E.cur[p]].sd[(size_t)p * 4 + 3];
+  }
+  s = Warp::sum(s);
+  return M.thermo ? s : s + probg;
+}
+
+IMA_KERNEL void k_eval_chains(EngineView E) {
+  IMA_SMEM_DECL
+  const int c = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (c >= E.d.nchains) return;
+  const DevModel &M = IMA_MODEL;
+  const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND;
+  ChainSm S = carve_chain_smem(IMA_SMEM + (size_t)ima_warp_in_block() * chain_smem_bytes(E.d), E.d);
+  // sum_treeinfo over loci in locus order (init_p, mcmcfile.cpp:188)
+  for (int i = lane; i < NI; i += IMA_WARP) {
+    int a = 0;
+    for (int li = 0; li < E.d.nloci; li++) { const int p = c * E.d.nloci + li; a += E.buf[E.cur[p]].gwi[(size_t)p * NI + i]; }
+    S.ai[i] = a; E.all_i[(size_t)c * NI + i] = a;
+  }
+  for (int i = lane; i < ND; i += IMA_WARP) {
+    double a = 0.0;
+    for (int li = 0; li < E.d.nloci; li++) { const int p = c * E.d.nloci + li; a += E.buf[E.cur[p]].gwd[(size_t)p * ND + i]; }
+    S.ad[i] = a; E.all_d[(size_t)c * ND + i] = a;
+  }
+  Warp::sync();
+  // initialize_integrate_tree_prob (update_gtree_common.cpp:2056-2134), one lane per parameter
+  double part = 0.0;
+  const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
+  for (int t = lane; t < nterms; t += IMA_WARP) {
+    double v;
+    if (t < M.nq) { int cc; double f, hc; gather_q(M, t, S.ai, S.ad, cc, f, hc); v = integrate_coalescent_term(E.mc, cc, f, hc, M.q_max[t], M.q_min[t]); E.qint[(size_t)c * kMaxParams + t] = v; }
+    else { int cm; double f; gather_m(M, t - M.nq, S.ai, S.ad, cm, f); v = mig_term(M, E.mc, t - M.nq, cm, f); E.mint[(size_t)c * kMaxParams + t - M.nq] = v; }
+    part += v;
+  }
+  double probg = Warp::sum(part);
+  if (!migration_allowed(M, S.ai)) probg = -kMyDblMax;
+  double pd = 0.0;
+  for (int li = lane; li < E.d.nloci; li += IMA_WARP) { const int p = c * E.d.nloci + li; pd += E.buf[E.cur[p]].sd[(size_t)p * 4 + 3]; }
+  pd = Warp::sum(pd);
+  const double ssum = chain_swapsum(E, M, c, probg);
+  if (lane == 0) { E.probg[c] = probg; E.pdgsum[c] = pd; E.swapsum[c] = ssum; }
+}
+
+IMA_KERNEL void k_propose(EngineView E) {
+  IMA_SMEM_DECL
+  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (p >= E.d.P) return;
+  const DevModel &M = IMA_MODEL;
+  const int c = p / E.d.nloci, li = p - c * E.d.nloci;
+  const DevLocus &L = E.loci[li];
+  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
+  const int cb = E.cur[p];
+  const PairBuf &B = E.buf[cb];
+  const PairBuf &Bn = E.buf[cb ^ 1];
+  const double *tv = E.tvals + (size_t)c * kMaxPeriods;
+  const int lane = Warp::lane();
+  stage_pair(E, B, p, L.nl, S);
+  if (lane == 0) {
+    Philox rng;
+    rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngPropose);
+    propose_move(M, E.d, tv, L.ng, L.nl, rng, S);
+  }
+  Warp::sync();
+  uint32_t flags = (uint32_t)S.ctl_i[kCiFlags];
+  bool ok = !(flags & kFlagOverflow);
+  if (ok) ok = eval_weights(M, E.d, L, tv, S);
+  const int total_mig = ok ? S.ctl_i[kCiMignum] : 0;
+  if (ok && total_mig > E.d.CAP) ok = false;
+  double pdga[kMaxLinked];
+  double pdg = 0.0;
+  if (ok) {
+    pdg = pair_likelihood(E, L, Bn, p, S, pdga);
+    flags = (uint32_t)S.ctl_i[kCiFlags];
+    if (pdg == kRejectIS) flags |= kFlagRejectIS;
+    if (lane == 0) S.ctl_d[kCdPdg] = pdg;
+    Warp::sync();
+    if (!(flags & (kFlagRejectIS | kFlagBadTree))) store_pair(E, Bn, p, L.nl, S, total_mig);
+  } else {
+    flags |= kFlagOverflow;
+  }
+  if (lane == 0) {
+    E.prop_flags[p] = flags;
+    E.prop_extra[p] = S.ctl_d[kCdMigw] + S.ctl_d[kCdSlidew] + S.ctl_d[kCdAterm];
+    E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw]; E.prop_dbg[(size_t)p * 4 + 1] = S.ctl_d[kCdSlidew];
+    E.prop_dbg[(size_t)p * 4 + 2] = S.ctl_d[kCdSlideDist]; E.prop_dbg[(size_t)p * 4 + 3] = (double)S.ctl_i[kCiEdge];
+  }
+}
+
+IMA_KERNEL void k_accept(EngineView E) {
+  IMA_SMEM_DECL
+  const int c = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (c >= E.d.nchains) return;
+  const DevModel &M = IMA_MODEL;
+  const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
+  ChainSm S = carve_chain_smem(IMA_SMEM + (size_t)ima_warp_in_block() * chain_smem_bytes(E.d), E.d);
+  for (int i = lane; i < NI; i += IMA_WARP) S.ai[i] = E.all_i[(size_t)c * NI + i];
+  for (int i = lane; i < ND; i += IMA_WARP) S.ad[i] = E.all_d[(size_t)c * ND + i];
+  for (int i = lane; i < M.nq; i += IMA_WARP) S.q[i] = E.qint[(size_t)c * kMaxParams + i];
+  for (int i = lane; i < M.nm; i += IMA_WARP) S.q[kMaxParams + i] = E.mint[(size_t)c * kMaxParams + i];
+  Warp::sync();
+  const double beta = E.beta[c];
+  double probg = E.probg[c], pdgsum = E.pdgsum[c];
+  const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
+  unsigned long long dropped = 0;
+  for (int li = 0; li < E.d.nloci; li++) {
+    const int p = c * E.d.nloci + li;
+    const uint32_t flags = E.prop_flags[p];
+    if (flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree)) { if (flags & kFlagOverflow) dropped++; continue; }
+    const int cb = E.cur[p], nb = cb ^ 1;
+    const int *oi = E.buf[cb].gwi + (size_t)p * NI, *ni = E.buf[nb].gwi + (size_t)p * NI;
+    const double *od = E.buf[cb].gwd + (size_t)p * ND, *nd = E.buf[nb].gwd + (size_t)p * ND;
+    // sum_subtract_treeinfo (ginfo.cpp:248-285): subtract old, add new, clamp fc and fm at 0
+    for (int i = lane; i < NI; i += IMA_WARP) S.ci[i] = S.ai[i] + (ni[i] - oi[i]);
+    for (int i = lane; i < ND; i += IMA_WARP) {
+      double x = S.ad[i];
+      x -= od[i];
+      x += nd[i];
+      if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
+      S.cd[i] = x;
+    }
+    Warp::sync();
+    // integrate_tree_prob (update_gtree_common.cpp:1944-2053) with the reuse rule :1997-2000, :2031-2034
+    double part = 0.0;
+    for (int t = lane; t < nterms; t += IMA_WARP) {
+      double v;
+      if (t < M.nq) {
+        int cn, co; double fn, fo, hn, ho;
+        gather_q(M, t, S.ci, S.cd, cn, fn, hn);
+        gather_q(M, t, S.ai, S.ad, co, fo, ho);
+        v = (cn == co && fn == fo) ? S.q[t] : integrate_coalescent_term(E.mc, cn, fn, hn, M.q_max[t], M.q_min[t]);
+        S.cq[t] = v;
+      } else {
+        const int tm = t - M.nq;
+        int cn, co; double fn, fo;
+        gather_m(M, tm, S.ci, S.cd, cn, fn);
+        gather_m(M, tm, S.ai, S.ad, co, fo);
+        v = (cn == co && fn == fo) ? S.q[kMaxParams + tm] : mig_term(M, E.mc, tm, cn, fn);
+        S.cq[kMaxParams + tm] = v;
+      }
+      part += v;
+    }
+    double newprobg = Warp::sum(part);
+    if (!migration_allowed(M, S.ci)) newprobg = -kMyDblMax;
+    const double oldpdg = E.buf[cb].sd[(size_t)p * 4 + 3], newpdg = E.buf[nb].sd[(size_t)p * 4 + 3];
+    int acc = 0;
+    if (lane == 0) {
+      const double tpw = newprobg - probg;
+      const double extra = E.prop_extra[p];
+      double mh;                                        // update_gtree.cpp:917-927
+      if (M.thermo) mh = exp(beta * M.gbeta * (newpdg - oldpdg) + tpw + extra);
+      else mh = exp(beta * (tpw + M.gbeta * (newpdg - oldpdg)) + extra);
+      Philox rng;
+      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngAccept);
+      const double U = rng.uniform();
+      acc = (U < fmin(1.0, mh)) ? 1 : 0;
+    }
+    acc = Warp::bcast(acc, 0);
+    if (acc) {
+      for (int i = lane; i < NI; i += IMA_WARP) S.ai[i] = S.ci[i];
+      for (int i = lane; i < ND; i += IMA_WARP) S.ad[i] = S.cd[i];
+      for (int i = lane; i < M.nq; i += IMA_WARP) S.q[i] = S.cq[i];
+      for (int i = lane; i < M.nm; i += IMA_WARP) S.q[kMaxParams + i] = S.cq[kMaxParams + i];
+      probg = newprobg;
+      pdgsum -= oldpdg;
+      pdgsum += newpdg;
+      if (lane == 0) {
+        E.cur[p] = (unsigned char)nb;
+        E.acc[(size_t)p * 3 + 0]++;
+        if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
+        if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
+      }
+    }
+    Warp::sync();
+  }
+  for (int i = lane; i < NI; i += IMA_WARP) E.all_i[(size_t)c * NI + i] = S.ai[i];
+  for (int i = lane; i < ND; i += IMA_WARP) E.all_d[(size_t)c * ND + i] = S.ad[i];
+  for (int i = lane; i < M.nq; i += IMA_WARP) E.qint[(size_t)c * kMaxParams + i] = S.q[i];
+  for (int i = lane; i < M.nm; i += IMA_WARP) E.mint[(size_t)c * kMaxParams + i] = S.q[kMaxParams + i];
+#if IMA_CUDA
+  __threadfence_block();
+#endif
+  Warp::sync();
+  const double ssum = chain_swapsum(E, M, c, probg);
+  if (lane == 0) {
+    E.probg[c] = probg; E.pdgsum[c] = pdgsum; E.swapsum[c] = ssum;
+    if (dropped) {
+#if IMA_CUDA
+      atomicAdd(E.overflow, dropped);
+#else
+      *E.overflow += dropped;
+#endif
+    }
+  }
+}
+
+// MC3 swaps in temperature-rank form (swapchains_bwprocesses, swapchains.cpp:192-523; accept rule
+// swapchains.cpp:57-62, 603-605): only betas move.  Every rank replays the same attempts on the same
+// all-gathered S with the same counter-based stream, so no further message is needed.
+struct SwapView {
+  const double *S_global;   // [nchains_global]
+  int *rank_of_chain;       // [nchains_global]
+  int *chain_of_rank;       // [nchains_global]
+  const double *beta_table; // [nchains_global] beta by temperature rank (rank 0 = cold)
+  unsigned long long *swap_counts;   // [2] attempts, accepts
+  int swaptries, advance_step;
+};
+
+IMA_KERNEL void k_swap(EngineView E, SwapView V) {
+  if (ima_block() != 0 || ima_warp_in_block() != 0 || Warp::lane() != 0) return;
+  const int N = E.d.nchains_global;
+  if (N > 1 && V.swaptries > 0) {
+    Philox rng;
+    rng_for(rng, E, 0xffffffffu, kRngSwap);
+    for (int x = 0; x < V.swaptries; x++) {
+      const int sa = rng.randint(N);
+      int sbmin = 0, sbrange = N;
+      if (N >= 2 * kSwapDist + 3) {
+        sbmin = sa - kSwapDist > 0 ? sa - kSwapDist : 0;
+        sbrange = (N < sa + kSwapDist ? N : sa + kSwapDist) - sbmin;
+      }
+      int sb;
+      do { sb = sbmin + rng.randint(sbrange); } while (sb == sa);
+      const int ca = V.chain_of_rank[sa], cb = V.chain_of_rank[sb];
+      const double w = exp((V.beta_table[sa] - V.beta_table[sb]) * (V.S_global[cb] - V.S_global[ca]));
+      V.swap_counts[0]++;
+      if (w >= 1.0 || w > rng.uniform()) {
+        V.chain_of_rank[sa] = cb; V.chain_of_rank[sb] = ca;
+        V.rank_of_chain[ca] = sb; V.rank_of_chain[cb] = sa;
+        V.swap_counts[1]++;
+      }
+    }
+    for (int c = 0; c < E.d.nchains; c++) E.beta[c] = V.beta_table[V.rank_of_chain[E.d.chain0 + c]];
+  }
+  if (V.advance_step) *E.nsteps += 1;
+}
+
+IMA_KERNEL void k_copy_swapsum(EngineView E, double *dst) {
+  const int i = ima_block() * kWarpsPerBlock * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
+  if (i < E.d.nchains) dst[i] = E.swapsum[i];
+}
+
+}  // namespace ima

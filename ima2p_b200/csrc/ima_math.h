@@ -1,0 +1,307 @@
+// Device numerics of the IMa2p hot path.
+//
+// "Within 1e-9 of the reference" means reproducing the reference's own recurrences and stopping rules
+// (SURVEY.md fact 3): incomplete-gamma series/continued fractions that stop at EPS 3e-7
+// (utilities.cpp:808-1122), Abramowitz-Stegun Bessel polynomials (utilities.cpp:54-124,1452-1491), the
+// 10-term eexp polynomial (utilities.cpp:1501-1539) and the LogDiff switches of the integrated prior
+// (update_gtree_common.cpp:108-304).  This translation unit is compiled with --fmad=false so that
+// no multiply-add is contracted (the reference is an FMA-free x86-64 build).
+#pragma once
+#include "ima_platform.h"
+
+namespace ima {
+
+struct MathCtx {
+  const double *logfact;   // logfact[i] = sum_{j<=i} log j, same running sum as setlogfact (utilities.cpp:1405-1414)
+  int logfact_n;
+  int *err;                // device error word (first error wins); 0 = none
+};
+
+enum DevErr { kErrNone = 0, kErrLogDiff = 14, kErrGamma = 15, kErrRange = 16 };
+
+IMA_DEV void raise(const MathCtx &mc, int code) {
+#if IMA_CUDA
+  atomicCAS(mc.err, 0, code);
+#else
+  if (*mc.err == 0) *mc.err = code;
+#endif
+}
+
+IMA_DEV double lfact(const MathCtx &mc, int n) {
+  if (n < 0 || n >= mc.logfact_n) { raise(mc, kErrRange); return 0.0; }
+  return mc.logfact[n];
+}
+
+constexpr int kItMax = 1000;       // ITMAX
+constexpr double kEps = 3.0e-7;    // EPS
+constexpr double kFpMin = 1.0e-30; // FPMIN
+
+// Lentz continued fraction shared by gcf / gcflog (utilities.cpp:811-877); returns h
+IMA_DEV double gamma_cf(const MathCtx &mc, double a, double x) {
+  double b = x + 1.0 - a, c = 1.0 / kFpMin, d = 1.0 / b, h = d;
+  int i;
+  for (i = 1; i <= kItMax; i++) {
+    double an = -i * (i - a);
+    b += 2.0;
+    d = an * d + b;
+    if (fabs(d) < kFpMin) d = kFpMin;
+    c = b + an / c;
+    if (fabs(c) < kFpMin) c = kFpMin;
+    d = 1.0 / d;
+    double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < kEps) break;
+  }
+  if (i > kItMax) raise(mc, kErrGamma);
+  return h;
+}
+
+// series shared by gser / gserlog (utilities.cpp:882-953); returns sum (0 when x <= 0)
+IMA_DEV double gamma_series(const MathCtx &mc, int a, double x) {
+  if (x <= 0.0) { if (x < 0.0) raise(mc, kErrGamma); return 0.0; }
+  double ap = a, del = 1.0 / a, sum = del;
+  for (int n = 1; n <= kItMax; n++) {
+    ap += 1.0;
+    del *= x / ap;
+    sum += del;
+    if (fabs(del) < fabs(sum) * kEps) return sum;
+  }
+  raise(mc, kErrGamma);
+  return 0.0;
+}
+
+// expint(1, x) as used by uppergamma(0, x) (utilities.cpp:962-1045, n == 1); result in log form
+IMA_DEV double log_expint1(const MathCtx &mc, double x) {
+  const double euler = 0.5772156649;
+  if (x <= 0.0) { raise(mc, kErrGamma); return 0.0; }
+  if (x > 1.0) {
+    double b = x + 1.0, c = 1.0 / kFpMin, d = 1.0 / b, h = d;
+    for (int i = 1; i <= 100; i++) {
+      double a = -(double)i * (double)i;       // -i*(nm1+i), nm1 = 0
+      b += 2.0;
+      d = 1.0 / (a * d + b);
+      c = b + a / c;
+      double del = c * d;
+      h *= del;
+      if (fabs(del - 1.0) < kEps) return log(h) - x;
+    }
+    raise(mc, kErrGamma);
+    return 0.0;
+  }
+  double ans = -log(x) - euler, fact = 1.0;
+  for (int i = 1; i <= 100; i++) {
+    fact *= -x / i;
+    double del = -fact / i;                    // i != nm1 (= 0) always
+    ans += del;
+    if (fabs(del) < fabs(ans) * kEps) return log(ans);
+  }
+  raise(mc, kErrGamma);
+  return 0.0;
+}
+
+// uppergamma utilities.cpp:1053-1090: log Gamma(a, x), integer a >= 0
+IMA_DEV double uppergamma(const MathCtx &mc, int a, double x) {
+  double p;
+  if (x < 0.0 || a < 0) { raise(mc, kErrGamma); return 0.0; }
+  if (a == 0) {
+    p = log_expint1(mc, x);
+  } else {
+    double gln = lfact(mc, a - 1);
+    if (x < a + 1.0) {
+      double s = gamma_series(mc, a, x);
+      double gamser = (x <= 0.0) ? 0.0 : s * exp(-x + a * log(x) - gln);
+      p = gln + log(1.0 - gamser);
+    } else {
+      double h = gamma_cf(mc, (double)a, x);
+      p = gln + ((-x + a * log(x) - gln) + log(h));
+    }
+  }
+  if (p < -1e200) p = -1e200;
+  return p;
+}
+
+// lowergamma utilities.cpp:1092-1122: log gamma(a, x), integer a >= 1
+IMA_DEV double lowergamma(const MathCtx &mc, int a, double x) {
+  double p;
+  if (x < 0.0 || a <= 0) { raise(mc, kErrGamma); return 0.0; }
+  double gln = lfact(mc, a - 1);
+  if (x < a + 1.0) {
+    double s = gamma_series(mc, a, x);
+    double gamserlog = (x <= 0.0) ? 0.0 : log(s) + (-x + a * log(x) - gln);
+    p = gln + gamserlog;
+  } else {
+    double h = gamma_cf(mc, (double)a, x);
+    double gammcf = exp(-x + a * log(x) - gln) * h;
+    p = gln + log(1 - gammcf);
+  }
+  if (p < -1e200) p = -1e200;
+  return p;
+}
+
+// LogDiff imamp.hpp:257-263; a <= b is fatal in the reference -> error word + huge negative value
+IMA_DEV bool logdiff(const MathCtx &mc, double &v, double a, double b) {
+  if (a <= b) { raise(mc, kErrLogDiff); v = -kMyDblMax; return false; }
+  v = (a - b < kLogDblMax) ? b + log(exp(a - b) - 1.0) : a;
+  return true;
+}
+
+// integrate_coalescent_term update_gtree_common.cpp:108-203 (MORESTABLE)
+IMA_DEV double integrate_coalescent_term(const MathCtx &mc, int cc, double fc, double hcc, double max, double min) {
+  double p, a, b, c, d;
+  if (cc > 0) {
+    if (min == 0) {
+      double ug = uppergamma(mc, cc - 1, 2 * fc / max);
+      if (cc > 1) {
+        double fullg = lfact(mc, cc - 2);
+        if (fullg - ug < 1e-15 || fullg - ug > kLogDblMax) {
+          double lg = lowergamma(mc, cc - 1, 2 * fc / max);
+          if (fullg > lg) {
+            double ugalt;
+            logdiff(mc, ugalt, fullg, lg);
+            if (fabs(ugalt - ug) > 1e-10) ug = ugalt;
+          }
+        }
+      }
+      p = ug + kLog2 - hcc + (1 - cc) * log(fc);
+    } else {
+      a = uppergamma(mc, cc - 1, 2 * fc / max);
+      b = uppergamma(mc, cc - 1, 2 * fc / min);
+      if (!logdiff(mc, p, a, b)) return p;
+      p += (kLog2 - hcc + (1 - cc) * log(fc));
+    }
+  } else if (2 * fc / max > 0) {
+    if (min == 0) {
+      a = log(max) - 2.0 * fc / max;
+      b = kLog2 + log(fc) + uppergamma(mc, 0, 2.0 * fc / max);
+      logdiff(mc, p, a, b);
+    } else {
+      a = uppergamma(mc, 0, 2 * fc / max);
+      b = uppergamma(mc, 0, 2 * fc / min);
+      if (!logdiff(mc, c, a, b)) return c;
+      c += kLog2 + log(fc);
+      a = log(max) - 2.0 * fc / max;
+      b = log(min) - 2.0 * fc / min;
+      if (!logdiff(mc, d, a, b)) return d;
+      logdiff(mc, p, d, c);
+    }
+  } else {
+    p = log(max - min);
+  }
+  return p;
+}
+
+// integrate_migration_term update_gtree_common.cpp:205-296 (MORESTABLE)
+IMA_DEV double integrate_migration_term(const MathCtx &mc, int cm, double fm, double max, double min) {
+  double p, a, b, c;
+  if (cm > 0) {
+    if (min == 0) {
+      double lg = lowergamma(mc, cm + 1, fm * max);
+      double fullg = lfact(mc, cm);
+      if (fullg - lg < 1e-15 || fullg - lg > kLogDblMax) {
+        double ug = uppergamma(mc, cm + 1, fm * max);
+        if (fullg > ug) {
+          double lgalt;
+          logdiff(mc, lgalt, fullg, ug);
+          if (fabs(lgalt - lg) > 1e-12) lg = lgalt;
+        }
+      }
+      p = (-1 - cm) * log(fm) + lg;
+    } else {
+      a = uppergamma(mc, cm + 1, fm * min);
+      b = uppergamma(mc, cm + 1, fm * max);
+      if (!logdiff(mc, c, a, b)) return c;
+      p = (-1 - cm) * log(fm) + c;
+    }
+  } else if (fm > kMPriorMin) {
+    if (min == 0) {
+      if (max == kMPriorMin) {
+        p = 0;
+      } else {
+        if (!logdiff(mc, c, 0.0, -fm * max)) return c;
+        p = c - log(fm);
+      }
+    } else {
+      if (!logdiff(mc, c, -fm * min, -fm * max)) return c;
+      p = c - log(fm);
+    }
+  } else {
+    p = log(max - min);
+  }
+  return p;
+}
+
+// integrate_migration_term_expo_prior update_gtree_common.cpp:298-304
+IMA_DEV double integrate_migration_term_expo(const MathCtx &mc, int cm, double fm, double exmean) {
+  return -log(exmean) + (-(cm + 1) * log(fm + 1.0 / exmean)) + lfact(mc, cm);
+}
+
+// utilities.cpp:239-255
+IMA_DEV double mylogcosh(double x) { return x < 100 ? log(cosh(x)) : x - kLog2; }
+IMA_DEV double mylogsinh(double x) { return x < 100 ? log(sinh(x)) : x - kLog2; }
+
+// calcmrate update_gtree_common.cpp:462-482
+IMA_DEV double calcmrate(int mcnt, double mt) {
+  if (mt <= 0.0) return 1.0;
+  if (mcnt == 0) return mt < 1 ? 0.1 : 0.1 / mt;
+  return mt < 1 ? (double)mcnt : ((double)mcnt) / mt;
+}
+
+// bessi0 / bessi1 / bessi: utilities.cpp:54-124, 1452-1491
+IMA_DEV double bessi0(double x) {
+  double ax = fabs(x), y;
+  if (ax < 3.75) {
+    y = x / 3.75; y *= y;
+    return 1.0 + y * (3.5156229 + y * (3.0899424 + y * (1.2067492 + y * (0.2659732 + y * (0.360768e-1 + y * 0.45813e-2)))));
+  }
+  y = 3.75 / ax;
+  return (exp(ax) / sqrt(ax)) * (0.39894228 + y * (0.1328592e-1 + y * (0.225319e-2 + y * (-0.157565e-2 + y * (0.916281e-2 +
+         y * (-0.2057706e-1 + y * (0.2635537e-1 + y * (-0.1647633e-1 + y * 0.392377e-2))))))));
+}
+IMA_DEV double bessi1(double x) {
+  double ax = fabs(x), y, ans;
+  if (ax < 3.75) {
+    y = x / 3.75; y *= y;
+    ans = ax * (0.5 + y * (0.87890594 + y * (0.51498869 + y * (0.15084934 + y * (0.2658733e-1 + y * (0.301532e-2 + y * 0.32411e-3))))));
+  } else {
+    y = 3.75 / ax;
+    ans = 0.2282967e-1 + y * (-0.2895312e-1 + y * (0.1787654e-1 - y * 0.420059e-2));
+    ans = 0.39894228 + y * (-0.3988024e-1 + y * (-0.362018e-2 + y * (0.163801e-2 + y * (-0.1031555e-1 + y * ans))));
+    ans *= (exp(ax) / sqrt(ax));
+  }
+  return x < 0.0 ? -ans : ans;
+}
+IMA_DEV double bessi(int n, double x) {
+  n = n < 0 ? -n : n;
+  if (x > 700) return kMyDblMax;
+  if (n == 0) return bessi0(x);
+  if (n == 1) return bessi1(x);
+  if (x == 0.0) return 0.0;
+  double tox = 2.0 / fabs(x), bip = 0.0, ans = 0.0, bi = 1.0;
+  for (int j = 2 * (n + (int)sqrt(40.0 * n)); j > 0; j--) {
+    double bim = bip + j * tox * bi;
+    bip = bi;
+    bi = bim;
+    if (fabs(bi) > 1.0e10) { ans *= 1.0e-10; bi *= 1.0e-10; bip *= 1.0e-10; }
+    if (j == n) ans = bip;
+  }
+  ans *= bessi0(x) / bi;
+  return (x < 0.0 && (n & 1)) ? -ans : ans;
+}
+
+// eexp utilities.cpp:1501-1539: exp(x) = m * 10^z with 1 <= |m| < 10
+IMA_DEV void eexp(double x, double &m, int &z) {
+  int n = (int)floor(x / kLog2);
+  double zr = 0.30102999566398119521 * (double)n;
+  z = (int)zr;
+  zr -= (double)z;
+  double u = x - (((double)n) * kLog2);
+  double t = 1 + u * (1.0 + u * (0.5 + u * (0.16666666666666666666666666667 + u * (0.04166666666666666666666666667 +
+             u * (0.00833333333333333333333333333 + u * (0.001388888888888888888888888889 +
+             u * (0.000198412698412698412698412698 + u * (0.000024801587301587301587301587301 +
+             u * (2.75573192239858906525573192239859e-6 + u * (2.75573192239858906525573192239e-7))))))))));
+  m = t * pow(10.0, zr);
+  if (fabs(m) > 10) { m = m / 10.0; z = z + 1; }
+  if (fabs(m) < 1) { m = m * 10.0; z = z - 1; }
+}
+
+}  // namespace ima

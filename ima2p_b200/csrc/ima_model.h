@@ -1,0 +1,108 @@
+// Device-resident tables and state layout of the engine (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include "ima_platform.h"
+#include "ima_math.h"
+
+namespace ima {
+
+// Chain-invariant model tables: population tree, per-period population lists, parameter ->
+// weight-position lists and priors (what setup_iparams builds, initialize.cpp:201-727).  Lives in
+// __constant__ memory on the device.
+struct DevModel {
+  int npops, nsplit, ntreepops, rootpop;
+  int nq, nm, ncc, nmc;                 // NI = ncc + nmc ints, ND = 2*ncc + nmc doubles per weight record
+  int nomigration, expoprior, thermo;
+  double gbeta;
+  signed char plist[kMaxPops][kMaxPops];
+  signed char addpop[kMaxPeriods], droppops[kMaxPeriods][2];
+  signed char pt_e[kMaxTreePops], pt_down[kMaxTreePops];
+  short cc_off[kMaxPeriods + 1], mc_off[kMaxPeriods + 1];
+  signed char q_n[kMaxParams], m_n[kMaxParams];
+  short q_idx[kMaxParams][kMaxWp], m_idx[kMaxParams][kMaxWp];
+  double q_max[kMaxParams], q_min[kMaxParams];
+  double m_max[kMaxParams], m_min[kMaxParams], m_mean[kMaxParams];
+  int nomig_n;
+  short nomig_idx[kMaxParams];
+};
+
+// weight record layout: ints  [cc(ncc) | mc(nmc)],  doubles [fc(ncc) | hcc(ncc) | fm(nmc)]
+IMA_HD int wi_cc(const DevModel &M, int k, int i) { return M.cc_off[k] + i; }
+IMA_HD int wi_mc(const DevModel &M, int k, int i, int j) { return M.ncc + M.mc_off[k] + i * (M.npops - k) + j; }
+IMA_HD int wd_fc(const DevModel &M, int k, int i) { return M.cc_off[k] + i; }
+IMA_HD int wd_hcc(const DevModel &M, int k, int i) { return M.ncc + M.cc_off[k] + i; }
+IMA_HD int wd_fm(const DevModel &M, int k, int i, int j) { return 2 * M.ncc + M.mc_off[k] + i * (M.npops - k) + j; }
+
+// Per-locus read-only data, shared by all chains (struct locus, imamp.hpp:894-936).
+struct DevLocus {
+  int model, ng, nl, nsites, nwords, totsites, nlinked;
+  int samppop[kMaxPops];
+  int minA[kMaxLinked], maxA[kMaxLinked];
+  double hval, sumlogk;
+  long long sitemask_off;   // uint32 [nsites][nwords]: carrier-tip bit masks of the segregating sites (IS)
+  long long seq_off;        // uint8  [ng][nsites]: bases 0..3 of the compressed site patterns (HKY)
+  long long mult_off;       // int    [nsites]: pattern multiplicities (HKY)
+};
+
+struct short4_t { short x, y, z, w; };       // up0, up1, down, pop
+struct ushort2_t { unsigned short x, y; };   // migration segment (start, count) in the pair's pool
+
+// One of the two state buffers.  Pair-major arrays: pair p = local_chain * nloci + locus.
+struct PairBuf {
+  short4_t *topo;       // [P][NL]
+  double *time;         // [P][NL]   time at the bottom of the edge (root: TIMEMAX)
+  ushort2_t *mseg;      // [P][NL]
+  double *mig_t;        // [P][CAP]
+  short *mig_p;         // [P][CAP]
+  double *sd;           // [P][4]    roottime, length, tlength, pdg
+  int *si;              // [P][2]    root, mignum
+  int *gwi;             // [P][NI]
+  double *gwd;          // [P][ND]
+  short *A;             // [P][kMaxLinked][NL]   stepwise allele states (only when some locus is stepwise)
+  double *dlikeA;       // [P][kMaxLinked][NL]
+  double *pdg_a;        // [P][kMaxLinked]
+};
+
+struct EngineDims {
+  int nchains;          // chains held by this GPU
+  int nchains_global;   // chains over all ranks
+  int chain0;           // global index of local chain 0
+  int nloci, P;
+  int NL, CAP, NI, ND, EVP, W, S;     // maxima over loci: numlines, pool capacity, record sizes, event slots, mask words, sites
+  int any_sw, any_hky;
+};
+
+// Everything a kernel needs, passed by value.
+struct EngineView {
+  EngineDims d;
+  MathCtx mc;
+  const DevLocus *loci;
+  const uint32_t *sitemask;
+  const unsigned char *seq;
+  const int *mult;
+  PairBuf buf[2];
+  unsigned char *cur;       // [P] which buffer holds the current state
+  double *uvals;            // [P][kMaxLinked] mutation-rate scalars
+  double *kappa;            // [P]
+  double *pi;               // [P][4]
+  // per chain
+  double *tvals;            // [nchains][kMaxPeriods] split times, TIMEMAX sentinel at [nsplit]
+  double *beta;             // [nchains]
+  int *all_i;               // [nchains][NI]
+  double *all_d;            // [nchains][ND]
+  double *qint;             // [nchains][kMaxParams]
+  double *mint;             // [nchains][kMaxParams]
+  double *probg;            // [nchains]
+  double *pdgsum;           // [nchains]  allpcalc.pdg
+  double *swapsum;          // [nchains]  sum_li pdg (+ probg): the S of swapweight
+  // proposal hand-off (propose kernel -> accept kernel)
+  double *prop_extra;       // [P] migweight + slideweight + Aterm
+  uint32_t *prop_flags;     // [P]
+  double *prop_dbg;         // [P][4] migweight, slideweight, slide distance drawn, edge moved (parity tests)
+  // counters
+  unsigned int *acc;        // [P][3] accepted: any, topology, tmrca
+  unsigned long long *nsteps;   // [1] steps done (device-side step counter, feeds the RNG streams)
+  unsigned long long *overflow; // [1] proposals dropped because the migration pool was full
+  unsigned long long seed;
+};
+
+}  // namespace ima

@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's function seam for the hot path.
+
+The reference drives its hot path through free functions over process-global state:
+``updategenealogy(ci, li)``, ``treeweight(ci, li)``, ``integrate_tree_prob``, ``likelihoodIS``,
+``swapchains``, ``savegsampinf`` (imamp.hpp:1167-1322) and, in L mode, ``margincalc`` / ``marginp`` /
+``jointp`` (imamp.hpp:1242-1248, 1420).  :class:`Engine` and :class:`LMode` expose the same operations,
+batched over all chains x loci, on top of the C ABI (include/ima2p_b200.h).  Nothing here computes:
+every method is one or two calls into the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+HEAT_LINEAR, HEAT_GEOMETRIC, HEAT_EVEN = 0, 1, 2     # HLINEAR / HGEOMETRIC / HEVEN, swapchains.cpp:94-110
+MODEL_IS, MODEL_HKY, MODEL_SW = 0, 1, 2
+MAXLINKED = 4
+
+
+def _ip(a):
+    return a.ctypes.data_as(capi.c_int_p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(capi.c_dbl_p)
+
+
+def _i32(x):
+    return np.ascontiguousarray(x, dtype=np.int32)
+
+
+def _f64(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+class Engine:
+    """All Metropolis-coupled chains x loci of one GPU, resident in HBM.
+
+    ``nchains`` chains live on this GPU; with several GPUs ``nchains_global`` is the total and ``chain0``
+    the global index of local chain 0 (chains shard by rank exactly like the reference's ``-hn`` chains
+    per MPI process, README.md:106).
+    """
+
+    def __init__(self, nchains, nloci, mig_capacity=64, seed=1, device=0, nchains_global=None, chain0=0, lib=None):
+        self.lib = lib if lib is not None else capi.lib()
+        self.nchains, self.nloci = nchains, nloci
+        self.nchains_global = nchains if nchains_global is None else nchains_global
+        self.chain0 = chain0
+        self._h = C.c_void_p()
+        self._ck(self.lib.ima2p_engine_create(C.byref(self._h), device, nchains, self.nchains_global, chain0, nloci,
+                                              mig_capacity, seed))
+        self._loci = {}
+        self.nsplit = None
+
+    def _ck(self, rc):
+        capi.check(self.lib, rc)
+
+    def close(self):
+        if self._h:
+            self.lib.ima2p_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- set-up (setup(), initialize.cpp:2074) -------------------------------------------------------------
+    def set_model(self, npops, nsplit, plist, addpop, droppops, pt_e, pt_down, rootpop, q_wp, q_max, q_min, m_wp,
+                  m_max, m_min, m_mean=None, nomig=(), nomigration=0, expoprior=0, thermo=0, gbeta=1.0):
+        """q_wp / m_wp: per parameter, the list of (period, row[, col]) weight positions (struct weightposition)."""
+        pl = -np.ones((npops, npops), dtype=np.int32)
+        for k, row in enumerate(plist):
+            pl[k, :len(row)] = row
+        q_off = _i32(np.cumsum([0] + [len(w) for w in q_wp]))
+        q_p = _i32([t[0] for w in q_wp for t in w]); q_r = _i32([t[1] for w in q_wp for t in w])
+        m_off = _i32(np.cumsum([0] + [len(w) for w in m_wp]))
+        m_p = _i32([t[0] for w in m_wp for t in w]); m_r = _i32([t[1] for w in m_wp for t in w])
+        m_c = _i32([t[2] for w in m_wp for t in w])
+        nm = len(m_wp)
+        m_mean = _f64(m_mean if m_mean is not None else np.zeros(max(nm, 1)))
+        n_p = _i32([t[0] for t in nomig]); n_r = _i32([t[1] for t in nomig]); n_c = _i32([t[2] for t in nomig])
+        self._ck(self.lib.ima2p_engine_set_model(
+            self._h, npops, nsplit, _ip(pl), _ip(_i32(addpop)), _ip(_i32(droppops).reshape(-1)), _ip(_i32(pt_e)),
+            _ip(_i32(pt_down)), rootpop, len(q_wp), _ip(q_off), _ip(q_p), _ip(q_r), _dp(_f64(q_max)), _dp(_f64(q_min)),
+            nm, _ip(m_off), _ip(m_p), _ip(m_r), _ip(m_c), _dp(_f64(m_max)), _dp(_f64(m_min)), _dp(m_mean), len(nomig),
+            _ip(n_p), _ip(n_r), _ip(n_c), nomigration, expoprior, thermo, float(gbeta)))
+        self.npops, self.nsplit, self.nq, self.nm = npops, nsplit, len(q_wp), nm
+
+    def set_model_flat(self, *create_args):
+        """Same tables in the flat CSR form of ima2p_engine_set_model (used by the tests' fixture loader)."""
+        self._ck(self.lib.ima2p_engine_set_model(self._h, *create_args))
+        self.npops, self.nsplit, self.nq, self.nm = create_args[0], create_args[1], create_args[8], create_args[14]
+
+    def set_locus(self, li, model, numgenes, numsites, samppop, seq=None, mult=None, hval=1.0, totsites=0, nlinked=1,
+                  minA=None, maxA=None, sumlogk=0.0):
+        seq_a = _i32(seq) if seq is not None and numsites > 0 else None
+        mult_a = _i32(mult) if mult is not None else None
+        mina = _i32(minA if minA is not None else [0] * nlinked)
+        maxa = _i32(maxA if maxA is not None else [0] * nlinked)
+        self._ck(self.lib.ima2p_engine_set_locus(
+            self._h, li, model, numgenes, numsites, totsites, float(hval), _ip(_i32(samppop)),
+            _ip(seq_a) if seq_a is not None else None, _ip(mult_a) if mult_a is not None else None, nlinked, _ip(mina),
+            _ip(maxa), float(sumlogk)))
+        self._loci[li] = dict(numgenes=numgenes, numlines=2 * numgenes - 1, nlinked=nlinked, model=model)
+
+    def finalize(self):
+        self._ck(self.lib.ima2p_engine_finalize(self._h))
+        d = _i32(np.zeros(5))
+        self._ck(self.lib.ima2p_engine_dims(self._h, _ip(d)))
+        self.NI, self.ND, self.NL, self.CAP, self.rowlen = (int(v) for v in d)
+
+    def set_heating(self, heatmode, hval1, hval2=0.0):
+        """setheat (swapchains.cpp:71-178)."""
+        self._ck(self.lib.ima2p_engine_set_heating(self._h, heatmode, float(hval1), float(hval2)))
+
+    def set_betas(self, betas_global):
+        self._ck(self.lib.ima2p_engine_set_betas(self._h, _dp(_f64(betas_global))))
+
+    # ---- state ---------------------------------------------------------------------------------------------
+    def set_chain(self, ci, tvals):
+        self._ck(self.lib.ima2p_engine_set_chain(self._h, ci, _dp(_f64(tvals))))
+
+    def set_genealogy(self, ci, li, up0, up1, down, pop, time, mig_off, mig_t, mig_p, root, roottime, uvals=(1.0,),
+                      kappa=2.0, pi=None, A=None):
+        mt, mp = _f64(np.append(_f64(mig_t), 0.0)), _i32(np.append(_i32(mig_p), 0))
+        a = _i32(A) if A is not None else None
+        self._ck(self.lib.ima2p_engine_set_genealogy(
+            self._h, ci, li, _ip(_i32(up0)), _ip(_i32(up1)), _ip(_i32(down)), _ip(_i32(pop)), _dp(_f64(time)),
+            _ip(_i32(mig_off)), _dp(mt), _ip(mp), int(root), float(roottime), _dp(_f64(uvals)), float(kappa),
+            _dp(_f64(pi)) if pi is not None else None, _ip(a) if a is not None else None))
+
+    def upload(self):
+        self._ck(self.lib.ima2p_engine_upload(self._h))
+
+    def get_genealogy(self, ci, li, which=0):
+        nl = self._loci[li]["numlines"]
+        up0, up1, down, pop = (np.zeros(nl, np.int32) for _ in range(4))
+        time, off = np.zeros(nl), np.zeros(nl + 1, np.int32)
+        mt, mp = np.zeros(self.CAP), np.zeros(self.CAP, np.int32)
+        root, rt = C.c_int(), C.c_double()
+        self._ck(self.lib.ima2p_engine_get_genealogy(self._h, ci, li, which, _ip(up0), _ip(up1), _ip(down), _ip(pop),
+                                                     _dp(time), _ip(off), _dp(mt), _ip(mp), self.CAP, C.byref(root),
+                                                     C.byref(rt)))
+        n = off[nl]
+        return dict(up0=up0, up1=up1, down=down, pop=pop, time=time, mig_off=off, mig_t=mt[:n], mig_p=mp[:n],
+                    root=root.value, roottime=rt.value)
+
+    # ---- evaluation of the loaded state: init_p (mcmcfile.cpp:130-193) ---------------------------------------
+    def eval(self):
+        self._ck(self.lib.ima2p_engine_eval(self._h))
+
+    def pair(self, ci, li):
+        """treeweight + likelihood results of one (chain, locus): C[ci]->G[li].gweight, pdg, length, ..."""
+        wi, wd = np.zeros(self.NI, np.int32), np.zeros(self.ND)
+        od, oi = np.zeros(4), np.zeros(2, np.int32)
+        self._ck(self.lib.ima2p_engine_get_pair(self._h, ci, li, _ip(wi), _dp(wd), _dp(od), _ip(oi)))
+        return dict(wi=wi, wd=wd, pdg=od[0], length=od[1], tlength=od[2], roottime=od[3], mignum=int(oi[0]),
+                    root=int(oi[1]))
+
+    def chain(self, ci):
+        """C[ci]->allgweight and allpcalc (struct probcalc)."""
+        wi, wd = np.zeros(self.NI, np.int32), np.zeros(self.ND)
+        q, m, od = np.zeros(max(self.nq, 1)), np.zeros(max(self.nm, 1)), np.zeros(3)
+        self._ck(self.lib.ima2p_engine_get_chain(self._h, ci, _ip(wi), _dp(wd), _dp(q), _dp(m), _dp(od)))
+        return dict(wi=wi, wd=wd, qintegrate=q[:self.nq], mintegrate=m[:self.nm], probg=od[0], pdg=od[1], beta=od[2])
+
+    # ---- M mode --------------------------------------------------------------------------------------------
+    def run(self, nsteps, swaptries=None, stream=None):
+        """nsteps x [updategenealogy for every chain x locus; swapchains(swaptries)] (qupdate)."""
+        if swaptries is None:
+            swaptries = max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0    # ima_main_mpi.cpp:1378
+        self._ck(self.lib.ima2p_engine_run(self._h, nsteps, swaptries, stream))
+
+    def update_genealogies(self, dev_S_local=None, stream=None):
+        self._ck(self.lib.ima2p_engine_update_genealogies(self._h, dev_S_local, stream))
+
+    def swap_replay(self, dev_S_global, swaptries, stream=None):
+        self._ck(self.lib.ima2p_engine_swap_replay(self._h, dev_S_global, swaptries, stream))
+
+    def sync(self):
+        self._ck(self.lib.ima2p_engine_sync(self._h))
+
+    def proposal(self, ci, li):
+        out, fl, buf = np.zeros(4), C.c_uint(), C.c_int()
+        self._ck(self.lib.ima2p_engine_get_proposal(self._h, ci, li, _dp(out), C.byref(fl), C.byref(buf)))
+        return dict(migweight=out[0], slideweight=out[1], slidedist=out[2], edge=int(out[3]), flags=fl.value,
+                    buffer=buf.value)
+
+    def counters(self):
+        out = np.zeros(8, np.uint64)
+        self._ck(self.lib.ima2p_engine_counters(self._h, out.ctypes.data_as(capi.c_u64_p)))
+        keys = ["steps", "updates", "accepted", "topology", "tmrca", "swap_attempts", "swaps", "dropped"]
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def betas(self):
+        b = np.zeros(self.nchains_global)
+        self._ck(self.lib.ima2p_engine_get_betas(self._h, _dp(b)))
+        return b
+
+    def cold_row(self):
+        """savegsampinf (ginfo.cpp:318-377) of the chain with beta == 1, or None when it lives on another GPU."""
+        row, present = np.zeros(self.rowlen, np.float32), C.c_int()
+        self._ck(self.lib.ima2p_engine_cold_row(self._h, row.ctypes.data_as(capi.c_flt_p), C.byref(present)))
+        return row if present.value else None
+
+    # ---- bulk state I/O in the engine's packed layout (end-to-end timing path) -----------------------------
+    def state_bytes(self):
+        out = np.zeros(8, np.uint64)
+        self._ck(self.lib.ima2p_engine_state_bytes(self._h, out.ctypes.data_as(capi.c_u64_p)))
+        return [int(v) for v in out]
+
+    def put_state(self, bufs, tvals, stream=None):
+        """bufs: 8 host buffers (objects with .ctypes or integer addresses) in state_bytes() order."""
+        ptrs = [b if isinstance(b, int) else b.ctypes.data for b in bufs]
+        tv = _f64(tvals)
+        self._ck(self.lib.ima2p_engine_put_state(self._h, *ptrs, _dp(tv), stream))
+
+    def fetch_state(self, bufs, stream=None):
+        ptrs = [b if isinstance(b, int) else b.ctypes.data for b in bufs]
+        self._ck(self.lib.ima2p_engine_fetch_state(self._h, *ptrs, stream))
+
+    def fetch_chain_summary(self, stream=None):
+        out = np.zeros((self.nchains, 4))
+        self._ck(self.lib.ima2p_engine_fetch_chain_summary(self._h, _dp(out), stream))
+        return out
+
+
+class LMode:
+    """L mode over the sampled-genealogy rows of a .ti file (``gsampinf``, ginfo.cpp:288-304)."""
+
+    def __init__(self, nq, nm, nsplit, q_max, q_min, m_max, m_min, m_mean=None, expoprior=0, device=0, lib=None):
+        self.lib = lib if lib is not None else capi.lib()
+        self.nq, self.nm, self.nsplit = nq, nm, nsplit
+        self._h = C.c_void_p()
+        mm = _f64(m_mean if m_mean is not None else np.zeros(max(nm, 1)))
+        capi.check(self.lib, self.lib.ima2p_lmode_create(C.byref(self._h), device, nq, nm, nsplit, _dp(_f64(q_max)),
+                                                         _dp(_f64(q_min)), _dp(_f64(m_max)), _dp(_f64(m_min)), _dp(mm),
+                                                         expoprior))
+        self.nrows = 0
+
+    def close(self):
+        if self._h:
+            self.lib.ima2p_lmode_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load(self, rows, nrows_total=None, row0=0):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        self.nrows, self.rowlen = rows.shape
+        self.nrows_total = self.nrows if nrows_total is None else nrows_total
+        self.row0 = row0
+        capi.check(self.lib, self.lib.ima2p_lmode_load(self._h, rows.ctypes.data_as(capi.c_flt_p), self.nrows,
+                                                       self.rowlen, self.nrows_total))
+
+    def marginal_sums(self, param, x, first=0, last=None, round_counts=1):
+        x = _f64(np.atleast_1d(x))
+        out = np.zeros(len(x))
+        capi.check(self.lib, self.lib.ima2p_lmode_marginal_sums(self._h, param, _dp(x), len(x), first,
+                                                                self.nrows if last is None else last, round_counts,
+                                                                _dp(out), None, None))
+        return out
+
+    def margincalc(self, x, yadjust, pi, logi):
+        """margincalc(x, yadjust, pi, logi) (surface_call_functions.cpp:119-173), vectorised over x."""
+        x = _f64(np.atleast_1d(x))
+        out = np.zeros(len(x))
+        capi.check(self.lib, self.lib.ima2p_lmode_margincalc(self._h, pi, _dp(x), len(x), float(yadjust), int(logi),
+                                                             _dp(out)))
+        return out
+
+    def marginp(self, param, firsttree, lasttree, x):
+        """marginp(param, firsttree, lasttree, x) (surface_call_functions.cpp:25-80), vectorised over x."""
+        x = _f64(np.atleast_1d(x))
+        out = np.zeros(len(x))
+        capi.check(self.lib, self.lib.ima2p_lmode_marginp(self._h, param, firsttree, lasttree, _dp(x), len(x), _dp(out)))
+        return out
+
+    def jointp(self, x, calc_ess=True):
+        """jointp(x, calc_ess, &ess) (jointfind.cpp:885-1047) for a batch of parameter vectors x[nvec][nq+nm]."""
+        x = _f64(np.atleast_2d(x))
+        q, ess = np.zeros(len(x)), np.zeros(len(x))
+        capi.check(self.lib, self.lib.ima2p_lmode_jointp(self._h, _dp(x), len(x), int(calc_ess), _dp(q), _dp(ess)))
+        return q, ess
+
+    # sharded form: see ima2p_lmode_joint_phase1/2 in include/ima2p_b200.h
+    def joint_phase1(self, x, seed_before=None):
+        x = _f64(np.atleast_2d(x))
+        out = np.zeros(len(x))
+        sb = _f64(seed_before) if seed_before is not None else None
+        capi.check(self.lib, self.lib.ima2p_lmode_joint_phase1(self._h, _dp(x), len(x), _dp(sb) if sb is not None else None,
+                                                               _dp(out)))
+        return out
+
+    def joint_phase2(self, nvec, globalmax):
+        rec = np.zeros((nvec, 6))
+        capi.check(self.lib, self.lib.ima2p_lmode_joint_phase2(self._h, nvec, _dp(_f64(globalmax)), self.row0, _dp(rec)))
+        return rec
+
+    def joint_finish(self, rec, globalmax, calc_ess=True):
+        q, ess = C.c_double(), C.c_double()
+        self.lib.ima2p_lmode_joint_finish(_dp(_f64(rec)), float(globalmax), self.nrows_total, int(calc_ess), C.byref(q),
+                                          C.byref(ess))
+        return q.value, ess.value

@@ -1,0 +1,175 @@
+/*
+ * ima2p_b200 -- C ABI of the B200-native engine for IMa2p's data-parallel hot path.
+ *
+ * The reference (arunsethuraman/ima2p) has no plugin/FFI interface: its hot path is a set of free
+ * functions over process-global state, called with (chain, locus) integer handles
+ * (SURVEY.md section 8b).  Each entry point below is the batched, handle-based replacement of one such
+ * seam function; the reference file:line it replaces is cited.  Plain pointers and sizes only.
+ * All functions return 0 on success or a negative IMA2P_E_* code; ima2p_last_error() gives the text.
+ * There is no CPU fallback: every call needs a CUDA device (IMA2P_E_CUDA otherwise).
+ *
+ * Conventions
+ *   - edges 0..n-1 are tips, n..2n-2 internal; edge.time is the time at the BOTTOM of the edge, the
+ *     root edge has down = -1 and time = 1e6 (TIMEMAX) (imamp.hpp:583-679).
+ *   - migration lists are CSR: mig_off[numlines+1], mig_t[], mig_p[] (imamp.hpp:601-605, (mt, mp) pairs).
+ *   - genealogy weights (struct genealogy_weights, imamp.hpp:878-887) are flat:
+ *       ints    wi[NI] = cc[k][i] (k = 0..nsplit, i < npops-k) followed by mc[k][i][j] (k < nsplit)
+ *       doubles wd[ND] = fc[k][i], then hcc[k][i], then fm[k][i][j]        NI = ncc+nmc, ND = 2*ncc+nmc
+ *   - chains are indexed locally (0..nchains_local-1); chain0 is the global index of local chain 0.
+ */
+#ifndef IMA2P_B200_H
+#define IMA2P_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMA2P_OK 0
+#define IMA2P_E_ARG (-1)        /* bad argument / call order */
+#define IMA2P_E_CUDA (-2)       /* CUDA runtime failure or no device */
+#define IMA2P_E_UNSUPPORTED (-3)        /* model feature not on the device path yet */
+#define IMA2P_E_DEVICE (-4)     /* error word raised by a kernel: IMERR_LOGDIFF / IMERR_*GAMMA equivalents
+                                   (utilities.hpp:18-72); the reference exit()s there */
+#define IMA2P_E_CAPACITY (-5)   /* a genealogy does not fit the configured migration capacity
+                                   (reference: IMERR_MIGARRAYTOOBIG / IMERR_TOOMANYMIG) */
+
+#define IMA2P_MODEL_IS 0        /* INFINITESITES */
+#define IMA2P_MODEL_HKY 1
+#define IMA2P_MODEL_SW 2        /* STEPWISE */
+#define IMA2P_MAXLINKED 4
+
+typedef struct ima2p_engine ima2p_engine;
+typedef struct ima2p_lmode ima2p_lmode;
+
+const char *ima2p_version (void);
+const char *ima2p_last_error (void);
+
+/* ---- set-up: replaces the global state built by setup() (initialize.cpp:2074) ------------------ */
+int ima2p_engine_create (ima2p_engine ** out, int device, int nchains_local, int nchains_global, int chain0,
+                         int nloci, int mig_capacity, uint64_t seed);
+void ima2p_engine_destroy (ima2p_engine * e);
+
+/* population tree, period lists, parameter -> weight-position lists, priors
+ * (setup_poptree build_poptree.cpp:628-709; setup_iparams initialize.cpp:201-727; nomigrationchecklist :760-809) */
+int ima2p_engine_set_model (ima2p_engine * e, int npops, int nsplit, const int *plist /* [npops*npops], -1 padded */ ,
+                            const int *addpop /* [nsplit+1] */ , const int *droppops /* [(nsplit+1)*2] */ ,
+                            const int *pt_e, const int *pt_down /* [2*npops-1] */ , int rootpop,
+                            int nq, const int *q_off, const int *q_p, const int *q_r, const double *q_max,
+                            const double *q_min, int nm, const int *m_off, const int *m_p, const int *m_r,
+                            const int *m_c, const double *m_max, const double *m_min, const double *m_mean,
+                            int nomig_n, const int *nomig_p, const int *nomig_r, const int *nomig_c,
+                            int nomigration, int expoprior, int thermo, double gbeta);
+
+/* struct locus (imamp.hpp:894-936) as produced by readdata (readata.cpp:1037): seq is [numgenes][numsites]
+ * (0/1 segregating sites for IS, bases 0..3 of the compressed patterns for HKY), mult[numsites] (HKY). */
+int ima2p_engine_set_locus (ima2p_engine * e, int li, int model, int numgenes, int numsites, int totsites,
+                            double hval, const int *samppop, const int *seq, const int *mult, int nlinked,
+                            const int *minA, const int *maxA, double sumlogk);
+
+/* allocate the HBM-resident state (call once after the model and every locus are set) */
+int ima2p_engine_finalize (ima2p_engine * e);
+
+/* heating schedule, setheat (swapchains.cpp:71-178): heatmode 0 linear, 1 geometric, 2 even */
+int ima2p_engine_set_heating (ima2p_engine * e, int heatmode, double hval1, double hval2);
+int ima2p_engine_set_betas (ima2p_engine * e, const double *betas_global /* [nchains_global] */ );
+
+/* ---- state upload / download: replaces C[ci]->G[li] (imamp.hpp:956-1012) and .mcf reload (mcmcfile.cpp:310-442) -- */
+int ima2p_engine_set_chain (ima2p_engine * e, int ci, const double *tvals /* [nsplit] */ );
+int ima2p_engine_set_genealogy (ima2p_engine * e, int ci, int li, const int *up0, const int *up1, const int *down,
+                                const int *pop, const double *time, const int *mig_off, const double *mig_t,
+                                const int *mig_p, int root, double roottime, const double *uvals, double kappa,
+                                const double *pi, const int *A /* [nlinked][numlines] or NULL */ );
+/* which = 0: the current genealogy; 1: the pair's other buffer, i.e. after a step the proposed genealogy when
+ * it was rejected, or the previous genealogy when it was accepted (restoreedges, update_gtree_common.cpp:705-814,
+ * becomes a buffer flip) */
+int ima2p_engine_get_genealogy (ima2p_engine * e, int ci, int li, int which, int *up0, int *up1, int *down, int *pop,
+                                double *time, int *mig_off, double *mig_t, int *mig_p, int mig_room, int *root,
+                                double *roottime);
+/* push everything staged by set_chain / set_genealogy to the device (one H2D per array) */
+int ima2p_engine_upload (ima2p_engine * e);
+
+/* ---- evaluation of a loaded state: what init_p() does after a reload (mcmcfile.cpp:130-193) ----
+ * per (chain, locus): treeweight (update_gtree_common.cpp:1679-1931) + likelihoodIS/HKY/SW
+ * (calc_prob_data.cpp:583-607, 731-836, 841-909); per chain: sum_treeinfo + initialize_integrate_tree_prob
+ * (update_gtree_common.cpp:2056-2134). */
+int ima2p_engine_eval (ima2p_engine * e);
+/* out_d = {pdg, length, tlength, roottime}, out_i = {mignum, root} */
+int ima2p_engine_get_pair (ima2p_engine * e, int ci, int li, int *wi, double *wd, double *out_d, int *out_i);
+/* out_d = {probg, pdg, beta} (struct probcalc imamp.hpp:858-865) */
+int ima2p_engine_get_chain (ima2p_engine * e, int ci, int *all_wi, double *all_wd, double *qintegrate,
+                            double *mintegrate, double *out_d);
+int ima2p_engine_dims (ima2p_engine * e, int *out /* {NI, ND, NL, CAP, rowlen} */ );
+
+/* ---- M mode -------------------------------------------------------------------------------------
+ * one step = updategenealogy(ci, li) for every chain x locus (qupdate ima_main_mpi.cpp:1821-1841 ->
+ * update_gtree.cpp:723-966) followed by swaptries MC3 temperature swaps (swapchains.cpp:526-653;
+ * temperature-rank form of swapchains_bwprocesses :192-523).  Single-GPU form: */
+int ima2p_engine_run (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream);
+/* Multi-GPU form (one process per GPU): genealogy updates of the local chains, then the per-chain
+ * S = sum_li pdg + probg (swapweight, swapchains.cpp:12-34) is written to dev_S_local[nchains_local]
+ * (device memory owned by the caller); the caller all-gathers it over NCCL into
+ * dev_S_global[nchains_global] and every rank replays the same swap attempts. */
+int ima2p_engine_update_genealogies (ima2p_engine * e, double *dev_S_local, void *cuda_stream);
+int ima2p_engine_swap_replay (ima2p_engine * e, const double *dev_S_global, int swaptries, void *cuda_stream);
+
+/* last proposal of a pair: out4 = {migweight (update_gtree.cpp:663), slideweight (:803-812), slide distance
+ * drawn (:783), edge moved}; flags bit0 infinite-sites reject, bit1 dropped for capacity, bit2 topology changed,
+ * bit3 root moved; buffer = index of the buffer that is current (flips on accept) */
+int ima2p_engine_get_proposal (ima2p_engine * e, int ci, int li, double *out4, unsigned int *flags, int *buffer);
+
+/* counters: out = {steps, updates tried, accepted, topology-changing accepted, tmrca-changing accepted,
+ *                  swap attempts, swaps accepted, proposals dropped for capacity} */
+int ima2p_engine_counters (ima2p_engine * e, uint64_t * out8);
+int ima2p_engine_get_betas (ima2p_engine * e, double *betas_global);
+/* savegsampinf (ginfo.cpp:318-377): the 4*nq+3*nm+2+nsplit float row of the chain with beta == 1;
+ * returns 1 in *present when that chain lives on this GPU */
+int ima2p_engine_cold_row (ima2p_engine * e, float *row, int *present);
+int ima2p_engine_sync (ima2p_engine * e);
+
+/* bulk state I/O in the engine's own packed layout (host buffers; used for end-to-end timing):
+ * sizes from ima2p_engine_state_bytes: {topo, time, mseg, mig_t, mig_p, scal_i, scal_d, uvals} */
+int ima2p_engine_state_bytes (ima2p_engine * e, uint64_t * out8);
+int ima2p_engine_put_state (ima2p_engine * e, const void *topo, const void *time, const void *mseg, const void *mig_t,
+                            const void *mig_p, const void *scal_i, const void *scal_d, const void *uvals,
+                            const double *tvals /* [nchains][nsplit] */ , void *cuda_stream);
+int ima2p_engine_fetch_state (ima2p_engine * e, void *topo, void *time, void *mseg, void *mig_t, void *mig_p,
+                              void *scal_i, void *scal_d, void *cuda_stream);
+/* per-chain summary after a run: out[ci] = {beta, probg, pdg, S} */
+int ima2p_engine_fetch_chain_summary (ima2p_engine * e, double *out4 /* [nchains_local][4] */ , void *cuda_stream);
+
+/* ---- L mode: replaces gsampinf + margincalc / marginp (surface_call_functions.cpp:25-173) and
+ * jointp (jointfind.cpp:885-1047) over the .ti rows (ginfo.cpp:288-304) -------------------------- */
+int ima2p_lmode_create (ima2p_lmode ** out, int device, int nq, int nm, int nsplit, const double *q_max,
+                        const double *q_min, const double *m_max, const double *m_min, const double *m_mean,
+                        int expoprior);
+void ima2p_lmode_destroy (ima2p_lmode * l);
+/* rows: host float [nrows][rowlen] (this rank's shard); nrows_total = rows over all ranks */
+int ima2p_lmode_load (ima2p_lmode * l, const float *rows, int nrows, int rowlen, long long nrows_total);
+/* sums[i] = sum over this rank's rows of the margincalc term of parameter `param` at x[i]
+ * (surface_call_functions.cpp:139-162; INTEGERROUND counts).  dev_sums may be NULL (then host_sums is
+ * filled) or device memory for an NCCL all-reduce by the caller. */
+int ima2p_lmode_marginal_sums (ima2p_lmode * l, int param, const double *x, int nx, int first, int last,
+                               int round_counts, double *host_sums, double *dev_sums, void *cuda_stream);
+/* margincalc (:119-173) / marginp (:25-80) on a single GPU holding all rows */
+int ima2p_lmode_margincalc (ima2p_lmode * l, int param, const double *x, int nx, double yadjust, int logi, double *out);
+int ima2p_lmode_marginp (ima2p_lmode * l, int param, int firsttree, int lasttree, const double *x, int nx, double *out);
+/* jointp for nvec parameter vectors x[nvec][nq+nm]; out_q[nvec] = -log joint density, out_ess[nvec] */
+int ima2p_lmode_jointp (ima2p_lmode * l, const double *x, int nvec, int calc_ess, double *out_q, double *out_ess);
+
+/* Sharded form (rows split over GPUs; the caller exchanges a few doubles per vector over NCCL):
+ *   phase 1: p_g of every local row for nvec (<= 32) vectors; seed_before[v] = max of p over the rows held by
+ *            lower ranks (NULL on rank 0); localmax_out[v] = max(seed, local rows)
+ *   phase 2: given the global maximum, records_out[v] = {inserted, kept, sum, sum of squares, smallest kept p,
+ *            its scaled term} over the local rows; global_row0 = global index of local row 0
+ *   finish : the closing arithmetic of jointp (:1011-1046) on the records summed over ranks */
+int ima2p_lmode_joint_phase1 (ima2p_lmode * l, const double *x, int nvec, const double *seed_before, double *localmax_out);
+int ima2p_lmode_joint_phase2 (ima2p_lmode * l, int nvec, const double *globalmax, long long global_row0,
+                              double *records_out);
+void ima2p_lmode_joint_finish (const double *rec6, double globalmax, long long nrows_total, int calc_ess, double *q,
+                               double *ess);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

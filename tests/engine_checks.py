@@ -1,0 +1,151 @@
+"""Parity checks shared by the GPU tests (-m gpu, product library) and the CPU tests that run the same
+kernel sources through the tests-only host-emulation build (tests/hostemu).  The checker is always the
+CPU oracle (pinned against the reference's own values) or the golden fixtures themselves."""
+import numpy as np
+
+from support import (FlatModel, OracleModel, check_static_eval, engine_from_fixture, f64, fp, dp, load_golden, oracle,
+                     rel_close, split_weights, tree_from_engine, _num)
+
+STATIC_FIXTURES = ["state_sim5_hn4", "state_sim50_hn3", "state_sim300_hn1", "state_sim2_hn2", "state_sim3_hn3",
+                   "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim3_sw_hn2"]
+STEP_FIXTURES = ["state_sim5_hn4", "state_sim3_hn3", "state_sim5_3pop_hn2", "state_sim2_hn2"]
+
+
+def static_eval_matches_reference(lib, name, rtol):
+    """a5 + a6 + a7 (+ a9): integers bit-exact, doubles within rtol of the reference's init_p values."""
+    d = load_golden(name)
+    eng, fm = engine_from_fixture(d, lib=lib)
+    eng.eval()
+    check_static_eval(eng, fm, d, rtol=rtol)
+    eng.close()
+
+
+def proposals_match_oracle(lib, name, nsteps, rtol=1e-9):
+    """a2-a4 on identical genealogies, no RNG-path matching: for every proposal the device makes, the oracle
+    recomputes from the (before, after) genealogies (i) the forward/reverse migration-path probabilities,
+    (ii) the slide weight when the root moved, (iii) the proposed genealogy's weights and likelihood."""
+    d = load_golden(name)
+    eng, fm = engine_from_fixture(d, lib=lib, mig_capacity=96)
+    om = OracleModel(fm)
+    eng.eval()
+    nch, nl = eng.nchains, eng.nloci
+    nchecked = nroot = nrej = 0
+    for _ in range(nsteps):
+        before = {(c, l): tree_from_engine(eng.get_genealogy(c, l, 0)) for c in range(nch) for l in range(nl)}
+        buf0 = {(c, l): eng.proposal(c, l)["buffer"] for c in range(nch) for l in range(nl)}
+        old = {(c, l): eng.pair(c, l) for c in range(nch) for l in range(nl)}
+        eng.run(1, swaptries=0)
+        eng.sync()
+        for c in range(nch):
+            tv = d["chains"][c]["tvals"]
+            for l in range(nl):
+                pr = eng.proposal(c, l)
+                if pr["flags"] & 2:
+                    continue                       # dropped for capacity (counted)
+                if pr["flags"] & 1:                # infinite-sites reject: state must be untouched
+                    nrej += 1
+                    assert pr["buffer"] == buf0[(c, l)]
+                    continue
+                accepted = pr["buffer"] != buf0[(c, l)]
+                after = tree_from_engine(eng.get_genealogy(c, l, 0 if accepted else 1))
+                b = before[(c, l)]
+                fwd, rev = om.migration_logprobs(tv, b, after, pr["edge"])
+                assert rel_close(rev - fwd, pr["migweight"], rtol, 1e-9), (name, c, l, fwd, rev, pr)
+                if b.root != after.root or b.roottime != after.roottime:
+                    sw = oracle().ora_slideweight(pr["slidedist"], b.roottime, after.roottime)
+                    assert rel_close(sw, pr["slideweight"], rtol, 1e-9), (sw, pr)
+                    nroot += 1
+                else:
+                    assert pr["slideweight"] == 0.0
+                loc = d["loci"][l]
+                w = om.treeweight(tv, loc, after)
+                assert w["mignum"] >= 0
+                new = eng.pair(c, l) if accepted else None
+                if accepted:
+                    ew = split_weights(fm, new["wi"], new["wd"])
+                    assert np.array_equal(ew["cc"], w["cc"]) and np.array_equal(ew["mc"], w["mc"])
+                    assert rel_close(ew["fc"], w["fc"], rtol) and rel_close(ew["fm"], w["fm"], rtol)
+                    assert new["mignum"] == w["mignum"]
+                    if loc["model"] == 0:
+                        u = d["chains"][c]["G"][l]["uvals"][0]
+                        assert rel_close(new["pdg"], om.likelihood_is(loc, after, w["length"], u), rtol)
+                else:
+                    assert eng.pair(c, l)["pdg"] == old[(c, l)]["pdg"]
+                nchecked += 1
+    cnt = eng.counters()
+    assert nchecked > 0 and nroot > 0, (nchecked, nroot)
+    assert 0.1 < cnt["accepted"] / cnt["updates"] < 0.7, cnt     # reference: 0.32-0.40
+    eng.close()
+    return cnt
+
+
+def incremental_sums_match_fresh_evaluation(lib, name, nsteps, rtol=1e-9):
+    """After many accepted/rejected updates (and swaps) the per-chain sums maintained by the accept kernel
+    (sum_subtract_treeinfo + integrate_tree_prob with its reuse rule) equal a from-scratch evaluation."""
+    d = load_golden(name)
+    eng, fm = engine_from_fixture(d, lib=lib)
+    eng.eval()
+    eng.run(nsteps)
+    eng.sync()
+    inc = [eng.chain(c) for c in range(eng.nchains)]
+    incp = [[eng.pair(c, l) for l in range(eng.nloci)] for c in range(eng.nchains)]
+    betas = eng.betas()
+    assert rel_close(sorted(betas), sorted(ch["beta"] for ch in d["chains"]), 0.0)   # swaps only permute betas
+    eng.eval()
+    for c in range(eng.nchains):
+        fresh = eng.chain(c)
+        assert np.array_equal(fresh["wi"], inc[c]["wi"])
+        assert rel_close(fresh["wd"], inc[c]["wd"], rtol, 1e-9)
+        assert rel_close(fresh["probg"], inc[c]["probg"], rtol) and rel_close(fresh["pdg"], inc[c]["pdg"], rtol)
+        for l in range(eng.nloci):
+            f = eng.pair(c, l)
+            assert np.array_equal(f["wi"], incp[c][l]["wi"]) and rel_close(f["pdg"], incp[c][l]["pdg"], 1e-12)
+    cnt = eng.counters()
+    row = eng.cold_row()
+    assert row is not None and row.shape == (fm.rowlen,)
+    eng.close()
+    return cnt
+
+
+def lmode_matches_reference(lib, name, rtol=1e-9):
+    """a14 + a15: margincalc / marginp / jointp against the reference's own values on the same rows."""
+    from ima2p_b200 import LMode
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    lm = LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=lib)
+    lm.load(rows)
+    G = len(rows)
+    tab = d["margincalc"]
+    for p in sorted(set(t[0] for t in tab)):
+        sel = [t for t in tab if t[0] == p]
+        x = np.array([t[1] for t in sel])
+        assert rel_close(lm.margincalc(x, 0.0, p, 0), [_num(t[2]) for t in sel], rtol, 1e-300)
+        assert rel_close(lm.margincalc(x, 0.25, p, 1), [_num(t[3]) for t in sel], rtol)
+        assert rel_close(lm.marginp(p, 0, G, x), [_num(t[4]) for t in sel], rtol, 1e-300)
+        assert rel_close(lm.marginp(p, G // 3, 2 * G // 3, x), [_num(t[5]) for t in sel], rtol, 1e-300)
+    xs = np.array([j["x"] for j in d["jointp"]])
+    q, ess = lm.jointp(xs, True)
+    assert rel_close(q, [j["q"] for j in d["jointp"]], rtol), (q[:4], [j["q"] for j in d["jointp"]][:4])
+    assert rel_close(ess, [j["ess"] for j in d["jointp"]], 1e-8)
+    # sharded form == single form (rows split in two, host-side exchange of the per-vector maxima)
+    half = G // 2 + 37
+    a = LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=lib)
+    b = LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=lib)
+    a.load(rows[:half], nrows_total=G, row0=0)
+    b.load(rows[half:], nrows_total=G, row0=half)
+    nv = min(len(xs), 32)
+    ma = a.joint_phase1(xs[:nv])
+    mb = b.joint_phase1(xs[:nv], seed_before=ma)
+    gmax = np.maximum(ma, mb)
+    ra, rb = a.joint_phase2(nv, gmax), b.joint_phase2(nv, gmax)
+    for v in range(nv):
+        rec = ra[v] + rb[v]
+        lo = ra[v] if ra[v][4] <= rb[v][4] else rb[v]
+        rec[4], rec[5] = lo[4], lo[5]
+        qv, ev = a.joint_finish(rec, gmax[v])
+        assert rel_close(qv, q[v], 1e-12) and rel_close(ev, ess[v], 1e-9)
+    s0 = lm.marginal_sums(0, xs[:8, 0])
+    assert rel_close(a.marginal_sums(0, xs[:8, 0]) + b.marginal_sums(0, xs[:8, 0]), s0, 1e-12)
+    for o in (lm, a, b):
+        o.close()

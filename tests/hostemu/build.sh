@@ -1,0 +1,8 @@
+#!/bin/sh
+# TESTS ONLY: compiles the kernel sources with a plain C++ compiler ("warp" of one lane, see
+# ima2p_b200/csrc/ima_platform.h) so that the CPU test-suite can exercise the kernel logic against the oracle.
+# The package never loads this library; it is not a fallback.
+set -e
+cd "$(dirname "$0")/../.."
+g++ -O2 -std=c++17 -DIMA_HOSTEMU -ffp-contract=off -Wall -Wno-unused-function -Wno-unknown-pragmas -fPIC -shared \
+    -x c++ ima2p_b200/csrc/ima_engine.cu -x c++ ima2p_b200/csrc/ima_lmode.cu -o tests/hostemu/libima2p_hostemu.so

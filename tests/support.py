@@ -263,3 +263,75 @@ def rel_close(a, b, rtol, atol=0.0):
     ok = np.zeros(a.shape, dtype=bool)
     ok[fin] = np.abs(a[fin] - b[fin]) <= atol + rtol * np.maximum(np.abs(a[fin]), np.abs(b[fin]))
     return bool(np.all(same | ok))
+
+
+# ---- engine loading helpers (shared by the hostemu CPU tests and the GPU parity tests) -------------------
+def engine_from_fixture(d, lib=None, chains=None, mig_capacity=64, seed=1234, betas=None):
+    """Build an ima2p_b200.Engine holding the chains of a "state" fixture (all loci)."""
+    from ima2p_b200 import Engine
+    fm = FlatModel(d["model"])
+    chains = list(range(len(d["chains"]))) if chains is None else chains
+    nloci = len(d["loci"])
+    eng = Engine(len(chains), nloci, mig_capacity=mig_capacity, seed=seed, lib=lib)
+    eng.set_model_flat(*fm.create_args())
+    for li, loc in enumerate(d["loci"]):
+        eng.set_locus(li, loc["model"], loc["numgenes"], loc["numsites"], loc["samppop"],
+                      seq=loc["seq"] if loc["seq"] else None, mult=loc.get("mult"), hval=loc["hval"],
+                      totsites=loc["totsites"], nlinked=loc["nlinked"], minA=loc["minA"], maxA=loc["maxA"],
+                      sumlogk=loc["sumlogk"])
+    eng.finalize()
+    eng.set_betas(betas if betas is not None else [d["chains"][c]["beta"] for c in chains])
+    for k, c in enumerate(chains):
+        ch = d["chains"][c]
+        eng.set_chain(k, ch["tvals"])
+        for li, g in enumerate(ch["G"]):
+            t = FlatTree(g["tree"])
+            A = np.stack(t.A) if t.A else None
+            eng.set_genealogy(k, li, t.up0, t.up1, t.down, t.pop, t.time, t.mig_off, t.mig_t[:-1], t.mig_p[:-1], t.root,
+                              t.roottime, uvals=g["uvals"], kappa=g["kappa"], pi=g["pi"], A=A)
+    eng.upload()
+    return eng, fm
+
+
+def tree_from_engine(g):
+    """Engine.get_genealogy() dict -> FlatTree-like object for the oracle."""
+    t = FlatTree.__new__(FlatTree)
+    t.root, t.roottime = g["root"], g["roottime"]
+    t.up0, t.up1, t.down, t.pop = i32(g["up0"]), i32(g["up1"]), i32(g["down"]), i32(g["pop"])
+    t.time = f64(g["time"])
+    t.numlines = len(t.up0)
+    t.numgenes = (t.numlines + 1) // 2
+    t.mig_off = i32(g["mig_off"])
+    t.mig_t, t.mig_p = f64(np.append(g["mig_t"], 0.0)), i32(np.append(g["mig_p"], 0))
+    t.A, t.dlikeA = [], []
+    return t
+
+
+def split_weights(fm, wi, wd):
+    """Engine weight records -> dict(cc, mc, fc, hcc, fm) in fixture order."""
+    return dict(cc=wi[:fm.ncc], mc=wi[fm.ncc:], fc=wd[:fm.ncc], hcc=wd[fm.ncc:2 * fm.ncc], fm=wd[2 * fm.ncc:])
+
+
+def check_static_eval(eng, fm, d, chains=None, rtol=1e-9):
+    """Engine.eval() results against the fixture's values (the reference's init_p): ints exact, doubles rtol."""
+    chains = list(range(len(d["chains"]))) if chains is None else chains
+    for k, c in enumerate(chains):
+        ch = d["chains"][c]
+        for li, g in enumerate(ch["G"]):
+            r = eng.pair(k, li)
+            w = split_weights(fm, r["wi"], r["wd"])
+            e = g["gweight"]
+            assert r["mignum"] == g["mignum"], (c, li)
+            assert np.array_equal(w["cc"], e["cc"]) and np.array_equal(w["mc"], e["mc"]), (c, li)
+            assert rel_close(w["fc"], e["fc"], rtol) and rel_close(w["fm"], e["fm"], rtol), (c, li)
+            assert rel_close(w["hcc"], e["hcc"], rtol, 1e-300), (c, li)
+            assert rel_close(r["length"], g["length"], rtol) and rel_close(r["tlength"], g["tlength"], rtol), (c, li)
+            assert rel_close(r["pdg"], g["pdg"], rtol), (c, li, r["pdg"], g["pdg"])
+        cr = eng.chain(k)
+        wa = split_weights(fm, cr["wi"], cr["wd"])
+        ea = ch["allgweight"]
+        assert np.array_equal(wa["cc"], ea["cc"]) and np.array_equal(wa["mc"], ea["mc"])
+        assert rel_close(wa["fc"], ea["fc"], rtol) and rel_close(wa["fm"], ea["fm"], rtol)
+        assert rel_close(cr["qintegrate"], ch["qintegrate"], rtol), (cr["qintegrate"], ch["qintegrate"])
+        assert rel_close(cr["mintegrate"], ch["mintegrate"], rtol)
+        assert rel_close(cr["probg"], ch["probg"], rtol) and rel_close(cr["pdg"], ch["pdg"], rtol)

@@ -1,0 +1,57 @@
+"""GPU parity tests (run with -m gpu on the B200): the product library libima2p_b200.so, called through
+the C ABI, against the CPU oracle and the reference-generated golden fixtures.
+
+Bars (BASELINE.json north_star): integer coalescent/migration counts bit-exact; likelihoods and priors
+within 1e-9 relative in fp64."""
+import numpy as np
+import pytest
+
+import engine_checks as ec
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from ima2p_b200 import capi
+    return capi.lib()
+
+
+@pytest.mark.parametrize("name", ec.STATIC_FIXTURES)
+def test_static_eval_matches_reference(lib, name):
+    ec.static_eval_matches_reference(lib, name, rtol=RTOL)
+
+
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 10), ("state_sim3_hn3", 20), ("state_sim5_3pop_hn2", 12),
+                                         ("state_sim2_hn2", 20)])
+def test_device_proposals_match_oracle(lib, name, nsteps):
+    ec.proposals_match_oracle(lib, name, nsteps, rtol=RTOL)
+
+
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 2000), ("state_sim5_3pop_hn2", 500), ("state_sim50_hn3", 300),
+                                         ("state_sim300_hn1", 100)])
+def test_incremental_sums_match_fresh_evaluation(lib, name, nsteps):
+    cnt = ec.incremental_sums_match_fresh_evaluation(lib, name, nsteps, rtol=RTOL)
+    assert cnt["steps"] == nsteps and cnt["dropped"] == 0
+
+
+@pytest.mark.parametrize("name", ["lmode_sim5_hn2", "lmode_sim5_expo_hn2"])
+def test_lmode_matches_reference(lib, name):
+    ec.lmode_matches_reference(lib, name, rtol=RTOL)
+
+
+def test_runs_are_reproducible_and_seed_dependent(lib):
+    from support import engine_from_fixture, load_golden
+    d = load_golden("state_sim5_hn4")
+    outs = []
+    for seed in (7, 7, 8):
+        eng, _ = engine_from_fixture(d, lib=lib, seed=seed)
+        eng.eval()
+        eng.run(50)
+        eng.sync()
+        outs.append(np.array([eng.chain(c)["probg"] for c in range(eng.nchains)]))
+        eng.close()
+    assert np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])

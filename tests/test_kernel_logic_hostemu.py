@@ -1,0 +1,41 @@
+"""CPU tests of the KERNEL SOURCES through the tests-only host-emulation build (tests/hostemu/build.sh):
+the same ima2p_b200/csrc/*.h|*.cu files compiled by g++ with a "warp" of one lane.  They check the kernel
+logic against the oracle and the golden fixtures where there is no GPU.  The product never loads this
+library -- the GPU parity tests proper are tests/test_gpu_parity.py (-m gpu) through libima2p_b200.so."""
+import os
+import subprocess
+
+import pytest
+
+import engine_checks as ec
+from ima2p_b200 import capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "hostemu", "libima2p_hostemu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run([os.path.join(HERE, "hostemu", "build.sh")], check=True)
+    return capi.bind(EMU)
+
+
+@pytest.mark.parametrize("name", ec.STATIC_FIXTURES)
+def test_static_eval(emu, name):
+    ec.static_eval_matches_reference(emu, name, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 12), ("state_sim3_hn3", 25), ("state_sim5_3pop_hn2", 15)])
+def test_proposals(emu, name, nsteps):
+    ec.proposals_match_oracle(emu, name, nsteps)
+
+
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 300), ("state_sim5_3pop_hn2", 150), ("state_sim50_hn3", 20)])
+def test_incremental_sums(emu, name, nsteps):
+    cnt = ec.incremental_sums_match_fresh_evaluation(emu, name, nsteps)
+    assert cnt["steps"] == nsteps and cnt["accepted"] > 0
+
+
+@pytest.mark.parametrize("name", ["lmode_sim5_hn2", "lmode_sim5_expo_hn2"])
+def test_lmode(emu, name):
+    ec.lmode_matches_reference(emu, name, rtol=1e-12)
