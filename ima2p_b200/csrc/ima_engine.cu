@@ -590,6 +590,45 @@ int ima2p_engine_run(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stre
   return IMA2P_OK;
 }
 
+// Same work as ima2p_engine_run, launched kernel by kernel with CUDA events recorded on the launching
+// stream around each kernel of every step; kernel_ms[3] receives the summed device time of
+// {propose, accept, swap} over the nsteps (bench.py's roofline numerator comes from here).
+int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms) {
+  if (!h || nsteps < 0 || swaptries < 0 || !kernel_ms) return fail(IMA2P_E_ARG, "run_timed: bad argument");
+  Engine &e = h->eng;
+  int rc = ensure_steppable(e);
+  if (rc) return rc;
+  if (e.d.nchains != e.d.nchains_global) return fail(IMA2P_E_ARG, "run_timed: engine holds a shard");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  kernel_ms[0] = kernel_ms[1] = kernel_ms[2] = 0.f;
+#if IMA_CUDA
+  const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int chunk = 256;
+  std::vector<cudaEvent_t> ev((size_t)chunk * 4);
+  for (auto &x : ev) if (!IMA_CUDA_OK(cudaEventCreate(&x))) return fail(IMA2P_E_CUDA, "event create failed");
+  for (int s0 = 0; s0 < nsteps; s0 += chunk) {
+    const int n = nsteps - s0 < chunk ? nsteps - s0 : chunk;
+    for (int i = 0; i < n; i++) {
+      cudaEventRecord(ev[i * 4 + 0], s);
+      IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v);
+      cudaEventRecord(ev[i * 4 + 1], s);
+      IMA_LAUNCH(k_accept, gc, kWarpsPerBlock, e.chain_smem * kWarpsPerBlock, s, e.v);
+      cudaEventRecord(ev[i * 4 + 2], s);
+      launch_swap(&e, s, e.v.swapsum, swaptries);
+      cudaEventRecord(ev[i * 4 + 3], s);
+    }
+    if (!IMA_CUDA_OK(cudaStreamSynchronize(s))) return fail(IMA2P_E_CUDA, "sync failed (run_timed)");
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < 3; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i * 4 + k], ev[i * 4 + k + 1]); kernel_ms[k] += ms; }
+  }
+  for (auto &x : ev) cudaEventDestroy(x);
+#else
+  for (int i = 0; i < nsteps; i++) { launch_update(&e, s); launch_swap(&e, s, e.v.swapsum, swaptries); }
+#endif
+  return IMA2P_OK;
+}
+
 int ima2p_engine_update_genealogies(ima2p_engine *h, double *dev_S_local, void *cuda_stream) {
   if (!h) return fail(IMA2P_E_ARG, "null engine");
   Engine &e = h->eng;

@@ -174,6 +174,16 @@ class Engine:
             swaptries = max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0    # ima_main_mpi.cpp:1378
         self._ck(self.lib.ima2p_engine_run(self._h, nsteps, swaptries, stream))
 
+    def default_swaptries(self):
+        return max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0             # ima_main_mpi.cpp:1378
+
+    def run_timed(self, nsteps, swaptries=None, stream=None):
+        """run() launched kernel by kernel; returns summed device ms of (propose, accept, swap)."""
+        ms = np.zeros(3, np.float32)
+        self._ck(self.lib.ima2p_engine_run_timed(self._h, nsteps, self.default_swaptries() if swaptries is None else swaptries,
+                                                 stream, ms.ctypes.data_as(capi.c_flt_p)))
+        return ms
+
     def update_genealogies(self, dev_S_local=None, stream=None):
         self._ck(self.lib.ima2p_engine_update_genealogies(self._h, dev_S_local, stream))
 

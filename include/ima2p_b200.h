@@ -106,6 +106,9 @@ int ima2p_engine_dims (ima2p_engine * e, int *out /* {NI, ND, NL, CAP, rowlen} *
  * update_gtree.cpp:723-966) followed by swaptries MC3 temperature swaps (swapchains.cpp:526-653;
  * temperature-rank form of swapchains_bwprocesses :192-523).  Single-GPU form: */
 int ima2p_engine_run (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream);
+/* same steps, launched kernel by kernel with CUDA events on the launching stream around each kernel;
+ * kernel_ms[3] = summed device time of {propose, accept, swap} (used for roofline accounting) */
+int ima2p_engine_run_timed (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms);
 /* Multi-GPU form (one process per GPU): genealogy updates of the local chains, then the per-chain
  * S = sum_li pdg + probg (swapweight, swapchains.cpp:12-34) is written to dev_S_local[nchains_local]
  * (device memory owned by the caller); the caller all-gathers it over NCCL into

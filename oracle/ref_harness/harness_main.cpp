@@ -738,33 +738,44 @@ mode_lmode (long burn, long rows, long every)
   fprintf (jo, "]}\n");
 }
 
+/* `chunks` timed chunks of `iters` sweeps each; a sweep = updategenealogy() for every chain x locus
+ * (full=0, the loop of qupdate ima_main_mpi.cpp:1821-1841) or one whole qupdate() step (full=1) */
 static void
-mode_bench (long burn, long iters, long full)
+mode_bench (long burn, long iters, long full, long chunks)
 {
-  long it, acc = 0, tries = 0;
+  long it, ch, acc = 0, tries = 0;
   int ci, li, a, b;
+  std::vector<double> secs;
   do_burn (burn);
-  double t0 = nowsec ();
-  for (it = 0; it < iters; it++)
+  double t00 = nowsec ();
+  for (ch = 0; ch < chunks; ch++)
   {
-    if (full)
+    double t0 = nowsec ();
+    for (it = 0; it < iters; it++)
     {
-      qupdate (0, 0, 1);
-      step++;
-      tries += (long) numchains *nloci;
+      if (full)
+      {
+        qupdate (0, 0, 1);
+        step++;
+        tries += (long) numchains *nloci;
+      }
+      else
+        for (ci = 0; ci < numchains; ci++)
+          for (li = 0; li < nloci; li++)
+          {
+            acc += updategenealogy (ci, li, &a, &b);
+            tries++;
+          }
     }
-    else
-      for (ci = 0; ci < numchains; ci++)
-        for (li = 0; li < nloci; li++)
-        {
-          acc += updategenealogy (ci, li, &a, &b);
-          tries++;
-        }
+    secs.push_back (nowsec () - t0);
   }
   double t1 = nowsec ();
-  fprintf (jo, "{\"mode\":\"%s\",\"chains\":%d,\"loci\":%d,\"iters\":%ld,\"updates\":%ld,\"accepted\":%ld,\"seconds\":%.6f,"
-           "\"updates_per_sec\":%.3f}\n", full ? "qupdate" : "updategenealogy", numchains, nloci, iters, tries, acc, t1 - t0,
-           tries / (t1 - t0));
+  fprintf (jo, "{\"mode\":\"%s\",\"chains\":%d,\"loci\":%d,\"iters\":%ld,\"chunks\":%ld,\"updates\":%ld,\"updates_per_chunk\":%ld,"
+           "\"accepted\":%ld,\"seconds\":%.6f,\"updates_per_sec\":%.3f,\"chunk_seconds\":[", full ? "qupdate" : "updategenealogy",
+           numchains, nloci, iters, chunks, tries, (long) numchains * nloci * iters, acc, t1 - t00, tries / (t1 - t00));
+  for (ch = 0; ch < chunks; ch++)
+    fprintf (jo, "%s%.6f", ch ? "," : "", secs[ch]);
+  fprintf (jo, "]}\n");
 }
 
 static void
@@ -870,7 +881,7 @@ main (int argc, char *argv[])
   else if (mode == "lmode")
     mode_lmode (burn, kvl ("rows", 500), kvl ("every", 5));
   else if (mode == "bench")
-    mode_bench (burn, kvl ("iters", 10), kvl ("full", 0));
+    mode_bench (burn, kvl ("iters", 10), kvl ("full", 0), kvl ("chunks", 1));
   else if (mode == "lbench")
     mode_lbench (burn, kvl ("rows", 100000), kvl ("evals", 50));
   else
