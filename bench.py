@@ -306,7 +306,7 @@ def main():
     mig_mean = float(outb["scal_i"][:, 1].mean())
     roof = None
     if kernel_ms is not None:
-        per = kernel_ms / args.steps                       # ms per launch: propose, accept, swap
+        per = np.asarray(kernel_ms, dtype=np.float64) / args.steps                       # ms per launch: propose, accept, swap
         names = ["k_propose", "k_accept", "k_swap"]
         dom = int(np.argmax(per))
         P = cpg * nloci
@@ -342,7 +342,7 @@ def main():
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean,
            "graph_replay_ms_per_step": (graph_ms / args.steps) if graph_ms else None, "lmode": lmode,
            "dropped_for_capacity": c1["dropped"], "swap_rate": (c1["swaps"] - c0["swaps"]) / max(1, c1["swap_attempts"] - c0["swap_attempts"])}
-    print(json.dumps(out))
+    print(json.dumps(out, default=float))
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,85 @@
+"""N > 1 path on CPU: two gloo ranks, each holding half of the chains in the tests-only host-emulation build of
+the kernels, must reproduce the single-process run bit for bit (random streams are keyed by GLOBAL chain and
+locus, swap attempts are replayed identically on every rank)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "hostemu", "libima2p_hostemu.so")
+FIXTURE, NSTEPS, SWAPTRIES = "state_sim5_hn4", 25, 3
+
+
+def _run_single():
+    from ima2p_b200 import capi
+    from support import engine_from_fixture, load_golden
+    d = load_golden(FIXTURE)
+    betas = [ch["beta"] for ch in d["chains"]]
+    eng, _ = engine_from_fixture(d, lib=capi.bind(EMU), seed=99, betas=betas)
+    eng.eval()
+    eng.run(NSTEPS, SWAPTRIES)
+    out = np.array([[eng.chain(c)["probg"], eng.chain(c)["pdg"]] for c in range(eng.nchains)])
+    return out, eng.betas(), eng.counters()
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ima2p_b200 import Engine, capi
+    from ima2p_b200.multirank import ShardedStepper
+    from support import FlatModel, FlatTree, load_golden
+    d = load_golden(FIXTURE)
+    fm = FlatModel(d["model"])
+    nglob = len(d["chains"])
+    per = nglob // world
+    eng = Engine(per, len(d["loci"]), seed=99, lib=capi.bind(EMU), nchains_global=nglob, chain0=per * rank)
+    eng.set_model_flat(*fm.create_args())
+    for li, loc in enumerate(d["loci"]):
+        eng.set_locus(li, loc["model"], loc["numgenes"], loc["numsites"], loc["samppop"], seq=loc["seq"], hval=loc["hval"],
+                      sumlogk=loc["sumlogk"])
+    eng.finalize()
+    eng.set_betas([ch["beta"] for ch in d["chains"]])
+    for k in range(per):
+        ch = d["chains"][per * rank + k]
+        eng.set_chain(k, ch["tvals"])
+        for li, g in enumerate(ch["G"]):
+            t = FlatTree(g["tree"])
+            eng.set_genealogy(k, li, t.up0, t.up1, t.down, t.pop, t.time, t.mig_off, t.mig_t[:-1], t.mig_p[:-1], t.root,
+                              t.roottime, uvals=g["uvals"])
+    eng.upload()
+    eng.eval()
+    ShardedStepper(eng, torch.device("cpu")).run(NSTEPS, SWAPTRIES)
+    out = np.array([[eng.chain(c)["probg"], eng.chain(c)["pdg"]] for c in range(per)])
+    q.put((rank, out, eng.betas(), eng.counters()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_reproduce_the_single_process_run():
+    subprocess.run([os.path.join(HERE, "hostemu", "build.sh")], check=True)
+    single, betas1, cnt1 = _run_single()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    both = np.concatenate([g[1] for g in got])
+    assert np.array_equal(both, single)                    # bit-identical chains regardless of sharding
+    for g in got:
+        assert np.array_equal(g[2], betas1)                # every rank ends with the same beta permutation
+        assert g[3]["swap_attempts"] == cnt1["swap_attempts"] and g[3]["swaps"] == cnt1["swaps"]
+    assert sum(g[3]["accepted"] for g in got) == cnt1["accepted"]
+    assert cnt1["swaps"] > 0
