@@ -45,6 +45,7 @@ SIGNATURES = {
     "ima2p_engine_update_genealogies": (_i, [_v, _v, _v]),
     "ima2p_engine_swap_replay": (_i, [_v, _v, _i, _v]),
     "ima2p_engine_get_proposal": (_i, [_v, _i, _i, c_dbl_p, c_u32_p, c_int_p]),
+    "ima2p_debug_gamma": (_i, [_i, c_int_p, c_dbl_p, _i, c_dbl_p]),
     "ima2p_engine_counters": (_i, [_v, c_u64_p]),
     "ima2p_engine_get_betas": (_i, [_v, c_dbl_p]),
     "ima2p_engine_cold_row": (_i, [_v, c_flt_p, c_int_p]),

@@ -114,7 +114,7 @@ static int launch_eval(Engine *e, stream_t s) {
 static void launch_update(Engine *e, stream_t s) {
   const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
   IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v);
-  IMA_LAUNCH(k_accept, gc, kWarpsPerBlock, e->chain_smem * kWarpsPerBlock, s, e->v);
+  IMA_LAUNCH(k_accept, gc, kWarpsPerBlock, e->chain_smem * kWarpsPerBlock, s, e->v, 0, e->d.nloci);
 }
 
 static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries) {
@@ -613,7 +613,7 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
       cudaEventRecord(ev[i * 4 + 0], s);
       IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v);
       cudaEventRecord(ev[i * 4 + 1], s);
-      IMA_LAUNCH(k_accept, gc, kWarpsPerBlock, e.chain_smem * kWarpsPerBlock, s, e.v);
+      IMA_LAUNCH(k_accept, gc, kWarpsPerBlock, e.chain_smem * kWarpsPerBlock, s, e.v, 0, e.d.nloci);
       cudaEventRecord(ev[i * 4 + 2], s);
       launch_swap(&e, s, e.v.swapsum, swaptries);
       cudaEventRecord(ev[i * 4 + 3], s);
@@ -670,6 +670,33 @@ int ima2p_engine_get_proposal(ima2p_engine *h, int ci, int li, double *out4, uns
   if (flags) *flags = fl;
   if (is_current) *is_current = cur;
   return IMA2P_OK;
+}
+
+// parity hook for the device numerics (a10): out[4*n] = uppergamma, lowergamma (scalar forms, one lane) and
+// their warp-cooperative forms for every (a, x); lowergamma entries are 0 where a == 0
+int ima2p_debug_gamma(int device, const int *a, const double *x, int n, double *out) {
+  if (!a || !x || !out || n < 1) return fail(IMA2P_E_ARG, "debug_gamma: bad argument");
+#if IMA_CUDA
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(IMA2P_E_CUDA, "no CUDA device: ima2p_b200 has no CPU path");
+  if (!IMA_CUDA_OK(cudaSetDevice(device))) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+#else
+  (void)device;
+#endif
+  const int nlf = 100 * 5000 + 1;
+  std::vector<double> lf(nlf);
+  lf[0] = 0;
+  for (int i = 1; i < nlf; i++) lf[i] = lf[i - 1] + log((double)i);
+  double *d_lf = (double *)dev_alloc(nlf * sizeof(double)), *d_x = (double *)dev_alloc(n * sizeof(double)), *d_out = (double *)dev_alloc((size_t)n * 4 * sizeof(double));
+  int *d_a = (int *)dev_alloc(n * sizeof(int)), *d_err = (int *)dev_alloc(sizeof(int));
+  bool ok = d_lf && d_x && d_out && d_a && d_err && h2d(d_lf, lf.data(), nlf * sizeof(double), 0) && h2d(d_x, x, n * sizeof(double), 0) && h2d(d_a, a, n * sizeof(int), 0);
+  if (ok) {
+    MathCtx mc; mc.logfact = d_lf; mc.logfact_n = nlf; mc.err = d_err;
+    IMA_LAUNCH(k_debug_gamma, (n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock, 0, 0, mc, d_a, d_x, n, d_out);
+    ok = d2h(out, d_out, (size_t)n * 4 * sizeof(double), 0) && dev_sync(0);
+  }
+  dev_free(d_lf); dev_free(d_x); dev_free(d_out); dev_free(d_a); dev_free(d_err);
+  return ok ? IMA2P_OK : fail(IMA2P_E_CUDA, "debug_gamma failed");
 }
 
 int ima2p_engine_sync(ima2p_engine *h) {

@@ -140,15 +140,24 @@ IMA_KERNEL void k_eval_chains(EngineView E) {
   }
   Warp::sync();
   // initialize_integrate_tree_prob (update_gtree_common.cpp:2056-2134), one lane per parameter
-  double part = 0.0;
+  double probg = 0.0;
   const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
-  for (int t = lane; t < nterms; t += IMA_WARP) {
+  for (int t = 0; t < nterms; t++) {                    // whole warp per term (see k_accept)
     double v;
-    if (t < M.nq) { int cc; double f, hc; gather_q(M, t, S.ai, S.ad, cc, f, hc); v = integrate_coalescent_term(E.mc, cc, f, hc, M.q_max[t], M.q_min[t]); E.qint[(size_t)c * kMaxParams + t] = v; }
-    else { int cm; double f; gather_m(M, t - M.nq, S.ai, S.ad, cm, f); v = mig_term(M, E.mc, t - M.nq, cm, f); E.mint[(size_t)c * kMaxParams + t - M.nq] = v; }
-    part += v;
+    if (t < M.nq) {
+      int cc; double f, hc;
+      gather_q(M, t, S.ai, S.ad, cc, f, hc);
+      v = integrate_coalescent_term_coop(E.mc, cc, f, hc, M.q_max[t], M.q_min[t]);
+      if (lane == 0) E.qint[(size_t)c * kMaxParams + t] = v;
+    } else {
+      const int tm = t - M.nq;
+      int cm; double f;
+      gather_m(M, tm, S.ai, S.ad, cm, f);
+      v = M.expoprior ? integrate_migration_term_expo(E.mc, cm, f, M.m_mean[tm]) : integrate_migration_term_coop(E.mc, cm, f, M.m_max[tm], M.m_min[tm]);
+      if (lane == 0) E.mint[(size_t)c * kMaxParams + tm] = v;
+    }
+    probg += v;
   }
-  double probg = Warp::sum(part);
   if (!migration_allowed(M, S.ai)) probg = -kMyDblMax;
   double pd = 0.0;
   for (int li = lane; li < E.d.nloci; li += IMA_WARP) { const int p = c * E.d.nloci + li; pd += E.buf[E.cur[p]].sd[(size_t)p * 4 + 3]; }
@@ -202,7 +211,23 @@ IMA_KERNEL void k_propose(EngineView E) {
   }
 }
 
-IMA_KERNEL void k_accept(EngineView E) {
+// what the accept sweep needs from one pair: per-lane slice of the weight records plus the scalars
+struct AcceptRecord { int dI, cb; uint32_t flags; double oD, nD, oldpdg, newpdg, extra; };
+IMA_DEV void fetch_accept_record(const EngineView &E, int p, int lane, int NI, int ND, AcceptRecord &r) {
+  r.flags = E.prop_flags[p];
+  r.cb = E.cur[p];
+  const PairBuf &O = E.buf[r.cb], &N = E.buf[r.cb ^ 1];
+  r.dI = (lane < NI) ? N.gwi[(size_t)p * NI + lane] - O.gwi[(size_t)p * NI + lane] : 0;
+  r.oD = (lane < ND) ? O.gwd[(size_t)p * ND + lane] : 0.0;
+  r.nD = (lane < ND) ? N.gwd[(size_t)p * ND + lane] : 0.0;
+  r.oldpdg = O.sd[(size_t)p * 4 + 3];
+  r.newpdg = N.sd[(size_t)p * 4 + 3];
+  r.extra = E.prop_extra[p];
+}
+
+// loci [l0, l1) of every chain; the all-locus sums travel through global memory between launches, so a step
+// may be cut into several launches (used to overlap the sweep with the next step's proposals)
+IMA_KERNEL void k_accept(EngineView E, int l0, int l1) {
   IMA_SMEM_DECL
   const int c = ima_block() * kWarpsPerBlock + ima_warp_in_block();
   if (c >= E.d.nchains) return;
@@ -218,50 +243,69 @@ IMA_KERNEL void k_accept(EngineView E) {
   double probg = E.probg[c], pdgsum = E.pdgsum[c];
   const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
   unsigned long long dropped = 0;
-  for (int li = 0; li < E.d.nloci; li++) {
+  // the records of locus li+1 are fetched while locus li is being decided (software prefetch: the sweep is a
+  // dependent chain, so global-memory latency would otherwise sit on the critical path of every locus)
+  AcceptRecord nxt;
+  fetch_accept_record(E, c * E.d.nloci + l0, lane, NI, ND, nxt);
+  for (int li = l0; li < l1; li++) {
     const int p = c * E.d.nloci + li;
-    const uint32_t flags = E.prop_flags[p];
+    const AcceptRecord rec = nxt;
+    if (li + 1 < l1) fetch_accept_record(E, p + 1, lane, NI, ND, nxt);
+    const uint32_t flags = rec.flags;
     if (flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree)) { if (flags & kFlagOverflow) dropped++; continue; }
-    const int cb = E.cur[p], nb = cb ^ 1;
-    const int *oi = E.buf[cb].gwi + (size_t)p * NI, *ni = E.buf[nb].gwi + (size_t)p * NI;
-    const double *od = E.buf[cb].gwd + (size_t)p * ND, *nd = E.buf[nb].gwd + (size_t)p * ND;
+    const int cb = rec.cb, nb = cb ^ 1;
     // sum_subtract_treeinfo (ginfo.cpp:248-285): subtract old, add new, clamp fc and fm at 0
-    for (int i = lane; i < NI; i += IMA_WARP) S.ci[i] = S.ai[i] + (ni[i] - oi[i]);
-    for (int i = lane; i < ND; i += IMA_WARP) {
-      double x = S.ad[i];
-      x -= od[i];
-      x += nd[i];
-      if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
-      S.cd[i] = x;
+    if (lane < NI) S.ci[lane] = S.ai[lane] + rec.dI;
+    if (lane < ND) {
+      double x = S.ad[lane];
+      x -= rec.oD;
+      x += rec.nD;
+      if ((lane < ncc || lane >= 2 * ncc) && 0.0 > x) x = 0.0;
+      S.cd[lane] = x;
+    }
+    if (NI > IMA_WARP || ND > IMA_WARP) {               // records wider than a warp (>= 4 populations): direct loads
+      const int *oi = E.buf[cb].gwi + (size_t)p * NI, *ni = E.buf[nb].gwi + (size_t)p * NI;
+      const double *od = E.buf[cb].gwd + (size_t)p * ND, *nd = E.buf[nb].gwd + (size_t)p * ND;
+      for (int i = lane + (IMA_WARP == 1 ? 1 : IMA_WARP); i < NI; i += IMA_WARP) S.ci[i] = S.ai[i] + (ni[i] - oi[i]);
+      for (int i = lane + (IMA_WARP == 1 ? 1 : IMA_WARP); i < ND; i += IMA_WARP) {
+        double x = S.ad[i];
+        x -= od[i];
+        x += nd[i];
+        if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
+        S.cd[i] = x;
+      }
     }
     Warp::sync();
-    // integrate_tree_prob (update_gtree_common.cpp:1944-2053) with the reuse rule :1997-2000, :2031-2034
-    double part = 0.0;
-    for (int t = lane; t < nterms; t += IMA_WARP) {
+    // integrate_tree_prob (update_gtree_common.cpp:1944-2053) with the reuse rule :1997-2000, :2031-2034.
+    // Terms are taken one after the other by the whole warp (uniform control flow, constant-bank broadcasts);
+    // inside a term the series / continued fraction runs 32 terms at a time (ima_math.h, *_coop).
+    double newprobg = 0.0;
+    for (int t = 0; t < nterms; t++) {
       double v;
       if (t < M.nq) {
         int cn, co; double fn, fo, hn, ho;
         gather_q(M, t, S.ci, S.cd, cn, fn, hn);
         gather_q(M, t, S.ai, S.ad, co, fo, ho);
-        v = (cn == co && fn == fo) ? S.q[t] : integrate_coalescent_term(E.mc, cn, fn, hn, M.q_max[t], M.q_min[t]);
-        S.cq[t] = v;
+        v = (cn == co && fn == fo) ? S.q[t] : integrate_coalescent_term_coop(E.mc, cn, fn, hn, M.q_max[t], M.q_min[t]);
+        if (lane == 0) S.cq[t] = v;
       } else {
         const int tm = t - M.nq;
         int cn, co; double fn, fo;
         gather_m(M, tm, S.ci, S.cd, cn, fn);
         gather_m(M, tm, S.ai, S.ad, co, fo);
-        v = (cn == co && fn == fo) ? S.q[kMaxParams + tm] : mig_term(M, E.mc, tm, cn, fn);
-        S.cq[kMaxParams + tm] = v;
+        v = (cn == co && fn == fo) ? S.q[kMaxParams + tm]
+            : (M.expoprior ? integrate_migration_term_expo(E.mc, cn, fn, M.m_mean[tm])
+                           : integrate_migration_term_coop(E.mc, cn, fn, M.m_max[tm], M.m_min[tm]));
+        if (lane == 0) S.cq[kMaxParams + tm] = v;
       }
-      part += v;
+      newprobg += v;
     }
-    double newprobg = Warp::sum(part);
     if (!migration_allowed(M, S.ci)) newprobg = -kMyDblMax;
-    const double oldpdg = E.buf[cb].sd[(size_t)p * 4 + 3], newpdg = E.buf[nb].sd[(size_t)p * 4 + 3];
+    const double oldpdg = rec.oldpdg, newpdg = rec.newpdg;
     int acc = 0;
     if (lane == 0) {
       const double tpw = newprobg - probg;
-      const double extra = E.prop_extra[p];
+      const double extra = rec.extra;
       double mh;                                        // update_gtree.cpp:917-927
       if (M.thermo) mh = exp(beta * M.gbeta * (newpdg - oldpdg) + tpw + extra);
       else mh = exp(beta * (tpw + M.gbeta * (newpdg - oldpdg)) + extra);
@@ -296,9 +340,10 @@ IMA_KERNEL void k_accept(EngineView E) {
   __threadfence_block();
 #endif
   Warp::sync();
-  const double ssum = chain_swapsum(E, M, c, probg);
+  const double ssum = (l1 == E.d.nloci) ? chain_swapsum(E, M, c, probg) : 0.0;
   if (lane == 0) {
-    E.probg[c] = probg; E.pdgsum[c] = pdgsum; E.swapsum[c] = ssum;
+    E.probg[c] = probg; E.pdgsum[c] = pdgsum;
+    if (l1 == E.d.nloci) E.swapsum[c] = ssum;
     if (dropped) {
 #if IMA_CUDA
       atomicAdd(E.overflow, dropped);
@@ -322,9 +367,11 @@ struct SwapView {
 };
 
 IMA_KERNEL void k_swap(EngineView E, SwapView V) {
-  if (ima_block() != 0 || ima_warp_in_block() != 0 || Warp::lane() != 0) return;
+  if (ima_block() != 0 || ima_warp_in_block() != 0) return;
   const int N = E.d.nchains_global;
+  const int lane = Warp::lane();
   if (N > 1 && V.swaptries > 0) {
+    if (lane == 0) {
     Philox rng;
     rng_for(rng, E, 0xffffffffu, kRngSwap);
     for (int x = 0; x < V.swaptries; x++) {
@@ -345,9 +392,28 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
         V.swap_counts[1]++;
       }
     }
-    for (int c = 0; c < E.d.nchains; c++) E.beta[c] = V.beta_table[V.rank_of_chain[E.d.chain0 + c]];
+    }
+#if IMA_CUDA
+    __threadfence_block();
+#endif
+    Warp::sync();
+    for (int c = lane; c < E.d.nchains; c += IMA_WARP) E.beta[c] = V.beta_table[V.rank_of_chain[E.d.chain0 + c]];
   }
-  if (V.advance_step) *E.nsteps += 1;
+  if (V.advance_step && lane == 0) *E.nsteps += 1;
+}
+
+// parity hook: one warp per (a, x) pair
+IMA_KERNEL void k_debug_gamma(MathCtx mc, const int *a, const double *x, int n, double *out) {
+  const int i = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (i >= n) return;
+  const double uc = uppergamma_coop(mc, a[i], x[i]);
+  const double lc = a[i] > 0 ? lowergamma_coop(mc, a[i], x[i]) : 0.0;
+  if (Warp::lane() == 0) {
+    out[4 * i + 0] = uppergamma(mc, a[i], x[i]);
+    out[4 * i + 1] = a[i] > 0 ? lowergamma(mc, a[i], x[i]) : 0.0;
+    out[4 * i + 2] = uc;
+    out[4 * i + 3] = lc;
+  }
 }
 
 IMA_KERNEL void k_copy_swapsum(EngineView E, double *dst) {

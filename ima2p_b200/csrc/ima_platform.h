@@ -81,6 +81,17 @@ struct Warp {
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane() >= o) v += t; }
     return v;
   }
+  IMA_DEV static double scan_add(double v) {
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, v, o); if (lane() >= o) v += t; }
+    return v;
+  }
+  IMA_DEV static double scan_mul(double v) {
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, v, o); if (lane() >= o) v *= t; }
+    return v;
+  }
+  IMA_DEV static double shfl_up(double v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
+  // index of the first lane whose predicate holds, or -1
+  IMA_DEV static int first(bool p) { unsigned m = __ballot_sync(0xffffffffu, p); return m ? __ffs(m) - 1 : -1; }
 #else
   static int lane() { return 0; }
   static void sync() {}
@@ -91,6 +102,10 @@ struct Warp {
   static double bcast(double v, int) { return v; }
   static bool any(bool p) { return p; }
   static int scan(int v) { return v; }
+  static double scan_add(double v) { return v; }
+  static double scan_mul(double v) { return v; }
+  static double shfl_up(double v, int) { return v; }
+  static int first(bool p) { return p ? 0 : -1; }
 #endif
 };
 

@@ -121,6 +121,10 @@ int ima2p_engine_swap_replay (ima2p_engine * e, const double *dev_S_global, int 
  * bit3 root moved; buffer = index of the buffer that is current (flips on accept) */
 int ima2p_engine_get_proposal (ima2p_engine * e, int ci, int li, double *out4, unsigned int *flags, int *buffer);
 
+/* parity hook for the device numerics (uppergamma / lowergamma utilities.cpp:1053-1122): out[4*i..] =
+ * {uppergamma, lowergamma} in their one-lane form and in their warp-cooperative form for (a[i], x[i]) */
+int ima2p_debug_gamma (int device, const int *a, const double *x, int n, double *out);
+
 /* counters: out = {steps, updates tried, accepted, topology-changing accepted, tmrca-changing accepted,
  *                  swap attempts, swaps accepted, proposals dropped for capacity} */
 int ima2p_engine_counters (ima2p_engine * e, uint64_t * out8);

@@ -149,3 +149,26 @@ def lmode_matches_reference(lib, name, rtol=1e-9):
     assert rel_close(a.marginal_sums(0, xs[:8, 0]) + b.marginal_sums(0, xs[:8, 0]), s0, 1e-12)
     for o in (lm, a, b):
         o.close()
+
+
+def gamma_tables_match_reference(lib, rtol=1e-10):
+    """a10: uppergamma / lowergamma on the device (one-lane and warp-cooperative forms) against the reference's
+    own values on a grid that straddles the series / continued-fraction switch at x = a + 1."""
+    import ctypes as C
+    k = load_golden("kat_sim5_hn4")
+    up = {(a, x): _num(v) for a, x, v in k["uppergamma"]}
+    lo = {(a, x): _num(v) for a, x, v in k["lowergamma"]}
+    keys = sorted(up)
+    a = np.array([t[0] for t in keys], np.int32)
+    x = np.array([t[1] for t in keys], np.float64)
+    out = np.zeros((len(keys), 4))
+    rc = lib.ima2p_debug_gamma(0, a.ctypes.data_as(C.POINTER(C.c_int)), x.ctypes.data_as(C.POINTER(C.c_double)), len(keys),
+                               out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0, lib.ima2p_last_error()
+    for i, key in enumerate(keys):
+        for col in (0, 2):
+            assert rel_close(out[i, col], up[key], rtol, 1e-12), ("uppergamma", key, col, out[i, col], up[key])
+        if key in lo:
+            for col in (1, 3):
+                assert rel_close(out[i, col], lo[key], rtol, 1e-12), ("lowergamma", key, col, out[i, col], lo[key])
+    return len(keys)

@@ -44,6 +44,10 @@ def test_lmode_matches_reference(lib, name):
     ec.lmode_matches_reference(lib, name, rtol=RTOL)
 
 
+def test_device_incomplete_gamma_matches_reference_tables(lib):
+    assert ec.gamma_tables_match_reference(lib, rtol=1e-10) > 400
+
+
 def test_runs_are_reproducible_and_seed_dependent(lib):
     from support import engine_from_fixture, load_golden
     d = load_golden("state_sim5_hn4")

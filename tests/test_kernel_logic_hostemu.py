@@ -39,3 +39,7 @@ def test_incremental_sums(emu, name, nsteps):
 @pytest.mark.parametrize("name", ["lmode_sim5_hn2", "lmode_sim5_expo_hn2"])
 def test_lmode(emu, name):
     ec.lmode_matches_reference(emu, name, rtol=1e-12)
+
+
+def test_gamma_tables(emu):
+    assert ec.gamma_tables_match_reference(emu, rtol=1e-12) > 400
