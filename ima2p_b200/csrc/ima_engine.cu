@@ -192,6 +192,8 @@ int ima2p_engine_set_model(ima2p_engine *h, int npops, int nsplit, const int *pl
     M.droppops[k][0] = (signed char)droppops[2 * k]; M.droppops[k][1] = (signed char)droppops[2 * k + 1];
   }
   for (int i = 0; i < M.ntreepops; i++) { M.pt_e[i] = (signed char)pt_e[i]; M.pt_down[i] = (signed char)pt_down[i]; }
+  for (int q = 0; q < M.ntreepops; q++)          // q contributes to itself and to every ancestor
+    for (int a = q, guard = 0; a >= 0 && guard < M.ntreepops; a = M.pt_down[a], guard++) M.desc_mask[a] |= 1 << q;
   M.cc_off[0] = M.mc_off[0] = 0;
   for (int k = 0; k <= nsplit; k++) {
     M.cc_off[k + 1] = (short)(M.cc_off[k] + (npops - k));
@@ -254,6 +256,12 @@ int ima2p_engine_set_locus(ima2p_engine *h, int li, int model, int numgenes, int
       }
       // a monomorphic column is IMERR_INFINITESITESFAIL in the reference (calc_prob_data.cpp:823-826)
       if (carriers == 0 || carriers == numgenes) return fail(IMA2P_E_ARG, "set_locus: non-segregating infinite-sites column");
+      // canonical key: a carrier set that contains gene 0 is stored as its complement (see build_tip_keys)
+      if (L.sitemask[(size_t)s * L.d.nwords] & 1u)
+        for (int w = 0; w < L.d.nwords; w++) {
+          const uint32_t full = (w == L.d.nwords - 1 && (numgenes & 31)) ? ((1u << (numgenes & 31)) - 1u) : 0xffffffffu;
+          L.sitemask[(size_t)s * L.d.nwords + w] = ~L.sitemask[(size_t)s * L.d.nwords + w] & full;
+        }
     }
   } else if (model == kHKY) {
     if (!seq || !mult) return fail(IMA2P_E_ARG, "set_locus: seq and mult required for HKY");
@@ -291,6 +299,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   if (d.NL > 32000) return fail(IMA2P_E_ARG, "finalize: sample too large for 16-bit edge indices");
   int ev = (maxng - 1) + d.CAP + e.model.nsplit;
   d.EVP = 1; while (d.EVP < ev) d.EVP <<= 1;
+  d.W64 = (e.model.ntreepops + 3) / 4;
   e.pair_smem = pair_smem_bytes(d);
   e.chain_smem = chain_smem_bytes(d);
 #if IMA_CUDA

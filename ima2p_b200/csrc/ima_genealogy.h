@@ -24,6 +24,8 @@ struct PairSm {
   short *pp;               // [4*CAP]
   double *evt;             // [EVP] event times (sort keys)
   int *evi;                // [EVP] packed event info
+  int *evk;                // [EVP] period of the event | lineages before it << 8
+  unsigned long long *pre; // [EVP*W64] exclusive prefix of the per-population lineage deltas (16-bit fields)
   uint32_t *mask;          // [NL*W] subtree tip masks
   int *moff;               // [NL+1] exclusive prefix of mcn
   int *gwi;                // [NI]
@@ -46,7 +48,8 @@ IMA_HD size_t pair_smem_bytes(const EngineDims &d) {
   b += align8(sizeof(double) * 4 * d.CAP);
   b += align8(sizeof(short) * 4 * d.CAP);
   b += align8(sizeof(double) * d.EVP);
-  b += align8(sizeof(int) * d.EVP);
+  b += align8(sizeof(int) * d.EVP) * 2;
+  b += align8(sizeof(unsigned long long) * d.EVP * d.W64);
   b += align8(sizeof(uint32_t) * d.NL * d.W);
   b += align8(sizeof(int) * (d.NL + 1));
   b += align8(sizeof(int) * d.NI);
@@ -63,6 +66,7 @@ IMA_DEV PairSm carve_pair_smem(unsigned char *base, const EngineDims &d) {
   s.time = (double *)take(sizeof(double) * d.NL);
   s.pt = (double *)take(sizeof(double) * 4 * d.CAP);
   s.evt = (double *)take(sizeof(double) * d.EVP);
+  s.pre = (unsigned long long *)take(sizeof(unsigned long long) * d.EVP * d.W64);
   s.gwd = (double *)take(sizeof(double) * d.ND);
   s.ctl_d = (double *)take(sizeof(double) * 8);
   s.up0 = (short *)take(sizeof(short) * d.NL);
@@ -73,6 +77,7 @@ IMA_DEV PairSm carve_pair_smem(unsigned char *base, const EngineDims &d) {
   s.mcn = (unsigned short *)take(sizeof(unsigned short) * d.NL);
   s.pp = (short *)take(sizeof(short) * 4 * d.CAP);
   s.evi = (int *)take(sizeof(int) * d.EVP);
+  s.evk = (int *)take(sizeof(int) * d.EVP);
   s.mask = (uint32_t *)take(sizeof(uint32_t) * d.NL * d.W);
   s.moff = (int *)take(sizeof(int) * (d.NL + 1));
   s.gwi = (int *)take(sizeof(int) * d.NI);
@@ -690,69 +695,138 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
       }
       Warp::sync();
     }
-  // tip masks
-  for (int i = lane; i < ng * W; i += IMA_WARP) {
-    const int tip = i / W, w = i - tip * W;
-    S.mask[i] = ((tip >> 5) == w) ? (1u << (tip & 31)) : 0u;
-  }
   for (int i = lane; i < d.NI; i += IMA_WARP) S.gwi[i] = 0;
   for (int i = lane; i < d.ND; i += IMA_WARP) S.gwd[i] = 0.0;
   Warp::sync();
-  // sweep (:1805-1921), lane 0; subtree masks are filled in coalescence-time order on the way
-  if (lane == 0) {
-    int n[kMaxTreePops];
-    const int npops = M.npops;
-    for (int i = 0; i < npops; i++) n[i] = L.samppop[i];
-    for (int i = npops; i < 2 * npops - 1; i++) n[i] = 0;
-    int nsum = ng, k = 0, bad = 0;
-    double lasttime = 0.0, length = 0.0, tlength = 0.0;
-    const double h2term = 1 / (2 * L.hval);
-    const double lastsplitt = M.nsplit > 0 ? tv[M.nsplit - 1] : kTimeMax;
-    for (int j = 0; j < nev; j++) {
-      const double t = S.evt[j];
-      const int info = S.evi[j];
-      const double dt = t - lasttime;
-      const double timeadd = nsum * dt;
-      length += timeadd;
-      if (t < lastsplitt) tlength += timeadd;
-      else if (lasttime < lastsplitt) tlength += nsum * (lastsplitt - lasttime);
-      lasttime = t;
-      const int np = npops - k;
-      for (int ii = 0; ii < np; ii++) {
-        const int ip = M.plist[k][ii];
-        S.gwd[wd_fc(M, k, ii)] += ((double)n[ip] * ((double)n[ip] - 1)) * dt * h2term;
-        if (!M.nomigration && k < M.nsplit) {
-          const double fmtemp = n[ip] * dt;
-          for (int jj = 0; jj < np; jj++) if (jj != ii) S.gwd[wd_fm(M, k, ii, jj)] += fmtemp;
+  // ---- sweep (:1805-1921), lane-parallel --------------------------------------------------------
+  // The reference walks the sorted events keeping lineage counts n[pop].  Here every event j gets its
+  // own view of the state just before it from exclusive prefix scans: the period k_j (splits before j),
+  // the number of lineages (coalescences before j) and, per tree population q, the running sum D_q of
+  // the events' +-1 effects.  A population that exists in period k holds
+  //     n = sum over q in desc(pop) of (samples_q + D_q)
+  // lineages (populations merge at splits and receive no events afterwards), so no sequential state is
+  // needed.  Integer counts are bit-exact; the double sums are added lane-wise then by a fixed-order
+  // warp reduction (the reference adds them in time order: differences are rounding only).
+  const int W64 = (M.ntreepops + 3) >> 2;              // 16-bit fields, four populations per 64-bit word
+  {
+    int carry_k = 0, carry_c = 0;
+    unsigned long long carry_w[(kMaxTreePops + 3) / 4];
+    for (int w = 0; w < W64; w++) carry_w[w] = 0ull;
+    for (int base = 0; base < nev; base += IMA_WARP) {
+      const int j = base + lane;
+      const bool valid = j < nev;
+      const int info = valid ? S.evi[j] : 0;
+      const int kind = valid ? (info & 3) : 3, ip = (info >> 2) & 31, jp = (info >> 7) & 31;
+      const int is_split = (kind == 2), is_coal = (kind == 0);
+      const int inc_k = Warp::scan(is_split), inc_c = Warp::scan(is_coal);
+      const int kj = carry_k + inc_k - is_split, cj = carry_c + inc_c - is_coal;
+      carry_k += Warp::bcast(inc_k, IMA_WARP - 1);
+      carry_c += Warp::bcast(inc_c, IMA_WARP - 1);
+      if (valid) S.evk[j] = kj | ((ng - cj) << 8);
+      for (int w = 0; w < W64; w++) {
+        unsigned long long own = 0ull;
+        if (valid) {
+          for (int f = 0; f < 4; f++) {
+            const int q = w * 4 + f;
+            if (q < M.ntreepops) {
+              int dq = 1;                                // biased by +1 so that every field stays non-negative
+              if (kind == 0 && ip == q) dq -= 1;
+              if (kind == 1) { if (ip == q) dq -= 1; if (jp == q) dq += 1; }
+              own |= (unsigned long long)dq << (16 * f);
+            }
+          }
         }
-      }
-      const int kind = info & 3, ip = (info >> 2) & 31, jp = (info >> 7) & 31;
-      if (kind == 0) {
-        int ii = 0;
-        while (ii < np && M.plist[k][ii] != ip) ii++;
-        if (ii >= np || n[ip] < 2) { bad = 1; break; }
-        S.gwi[wi_cc(M, k, ii)]++;
-        n[ip]--; nsum--;
-        const int node = info >> 12, a = S.up0[node], b = S.up1[node];
-        for (int w = 0; w < W; w++) S.mask[node * W + w] = S.mask[a * W + w] | S.mask[b * W + w];
-      } else if (kind == 1) {
-        int ii = 0, jj = 0;
-        while (ii < np && M.plist[k][ii] != ip) ii++;
-        while (jj < np && M.plist[k][jj] != jp) jj++;
-        if (ii >= np || jj >= np || n[ip] < 1 || k >= M.nsplit) { bad = 1; break; }
-        S.gwi[wi_mc(M, k, ii, jj)]++;
-        n[ip]--; n[jp]++;
-      } else {
-        k++;
-        n[M.addpop[k]] = n[M.droppops[k][0]] + n[M.droppops[k][1]];
-        n[M.droppops[k][0]] = n[M.droppops[k][1]] = 0;
+        unsigned long long inc = own;
+#if IMA_CUDA
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
+#else
+        const unsigned long long tot = inc;
+#endif
+        if (valid) S.pre[(size_t)j * W64 + w] = carry_w[w] + inc - own;
+        carry_w[w] += tot;
       }
     }
-    const double hlog = log(L.hval);
-    if (hlog != 0.0)
-      for (int kk = 0; kk <= M.nsplit; kk++)
-        for (int i = 0; i < npops - kk; i++) S.gwd[wd_hcc(M, kk, i)] += hlog * S.gwi[wi_cc(M, kk, i)];
-    if (nsum != 1) bad = 1;
+  }
+  Warp::sync();
+  // number of lineages in tree population `pop` just before event j
+  auto lineages = [&](int pop, int j) {
+    int n = 0;
+    const unsigned dm = (unsigned)M.desc_mask[pop];
+    for (int q = 0; q < M.ntreepops; q++)
+      if (dm & (1u << q)) {
+        const int dq = (int)((S.pre[(size_t)j * W64 + (q >> 2)] >> (16 * (q & 3))) & 0xffffull) - j;   // remove the +1 bias
+        n += dq + (q < M.npops ? L.samppop[q] : 0);
+      }
+    return n;
+  };
+  const double h2term = 1 / (2 * L.hval);
+  const double lastsplitt = M.nsplit > 0 ? tv[M.nsplit - 1] : kTimeMax;
+  double length = 0.0, tlength = 0.0;
+  int bad = 0;
+  for (int j = lane; j < nev; j += IMA_WARP) {
+    const double t = S.evt[j], lasttime = j > 0 ? S.evt[j - 1] : 0.0;
+    const double dt = t - lasttime;
+    const int kj = S.evk[j] & 0xff, nsum = S.evk[j] >> 8;
+    const double timeadd = nsum * dt;
+    length += timeadd;
+    if (t < lastsplitt) tlength += timeadd;
+    else if (lasttime < lastsplitt) tlength += nsum * (lastsplitt - lasttime);
+    const int info = S.evi[j], kind = info & 3, ip = (info >> 2) & 31, jp = (info >> 7) & 31;
+    const int np = M.npops - kj;
+    if (kind == 0) {
+      int ii = 0;
+      while (ii < np && M.plist[kj][ii] != ip) ii++;
+      if (ii >= np || lineages(ip, j) < 2) bad = 1;
+      else {
+#if IMA_CUDA
+        atomicAdd(&S.gwi[wi_cc(M, kj, ii)], 1);
+#else
+        S.gwi[wi_cc(M, kj, ii)]++;
+#endif
+      }
+    } else if (kind == 1) {
+      int ii = 0, jj = 0;
+      while (ii < np && M.plist[kj][ii] != ip) ii++;
+      while (jj < np && M.plist[kj][jj] != jp) jj++;
+      if (ii >= np || jj >= np || kj >= M.nsplit || lineages(ip, j) < 1) bad = 1;
+      else {
+#if IMA_CUDA
+        atomicAdd(&S.gwi[wi_mc(M, kj, ii, jj)], 1);
+#else
+        S.gwi[wi_mc(M, kj, ii, jj)]++;
+#endif
+      }
+    }
+  }
+  length = Warp::sum(length);
+  tlength = Warp::sum(tlength);
+  bad = Warp::any(bad != 0) ? 1 : 0;
+  // fc[k][ii] += n(n-1) dt / (2h) and fm[k][ii][*] += n dt: one target (k, ii) at a time
+  for (int k = 0; k <= M.nsplit; k++)
+    for (int ii = 0; ii < M.npops - k; ii++) {
+      const int ip = M.plist[k][ii];
+      double fcacc = 0.0, fmacc = 0.0;
+      for (int j = lane; j < nev; j += IMA_WARP)
+        if ((S.evk[j] & 0xff) == k) {
+          const double dt = S.evt[j] - (j > 0 ? S.evt[j - 1] : 0.0);
+          const int n = lineages(ip, j);
+          fcacc += ((double)n * ((double)n - 1)) * dt * h2term;
+          fmacc += n * dt;
+        }
+      fcacc = Warp::sum(fcacc);
+      fmacc = Warp::sum(fmacc);
+      if (lane == 0) {
+        S.gwd[wd_fc(M, k, ii)] = fcacc;
+        if (!M.nomigration && k < M.nsplit)
+          for (int jj = 0; jj < M.npops - k; jj++) if (jj != ii) S.gwd[wd_fm(M, k, ii, jj)] = fmacc;
+      }
+    }
+  Warp::sync();
+  const double hlog = log(L.hval);
+  if (hlog != 0.0)
+    for (int i = lane; i < M.ncc; i += IMA_WARP) S.gwd[M.ncc + i] += hlog * S.gwi[i];
+  if (lane == 0) {
     if (bad) S.ctl_i[kCiFlags] |= (int)kFlagBadTree;
     S.ctl_d[kCdLength] = length;
     S.ctl_d[kCdTlength] = tlength;
@@ -763,30 +837,62 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
   return true;
 }
 
+// Subtree tip sets as canonical keys: every tip walks to the root OR-ing its bit into the edges it passes
+// (order-independent, so deterministic); a set that contains tip 0 is replaced by its complement, which makes
+// "equals the carrier set or its complement" a single comparison against the (canonical) site key.
+IMA_DEV void build_tip_keys(const DevLocus &L, PairSm &S) {
+  const int lane = Warp::lane();
+  const int ng = L.ng, nl = L.nl, W = L.nwords;
+  for (int i = lane; i < nl * W; i += IMA_WARP) {
+    const int e = i / W, w = i - e * W;
+    S.mask[i] = (e < ng && (e >> 5) == w) ? (1u << (e & 31)) : 0u;
+  }
+  Warp::sync();
+  for (int tip = lane; tip < ng; tip += IMA_WARP) {
+    const uint32_t bit = 1u << (tip & 31);
+    const int w = tip >> 5;
+    for (int e = S.down[tip], guard = 0; e != -1 && guard < nl; e = S.down[e], guard++) {
+#if IMA_CUDA
+      atomicOr(&S.mask[e * W + w], bit);
+#else
+      S.mask[e * W + w] |= bit;
+#endif
+    }
+  }
+  Warp::sync();
+  for (int e = lane; e < nl; e += IMA_WARP)
+    if (S.mask[e * W] & 1u)
+      for (int w = 0; w < W; w++) {
+        const uint32_t full = (w == W - 1 && (ng & 31)) ? ((1u << (ng & 31)) - 1u) : 0xffffffffu;
+        S.mask[e * W + w] = ~S.mask[e * W + w] & full;
+      }
+  Warp::sync();
+}
+
 // ------------------------------------------------------------------------------------------------
 // infinite sites: calc_prob_data.cpp:731-836.  A site is compatible iff exactly one branch carries
 // its mutation, i.e. iff some non-root edge's subtree tip set equals the site's carrier set or its
 // complement (same accept/reject and same branch as labelgtree's Fitch pass).
 // Every lane returns the likelihood (or kRejectIS).
 // ------------------------------------------------------------------------------------------------
-IMA_DEV double likelihood_is(const EngineView &E, const DevLocus &L, const PairSm &S, double mutrate) {
+IMA_DEV double likelihood_is(const EngineView &E, const DevLocus &L, PairSm &S, double mutrate) {
   const int lane = Warp::lane();
   const int ng = L.ng, nl = L.nl, W = L.nwords, root = S.ctl_i[kCiRoot];
-  const uint32_t *sm = E.sitemask + L.sitemask_off;
+  build_tip_keys(L, S);
+  const uint32_t *sm = E.sitemask + L.sitemask_off;     // canonical site keys (set_locus)
   double acc = 0.0;
   bool reject = false;
   for (int s = lane; s < L.nsites; s += IMA_WARP) {
     int found = -1;
-    for (int b = 0; b < nl && found < 0; b++) {
-      if (b == root) continue;
-      bool eq = true, ceq = true;
-      for (int w = 0; w < W; w++) {
-        const uint32_t full = (w == W - 1 && (ng & 31)) ? ((1u << (ng & 31)) - 1u) : 0xffffffffu;
-        const uint32_t m = S.mask[b * W + w], v = sm[(size_t)s * W + w];
-        eq = eq && (m == v);
-        ceq = ceq && (m == (~v & full));
+    if (W == 1) {
+      const uint32_t key = sm[s];
+      for (int b = 0; b < nl; b++) if (S.mask[b] == key) found = b;      // the root's key is 0: never a site key
+    } else {
+      for (int b = 0; b < nl && found < 0; b++) {
+        bool eq = true;
+        for (int w = 0; w < W; w++) eq = eq && (S.mask[b * W + w] == sm[(size_t)s * W + w]);
+        if (eq) found = b;
       }
-      if (eq || ceq) found = b;
     }
     if (found < 0) { reject = true; continue; }
     double ptime = S.time[found] - edge_top_time(S, ng, found);

@@ -166,7 +166,15 @@ IMA_KERNEL void k_eval_chains(EngineView E) {
   if (lane == 0) { E.probg[c] = probg; E.pdgsum[c] = pd; E.swapsum[c] = ssum; }
 }
 
-IMA_KERNEL void k_propose(EngineView E) {
+#ifndef IMA_PROPOSE_MINBLOCKS
+#define IMA_PROPOSE_MINBLOCKS 6      // 80 registers/thread: 24 resident warps per SM (the kernel is latency-bound)
+#endif
+#if IMA_CUDA
+#define IMA_PROPOSE_BOUNDS __launch_bounds__(kWarpsPerBlock * 32, IMA_PROPOSE_MINBLOCKS)
+#else
+#define IMA_PROPOSE_BOUNDS
+#endif
+IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E) {
   IMA_SMEM_DECL
   const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
   if (p >= E.d.P) return;

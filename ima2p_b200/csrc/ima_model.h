@@ -16,6 +16,7 @@ struct DevModel {
   signed char plist[kMaxPops][kMaxPops];
   signed char addpop[kMaxPeriods], droppops[kMaxPeriods][2];
   signed char pt_e[kMaxTreePops], pt_down[kMaxTreePops];
+  int desc_mask[kMaxTreePops];          // bit q set: tree population q is this population or one of its descendants
   short cc_off[kMaxPeriods + 1], mc_off[kMaxPeriods + 1];
   signed char q_n[kMaxParams], m_n[kMaxParams];
   short q_idx[kMaxParams][kMaxWp], m_idx[kMaxParams][kMaxWp];
@@ -67,7 +68,7 @@ struct EngineDims {
   int nchains_global;   // chains over all ranks
   int chain0;           // global index of local chain 0
   int nloci, P;
-  int NL, CAP, NI, ND, EVP, W, S;     // maxima over loci: numlines, pool capacity, record sizes, event slots, mask words, sites
+  int NL, CAP, NI, ND, EVP, W, S, W64;     // maxima over loci: numlines, pool capacity, record sizes, event slots, mask words, sites
   int any_sw, any_hky;
 };
 
