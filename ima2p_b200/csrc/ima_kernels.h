@@ -94,9 +94,9 @@ IMA_DEV double mig_term(const DevModel &M, const MathCtx &mc, int t, int c, doub
 }
 
 // shared-memory scratch of the per-chain kernels
-struct ChainSm { int *ai, *ci; double *ad, *cd, *q, *cq; };
+struct ChainSm { int *ai, *ci, *ic; double *ad, *cd, *q, *cq, *dc; };
 IMA_HD size_t chain_smem_bytes(const EngineDims &d) {
-  return 2 * align8(sizeof(int) * d.NI) + 2 * align8(sizeof(double) * d.ND) + 2 * align8(sizeof(double) * 2 * kMaxParams);
+  return 2 * align8(sizeof(int) * d.NI) + 2 * align8(sizeof(double) * d.ND) + 2 * align8(sizeof(double) * 2 * kMaxParams) + 64 + 32;
 }
 IMA_DEV ChainSm carve_chain_smem(unsigned char *base, const EngineDims &d) {
   ChainSm s; unsigned char *p = base;
@@ -104,8 +104,10 @@ IMA_DEV ChainSm carve_chain_smem(unsigned char *base, const EngineDims &d) {
   s.cd = (double *)p; p += align8(sizeof(double) * d.ND);
   s.q = (double *)p; p += align8(sizeof(double) * 2 * kMaxParams);
   s.cq = (double *)p; p += align8(sizeof(double) * 2 * kMaxParams);
+  s.dc = (double *)p; p += 64;
   s.ai = (int *)p; p += align8(sizeof(int) * d.NI);
-  s.ci = (int *)p;
+  s.ci = (int *)p; p += align8(sizeof(int) * d.NI);
+  s.ic = (int *)p;
   return s;
 }
 
@@ -174,12 +176,15 @@ IMA_KERNEL void k_eval_chains(EngineView E) {
 #else
 #define IMA_PROPOSE_BOUNDS
 #endif
-IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E) {
+// loci [l0, l1) of every chain (one warp per pair); see launch_update for why a step is cut into pieces
+IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E, int l0, int l1) {
   IMA_SMEM_DECL
-  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
-  if (p >= E.d.P) return;
+  const int idx = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  const int nsub = l1 - l0;
+  if (idx >= E.d.nchains * nsub) return;
   const DevModel &M = IMA_MODEL;
-  const int c = p / E.d.nloci, li = p - c * E.d.nloci;
+  const int c = idx / nsub, li = l0 + (idx - c * nsub);
+  const int p = c * E.d.nloci + li;
   const DevLocus &L = E.loci[li];
   PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
   const int cb = E.cur[p];
@@ -233,62 +238,86 @@ IMA_DEV void fetch_accept_record(const EngineView &E, int p, int lane, int NI, i
   r.extra = E.prop_extra[p];
 }
 
-// loci [l0, l1) of every chain; the all-locus sums travel through global memory between launches, so a step
-// may be cut into several launches (used to overlap the sweep with the next step's proposals)
+// One block per chain.  The loci of a chain are swept in order (they are coupled through the integrated prior,
+// SURVEY.md fact 1); inside a locus the nq + nm prior terms are independent, so each is given to its own warp
+// (which evaluates the term's series / continued fraction 32 terms per round, ima_math.h *_coop):
+//   warp 0      fetch (prefetched one locus ahead) the pair's weight records, build all +- weights with the clamps
+//   warp t      term t: gather (c, f, hc); reuse rule (:1997-2000, :2031-2034) or integrate_*_term
+//   thread 0    sum the terms in parameter order, MH decision (update_gtree.cpp:917-927)
+//   all         commit on accept
+// Loci [l0, l1): the sums travel through global memory between launches, so a step may be cut into pieces.
+#if IMA_CUDA
+constexpr int kAcceptWarps = 8;
+IMA_DEV void block_sync() { __syncthreads(); }
+#else
+constexpr int kAcceptWarps = 1;      // host emulation: one "warp" takes the terms one after the other
+IMA_DEV void block_sync() {}
+#endif
+enum { kAcFlags = 0, kAcCb, kAcAccept };
+enum { kAdOldPdg = 0, kAdNewPdg, kAdExtra, kAdNewProbg };
+
 IMA_KERNEL void k_accept(EngineView E, int l0, int l1) {
   IMA_SMEM_DECL
-  const int c = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  const int c = ima_block();
   if (c >= E.d.nchains) return;
   const DevModel &M = IMA_MODEL;
-  const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
-  ChainSm S = carve_chain_smem(IMA_SMEM + (size_t)ima_warp_in_block() * chain_smem_bytes(E.d), E.d);
-  for (int i = lane; i < NI; i += IMA_WARP) S.ai[i] = E.all_i[(size_t)c * NI + i];
-  for (int i = lane; i < ND; i += IMA_WARP) S.ad[i] = E.all_d[(size_t)c * ND + i];
-  for (int i = lane; i < M.nq; i += IMA_WARP) S.q[i] = E.qint[(size_t)c * kMaxParams + i];
-  for (int i = lane; i < M.nm; i += IMA_WARP) S.q[kMaxParams + i] = E.mint[(size_t)c * kMaxParams + i];
-  Warp::sync();
+  const int lane = Warp::lane(), w = ima_warp_in_block(), tid = w * IMA_WARP + lane, nth = kAcceptWarps * IMA_WARP;
+  const int NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
+  ChainSm S = carve_chain_smem(IMA_SMEM, E.d);
+  for (int i = tid; i < NI; i += nth) S.ai[i] = E.all_i[(size_t)c * NI + i];
+  for (int i = tid; i < ND; i += nth) S.ad[i] = E.all_d[(size_t)c * ND + i];
+  for (int i = tid; i < M.nq; i += nth) S.q[i] = E.qint[(size_t)c * kMaxParams + i];
+  for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = E.mint[(size_t)c * kMaxParams + i];
   const double beta = E.beta[c];
   double probg = E.probg[c], pdgsum = E.pdgsum[c];
   const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
   unsigned long long dropped = 0;
-  // the records of locus li+1 are fetched while locus li is being decided (software prefetch: the sweep is a
-  // dependent chain, so global-memory latency would otherwise sit on the critical path of every locus)
   AcceptRecord nxt;
-  fetch_accept_record(E, c * E.d.nloci + l0, lane, NI, ND, nxt);
+  if (w == 0) fetch_accept_record(E, c * E.d.nloci + l0, lane, NI, ND, nxt);
+  block_sync();
   for (int li = l0; li < l1; li++) {
     const int p = c * E.d.nloci + li;
-    const AcceptRecord rec = nxt;
-    if (li + 1 < l1) fetch_accept_record(E, p + 1, lane, NI, ND, nxt);
-    const uint32_t flags = rec.flags;
-    if (flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree)) { if (flags & kFlagOverflow) dropped++; continue; }
-    const int cb = rec.cb, nb = cb ^ 1;
-    // sum_subtract_treeinfo (ginfo.cpp:248-285): subtract old, add new, clamp fc and fm at 0
-    if (lane < NI) S.ci[lane] = S.ai[lane] + rec.dI;
-    if (lane < ND) {
-      double x = S.ad[lane];
-      x -= rec.oD;
-      x += rec.nD;
-      if ((lane < ncc || lane >= 2 * ncc) && 0.0 > x) x = 0.0;
-      S.cd[lane] = x;
-    }
-    if (NI > IMA_WARP || ND > IMA_WARP) {               // records wider than a warp (>= 4 populations): direct loads
-      const int *oi = E.buf[cb].gwi + (size_t)p * NI, *ni = E.buf[nb].gwi + (size_t)p * NI;
-      const double *od = E.buf[cb].gwd + (size_t)p * ND, *nd = E.buf[nb].gwd + (size_t)p * ND;
-      for (int i = lane + (IMA_WARP == 1 ? 1 : IMA_WARP); i < NI; i += IMA_WARP) S.ci[i] = S.ai[i] + (ni[i] - oi[i]);
-      for (int i = lane + (IMA_WARP == 1 ? 1 : IMA_WARP); i < ND; i += IMA_WARP) {
-        double x = S.ad[i];
-        x -= od[i];
-        x += nd[i];
-        if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
-        S.cd[i] = x;
+    if (w == 0) {
+      // records of locus li+1 are fetched while locus li is being decided (the sweep is a dependent chain, so
+      // global-memory latency would otherwise sit on the critical path of every locus)
+      const AcceptRecord rec = nxt;
+      if (li + 1 < l1) fetch_accept_record(E, p + 1, lane, NI, ND, nxt);
+      const int cb = rec.cb, nb = cb ^ 1;
+      // sum_subtract_treeinfo (ginfo.cpp:248-285): subtract old, add new, clamp fc and fm at 0
+      if (lane < NI) S.ci[lane] = S.ai[lane] + rec.dI;
+      if (lane < ND) {
+        double x = S.ad[lane];
+        x -= rec.oD;
+        x += rec.nD;
+        if ((lane < ncc || lane >= 2 * ncc) && 0.0 > x) x = 0.0;
+        S.cd[lane] = x;
+      }
+      if (NI > IMA_WARP || ND > IMA_WARP) {             // records wider than a warp (>= 4 populations): direct loads
+        const int *oi = E.buf[cb].gwi + (size_t)p * NI, *ni = E.buf[nb].gwi + (size_t)p * NI;
+        const double *od = E.buf[cb].gwd + (size_t)p * ND, *nd = E.buf[nb].gwd + (size_t)p * ND;
+        for (int i = lane + (IMA_WARP == 1 ? 1 : IMA_WARP); i < NI; i += IMA_WARP) S.ci[i] = S.ai[i] + (ni[i] - oi[i]);
+        for (int i = lane + (IMA_WARP == 1 ? 1 : IMA_WARP); i < ND; i += IMA_WARP) {
+          double x = S.ad[i];
+          x -= od[i];
+          x += nd[i];
+          if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
+          S.cd[i] = x;
+        }
+      }
+      if (lane == 0) {
+        S.ic[kAcFlags] = (int)rec.flags; S.ic[kAcCb] = cb;
+        S.dc[kAdOldPdg] = rec.oldpdg; S.dc[kAdNewPdg] = rec.newpdg; S.dc[kAdExtra] = rec.extra;
       }
     }
-    Warp::sync();
-    // integrate_tree_prob (update_gtree_common.cpp:1944-2053) with the reuse rule :1997-2000, :2031-2034.
-    // Terms are taken one after the other by the whole warp (uniform control flow, constant-bank broadcasts);
-    // inside a term the series / continued fraction runs 32 terms at a time (ima_math.h, *_coop).
-    double newprobg = 0.0;
-    for (int t = 0; t < nterms; t++) {
+    block_sync();
+    const uint32_t flags = (uint32_t)S.ic[kAcFlags];
+    if (flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree)) {
+      if (flags & kFlagOverflow) dropped++;
+      block_sync();                                      // warp 0 may not overwrite the control words before all have read them
+      continue;
+    }
+    // integrate_tree_prob (update_gtree_common.cpp:1944-2053): term t on warp t
+    for (int t = w; t < nterms; t += kAcceptWarps) {
       double v;
       if (t < M.nq) {
         int cn, co; double fn, fo, hn, ho;
@@ -306,58 +335,61 @@ IMA_KERNEL void k_accept(EngineView E, int l0, int l1) {
                            : integrate_migration_term_coop(E.mc, cn, fn, M.m_max[tm], M.m_min[tm]));
         if (lane == 0) S.cq[kMaxParams + tm] = v;
       }
-      newprobg += v;
     }
-    if (!migration_allowed(M, S.ci)) newprobg = -kMyDblMax;
-    const double oldpdg = rec.oldpdg, newpdg = rec.newpdg;
-    int acc = 0;
-    if (lane == 0) {
-      const double tpw = newprobg - probg;
-      const double extra = rec.extra;
+    block_sync();
+    if (tid == 0) {
+      double newprobg = 0.0;
+      for (int t = 0; t < M.nq; t++) newprobg += S.cq[t];
+      if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[kMaxParams + t];
+      if (!migration_allowed(M, S.ci)) newprobg = -kMyDblMax;
+      const double tpw = newprobg - probg, dpdg = S.dc[kAdNewPdg] - S.dc[kAdOldPdg], extra = S.dc[kAdExtra];
       double mh;                                        // update_gtree.cpp:917-927
-      if (M.thermo) mh = exp(beta * M.gbeta * (newpdg - oldpdg) + tpw + extra);
-      else mh = exp(beta * (tpw + M.gbeta * (newpdg - oldpdg)) + extra);
+      if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
+      else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
       Philox rng;
       rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngAccept);
       const double U = rng.uniform();
-      acc = (U < fmin(1.0, mh)) ? 1 : 0;
+      S.ic[kAcAccept] = (U < fmin(1.0, mh)) ? 1 : 0;
+      S.dc[kAdNewProbg] = newprobg;
     }
-    acc = Warp::bcast(acc, 0);
-    if (acc) {
-      for (int i = lane; i < NI; i += IMA_WARP) S.ai[i] = S.ci[i];
-      for (int i = lane; i < ND; i += IMA_WARP) S.ad[i] = S.cd[i];
-      for (int i = lane; i < M.nq; i += IMA_WARP) S.q[i] = S.cq[i];
-      for (int i = lane; i < M.nm; i += IMA_WARP) S.q[kMaxParams + i] = S.cq[kMaxParams + i];
-      probg = newprobg;
-      pdgsum -= oldpdg;
-      pdgsum += newpdg;
-      if (lane == 0) {
-        E.cur[p] = (unsigned char)nb;
+    block_sync();
+    if (S.ic[kAcAccept]) {
+      for (int i = tid; i < NI; i += nth) S.ai[i] = S.ci[i];
+      for (int i = tid; i < ND; i += nth) S.ad[i] = S.cd[i];
+      for (int i = tid; i < M.nq; i += nth) S.q[i] = S.cq[i];
+      for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = S.cq[kMaxParams + i];
+      probg = S.dc[kAdNewProbg];
+      pdgsum -= S.dc[kAdOldPdg];
+      pdgsum += S.dc[kAdNewPdg];
+      if (tid == 0) {
+        E.cur[p] = (unsigned char)(S.ic[kAcCb] ^ 1);
         E.acc[(size_t)p * 3 + 0]++;
         if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
         if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
       }
     }
-    Warp::sync();
+    block_sync();
   }
-  for (int i = lane; i < NI; i += IMA_WARP) E.all_i[(size_t)c * NI + i] = S.ai[i];
-  for (int i = lane; i < ND; i += IMA_WARP) E.all_d[(size_t)c * ND + i] = S.ad[i];
-  for (int i = lane; i < M.nq; i += IMA_WARP) E.qint[(size_t)c * kMaxParams + i] = S.q[i];
-  for (int i = lane; i < M.nm; i += IMA_WARP) E.mint[(size_t)c * kMaxParams + i] = S.q[kMaxParams + i];
+  for (int i = tid; i < NI; i += nth) E.all_i[(size_t)c * NI + i] = S.ai[i];
+  for (int i = tid; i < ND; i += nth) E.all_d[(size_t)c * ND + i] = S.ad[i];
+  for (int i = tid; i < M.nq; i += nth) E.qint[(size_t)c * kMaxParams + i] = S.q[i];
+  for (int i = tid; i < M.nm; i += nth) E.mint[(size_t)c * kMaxParams + i] = S.q[kMaxParams + i];
 #if IMA_CUDA
   __threadfence_block();
 #endif
-  Warp::sync();
-  const double ssum = (l1 == E.d.nloci) ? chain_swapsum(E, M, c, probg) : 0.0;
-  if (lane == 0) {
-    E.probg[c] = probg; E.pdgsum[c] = pdgsum;
-    if (l1 == E.d.nloci) E.swapsum[c] = ssum;
-    if (dropped) {
+  block_sync();
+  if (w == 0) {
+    const double ssum = (l1 == E.d.nloci) ? chain_swapsum(E, M, c, probg) : 0.0;
+    if (lane == 0) {
+      E.probg[c] = probg; E.pdgsum[c] = pdgsum;
+      if (l1 == E.d.nloci) E.swapsum[c] = ssum;
+      if (dropped) {
 #if IMA_CUDA
-      atomicAdd(E.overflow, dropped);
+        atomicAdd(E.overflow, dropped);
 #else
-      *E.overflow += dropped;
+        *E.overflow += dropped;
 #endif
+      }
     }
   }
 }

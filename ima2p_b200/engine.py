@@ -174,6 +174,10 @@ class Engine:
             swaptries = max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0    # ima_main_mpi.cpp:1378
         self._ck(self.lib.ima2p_engine_run(self._h, nsteps, swaptries, stream))
 
+    def set_pieces(self, pieces):
+        """Cut a step into `pieces` locus ranges (accept sweep of one range overlaps the proposals of the next)."""
+        self._ck(self.lib.ima2p_engine_set_pieces(self._h, pieces))
+
     def default_swaptries(self):
         return max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0             # ima_main_mpi.cpp:1378
 

@@ -106,6 +106,9 @@ int ima2p_engine_dims (ima2p_engine * e, int *out /* {NI, ND, NL, CAP, rowlen} *
  * update_gtree.cpp:723-966) followed by swaptries MC3 temperature swaps (swapchains.cpp:526-653;
  * temperature-rank form of swapchains_bwprocesses :192-523).  Single-GPU form: */
 int ima2p_engine_run (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream);
+/* number of locus ranges a step is cut into so that the accept sweep of one range overlaps the proposals of the
+ * next (default 4; 1 = propose everything, then sweep) */
+int ima2p_engine_set_pieces (ima2p_engine * e, int pieces);
 /* same steps, launched kernel by kernel with CUDA events on the launching stream around each kernel;
  * kernel_ms[3] = summed device time of {propose, accept, swap} (used for roofline accounting) */
 int ima2p_engine_run_timed (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms);

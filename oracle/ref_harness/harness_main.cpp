@@ -741,12 +741,18 @@ mode_lmode (long burn, long rows, long every)
 /* `chunks` timed chunks of `iters` sweeps each; a sweep = updategenealogy() for every chain x locus
  * (full=0, the loop of qupdate ima_main_mpi.cpp:1821-1841) or one whole qupdate() step (full=1) */
 static void
-mode_bench (long burn, long iters, long full, long chunks)
+mode_bench (long burn, long iters, long full, long chunks, long gburn)
 {
   long it, ch, acc = 0, tries = 0;
   int ci, li, a, b;
   std::vector<double> secs;
   do_burn (burn);
+  /* gburn untimed sweeps of updategenealogy() only: the split times stay where start() put them
+   * ((i+1)/(nsplit+1) of the prior maximum, initialize.cpp:1959), which is what the GPU arm also uses */
+  for (it = 0; it < gburn; it++)
+    for (ci = 0; ci < numchains; ci++)
+      for (li = 0; li < nloci; li++)
+        updategenealogy (ci, li, &a, &b);
   double t00 = nowsec ();
   for (ch = 0; ch < chunks; ch++)
   {
@@ -881,7 +887,7 @@ main (int argc, char *argv[])
   else if (mode == "lmode")
     mode_lmode (burn, kvl ("rows", 500), kvl ("every", 5));
   else if (mode == "bench")
-    mode_bench (burn, kvl ("iters", 10), kvl ("full", 0), kvl ("chunks", 1));
+    mode_bench (burn, kvl ("iters", 10), kvl ("full", 0), kvl ("chunks", 1), kvl ("gburn", 0));
   else if (mode == "lbench")
     mode_lbench (burn, kvl ("rows", 100000), kvl ("evals", 50));
   else
