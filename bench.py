@@ -111,7 +111,7 @@ def algorithmic_bytes_per_update(n, mig_per_genealogy, p_acc, NI, ND):
     return 24.0 * (2 * n - 1) + 12.0 * M + W_g + 24.0 + p_acc * (72.0 + 12.0 * M_e + W_g + 16.0)
 
 
-def run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn, full, tmp, budget_s=20.0, gburn=30):
+def run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn, full, tmp, budget_s=20.0, gburn=1000):
     """The reference's own updategenealogy()/qupdate() loop (oracle/_ref/ref_harness `bench` mode) in nproc
     independent serial processes, each holding total_chains/nproc chains (no MPI in this image: no cross-process
     swaps, which makes this an upper bound on the reference's MPI build)."""
@@ -176,7 +176,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sim50x128", choices=sorted(WORKLOADS))
-    ap.add_argument("--burn", type=int, default=300, help="untimed burn-in steps before warm-up")
+    ap.add_argument("--burn", type=int, default=3000, help="untimed burn-in steps before warm-up (migration counts need ~3000 steps to settle)")
+    ap.add_argument("--pieces", type=int, default=0, help="locus ranges per step (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lmode", action="store_true")
     args = ap.parse_args()
@@ -210,6 +211,8 @@ def main():
         dist.init_process_group("nccl")
     dev = torch.device("cuda", torch.cuda.current_device())
     eng, loci, st = build_engine(wl, rank, world)
+    if args.pieces > 0:
+        eng.set_pieces(args.pieces)
     work_stream = torch.cuda.Stream()              # a real (non-default) stream: kernels, NCCL and the timing events all go here
     torch.cuda.set_stream(work_stream)
     stream = work_stream.cuda_stream
@@ -279,12 +282,17 @@ def main():
         g0.record(); eng.run(args.steps, swaptries, stream); g1.record()
         torch.cuda.synchronize()
         graph_ms = g0.elapsed_time(g1)
-        eng.set_pieces(4)
+        eng.set_pieces(args.pieces if args.pieces > 0 else 4)
 
     # ---- end to end through the C ABI with HOST buffers: every step uploads the genealogies from pinned host
     # memory (H2D), evaluates them, runs one M-mode step and reads the per-chain results back (D2H)
     ke = min(args.steps, 50)
     sb = eng.state_bytes()
+    # the burned-in genealogies come back to pinned host memory once (untimed); they are what every e2e step uploads
+    eng.fetch_state([pinned[k].data_ptr() for k in STATE_KEYS[:7]], stream)
+    torch.cuda.synchronize()
+    mig_mean = float(pinned["scal_i"].numpy()[:, 1].mean())
+    mig_max = int(pinned["scal_i"].numpy()[:, 1].max())
     h2d = int(sum(sb)) + st["tvals"].nbytes
     d2h = cpg * 4 * 8 + eng.rowlen * 4
     for _ in range(3):
@@ -308,10 +316,6 @@ def main():
     if rank != 0:
         return
     pk, pk_kind = peaks()
-    # migration events per genealogy (for the algorithmic-bytes formula): read the current state back
-    outb = {k: np.empty_like(st[k]) for k in STATE_KEYS[:7]}
-    eng.fetch_state([outb[k] for k in STATE_KEYS[:7]])
-    mig_mean = float(outb["scal_i"][:, 1].mean())
     roof = None
     if kernel_ms is not None:
         per = np.asarray(kernel_ms, dtype=np.float64) / args.steps                       # ms per launch: propose, accept, swap
@@ -347,7 +351,7 @@ def main():
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
            "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke},
            "gpu_launches": 3 * args.steps if world == 1 else 3 * args.steps,
-           "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean,
+           "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
            "unpipelined_ms_per_step": (graph_ms / args.steps) if graph_ms else None, "lmode": lmode,
            "dropped_for_capacity": c1["dropped"], "swap_rate": (c1["swaps"] - c0["swaps"]) / max(1, c1["swap_attempts"] - c0["swap_attempts"])}
     print(json.dumps(out, default=float))

@@ -24,7 +24,9 @@ inline int dev_check(cudaError_t e, const char *what, const char *file, int line
 inline void *dev_alloc(size_t bytes) {
   void *p = nullptr;
   if (!IMA_CUDA_OK(cudaMalloc(&p, bytes ? bytes : 1))) return nullptr;
-  cudaMemset(p, 0, bytes ? bytes : 1);
+  // cudaMemset runs on the legacy default stream, asynchronously to the host and NOT ordered with the engine's
+  // non-blocking streams: wait for it, or it could zero a buffer after a later upload/kernel has written it
+  if (!IMA_CUDA_OK(cudaMemset(p, 0, bytes ? bytes : 1)) || !IMA_CUDA_OK(cudaStreamSynchronize(cudaStreamLegacy))) { cudaFree(p); return nullptr; }
   return p;
 }
 inline void dev_free(void *p) { if (p) cudaFree(p); }
