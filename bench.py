@@ -272,7 +272,7 @@ def main():
     value = updates_all / (ms * 1e-3)
     p_acc = (c1["accepted"] - c0["accepted"]) / max(1, c1["updates"] - c0["updates"])
 
-    # the same K steps with the step NOT cut into overlapped pieces (propose everything, then sweep), for the record
+    # the same K steps through the default (un-pieced) graph again, for the record
     graph_ms = None
     if world == 1:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -282,7 +282,7 @@ def main():
         g0.record(); eng.run(args.steps, swaptries, stream); g1.record()
         torch.cuda.synchronize()
         graph_ms = g0.elapsed_time(g1)
-        eng.set_pieces(args.pieces if args.pieces > 0 else 4)
+        eng.set_pieces(args.pieces if args.pieces > 0 else 1)
 
     # ---- end to end through the C ABI with HOST buffers: every step uploads the genealogies from pinned host
     # memory (H2D), evaluates them, runs one M-mode step and reads the per-chain results back (D2H)

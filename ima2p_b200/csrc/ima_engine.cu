@@ -56,8 +56,8 @@ struct Engine {
   cudaStream_t own_stream = nullptr, aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_piece[16] = {};
 #endif
-  int pieces = 4;
-  size_t pair_smem = 0, chain_smem = 0;
+  int pieces = 1;      // measured on B200: overlapping the sweep with proposals does not pay
+  size_t pair_smem = 0, chain_smem = 0, overlap_smem = 0;
 
   template <class T> T *alloc(size_t n) {
     T *p = (T *)dev_alloc(n * sizeof(T));
@@ -132,7 +132,9 @@ static void launch_update(Engine *e, stream_t s) {
     for (int q = 0; q < Q; q++) {
       const int l0 = (int)((long long)L * q / Q), l1 = (int)((long long)L * (q + 1) / Q);
       const int gp = (e->d.nchains * (l1 - l0) + kWarpsPerBlock - 1) / kWarpsPerBlock;
-      IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, e->aux_stream, e->v, l0, l1);
+      // padded dynamic shared memory caps the proposal kernel at 4 blocks per SM, which leaves registers for one
+      // accept block (256 threads) on every SM: the two kernels then really run side by side
+      IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e->overlap_smem, e->aux_stream, e->v, l0, l1);
       cudaEventRecord(e->ev_piece[q], e->aux_stream);
     }
     for (int q = 0; q < Q; q++) {
@@ -189,8 +191,12 @@ int ima2p_engine_create(ima2p_engine **out, int device, int nchains_local, int n
   e.loci.resize(nloci);
   if (!use_device(&e)) { delete h; return fail(IMA2P_E_CUDA, "cudaSetDevice failed"); }
 #if IMA_CUDA
-  if (!IMA_CUDA_OK(cudaStreamCreateWithFlags(&e.own_stream, cudaStreamNonBlocking)) ||
-      !IMA_CUDA_OK(cudaStreamCreateWithFlags(&e.aux_stream, cudaStreamNonBlocking)) ||
+  // the accept sweep is the latency-critical chain: its stream gets the highest priority so that its blocks are
+  // placed ahead of the (throughput-oriented) proposal blocks of the aux stream whenever an SM frees resources
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (!IMA_CUDA_OK(cudaStreamCreateWithPriority(&e.own_stream, cudaStreamNonBlocking, prio_hi)) ||
+      !IMA_CUDA_OK(cudaStreamCreateWithPriority(&e.aux_stream, cudaStreamNonBlocking, prio_lo)) ||
       !IMA_CUDA_OK(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming))) { delete h; return fail(IMA2P_E_CUDA, "stream create failed"); }
   for (auto &x : e.ev_piece) if (!IMA_CUDA_OK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming))) { delete h; return fail(IMA2P_E_CUDA, "event create failed"); }
 #endif
@@ -338,7 +344,8 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   e.chain_smem = chain_smem_bytes(d);
 #if IMA_CUDA
   if (e.pair_smem * kWarpsPerBlock > 227 * 1024) return fail(IMA2P_E_ARG, "finalize: pair does not fit in shared memory; lower mig_capacity");
-  if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
+  e.overlap_smem = e.pair_smem * kWarpsPerBlock;
+  if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
   if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");

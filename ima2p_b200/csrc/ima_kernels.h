@@ -254,9 +254,14 @@ constexpr int kAcceptWarps = 1;      // host emulation: one "warp" takes the ter
 IMA_DEV void block_sync() {}
 #endif
 enum { kAcFlags = 0, kAcCb, kAcAccept };
-enum { kAdOldPdg = 0, kAdNewPdg, kAdExtra, kAdNewProbg };
+enum { kAdOldPdg = 0, kAdNewPdg, kAdExtra, kAdNewProbg, kAdUniform };
 
-IMA_KERNEL void k_accept(EngineView E, int l0, int l1) {
+#if IMA_CUDA
+#define IMA_ACCEPT_BOUNDS __launch_bounds__(kAcceptWarps * 32, 2)
+#else
+#define IMA_ACCEPT_BOUNDS
+#endif
+IMA_KERNEL void IMA_ACCEPT_BOUNDS k_accept(EngineView E, int l0, int l1) {
   IMA_SMEM_DECL
   const int c = ima_block();
   if (c >= E.d.nchains) return;
@@ -316,6 +321,12 @@ IMA_KERNEL void k_accept(EngineView E, int l0, int l1) {
       block_sync();                                      // warp 0 may not overwrite the control words before all have read them
       continue;
     }
+    // the MH uniform of this locus is drawn by the last warp while the terms are being evaluated
+    if (w == kAcceptWarps - 1 && lane == 0) {
+      Philox rng;
+      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngAccept);
+      S.dc[kAdUniform] = rng.uniform();
+    }
     // integrate_tree_prob (update_gtree_common.cpp:1944-2053): term t on warp t
     for (int t = w; t < nterms; t += kAcceptWarps) {
       double v;
@@ -346,10 +357,7 @@ IMA_KERNEL void k_accept(EngineView E, int l0, int l1) {
       double mh;                                        // update_gtree.cpp:917-927
       if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
       else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
-      Philox rng;
-      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngAccept);
-      const double U = rng.uniform();
-      S.ic[kAcAccept] = (U < fmin(1.0, mh)) ? 1 : 0;
+      S.ic[kAcAccept] = (S.dc[kAdUniform] < fmin(1.0, mh)) ? 1 : 0;
       S.dc[kAdNewProbg] = newprobg;
     }
     block_sync();
