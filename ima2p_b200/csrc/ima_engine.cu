@@ -375,6 +375,13 @@ int ima2p_engine_finalize(ima2p_engine *h) {
     if (d.any_sw) { B.A = e.alloc<short>(P * kMaxLinked * NL); B.dlikeA = e.alloc<double>(P * kMaxLinked * NL); B.pdg_a = e.alloc<double>(P * kMaxLinked); }
     else { B.A = nullptr; B.dlikeA = nullptr; B.pdg_a = nullptr; }
   }
+  if (d.any_hky) {
+    int hs = 0, hg = 0;
+    for (int li = 0; li < d.nloci; li++) if (e.loci[li].d.model == kHKY) { if (e.loci[li].d.nsites > hs) hs = e.loci[li].d.nsites; if (e.loci[li].d.ng > hg) hg = e.loci[li].d.ng; }
+    v.d.hky_stride = d.hky_stride = (long long)(hg - 1) * hs * 5;
+    v.hky_scratch = e.alloc<double>((size_t)P * d.hky_stride);
+    if (!v.hky_scratch) return fail(IMA2P_E_CUDA, "device allocation failed (HKY scratch)");
+  }
   v.cur = e.alloc<unsigned char>(P);
   v.uvals = e.alloc<double>(P * kMaxLinked); v.kappa = e.alloc<double>(P); v.pi = e.alloc<double>(P * 4);
   v.tvals = e.alloc<double>(C * kMaxPeriods); v.beta = e.alloc<double>(C);
@@ -515,7 +522,6 @@ int ima2p_engine_upload(ima2p_engine *h) {
 int ima2p_engine_eval(ima2p_engine *h) {
   if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "eval: not finalized");
   Engine &e = h->eng;
-  if (e.d.any_hky) return fail(IMA2P_E_UNSUPPORTED, "eval: HKY loci are not on the device path yet");
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, nullptr);
   int rc = launch_eval(&e, s);
@@ -608,7 +614,7 @@ int ima2p_engine_get_genealogy(ima2p_engine *h, int ci, int li, int which, int *
 
 static int ensure_steppable(Engine &e) {
   if (!e.finalized) return fail(IMA2P_E_ARG, "engine not finalized");
-  if (e.d.any_hky || e.d.any_sw) return fail(IMA2P_E_UNSUPPORTED, "M-mode stepping: only infinite-sites loci are on the device path in this build");
+  if (e.d.any_sw) return fail(IMA2P_E_UNSUPPORTED, "M-mode stepping: the stepwise allele update (finishSWupdateA) is not on the device path in this build");
   if (e.model.nomigration) return fail(IMA2P_E_UNSUPPORTED, "M-mode stepping: the no-migration slider is not on the device path in this build");
   return IMA2P_OK;
 }

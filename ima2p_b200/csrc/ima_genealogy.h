@@ -909,6 +909,73 @@ IMA_DEV double likelihood_is(const EngineView &E, const DevLocus &L, PairSm &S, 
   return -S.ctl_d[kCdLength] * mutrate + acc - L.sumlogk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// HKY: calc_prob_data.cpp:26-41 (pijt), 118-471 (makefrac), 473-493 (getstandfactor), 583-607.
+// The reference keeps frac/newfrac per internal node and recomputes only the nodes above the touched
+// edges (a CPU economy).  Here every call prunes the whole genealogy: nodes are visited in coalescence
+// order (children first -- the order eval_weights' sorted event list already gives), the 32 lanes first
+// compute the 2 x 16 transition probabilities of the node's two child branches (one entry each), then take
+// one compressed site pattern each.  Partial likelihoods of a pair live in an L2-resident scratch slab;
+// nothing HKY-specific has to be kept between calls, so accept/reject stays a buffer flip.
+// ------------------------------------------------------------------------------------------------
+IMA_DEV double hky_pijt(const double *pi, double mutrate, double t, double kappa, int from, int to) {
+  const double PIj = (to == 0 || to == 2) ? pi[0] + pi[2] : pi[1] + pi[3];
+  const double A = 1.0 + PIj * (kappa - 1.0);
+  if (from == to) return pi[to] + pi[to] * exp(-mutrate * t) * (1.0 / PIj - 1.0) + exp(-mutrate * t * A) * ((PIj - pi[to]) / PIj);
+  if (from + to == 2 || from + to == 4) return pi[to] + pi[to] * (1.0 / PIj - 1.0) * exp(-mutrate * t) - (pi[to] / PIj) * exp(-mutrate * t * A);
+  return pi[to] * (1.0 - exp(-mutrate * t));
+}
+
+IMA_DEV double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S, int p, double u, double kappa, const double *pi) {
+  const int lane = Warp::lane();
+  const int ng = L.ng, ns = L.nsites, nev = S.ctl_i[kCiNev], root = S.ctl_i[kCiRoot];
+  double *slab = E.hky_scratch + (size_t)p * E.d.hky_stride;      // [internal node][pattern][4 partials + scale]
+  const unsigned char *seq = E.seq + L.seq_off;
+  const int *mult = E.mult + L.mult_off;
+  double sf = 0.0;                                                 // getstandfactor :473-493
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      if (i != j) sf += (i + j == 2 || i + j == 4) ? pi[i] * pi[j] * kappa : pi[i] * pi[j];
+  const double mu = u / (L.totsites * sf);                         // :593
+  double *P = (double *)S.pre;                                     // 32 doubles; the prefix table is free after the sweep
+  for (int j = 0; j < nev; j++) {
+    const int info = S.evi[j];
+    if ((info & 3) != 0) continue;
+    const int node = info >> 12, a = S.up0[node], b = S.up1[node];
+    const double ta = S.time[a] - edge_top_time(S, ng, a), tb = S.time[b] - edge_top_time(S, ng, b);
+    for (int e = lane; e < 32; e += IMA_WARP) P[e] = hky_pijt(pi, mu, (e >> 4) ? tb : ta, kappa, (e >> 2) & 3, e & 3);
+    Warp::sync();
+    double *out = slab + (size_t)(node - ng) * ns * 5;
+    const double *fa = slab + (size_t)(a - ng) * ns * 5, *fb = slab + (size_t)(b - ng) * ns * 5;
+    for (int s = lane; s < ns; s += IMA_WARP) {
+      double v[4], mx = 0.0;
+      for (int from = 0; from < 4; from++) {
+        double sa, sb;
+        if (a < ng) sa = P[from * 4 + seq[(size_t)a * ns + s]];
+        else { sa = 0.0; for (int k = 0; k < 4; k++) sa += P[from * 4 + k] * fa[s * 5 + k]; }
+        if (b < ng) sb = P[16 + from * 4 + seq[(size_t)b * ns + s]];
+        else { sb = 0.0; for (int k = 0; k < 4; k++) sb += P[16 + from * 4 + k] * fb[s * 5 + k]; }
+        v[from] = sa * sb;
+        if (v[from] > mx) mx = v[from];
+      }
+      for (int k = 0; k < 4; k++) out[s * 5 + k] = v[k] / mx;
+      out[s * 5 + 4] = (a < ng ? 0.0 : fa[s * 5 + 4]) + (b < ng ? 0.0 : fb[s * 5 + 4]) + log(mx);
+    }
+#if IMA_CUDA
+    __threadfence_block();
+#endif
+    Warp::sync();
+  }
+  const double *fr = slab + (size_t)(root - ng) * ns * 5;
+  double acc = 0.0;
+  for (int s = lane; s < ns; s += IMA_WARP) {
+    double fracp = 0.0;
+    for (int k = 0; k < 4; k++) fracp += pi[k] * fr[s * 5 + k];
+    acc += mult[s] * (log(fracp) + fr[s * 5 + 4]);
+  }
+  return Warp::sum(acc);
+}
+
 // stepwise: calc_prob_data.cpp:841-909 (full evaluation of one linked portion); A/dlikeA in global memory
 IMA_DEV double likelihood_sw(const DevLocus &L, const PairSm &S, const short *A, double *dlikeA, double u) {
   const int lane = Warp::lane();

@@ -45,6 +45,11 @@ IMA_DEV double pair_likelihood(const EngineView &E, const DevLocus &L, const Pai
     }
     return tot;
   }
+  if (L.model == kHKY) {
+    const double v = likelihood_hky(E, L, S, p, u[0], E.kappa[p], E.pi + (size_t)p * 4);
+    pdg_a_out[0] = v;
+    return v;
+  }
   pdg_a_out[0] = 0.0;
   return 0.0;
 }

@@ -70,6 +70,7 @@ struct EngineDims {
   int nloci, P;
   int NL, CAP, NI, ND, EVP, W, S, W64;     // maxima over loci: numlines, pool capacity, record sizes, event slots, mask words, sites
   int any_sw, any_hky;
+  long long hky_stride; // doubles of HKY scratch per pair: (max genes - 1) * (max patterns) * 5
 };
 
 // Everything a kernel needs, passed by value.
@@ -85,6 +86,7 @@ struct EngineView {
   double *uvals;            // [P][kMaxLinked] mutation-rate scalars
   double *kappa;            // [P]
   double *pi;               // [P][4]
+  double *hky_scratch;      // [P][hky_stride] partial likelihoods (scratch, recomputed by every call)
   // per chain
   double *tvals;            // [nchains][kMaxPeriods] split times, TIMEMAX sentinel at [nsplit]
   double *beta;             // [nchains]

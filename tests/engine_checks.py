@@ -7,7 +7,7 @@ from support import (FlatModel, OracleModel, check_static_eval, engine_from_fixt
                      rel_close, split_weights, tree_from_engine, _num)
 
 STATIC_FIXTURES = ["state_sim5_hn4", "state_sim50_hn3", "state_sim300_hn1", "state_sim2_hn2", "state_sim3_hn3",
-                   "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim3_sw_hn2"]
+                   "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim3_sw_hn2", "state_sim5_hky_hn2"]
 STEP_FIXTURES = ["state_sim5_hn4", "state_sim3_hn3", "state_sim5_3pop_hn2", "state_sim2_hn2"]
 
 
@@ -66,9 +66,11 @@ def proposals_match_oracle(lib, name, nsteps, rtol=1e-9, need_root_moves=True):
                     assert np.array_equal(ew["cc"], w["cc"]) and np.array_equal(ew["mc"], w["mc"])
                     assert rel_close(ew["fc"], w["fc"], rtol) and rel_close(ew["fm"], w["fm"], rtol)
                     assert new["mignum"] == w["mignum"]
+                    gj = d["chains"][c]["G"][l]
                     if loc["model"] == 0:
-                        u = d["chains"][c]["G"][l]["uvals"][0]
-                        assert rel_close(new["pdg"], om.likelihood_is(loc, after, w["length"], u), rtol)
+                        assert rel_close(new["pdg"], om.likelihood_is(loc, after, w["length"], gj["uvals"][0]), rtol)
+                    elif loc["model"] == 1:
+                        assert rel_close(new["pdg"], om.likelihood_hky(loc, after, gj["pi"], gj["uvals"][0], gj["kappa"]), rtol)
                 else:
                     assert eng.pair(c, l)["pdg"] == old[(c, l)]["pdg"]
                 nchecked += 1

@@ -26,14 +26,14 @@ def test_static_eval_matches_reference(lib, name):
 
 
 @pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 10), ("state_sim3_hn3", 20), ("state_sim5_3pop_hn2", 12),
-                                         ("state_sim2_hn2", 20)])
+                                         ("state_sim2_hn2", 20), ("state_sim5_hky_hn2", 12)])
 def test_device_proposals_match_oracle(lib, name, nsteps):
     # Sim2 is one locus of 100 genes: root moves are rare in 40 proposals, so they are not demanded there
     ec.proposals_match_oracle(lib, name, nsteps, rtol=RTOL, need_root_moves=(name != "state_sim2_hn2"))
 
 
 @pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 2000), ("state_sim5_3pop_hn2", 500), ("state_sim50_hn3", 300),
-                                         ("state_sim300_hn1", 100)])
+                                         ("state_sim300_hn1", 100), ("state_sim5_hky_hn2", 300)])
 def test_incremental_sums_match_fresh_evaluation(lib, name, nsteps):
     cnt = ec.incremental_sums_match_fresh_evaluation(lib, name, nsteps, rtol=RTOL)
     assert cnt["steps"] == nsteps and cnt["dropped"] == 0

@@ -25,7 +25,7 @@ def test_static_eval(emu, name):
     ec.static_eval_matches_reference(emu, name, rtol=1e-12)
 
 
-@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 12), ("state_sim3_hn3", 25), ("state_sim5_3pop_hn2", 15)])
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 12), ("state_sim3_hn3", 25), ("state_sim5_3pop_hn2", 15), ("state_sim5_hky_hn2", 10)])
 def test_proposals(emu, name, nsteps):
     ec.proposals_match_oracle(emu, name, nsteps)
 
