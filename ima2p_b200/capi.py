@@ -35,6 +35,7 @@ SIGNATURES = {
                                         _i, _d, c_dbl_p, _d, c_dbl_p, c_int_p]),
     "ima2p_engine_get_genealogy": (_i, [_v, _i, _i, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p, c_dbl_p,
                                         c_int_p, _i, c_int_p, c_dbl_p]),
+    "ima2p_engine_get_alleles": (_i, [_v, _i, _i, _i, c_int_p, c_dbl_p, c_dbl_p]),
     "ima2p_engine_upload": (_i, [_v]),
     "ima2p_engine_eval": (_i, [_v]),
     "ima2p_engine_get_pair": (_i, [_v, _i, _i, c_int_p, c_dbl_p, c_dbl_p, c_int_p]),

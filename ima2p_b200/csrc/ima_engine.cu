@@ -612,9 +612,31 @@ int ima2p_engine_get_genealogy(ima2p_engine *h, int ci, int li, int which, int *
   return IMA2P_OK;
 }
 
+int ima2p_engine_get_alleles(ima2p_engine *h, int ci, int li, int which, int *A, double *dlikeA, double *pdg_a) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "get_alleles: not finalized");
+  Engine &e = h->eng;
+  if (ci < 0 || ci >= e.d.nchains || li < 0 || li >= e.d.nloci || !e.d.any_sw) return fail(IMA2P_E_ARG, "get_alleles: bad index or no stepwise locus");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const DevLocus &L = e.loci[li].d;
+  const size_t p = (size_t)ci * e.d.nloci + li, NL = e.d.NL;
+  unsigned char cur = 0;
+  if (!d2h(&cur, e.v.cur + p, 1, s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  const PairBuf &B = e.v.buf[which ? (cur ^ 1) : cur];
+  std::vector<short> a((size_t)kMaxLinked * NL);
+  std::vector<double> dl((size_t)kMaxLinked * NL), pa(kMaxLinked);
+  bool ok = d2h(a.data(), B.A + p * kMaxLinked * NL, a.size() * sizeof(short), s) && d2h(dl.data(), B.dlikeA + p * kMaxLinked * NL, dl.size() * sizeof(double), s) &&
+            d2h(pa.data(), B.pdg_a + p * kMaxLinked, kMaxLinked * sizeof(double), s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  for (int ai = 0; ai < L.nlinked; ai++) {
+    for (int i = 0; i < L.nl; i++) { if (A) A[(size_t)ai * L.nl + i] = a[(size_t)ai * NL + i]; if (dlikeA) dlikeA[(size_t)ai * L.nl + i] = dl[(size_t)ai * NL + i]; }
+    if (pdg_a) pdg_a[ai] = pa[ai];
+  }
+  return IMA2P_OK;
+}
+
 static int ensure_steppable(Engine &e) {
   if (!e.finalized) return fail(IMA2P_E_ARG, "engine not finalized");
-  if (e.d.any_sw) return fail(IMA2P_E_UNSUPPORTED, "M-mode stepping: the stepwise allele update (finishSWupdateA) is not on the device path in this build");
   if (e.model.nomigration) return fail(IMA2P_E_UNSUPPORTED, "M-mode stepping: the no-migration slider is not on the device path in this build");
   return IMA2P_OK;
 }
@@ -721,7 +743,8 @@ int ima2p_engine_get_proposal(ima2p_engine *h, int ci, int li, double *out4, uns
   const size_t p = (size_t)ci * e.d.nloci + li;
   unsigned char cur = 0;
   uint32_t fl = 0;
-  bool ok = d2h(out4, e.v.prop_dbg + p * 4, 4 * sizeof(double), s) && d2h(&fl, e.v.prop_flags + p, sizeof fl, s) && d2h(&cur, e.v.cur + p, 1, s);
+  bool ok = d2h(out4, e.v.prop_dbg + p * 4, 4 * sizeof(double), s) && d2h(out4 + 4, e.v.prop_extra + p, sizeof(double), s) &&
+            d2h(&fl, e.v.prop_flags + p, sizeof fl, s) && d2h(&cur, e.v.cur + p, 1, s);
   if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   if (flags) *flags = fl;
   if (is_current) *is_current = cur;

@@ -31,11 +31,11 @@ struct PairSm {
   int *gwi;                // [NI]
   double *gwd;             // [ND]
   double *ctl_d;           // [8]  roottime, length, tlength, migweight, slideweight, pdg, Aterm, slide distance
-  int *ctl_i;              // [8]  root, mignum, flags, nev, edge, freed, oldsis, newsis
+  int *ctl_i;              // [12] root, mignum, flags, nev, edge, freed, oldsis, newsis, parent of freed before the move
 };
 
 enum { kCdRoottime = 0, kCdLength, kCdTlength, kCdMigw, kCdSlidew, kCdPdg, kCdAterm, kCdSlideDist };
-enum { kCiRoot = 0, kCiMignum, kCiFlags, kCiNev, kCiEdge, kCiFreed, kCiOldsis, kCiNewsis };
+enum { kCiRoot = 0, kCiMignum, kCiFlags, kCiNev, kCiEdge, kCiFreed, kCiOldsis, kCiNewsis, kCiOldDownDown };
 
 IMA_HD size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
 
@@ -55,7 +55,7 @@ IMA_HD size_t pair_smem_bytes(const EngineDims &d) {
   b += align8(sizeof(int) * d.NI);
   b += align8(sizeof(double) * d.ND);
   b += align8(sizeof(double) * 8);
-  b += align8(sizeof(int) * 8);
+  b += align8(sizeof(int) * 12);
   return b;
 }
 
@@ -81,7 +81,7 @@ IMA_DEV PairSm carve_pair_smem(unsigned char *base, const EngineDims &d) {
   s.mask = (uint32_t *)take(sizeof(uint32_t) * d.NL * d.W);
   s.moff = (int *)take(sizeof(int) * (d.NL + 1));
   s.gwi = (int *)take(sizeof(int) * d.NI);
-  s.ctl_i = (int *)take(sizeof(int) * 8);
+  s.ctl_i = (int *)take(sizeof(int) * 12);
   return s;
 }
 
@@ -511,6 +511,7 @@ IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *
     } else if (n2 > 0) { S.ms[oldsis] = S.ms[freed]; S.mcn[oldsis] = (unsigned short)n2; }
     S.time[oldsis] = S.time[freed];
     const int dd = S.down[freed];
+    S.ctl_i[kCiOldDownDown] = dd;
     S.down[oldsis] = (short)dd;
     if (dd != -1) {
       rootmove = 0;
@@ -974,6 +975,63 @@ IMA_DEV double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S,
     acc += mult[s] * (log(fracp) + fr[s * 5 + 4]);
   }
   return Warp::sum(acc);
+}
+
+// finishSWupdateA update_gtree_common.cpp:2218-2362 (lane 0): after the edge has been re-attached, draw the
+// allele state of the new junction node around its neighbours (geometric step), refresh the branch terms of the
+// (at most four) branches whose ends changed, and return the change of log-likelihood; *aterm is the Hastings
+// term of the allele draw.  Aold/dlold: the pair's current arrays; Anew/dlnew: the proposal buffer (already a copy).
+IMA_DEV double sw_update_alleles(const DevLocus &L, const PairSm &S, int ai, Philox &rng, const short *Aold, const double *dlold,
+                                 short *Anew, double *dlnew, int edge, int downedge, int sisedge, int newsisedge,
+                                 int old_downdown, double u, double *aterm) {
+  const int ng = L.ng;
+  const int oldA = Anew[downedge];                     // the junction keeps its number; its old state is the starting point
+  const double holdsis = (newsisedge != sisedge) ? dlold[newsisedge] : 0.0;
+  // old terms of edge, sister and (when it was not the root) the freed edge: copyedge[0..2].dlikeA (storeAinfo :822-847)
+  const double oldlikeadj = dlold[edge] + dlold[sisedge] + (old_downdown != -1 ? dlold[downedge] : 0.0) + holdsis;
+  const int e[3] = { edge, newsisedge, downedge };
+  double t[3];
+  int wsumdiff = 0, j = 0;
+  for (int i = 0; i < 3; i++)
+    if (S.down[e[i]] != -1) {
+      t[i] = S.time[e[i]] - edge_top_time(S, ng, e[i]);
+      const int d = (i < 2 ? Anew[e[i]] : Anew[S.down[e[i]]]) - oldA;
+      wsumdiff += d < 0 ? -d : d;
+      j++;
+    }
+  double geonew = j / ((double)(wsumdiff + j));
+  if (geonew > 0.95) geonew = 0.95;
+  int dA = (int)ceil(log(rng.uniform()) / log(1.0 - geonew)) - 1;           // geometric(p) - 1, utilities.cpp:608-617
+  if (rng.bit()) dA = -dA;
+  int newA;
+  if (dA >= 0) newA = (oldA + dA < L.maxA[ai]) ? oldA + dA : L.maxA[ai];
+  else newA = (oldA + dA > L.minA[ai]) ? oldA + dA : L.minA[ai];
+  Anew[downedge] = (short)newA;
+  dA = newA - oldA;
+  if (S.down[sisedge] != -1 && sisedge != newsisedge) {                      // old sister now runs on through the old junction
+    const double ts = S.time[sisedge] - edge_top_time(S, ng, sisedge);
+    dlnew[sisedge] = -(ts * u) + log(bessi(Anew[sisedge] - Anew[S.down[sisedge]], ts * u));
+  } else {
+    dlnew[sisedge] = 0.0;
+  }
+  double likeadj = dlnew[sisedge];
+  for (int i = 0; i < 3; i++)
+    if (S.down[e[i]] != -1) {
+      const int d = (i < 2 ? Anew[e[i]] : Anew[S.down[e[i]]]) - newA;
+      dlnew[e[i]] = -(t[i] * u) + log(bessi(d, t[i] * u));
+      likeadj += dlnew[e[i]];
+    } else {
+      dlnew[e[i]] = 0.0;                               // the root edge carries no term (update_gtree.cpp:448-450, 486-488)
+    }
+  // reverse move: the old junction (children edge and old sister, parent old_downdown) seen from newA
+  wsumdiff = 0; j = 0;
+  { int d = Aold[edge] - newA; wsumdiff += d < 0 ? -d : d; j++; d = Aold[sisedge] - newA; wsumdiff += d < 0 ? -d : d; j++; }
+  if (old_downdown != -1) { const int d = Aold[old_downdown] - newA; wsumdiff += d < 0 ? -d : d; j++; }
+  double geoold = j / ((double)(wsumdiff + j));
+  if (geoold > 0.95) geoold = 0.95;
+  const int adA = dA < 0 ? -dA : dA;
+  *aterm = (adA * log(1 - geoold) + log(geoold)) - (adA * log(1 - geonew) + log(geonew));
+  return likeadj - oldlikeadj;
 }
 
 // stepwise: calc_prob_data.cpp:841-909 (full evaluation of one linked portion); A/dlikeA in global memory

@@ -211,7 +211,38 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E, int l0, int l1) {
   if (ok && total_mig > E.d.CAP) ok = false;
   double pdga[kMaxLinked];
   double pdg = 0.0;
-  if (ok) {
+  if (ok && L.model == kStepwise) {
+    // stepwise loci: incremental update of the allele states and branch terms (update_gtree.cpp:857-868)
+    const size_t ao = (size_t)p * kMaxLinked * E.d.NL;
+    for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) { Bn.A[ao + i] = B.A[ao + i]; Bn.dlikeA[ao + i] = B.dlikeA[ao + i]; }
+#if IMA_CUDA
+    __threadfence_block();
+#endif
+    Warp::sync();
+    if (lane == 0) {
+      Philox rng;
+      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngAlleles);
+      double atermsum = 0.0, tot = 0.0;
+      for (int ai = 0; ai < L.nlinked; ai++) {
+        double aterm = 0.0;
+        const double dl = sw_update_alleles(L, S, ai, rng, B.A + ao + (size_t)ai * E.d.NL, B.dlikeA + ao + (size_t)ai * E.d.NL,
+                                            Bn.A + ao + (size_t)ai * E.d.NL, Bn.dlikeA + ao + (size_t)ai * E.d.NL, S.ctl_i[kCiEdge],
+                                            S.ctl_i[kCiFreed], S.ctl_i[kCiOldsis], S.ctl_i[kCiNewsis], S.ctl_i[kCiOldDownDown],
+                                            E.uvals[(size_t)p * kMaxLinked + ai], &aterm);
+        const double v = B.pdg_a[(size_t)p * kMaxLinked + ai] + dl;
+        Bn.pdg_a[(size_t)p * kMaxLinked + ai] = v;
+        tot += v;
+        atermsum += aterm;
+      }
+      S.ctl_d[kCdAterm] = atermsum;
+      S.ctl_d[kCdPdg] = tot;
+    }
+    Warp::sync();
+    pdg = S.ctl_d[kCdPdg];
+    flags = (uint32_t)S.ctl_i[kCiFlags];
+    if (!(pdg > -DBL_MAX)) flags |= kFlagRejectIS;       // a branch term of -inf (bessi == 0): the move cannot be accepted
+    if (!(flags & (kFlagRejectIS | kFlagBadTree))) store_pair(E, Bn, p, L.nl, S, total_mig);
+  } else if (ok) {
     pdg = pair_likelihood(E, L, Bn, p, S, pdga);
     flags = (uint32_t)S.ctl_i[kCiFlags];
     if (pdg == kRejectIS) flags |= kFlagRejectIS;

@@ -168,6 +168,6 @@ struct Philox {
   }
 };
 
-enum RngPurpose : uint32_t { kRngPropose = 1, kRngAccept = 2, kRngSwap = 3 };
+enum RngPurpose : uint32_t { kRngPropose = 1, kRngAccept = 2, kRngSwap = 3, kRngAlleles = 4 };
 
 }  // namespace ima

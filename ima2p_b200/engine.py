@@ -148,6 +148,12 @@ class Engine:
         return dict(up0=up0, up1=up1, down=down, pop=pop, time=time, mig_off=off, mig_t=mt[:n], mig_p=mp[:n],
                     root=root.value, roottime=rt.value)
 
+    def get_alleles(self, ci, li, which=0):
+        nl, k = self._loci[li]["numlines"], self._loci[li]["nlinked"]
+        A, dl, pa = np.zeros((k, nl), np.int32), np.zeros((k, nl)), np.zeros(k)
+        self._ck(self.lib.ima2p_engine_get_alleles(self._h, ci, li, which, _ip(A), _dp(dl), _dp(pa)))
+        return dict(A=A, dlikeA=dl, pdg_a=pa)
+
     # ---- evaluation of the loaded state: init_p (mcmcfile.cpp:130-193) ---------------------------------------
     def eval(self):
         self._ck(self.lib.ima2p_engine_eval(self._h))
@@ -198,10 +204,10 @@ class Engine:
         self._ck(self.lib.ima2p_engine_sync(self._h))
 
     def proposal(self, ci, li):
-        out, fl, buf = np.zeros(4), C.c_uint(), C.c_int()
+        out, fl, buf = np.zeros(5), C.c_uint(), C.c_int()
         self._ck(self.lib.ima2p_engine_get_proposal(self._h, ci, li, _dp(out), C.byref(fl), C.byref(buf)))
-        return dict(migweight=out[0], slideweight=out[1], slidedist=out[2], edge=int(out[3]), flags=fl.value,
-                    buffer=buf.value)
+        return dict(migweight=out[0], slideweight=out[1], slidedist=out[2], edge=int(out[3]), extra=out[4],
+                    aterm=out[4] - out[0] - out[1], flags=fl.value, buffer=buf.value)
 
     def counters(self):
         out = np.zeros(8, np.uint64)

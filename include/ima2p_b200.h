@@ -86,6 +86,9 @@ int ima2p_engine_set_genealogy (ima2p_engine * e, int ci, int li, const int *up0
 int ima2p_engine_get_genealogy (ima2p_engine * e, int ci, int li, int which, int *up0, int *up1, int *down, int *pop,
                                 double *time, int *mig_off, double *mig_t, int *mig_p, int mig_room, int *root,
                                 double *roottime);
+/* stepwise loci: allele states A[nlinked][numlines] at the top of every edge, the per-branch terms dlikeA and the
+ * per-portion likelihoods pdg_a (struct edge A/dlikeA imamp.hpp:651-679, genealogy.pdg_a :956-987) */
+int ima2p_engine_get_alleles (ima2p_engine * e, int ci, int li, int which, int *A, double *dlikeA, double *pdg_a);
 /* push everything staged by set_chain / set_genealogy to the device (one H2D per array) */
 int ima2p_engine_upload (ima2p_engine * e);
 
@@ -119,8 +122,8 @@ int ima2p_engine_run_timed (ima2p_engine * e, int nsteps, int swaptries, void *c
 int ima2p_engine_update_genealogies (ima2p_engine * e, double *dev_S_local, void *cuda_stream);
 int ima2p_engine_swap_replay (ima2p_engine * e, const double *dev_S_global, int swaptries, void *cuda_stream);
 
-/* last proposal of a pair: out4 = {migweight (update_gtree.cpp:663), slideweight (:803-812), slide distance
- * drawn (:783), edge moved}; flags bit0 infinite-sites reject, bit1 dropped for capacity, bit2 topology changed,
+/* last proposal of a pair: out4[5] = {migweight (update_gtree.cpp:663), slideweight (:803-812), slide distance
+ * drawn (:783), edge moved, migweight + slideweight + Atermsum (the non-likelihood part of the MH exponent, :919-924)}; flags bit0 infinite-sites reject, bit1 dropped for capacity, bit2 topology changed,
  * bit3 root moved; buffer = index of the buffer that is current (flips on accept) */
 int ima2p_engine_get_proposal (ima2p_engine * e, int ci, int li, double *out4, unsigned int *flags, int *buffer);
 

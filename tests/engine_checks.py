@@ -3,7 +3,7 @@ kernel sources through the tests-only host-emulation build (tests/hostemu).  The
 CPU oracle (pinned against the reference's own values) or the golden fixtures themselves."""
 import numpy as np
 
-from support import (FlatModel, OracleModel, check_static_eval, engine_from_fixture, f64, fp, dp, load_golden, oracle,
+from support import (FlatModel, OracleModel, check_static_eval, engine_from_fixture, f64, fp, dp, i32, load_golden, oracle,
                      rel_close, split_weights, tree_from_engine, _num)
 
 STATIC_FIXTURES = ["state_sim5_hn4", "state_sim50_hn3", "state_sim300_hn1", "state_sim2_hn2", "state_sim3_hn3",
@@ -174,3 +174,61 @@ def gamma_tables_match_reference(lib, rtol=1e-10):
             for col in (1, 3):
                 assert rel_close(out[i, col], lo[key], rtol, 1e-12), ("lowergamma", key, col, out[i, col], lo[key])
     return len(keys)
+
+
+def stepwise_updates_match_oracle(lib, name, nsteps, rtol=1e-9):
+    """a9: for every stepwise proposal the device makes, (i) the incrementally updated branch terms and locus
+    likelihood equal the oracle's full likelihoodSW of the proposed genealogy and allele states, (ii) the Hastings
+    term of the junction-allele draw equals the ratio of the two geometric probabilities of finishSWupdateA
+    (update_gtree_common.cpp:2264-2359), recomputed here from the before/after states."""
+    import math
+    d = load_golden(name)
+    eng, fm = engine_from_fixture(d, lib=lib)
+    om = OracleModel(fm)
+    eng.eval()
+    nch, nl = eng.nchains, eng.nloci
+    geo = lambda j, w: min(j / (w + j), 0.95)
+    nchk = nmoved = 0
+    for _ in range(nsteps):
+        before = {(c, l): (tree_from_engine(eng.get_genealogy(c, l, 0)), eng.get_alleles(c, l, 0)) for c in range(nch) for l in range(nl)}
+        buf0 = {(c, l): eng.proposal(c, l)["buffer"] for c in range(nch) for l in range(nl)}
+        eng.run(1, swaptries=0)
+        eng.sync()
+        for c in range(nch):
+            for l in range(nl):
+                pr = eng.proposal(c, l)
+                if pr["flags"] & 3:
+                    continue
+                acc = pr["buffer"] != buf0[(c, l)]
+                after = tree_from_engine(eng.get_genealogy(c, l, 0 if acc else 1))
+                al = eng.get_alleles(c, l, 0 if acc else 1)
+                bt, bal = before[(c, l)]
+                g = d["chains"][c]["G"][l]
+                aterm = 0.0
+                for ai in range(d["loci"][l]["nlinked"]):
+                    after.A = [i32(a) for a in al["A"]]
+                    like, dl = om.likelihood_sw(after, ai, g["uvals"][ai])
+                    assert rel_close(al["pdg_a"][ai], like, rtol), (c, l, al["pdg_a"], like)
+                    nz = after.down != -1
+                    assert rel_close(al["dlikeA"][ai][nz], dl[nz], rtol, 1e-12) and np.all(al["dlikeA"][ai][~nz] == 0)
+                    # Hastings term of the allele draw
+                    edge = pr["edge"]
+                    junction = int(bt.down[edge])                 # the freed edge keeps its number
+                    A0, A1 = bal["A"][ai], al["A"][ai]
+                    oldA, newA = int(A0[junction]), int(A1[junction])
+                    nb_new = [A1[edge], A1[after.up0[junction] if after.up0[junction] != edge else after.up1[junction]]]
+                    if after.down[junction] != -1:
+                        nb_new.append(A1[after.down[junction]])
+                    oldsis = bt.up0[junction] if bt.up0[junction] != edge else bt.up1[junction]
+                    nb_old = [A0[edge], A0[oldsis]] + ([A0[bt.down[junction]]] if bt.down[junction] != -1 else [])
+                    gn = geo(len(nb_new), sum(abs(int(a) - oldA) for a in nb_new))
+                    go = geo(len(nb_old), sum(abs(int(a) - newA) for a in nb_old))
+                    dA = abs(newA - oldA)
+                    aterm += (dA * math.log(1 - go) + math.log(go)) - (dA * math.log(1 - gn) + math.log(gn))
+                    nmoved += dA > 0
+                assert abs(aterm - pr["aterm"]) < 1e-9 * max(1.0, abs(aterm)), (aterm, pr)
+                nchk += 1
+    assert nchk > 0 and nmoved > 0
+    cnt = eng.counters()
+    eng.close()
+    return cnt

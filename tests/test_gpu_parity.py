@@ -33,7 +33,7 @@ def test_device_proposals_match_oracle(lib, name, nsteps):
 
 
 @pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 2000), ("state_sim5_3pop_hn2", 500), ("state_sim50_hn3", 300),
-                                         ("state_sim300_hn1", 100), ("state_sim5_hky_hn2", 300)])
+                                         ("state_sim300_hn1", 100), ("state_sim5_hky_hn2", 300), ("state_sim3_sw_hn2", 400)])
 def test_incremental_sums_match_fresh_evaluation(lib, name, nsteps):
     cnt = ec.incremental_sums_match_fresh_evaluation(lib, name, nsteps, rtol=RTOL)
     assert cnt["steps"] == nsteps and cnt["dropped"] == 0
@@ -42,6 +42,10 @@ def test_incremental_sums_match_fresh_evaluation(lib, name, nsteps):
 @pytest.mark.parametrize("name", ["lmode_sim5_hn2", "lmode_sim5_expo_hn2"])
 def test_lmode_matches_reference(lib, name):
     ec.lmode_matches_reference(lib, name, rtol=RTOL)
+
+
+def test_stepwise_updates_match_oracle(lib):
+    ec.stepwise_updates_match_oracle(lib, "state_sim3_sw_hn2", 40, rtol=RTOL)
 
 
 def test_device_incomplete_gamma_matches_reference_tables(lib):

@@ -43,3 +43,7 @@ def test_lmode(emu, name):
 
 def test_gamma_tables(emu):
     assert ec.gamma_tables_match_reference(emu, rtol=1e-12) > 400
+
+
+def test_stepwise_updates(emu):
+    ec.stepwise_updates_match_oracle(emu, "state_sim3_sw_hn2", 40, rtol=1e-10)
