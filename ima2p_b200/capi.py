@@ -55,6 +55,7 @@ SIGNATURES = {
     "ima2p_engine_state_bytes": (_i, [_v, c_u64_p]),
     "ima2p_engine_put_state": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v, c_dbl_p, _v]),
     "ima2p_engine_fetch_state": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v]),
+    "ima2p_engine_fetch_pair_summaries": (_i, [_v, c_dbl_p, c_int_p, c_int_p, _v]),
     "ima2p_engine_fetch_chain_summary": (_i, [_v, c_dbl_p, _v]),
     "ima2p_lmode_create": (_i, [C.POINTER(_v), _i, _i, _i, _i, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, _i]),
     "ima2p_lmode_destroy": (None, [_v]),

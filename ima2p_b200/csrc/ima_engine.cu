@@ -919,6 +919,31 @@ int ima2p_engine_fetch_state(ima2p_engine *h, void *topo, void *time, void *mseg
   return check_device_error(&e, s);
 }
 
+// per-pair summaries of the CURRENT genealogies in one call: sd[P][4] = roottime, length, tlength, pdg;
+// si[P][2] = root, mignum; wi[P][NI] = cc | mc counts (any pointer may be NULL)
+int ima2p_engine_fetch_pair_summaries(ima2p_engine *h, double *sd, int *si, int *wi, void *cuda_stream) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "fetch_pair_summaries: not finalized");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  const size_t P = e.d.P, NI = e.d.NI;
+  std::vector<unsigned char> cur(P);
+  if (!d2h(cur.data(), e.v.cur, P, s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  bool ok = true;
+  for (size_t p0 = 0; p0 < P && ok;) {
+    size_t p1 = p0 + 1;
+    while (p1 < P && cur[p1] == cur[p0]) p1++;
+    const PairBuf &B = e.v.buf[cur[p0]];
+    const size_t n = p1 - p0;
+    if (sd) ok = ok && d2h(sd + p0 * 4, B.sd + p0 * 4, n * 4 * sizeof(double), s);
+    if (si) ok = ok && d2h(si + p0 * 2, B.si + p0 * 2, n * 2 * sizeof(int), s);
+    if (wi) ok = ok && d2h(wi + p0 * NI, B.gwi + p0 * NI, n * NI * sizeof(int), s);
+    p0 = p1;
+  }
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  return IMA2P_OK;
+}
+
 int ima2p_engine_fetch_chain_summary(ima2p_engine *h, double *out4, void *cuda_stream) {
   if (!h || !h->eng.finalized || !out4) return fail(IMA2P_E_ARG, "fetch_chain_summary: bad argument");
   Engine &e = h->eng;

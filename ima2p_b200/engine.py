@@ -242,6 +242,13 @@ class Engine:
         ptrs = [b if isinstance(b, int) else b.ctypes.data for b in bufs]
         self._ck(self.lib.ima2p_engine_fetch_state(self._h, *ptrs, stream))
 
+    def fetch_pair_summaries(self, stream=None):
+        """(sd[P][4] = roottime, length, tlength, pdg; si[P][2] = root, mignum; wi[P][NI]) of the current genealogies."""
+        P = self.nchains * self.nloci
+        sd, si, wi = np.zeros((P, 4)), np.zeros((P, 2), np.int32), np.zeros((P, self.NI), np.int32)
+        self._ck(self.lib.ima2p_engine_fetch_pair_summaries(self._h, _dp(sd), _ip(si), _ip(wi), stream))
+        return sd, si, wi
+
     def fetch_chain_summary(self, stream=None):
         out = np.zeros((self.nchains, 4))
         self._ck(self.lib.ima2p_engine_fetch_chain_summary(self._h, _dp(out), stream))

@@ -148,6 +148,9 @@ int ima2p_engine_put_state (ima2p_engine * e, const void *topo, const void *time
                             const double *tvals /* [nchains][nsplit] */ , void *cuda_stream);
 int ima2p_engine_fetch_state (ima2p_engine * e, void *topo, void *time, void *mseg, void *mig_t, void *mig_p,
                               void *scal_i, void *scal_d, void *cuda_stream);
+/* per-pair summaries of the current genealogies: sd[P][4] = {roottime, length, tlength, pdg}, si[P][2] = {root, mignum},
+ * wi[P][NI] = coalescence | migration counts (struct genealogy fields imamp.hpp:956-987); NULL pointers are skipped */
+int ima2p_engine_fetch_pair_summaries (ima2p_engine * e, double *sd, int *si, int *wi, void *cuda_stream);
 /* per-chain summary after a run: out[ci] = {beta, probg, pdg, S} */
 int ima2p_engine_fetch_chain_summary (ima2p_engine * e, double *out4 /* [nchains_local][4] */ , void *cuda_stream);
 

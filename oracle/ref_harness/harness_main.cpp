@@ -346,6 +346,30 @@ dump_state (void)
   fprintf (jo, "]}\n");
 }
 
+static std::string g_start_trees;
+static void
+capture_start_trees (void)      /* chain 0's genealogies as JSON, kept for the trace fixture */
+{
+  char *buf = NULL;
+  size_t blen = 0;
+  FILE *keep = jo;
+  jo = open_memstream (&buf, &blen);
+  fputc ('[', jo);
+  for (int li = 0; li < nloci; li++)
+    dump_tree (0, li, li + 1 < nloci ? "," : "");
+  fputc (']', jo);
+  fclose (jo);
+  jo = keep;
+  g_start_trees = buf;
+  free (buf);
+}
+
+static void
+dump_tree_all (void)
+{
+  fputs (g_start_trees.c_str (), jo);
+}
+
 static void
 do_burn (long burn)
 {
@@ -784,6 +808,77 @@ mode_bench (long burn, long iters, long full, long chunks, long gburn)
   fprintf (jo, "]}\n");
 }
 
+/* long-run summary statistics of the reference sampler with split times and mutation scalars held at their start
+ * values: `sweeps` sweeps of updategenealogy() over every chain x locus after `gburn` untimed ones; per locus the
+ * mean (over sweeps and chains) of tree length, root time, migration count and per-population coalescence counts,
+ * with batch-means standard errors (nbatch batches).  Used for the statistical parity fixture. */
+static void
+mode_trace (long gburn, long sweeps, long nbatch)
+{
+  int ci, li, a, b, k;
+  long it, bi;
+  for (it = 0; it < gburn; it++)
+    for (ci = 0; ci < numchains; ci++)
+      for (li = 0; li < nloci; li++)
+        updategenealogy (ci, li, &a, &b);
+  const int NS = 6;             /* length, roottime, mignum, cc0, cc1, cc2(+) */
+  std::vector<double> bsum ((size_t) nbatch * nloci * NS, 0.0);
+  long per = sweeps / nbatch, acc = 0, tries = 0;
+  for (bi = 0; bi < nbatch; bi++)
+    for (it = 0; it < per; it++)
+      for (ci = 0; ci < numchains; ci++)
+        for (li = 0; li < nloci; li++)
+        {
+          acc += updategenealogy (ci, li, &a, &b);
+          tries++;
+          struct genealogy *G = &C[ci]->G[li];
+          double *o = &bsum[((size_t) bi * nloci + li) * NS];
+          o[0] += G->length;
+          o[1] += G->roottime;
+          o[2] += G->mignum;
+          o[3] += G->gweight.cc[0][0];
+          o[4] += npops > 1 ? G->gweight.cc[0][1] : 0;
+          for (k = 1; k <= numsplittimes; k++)
+            o[5] += G->gweight.cc[k][0];
+        }
+  fprintf (jo, "{");
+  dump_model ();
+  fprintf (jo, "\"sweeps\":%ld,\"chains\":%d,\"nbatch\":%ld,\"accept\":%.6f,\"tvals\":[", per * nbatch, numchains, nbatch, (double) acc / tries);
+  for (k = 0; k < numsplittimes; k++)
+  {
+    if (k)
+      fputc (',', jo);
+    jd (C[0]->tvals[k]);
+  }
+  fprintf (jo, "],\"uvals\":[");
+  for (li = 0; li < nloci; li++)
+  {
+    if (li)
+      fputc (',', jo);
+    jd (C[0]->G[li].uvals[0]);
+  }
+  fprintf (jo, "],\"batch_means\":[");
+  for (bi = 0; bi < nbatch; bi++)
+  {
+    fprintf (jo, "%s[", bi ? "," : "");
+    for (li = 0; li < nloci; li++)
+    {
+      fprintf (jo, "%s[", li ? "," : "");
+      for (k = 0; k < NS; k++)
+      {
+        if (k)
+          fputc (',', jo);
+        jd (bsum[((size_t) bi * nloci + li) * NS + k] / ((double) per * numchains));
+      }
+      fputc (']', jo);
+    }
+    fputc (']', jo);
+  }
+  fprintf (jo, "],\"start\":");
+  dump_tree_all ();
+  fprintf (jo, "}\n");
+}
+
 static void
 mode_lbench (long burn, long rows, long evals)
 {
@@ -888,6 +983,11 @@ main (int argc, char *argv[])
     mode_lmode (burn, kvl ("rows", 500), kvl ("every", 5));
   else if (mode == "bench")
     mode_bench (burn, kvl ("iters", 10), kvl ("full", 0), kvl ("chunks", 1), kvl ("gburn", 0));
+  else if (mode == "trace")
+  {
+    capture_start_trees ();
+    mode_trace (kvl ("gburn", 1000), kvl ("sweeps", 20000), kvl ("nbatch", 20));
+  }
   else if (mode == "lbench")
     mode_lbench (burn, kvl ("rows", 100000), kvl ("evals", 50));
   else

@@ -3,7 +3,7 @@ kernel sources through the tests-only host-emulation build (tests/hostemu).  The
 CPU oracle (pinned against the reference's own values) or the golden fixtures themselves."""
 import numpy as np
 
-from support import (FlatModel, OracleModel, check_static_eval, engine_from_fixture, f64, fp, dp, i32, load_golden, oracle,
+from support import (FlatModel, FlatTree, OracleModel, check_static_eval, engine_from_fixture, f64, fp, dp, i32, load_golden, oracle,
                      rel_close, split_weights, tree_from_engine, _num)
 
 STATIC_FIXTURES = ["state_sim5_hn4", "state_sim50_hn3", "state_sim300_hn1", "state_sim2_hn2", "state_sim3_hn3",
@@ -232,3 +232,53 @@ def stepwise_updates_match_oracle(lib, name, nsteps, rtol=1e-9):
     cnt = eng.counters()
     eng.close()
     return cnt
+
+
+def long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=5.0):
+    """Statistical parity (no RNG matching): with split times and mutation scalars held at the reference's start
+    values, the engine's long-run per-locus means of tree length, root time, migration count and per-population
+    coalescence counts agree with the reference's own updategenealogy() sampler (fixture written by
+    `ref_harness trace`) within nsigma combined standard errors."""
+    from ima2p_b200 import Engine
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    nloci = len(d["loci"])
+    eng = Engine(nchains, nloci, mig_capacity=96, seed=4242, lib=lib)
+    eng.set_model_flat(*fm.create_args())
+    for li, loc in enumerate(d["loci"]):
+        eng.set_locus(li, loc["model"], loc["numgenes"], loc["numsites"], loc["samppop"], seq=loc["seq"], hval=loc["hval"])
+    eng.finalize()
+    eng.set_betas([1.0] * nchains)                      # independent cold chains, no swapping
+    for c in range(nchains):
+        eng.set_chain(c, d["tvals"])
+        for li in range(nloci):
+            t = FlatTree(d["start"][li])
+            eng.set_genealogy(c, li, t.up0, t.up1, t.down, t.pop, t.time, t.mig_off, t.mig_t[:-1], t.mig_p[:-1], t.root,
+                              t.roottime, uvals=[d["uvals"][li]])
+    eng.upload()
+    eng.eval()
+    eng.run(burn, swaptries=0)
+    acc = np.zeros((nchains, nloci, 6))
+    ncc = fm.ncc
+    for _ in range(sweeps):
+        eng.run(1, swaptries=0)
+        sd, si, wi = eng.fetch_pair_summaries()
+        sd, si, wi = sd.reshape(nchains, nloci, 4), si.reshape(nchains, nloci, 2), wi.reshape(nchains, nloci, -1)
+        acc[:, :, 0] += sd[:, :, 1]
+        acc[:, :, 1] += sd[:, :, 0]
+        acc[:, :, 2] += si[:, :, 1]
+        acc[:, :, 3] += wi[:, :, 0]
+        acc[:, :, 4] += wi[:, :, 1] if fm.npops > 1 else 0
+        acc[:, :, 5] += wi[:, :, fm.npops:ncc].sum(axis=2)
+    chain_means = acc / sweeps
+    m_e, se_e = chain_means.mean(axis=0), chain_means.std(axis=0, ddof=1) / np.sqrt(nchains)
+    bm = np.array(d["batch_means"])
+    m_r, se_r = bm.mean(axis=0), bm.std(axis=0, ddof=1) / np.sqrt(len(bm))
+    z = (m_e - m_r) / np.sqrt(se_e ** 2 + se_r ** 2 + 1e-300)
+    cnt = eng.counters()
+    ref_acc = float(np.mean(d["accept"]))
+    eng_acc = cnt["accepted"] / cnt["updates"]
+    eng.close()
+    assert np.all(np.abs(z) < nsigma), (z, m_e, m_r)
+    assert abs(eng_acc - ref_acc) < 0.03, (eng_acc, ref_acc)
+    return z, m_e, m_r, eng_acc, ref_acc

@@ -41,6 +41,34 @@ def run(mode, name, ufile, hn, kv, extra=()):
     print("wrote", name + ".json.gz", os.path.getsize(os.path.join(HERE, name + ".json.gz")), "bytes")
 
 
+def run_trace(name, ufile, seeds, kv):
+    """Long-run summary statistics of the reference's updategenealogy sampler (split times and mutation scalars held
+    at their start values): several independently seeded runs merged into one fixture."""
+    import json
+    merged = None
+    for sd in seeds:
+        out = os.path.join(TMP, "%s_%d.json" % (name, sd))
+        cmd = [HARNESS, "trace", out, "seed=%d" % sd] + ["%s=%s" % p for p in kv.items()] + ["--", "-i", ufile, "-o",
+              os.path.join(TMP, name + ".out")] + PRIORS + COMMON + ["-hn", "1"]
+        try:    # the reference itself occasionally spins forever for some seeds; such a run is dropped
+            with open(os.path.join(TMP, name + ".log"), "w") as log:
+                subprocess.run(cmd, check=True, stdout=log, stderr=subprocess.STDOUT, cwd=TMP, timeout=120)
+        except subprocess.TimeoutExpired:
+            print("seed", sd, "did not finish (reference hang); skipped")
+            continue
+        d = json.load(open(out))
+        if merged is None:
+            merged = d
+            merged["accept"] = [d["accept"]]
+        else:
+            assert d["tvals"] == merged["tvals"] and d["uvals"] == merged["uvals"]
+            merged["batch_means"] += d["batch_means"]
+            merged["accept"].append(d["accept"])
+    with gzip.GzipFile(os.path.join(HERE, name + ".json.gz"), "wb", mtime=0) as g:
+        g.write(json.dumps(merged).encode())
+    print("wrote", name + ".json.gz", os.path.getsize(os.path.join(HERE, name + ".json.gz")), "bytes")
+
+
 def relabel(src, dst, fn):
     """Copy a .u file, passing each locus header line through fn(fields) -> fields."""
     lines = open(src).read().split("\n")
@@ -120,6 +148,9 @@ def main():
     run("kat", "kat_sim5_hn4", s5, 4, {"burn": 100})
     run("lmode", "lmode_sim5_hn2", s5, 2, {"burn": 200, "rows": 600, "every": 3})
     run("lmode", "lmode_sim5_expo_hn2", s5, 2, {"burn": 200, "rows": 300, "every": 3}, extra=["-j7"])
+    # statistical parity (north_star: posterior summaries from long runs agree with the reference)
+    run_trace("trace_sim5", s5, [1, 2, 3, 4, 5, 6], {"gburn": 3000, "sweeps": 60000, "nbatch": 12})
+    run_trace("trace_sim3", s3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12})
 
 
 if __name__ == "__main__":

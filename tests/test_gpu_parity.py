@@ -48,6 +48,13 @@ def test_stepwise_updates_match_oracle(lib):
     ec.stepwise_updates_match_oracle(lib, "state_sim3_sw_hn2", 40, rtol=RTOL)
 
 
+@pytest.mark.parametrize("name,nchains,burn,sweeps", [("trace_sim3", 256, 6000, 4000), ("trace_sim5", 256, 6000, 4000)])
+def test_long_run_statistics_match_reference_sampler(lib, name, nchains, burn, sweeps):
+    """north_star: posterior summaries from long runs agree with the reference statistically."""
+    z, m_e, m_r, eng_acc, ref_acc = ec.long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=5.0)
+    assert abs(z).max() < 5.0
+
+
 def test_device_incomplete_gamma_matches_reference_tables(lib):
     assert ec.gamma_tables_match_reference(lib, rtol=1e-10) > 400
 

@@ -47,3 +47,9 @@ def test_gamma_tables(emu):
 
 def test_stepwise_updates(emu):
     ec.stepwise_updates_match_oracle(emu, "state_sim3_sw_hn2", 40, rtol=1e-10)
+
+
+def test_long_run_statistics_match_reference_sampler(emu):
+    # statistical parity of the whole sampler (proposal distributions, Hastings terms, prior, likelihood)
+    z, _, _, eng_acc, ref_acc = ec.long_run_summaries_match_reference(emu, "trace_sim3", 64, 5000, 3000)
+    assert abs(z).max() < 5.0
