@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libima2p_b200.so")
+# IMA2P_B200_LIB selects another BUILD of the same CUDA library (e.g. a tuning variant); there is no non-CUDA build
+LIB_PATH = os.environ.get("IMA2P_B200_LIB", os.path.join(HERE, "libima2p_b200.so"))
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)
@@ -43,6 +44,7 @@ SIGNATURES = {
     "ima2p_engine_dims": (_i, [_v, c_int_p]),
     "ima2p_engine_run": (_i, [_v, _i, _i, _v]),
     "ima2p_engine_set_pieces": (_i, [_v, _i]),
+    "ima2p_engine_set_speculation": (_i, [_v, _i]),
     "ima2p_engine_run_timed": (_i, [_v, _i, _i, _v, c_flt_p]),
     "ima2p_engine_update_genealogies": (_i, [_v, _v, _v]),
     "ima2p_engine_swap_replay": (_i, [_v, _v, _i, _v]),

@@ -57,7 +57,8 @@ struct Engine {
   cudaEvent_t ev_fork = nullptr, ev_piece[16] = {};
 #endif
   int pieces = 1;      // measured on B200: overlapping the sweep with proposals does not pay
-  size_t pair_smem = 0, chain_smem = 0, overlap_smem = 0;
+  size_t pair_smem = 0, chain_smem = 0, overlap_smem = 0, accept_smem = 0;
+  int spec = 3;        // speculative depth of the accept sweep (see k_accept)
 
   template <class T> T *alloc(size_t n) {
     T *p = (T *)dev_alloc(n * sizeof(T));
@@ -116,6 +117,7 @@ static int launch_eval(Engine *e, stream_t s) {
   return IMA2P_OK;
 }
 
+static int accept_block_warps(int spec);
 // One step's genealogy updates.  The accept sweep is a dependent chain over the loci of a chain, the
 // proposals are independent per pair, and a proposal only needs its own pair's state -- so the loci are cut
 // into `pieces` ranges and the sweep of range q (stream s) overlaps the proposals of range q+1 (aux stream):
@@ -140,15 +142,19 @@ static void launch_update(Engine *e, stream_t s) {
     for (int q = 0; q < Q; q++) {
       const int l0 = (int)((long long)L * q / Q), l1 = (int)((long long)L * (q + 1) / Q);
       cudaStreamWaitEvent(s, e->ev_piece[q], 0);
-      IMA_LAUNCH(k_accept, e->d.nchains, kAcceptWarps, e->chain_smem, s, e->v, l0, l1);
+      IMA_LAUNCH(k_accept, e->d.nchains, accept_block_warps(e->spec), e->accept_smem, s, e->v, l0, l1, e->spec);
     }
     return;
   }
 #endif
   const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
   IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, 0, L);
-  IMA_LAUNCH(k_accept, e->d.nchains, kAcceptWarps, e->chain_smem, s, e->v, 0, L);
+  IMA_LAUNCH(k_accept, e->d.nchains, accept_block_warps(e->spec), e->accept_smem, s, e->v, 0, L, e->spec);
 }
+
+// warps per accept block: one per (speculative locus, term slot) plus the loader; the host emulation plays all of
+// them from a single thread (IMA_FOR_WARPS)
+static int accept_block_warps(int spec) { return IMA_CUDA ? spec * kTermWarps + 1 : 1; }
 
 static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries) {
   SwapView sv = e->sv;
@@ -342,6 +348,9 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   d.W64 = (e.model.ntreepops + 3) / 4;
   e.pair_smem = pair_smem_bytes(d);
   e.chain_smem = chain_smem_bytes(d);
+  e.accept_smem = accept_smem_bytes(d);
+  // deep speculation needs a 16-warp block per chain (one per SM); with more chains than SMs two 11-warp blocks per SM win
+  e.spec = d.nchains <= 148 ? 3 : 2;
 #if IMA_CUDA
   if (e.pair_smem * kWarpsPerBlock > 227 * 1024) return fail(IMA2P_E_ARG, "finalize: pair does not fit in shared memory; lower mig_capacity");
   e.overlap_smem = e.pair_smem * kWarpsPerBlock;
@@ -691,7 +700,7 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
       cudaEventRecord(ev[i * 4 + 0], s);
       IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, 0, e.d.nloci);
       cudaEventRecord(ev[i * 4 + 1], s);
-      IMA_LAUNCH(k_accept, e.d.nchains, kAcceptWarps, e.chain_smem, s, e.v, 0, e.d.nloci);
+      IMA_LAUNCH(k_accept, e.d.nchains, accept_block_warps(e.spec), e.accept_smem, s, e.v, 0, e.d.nloci, e.spec);
       cudaEventRecord(ev[i * 4 + 2], s);
       launch_swap(&e, s, e.v.swapsum, swaptries);
       cudaEventRecord(ev[i * 4 + 3], s);
@@ -776,6 +785,13 @@ int ima2p_debug_gamma(int device, const int *a, const double *x, int n, double *
   }
   dev_free(d_lf); dev_free(d_x); dev_free(d_out); dev_free(d_a); dev_free(d_err);
   return ok ? IMA2P_OK : fail(IMA2P_E_CUDA, "debug_gamma failed");
+}
+
+int ima2p_engine_set_speculation(ima2p_engine *h, int depth) {
+  if (!h || depth < 1 || depth > kSpecMax) return fail(IMA2P_E_ARG, "set_speculation: 1..3");
+  h->eng.spec = depth;
+  h->eng.graph_ready = false;
+  return IMA2P_OK;
 }
 
 int ima2p_engine_set_pieces(ima2p_engine *h, int pieces) {

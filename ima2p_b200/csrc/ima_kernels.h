@@ -174,7 +174,7 @@ IMA_KERNEL void k_eval_chains(EngineView E) {
 }
 
 #ifndef IMA_PROPOSE_MINBLOCKS
-#define IMA_PROPOSE_MINBLOCKS 6      // 80 registers/thread: 24 resident warps per SM (the kernel is latency-bound)
+#define IMA_PROPOSE_MINBLOCKS 5      // <= 102 registers/thread, 20 resident warps per SM: best of 5/6/8 measured on B200
 #endif
 #if IMA_CUDA
 #define IMA_PROPOSE_BOUNDS __launch_bounds__(kWarpsPerBlock * 32, IMA_PROPOSE_MINBLOCKS)
@@ -274,165 +274,243 @@ IMA_DEV void fetch_accept_record(const EngineView &E, int p, int lane, int NI, i
   r.extra = E.prop_extra[p];
 }
 
-// One block per chain.  The loci of a chain are swept in order (they are coupled through the integrated prior,
-// SURVEY.md fact 1); inside a locus the nq + nm prior terms are independent, so each is given to its own warp
-// (which evaluates the term's series / continued fraction 32 terms per round, ima_math.h *_coop):
-//   warp 0      fetch (prefetched one locus ahead) the pair's weight records, build all +- weights with the clamps
-//   warp t      term t: gather (c, f, hc); reuse rule (:1997-2000, :2031-2034) or integrate_*_term
-//   thread 0    sum the terms in parameter order, MH decision (update_gtree.cpp:917-927)
-//   all         commit on accept
-// Loci [l0, l1): the sums travel through global memory between launches, so a step may be cut into pieces.
+// ---- accept sweep ---------------------------------------------------------------------------------------
+// One block per chain.  The loci of a chain must be decided in order: they are coupled through the integrated
+// prior, so locus li sees the sums left by every accepted update before it.  Two things
+// shorten that dependent chain without changing its result:
+//   * inside a locus the nq + nm prior terms are independent: each goes to its own warp, which runs the term's
+//     series / continued fraction 32 terms per round (ima_math.h *_coop);
+//   * the next B-1 loci are evaluated SPECULATIVELY in the same round, against the same sums.  Decisions are then
+//     taken in locus order; the first acceptance changes the sums, so every speculative locus after it is
+//     thrown away and re-evaluated in the next round.  About two thirds of the updates are rejected, so a round
+//     decides 1 + q + q^2 ... loci on average (q = rejection rate).  The random number of a locus depends only on
+//     (chain, locus, step), so the outcome is identical to the one-locus-at-a-time sweep.
+// A loader warp streams the pairs' weight records (and draws the uniforms) a few loci ahead into a ring in
+// shared memory, so global-memory latency is off the critical path.
+// Loci [l0, l1): the sums travel through global memory between launches.
 #if IMA_CUDA
-constexpr int kAcceptWarps = 8;
+constexpr int kSpecMax = 3;          // speculative depth B
+constexpr int kTermWarps = 5;        // warps per speculative locus (terms are strided over them)
 IMA_DEV void block_sync() { __syncthreads(); }
+#define IMA_FOR_WARPS(wv, nw) for (int wv = ima_warp_in_block(), once_ = 1; once_; once_ = 0)
 #else
-constexpr int kAcceptWarps = 1;      // host emulation: one "warp" takes the terms one after the other
+constexpr int kSpecMax = 3;
+constexpr int kTermWarps = 5;
 IMA_DEV void block_sync() {}
+#define IMA_FOR_WARPS(wv, nw) for (int wv = 0; wv < (nw); wv++)      // host emulation: one thread plays every warp in turn
 #endif
-enum { kAcFlags = 0, kAcCb, kAcAccept };
-enum { kAdOldPdg = 0, kAdNewPdg, kAdExtra, kAdNewProbg, kAdUniform };
+constexpr int kRing = 8;             // loci buffered ahead
+
+struct AcceptSm {
+  int *ai; double *ad, *q;                                   // all-locus sums and current prior terms
+  double *cq;                                                // [kSpecMax][2*kMaxParams] candidate terms per speculative locus
+  int *r_dI; double *r_oD, *r_nD, *r_sc; int *r_ic;          // ring: [kRing] records
+  int *ctl;                                                  // [4]: accepted group (or -1), advance
+  double *dctl;                                              // [2]: new probg
+};
+IMA_HD size_t accept_smem_bytes(const EngineDims &d) {
+  return align8(sizeof(int) * d.NI) + align8(sizeof(double) * d.ND) + align8(sizeof(double) * 2 * kMaxParams) +
+         align8(sizeof(double) * kSpecMax * 2 * kMaxParams) + kRing * (align8(sizeof(int) * d.NI) + 2 * align8(sizeof(double) * d.ND) + 5 * 8 + 16) + 64;
+}
+IMA_DEV AcceptSm carve_accept_smem(unsigned char *base, const EngineDims &d) {
+  AcceptSm s; unsigned char *p = base;
+  s.ad = (double *)p; p += align8(sizeof(double) * d.ND);
+  s.q = (double *)p; p += align8(sizeof(double) * 2 * kMaxParams);
+  s.cq = (double *)p; p += align8(sizeof(double) * kSpecMax * 2 * kMaxParams);
+  s.r_oD = (double *)p; p += kRing * align8(sizeof(double) * d.ND);
+  s.r_nD = (double *)p; p += kRing * align8(sizeof(double) * d.ND);
+  s.r_sc = (double *)p; p += kRing * 5 * 8;                  // oldpdg, newpdg, extra, uniform, (pad)
+  s.dctl = (double *)p; p += 16;
+  s.ai = (int *)p; p += align8(sizeof(int) * d.NI);
+  s.r_dI = (int *)p; p += kRing * align8(sizeof(int) * d.NI);
+  s.r_ic = (int *)p; p += kRing * 16;                        // flags, cb
+  s.ctl = (int *)p;
+  return s;
+}
 
 #if IMA_CUDA
-#define IMA_ACCEPT_BOUNDS __launch_bounds__(kAcceptWarps * 32, 2)
+#define IMA_ACCEPT_BOUNDS __launch_bounds__((kSpecMax * kTermWarps + 1) * 32, 1)
 #else
 #define IMA_ACCEPT_BOUNDS
 #endif
-IMA_KERNEL void IMA_ACCEPT_BOUNDS k_accept(EngineView E, int l0, int l1) {
+IMA_KERNEL void IMA_ACCEPT_BOUNDS k_accept(EngineView E, int l0, int l1, int spec) {
   IMA_SMEM_DECL
   const int c = ima_block();
   if (c >= E.d.nchains) return;
   const DevModel &M = IMA_MODEL;
-  const int lane = Warp::lane(), w = ima_warp_in_block(), tid = w * IMA_WARP + lane, nth = kAcceptWarps * IMA_WARP;
-  const int NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
-  ChainSm S = carve_chain_smem(IMA_SMEM, E.d);
-  for (int i = tid; i < NI; i += nth) S.ai[i] = E.all_i[(size_t)c * NI + i];
-  for (int i = tid; i < ND; i += nth) S.ad[i] = E.all_d[(size_t)c * ND + i];
-  for (int i = tid; i < M.nq; i += nth) S.q[i] = E.qint[(size_t)c * kMaxParams + i];
-  for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = E.mint[(size_t)c * kMaxParams + i];
+  const int B = spec < 1 ? 1 : (spec > kSpecMax ? kSpecMax : spec);
+  const int NW = B * kTermWarps + 1, LOADER = B * kTermWarps;       // warps in the block; the last one loads
+  const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
+  const int sI = (int)(align8(sizeof(int) * NI) / sizeof(int)), sD = (int)(align8(sizeof(double) * ND) / sizeof(double));
+  AcceptSm S = carve_accept_smem(IMA_SMEM, E.d);
+  const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
+  // ring slot of locus l: l % kRing.  The loader fills loci [filled, upto).
+  auto load_records = [&](int from, int upto) {
+    for (int l = from; l < upto; l++) {
+      const int p = c * E.d.nloci + l, slot = l % kRing;
+      const int cb = E.cur[p];
+      const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
+      for (int i = lane; i < NI; i += IMA_WARP) S.r_dI[slot * sI + i] = N.gwi[(size_t)p * NI + i] - O.gwi[(size_t)p * NI + i];
+      for (int i = lane; i < ND; i += IMA_WARP) { S.r_oD[slot * sD + i] = O.gwd[(size_t)p * ND + i]; S.r_nD[slot * sD + i] = N.gwd[(size_t)p * ND + i]; }
+      if (lane == 0) {
+        S.r_ic[slot * 4 + 0] = (int)E.prop_flags[p]; S.r_ic[slot * 4 + 1] = cb;
+        S.r_sc[slot * 5 + 0] = O.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 5 + 1] = N.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 5 + 2] = E.prop_extra[p];
+        Philox rng;
+        rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + l), kRngAccept);
+        S.r_sc[slot * 5 + 3] = rng.uniform();
+      }
+    }
+  };
+  IMA_FOR_WARPS(w, NW) {
+    const int tid = w * IMA_WARP + lane, nth = NW * IMA_WARP;
+    for (int i = tid; i < NI; i += nth) S.ai[i] = E.all_i[(size_t)c * NI + i];
+    for (int i = tid; i < ND; i += nth) S.ad[i] = E.all_d[(size_t)c * ND + i];
+    for (int i = tid; i < M.nq; i += nth) S.q[i] = E.qint[(size_t)c * kMaxParams + i];
+    for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = E.mint[(size_t)c * kMaxParams + i];
+    if (w == LOADER) load_records(l0, (l0 + kRing < l1) ? l0 + kRing : l1);
+  }
   const double beta = E.beta[c];
   double probg = E.probg[c], pdgsum = E.pdgsum[c];
-  const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
   unsigned long long dropped = 0;
-  AcceptRecord nxt;
-  if (w == 0) fetch_accept_record(E, c * E.d.nloci + l0, lane, NI, ND, nxt);
+  int filled = (l0 + kRing < l1) ? l0 + kRing : l1;
   block_sync();
-  for (int li = l0; li < l1; li++) {
-    const int p = c * E.d.nloci + li;
-    if (w == 0) {
-      // records of locus li+1 are fetched while locus li is being decided (the sweep is a dependent chain, so
-      // global-memory latency would otherwise sit on the critical path of every locus)
-      const AcceptRecord rec = nxt;
-      if (li + 1 < l1) fetch_accept_record(E, p + 1, lane, NI, ND, nxt);
-      const int cb = rec.cb, nb = cb ^ 1;
-      // sum_subtract_treeinfo (ginfo.cpp:248-285): subtract old, add new, clamp fc and fm at 0
-      if (lane < NI) S.ci[lane] = S.ai[lane] + rec.dI;
-      if (lane < ND) {
-        double x = S.ad[lane];
-        x -= rec.oD;
-        x += rec.nD;
-        if ((lane < ncc || lane >= 2 * ncc) && 0.0 > x) x = 0.0;
-        S.cd[lane] = x;
-      }
-      if (NI > IMA_WARP || ND > IMA_WARP) {             // records wider than a warp (>= 4 populations): direct loads
-        const int *oi = E.buf[cb].gwi + (size_t)p * NI, *ni = E.buf[nb].gwi + (size_t)p * NI;
-        const double *od = E.buf[cb].gwd + (size_t)p * ND, *nd = E.buf[nb].gwd + (size_t)p * ND;
-        for (int i = lane + (IMA_WARP == 1 ? 1 : IMA_WARP); i < NI; i += IMA_WARP) S.ci[i] = S.ai[i] + (ni[i] - oi[i]);
-        for (int i = lane + (IMA_WARP == 1 ? 1 : IMA_WARP); i < ND; i += IMA_WARP) {
-          double x = S.ad[i];
-          x -= od[i];
-          x += nd[i];
-          if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
-          S.cd[i] = x;
+  for (int li = l0; li < l1;) {
+    const int nb = (l1 - li < B) ? l1 - li : B;
+    // ---- phase 1: term t of speculative locus li+g on warp g*kTermWarps + (t % kTermWarps) -------------------
+    const int upto = (li + kRing < l1) ? li + kRing : l1;   // loci < li are decided: their ring slots are free again
+    IMA_FOR_WARPS(w, NW) {
+      const int g = w / kTermWarps, t0 = w - g * kTermWarps;
+      if (w == LOADER) load_records(filled, upto);
+      if (w != LOADER && g < nb) {
+        const int slot = (li + g) % kRing;
+        const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
+        if (!(flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree))) {
+          const int *dI = S.r_dI + slot * sI;
+          const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
+          // candidate sums = sum_subtract_treeinfo (ginfo.cpp:248-285) on the entries this term reads: subtract old, add
+          // new, clamp fc and fm at 0; then integrate_tree_prob's reuse rule (:1997-2000, :2031-2034) or the integral
+          for (int t = t0; t < nterms; t += kTermWarps) {
+            double v;
+            if (t < M.nq) {
+              int cn = 0, co = 0; double fn = 0.0, fo = 0.0, hn = 0.0;
+              for (int j = 0; j < M.q_n[t]; j++) {
+                const int x = M.q_idx[t][j];
+                co += S.ai[x]; cn += S.ai[x] + dI[x];
+                fo += S.ad[x];
+                double f = S.ad[x]; f -= oD[x]; f += nD[x]; if (0.0 > f) f = 0.0;
+                fn += f;
+                double hh = S.ad[ncc + x]; hh -= oD[ncc + x]; hh += nD[ncc + x];
+                hn += hh;
+              }
+              v = (cn == co && fn == fo) ? S.q[t] : integrate_coalescent_term_coop(E.mc, cn, fn, hn, M.q_max[t], M.q_min[t]);
+              if (lane == 0) S.cq[g * 2 * kMaxParams + t] = v;
+            } else {
+              const int tm = t - M.nq;
+              int cn = 0, co = 0; double fn = 0.0, fo = 0.0;
+              for (int j = 0; j < M.m_n[tm]; j++) {
+                const int x = M.m_idx[tm][j];
+                co += S.ai[ncc + x]; cn += S.ai[ncc + x] + dI[ncc + x];
+                fo += S.ad[2 * ncc + x];
+                double f = S.ad[2 * ncc + x]; f -= oD[2 * ncc + x]; f += nD[2 * ncc + x]; if (0.0 > f) f = 0.0;
+                fn += f;
+              }
+              v = (cn == co && fn == fo) ? S.q[kMaxParams + tm]
+                  : (M.expoprior ? integrate_migration_term_expo(E.mc, cn, fn, M.m_mean[tm])
+                                 : integrate_migration_term_coop(E.mc, cn, fn, M.m_max[tm], M.m_min[tm]));
+              if (lane == 0) S.cq[g * 2 * kMaxParams + kMaxParams + tm] = v;
+            }
+          }
         }
       }
-      if (lane == 0) {
-        S.ic[kAcFlags] = (int)rec.flags; S.ic[kAcCb] = cb;
-        S.dc[kAdOldPdg] = rec.oldpdg; S.dc[kAdNewPdg] = rec.newpdg; S.dc[kAdExtra] = rec.extra;
+    }
+    block_sync();
+    // ---- phase 2: decisions in locus order (update_gtree.cpp:917-927) ----------------------------------------
+    IMA_FOR_WARPS(w, NW) {
+      if (w == 0 && lane == 0) {
+        int accepted = -1, adv = nb;
+        for (int g = 0; g < nb && accepted < 0; g++) {
+          const int slot = (li + g) % kRing;
+          const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
+          if (flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree)) continue;
+          double newprobg = 0.0;
+          for (int t = 0; t < M.nq; t++) newprobg += S.cq[g * 2 * kMaxParams + t];
+          if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
+          if (M.nomigration == 0)
+            for (int i = 0; i < M.nomig_n; i++)
+              if (S.ai[ncc + M.nomig_idx[i]] + S.r_dI[slot * sI + ncc + M.nomig_idx[i]] != 0) newprobg = -kMyDblMax;
+          const double tpw = newprobg - probg, dpdg = S.r_sc[slot * 5 + 1] - S.r_sc[slot * 5 + 0], extra = S.r_sc[slot * 5 + 2];
+          double mh;
+          if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
+          else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
+          if (S.r_sc[slot * 5 + 3] < fmin(1.0, mh)) { accepted = g; adv = g + 1; S.dctl[0] = newprobg; }
+        }
+        S.ctl[0] = accepted; S.ctl[1] = adv;
       }
     }
     block_sync();
-    const uint32_t flags = (uint32_t)S.ic[kAcFlags];
-    if (flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree)) {
-      if (flags & kFlagOverflow) dropped++;
-      block_sync();                                      // warp 0 may not overwrite the control words before all have read them
-      continue;
-    }
-    // the MH uniform of this locus is drawn by the last warp while the terms are being evaluated
-    if (w == kAcceptWarps - 1 && lane == 0) {
-      Philox rng;
-      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngAccept);
-      S.dc[kAdUniform] = rng.uniform();
-    }
-    // integrate_tree_prob (update_gtree_common.cpp:1944-2053): term t on warp t
-    for (int t = w; t < nterms; t += kAcceptWarps) {
-      double v;
-      if (t < M.nq) {
-        int cn, co; double fn, fo, hn, ho;
-        gather_q(M, t, S.ci, S.cd, cn, fn, hn);
-        gather_q(M, t, S.ai, S.ad, co, fo, ho);
-        v = (cn == co && fn == fo) ? S.q[t] : integrate_coalescent_term_coop(E.mc, cn, fn, hn, M.q_max[t], M.q_min[t]);
-        if (lane == 0) S.cq[t] = v;
-      } else {
-        const int tm = t - M.nq;
-        int cn, co; double fn, fo;
-        gather_m(M, tm, S.ci, S.cd, cn, fn);
-        gather_m(M, tm, S.ai, S.ad, co, fo);
-        v = (cn == co && fn == fo) ? S.q[kMaxParams + tm]
-            : (M.expoprior ? integrate_migration_term_expo(E.mc, cn, fn, M.m_mean[tm])
-                           : integrate_migration_term_coop(E.mc, cn, fn, M.m_max[tm], M.m_min[tm]));
-        if (lane == 0) S.cq[kMaxParams + tm] = v;
+    // ---- phase 3: commit the accepted locus (if any) -----------------------------------------------------
+    const int accepted = S.ctl[0], adv = S.ctl[1];
+    for (int g = 0; g < adv; g++) if ((uint32_t)S.r_ic[((li + g) % kRing) * 4] & kFlagOverflow) dropped++;
+    IMA_FOR_WARPS(w, NW) {
+      const int tid = w * IMA_WARP + lane, nth = (NW - 1) * IMA_WARP;
+      if (w != LOADER && accepted >= 0) {
+        const int slot = (li + accepted) % kRing;
+        const int *dI = S.r_dI + slot * sI;
+        const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
+        for (int i = tid; i < NI; i += nth) S.ai[i] += dI[i];
+        for (int i = tid; i < ND; i += nth) {
+          double x = S.ad[i];
+          x -= oD[i];
+          x += nD[i];
+          if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
+          S.ad[i] = x;
+        }
+        for (int i = tid; i < M.nq; i += nth) S.q[i] = S.cq[accepted * 2 * kMaxParams + i];
+        for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = S.cq[accepted * 2 * kMaxParams + kMaxParams + i];
+        if (tid == 0) {
+          const int p = c * E.d.nloci + li + accepted;
+          const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
+          E.cur[p] = (unsigned char)(S.r_ic[slot * 4 + 1] ^ 1);
+          E.acc[(size_t)p * 3 + 0]++;
+          if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
+          if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
+        }
       }
     }
-    block_sync();
-    if (tid == 0) {
-      double newprobg = 0.0;
-      for (int t = 0; t < M.nq; t++) newprobg += S.cq[t];
-      if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[kMaxParams + t];
-      if (!migration_allowed(M, S.ci)) newprobg = -kMyDblMax;
-      const double tpw = newprobg - probg, dpdg = S.dc[kAdNewPdg] - S.dc[kAdOldPdg], extra = S.dc[kAdExtra];
-      double mh;                                        // update_gtree.cpp:917-927
-      if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
-      else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
-      S.ic[kAcAccept] = (S.dc[kAdUniform] < fmin(1.0, mh)) ? 1 : 0;
-      S.dc[kAdNewProbg] = newprobg;
+    filled = upto;
+    if (accepted >= 0) {
+      const int slot = (li + accepted) % kRing;
+      probg = S.dctl[0];
+      pdgsum -= S.r_sc[slot * 5 + 0];
+      pdgsum += S.r_sc[slot * 5 + 1];
     }
-    block_sync();
-    if (S.ic[kAcAccept]) {
-      for (int i = tid; i < NI; i += nth) S.ai[i] = S.ci[i];
-      for (int i = tid; i < ND; i += nth) S.ad[i] = S.cd[i];
-      for (int i = tid; i < M.nq; i += nth) S.q[i] = S.cq[i];
-      for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = S.cq[kMaxParams + i];
-      probg = S.dc[kAdNewProbg];
-      pdgsum -= S.dc[kAdOldPdg];
-      pdgsum += S.dc[kAdNewPdg];
-      if (tid == 0) {
-        E.cur[p] = (unsigned char)(S.ic[kAcCb] ^ 1);
-        E.acc[(size_t)p * 3 + 0]++;
-        if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
-        if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
-      }
-    }
+    li += adv;
     block_sync();
   }
-  for (int i = tid; i < NI; i += nth) E.all_i[(size_t)c * NI + i] = S.ai[i];
-  for (int i = tid; i < ND; i += nth) E.all_d[(size_t)c * ND + i] = S.ad[i];
-  for (int i = tid; i < M.nq; i += nth) E.qint[(size_t)c * kMaxParams + i] = S.q[i];
-  for (int i = tid; i < M.nm; i += nth) E.mint[(size_t)c * kMaxParams + i] = S.q[kMaxParams + i];
+  IMA_FOR_WARPS(w, NW) {
+    const int tid = w * IMA_WARP + lane, nth = NW * IMA_WARP;
+    for (int i = tid; i < NI; i += nth) E.all_i[(size_t)c * NI + i] = S.ai[i];
+    for (int i = tid; i < ND; i += nth) E.all_d[(size_t)c * ND + i] = S.ad[i];
+    for (int i = tid; i < M.nq; i += nth) E.qint[(size_t)c * kMaxParams + i] = S.q[i];
+    for (int i = tid; i < M.nm; i += nth) E.mint[(size_t)c * kMaxParams + i] = S.q[kMaxParams + i];
+  }
 #if IMA_CUDA
   __threadfence_block();
 #endif
   block_sync();
-  if (w == 0) {
-    const double ssum = (l1 == E.d.nloci) ? chain_swapsum(E, M, c, probg) : 0.0;
-    if (lane == 0) {
-      E.probg[c] = probg; E.pdgsum[c] = pdgsum;
-      if (l1 == E.d.nloci) E.swapsum[c] = ssum;
-      if (dropped) {
+  IMA_FOR_WARPS(w, NW) {
+    if (w == 0) {
+      const double ssum = (l1 == E.d.nloci) ? chain_swapsum(E, M, c, probg) : 0.0;
+      if (lane == 0) {
+        E.probg[c] = probg; E.pdgsum[c] = pdgsum;
+        if (l1 == E.d.nloci) E.swapsum[c] = ssum;
+        if (dropped) {
 #if IMA_CUDA
-        atomicAdd(E.overflow, dropped);
+          atomicAdd(E.overflow, dropped);
 #else
-        *E.overflow += dropped;
+          *E.overflow += dropped;
 #endif
+        }
       }
     }
   }

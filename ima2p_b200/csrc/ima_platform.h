@@ -147,12 +147,9 @@ struct Philox {
     if (have == 0) refill();
     return out[4 - (have--)];
   }
-  // uniform on the open interval (0,1), 53 bits (reference: genrand_real3, utilities.cpp:418)
-  IMA_HD double uniform() {
-    uint64_t a = next32(), b = next32();
-    uint64_t x = ((a << 32) | b) >> 11;
-    return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
-  }
+  // uniform on the open interval (0,1) with 32-bit resolution, exactly the grid of the reference's
+  // genrand_real3 (utilities.cpp:418 -> ((double)genrand_int32() + 0.5) / 2^32)
+  IMA_HD double uniform() { return ((double)next32() + 0.5) * (1.0 / 4294967296.0); }
   IMA_HD int randint(int n) { int v = (int)floor(uniform() * n); return v < n ? v : n - 1; }  // randposint :433
   IMA_HD int bit() { return (int)(next32() >> 31); }                                           // bitran :443
   // normdev utilities.cpp:472-500 (polar Box-Muller; the cached second deviate is not kept)

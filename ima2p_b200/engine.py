@@ -184,6 +184,10 @@ class Engine:
         """Cut a step into `pieces` locus ranges (accept sweep of one range overlaps the proposals of the next)."""
         self._ck(self.lib.ima2p_engine_set_pieces(self._h, pieces))
 
+    def set_speculation(self, depth):
+        """Loci evaluated per round of the accept sweep (1..3); the results do not depend on it."""
+        self._ck(self.lib.ima2p_engine_set_speculation(self._h, depth))
+
     def default_swaptries(self):
         return max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0             # ima_main_mpi.cpp:1378
 

@@ -112,6 +112,9 @@ int ima2p_engine_run (ima2p_engine * e, int nsteps, int swaptries, void *cuda_st
 /* number of locus ranges a step is cut into so that the accept sweep of one range overlaps the proposals of the
  * next (default 4; 1 = propose everything, then sweep) */
 int ima2p_engine_set_pieces (ima2p_engine * e, int pieces);
+/* speculative depth of the accept sweep (1..3): how many consecutive loci of a chain are evaluated per round against
+ * the same all-locus sums; results are identical for every depth (see csrc/ima_kernels.h k_accept) */
+int ima2p_engine_set_speculation (ima2p_engine * e, int depth);
 /* same steps, launched kernel by kernel with CUDA events on the launching stream around each kernel;
  * kernel_ms[3] = summed device time of {propose, accept, swap} (used for roofline accounting) */
 int ima2p_engine_run_timed (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms);
