@@ -117,7 +117,13 @@ static int launch_eval(Engine *e, stream_t s) {
   return IMA2P_OK;
 }
 
-static int accept_block_warps(int spec);
+static int accept_block_warps(int spec) { return IMA_CUDA ? spec * kTermWarps + 1 : 1; }
+static void launch_accept(Engine *e, stream_t s, int l0, int l1) {
+  const int nw = accept_block_warps(e->spec);
+  if (e->spec >= 3) IMA_LAUNCH(k_accept<3>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
+  else if (e->spec == 2) IMA_LAUNCH(k_accept<2>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
+  else IMA_LAUNCH(k_accept<1>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
+}
 // One step's genealogy updates.  The accept sweep is a dependent chain over the loci of a chain, the
 // proposals are independent per pair, and a proposal only needs its own pair's state -- so the loci are cut
 // into `pieces` ranges and the sweep of range q (stream s) overlaps the proposals of range q+1 (aux stream):
@@ -142,19 +148,15 @@ static void launch_update(Engine *e, stream_t s) {
     for (int q = 0; q < Q; q++) {
       const int l0 = (int)((long long)L * q / Q), l1 = (int)((long long)L * (q + 1) / Q);
       cudaStreamWaitEvent(s, e->ev_piece[q], 0);
-      IMA_LAUNCH(k_accept, e->d.nchains, accept_block_warps(e->spec), e->accept_smem, s, e->v, l0, l1, e->spec);
+      launch_accept(e, s, l0, l1);
     }
     return;
   }
 #endif
   const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
   IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, 0, L);
-  IMA_LAUNCH(k_accept, e->d.nchains, accept_block_warps(e->spec), e->accept_smem, s, e->v, 0, L, e->spec);
+  launch_accept(e, s, 0, L);
 }
-
-// warps per accept block: one per (speculative locus, term slot) plus the loader; the host emulation plays all of
-// them from a single thread (IMA_FOR_WARPS)
-static int accept_block_warps(int spec) { return IMA_CUDA ? spec * kTermWarps + 1 : 1; }
 
 static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries) {
   SwapView sv = e->sv;
@@ -700,7 +702,7 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
       cudaEventRecord(ev[i * 4 + 0], s);
       IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, 0, e.d.nloci);
       cudaEventRecord(ev[i * 4 + 1], s);
-      IMA_LAUNCH(k_accept, e.d.nchains, accept_block_warps(e.spec), e.accept_smem, s, e.v, 0, e.d.nloci, e.spec);
+      launch_accept(&e, s, 0, e.d.nloci);
       cudaEventRecord(ev[i * 4 + 2], s);
       launch_swap(&e, s, e.v.swapsum, swaptries);
       cudaEventRecord(ev[i * 4 + 3], s);

@@ -328,37 +328,46 @@ IMA_DEV AcceptSm carve_accept_smem(unsigned char *base, const EngineDims &d) {
   return s;
 }
 
+// depth 3: one 16-warp block per SM (<= 128 registers); depth 1 and 2: two blocks per SM (<= 93 registers), which is
+// what a GPU holding more chains than it has SMs needs
 #if IMA_CUDA
-#define IMA_ACCEPT_BOUNDS __launch_bounds__((kSpecMax * kTermWarps + 1) * 32, 1)
+#define IMA_ACCEPT_BOUNDS(B) __launch_bounds__(((B) * kTermWarps + 1) * 32, (B) == 3 ? 1 : 2)
 #else
-#define IMA_ACCEPT_BOUNDS
+#define IMA_ACCEPT_BOUNDS(B)
 #endif
-IMA_KERNEL void IMA_ACCEPT_BOUNDS k_accept(EngineView E, int l0, int l1, int spec) {
+template <int B>
+IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
   IMA_SMEM_DECL
   const int c = ima_block();
   if (c >= E.d.nchains) return;
   const DevModel &M = IMA_MODEL;
-  const int B = spec < 1 ? 1 : (spec > kSpecMax ? kSpecMax : spec);
   const int NW = B * kTermWarps + 1, LOADER = B * kTermWarps;       // warps in the block; the last one loads
   const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
   const int sI = (int)(align8(sizeof(int) * NI) / sizeof(int)), sD = (int)(align8(sizeof(double) * ND) / sizeof(double));
   AcceptSm S = carve_accept_smem(IMA_SMEM, E.d);
   const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
-  // ring slot of locus l: l % kRing.  The loader fills loci [filled, upto).
+  // ring slot of locus l: l % kRing.  The loader fills loci [from, upto): every load of every locus of the batch is
+  // issued before any is consumed (independent addresses), and the uniforms are drawn one locus per lane.
   auto load_records = [&](int from, int upto) {
-    for (int l = from; l < upto; l++) {
+    for (int l = from + lane; l < upto; l += IMA_WARP) {
       const int p = c * E.d.nloci + l, slot = l % kRing;
       const int cb = E.cur[p];
       const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
-      for (int i = lane; i < NI; i += IMA_WARP) S.r_dI[slot * sI + i] = N.gwi[(size_t)p * NI + i] - O.gwi[(size_t)p * NI + i];
-      for (int i = lane; i < ND; i += IMA_WARP) { S.r_oD[slot * sD + i] = O.gwd[(size_t)p * ND + i]; S.r_nD[slot * sD + i] = N.gwd[(size_t)p * ND + i]; }
-      if (lane == 0) {
-        S.r_ic[slot * 4 + 0] = (int)E.prop_flags[p]; S.r_ic[slot * 4 + 1] = cb;
-        S.r_sc[slot * 5 + 0] = O.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 5 + 1] = N.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 5 + 2] = E.prop_extra[p];
-        Philox rng;
-        rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + l), kRngAccept);
-        S.r_sc[slot * 5 + 3] = rng.uniform();
-      }
+      S.r_ic[slot * 4 + 0] = (int)E.prop_flags[p]; S.r_ic[slot * 4 + 1] = cb;
+      S.r_sc[slot * 5 + 0] = O.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 5 + 1] = N.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 5 + 2] = E.prop_extra[p];
+      Philox rng;
+      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + l), kRngAccept);
+      S.r_sc[slot * 5 + 3] = rng.uniform();
+    }
+    const int nl = upto - from, per = NI + 2 * ND;
+    for (int k = lane; k < nl * per; k += IMA_WARP) {
+      const int l = from + k / per, i = k - (l - from) * per;
+      const int p = c * E.d.nloci + l, slot = l % kRing;
+      const int cb = E.cur[p];
+      const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
+      if (i < NI) S.r_dI[slot * sI + i] = N.gwi[(size_t)p * NI + i] - O.gwi[(size_t)p * NI + i];
+      else if (i < NI + ND) S.r_oD[slot * sD + (i - NI)] = O.gwd[(size_t)p * ND + (i - NI)];
+      else S.r_nD[slot * sD + (i - NI - ND)] = N.gwd[(size_t)p * ND + (i - NI - ND)];
     }
   };
   IMA_FOR_WARPS(w, NW) {
@@ -426,25 +435,53 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS k_accept(EngineView E, int l0, int l1, int spe
     block_sync();
     // ---- phase 2: decisions in locus order (update_gtree.cpp:917-927) ----------------------------------------
     IMA_FOR_WARPS(w, NW) {
-      if (w == 0 && lane == 0) {
-        int accepted = -1, adv = nb;
+      if (w == 0) {
+        // lane g evaluates the MH ratio of speculative locus li+g (all against the same sums); the first accepting
+        // lane in locus order wins
+        bool acc = false;
+        double newprobg = 0.0;
+        if (lane < nb) {
+          const int g = lane, slot = (li + g) % kRing;
+          const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
+          if (!(flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree))) {
+            for (int t = 0; t < M.nq; t++) newprobg += S.cq[g * 2 * kMaxParams + t];
+            if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
+            if (M.nomigration == 0)
+              for (int i = 0; i < M.nomig_n; i++)
+                if (S.ai[ncc + M.nomig_idx[i]] + S.r_dI[slot * sI + ncc + M.nomig_idx[i]] != 0) newprobg = -kMyDblMax;
+            const double tpw = newprobg - probg, dpdg = S.r_sc[slot * 5 + 1] - S.r_sc[slot * 5 + 0], extra = S.r_sc[slot * 5 + 2];
+            double mh;
+            if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
+            else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
+            acc = S.r_sc[slot * 5 + 3] < fmin(1.0, mh);
+          }
+        }
+#if IMA_CUDA
+        const int accepted = Warp::first(acc);
+        const double np = Warp::bcast(newprobg, accepted < 0 ? 0 : accepted);
+        if (lane == 0) { S.ctl[0] = accepted; S.ctl[1] = accepted < 0 ? nb : accepted + 1; if (accepted >= 0) S.dctl[0] = np; }
+#else
+        // one lane: walk the speculative loci in order
+        int accepted = -1;
         for (int g = 0; g < nb && accepted < 0; g++) {
           const int slot = (li + g) % kRing;
           const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
           if (flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree)) continue;
-          double newprobg = 0.0;
-          for (int t = 0; t < M.nq; t++) newprobg += S.cq[g * 2 * kMaxParams + t];
-          if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
+          double npg = 0.0;
+          for (int t = 0; t < M.nq; t++) npg += S.cq[g * 2 * kMaxParams + t];
+          if (!M.nomigration) for (int t = 0; t < M.nm; t++) npg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
           if (M.nomigration == 0)
             for (int i = 0; i < M.nomig_n; i++)
-              if (S.ai[ncc + M.nomig_idx[i]] + S.r_dI[slot * sI + ncc + M.nomig_idx[i]] != 0) newprobg = -kMyDblMax;
-          const double tpw = newprobg - probg, dpdg = S.r_sc[slot * 5 + 1] - S.r_sc[slot * 5 + 0], extra = S.r_sc[slot * 5 + 2];
+              if (S.ai[ncc + M.nomig_idx[i]] + S.r_dI[slot * sI + ncc + M.nomig_idx[i]] != 0) npg = -kMyDblMax;
+          const double tpw = npg - probg, dpdg = S.r_sc[slot * 5 + 1] - S.r_sc[slot * 5 + 0], extra = S.r_sc[slot * 5 + 2];
           double mh;
           if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
           else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
-          if (S.r_sc[slot * 5 + 3] < fmin(1.0, mh)) { accepted = g; adv = g + 1; S.dctl[0] = newprobg; }
+          if (S.r_sc[slot * 5 + 3] < fmin(1.0, mh)) { accepted = g; S.dctl[0] = npg; }
         }
-        S.ctl[0] = accepted; S.ctl[1] = adv;
+        S.ctl[0] = accepted; S.ctl[1] = accepted < 0 ? nb : accepted + 1;
+        (void)acc; (void)newprobg;
+#endif
       }
     }
     block_sync();
