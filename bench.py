@@ -213,6 +213,8 @@ def main():
     eng, loci, st = build_engine(wl, rank, world)
     if args.pieces > 0:
         eng.set_pieces(args.pieces)
+    if os.environ.get("IMA_SPEC"):
+        eng.set_speculation(int(os.environ["IMA_SPEC"]))
     work_stream = torch.cuda.Stream()              # a real (non-default) stream: kernels, NCCL and the timing events all go here
     torch.cuda.set_stream(work_stream)
     stream = work_stream.cuda_stream

@@ -286,13 +286,13 @@ IMA_DEV double gamma_cf_coop(const MathCtx &mc, double a, double x) {
   for (int i0 = 1; i0 <= kItMax; i0 += IMA_WARP) {
     const int i = i0 + lane;
     const double an = -i * (i - a), b = b0 + 2.0 * i;
-    Mat2 md, mcm;
-    md.a = 0.0; md.b = 1.0; md.c = an; md.d = b;         // (N, D) <- (D, an N + b D)
-    mcm.a = b; mcm.b = an; mcm.c = 1.0; mcm.d = 0.0;     // (U, V) <- (b U + an V, U)
-    md = mat2_scan(md);
-    mcm = mat2_scan(mcm);
-    const double N = md.a * dprev + md.b, D = md.c * dprev + md.d;       // applied to (dprev, 1)
-    const double U = mcm.a * cprev + mcm.b, V = mcm.c * cprev + mcm.d;   // applied to (cprev, 1)
+    // c-recurrence matrix C_i = [[b, an], [1, 0]] acting on (U, V); the d-recurrence matrix is J C_i J (J swaps the two
+    // coordinates), so the product of the d-matrices is J (product of the C_i) J: one matrix scan serves both
+    Mat2 pc;
+    pc.a = b; pc.b = an; pc.c = 1.0; pc.d = 0.0;
+    pc = mat2_scan(pc);
+    const double U = pc.a * cprev + pc.b, V = pc.c * cprev + pc.d;       // applied to (cprev, 1)
+    const double N = pc.d * dprev + pc.c, D = pc.b * dprev + pc.a;       // J P J applied to (dprev, 1)
     // the reference clamps |an d + b| and |c| at FPMIN; if that would ever trigger, redo the call sequentially
     const bool guard = (fabs(D) < kFpMin * fabs(N)) || (fabs(U) < kFpMin * fabs(V)) || !(fabs(D) < DBL_MAX) || !(fabs(U) < DBL_MAX);
     if (Warp::any(guard)) return gamma_cf(mc, a, x);
