@@ -170,6 +170,7 @@ def reference_throughput(wl, world, steps, warmup, budget_s):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keeps NCCL's version banner off stdout (one JSON line only)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -314,6 +315,14 @@ def main():
         e2e_s = float(t.item())
     e2e_value = cpg * world * nloci * ke / e2e_s
     assert np.isfinite(summ).all()
+    # where an end-to-end step goes (each part synchronised on its own; untimed for the metric)
+    parts = {"upload_and_evaluate": 0.0, "step": 0.0, "read_back": 0.0}
+    for _ in range(10):
+        t0 = time.perf_counter(); eng.put_state(bufs, st["tvals"], stream); torch.cuda.synchronize()
+        t1 = time.perf_counter(); run_steps(1); torch.cuda.synchronize()
+        t2 = time.perf_counter(); eng.fetch_chain_summary(stream); eng.cold_row(); torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        parts["upload_and_evaluate"] += (t1 - t0) * 100; parts["step"] += (t2 - t1) * 100; parts["read_back"] += (t3 - t2) * 100
 
     if rank != 0:
         return
@@ -351,7 +360,7 @@ def main():
     config["l2"] = "working set %.1f MB per GPU (both state buffers) vs 126 MB L2: L2-resident; no flush (state is reused every step by design)" % (2 * sum(sb) / 1e6)
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-           "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke},
+           "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke, "parts_ms": parts},
            "gpu_launches": 3 * args.steps if world == 1 else 3 * args.steps,
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
            "unpipelined_ms_per_step": (graph_ms / args.steps) if graph_ms else None, "lmode": lmode,

@@ -444,6 +444,21 @@ int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const do
   return IMA2P_OK;
 }
 
+// recompute the running-maximum prefixes of the batch evaluated by the last phase-1 call with a (new) seed: the
+// maximum over the rows held by lower ranks, known only after the ranks have exchanged their local maxima
+int ima2p_lmode_joint_reseed(ima2p_lmode *h, int nvec, const double *seed_before, double *localmax_out) {
+  if (!h || !h->lm.d_cols || nvec < 1 || nvec > kJointVecMax || !localmax_out) return lfail(IMA2P_E_ARG, "joint_reseed: bad argument");
+  Lmode &l = h->lm;
+  if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = lm_stream(&l, nullptr);
+  const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
+  double *d_seed = nullptr;
+  if (seed_before) { d_seed = l.d_jout; if (!h2d(d_seed, seed_before, nvec * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed"); }
+  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, d_seed, l.d_prefix, l.d_lmax);
+  if (!d2h(localmax_out, l.d_lmax, nvec * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+  return IMA2P_OK;
+}
+
 int ima2p_lmode_joint_phase2(ima2p_lmode *h, int nvec, const double *globalmax, long long global_row0, double *records_out /* [nvec][6] */) {
   if (!h || !h->lm.d_cols || nvec < 1 || nvec > kJointVecMax || !globalmax || !records_out) return lfail(IMA2P_E_ARG, "joint_phase2: bad argument");
   Lmode &l = h->lm;

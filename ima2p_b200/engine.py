@@ -330,6 +330,12 @@ class LMode:
                                                                _dp(out)))
         return out
 
+    def joint_reseed(self, nvec, seed_before):
+        out = np.zeros(nvec)
+        sb = _f64(seed_before)
+        capi.check(self.lib, self.lib.ima2p_lmode_joint_reseed(self._h, nvec, _dp(sb), _dp(out)))
+        return out
+
     def joint_phase2(self, nvec, globalmax):
         rec = np.zeros((nvec, 6))
         capi.check(self.lib, self.lib.ima2p_lmode_joint_phase2(self._h, nvec, _dp(_f64(globalmax)), self.row0, _dp(rec)))

@@ -29,3 +29,53 @@ class ShardedStepper:
         st = self.eng.default_swaptries() if swaptries is None else swaptries
         for _ in range(nsteps):
             self.step(st)
+
+
+# ---- L mode: the sampled genealogies (.ti rows) shard by rank; README.md:117 of the reference: "a separate L mode run
+# will run in serial" -- here every evaluation is local partial sums plus one tiny collective ----------------------
+
+def sharded_margincalc(lm, x, yadjust, pi, logi, device="cpu"):
+    """margincalc (surface_call_functions.cpp:119-173) over rows sharded across ranks: all-reduce of nx doubles."""
+    import numpy as np
+    sums = torch.from_numpy(lm.marginal_sums(pi, x, round_counts=1)).to(device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    s = sums.cpu().numpy() / lm.nrows_total
+    if logi:
+        s = np.where(s <= 0, -1e200, np.log(np.where(s <= 0, 1.0, s)))
+    return s - yadjust
+
+
+def sharded_jointp(lm, x, calc_ess=True, device="cpu"):
+    """jointp (jointfind.cpp:885-1047) over rows sharded across ranks, <= 32 vectors per call.  Exchanges: the local
+    maxima (all-gather, gives every rank the maximum of the rows before it and the global maximum), then six doubles
+    per vector (sums all-reduced; the smallest kept term is the minimum over ranks)."""
+    import numpy as np
+    x = np.atleast_2d(x)
+    nv = len(x)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    local = torch.from_numpy(np.ascontiguousarray(lm.joint_phase1(x)).reshape(-1)).to(device)
+    if world > 1:
+        allmax = torch.zeros(world * nv, dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(allmax, local)
+        allmax = allmax.cpu().numpy().reshape(world, nv)
+    else:
+        allmax = local.cpu().numpy().reshape(1, nv)
+    gmax = allmax.max(axis=0)
+    if rank > 0:
+        lm.joint_reseed(nv, allmax[:rank].max(axis=0))
+    rec = torch.from_numpy(np.ascontiguousarray(lm.joint_phase2(nv, gmax)).reshape(-1)).to(device)
+    if world > 1:
+        allrec = torch.zeros(world * nv * 6, dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(allrec, rec)
+        allrec = allrec.cpu().numpy().reshape(world, nv, 6)
+    else:
+        allrec = rec.cpu().numpy().reshape(1, nv, 6)
+    q, ess = np.zeros(nv), np.zeros(nv)
+    for v in range(nv):
+        tot = allrec[:, v, :].sum(axis=0)
+        k = int(np.argmin(allrec[:, v, 4]))
+        tot[4], tot[5] = allrec[k, v, 4], allrec[k, v, 5]
+        q[v], ess[v] = lm.joint_finish(tot, gmax[v], calc_ess)
+    return q, ess

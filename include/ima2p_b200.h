@@ -179,10 +179,12 @@ int ima2p_lmode_jointp (ima2p_lmode * l, const double *x, int nvec, int calc_ess
 /* Sharded form (rows split over GPUs; the caller exchanges a few doubles per vector over NCCL):
  *   phase 1: p_g of every local row for nvec (<= 32) vectors; seed_before[v] = max of p over the rows held by
  *            lower ranks (NULL on rank 0); localmax_out[v] = max(seed, local rows)
+ *   reseed : same prefixes recomputed with the seed once it is known (after the ranks exchanged their local maxima)
  *   phase 2: given the global maximum, records_out[v] = {inserted, kept, sum, sum of squares, smallest kept p,
  *            its scaled term} over the local rows; global_row0 = global index of local row 0
  *   finish : the closing arithmetic of jointp (:1011-1046) on the records summed over ranks */
 int ima2p_lmode_joint_phase1 (ima2p_lmode * l, const double *x, int nvec, const double *seed_before, double *localmax_out);
+int ima2p_lmode_joint_reseed (ima2p_lmode * l, int nvec, const double *seed_before, double *localmax_out);
 int ima2p_lmode_joint_phase2 (ima2p_lmode * l, int nvec, const double *globalmax, long long global_row0,
                               double *records_out);
 void ima2p_lmode_joint_finish (const double *rec6, double globalmax, long long nrows_total, int calc_ess, double *q,

@@ -83,3 +83,49 @@ def test_two_ranks_reproduce_the_single_process_run():
         assert g[3]["swap_attempts"] == cnt1["swap_attempts"] and g[3]["swaps"] == cnt1["swaps"]
     assert sum(g[3]["accepted"] for g in got) == cnt1["accepted"]
     assert cnt1["swaps"] > 0
+
+
+def _lmode_worker(rank, world, port, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ima2p_b200 import LMode, capi
+    from ima2p_b200.multirank import sharded_jointp, sharded_margincalc
+    from support import FlatModel, load_golden
+    d = load_golden("lmode_sim5_hn2")
+    fm = FlatModel(d["model"])
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    G = len(rows)
+    cut = [0, G // 3 + 11, G]          # uneven shards
+    lm = LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=capi.bind(EMU))
+    lm.load(rows[cut[rank]:cut[rank + 1]], nrows_total=G, row0=cut[rank])
+    xs = np.array([j["x"] for j in d["jointp"]])[:32]
+    qv, ess = sharded_jointp(lm, xs)
+    tab = [t for t in d["margincalc"] if t[0] == 1]
+    mc = sharded_margincalc(lm, np.array([t[1] for t in tab]), 0.25, 1, 1)
+    q.put((rank, qv, ess, mc))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lmode_sharded_over_two_ranks_matches_reference():
+    from support import _num, load_golden, rel_close
+    subprocess.run([os.path.join(HERE, "hostemu", "build.sh")], check=True)
+    d = load_golden("lmode_sim5_hn2")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_lmode_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref_q = [j["q"] for j in d["jointp"]][:32]
+    ref_e = [j["ess"] for j in d["jointp"]][:32]
+    ref_mc = [_num(t[3]) for t in d["margincalc"] if t[0] == 1]
+    for _, qv, ess, mc in got:          # every rank ends with the same, reference-matching values
+        assert rel_close(qv, ref_q, 1e-10) and rel_close(ess, ref_e, 1e-8)
+        assert rel_close(mc, ref_mc, 1e-10)
