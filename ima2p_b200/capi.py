@@ -51,6 +51,9 @@ SIGNATURES = {
     "ima2p_engine_get_proposal": (_i, [_v, _i, _i, c_dbl_p, c_u32_p, c_int_p]),
     "ima2p_debug_gamma": (_i, [_i, c_int_p, c_dbl_p, _i, c_dbl_p]),
     "ima2p_engine_counters": (_i, [_v, c_u64_p]),
+    "ima2p_engine_thermo_accumulate": (_i, [_v, _v]),
+    "ima2p_engine_thermo_sums": (_i, [_v, c_dbl_p, _i]),
+    "ima2p_thermo_marginlike": (_i, [c_dbl_p, _i, _i, c_dbl_p]),
     "ima2p_engine_get_betas": (_i, [_v, c_dbl_p]),
     "ima2p_engine_cold_row": (_i, [_v, c_flt_p, c_int_p]),
     "ima2p_engine_sync": (_i, [_v]),

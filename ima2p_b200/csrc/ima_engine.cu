@@ -50,6 +50,7 @@ struct Engine {
   DevLocus *d_loci = nullptr;
   double *d_beta_table = nullptr;
   unsigned long long *d_swap_counts = nullptr;
+  double *d_thermosum = nullptr;
 #if IMA_CUDA
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -408,6 +409,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   e.sv.rank_of_chain = e.alloc<int>(G); e.sv.chain_of_rank = e.alloc<int>(G);
   e.d_beta_table = e.alloc<double>(G); e.sv.beta_table = e.d_beta_table;
   e.d_swap_counts = e.alloc<unsigned long long>(2); e.sv.swap_counts = e.d_swap_counts;
+  e.d_thermosum = e.alloc<double>(G);
   if (!v.acc || !v.buf[1].gwd || !e.d_swap_counts || !v.overflow) return fail(IMA2P_E_CUDA, "device allocation failed");
   stream_t s = pick_stream(&e, nullptr);
   bool ok = h2d(e.d_logfact, lf.data(), nlf * sizeof(double), s) && h2d(e.d_loci, dl.data(), dl.size() * sizeof(DevLocus), s);
@@ -826,6 +828,48 @@ int ima2p_engine_counters(ima2p_engine *h, uint64_t *out8) {
   uint64_t a = 0, t = 0, m = 0;
   for (size_t p = 0; p < (size_t)e.d.P; p++) { a += acc[p * 3]; t += acc[p * 3 + 1]; m += acc[p * 3 + 2]; }
   out8[0] = steps; out8[1] = steps * (uint64_t)e.d.P; out8[2] = a; out8[3] = t; out8[4] = m; out8[5] = sw[0]; out8[6] = sw[1]; out8[7] = ovf;
+  return IMA2P_OK;
+}
+
+// ---- thermodynamic integration (marglike.cpp) ------------------------------------------------------------------
+int ima2p_engine_thermo_accumulate(ima2p_engine *h, void *cuda_stream) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "thermo_accumulate: not finalized");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  const int per = kWarpsPerBlock * IMA_WARP;
+  IMA_LAUNCH(k_thermo_accumulate, (e.d.nchains + per - 1) / per, kWarpsPerBlock, 0, s, e.v, (const int *)e.sv.rank_of_chain, e.d_thermosum);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (thermo)");
+#endif
+  return IMA2P_OK;
+}
+
+// this rank's share of thermosum[] (zero where the chain at that temperature lives on another rank): sum over ranks
+int ima2p_engine_thermo_sums(ima2p_engine *h, double *thermosum_global, int reset) {
+  if (!h || !h->eng.finalized || !thermosum_global) return fail(IMA2P_E_ARG, "thermo_sums: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const size_t G = e.d.nchains_global;
+  if (!d2h(thermosum_global, e.d_thermosum, G * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  if (reset) {
+    std::vector<double> z(G, 0.0);
+    if (!h2d(e.d_thermosum, z.data(), G * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "upload failed");
+  }
+  return IMA2P_OK;
+}
+
+// thermomarginlikecalc (marglike.cpp:121-150): Simpson's rule over the evenly spaced betas, the hottest chain
+// (beta = 0) contributing 0; host arithmetic on numchains doubles, needs no device
+int ima2p_thermo_marginlike(const double *thermosum, int numchains, int k, double *out) {
+  if (!thermosum || !out || numchains < 2 || k < 1) return fail(IMA2P_E_ARG, "thermo_marginlike: bad argument");
+  const double width = 1.0 / (float)(numchains - 1);
+  double sum = 0.0;
+  for (int i = 0; i <= numchains - 1; i += 2)
+    if (i != numchains - 1) sum += 4.0 * (thermosum[i] / k);
+  for (int i = 1; i <= numchains - 2; i += 2) sum += 2.0 * (thermosum[i] / k);
+  *out = width * sum / 3.0;
   return IMA2P_OK;
 }
 

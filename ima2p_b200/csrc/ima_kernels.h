@@ -615,6 +615,13 @@ IMA_KERNEL void k_debug_gamma(MathCtx mc, const int *a, const double *x, int n, 
   }
 }
 
+// summarginlikecalc (marglike.cpp:51-87): thermosum[i] += allpcalc.pdg of the chain heated at beta_i.  Whole chains
+// move between temperatures in the serial reference; here only betas move, so the slot is the temperature rank.
+IMA_KERNEL void k_thermo_accumulate(EngineView E, const int *rank_of_chain, double *thermosum) {
+  const int i = ima_block() * kWarpsPerBlock * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
+  if (i < E.d.nchains) thermosum[rank_of_chain[E.d.chain0 + i]] += E.pdgsum[i];
+}
+
 IMA_KERNEL void k_copy_swapsum(EngineView E, double *dst) {
   const int i = ima_block() * kWarpsPerBlock * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
   if (i < E.d.nchains) dst[i] = E.swapsum[i];

@@ -219,6 +219,22 @@ class Engine:
         keys = ["steps", "updates", "accepted", "topology", "tmrca", "swap_attempts", "swaps", "dropped"]
         return dict(zip(keys, (int(v) for v in out)))
 
+    def thermo_accumulate(self, stream=None):
+        """summarginlikecalc (marglike.cpp:51-87) for the local chains."""
+        self._ck(self.lib.ima2p_engine_thermo_accumulate(self._h, stream))
+
+    def thermo_sums(self, reset=False):
+        out = np.zeros(self.nchains_global)
+        self._ck(self.lib.ima2p_engine_thermo_sums(self._h, _dp(out), int(reset)))
+        return out
+
+    def thermo_marginlike(self, thermosum, k):
+        """thermomarginlikecalc (marglike.cpp:121-150)."""
+        t = _f64(thermosum)
+        out = C.c_double()
+        self._ck(self.lib.ima2p_thermo_marginlike(_dp(t), len(t), int(k), C.byref(out)))
+        return out.value
+
     def betas(self):
         b = np.zeros(self.nchains_global)
         self._ck(self.lib.ima2p_engine_get_betas(self._h, _dp(b)))

@@ -134,6 +134,14 @@ int ima2p_engine_get_proposal (ima2p_engine * e, int ci, int li, double *out4, u
  * {uppergamma, lowergamma} in their one-lane form and in their warp-cooperative form for (a[i], x[i]) */
 int ima2p_debug_gamma (int device, const int *a, const double *x, int n, double *out);
 
+/* Thermodynamic integration (marglike.cpp:51-87 summarginlikecalc, :121-150 thermomarginlikecalc).
+ * accumulate: thermosum[slot of the chain's beta] += allpcalc.pdg for every local chain (call once per recorded step);
+ * thermo_sums: this rank's share of thermosum[nchains_global] (sum the shares over ranks), optionally reset;
+ * thermo_marginlike: the reference's Simpson rule over k recorded steps (host arithmetic). */
+int ima2p_engine_thermo_accumulate (ima2p_engine * e, void *cuda_stream);
+int ima2p_engine_thermo_sums (ima2p_engine * e, double *thermosum_global, int reset);
+int ima2p_thermo_marginlike (const double *thermosum, int numchains, int k, double *out);
+
 /* counters: out = {steps, updates tried, accepted, topology-changing accepted, tmrca-changing accepted,
  *                  swap attempts, swaps accepted, proposals dropped for capacity} */
 int ima2p_engine_counters (ima2p_engine * e, uint64_t * out8);

@@ -1917,3 +1917,146 @@ ora_jointp (const ora_model * m, const float *rows, int rowlen, int nrows, const
   free (ez);
   return log ((double) nrows) - sum;
 }
+
+
+/* ------------------------------------------------------------------------------------------- */
+/* changet_RY1: update_t_RY.cpp:52-80 (aftersplit, beforesplit), 222-517; getnewt               */
+/* update_gtree_common.cpp:2501-2519                                                            */
+/* ------------------------------------------------------------------------------------------- */
+
+double
+ora_getnewt (double U, int nloci, int npops, int timeperiod, double t_u_prior, double t_d_prior, double oldt)
+{
+  double twin, newt;
+  twin = (t_d_prior - t_u_prior) / (log ((double) nloci + 1) * (npops - timeperiod));
+  newt = (oldt - twin / 2) + U * twin;
+  if (newt >= t_d_prior)
+    newt = 2.0 * t_d_prior - newt;
+  else if (newt <= t_u_prior)
+    newt = 2.0 * t_u_prior - newt;
+  return newt;
+}
+
+static double
+ry_aftersplit (int tnode, int lastperiodnumber, double oldt, double newt, double tau_d, double ptime)
+{
+  if (tnode == lastperiodnumber - 1)
+    return ptime + newt - oldt;
+  return tau_d - (tau_d - newt) * (tau_d - ptime) / (tau_d - oldt);
+}
+
+static double
+ry_beforesplit (int tnode, double oldt, double newt, double tau_u, double ptime)
+{
+  if (tnode == 0)
+    return ptime * newt / oldt;
+  return tau_u + (ptime - tau_u) * (newt - tau_u) / (oldt - tau_u);
+}
+
+void
+ora_ry1_rescale (int numlines, const int *down, double *time, int nmig, double *mig_t, double *roottime,
+                 int timeperiod, int lastperiodnumber, double oldt, double newt, double t_u, double t_d, int *counts)
+{
+  int i;
+  /* :268-320; migration events sit on non-root edges only, so the per-edge loop over them is a flat one here */
+  for (i = 0; i < numlines; i++)
+    if (down[i] != -1)
+    {
+      if (time[i] <= oldt && time[i] > t_u)
+      {
+        time[i] = ry_beforesplit (timeperiod, oldt, newt, t_u, time[i]);
+        counts[0]++;
+      }
+      else if (time[i] > oldt && time[i] < t_d)
+      {
+        time[i] = ry_aftersplit (timeperiod, lastperiodnumber, oldt, newt, t_d, time[i]);
+        counts[1]++;
+      }
+    }
+  for (i = 0; i < nmig; i++)
+  {
+    if (mig_t[i] <= oldt && mig_t[i] > t_u)
+    {
+      mig_t[i] = ry_beforesplit (timeperiod, oldt, newt, t_u, mig_t[i]);
+      counts[2]++;
+    }
+    else if (mig_t[i] > oldt && mig_t[i] < t_d)
+    {
+      mig_t[i] = ry_aftersplit (timeperiod, lastperiodnumber, oldt, newt, t_d, mig_t[i]);
+      counts[3]++;
+    }
+  }
+  /* :321-328 */
+  if (*roottime <= oldt && *roottime > t_u)
+    *roottime = ry_beforesplit (timeperiod, oldt, newt, t_u, *roottime);
+  else if (*roottime > oldt && *roottime < t_d)
+    *roottime = ry_aftersplit (timeperiod, lastperiodnumber, oldt, newt, t_d, *roottime);
+}
+
+double
+ora_ry1_hastings (int timeperiod, int lastperiodnumber, double oldt, double newt, double t_u, double t_d, int ecu,
+                  int ecd, int emu, int emd)
+{
+  double t_u_hterm = (newt - t_u) / (oldt - t_u), t_d_hterm;
+  if (timeperiod == lastperiodnumber - 1)
+    t_d_hterm = 1;
+  else
+    t_d_hterm = (t_d - newt) / (t_d - oldt);
+  return (ecd + emd) * log (t_d_hterm) + (ecu + emu) * log (t_u_hterm);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* changeu / changekappa proposals: update_mc_params.cpp:201-212, 258-272                       */
+/* ------------------------------------------------------------------------------------------- */
+
+double
+ora_changeu_newr (double U, double r, double windowsize, double maxratio, double *d)
+{
+  double newr;
+  if (U > 0.5)
+    newr = r + (2.0 * U - 1.0) * windowsize;
+  else
+    newr = r - windowsize * U * 2.0;
+  if (newr > maxratio)
+    newr = 2.0 * maxratio - newr;
+  else if (newr < -maxratio)
+    newr = 2.0 * (-maxratio) - newr;
+  *d = exp ((newr - r) / 2);
+  return newr;
+}
+
+double
+ora_new_kappa (double U, double kappa, double win, double max)
+{
+  double nk;
+  if (U > 0.5)
+  {
+    nk = kappa + (2.0 * U - 1.0) * win;
+    if (nk > max)
+      nk = 2.0 * max - nk;
+  }
+  else
+  {
+    nk = kappa - win * U * 2.0;
+    if (nk < 0)
+      nk = -nk;
+  }
+  return nk;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* thermomarginlikecalc: marglike.cpp:121-150 (Simpson's rule; the beta = 0 chain contributes 0) */
+/* ------------------------------------------------------------------------------------------- */
+
+double
+ora_thermomarginlike (const double *thermosum, int numchains, int k)
+{
+  int i;
+  double width = 1.0 / (float) (numchains - 1), sum = 0.0;
+  for (i = 0; i <= numchains - 1; i += 2)
+    if (i != numchains - 1)
+      sum += 4.0 * (thermosum[i] / k);
+  for (i = 1; i <= numchains - 2; i += 2)
+    sum += 2.0 * (thermosum[i] / k);
+  return width * sum / 3.0;
+}

@@ -41,8 +41,27 @@ extern struct edgemiginfo oldedgemig, oldsismig, newedgemig, newsismig;
 void harness_init_p (void);                             /* mcmcfile.cpp:130, file-static */
 extern int rootmove;
 
+double harness_ry_last_mh (void);
+double harness_mc_last_mh (void);
+extern double thermosum[];                              /* marglike.cpp:23 */
+
 static FILE *jo;
 static std::map<std::string, std::string> kv;
+
+/* hooks named by the uniform() macro of the update_t_RY / update_mc_params shims */
+static int g_force_accept = 0;
+static std::vector<double> g_ulog;
+double harness_uniform_ry ()
+{
+  double u = uniform ();
+  return g_force_accept ? 1e-300 : u;       /* log(1e-300) is below any finite Metropolis-Hastings term */
+}
+double harness_uniform_mc ()
+{
+  double u = uniform ();
+  g_ulog.push_back (u);
+  return u;
+}
 
 static long
 kvl (const char *k, long dflt)
@@ -298,6 +317,7 @@ recompute_all (void)
   harness_init_p ();
 }
 
+static void dump_chain (int ci);
 static void
 dump_state (void)
 {
@@ -307,7 +327,18 @@ dump_state (void)
   fprintf (jo, "\"chains\":[");
   for (ci = 0; ci < numchains; ci++)
   {
-    fprintf (jo, "%s{\"beta\":", ci ? ",\n" : "");
+    fprintf (jo, "%s", ci ? ",\n" : "");
+    dump_chain (ci);
+  }
+  fprintf (jo, "]}\n");
+}
+
+static void
+dump_chain (int ci)
+{
+  int li;
+  {
+    fprintf (jo, "{\"beta\":");
     jd (beta[ci]);
     fputc (',', jo);
     jdarr ("tvals", C[ci]->tvals, numsplittimes, ",");
@@ -343,7 +374,6 @@ dump_state (void)
     }
     fprintf (jo, "]}");
   }
-  fprintf (jo, "]}\n");
 }
 
 static std::string g_start_trees;
@@ -808,6 +838,134 @@ mode_bench (long burn, long iters, long full, long chunks, long gburn)
   fprintf (jo, "]}\n");
 }
 
+/* split-time updates: changet_RY1() (update_t_RY.cpp:222-517) with the accept draw forced, so that the proposed
+ * state is visible afterwards; the Metropolis-Hastings term is what the reference passed to DMIN at :425 */
+static void
+mode_tupdates (long burn, long n, long between)
+{
+  do_burn (burn);
+  recompute_all ();
+  fprintf (jo, "{");
+  dump_model ();
+  fprintf (jo, "\"tprior_max\":[");
+  for (int k = 0; k < numsplittimes; k++)
+  {
+    if (k) fputc (',', jo);
+    jd (T[k].pr.max);
+  }
+  fprintf (jo, "],\"tprior_min\":[");
+  for (int k = 0; k < numsplittimes; k++)
+  {
+    if (k) fputc (',', jo);
+    jd (T[k].pr.min);
+  }
+  fprintf (jo, "],\n\"getnewt\":[");
+  for (int i = 0; i < 40; i++)
+  {
+    /* getnewt (update_gtree_common.cpp:2501-2519): the same generator state gives U and then newt(U) */
+    int period = i % numsplittimes;
+    double tu = 0.05 * (i % 3), td = T[period].pr.max - 0.1 * (i % 4), oldt = tu + (td - tu) * (0.03 + 0.94 * ((i * 7) % 40) / 40.0);
+    setseeds (1000 + i);
+    double u = uniform ();
+    setseeds (1000 + i);
+    double nt = getnewt (period, tu, td, oldt, 1);
+    fprintf (jo, "%s[%d,", i ? "," : "", period);
+    jd (tu); fputc (',', jo); jd (td); fputc (',', jo); jd (oldt); fputc (',', jo); jd (u); fputc (',', jo); jd (nt);
+    fputc (']', jo);
+  }
+  setseeds (77);
+  fprintf (jo, "],\n\"records\":[");
+  for (long it = 0; it < n; it++)
+  {
+    int ci = (int) (it % numchains), period = (int) ((it / numchains) % numsplittimes);
+    for (long b = 0; b < between; b++)
+    {
+      qupdate (0, 0, 1);
+      step++;
+    }
+    recompute_all ();
+    fprintf (jo, "%s{\"ci\":%d,\"period\":%d,\"before\":", it ? ",\n" : "", ci, period);
+    dump_chain (ci);
+    g_force_accept = 1;
+    int acc = changet_RY1 (ci, period);
+    g_force_accept = 0;
+    fprintf (jo, ",\"accepted\":%d,\"mh\":", acc);
+    jd (harness_ry_last_mh ());
+    fprintf (jo, ",\"after\":");
+    dump_chain (ci);
+    fputc ('}', jo);
+  }
+  fprintf (jo, "]}\n");
+}
+
+/* mutation-scalar updates: changeu() (update_mc_params.cpp:23-370), unforced; every uniform() the call drew is
+ * logged, the Metropolis-Hastings term is DMIN's second argument at :294 */
+static void
+mode_uupdates (long burn, long n, long between)
+{
+  do_burn (burn);
+  recompute_all ();
+  fprintf (jo, "{");
+  dump_model ();
+  fprintf (jo, "\"nurates\":%d,\"ul\":[", nurates);
+  for (int i = 0; i < nurates; i++)
+    fprintf (jo, "%s[%d,%d]", i ? "," : "", ul[i].l, ul[i].u);
+  fprintf (jo, "],\"u_prmax\":");
+  jd (L[0].u_rec[0].pr.max);
+  fprintf (jo, ",\"u_win\":");
+  jd (L[0].u_rec[0].win);
+  fprintf (jo, ",\"kappa_win\":");
+  jd (L[0].model == HKY ? L[0].kappa_rec->win : 0.0);
+  fprintf (jo, ",\"kappa_max\":");
+  jd (L[0].model == HKY ? L[0].kappa_rec->pr.max : 0.0);
+  fprintf (jo, ",\n\"records\":[");
+  for (long it = 0; it < n; it++)
+  {
+    int ci = (int) (it % numchains), j = (int) ((it / numchains) % (nurates - (nurates == 2))), k = -1;
+    for (long b = 0; b < between; b++)
+    {
+      qupdate (0, 0, 1);
+      step++;
+    }
+    recompute_all ();
+    fprintf (jo, "%s{\"ci\":%d,\"j\":%d,\"before\":", it ? ",\n" : "", ci, j);
+    dump_chain (ci);
+    g_ulog.clear ();
+    int acc = changeu (ci, j, &k);
+    fprintf (jo, ",\"k\":%d,\"accepted\":%d,\"mh\":", k, acc);
+    jd (harness_mc_last_mh ());
+    fputc (',', jo);
+    jdarr ("U", g_ulog.data (), (int) g_ulog.size (), ",");
+    fprintf (jo, "\"after\":");
+    dump_chain (ci);
+    fputc ('}', jo);
+  }
+  fprintf (jo, "]}\n");
+}
+
+/* thermomarginlikecalc (marglike.cpp:121-150) on synthetic per-temperature sums */
+static void
+mode_thermo (void)
+{
+  static const int ns[] = { 3, 4, 5, 8, 9, 16, 33, 128 };
+  const int keepn = numchains;
+  fprintf (jo, "{\"thermo\":[");
+  for (size_t t = 0; t < sizeof (ns) / sizeof (ns[0]); t++)
+  {
+    const int n = ns[t], k = 10 + 7 * (int) t;
+    numchains = n;
+    for (int i = 0; i < n; i++)
+      thermosum[i] = -k * (300.0 + 40.0 * sin (0.7 * i + t) + 2.5 * i);
+    fprintf (jo, "%s{\"k\":%d,", t ? ",\n" : "", k);
+    jdarr ("sums", thermosum, n, ",");
+    fprintf (jo, "\"value\":");
+    jd (thermomarginlikecalc (k));
+    fputc ('}', jo);
+  }
+  numchains = keepn;
+  fprintf (jo, "]}\n");
+}
+
 /* long-run summary statistics of the reference sampler with split times and mutation scalars held at their start
  * values: `sweeps` sweeps of updategenealogy() over every chain x locus after `gburn` untimed ones; per locus the
  * mean (over sweeps and chains) of tree length, root time, migration count and per-population coalescence counts,
@@ -988,6 +1146,12 @@ main (int argc, char *argv[])
     capture_start_trees ();
     mode_trace (kvl ("gburn", 1000), kvl ("sweeps", 20000), kvl ("nbatch", 20));
   }
+  else if (mode == "tupdates")
+    mode_tupdates (burn, kvl ("n", 40), kvl ("between", 3));
+  else if (mode == "uupdates")
+    mode_uupdates (burn, kvl ("n", 40), kvl ("between", 3));
+  else if (mode == "thermo")
+    mode_thermo ();
   else if (mode == "lbench")
     mode_lbench (burn, kvl ("rows", 100000), kvl ("evals", 50));
   else

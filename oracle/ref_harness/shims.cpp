@@ -53,6 +53,21 @@ double harness_get_sumlogk (int li) { return sumlogk[li] ? *sumlogk[li] : 0.0; }
 #include "mcmcfile.cpp"
 /* mcmcfile.cpp:130 is file-static */
 void harness_init_p (void) { init_p (); }
+#elif defined(SHIM_T_RY)
+/* every uniform() call of this file (the accept draw, update_t_RY.cpp:424) goes through a hook defined in
+ * harness_main.cpp, which can force acceptance; DMIN's second argument at :425 is the Metropolis-Hastings term */
+#define uniform harness_uniform_ry
+#include "update_t_RY.cpp"
+#undef uniform
+double harness_ry_last_mh (void) { return dminarg2; }
+
+#elif defined(SHIM_MC_PARAMS)
+/* uniform() calls of this file are logged (pick of k, the ratio draw, kappa draws, the accept draw) */
+#define uniform harness_uniform_mc
+#include "update_mc_params.cpp"
+#undef uniform
+double harness_mc_last_mh (void) { return dminarg2; }
+
 #else
 #error "select a shim"
 #endif

@@ -30,7 +30,12 @@ HEAT_LINEAR = ["-hfl", "-ha", "0.05"]
 COMMON = ["-b", "100", "-l", "100", "-p01", "-z", "100000000"]
 
 
+ONLY = set(sys.argv[1:])        # optional fixture names: regenerate just those
+
+
 def run(mode, name, ufile, hn, kv, extra=()):
+    if ONLY and name not in ONLY:
+        return
     out = os.path.join(TMP, name + ".json")
     cmd = [HARNESS, mode, out] + ["%s=%s" % p for p in kv.items()] + ["--", "-i", ufile, "-o",
           os.path.join(TMP, name + ".out")] + PRIORS + COMMON + ["-hn", str(hn)] + (HEAT if hn >= 4 else HEAT_LINEAR if hn > 1 else []) + list(extra)
@@ -44,6 +49,8 @@ def run(mode, name, ufile, hn, kv, extra=()):
 def run_trace(name, ufile, seeds, kv):
     """Long-run summary statistics of the reference's updategenealogy sampler (split times and mutation scalars held
     at their start values): several independently seeded runs merged into one fixture."""
+    if ONLY and name not in ONLY:
+        return
     import json
     merged = None
     for sd in seeds:
@@ -148,6 +155,14 @@ def main():
     run("kat", "kat_sim5_hn4", s5, 4, {"burn": 100})
     run("lmode", "lmode_sim5_hn2", s5, 2, {"burn": 200, "rows": 600, "every": 3})
     run("lmode", "lmode_sim5_expo_hn2", s5, 2, {"burn": 200, "rows": 300, "every": 3}, extra=["-j7"])
+    # split-time, mutation-scalar updates (section 8 f1) and thermodynamic integration (a16)
+    run("tupdates", "tupdates_sim5_hn2", s5, 2, {"burn": 100, "n": 30, "between": 3})
+    run("tupdates", "tupdates_sim5_3pop_hn2", p3, 2, {"burn": 100, "n": 24, "between": 3})
+    run("tupdates", "tupdates_sim3_sw_hn2", sw3, 2, {"burn": 100, "n": 12, "between": 3})
+    run("uupdates", "uupdates_sim5_hn2", s5, 2, {"burn": 100, "n": 40, "between": 2})
+    run("uupdates", "uupdates_sim5_hky_hn2", hky5, 2, {"burn": 60, "n": 20, "between": 2})
+    run("uupdates", "uupdates_sim3_sw_hn2", sw3, 2, {"burn": 100, "n": 16, "between": 2})
+    run("thermo", "kat_thermo", s5, 2, {})
     # statistical parity (north_star: posterior summaries from long runs agree with the reference)
     run_trace("trace_sim5", s5, [1, 2, 3, 4, 5, 6], {"gburn": 3000, "sweeps": 60000, "nbatch": 12})
     run_trace("trace_sim3", s3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12})

@@ -188,6 +188,17 @@ def oracle():
     lib.ora_margincalc.argtypes = [v, c_flt_p, i, i, d, d, i, i]
     lib.ora_jointp.restype = d
     lib.ora_jointp.argtypes = [v, c_flt_p, i, i, c_dbl_p, i, c_dbl_p]
+    lib.ora_getnewt.restype = d
+    lib.ora_getnewt.argtypes = [d, i, i, i, d, d, d]
+    lib.ora_ry1_rescale.argtypes = [i, c_int_p, c_dbl_p, i, c_dbl_p, c_dbl_p, i, i, d, d, d, d, c_int_p]
+    lib.ora_ry1_hastings.restype = d
+    lib.ora_ry1_hastings.argtypes = [i, i, d, d, d, d, i, i, i, i]
+    lib.ora_changeu_newr.restype = d
+    lib.ora_changeu_newr.argtypes = [d, d, d, d, c_dbl_p]
+    lib.ora_new_kappa.restype = d
+    lib.ora_new_kappa.argtypes = [d, d, d, d]
+    lib.ora_thermomarginlike.restype = d
+    lib.ora_thermomarginlike.argtypes = [c_dbl_p, i, i]
     lib.ora_last_error.restype = i
     _ORACLE = lib
     return lib
@@ -335,3 +346,36 @@ def check_static_eval(eng, fm, d, chains=None, rtol=1e-9):
         assert rel_close(cr["qintegrate"], ch["qintegrate"], rtol), (cr["qintegrate"], ch["qintegrate"])
         assert rel_close(cr["mintegrate"], ch["mintegrate"], rtol)
         assert rel_close(cr["probg"], ch["probg"], rtol) and rel_close(cr["pdg"], ch["pdg"], rtol)
+
+
+# ---- split-time (Rannala-Yang) and mutation-scalar updates: shared pieces of the oracle-side restatement -------------
+TIMEMAX = 1000000.0
+
+
+def ry1_bounds(tvals, period, nsplit):
+    """t_u, t_d of changet_RY1 (update_t_RY.cpp:242-246)."""
+    t_u = 0.0 if period == 0 else tvals[period - 1]
+    t_d = TIMEMAX if period == nsplit - 1 else tvals[period + 1]
+    return t_u, t_d
+
+
+def ry1_rescale_tree(tree, period, nsplit, oldt, newt, t_u, t_d, counts):
+    """In-place oracle rescaling of one FlatTree; counts (int32[4]) accumulates."""
+    rt = C.c_double(tree.roottime)
+    nmig = int(tree.mig_off[-1])
+    oracle().ora_ry1_rescale(tree.numlines, ip(tree.down), dp(tree.time), nmig, dp(tree.mig_t), C.byref(rt), period, nsplit,
+                             oldt, newt, t_u, t_d, ip(counts))
+    tree.roottime = rt.value
+
+
+def changeu_replay(U, j, nurates):
+    """The draws of one changeu() call in order (update_mc_params.cpp:78-90, 201-212): returns k and the ratio draw."""
+    it = iter(U)
+    if nurates > 2:
+        while True:
+            k = int(next(it) * nurates)
+            if k != j and 0 <= k < nurates:
+                break
+    else:
+        k = 1
+    return k, next(it), list(it)

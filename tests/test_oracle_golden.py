@@ -5,6 +5,8 @@ written by oracle/_ref/ref_harness, i.e. by the reference's own functions (tests
 Tolerances: integers bit-exact; doubles 1e-12 relative (same recurrences, same operation order, both
 sides FMA-free gcc builds) unless noted.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -181,3 +183,88 @@ def test_ti_row_packer_matches_reference_rows():
     assert row[3 * nq + 2 * nm + nq + nm] == np.float32(ch["pdg"])
     assert row[-1] == np.float32(ch["tvals"][0])
     assert row[nq:2 * nq].tolist() == [np.float32(v) for v in w["fc"]]
+
+
+# ---- section 8 (f1): split-time and mutation-scalar updates; a16 thermodynamic integration -----------------------
+def test_getnewt_matches_reference():
+    d = load_golden("tupdates_sim5_hn2")
+    nloci, npops = len(d["loci"]), d["model"]["npops"]
+    for period, tu, td, oldt, U, newt in d["getnewt"]:
+        assert oracle().ora_getnewt(U, nloci, npops, period, tu, td, oldt) == newt
+
+
+@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2"])
+def test_rannala_yang_rescaling_matches_reference(name):
+    """changet_RY1 with the accept draw forced: the oracle's rescaled genealogies equal the reference's bit for bit
+    and its Hastings term + the reference's own likelihood/prior differences give the reference's MH term."""
+    from support import ry1_bounds, ry1_rescale_tree
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    om = OracleModel(fm)
+    for rec in d["records"]:
+        b, a, period = rec["before"], rec["after"], rec["period"]
+        assert rec["accepted"] == 1
+        oldt, newt = b["tvals"][period], a["tvals"][period]
+        t_u, t_d = ry1_bounds(b["tvals"], period, fm.nsplit)
+        counts = np.zeros(4, np.int32)
+        for li, (gb, ga) in enumerate(zip(b["G"], a["G"])):
+            t, ta = FlatTree(gb["tree"]), FlatTree(ga["tree"])
+            ry1_rescale_tree(t, period, fm.nsplit, oldt, newt, t_u, t_d, counts)
+            assert np.array_equal(t.time, ta.time) and np.array_equal(t.mig_t, ta.mig_t) and t.roottime == ta.roottime
+            # the rescaled genealogy evaluates to the reference's new weights and likelihood
+            w = om.treeweight(a["tvals"], d["loci"][li], t)
+            assert np.array_equal(w["cc"], ga["gweight"]["cc"]) and np.array_equal(w["mc"], ga["gweight"]["mc"])
+            assert rel_close(w["fc"], ga["gweight"]["fc"], 1e-12) and rel_close(w["fm"], ga["gweight"]["fm"], 1e-12)
+        assert counts[0] % 2 == 0 and counts[1] % 2 == 0
+        h = oracle().ora_ry1_hastings(period, fm.nsplit, oldt, newt, t_u, t_d, int(counts[0]) // 2, int(counts[1]) // 2,
+                                      int(counts[2]), int(counts[3]))
+        mh = b["beta"] * ((a["pdg"] - b["pdg"]) + (a["probg"] - b["probg"])) + h
+        assert rel_close(mh, rec["mh"], 1e-10, 1e-10), (mh, rec["mh"])
+
+
+@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2"])
+def test_mutation_scalar_update_matches_reference(name):
+    """changeu replayed from the uniforms the reference drew: same partner k, same new scalars, same MH term."""
+    from support import changeu_replay
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    om = OracleModel(fm)
+    nur, ul = d["nurates"], d["ul"]
+    win, maxratio = d["u_win"], 3.0 * d["u_prmax"]
+    for rec in d["records"]:
+        b, a, j = rec["before"], rec["after"], rec["j"]
+        k, U, rest = changeu_replay(rec["U"], j, nur)
+        assert k == rec["k"]
+        (lj, aj), (lk, ak) = ul[j], ul[k]
+        uj, uk = b["G"][lj]["uvals"][aj], b["G"][lk]["uvals"][ak]
+        dd = C.c_double()
+        oracle().ora_changeu_newr(U, float(np.log(uj / uk)), win, maxratio, C.byref(dd))
+        nuj, nuk = uj * dd.value, uk / dd.value
+        if rec["accepted"]:
+            assert a["G"][lj]["uvals"][aj] == nuj and a["G"][lk]["uvals"][ak] == nuk
+        likenewsum = 0.0
+        for (li, ai, unew) in ((lj, aj, nuj), (lk, ak, nuk)):
+            g, loc = b["G"][li], d["loci"][li]
+            t = FlatTree(g["tree"])
+            if loc["model"] == 0:
+                new = om.likelihood_is(loc, t, g["length"], unew)
+            elif loc["model"] == 1:
+                nk = oracle().ora_new_kappa(rest.pop(0), g["kappa"], d["kappa_win"], d["kappa_max"])
+                if rec["accepted"]:
+                    assert a["G"][li]["kappa"] == nk
+                new = om.likelihood_hky(loc, t, g["pi"], unew, nk)
+            else:
+                new, _ = om.likelihood_sw(t, ai, unew)
+            if rec["accepted"]:
+                assert rel_close(new, a["G"][li]["pdg_a"][ai], 1e-12)
+            likenewsum += new - g["pdg_a"][ai]
+        assert len(rest) == 1                      # only the accept draw is left
+        mh = float(np.exp(b["beta"] * fm.gbeta * likenewsum))
+        assert rel_close(mh, rec["mh"], 1e-9, 1e-300), (mh, rec["mh"])
+        assert rec["accepted"] == int(rest[0] < min(1.0, mh))
+
+
+def test_thermodynamic_integration_matches_reference():
+    for t in load_golden("kat_thermo")["thermo"]:
+        s = f64(t["sums"])
+        assert rel_close(oracle().ora_thermomarginlike(dp(s), len(s), t["k"]), t["value"], 1e-14)
