@@ -51,6 +51,14 @@ SIGNATURES = {
     "ima2p_engine_get_proposal": (_i, [_v, _i, _i, c_dbl_p, c_u32_p, c_int_p]),
     "ima2p_debug_gamma": (_i, [_i, c_int_p, c_dbl_p, _i, c_dbl_p]),
     "ima2p_engine_counters": (_i, [_v, c_u64_p]),
+    "ima2p_engine_set_update_schedule": (_i, [_v, _i, _i]),
+    "ima2p_engine_set_update_priors": (_i, [_v, c_dbl_p, c_dbl_p, _d, _d, _d, _d]),
+    "ima2p_engine_update_counters": (_i, [_v, c_u64_p]),
+    "ima2p_engine_get_split_times": (_i, [_v, _i, c_dbl_p]),
+    "ima2p_engine_fetch_parameters": (_i, [_v, c_dbl_p, c_dbl_p, c_dbl_p]),
+    "ima2p_engine_get_scalars": (_i, [_v, _i, _i, c_dbl_p, c_dbl_p]),
+    "ima2p_engine_debug_split_time": (_i, [_v, _i, c_dbl_p, _i, c_dbl_p]),
+    "ima2p_engine_debug_changeu": (_i, [_v, _i, _i, _i, _d, _d, _d, c_dbl_p]),
     "ima2p_engine_thermo_accumulate": (_i, [_v, _v]),
     "ima2p_engine_thermo_sums": (_i, [_v, c_dbl_p, _i]),
     "ima2p_thermo_marginlike": (_i, [c_dbl_p, _i, _i, c_dbl_p]),
@@ -75,6 +83,7 @@ SIGNATURES = {
     "ima2p_lmode_joint_finish": (None, [c_dbl_p, _d, _ll, _i, c_dbl_p, c_dbl_p]),
 }
 
+MAX_LINKED = 4          # IMA2P_MAX_LINKED
 E_ARG, E_CUDA, E_UNSUPPORTED, E_DEVICE, E_CAPACITY = -1, -2, -3, -4, -5
 
 

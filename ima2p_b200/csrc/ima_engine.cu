@@ -5,6 +5,7 @@
 // replayed; the step counter that feeds the counter-based RNG lives on the device so the graph needs no
 // parameter updates.
 #include "ima_kernels.h"
+#include "ima_updates.h"
 #include "../../include/ima2p_b200.h"
 #include <string>
 #include <vector>
@@ -51,6 +52,9 @@ struct Engine {
   double *d_beta_table = nullptr;
   unsigned long long *d_swap_counts = nullptr;
   double *d_thermosum = nullptr;
+  UpdateView uv{};              // split-time / mutation-scalar updates
+  int t_updates = 0, u_every = 0;
+  std::vector<int> h_ul_l, h_ul_a;
 #if IMA_CUDA
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -130,7 +134,28 @@ static void launch_accept(Engine *e, stream_t s, int l0, int l1) {
 // into `pieces` ranges and the sweep of range q (stream s) overlaps the proposals of range q+1 (aux stream):
 //     P0 -> [A0 | P1] -> [A1 | P2] -> ... -> A(Q-1)          step time ~ P/Q + A instead of P + A.
 // Works under stream capture too (the event record/wait pairs become graph edges).
+// the rest of qupdate's schedule (ima_main_mpi.cpp:1867-1945): a split-time update of every chain each step
+// (TUPDATEINC 0), the mutation scalars every u_every-th step (UUPDATEINC 4); both are local to a chain
+static void launch_param_updates(Engine *e, stream_t s) {
+  const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (e->t_updates && e->model.nsplit > 0) {
+    IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
+    IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e->d) * kWarpsPerBlock, s, e->v, e->uv);
+  }
+  if (e->u_every > 0 && (e->uv.nurates > 1 || e->loci[0].d.model == kHKY)) {
+    UpdateView u = e->uv;
+    u.u_every = e->u_every;
+    IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, u);
+  }
+}
+
+static void launch_update_genealogies(Engine *e, stream_t s);
 static void launch_update(Engine *e, stream_t s) {
+  launch_update_genealogies(e, s);
+  launch_param_updates(e, s);
+}
+
+static void launch_update_genealogies(Engine *e, stream_t s) {
   const int gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock, L = e->d.nloci;
   int Q = e->pieces < 1 ? 1 : e->pieces;
   if (Q > L) Q = L;
@@ -358,7 +383,9 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   if (e.pair_smem * kWarpsPerBlock > 227 * 1024) return fail(IMA2P_E_ARG, "finalize: pair does not fit in shared memory; lower mig_capacity");
   e.overlap_smem = e.pair_smem * kWarpsPerBlock;
   if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
-      !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))))
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_rescale_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
   if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");
 #else
@@ -410,6 +437,25 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   e.d_beta_table = e.alloc<double>(G); e.sv.beta_table = e.d_beta_table;
   e.d_swap_counts = e.alloc<unsigned long long>(2); e.sv.swap_counts = e.d_swap_counts;
   e.d_thermosum = e.alloc<double>(G);
+  {
+    // mutation-rate scalars in the order of readata.cpp:832-834; update parameters start at the reference's defaults
+    for (int li = 0; li < d.nloci; li++) for (int a = 0; a < e.loci[li].d.nlinked; a++) { e.h_ul_l.push_back(li); e.h_ul_a.push_back(a); }
+    UpdateView &u = e.uv;
+    u.nurates = (int)e.h_ul_l.size();
+    int *ul_l = e.alloc<int>(u.nurates), *ul_a = e.alloc<int>(u.nurates);
+    u.ul_l = ul_l; u.ul_a = ul_a;
+    u.t_counts = e.alloc<int>(P * 4); u.t_out = e.alloc<double>(C * 4); u.u_out = e.alloc<double>(C * 4);
+    u.stats = e.alloc<unsigned long long>(4);
+    if (!u.stats || !u.u_out) return fail(IMA2P_E_CUDA, "device allocation failed");
+    stream_t s0 = pick_stream(&e, nullptr);
+    if (!h2d(ul_l, e.h_ul_l.data(), u.nurates * sizeof(int), s0) || !h2d(ul_a, e.h_ul_a.data(), u.nurates * sizeof(int), s0) || !dev_sync(s0))
+      return fail(IMA2P_E_CUDA, "table upload failed");
+    for (int k = 0; k < kMaxPeriods; k++) { u.t_max[k] = kTimeMax; u.t_min[k] = 0.0; }
+    const double umax = log(10000.0);                      // UMAX, imamp.hpp:152; initialize.cpp:1448-1450, update_mc_params.cpp:52-56
+    u.u_win = umax / d.nloci; u.u_maxratio = 3.0 * umax;
+    u.kappa_win = 2.0; u.kappa_max = 100.0;                // initialize.cpp:1499-1501
+    u.t_forced = nullptr; u.t_forced_period = 0; u.t_force_accept = -1; u.u_forced = 0; u.u_every = 5;
+  }
   if (!v.acc || !v.buf[1].gwd || !e.d_swap_counts || !v.overflow) return fail(IMA2P_E_CUDA, "device allocation failed");
   stream_t s = pick_stream(&e, nullptr);
   bool ok = h2d(e.d_logfact, lf.data(), nlf * sizeof(double), s) && h2d(e.d_loci, dl.data(), dl.size() * sizeof(DevLocus), s);
@@ -828,6 +874,132 @@ int ima2p_engine_counters(ima2p_engine *h, uint64_t *out8) {
   uint64_t a = 0, t = 0, m = 0;
   for (size_t p = 0; p < (size_t)e.d.P; p++) { a += acc[p * 3]; t += acc[p * 3 + 1]; m += acc[p * 3 + 2]; }
   out8[0] = steps; out8[1] = steps * (uint64_t)e.d.P; out8[2] = a; out8[3] = t; out8[4] = m; out8[5] = sw[0]; out8[6] = sw[1]; out8[7] = ovf;
+  return IMA2P_OK;
+}
+
+// ---- split-time and mutation-scalar updates (update_t_RY.cpp, update_mc_params.cpp) ------------------------------
+int ima2p_engine_set_update_schedule(ima2p_engine *h, int t_updates, int u_every) {
+  if (!h || !h->eng.finalized || t_updates < 0 || u_every < 0) return fail(IMA2P_E_ARG, "set_update_schedule: bad argument");
+  Engine &e = h->eng;
+  if (e.t_updates != t_updates || e.u_every != u_every) e.graph_ready = false;
+  e.t_updates = t_updates; e.u_every = u_every;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_set_update_priors(ima2p_engine *h, const double *t_max, const double *t_min, double u_prior_max, double u_window,
+                                   double kappa_window, double kappa_max) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "set_update_priors: not finalized");
+  Engine &e = h->eng;
+  for (int k = 0; k < e.model.nsplit; k++) {
+    if (t_max) e.uv.t_max[k] = t_max[k];
+    if (t_min) e.uv.t_min[k] = t_min[k];
+  }
+  if (u_prior_max > 0) { e.uv.u_maxratio = 3.0 * u_prior_max; e.uv.u_win = u_window > 0 ? u_window : u_prior_max / e.d.nloci; }
+  else if (u_window > 0) e.uv.u_win = u_window;
+  if (kappa_window > 0) e.uv.kappa_win = kappa_window;
+  if (kappa_max > 0) e.uv.kappa_max = kappa_max;
+  e.graph_ready = false;
+  return IMA2P_OK;
+}
+
+// parity hook: one changet_RY1 on every chain with the proposed split times given (newt[nchains]); force_accept
+// -1 = draw, 0 = reject, 1 = accept; out[nchains][4] = period, proposed time, MH term, accepted
+int ima2p_engine_debug_split_time(ima2p_engine *h, int period, const double *newt, int force_accept, double *out) {
+  if (!h || !out) return fail(IMA2P_E_ARG, "debug_split_time: bad argument");
+  Engine &e = h->eng;
+  int rc = ensure_steppable(e);
+  if (rc) return rc;
+  if (e.model.nsplit < 1 || period < 0 || period >= e.model.nsplit) return fail(IMA2P_E_ARG, "debug_split_time: no such split time");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const size_t C = e.d.nchains;
+  double *d_newt = nullptr;
+  UpdateView u = e.uv;
+  if (newt) {
+    d_newt = e.alloc<double>(C);
+    if (!d_newt || !h2d(d_newt, newt, C * sizeof(double), s)) return fail(IMA2P_E_CUDA, "upload failed");
+    u.t_forced = d_newt; u.t_forced_period = period; u.t_force_accept = force_accept;
+  }
+  const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
+  IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e.d) * kWarpsPerBlock, s, e.v, u);
+  if (!d2h(out, e.uv.t_out, C * 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  return check_device_error(&e, s);
+}
+
+// parity hook: evaluates (never applies) one changeu proposal on one chain: scalars j and k, u_j *= d, u_k /= d, and
+// the proposed kappas of their loci when those are HKY; out[4] = new P(D|G) of j's part, of k's part, MH term, 0
+int ima2p_engine_debug_changeu(ima2p_engine *h, int chain, int j, int k, double d, double kappa_j, double kappa_k, double *out) {
+  if (!h || !out) return fail(IMA2P_E_ARG, "debug_changeu: bad argument");
+  Engine &e = h->eng;
+  int rc = ensure_steppable(e);
+  if (rc) return rc;
+  const int nur = e.uv.nurates;
+  if (chain < 0 || chain >= e.d.nchains || !(d > 0)) return fail(IMA2P_E_ARG, "debug_changeu: bad argument");
+  if (nur > 1 && (j < 0 || j >= nur || k < 0 || k >= nur || j == k)) return fail(IMA2P_E_ARG, "debug_changeu: bad scalar index");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  UpdateView u = e.uv;
+  u.u_forced = 1; u.u_chain = chain; u.u_j = j; u.u_k = k; u.u_d = d; u.u_kappa[0] = kappa_j; u.u_kappa[1] = kappa_k; u.u_every = 1;
+  const int gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
+  if (!d2h(out, e.uv.u_out + (size_t)chain * 4, 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  return check_device_error(&e, s);
+}
+
+// tries / accepts of the split-time and the mutation-scalar updates since the engine was created
+int ima2p_engine_update_counters(ima2p_engine *h, uint64_t *out4) {
+  if (!h || !h->eng.finalized || !out4) return fail(IMA2P_E_ARG, "update_counters: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  unsigned long long v[4];
+  if (!d2h(v, e.uv.stats, sizeof(v), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  for (int i = 0; i < 4; i++) out4[i] = v[i];
+  return IMA2P_OK;
+}
+
+// current split times of one chain: tvals[nsplit]
+int ima2p_engine_get_split_times(ima2p_engine *h, int ci, double *tvals) {
+  if (!h || !h->eng.finalized || !tvals) return fail(IMA2P_E_ARG, "get_split_times: bad argument");
+  Engine &e = h->eng;
+  if (ci < 0 || ci >= e.d.nchains) return fail(IMA2P_E_ARG, "get_split_times: index out of range");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  if (e.model.nsplit > 0 && (!d2h(tvals, e.v.tvals + (size_t)ci * kMaxPeriods, e.model.nsplit * sizeof(double), s) || !dev_sync(s)))
+    return fail(IMA2P_E_CUDA, "download failed");
+  return IMA2P_OK;
+}
+
+// every chain's split times (tvals[nchains][nsplit]) and every pair's scalars (uvals[P][IMA2P_MAX_LINKED], kappa[P]) in one call
+int ima2p_engine_fetch_parameters(ima2p_engine *h, double *tvals, double *uvals, double *kappa) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "fetch_parameters: not finalized");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const size_t C = e.d.nchains, P = e.d.P;
+  std::vector<double> tv(C * kMaxPeriods);
+  bool ok = true;
+  if (tvals) ok = ok && d2h(tv.data(), e.v.tvals, tv.size() * sizeof(double), s);
+  if (uvals) ok = ok && d2h(uvals, e.v.uvals, P * kMaxLinked * sizeof(double), s);
+  if (kappa) ok = ok && d2h(kappa, e.v.kappa, P * sizeof(double), s);
+  if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  if (tvals) for (size_t c = 0; c < C; c++) for (int k = 0; k < e.model.nsplit; k++) tvals[c * e.model.nsplit + k] = tv[c * kMaxPeriods + k];
+  return IMA2P_OK;
+}
+
+// current mutation-rate scalars and kappa of one (chain, locus): uvals[IMA2P_MAX_LINKED]
+int ima2p_engine_get_scalars(ima2p_engine *h, int ci, int li, double *uvals, double *kappa) {
+  if (!h || !h->eng.finalized || !uvals) return fail(IMA2P_E_ARG, "get_scalars: bad argument");
+  Engine &e = h->eng;
+  if (ci < 0 || ci >= e.d.nchains || li < 0 || li >= e.d.nloci) return fail(IMA2P_E_ARG, "get_scalars: bad index");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const size_t p = (size_t)ci * e.d.nloci + li;
+  double k = 0.0;
+  if (!d2h(uvals, e.v.uvals + p * kMaxLinked, kMaxLinked * sizeof(double), s) || !d2h(&k, e.v.kappa + p, sizeof(double), s) || !dev_sync(s))
+    return fail(IMA2P_E_CUDA, "download failed");
+  if (kappa) *kappa = k;
   return IMA2P_OK;
 }
 

@@ -171,7 +171,10 @@ class Engine:
         wi, wd = np.zeros(self.NI, np.int32), np.zeros(self.ND)
         q, m, od = np.zeros(max(self.nq, 1)), np.zeros(max(self.nm, 1)), np.zeros(3)
         self._ck(self.lib.ima2p_engine_get_chain(self._h, ci, _ip(wi), _dp(wd), _dp(q), _dp(m), _dp(od)))
-        return dict(wi=wi, wd=wd, qintegrate=q[:self.nq], mintegrate=m[:self.nm], probg=od[0], pdg=od[1], beta=od[2])
+        tv = np.zeros(max(self.nsplit, 1))
+        self._ck(self.lib.ima2p_engine_get_split_times(self._h, ci, _dp(tv)))
+        return dict(wi=wi, wd=wd, qintegrate=q[:self.nq], mintegrate=m[:self.nm], probg=od[0], pdg=od[1], beta=od[2],
+                    tvals=tv[:self.nsplit])
 
     # ---- M mode --------------------------------------------------------------------------------------------
     def run(self, nsteps, swaptries=None, stream=None):
@@ -218,6 +221,46 @@ class Engine:
         self._ck(self.lib.ima2p_engine_counters(self._h, out.ctypes.data_as(capi.c_u64_p)))
         keys = ["steps", "updates", "accepted", "topology", "tmrca", "swap_attempts", "swaps", "dropped"]
         return dict(zip(keys, (int(v) for v in out)))
+
+    def set_update_schedule(self, t_updates=True, u_every=5):
+        """Split-time updates every step and mutation-scalar updates every ``u_every``-th (ima_main_mpi.cpp:1784-1785)."""
+        self._ck(self.lib.ima2p_engine_set_update_schedule(self._h, int(bool(t_updates)), int(u_every)))
+
+    def set_update_priors(self, t_max=None, t_min=None, u_prior_max=0.0, u_window=0.0, kappa_window=0.0, kappa_max=0.0):
+        tm = None if t_max is None else _f64(np.atleast_1d(t_max))
+        tn = None if t_min is None else _f64(np.atleast_1d(t_min))
+        self._ck(self.lib.ima2p_engine_set_update_priors(self._h, None if tm is None else _dp(tm), None if tn is None else _dp(tn),
+                                                         u_prior_max, u_window, kappa_window, kappa_max))
+
+    def update_counters(self):
+        out = (C.c_uint64 * 4)()
+        self._ck(self.lib.ima2p_engine_update_counters(self._h, out))
+        return dict(t_tries=out[0], t_accepts=out[1], u_tries=out[2], u_accepts=out[3])
+
+    def scalars(self, chain, locus):
+        u = np.zeros(capi.MAX_LINKED)
+        k = C.c_double()
+        self._ck(self.lib.ima2p_engine_get_scalars(self._h, chain, locus, _dp(u), C.byref(k)))
+        return u, k.value
+
+    def fetch_parameters(self):
+        """(tvals[nchains][nsplit], uvals[nchains][nloci][MAX_LINKED], kappa[nchains][nloci]) of the current state."""
+        tv = np.zeros((self.nchains, max(self.nsplit, 1)))
+        u = np.zeros((self.nchains, self.nloci, capi.MAX_LINKED))
+        k = np.zeros((self.nchains, self.nloci))
+        self._ck(self.lib.ima2p_engine_fetch_parameters(self._h, _dp(tv) if self.nsplit else None, _dp(u), _dp(k)))
+        return tv[:, :self.nsplit], u, k
+
+    def debug_split_time(self, period, newt=None, force_accept=-1):
+        out = np.zeros((self.nchains, 4))
+        nt = None if newt is None else _f64(newt)
+        self._ck(self.lib.ima2p_engine_debug_split_time(self._h, period, None if nt is None else _dp(nt), force_accept, _dp(out)))
+        return out
+
+    def debug_changeu(self, chain, j, k, d, kappa_j=0.0, kappa_k=0.0):
+        out = np.zeros(4)
+        self._ck(self.lib.ima2p_engine_debug_changeu(self._h, chain, j, k, d, kappa_j, kappa_k, _dp(out)))
+        return out
 
     def thermo_accumulate(self, stream=None):
         """summarginlikecalc (marglike.cpp:51-87) for the local chains."""

@@ -37,6 +37,7 @@ extern "C" {
 #define IMA2P_MODEL_IS 0        /* INFINITESITES */
 #define IMA2P_MODEL_HKY 1
 #define IMA2P_MODEL_SW 2        /* STEPWISE */
+#define IMA2P_MAX_LINKED 4       /* linked parts per locus kept on the device (reference MAXLINKED 15) */
 #define IMA2P_MAXLINKED 4
 
 typedef struct ima2p_engine ima2p_engine;
@@ -133,6 +134,33 @@ int ima2p_engine_get_proposal (ima2p_engine * e, int ci, int li, double *out4, u
 /* parity hook for the device numerics (uppergamma / lowergamma utilities.cpp:1053-1122): out[4*i..] =
  * {uppergamma, lowergamma} in their one-lane form and in their warp-cooperative form for (a[i], x[i]) */
 int ima2p_debug_gamma (int device, const int *a, const double *x, int n, double *out);
+
+/* The rest of one qupdate step (ima_main_mpi.cpp:1867-1945), local to each chain:
+ *   t_updates != 0 : a split-time update of every chain in every step -- changet_RY1, update_t_RY.cpp:222-517 (the
+ *                    reference picks between this and changet_NW at random);
+ *   u_every  > 0   : changeu for every mutation-rate scalar (update_mc_params.cpp:23-370; changekappa :381-431 when a
+ *                    single HKY locus is all there is) in every u_every-th step (the reference: 5, UUPDATEINC 4).
+ * Both default to off; ima2p_engine_run / update_genealogies then perform them after the genealogy updates.
+ * set_update_priors: split-time prior bounds T[].pr (t_max/t_min[nsplit], NULL keeps the current ones), the mutation
+ * scalar prior bound log(UMAX) and window (<= 0 keeps / derives initialize.cpp:1448-1450), kappa window and bound. */
+int ima2p_engine_set_update_schedule (ima2p_engine * e, int t_updates, int u_every);
+int ima2p_engine_set_update_priors (ima2p_engine * e, const double *t_max, const double *t_min, double u_prior_max,
+                                    double u_window, double kappa_window, double kappa_max);
+/* tries / accepts: out4 = split-time tries, accepts, mutation-scalar tries, accepts */
+int ima2p_engine_update_counters (ima2p_engine * e, uint64_t * out4);
+/* current split times C[ci]->tvals[nsplit] of one chain */
+int ima2p_engine_get_split_times (ima2p_engine * e, int chain, double *tvals);
+/* all of them at once: tvals[nchains][nsplit], uvals[P][IMA2P_MAX_LINKED], kappa[P] (any pointer may be NULL) */
+int ima2p_engine_fetch_parameters (ima2p_engine * e, double *tvals, double *uvals, double *kappa);
+/* mutation-rate scalars (uvals[IMA2P_MAX_LINKED]) and kappa of one (chain, locus) */
+int ima2p_engine_get_scalars (ima2p_engine * e, int chain, int locus, double *uvals, double *kappa);
+/* parity hooks (tests): one changet_RY1 with the proposed times given, newt[nchains] (NULL: drawn); force_accept -1
+ * draws the decision, 0 rejects, 1 accepts; out[nchains][4] = period, proposed time, log MH term, accepted.
+ * debug_changeu evaluates, and never applies, the proposal u_j *= d, u_k /= d on one chain:
+ * out[4] = new P(D|G) of j's part, of k's part, MH term (update_mc_params.cpp:291), 0 */
+int ima2p_engine_debug_split_time (ima2p_engine * e, int period, const double *newt, int force_accept, double *out);
+int ima2p_engine_debug_changeu (ima2p_engine * e, int chain, int j, int k, double d, double kappa_j, double kappa_k,
+                                double *out);
 
 /* Thermodynamic integration (marglike.cpp:51-87 summarginlikecalc, :121-150 thermomarginlikecalc).
  * accumulate: thermosum[slot of the chain's beta] += allpcalc.pdg for every local chain (call once per recorded step);

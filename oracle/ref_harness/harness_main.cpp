@@ -970,25 +970,83 @@ mode_thermo (void)
  * values: `sweeps` sweeps of updategenealogy() over every chain x locus after `gburn` untimed ones; per locus the
  * mean (over sweeps and chains) of tree length, root time, migration count and per-population coalescence counts,
  * with batch-means standard errors (nbatch batches).  Used for the statistical parity fixture. */
+/* diagnostic schedules built from the reference's own update functions: full=2 the engine's schedule (RY1 every
+ * step, changeu every 5th), full=3 NW only, full=4 RY1 only without changeu */
 static void
-mode_trace (long gburn, long sweeps, long nbatch)
+ry_only_rest (long it, long full)
+{
+  int k;
+  for (int ci = 0; ci < numchains; ci++)
+  {
+    int period = randposint (numsplittimes);
+    if (full == 3)
+      changet_NW (ci, period);
+    else
+      changet_RY1 (ci, period);
+  }
+  if ((it + 1) % 5 == 0 && nurates > 1 && full != 4)
+    for (int ci = 0; ci < numchains; ci++)
+      for (int j = 0; j < (nurates - (nurates == 2)); j++)
+        changeu (ci, j, &k);
+}
+
+static void
+mode_trace (long gburn, long sweeps, long nbatch, long full)
 {
   int ci, li, a, b, k;
   long it, bi;
+  /* full=1: whole qupdate() steps (genealogies, split times by RY1 or NW, mutation scalars); the split times and
+   * the log scalars are then summarised too */
+  std::vector<double> t0v, u0v;
+  for (k = 0; k < numsplittimes; k++)
+    t0v.push_back (C[0]->tvals[k]);
+  for (li = 0; li < nloci; li++)
+    u0v.push_back (C[0]->G[li].uvals[0]);
   for (it = 0; it < gburn; it++)
+  {
+    if (full == 1)
+    {
+      qupdate (0, 0, 1);
+      step++;
+      continue;
+    }
     for (ci = 0; ci < numchains; ci++)
       for (li = 0; li < nloci; li++)
         updategenealogy (ci, li, &a, &b);
+    if (full >= 2)
+      ry_only_rest (it, full);
+  }
   const int NS = 6;             /* length, roottime, mignum, cc0, cc1, cc2(+) */
   std::vector<double> bsum ((size_t) nbatch * nloci * NS, 0.0);
+  std::vector<double> tsum ((size_t) nbatch * (numsplittimes + 1), 0.0), usum ((size_t) nbatch * nloci, 0.0);
   long per = sweeps / nbatch, acc = 0, tries = 0;
   for (bi = 0; bi < nbatch; bi++)
     for (it = 0; it < per; it++)
+    {
+      if (full == 1)
+      {
+        qupdate (0, 0, 1);
+        step++;
+      }
+      if (full >= 2)
+      {
+        for (ci = 0; ci < numchains; ci++)
+          for (li = 0; li < nloci; li++)
+            updategenealogy (ci, li, &a, &b);
+        ry_only_rest (bi * per + it, full);
+      }
       for (ci = 0; ci < numchains; ci++)
+      {
+        for (k = 0; k < numsplittimes; k++)
+          tsum[(size_t) bi * (numsplittimes + 1) + k] += C[ci]->tvals[k];
         for (li = 0; li < nloci; li++)
         {
-          acc += updategenealogy (ci, li, &a, &b);
-          tries++;
+          if (!full)
+          {
+            acc += updategenealogy (ci, li, &a, &b);
+            tries++;
+          }
+          usum[(size_t) bi * nloci + li] += log (C[ci]->G[li].uvals[0]);
           struct genealogy *G = &C[ci]->G[li];
           double *o = &bsum[((size_t) bi * nloci + li) * NS];
           o[0] += G->length;
@@ -999,21 +1057,55 @@ mode_trace (long gburn, long sweeps, long nbatch)
           for (k = 1; k <= numsplittimes; k++)
             o[5] += G->gweight.cc[k][0];
         }
+      }
+    }
   fprintf (jo, "{");
   dump_model ();
-  fprintf (jo, "\"sweeps\":%ld,\"chains\":%d,\"nbatch\":%ld,\"accept\":%.6f,\"tvals\":[", per * nbatch, numchains, nbatch, (double) acc / tries);
+  fprintf (jo, "\"sweeps\":%ld,\"chains\":%d,\"nbatch\":%ld,\"full\":%ld,\"accept\":%.6f,\"tvals\":[", per * nbatch, numchains, nbatch, full,
+           tries ? (double) acc / tries : -1.0);
   for (k = 0; k < numsplittimes; k++)
   {
     if (k)
       fputc (',', jo);
-    jd (C[0]->tvals[k]);
+    jd (t0v[k]);
   }
   fprintf (jo, "],\"uvals\":[");
   for (li = 0; li < nloci; li++)
   {
     if (li)
       fputc (',', jo);
-    jd (C[0]->G[li].uvals[0]);
+    jd (u0v[li]);
+  }
+  fprintf (jo, "],\"tprior_max\":[");
+  for (k = 0; k < numsplittimes; k++)
+  {
+    if (k)
+      fputc (',', jo);
+    jd (T[k].pr.max);
+  }
+  fprintf (jo, "],\"t_batch_means\":[");
+  for (bi = 0; bi < nbatch; bi++)
+  {
+    fprintf (jo, "%s[", bi ? "," : "");
+    for (k = 0; k < numsplittimes; k++)
+    {
+      if (k)
+        fputc (',', jo);
+      jd (tsum[(size_t) bi * (numsplittimes + 1) + k] / ((double) per * numchains));
+    }
+    fputc (']', jo);
+  }
+  fprintf (jo, "],\"logu_batch_means\":[");
+  for (bi = 0; bi < nbatch; bi++)
+  {
+    fprintf (jo, "%s[", bi ? "," : "");
+    for (li = 0; li < nloci; li++)
+    {
+      if (li)
+        fputc (',', jo);
+      jd (usum[(size_t) bi * nloci + li] / ((double) per * numchains));
+    }
+    fputc (']', jo);
   }
   fprintf (jo, "],\"batch_means\":[");
   for (bi = 0; bi < nbatch; bi++)
@@ -1144,7 +1236,7 @@ main (int argc, char *argv[])
   else if (mode == "trace")
   {
     capture_start_trees ();
-    mode_trace (kvl ("gburn", 1000), kvl ("sweeps", 20000), kvl ("nbatch", 20));
+    mode_trace (kvl ("gburn", 1000), kvl ("sweeps", 20000), kvl ("nbatch", 20), kvl ("full", 0));
   }
   else if (mode == "tupdates")
     mode_tupdates (burn, kvl ("n", 40), kvl ("between", 3));

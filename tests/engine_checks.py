@@ -81,14 +81,29 @@ def proposals_match_oracle(lib, name, nsteps, rtol=1e-9, need_root_moves=True):
     return cnt
 
 
-def incremental_sums_match_fresh_evaluation(lib, name, nsteps, rtol=1e-9):
+def incremental_sums_match_fresh_evaluation(lib, name, nsteps, rtol=1e-9, full_schedule=False):
     """After many accepted/rejected updates (and swaps) the per-chain sums maintained by the accept kernel
     (sum_subtract_treeinfo + integrate_tree_prob with its reuse rule) equal a from-scratch evaluation."""
     d = load_golden(name)
     eng, fm = engine_from_fixture(d, lib=lib)
     eng.eval()
+    if full_schedule:           # split-time update every step, mutation scalars every 5th (qupdate's schedule)
+        eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+        eng.set_update_schedule(True, 5)
     eng.run(nsteps)
     eng.sync()
+    if full_schedule:
+        uc = eng.update_counters()
+        assert uc["t_tries"] == nsteps * eng.nchains and 0 < uc["t_accepts"] < uc["t_tries"]
+        nur = sum(l["nlinked"] for l in d["loci"])
+        if nur > 1:
+            assert uc["u_tries"] == (nsteps // 5) * eng.nchains * (nur - (nur == 2)) and 0 < uc["u_accepts"] < uc["u_tries"]
+        for c in range(eng.nchains):
+            tv = eng.chain(c)["tvals"][:fm.nsplit]
+            assert np.all(np.diff(np.concatenate([[0.0], tv, [3.0]])) > 0)          # ordered, inside the prior
+            logu = sum(float(np.sum(np.log(eng.scalars(c, l)[0][:d["loci"][l]["nlinked"]]))) for l in range(eng.nloci))
+            start = sum(float(np.sum(np.log(g["uvals"]))) for g in d["chains"][c]["G"])
+            assert abs(logu - start) < 1e-9                                         # the product of the scalars is invariant
     inc = [eng.chain(c) for c in range(eng.nchains)]
     incp = [[eng.pair(c, l) for l in range(eng.nloci)] for c in range(eng.nchains)]
     betas = eng.betas()
@@ -234,7 +249,7 @@ def stepwise_updates_match_oracle(lib, name, nsteps, rtol=1e-9):
     return cnt
 
 
-def long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=5.0):
+def long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=5.0, full_schedule=False):
     """Statistical parity (no RNG matching): with split times and mutation scalars held at the reference's start
     values, the engine's long-run per-locus means of tree length, root time, migration count and per-population
     coalescence counts agree with the reference's own updategenealogy() sampler (fixture written by
@@ -257,11 +272,21 @@ def long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=
                               t.roottime, uvals=[d["uvals"][li]])
     eng.upload()
     eng.eval()
+    if full_schedule:
+        # the whole qupdate schedule.  The reference mixes two split-time kernels (RY1 / NW), the engine uses RY1 only:
+        # different kernels, same stationary distribution, so the posterior summaries of t and of the scalars must agree
+        eng.set_update_priors(t_max=d["tprior_max"])
+        eng.set_update_schedule(True, 5)
     eng.run(burn, swaptries=0)
     acc = np.zeros((nchains, nloci, 6))
+    tacc, uacc = np.zeros((nchains, fm.nsplit)), np.zeros((nchains, nloci))
     ncc = fm.ncc
     for _ in range(sweeps):
         eng.run(1, swaptries=0)
+        if full_schedule:
+            tv, uv, _ = eng.fetch_parameters()
+            tacc += tv
+            uacc += np.log(uv[:, :, 0])
         sd, si, wi = eng.fetch_pair_summaries()
         sd, si, wi = sd.reshape(nchains, nloci, 4), si.reshape(nchains, nloci, 2), wi.reshape(nchains, nloci, -1)
         acc[:, :, 0] += sd[:, :, 1]
@@ -278,7 +303,87 @@ def long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=
     cnt = eng.counters()
     ref_acc = float(np.mean(d["accept"]))
     eng_acc = cnt["accepted"] / cnt["updates"]
+    if full_schedule:
+        def zscore(e, r):
+            e, r = e / sweeps, np.array(r)
+            return (e.mean(axis=0) - r.mean(axis=0)) / np.sqrt(e.var(axis=0, ddof=1) / nchains + r.var(axis=0, ddof=1) / len(r) + 1e-300)
+        zt, zu = zscore(tacc, d["t_batch_means"]), zscore(uacc, d["logu_batch_means"])
+        uc = eng.update_counters()
+        eng.close()
+        assert np.all(np.abs(z) < nsigma), (z, m_e, m_r)
+        assert np.all(np.abs(zt) < nsigma) and np.all(np.abs(zu) < nsigma), (zt, zu, tacc.mean(axis=0) / sweeps, uacc.mean(axis=0) / sweeps)
+        return z, zt, zu, tacc.mean(axis=0) / sweeps, np.array(d["t_batch_means"]).mean(axis=0), uc
     eng.close()
     assert np.all(np.abs(z) < nsigma), (z, m_e, m_r)
     assert abs(eng_acc - ref_acc) < 0.03, (eng_acc, ref_acc)
     return z, m_e, m_r, eng_acc, ref_acc
+
+
+def _one_chain_fixture(d, chain):
+    return {"model": d["model"], "loci": d["loci"], "chains": [chain]}
+
+
+def split_time_update_matches_reference(lib, name, rtol=1e-9):
+    """changet_RY1 (section 8 f1): with the reference's proposed time, the device's rescaled genealogies, weights,
+    likelihoods, prior and Metropolis-Hastings term equal the reference's (accept forced on both sides)."""
+    d = load_golden(name)
+    for rec in d["records"]:
+        b, a, period = rec["before"], rec["after"], rec["period"]
+        eng, fm = engine_from_fixture(_one_chain_fixture(d, b), lib=lib)
+        eng.eval()
+        eng.set_update_priors(t_max=d["tprior_max"], t_min=d["tprior_min"])
+        newt = a["tvals"][period]
+        # rejected first: nothing may move
+        out = eng.debug_split_time(period, [newt], force_accept=0)
+        assert out[0, 3] == 0 and rel_close(out[0, 2], rec["mh"], rtol, 1e-8), (out[0], rec["mh"])
+        check_static_eval(eng, fm, _one_chain_fixture(d, b), rtol=rtol)
+        out = eng.debug_split_time(period, [newt], force_accept=1)
+        assert out[0, 0] == period and out[0, 1] == newt and out[0, 3] == 1
+        assert rel_close(out[0, 2], rec["mh"], rtol, 1e-8), (out[0], rec["mh"])
+        check_static_eval(eng, fm, _one_chain_fixture(d, a), rtol=rtol)            # stored values == the reference's after the move
+        assert rel_close(eng.chain(0)["tvals"][:fm.nsplit], a["tvals"], 0.0)
+        for li, ga in enumerate(a["G"]):
+            t, ta = tree_from_engine(eng.get_genealogy(0, li)), FlatTree(ga["tree"])
+            assert rel_close(t.time, ta.time, 1e-14) and rel_close(t.roottime, ta.roottime, 1e-14)
+            assert rel_close(np.sort(t.mig_t[:-1]), np.sort(ta.mig_t[:-1]), 1e-14)
+        eng.eval()                                                                  # and a fresh evaluation agrees with them
+        check_static_eval(eng, fm, _one_chain_fixture(d, a), rtol=rtol)
+        eng.close()
+
+
+def mutation_scalar_update_matches_reference(lib, name, rtol=1e-8):
+    """changeu (section 8 f1): the reference's own proposals (partner, ratio step, kappas replayed from the uniforms
+    it drew) evaluated on the device give the reference's new likelihoods and Metropolis-Hastings term."""
+    import ctypes as C
+    from support import changeu_replay
+    d = load_golden(name)
+    nur, ul = d["nurates"], d["ul"]
+    for rec in d["records"]:
+        b, a, j = rec["before"], rec["after"], rec["j"]
+        k, U, rest = changeu_replay(rec["U"], j, nur)
+        (lj, aj), (lk, ak) = ul[j], ul[k]
+        uj, uk = b["G"][lj]["uvals"][aj], b["G"][lk]["uvals"][ak]
+        dd = C.c_double()
+        oracle().ora_changeu_newr(U, float(np.log(uj / uk)), d["u_win"], 3.0 * d["u_prmax"], C.byref(dd))
+        kap = [0.0, 0.0]
+        for i, li in enumerate((lj, lk)):
+            if d["loci"][li]["model"] == 1:
+                kap[i] = oracle().ora_new_kappa(rest.pop(0), b["G"][li]["kappa"], d["kappa_win"], d["kappa_max"])
+        eng, fm = engine_from_fixture(_one_chain_fixture(d, b), lib=lib)
+        eng.eval()
+        out = eng.debug_changeu(0, j, k, dd.value, kap[0], kap[1])
+        assert rel_close(out[2], rec["mh"], rtol, 1e-300), (out, rec["mh"])
+        if rec["accepted"]:
+            assert rel_close(out[0], a["G"][lj]["pdg_a"][aj], 1e-9) and rel_close(out[1], a["G"][lk]["pdg_a"][ak], 1e-9)
+        check_static_eval(eng, fm, _one_chain_fixture(d, b), rtol=1e-9)             # a debug evaluation changes nothing
+        eng.close()
+
+
+def thermodynamic_integration_matches_reference(lib):
+    from ima2p_b200 import Engine  # noqa: F401  (the Simpson rule is a host function of the same library)
+    import ctypes as C
+    for t in load_golden("kat_thermo")["thermo"]:
+        s = f64(t["sums"])
+        out = C.c_double()
+        assert lib.ima2p_thermo_marginlike(dp(s), len(s), t["k"], C.byref(out)) == 0
+        assert rel_close(out.value, t["value"], 1e-14)

@@ -46,7 +46,7 @@ def run(mode, name, ufile, hn, kv, extra=()):
     print("wrote", name + ".json.gz", os.path.getsize(os.path.join(HERE, name + ".json.gz")), "bytes")
 
 
-def run_trace(name, ufile, seeds, kv):
+def run_trace(name, ufile, seeds, kv, priors=None):
     """Long-run summary statistics of the reference's updategenealogy sampler (split times and mutation scalars held
     at their start values): several independently seeded runs merged into one fixture."""
     if ONLY and name not in ONLY:
@@ -56,7 +56,7 @@ def run_trace(name, ufile, seeds, kv):
     for sd in seeds:
         out = os.path.join(TMP, "%s_%d.json" % (name, sd))
         cmd = [HARNESS, "trace", out, "seed=%d" % sd] + ["%s=%s" % p for p in kv.items()] + ["--", "-i", ufile, "-o",
-              os.path.join(TMP, name + ".out")] + PRIORS + COMMON + ["-hn", "1"]
+              os.path.join(TMP, name + ".out")] + (priors or PRIORS) + COMMON + ["-hn", "1"]
         try:    # the reference itself occasionally spins forever for some seeds; such a run is dropped
             with open(os.path.join(TMP, name + ".log"), "w") as log:
                 subprocess.run(cmd, check=True, stdout=log, stderr=subprocess.STDOUT, cwd=TMP, timeout=120)
@@ -70,6 +70,8 @@ def run_trace(name, ufile, seeds, kv):
         else:
             assert d["tvals"] == merged["tvals"] and d["uvals"] == merged["uvals"]
             merged["batch_means"] += d["batch_means"]
+            merged["t_batch_means"] += d["t_batch_means"]
+            merged["logu_batch_means"] += d["logu_batch_means"]
             merged["accept"].append(d["accept"])
     with gzip.GzipFile(os.path.join(HERE, name + ".json.gz"), "wb", mtime=0) as g:
         g.write(json.dumps(merged).encode())
@@ -166,6 +168,11 @@ def main():
     # statistical parity (north_star: posterior summaries from long runs agree with the reference)
     run_trace("trace_sim5", s5, [1, 2, 3, 4, 5, 6], {"gburn": 3000, "sweeps": 60000, "nbatch": 12})
     run_trace("trace_sim3", s3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12})
+    # the same with a recent split time (most of every genealogy lies in the ancestral population)
+    run_trace("trace_sim3_recent", s3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12}, priors=["-q", "10", "-m", "1", "-t", "0.5"])
+    # whole qupdate steps: genealogies + split time (RY1 or NW) + mutation scalars; the posterior of t and of the scalars
+    run_trace("trace_full_sim5", s5, [11, 12, 13, 14, 15, 16], {"gburn": 5000, "sweeps": 60000, "nbatch": 12, "full": 1})
+    run_trace("trace_full_sim3", s3, [11, 12, 13, 14], {"gburn": 5000, "sweeps": 60000, "nbatch": 12, "full": 1})
 
 
 if __name__ == "__main__":

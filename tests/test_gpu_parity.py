@@ -71,3 +71,47 @@ def test_runs_are_reproducible_and_seed_dependent(lib):
         outs.append(np.array([eng.chain(c)["probg"] for c in range(eng.nchains)]))
         eng.close()
     assert np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])
+
+
+# ---- section 8 (f1): the rest of the step on the device ------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2"])
+def test_split_time_update_matches_reference(lib, name):
+    ec.split_time_update_matches_reference(lib, name)
+
+
+@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2"])
+def test_mutation_scalar_update_matches_reference(lib, name):
+    ec.mutation_scalar_update_matches_reference(lib, name)
+
+
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 2000), ("state_sim5_3pop_hn2", 500), ("state_sim50_hn3", 300),
+                                         ("state_sim3_sw_hn2", 300), ("state_sim5_hky_hn2", 100)])
+def test_incremental_sums_with_full_schedule(lib, name, nsteps):
+    ec.incremental_sums_match_fresh_evaluation(lib, name, nsteps, full_schedule=True)
+
+
+@pytest.mark.parametrize("name,nchains,burn,sweeps", [("trace_full_sim3", 64, 15000, 20000), ("trace_full_sim5", 64, 15000, 20000)])
+def test_full_schedule_posterior_matches_reference_sampler(lib, name, nchains, burn, sweeps):
+    z, zt, zu, tm, tr, uc = ec.long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, full_schedule=True)
+    assert abs(zt).max() < 5.0 and abs(zu).max() < 5.0
+
+
+def test_recent_split_time_statistics(lib):
+    z, _, _, _, _ = ec.long_run_summaries_match_reference(lib, "trace_sim3_recent", 256, 4000, 4000)
+    assert abs(z).max() < 5.0
+
+
+def test_thermodynamic_integration(lib):
+    ec.thermodynamic_integration_matches_reference(lib)
+    # accumulators: after k recorded steps every temperature slot holds k chain likelihood sums
+    d = ec.load_golden("state_sim5_hn4")
+    eng, fm = ec.engine_from_fixture(d, lib=lib)
+    eng.eval()
+    tot = 0.0
+    for _ in range(7):
+        eng.run(3)
+        eng.thermo_accumulate()
+        tot += sum(eng.chain(c)["pdg"] for c in range(eng.nchains))
+    s = eng.thermo_sums(reset=True)
+    assert ec.rel_close(s.sum(), tot, 1e-12) and np.all(s < 0) and np.all(eng.thermo_sums() == 0)
+    eng.close()

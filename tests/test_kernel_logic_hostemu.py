@@ -53,3 +53,35 @@ def test_long_run_statistics_match_reference_sampler(emu):
     # statistical parity of the whole sampler (proposal distributions, Hastings terms, prior, likelihood)
     z, _, _, eng_acc, ref_acc = ec.long_run_summaries_match_reference(emu, "trace_sim3", 64, 5000, 3000)
     assert abs(z).max() < 5.0
+
+
+@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2"])
+def test_split_time_update(emu, name):
+    ec.split_time_update_matches_reference(emu, name)
+
+
+@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2"])
+def test_mutation_scalar_update(emu, name):
+    ec.mutation_scalar_update_matches_reference(emu, name)
+
+
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 200), ("state_sim5_3pop_hn2", 100), ("state_sim3_sw_hn2", 60), ("state_sim5_hky_hn2", 30)])
+def test_incremental_sums_full_schedule(emu, name, nsteps):
+    ec.incremental_sums_match_fresh_evaluation(emu, name, nsteps, full_schedule=True)
+
+
+def test_thermodynamic_integration(emu):
+    ec.thermodynamic_integration_matches_reference(emu)
+
+
+def test_full_schedule_posterior_matches_reference_sampler(emu):
+    # genealogies + split time + mutation scalars: the posterior of t and of the scalars against whole qupdate() runs
+    # of the reference (the split time mixes slowly: a long burn-in is part of the test)
+    z, zt, zu, _, _, uc = ec.long_run_summaries_match_reference(emu, "trace_full_sim3", 8, 15000, 40000, full_schedule=True)
+    assert abs(zt).max() < 5.0 and abs(zu).max() < 5.0 and uc["t_accepts"] > 0 and uc["u_accepts"] > 0
+
+
+def test_recent_split_time_statistics(emu):
+    # the genealogy sampler where most of every genealogy lies in the ancestral population
+    z, _, _, _, _ = ec.long_run_summaries_match_reference(emu, "trace_sim3_recent", 16, 3000, 6000)
+    assert abs(z).max() < 5.0
