@@ -140,7 +140,7 @@ def run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn, ful
     return res, len(res)
 
 
-def reference_throughput(wl, world, steps, warmup, budget_s):
+def reference_throughput(wl, world, steps, warmup, budget_s, full=1):
     """(value updates/s over all host cores, ms per step, cores, sample description); each step is one chunk."""
     from ima2p_b200 import synth
     if not os.path.exists(HARNESS):
@@ -153,18 +153,18 @@ def reference_throughput(wl, world, steps, warmup, budget_s):
     ufile = os.path.join(tmp, "synthetic.u")
     synth.write_u(ufile, synth.make_dataset(nloci, n0, n1, seed=11))
     chains_pp = -(-total_chains // nproc)
-    est = 30000.0                                          # updates/s/core, survey probe
+    est = 30000.0 if not full else 17000.0                 # updates/s/core, survey probe
     chunks = steps + warmup
     iters = max(1, int(budget_s * est / (chunks * chains_pp * nloci)))
-    res, used = run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn=0, full=0, tmp=tmp, budget_s=budget_s)
+    res, used = run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn=0, full=full, tmp=tmp, budget_s=budget_s)
     if not res:
         return None
     chunk_s = np.array([r["chunk_seconds"] for r in res])            # [proc][chunk]
     upd = sum(r["updates_per_chunk"] for r in res)
     timed = chunk_s[:, warmup:]
     step_s = timed.max(axis=0).mean()
-    sample = "%d serial reference processes x %d chains, %d loci; %d updategenealogy sweeps per step" % (
-        used, chains_pp, nloci, iters)
+    sample = "%d serial reference processes x %d chains, %d loci; %d %s per step" % (
+        used, chains_pp, nloci, iters, "whole qupdate() steps" if full else "updategenealogy sweeps")
     return dict(value=upd / step_s, ms_per_step=step_s * 1e3, cores=used, sample=sample,
                 accept=sum(r["accepted"] for r in res) / max(1, sum(r["updates"] for r in res)))
 
@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--workload", default="sim50x128", choices=sorted(WORKLOADS))
     ap.add_argument("--burn", type=int, default=3000, help="untimed burn-in steps before warm-up (migration counts need ~3000 steps to settle)")
     ap.add_argument("--pieces", type=int, default=0, help="locus ranges per step (0 = engine default)")
+    ap.add_argument("--schedule", default="full", choices=["full", "genealogy"],
+                    help="full: qupdate's schedule (genealogies, split time every step, mutation scalars every 5th, swaps); "
+                         "genealogy: updategenealogy + swaps only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lmode", action="store_true")
     args = ap.parse_args()
@@ -189,12 +192,15 @@ def main():
     metric, unit = "chain_x_locus_genealogy_updates_per_sec", "updates/s"
     config = {"workload": desc, "chains_total": cpg * max(world, 1), "loci": nloci, "genes_per_locus": n0 + n1,
               "priors": "-q %g -m %g" % (PRIOR_Q, PRIOR_M), "heating": "-hfg -ha 0.96 -hb 0.9", "parallelism": "chains sharded by rank x%d" % world,
-              "l2": "inputs %s L2: state of all pairs is re-read every step; see l2_note" % "vs"}
+              "l2": "inputs %s L2: state of all pairs is re-read every step; see l2_note" % "vs",
+              "schedule": ("qupdate: updategenealogy for every chain x locus, split-time update of every chain (-t %g), mutation scalars "
+                           "every 5th step, swaps" % PRIOR_T) if args.schedule == "full" else "updategenealogy for every chain x locus + swaps"}
+    full = 1 if args.schedule == "full" else 0
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = reference_throughput(wl, world, args.steps, W, budget_s=100.0)
+        r = reference_throughput(wl, world, args.steps, W, budget_s=100.0, full=full)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness was not built (needs /root/reference at build time)"}))
             return
@@ -212,6 +218,9 @@ def main():
         dist.init_process_group("nccl")
     dev = torch.device("cuda", torch.cuda.current_device())
     eng, loci, st = build_engine(wl, rank, world)
+    eng.set_update_priors(t_max=[PRIOR_T])
+    if full:
+        eng.set_update_schedule(True, 5)
     if args.pieces > 0:
         eng.set_pieces(args.pieces)
     if os.environ.get("IMA_SPEC"):
@@ -275,17 +284,17 @@ def main():
     value = updates_all / (ms * 1e-3)
     p_acc = (c1["accepted"] - c0["accepted"]) / max(1, c1["updates"] - c0["updates"])
 
-    # the same K steps through the default (un-pieced) graph again, for the record
+    # the same K steps with the genealogy updates + swaps only (no split-time / scalar updates), for the record
     graph_ms = None
-    if world == 1:
+    if world == 1 and full:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eng.set_pieces(1)
+        eng.set_update_schedule(False, 0)
         eng.run(3, swaptries, stream)
         torch.cuda.synchronize()
         g0.record(); eng.run(args.steps, swaptries, stream); g1.record()
         torch.cuda.synchronize()
         graph_ms = g0.elapsed_time(g1)
-        eng.set_pieces(args.pieces if args.pieces > 0 else 1)
+        eng.set_update_schedule(True, 5)
 
     # ---- end to end through the C ABI with HOST buffers: every step uploads the genealogies from pinned host
     # memory (H2D), evaluates them, runs one M-mode step and reads the per-chain results back (D2H)
@@ -329,14 +338,16 @@ def main():
     pk, pk_kind = peaks()
     roof = None
     if kernel_ms is not None:
-        per = np.asarray(kernel_ms, dtype=np.float64) / args.steps                       # ms per launch: propose, accept, swap
-        names = ["k_propose", "k_accept", "k_swap"]
+        per = np.asarray(kernel_ms, dtype=np.float64) / args.steps                       # ms per launch
+        names = ["k_propose", "k_accept", "k_swap", "k_rescale_t", "k_accept_t", "k_changeu"]
         dom = int(np.argmax(per))
         P = cpg * nloci
         b_update = algorithmic_bytes_per_update(n0 + n1, mig_mean, p_acc, eng.NI, eng.ND)
         W_g = 4 * eng.NI + 8 * eng.ND
         b_accept = 2 * W_g + 16 + 12 + 1 + (W_g + 8 * (eng.nq + eng.nm) + 40) / nloci
-        alg = {"k_propose": b_update * P, "k_accept": b_accept * P, "k_swap": 16.0 * cpg}[names[dom]]
+        b_pair = 24.0 * (2 * (n0 + n1) - 1) + 12.0 * mig_mean + W_g + 24.0                # one genealogy with its weights
+        alg = {"k_propose": b_update * P, "k_accept": b_accept * P, "k_swap": 16.0 * cpg, "k_rescale_t": 2.0 * b_pair * P,
+               "k_accept_t": (W_g + 8 + 16 + 1) * P, "k_changeu": 48.0 * P}[names[dom]]
         achieved = alg / (per[dom] * 1e-3) / 1e9
         traffic = None
         tf = os.path.join(ROOT, "profiles", "traffic.json")
@@ -348,7 +359,7 @@ def main():
                 "note": "latency/dependency-bound path: small FP64/integer work per pair, see DESIGN.md"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = reference_throughput(wl, 1, 3, 1, budget_s=12.0)
+        r = reference_throughput(wl, 1, 3, 1, budget_s=12.0, full=full)
         if r is not None:
             cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference", "sample": r["sample"], "accept_rate": r["accept"]}
     lmode = None
@@ -361,10 +372,12 @@ def main():
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
            "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke, "parts_ms": parts},
-           "gpu_launches": 3 * args.steps if world == 1 else 3 * args.steps,
+           "gpu_launches": (6 if full else 3) * args.steps,
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
-           "unpipelined_ms_per_step": (graph_ms / args.steps) if graph_ms else None, "lmode": lmode,
-           "dropped_for_capacity": c1["dropped"], "swap_rate": (c1["swaps"] - c0["swaps"]) / max(1, c1["swap_attempts"] - c0["swap_attempts"])}
+           "genealogy_updates_only": ({"ms_per_step": graph_ms / args.steps, "value": updates_all / (graph_ms * 1e-3), "unit": unit}
+                                      if graph_ms else None), "lmode": lmode,
+           "dropped_for_capacity": c1["dropped"], "split_time_mean": float(np.mean(eng.fetch_parameters()[0])),
+           "update_counters": {k: int(v) for k, v in eng.update_counters().items()}, "swap_rate": (c1["swaps"] - c0["swaps"]) / max(1, c1["swap_attempts"] - c0["swap_attempts"])}
     print(json.dumps(out, default=float))
     if world > 1:
         dist.destroy_process_group()

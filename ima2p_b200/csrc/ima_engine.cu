@@ -728,8 +728,8 @@ int ima2p_engine_run(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stre
 }
 
 // Same work as ima2p_engine_run, launched kernel by kernel with CUDA events recorded on the launching
-// stream around each kernel of every step; kernel_ms[3] receives the summed device time of
-// {propose, accept, swap} over the nsteps (bench.py's roofline numerator comes from here).
+// stream around each kernel of every step; kernel_ms[6] receives the summed device time of
+// {propose, accept, swap, rescale_t, accept_t, changeu} over the nsteps (bench.py's roofline numerator comes from here).
 int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms) {
   if (!h || nsteps < 0 || swaptries < 0 || !kernel_ms) return fail(IMA2P_E_ARG, "run_timed: bad argument");
   Engine &e = h->eng;
@@ -738,26 +738,36 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
   if (e.d.nchains != e.d.nchains_global) return fail(IMA2P_E_ARG, "run_timed: engine holds a shard");
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, cuda_stream);
-  kernel_ms[0] = kernel_ms[1] = kernel_ms[2] = 0.f;
+  for (int k = 0; k < 6; k++) kernel_ms[k] = 0.f;
 #if IMA_CUDA
   const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int chunk = 256;
-  std::vector<cudaEvent_t> ev((size_t)chunk * 4);
+  std::vector<cudaEvent_t> ev((size_t)chunk * 7);
+  const bool do_t = e.t_updates && e.model.nsplit > 0, do_u = e.u_every > 0 && (e.uv.nurates > 1 || e.loci[0].d.model == kHKY);
+  UpdateView uvu = e.uv;
+  uvu.u_every = e.u_every > 0 ? e.u_every : 1;
   for (auto &x : ev) if (!IMA_CUDA_OK(cudaEventCreate(&x))) return fail(IMA2P_E_CUDA, "event create failed");
   for (int s0 = 0; s0 < nsteps; s0 += chunk) {
     const int n = nsteps - s0 < chunk ? nsteps - s0 : chunk;
     for (int i = 0; i < n; i++) {
-      cudaEventRecord(ev[i * 4 + 0], s);
+      cudaEventRecord(ev[i * 7 + 0], s);
       IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, 0, e.d.nloci);
-      cudaEventRecord(ev[i * 4 + 1], s);
+      cudaEventRecord(ev[i * 7 + 1], s);
       launch_accept(&e, s, 0, e.d.nloci);
-      cudaEventRecord(ev[i * 4 + 2], s);
+      cudaEventRecord(ev[i * 7 + 2], s);
+      if (do_t) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
+      cudaEventRecord(ev[i * 7 + 3], s);
+      if (do_t) IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e.d) * kWarpsPerBlock, s, e.v, e.uv);
+      cudaEventRecord(ev[i * 7 + 4], s);
+      if (do_u) IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, uvu);
+      cudaEventRecord(ev[i * 7 + 5], s);
       launch_swap(&e, s, e.v.swapsum, swaptries);
-      cudaEventRecord(ev[i * 4 + 3], s);
+      cudaEventRecord(ev[i * 7 + 6], s);
     }
     if (!IMA_CUDA_OK(cudaStreamSynchronize(s))) return fail(IMA2P_E_CUDA, "sync failed (run_timed)");
+    static const int slot[6] = {0, 1, 3, 4, 5, 2};      // event interval -> kernel_ms index
     for (int i = 0; i < n; i++)
-      for (int k = 0; k < 3; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i * 4 + k], ev[i * 4 + k + 1]); kernel_ms[k] += ms; }
+      for (int k = 0; k < 6; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i * 7 + k], ev[i * 7 + k + 1]); kernel_ms[slot[k]] += ms; }
   }
   for (auto &x : ev) cudaEventDestroy(x);
 #else
