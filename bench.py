@@ -303,16 +303,20 @@ def main():
     # the burned-in genealogies come back to pinned host memory once (untimed); they are what every e2e step uploads
     eng.fetch_state([pinned[k].data_ptr() for k in STATE_KEYS[:7]], stream)
     torch.cuda.synchronize()
+    tv_now, uv_now, _ = eng.fetch_parameters()          # the split times and scalars the burned-in genealogies belong to
+    tv_now = np.ascontiguousarray(tv_now)
+    pinned["uvals"].numpy()[:] = uv_now.reshape(pinned["uvals"].shape)
+    split_time_mean = float(tv_now.mean())
     mig_mean = float(pinned["scal_i"].numpy()[:, 1].mean())
     mig_max = int(pinned["scal_i"].numpy()[:, 1].max())
-    h2d = int(sum(sb)) + st["tvals"].nbytes
+    h2d = int(sum(sb)) + tv_now.nbytes
     d2h = cpg * 4 * 8 + eng.rowlen * 4
     for _ in range(3):
-        eng.put_state(bufs, st["tvals"], stream); run_steps(1); eng.fetch_chain_summary(stream)
+        eng.put_state(bufs, tv_now, stream); run_steps(1); eng.fetch_chain_summary(stream)
     barrier()
     t0 = time.perf_counter()
     for _ in range(ke):
-        eng.put_state(bufs, st["tvals"], stream)
+        eng.put_state(bufs, tv_now, stream)
         run_steps(1)
         summ = eng.fetch_chain_summary(stream)
         eng.cold_row()
@@ -327,7 +331,7 @@ def main():
     # where an end-to-end step goes (each part synchronised on its own; untimed for the metric)
     parts = {"upload_and_evaluate": 0.0, "step": 0.0, "read_back": 0.0}
     for _ in range(10):
-        t0 = time.perf_counter(); eng.put_state(bufs, st["tvals"], stream); torch.cuda.synchronize()
+        t0 = time.perf_counter(); eng.put_state(bufs, tv_now, stream); torch.cuda.synchronize()
         t1 = time.perf_counter(); run_steps(1); torch.cuda.synchronize()
         t2 = time.perf_counter(); eng.fetch_chain_summary(stream); eng.cold_row(); torch.cuda.synchronize()
         t3 = time.perf_counter()
@@ -376,7 +380,7 @@ def main():
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
            "genealogy_updates_only": ({"ms_per_step": graph_ms / args.steps, "value": updates_all / (graph_ms * 1e-3), "unit": unit}
                                       if graph_ms else None), "lmode": lmode,
-           "dropped_for_capacity": c1["dropped"], "split_time_mean": float(np.mean(eng.fetch_parameters()[0])),
+           "dropped_for_capacity": c1["dropped"], "split_time_mean": split_time_mean,
            "update_counters": {k: int(v) for k, v in eng.update_counters().items()}, "swap_rate": (c1["swaps"] - c0["swaps"]) / max(1, c1["swap_attempts"] - c0["swap_attempts"])}
     print(json.dumps(out, default=float))
     if world > 1:

@@ -308,7 +308,8 @@ int ima2p_engine_set_locus(ima2p_engine *h, int li, int model, int numgenes, int
   if (!e.model_set || e.finalized) return fail(IMA2P_E_ARG, "set_locus: call after set_model and before finalize");
   if (li < 0 || li >= e.d.nloci || numgenes < 2 || numgenes > 16000 || numsites < 0 || nlinked < 1 || nlinked > kMaxLinked)
     return fail(IMA2P_E_ARG, "set_locus: bad argument");
-  if (model != kInfiniteSites && model != kHKY && model != kStepwise) return fail(IMA2P_E_UNSUPPORTED, "set_locus: mutation model not supported");
+  if (model != kInfiniteSites && model != kHKY && model != kStepwise && model != kJointISSW) return fail(IMA2P_E_UNSUPPORTED, "set_locus: mutation model not supported");
+  if (model == kJointISSW && nlinked < 2) return fail(IMA2P_E_ARG, "set_locus: a joint locus has an infinite-sites part and at least one stepwise part");
   HostLocus &L = e.loci[li];
   memset(&L.d, 0, sizeof L.d);
   L.d.model = model; L.d.ng = numgenes; L.d.nl = 2 * numgenes - 1; L.d.nsites = numsites; L.d.totsites = totsites;
@@ -318,7 +319,7 @@ int ima2p_engine_set_locus(ima2p_engine *h, int li, int model, int numgenes, int
   if (tot != numgenes) return fail(IMA2P_E_ARG, "set_locus: samppop does not sum to numgenes");
   for (int i = 0; i < nlinked; i++) { L.d.minA[i] = minA ? minA[i] : 0; L.d.maxA[i] = maxA ? maxA[i] : 0; }
   L.sitemask.clear(); L.seq.clear(); L.mult.clear();
-  if (model == kInfiniteSites) {
+  if (has_infinite_sites(model)) {
     if (numsites > 0 && !seq) return fail(IMA2P_E_ARG, "set_locus: seq required");
     L.sitemask.assign((size_t)numsites * L.d.nwords, 0u);
     for (int s = 0; s < numsites; s++) {
@@ -363,7 +364,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
     if (L.d.nwords > d.W) d.W = L.d.nwords;
     if (L.d.nsites > d.S) d.S = L.d.nsites;
     if (L.d.ng > maxng) maxng = L.d.ng;
-    if (L.d.model == kStepwise) d.any_sw = 1;
+    if (has_stepwise(L.d.model)) d.any_sw = 1;
     if (L.d.model == kHKY) d.any_hky = 1;
     L.d.sitemask_off = (long long)sm.size(); sm.insert(sm.end(), L.sitemask.begin(), L.sitemask.end());
     L.d.seq_off = (long long)sq.size(); sq.insert(sq.end(), L.seq.begin(), L.seq.end());
@@ -696,7 +697,6 @@ int ima2p_engine_get_alleles(ima2p_engine *h, int ci, int li, int which, int *A,
 
 static int ensure_steppable(Engine &e) {
   if (!e.finalized) return fail(IMA2P_E_ARG, "engine not finalized");
-  if (e.model.nomigration) return fail(IMA2P_E_UNSUPPORTED, "M-mode stepping: the no-migration slider is not on the device path in this build");
   return IMA2P_OK;
 }
 

@@ -479,6 +479,26 @@ IMA_DEV double log_normprob(double stdev, double val) {
 // ------------------------------------------------------------------------------------------------
 // the proposal (lane 0): update_gtree.cpp:755-825
 // ------------------------------------------------------------------------------------------------
+// findjointime update_gtree.cpp:34-76: the time from which two lineages, in populations slidepop and sispop at the
+// tops of their edges, are in the same population (no-migration slider)
+IMA_DEV double findjointime(const DevModel &M, const double *tv, int slidepop, int sispop, double edgeuptime, double sisuptime) {
+  int edgeperiod = findperiod(M, tv, edgeuptime), sisperiod = findperiod(M, tv, sisuptime);
+  while (edgeperiod < sisperiod) {
+    edgeperiod++;
+    if (slidepop == M.droppops[edgeperiod][0] || slidepop == M.droppops[edgeperiod][1]) slidepop = M.pt_down[slidepop];
+  }
+  while (sisperiod < edgeperiod) {
+    sisperiod++;
+    if (sispop == M.droppops[sisperiod][0] || sispop == M.droppops[sisperiod][1]) sispop = M.pt_down[sispop];
+  }
+  while (slidepop != sispop) {
+    edgeperiod++;
+    if (slidepop == M.droppops[edgeperiod][0] || slidepop == M.droppops[edgeperiod][1]) slidepop = M.pt_down[slidepop];
+    if (sispop == M.droppops[edgeperiod][0] || sispop == M.droppops[edgeperiod][1]) sispop = M.pt_down[sispop];
+  }
+  return edgeperiod == 0 ? 0.0 : tv[edgeperiod - 1];
+}
+
 IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *tv, int ng, int nl, Philox &rng, PairSm &S) {
   const int CAP = d.CAP;
   int root = S.ctl_i[kCiRoot];
@@ -529,7 +549,26 @@ IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *
   double tp = S.time[edge];
   for (int iter = 0;; iter++) {
     if (iter > 100000) { flags |= kFlagOverflow; break; }
-    if (slidedist < 0) {
+    if (slidedist < 0 && M.nomigration) {
+      // slider_nomigration :78-253: without migration the sliding edge may only meet a sister that is in its own
+      // population, so the upper limit is also bounded by the time the two populations join
+      slidedist = -slidedist;
+      const double edgeuptime = edge_top_time(S, ng, edge), sisuptime = edge_top_time(S, ng, newsis);
+      const int slidepop = S.pop[edge], sispop = S.pop[newsis];
+      const double popjointime = slidepop != sispop ? findjointime(M, tv, slidepop, sispop, edgeuptime, sisuptime) : 0.0;
+      if (popjointime > edgeuptime && popjointime > sisuptime) {
+        if (slidedist < tp - popjointime) { tp -= slidedist; break; }
+        slidedist -= tp - popjointime; tp = popjointime;                              // reflect, continue downwards
+      } else if (sisuptime == 0 || edgeuptime >= sisuptime) {
+        if (slidedist < tp - edgeuptime) { tp -= slidedist; break; }
+        slidedist -= tp - edgeuptime; tp = edgeuptime;
+      } else {
+        if (slidedist < tp - sisuptime) { tp -= slidedist; break; }
+        slidedist -= tp - sisuptime; tp = sisuptime;
+        newsis = rng.bit() ? S.up0[newsis] : S.up1[newsis];
+        slidedist = -slidedist;                                                      // keep going up
+      }
+    } else if (slidedist < 0) {
       slidedist = -slidedist;
       const double uplimit = edge_top_time(S, ng, edge);
       const int su = S.up0[newsis];
@@ -589,7 +628,7 @@ IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *
 
   // addmigration :588-665
   double migweight = 0.0;
-  if (!(flags & kFlagOverflow)) {
+  if (!M.nomigration && !(flags & kFlagOverflow)) {                                 // :815-822 (no migration: nothing to simulate)
     emi_reset(ne); emi_reset(ns);
     ne.edgeid = edge;
     ne.upt = edge_top_time(S, ng, edge);

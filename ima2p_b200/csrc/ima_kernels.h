@@ -34,9 +34,14 @@ IMA_DEV double pair_likelihood(const EngineView &E, const DevLocus &L, const Pai
     pdg_a_out[0] = v;
     return v;
   }
-  if (L.model == kStepwise) {
+  if (has_stepwise(L.model)) {
     double tot = 0.0;
-    for (int ai = 0; ai < L.nlinked; ai++) {
+    if (L.model == kJointISSW) {                          // part 0 is the infinite-sites part (calc_prob_data / update_gtree.cpp:871-883)
+      tot = likelihood_is(E, L, S, u[0]);
+      pdg_a_out[0] = tot;
+      if (tot == kRejectIS) return kRejectIS;
+    }
+    for (int ai = sw_first(L.model); ai < L.nlinked; ai++) {
       const short *A = B.A + ((size_t)p * kMaxLinked + ai) * E.d.NL;
       double *dl = B.dlikeA + ((size_t)p * kMaxLinked + ai) * E.d.NL;
       const double v = likelihood_sw(L, S, A, dl, u[ai]);
@@ -211,7 +216,7 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E, int l0, int l1) {
   if (ok && total_mig > E.d.CAP) ok = false;
   double pdga[kMaxLinked];
   double pdg = 0.0;
-  if (ok && L.model == kStepwise) {
+  if (ok && has_stepwise(L.model)) {
     // stepwise loci: incremental update of the allele states and branch terms (update_gtree.cpp:857-868)
     const size_t ao = (size_t)p * kMaxLinked * E.d.NL;
     for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) { Bn.A[ao + i] = B.A[ao + i]; Bn.dlikeA[ao + i] = B.dlikeA[ao + i]; }
@@ -219,11 +224,17 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E, int l0, int l1) {
     __threadfence_block();
 #endif
     Warp::sync();
+    double pis = 0.0;
+    if (L.model == kJointISSW) {                          // the infinite-sites part is evaluated in full, as for an I locus
+      pis = likelihood_is(E, L, S, E.uvals[(size_t)p * kMaxLinked]);
+      if (lane == 0) { Bn.pdg_a[(size_t)p * kMaxLinked] = pis; if (pis == kRejectIS) S.ctl_i[kCiFlags] |= kFlagRejectIS; }
+      Warp::sync();
+    }
     if (lane == 0) {
       Philox rng;
       rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngAlleles);
-      double atermsum = 0.0, tot = 0.0;
-      for (int ai = 0; ai < L.nlinked; ai++) {
+      double atermsum = 0.0, tot = pis;
+      for (int ai = sw_first(L.model); ai < L.nlinked; ai++) {
         double aterm = 0.0;
         const double dl = sw_update_alleles(L, S, ai, rng, B.A + ao + (size_t)ai * E.d.NL, B.dlikeA + ao + (size_t)ai * E.d.NL,
                                             Bn.A + ao + (size_t)ai * E.d.NL, Bn.dlikeA + ao + (size_t)ai * E.d.NL, S.ctl_i[kCiEdge],

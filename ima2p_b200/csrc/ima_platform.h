@@ -46,6 +46,10 @@ constexpr int kAddMigMax = 1000;         // ADDMIGMAX
 constexpr int kSwapDist = 7;             // swapchains.cpp:220
 
 enum MutModel { kInfiniteSites = 0, kHKY = 1, kStepwise = 2, kJointISSW = 3 };
+// linked parts [sw_first, nlinked) of a locus are stepwise: all of them (S), all but part 0 (J: part 0 is infinite sites), none
+IMA_HD bool has_stepwise(int model) { return model == kStepwise || model == kJointISSW; }
+IMA_HD bool has_infinite_sites(int model) { return model == kInfiniteSites || model == kJointISSW; }
+IMA_HD int sw_first(int model) { return model == kJointISSW ? 1 : 0; }
 
 // per-pair proposal flags
 enum : uint32_t {

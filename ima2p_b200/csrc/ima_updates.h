@@ -113,7 +113,7 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_rescale_t(EngineView E, UpdateView U) {
   if (ok && total_mig > E.d.CAP) ok = false;
   uint32_t flags = ok ? (uint32_t)S.ctl_i[kCiFlags] : (uint32_t)kFlagOverflow;
   if (ok) {
-    if (L.model == kStepwise) {            // the allele states do not move; the branch terms are recomputed below
+    if (has_stepwise(L.model)) {           // the allele states do not move; the branch terms are recomputed below
       const size_t ao = (size_t)p * kMaxLinked * E.d.NL;
       for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) Bn.A[ao + i] = B.A[ao + i];
 #if IMA_CUDA
@@ -230,6 +230,15 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   }
 }
 
+// current P(D|G) of one linked part: only stepwise loci keep per-part values (pdg_a); elsewhere the part is the locus
+IMA_DEV double part_pdg(const DevLocus &L, const PairBuf &B, int p, int ai) {
+  return has_stepwise(L.model) ? B.pdg_a[(size_t)p * kMaxLinked + ai] : B.sd[(size_t)p * 4 + 3];
+}
+IMA_DEV void set_part_pdg(const DevLocus &L, const PairBuf &B, int p, int ai, double v) {
+  if (has_stepwise(L.model)) { B.sd[(size_t)p * 4 + 3] += v - B.pdg_a[(size_t)p * kMaxLinked + ai]; B.pdg_a[(size_t)p * kMaxLinked + ai] = v; }
+  else B.sd[(size_t)p * 4 + 3] = v;
+}
+
 // P(D|G) of linked part `ai` of pair p under a new scalar (and kappa); the genealogy does not move.
 //   infinite sites: -length u + sum_s log(ptime_s u) - sumlogk  ->  old - length (u' - u) + S log(u'/u)
 //   stepwise / HKY: recomputed from the staged genealogy (S is scratch for one warp)
@@ -237,26 +246,17 @@ IMA_DEV double scalar_likelihood(const EngineView &E, const DevModel &M, int c, 
                                  double kappa_new, PairSm &S, const PairBuf &B, const PairBuf &Bscratch) {
   const DevLocus &L = E.loci[li];
   const int p = c * E.d.nloci + li;
-  if (L.model == kInfiniteSites) {
+  if (has_infinite_sites(L.model) && ai == 0) {
     const double uold = E.uvals[(size_t)p * kMaxLinked];
-    return B.sd[(size_t)p * 4 + 3] - B.sd[(size_t)p * 4 + 1] * (unew - uold) + L.nsites * logratio;
+    return part_pdg(L, B, p, 0) - B.sd[(size_t)p * 4 + 1] * (unew - uold) + L.nsites * logratio;
   }
   stage_pair(E, B, p, L.nl, S);
-  if (L.model == kStepwise) {
+  if (has_stepwise(L.model)) {
     const size_t ao = ((size_t)p * kMaxLinked + ai) * E.d.NL;
     return likelihood_sw(L, S, B.A + ao, Bscratch.dlikeA + ao, unew);          // new branch terms go to the other buffer
   }
   if (!eval_weights(M, E.d, L, E.tvals + (size_t)c * kMaxPeriods, S)) return kRejectIS;
   return likelihood_hky(E, L, S, p, unew, kappa_new, E.pi + (size_t)p * 4);
-}
-
-// current P(D|G) of one linked part: only stepwise loci keep per-part values (pdg_a); elsewhere the part is the locus
-IMA_DEV double part_pdg(const DevLocus &L, const PairBuf &B, int p, int ai) {
-  return L.model == kStepwise ? B.pdg_a[(size_t)p * kMaxLinked + ai] : B.sd[(size_t)p * 4 + 3];
-}
-IMA_DEV void set_part_pdg(const DevLocus &L, const PairBuf &B, int p, int ai, double v) {
-  if (L.model == kStepwise) { B.sd[(size_t)p * 4 + 3] += v - B.pdg_a[(size_t)p * kMaxLinked + ai]; B.pdg_a[(size_t)p * kMaxLinked + ai] = v; }
-  else B.sd[(size_t)p * 4 + 3] = v;
 }
 
 IMA_DEV double reflect_kappa(double u, double kappa, double win, double kmax) {       // update_mc_params.cpp:258-272
@@ -341,7 +341,7 @@ IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
         const int li = i ? lk : lj, ai = i ? ak : aj, p = i ? pk : pj;
         const DevLocus &L = E.loci[li];
         const PairBuf &B = E.buf[E.cur[p]], &Bo = E.buf[E.cur[p] ^ 1];
-        if (L.model == kStepwise) {
+        if (has_stepwise(L.model) && ai >= sw_first(L.model)) {
           const size_t ao = ((size_t)p * kMaxLinked + ai) * E.d.NL;
           for (int e = lane; e < L.nl; e += IMA_WARP) B.dlikeA[ao + e] = Bo.dlikeA[ao + e];
         }

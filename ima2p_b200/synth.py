@@ -42,13 +42,60 @@ def _coalescent_tree(n, rng):
     return up0, up1, down, height
 
 
-def make_dataset(nloci, n0, n1, seed=1, theta=6.2, min_sites=8):
-    """nloci infinite-sites loci with n0 + n1 genes; returns a list of dicts (seq is [n][S] 0/1)."""
+def _im_tree(n0, n1, rng, split, mig):
+    """Genealogy of n0 + n1 genes under the isolation-with-migration model the shipped inputs were simulated from
+    (their headers: ms ... -I 2 n0 n1 ... split time 0.1): two populations of equal size exchanging migrants until
+    they merge, backwards in time, at `split`.  Time in units of 2N generations (pairwise coalescence rate 1);
+    `mig` = 4Nm, i.e. rate mig/4 per lineage in these units.  Tips 0..n0-1 are population 0."""
+    n = n0 + n1
+    nl = 2 * n - 1
+    up0, up1, down = -np.ones(nl, int), -np.ones(nl, int), -np.ones(nl, int)
+    height = np.zeros(nl)
+    pops = [list(range(n0)), list(range(n0, n))]
+    t, k = 0.0, n
+    while k < nl:
+        if t < split:
+            rc = [len(p) * (len(p) - 1) / 2.0 for p in pops]
+            rm = [len(p) * mig / 4.0 for p in pops]
+            tot = sum(rc) + sum(rm)
+            dt = rng.exponential(1.0 / tot) if tot > 0 else np.inf
+            if t + dt >= split:
+                t = split
+                pops = [pops[0] + pops[1], []]
+                continue
+            t += dt
+            x = rng.uniform(0, tot)
+            if x < rc[0] + rc[1]:
+                p = pops[0] if x < rc[0] else pops[1]
+            else:
+                src = 0 if x < rc[0] + rc[1] + rm[0] else 1
+                e = pops[src].pop(int(rng.integers(len(pops[src]))))
+                pops[1 - src].append(e)
+                continue
+        else:
+            p = pops[0]
+            m = len(p)
+            t += rng.exponential(2.0 / (m * (m - 1)))
+        i, j = rng.choice(len(p), 2, replace=False)
+        a, b = p[i], p[j]
+        up0[k], up1[k] = a, b
+        down[a] = down[b] = k
+        height[k] = t
+        p[:] = [e for e in p if e not in (a, b)] + [k]
+        k += 1
+    return up0, up1, down, height
+
+
+def make_dataset(nloci, n0, n1, seed=1, theta=5.0, min_sites=8, split=0.2, mig=1.0, structured=True):
+    """nloci infinite-sites loci with n0 + n1 genes; returns a list of dicts (seq is [n][S] 0/1).
+
+    structured: isolation-with-migration genealogies (ms -t 5 -I 2 n0 n1, split at 0.1 x 4N generations like
+    Simulations/Sim1_*.u); otherwise one panmictic population with genes dealt to the two samples at random."""
     rng = np.random.default_rng(seed)
     n = n0 + n1
     loci = []
     while len(loci) < nloci:
-        up0, up1, down, height = _coalescent_tree(n, rng)
+        up0, up1, down, height = _im_tree(n0, n1, rng, split, mig) if structured else _coalescent_tree(n, rng)
         nl = 2 * n - 1
         tips = [None] * nl
         for e in range(nl):
@@ -67,8 +114,8 @@ def make_dataset(nloci, n0, n1, seed=1, theta=6.2, min_sites=8):
         # the reference codes the base of the first sequence as 0 at every segregating site (readseqIS)
         flip = seq[0] == 1
         seq[:, flip] = 1 - seq[:, flip]
-        # random assignment of genes to populations (tips 0..n0-1 are population 0)
-        perm = rng.permutation(n)
+        # panmictic case: random assignment of genes to populations (tips 0..n0-1 are population 0)
+        perm = np.arange(n) if structured else rng.permutation(n)
         seq = seq[perm]
         flip = seq[0] == 1
         seq[:, flip] = 1 - seq[:, flip]

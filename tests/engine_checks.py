@@ -7,7 +7,8 @@ from support import (FlatModel, FlatTree, OracleModel, check_static_eval, engine
                      rel_close, split_weights, tree_from_engine, _num)
 
 STATIC_FIXTURES = ["state_sim5_hn4", "state_sim50_hn3", "state_sim300_hn1", "state_sim2_hn2", "state_sim3_hn3",
-                   "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim3_sw_hn2", "state_sim5_hky_hn2"]
+                   "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim3_sw_hn2", "state_sim5_hky_hn2", "state_sim3_joint_hn2",
+                   "state_sim5_nomig_hn2", "state_sim5_3pop_nomig_hn2"]
 STEP_FIXTURES = ["state_sim5_hn4", "state_sim3_hn3", "state_sim5_3pop_hn2", "state_sim2_hn2"]
 
 
@@ -50,7 +51,10 @@ def proposals_match_oracle(lib, name, nsteps, rtol=1e-9, need_root_moves=True):
                 after = tree_from_engine(eng.get_genealogy(c, l, 0 if accepted else 1))
                 b = before[(c, l)]
                 fwd, rev = om.migration_logprobs(tv, b, after, pr["edge"])
-                assert rel_close(rev - fwd, pr["migweight"], rtol, 1e-9), (name, c, l, fwd, rev, pr)
+                if fm.nomigration:          # update_gtree.cpp:815-818: no migration path is simulated, the weight is 0
+                    assert pr["migweight"] == 0.0 and after.mig_off[-1] == 0
+                else:
+                    assert rel_close(rev - fwd, pr["migweight"], rtol, 1e-9), (name, c, l, fwd, rev, pr)
                 if b.root != after.root or b.roottime != after.roottime:
                     sw = oracle().ora_slideweight(pr["slidedist"], b.roottime, after.roottime)
                     assert rel_close(sw, pr["slideweight"], rtol, 1e-9), (sw, pr)
@@ -220,7 +224,11 @@ def stepwise_updates_match_oracle(lib, name, nsteps, rtol=1e-9):
                 bt, bal = before[(c, l)]
                 g = d["chains"][c]["G"][l]
                 aterm = 0.0
-                for ai in range(d["loci"][l]["nlinked"]):
+                joint = d["loci"][l]["model"] == 3
+                if joint:           # part 0 of a J locus is the infinite-sites part, evaluated in full
+                    w = om.treeweight(d["chains"][c]["tvals"], d["loci"][l], after)
+                    assert rel_close(al["pdg_a"][0], om.likelihood_is(d["loci"][l], after, w["length"], g["uvals"][0]), rtol)
+                for ai in range(1 if joint else 0, d["loci"][l]["nlinked"]):
                     after.A = [i32(a) for a in al["A"]]
                     like, dl = om.likelihood_sw(after, ai, g["uvals"][ai])
                     assert rel_close(al["pdg_a"][ai], like, rtol), (c, l, al["pdg_a"], like)
@@ -280,7 +288,7 @@ def long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=
     eng.run(burn, swaptries=0)
     acc = np.zeros((nchains, nloci, 6))
     tacc, uacc = np.zeros((nchains, fm.nsplit)), np.zeros((nchains, nloci))
-    ncc = fm.ncc
+    first_of_period = np.cumsum([0] + [fm.npops - k for k in range(fm.nsplit)])
     for _ in range(sweeps):
         eng.run(1, swaptries=0)
         if full_schedule:
@@ -294,7 +302,7 @@ def long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=
         acc[:, :, 2] += si[:, :, 1]
         acc[:, :, 3] += wi[:, :, 0]
         acc[:, :, 4] += wi[:, :, 1] if fm.npops > 1 else 0
-        acc[:, :, 5] += wi[:, :, fm.npops:ncc].sum(axis=2)
+        acc[:, :, 5] += wi[:, :, first_of_period[1:]].sum(axis=2)       # cc[k][0], k >= 1 (what the trace fixture sums)
     chain_means = acc / sweeps
     m_e, se_e = chain_means.mean(axis=0), chain_means.std(axis=0, ddof=1) / np.sqrt(nchains)
     bm = np.array(d["batch_means"])

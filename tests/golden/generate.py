@@ -33,12 +33,12 @@ COMMON = ["-b", "100", "-l", "100", "-p01", "-z", "100000000"]
 ONLY = set(sys.argv[1:])        # optional fixture names: regenerate just those
 
 
-def run(mode, name, ufile, hn, kv, extra=()):
+def run(mode, name, ufile, hn, kv, extra=(), priors=None):
     if ONLY and name not in ONLY:
         return
     out = os.path.join(TMP, name + ".json")
     cmd = [HARNESS, mode, out] + ["%s=%s" % p for p in kv.items()] + ["--", "-i", ufile, "-o",
-          os.path.join(TMP, name + ".out")] + PRIORS + COMMON + ["-hn", str(hn)] + (HEAT if hn >= 4 else HEAT_LINEAR if hn > 1 else []) + list(extra)
+          os.path.join(TMP, name + ".out")] + (priors or PRIORS) + COMMON + ["-hn", str(hn)] + (HEAT if hn >= 4 else HEAT_LINEAR if hn > 1 else []) + list(extra)
     with open(os.path.join(TMP, name + ".log"), "w") as log:
         subprocess.run(cmd, check=True, stdout=log, stderr=subprocess.STDOUT, cwd=TMP)
     with open(out, "rb") as f, gzip.GzipFile(os.path.join(HERE, name + ".json.gz"), "wb", mtime=0) as g:
@@ -109,6 +109,13 @@ def to_sw(f, rows, npops, rng=random.Random(1)):
     return f, rows
 
 
+def to_joint(f, rows, npops, rng=random.Random(2)):
+    # J1 locus: the infinite-sites columns as they are plus one stepwise allele column in front (readata.cpp:93-97, 428-440)
+    f = list(f); f[2 + npops] = "J1"
+    rows = ["%-10s%d %s" % (r[:10].strip(), rng.randint(10, 16), r[10:].strip()) for r in rows]
+    return f, rows
+
+
 def three_pops(src, dst):
     """Same samples as `src`, re-divided into 3 populations with tree ((0,1):3,2):4."""
     lines = open(src).read().split("\n")
@@ -138,6 +145,7 @@ def main():
     hky5 = os.path.join(TMP, "Sim1_5loci_HKY.u"); relabel(s5, hky5, to_hky)
     sw3 = os.path.join(TMP, "Sim3_SW.u"); relabel(s3, sw3, to_sw)
     p3 = os.path.join(TMP, "Sim1_5loci_3pop.u"); three_pops(s5, p3)
+    j3 = os.path.join(TMP, "Sim3_JOINT.u"); relabel(s3, j3, to_joint)
 
     # static-evaluation fixtures (a5, a6, a7, a8, a9, a13): states after a short burn-in
     run("state", "state_sim5_hn4", s5, 4, {"burn": 200})                 # BASELINE config 1
@@ -149,6 +157,10 @@ def main():
     run("state", "state_sim5_expo_hn2", s5, 2, {"burn": 100}, extra=["-j7"])   # exponential m prior
     run("state", "state_sim5_hky_hn2", hky5, 2, {"burn": 60})
     run("state", "state_sim3_sw_hn2", sw3, 2, {"burn": 100})
+    run("state", "state_sim3_joint_hn2", j3, 2, {"burn": 100})
+    nomig = ["-q", "10", "-m", "0", "-t", "3"]                       # -m 0 sets NOMIGRATION (ima_main_mpi.cpp:822-823)
+    run("state", "state_sim5_nomig_hn2", s5, 2, {"burn": 100}, priors=nomig)
+    run("state", "state_sim5_3pop_nomig_hn2", p3, 2, {"burn": 100}, priors=nomig)
     # proposal known-answer fixtures (a2-a4): accepted updategenealogy() calls
     run("updates", "updates_sim5_hn2", s5, 2, {"burn": 50, "n": 250})
     run("updates", "updates_sim3_hn2", s3, 2, {"burn": 50, "n": 250})
@@ -164,12 +176,17 @@ def main():
     run("uupdates", "uupdates_sim5_hn2", s5, 2, {"burn": 100, "n": 40, "between": 2})
     run("uupdates", "uupdates_sim5_hky_hn2", hky5, 2, {"burn": 60, "n": 20, "between": 2})
     run("uupdates", "uupdates_sim3_sw_hn2", sw3, 2, {"burn": 100, "n": 16, "between": 2})
+    run("tupdates", "tupdates_sim3_joint_hn2", j3, 2, {"burn": 100, "n": 12, "between": 3})
+    run("uupdates", "uupdates_sim3_joint_hn2", j3, 2, {"burn": 100, "n": 24, "between": 2})
     run("thermo", "kat_thermo", s5, 2, {})
     # statistical parity (north_star: posterior summaries from long runs agree with the reference)
     run_trace("trace_sim5", s5, [1, 2, 3, 4, 5, 6], {"gburn": 3000, "sweeps": 60000, "nbatch": 12})
     run_trace("trace_sim3", s3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12})
     # the same with a recent split time (most of every genealogy lies in the ancestral population)
     run_trace("trace_sim3_recent", s3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12}, priors=["-q", "10", "-m", "1", "-t", "0.5"])
+    # no migration: the other slider (slider_nomigration)
+    run_trace("trace_sim3_nomig", s3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12}, priors=nomig)
+    run_trace("trace_sim5_3pop_nomig", p3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12}, priors=nomig)
     # whole qupdate steps: genealogies + split time (RY1 or NW) + mutation scalars; the posterior of t and of the scalars
     run_trace("trace_full_sim5", s5, [11, 12, 13, 14, 15, 16], {"gburn": 5000, "sweeps": 60000, "nbatch": 12, "full": 1})
     run_trace("trace_full_sim3", s3, [11, 12, 13, 14], {"gburn": 5000, "sweeps": 60000, "nbatch": 12, "full": 1})

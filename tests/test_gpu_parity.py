@@ -44,8 +44,9 @@ def test_lmode_matches_reference(lib, name):
     ec.lmode_matches_reference(lib, name, rtol=RTOL)
 
 
-def test_stepwise_updates_match_oracle(lib):
-    ec.stepwise_updates_match_oracle(lib, "state_sim3_sw_hn2", 40, rtol=RTOL)
+@pytest.mark.parametrize("name", ["state_sim3_sw_hn2", "state_sim3_joint_hn2"])
+def test_stepwise_updates_match_oracle(lib, name):
+    ec.stepwise_updates_match_oracle(lib, name, 40, rtol=RTOL)
 
 
 @pytest.mark.parametrize("name,nchains,burn,sweeps", [("trace_sim3", 256, 6000, 4000), ("trace_sim5", 256, 6000, 4000)])
@@ -74,18 +75,18 @@ def test_runs_are_reproducible_and_seed_dependent(lib):
 
 
 # ---- section 8 (f1): the rest of the step on the device ------------------------------------------------------------
-@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2"])
+@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2", "tupdates_sim3_joint_hn2"])
 def test_split_time_update_matches_reference(lib, name):
     ec.split_time_update_matches_reference(lib, name)
 
 
-@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2"])
+@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2", "uupdates_sim3_joint_hn2"])
 def test_mutation_scalar_update_matches_reference(lib, name):
     ec.mutation_scalar_update_matches_reference(lib, name)
 
 
 @pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 2000), ("state_sim5_3pop_hn2", 500), ("state_sim50_hn3", 300),
-                                         ("state_sim3_sw_hn2", 300), ("state_sim5_hky_hn2", 100)])
+                                         ("state_sim3_sw_hn2", 300), ("state_sim5_hky_hn2", 100), ("state_sim3_joint_hn2", 300)])
 def test_incremental_sums_with_full_schedule(lib, name, nsteps):
     ec.incremental_sums_match_fresh_evaluation(lib, name, nsteps, full_schedule=True)
 
@@ -115,3 +116,16 @@ def test_thermodynamic_integration(lib):
     s = eng.thermo_sums(reset=True)
     assert ec.rel_close(s.sum(), tot, 1e-12) and np.all(s < 0) and np.all(eng.thermo_sums() == 0)
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["state_sim5_nomig_hn2", "state_sim5_3pop_nomig_hn2"])
+def test_no_migration_model(lib, name):
+    ec.proposals_match_oracle(lib, name, 15, need_root_moves=False)
+    cnt = ec.incremental_sums_match_fresh_evaluation(lib, name, 500)
+    assert cnt["accepted"] > 0 and cnt["topology"] > 0
+
+
+@pytest.mark.parametrize("name", ["trace_sim3_nomig", "trace_sim5_3pop_nomig"])
+def test_no_migration_statistics(lib, name):
+    z, _, _, _, _ = ec.long_run_summaries_match_reference(lib, name, 256, 4000, 4000)
+    assert abs(z).max() < 5.0

@@ -45,8 +45,9 @@ def test_gamma_tables(emu):
     assert ec.gamma_tables_match_reference(emu, rtol=1e-12) > 400
 
 
-def test_stepwise_updates(emu):
-    ec.stepwise_updates_match_oracle(emu, "state_sim3_sw_hn2", 40, rtol=1e-10)
+@pytest.mark.parametrize("name", ["state_sim3_sw_hn2", "state_sim3_joint_hn2"])
+def test_stepwise_updates(emu, name):
+    ec.stepwise_updates_match_oracle(emu, name, 40, rtol=1e-10)
 
 
 def test_long_run_statistics_match_reference_sampler(emu):
@@ -55,17 +56,17 @@ def test_long_run_statistics_match_reference_sampler(emu):
     assert abs(z).max() < 5.0
 
 
-@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2"])
+@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2", "tupdates_sim3_joint_hn2"])
 def test_split_time_update(emu, name):
     ec.split_time_update_matches_reference(emu, name)
 
 
-@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2"])
+@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2", "uupdates_sim3_joint_hn2"])
 def test_mutation_scalar_update(emu, name):
     ec.mutation_scalar_update_matches_reference(emu, name)
 
 
-@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 200), ("state_sim5_3pop_hn2", 100), ("state_sim3_sw_hn2", 60), ("state_sim5_hky_hn2", 30)])
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 200), ("state_sim5_3pop_hn2", 100), ("state_sim3_sw_hn2", 60), ("state_sim5_hky_hn2", 30), ("state_sim3_joint_hn2", 60)])
 def test_incremental_sums_full_schedule(emu, name, nsteps):
     ec.incremental_sums_match_fresh_evaluation(emu, name, nsteps, full_schedule=True)
 
@@ -84,4 +85,17 @@ def test_full_schedule_posterior_matches_reference_sampler(emu):
 def test_recent_split_time_statistics(emu):
     # the genealogy sampler where most of every genealogy lies in the ancestral population
     z, _, _, _, _ = ec.long_run_summaries_match_reference(emu, "trace_sim3_recent", 16, 3000, 6000)
+    assert abs(z).max() < 5.0
+
+
+@pytest.mark.parametrize("name", ["state_sim5_nomig_hn2", "state_sim5_3pop_nomig_hn2"])
+def test_no_migration_model(emu, name):
+    # -m 0: slider_nomigration (update_gtree.cpp:78-253), no migration path, no migration terms in the prior
+    ec.proposals_match_oracle(emu, name, 15, need_root_moves=False)
+    cnt = ec.incremental_sums_match_fresh_evaluation(emu, name, 200)
+    assert cnt["accepted"] > 0 and cnt["topology"] > 0
+
+
+def test_no_migration_statistics(emu):
+    z, _, _, _, _ = ec.long_run_summaries_match_reference(emu, "trace_sim5_3pop_nomig", 16, 2000, 6000)
     assert abs(z).max() < 5.0

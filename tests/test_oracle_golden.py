@@ -14,7 +14,8 @@ from support import (FlatModel, FlatTree, OracleModel, _num, f64, fp, dp, i32, i
                      weights_from_json)
 
 STATE_FIXTURES = ["state_sim5_hn4", "state_sim50_hn3", "state_sim300_hn1", "state_sim2_hn2", "state_sim3_hn3",
-                  "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim5_hky_hn2", "state_sim3_sw_hn2"]
+                  "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim5_hky_hn2", "state_sim3_sw_hn2", "state_sim3_joint_hn2",
+                  "state_sim5_nomig_hn2", "state_sim5_3pop_nomig_hn2"]
 IS, HKY, SW = 0, 1, 2           # imamp.hpp mutation model enum order (INFINITESITES, HKY, STEPWISE)
 
 
@@ -47,8 +48,13 @@ def test_data_likelihood_matches_reference(name):
             elif loc["model"] == SW:
                 p, dl = om.likelihood_sw(tree, 0, g["uvals"][0])
                 assert rel_close(dl, tree.dlikeA[0], 1e-12, 1e-300)
-            else:
-                pytest.skip("joint model not in fixtures")
+            else:                           # JOINT_IS_SW: part 0 infinite sites, parts 1.. stepwise
+                p = om.likelihood_is(loc, tree, g["length"], g["uvals"][0])
+                assert rel_close(p, g["pdg_a"][0], 1e-12)
+                for ai in range(1, loc["nlinked"]):
+                    pa, dl = om.likelihood_sw(tree, ai, g["uvals"][ai])
+                    assert rel_close(pa, g["pdg_a"][ai], 1e-12) and rel_close(dl, tree.dlikeA[ai], 1e-12, 1e-300)
+                    p += pa
             assert rel_close(p, g["pdg"], 1e-12), (li, p, g["pdg"])
 
 
@@ -193,7 +199,7 @@ def test_getnewt_matches_reference():
         assert oracle().ora_getnewt(U, nloci, npops, period, tu, td, oldt) == newt
 
 
-@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2"])
+@pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2", "tupdates_sim3_joint_hn2"])
 def test_rannala_yang_rescaling_matches_reference(name):
     """changet_RY1 with the accept draw forced: the oracle's rescaled genealogies equal the reference's bit for bit
     and its Hastings term + the reference's own likelihood/prior differences give the reference's MH term."""
@@ -222,7 +228,7 @@ def test_rannala_yang_rescaling_matches_reference(name):
         assert rel_close(mh, rec["mh"], 1e-10, 1e-10), (mh, rec["mh"])
 
 
-@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2"])
+@pytest.mark.parametrize("name", ["uupdates_sim5_hn2", "uupdates_sim5_hky_hn2", "uupdates_sim3_sw_hn2", "uupdates_sim3_joint_hn2"])
 def test_mutation_scalar_update_matches_reference(name):
     """changeu replayed from the uniforms the reference drew: same partner k, same new scalars, same MH term."""
     from support import changeu_replay
@@ -246,7 +252,7 @@ def test_mutation_scalar_update_matches_reference(name):
         for (li, ai, unew) in ((lj, aj, nuj), (lk, ak, nuk)):
             g, loc = b["G"][li], d["loci"][li]
             t = FlatTree(g["tree"])
-            if loc["model"] == 0:
+            if loc["model"] == 0 or (loc["model"] == 3 and ai == 0):
                 new = om.likelihood_is(loc, t, g["length"], unew)
             elif loc["model"] == 1:
                 nk = oracle().ora_new_kappa(rest.pop(0), g["kappa"], d["kappa_win"], d["kappa_max"])
