@@ -220,7 +220,7 @@ def main():
     eng, loci, st = build_engine(wl, rank, world)
     eng.set_update_priors(t_max=[PRIOR_T])
     if full:
-        eng.set_update_schedule(True, 5)
+        eng.set_update_schedule(3, 5)
     if args.pieces > 0:
         eng.set_pieces(args.pieces)
     if os.environ.get("IMA_SPEC"):
@@ -294,7 +294,7 @@ def main():
         g0.record(); eng.run(args.steps, swaptries, stream); g1.record()
         torch.cuda.synchronize()
         graph_ms = g0.elapsed_time(g1)
-        eng.set_update_schedule(True, 5)
+        eng.set_update_schedule(3, 5)
 
     # ---- end to end through the C ABI with HOST buffers: every step uploads the genealogies from pinned host
     # memory (H2D), evaluates them, runs one M-mode step and reads the per-chain results back (D2H)

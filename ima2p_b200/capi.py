@@ -57,7 +57,7 @@ SIGNATURES = {
     "ima2p_engine_get_split_times": (_i, [_v, _i, c_dbl_p]),
     "ima2p_engine_fetch_parameters": (_i, [_v, c_dbl_p, c_dbl_p, c_dbl_p]),
     "ima2p_engine_get_scalars": (_i, [_v, _i, _i, c_dbl_p, c_dbl_p]),
-    "ima2p_engine_debug_split_time": (_i, [_v, _i, c_dbl_p, _i, c_dbl_p]),
+    "ima2p_engine_debug_split_time": (_i, [_v, _i, _i, c_dbl_p, _i, c_dbl_p]),
     "ima2p_engine_debug_changeu": (_i, [_v, _i, _i, _i, _d, _d, _d, c_dbl_p]),
     "ima2p_engine_thermo_accumulate": (_i, [_v, _v]),
     "ima2p_engine_thermo_sums": (_i, [_v, c_dbl_p, _i]),

@@ -139,7 +139,9 @@ static void launch_accept(Engine *e, stream_t s, int l0, int l1) {
 static void launch_param_updates(Engine *e, stream_t s) {
   const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (e->t_updates && e->model.nsplit > 0) {
-    IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
+    // every chain picks one of the two split-time updates (t_proposal); a warp whose chain picked the other one returns at once
+    if ((e->t_updates & 2) && !e->model.nomigration) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
+    if ((e->t_updates & 1) || e->model.nomigration) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
     IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e->d) * kWarpsPerBlock, s, e->v, e->uv);
   }
   if (e->u_every > 0 && (e->uv.nurates > 1 || e->loci[0].d.model == kHKY)) {
@@ -386,6 +388,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_rescale_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_nw_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
   if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");
@@ -455,7 +458,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
     const double umax = log(10000.0);                      // UMAX, imamp.hpp:152; initialize.cpp:1448-1450, update_mc_params.cpp:52-56
     u.u_win = umax / d.nloci; u.u_maxratio = 3.0 * umax;
     u.kappa_win = 2.0; u.kappa_max = 100.0;                // initialize.cpp:1499-1501
-    u.t_forced = nullptr; u.t_forced_period = 0; u.t_force_accept = -1; u.u_forced = 0; u.u_every = 5;
+    u.t_forced = nullptr; u.t_forced_period = 0; u.t_force_accept = -1; u.t_forced_method = 0; u.t_methods = 1; u.u_forced = 0; u.u_every = 5;
   }
   if (!v.acc || !v.buf[1].gwd || !e.d_swap_counts || !v.overflow) return fail(IMA2P_E_CUDA, "device allocation failed");
   stream_t s = pick_stream(&e, nullptr);
@@ -755,7 +758,8 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
       cudaEventRecord(ev[i * 7 + 1], s);
       launch_accept(&e, s, 0, e.d.nloci);
       cudaEventRecord(ev[i * 7 + 2], s);
-      if (do_t) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
+      if (do_t && (e.t_updates & 2) && !e.model.nomigration) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
+      if (do_t && ((e.t_updates & 1) || e.model.nomigration)) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
       cudaEventRecord(ev[i * 7 + 3], s);
       if (do_t) IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e.d) * kWarpsPerBlock, s, e.v, e.uv);
       cudaEventRecord(ev[i * 7 + 4], s);
@@ -889,10 +893,11 @@ int ima2p_engine_counters(ima2p_engine *h, uint64_t *out8) {
 
 // ---- split-time and mutation-scalar updates (update_t_RY.cpp, update_mc_params.cpp) ------------------------------
 int ima2p_engine_set_update_schedule(ima2p_engine *h, int t_updates, int u_every) {
-  if (!h || !h->eng.finalized || t_updates < 0 || u_every < 0) return fail(IMA2P_E_ARG, "set_update_schedule: bad argument");
+  if (!h || !h->eng.finalized || t_updates < 0 || t_updates > 3 || u_every < 0) return fail(IMA2P_E_ARG, "set_update_schedule: bad argument");
   Engine &e = h->eng;
   if (e.t_updates != t_updates || e.u_every != u_every) e.graph_ready = false;
   e.t_updates = t_updates; e.u_every = u_every;
+  e.uv.t_methods = t_updates;
   return IMA2P_OK;
 }
 
@@ -914,12 +919,12 @@ int ima2p_engine_set_update_priors(ima2p_engine *h, const double *t_max, const d
 
 // parity hook: one changet_RY1 on every chain with the proposed split times given (newt[nchains]); force_accept
 // -1 = draw, 0 = reject, 1 = accept; out[nchains][4] = period, proposed time, MH term, accepted
-int ima2p_engine_debug_split_time(ima2p_engine *h, int period, const double *newt, int force_accept, double *out) {
+int ima2p_engine_debug_split_time(ima2p_engine *h, int method, int period, const double *newt, int force_accept, double *out) {
   if (!h || !out) return fail(IMA2P_E_ARG, "debug_split_time: bad argument");
   Engine &e = h->eng;
   int rc = ensure_steppable(e);
   if (rc) return rc;
-  if (e.model.nsplit < 1 || period < 0 || period >= e.model.nsplit) return fail(IMA2P_E_ARG, "debug_split_time: no such split time");
+  if (e.model.nsplit < 1 || period < 0 || period >= e.model.nsplit || method < 0 || method > 1) return fail(IMA2P_E_ARG, "debug_split_time: no such split time / update");
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, nullptr);
   const size_t C = e.d.nchains;
@@ -928,10 +933,11 @@ int ima2p_engine_debug_split_time(ima2p_engine *h, int period, const double *new
   if (newt) {
     d_newt = e.alloc<double>(C);
     if (!d_newt || !h2d(d_newt, newt, C * sizeof(double), s)) return fail(IMA2P_E_CUDA, "upload failed");
-    u.t_forced = d_newt; u.t_forced_period = period; u.t_force_accept = force_accept;
-  }
+    u.t_forced = d_newt; u.t_forced_period = period; u.t_force_accept = force_accept; u.t_forced_method = method;
+  } else u.t_methods = method ? 2 : 1;
   const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
+  if (method == 1) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
+  else IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
   IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e.d) * kWarpsPerBlock, s, e.v, u);
   if (!d2h(out, e.uv.t_out, C * 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   return check_device_error(&e, s);

@@ -27,7 +27,8 @@ struct UpdateView {
   double *u_out;                                   // [nchains][4] debug: new pdg of j, new pdg of k, MH term, accepted
   unsigned long long *stats;                       // [4] t tries, t accepts, u tries, u accepts
   const double *t_forced;                          // [nchains] tests: proposed time to use instead of the draw (or null)
-  int t_forced_period, t_force_accept;
+  int t_forced_period, t_force_accept, t_forced_method;
+  int t_methods;                                   // bit 0: Rannala-Yang, bit 1: Nielsen-Wakeley
   // tests: one forced changeu proposal per launch
   int u_forced;                                    // 0: production sweep; 1: evaluate (u_j, u_k, d, kappas) below on u_chain only
   int u_chain, u_j, u_k, u_every;
@@ -43,7 +44,7 @@ IMA_DEV double ry_aftersplit(int tnode, int lastperiod, double oldt, double newt
   return tau_d - (tau_d - newt) * (tau_d - ptime) / (tau_d - oldt);
 }
 
-struct TProposal { int period; double oldt, newt, t_u, t_d; };
+struct TProposal { int period, method; double oldt, newt, t_u, t_d; };     // method 0 = Rannala-Yang, 1 = Nielsen-Wakeley
 
 // period pick, getnewt (update_gtree_common.cpp:2501-2519): every warp of a chain derives the same proposal
 IMA_DEV TProposal t_proposal(const EngineView &E, const UpdateView &U, const DevModel &M, int c) {
@@ -53,7 +54,10 @@ IMA_DEV TProposal t_proposal(const EngineView &E, const UpdateView &U, const Dev
   TProposal t;
   t.period = rng.randint(M.nsplit);
   const double u = rng.uniform();
-  if (U.t_forced) t.period = U.t_forced_period;
+  // ima_main_mpi.cpp:1871-1872: one of the two update types at random (NW adds migration events, which a
+  // no-migration model must not have: Rannala-Yang only there)
+  t.method = (U.t_methods == 3 && !M.nomigration) ? rng.randint(2) : (U.t_methods == 2 && !M.nomigration ? 1 : 0);
+  if (U.t_forced) { t.period = U.t_forced_period; t.method = U.t_forced_method; }
   t.oldt = tv[t.period];
   t.t_u = t.period == 0 ? 0.0 : tv[t.period - 1];
   t.t_d = t.period == M.nsplit - 1 ? kTimeMax : tv[t.period + 1];
@@ -65,6 +69,225 @@ IMA_DEV TProposal t_proposal(const EngineView &E, const UpdateView &U, const Dev
   else if (newt <= t_u_prior) newt = 2.0 * t_u_prior - newt;
   t.newt = U.t_forced ? U.t_forced[c] : newt;
   return t;
+}
+
+// ---- Nielsen-Wakeley split-time update: update_t_NW.cpp -----------------------------------------------------
+// The split time moves from oldt to newt and nothing else does; every stretch of edge inside the interval
+// (tu, td) = (min, max)(oldt, newt) changes the set of populations it may be in, so its migration events there are
+// erased and re-simulated.  One lane walks the edges (as the reference does, the work is a chain of small dependent
+// decisions); the weights are rebuilt by the whole warp afterwards.
+
+// nowedgepop update_gtree_common.cpp:1638-1655, population tree times from the chain's CURRENT split times
+IMA_DEV int nw_nowpop(const DevModel &M, const double *tv, const PairSm &S, int e, double ptime) {
+  int pop = S.pop[e];
+  const int s0 = S.ms[e], n = S.mcn[e];
+  for (int j = 0; j < n && S.pt[s0 + j] < ptime; j++) pop = S.pp[s0 + j];
+  while (pop != -1 && ptime > (M.pt_e[pop] == -1 ? kTimeMax : tv[M.pt_e[pop] - 1])) pop = M.pt_down[pop];
+  return pop;
+}
+
+IMA_DEV double nw_logpf(int code) {            // the seven values logpfpop / logpfpop_r take (:372-583, MIGSIMFRAC 0.999)
+  switch (code) {
+    case 1: return log(0.999);
+    case 2: return log(1.0 - 0.999);
+    case 3: return -kLog2;
+    case 4: return log(0.999) / 2.0;
+    case 5: return log(1.0 - 0.999) / 2.0;
+    case 6: return -0.34657359027997265470861606073;      // LOG2HALF, imamp.hpp:189
+    default: return 0.0;
+  }
+}
+
+// getmprob_NW :291-330
+IMA_DEV double nw_getmprob(const DevModel &M, int period, double mrate, double mtime, int mcount, int uppop, int dpop, int cm2pop, int numpops) {
+  if (period == M.nsplit) return 0.0;
+  if (period == M.nsplit - 1) return mcount * log(mrate / mtime) - ((mcount & 1) ? mylogsinh(mrate) : mylogcosh(mrate));
+  const double logs = uppop == dpop ? log(1 - mrate * exp(-mrate)) : log(1 - exp(-mrate));
+  if (mcount == 0) return -mrate - logs;
+  if (mcount == 1) return log(mrate / mtime) - mrate - logs;
+  const double lognp = log((double)numpops - 1);
+  const double logb = cm2pop == dpop ? -lognp : -log((double)numpops - 2);
+  return mcount * log(mrate / mtime) + (2 - mcount) * lognp + logb - mrate - logs;
+}
+
+// update_mig_tNW :336-786 for the staged genealogy; returns the log Hastings ratio of the migration events
+// (mproposenum - mproposedenom).  *overflow is set when the rewritten lists do not fit the pool.
+IMA_DEV double nw_update_pair(const DevModel &M, const EngineDims &d, const double *tv, int period, double oldt, double newt,
+                              int ng, int nl, Philox &rng, PairSm &S, bool *overflow) {
+  const int CAP = d.CAP, root = S.ctl_i[kCiRoot];
+  const bool up = newt > oldt;                        // the split moves back in time
+  const double tu = up ? oldt : newt, td = up ? newt : oldt;
+  const int period_a = up ? period : period + 1, period_b = up ? period + 1 : period, p1 = period + 1;
+  const int addp = M.addpop[p1], d0 = M.droppops[p1][0], d1 = M.droppops[p1][1];
+  int *rec = S.moff;                                  // per edge: db | da << 5 | codef << 10 | coder << 13 | two << 16 | first << 17 | set << 18
+  for (int i = 0; i < nl; i++) rec[i] = 0;
+  // which edges have a stretch inside the interval, and where their lower ends are before (db) and after (da) the update
+  for (int i = 0; i < nl; i++) {
+    const double uptime = edge_top_time(S, ng, i);
+    if (!(S.time[i] > tu && uptime <= td) || (rec[i] >> 18)) continue;
+    int db, da, cf = 0, cr = 0, two = 0, sis = -1;
+    if (S.time[i] > td) {                             // the edge leaves the interval at its lower end: on its own
+      db = nw_nowpop(M, tv, S, i, td);
+      if (up) {
+        if (db == addp) {
+          const int c0 = nw_nowpop(M, tv, S, i, tu);
+          if (uptime < tu && (c0 == d0 || c0 == d1)) {
+            if (rng.uniform() < 0.999) { da = c0; cf = 1; } else { da = c0 == d0 ? d1 : d0; cf = 2; }
+          } else { cf = 3; da = rng.bit() ? d1 : d0; }
+        } else da = db;
+      } else {
+        if (db == d0 || db == d1) {
+          da = addp;
+          const int c0 = nw_nowpop(M, tv, S, i, tu);
+          if (uptime < tu && (c0 == d0 || c0 == d1)) cr = c0 == db ? 1 : 2; else cr = 3;
+        } else da = db;
+      }
+    } else {                                          // the edge ends in a coalescence inside the interval: with its sister
+      two = 1;
+      const int dn = S.down[i];
+      sis = S.up0[dn] == i ? S.up1[dn] : S.up0[dn];
+      const double uptime1 = edge_top_time(S, ng, sis);
+      db = nw_nowpop(M, tv, S, i, S.time[i]);
+      if (up) {
+        if (db == addp) {
+          const int c0 = nw_nowpop(M, tv, S, i, tu), c1 = nw_nowpop(M, tv, S, sis, tu);
+          if (uptime < tu && uptime1 < tu && c0 == c1 && (c0 == d0 || c0 == d1)) {
+            if (rng.uniform() < 0.999) { da = c0; cf = 4; } else { da = c0 == d0 ? d1 : d0; cf = 5; }
+          } else { cf = 6; da = rng.bit() ? d1 : d0; }
+        } else da = db;
+      } else {
+        if (db == d0 || db == d1) {
+          const int c0 = nw_nowpop(M, tv, S, i, tu), c1 = nw_nowpop(M, tv, S, sis, tu);
+          da = addp;
+          if (uptime < tu && uptime1 < tu && c0 == c1 && (c0 == d0 || c0 == d1)) cr = c0 == db ? 4 : 5; else cr = 6;
+        } else da = db;
+      }
+    }
+    const int v = db | (da << 5) | (cf << 10) | (cr << 13) | (two << 16) | (1 << 18);
+    rec[i] = v | (1 << 17);
+    if (two) rec[sis] = v;
+  }
+  // per record: population at the upper end before / after, migration counts and rates, new paths, Hastings terms
+  double num = 0.0, denom = 0.0;
+  int freep = CAP;                                    // rewritten lists are appended to the scratch part of the pool
+  for (int i = 0; i < nl; i++) {
+    if (!((rec[i] >> 17) & 1)) continue;
+    const int db = rec[i] & 31, da = (rec[i] >> 5) & 31, two = (rec[i] >> 16) & 1;
+    const double logpf = nw_logpf((rec[i] >> 10) & 7), logpf_r = nw_logpf((rec[i] >> 13) & 7);
+    for (int k = 0; k <= two; k++) {
+      int ei = i;
+      if (k) { const int dn = S.down[i]; ei = S.up0[dn] == i ? S.up1[dn] : S.up0[dn]; }
+      const double uptime = edge_top_time(S, ng, ei);
+      int upb, upa;
+      if (uptime < tu) {
+        if (!up) { upb = nw_nowpop(M, tv, S, ei, tu); upa = (upb == d0 || upb == d1) ? addp : upb; }
+        else { upb = nw_nowpop(M, tv, S, ei, tu * (1 + DBL_EPSILON)); upa = upb == addp ? nw_nowpop(M, tv, S, ei, tu) : upb; }
+      } else {                                        // the upper end is a node inside the interval: its daughters' record
+        const int r = rec[S.up0[ei]];
+        upb = r & 31; upa = (r >> 5) & 31;
+        S.pop[ei] = (short)upa;
+      }
+      if (ei == root) continue;
+      const double bottom = td < S.time[ei] ? td : S.time[ei], top = tu > uptime ? tu : uptime;
+      const double mtime = bottom - top;
+      const int s0 = S.ms[ei], n = S.mcn[ei];
+      int kk = 0, mi = 0, mstart = -1;
+      while (kk < n && S.pt[s0 + kk] < td) { if (S.pt[s0 + kk] > tu) { if (mi == 0) mstart = kk; mi++; } kk++; }
+      int cm2_b = -1, cm2_a = -1;
+      if (kk >= 2 && mstart >= 0 && kk - mstart >= 2) cm2_b = kk == 2 ? upb : (int)S.pp[s0 + kk - 3];
+      const int mcount = mi, npopsa = M.npops - period_a, npopsb = M.npops - period_b;
+      const double mrate = period_a < M.nsplit ? calcmrate(mcount, mtime) * mtime : 0.0;
+      int mnew;
+      if (npopsa == 1) mnew = 0;
+      else if (npopsa == 2) mnew = poisson_cond(rng, mrate, upa == da ? 0 : 1);
+      else mnew = poisson_cond(rng, mrate, upa == da ? 3 : 2);
+      const double mrate_r = period_b < M.nsplit ? calcmrate(mnew, mtime) * mtime : 0.0;
+      // addmigration_NW :208-289: keep the events above tu and below td, replace those in between
+      int above = 0;
+      if (uptime < tu) while (above < n && S.pt[s0 + above] < tu) above++;
+      int below = above;
+      while (below < n && S.pt[s0 + below] < td) below++;
+      const int numskip = below - above, numheld = n - below;
+      if (!up && period_a == M.nsplit) {
+        S.mcn[ei] = (unsigned short)above;
+      } else if (mnew > 0 || numskip > 0) {
+        const int total = above + mnew + numheld;
+        if (freep + total > 4 * CAP) { *overflow = true; return 0.0; }
+        for (int j = 0; j < above; j++) { S.pt[freep + j] = S.pt[s0 + j]; S.pp[freep + j] = S.pp[s0 + j]; }
+        if (mnew > 0) {
+          Emi em; em.seg = freep + above; em.nmig = 0;
+          simmpath(M, rng, S, em, 4 * CAP, period_a, mnew, mtime, top, upa, da);
+          if (mnew >= 2) cm2_a = mnew == 2 ? upa : (int)S.pp[freep + above + mnew - 3];
+        }
+        for (int j = 0; j < numheld; j++) { S.pt[freep + above + mnew + j] = S.pt[s0 + below + j]; S.pp[freep + above + mnew + j] = S.pp[s0 + below + j]; }
+        S.ms[ei] = (unsigned short)freep; S.mcn[ei] = (unsigned short)total;
+        freep += total;
+      }
+      if (mrate > 0) denom += logpf + nw_getmprob(M, period_a, mrate, mtime, mnew, upa, da, cm2_a, npopsa);
+      if (mrate_r > 0) num += logpf_r + nw_getmprob(M, period_b, mrate_r, mtime, mcount, upb, db, cm2_b, npopsb);
+    }
+  }
+  return num - denom;
+}
+
+IMA_KERNEL void IMA_PROPOSE_BOUNDS k_nw_t(EngineView E, UpdateView U) {
+  IMA_SMEM_DECL
+  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (p >= E.d.P) return;
+  const DevModel &M = IMA_MODEL;
+  const int c = p / E.d.nloci, li = p - c * E.d.nloci;
+  const TProposal t = t_proposal(E, U, M, c);
+  if (t.method != 1) return;
+  const DevLocus &L = E.loci[li];
+  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
+  const int cb = E.cur[p];
+  const PairBuf &B = E.buf[cb];
+  const PairBuf &Bn = E.buf[cb ^ 1];
+  const int lane = Warp::lane();
+  double tvo[kMaxPeriods], tvn[kMaxPeriods];
+  for (int k = 0; k < kMaxPeriods; k++) tvo[k] = tvn[k] = E.tvals[(size_t)c * kMaxPeriods + k];
+  tvn[t.period] = t.newt;
+  stage_pair(E, B, p, L.nl, S);
+  const double roottime = S.ctl_d[kCdRoottime];
+  // :967-969: a genealogy whose root is younger than both split times is not touched
+  const bool touched = (t.newt > t.oldt && roottime > t.oldt) || (t.newt < t.oldt && roottime > t.newt);
+  if (lane == 0) {
+    double mw = 0.0;
+    bool ovf = false;
+    if (touched) {
+      Philox rng;
+      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngSplitMig);
+      mw = nw_update_pair(M, E.d, tvo, t.period, t.oldt, t.newt, L.ng, L.nl, rng, S, &ovf);
+    }
+    S.ctl_d[kCdMigw] = mw;
+    S.ctl_i[kCiFlags] = ovf ? (int)kFlagOverflow : 0;
+  }
+#if IMA_CUDA
+  __threadfence_block();
+#endif
+  Warp::sync();
+  bool ok = !(S.ctl_i[kCiFlags] & kFlagOverflow);
+  if (ok) ok = eval_weights(M, E.d, L, tvn, S);
+  const int total_mig = ok ? S.ctl_i[kCiMignum] : 0;
+  if (ok && total_mig > E.d.CAP) ok = false;
+  if (ok) {
+    // branch lengths do not change: P(D|G) and everything it is built from are carried over (:908)
+    if (has_stepwise(L.model)) {
+      const size_t ao = (size_t)p * kMaxLinked * E.d.NL;
+      for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) { Bn.A[ao + i] = B.A[ao + i]; Bn.dlikeA[ao + i] = B.dlikeA[ao + i]; }
+      for (int ai = lane; ai < L.nlinked; ai += IMA_WARP) Bn.pdg_a[(size_t)p * kMaxLinked + ai] = B.pdg_a[(size_t)p * kMaxLinked + ai];
+    }
+    if (lane == 0) S.ctl_d[kCdPdg] = B.sd[(size_t)p * 4 + 3];
+    Warp::sync();
+    store_pair(E, Bn, p, L.nl, S, total_mig);
+  }
+  if (lane == 0) {
+    E.prop_flags[p] = ok ? 0u : (uint32_t)kFlagOverflow;
+    E.prop_extra[p] = S.ctl_d[kCdMigw];
+    E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw];
+    int *o = U.t_counts + (size_t)p * 4;
+    o[0] = o[1] = o[2] = o[3] = 0;
+  }
 }
 
 IMA_KERNEL void IMA_PROPOSE_BOUNDS k_rescale_t(EngineView E, UpdateView U) {
@@ -80,6 +303,7 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_rescale_t(EngineView E, UpdateView U) {
   const PairBuf &Bn = E.buf[cb ^ 1];
   const int lane = Warp::lane();
   const TProposal t = t_proposal(E, U, M, c);
+  if (t.method != 0) return;
   double tvn[kMaxPeriods];
   for (int k = 0; k < kMaxPeriods; k++) tvn[k] = E.tvals[(size_t)c * kMaxPeriods + k];
   tvn[t.period] = t.newt;
@@ -177,17 +401,19 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
     probg += v;
   }
   if (!migration_allowed(M, S.ai)) probg = -kMyDblMax;
-  double pdgnew = 0.0;
+  double pdgnew = 0.0, migw = 0.0;
   int n_eu = 0, n_ed = 0, n_mu = 0, n_md = 0;
   uint32_t bad = 0;
   for (int li = lane; li < nloci; li += IMA_WARP) {
     const int p = c * nloci + li;
     pdgnew += E.buf[E.cur[p] ^ 1].sd[(size_t)p * 4 + 3];
+    if (t.method == 1) migw += E.prop_extra[p];
     const int *o = U.t_counts + (size_t)p * 4;
     n_eu += o[0]; n_ed += o[1]; n_mu += o[2]; n_md += o[3];
     bad |= E.prop_flags[p] & (kFlagOverflow | kFlagRejectIS | kFlagBadTree);
   }
   pdgnew = Warp::sum(pdgnew);
+  migw = Warp::sum(migw);
   n_eu = Warp::sum(n_eu); n_ed = Warp::sum(n_ed); n_mu = Warp::sum(n_mu); n_md = Warp::sum(n_md);
   const bool anybad = Warp::any(bad != 0);
   // every coalescent node was met on both of its daughter edges (:405-408)
@@ -201,8 +427,18 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   else { tpw += probg - E.probg[c]; mh = beta * tpw + hast; }                     // :419-421
   Philox rng;
   rng_for(rng, E, (uint32_t)(E.d.nchains_global + E.d.chain0 + c), kRngSplitTime);
-  const double lu = log(rng.uniform());
-  bool accept = !anybad && lu < (mh < 1.0 ? mh : 1.0);                            // :424-425
+  const double uacc = rng.uniform();
+  bool accept;
+  if (t.method == 1) {
+    // changet_NW update_t_NW.cpp:993-1005: no likelihood term (branch lengths are unchanged), the migration events'
+    // Hastings ratio instead; the decision is taken on the natural scale
+    const double dprobg = probg - E.probg[c];
+    mh = exp((M.thermo ? dprobg : beta * dprobg) + migw);
+    pdgnew = E.pdgsum[c];
+    accept = !anybad && uacc < (mh < 1.0 ? mh : 1.0);
+  } else {
+    accept = !anybad && log(uacc) < (mh < 1.0 ? mh : 1.0);                        // update_t_RY.cpp:424-425
+  }
   if (U.t_forced && U.t_force_accept >= 0) accept = !anybad && U.t_force_accept != 0;
   if (accept) {
     for (int i = lane; i < NI; i += IMA_WARP) E.all_i[(size_t)c * NI + i] = S.ai[i];

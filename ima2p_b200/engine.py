@@ -222,9 +222,10 @@ class Engine:
         keys = ["steps", "updates", "accepted", "topology", "tmrca", "swap_attempts", "swaps", "dropped"]
         return dict(zip(keys, (int(v) for v in out)))
 
-    def set_update_schedule(self, t_updates=True, u_every=5):
-        """Split-time updates every step and mutation-scalar updates every ``u_every``-th (ima_main_mpi.cpp:1784-1785)."""
-        self._ck(self.lib.ima2p_engine_set_update_schedule(self._h, int(bool(t_updates)), int(u_every)))
+    def set_update_schedule(self, t_updates=3, u_every=5):
+        """Split-time updates every step (1 Rannala-Yang, 2 Nielsen-Wakeley, 3 either at random as the reference does)
+        and mutation-scalar updates every ``u_every``-th (ima_main_mpi.cpp:1784-1785, 1871-1872)."""
+        self._ck(self.lib.ima2p_engine_set_update_schedule(self._h, int(t_updates), int(u_every)))
 
     def set_update_priors(self, t_max=None, t_min=None, u_prior_max=0.0, u_window=0.0, kappa_window=0.0, kappa_max=0.0):
         tm = None if t_max is None else _f64(np.atleast_1d(t_max))
@@ -251,10 +252,11 @@ class Engine:
         self._ck(self.lib.ima2p_engine_fetch_parameters(self._h, _dp(tv) if self.nsplit else None, _dp(u), _dp(k)))
         return tv[:, :self.nsplit], u, k
 
-    def debug_split_time(self, period, newt=None, force_accept=-1):
+    def debug_split_time(self, period, newt=None, force_accept=-1, method=0):
+        """One changet_RY1 (method 0) / changet_NW (method 1) on every chain; rows of (period, newt, MH term, accepted)."""
         out = np.zeros((self.nchains, 4))
         nt = None if newt is None else _f64(newt)
-        self._ck(self.lib.ima2p_engine_debug_split_time(self._h, period, None if nt is None else _dp(nt), force_accept, _dp(out)))
+        self._ck(self.lib.ima2p_engine_debug_split_time(self._h, method, period, None if nt is None else _dp(nt), force_accept, _dp(out)))
         return out
 
     def debug_changeu(self, chain, j, k, d, kappa_j=0.0, kappa_k=0.0):

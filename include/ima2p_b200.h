@@ -136,8 +136,9 @@ int ima2p_engine_get_proposal (ima2p_engine * e, int ci, int li, double *out4, u
 int ima2p_debug_gamma (int device, const int *a, const double *x, int n, double *out);
 
 /* The rest of one qupdate step (ima_main_mpi.cpp:1867-1945), local to each chain:
- *   t_updates != 0 : a split-time update of every chain in every step -- changet_RY1, update_t_RY.cpp:222-517 (the
- *                    reference picks between this and changet_NW at random);
+ *   t_updates      : a split-time update of every chain in every step: 1 = changet_RY1 (update_t_RY.cpp:222-517),
+ *                    2 = changet_NW (update_t_NW.cpp:919-1032), 3 = one of the two at random per chain, as the
+ *                    reference does (ima_main_mpi.cpp:1871-1872); 0 = none;
  *   u_every  > 0   : changeu for every mutation-rate scalar (update_mc_params.cpp:23-370; changekappa :381-431 when a
  *                    single HKY locus is all there is) in every u_every-th step (the reference: 5, UUPDATEINC 4).
  * Both default to off; ima2p_engine_run / update_genealogies then perform them after the genealogy updates.
@@ -154,11 +155,13 @@ int ima2p_engine_get_split_times (ima2p_engine * e, int chain, double *tvals);
 int ima2p_engine_fetch_parameters (ima2p_engine * e, double *tvals, double *uvals, double *kappa);
 /* mutation-rate scalars (uvals[IMA2P_MAX_LINKED]) and kappa of one (chain, locus) */
 int ima2p_engine_get_scalars (ima2p_engine * e, int chain, int locus, double *uvals, double *kappa);
-/* parity hooks (tests): one changet_RY1 with the proposed times given, newt[nchains] (NULL: drawn); force_accept -1
+/* parity hooks (tests): one changet_RY1 (method 0) or changet_NW (method 1) with the proposed times given,
+ * newt[nchains] (NULL: drawn); force_accept -1
  * draws the decision, 0 rejects, 1 accepts; out[nchains][4] = period, proposed time, log MH term, accepted.
  * debug_changeu evaluates, and never applies, the proposal u_j *= d, u_k /= d on one chain:
  * out[4] = new P(D|G) of j's part, of k's part, MH term (update_mc_params.cpp:291), 0 */
-int ima2p_engine_debug_split_time (ima2p_engine * e, int period, const double *newt, int force_accept, double *out);
+int ima2p_engine_debug_split_time (ima2p_engine * e, int method, int period, const double *newt, int force_accept,
+                                   double *out);
 int ima2p_engine_debug_changeu (ima2p_engine * e, int chain, int j, int k, double d, double kappa_j, double kappa_k,
                                 double *out);
 

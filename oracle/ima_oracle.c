@@ -2060,3 +2060,224 @@ ora_thermomarginlike (const double *thermosum, int numchains, int k)
     sum += 2.0 * (thermosum[i] / k);
   return width * sum / 3.0;
 }
+
+
+/* ------------------------------------------------------------------------------------------- */
+/* changet_NW, replayed: update_t_NW.cpp:291-330 (getmprob_NW), 336-786 (update_mig_tNW);       */
+/* nowedgepop update_gtree_common.cpp:1638-1655                                                 */
+/* ------------------------------------------------------------------------------------------- */
+
+static int
+nw_nowedgepop (const ora_model * m, const double *tv, int pop, const int *off, const double *mt, const int *mp, int e,
+               double ptime)
+{
+  int j;
+  for (j = off[e]; j < off[e + 1] && mt[j] < ptime; j++)
+    pop = mp[j];
+  while (pop != -1 && ptime > (m->pt_e[pop] == -1 ? ORA_TIMEMAX : tv[m->pt_e[pop] - 1]))
+    pop = m->pt_down[pop];
+  return pop;
+}
+
+static double
+nw_getmprob (const ora_model * m, int period, double mrate, double mtime, int mcount, int uppop, int dpop, int cm2pop,
+             int numpops)
+{
+  double logb, logs, lognp;
+  if (period == m->nsplit)
+    return 0;
+  if (period == m->nsplit - 1)
+  {
+    if (mcount & 1)
+      return mcount * log (mrate / mtime) - ora_mylogsinh (mrate);
+    return mcount * log (mrate / mtime) - ora_mylogcosh (mrate);
+  }
+  if (uppop == dpop)
+    logs = log (1 - mrate * exp (-mrate));
+  else
+    logs = log (1 - exp (-mrate));
+  switch (mcount)
+  {
+  case 0:
+    return -mrate - logs;
+  case 1:
+    return log (mrate / mtime) - mrate - logs;
+  default:
+    lognp = log ((double) numpops - 1);
+    if (cm2pop == dpop)
+      logb = -lognp;
+    else
+      logb = -log ((double) numpops - 2);
+    return mcount * log (mrate / mtime) + (2 - mcount) * lognp + logb - mrate - logs;
+  }
+}
+
+#define NW_MIGSIMFRAC 0.999
+#define NW_LOG2HALF 0.34657359027997265470861606073
+
+double
+ora_nw_migweight (const ora_model * m, const double *tvals, int period, double newt, int numgenes, int root,
+                  const int *up0, const int *up1, const int *down, const double *time, const int *b_pop,
+                  const int *b_mig_off, const double *b_mig_t, const int *b_mig_p, const int *a_pop,
+                  const int *a_mig_off, const double *a_mig_t, const int *a_mig_p)
+{
+  const int ng = numgenes, nl = 2 * ng - 1, p1 = period + 1;
+  const double oldt = tvals[period];
+  const int up = newt > oldt;
+  const double tu = up ? oldt : newt, td = up ? newt : oldt;
+  const int period_a = up ? period : period + 1, period_b = up ? period + 1 : period;
+  const int addp = m->addpop[p1], d0 = m->droppops[p1][0], d1 = m->droppops[p1][1];
+  double tvn[ORA_MAXPERIODS + 1], num = 0, denom = 0;
+  int i, k, *setf = (int *) malloc (nl * sizeof (int)), *rdb = (int *) malloc (nl * sizeof (int)), *rda =
+    (int *) malloc (nl * sizeof (int)), *first = (int *) calloc (nl, sizeof (int)), *two = (int *) calloc (nl, sizeof (int));
+  double *lpf = (double *) calloc (nl, sizeof (double)), *lpfr = (double *) calloc (nl, sizeof (double));
+  for (k = 0; k <= m->nsplit; k++)
+    tvn[k] = k < m->nsplit ? tvals[k] : ORA_TIMEMAX;
+  tvn[period] = newt;
+#define UPT(e) ((e) < ng ? 0.0 : time[up0[e]])
+#define POPB(e, t) nw_nowedgepop (m, tvals, b_pop[e], b_mig_off, b_mig_t, b_mig_p, e, t)
+#define POPA(e, t) nw_nowedgepop (m, tvn, a_pop[e], a_mig_off, a_mig_t, a_mig_p, e, t)
+#define ISDROP(p) ((p) == d0 || (p) == d1)
+  for (i = 0; i < nl; i++)
+    setf[i] = -1;
+  /* :355-583, the simulated population below the interval taken from the genealogy after the move */
+  for (i = 0; i < nl; i++)
+  {
+    double uptime = UPT (i);
+    if (!(time[i] > tu && uptime <= td) || setf[i] != -1)
+      continue;
+    int db, da, c0, c1, sis = -1;
+    double f = 0, fr = 0;
+    if (time[i] > td)
+    {
+      db = POPB (i, td);
+      da = db;
+      if (up)
+      {
+        if (db == addp)
+        {
+          c0 = POPB (i, tu);
+          da = POPA (i, td);
+          if (uptime < tu && ISDROP (c0))
+            f = da == c0 ? log (NW_MIGSIMFRAC) : log (1.0 - NW_MIGSIMFRAC);
+          else
+            f = -0.69314718055994530941723212146;   /* LOG2, imamp.hpp:188 */
+        }
+      }
+      else if (ISDROP (db))
+      {
+        da = addp;
+        c0 = POPB (i, tu);
+        if (uptime < tu && ISDROP (c0))
+          fr = c0 == db ? log (NW_MIGSIMFRAC) : log (1.0 - NW_MIGSIMFRAC);
+        else
+          fr = -0.69314718055994530941723212146;   /* LOG2, imamp.hpp:188 */
+      }
+    }
+    else
+    {
+      sis = up0[down[i]] == i ? up1[down[i]] : up0[down[i]];
+      double uptime1 = UPT (sis);
+      two[i] = 1;
+      db = POPB (i, time[i]);
+      da = db;
+      if (up)
+      {
+        if (db == addp)
+        {
+          c0 = POPB (i, tu);
+          c1 = POPB (sis, tu);
+          da = POPA (i, time[i]);
+          if (uptime < tu && uptime1 < tu && c0 == c1 && ISDROP (c0))
+            f = (da == c0 ? log (NW_MIGSIMFRAC) : log (1.0 - NW_MIGSIMFRAC)) / 2.0;
+          else
+            f = -NW_LOG2HALF;
+        }
+      }
+      else if (ISDROP (db))
+      {
+        c0 = POPB (i, tu);
+        c1 = POPB (sis, tu);
+        da = addp;
+        if (uptime < tu && uptime1 < tu && c0 == c1 && ISDROP (c0))
+          fr = (c0 == db ? log (NW_MIGSIMFRAC) : log (1.0 - NW_MIGSIMFRAC)) / 2.0;
+        else
+          fr = -NW_LOG2HALF;
+      }
+    }
+    setf[i] = i;
+    first[i] = 1;
+    rdb[i] = db;
+    rda[i] = da;
+    lpf[i] = f;
+    lpfr[i] = fr;
+    if (sis >= 0)
+    {
+      setf[sis] = i;
+      rdb[sis] = db;
+      rda[sis] = da;
+    }
+  }
+  /* :586-757 */
+  for (i = 0; i < nl; i++)
+  {
+    if (!first[i])
+      continue;
+    for (k = 0; k <= two[i]; k++)
+    {
+      int ei = k ? (up0[down[i]] == i ? up1[down[i]] : up0[down[i]]) : i, upb, upa, j, mi, mstart, kk, cm2_b = -1, cm2_a = -1;
+      int mcount, mnew, npopsa = m->npops - period_a, npopsb = m->npops - period_b;
+      double uptime = UPT (ei), mtime, mrate, mrate_r, top;
+      if (uptime < tu)
+      {
+        if (!up)
+        {
+          upb = POPB (ei, tu);
+          upa = ISDROP (upb) ? addp : upb;
+        }
+        else
+        {
+          upb = POPB (ei, tu * (1 + DBL_EPSILON));
+          upa = upb == addp ? POPB (ei, tu) : upb;
+        }
+      }
+      else
+      {
+        upb = rdb[up0[ei]];
+        upa = rda[up0[ei]];
+      }
+      if (ei == root)
+        continue;
+      top = tu > uptime ? tu : uptime;
+      mtime = (td < time[ei] ? td : time[ei]) - top;
+      for (j = b_mig_off[ei], kk = 0, mi = 0, mstart = -1; j < b_mig_off[ei + 1] && b_mig_t[j] < td; j++, kk++)
+        if (b_mig_t[j] > tu)
+        {
+          if (mi == 0)
+            mstart = kk;
+          mi++;
+        }
+      if (kk >= 2 && mstart >= 0 && kk - mstart >= 2)
+        cm2_b = kk == 2 ? upb : b_mig_p[b_mig_off[ei] + kk - 3];
+      mcount = mi;
+      mrate = period_a < m->nsplit ? ora_calcmrate (mcount, mtime) * mtime : 0;
+      /* the number of events simulated, and the population before the second to last of them, from the result */
+      for (j = a_mig_off[ei], kk = 0, mnew = 0; j < a_mig_off[ei + 1] && a_mig_t[j] < td; j++, kk++)
+        if (a_mig_t[j] > tu)
+          mnew++;
+      if (mnew >= 2)
+        cm2_a = mnew == 2 ? upa : a_mig_p[a_mig_off[ei] + kk - 3];
+      mrate_r = period_b < m->nsplit ? ora_calcmrate (mnew, mtime) * mtime : 0;
+      if (mrate > 0)
+        denom += lpf[setf[ei]] + nw_getmprob (m, period_a, mrate, mtime, mnew, upa, rda[ei], cm2_a, npopsa);
+      if (mrate_r > 0)
+        num += lpfr[setf[ei]] + nw_getmprob (m, period_b, mrate_r, mtime, mcount, upb, rdb[ei], cm2_b, npopsb);
+    }
+  }
+  free (setf); free (rdb); free (rda); free (first); free (two); free (lpf); free (lpfr);
+  return num - denom;
+#undef UPT
+#undef POPB
+#undef POPA
+#undef ISDROP
+}

@@ -56,6 +56,14 @@ double harness_uniform_ry ()
   double u = uniform ();
   return g_force_accept ? 1e-300 : u;       /* log(1e-300) is below any finite Metropolis-Hastings term */
 }
+static long g_nw_count = 0, g_nw_force = -1;
+double harness_nw_last_mh (void);
+double harness_uniform_nw ()
+{
+  double u = uniform ();
+  g_nw_count++;
+  return g_nw_count == g_nw_force ? 0.0 : u;
+}
 double harness_uniform_mc ()
 {
   double u = uniform ();
@@ -898,6 +906,61 @@ mode_tupdates (long burn, long n, long between)
   fprintf (jo, "]}\n");
 }
 
+/* split-time updates, Nielsen-Wakeley: changet_NW() (update_t_NW.cpp:919-1032).  The call is made from a fixed seed; if it
+ * rejects (the reference then restores everything) it is repeated from the same seed with its last uniform() -- the
+ * accept draw -- replaced by 0, so that the proposed state stays visible */
+static void
+mode_nwupdates (long burn, long n, long between)
+{
+  do_burn (burn);
+  recompute_all ();
+  fprintf (jo, "{");
+  dump_model ();
+  fprintf (jo, "\"records\":[");
+  int first = 1;
+  for (long it = 0; it < n; it++)
+  {
+    int ci = (int) (it % numchains), period = (int) ((it / numchains) % numsplittimes);
+    for (long b = 0; b < between; b++)
+    {
+      qupdate (0, 0, 1);
+      step++;
+    }
+    recompute_all ();
+    char *buf = NULL;
+    size_t blen = 0;
+    FILE *keep = jo;
+    jo = open_memstream (&buf, &blen);
+    dump_chain (ci);
+    fclose (jo);
+    jo = keep;
+    setseeds (5000 + (int) it);
+    g_nw_count = 0;
+    g_nw_force = -1;
+    int acc = changet_NW (ci, period), natural = acc;
+    long ncalls = g_nw_count;
+    if (!acc)
+    {
+      setseeds (5000 + (int) it);
+      g_nw_count = 0;
+      g_nw_force = ncalls;
+      acc = changet_NW (ci, period);
+      g_nw_force = -1;
+    }
+    if (acc)
+    {
+      fprintf (jo, "%s{\"ci\":%d,\"period\":%d,\"natural\":%d,\"mh\":", first ? "" : ",\n", ci, period, natural);
+      jd (harness_nw_last_mh ());
+      fprintf (jo, ",\"before\":%s,\"after\":", buf);
+      dump_chain (ci);
+      fputc ('}', jo);
+      first = 0;
+    }
+    free (buf);
+  }
+  fprintf (jo, "]}\n");
+}
+
 /* mutation-scalar updates: changeu() (update_mc_params.cpp:23-370), unforced; every uniform() the call drew is
  * logged, the Metropolis-Hastings term is DMIN's second argument at :294 */
 static void
@@ -1240,6 +1303,8 @@ main (int argc, char *argv[])
   }
   else if (mode == "tupdates")
     mode_tupdates (burn, kvl ("n", 40), kvl ("between", 3));
+  else if (mode == "nwupdates")
+    mode_nwupdates (burn, kvl ("n", 40), kvl ("between", 3));
   else if (mode == "uupdates")
     mode_uupdates (burn, kvl ("n", 40), kvl ("between", 3));
   else if (mode == "thermo")

@@ -68,6 +68,14 @@ double harness_ry_last_mh (void) { return dminarg2; }
 #undef uniform
 double harness_mc_last_mh (void) { return dminarg2; }
 
+#elif defined(SHIM_T_NW)
+/* uniform() calls of this file: the MIGSIMFRAC draws, the migration times, and last the accept draw (:1007);
+ * the hook counts them and can replace the n-th by 0 */
+#define uniform harness_uniform_nw
+#include "update_t_NW.cpp"
+#undef uniform
+double harness_nw_last_mh (void) { return dminarg2; }
+
 #else
 #error "select a shim"
 #endif

@@ -93,7 +93,7 @@ def incremental_sums_match_fresh_evaluation(lib, name, nsteps, rtol=1e-9, full_s
     eng.eval()
     if full_schedule:           # split-time update every step, mutation scalars every 5th (qupdate's schedule)
         eng.set_update_priors(t_max=[3.0] * fm.nsplit)
-        eng.set_update_schedule(True, 5)
+        eng.set_update_schedule(3, 5)
     eng.run(nsteps)
     eng.sync()
     if full_schedule:
@@ -281,10 +281,10 @@ def long_run_summaries_match_reference(lib, name, nchains, burn, sweeps, nsigma=
     eng.upload()
     eng.eval()
     if full_schedule:
-        # the whole qupdate schedule.  The reference mixes two split-time kernels (RY1 / NW), the engine uses RY1 only:
-        # different kernels, same stationary distribution, so the posterior summaries of t and of the scalars must agree
+        # the whole qupdate schedule (genealogies, RY1 or NW split-time update at random, mutation scalars): the posterior
+        # summaries of t and of the scalars must agree with the reference's
         eng.set_update_priors(t_max=d["tprior_max"])
-        eng.set_update_schedule(True, 5)
+        eng.set_update_schedule(3, 5)
     eng.run(burn, swaptries=0)
     acc = np.zeros((nchains, nloci, 6))
     tacc, uacc = np.zeros((nchains, fm.nsplit)), np.zeros((nchains, nloci))
@@ -395,3 +395,53 @@ def thermodynamic_integration_matches_reference(lib):
         out = C.c_double()
         assert lib.ima2p_thermo_marginlike(dp(s), len(s), t["k"], C.byref(out)) == 0
         assert rel_close(out.value, t["value"], 1e-14)
+
+
+def nielsen_wakeley_update_matches_oracle(lib, name, rtol=1e-9):
+    """changet_NW on the device, from the reference's states and proposed split times, no RNG matching: for the move the
+    device makes, the oracle (pinned to the reference's own NW moves) recomputes the migration Hastings term of every
+    locus from the (before, proposed) genealogies, and the weights / prior of the proposed state."""
+    d = load_golden(name)
+    nmoved = nup = ndown = 0
+    for rec in d["records"]:
+        b, a, period = rec["before"], rec["after"], rec["period"]
+        eng, fm = engine_from_fixture(_one_chain_fixture(d, b), lib=lib, mig_capacity=96)
+        om = OracleModel(fm)
+        eng.eval()
+        oldt, newt = b["tvals"][period], a["tvals"][period]
+        out = eng.debug_split_time(period, [newt], force_accept=0, method=1)
+        assert out[0, 3] == 0
+        check_static_eval(eng, fm, _one_chain_fixture(d, b), rtol=rtol)          # a rejected move leaves nothing behind
+        tvn = list(b["tvals"]); tvn[period] = newt
+        acc = dict(cc=np.zeros(fm.ncc, np.int64), mc=np.zeros(fm.nmc, np.int64), fc=np.zeros(fm.ncc), hcc=np.zeros(fm.ncc), fm=np.zeros(fm.nmc))
+        migw = 0.0
+        for li, gb in enumerate(b["G"]):
+            tb = FlatTree(gb["tree"])
+            tp = tree_from_engine(eng.get_genealogy(0, li, 1))                    # the proposed genealogy (other buffer)
+            assert np.array_equal(tb.time, tp.time) and np.array_equal(tb.up0, tp.up0) and tb.root == tp.root
+            touched = (newt > oldt and tb.roottime > oldt) or (newt < oldt and tb.roottime > newt)
+            w = om.nw_migweight(b["tvals"], period, newt, tb, tp) if touched else 0.0
+            pr = eng.proposal(0, li)
+            assert abs(w - pr["migweight"]) <= 1e-9 * max(1.0, abs(w)), (li, w, pr)
+            migw += w
+            tw = om.treeweight(tvn, d["loci"][li], tp)                           # consistent populations, new weights
+            assert tw["mignum"] == tp.mig_off[-1]
+            for k in acc:
+                acc[k] = acc[k] + tw[k]
+            nmoved += int(tp.mig_off[-1] != tb.mig_off[-1])
+        probg, _, _ = om.init_integrate(acc)
+        mh = float(np.exp(b["beta"] * (probg - b["probg"]) + migw))
+        assert rel_close(out[0, 2], mh, rtol, 1e-300), (out[0], mh)
+        # the same proposal again (same step, same streams), accepted: stored sums equal a fresh evaluation
+        out = eng.debug_split_time(period, [newt], force_accept=1, method=1)
+        assert out[0, 3] == 1 and rel_close(out[0, 2], mh, rtol, 1e-300)
+        inc = eng.chain(0)
+        assert rel_close(inc["probg"], probg, rtol) and rel_close(inc["tvals"], tvn, 0.0) and rel_close(inc["pdg"], b["pdg"], 1e-12)
+        eng.eval()
+        fresh = eng.chain(0)
+        assert np.array_equal(inc["wi"], fresh["wi"]) and rel_close(inc["wd"], fresh["wd"], rtol, 1e-12)
+        assert rel_close(inc["probg"], fresh["probg"], rtol) and rel_close(inc["pdg"], fresh["pdg"], rtol)
+        nup += newt > oldt
+        ndown += newt < oldt
+        eng.close()
+    assert nmoved > 0 and nup > 0 and ndown > 0

@@ -173,6 +173,9 @@ def main():
     run("tupdates", "tupdates_sim5_hn2", s5, 2, {"burn": 100, "n": 30, "between": 3})
     run("tupdates", "tupdates_sim5_3pop_hn2", p3, 2, {"burn": 100, "n": 24, "between": 3})
     run("tupdates", "tupdates_sim3_sw_hn2", sw3, 2, {"burn": 100, "n": 12, "between": 3})
+    run("nwupdates", "nwupdates_sim5_hn2", s5, 2, {"burn": 100, "n": 30, "between": 3})
+    run("nwupdates", "nwupdates_sim3_hn2", s3, 2, {"burn": 100, "n": 30, "between": 3})
+    run("nwupdates", "nwupdates_sim5_3pop_hn2", p3, 2, {"burn": 100, "n": 40, "between": 3})
     run("uupdates", "uupdates_sim5_hn2", s5, 2, {"burn": 100, "n": 40, "between": 2})
     run("uupdates", "uupdates_sim5_hky_hn2", hky5, 2, {"burn": 60, "n": 20, "between": 2})
     run("uupdates", "uupdates_sim3_sw_hn2", sw3, 2, {"burn": 100, "n": 16, "between": 2})

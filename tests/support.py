@@ -209,6 +209,9 @@ def oracle():
     lib.ora_ry1_rescale.argtypes = [i, c_int_p, c_dbl_p, i, c_dbl_p, c_dbl_p, i, i, d, d, d, d, c_int_p]
     lib.ora_ry1_hastings.restype = d
     lib.ora_ry1_hastings.argtypes = [i, i, d, d, d, d, i, i, i, i]
+    lib.ora_nw_migweight.restype = d
+    lib.ora_nw_migweight.argtypes = [v, c_dbl_p, i, d, i, i, c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p, c_int_p, c_dbl_p,
+                                     c_int_p, c_int_p, c_int_p, c_dbl_p, c_int_p]
     lib.ora_changeu_newr.restype = d
     lib.ora_changeu_newr.argtypes = [d, d, d, d, c_dbl_p]
     lib.ora_new_kappa.restype = d
@@ -270,6 +273,13 @@ class OracleModel:
         probg = self.lib.ora_initialize_integrate_tree_prob(self.h, ip(i32(w["cc"])), dp(f64(w["fc"])), dp(f64(w["hcc"])),
                                                             ip(mc), dp(fmw), dp(qint), dp(mint))
         return probg, qint[:self.fm.nq], mint[:self.fm.nm]
+
+    def nw_migweight(self, tvals, period, newt, before, after):
+        """log Hastings ratio of the migration events of one changet_NW() move (oracle replay of update_mig_tNW)."""
+        tv = f64(tvals)
+        return self.lib.ora_nw_migweight(self.h, dp(tv), period, newt, before.numgenes, before.root, ip(before.up0), ip(before.up1),
+                                         ip(before.down), dp(before.time), ip(before.pop), ip(before.mig_off), dp(before.mig_t),
+                                         ip(before.mig_p), ip(after.pop), ip(after.mig_off), dp(after.mig_t), ip(after.mig_p))
 
     def migration_logprobs(self, tvals, before, after, edge):
         out = np.zeros(2)

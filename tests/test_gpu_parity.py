@@ -129,3 +129,8 @@ def test_no_migration_model(lib, name):
 def test_no_migration_statistics(lib, name):
     z, _, _, _, _ = ec.long_run_summaries_match_reference(lib, name, 256, 4000, 4000)
     assert abs(z).max() < 5.0
+
+
+@pytest.mark.parametrize("name", ["nwupdates_sim5_hn2", "nwupdates_sim3_hn2", "nwupdates_sim5_3pop_hn2"])
+def test_nielsen_wakeley_update_matches_oracle(lib, name):
+    ec.nielsen_wakeley_update_matches_oracle(lib, name)

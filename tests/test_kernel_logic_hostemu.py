@@ -78,7 +78,7 @@ def test_thermodynamic_integration(emu):
 def test_full_schedule_posterior_matches_reference_sampler(emu):
     # genealogies + split time + mutation scalars: the posterior of t and of the scalars against whole qupdate() runs
     # of the reference (the split time mixes slowly: a long burn-in is part of the test)
-    z, zt, zu, _, _, uc = ec.long_run_summaries_match_reference(emu, "trace_full_sim3", 8, 15000, 40000, full_schedule=True)
+    z, zt, zu, _, _, uc = ec.long_run_summaries_match_reference(emu, "trace_full_sim3", 8, 8000, 30000, full_schedule=True)
     assert abs(zt).max() < 5.0 and abs(zu).max() < 5.0 and uc["t_accepts"] > 0 and uc["u_accepts"] > 0
 
 
@@ -99,3 +99,8 @@ def test_no_migration_model(emu, name):
 def test_no_migration_statistics(emu):
     z, _, _, _, _ = ec.long_run_summaries_match_reference(emu, "trace_sim5_3pop_nomig", 16, 2000, 6000)
     assert abs(z).max() < 5.0
+
+
+@pytest.mark.parametrize("name", ["nwupdates_sim5_hn2", "nwupdates_sim3_hn2", "nwupdates_sim5_3pop_hn2"])
+def test_nielsen_wakeley_update(emu, name):
+    ec.nielsen_wakeley_update_matches_oracle(emu, name)

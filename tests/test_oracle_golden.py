@@ -274,3 +274,31 @@ def test_thermodynamic_integration_matches_reference():
     for t in load_golden("kat_thermo")["thermo"]:
         s = f64(t["sums"])
         assert rel_close(oracle().ora_thermomarginlike(dp(s), len(s), t["k"]), t["value"], 1e-14)
+
+
+@pytest.mark.parametrize("name", ["nwupdates_sim5_hn2", "nwupdates_sim3_hn2", "nwupdates_sim5_3pop_hn2"])
+def test_nielsen_wakeley_hastings_term_matches_reference(name):
+    """changet_NW: the oracle's replay of update_mig_tNW on the reference's (before, after) genealogies gives, with the
+    reference's own prior values, the Metropolis-Hastings term the reference computed."""
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    om = OracleModel(fm)
+    nup = ndown = nmoved = 0
+    for rec in d["records"]:
+        b, a, period = rec["before"], rec["after"], rec["period"]
+        oldt, newt = b["tvals"][period], a["tvals"][period]
+        migw = 0.0
+        for li, (gb, ga) in enumerate(zip(b["G"], a["G"])):
+            tb, ta = FlatTree(gb["tree"]), FlatTree(ga["tree"])
+            assert np.array_equal(tb.time, ta.time) and np.array_equal(tb.up0, ta.up0)       # only populations and migrations move
+            touched = (newt > oldt and tb.roottime > oldt) or (newt < oldt and tb.roottime > newt)
+            if touched:
+                migw += om.nw_migweight(b["tvals"], period, newt, tb, ta)
+                nmoved += int(ga["mignum"] != gb["mignum"])
+            else:
+                assert np.array_equal(tb.mig_t, ta.mig_t)
+        mh = float(np.exp(b["beta"] * (a["probg"] - b["probg"]) + migw))
+        assert rel_close(mh, rec["mh"], 1e-9, 1e-300), (mh, rec["mh"], migw)
+        nup += newt > oldt
+        ndown += newt < oldt
+    assert nup > 0 and ndown > 0 and nmoved > 0
