@@ -23,8 +23,10 @@ def _run_single():
     betas = [ch["beta"] for ch in d["chains"]]
     eng, _ = engine_from_fixture(d, lib=capi.bind(EMU), seed=99, betas=betas)
     eng.eval()
+    eng.set_update_priors(t_max=[3.0])
+    eng.set_update_schedule(3, 5)              # the whole qupdate step: split-time and scalar updates are local to a chain
     eng.run(NSTEPS, SWAPTRIES)
-    out = np.array([[eng.chain(c)["probg"], eng.chain(c)["pdg"]] for c in range(eng.nchains)])
+    out = np.array([[eng.chain(c)["probg"], eng.chain(c)["pdg"], eng.chain(c)["tvals"][0]] for c in range(eng.nchains)])
     return out, eng.betas(), eng.counters()
 
 
@@ -56,8 +58,10 @@ def _worker(rank, world, port, q):
                               t.roottime, uvals=g["uvals"])
     eng.upload()
     eng.eval()
+    eng.set_update_priors(t_max=[3.0])
+    eng.set_update_schedule(3, 5)
     ShardedStepper(eng, torch.device("cpu")).run(NSTEPS, SWAPTRIES)
-    out = np.array([[eng.chain(c)["probg"], eng.chain(c)["pdg"]] for c in range(per)])
+    out = np.array([[eng.chain(c)["probg"], eng.chain(c)["pdg"], eng.chain(c)["tvals"][0]] for c in range(per)])
     q.put((rank, out, eng.betas(), eng.counters()))
     dist.barrier()
     dist.destroy_process_group()
@@ -82,7 +86,7 @@ def test_two_ranks_reproduce_the_single_process_run():
         assert np.array_equal(g[2], betas1)                # every rank ends with the same beta permutation
         assert g[3]["swap_attempts"] == cnt1["swap_attempts"] and g[3]["swaps"] == cnt1["swaps"]
     assert sum(g[3]["accepted"] for g in got) == cnt1["accepted"]
-    assert cnt1["swaps"] > 0
+    assert cnt1["swaps"] > 0 and len(set(single[:, 2])) > 1      # split times moved
 
 
 def _lmode_worker(rank, world, port, q):
