@@ -70,6 +70,11 @@ SIGNATURES = {
     "ima2p_engine_fetch_state": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v]),
     "ima2p_engine_fetch_pair_summaries": (_i, [_v, c_dbl_p, c_int_p, c_int_p, _v]),
     "ima2p_engine_fetch_chain_summary": (_i, [_v, c_dbl_p, _v]),
+    "ima2p_dataset_read": (_i, [C.c_char_p, C.POINTER(_v)]),
+    "ima2p_dataset_free": (None, [_v]),
+    "ima2p_dataset_dims": (_i, [_v, c_int_p, c_int_p, C.c_char_p, _i]),
+    "ima2p_dataset_locus": (_i, [_v, _i, c_int_p, c_dbl_p, c_int_p, C.c_char_p, _i]),
+    "ima2p_dataset_locus_data": (_i, [_v, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
     "ima2p_lmode_create": (_i, [C.POINTER(_v), _i, _i, _i, _i, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, _i]),
     "ima2p_lmode_destroy": (None, [_v]),
     "ima2p_lmode_load": (_i, [_v, c_flt_p, _i, _i, _ll]),

@@ -110,27 +110,42 @@ IMA_DEV double nw_getmprob(const DevModel &M, int period, double mrate, double m
   return mcount * log(mrate / mtime) + (2 - mcount) * lognp + logb - mrate - logs;
 }
 
-// update_mig_tNW :336-786 for the staged genealogy; returns the log Hastings ratio of the migration events
-// (mproposenum - mproposedenom).  *overflow is set when the rewritten lists do not fit the pool.
-IMA_DEV double nw_update_pair(const DevModel &M, const EngineDims &d, const double *tv, int period, double oldt, double newt,
-                              int ng, int nl, Philox &rng, PairSm &S, bool *overflow) {
-  const int CAP = d.CAP, root = S.ctl_i[kCiRoot];
+// update_mig_tNW :336-786 for the staged genealogy, by the whole warp; every lane returns the log Hastings ratio of the
+// migration events (mproposenum - mproposedenom).  The reference walks the edges one after another; nothing in that
+// walk couples two edges except (i) an edge whose upper node lies inside the interval takes its upper populations from
+// its daughters' record and (ii) the random draws, so here lanes take edges: a first pass decides the lower end of every
+// stretch (one draw stream per edge), a second pass re-simulates every stretch against those decisions.
+IMA_DEV void nw_edge_rng(Philox &rng, const EngineView &E, int pair_global, int nl_max, int edge) {
+  const unsigned long long step = *E.nsteps;
+  rng.init(E.seed, (uint32_t)(pair_global * nl_max + edge), (uint32_t)step, kRngSplitMig | ((uint32_t)(step >> 32) << 8));
+}
+
+IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const double *tv, int period, double oldt, double newt,
+                              int ng, int nl, int pair_global, PairSm &S) {
+  const int CAP = E.d.CAP, root = S.ctl_i[kCiRoot], lane = Warp::lane();
   const bool up = newt > oldt;                        // the split moves back in time
   const double tu = up ? oldt : newt, td = up ? newt : oldt;
   const int period_a = up ? period : period + 1, period_b = up ? period + 1 : period, p1 = period + 1;
   const int addp = M.addpop[p1], d0 = M.droppops[p1][0], d1 = M.droppops[p1][1];
-  int *rec = S.moff;                                  // per edge: db | da << 5 | codef << 10 | coder << 13 | two << 16 | first << 17 | set << 18
-  for (int i = 0; i < nl; i++) rec[i] = 0;
+  int *rec = S.moff;                                  // per edge: db | da << 5 | codef << 10 | coder << 13 | set << 18
+  for (int i = lane; i < nl; i += IMA_WARP) rec[i] = 0;
+  if (lane == 0) S.ctl_i[kCiNev] = CAP;               // rewritten lists are appended to the scratch part of the pool
+#if IMA_CUDA
+  __threadfence_block();
+#endif
+  Warp::sync();
   // which edges have a stretch inside the interval, and where their lower ends are before (db) and after (da) the update
-  for (int i = 0; i < nl; i++) {
+  for (int i = lane; i < nl; i += IMA_WARP) {
     const double uptime = edge_top_time(S, ng, i);
-    if (!(S.time[i] > tu && uptime <= td) || (rec[i] >> 18)) continue;
-    int db, da, cf = 0, cr = 0, two = 0, sis = -1;
+    if (!(S.time[i] > tu && uptime <= td)) continue;
+    int db, da, cf = 0, cr = 0, sis = -1;
+    Philox rng;
     if (S.time[i] > td) {                             // the edge leaves the interval at its lower end: on its own
       db = nw_nowpop(M, tv, S, i, td);
       if (up) {
         if (db == addp) {
           const int c0 = nw_nowpop(M, tv, S, i, tu);
+          nw_edge_rng(rng, E, pair_global, E.d.NL, i);
           if (uptime < tu && (c0 == d0 || c0 == d1)) {
             if (rng.uniform() < 0.999) { da = c0; cf = 1; } else { da = c0 == d0 ? d1 : d0; cf = 2; }
           } else { cf = 3; da = rng.bit() ? d1 : d0; }
@@ -143,14 +158,15 @@ IMA_DEV double nw_update_pair(const DevModel &M, const EngineDims &d, const doub
         } else da = db;
       }
     } else {                                          // the edge ends in a coalescence inside the interval: with its sister
-      two = 1;
       const int dn = S.down[i];
       sis = S.up0[dn] == i ? S.up1[dn] : S.up0[dn];
+      if (sis < i) continue;                          // the record of a pair of sisters is made from the lower-numbered one
       const double uptime1 = edge_top_time(S, ng, sis);
       db = nw_nowpop(M, tv, S, i, S.time[i]);
       if (up) {
         if (db == addp) {
           const int c0 = nw_nowpop(M, tv, S, i, tu), c1 = nw_nowpop(M, tv, S, sis, tu);
+          nw_edge_rng(rng, E, pair_global, E.d.NL, i);
           if (uptime < tu && uptime1 < tu && c0 == c1 && (c0 == d0 || c0 == d1)) {
             if (rng.uniform() < 0.999) { da = c0; cf = 4; } else { da = c0 == d0 ? d1 : d0; cf = 5; }
           } else { cf = 6; da = rng.bit() ? d1 : d0; }
@@ -163,71 +179,79 @@ IMA_DEV double nw_update_pair(const DevModel &M, const EngineDims &d, const doub
         } else da = db;
       }
     }
-    const int v = db | (da << 5) | (cf << 10) | (cr << 13) | (two << 16) | (1 << 18);
-    rec[i] = v | (1 << 17);
-    if (two) rec[sis] = v;
+    const int v = db | (da << 5) | (cf << 10) | (cr << 13) | (1 << 18);
+    rec[i] = v;
+    if (sis >= 0) rec[sis] = v;
   }
-  // per record: population at the upper end before / after, migration counts and rates, new paths, Hastings terms
+#if IMA_CUDA
+  __threadfence_block();
+#endif
+  Warp::sync();
+  // per stretch: population at the upper end before / after, migration counts and rates, the new path, Hastings terms
   double num = 0.0, denom = 0.0;
-  int freep = CAP;                                    // rewritten lists are appended to the scratch part of the pool
-  for (int i = 0; i < nl; i++) {
-    if (!((rec[i] >> 17) & 1)) continue;
-    const int db = rec[i] & 31, da = (rec[i] >> 5) & 31, two = (rec[i] >> 16) & 1;
-    const double logpf = nw_logpf((rec[i] >> 10) & 7), logpf_r = nw_logpf((rec[i] >> 13) & 7);
-    for (int k = 0; k <= two; k++) {
-      int ei = i;
-      if (k) { const int dn = S.down[i]; ei = S.up0[dn] == i ? S.up1[dn] : S.up0[dn]; }
-      const double uptime = edge_top_time(S, ng, ei);
-      int upb, upa;
-      if (uptime < tu) {
-        if (!up) { upb = nw_nowpop(M, tv, S, ei, tu); upa = (upb == d0 || upb == d1) ? addp : upb; }
-        else { upb = nw_nowpop(M, tv, S, ei, tu * (1 + DBL_EPSILON)); upa = upb == addp ? nw_nowpop(M, tv, S, ei, tu) : upb; }
-      } else {                                        // the upper end is a node inside the interval: its daughters' record
-        const int r = rec[S.up0[ei]];
-        upb = r & 31; upa = (r >> 5) & 31;
-        S.pop[ei] = (short)upa;
-      }
-      if (ei == root) continue;
-      const double bottom = td < S.time[ei] ? td : S.time[ei], top = tu > uptime ? tu : uptime;
-      const double mtime = bottom - top;
-      const int s0 = S.ms[ei], n = S.mcn[ei];
-      int kk = 0, mi = 0, mstart = -1;
-      while (kk < n && S.pt[s0 + kk] < td) { if (S.pt[s0 + kk] > tu) { if (mi == 0) mstart = kk; mi++; } kk++; }
-      int cm2_b = -1, cm2_a = -1;
-      if (kk >= 2 && mstart >= 0 && kk - mstart >= 2) cm2_b = kk == 2 ? upb : (int)S.pp[s0 + kk - 3];
-      const int mcount = mi, npopsa = M.npops - period_a, npopsb = M.npops - period_b;
-      const double mrate = period_a < M.nsplit ? calcmrate(mcount, mtime) * mtime : 0.0;
-      int mnew;
-      if (npopsa == 1) mnew = 0;
-      else if (npopsa == 2) mnew = poisson_cond(rng, mrate, upa == da ? 0 : 1);
-      else mnew = poisson_cond(rng, mrate, upa == da ? 3 : 2);
-      const double mrate_r = period_b < M.nsplit ? calcmrate(mnew, mtime) * mtime : 0.0;
-      // addmigration_NW :208-289: keep the events above tu and below td, replace those in between
-      int above = 0;
-      if (uptime < tu) while (above < n && S.pt[s0 + above] < tu) above++;
-      int below = above;
-      while (below < n && S.pt[s0 + below] < td) below++;
-      const int numskip = below - above, numheld = n - below;
-      if (!up && period_a == M.nsplit) {
-        S.mcn[ei] = (unsigned short)above;
-      } else if (mnew > 0 || numskip > 0) {
-        const int total = above + mnew + numheld;
-        if (freep + total > 4 * CAP) { *overflow = true; return 0.0; }
-        for (int j = 0; j < above; j++) { S.pt[freep + j] = S.pt[s0 + j]; S.pp[freep + j] = S.pp[s0 + j]; }
-        if (mnew > 0) {
-          Emi em; em.seg = freep + above; em.nmig = 0;
-          simmpath(M, rng, S, em, 4 * CAP, period_a, mnew, mtime, top, upa, da);
-          if (mnew >= 2) cm2_a = mnew == 2 ? upa : (int)S.pp[freep + above + mnew - 3];
-        }
-        for (int j = 0; j < numheld; j++) { S.pt[freep + above + mnew + j] = S.pt[s0 + below + j]; S.pp[freep + above + mnew + j] = S.pp[s0 + below + j]; }
-        S.ms[ei] = (unsigned short)freep; S.mcn[ei] = (unsigned short)total;
-        freep += total;
-      }
-      if (mrate > 0) denom += logpf + nw_getmprob(M, period_a, mrate, mtime, mnew, upa, da, cm2_a, npopsa);
-      if (mrate_r > 0) num += logpf_r + nw_getmprob(M, period_b, mrate_r, mtime, mcount, upb, db, cm2_b, npopsb);
+  bool overflow = false;
+  for (int ei = lane; ei < nl; ei += IMA_WARP) {
+    if (!(rec[ei] >> 18)) continue;
+    const int db = rec[ei] & 31, da = (rec[ei] >> 5) & 31;
+    const double logpf = nw_logpf((rec[ei] >> 10) & 7), logpf_r = nw_logpf((rec[ei] >> 13) & 7);
+    const double uptime = edge_top_time(S, ng, ei);
+    int upb, upa;
+    if (uptime < tu) {
+      if (!up) { upb = nw_nowpop(M, tv, S, ei, tu); upa = (upb == d0 || upb == d1) ? addp : upb; }
+      else { upb = nw_nowpop(M, tv, S, ei, tu * (1 + DBL_EPSILON)); upa = upb == addp ? nw_nowpop(M, tv, S, ei, tu) : upb; }
+    } else {                                          // the upper end is a node inside the interval: its daughters' record
+      const int r = rec[S.up0[ei]];
+      upb = r & 31; upa = (r >> 5) & 31;
+      S.pop[ei] = (short)upa;
     }
+    if (ei == root) continue;
+    const double bottom = td < S.time[ei] ? td : S.time[ei], top = tu > uptime ? tu : uptime;
+    const double mtime = bottom - top;
+    const int s0 = S.ms[ei], n = S.mcn[ei];
+    int kk = 0, mi = 0, mstart = -1;
+    while (kk < n && S.pt[s0 + kk] < td) { if (S.pt[s0 + kk] > tu) { if (mi == 0) mstart = kk; mi++; } kk++; }
+    int cm2_b = -1, cm2_a = -1;
+    if (kk >= 2 && mstart >= 0 && kk - mstart >= 2) cm2_b = kk == 2 ? upb : (int)S.pp[s0 + kk - 3];
+    const int mcount = mi, npopsa = M.npops - period_a, npopsb = M.npops - period_b;
+    const double mrate = period_a < M.nsplit ? calcmrate(mcount, mtime) * mtime : 0.0;
+    Philox rng;
+    nw_edge_rng(rng, E, pair_global, E.d.NL, E.d.NL + ei);          // second block of streams: the simulation draws
+    int mnew;
+    if (npopsa == 1) mnew = 0;
+    else if (npopsa == 2) mnew = poisson_cond(rng, mrate, upa == da ? 0 : 1);
+    else mnew = poisson_cond(rng, mrate, upa == da ? 3 : 2);
+    const double mrate_r = period_b < M.nsplit ? calcmrate(mnew, mtime) * mtime : 0.0;
+    // addmigration_NW :208-289: keep the events above tu and below td, replace those in between
+    int above = 0;
+    if (uptime < tu) while (above < n && S.pt[s0 + above] < tu) above++;
+    int below = above;
+    while (below < n && S.pt[s0 + below] < td) below++;
+    const int numskip = below - above, numheld = n - below;
+    if (!up && period_a == M.nsplit) {
+      S.mcn[ei] = (unsigned short)above;
+    } else if (mnew > 0 || numskip > 0) {
+      const int total = above + mnew + numheld;
+#if IMA_CUDA
+      const int at = atomicAdd(&S.ctl_i[kCiNev], total);
+#else
+      const int at = S.ctl_i[kCiNev];
+      S.ctl_i[kCiNev] += total;
+#endif
+      if (at + total > 4 * CAP) { overflow = true; continue; }
+      for (int j = 0; j < above; j++) { S.pt[at + j] = S.pt[s0 + j]; S.pp[at + j] = S.pp[s0 + j]; }
+      if (mnew > 0) {
+        Emi em; em.seg = at + above; em.nmig = 0;
+        simmpath(M, rng, S, em, 4 * CAP, period_a, mnew, mtime, top, upa, da);
+        if (mnew >= 2) cm2_a = mnew == 2 ? upa : (int)S.pp[at + above + mnew - 3];
+      }
+      for (int j = 0; j < numheld; j++) { S.pt[at + above + mnew + j] = S.pt[s0 + below + j]; S.pp[at + above + mnew + j] = S.pp[s0 + below + j]; }
+      S.ms[ei] = (unsigned short)at; S.mcn[ei] = (unsigned short)total;
+    }
+    if (mrate > 0) denom += logpf + nw_getmprob(M, period_a, mrate, mtime, mnew, upa, da, cm2_a, npopsa);
+    if (mrate_r > 0) num += logpf_r + nw_getmprob(M, period_b, mrate_r, mtime, mcount, upb, db, cm2_b, npopsb);
   }
-  return num - denom;
+  if (Warp::any(overflow) && lane == 0) S.ctl_i[kCiFlags] |= (int)kFlagOverflow;
+  return Warp::sum(num - denom);
 }
 
 IMA_KERNEL void IMA_PROPOSE_BOUNDS k_nw_t(EngineView E, UpdateView U) {
@@ -251,17 +275,9 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_nw_t(EngineView E, UpdateView U) {
   const double roottime = S.ctl_d[kCdRoottime];
   // :967-969: a genealogy whose root is younger than both split times is not touched
   const bool touched = (t.newt > t.oldt && roottime > t.oldt) || (t.newt < t.oldt && roottime > t.newt);
-  if (lane == 0) {
-    double mw = 0.0;
-    bool ovf = false;
-    if (touched) {
-      Philox rng;
-      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngSplitMig);
-      mw = nw_update_pair(M, E.d, tvo, t.period, t.oldt, t.newt, L.ng, L.nl, rng, S, &ovf);
-    }
-    S.ctl_d[kCdMigw] = mw;
-    S.ctl_i[kCiFlags] = ovf ? (int)kFlagOverflow : 0;
-  }
+  double mw = 0.0;
+  if (touched) mw = nw_update_pair(E, M, tvo, t.period, t.oldt, t.newt, L.ng, L.nl, (E.d.chain0 + c) * E.d.nloci + li, S);
+  if (lane == 0) S.ctl_d[kCdMigw] = mw;
 #if IMA_CUDA
   __threadfence_block();
 #endif

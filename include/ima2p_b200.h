@@ -37,6 +37,7 @@ extern "C" {
 #define IMA2P_MODEL_IS 0        /* INFINITESITES */
 #define IMA2P_MODEL_HKY 1
 #define IMA2P_MODEL_SW 2        /* STEPWISE */
+#define IMA2P_MODEL_JOINT 3     /* JOINT_IS_SW: part 0 infinite sites, parts 1.. stepwise */
 #define IMA2P_MAX_LINKED 4       /* linked parts per locus kept on the device (reference MAXLINKED 15) */
 #define IMA2P_MAXLINKED 4
 
@@ -228,6 +229,24 @@ int ima2p_lmode_joint_phase2 (ima2p_lmode * l, int nvec, const double *globalmax
                               double *records_out);
 void ima2p_lmode_joint_finish (const double *rec6, double globalmax, long long nrows_total, int calc_ess, double *q,
                                double *ess);
+
+/* ---- the .u input file (readata.cpp): host code, needs no device -------------------------------------------------
+ * dataset_read = readdata (readata.cpp:1038-1123): top lines (:891-1036), locus header lines (parse_locus_info
+ * :618-866), and the data with the reference's site handling: infinite-sites / joint loci keep the segregating,
+ * two-state, all-acgt columns recoded 0/1 against the first gene (findsegsites :34-178, readseqIS :347-497); HKY loci
+ * drop gapped columns and merge identical ones with multiplicities (readseqHKY :246-345, eliminategaps, sortseq);
+ * stepwise parts give allele lengths and their range (readseqSW :500-588).  Malformed input is a negative return
+ * code where the reference calls IM_err. */
+typedef struct ima2p_dataset ima2p_dataset;
+int ima2p_dataset_read (const char *path, ima2p_dataset ** out);
+void ima2p_dataset_free (ima2p_dataset * d);
+int ima2p_dataset_dims (const ima2p_dataset * d, int *npops, int *nloci, char *tree, int tree_len);
+/* info[8] = model, numgenes, numsites, totsites, numbases, nlinked, mutation rates given on the header line, 0 */
+int ima2p_dataset_locus (const ima2p_dataset * d, int locus, int *info, double *hval, int *samppop, char *name,
+                         int name_len);
+/* seq[numgenes][numsites]; mult[numsites] (HKY); A[nlinked][numgenes]; minA, maxA[nlinked]; pi[4] (HKY); urate[info[6]] */
+int ima2p_dataset_locus_data (const ima2p_dataset * d, int locus, int *seq, int *mult, int *A, int *minA, int *maxA,
+                              double *pi, double *urate);
 
 #ifdef __cplusplus
 }

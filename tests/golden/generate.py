@@ -135,6 +135,93 @@ def three_pops(src, dst):
     open(dst, "w").write("\n".join(out) + "\n")
 
 
+def make_parse_inputs():
+    """Small .u files of our own making that exercise the reader's corner cases (kept columns vs monomorphic, three-state
+    and non-acgt columns; gaps and repeated columns under HKY, interleaved blocks; linked stepwise parts; a joint locus;
+    the optional tree line; comment lines; blanks inside sequences).  The infinite-sites columns come from genealogies,
+    so that the reference accepts the files; the expected parse is then the reference's own (state fixtures below)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import numpy as np
+    from ima2p_b200 import synth
+    rng = np.random.default_rng(5)
+    out = os.path.join(HERE, "inputs")
+    os.makedirs(out, exist_ok=True)
+
+    def is_rows(L, junk=True):
+        n, cols = L["n"], []
+        for s in range(L["numsites"]):
+            anc, der = rng.choice(list("ACGT"), 2, replace=False)
+            cols.append([der if L["seq"][j][s] else anc for j in range(n)])
+            if junk and s % 3 == 0:                      # a monomorphic column
+                cols.append([str(rng.choice(list("ACGT")))] * n)
+            if junk and s % 5 == 1:                      # three states: dropped
+                c = [str(x) for x in rng.choice(list("ACG"), n)]
+                c[0], c[1], c[2] = "A", "C", "G"
+                cols.append(c)
+            if junk and s % 7 == 2:                      # an unknown base: dropped
+                c = ["T"] * n
+                c[int(rng.integers(1, n))] = "N"
+                c[int(rng.integers(1, n))] = "C"
+                cols.append(c)
+        rows = ["".join(cols[s][j] for s in range(len(cols))) for j in range(n)]
+        return rows, len(cols)
+
+    def case(rows):                                      # lower case on odd rows, a blank in the middle of even rows
+        return [r.lower() if j % 2 else r[:len(r) // 2] + " " + r[len(r) // 2:] for j, r in enumerate(rows)]
+
+    # 1: infinite sites, 3 populations, tree line, comments, inheritance scalars, a mutation rate
+    loci = synth.make_dataset(4, 6, 8, seed=21, min_sites=5)
+    with open(os.path.join(out, "parse_is_3pop.u"), "w") as f:
+        f.write("parser corner cases, infinite sites\n# a comment line\n#another\n3\npopA popB popC\n((0,1):3,2):4\n4\n")
+        for k, L in enumerate(loci):
+            rows, nb = is_rows(L)
+            tail = ["", " 0.75", " 0.25 0.0000012", " 1"][k]
+            f.write("loc%d 6 5 3 %d I%s\n" % (k, nb, tail))
+            for j, r in enumerate(case(rows)):
+                f.write("%-10s%s\n" % ("g%d_%d" % (k, j), r))
+    # 2: HKY, 2 populations; gaps, repeated columns, u for t, an interleaved locus
+    with open(os.path.join(out, "parse_hky.u"), "w") as f:
+        f.write("parser corner cases, HKY\n2\npop0 pop1\n(0,1):2\n3\n")
+        for k in range(3):
+            n0, n1, nb = 5, 4 + k, 40 + 7 * k
+            base = rng.choice(list("ACGT"), nb)
+            rows = []
+            for j in range(n0 + n1):
+                r = base.copy()
+                mut = rng.random(nb) < 0.08
+                r[mut] = rng.choice(list("ACGT"), mut.sum())
+                gap = rng.random(nb) < 0.02
+                r[gap] = rng.choice(list("N-."), gap.sum())
+                r = "".join(r)
+                rows.append(r.replace("T", "U") if j == 2 else (r.lower() if j % 3 == 1 else r))
+            f.write("hloc%d %d %d %d H %s\n" % (k, n0, n1, nb, ["1", "0.5", "1"][k]))
+            if k == 1:                                   # two interleaved blocks
+                cut = nb // 2
+                for j, r in enumerate(rows):
+                    f.write("%-10s%s\n" % ("h%d" % j, r[:cut]))
+                for j, r in enumerate(rows):
+                    f.write("%-10s%s\n" % ("h%d" % j, r[cut:]))
+            else:
+                for j, r in enumerate(rows):
+                    f.write("%-10s%s %s\n" % ("h%d" % j, r[:10], r[10:]))
+    # 3: stepwise with two linked parts, a joint locus, an infinite-sites locus; 2 populations with the tree line
+    loci = synth.make_dataset(2, 7, 6, seed=23, min_sites=6)
+    with open(os.path.join(out, "parse_sw_joint.u"), "w") as f:
+        f.write("parser corner cases, stepwise and joint\n#c\n2\nwest east\n(0,1):2\n3\n")
+        f.write("str2 7 6 2 S2 1\n")
+        for j in range(13):
+            f.write("%-10s%d %d\n" % ("s%d" % j, rng.integers(8, 15), rng.integers(20, 31)))
+        rows, nb = is_rows(loci[0])
+        f.write("joint 7 6 %d J1 0.5\n" % nb)
+        for j, r in enumerate(rows):
+            f.write("%-10s%d %s\n" % ("j%d" % j, rng.integers(9, 14), r))
+        rows, nb = is_rows(loci[1], junk=False)
+        f.write("plain 7 6 %d I 1\n" % nb)
+        for j, r in enumerate(rows):
+            f.write("%-10s%s\n" % ("p%d" % j, r))
+    return [os.path.join(out, n) for n in ("parse_is_3pop.u", "parse_hky.u", "parse_sw_joint.u")]
+
+
 def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the reference harness first: make -C oracle ref")
@@ -161,6 +248,12 @@ def main():
     nomig = ["-q", "10", "-m", "0", "-t", "3"]                       # -m 0 sets NOMIGRATION (ima_main_mpi.cpp:822-823)
     run("state", "state_sim5_nomig_hn2", s5, 2, {"burn": 100}, priors=nomig)
     run("state", "state_sim5_3pop_nomig_hn2", p3, 2, {"burn": 100}, priors=nomig)
+    # the .u reader (section 8 f2): our own corner-case inputs, parsed by the reference
+    if not ONLY or any(n.startswith("parse_") for n in ONLY):
+        u1, u2, u3 = make_parse_inputs()
+        run("state", "parse_is_3pop", u1, 1, {"burn": 0})
+        run("state", "parse_hky", u2, 1, {"burn": 0})
+        run("state", "parse_sw_joint", u3, 1, {"burn": 0})
     # proposal known-answer fixtures (a2-a4): accepted updategenealogy() calls
     run("updates", "updates_sim5_hn2", s5, 2, {"burn": 50, "n": 250})
     run("updates", "updates_sim3_hn2", s3, 2, {"burn": 50, "n": 250})
