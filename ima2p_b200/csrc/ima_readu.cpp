@@ -350,4 +350,73 @@ int ima2p_dataset_locus_data(const ima2p_dataset *d, int li, int *seq, int *mult
   return IMA2P_OK;
 }
 
+// ---- the .ti file of sampled genealogies (written in M mode, read back in L mode) ---------------------------------
+// header block + "VALUESSTART" (ima_main_mpi.cpp:2123-2141), then one line per sampled genealogy, every value as
+// "%.6f\t" (savegenealogyfile, output.cpp:662-685); read back by loadgenealogyvalues (ima_main_mpi.cpp:3216-3440)
+int ima2p_ti_create(const char *path, const char *header_text) {
+  if (!path) return ufail(IMA2P_E_ARG, "ti_create: bad argument");
+  FILE *f = fopen(path, "w");
+  if (!f) return ufail(IMA2P_E_ARG, "Error creating file for holding genealogy information");
+  const char *bar = "-------------------------------------------\n\n";
+  fprintf(f, "%s", bar);
+  fprintf(f, "Header for genealogy file:  %s\n\n", path);
+  fprintf(f, "%s", bar);
+  fprintf(f, "%s\n", header_text ? header_text : "");
+  fprintf(f, "%s", bar);
+  fprintf(f, "End of header for genealogy file:  %s\n\n", path);
+  fprintf(f, "%s", bar);
+  fprintf(f, "VALUESSTART\n");
+  fclose(f);
+  return IMA2P_OK;
+}
+
+int ima2p_ti_append(const char *path, const float *rows, long long nrows, int rowlen) {
+  if (!path || !rows || nrows < 0 || rowlen < 1) return ufail(IMA2P_E_ARG, "ti_append: bad argument");
+  FILE *f = fopen(path, "a");
+  if (!f) return ufail(IMA2P_E_ARG, "Error opening treeinfosave file for writing");
+  for (long long j = 0; j < nrows; j++) {
+    for (int i = 0; i < rowlen; i++) fprintf(f, "%.6f\t", (float)rows[(size_t)j * rowlen + i]);
+    fprintf(f, "\n");
+  }
+  fclose(f);
+  return IMA2P_OK;
+}
+
+// rows == NULL: only counts the genealogies in the file.  Otherwise loads up to max_rows of them (all when the file
+// holds fewer); a line with fewer or more than rowlen values is an error, as in the reference (IMERR_TIFILE).
+int ima2p_ti_load(const char *path, int rowlen, float *rows, long long max_rows, long long *nrows_out) {
+  if (!path || rowlen < 1 || !nrows_out) return ufail(IMA2P_E_ARG, "ti_load: bad argument");
+  FILE *f = fopen(path, "r");
+  if (!f) return ufail(IMA2P_E_ARG, " cannot open .ti file");
+  std::string line;
+  int ch;
+  bool started = false;
+  long long n = 0;
+  auto getline = [&]() { line.clear(); while ((ch = fgetc(f)) != EOF && ch != '\n') line.push_back((char)ch); return ch != EOF || !line.empty(); };
+  while (getline()) if (line.find("VALUESSTART") != std::string::npos) { started = true; break; }
+  if (!started) { fclose(f); return ufail(IMA2P_E_ARG, "no VALUESSTART line in .ti file"); }
+  while (getline()) {
+    if (rows && n >= max_rows) break;
+    const char *c = line.c_str();
+    int got = 0;
+    for (;;) {
+      while (*c && isspace((unsigned char)*c)) c++;
+      if (!*c) break;
+      char *end = nullptr;
+      const float v = strtof(c, &end);
+      if (end == c) { fclose(f); return ufail(IMA2P_E_ARG, "Problem in .ti file: not a number"); }
+      if (got < rowlen && rows) rows[(size_t)n * rowlen + got] = v;
+      got++;
+      c = end;
+    }
+    if (got == 0) continue;
+    if (got < rowlen) { fclose(f); return ufail(IMA2P_E_ARG, "Problem in .ti file, too few values per genealogy, .ti file may have been generated with a different program"); }
+    if (got > rowlen) { fclose(f); return ufail(IMA2P_E_ARG, "Problem in .ti file, too many values per genealogy, .ti file may have been generated with a different program"); }
+    n++;
+  }
+  fclose(f);
+  *nrows_out = n;
+  return IMA2P_OK;
+}
+
 }  // extern "C"

@@ -36,3 +36,25 @@ def read_u(path, lib=None):
         return dict(npops=npops.value, tree=tree.value.decode(), loci=loci)
     finally:
         l.ima2p_dataset_free(h)
+
+
+def ti_create(path, header="", lib=None):
+    l = lib or capi.lib()
+    capi.check(l, l.ima2p_ti_create(str(path).encode(), header.encode()))
+
+
+def ti_append(path, rows, lib=None):
+    l = lib or capi.lib()
+    r = np.ascontiguousarray(rows, dtype=np.float32)
+    capi.check(l, l.ima2p_ti_append(str(path).encode(), r.ctypes.data_as(capi.c_flt_p), r.shape[0], r.shape[1]))
+
+
+def ti_load(path, rowlen, max_rows=None, lib=None):
+    """Rows of a .ti file as float32 [G][rowlen] (loadgenealogyvalues)."""
+    l = lib or capi.lib()
+    n = C.c_longlong()
+    capi.check(l, l.ima2p_ti_load(str(path).encode(), rowlen, None, 0, C.byref(n)))
+    want = n.value if max_rows is None else min(n.value, max_rows)
+    rows = np.zeros((want, rowlen), np.float32)
+    capi.check(l, l.ima2p_ti_load(str(path).encode(), rowlen, rows.ctypes.data_as(capi.c_flt_p), want, C.byref(n)))
+    return rows[:n.value]

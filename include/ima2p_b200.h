@@ -248,6 +248,14 @@ int ima2p_dataset_locus (const ima2p_dataset * d, int locus, int *info, double *
 int ima2p_dataset_locus_data (const ima2p_dataset * d, int locus, int *seq, int *mult, int *A, int *minA, int *maxA,
                               double *pi, double *urate);
 
+/* ---- the .ti file of sampled genealogies: M mode writes it, L mode reads it back ---------------------------------
+ * ti_create: header block ending in "VALUESSTART" (ima_main_mpi.cpp:2123-2141); ti_append: one line per row, every value
+ * "%.6f\t" (savegenealogyfile, output.cpp:662-685); ti_load (loadgenealogyvalues, ima_main_mpi.cpp:3216-3440):
+ * rows == NULL counts the genealogies, else up to max_rows rows of rowlen floats are read; *nrows_out = rows read. */
+int ima2p_ti_create (const char *path, const char *header_text);
+int ima2p_ti_append (const char *path, const float *rows, long long nrows, int rowlen);
+int ima2p_ti_load (const char *path, int rowlen, float *rows, long long max_rows, long long *nrows_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -735,6 +735,16 @@ mode_lmode (long burn, long rows, long every)
   do_burn (burn);
   collect_rows (rows, every);
   np = numpopsizeparams + nummigrateparams;
+  if (kv.count ("ti"))
+  {
+    /* the rows as the reference writes them to a .ti file: savegenealogyfile (output.cpp:662-685) appends to a file
+     * that the run created with a header ending in VALUESSTART (ima_main_mpi.cpp:2123-2141) */
+    FILE *tf = fopen (kv["ti"].c_str (), "w");
+    fprintf (tf, "header written by the harness\n\nVALUESSTART\n");
+    fclose (tf);
+    int last = -1;
+    savegenealogyfile (const_cast<char *> (kv["ti"].c_str ()), NULL, &last, gsampinflength);
+  }
   fprintf (jo, "{");
   dump_model ();
   fprintf (jo, "\"rows\":[");

@@ -261,6 +261,8 @@ def main():
     # numerics tables (a10, a13) and L mode (a14, a15)
     run("kat", "kat_sim5_hn4", s5, 4, {"burn": 100})
     run("lmode", "lmode_sim5_hn2", s5, 2, {"burn": 200, "rows": 600, "every": 3})
+    os.makedirs(os.path.join(HERE, "inputs"), exist_ok=True)
+    run("lmode", "lmode_ti_sim3_hn2", s3, 2, {"burn": 100, "rows": 60, "every": 2, "ti": os.path.join(HERE, "inputs", "sample_sim3.ti")})
     run("lmode", "lmode_sim5_expo_hn2", s5, 2, {"burn": 200, "rows": 300, "every": 3}, extra=["-j7"])
     # split-time, mutation-scalar updates (section 8 f1) and thermodynamic integration (a16)
     run("tupdates", "tupdates_sim5_hn2", s5, 2, {"burn": 100, "n": 30, "between": 3})

@@ -75,3 +75,27 @@ def test_reader_rejects_malformed_files(lib, tmp_path):
             read_u(p, lib)
     with pytest.raises(Ima2pError):
         read_u(tmp_path / "missing.u", lib)
+
+
+def test_ti_file_round_trip_matches_reference_text(lib, tmp_path):
+    """.ti rows: the loader reads what the reference's savegenealogyfile wrote; the writer reproduces that text byte for
+    byte; L-mode values computed from the loaded file agree with the reference's (which used the in-memory rows)."""
+    from ima2p_b200.readu import ti_append, ti_create, ti_load
+    ref = load_golden("lmode_ti_sim3_hn2")
+    rows = np.array(ref["rows"], dtype=np.float32)
+    src = os.path.join(HERE, "golden", "inputs", "sample_sim3.ti")
+    got = ti_load(src, rows.shape[1], lib=lib)
+    assert got.shape == rows.shape
+    assert np.array_equal(got, np.array([[np.float32("%.6f" % v) for v in r] for r in rows]))     # %.6f text of each float
+    assert len(ti_load(src, rows.shape[1], max_rows=7, lib=lib)) == 7
+    out = tmp_path / "mine.ti"
+    ti_create(out, "a header", lib=lib)
+    ti_append(out, rows[:25], lib=lib)
+    ti_append(out, rows[25:], lib=lib)
+    body = lambda p: open(p).read().split("VALUESSTART\n", 1)[1]
+    assert body(out) == body(src)
+    from ima2p_b200.capi import Ima2pError
+    with pytest.raises(Ima2pError):
+        ti_load(src, rows.shape[1] + 1, lib=lib)                  # too few values per genealogy
+    with pytest.raises(Ima2pError):
+        ti_load(src, rows.shape[1] - 1, lib=lib)                  # too many
