@@ -356,7 +356,7 @@ def main():
     roof = None
     if kernel_ms is not None:
         per = np.asarray(kernel_ms, dtype=np.float64) / args.steps                       # ms per launch
-        names = ["k_propose", "k_accept", "k_swap", "k_rescale_t", "k_accept_t", "k_changeu"]
+        names = ["k_propose", "k_accept", "k_swap", "k_rescale_t", "k_accept_t", "k_changeu", "k_nw_t"]
         dom = int(np.argmax(per))
         P = cpg * nloci
         b_update = algorithmic_bytes_per_update(n0 + n1, mig_mean, p_acc, eng.NI, eng.ND)
@@ -364,7 +364,7 @@ def main():
         b_accept = 2 * W_g + 16 + 12 + 1 + (W_g + 8 * (eng.nq + eng.nm) + 40) / nloci
         b_pair = 24.0 * (2 * (n0 + n1) - 1) + 12.0 * mig_mean + W_g + 24.0                # one genealogy with its weights
         alg = {"k_propose": b_update * P, "k_accept": b_accept * P, "k_swap": 16.0 * cpg, "k_rescale_t": 2.0 * b_pair * P,
-               "k_accept_t": (W_g + 8 + 16 + 1) * P, "k_changeu": 48.0 * P}[names[dom]]
+               "k_accept_t": (W_g + 8 + 16 + 1) * P, "k_changeu": 48.0 * P, "k_nw_t": 2.0 * b_pair * P}[names[dom]]
         achieved = alg / (per[dom] * 1e-3) / 1e9
         traffic = None
         tf = os.path.join(ROOT, "profiles", "traffic.json")
@@ -389,7 +389,7 @@ def main():
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
            "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke, "parts_ms": parts},
-           "gpu_launches": (6 if full else 3) * args.steps,
+           "gpu_launches": (7 if full else 3) * args.steps,
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
            "genealogy_updates_only": ({"ms_per_step": graph_ms / args.steps, "value": updates_all / (graph_ms * 1e-3), "unit": unit}
                                       if graph_ms else None), "lmode": lmode,

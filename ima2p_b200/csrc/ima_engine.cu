@@ -134,6 +134,11 @@ static void launch_accept(Engine *e, stream_t s, int l0, int l1) {
 // into `pieces` ranges and the sweep of range q (stream s) overlaps the proposals of range q+1 (aux stream):
 //     P0 -> [A0 | P1] -> [A1 | P2] -> ... -> A(Q-1)          step time ~ P/Q + A instead of P + A.
 // Works under stream capture too (the event record/wait pairs become graph edges).
+static size_t changeu_smem(const Engine *e) {
+  const size_t need = changeu_smem_doubles(e->d.nloci) * sizeof(double);
+  return need > e->pair_smem ? need : e->pair_smem;
+}
+
 // the rest of qupdate's schedule (ima_main_mpi.cpp:1867-1945): a split-time update of every chain each step
 // (TUPDATEINC 0), the mutation scalars every u_every-th step (UUPDATEINC 4); both are local to a chain
 static void launch_param_updates(Engine *e, stream_t s) {
@@ -147,7 +152,7 @@ static void launch_param_updates(Engine *e, stream_t s) {
   if (e->u_every > 0 && (e->uv.nurates > 1 || e->loci[0].d.model == kHKY)) {
     UpdateView u = e->uv;
     u.u_every = e->u_every;
-    IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, u);
+    IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, changeu_smem(e) * kWarpsPerBlock, s, e->v, u);
   }
 }
 
@@ -191,7 +196,9 @@ static void launch_swap(Engine *e, stream_t s, const double *S_global, int swapt
   sv.S_global = S_global;
   sv.swaptries = swaptries;
   sv.advance_step = 1;
-  IMA_LAUNCH(k_swap, 1, 1, 0, s, e->v, sv);
+  const int G = e->d.nchains_global;
+  sv.smem_chains = G <= 4000 ? G : 0;                        // 24 bytes per chain, 96 KB opted in at finalize
+  IMA_LAUNCH(k_swap, 1, 1, (size_t)sv.smem_chains * 24 + 16, s, e->v, sv);
 }
 
 }  // namespace ima
@@ -388,8 +395,9 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_rescale_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * 24 + 16)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_nw_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
-      !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))))
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(changeu_smem(&e) * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
   if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");
 #else
@@ -731,8 +739,8 @@ int ima2p_engine_run(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stre
 }
 
 // Same work as ima2p_engine_run, launched kernel by kernel with CUDA events recorded on the launching
-// stream around each kernel of every step; kernel_ms[6] receives the summed device time of
-// {propose, accept, swap, rescale_t, accept_t, changeu} over the nsteps (bench.py's roofline numerator comes from here).
+// stream around each kernel of every step; kernel_ms[7] receives the summed device time of
+// {propose, accept, swap, rescale_t, accept_t, changeu, nw_t} over the nsteps (bench.py's roofline numerator comes from here).
 int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms) {
   if (!h || nsteps < 0 || swaptries < 0 || !kernel_ms) return fail(IMA2P_E_ARG, "run_timed: bad argument");
   Engine &e = h->eng;
@@ -741,11 +749,11 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
   if (e.d.nchains != e.d.nchains_global) return fail(IMA2P_E_ARG, "run_timed: engine holds a shard");
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, cuda_stream);
-  for (int k = 0; k < 6; k++) kernel_ms[k] = 0.f;
+  for (int k = 0; k < 7; k++) kernel_ms[k] = 0.f;
 #if IMA_CUDA
   const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int chunk = 256;
-  std::vector<cudaEvent_t> ev((size_t)chunk * 7);
+  std::vector<cudaEvent_t> ev((size_t)chunk * 8);
   const bool do_t = e.t_updates && e.model.nsplit > 0, do_u = e.u_every > 0 && (e.uv.nurates > 1 || e.loci[0].d.model == kHKY);
   UpdateView uvu = e.uv;
   uvu.u_every = e.u_every > 0 ? e.u_every : 1;
@@ -753,25 +761,26 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
   for (int s0 = 0; s0 < nsteps; s0 += chunk) {
     const int n = nsteps - s0 < chunk ? nsteps - s0 : chunk;
     for (int i = 0; i < n; i++) {
-      cudaEventRecord(ev[i * 7 + 0], s);
+      cudaEventRecord(ev[i * 8 + 0], s);
       IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, 0, e.d.nloci);
-      cudaEventRecord(ev[i * 7 + 1], s);
+      cudaEventRecord(ev[i * 8 + 1], s);
       launch_accept(&e, s, 0, e.d.nloci);
-      cudaEventRecord(ev[i * 7 + 2], s);
+      cudaEventRecord(ev[i * 8 + 2], s);
       if (do_t && (e.t_updates & 2) && !e.model.nomigration) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
+      cudaEventRecord(ev[i * 8 + 3], s);
       if (do_t && ((e.t_updates & 1) || e.model.nomigration)) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
-      cudaEventRecord(ev[i * 7 + 3], s);
+      cudaEventRecord(ev[i * 8 + 4], s);
       if (do_t) IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e.d) * kWarpsPerBlock, s, e.v, e.uv);
-      cudaEventRecord(ev[i * 7 + 4], s);
-      if (do_u) IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, uvu);
-      cudaEventRecord(ev[i * 7 + 5], s);
+      cudaEventRecord(ev[i * 8 + 5], s);
+      if (do_u) IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, changeu_smem(&e) * kWarpsPerBlock, s, e.v, uvu);
+      cudaEventRecord(ev[i * 8 + 6], s);
       launch_swap(&e, s, e.v.swapsum, swaptries);
-      cudaEventRecord(ev[i * 7 + 6], s);
+      cudaEventRecord(ev[i * 8 + 7], s);
     }
     if (!IMA_CUDA_OK(cudaStreamSynchronize(s))) return fail(IMA2P_E_CUDA, "sync failed (run_timed)");
-    static const int slot[6] = {0, 1, 3, 4, 5, 2};      // event interval -> kernel_ms index
+    static const int slot[7] = {0, 1, 6, 3, 4, 5, 2};      // event interval -> kernel_ms index
     for (int i = 0; i < n; i++)
-      for (int k = 0; k < 6; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i * 7 + k], ev[i * 7 + k + 1]); kernel_ms[slot[k]] += ms; }
+      for (int k = 0; k < 7; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i * 8 + k], ev[i * 8 + k + 1]); kernel_ms[slot[k]] += ms; }
   }
   for (auto &x : ev) cudaEventDestroy(x);
 #else
@@ -958,7 +967,7 @@ int ima2p_engine_debug_changeu(ima2p_engine *h, int chain, int j, int k, double 
   UpdateView u = e.uv;
   u.u_forced = 1; u.u_chain = chain; u.u_j = j; u.u_k = k; u.u_d = d; u.u_kappa[0] = kappa_j; u.u_kappa[1] = kappa_k; u.u_every = 1;
   const int gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
+  IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, changeu_smem(&e) * kWarpsPerBlock, s, e.v, u);
   if (!d2h(out, e.uv.u_out + (size_t)chain * 4, 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   return check_device_error(&e, s);
 }

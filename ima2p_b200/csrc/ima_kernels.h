@@ -574,40 +574,59 @@ struct SwapView {
   const double *beta_table; // [nchains_global] beta by temperature rank (rank 0 = cold)
   unsigned long long *swap_counts;   // [2] attempts, accepts
   int swaptries, advance_step;
+  int smem_chains;          // chains the launch's shared memory can stage (0: work on global memory)
 };
 
 IMA_KERNEL void k_swap(EngineView E, SwapView V) {
+  IMA_SMEM_DECL
   if (ima_block() != 0 || ima_warp_in_block() != 0) return;
   const int N = E.d.nchains_global;
   const int lane = Warp::lane();
   if (N > 1 && V.swaptries > 0) {
-    if (lane == 0) {
-    Philox rng;
-    rng_for(rng, E, 0xffffffffu, kRngSwap);
-    for (int x = 0; x < V.swaptries; x++) {
-      const int sa = rng.randint(N);
-      int sbmin = 0, sbrange = N;
-      if (N >= 2 * kSwapDist + 3) {
-        sbmin = sa - kSwapDist > 0 ? sa - kSwapDist : 0;
-        sbrange = (N < sa + kSwapDist ? N : sa + kSwapDist) - sbmin;
-      }
-      int sb;
-      do { sb = sbmin + rng.randint(sbrange); } while (sb == sa);
-      const int ca = V.chain_of_rank[sa], cb = V.chain_of_rank[sb];
-      const double w = exp((V.beta_table[sa] - V.beta_table[sb]) * (V.S_global[cb] - V.S_global[ca]));
-      V.swap_counts[0]++;
-      if (w >= 1.0 || w > rng.uniform()) {
-        V.chain_of_rank[sa] = cb; V.chain_of_rank[sb] = ca;
-        V.rank_of_chain[ca] = sb; V.rank_of_chain[cb] = sa;
-        V.swap_counts[1]++;
-      }
+    // the attempts are a dependent chain of small decisions over (beta, S, rank): the warp stages those in shared memory
+    // (when they fit) so that one lane walks the attempts without waiting on global memory, and writes the ranks back
+    const bool staged = V.smem_chains >= N;
+    double *sS = (double *)IMA_SMEM, *sB = sS + (staged ? N : 0);
+    int *sC = (int *)(sB + (staged ? N : 0)), *sR = sC + (staged ? N : 0);
+    if (staged) {
+      for (int i = lane; i < N; i += IMA_WARP) { sS[i] = V.S_global[i]; sB[i] = V.beta_table[i]; sC[i] = V.chain_of_rank[i]; sR[i] = V.rank_of_chain[i]; }
+#if IMA_CUDA
+      __threadfence_block();
+#endif
+      Warp::sync();
     }
+    const double *Sg = staged ? sS : V.S_global, *Bt = staged ? sB : V.beta_table;
+    int *cor = staged ? sC : V.chain_of_rank, *roc = staged ? sR : V.rank_of_chain;
+    if (lane == 0) {
+      Philox rng;
+      rng_for(rng, E, 0xffffffffu, kRngSwap);
+      unsigned long long nacc = 0;
+      for (int x = 0; x < V.swaptries; x++) {
+        const int sa = rng.randint(N);
+        int sbmin = 0, sbrange = N;
+        if (N >= 2 * kSwapDist + 3) {
+          sbmin = sa - kSwapDist > 0 ? sa - kSwapDist : 0;
+          sbrange = (N < sa + kSwapDist ? N : sa + kSwapDist) - sbmin;
+        }
+        int sb;
+        do { sb = sbmin + rng.randint(sbrange); } while (sb == sa);
+        const int ca = cor[sa], cb = cor[sb];
+        const double w = exp((Bt[sa] - Bt[sb]) * (Sg[cb] - Sg[ca]));
+        if (w >= 1.0 || w > rng.uniform()) {
+          cor[sa] = cb; cor[sb] = ca;
+          roc[ca] = sb; roc[cb] = sa;
+          nacc++;
+        }
+      }
+      V.swap_counts[0] += (unsigned long long)V.swaptries;
+      V.swap_counts[1] += nacc;
     }
 #if IMA_CUDA
     __threadfence_block();
 #endif
     Warp::sync();
-    for (int c = lane; c < E.d.nchains; c += IMA_WARP) E.beta[c] = V.beta_table[V.rank_of_chain[E.d.chain0 + c]];
+    if (staged) for (int i = lane; i < N; i += IMA_WARP) { V.chain_of_rank[i] = sC[i]; V.rank_of_chain[i] = sR[i]; }
+    for (int c = lane; c < E.d.nchains; c += IMA_WARP) E.beta[c] = Bt[roc[E.d.chain0 + c]];
   }
   if (V.advance_step && lane == 0) *E.nsteps += 1;
 }

@@ -387,16 +387,23 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   ChainSm S = carve_chain_smem(IMA_SMEM + (size_t)ima_warp_in_block() * chain_smem_bytes(E.d), E.d);
   const TProposal t = t_proposal(E, U, M, c);
   // setzero + sum_treeinfo over loci in locus order (:256, 331), from the proposed (other) buffers
-  for (int i = lane; i < NI; i += IMA_WARP) {
+  // (lanes take loci, a warp reduction per weight: the loads of one weight are independent of each other, where a
+  // lane walking the loci of one weight in order would wait for each in turn)
+  for (int i = 0; i < NI; i++) {
     int a = 0;
-    for (int li = 0; li < nloci; li++) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwi[(size_t)p * NI + i]; }
-    S.ai[i] = a;
+    for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwi[(size_t)p * NI + i]; }
+    a = Warp::sum(a);
+    if (lane == 0) S.ai[i] = a;
   }
-  for (int i = lane; i < ND; i += IMA_WARP) {
+  for (int i = 0; i < ND; i++) {
     double a = 0.0;
-    for (int li = 0; li < nloci; li++) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwd[(size_t)p * ND + i]; }
-    S.ad[i] = a;
+    for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwd[(size_t)p * ND + i]; }
+    a = Warp::sum(a);
+    if (lane == 0) S.ad[i] = a;
   }
+#if IMA_CUDA
+  __threadfence_block();
+#endif
   Warp::sync();
   // integrate_tree_prob (:410): a term whose (c, f) did not change evaluates to the value it had, so the reuse rule
   // of update_gtree_common.cpp:1997-2000 and a fresh evaluation agree
@@ -518,6 +525,10 @@ IMA_DEV double reflect_kappa(double u, double kappa, double win, double kmax) { 
   return nk;
 }
 
+// shared memory of the all-infinite-sites fast path of k_changeu, per warp: u, pdg, length, step draw, log accept draw
+// (doubles) and the partner (int) of every locus
+IMA_HD size_t changeu_smem_doubles(int nloci) { return (size_t)5 * nloci + (nloci + 1) / 2 + 1; }
+
 IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
   IMA_SMEM_DECL
   const int c = ima_block() * kWarpsPerBlock + ima_warp_in_block();
@@ -529,6 +540,74 @@ IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
   Philox rng;
   rng_for(rng, E, (uint32_t)(E.d.chain0 + c), kRngScalars);
   const double beta = E.beta[c];
+  if (!U.u_forced && nur > 2 && nur == nloci && !E.d.any_sw && !E.d.any_hky) {
+    // All loci infinite sites, one scalar each (every shipped input): a proposal touches two numbers per locus and costs
+    // a logarithm and two exponentials, so the walk is bound by the latency of fetching them.  The chain's scalars,
+    // likelihoods and tree lengths are staged in shared memory by the warp, every proposal's draws (partner, step,
+    // accept) are made by the lane of that proposal from its own stream, one lane then walks the proposals in order
+    // on shared memory, and the warp writes the result back.
+    double *su = (double *)IMA_SMEM + (size_t)ima_warp_in_block() * changeu_smem_doubles(nloci);
+    double *spdg = su + nloci, *slen = spdg + nloci, *sdraw = slen + nloci, *slacc = sdraw + nloci;
+    int *sk = (int *)(slacc + nloci);
+    for (int li = lane; li < nloci; li += IMA_WARP) {
+      const int p = c * nloci + li;
+      const PairBuf &B = E.buf[E.cur[p]];
+      su[li] = E.uvals[(size_t)p * kMaxLinked];
+      spdg[li] = B.sd[(size_t)p * 4 + 3];
+      slen[li] = B.sd[(size_t)p * 4 + 1];
+      Philox r2;
+      const unsigned long long step = *E.nsteps;
+      r2.init(E.seed, (uint32_t)((E.d.chain0 + c) * nloci + li), (uint32_t)step, kRngScalars | ((uint32_t)(step >> 32) << 8));
+      int k;
+      do { k = (int)(r2.uniform() * nur); } while (k == li || k < 0 || k >= nur);          // :78-90
+      sk[li] = k;
+      sdraw[li] = r2.uniform();
+      slacc[li] = log(r2.uniform());
+    }
+#if IMA_CUDA
+    __threadfence_block();
+#endif
+    Warp::sync();
+    if (lane == 0) {
+      double total = 0.0;
+      unsigned long long nacc = 0;
+      for (int j = 0; j < nur; j++) {
+        const int k = sk[j];
+        const double olduj = su[j], olduk = su[k], r = log(olduj / olduk), u = sdraw[j];
+        double newr = u > 0.5 ? r + (2.0 * u - 1.0) * U.u_win : r - U.u_win * u * 2.0;      // :201-212
+        if (newr > U.u_maxratio) newr = 2.0 * U.u_maxratio - newr;
+        else if (newr < -U.u_maxratio) newr = 2.0 * (-U.u_maxratio) - newr;
+        const double logd = (newr - r) / 2, d = exp(logd);
+        const double newuj = olduj * d, newuk = olduk / d;
+        const double npj = spdg[j] - slen[j] * (newuj - olduj) + E.loci[j].nsites * logd;
+        const double npk = spdg[k] - slen[k] * (newuk - olduk) - E.loci[k].nsites * logd;
+        const double likenewsum = (npj - spdg[j]) + (npk - spdg[k]);
+        const double x = beta * M.gbeta * likenewsum;                                      // log of :291
+        if (slacc[j] < (x < 0.0 ? x : 0.0)) {                                              // U < min(1, e^x), :294
+          su[j] = newuj; su[k] = newuk; spdg[j] = npj; spdg[k] = npk;
+          total += likenewsum;
+          nacc++;
+        }
+      }
+      E.pdgsum[c] += total; E.swapsum[c] += total;
+#if IMA_CUDA
+      atomicAdd(U.stats + 2, (unsigned long long)nur);
+      atomicAdd(U.stats + 3, nacc);
+#else
+      U.stats[2] += nur; U.stats[3] += nacc;
+#endif
+    }
+#if IMA_CUDA
+    __threadfence_block();
+#endif
+    Warp::sync();
+    for (int li = lane; li < nloci; li += IMA_WARP) {
+      const int p = c * nloci + li;
+      E.uvals[(size_t)p * kMaxLinked] = su[li];
+      E.buf[E.cur[p]].sd[(size_t)p * 4 + 3] = spdg[li];
+    }
+    return;
+  }
   if (nur == 1) {
     // changekappa (:381-431): a single HKY locus has nothing to trade its scalar against
     if (E.loci[0].model != kHKY) return;
