@@ -75,6 +75,8 @@ SIGNATURES = {
     "ima2p_dataset_dims": (_i, [_v, c_int_p, c_int_p, C.c_char_p, _i]),
     "ima2p_dataset_locus": (_i, [_v, _i, c_int_p, c_dbl_p, c_int_p, C.c_char_p, _i]),
     "ima2p_dataset_locus_data": (_i, [_v, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
+    "ima2p_engine_write_mcf": (_i, [_v, C.c_char_p]),
+    "ima2p_engine_read_mcf": (_i, [_v, C.c_char_p]),
     "ima2p_ti_create": (_i, [C.c_char_p, C.c_char_p]),
     "ima2p_ti_append": (_i, [C.c_char_p, c_flt_p, _ll, _i]),
     "ima2p_ti_load": (_i, [C.c_char_p, _i, c_flt_p, _ll, C.POINTER(_ll)]),

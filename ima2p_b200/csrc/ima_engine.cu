@@ -147,7 +147,7 @@ static void launch_param_updates(Engine *e, stream_t s) {
     // every chain picks one of the two split-time updates (t_proposal); a warp whose chain picked the other one returns at once
     if ((e->t_updates & 2) && !e->model.nomigration) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
     if ((e->t_updates & 1) || e->model.nomigration) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
-    IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e->d) * kWarpsPerBlock, s, e->v, e->uv);
+    IMA_LAUNCH(k_accept_t, e->d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e->d), s, e->v, e->uv);
   }
   if (e->u_every > 0 && (e->uv.nurates > 1 || e->loci[0].d.model == kHKY)) {
     UpdateView u = e->uv;
@@ -770,7 +770,7 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
       cudaEventRecord(ev[i * 8 + 3], s);
       if (do_t && ((e.t_updates & 1) || e.model.nomigration)) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
       cudaEventRecord(ev[i * 8 + 4], s);
-      if (do_t) IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e.d) * kWarpsPerBlock, s, e.v, e.uv);
+      if (do_t) IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e.d), s, e.v, e.uv);
       cudaEventRecord(ev[i * 8 + 5], s);
       if (do_u) IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, changeu_smem(&e) * kWarpsPerBlock, s, e.v, uvu);
       cudaEventRecord(ev[i * 8 + 6], s);
@@ -947,7 +947,7 @@ int ima2p_engine_debug_split_time(ima2p_engine *h, int method, int period, const
   const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (method == 1) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
   else IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
-  IMA_LAUNCH(k_accept_t, gc, kWarpsPerBlock, chain_smem_bytes(e.d) * kWarpsPerBlock, s, e.v, u);
+  IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e.d), s, e.v, u);
   if (!d2h(out, e.uv.t_out, C * 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   return check_device_error(&e, s);
 }
@@ -1217,3 +1217,5 @@ int ima2p_engine_fetch_chain_summary(ima2p_engine *h, double *out4, void *cuda_s
 }
 
 }  // extern "C"
+
+#include "ima_mcf.h"

@@ -378,51 +378,56 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_rescale_t(EngineView E, UpdateView U) {
   }
 }
 
+constexpr int kTWarps = 8;            // warps of a k_accept_t block (one block per chain)
+
 IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   IMA_SMEM_DECL
-  const int c = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  const int c = ima_block();
   if (c >= E.d.nchains) return;
   const DevModel &M = IMA_MODEL;
   const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, nloci = E.d.nloci;
-  ChainSm S = carve_chain_smem(IMA_SMEM + (size_t)ima_warp_in_block() * chain_smem_bytes(E.d), E.d);
+  ChainSm S = carve_chain_smem(IMA_SMEM, E.d);
   const TProposal t = t_proposal(E, U, M, c);
-  // setzero + sum_treeinfo over loci in locus order (:256, 331), from the proposed (other) buffers
-  // (lanes take loci, a warp reduction per weight: the loads of one weight are independent of each other, where a
-  // lane walking the loci of one weight in order would wait for each in turn)
-  for (int i = 0; i < NI; i++) {
-    int a = 0;
-    for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwi[(size_t)p * NI + i]; }
-    a = Warp::sum(a);
-    if (lane == 0) S.ai[i] = a;
-  }
-  for (int i = 0; i < ND; i++) {
-    double a = 0.0;
-    for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwd[(size_t)p * ND + i]; }
-    a = Warp::sum(a);
-    if (lane == 0) S.ad[i] = a;
-  }
-#if IMA_CUDA
-  __threadfence_block();
-#endif
-  Warp::sync();
-  // integrate_tree_prob (:410): a term whose (c, f) did not change evaluates to the value it had, so the reuse rule
-  // of update_gtree_common.cpp:1997-2000 and a fresh evaluation agree
-  double probg = 0.0;
   const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
-  for (int k = 0; k < nterms; k++) {
-    double v;
-    if (k < M.nq) {
-      int cc; double f, hc;
-      gather_q(M, k, S.ai, S.ad, cc, f, hc);
-      v = integrate_coalescent_term_coop(E.mc, cc, f, hc, M.q_max[k], M.q_min[k]);
-    } else {
-      int cm; double f;
-      gather_m(M, k - M.nq, S.ai, S.ad, cm, f);
-      v = M.expoprior ? integrate_migration_term_expo(E.mc, cm, f, M.m_mean[k - M.nq]) : integrate_migration_term_coop(E.mc, cm, f, M.m_max[k - M.nq], M.m_min[k - M.nq]);
+  // setzero + sum_treeinfo over the loci (:256, 331), from the proposed (other) buffers: warps take weights, lanes take
+  // loci, one warp reduction per weight (the loads of one weight do not wait for each other)
+  IMA_FOR_WARPS(w, kTWarps) {
+    for (int i = w; i < NI + ND; i += kTWarps) {
+      if (i < NI) {
+        int a = 0;
+        for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwi[(size_t)p * NI + i]; }
+        a = Warp::sum(a);
+        if (lane == 0) S.ai[i] = a;
+      } else {
+        double a = 0.0;
+        for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwd[(size_t)p * ND + i - NI]; }
+        a = Warp::sum(a);
+        if (lane == 0) S.ad[i - NI] = a;
+      }
     }
-    if (lane == 0) S.q[k] = v;
-    probg += v;
   }
+  block_sync();
+  // integrate_tree_prob (:410): a term whose (c, f) did not change evaluates to the value it had, so the reuse rule
+  // of update_gtree_common.cpp:1997-2000 and a fresh evaluation agree.  One warp per term.
+  IMA_FOR_WARPS(w, kTWarps) {
+    for (int k = w; k < nterms; k += kTWarps) {
+      double v;
+      if (k < M.nq) {
+        int cc; double f, hc;
+        gather_q(M, k, S.ai, S.ad, cc, f, hc);
+        v = integrate_coalescent_term_coop(E.mc, cc, f, hc, M.q_max[k], M.q_min[k]);
+      } else {
+        int cm; double f;
+        gather_m(M, k - M.nq, S.ai, S.ad, cm, f);
+        v = M.expoprior ? integrate_migration_term_expo(E.mc, cm, f, M.m_mean[k - M.nq]) : integrate_migration_term_coop(E.mc, cm, f, M.m_max[k - M.nq], M.m_min[k - M.nq]);
+      }
+      if (lane == 0) S.q[k] = v;
+    }
+  }
+  block_sync();
+  if (ima_warp_in_block() != 0) return;              // the decision and the commit are one warp's work
+  double probg = 0.0;
+  for (int k = 0; k < nterms; k++) probg += S.q[k];
   if (!migration_allowed(M, S.ai)) probg = -kMyDblMax;
   double pdgnew = 0.0, migw = 0.0;
   int n_eu = 0, n_ed = 0, n_mu = 0, n_md = 0;

@@ -264,6 +264,14 @@ class Engine:
         self._ck(self.lib.ima2p_engine_debug_changeu(self._h, chain, j, k, d, kappa_j, kappa_k, _dp(out)))
         return out
 
+    def write_mcf(self, path):
+        """writemcf (mcmcfile.cpp:203-296): the state of the local chains in the reference's .mcf format."""
+        self._ck(self.lib.ima2p_engine_write_mcf(self._h, str(path).encode()))
+
+    def read_mcf(self, path):
+        """readmcf (mcmcfile.cpp:310-442) + init_p: load, upload and evaluate."""
+        self._ck(self.lib.ima2p_engine_read_mcf(self._h, str(path).encode()))
+
     def thermo_accumulate(self, stream=None):
         """summarginlikecalc (marglike.cpp:51-87) for the local chains."""
         self._ck(self.lib.ima2p_engine_thermo_accumulate(self._h, stream))

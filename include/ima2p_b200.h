@@ -248,6 +248,13 @@ int ima2p_dataset_locus (const ima2p_dataset * d, int locus, int *info, double *
 int ima2p_dataset_locus_data (const ima2p_dataset * d, int locus, int *seq, int *mult, int *A, int *minA, int *maxA,
                               double *pi, double *urate);
 
+/* ---- the MCMC state file (.mcf): writemcf / readmcf, mcmcfile.cpp:203-442 --------------------------------------
+ * write_mcf: the chains this engine holds, in the reference's record stream ("name type count values", doubles as
+ * %.10lg); read_mcf: loads such a file into the engine's chains (read again from the top when it holds fewer, as the
+ * reference does), uploads and evaluates (init_p, :130-193). */
+int ima2p_engine_write_mcf (ima2p_engine * e, const char *path);
+int ima2p_engine_read_mcf (ima2p_engine * e, const char *path);
+
 /* ---- the .ti file of sampled genealogies: M mode writes it, L mode reads it back ---------------------------------
  * ti_create: header block ending in "VALUESSTART" (ima_main_mpi.cpp:2123-2141); ti_append: one line per row, every value
  * "%.6f\t" (savegenealogyfile, output.cpp:662-685); ti_load (loadgenealogyvalues, ima_main_mpi.cpp:3216-3440):

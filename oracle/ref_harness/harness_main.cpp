@@ -1313,6 +1313,16 @@ main (int argc, char *argv[])
   }
   else if (mode == "tupdates")
     mode_tupdates (burn, kvl ("n", 40), kvl ("between", 3));
+  else if (mode == "mcf")
+  {
+    /* the reference's own state file: written, read back (readmcf ends in init_p), then dumped -- both sides of the
+     * parity test parse the same text */
+    do_burn (burn);
+    if (kv.count ("load") == 0)
+      writemcf (const_cast<char *> (kv["mcf"].c_str ()));
+    readmcf (const_cast<char *> (kv["mcf"].c_str ()));
+    dump_state ();
+  }
   else if (mode == "nwupdates")
     mode_nwupdates (burn, kvl ("n", 40), kvl ("between", 3));
   else if (mode == "uupdates")

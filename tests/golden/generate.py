@@ -254,6 +254,30 @@ def main():
         run("state", "parse_is_3pop", u1, 1, {"burn": 0})
         run("state", "parse_hky", u2, 1, {"burn": 0})
         run("state", "parse_sw_joint", u3, 1, {"burn": 0})
+    # the .mcf state file: written by the reference (inputs/*.mcf.gz) and by the engine (inputs/*_ours.mcf.gz), each
+    # read back by the reference's readmcf and dumped
+    for nm, uf, hn, burn in (("mcf_sim5_hn2", s5, 2, 60), ("mcf_sim3_sw_hn2", sw3, 2, 60), ("mcf_sim5_hky_hn2", hky5, 2, 30),
+                             ("mcf_sim3_joint_hn2", j3, 2, 60)):
+        if ONLY and nm not in ONLY:
+            continue
+        mcf = os.path.join(TMP, nm + ".mcf")
+        run("mcf", nm, uf, hn, {"burn": burn, "mcf": mcf})
+        with open(mcf, "rb") as f, gzip.GzipFile(os.path.join(HERE, "inputs", nm + ".mcf.gz"), "wb", mtime=0) as g:
+            shutil.copyfileobj(f, g)
+        # the same state written by the engine (host-emulation build), read by the reference
+        sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+        from support import engine_from_fixture, load_golden
+        from ima2p_b200 import capi
+        emu = capi.bind(os.path.join(os.path.dirname(HERE), "hostemu", "libima2p_hostemu.so"))
+        eng, _ = engine_from_fixture(load_golden(nm), lib=emu)
+        eng.eval()
+        ours = os.path.join(TMP, nm + "_ours.mcf")
+        eng.write_mcf(ours)
+        eng.close()
+        ONLY.add(nm + "_ours") if ONLY else None
+        run("mcf", nm + "_ours", uf, hn, {"burn": 0, "mcf": ours, "load": 1})
+        with open(ours, "rb") as f, gzip.GzipFile(os.path.join(HERE, "inputs", nm + "_ours.mcf.gz"), "wb", mtime=0) as g:
+            shutil.copyfileobj(f, g)
     # proposal known-answer fixtures (a2-a4): accepted updategenealogy() calls
     run("updates", "updates_sim5_hn2", s5, 2, {"burn": 50, "n": 250})
     run("updates", "updates_sim3_hn2", s3, 2, {"burn": 50, "n": 250})

@@ -134,3 +134,9 @@ def test_no_migration_statistics(lib, name):
 @pytest.mark.parametrize("name", ["nwupdates_sim5_hn2", "nwupdates_sim3_hn2", "nwupdates_sim5_3pop_hn2"])
 def test_nielsen_wakeley_update_matches_oracle(lib, name):
     ec.nielsen_wakeley_update_matches_oracle(lib, name)
+
+
+@pytest.mark.parametrize("name", ["mcf_sim5_hn2", "mcf_sim3_sw_hn2", "mcf_sim5_hky_hn2", "mcf_sim3_joint_hn2"])
+def test_reference_state_file_evaluates_to_reference_values(lib, name, tmp_path):
+    from test_mcf import mcf_read_matches_reference
+    mcf_read_matches_reference(lib, name, tmp_path, rtol=RTOL)
