@@ -350,21 +350,29 @@ def main():
         t3 = time.perf_counter()
         parts["upload_and_evaluate"] += (t1 - t0) * 100; parts["step"] += (t2 - t1) * 100; parts["read_back"] += (t3 - t2) * 100
 
+    lmode_multi = None
+    if world > 1 and not args.no_lmode:
+        try:
+            lmode_multi = lmode_bench_sharded(eng, dev, rank, world, step_multi)
+        except Exception as ex:
+            lmode_multi = {"error": str(ex)}
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     pk, pk_kind = peaks()
     roof = None
     if kernel_ms is not None:
         per = np.asarray(kernel_ms, dtype=np.float64) / args.steps                       # ms per launch
-        names = ["k_propose", "k_accept", "k_swap", "k_rescale_t", "k_accept_t", "k_changeu", "k_nw_t"]
+        names = ["k_propose", "k_accept", "k_swap", "k_split_t", "k_accept_t", "k_changeu"]
         dom = int(np.argmax(per))
         P = cpg * nloci
         b_update = algorithmic_bytes_per_update(n0 + n1, mig_mean, p_acc, eng.NI, eng.ND)
         W_g = 4 * eng.NI + 8 * eng.ND
         b_accept = 2 * W_g + 16 + 12 + 1 + (W_g + 8 * (eng.nq + eng.nm) + 40) / nloci
         b_pair = 24.0 * (2 * (n0 + n1) - 1) + 12.0 * mig_mean + W_g + 24.0                # one genealogy with its weights
-        alg = {"k_propose": b_update * P, "k_accept": b_accept * P, "k_swap": 16.0 * cpg, "k_rescale_t": 2.0 * b_pair * P,
-               "k_accept_t": (W_g + 8 + 16 + 1) * P, "k_changeu": 48.0 * P, "k_nw_t": 2.0 * b_pair * P}[names[dom]]
+        alg = {"k_propose": b_update * P, "k_accept": b_accept * P, "k_swap": 16.0 * cpg, "k_split_t": 2.0 * b_pair * P,
+               "k_accept_t": (W_g + 8 + 16 + 1) * P, "k_changeu": 48.0 * P}[names[dom]]
         achieved = alg / (per[dom] * 1e-3) / 1e9
         traffic = None
         tf = os.path.join(ROOT, "profiles", "traffic.json")
@@ -379,7 +387,7 @@ def main():
         r = reference_throughput(wl, 1, 3, 1, budget_s=12.0, full=full)
         if r is not None:
             cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference", "sample": r["sample"], "accept_rate": r["accept"]}
-    lmode = None
+    lmode = lmode_multi
     if not args.no_lmode and world == 1:
         try:
             lmode = lmode_bench(eng, dev)
@@ -389,7 +397,7 @@ def main():
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
            "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke, "parts_ms": parts},
-           "gpu_launches": (7 if full else 3) * args.steps,
+           "gpu_launches": (6 if full else 3) * args.steps,
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
            "genealogy_updates_only": ({"ms_per_step": graph_ms / args.steps, "value": updates_all / (graph_ms * 1e-3), "unit": unit}
                                       if graph_ms else None), "lmode": lmode,
@@ -431,6 +439,51 @@ def lmode_bench(eng, dev, G=1000000):
     lm.close()
     return {"rows": G, "margincalc_geneval_per_sec": 5 * 1000 * G / (t1 - t0), "jointp_geneval_per_sec": 64 * G / (t3 - t2),
             "unit": "genealogy evals/s", "timing": "host wall clock around the C-ABI calls (includes H2D of x and D2H of results)"}
+
+
+def lmode_bench_sharded(eng, dev, rank, world, step_multi, G=1000000):
+    """The same L-mode evaluations with the G rows sharded over the ranks (BASELINE config 4): every evaluation is local
+    partial sums plus one small collective (ima2p_b200/multirank.py).  Whole-job evals/s, slowest rank."""
+    import torch
+    import torch.distributed as dist
+    from ima2p_b200 import LMode
+    from ima2p_b200.multirank import sharded_jointp, sharded_margincalc
+    mine = []
+    for _ in range(200):                              # cold-chain rows of this run, wherever the cold chain lives
+        step_multi(); step_multi()
+        r = eng.cold_row()
+        if r is not None:
+            mine.append(r.copy())
+    every = [None] * world
+    dist.all_gather_object(every, mine)
+    base = np.stack([r for part in every for r in part])
+    rng = np.random.default_rng(5)
+    big = base[rng.integers(0, len(base), G)]
+    lo, hi = G * rank // world, G * (rank + 1) // world
+    lm = LMode(eng.nq, eng.nm, eng.nsplit, [PRIOR_Q] * 3, [0.0] * 3, [PRIOR_M] * 2, [0.0] * 2, device=torch.cuda.current_device())
+    lm.load(big[lo:hi], nrows_total=G, row0=lo)
+    grid = [(np.arange(1000) + 0.5) / 1000 * (PRIOR_Q if p < 3 else PRIOR_M) for p in range(5)]
+    sharded_margincalc(lm, grid[0], 0.0, 0, 0, device=dev)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for p in range(5):
+        sharded_margincalc(lm, grid[p], 0.0, p, 0, device=dev)
+    torch.cuda.synchronize(); dist.barrier()
+    t1 = time.perf_counter()
+    xs = np.column_stack([rng.uniform(0.05, 0.9, 64) * (PRIOR_Q if p < 3 else PRIOR_M) for p in range(5)])
+    sharded_jointp(lm, xs[:32], device=dev)
+    torch.cuda.synchronize(); dist.barrier()
+    t2 = time.perf_counter()
+    q1, _ = sharded_jointp(lm, xs[:32], device=dev)
+    q2, _ = sharded_jointp(lm, xs[32:], device=dev)
+    torch.cuda.synchronize(); dist.barrier()
+    t3 = time.perf_counter()
+    lm.close()
+    t = torch.tensor([t1 - t0, t3 - t2], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"rows": G, "rows_per_rank": hi - lo, "margincalc_geneval_per_sec": 5 * 1000 * G / float(t[0]), "jointp_geneval_per_sec": 64 * G / float(t[1]),
+            "unit": "genealogy evals/s", "checksum": float(np.sum(q1) + np.sum(q2)),
+            "timing": "host wall clock around the sharded calls incl. the collectives, max over ranks"}
 
 
 if __name__ == "__main__":

@@ -145,8 +145,7 @@ static void launch_param_updates(Engine *e, stream_t s) {
   const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (e->t_updates && e->model.nsplit > 0) {
     // every chain picks one of the two split-time updates (t_proposal); a warp whose chain picked the other one returns at once
-    if ((e->t_updates & 2) && !e->model.nomigration) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
-    if ((e->t_updates & 1) || e->model.nomigration) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
+    IMA_LAUNCH(k_split_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
     IMA_LAUNCH(k_accept_t, e->d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e->d), s, e->v, e->uv);
   }
   if (e->u_every > 0 && (e->uv.nurates > 1 || e->loci[0].d.model == kHKY)) {
@@ -394,9 +393,8 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   e.overlap_smem = e.pair_smem * kWarpsPerBlock;
   if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
-      !IMA_CUDA_OK(cudaFuncSetAttribute(k_rescale_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * 24 + 16)) ||
-      !IMA_CUDA_OK(cudaFuncSetAttribute(k_nw_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(changeu_smem(&e) * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
   if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");
@@ -740,7 +738,7 @@ int ima2p_engine_run(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stre
 
 // Same work as ima2p_engine_run, launched kernel by kernel with CUDA events recorded on the launching
 // stream around each kernel of every step; kernel_ms[7] receives the summed device time of
-// {propose, accept, swap, rescale_t, accept_t, changeu, nw_t} over the nsteps (bench.py's roofline numerator comes from here).
+// {propose, accept, swap, split_t, accept_t, changeu, 0} over the nsteps (bench.py's roofline numerator comes from here).
 int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms) {
   if (!h || nsteps < 0 || swaptries < 0 || !kernel_ms) return fail(IMA2P_E_ARG, "run_timed: bad argument");
   Engine &e = h->eng;
@@ -766,9 +764,8 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
       cudaEventRecord(ev[i * 8 + 1], s);
       launch_accept(&e, s, 0, e.d.nloci);
       cudaEventRecord(ev[i * 8 + 2], s);
-      if (do_t && (e.t_updates & 2) && !e.model.nomigration) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
       cudaEventRecord(ev[i * 8 + 3], s);
-      if (do_t && ((e.t_updates & 1) || e.model.nomigration)) IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
+      if (do_t) IMA_LAUNCH(k_split_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
       cudaEventRecord(ev[i * 8 + 4], s);
       if (do_t) IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e.d), s, e.v, e.uv);
       cudaEventRecord(ev[i * 8 + 5], s);
@@ -945,8 +942,7 @@ int ima2p_engine_debug_split_time(ima2p_engine *h, int method, int period, const
     u.t_forced = d_newt; u.t_forced_period = period; u.t_force_accept = force_accept; u.t_forced_method = method;
   } else u.t_methods = method ? 2 : 1;
   const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  if (method == 1) IMA_LAUNCH(k_nw_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
-  else IMA_LAUNCH(k_rescale_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
+  IMA_LAUNCH(k_split_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
   IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e.d), s, e.v, u);
   if (!d2h(out, e.uv.t_out, C * 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   return check_device_error(&e, s);

@@ -254,16 +254,8 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
   return Warp::sum(num - denom);
 }
 
-IMA_KERNEL void IMA_PROPOSE_BOUNDS k_nw_t(EngineView E, UpdateView U) {
-  IMA_SMEM_DECL
-  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
-  if (p >= E.d.P) return;
-  const DevModel &M = IMA_MODEL;
-  const int c = p / E.d.nloci, li = p - c * E.d.nloci;
-  const TProposal t = t_proposal(E, U, M, c);
-  if (t.method != 1) return;
+IMA_DEV void nw_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S) {
   const DevLocus &L = E.loci[li];
-  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
   const int cb = E.cur[p];
   const PairBuf &B = E.buf[cb];
   const PairBuf &Bn = E.buf[cb ^ 1];
@@ -306,20 +298,12 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_nw_t(EngineView E, UpdateView U) {
   }
 }
 
-IMA_KERNEL void IMA_PROPOSE_BOUNDS k_rescale_t(EngineView E, UpdateView U) {
-  IMA_SMEM_DECL
-  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
-  if (p >= E.d.P) return;
-  const DevModel &M = IMA_MODEL;
-  const int c = p / E.d.nloci, li = p - c * E.d.nloci;
+IMA_DEV void rescale_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S) {
   const DevLocus &L = E.loci[li];
-  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
   const int cb = E.cur[p];
   const PairBuf &B = E.buf[cb];
   const PairBuf &Bn = E.buf[cb ^ 1];
   const int lane = Warp::lane();
-  const TProposal t = t_proposal(E, U, M, c);
-  if (t.method != 0) return;
   double tvn[kMaxPeriods];
   for (int k = 0; k < kMaxPeriods; k++) tvn[k] = E.tvals[(size_t)c * kMaxPeriods + k];
   tvn[t.period] = t.newt;
@@ -376,6 +360,19 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_rescale_t(EngineView E, UpdateView U) {
     int *o = U.t_counts + (size_t)p * 4;
     o[0] = n_eu; o[1] = n_ed; o[2] = n_mu; o[3] = n_md;
   }
+}
+
+// One launch for both split-time updates: every chain drew its update type (t_proposal), every warp follows its chain.
+IMA_KERNEL void IMA_PROPOSE_BOUNDS k_split_t(EngineView E, UpdateView U) {
+  IMA_SMEM_DECL
+  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (p >= E.d.P) return;
+  const DevModel &M = IMA_MODEL;
+  const int c = p / E.d.nloci, li = p - c * E.d.nloci;
+  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
+  const TProposal t = t_proposal(E, U, M, c);
+  if (t.method == 1) nw_t_pair(E, U, M, t, p, c, li, S);
+  else rescale_t_pair(E, U, M, t, p, c, li, S);
 }
 
 constexpr int kTWarps = 8;            // warps of a k_accept_t block (one block per chain)

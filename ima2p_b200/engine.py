@@ -195,7 +195,7 @@ class Engine:
         return max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0             # ima_main_mpi.cpp:1378
 
     def run_timed(self, nsteps, swaptries=None, stream=None):
-        """run() launched kernel by kernel; returns summed device ms of (propose, accept, swap, rescale_t, accept_t, changeu, nw_t)."""
+        """run() launched kernel by kernel; returns summed device ms of (propose, accept, swap, split_t, accept_t, changeu, unused)."""
         ms = np.zeros(7, np.float32)
         self._ck(self.lib.ima2p_engine_run_timed(self._h, nsteps, self.default_swaptries() if swaptries is None else swaptries,
                                                  stream, ms.ctypes.data_as(capi.c_flt_p)))

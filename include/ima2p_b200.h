@@ -118,7 +118,7 @@ int ima2p_engine_set_pieces (ima2p_engine * e, int pieces);
  * the same all-locus sums; results are identical for every depth (see csrc/ima_kernels.h k_accept) */
 int ima2p_engine_set_speculation (ima2p_engine * e, int depth);
 /* same steps, launched kernel by kernel with CUDA events on the launching stream around each kernel;
- * kernel_ms[7] = summed device time of {propose, accept, swap, rescale_t, accept_t, changeu, nw_t} (roofline accounting) */
+ * kernel_ms[7] = summed device time of {propose, accept, swap, split_t, accept_t, changeu, (unused)} (roofline accounting) */
 int ima2p_engine_run_timed (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms);
 /* Multi-GPU form (one process per GPU): genealogy updates of the local chains, then the per-chain
  * S = sum_li pdg + probg (swapweight, swapchains.cpp:12-34) is written to dev_S_local[nchains_local]
