@@ -70,6 +70,11 @@ SIGNATURES = {
     "ima2p_engine_fetch_state": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v]),
     "ima2p_engine_fetch_pair_summaries": (_i, [_v, c_dbl_p, c_int_p, c_int_p, _v]),
     "ima2p_engine_fetch_chain_summary": (_i, [_v, c_dbl_p, _v]),
+    "ima2p_modelspec_create": (_i, [C.POINTER(_v), _i, C.c_char_p, _d, _d, _i, _d, _i, _d]),
+    "ima2p_modelspec_free": (None, [_v]),
+    "ima2p_modelspec_dims": (_i, [_v, c_int_p]),
+    "ima2p_modelspec_tables": (_i, [_v] + [c_int_p] * 13),
+    "ima2p_engine_set_model_spec": (_i, [_v, _v]),
     "ima2p_dataset_read": (_i, [C.c_char_p, C.POINTER(_v)]),
     "ima2p_dataset_free": (None, [_v]),
     "ima2p_dataset_dims": (_i, [_v, c_int_p, c_int_p, C.c_char_p, _i]),

@@ -94,6 +94,21 @@ class Engine:
         self._ck(self.lib.ima2p_engine_set_model(self._h, *create_args))
         self.npops, self.nsplit, self.nq, self.nm = create_args[0], create_args[1], create_args[8], create_args[14]
 
+    def set_model_from_tree(self, npops, tree, qmax, mmax, expo_prior=0, m_mean=0.0, thermo=0, gbeta=1.0):
+        """Default model from the population tree string and the priors (setup_poptree + setup_iparams)."""
+        h = C.c_void_p()
+        self._ck(self.lib.ima2p_modelspec_create(C.byref(h), npops, tree.encode(), qmax, mmax, expo_prior, m_mean, thermo, gbeta))
+        try:
+            dims = (C.c_int * 6)()
+            self._ck(self.lib.ima2p_modelspec_dims(h, dims))
+            self._ck(self.lib.ima2p_engine_set_model_spec(self._h, h))
+            self.adopt_model_dims(dims[0], dims[1], dims[3], dims[4])
+        finally:
+            self.lib.ima2p_modelspec_free(h)
+
+    def adopt_model_dims(self, npops, nsplit, nq, nm):
+        self.npops, self.nsplit, self.nq, self.nm = npops, nsplit, nq, nm
+
     def set_locus(self, li, model, numgenes, numsites, samppop, seq=None, mult=None, hval=1.0, totsites=0, nlinked=1,
                   minA=None, maxA=None, sumlogk=0.0):
         seq_a = _i32(seq) if seq is not None and numsites > 0 else None

@@ -39,7 +39,6 @@ extern "C" {
 #define IMA2P_MODEL_SW 2        /* STEPWISE */
 #define IMA2P_MODEL_JOINT 3     /* JOINT_IS_SW: part 0 infinite sites, parts 1.. stepwise */
 #define IMA2P_MAX_LINKED 4       /* linked parts per locus kept on the device (reference MAXLINKED 15) */
-#define IMA2P_MAXLINKED 4
 
 typedef struct ima2p_engine ima2p_engine;
 typedef struct ima2p_lmode ima2p_lmode;
@@ -62,6 +61,20 @@ int ima2p_engine_set_model (ima2p_engine * e, int npops, int nsplit, const int *
                             const int *m_c, const double *m_max, const double *m_min, const double *m_mean,
                             int nomig_n, const int *nomig_p, const int *nomig_r, const int *nomig_c,
                             int nomigration, int expoprior, int thermo, double gbeta);
+
+/* The same tables built from the population tree string and the priors, for the default model: one size parameter per
+ * population of the tree (-q qmax), two migration parameters for every pair of populations that coexist (-m mmax; 0 =
+ * no migration; expo_prior: -j7 with mean m_mean), setup_poptree build_poptree.cpp:391-448,508-539,628-709 and
+ * setup_iparams initialize.cpp:201-727.  dims[6] = npops, nsplit, numtreepops, numpopsizeparams, nummigrateparams,
+ * migration weight positions. */
+typedef struct ima2p_modelspec ima2p_modelspec;
+int ima2p_modelspec_create (ima2p_modelspec ** out, int npops, const char *tree, double qmax, double mmax,
+                            int expo_prior, double m_mean, int thermo, double gbeta);
+void ima2p_modelspec_free (ima2p_modelspec * s);
+int ima2p_modelspec_dims (const ima2p_modelspec * s, int *dims);
+int ima2p_modelspec_tables (const ima2p_modelspec * s, int *plist, int *addpop, int *droppops, int *pt_b, int *pt_e,
+                            int *pt_down, int *q_off, int *q_p, int *q_r, int *m_off, int *m_p, int *m_r, int *m_c);
+int ima2p_engine_set_model_spec (ima2p_engine * e, const ima2p_modelspec * s);
 
 /* struct locus (imamp.hpp:894-936) as produced by readdata (readata.cpp:1037): seq is [numgenes][numsites]
  * (0/1 segregating sites for IS, bases 0..3 of the compressed patterns for HKY), mult[numsites] (HKY). */

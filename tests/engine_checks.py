@@ -8,7 +8,7 @@ from support import (FlatModel, FlatTree, OracleModel, check_static_eval, engine
 
 STATIC_FIXTURES = ["state_sim5_hn4", "state_sim50_hn3", "state_sim300_hn1", "state_sim2_hn2", "state_sim3_hn3",
                    "state_sim5_3pop_hn2", "state_sim5_expo_hn2", "state_sim3_sw_hn2", "state_sim5_hky_hn2", "state_sim3_joint_hn2",
-                   "state_sim5_nomig_hn2", "state_sim5_3pop_nomig_hn2"]
+                   "state_sim5_nomig_hn2", "state_sim5_3pop_nomig_hn2", "state_sim5_4popA_hn2", "state_sim5_4popB_hn2"]
 STEP_FIXTURES = ["state_sim5_hn4", "state_sim3_hn3", "state_sim5_3pop_hn2", "state_sim2_hn2"]
 
 

@@ -222,6 +222,24 @@ def make_parse_inputs():
     return [os.path.join(out, n) for n in ("parse_is_3pop.u", "parse_hky.u", "parse_sw_joint.u")]
 
 
+def four_pops(src, dst, tree):
+    """Same samples as `src` (two populations of 10), re-divided into 4 populations of 5 with the given tree."""
+    lines = open(src).read().split("\n")
+    out, i = [lines[0]], 1
+    while lines[i].startswith("#"):
+        out.append(lines[i]); i += 1
+    i += 3
+    out += ["4", "popA popB popC popD", tree]
+    nloci = int(lines[i].split()[0]); out.append(lines[i]); i += 1
+    for _ in range(nloci):
+        f = lines[i].split(); i += 1
+        n0, n1 = int(f[1]), int(f[2])
+        rows = lines[i:i + n0 + n1]; i += n0 + n1
+        out.append(" ".join([f[0], str(n0 // 2), str(n0 - n0 // 2), str(n1 // 2), str(n1 - n1 // 2)] + f[3:]))
+        out.extend(rows)
+    open(dst, "w").write("\n".join(out) + "\n")
+
+
 def main():
     if not os.path.exists(HARNESS):
         sys.exit("build the reference harness first: make -C oracle ref")
@@ -245,6 +263,10 @@ def main():
     run("state", "state_sim5_hky_hn2", hky5, 2, {"burn": 60})
     run("state", "state_sim3_sw_hn2", sw3, 2, {"burn": 100})
     run("state", "state_sim3_joint_hn2", j3, 2, {"burn": 100})
+    p4a = os.path.join(TMP, "Sim1_5loci_4popA.u"); four_pops(s5, p4a, "((0,1):4,(2,3):5):6")
+    p4b = os.path.join(TMP, "Sim1_5loci_4popB.u"); four_pops(s5, p4b, "(((0,1):4,2):5,3):6")
+    run("state", "state_sim5_4popA_hn2", p4a, 2, {"burn": 100})
+    run("state", "state_sim5_4popB_hn2", p4b, 2, {"burn": 100})
     nomig = ["-q", "10", "-m", "0", "-t", "3"]                       # -m 0 sets NOMIGRATION (ima_main_mpi.cpp:822-823)
     run("state", "state_sim5_nomig_hn2", s5, 2, {"burn": 100}, priors=nomig)
     run("state", "state_sim5_3pop_nomig_hn2", p3, 2, {"burn": 100}, priors=nomig)

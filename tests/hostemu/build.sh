@@ -5,4 +5,4 @@
 set -e
 cd "$(dirname "$0")/../.."
 g++ -O2 -std=c++17 -DIMA_HOSTEMU -ffp-contract=off -Wall -Wno-unused-function -Wno-unknown-pragmas -fPIC -shared \
-    -x c++ ima2p_b200/csrc/ima_engine.cu -x c++ ima2p_b200/csrc/ima_lmode.cu ima2p_b200/csrc/ima_readu.cpp -o tests/hostemu/libima2p_hostemu.so
+    -x c++ ima2p_b200/csrc/ima_engine.cu -x c++ ima2p_b200/csrc/ima_lmode.cu ima2p_b200/csrc/ima_readu.cpp ima2p_b200/csrc/ima_modelspec.cpp -o tests/hostemu/libima2p_hostemu.so

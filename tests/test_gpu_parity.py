@@ -26,7 +26,8 @@ def test_static_eval_matches_reference(lib, name):
 
 
 @pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 10), ("state_sim3_hn3", 20), ("state_sim5_3pop_hn2", 12),
-                                         ("state_sim2_hn2", 20), ("state_sim5_hky_hn2", 12)])
+                                         ("state_sim2_hn2", 20), ("state_sim5_hky_hn2", 12), ("state_sim5_4popA_hn2", 10),
+                                         ("state_sim5_4popB_hn2", 10)])
 def test_device_proposals_match_oracle(lib, name, nsteps):
     # Sim2 is one locus of 100 genes: root moves are rare in 40 proposals, so they are not demanded there
     ec.proposals_match_oracle(lib, name, nsteps, rtol=RTOL, need_root_moves=(name != "state_sim2_hn2"))
@@ -86,7 +87,8 @@ def test_mutation_scalar_update_matches_reference(lib, name):
 
 
 @pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 2000), ("state_sim5_3pop_hn2", 500), ("state_sim50_hn3", 300),
-                                         ("state_sim3_sw_hn2", 300), ("state_sim5_hky_hn2", 100), ("state_sim3_joint_hn2", 300)])
+                                         ("state_sim3_sw_hn2", 300), ("state_sim5_hky_hn2", 100), ("state_sim3_joint_hn2", 300),
+                                         ("state_sim5_4popA_hn2", 300), ("state_sim5_4popB_hn2", 300)])
 def test_incremental_sums_with_full_schedule(lib, name, nsteps):
     ec.incremental_sums_match_fresh_evaluation(lib, name, nsteps, full_schedule=True)
 

@@ -25,7 +25,7 @@ def test_static_eval(emu, name):
     ec.static_eval_matches_reference(emu, name, rtol=1e-12)
 
 
-@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 12), ("state_sim3_hn3", 25), ("state_sim5_3pop_hn2", 15), ("state_sim5_hky_hn2", 10)])
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 12), ("state_sim3_hn3", 25), ("state_sim5_3pop_hn2", 15), ("state_sim5_hky_hn2", 10), ("state_sim5_4popA_hn2", 10), ("state_sim5_4popB_hn2", 10)])
 def test_proposals(emu, name, nsteps):
     ec.proposals_match_oracle(emu, name, nsteps)
 
@@ -66,7 +66,8 @@ def test_mutation_scalar_update(emu, name):
     ec.mutation_scalar_update_matches_reference(emu, name)
 
 
-@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 200), ("state_sim5_3pop_hn2", 100), ("state_sim3_sw_hn2", 60), ("state_sim5_hky_hn2", 30), ("state_sim3_joint_hn2", 60)])
+@pytest.mark.parametrize("name,nsteps", [("state_sim5_hn4", 200), ("state_sim5_3pop_hn2", 100), ("state_sim3_sw_hn2", 60), ("state_sim5_hky_hn2", 30), ("state_sim3_joint_hn2", 60), ("state_sim5_4popA_hn2", 80),
+                                         ("state_sim5_4popB_hn2", 80)])
 def test_incremental_sums_full_schedule(emu, name, nsteps):
     ec.incremental_sums_match_fresh_evaluation(emu, name, nsteps, full_schedule=True)
 
