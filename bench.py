@@ -322,17 +322,17 @@ def main():
     split_time_mean = float(tv_now.mean())
     mig_mean = float(pinned["scal_i"].numpy()[:, 1].mean())
     mig_max = int(pinned["scal_i"].numpy()[:, 1].max())
-    h2d = int(sum(sb)) + tv_now.nbytes
-    d2h = cpg * 4 * 8 + eng.rowlen * 4
+    # the migration pools travel as their used columns only (ima2p_engine_put_state)
+    h2d = int(sum(sb)) - int(sb[3] + sb[4]) + cpg * nloci * mig_max * 10 + tv_now.nbytes
+    d2h = (cpg * 4 + eng.rowlen + 2) * 8          # the packed step report (ima2p_engine_step_report)
     for _ in range(3):
-        eng.put_state(bufs, tv_now, stream); run_steps(1); eng.fetch_chain_summary(stream)
+        eng.put_state(bufs, tv_now, stream); run_steps(1); eng.step_report(stream)
     barrier()
     t0 = time.perf_counter()
     for _ in range(ke):
         eng.put_state(bufs, tv_now, stream)
         run_steps(1)
-        summ = eng.fetch_chain_summary(stream)
-        eng.cold_row()
+        summ, _row = eng.step_report(stream)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -346,7 +346,7 @@ def main():
     for _ in range(10):
         t0 = time.perf_counter(); eng.put_state(bufs, tv_now, stream); torch.cuda.synchronize()
         t1 = time.perf_counter(); run_steps(1); torch.cuda.synchronize()
-        t2 = time.perf_counter(); eng.fetch_chain_summary(stream); eng.cold_row(); torch.cuda.synchronize()
+        t2 = time.perf_counter(); eng.step_report(stream); torch.cuda.synchronize()
         t3 = time.perf_counter()
         parts["upload_and_evaluate"] += (t1 - t0) * 100; parts["step"] += (t2 - t1) * 100; parts["read_back"] += (t3 - t2) * 100
 

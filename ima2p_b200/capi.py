@@ -80,6 +80,7 @@ SIGNATURES = {
     "ima2p_dataset_dims": (_i, [_v, c_int_p, c_int_p, C.c_char_p, _i]),
     "ima2p_dataset_locus": (_i, [_v, _i, c_int_p, c_dbl_p, c_int_p, C.c_char_p, _i]),
     "ima2p_dataset_locus_data": (_i, [_v, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
+    "ima2p_engine_step_report": (_i, [_v, c_dbl_p, c_flt_p, c_int_p, _v]),
     "ima2p_engine_write_mcf": (_i, [_v, C.c_char_p]),
     "ima2p_engine_read_mcf": (_i, [_v, C.c_char_p]),
     "ima2p_ti_create": (_i, [C.c_char_p, C.c_char_p]),

@@ -52,6 +52,7 @@ struct Engine {
   double *d_beta_table = nullptr;
   unsigned long long *d_swap_counts = nullptr;
   double *d_thermosum = nullptr;
+  double *d_report = nullptr, *h_report = nullptr;      // step_report: device staging and its pinned host mirror
   UpdateView uv{};              // split-time / mutation-scalar updates
   int t_updates = 0, u_every = 0;
   std::vector<int> h_ul_l, h_ul_a;
@@ -1132,8 +1133,22 @@ int ima2p_engine_put_state(ima2p_engine *h, const void *topo, const void *time, 
   uint64_t b[8];
   ima2p_engine_state_bytes(h, b);
   PairBuf &B = e.v.buf[0];
-  bool ok = h2d(B.topo, topo, b[0], s) && h2d(B.time, time, b[1], s) && h2d(B.mseg, mseg, b[2], s) && h2d(B.mig_t, mig_t, b[3], s) &&
-            h2d(B.mig_p, mig_p, b[4], s) && h2d(B.si, scal_i, b[5], s) && h2d(B.sd, scal_d, b[6], s) && h2d(e.v.uvals, uvals, b[7], s);
+  bool ok = h2d(B.topo, topo, b[0], s) && h2d(B.time, time, b[1], s) && h2d(B.mseg, mseg, b[2], s) &&
+            h2d(B.si, scal_i, b[5], s) && h2d(B.sd, scal_d, b[6], s) && h2d(e.v.uvals, uvals, b[7], s);
+  // the migration pools are [P][CAP] with only the first mignum entries of a row in use: copy that many columns
+  {
+    const int *si = (const int *)scal_i;
+    int maxmig = 0;
+    for (size_t p = 0; p < (size_t)e.d.P; p++) if (si[2 * p + 1] > maxmig) maxmig = si[2 * p + 1];
+    if (maxmig > e.d.CAP) return fail(IMA2P_E_CAPACITY, "put_state: more migration events than mig_capacity");
+#if IMA_CUDA
+    if (maxmig > 0)
+      ok = ok && IMA_CUDA_OK(cudaMemcpy2DAsync(B.mig_t, (size_t)e.d.CAP * 8, mig_t, (size_t)e.d.CAP * 8, (size_t)maxmig * 8, e.d.P, cudaMemcpyHostToDevice, s)) &&
+           IMA_CUDA_OK(cudaMemcpy2DAsync(B.mig_p, (size_t)e.d.CAP * 2, mig_p, (size_t)e.d.CAP * 2, (size_t)maxmig * 2, e.d.P, cudaMemcpyHostToDevice, s));
+#else
+    ok = ok && h2d(B.mig_t, mig_t, b[3], s) && h2d(B.mig_p, mig_p, b[4], s);
+#endif
+  }
   if (tvals) {
     for (int c = 0; c < e.d.nchains; c++) for (int k = 0; k < kMaxPeriods; k++) e.h_tvals[(size_t)c * kMaxPeriods + k] = k < e.model.nsplit ? tvals[(size_t)c * e.model.nsplit + k] : kTimeMax;
     ok = ok && h2d(e.v.tvals, e.h_tvals.data(), e.h_tvals.size() * sizeof(double), s);
@@ -1196,6 +1211,40 @@ int ima2p_engine_fetch_pair_summaries(ima2p_engine *h, double *sd, int *si, int 
     p0 = p1;
   }
   if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  return IMA2P_OK;
+}
+
+// The per-step read-back in one kernel, one copy and one synchronisation: chain4[nchains][4] = beta, probg, pdg, S;
+// row[rowlen] = the cold chain's .ti row when it lives on this rank (*present), as ima2p_engine_cold_row
+int ima2p_engine_step_report(ima2p_engine *h, double *chain4, float *row, int *present, void *cuda_stream) {
+  if (!h || !h->eng.finalized || !chain4 || !row || !present) return fail(IMA2P_E_ARG, "step_report: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  int dims[5];
+  ima2p_engine_dims(h, dims);
+  const int rowlen = dims[4], C = e.d.nchains;
+  const size_t n = 4 * (size_t)C + rowlen + 2;
+  if (!e.d_report) {
+    e.d_report = e.alloc<double>(n);
+#if IMA_CUDA
+    if (!IMA_CUDA_OK(cudaMallocHost((void **)&e.h_report, n * sizeof(double)))) return fail(IMA2P_E_CUDA, "pinned allocation failed");
+#else
+    e.h_report = (double *)malloc(n * sizeof(double));
+#endif
+    if (!e.d_report || !e.h_report) return fail(IMA2P_E_CUDA, "allocation failed (step report)");
+  }
+  IMA_LAUNCH(k_pack_report, 1, 1, 0, s, e.v, (const int *)e.sv.chain_of_rank, rowlen, e.d_report);
+  if (!d2h(e.h_report, e.d_report, n * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  memcpy(chain4, e.h_report, 4 * (size_t)C * sizeof(double));
+  const double *r = e.h_report + 4 * (size_t)C;
+  *present = r[rowlen] != 0.0;
+  if (*present) for (int i = 0; i < rowlen; i++) row[i] = (float)r[i];
+  if (r[rowlen + 1] != 0.0) {
+    char buf[120];
+    snprintf(buf, sizeof buf, "device error word %d raised by a kernel", (int)r[rowlen + 1]);
+    return fail(IMA2P_E_DEVICE, buf);
+  }
   return IMA2P_OK;
 }
 

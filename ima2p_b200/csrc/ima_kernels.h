@@ -652,6 +652,41 @@ IMA_KERNEL void k_thermo_accumulate(EngineView E, const int *rank_of_chain, doub
   if (i < E.d.nchains) thermosum[rank_of_chain[E.d.chain0 + i]] += E.pdgsum[i];
 }
 
+// What the host reads after a step, packed for one copy: out[0 .. 4 nchains) = beta, probg, pdg, S of every local chain;
+// then rowlen floats (as doubles) = the cold chain's .ti row, savegsampinf ginfo.cpp:318-377 with its float sums; then
+// 1 if the cold chain lives here; then the device error word.
+IMA_KERNEL void k_pack_report(EngineView E, const int *chain_of_rank, int rowlen, double *out) {
+  if (ima_block() != 0 || ima_warp_in_block() != 0) return;
+  const DevModel &M = IMA_MODEL;
+  const int lane = Warp::lane(), C = E.d.nchains;
+  for (int c = lane; c < C; c += IMA_WARP) {
+    out[4 * c] = E.beta[c]; out[4 * c + 1] = E.probg[c]; out[4 * c + 2] = E.pdgsum[c]; out[4 * c + 3] = E.swapsum[c];
+  }
+  if (lane != 0) return;
+  double *row = out + 4 * (size_t)C;
+  const int c = chain_of_rank[0] - E.d.chain0;
+  const bool here = c >= 0 && c < C;
+  row[rowlen] = here ? 1.0 : 0.0;
+  row[rowlen + 1] = (double)*E.mc.err;
+  if (!here) return;
+  const int *wi = E.all_i + (size_t)c * E.d.NI;
+  const double *wd = E.all_d + (size_t)c * E.d.ND;
+  const int nq = M.nq, nm = M.nomigration ? 0 : M.nm;
+  const int fcp = nq, hccp = 2 * nq, mcp = 3 * nq, fmp = mcp + nm, qip = fmp + nm, mip = qip + nq, pdgp = mip + nm;
+  for (int i = 0; i < nq; i++) {
+    int cc = 0; float f = 0.f, hc = 0.f;
+    for (int j = 0; j < M.q_n[i]; j++) { const int x = M.q_idx[i][j]; cc += wi[x]; f += (float)wd[x]; hc += (float)wd[M.ncc + x]; }
+    row[i] = (float)cc; row[fcp + i] = f; row[hccp + i] = hc; row[qip + i] = (float)E.qint[(size_t)c * kMaxParams + i];
+  }
+  for (int i = 0; i < nm; i++) {
+    int cm = 0; float f = 0.f;
+    for (int j = 0; j < M.m_n[i]; j++) { const int x = M.m_idx[i][j]; cm += wi[M.ncc + x]; f += (float)wd[2 * M.ncc + x]; }
+    row[mcp + i] = (float)cm; row[fmp + i] = f; row[mip + i] = (float)E.mint[(size_t)c * kMaxParams + i];
+  }
+  row[pdgp] = (float)E.pdgsum[c]; row[pdgp + 1] = (float)E.probg[c];
+  for (int i = 0; i < M.nsplit; i++) row[pdgp + 2 + i] = (float)E.tvals[(size_t)c * kMaxPeriods + i];
+}
+
 IMA_KERNEL void k_copy_swapsum(EngineView E, double *dst) {
   const int i = ima_block() * kWarpsPerBlock * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
   if (i < E.d.nchains) dst[i] = E.swapsum[i];

@@ -279,6 +279,14 @@ class Engine:
         self._ck(self.lib.ima2p_engine_debug_changeu(self._h, chain, j, k, d, kappa_j, kappa_k, _dp(out)))
         return out
 
+    def step_report(self, stream=None):
+        """(chain summary [nchains][4] = beta, probg, pdg, S; cold-chain .ti row or None) with one device-to-host copy."""
+        out = np.zeros((self.nchains, 4))
+        row = np.zeros(self.rowlen, np.float32)
+        present = C.c_int()
+        self._ck(self.lib.ima2p_engine_step_report(self._h, _dp(out), row.ctypes.data_as(capi.c_flt_p), C.byref(present), stream))
+        return out, (row if present.value else None)
+
     def write_mcf(self, path):
         """writemcf (mcmcfile.cpp:203-296): the state of the local chains in the reference's .mcf format."""
         self._ck(self.lib.ima2p_engine_write_mcf(self._h, str(path).encode()))

@@ -261,6 +261,11 @@ int ima2p_dataset_locus (const ima2p_dataset * d, int locus, int *info, double *
 int ima2p_dataset_locus_data (const ima2p_dataset * d, int locus, int *seq, int *mult, int *A, int *minA, int *maxA,
                               double *pi, double *urate);
 
+/* What the host reads after a step (recording, ima_main_mpi.cpp:2891, 3035) in one kernel, one copy and one
+ * synchronisation: chain4[nchains][4] = beta, probg, P(D|G), swap sum of every local chain; row = the cold chain's .ti
+ * row (ima2p_engine_cold_row) when it lives on this rank (*present). */
+int ima2p_engine_step_report (ima2p_engine * e, double *chain4, float *row, int *present, void *cuda_stream);
+
 /* ---- the MCMC state file (.mcf): writemcf / readmcf, mcmcfile.cpp:203-442 --------------------------------------
  * write_mcf: the chains this engine holds, in the reference's record stream ("name type count values", doubles as
  * %.10lg); read_mcf: loads such a file into the engine's chains (read again from the top when it holds fewer, as the

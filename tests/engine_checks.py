@@ -445,3 +445,16 @@ def nielsen_wakeley_update_matches_oracle(lib, name, rtol=1e-9):
         ndown += newt < oldt
         eng.close()
     assert nmoved > 0 and nup > 0 and ndown > 0
+
+
+def step_report_matches_separate_reads(lib, name="state_sim5_hn4"):
+    """ima2p_engine_step_report == fetch_chain_summary + cold_row (the packed read-back used per step)."""
+    d = load_golden(name)
+    eng, fm = engine_from_fixture(d, lib=lib)
+    eng.eval()
+    eng.run(7)
+    summ, row = eng.step_report()
+    assert np.array_equal(summ, eng.fetch_chain_summary())
+    ref_row = eng.cold_row()
+    assert (row is None) == (ref_row is None) and (row is None or np.array_equal(row, ref_row))
+    eng.close()

@@ -142,3 +142,7 @@ def test_nielsen_wakeley_update_matches_oracle(lib, name):
 def test_reference_state_file_evaluates_to_reference_values(lib, name, tmp_path):
     from test_mcf import mcf_read_matches_reference
     mcf_read_matches_reference(lib, name, tmp_path, rtol=RTOL)
+
+
+def test_step_report(lib):
+    ec.step_report_matches_separate_reads(lib)

@@ -105,3 +105,7 @@ def test_no_migration_statistics(emu):
 @pytest.mark.parametrize("name", ["nwupdates_sim5_hn2", "nwupdates_sim3_hn2", "nwupdates_sim5_3pop_hn2"])
 def test_nielsen_wakeley_update(emu, name):
     ec.nielsen_wakeley_update_matches_oracle(emu, name)
+
+
+def test_step_report(emu):
+    ec.step_report_matches_separate_reads(emu)
