@@ -1,0 +1,250 @@
+// Command-line front end over the C ABI: an M-mode run from a .u file to a .ti file, with the reference's flags for the
+// things this repository implements (ima_main_mpi.cpp:252-1561 option scan, :4317-4560 main loop):
+//
+//   IMa2p_b200 -i data.u -o out -q QMAX -m MMAX -t TMAX -b BURNSTEPS -l GENEALOGIES [-d STEPS_BETWEEN_SAVES (100)]
+//              [-hn CHAINS] [-hfg | -hfl | -hfs] [-ha A] [-hb B] [-s SEED] [-j7] [-r3 (write out.mcf at the end)] [-f file.mcf]
+//
+// What it does in the reference's order: readdata -> setup_poptree / setup_iparams -> a starting genealogy for every
+// locus (any valid one: infinite-sites loci get a perfect phylogeny of their 0/1 columns, everything coalescing in the
+// root population above the last split time; see start_genealogy) -> setheat -> burn-in -> every -d steps the cold chain's
+// row (savegsampinf) is appended to out.ti -> a short report.  Values are arguments attached to the flag ("-q10") or
+// the next word ("-q 10"), as the reference accepts.  Options of the reference outside this path are refused, not ignored.
+#include "../../include/ima2p_b200.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+[[noreturn]] void die(const std::string &m, int code = 1) {
+  fprintf(stderr, "IMa2: %s\n", m.c_str());
+  exit(code);
+}
+void ck(int rc, const char *what) {
+  if (rc != IMA2P_OK) die(std::string(what) + ": " + ima2p_last_error(), rc < 0 ? -rc : rc);
+}
+
+struct Locus { int info[8]; double hval; std::vector<int> samppop, seq, mult, A, minA, maxA; double pi[4]; };
+
+// One valid genealogy for a locus, every coalescence above `tbase` (so every lineage has reached the root population
+// by the population tree alone and no migration event is needed).  Infinite-sites columns (0 = the first gene's base)
+// define nested-or-disjoint gene sets because the first gene is in none of them; those sets are made clades.
+struct Tree { std::vector<int> up0, up1, down, pop; std::vector<double> time; int root; double roottime; };
+
+Tree start_genealogy(const Locus &L, int npops, int rootpop, double tbase, unsigned &rng) {
+  const int n = L.info[1], ns = (L.info[0] == IMA2P_MODEL_IS || L.info[0] == IMA2P_MODEL_JOINT) ? L.info[2] : 0, nl = 2 * n - 1;
+  Tree T;
+  T.up0.assign(nl, -1); T.up1.assign(nl, -1); T.down.assign(nl, -1); T.pop.assign(nl, rootpop); T.time.assign(nl, 0.0);
+  for (int i = 0, p = 0, e = L.samppop[0]; i < n; i++) { while (i >= e) e += L.samppop[++p]; T.pop[i] = p; }
+  // distinct carrier sets, largest first
+  std::vector<std::vector<char>> sets;
+  for (int s = 0; s < ns; s++) {
+    std::vector<char> c(n);
+    int k = 0;
+    for (int j = 0; j < n; j++) { c[j] = (char)L.seq[(size_t)j * ns + s]; k += c[j]; }
+    if (k < 2) continue;                               // a singleton is a tip branch already
+    bool dup = false;
+    for (auto &o : sets) dup |= o == c;
+    if (!dup) sets.push_back(c);
+  }
+  auto size_of = [&](const std::vector<char> &c) { int k = 0; for (char x : c) k += x; return k; };
+  for (size_t a = 0; a < sets.size(); a++) for (size_t b = a + 1; b < sets.size(); b++) if (size_of(sets[b]) > size_of(sets[a])) std::swap(sets[a], sets[b]);
+  // member lists per set; the implicit outermost set holds every gene
+  std::vector<int> node_of(n);                         // current tree node standing for gene j's lineage
+  std::vector<int> ntips(nl, 1);
+  for (int j = 0; j < n; j++) node_of[j] = j;
+  int next = n;
+  auto join = [&](int a, int b) {
+    const int k = next++;
+    T.up0[k] = a; T.up1[k] = b; T.down[a] = T.down[b] = k;
+    ntips[k] = ntips[a] + ntips[b];
+    return k;
+  };
+  // smallest sets first: each set's current lineages are merged into one clade (sets inside it are single lineages by then)
+  for (int si = (int)sets.size() - 1; si >= -1; si--) {
+    std::vector<int> members;
+    for (int j = 0; j < n; j++) if (si < 0 || sets[si][j]) { bool seen = false; for (int m : members) seen |= m == node_of[j]; if (!seen) members.push_back(node_of[j]); }
+    while (members.size() > 1) {
+      rng = rng * 1664525u + 1013904223u;
+      const size_t a = (rng >> 8) % members.size();
+      size_t b = (rng >> 20) % (members.size() - 1);
+      if (b >= a) b++;
+      const int k = join(members[a], members[b]);
+      members[a] = k; members.erase(members.begin() + b);
+    }
+    for (int j = 0; j < n; j++) if (si < 0 || sets[si][j]) node_of[j] = members[0];
+    if (si < 0) T.root = members[0];
+  }
+  if (next != nl) die("starting genealogy: data not compatible with the infinite sites model", 36);
+  // node heights grow with the number of tips below, all above tbase
+  const double step = tbase > 0 ? 0.05 * tbase : 0.05;
+  std::vector<double> height(nl, 0.0);
+  for (int k = n; k < nl; k++) height[k] = (tbase > 0 ? 1.1 * tbase : 0.1) + step * (ntips[k] - 1);
+  for (int e = 0; e < nl; e++) T.time[e] = T.down[e] == -1 ? 1000000.0 : height[T.down[e]];
+  T.roottime = height[T.root];
+  return T;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  std::map<std::string, std::string> opt;
+  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", nullptr};
+  for (int a = 1; a < argc; a++) {
+    if (argv[a][0] != '-') die(std::string("command line: unexpected word ") + argv[a], 5);
+    const std::string w = argv[a] + 1;
+    std::string key;
+    for (int k = 0; known[k]; k++) if (w.compare(0, strlen(known[k]), known[k]) == 0) { key = known[k]; break; }
+    if (key.empty()) die("command line: option -" + w + " is not part of this build (M-mode hot path only)", 5);
+    std::string val = w.substr(key.size());
+    const bool flag_only = key == "hf" || key == "j" || key == "r" || key == "p";
+    if (val.empty() && !flag_only) { if (a + 1 >= argc) die("command line: -" + key + " needs a value", 5); val = argv[++a]; }
+    if (key == "j" && val != "7") die("model option -j" + val + " is not part of this build", 5);
+    opt[key] = val;
+  }
+  for (const char *need : {"i", "o", "q", "t", "b", "l"}) if (!opt.count(need)) die(std::string("command line: -") + need + " is required", 5);
+  const double qmax = atof(opt["q"].c_str()), mmax = opt.count("m") ? atof(opt["m"].c_str()) : 0.0, tmax = atof(opt["t"].c_str());
+  const int nchains = opt.count("hn") ? atoi(opt["hn"].c_str()) : 1, expo = opt.count("j") ? 1 : 0;
+  const long burn = atol(opt["b"].c_str()), nsave = atol(opt["l"].c_str()), every = opt.count("d") ? atol(opt["d"].c_str()) : 100;
+  const unsigned long long seed = opt.count("s") ? strtoull(opt["s"].c_str(), nullptr, 10) : 1ull;
+  if (nchains < 1 || burn < 0 || nsave < 1 || every < 1 || !(tmax > 0)) die("command line: bad value", 5);
+
+  ima2p_dataset *D = nullptr;
+  ck(ima2p_dataset_read(opt["i"].c_str(), &D), "reading data");
+  int npops = 0, nloci = 0;
+  char tree[256];
+  ck(ima2p_dataset_dims(D, &npops, &nloci, tree, sizeof tree), "data");
+  ima2p_modelspec *S = nullptr;
+  ck(ima2p_modelspec_create(&S, npops, tree, qmax, expo ? 20.0 * mmax : mmax, expo, expo ? mmax : 0.0, 0, 1.0), "model");   // -j7: -m is the mean, plotted to 20 means
+  int md[6];
+  ima2p_modelspec_dims(S, md);
+  const int nsplit = md[1], rootpop = 2 * npops - 2;
+
+  std::vector<Locus> loci(nloci);
+  for (int li = 0; li < nloci; li++) {
+    Locus &L = loci[li];
+    L.samppop.resize(npops);
+    char name[64];
+    ck(ima2p_dataset_locus(D, li, L.info, &L.hval, L.samppop.data(), name, sizeof name), "locus");
+    const int n = L.info[1], ns = L.info[2], nlinked = L.info[5];
+    L.seq.assign((size_t)n * (ns > 0 ? ns : 1), 0); L.mult.assign(ns > 0 ? ns : 1, 1); L.A.assign((size_t)nlinked * n, 0);
+    L.minA.assign(nlinked, 0); L.maxA.assign(nlinked, 0);
+    ck(ima2p_dataset_locus_data(D, li, L.seq.data(), L.mult.data(), L.A.data(), L.minA.data(), L.maxA.data(), L.pi, nullptr), "locus data");
+    if (nlinked > IMA2P_MAX_LINKED) die("more linked stepwise parts than this build keeps on the device", 5);
+  }
+
+  ima2p_engine *E = nullptr;
+  ck(ima2p_engine_create(&E, 0, nchains, nchains, 0, nloci, 96, seed), "engine");
+  ck(ima2p_engine_set_model_spec(E, S), "model");
+  for (int li = 0; li < nloci; li++) {
+    Locus &L = loci[li];
+    const int model = L.info[0], n = L.info[1], ns = L.info[2], nlinked = L.info[5];
+    // sumlogk (calc_prob_data.cpp:609-719): log k! over the branches carrying k mutations, i.e. over repeated columns
+    double sumlogk = 0.0;
+    if (model == IMA2P_MODEL_IS || model == IMA2P_MODEL_JOINT) {
+      std::vector<char> done(ns, 0);
+      for (int s = 0; s < ns; s++) {
+        if (done[s]) continue;
+        int k = 0;
+        for (int r = s; r < ns; r++) {
+          bool same = true, comp = true;
+          for (int j = 0; j < n && (same || comp); j++) { const int a = L.seq[(size_t)j * ns + s], b = L.seq[(size_t)j * ns + r]; same &= a == b; comp &= a != b; }
+          if (same || comp) { done[r] = 1; k++; }
+        }
+        sumlogk += lgamma(k + 1.0);
+      }
+    }
+    std::vector<int> lo(nlinked, 0), hi(nlinked, 0);          // allele range rule of build_gtree.cpp:519-520, 721-722
+    for (int a = (model == IMA2P_MODEL_JOINT); a < nlinked && (model == IMA2P_MODEL_SW || model == IMA2P_MODEL_JOINT); a++) {
+      const int mn = L.minA[a], mx = L.maxA[a];
+      lo[a] = (mx + mn) / 2 - (mx - mn) > 1 ? (mx + mn) / 2 - (mx - mn) : 1;
+      hi[a] = (mx + mn) / 2 + (mx - mn) < 1000 ? (mx + mn) / 2 + (mx - mn) : 1000;
+    }
+    ck(ima2p_engine_set_locus(E, li, model, n, ns, L.info[3], L.hval, L.samppop.data(), ns > 0 ? L.seq.data() : nullptr,
+                              model == IMA2P_MODEL_HKY ? L.mult.data() : nullptr, nlinked, lo.data(), hi.data(), sumlogk), "locus");
+  }
+  ck(ima2p_engine_finalize(E), "finalize");
+  if (nchains > 1) {
+    const int mode = opt.count("hf") ? (opt["hf"] == "g" ? 1 : opt["hf"] == "s" ? 2 : 0) : 0;
+    ck(ima2p_engine_set_heating(E, mode, opt.count("ha") ? atof(opt["ha"].c_str()) : 0.05, opt.count("hb") ? atof(opt["hb"].c_str()) : 0.0), "heating");
+  }
+  std::vector<double> tmaxv(nsplit > 0 ? nsplit : 1, tmax), tminv(nsplit > 0 ? nsplit : 1, 0.0);
+  ck(ima2p_engine_set_update_priors(E, tmaxv.data(), tminv.data(), 0.0, 0.0, 0.0, 0.0), "priors");
+
+  if (opt.count("f")) {
+    ck(ima2p_engine_read_mcf(E, opt["f"].c_str()), "loading the state file");
+  } else {
+    // set_tvalues (initialize.cpp:1945-1960): split times evenly spaced inside the prior
+    std::vector<double> tv(nsplit > 0 ? nsplit : 1);
+    for (int k = 0; k < nsplit; k++) tv[k] = (k + 1.0) / (nsplit + 1.0) * tmax;
+    unsigned rng = (unsigned)seed * 2654435761u + 12345u;
+    for (int li = 0; li < nloci; li++) {
+      const Locus &L = loci[li];
+      const int n = L.info[1], nl = 2 * n - 1, nlinked = L.info[5];
+      const Tree T = start_genealogy(L, npops, rootpop, nsplit > 0 ? tv[nsplit - 1] : 0.0, rng);
+      std::vector<int> moff(nl + 1, 0), mp(1, 0), A((size_t)nlinked * nl, 0);
+      std::vector<double> mt(1, 0.0), u(IMA2P_MAX_LINKED, 1.0);
+      for (int a = 0; a < nlinked; a++) {                     // internal allele states: those of a descendant tip
+        for (int i = 0; i < n; i++) A[(size_t)a * nl + i] = L.A[(size_t)a * n + i];
+        for (int k = n; k < nl; k++) A[(size_t)a * nl + k] = A[(size_t)a * nl + T.up0[k]];
+      }
+      for (int c = 0; c < nchains; c++) {
+        if (li == 0) ck(ima2p_engine_set_chain(E, c, tv.data()), "chain");
+        ck(ima2p_engine_set_genealogy(E, c, li, T.up0.data(), T.up1.data(), T.down.data(), T.pop.data(), T.time.data(), moff.data(), mt.data(),
+                                      mp.data(), T.root, T.roottime, u.data(), 2.0, L.pi, nlinked > 0 && (L.info[0] == IMA2P_MODEL_SW || L.info[0] == IMA2P_MODEL_JOINT) ? A.data() : nullptr),
+           "starting genealogy");
+      }
+    }
+    ck(ima2p_engine_upload(E), "upload");
+    ck(ima2p_engine_eval(E), "evaluating the starting state");
+  }
+  ck(ima2p_engine_set_update_schedule(E, nsplit > 0 ? 3 : 0, 5), "schedule");
+
+  const int swaptries = nchains > 1 ? (nchains / 10 > 1 ? nchains / 10 : 1) : 0;                 // ima_main_mpi.cpp:1378
+  int dims[5];
+  ima2p_engine_dims(E, dims);
+  const int rowlen = dims[4];
+  const std::string ti = opt["o"] + ".ti";
+  std::string header = "Command line string : ";
+  for (int a = 0; a < argc; a++) header += std::string(argv[a]) + " ";
+  ck(ima2p_ti_create(ti.c_str(), header.c_str()), "creating the .ti file");
+  printf("IMa2p_b200: %d populations %s, %d loci, %d chains, burn %ld steps, %ld genealogies every %ld steps\n", npops, tree, nloci, nchains, burn, nsave, every);
+  for (long done = 0; done < burn;) { const int n = burn - done > 1000 ? 1000 : (int)(burn - done); ck(ima2p_engine_run(E, n, swaptries, nullptr), "burn-in"); done += n; }
+  std::vector<double> chain4((size_t)nchains * 4);
+  std::vector<float> rows, row(rowlen);
+  std::vector<double> tsum(nsplit > 0 ? nsplit : 1, 0.0);
+  long saved = 0;
+  while (saved < nsave) {
+    ck(ima2p_engine_run(E, (int)every, swaptries, nullptr), "run");
+    int present = 0;
+    ck(ima2p_engine_step_report(E, chain4.data(), row.data(), &present, nullptr), "reading the cold chain");
+    if (!present) die("the cold chain is not on this device");
+    rows.insert(rows.end(), row.begin(), row.end());
+    for (int k = 0; k < nsplit; k++) tsum[k] += row[rowlen - nsplit + k];
+    saved++;
+    if (rows.size() >= (size_t)rowlen * 256 || saved == nsave) { ck(ima2p_ti_append(ti.c_str(), rows.data(), (long long)(rows.size() / rowlen), rowlen), "writing the .ti file"); rows.clear(); }
+  }
+  uint64_t cnt[8], ucnt[4];
+  ck(ima2p_engine_counters(E, cnt), "counters");
+  ck(ima2p_engine_update_counters(E, ucnt), "counters");
+  const std::string outname = opt["o"];
+  FILE *f = fopen(outname.c_str(), "w");
+  if (!f) die("cannot create the output file", 2);
+  fprintf(f, "IMa2p_b200 run summary\n%s\n\nsteps %llu  genealogy updates %llu  accepted %.4f  topology changes %.4f\n", header.c_str(), (unsigned long long)cnt[0],
+          (unsigned long long)cnt[1], (double)cnt[2] / (double)(cnt[1] ? cnt[1] : 1), (double)cnt[3] / (double)(cnt[1] ? cnt[1] : 1));
+  fprintf(f, "chain swaps %llu of %llu attempts\nsplit-time updates accepted %llu of %llu   mutation-scalar updates accepted %llu of %llu\n", (unsigned long long)cnt[6],
+          (unsigned long long)cnt[5], (unsigned long long)ucnt[1], (unsigned long long)ucnt[0], (unsigned long long)ucnt[3], (unsigned long long)ucnt[2]);
+  fprintf(f, "proposals dropped for migration capacity %llu\ngenealogies saved %ld in %s\n", (unsigned long long)cnt[7], saved, ti.c_str());
+  for (int k = 0; k < nsplit; k++) fprintf(f, "mean of t%d over the saved genealogies %.6f\n", k, tsum[k] / saved);
+  fclose(f);
+  if (opt.count("r")) ck(ima2p_engine_write_mcf(E, (outname + ".mcf").c_str()), "writing the state file");
+  printf("IMa2p_b200: done, %ld genealogies in %s\n", saved, ti.c_str());
+  ima2p_engine_destroy(E);
+  ima2p_modelspec_free(S);
+  ima2p_dataset_free(D);
+  return 0;
+}

@@ -1,0 +1,64 @@
+"""The command-line front end (csrc/ima_frontend.cpp) over the C ABI, built here against the host-emulation library:
+host logic only -- option scan, .u -> model -> starting genealogies -> schedule -> .ti / .mcf / report files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EXE = os.path.join(HERE, "hostemu", "IMa2p_hostemu")
+INPUTS = os.path.join(HERE, "golden", "inputs")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    subprocess.run([os.path.join(HERE, "hostemu", "build.sh")], check=True)
+    return EXE
+
+
+def _run(exe, args, **kw):
+    return subprocess.run([exe] + args, capture_output=True, text=True, timeout=600, **kw)
+
+
+@pytest.mark.parametrize("name,genes", [("parse_is_3pop", [14] * 4), ("parse_sw_joint", [13] * 3), ("parse_hky", [9, 10, 11])])
+def test_run_from_u_file_to_ti_file(exe, tmp_path, name, genes):
+    from ima2p_b200 import capi
+    from ima2p_b200.readu import read_u, ti_load
+    lib = capi.bind(os.path.join(HERE, "hostemu", "libima2p_hostemu.so"))
+    out = tmp_path / name
+    r = _run(exe, ["-i", os.path.join(INPUTS, name + ".u"), "-o", str(out), "-q10", "-m", "1", "-t3", "-b", "150", "-l", "12", "-d", "5",
+                   "-hn3", "-hfl", "-ha", "0.05", "-s", "11", "-r3"])
+    assert r.returncode == 0, r.stderr
+    d = read_u(os.path.join(INPUTS, name + ".u"), lib)
+    npops = d["npops"]
+    nq, nm = 2 * npops - 1, {2: 2, 3: 8}[npops]
+    rowlen = 4 * nq + 3 * nm + 2 + (npops - 1)
+    rows = ti_load(str(out) + ".ti", rowlen, lib=lib)
+    assert rows.shape == (12, rowlen)
+    cc = rows[:, :nq]
+    assert np.all(cc == np.round(cc)) and np.all(cc >= 0)
+    assert np.all(cc.sum(axis=1) == sum(g - 1 for g in genes))        # every coalescence is in exactly one population
+    mc = rows[:, 3 * nq:3 * nq + nm]
+    assert np.all(mc == np.round(mc)) and np.all(mc >= 0)
+    t = rows[:, rowlen - (npops - 1):]
+    assert np.all(t > 0) and np.all(t < 3) and np.all(np.diff(t, axis=1) > 0)
+    rep = open(out).read()
+    assert "genealogies saved 12" in rep and "proposals dropped for migration capacity 0" in rep
+    assert os.path.getsize(str(out) + ".mcf") > 1000
+    # the state file it wrote restarts a run (-f)
+    r2 = _run(exe, ["-i", os.path.join(INPUTS, name + ".u"), "-o", str(tmp_path / "again"), "-q10", "-m1", "-t3", "-b0", "-l3", "-d2", "-hn3", "-hfl",
+                    "-ha0.05", "-f", str(out) + ".mcf"])
+    assert r2.returncode == 0, r2.stderr
+    assert len(ti_load(str(tmp_path / "again") + ".ti", rowlen, lib=lib)) == 3
+
+
+def test_refuses_what_it_does_not_implement(exe, tmp_path):
+    u = os.path.join(INPUTS, "parse_hky.u")
+    for bad in (["-a1"], ["-j3"], ["-c0"]):
+        r = _run(exe, ["-i", u, "-o", str(tmp_path / "x"), "-q10", "-m1", "-t3", "-b1", "-l1"] + bad)
+        assert r.returncode != 0 and r.stderr.startswith("IMa2:")
+    r = _run(exe, ["-i", str(tmp_path / "nothere.u"), "-o", str(tmp_path / "x"), "-q10", "-m1", "-t3", "-b1", "-l1"])
+    assert r.returncode != 0 and "can't be opened" in r.stderr
+    r = _run(exe, ["-i", u, "-q10", "-m1", "-t3", "-b1", "-l1"])
+    assert r.returncode != 0 and "-o is required" in r.stderr
