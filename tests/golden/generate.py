@@ -333,6 +333,10 @@ def main():
     run_trace("trace_sim5_3pop_nomig", p3, [1, 2, 3, 4], {"gburn": 3000, "sweeps": 60000, "nbatch": 12}, priors=nomig)
     # whole qupdate steps: genealogies + split time (RY1 or NW) + mutation scalars; the posterior of t and of the scalars
     run_trace("trace_full_sim5", s5, [11, 12, 13, 14, 15, 16], {"gburn": 5000, "sweeps": 60000, "nbatch": 12, "full": 1})
+    # the same on one of our own input files: what the command-line front end is compared with
+    if not ONLY or "trace_full_parse_is_3pop" in ONLY:
+        u1 = os.path.join(HERE, "inputs", "parse_is_3pop.u")
+        run_trace("trace_full_parse_is_3pop", u1, [11, 12, 13, 14, 15, 16], {"gburn": 5000, "sweeps": 60000, "nbatch": 12, "full": 1})
     run_trace("trace_full_sim3", s3, [11, 12, 13, 14], {"gburn": 5000, "sweeps": 60000, "nbatch": 12, "full": 1})
 
 

@@ -62,3 +62,28 @@ def test_refuses_what_it_does_not_implement(exe, tmp_path):
     assert r.returncode != 0 and "can't be opened" in r.stderr
     r = _run(exe, ["-i", u, "-q10", "-m1", "-t3", "-b1", "-l1"])
     assert r.returncode != 0 and "-o is required" in r.stderr
+
+
+def frontend_posterior_matches_reference(exe, lib, tmp_path, nsigma=5.0):
+    """A run of the front end from the .u file alone (its own model tables, starting genealogies and schedule) samples the
+    posterior the reference samples with whole qupdate() steps on the same file: split times, coalescences per sampled
+    population and migration events (fixture trace_full_parse_is_3pop, written by the reference)."""
+    from ima2p_b200.readu import ti_load
+    from support import load_golden
+    out = tmp_path / "long"
+    r = _run(exe, ["-i", os.path.join(INPUTS, "parse_is_3pop.u"), "-o", str(out), "-q10", "-m1", "-t3", "-b10000", "-l3000", "-d20", "-hn1", "-s5"])
+    assert r.returncode == 0, r.stderr
+    rows = ti_load(str(out) + ".ti", 4 * 5 + 3 * 8 + 2 + 2, lib=lib)
+    d = load_golden("trace_full_parse_is_3pop")
+    t, b = np.array(d["t_batch_means"]), np.array(d["batch_means"]).sum(axis=1)
+    pairs = {"t0": (rows[:, -2], t[:, 0]), "t1": (rows[:, -1], t[:, 1]), "cc0": (rows[:, 0], b[:, 3]), "cc1": (rows[:, 1], b[:, 4]),
+             "migrations": (rows[:, 15:23].sum(axis=1), b[:, 2])}
+    for k, (mine, ref) in pairs.items():
+        bm = mine[:3000].reshape(30, -1).mean(axis=1)                     # batch means of the correlated series
+        z = (bm.mean() - ref.mean()) / np.hypot(bm.std(ddof=1) / np.sqrt(30), ref.std(ddof=1) / np.sqrt(len(ref)))
+        assert abs(z) < nsigma, (k, bm.mean(), ref.mean(), z)
+
+
+def test_front_end_samples_the_reference_posterior(exe, tmp_path):
+    from ima2p_b200 import capi
+    frontend_posterior_matches_reference(exe, capi.bind(os.path.join(HERE, "hostemu", "libima2p_hostemu.so")), tmp_path)

@@ -146,3 +146,12 @@ def test_reference_state_file_evaluates_to_reference_values(lib, name, tmp_path)
 
 def test_step_report(lib):
     ec.step_report_matches_separate_reads(lib)
+
+
+def test_front_end_on_the_device(lib, tmp_path):
+    """ima2p_b200/IMa2p_b200 (the product executable) from a .u file: posterior summaries against the reference's."""
+    import os
+    from test_frontend import frontend_posterior_matches_reference
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ima2p_b200", "IMa2p_b200")
+    assert os.path.exists(exe), "build the front end with __graft_entry__.build()"
+    frontend_posterior_matches_reference(exe, lib, tmp_path)
