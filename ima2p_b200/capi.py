@@ -109,8 +109,9 @@ class Ima2pError(RuntimeError):
         self.code = code
 
 
-def bind(path=LIB_PATH):
+def bind(path=None):
     """Load a build of the C ABI and set the prototypes of every declared symbol."""
+    path = path or LIB_PATH
     if not os.path.exists(path):
         raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(ima2p_b200 has no CPU fallback)" % path)
@@ -126,9 +127,15 @@ _LIB = None
 
 
 def lib():
+    """The product library.  Only a CUDA build is accepted here: the tests-only host emulation of the kernels
+    (tests/hostemu) identifies itself in ima2p_version() and is refused, whatever IMA2P_B200_LIB says."""
     global _LIB
     if _LIB is None:
-        _LIB = bind()
+        l = bind()
+        v = l.ima2p_version().decode()
+        if "sm_100a" not in v:
+            raise ImportError("%s is not a CUDA build of ima2p_b200 (%s): there is no CPU path" % (LIB_PATH, v))
+        _LIB = l
     return _LIB
 
 

@@ -209,7 +209,11 @@ struct ima2p_engine { Engine eng; };
 
 extern "C" {
 
+#if IMA_CUDA
 const char *ima2p_version(void) { return "ima2p_b200 0.1 (sm_100a)"; }
+#else
+const char *ima2p_version(void) { return "ima2p_b200 0.1 (host emulation of the kernels: tests only, not a product build)"; }
+#endif
 const char *ima2p_last_error(void) { return g_last_error.c_str(); }
 void ima2p_internal_set_error(const char *msg) { g_last_error = msg ? msg : ""; }
 

@@ -44,3 +44,16 @@ def test_no_cpu_fallback_without_a_device(product_lib):
     z = (C.c_double * 4)()
     rc = product_lib.ima2p_lmode_create(C.byref(l), 0, 3, 2, 1, z, z, z, z, z, 0)
     assert rc == capi.E_CUDA
+
+
+def test_product_binding_refuses_the_test_emulation(monkeypatch):
+    """The host emulation of the kernels exists for the CPU test-suite only: the package's own loader rejects it."""
+    import subprocess
+    subprocess.run([os.path.join(ROOT, "tests", "hostemu", "build.sh")], check=True)
+    emu = os.path.join(ROOT, "tests", "hostemu", "libima2p_hostemu.so")
+    assert b"tests only" in capi.bind(emu).ima2p_version()
+    monkeypatch.setattr(capi, "LIB_PATH", emu)
+    monkeypatch.setattr(capi, "_LIB", None)
+    with pytest.raises(ImportError):
+        capi.lib()
+    monkeypatch.setattr(capi, "_LIB", None)
