@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--schedule", default="full", choices=["full", "genealogy"],
                     help="full: qupdate's schedule (genealogies, split time every step, mutation scalars every 5th, swaps); "
                          "genealogy: updategenealogy + swaps only")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lmode", action="store_true")
     args = ap.parse_args()
@@ -254,12 +255,16 @@ def main():
         dist.all_gather_into_tensor(S_global, S_local)
         eng.swap_replay(S_global.data_ptr(), swaptries, stream)
 
+    stepper = None
+    if world > 1:
+        from ima2p_b200.multirank import ShardedStepper
+        stepper = ShardedStepper(eng, dev, stream)
+
     def run_steps(n):
         if world == 1:
             eng.run(n, swaptries, stream)
         else:
-            for _ in range(n):
-                step_multi()
+            stepper.run(n, swaptries)
 
     def barrier():
         torch.cuda.synchronize()
@@ -267,6 +272,15 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    graphed = False
+    if world > 1 and not args.no_graph:
+        with torch.cuda.stream(work_stream):
+            graphed = stepper.capture(swaptries)      # kernels + the NCCL all-gather of one step as one CUDA graph
+        flag = torch.tensor([1.0 if graphed else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # all ranks replay a graph, or none does
+        if float(flag.item()) == 0.0:
+            stepper._graph = None
+            graphed = False
     run_steps(args.burn)          # burn-in: leave the artificial starting genealogies behind (untimed)
     run_steps(W)
     barrier()
@@ -401,6 +415,7 @@ def main():
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
            "genealogy_updates_only": ({"ms_per_step": graph_ms / args.steps, "value": updates_all / (graph_ms * 1e-3), "unit": unit}
                                       if graph_ms else None), "lmode": lmode,
+           "multi_gpu_step": (("cuda graph (kernels + NCCL all-gather)" if graphed else "eager launches") if world > 1 else None),
            "dropped_for_capacity": c1["dropped"], "split_time_mean": split_time_mean,
            "update_counters": {k: int(v) for k, v in eng.update_counters().items()}, "swap_rate": (c1["swaps"] - c0["swaps"]) / max(1, c1["swap_attempts"] - c0["swap_attempts"])}
     print(json.dumps(out, default=float))
@@ -437,8 +452,16 @@ def lmode_bench(eng, dev, G=1000000):
     lm.jointp(xs)
     t3 = time.perf_counter()
     lm.close()
+    # the marginal kernel serves 8 evaluation points per pass over the rows (4 columns for a size parameter, 3 for a migration
+    # parameter, 4 bytes each): bytes it streams, against the HBM figure; the 84 MB of rows stay in the 126 MB L2 after
+    # the first pass, so the kernel is bound by FP64 exp throughput (one exp per genealogy-eval), not by HBM
+    passes = -(-1000 // 8)
+    streamed = G * 4.0 * passes * (3 * 4 + 2 * 3)
+    pk, _ = peaks()
     return {"rows": G, "margincalc_geneval_per_sec": 5 * 1000 * G / (t1 - t0), "jointp_geneval_per_sec": 64 * G / (t3 - t2),
-            "unit": "genealogy evals/s", "timing": "host wall clock around the C-ABI calls (includes H2D of x and D2H of results)"}
+            "unit": "genealogy evals/s", "timing": "host wall clock around the C-ABI calls (includes H2D of x and D2H of results)",
+            "margincalc_streamed_GBps": streamed / (t1 - t0) / 1e9, "margincalc_streamed_frac_of_hbm_peak": streamed / (t1 - t0) / 1e9 / pk["hbm_gbs"],
+            "margincalc_algorithmic_GBps_one_pass_per_x": 5 * 1000 * G * 15.2 / (t1 - t0) / 1e9}
 
 
 def lmode_bench_sharded(eng, dev, rank, world, step_multi, G=1000000):

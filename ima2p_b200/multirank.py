@@ -25,8 +25,34 @@ class ShardedStepper:
             self.S_global.copy_(self.S_local)
         self.eng.swap_replay(self.S_global.data_ptr(), swaptries, self.stream)
 
+    def capture(self, swaptries):
+        """One step (kernels + the NCCL all-gather) as a CUDA graph on the current torch stream: the step is a handful
+        of short launches, so at 2-8 GPUs the launch gaps between them are what the graph removes.  Returns False and
+        keeps the eager path when the capture is not possible (CPU/gloo, or a torch/NCCL that cannot capture)."""
+        if not torch.cuda.is_available() or self.S_local.device.type != "cuda":
+            return False
+        try:
+            for _ in range(3):                      # warm-up outside the capture (NCCL channels, lazy allocations)
+                self.step(swaptries)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream()
+            self.stream = cur.cuda_stream
+            with torch.cuda.graph(g, stream=cur):
+                self.step(swaptries)
+            self._graph, self._graph_swaptries = g, swaptries
+            return True
+        except Exception:
+            self._graph = None
+            return False
+
     def run(self, nsteps, swaptries=None):
         st = self.eng.default_swaptries() if swaptries is None else swaptries
+        g = getattr(self, "_graph", None)
+        if g is not None and self._graph_swaptries == st:
+            for _ in range(nsteps):
+                g.replay()
+            return
         for _ in range(nsteps):
             self.step(st)
 
