@@ -394,17 +394,25 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
   unsigned long long dropped = 0;
   int filled = (l0 + kRing < l1) ? l0 + kRing : l1;
   block_sync();
+  constexpr uint32_t kNoGo = kFlagRejectIS | kFlagOverflow | kFlagBadTree;
   for (int li = l0; li < l1;) {
-    const int nb = (l1 - li < B) ? l1 - li : B;
-    // ---- phase 1: term t of speculative locus li+g on warp g*kTermWarps + (t % kTermWarps) -------------------
+    // A proposal that arrives flagged (the data rule it out, or it was dropped) is rejected whatever the prior says: such
+    // loci are passed over without spending a speculative slot on them.  cand[g] = offset from li of the g-th locus that
+    // needs a decision among the loci already in the ring, span = loci consumed when none of them is accepted.
+    int cand[B], nb = 0;
+    const int visible = filled - li;
+    for (int k = 0; k < visible && nb < B; k++)
+      if (!((uint32_t)S.r_ic[((li + k) % kRing) * 4] & kNoGo)) cand[nb++] = k;
+    for (int g = nb; g < B; g++) cand[g] = 0;
+    const int span = nb == B ? cand[B - 1] + 1 : visible;
+    // ---- phase 1: term t of speculative candidate g on warp g*kTermWarps + (t % kTermWarps) ------------------
     const int upto = (li + kRing < l1) ? li + kRing : l1;   // loci < li are decided: their ring slots are free again
     IMA_FOR_WARPS(w, NW) {
       const int g = w / kTermWarps, t0 = w - g * kTermWarps;
       if (w == LOADER) load_records(filled, upto);
       if (w != LOADER && g < nb) {
-        const int slot = (li + g) % kRing;
-        const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
-        if (!(flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree))) {
+        const int slot = (li + cand[g]) % kRing;
+        {
           const int *dI = S.r_dI + slot * sI;
           const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
           // candidate sums = sum_subtract_treeinfo (ginfo.cpp:248-285) on the entries this term reads: subtract old, add
@@ -452,9 +460,8 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
         bool acc = false;
         double newprobg = 0.0;
         if (lane < nb) {
-          const int g = lane, slot = (li + g) % kRing;
-          const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
-          if (!(flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree))) {
+          const int g = lane, slot = (li + cand[lane]) % kRing;
+          {
             for (int t = 0; t < M.nq; t++) newprobg += S.cq[g * 2 * kMaxParams + t];
             if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
             if (M.nomigration == 0)
@@ -470,14 +477,15 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
 #if IMA_CUDA
         const int accepted = Warp::first(acc);
         const double np = Warp::bcast(newprobg, accepted < 0 ? 0 : accepted);
-        if (lane == 0) { S.ctl[0] = accepted; S.ctl[1] = accepted < 0 ? nb : accepted + 1; if (accepted >= 0) S.dctl[0] = np; }
+        if (lane == 0) {
+          S.ctl[0] = accepted; S.ctl[1] = accepted < 0 ? span : cand[accepted < 0 ? 0 : accepted] + 1; S.ctl[2] = accepted < 0 ? 0 : cand[accepted];
+          if (accepted >= 0) S.dctl[0] = np;
+        }
 #else
         // one lane: walk the speculative loci in order
         int accepted = -1;
         for (int g = 0; g < nb && accepted < 0; g++) {
-          const int slot = (li + g) % kRing;
-          const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
-          if (flags & (kFlagRejectIS | kFlagOverflow | kFlagBadTree)) continue;
+          const int slot = (li + cand[g]) % kRing;
           double npg = 0.0;
           for (int t = 0; t < M.nq; t++) npg += S.cq[g * 2 * kMaxParams + t];
           if (!M.nomigration) for (int t = 0; t < M.nm; t++) npg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
@@ -490,19 +498,19 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
           else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
           if (S.r_sc[slot * 5 + 3] < fmin(1.0, mh)) { accepted = g; S.dctl[0] = npg; }
         }
-        S.ctl[0] = accepted; S.ctl[1] = accepted < 0 ? nb : accepted + 1;
+        S.ctl[0] = accepted; S.ctl[1] = accepted < 0 ? span : cand[accepted] + 1; S.ctl[2] = accepted < 0 ? 0 : cand[accepted];
         (void)acc; (void)newprobg;
 #endif
       }
     }
     block_sync();
     // ---- phase 3: commit the accepted locus (if any) -----------------------------------------------------
-    const int accepted = S.ctl[0], adv = S.ctl[1];
+    const int accepted = S.ctl[0], adv = S.ctl[1], aoff = S.ctl[2];      // accepted candidate (or -1), loci consumed, its offset
     for (int g = 0; g < adv; g++) if ((uint32_t)S.r_ic[((li + g) % kRing) * 4] & kFlagOverflow) dropped++;
     IMA_FOR_WARPS(w, NW) {
       const int tid = w * IMA_WARP + lane, nth = (NW - 1) * IMA_WARP;
       if (w != LOADER && accepted >= 0) {
-        const int slot = (li + accepted) % kRing;
+        const int slot = (li + aoff) % kRing;
         const int *dI = S.r_dI + slot * sI;
         const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
         for (int i = tid; i < NI; i += nth) S.ai[i] += dI[i];
@@ -516,7 +524,7 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
         for (int i = tid; i < M.nq; i += nth) S.q[i] = S.cq[accepted * 2 * kMaxParams + i];
         for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = S.cq[accepted * 2 * kMaxParams + kMaxParams + i];
         if (tid == 0) {
-          const int p = c * E.d.nloci + li + accepted;
+          const int p = c * E.d.nloci + li + aoff;
           const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
           E.cur[p] = (unsigned char)(S.r_ic[slot * 4 + 1] ^ 1);
           E.acc[(size_t)p * 3 + 0]++;
@@ -527,7 +535,7 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
     }
     filled = upto;
     if (accepted >= 0) {
-      const int slot = (li + accepted) % kRing;
+      const int slot = (li + aoff) % kRing;
       probg = S.dctl[0];
       pdgsum -= S.r_sc[slot * 5 + 0];
       pdgsum += S.r_sc[slot * 5 + 1];
