@@ -374,6 +374,8 @@ def main():
             lmode_multi = {"error": str(ex)}
     if rank != 0:
         if world > 1:
+            if graphed:
+                os._exit(0)         # see --graph-multi
             dist.destroy_process_group()
         return
     pk, pk_kind = peaks()
