@@ -123,10 +123,11 @@ static int launch_eval(Engine *e, stream_t s) {
   return IMA2P_OK;
 }
 
-static int accept_block_warps(int spec) { return IMA_CUDA ? spec * kTermWarps + 1 : 1; }
+static int accept_block_warps(int spec) { return IMA_CUDA ? spec * kTermWarps : 1; }
 static void launch_accept(Engine *e, stream_t s, int l0, int l1) {
   const int nw = accept_block_warps(e->spec);
-  if (e->spec >= 3) IMA_LAUNCH(k_accept<3>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
+  if (e->spec >= 4) IMA_LAUNCH(k_accept<4>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
+  else if (e->spec == 3) IMA_LAUNCH(k_accept<3>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
   else if (e->spec == 2) IMA_LAUNCH(k_accept<2>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
   else IMA_LAUNCH(k_accept<1>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
 }
@@ -391,12 +392,16 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   e.pair_smem = pair_smem_bytes(d);
   e.chain_smem = chain_smem_bytes(d);
   e.accept_smem = accept_smem_bytes(d);
-  // deep speculation needs a 16-warp block per chain (one per SM); with more chains than SMs two 11-warp blocks per SM win
+  // deep speculation needs a 15- or 20-warp block per chain (one per SM); with more chains than SMs two 10-warp blocks per SM win
   e.spec = d.nchains <= 148 ? 3 : 2;
 #if IMA_CUDA
   if (e.pair_smem * kWarpsPerBlock > 227 * 1024) return fail(IMA2P_E_ARG, "finalize: pair does not fit in shared memory; lower mig_capacity");
   e.overlap_smem = e.pair_smem * kWarpsPerBlock;
-  if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
+  if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * 24 + 16)) ||
@@ -863,7 +868,7 @@ int ima2p_debug_gamma(int device, const int *a, const double *x, int n, double *
 }
 
 int ima2p_engine_set_speculation(ima2p_engine *h, int depth) {
-  if (!h || depth < 1 || depth > kSpecMax) return fail(IMA2P_E_ARG, "set_speculation: 1..3");
+  if (!h || depth < 1 || depth > kSpecMax) return fail(IMA2P_E_ARG, "set_speculation: 1..4");
   h->eng.spec = depth;
   h->eng.graph_ready = false;
   return IMA2P_OK;

@@ -178,6 +178,14 @@ IMA_KERNEL void k_eval_chains(EngineView E) {
   if (lane == 0) { E.probg[c] = probg; E.pdgsum[c] = pd; E.swapsum[c] = ssum; }
 }
 
+// IMA_PROF (tuning builds only): a few warps / blocks print the clock cycles they spent per stage
+#if defined(IMA_PROF) && IMA_CUDA
+#define IMA_PROF_DECL(n) long long prof_t_[n]; int prof_i_ = 0; prof_t_[0] = clock64();
+#define IMA_PROF_MARK() prof_t_[++prof_i_] = clock64();
+#else
+#define IMA_PROF_DECL(n)
+#define IMA_PROF_MARK()
+#endif
 #ifndef IMA_PROPOSE_MINBLOCKS
 #define IMA_PROPOSE_MINBLOCKS 5      // <= 102 registers/thread, 20 resident warps per SM: best of 5/6/8 measured on B200
 #endif
@@ -202,16 +210,20 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E, int l0, int l1) {
   const PairBuf &Bn = E.buf[cb ^ 1];
   const double *tv = E.tvals + (size_t)c * kMaxPeriods;
   const int lane = Warp::lane();
+  IMA_PROF_DECL(8)
   stage_pair(E, B, p, L.nl, S);
+  IMA_PROF_MARK()
   if (lane == 0) {
     Philox rng;
     rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngPropose);
     propose_move(M, E.d, tv, L.ng, L.nl, rng, S);
   }
   Warp::sync();
+  IMA_PROF_MARK()
   uint32_t flags = (uint32_t)S.ctl_i[kCiFlags];
   bool ok = !(flags & kFlagOverflow);
   if (ok) ok = eval_weights(M, E.d, L, tv, S);
+  IMA_PROF_MARK()
   const int total_mig = ok ? S.ctl_i[kCiMignum] : 0;
   if (ok && total_mig > E.d.CAP) ok = false;
   double pdga[kMaxLinked];
@@ -255,11 +267,18 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E, int l0, int l1) {
     if (!(flags & (kFlagRejectIS | kFlagBadTree))) store_pair(E, Bn, p, L.nl, S, total_mig);
   } else if (ok) {
     pdg = pair_likelihood(E, L, Bn, p, S, pdga);
+    IMA_PROF_MARK()
     flags = (uint32_t)S.ctl_i[kCiFlags];
     if (pdg == kRejectIS) flags |= kFlagRejectIS;
     if (lane == 0) S.ctl_d[kCdPdg] = pdg;
     Warp::sync();
     if (!(flags & (kFlagRejectIS | kFlagBadTree))) store_pair(E, Bn, p, L.nl, S, total_mig);
+    IMA_PROF_MARK()
+#if defined(IMA_PROF) && IMA_CUDA
+    if (lane == 0 && idx % 641 == 0 && prof_i_ == 5)
+      printf("PROFP %d stage %lld move %lld weights %lld like %lld store %lld flags %u\n", idx, prof_t_[1] - prof_t_[0], prof_t_[2] - prof_t_[1],
+             prof_t_[3] - prof_t_[2], prof_t_[4] - prof_t_[3], prof_t_[5] - prof_t_[4], flags);
+#endif
   } else {
     flags |= kFlagOverflow;
   }
@@ -287,7 +306,7 @@ IMA_DEV void fetch_accept_record(const EngineView &E, int p, int lane, int NI, i
 
 // ---- accept sweep ---------------------------------------------------------------------------------------
 // One block per chain.  The loci of a chain must be decided in order: they are coupled through the integrated
-// prior, so locus li sees the sums left by every accepted update before it.  Two things
+// prior, so locus li sees the sums left by every accepted update before it.  Three things
 // shorten that dependent chain without changing its result:
 //   * inside a locus the nq + nm prior terms are independent: each goes to its own warp, which runs the term's
 //     series / continued fraction 32 terms per round (ima_math.h *_coop);
@@ -295,54 +314,67 @@ IMA_DEV void fetch_accept_record(const EngineView &E, int p, int lane, int NI, i
 //     taken in locus order; the first acceptance changes the sums, so every speculative locus after it is
 //     thrown away and re-evaluated in the next round.  About two thirds of the updates are rejected, so a round
 //     decides 1 + q + q^2 ... loci on average (q = rejection rate).  The random number of a locus depends only on
-//     (chain, locus, step), so the outcome is identical to the one-locus-at-a-time sweep.
-// A loader warp streams the pairs' weight records (and draws the uniforms) a few loci ahead into a ring in
-// shared memory, so global-memory latency is off the critical path.
+//     (chain, locus, step), so the outcome is identical to the one-locus-at-a-time sweep;
+//   * nothing on the per-round path touches global memory: the weight records of a whole run of loci (all of them
+//     when they fit, else chunks of accept_chunk()) are brought into shared memory by every thread of the block at
+//     once, with the uniforms drawn one locus per thread, before the rounds start.  A round is then
+//     terms -> barrier -> warp 0 decides and commits -> barrier.
 // Loci [l0, l1): the sums travel through global memory between launches.
 #if IMA_CUDA
-constexpr int kSpecMax = 3;          // speculative depth B
+constexpr int kSpecMax = 4;          // speculative depth B
 constexpr int kTermWarps = 5;        // warps per speculative locus (terms are strided over them)
 IMA_DEV void block_sync() { __syncthreads(); }
 #define IMA_FOR_WARPS(wv, nw) for (int wv = ima_warp_in_block(), once_ = 1; once_; once_ = 0)
 #else
-constexpr int kSpecMax = 3;
+constexpr int kSpecMax = 4;
 constexpr int kTermWarps = 5;
 IMA_DEV void block_sync() {}
 #define IMA_FOR_WARPS(wv, nw) for (int wv = 0; wv < (nw); wv++)      // host emulation: one thread plays every warp in turn
 #endif
-constexpr int kRing = 8;             // loci buffered ahead
+constexpr int kAcceptSmemBudget = 100 * 1024;   // two blocks per SM stay possible
 
 struct AcceptSm {
   int *ai; double *ad, *q;                                   // all-locus sums and current prior terms
   double *cq;                                                // [kSpecMax][2*kMaxParams] candidate terms per speculative locus
-  int *r_dI; double *r_oD, *r_nD, *r_sc; int *r_ic;          // ring: [kRing] records
-  int *ctl;                                                  // [4]: accepted group (or -1), advance
-  double *dctl;                                              // [2]: new probg
+  int *cflag;                                                // [kSpecMax] candidate would put migration where the model forbids it
+  int *r_dI; double *r_oD, *r_nD, *r_sc; int *r_ic;          // [chunk] records
+  int *ctl;                                                  // [2]: loci consumed by the round
 };
-IMA_HD size_t accept_smem_bytes(const EngineDims &d) {
+IMA_HD size_t accept_fixed_bytes(const EngineDims &d) {
   return align8(sizeof(int) * d.NI) + align8(sizeof(double) * d.ND) + align8(sizeof(double) * 2 * kMaxParams) +
-         align8(sizeof(double) * kSpecMax * 2 * kMaxParams) + kRing * (align8(sizeof(int) * d.NI) + 2 * align8(sizeof(double) * d.ND) + 5 * 8 + 16) + 64;
+         align8(sizeof(double) * kSpecMax * 2 * kMaxParams) + align8(sizeof(int) * kSpecMax) + 16;
 }
-IMA_DEV AcceptSm carve_accept_smem(unsigned char *base, const EngineDims &d) {
+IMA_HD size_t accept_record_bytes(const EngineDims &d) {
+  return align8(sizeof(int) * d.NI) + 2 * align8(sizeof(double) * d.ND) + 4 * 8 + 8;
+}
+// loci whose records are resident at a time
+IMA_HD int accept_chunk(const EngineDims &d) {
+  long long k = ((long long)kAcceptSmemBudget - (long long)accept_fixed_bytes(d)) / (long long)accept_record_bytes(d);
+  if (k > d.nloci) k = d.nloci;
+  if (k < 1) k = 1;
+  return (int)k;
+}
+IMA_HD size_t accept_smem_bytes(const EngineDims &d) { return accept_fixed_bytes(d) + (size_t)accept_chunk(d) * accept_record_bytes(d); }
+IMA_DEV AcceptSm carve_accept_smem(unsigned char *base, const EngineDims &d, int K) {
   AcceptSm s; unsigned char *p = base;
   s.ad = (double *)p; p += align8(sizeof(double) * d.ND);
   s.q = (double *)p; p += align8(sizeof(double) * 2 * kMaxParams);
   s.cq = (double *)p; p += align8(sizeof(double) * kSpecMax * 2 * kMaxParams);
-  s.r_oD = (double *)p; p += kRing * align8(sizeof(double) * d.ND);
-  s.r_nD = (double *)p; p += kRing * align8(sizeof(double) * d.ND);
-  s.r_sc = (double *)p; p += kRing * 5 * 8;                  // oldpdg, newpdg, extra, uniform, (pad)
-  s.dctl = (double *)p; p += 16;
+  s.r_oD = (double *)p; p += (size_t)K * align8(sizeof(double) * d.ND);
+  s.r_nD = (double *)p; p += (size_t)K * align8(sizeof(double) * d.ND);
+  s.r_sc = (double *)p; p += (size_t)K * 4 * 8;              // oldpdg, newpdg, extra, uniform
   s.ai = (int *)p; p += align8(sizeof(int) * d.NI);
-  s.r_dI = (int *)p; p += kRing * align8(sizeof(int) * d.NI);
-  s.r_ic = (int *)p; p += kRing * 16;                        // flags, cb
+  s.r_dI = (int *)p; p += (size_t)K * align8(sizeof(int) * d.NI);
+  s.r_ic = (int *)p; p += (size_t)K * 8;                     // flags, cb
+  s.cflag = (int *)p; p += align8(sizeof(int) * kSpecMax);
   s.ctl = (int *)p;
   return s;
 }
 
-// depth 3: one 16-warp block per SM (<= 128 registers); depth 1 and 2: two blocks per SM (<= 93 registers), which is
-// what a GPU holding more chains than it has SMs needs
+// depth 3 and 4: one block per SM; depth 1 and 2: two blocks per SM, which is what a GPU holding more chains than it
+// has SMs needs
 #if IMA_CUDA
-#define IMA_ACCEPT_BOUNDS(B) __launch_bounds__(((B) * kTermWarps + 1) * 32, (B) == 3 ? 1 : 2)
+#define IMA_ACCEPT_BOUNDS(B) __launch_bounds__((B) * kTermWarps * 32, (B) >= 3 ? 1 : 2)
 #else
 #define IMA_ACCEPT_BOUNDS(B)
 #endif
@@ -352,69 +384,84 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
   const int c = ima_block();
   if (c >= E.d.nchains) return;
   const DevModel &M = IMA_MODEL;
-  const int NW = B * kTermWarps + 1, LOADER = B * kTermWarps;       // warps in the block; the last one loads
+  const int NW = B * kTermWarps;                                     // warps in the block
   const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
   const int sI = (int)(align8(sizeof(int) * NI) / sizeof(int)), sD = (int)(align8(sizeof(double) * ND) / sizeof(double));
-  AcceptSm S = carve_accept_smem(IMA_SMEM, E.d);
+  const int K = accept_chunk(E.d);
+  AcceptSm S = carve_accept_smem(IMA_SMEM, E.d, K);
   const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
-  // ring slot of locus l: l % kRing.  The loader fills loci [from, upto): every load of every locus of the batch is
-  // issued before any is consumed (independent addresses), and the uniforms are drawn one locus per lane.
-  auto load_records = [&](int from, int upto) {
-    for (int l = from + lane; l < upto; l += IMA_WARP) {
-      const int p = c * E.d.nloci + l, slot = l % kRing;
-      const int cb = E.cur[p];
-      const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
-      S.r_ic[slot * 4 + 0] = (int)E.prop_flags[p]; S.r_ic[slot * 4 + 1] = cb;
-      S.r_sc[slot * 5 + 0] = O.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 5 + 1] = N.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 5 + 2] = E.prop_extra[p];
-      Philox rng;
-      rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + l), kRngAccept);
-      S.r_sc[slot * 5 + 3] = rng.uniform();
-    }
-    const int nl = upto - from, per = NI + 2 * ND;
-    for (int k = lane; k < nl * per; k += IMA_WARP) {
-      const int l = from + k / per, i = k - (l - from) * per;
-      const int p = c * E.d.nloci + l, slot = l % kRing;
-      const int cb = E.cur[p];
-      const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
-      if (i < NI) S.r_dI[slot * sI + i] = N.gwi[(size_t)p * NI + i] - O.gwi[(size_t)p * NI + i];
-      else if (i < NI + ND) S.r_oD[slot * sD + (i - NI)] = O.gwd[(size_t)p * ND + (i - NI)];
-      else S.r_nD[slot * sD + (i - NI - ND)] = N.gwd[(size_t)p * ND + (i - NI - ND)];
-    }
-  };
   IMA_FOR_WARPS(w, NW) {
     const int tid = w * IMA_WARP + lane, nth = NW * IMA_WARP;
     for (int i = tid; i < NI; i += nth) S.ai[i] = E.all_i[(size_t)c * NI + i];
     for (int i = tid; i < ND; i += nth) S.ad[i] = E.all_d[(size_t)c * ND + i];
     for (int i = tid; i < M.nq; i += nth) S.q[i] = E.qint[(size_t)c * kMaxParams + i];
     for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = E.mint[(size_t)c * kMaxParams + i];
-    if (w == LOADER) load_records(l0, (l0 + kRing < l1) ? l0 + kRing : l1);
   }
   const double beta = E.beta[c];
-  double probg = E.probg[c], pdgsum = E.pdgsum[c];
+  double probg = E.probg[c], pdgsum = E.pdgsum[c];                    // kept by warp 0
   unsigned long long dropped = 0;
-  int filled = (l0 + kRing < l1) ? l0 + kRing : l1;
-  block_sync();
   constexpr uint32_t kNoGo = kFlagRejectIS | kFlagOverflow | kFlagBadTree;
-  for (int li = l0; li < l1;) {
-    // A proposal that arrives flagged (the data rule it out, or it was dropped) is rejected whatever the prior says: such
-    // loci are passed over without spending a speculative slot on them.  cand[g] = offset from li of the g-th locus that
-    // needs a decision among the loci already in the ring, span = loci consumed when none of them is accepted.
-    int cand[B], nb = 0;
-    const int visible = filled - li;
-    for (int k = 0; k < visible && nb < B; k++)
-      if (!((uint32_t)S.r_ic[((li + k) % kRing) * 4] & kNoGo)) cand[nb++] = k;
-    for (int g = nb; g < B; g++) cand[g] = 0;
-    const int span = nb == B ? cand[B - 1] + 1 : visible;
-    // ---- phase 1: term t of speculative candidate g on warp g*kTermWarps + (t % kTermWarps) ------------------
-    const int upto = (li + kRing < l1) ? li + kRing : l1;   // loci < li are decided: their ring slots are free again
+#if defined(IMA_PROF) && IMA_CUDA
+  auto pclk_ = []() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; };
+  long long pf_[6] = {0, 0, 0, 0, 0, 0}, pt_ = pclk_(), pt0_ = pt_; int prounds_ = 0;
+#define IMA_PF(k) { const long long n_ = pclk_(); pf_[k] += n_ - pt_; pt_ = n_; }
+#else
+#define IMA_PF(k)
+#endif
+  for (int ch0 = l0; ch0 < l1; ch0 += K) {
+    const int ch1 = (ch0 + K < l1) ? ch0 + K : l1;
+    block_sync();                                                    // the previous chunk's records are no longer read
+    // every record of loci [ch0, ch1): slot = l - ch0.  All loads are independent, one pass of the whole block.
     IMA_FOR_WARPS(w, NW) {
-      const int g = w / kTermWarps, t0 = w - g * kTermWarps;
-      if (w == LOADER) load_records(filled, upto);
-      if (w != LOADER && g < nb) {
-        const int slot = (li + cand[g]) % kRing;
-        {
+      const int tid = w * IMA_WARP + lane, nth = NW * IMA_WARP;
+      for (int l = ch0 + tid; l < ch1; l += nth) {
+        const int p = c * E.d.nloci + l, slot = l - ch0;
+        const int cb = E.cur[p];
+        const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
+        S.r_ic[slot * 2 + 0] = (int)E.prop_flags[p]; S.r_ic[slot * 2 + 1] = cb;
+        S.r_sc[slot * 4 + 0] = O.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 4 + 1] = N.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 4 + 2] = E.prop_extra[p];
+        Philox rng;
+        rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + l), kRngAccept);
+        S.r_sc[slot * 4 + 3] = rng.uniform();
+      }
+      const int nl = ch1 - ch0, per = NI + 2 * ND;
+      for (int k = tid; k < nl * per; k += nth) {
+        const int slot = k / per, i = k - slot * per;
+        const int p = c * E.d.nloci + ch0 + slot;
+        const int cb = E.cur[p];
+        const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
+        if (i < NI) S.r_dI[slot * sI + i] = N.gwi[(size_t)p * NI + i] - O.gwi[(size_t)p * NI + i];
+        else if (i < NI + ND) S.r_oD[slot * sD + (i - NI)] = O.gwd[(size_t)p * ND + (i - NI)];
+        else S.r_nD[slot * sD + (i - NI - ND)] = N.gwd[(size_t)p * ND + (i - NI - ND)];
+      }
+    }
+    block_sync();
+    IMA_PF(3)
+    for (int li = ch0; li < ch1;) {
+      // A proposal that arrives flagged (the data rule it out, or it was dropped) is rejected whatever the prior says: such
+      // loci are passed over without spending a speculative slot on them.  cand[g] = offset from li of the g-th locus that
+      // needs a decision, span = loci consumed when none of them is accepted.
+      int cand[B], nb = 0;
+      const int visible = ch1 - li;
+      int k = 0;
+      for (; k < visible && nb < B; k++)
+        if (!((uint32_t)S.r_ic[(li - ch0 + k) * 2] & kNoGo)) cand[nb++] = k;
+      for (int g = nb; g < B; g++) cand[g] = 0;
+      const int span = k;                    // nb == B: up to and including the last candidate; else everything left in the chunk
+      // ---- phase 1: term t of speculative candidate g on warp g*kTermWarps + (t % kTermWarps) ------------------
+      IMA_FOR_WARPS(w, NW) {
+        const int g = w / kTermWarps, t0 = w - g * kTermWarps;
+        if (g < nb) {
+          const int slot = li - ch0 + cand[g];
           const int *dI = S.r_dI + slot * sI;
           const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
+          if (t0 == 0 && lane == 0) {
+            int bad = 0;
+            if (M.nomigration == 0)
+              for (int i = 0; i < M.nomig_n; i++)
+                if (S.ai[ncc + M.nomig_idx[i]] + dI[ncc + M.nomig_idx[i]] != 0) bad = 1;
+            S.cflag[g] = bad;
+          }
           // candidate sums = sum_subtract_treeinfo (ginfo.cpp:248-285) on the entries this term reads: subtract old, add
           // new, clamp fc and fm at 0; then integrate_tree_prob's reuse rule (:1997-2000, :2031-2034) or the integral
           for (int t = t0; t < nterms; t += kTermWarps) {
@@ -450,112 +497,112 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
           }
         }
       }
-    }
-    block_sync();
-    // ---- phase 2: decisions in locus order (update_gtree.cpp:917-927) ----------------------------------------
-    IMA_FOR_WARPS(w, NW) {
-      if (w == 0) {
-        // lane g evaluates the MH ratio of speculative locus li+g (all against the same sums); the first accepting
-        // lane in locus order wins
-        bool acc = false;
-        double newprobg = 0.0;
-        if (lane < nb) {
-          const int g = lane, slot = (li + cand[lane]) % kRing;
+      IMA_PF(0)
+      block_sync();
+      IMA_PF(1)
+      // ---- phase 2: warp 0 decides in locus order (update_gtree.cpp:917-927) and commits the accepted locus ------
+      IMA_FOR_WARPS(w, NW) {
+        if (w == 0) {
+          int accepted = -1;
+          double np = 0.0;
+#if IMA_CUDA
           {
-            for (int t = 0; t < M.nq; t++) newprobg += S.cq[g * 2 * kMaxParams + t];
-            if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
-            if (M.nomigration == 0)
-              for (int i = 0; i < M.nomig_n; i++)
-                if (S.ai[ncc + M.nomig_idx[i]] + S.r_dI[slot * sI + ncc + M.nomig_idx[i]] != 0) newprobg = -kMyDblMax;
-            const double tpw = newprobg - probg, dpdg = S.r_sc[slot * 5 + 1] - S.r_sc[slot * 5 + 0], extra = S.r_sc[slot * 5 + 2];
+            // lane g evaluates the MH ratio of speculative candidate g (all against the same sums); the first accepting
+            // lane in locus order wins
+            bool acc = false;
+            double newprobg = 0.0;
+            if (lane < nb) {
+              const int g = lane, slot = li - ch0 + cand[lane];
+              for (int t = 0; t < M.nq; t++) newprobg += S.cq[g * 2 * kMaxParams + t];
+              if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
+              if (S.cflag[g]) newprobg = -kMyDblMax;
+              const double tpw = newprobg - probg, dpdg = S.r_sc[slot * 4 + 1] - S.r_sc[slot * 4 + 0], extra = S.r_sc[slot * 4 + 2];
+              double mh;
+              if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
+              else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
+              acc = S.r_sc[slot * 4 + 3] < fmin(1.0, mh);
+            }
+            accepted = Warp::first(acc);
+            np = Warp::bcast(newprobg, accepted < 0 ? 0 : accepted);
+            IMA_PF(4)
+          }
+#else
+          for (int g = 0; g < nb && accepted < 0; g++) {       // one lane: walk the speculative loci in order
+            const int slot = li - ch0 + cand[g];
+            double npg = 0.0;
+            for (int t = 0; t < M.nq; t++) npg += S.cq[g * 2 * kMaxParams + t];
+            if (!M.nomigration) for (int t = 0; t < M.nm; t++) npg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
+            if (S.cflag[g]) npg = -kMyDblMax;
+            const double tpw = npg - probg, dpdg = S.r_sc[slot * 4 + 1] - S.r_sc[slot * 4 + 0], extra = S.r_sc[slot * 4 + 2];
             double mh;
             if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
             else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
-            acc = S.r_sc[slot * 5 + 3] < fmin(1.0, mh);
+            if (S.r_sc[slot * 4 + 3] < fmin(1.0, mh)) { accepted = g; np = npg; }
+          }
+#endif
+          const int aoff = accepted < 0 ? 0 : cand[accepted];
+          const int adv = accepted < 0 ? span : aoff + 1;
+          if (lane == 0) S.ctl[0] = adv;
+          for (int g = 0; g < adv; g++) if ((uint32_t)S.r_ic[(li - ch0 + g) * 2] & kFlagOverflow) dropped++;
+          if (accepted >= 0) {
+            const int slot = li - ch0 + aoff;
+            const int *dI = S.r_dI + slot * sI;
+            const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
+            for (int i = lane; i < NI; i += IMA_WARP) S.ai[i] += dI[i];
+            for (int i = lane; i < ND; i += IMA_WARP) {
+              double x = S.ad[i];
+              x -= oD[i];
+              x += nD[i];
+              if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
+              S.ad[i] = x;
+            }
+            for (int i = lane; i < M.nq; i += IMA_WARP) S.q[i] = S.cq[accepted * 2 * kMaxParams + i];
+            for (int i = lane; i < M.nm; i += IMA_WARP) S.q[kMaxParams + i] = S.cq[accepted * 2 * kMaxParams + kMaxParams + i];
+            if (lane == 0) {
+              const int p = c * E.d.nloci + li + aoff;
+              const uint32_t flags = (uint32_t)S.r_ic[slot * 2];
+              E.cur[p] = (unsigned char)(S.r_ic[slot * 2 + 1] ^ 1);
+#if IMA_CUDA
+              atomicAdd(&E.acc[(size_t)p * 3 + 0], 1u);                 // fire and forget: nothing waits for the old value
+              if (flags & kFlagTopol) atomicAdd(&E.acc[(size_t)p * 3 + 1], 1u);
+              if (flags & kFlagTmrca) atomicAdd(&E.acc[(size_t)p * 3 + 2], 1u);
+#else
+              E.acc[(size_t)p * 3 + 0]++;
+              if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
+              if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
+#endif
+            }
+            probg = np;
+            pdgsum -= S.r_sc[slot * 4 + 0];
+            pdgsum += S.r_sc[slot * 4 + 1];
           }
         }
-#if IMA_CUDA
-        const int accepted = Warp::first(acc);
-        const double np = Warp::bcast(newprobg, accepted < 0 ? 0 : accepted);
-        if (lane == 0) {
-          S.ctl[0] = accepted; S.ctl[1] = accepted < 0 ? span : cand[accepted < 0 ? 0 : accepted] + 1; S.ctl[2] = accepted < 0 ? 0 : cand[accepted];
-          if (accepted >= 0) S.dctl[0] = np;
-        }
-#else
-        // one lane: walk the speculative loci in order
-        int accepted = -1;
-        for (int g = 0; g < nb && accepted < 0; g++) {
-          const int slot = (li + cand[g]) % kRing;
-          double npg = 0.0;
-          for (int t = 0; t < M.nq; t++) npg += S.cq[g * 2 * kMaxParams + t];
-          if (!M.nomigration) for (int t = 0; t < M.nm; t++) npg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
-          if (M.nomigration == 0)
-            for (int i = 0; i < M.nomig_n; i++)
-              if (S.ai[ncc + M.nomig_idx[i]] + S.r_dI[slot * sI + ncc + M.nomig_idx[i]] != 0) npg = -kMyDblMax;
-          const double tpw = npg - probg, dpdg = S.r_sc[slot * 5 + 1] - S.r_sc[slot * 5 + 0], extra = S.r_sc[slot * 5 + 2];
-          double mh;
-          if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
-          else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
-          if (S.r_sc[slot * 5 + 3] < fmin(1.0, mh)) { accepted = g; S.dctl[0] = npg; }
-        }
-        S.ctl[0] = accepted; S.ctl[1] = accepted < 0 ? span : cand[accepted] + 1; S.ctl[2] = accepted < 0 ? 0 : cand[accepted];
-        (void)acc; (void)newprobg;
-#endif
       }
-    }
-    block_sync();
-    // ---- phase 3: commit the accepted locus (if any) -----------------------------------------------------
-    const int accepted = S.ctl[0], adv = S.ctl[1], aoff = S.ctl[2];      // accepted candidate (or -1), loci consumed, its offset
-    for (int g = 0; g < adv; g++) if ((uint32_t)S.r_ic[((li + g) % kRing) * 4] & kFlagOverflow) dropped++;
-    IMA_FOR_WARPS(w, NW) {
-      const int tid = w * IMA_WARP + lane, nth = (NW - 1) * IMA_WARP;
-      if (w != LOADER && accepted >= 0) {
-        const int slot = (li + aoff) % kRing;
-        const int *dI = S.r_dI + slot * sI;
-        const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
-        for (int i = tid; i < NI; i += nth) S.ai[i] += dI[i];
-        for (int i = tid; i < ND; i += nth) {
-          double x = S.ad[i];
-          x -= oD[i];
-          x += nD[i];
-          if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
-          S.ad[i] = x;
-        }
-        for (int i = tid; i < M.nq; i += nth) S.q[i] = S.cq[accepted * 2 * kMaxParams + i];
-        for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = S.cq[accepted * 2 * kMaxParams + kMaxParams + i];
-        if (tid == 0) {
-          const int p = c * E.d.nloci + li + aoff;
-          const uint32_t flags = (uint32_t)S.r_ic[slot * 4];
-          E.cur[p] = (unsigned char)(S.r_ic[slot * 4 + 1] ^ 1);
-          E.acc[(size_t)p * 3 + 0]++;
-          if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
-          if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
-        }
-      }
-    }
-    filled = upto;
-    if (accepted >= 0) {
-      const int slot = (li + aoff) % kRing;
-      probg = S.dctl[0];
-      pdgsum -= S.r_sc[slot * 5 + 0];
-      pdgsum += S.r_sc[slot * 5 + 1];
-    }
-    li += adv;
-    block_sync();
-  }
-  IMA_FOR_WARPS(w, NW) {
-    const int tid = w * IMA_WARP + lane, nth = NW * IMA_WARP;
-    for (int i = tid; i < NI; i += nth) E.all_i[(size_t)c * NI + i] = S.ai[i];
-    for (int i = tid; i < ND; i += nth) E.all_d[(size_t)c * ND + i] = S.ad[i];
-    for (int i = tid; i < M.nq; i += nth) E.qint[(size_t)c * kMaxParams + i] = S.q[i];
-    for (int i = tid; i < M.nm; i += nth) E.mint[(size_t)c * kMaxParams + i] = S.q[kMaxParams + i];
-  }
-#if IMA_CUDA
-  __threadfence_block();
+      IMA_PF(2)
+      block_sync();
+      IMA_PF(3)
+      li += S.ctl[0];
+#if defined(IMA_PROF) && IMA_CUDA
+      prounds_++;
 #endif
-  block_sync();
+    }
+  }
+#if defined(IMA_PROF) && IMA_CUDA
+  if ((c == 0 || c == 77) && lane == 0)
+    printf("PROFA chain %d warp %d rounds %d phase1 %lld wait1 %lld decide %lld commit %lld wait2 %lld total %lld\n", c, ima_warp_in_block(), prounds_, pf_[0], pf_[1],
+           pf_[4], pf_[2], pf_[3], pclk_() - pt0_);
+#endif
+  // warp 0 wrote the sums last and holds probg / pdgsum: it writes the chain's state back
   IMA_FOR_WARPS(w, NW) {
     if (w == 0) {
+      for (int i = lane; i < NI; i += IMA_WARP) E.all_i[(size_t)c * NI + i] = S.ai[i];
+      for (int i = lane; i < ND; i += IMA_WARP) E.all_d[(size_t)c * ND + i] = S.ad[i];
+      for (int i = lane; i < M.nq; i += IMA_WARP) E.qint[(size_t)c * kMaxParams + i] = S.q[i];
+      for (int i = lane; i < M.nm; i += IMA_WARP) E.mint[(size_t)c * kMaxParams + i] = S.q[kMaxParams + i];
+#if IMA_CUDA
+      __threadfence_block();
+      __syncwarp();
+#endif
       const double ssum = (l1 == E.d.nloci) ? chain_swapsum(E, M, c, probg) : 0.0;
       if (lane == 0) {
         E.probg[c] = probg; E.pdgsum[c] = pdgsum;

@@ -346,22 +346,64 @@ IMA_DEV double lowergamma_coop(const MathCtx &mc, int a, double x) {
   return p;
 }
 
+// The reference falls back from one incomplete gamma to the complementary one at the SAME (a, x) when the first is
+// indistinguishable from the complete gamma (update_gtree_common.cpp:128-141, :222-237).  Both evaluate the same
+// series / continued fraction and the same exponent, so the cooperative forms compute them once: GammaCore holds the
+// shared pieces, upper_of / lower_of finish either function with the arithmetic of uppergamma / lowergamma above.
+struct GammaCore { double gln, t, v; bool series; };    // v = series sum (x < a+1) or continued fraction h
+IMA_DEV GammaCore gamma_core_coop(const MathCtx &mc, int a, double x) {      // a >= 1, x >= 0
+  GammaCore g;
+  g.gln = lfact(mc, a - 1);
+  g.series = x < a + 1.0;
+  g.v = g.series ? gamma_series_coop(mc, a, x) : gamma_cf_coop(mc, (double)a, x);
+  g.t = -x + a * log(x) - g.gln;
+  return g;
+}
+IMA_DEV double upper_of(const GammaCore &g, double x) {
+  double p;
+  if (g.series) {
+    const double gamser = (x <= 0.0) ? 0.0 : g.v * exp(g.t);
+    p = g.gln + log(1.0 - gamser);
+  } else {
+    p = g.gln + (g.t + log(g.v));
+  }
+  if (p < -1e200) p = -1e200;
+  return p;
+}
+IMA_DEV double lower_of(const GammaCore &g, double x) {
+  double p;
+  if (g.series) {
+    const double gamserlog = (x <= 0.0) ? 0.0 : log(g.v) + g.t;
+    p = g.gln + gamserlog;
+  } else {
+    const double gammcf = exp(g.t) * g.v;
+    p = g.gln + log(1 - gammcf);
+  }
+  if (p < -1e200) p = -1e200;
+  return p;
+}
+
 // integrate_coalescent_term / integrate_migration_term with the cooperative gamma functions
 IMA_DEV double integrate_coalescent_term_coop(const MathCtx &mc, int cc, double fc, double hcc, double max, double min) {
   double p, a, b, c, d;
   if (cc > 0) {
     if (min == 0) {
-      double ug = uppergamma_coop(mc, cc - 1, 2 * fc / max);
-      if (cc > 1) {
-        const double fullg = lfact(mc, cc - 2);
+      const double x = 2 * fc / max;
+      double ug;
+      if (cc > 1 && x >= 0.0) {
+        const GammaCore g = gamma_core_coop(mc, cc - 1, x);
+        ug = upper_of(g, x);
+        const double fullg = g.gln;                        // lfact(cc - 2)
         if (fullg - ug < 1e-15 || fullg - ug > kLogDblMax) {
-          const double lg = lowergamma_coop(mc, cc - 1, 2 * fc / max);
+          const double lg = lower_of(g, x);
           if (fullg > lg) {
             double ugalt;
             logdiff(mc, ugalt, fullg, lg);
             if (fabs(ugalt - ug) > 1e-10) ug = ugalt;
           }
         }
+      } else {
+        ug = uppergamma_coop(mc, cc - 1, x);
       }
       p = ug + kLog2 - hcc + (1 - cc) * log(fc);
     } else {
@@ -395,10 +437,13 @@ IMA_DEV double integrate_migration_term_coop(const MathCtx &mc, int cm, double f
   double p, a, b, c;
   if (cm > 0) {
     if (min == 0) {
-      double lg = lowergamma_coop(mc, cm + 1, fm * max);
-      const double fullg = lfact(mc, cm);
+      const double x = fm * max;
+      if (x < 0.0) { raise(mc, kErrGamma); return 0.0; }
+      const GammaCore g = gamma_core_coop(mc, cm + 1, x);
+      double lg = lower_of(g, x);
+      const double fullg = g.gln;                          // lfact(cm)
       if (fullg - lg < 1e-15 || fullg - lg > kLogDblMax) {
-        const double ug = uppergamma_coop(mc, cm + 1, fm * max);
+        const double ug = upper_of(g, x);
         if (fullg > ug) {
           double lgalt;
           logdiff(mc, lgalt, fullg, ug);

@@ -203,7 +203,7 @@ class Engine:
         self._ck(self.lib.ima2p_engine_set_pieces(self._h, pieces))
 
     def set_speculation(self, depth):
-        """Loci evaluated per round of the accept sweep (1..3); the results do not depend on it."""
+        """Loci evaluated per round of the accept sweep (1..4); the results do not depend on it."""
         self._ck(self.lib.ima2p_engine_set_speculation(self._h, depth))
 
     def default_swaptries(self):

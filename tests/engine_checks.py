@@ -458,3 +458,25 @@ def step_report_matches_separate_reads(lib, name="state_sim5_hn4"):
     ref_row = eng.cold_row()
     assert (row is None) == (ref_row is None) and (row is None or np.array_equal(row, ref_row))
     eng.close()
+
+
+def speculation_depth_does_not_change_the_run(lib, name="state_sim50_hn3", nsteps=60):
+    """The accept sweep evaluates several loci of a chain per round speculatively (k_accept<B>); whatever the depth B, the
+    run must be the one-locus-at-a-time sweep of update_gtree.cpp:917-927: same acceptances, same sums, same genealogies."""
+    from support import engine_from_fixture, load_golden
+    d = load_golden(name)
+    outs = []
+    for depth in (1, 2, 3, 4):
+        eng, _ = engine_from_fixture(d, lib=lib, seed=31)
+        eng.set_speculation(depth)
+        eng.eval()
+        eng.run(nsteps)
+        eng.sync()
+        ch = [eng.chain(c) for c in range(eng.nchains)]
+        outs.append((eng.counters(), np.concatenate([np.r_[c["probg"], c["pdg"], c["wd"], c["wi"]] for c in ch])))
+        eng.close()
+    assert outs[0][0]["accepted"] > 0
+    for k in (1, 2, 3):
+        assert outs[k][0] == outs[0][0], (k, outs[k][0], outs[0][0])
+        assert np.array_equal(outs[k][1], outs[0][1]), k
+    return outs[0][0]

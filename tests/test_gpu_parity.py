@@ -75,6 +75,10 @@ def test_runs_are_reproducible_and_seed_dependent(lib):
     assert np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])
 
 
+def test_speculation_depth_does_not_change_the_run(lib):
+    ec.speculation_depth_does_not_change_the_run(lib)
+
+
 # ---- section 8 (f1): the rest of the step on the device ------------------------------------------------------------
 @pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2", "tupdates_sim3_joint_hn2"])
 def test_split_time_update_matches_reference(lib, name):

@@ -41,6 +41,10 @@ def test_lmode(emu, name):
     ec.lmode_matches_reference(emu, name, rtol=1e-12)
 
 
+def test_speculation_depth_does_not_change_the_run(emu):
+    ec.speculation_depth_does_not_change_the_run(emu, nsteps=25)
+
+
 def test_gamma_tables(emu):
     assert ec.gamma_tables_match_reference(emu, rtol=1e-12) > 400
 
