@@ -261,6 +261,297 @@ IMA_KERNEL void k_joint_fold(const double *partials, int nchunks, int nvec, doub
   r[0] = ins; r[1] = kept; r[2] = sum; r[3] = sq; r[4] = minp; r[5] = minterm;
 }
 
+
+// ---- section 8 (f3): the other evaluators that stream over the rows -------------------------------------------------
+// calcx moments (output.cpp:14-134, 687-745) and the densities of the product 2NM (popmig.cpp:9-357).  Same shape as
+// k_marginal -- one pass over the column-major rows, per-block partials folded in block order -- but every row costs a
+// few incomplete gamma functions (scalar forms of ima_math.h, one lane each), so these are bound by FP64 throughput.
+struct LmPriors { double q_max[kMaxParams], m_max[kMaxParams], m_mean[kMaxParams]; };
+constexpr double kMinParamVal = 0.0000001;       // MINPARAMVAL imamp.hpp:130
+constexpr int kMomentsMaxParams = 32;
+
+// calcx output.cpp:14-134: E[x] (mode 0) or E[x^2] (mode 1) of parameter pnum given genealogy row r
+IMA_DEV double calcx_row(const LmView &V, const MathCtx &mc, const LmPriors &P, long long r, int pnum, int mode) {
+  double tempval;
+  if (pnum < V.nq) {
+    const int p = pnum;
+    const double max = P.q_max[p];
+    if (max <= kMinParamVal) return -1;
+    const int cc = (int)V.cols[(size_t)(V.ccp + p) * V.G + r];
+    const double fc = V.cols[(size_t)(V.fcp + p) * V.G + r];
+    const double hval = V.cols[(size_t)(V.hccp + p) * V.G + r];
+    const double denom = V.cols[(size_t)(V.qip + p) * V.G + r];
+    if (mode == 0) {
+      if (cc == 0 && fc == 0) tempval = (max * max / 2) / exp(denom);
+      else if (cc > 1) tempval = exp(2 * kLog2 - hval + (2 - cc) * log(fc) + uppergamma(mc, cc - 2, 2 * fc / max) - denom);
+      else if (cc == 1) tempval = exp(kLog2 - hval + log(max * exp(-2 * fc / max) - 2 * fc * exp(uppergamma(mc, 0, 2 * fc / max))) - denom);
+      else tempval = exp(log((max / 2) * (max - 2 * fc) * exp(-2 * fc / max) + 2 * (fc * fc) * exp(uppergamma(mc, 0, 2 * fc / max))) - denom);
+    } else {
+      if (cc == 0 && fc == 0) tempval = (max * (max * max) / 3) / exp(denom);
+      else if (cc > 2) tempval = exp(uppergamma(mc, cc - 3, 2 * fc / max) + 3 * kLog2 - hval + (3 - cc) * log(fc) - denom);
+      else if (cc == 2) tempval = exp(2 * kLog2 - hval + log(max * exp(-2 * fc / max) - 2 * fc * exp(uppergamma(mc, 0, 2 * fc / max))) - denom);
+      else if (cc == 1) tempval = exp(-hval + log(max * (max - 2 * fc) * exp(-2 * fc / max) + 4 * (fc * fc) * exp(uppergamma(mc, 0, 2 * fc / max))) - denom);
+      else tempval = exp(-log(3.0) + log(max * (2 * (fc * fc) - fc * max + (max * max)) * exp(-2 * fc / max) - 4 * pow(fc, 3.0) * exp(uppergamma(mc, 0, 2 * fc / max))) - denom);
+    }
+  } else {
+    const int p = pnum - V.nq;
+    const double max = P.m_max[p];
+    if (max <= kMinParamVal) return -1;
+    const int mcnt = (int)V.cols[(size_t)(V.mcp + p) * V.G + r];
+    const double fm = V.cols[(size_t)(V.fmp + p) * V.G + r];
+    const double denom = V.cols[(size_t)(V.mip + p) * V.G + r];
+    if (mode == 0) {
+      if (mcnt == 0 && fm == 0) tempval = (max * max / 2) / exp(denom);
+      else if (mcnt > 0) tempval = exp(lowergamma(mc, mcnt + 2, fm * max) - (mcnt + 2) * log(fm) - denom);
+      else tempval = (1 - (1 + fm * max) * exp(-fm * max)) / (fm * fm) / exp(denom);
+    } else {
+      if (mcnt == 0 && fm == 0) tempval = (pow(max, 3.0) / 3) / exp(denom);
+      else tempval = exp(lowergamma(mc, mcnt + 3, fm * max) - (mcnt + 3) * log(fm) - denom);
+    }
+  }
+  return tempval;
+}
+
+IMA_KERNEL void k_upper0(MathCtx mc, const double *x, int n, double *out) {
+  const int i = ima_block() * IMA_WARP + Warp::lane();
+  if (i < n) out[i] = uppergamma(mc, 0, x[i]);
+}
+
+// partials[chunk][2 np + np (np-1)/2]: sums over the chunk's rows of calcx(.,p,0), calcx(.,p,1) and of the products
+// calcx(.,p,0) calcx(.,q,0), p < q (output.cpp:704-728)
+IMA_KERNEL void k_moments(LmView V, MathCtx mc, const LmPriors *pri, double *partials) {
+  IMA_SMEM_DECL
+  const int lane = Warp::lane(), warp = ima_warp_in_block();
+  const int chunk = ima_block();
+  const long long r0 = (long long)chunk * kRowsPerBlock;
+  long long r1 = r0 + kRowsPerBlock;
+  if (r1 > V.G) r1 = V.G;
+  const int np = V.nq + V.nm, nacc = 2 * np + np * (np - 1) / 2;
+  double *sm = (double *)IMA_SMEM + (size_t)warp * nacc;       // [kLmWarps][nacc]
+  for (int i = lane; i < nacc; i += IMA_WARP) sm[i] = 0.0;
+  Warp::sync();
+  const LmPriors &P = *pri;
+  for (long long base = r0 + (long long)warp * IMA_WARP; base < r1; base += kLmWarps * IMA_WARP) {
+    const long long r = base + lane;
+    const bool valid = r < r1;
+    double x0[kMomentsMaxParams];
+    for (int p = 0; p < np; p++) {
+      const double a = valid ? calcx_row(V, mc, P, r, p, 0) : 0.0, b = valid ? calcx_row(V, mc, P, r, p, 1) : 0.0;
+      x0[p] = a;
+      const double sa = Warp::sum(a), sb = Warp::sum(b);
+      if (lane == 0) { sm[p] += sa; sm[np + p] += sb; }
+    }
+    int k = 2 * np;
+    for (int p = 0; p < np - 1; p++)
+      for (int q = p + 1; q < np; q++, k++) {
+        const double s = Warp::sum(x0[p] * x0[q]);
+        if (lane == 0) sm[k] += s;
+      }
+  }
+#if IMA_CUDA
+  __syncthreads();
+  const double *all = (const double *)IMA_SMEM;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < kLmWarps; w++) s += all[(size_t)w * nacc + i];
+    partials[(size_t)chunk * nacc + i] = s;
+  }
+#else
+  if (warp == kLmWarps - 1) {
+    const double *all = (const double *)IMA_SMEM;
+    for (int i = 0; i < nacc; i++) {
+      double s = 0.0;
+      for (int w = 0; w < kLmWarps; w++) s += all[(size_t)w * nacc + i];
+      partials[(size_t)chunk * nacc + i] = s;
+    }
+  }
+#endif
+}
+
+// one row's term of calc_popmig / marginpopmig (popmig.cpp:29-89, 213-262); false when the reference skips the row
+IMA_DEV bool popmig_term(const LmView &V, const MathCtx &mc, long long r, int thetai, int mi, double x, double qmax, double mmax, double &val) {
+  const int cc = (int)V.cols[(size_t)(V.ccp + thetai) * V.G + r];
+  const double fc = V.cols[(size_t)(V.fcp + thetai) * V.G + r];
+  const double hc = V.cols[(size_t)(V.hccp + thetai) * V.G + r];
+  const int mcnt = (int)V.cols[(size_t)(V.mcp + mi) * V.G + r];
+  const double fm = V.cols[(size_t)(V.fmp + mi) * V.G + r];
+  const double qintg = V.cols[(size_t)(V.qip + thetai) * V.G + r];
+  const double mintg = V.cols[(size_t)(V.mip + mi) * V.G + r];
+  double temp1, temp2;
+  if (fc == 0 && cc == 0 && fm > 0) {
+    temp1 = kLog2 - (mcnt * log(fm)) - hc - qintg - mintg;
+    temp2 = log(exp(uppergamma(mc, mcnt, 2 * fm * x / qmax)) - exp(uppergamma(mc, mcnt, mmax * fm)));
+  } else if (fm == 0 && mcnt == 0 && fc > 0) {
+    temp1 = kLog2 - (cc * log(fc)) - hc - qintg - mintg;
+    temp2 = log(exp(uppergamma(mc, cc, 2 * fc / qmax)) - exp(uppergamma(mc, cc, fc * mmax / x)));
+  } else if (fc == 0 && cc == 0 && mcnt == 0 && fm == 0) {
+    temp1 = log(2 * log(mmax * qmax / (2 * x))) - hc - qintg - mintg;
+    temp2 = 0;
+  } else {
+    temp1 = kLog2 + (mcnt * log(x)) - ((cc + mcnt) * log(fc + fm * x)) - hc - qintg - mintg;
+    double a = uppergamma(mc, cc + mcnt, 2 * (fc + fm * x) / qmax);
+    double b = uppergamma(mc, cc + mcnt, mmax * (fm + fc / x));
+    if (a == b) {                     // both saturated: the difference of the lower gammas carries the information (:62-66)
+      b = lowergamma(mc, cc + mcnt, 2 * (fc + fm * x) / qmax);
+      a = lowergamma(mc, cc + mcnt, mmax * (fm + fc / x));
+    }
+    if (a > b) logdiff(mc, temp2, a, b);               // LogDiff imamp.hpp:257-263
+    else temp1 = temp2 = 0.0;
+  }
+  if ((temp1 + temp2 < 700) && (temp1 + temp2 > -700)) { val = exp(temp1 + temp2); return true; }
+  return false;
+}
+
+// sums over rows [first, last) of the 2NM density terms at nx points; layout of blocks and partials as k_marginal
+IMA_KERNEL void k_popmig(LmView V, MathCtx mc, const LmPriors *pri, int thetai, int mi, const double *x, int nx, long long first, long long last,
+                         double *partials) {
+  IMA_SMEM_DECL
+  const int lane = Warp::lane(), warp = ima_warp_in_block();
+  const int nxt = (nx + kXT - 1) / kXT;
+  const int chunk = ima_block() / nxt, xt = ima_block() - chunk * nxt;
+  const long long r0 = first + (long long)chunk * kRowsPerBlock;
+  long long r1 = r0 + kRowsPerBlock;
+  if (r1 > last) r1 = last;
+  const double qmax = pri->q_max[thetai], mmax = pri->m_max[mi];
+  double acc[kXT];
+  for (int j = 0; j < kXT; j++) acc[j] = 0.0;
+  for (long long r = r0 + warp * IMA_WARP + lane; r < r1; r += kLmWarps * IMA_WARP)
+    for (int j = 0; j < kXT; j++) {
+      const int ix = xt * kXT + j;
+      double v;
+      if (ix < nx && popmig_term(V, mc, r, thetai, mi, x[ix], qmax, mmax, v)) acc[j] += v;
+    }
+  double *sm = (double *)IMA_SMEM;     // [kLmWarps][kXT]
+  for (int j = 0; j < kXT; j++) {
+    const double s = Warp::sum(acc[j]);
+    if (lane == 0) sm[warp * kXT + j] = s;
+  }
+#if IMA_CUDA
+  __syncthreads();
+  if (threadIdx.x < kXT) {
+    double s = 0.0;
+    for (int w = 0; w < kLmWarps; w++) s += sm[w * kXT + threadIdx.x];
+    partials[(size_t)chunk * (nxt * kXT) + xt * kXT + threadIdx.x] = s;
+  }
+#else
+  if (warp == kLmWarps - 1)
+    for (int j = 0; j < kXT; j++) {
+      double s = 0.0;
+      for (int w = 0; w < kLmWarps; w++) s += sm[w * kXT + j];
+      partials[(size_t)chunk * (nxt * kXT) + xt * kXT + j] = s;
+    }
+#endif
+}
+
+// exponential migration prior (popmig.cpp:101-170, 272-357): the log term of every row (temp2) goes to tbuf[ix][row - first]
+// and the largest base-10 exponent eexp gives any of them to zmax[ix][chunk]; k_expomig_sum then adds the mantissas on the
+// common exponent maxz - OCUTOFF
+IMA_DEV double expomig_term(const LmView &V, const MathCtx &mc, long long r, int thetai, int mi, double x, double qmax, double mmean) {
+  const int cc = (int)V.cols[(size_t)(V.ccp + thetai) * V.G + r];
+  const double fc = V.cols[(size_t)(V.fcp + thetai) * V.G + r];
+  const double hc = V.cols[(size_t)(V.hccp + thetai) * V.G + r];
+  const int mcnt = (int)V.cols[(size_t)(V.mcp + mi) * V.G + r];
+  const double fm = V.cols[(size_t)(V.fmp + mi) * V.G + r];
+  const double qintg = V.cols[(size_t)(V.qip + thetai) * V.G + r];
+  const double mintg = V.cols[(size_t)(V.mip + mi) * V.G + r];
+  const double temp1 = x + fc * mmean + fm * mmean * x;
+  double temp2 = kLog2 - hc - log(mmean) - qintg - mintg;
+  double temp3 = 2 * temp1 / (mmean * qmax);
+  if (mcnt == 0 && cc == 0) {
+    temp3 = uppergamma(mc, 0, temp3);
+    temp2 += temp3;
+  } else if (cc == 0) {
+    temp3 = uppergamma(mc, mcnt, temp3);
+    temp2 += temp3 - mcnt * log(fm + 1 / mmean);
+  } else if (mcnt == 0) {
+    temp3 = uppergamma(mc, cc, temp3);
+    temp2 += temp3 + -cc * log(fc + x * (fm + 1 / mmean));
+  } else {
+    temp3 = uppergamma(mc, mcnt + cc, temp3);
+    temp2 += temp3 - cc * log(x) + (cc + mcnt) * log(mmean * x / temp1);
+  }
+  return temp2;
+}
+
+IMA_KERNEL void k_expomig_terms(LmView V, MathCtx mc, const LmPriors *pri, int thetai, int mi, const double *x, int nx, long long first, long long last,
+                                double *tbuf, double *zmax) {
+  IMA_SMEM_DECL
+  const int lane = Warp::lane(), warp = ima_warp_in_block();
+  const int chunk = ima_block();
+  const int nchunks = (int)((last - first + kRowsPerBlock - 1) / kRowsPerBlock);
+  const long long r0 = first + (long long)chunk * kRowsPerBlock;
+  long long r1 = r0 + kRowsPerBlock;
+  if (r1 > last) r1 = last;
+  const double qmax = pri->q_max[thetai], mmean = pri->m_mean[mi];
+  double *sm = (double *)IMA_SMEM;     // [kLmWarps][kJointVecMax]
+  for (int ix = 0; ix < nx; ix++) {
+    double zm = -1e300;
+    for (long long r = r0 + warp * IMA_WARP + lane; r < r1; r += kLmWarps * IMA_WARP) {
+      const double t2 = expomig_term(V, mc, r, thetai, mi, x[ix], qmax, mmean);
+      tbuf[(size_t)ix * (last - first) + (r - first)] = t2;
+      double m; int z;
+      eexp(t2, m, z);
+      if ((double)z > zm) zm = (double)z;
+    }
+#if IMA_CUDA
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, zm, o); zm = t > zm ? t : zm; }
+#endif
+    if (lane == 0) sm[warp * kJointVecMax + ix] = zm;
+  }
+#if IMA_CUDA
+  __syncthreads();
+  if ((int)threadIdx.x < nx) {
+    double m = -1e300;
+    for (int w = 0; w < kLmWarps; w++) m = sm[w * kJointVecMax + threadIdx.x] > m ? sm[w * kJointVecMax + threadIdx.x] : m;
+    zmax[(size_t)threadIdx.x * nchunks + chunk] = m;
+  }
+#else
+  if (warp == kLmWarps - 1)
+    for (int ix = 0; ix < nx; ix++) {
+      double m = -1e300;
+      for (int w = 0; w < kLmWarps; w++) m = sm[w * kJointVecMax + ix] > m ? sm[w * kJointVecMax + ix] : m;
+      zmax[(size_t)ix * nchunks + chunk] = m;
+    }
+#endif
+}
+
+// partials[chunk][ix] = sum over the chunk's rows of m 10^(z - (maxz - OCUTOFF)) (popmig.cpp:157-162)
+IMA_KERNEL void k_expomig_sum(const double *tbuf, int nx, long long nrows, const double *maxz, double *partials) {
+  IMA_SMEM_DECL
+  const int lane = Warp::lane(), warp = ima_warp_in_block();
+  const int chunk = ima_block();
+  const long long r0 = (long long)chunk * kRowsPerBlock;
+  long long r1 = r0 + kRowsPerBlock;
+  if (r1 > nrows) r1 = nrows;
+  double *sm = (double *)IMA_SMEM;     // [kLmWarps][kJointVecMax]
+  for (int ix = 0; ix < nx; ix++) {
+    const int base = (int)maxz[ix] - 10;
+    double acc = 0.0;
+    for (long long r = r0 + warp * IMA_WARP + lane; r < r1; r += kLmWarps * IMA_WARP) {
+      double m; int z;
+      eexp(tbuf[(size_t)ix * nrows + r], m, z);
+      acc += m * pow(10.0, (double)(z - base));
+    }
+    acc = Warp::sum(acc);
+    if (lane == 0) sm[warp * kJointVecMax + ix] = acc;
+  }
+#if IMA_CUDA
+  __syncthreads();
+  if ((int)threadIdx.x < nx) {
+    double s = 0.0;
+    for (int w = 0; w < kLmWarps; w++) s += sm[w * kJointVecMax + threadIdx.x];
+    partials[(size_t)chunk * kJointVecMax + threadIdx.x] = s;
+  }
+#else
+  if (warp == kLmWarps - 1)
+    for (int ix = 0; ix < nx; ix++) {
+      double s = 0.0;
+      for (int w = 0; w < kLmWarps; w++) s += sm[w * kJointVecMax + ix];
+      partials[(size_t)chunk * kJointVecMax + ix] = s;
+    }
+#endif
+}
+
 }  // namespace ima
 extern "C" void ima2p_internal_set_error(const char *msg);   // ima_engine.cu: one error string for the whole library
 namespace ima {
@@ -275,6 +566,10 @@ struct Lmode {
          *d_lmax = nullptr, *d_jpart = nullptr, *d_jout = nullptr;
   JointXs *d_xs = nullptr;
   size_t cap_x = 0, cap_partials = 0;
+  struct LmPriors *d_pri = nullptr;            // section 8 (f3) evaluators: priors, logfact table and error word, made on first use
+  double *d_logfact = nullptr;
+  int *d_err = nullptr;
+  MathCtx mc{};
   std::vector<void *> allocs;
 #if IMA_CUDA
   cudaStream_t stream = nullptr;
@@ -515,6 +810,200 @@ int ima2p_lmode_jointp(ima2p_lmode *h, const double *x, int nvec, int calc_ess, 
       ima2p_lmode_joint_finish(rec + (size_t)v * kJP, lmax[v], l.v.G_total, calc_ess, &out_q[v0 + v], &e);
       if (out_ess) out_ess[v0 + v] = e;
     }
+  }
+  return IMA2P_OK;
+}
+
+}  // extern "C"
+
+namespace ima {
+// ---- section 8 (f3) entry points ---------------------------------------------------------------------------------
+static int lm_prepare_extra(Lmode &l) {
+  if (l.d_pri) return IMA2P_OK;
+  const int nlf = 100 * 5000 + 1;                      // logfact: same running sum as setlogfact (utilities.cpp:1405-1414)
+  std::vector<double> lf(nlf);
+  lf[0] = 0;
+  for (int i = 1; i < nlf; i++) lf[i] = lf[i - 1] + log((double)i);
+  LmPriors pr;
+  for (int i = 0; i < kMaxParams; i++) { pr.q_max[i] = l.q_max[i]; pr.m_max[i] = l.m_max[i]; pr.m_mean[i] = l.m_mean[i]; }
+  l.d_logfact = l.alloc<double>(nlf);
+  l.d_err = l.alloc<int>(1);
+  LmPriors *dp = l.alloc<LmPriors>(1);
+  if (!l.d_logfact || !l.d_err || !dp) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  stream_t s = lm_stream(&l, nullptr);
+  int zero = 0;
+  if (!h2d(l.d_logfact, lf.data(), nlf * sizeof(double), s) || !h2d(dp, &pr, sizeof pr, s) || !h2d(l.d_err, &zero, sizeof zero, s) || !dev_sync(s))
+    return lfail(IMA2P_E_CUDA, "upload failed");
+  l.mc.logfact = l.d_logfact; l.mc.logfact_n = nlf; l.mc.err = l.d_err;
+  l.d_pri = dp;
+  return IMA2P_OK;
+}
+static int lm_check_err(Lmode &l, stream_t s, const char *what) {
+  int code = 0;
+  if (!d2h(&code, l.d_err, sizeof code, s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+  if (code) {
+    int zero = 0;
+    h2d(l.d_err, &zero, sizeof zero, s); dev_sync(s);
+    return lfail(IMA2P_E_DEVICE, std::string(what) + ": device error word raised (14 = LogDiff a<=b, 15 = incomplete gamma, 16 = logfact range)");
+  }
+  return IMA2P_OK;
+}
+// uppergamma(0, x) = log E1(x) evaluated by the device routine (one lane)
+static int lm_upper0(Lmode &l, double x, double *out) {
+  stream_t s = lm_stream(&l, nullptr);
+  if ((size_t)1 > l.cap_x) { l.d_x = l.alloc<double>(8); l.d_out = l.alloc<double>(8); l.cap_x = 8; }
+  if (!l.d_x || !l.d_out) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  if (!h2d(l.d_x, &x, sizeof x, s)) return lfail(IMA2P_E_CUDA, "upload failed");
+  IMA_LAUNCH(k_upper0, 1, 1, 0, s, l.mc, l.d_x, 1, l.d_out);
+  if (!d2h(out, l.d_out, sizeof *out, s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+  return IMA2P_OK;
+}
+static bool lm_grow_partials(Lmode &l, size_t n) {
+  if (n > l.cap_partials) { l.d_partials = l.alloc<double>(n); l.cap_partials = n; }
+  return l.d_partials != nullptr;
+}
+
+}  // namespace ima
+using namespace ima;
+extern "C" {
+
+// print_means_variances_correlations output.cpp:687-745: sums of calcx over every row, then the reference's finishing
+// (means, variances = E[x^2] - mean^2, correlations of the p < q pairs; -1 marks a parameter whose prior maximum is ~0)
+int ima2p_lmode_moments(ima2p_lmode *h, double *means, double *variances, double *correlations, double *raw_sums) {
+  if (!h || !h->lm.d_cols || !means || !variances) return lfail(IMA2P_E_ARG, "moments: bad argument / rows not loaded");
+  Lmode &l = h->lm;
+  const int np = l.v.nq + l.v.nm, nacc = 2 * np + np * (np - 1) / 2;
+  if (np > kMomentsMaxParams) return lfail(IMA2P_E_ARG, "moments: more than 32 parameters");
+  if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  int rc = lm_prepare_extra(l);
+  if (rc) return rc;
+  stream_t s = lm_stream(&l, nullptr);
+  const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
+  if (!lm_grow_partials(l, (size_t)nchunks * nacc)) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  double *d_sums = l.alloc<double>(nacc);
+  if (!d_sums) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  IMA_LAUNCH(k_moments, nchunks, kLmWarps, (size_t)kLmWarps * nacc * sizeof(double), s, l.v, l.mc, l.d_pri, l.d_partials);
+  IMA_LAUNCH(k_reduce_partials, (nacc + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_partials, nchunks, nacc, nacc, d_sums);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (moments)");
+#endif
+  std::vector<double> sums(nacc);
+  if (!d2h(sums.data(), d_sums, nacc * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+  if ((rc = lm_check_err(l, s, "moments"))) return rc;
+  const double G = (double)l.v.G;
+  for (int p = 0; p < np; p++) {
+    means[p] = sums[p]; variances[p] = sums[np + p];
+    if (means[p] >= 0.0) means[p] /= G;                                          // output.cpp:712-713
+    if (variances[p] >= 0.0) { variances[p] /= G; variances[p] -= means[p] * means[p]; }   // :714-718
+  }
+  if (correlations) {
+    for (int i = 0; i < np * np; i++) correlations[i] = 0.0;
+    int k = 2 * np;
+    for (int p = 0; p < np - 1; p++)
+      for (int q = p + 1; q < np; q++, k++) {
+        double c = sums[k];
+        if (c >= 0.0) { c /= G; c -= means[p] * means[q]; c /= sqrt(variances[p] * variances[q]); }   // :731-737
+        else c = -1.0;
+        correlations[p * np + q] = c;
+      }
+  }
+  if (raw_sums) {
+    for (int i = 0; i < 2 * np + np * np; i++) raw_sums[i] = 0.0;
+    for (int p = 0; p < np; p++) { raw_sums[p] = sums[p]; raw_sums[np + p] = sums[np + p]; }
+    int k = 2 * np;
+    for (int p = 0; p < np - 1; p++) for (int q = p + 1; q < np; q++, k++) raw_sums[2 * np + p * np + q] = sums[k];
+  }
+  return IMA2P_OK;
+}
+
+// sums over rows [first, last) of the 2NM density terms; uniform prior: one pass; exponential prior: terms, maximum
+// exponent, mantissa sum.  out[ix] = the row sum (uniform) or exp(log(acumm) + (maxz - OCUTOFF) LOG10) (exponential),
+// not yet divided by the number of rows
+static int lm_popmig_sums(Lmode &l, int thetai, int mi, const double *x, int nx, long long first, long long last, double *out) {
+  if (thetai < 0 || thetai >= l.v.nq || mi < 0 || mi >= l.v.nm || first < 0 || last > l.v.G || first >= last || nx < 1)
+    return lfail(IMA2P_E_ARG, "popmig: bad argument");
+  if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  int rc = lm_prepare_extra(l);
+  if (rc) return rc;
+  stream_t s = lm_stream(&l, nullptr);
+  const long long nrows = last - first;
+  const int nchunks = (int)((nrows + kRowsPerBlock - 1) / kRowsPerBlock);
+  if ((size_t)nx > l.cap_x) { l.d_x = l.alloc<double>(nx); l.d_out = l.alloc<double>(((nx + kXT - 1) / kXT) * kXT); l.cap_x = nx; }
+  if (!l.d_x || !l.d_out) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  if (!h2d(l.d_x, x, nx * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed");
+  if (!l.v.expoprior) {
+    const int nxt = (nx + kXT - 1) / kXT, width = nxt * kXT;
+    if (!lm_grow_partials(l, (size_t)nchunks * width)) return lfail(IMA2P_E_CUDA, "device allocation failed");
+    IMA_LAUNCH(k_popmig, nchunks * nxt, kLmWarps, kLmWarps * kXT * sizeof(double), s, l.v, l.mc, l.d_pri, thetai, mi, l.d_x, nx, first, last, l.d_partials);
+    IMA_LAUNCH(k_reduce_partials, (nx + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_partials, nchunks, width, nx, l.d_out);
+#if IMA_CUDA
+    if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (popmig)");
+#endif
+    if (!d2h(out, l.d_out, nx * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+  } else {
+    // batches of kJointVecMax points reuse the joint-density term buffer ([kJointVecMax][rows])
+    std::vector<double> zm((size_t)kJointVecMax * nchunks), mz(kJointVecMax), part((size_t)nchunks * kJointVecMax);
+    if (!lm_grow_partials(l, (size_t)nchunks * kJointVecMax)) return lfail(IMA2P_E_CUDA, "device allocation failed");
+    for (int x0 = 0; x0 < nx; x0 += kJointVecMax) {
+      const int nb = nx - x0 < kJointVecMax ? nx - x0 : kJointVecMax;
+      IMA_LAUNCH(k_expomig_terms, nchunks, kLmWarps, kLmWarps * kJointVecMax * sizeof(double), s, l.v, l.mc, l.d_pri, thetai, mi, l.d_x + x0, nb, first, last,
+                 l.d_pbuf, l.d_chunkmax);
+      if (!d2h(zm.data(), l.d_chunkmax, (size_t)nb * nchunks * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+      for (int i = 0; i < nb; i++) { double m = -1e300; for (int c = 0; c < nchunks; c++) m = zm[(size_t)i * nchunks + c] > m ? zm[(size_t)i * nchunks + c] : m; mz[i] = m; }
+      if (!h2d(l.d_lmax, mz.data(), nb * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed");
+      IMA_LAUNCH(k_expomig_sum, nchunks, kLmWarps, kLmWarps * kJointVecMax * sizeof(double), s, l.d_pbuf, nb, nrows, l.d_lmax, l.d_partials);
+#if IMA_CUDA
+      if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (expomig)");
+#endif
+      if (!d2h(part.data(), l.d_partials, (size_t)nchunks * kJointVecMax * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+      for (int i = 0; i < nb; i++) {
+        double acumm = 0.0;
+        for (int c = 0; c < nchunks; c++) acumm += part[(size_t)c * kJointVecMax + i];
+        out[x0 + i] = log(acumm) + (mz[i] - 10) * 2.3025850929940456840;      // :162, LOG10
+      }
+    }
+  }
+  return lm_check_err(l, s, "popmig");
+}
+
+// calc_popmig popmig.cpp:9-97 / calc_pop_expomig :101-170 (the choice follows the model's migration prior)
+int ima2p_lmode_popmig(ima2p_lmode *h, int thetai, int mi, const double *x, int nx, int prob_or_like, double *out) {
+  if (!h || !h->lm.d_cols || !x || !out) return lfail(IMA2P_E_ARG, "popmig: bad argument / rows not loaded");
+  Lmode &l = h->lm;
+  int rc = lm_popmig_sums(l, thetai, mi, x, nx, 0, l.v.G, out);
+  if (rc) return rc;
+  const double qmax = l.q_max[thetai];
+  for (int i = 0; i < nx; i++) {
+    double sum;
+    if (!l.v.expoprior) {
+      sum = out[i] / (double)l.v.G;
+      if (prob_or_like) sum /= 2 * (log(qmax) + log(l.m_max[mi]) - log(2 * x[i])) / (qmax * l.m_max[mi]);
+    } else {
+      sum = exp(out[i] - log((double)l.v.G));
+      if (prob_or_like) {
+        double ug = 0.0;                                  // prior density of 2NM: 2 exp(uppergamma(0, 2x/(mmean qmax))) / (qmax mmean) (:166)
+        if ((rc = lm_upper0(l, 2 * x[i] / (l.m_mean[mi] * qmax), &ug))) return rc;
+        sum /= 2 * exp(ug) / (qmax * l.m_mean[mi]);
+      }
+    }
+    out[i] = sum;
+  }
+  return IMA2P_OK;
+}
+
+// marginpopmig popmig.cpp:176-268 / marginpop_expomig :272-357: minus the mean over rows [firsttree, lasttree), with the
+// reference's divisor and its OFFSCALEVAL = 1 outside the plotted range
+int ima2p_lmode_marginpopmig(ima2p_lmode *h, int thetai, int mi, int firsttree, int lasttree, const double *x, int nx, double *out) {
+  if (!h || !h->lm.d_cols || !x || !out) return lfail(IMA2P_E_ARG, "marginpopmig: bad argument / rows not loaded");
+  Lmode &l = h->lm;
+  int rc = lm_popmig_sums(l, thetai, mi, x, nx, firsttree, lasttree, out);
+  if (rc) return rc;
+  const double hi = l.v.expoprior ? 20 * l.m_mean[mi] : l.q_max[thetai] * l.m_max[mi] / 2.0;     // EXPOMIGPLOTSCALE imamp.hpp:156
+  const double div = (double)lasttree - firsttree + (firsttree == 0);
+  for (int i = 0; i < nx; i++) {
+    if (x[i] < 0 || x[i] > hi) out[i] = 1.0;
+    else if (!l.v.expoprior) out[i] = -(out[i] / div);
+    else out[i] = -exp(out[i] - log(div));
   }
   return IMA2P_OK;
 }

@@ -406,6 +406,28 @@ class LMode:
         capi.check(self.lib, self.lib.ima2p_lmode_marginp(self._h, param, firsttree, lasttree, _dp(x), len(x), _dp(out)))
         return out
 
+    def moments(self):
+        """print_means_variances_correlations (output.cpp:687-745): means, variances, correlations (p < q entries) of the
+        parameters from the calcx sums over every row, plus the raw sums (sum0[np], sum1[np], cross[np][np])."""
+        n = self.nq + self.nm
+        means, var, corr, raw = np.zeros(n), np.zeros(n), np.zeros((n, n)), np.zeros(2 * n + n * n)
+        capi.check(self.lib, self.lib.ima2p_lmode_moments(self._h, _dp(means), _dp(var), _dp(corr), _dp(raw)))
+        return means, var, corr, {"sum0": raw[:n].copy(), "sum1": raw[n:2 * n].copy(), "cross": raw[2 * n:].reshape(n, n).copy()}
+
+    def popmig(self, thetai, mi, x, prob_or_like=0):
+        """calc_popmig / calc_pop_expomig (popmig.cpp:9-170): density of 2NM at x, vectorised over x."""
+        x = _f64(np.atleast_1d(x))
+        out = np.zeros(len(x))
+        capi.check(self.lib, self.lib.ima2p_lmode_popmig(self._h, thetai, mi, _dp(x), len(x), int(prob_or_like), _dp(out)))
+        return out
+
+    def marginpopmig(self, mi, firsttree, lasttree, x, thetai):
+        """marginpopmig / marginpop_expomig (popmig.cpp:176-357), argument order of the reference, vectorised over x."""
+        x = _f64(np.atleast_1d(x))
+        out = np.zeros(len(x))
+        capi.check(self.lib, self.lib.ima2p_lmode_marginpopmig(self._h, thetai, mi, firsttree, lasttree, _dp(x), len(x), _dp(out)))
+        return out
+
     def jointp(self, x, calc_ess=True):
         """jointp(x, calc_ess, &ess) (jointfind.cpp:885-1047) for a batch of parameter vectors x[nvec][nq+nm]."""
         x = _f64(np.atleast_2d(x))

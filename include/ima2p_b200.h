@@ -243,6 +243,19 @@ int ima2p_lmode_joint_phase2 (ima2p_lmode * l, int nvec, const double *globalmax
 void ima2p_lmode_joint_finish (const double *rec6, double globalmax, long long nrows_total, int calc_ess, double *q,
                                double *ess);
 
+/* ---- L mode, the other evaluators that stream over the rows ------------------------------
+ * moments = print_means_variances_correlations (output.cpp:687-745) over calcx (output.cpp:14-134): means[np],
+ * variances[np] (E[x^2] - mean^2), correlations[np][np] (entries p < q; may be NULL); np = nq + nm <= 32.  raw_sums
+ * (may be NULL) receives the row sums themselves: [np] of calcx(.,p,0), [np] of calcx(.,p,1), [np][np] of the products. */
+int ima2p_lmode_moments (ima2p_lmode * l, double *means, double *variances, double *correlations, double *raw_sums);
+/* density of the product 2NM = theta_thetai * m_mi / 2 at x[nx]: calc_popmig (popmig.cpp:9-97) or, when the handle was
+ * created with the exponential migration prior, calc_pop_expomig (:101-170); prob_or_like = 1 divides by the prior density */
+int ima2p_lmode_popmig (ima2p_lmode * l, int thetai, int mi, const double *x, int nx, int prob_or_like, double *out);
+/* marginpopmig (popmig.cpp:176-268) / marginpop_expomig (:272-357): minus the mean over rows [firsttree, lasttree) with
+ * the reference's divisor; 1 (OFFSCALEVAL) outside the plotted range.  The function marginalopt_popmig minimises. */
+int ima2p_lmode_marginpopmig (ima2p_lmode * l, int thetai, int mi, int firsttree, int lasttree, const double *x, int nx,
+                              double *out);
+
 /* ---- the .u input file (readata.cpp): host code, needs no device -------------------------------------------------
  * dataset_read = readdata (readata.cpp:1038-1123): top lines (:891-1036), locus header lines (parse_locus_info
  * :618-866), and the data with the reference's site handling: infinite-sites / joint loci keep the segregating,

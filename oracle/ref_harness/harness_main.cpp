@@ -35,6 +35,12 @@ double harness_swapweight (int ci, int cj);
 double harness_swapweight_bwprocesses (double sumi, double sumj, double betai, double betaj);
 double harness_marginp (int param, int firsttree, int lasttree, double x);
 void harness_jointp_setup (void);
+double harness_calcx (int ei, int pnum, int mode);
+double calc_popmig (int thetai, int mi, double x, int prob_or_like);
+double calc_pop_expomig (int thetai, int mi, double x, int prob_or_like);
+double marginpopmig (int mi, int firsttree, int lasttree, double x, int thetai);
+double marginpop_expomig (int mi, int firsttree, int lasttree, double x, int thetai);
+void print_means_variances_correlations (FILE * outfile);
 double harness_get_sumlogk (int li);
 double jointp (double *x, int calc_ess, double *effective_n);
 extern struct edgemiginfo oldedgemig, oldsismig, newedgemig, newsismig;
@@ -807,7 +813,81 @@ mode_lmode (long burn, long rows, long every)
       fputc ('}', jo);
     }
   }
-  fprintf (jo, "]}\n");
+  fprintf (jo, "]");
+  if (kv.count ("extra"))
+  {
+    /* section 8 (f3): the other evaluators that stream over the rows.  calcx sums in row order exactly as
+     * print_means_variances_correlations accumulates them (output.cpp:704-728), the table it prints, and the 2NM
+     * densities calc_popmig / marginpopmig (popmig.cpp:9-97,176-268) or their exponential-prior forms (:101-170,:272-357) */
+    int q, expo = modeloptions[EXPOMIGRATIONPRIOR];
+    std::vector<double> m0 (np, 0.0), m1 (np, 0.0), cr (np * np, 0.0);
+    for (g = 0; g < rows; g++)
+      for (p = 0; p < np; p++)
+      {
+        m0[p] += harness_calcx ((int) g, p, 0);
+        m1[p] += harness_calcx ((int) g, p, 1);
+      }
+    for (g = 0; g < rows; g++)
+      for (p = 0; p < np - 1; p++)
+        for (q = p + 1; q < np; q++)
+          cr[p * np + q] += harness_calcx ((int) g, p, 0) * harness_calcx ((int) g, q, 0);
+    fprintf (jo, ",\n\"calcx\":{");
+    jdarr ("sum0", &m0[0], np, ",");
+    jdarr ("sum1", &m1[0], np, ",");
+    jdarr ("cross", &cr[0], np * np, ",");
+    fprintf (jo, "\"sample\":[");
+    for (g = 0; g < rows && g < 8; g++)
+      for (p = 0; p < np; p++)
+      {
+        fprintf (jo, "%s[%ld,%d,", (g || p) ? "," : "", g, p);
+        jd (harness_calcx ((int) g, p, 0));
+        fputc (',', jo);
+        jd (harness_calcx ((int) g, p, 1));
+        fputc (']', jo);
+      }
+    fprintf (jo, "],\"table\":\"");
+    {
+      FILE *tf = tmpfile ();
+      int ch;
+      print_means_variances_correlations (tf);
+      rewind (tf);
+      while ((ch = fgetc (tf)) != EOF)
+      {
+        if (ch == '\n') fputs ("\\n", jo);
+        else if (ch == '\t') fputs ("\\t", jo);
+        else if (ch == '"' || ch == '\\') { fputc ('\\', jo); fputc (ch, jo); }
+        else fputc (ch, jo);
+      }
+      fclose (tf);
+    }
+    fprintf (jo, "\"},\n\"popmig\":[");
+    for (first = 1, p = 0; p < numpopsizeparams; p++)
+      for (q = 0; q < nummigrateparams; q++)
+      {
+        double hi = expo ? EXPOMIGPLOTSCALE * imig[q].pr.mean : itheta[p].pr.max * imig[q].pr.max / 2.0;
+        for (i = 0; i < 14; i++, first = 0)
+        {
+          double x = hi * (i + 0.5) / 14.0;
+          if (i == 0)
+            x = hi * 0.5 / GRIDSIZE;
+          if (i == 13)
+            x = hi * (GRIDSIZE - 0.5) / GRIDSIZE;
+          fprintf (jo, "%s[%d,%d,", first ? "" : ",", p, q);
+          jd (x);
+          fputc (',', jo);
+          jd (expo ? calc_pop_expomig (p, q, x, 0) : calc_popmig (p, q, x, 0));
+          fputc (',', jo);
+          jd (expo ? calc_pop_expomig (p, q, x, 1) : calc_popmig (p, q, x, 1));
+          fputc (',', jo);
+          jd (expo ? marginpop_expomig (q, 0, (int) rows, x, p) : marginpopmig (q, 0, (int) rows, x, p));
+          fputc (',', jo);
+          jd (expo ? marginpop_expomig (q, (int) (rows / 3), (int) (2 * rows / 3), x, p) : marginpopmig (q, (int) (rows / 3), (int) (2 * rows / 3), x, p));
+          fputc (']', jo);
+        }
+      }
+    fprintf (jo, "]");
+  }
+  fprintf (jo, "}\n");
 }
 
 /* `chunks` timed chunks of `iters` sweeps each; a sweep = updategenealogy() for every chain x locus

@@ -76,6 +76,11 @@ double harness_mc_last_mh (void) { return dminarg2; }
 #undef uniform
 double harness_nw_last_mh (void) { return dminarg2; }
 
+#elif defined(SHIM_OUTPUT)
+#include "output.cpp"
+/* output.cpp:14 is file-static */
+double harness_calcx (int ei, int pnum, int mode) { return calcx (ei, pnum, mode); }
+
 #else
 #error "select a shim"
 #endif

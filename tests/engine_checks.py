@@ -172,6 +172,57 @@ def lmode_matches_reference(lib, name, rtol=1e-9):
         o.close()
 
 
+def lmode_moments_and_popmig_match_reference(lib, name, rtol=1e-9):
+    """section 8 (f3): the calcx sums behind print_means_variances_correlations (output.cpp:14-134, 687-745), the table it
+    prints, and the 2NM densities calc_popmig / marginpopmig or their exponential-prior forms (popmig.cpp:9-357) against
+    the reference's own values on the same rows."""
+    from ima2p_b200 import LMode
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    lm = LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=lib)
+    lm.load(rows)
+    G, n = len(rows), fm.nq + fm.nm
+    means, var, corr, raw = lm.moments()
+    cx = d["calcx"]
+    ref0, ref1 = np.array([_num(v) for v in cx["sum0"]]), np.array([_num(v) for v in cx["sum1"]])
+    refc = np.array([_num(v) for v in cx["cross"]]).reshape(n, n)
+    ok = np.isfinite(ref0) & np.isfinite(ref1)          # the reference's own sums overflow for the exponential-prior terms
+    assert ok[:fm.nq].all()
+    assert rel_close(raw["sum0"][ok], ref0[ok], rtol) and rel_close(raw["sum1"][ok], ref1[ok], rtol)
+    okc = np.isfinite(refc) & np.outer(ok, ok)
+    assert rel_close(raw["cross"][okc], refc[okc], rtol)
+    # the printed table (%.3lf): Mean and Stdv lines
+    lines = cx["table"].split("\n")
+    mean_line = [ln for ln in lines if ln.startswith("Mean:")][0].split("\t")[1:]
+    sd_line = [ln for ln in lines if ln.startswith("Stdv:")][0].split("\t")[1:]
+    for p in range(n):
+        if ok[p] and "nan" not in mean_line[p]:
+            assert abs(float(mean_line[p]) - means[p]) <= 0.00051, (p, mean_line[p], means[p])
+        if ok[p] and "nan" not in sd_line[p]:
+            assert abs(float(sd_line[p]) - np.sqrt(var[p])) <= 0.00051, (p, sd_line[p], var[p])
+    # finishing arithmetic of output.cpp:709-739 redone here from the reference's own sums
+    rm = ref0 / G
+    rv = ref1 / G - rm * rm
+    assert rel_close(means[ok], rm[ok], rtol) and rel_close(var[ok], rv[ok], 1e-7)
+    for p in range(n - 1):
+        for q in range(p + 1, n):
+            if okc[p, q] and rv[p] > 0 and rv[q] > 0:
+                assert abs(corr[p, q] - (refc[p, q] / G - rm[p] * rm[q]) / np.sqrt(rv[p] * rv[q])) < 1e-6
+    tab = d["popmig"]
+    npairs = 0
+    for (ti, mi) in sorted(set((t[0], t[1]) for t in tab)):
+        sel = [t for t in tab if t[0] == ti and t[1] == mi]
+        x = np.array([t[2] for t in sel])
+        assert rel_close(lm.popmig(ti, mi, x, 0), [_num(t[3]) for t in sel], rtol, 1e-300), (ti, mi)
+        assert rel_close(lm.popmig(ti, mi, x, 1), [_num(t[4]) for t in sel], rtol, 1e-300), (ti, mi)
+        assert rel_close(lm.marginpopmig(mi, 0, G, x, ti), [_num(t[5]) for t in sel], rtol, 1e-300), (ti, mi)
+        assert rel_close(lm.marginpopmig(mi, G // 3, 2 * G // 3, x, ti), [_num(t[6]) for t in sel], rtol, 1e-300), (ti, mi)
+        npairs += 1
+    lm.close()
+    return npairs
+
+
 def gamma_tables_match_reference(lib, rtol=1e-10):
     """a10: uppergamma / lowergamma on the device (one-lane and warp-cooperative forms) against the reference's
     own values on a grid that straddles the series / continued-fraction switch at x = a + 1."""

@@ -310,6 +310,10 @@ def main():
     os.makedirs(os.path.join(HERE, "inputs"), exist_ok=True)
     run("lmode", "lmode_ti_sim3_hn2", s3, 2, {"burn": 100, "rows": 60, "every": 2, "ti": os.path.join(HERE, "inputs", "sample_sim3.ti")})
     run("lmode", "lmode_sim5_expo_hn2", s5, 2, {"burn": 200, "rows": 300, "every": 3}, extra=["-j7"])
+    # section 8 (f3): calcx moments and the 2NM densities over the rows (uniform and exponential migration priors, 3 populations)
+    run("lmode", "lmode_extra_sim5_hn2", s5, 2, {"burn": 200, "rows": 400, "every": 3, "extra": 1})
+    run("lmode", "lmode_extra_sim5_expo_hn2", s5, 2, {"burn": 200, "rows": 300, "every": 3, "extra": 1}, extra=["-j7"])
+    run("lmode", "lmode_extra_sim5_3pop_hn2", p3, 2, {"burn": 150, "rows": 200, "every": 3, "extra": 1})
     # split-time, mutation-scalar updates (section 8 f1) and thermodynamic integration (a16)
     run("tupdates", "tupdates_sim5_hn2", s5, 2, {"burn": 100, "n": 30, "between": 3})
     run("tupdates", "tupdates_sim5_3pop_hn2", p3, 2, {"burn": 100, "n": 24, "between": 3})

@@ -57,6 +57,11 @@ def test_long_run_statistics_match_reference_sampler(lib, name, nchains, burn, s
     assert abs(z).max() < 5.0
 
 
+@pytest.mark.parametrize("name", ["lmode_extra_sim5_hn2", "lmode_extra_sim5_expo_hn2", "lmode_extra_sim5_3pop_hn2"])
+def test_lmode_moments_and_popmig(lib, name):
+    assert ec.lmode_moments_and_popmig_match_reference(lib, name) >= 6
+
+
 def test_device_incomplete_gamma_matches_reference_tables(lib):
     assert ec.gamma_tables_match_reference(lib, rtol=1e-10) > 400
 

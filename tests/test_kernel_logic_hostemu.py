@@ -45,6 +45,11 @@ def test_speculation_depth_does_not_change_the_run(emu):
     ec.speculation_depth_does_not_change_the_run(emu, nsteps=25)
 
 
+@pytest.mark.parametrize("name", ["lmode_extra_sim5_hn2", "lmode_extra_sim5_expo_hn2", "lmode_extra_sim5_3pop_hn2"])
+def test_lmode_moments_and_popmig(emu, name):
+    assert ec.lmode_moments_and_popmig_match_reference(emu, name) >= 6
+
+
 def test_gamma_tables(emu):
     assert ec.gamma_tables_match_reference(emu, rtol=1e-12) > 400
 
