@@ -552,6 +552,198 @@ IMA_KERNEL void k_expomig_sum(const double *tbuf, int nx, long long nrows, const
 #endif
 }
 
+
+// ---- greater-than probabilities gtint.cpp:26-330: P(parameter i > parameter j) as the mean over (a thinned set of)
+// rows of a closed form or of a trapezoid quadrature (qtrap, EPS 1e-4, JMAX 20) of the reference's integrands.  One
+// lane per row; the quadrature is evaluated in the reference's own order so that it stops at the same refinement.
+struct GtRow { int cci, ccj, wi, wj; double fci, fcj, hval, denom, qmax, fmi, fmj, mmax; };
+constexpr double kGtSwitchLower = 1e-15;          // SWITCH_TO_LOWERGAMMA_CRIT gtint.cpp:23
+
+IMA_DEV double mgt_wj_gt_0(const MathCtx &mc, const GtRow &g, double mi) {      // gtint.cpp:26-47
+  if (mi < kMinParamVal) return 0.0;
+  const double a = lfact(mc, g.wj);
+  const double b = uppergamma(mc, g.wj + 1, g.fmj * mi);
+  if (a <= b) return 0.0;
+  double temp1;
+  if ((a - b) < kGtSwitchLower) temp1 = lowergamma(mc, g.wj + 1, g.fmj * mi);
+  else logdiff(mc, temp1, a, b);
+  double temp2 = g.wi * log(mi) - g.fmi * mi - (g.wj + 1) * log(g.fmj) + temp1;
+  temp2 -= g.denom;
+  return exp(temp2);
+}
+
+IMA_DEV double pgt_fcj_gt_0(const MathCtx &mc, const GtRow &g, double qi) {      // gtint.cpp:49-79
+  if (qi < kMinParamVal) return 0.0;
+  const double fcj2 = 2 * g.fcj, fci2 = 2 * g.fci;
+  if (g.ccj == 0) {
+    const double a = log(qi) - fcj2 / qi;
+    const double b = log(fcj2) + uppergamma(mc, 0, fcj2 / qi);
+    if (a > b) {
+      double temp1;
+      logdiff(mc, temp1, a, b);
+      const double temp2 = -fci2 / qi + g.cci * log(2 / qi);
+      return exp(temp1 + temp2 - g.hval - g.denom);
+    }
+    return 0.0;
+  }
+  const double temp1 = uppergamma(mc, g.ccj - 1, fcj2 / qi);
+  const double temp2 = kLog2 + g.cci * log(2 / qi) + (1 - g.ccj) * log(g.fcj) - fci2 / qi;
+  return exp(temp2 + temp1 - g.hval - g.denom);
+}
+
+// qtrap / trapzd gtint.cpp:83-125 (Numerical Recipes): refinement j adds 2^(j-2) midpoints, summed in order
+template <int MIG>
+IMA_DEV double gt_qtrap(const MathCtx &mc, const GtRow &g, double a, double b) {
+  auto f = [&](double x) { return MIG ? mgt_wj_gt_0(mc, g, x) : pgt_fcj_gt_0(mc, g, x); };
+  double s = 0.0, olds = -1.0e100;
+  for (int j = 1; j <= 20; j++) {
+    if (j == 1) s = 0.5 * (b - a) * (f(a) + f(b));
+    else {
+      int it = 1;
+      for (int k = 1; k < j - 1; k++) it <<= 1;
+      const double tnm = it, del = (b - a) / tnm;
+      double x = a + 0.5 * del, sum = 0.0;
+      for (int k = 1; k <= it; k++, x += del) sum += f(x);
+      s = 0.5 * (s + (b - a) * sum / tnm);
+    }
+    if (j > 5 && (fabs(s - olds) < 1.0e-4 * fabs(olds) || (s == 0.0 && olds == 0.0))) return s;
+    olds = s;
+  }
+  return s;
+}
+
+IMA_DEV double gtmig_row(const LmView &V, const MathCtx &mc, long long r, int mi, int mj, double mmax) {   // gtint.cpp:137-245
+  GtRow g;
+  g.mmax = mmax;
+  g.fmi = V.cols[(size_t)(V.fmp + mi) * V.G + r];
+  g.fmj = V.cols[(size_t)(V.fmp + mj) * V.G + r];
+  g.wi = (int)V.cols[(size_t)(V.mcp + mi) * V.G + r];
+  g.wj = (int)V.cols[(size_t)(V.mcp + mj) * V.G + r];
+  g.denom = V.cols[(size_t)(V.mip + mi) * V.G + r] + V.cols[(size_t)(V.mip + mj) * V.G + r];      // float sum, as gtint.cpp:144
+  const double fmi = g.fmi, fmj = g.fmj, denom = g.denom;
+  const int wi = g.wi;
+  double temp;
+  if (g.wj == 0) {
+    if (fmj > 0.0) {
+      if (wi > 0) {
+        const double a = lfact(mc, wi);
+        const double b = uppergamma(mc, wi + 1, (fmi + fmj) * mmax);
+        const double c = uppergamma(mc, wi + 1, fmi * mmax);
+        if (a <= b || a <= c) temp = 0.0;
+        else {
+          double temp1, temp2;
+          if ((a - b) < kGtSwitchLower) temp1 = lowergamma(mc, wi + 1, (fmi + fmj) * mmax);
+          else logdiff(mc, temp1, a, b);
+          temp1 += -(wi + 1) * log(fmi + fmj);
+          if ((a - c) < kGtSwitchLower) temp2 = lowergamma(mc, wi + 1, fmi * mmax);
+          else logdiff(mc, temp2, a, c);
+          temp2 += -(wi + 1) * log(fmi);
+          if (temp2 <= temp1) temp = 0.0;
+          else {
+            double temp3;
+            logdiff(mc, temp3, temp2, temp1);
+            temp = exp(temp3 - log(fmj) - denom);
+          }
+        }
+      } else if (fmi > 0.0) {
+        const double temp1 = fmi * (exp(-(fmi + fmj) * mmax) - exp(-fmi * mmax));
+        const double temp2 = fmj * (1 - exp(-fmi * mmax));
+        const double temp3 = (temp1 + temp2) / (fmi * fmj * (fmi + fmj));
+        temp = exp(log(temp3) - denom);
+      } else {
+        const double temp1 = (fmj * mmax - 1.0 + exp(-fmj * mmax)) / (fmj * fmj);
+        temp = exp(log(temp1) - denom);
+      }
+    } else {
+      if (wi > 0) {
+        const double a = lfact(mc, wi + 1);
+        const double b = uppergamma(mc, wi + 2, fmi * mmax);
+        if (a <= b) temp = 0.0;
+        else {
+          double temp1;
+          if ((a - b) < kGtSwitchLower) temp1 = lowergamma(mc, wi + 2, fmi * mmax);
+          else logdiff(mc, temp1, a, b);
+          const double temp2 = -(wi + 2) * log(fmi);
+          temp = exp(temp2 + temp1 - denom);
+        }
+      } else if (fmi > 0.0) {
+        const double temp1 = (1.0 - exp(-fmi * mmax) * (fmi * mmax + 1.0)) / (fmi * fmi);
+        temp = exp(log(temp1) - denom);
+      } else {
+        temp = exp(log(mmax * mmax / 2.0) - denom);
+      }
+    }
+  } else {
+    temp = gt_qtrap<1>(mc, g, kMinParamVal, mmax);
+  }
+  return temp < 1.0 ? temp : 1.0;          // DMIN(1.0, temp) :240
+}
+
+IMA_DEV double gtpops_row(const LmView &V, const MathCtx &mc, long long r, int pi, int pj, double qmax) {   // gtint.cpp:248-318
+  GtRow g;
+  g.qmax = qmax;
+  g.cci = (int)V.cols[(size_t)(V.ccp + pi) * V.G + r];
+  g.ccj = (int)V.cols[(size_t)(V.ccp + pj) * V.G + r];
+  g.fci = V.cols[(size_t)(V.fcp + pi) * V.G + r];
+  g.fcj = V.cols[(size_t)(V.fcp + pj) * V.G + r];
+  // the reference adds the two float row entries before widening (gtint.cpp:266-267): a float sum
+  g.hval = V.cols[(size_t)(V.hccp + pi) * V.G + r] + V.cols[(size_t)(V.hccp + pj) * V.G + r];
+  g.denom = V.cols[(size_t)(V.qip + pi) * V.G + r] + V.cols[(size_t)(V.qip + pj) * V.G + r];
+  const double fci = g.fci, hval = g.hval, denom = g.denom;
+  const int cci = g.cci;
+  double temp;
+  if (g.ccj == 0 && g.fcj == 0) {
+    if (fci == 0) temp = exp(2.0 * log(qmax) - kLog2 - hval - denom);
+    else if (cci >= 2) {
+      const double temp1 = 2 * kLog2 + (2 - cci) * log(fci);
+      const double temp2 = uppergamma(mc, cci - 2, 2 * fci / qmax);
+      temp = exp(temp1 + temp2 - hval - denom);
+    } else if (cci == 1) {
+      const double temp1 = 4 * fci * exp(uppergamma(mc, 0, 2 * fci / qmax));
+      const double temp2 = 2 * qmax * exp(-2 * fci / qmax) - temp1;
+      temp = exp(log(temp2) - hval - denom);
+    } else {
+      const double temp1 = exp(uppergamma(mc, 0, 2 * fci / qmax));
+      const double temp2 = (qmax / 2) * (qmax - 2 * fci) * exp(-2 * fci / qmax) + 2 * fci * fci * temp1;
+      temp = exp(log(temp2) - hval - denom);
+    }
+  } else {
+    temp = gt_qtrap<0>(mc, g, kMinParamVal, qmax);
+  }
+  return temp < 1.0 ? temp : 1.0;
+}
+
+// partials[chunk] = sum over the chunk's used rows (row = index * treeinc) of the row terms; kind 0 = gtpops, 1 = gtmig
+IMA_KERNEL void k_greater_than(LmView V, MathCtx mc, const LmPriors *pri, int kind, int pi, int pj, int treeinc, int nused, double *partials) {
+  IMA_SMEM_DECL
+  const int lane = Warp::lane(), warp = ima_warp_in_block();
+  const int chunk = ima_block();
+  const int rowsper = kLmWarps * IMA_WARP;                         // one row per thread: the quadrature is long
+  const int i = chunk * rowsper + warp * IMA_WARP + lane;
+  double v = 0.0;
+  if (i < nused) {
+    const long long r = (long long)i * treeinc;
+    v = kind == 0 ? gtpops_row(V, mc, r, pi, pj, pri->q_max[pi]) : gtmig_row(V, mc, r, pi, pj, pri->m_max[pi]);
+  }
+  double *sm = (double *)IMA_SMEM;     // [kLmWarps]
+  v = Warp::sum(v);
+  if (lane == 0) sm[warp] = v;
+#if IMA_CUDA
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kLmWarps; w++) s += sm[w];
+    partials[chunk] = s;
+  }
+#else
+  if (warp == kLmWarps - 1) {
+    double s = 0.0;
+    for (int w = 0; w < kLmWarps; w++) s += sm[w];
+    partials[chunk] = s;
+  }
+#endif
+}
+
 }  // namespace ima
 extern "C" void ima2p_internal_set_error(const char *msg);   // ima_engine.cu: one error string for the whole library
 namespace ima {
@@ -1008,4 +1200,40 @@ int ima2p_lmode_marginpopmig(ima2p_lmode *h, int thetai, int mi, int firsttree, 
   return IMA2P_OK;
 }
 
+}  // extern "C"
+
+extern "C" {
+// gtpops / gtmig gtint.cpp:128-330 with the row thinning of print_greater_than_tests (:341-351, at most 20000 rows).
+// kind 0: population sizes, 1: migration rates.  *out = -1 for the pairs the reference does not compute (i == j, different
+// prior maxima, a migration maximum of ~0); migration rates under the exponential prior are not implemented there either.
+int ima2p_lmode_greater_than(ima2p_lmode *h, int kind, int i, int j, double *out) {
+  if (!h || !h->lm.d_cols || !out || (kind != 0 && kind != 1)) return lfail(IMA2P_E_ARG, "greater_than: bad argument / rows not loaded");
+  Lmode &l = h->lm;
+  const int n = kind == 0 ? l.v.nq : l.v.nm;
+  if (i < 0 || j < 0 || i >= n || j >= n) return lfail(IMA2P_E_ARG, "greater_than: bad parameter index");
+  if (kind == 1 && l.v.expoprior) return lfail(IMA2P_E_ARG, "greater_than: not defined for migration rates with exponential priors (gtint.cpp:404)");
+  const double *mx = kind == 0 ? l.q_max : l.m_max;
+  if (i == j || mx[i] != mx[j] || (kind == 1 && !(mx[i] > kMinParamVal && mx[j] > kMinParamVal))) { *out = -1.0; return IMA2P_OK; }
+  if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  int rc = lm_prepare_extra(l);
+  if (rc) return rc;
+  stream_t s = lm_stream(&l, nullptr);
+  const long long G = l.v.G;
+  int treeinc = 1; long long nused = G;
+  if (G > 20000) { treeinc = (int)(G / 20000); nused = 20000; }      // USETREESMAX gtint.cpp:24
+  const int rowsper = kLmWarps * IMA_WARP, nchunks = (int)((nused + rowsper - 1) / rowsper);
+  if (!lm_grow_partials(l, (size_t)nchunks)) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  if (l.cap_x < 1) { l.d_x = l.alloc<double>(8); l.d_out = l.alloc<double>(8); l.cap_x = 8; }
+  if (!l.d_out) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  IMA_LAUNCH(k_greater_than, nchunks, kLmWarps, kLmWarps * sizeof(double), s, l.v, l.mc, l.d_pri, kind, i, j, treeinc, (int)nused, l.d_partials);
+  IMA_LAUNCH(k_reduce_partials, 1, kLmWarps, 0, s, l.d_partials, nchunks, 1, 1, l.d_out);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (greater_than)");
+#endif
+  double sum = 0.0;
+  if (!d2h(&sum, l.d_out, sizeof sum, s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+  if ((rc = lm_check_err(l, s, "greater_than"))) return rc;
+  *out = sum / (double)nused;
+  return IMA2P_OK;
+}
 }  // extern "C"

@@ -428,6 +428,12 @@ class LMode:
         capi.check(self.lib, self.lib.ima2p_lmode_marginpopmig(self._h, thetai, mi, firsttree, lasttree, _dp(x), len(x), _dp(out)))
         return out
 
+    def greater_than(self, kind, i, j):
+        """gtpops(i, j) (kind 0) / gtmig(i, j) (kind 1) (gtint.cpp:128-330): P(parameter i > parameter j); -1 = "na"."""
+        out = C.c_double(0.0)
+        capi.check(self.lib, self.lib.ima2p_lmode_greater_than(self._h, int(kind), int(i), int(j), C.byref(out)))
+        return out.value
+
     def jointp(self, x, calc_ess=True):
         """jointp(x, calc_ess, &ess) (jointfind.cpp:885-1047) for a batch of parameter vectors x[nvec][nq+nm]."""
         x = _f64(np.atleast_2d(x))

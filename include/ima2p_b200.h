@@ -256,6 +256,10 @@ int ima2p_lmode_popmig (ima2p_lmode * l, int thetai, int mi, const double *x, in
 int ima2p_lmode_marginpopmig (ima2p_lmode * l, int thetai, int mi, int firsttree, int lasttree, const double *x, int nx,
                               double *out);
 
+/* gtpops / gtmig (gtint.cpp:128-330): probability that parameter i is greater than parameter j (kind 0: population sizes,
+ * 1: migration rates), over the rows print_greater_than_tests uses (:341-351); *out = -1 where the reference prints "na" */
+int ima2p_lmode_greater_than (ima2p_lmode * l, int kind, int i, int j, double *out);
+
 /* ---- the .u input file (readata.cpp): host code, needs no device -------------------------------------------------
  * dataset_read = readdata (readata.cpp:1038-1123): top lines (:891-1036), locus header lines (parse_locus_info
  * :618-866), and the data with the reference's site handling: infinite-sites / joint loci keep the segregating,

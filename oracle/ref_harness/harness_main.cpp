@@ -36,6 +36,8 @@ double harness_swapweight_bwprocesses (double sumi, double sumj, double betai, d
 double harness_marginp (int param, int firsttree, int lasttree, double x);
 void harness_jointp_setup (void);
 double harness_calcx (int ei, int pnum, int mode);
+double harness_greater_than (int kind, int i, int j);
+void print_greater_than_tests (FILE * outfile);
 double calc_popmig (int thetai, int mi, double x, int prob_or_like);
 double calc_pop_expomig (int thetai, int mi, double x, int prob_or_like);
 double marginpopmig (int mi, int firsttree, int lasttree, double x, int thetai);
@@ -885,6 +887,28 @@ mode_lmode (long burn, long rows, long every)
           fputc (']', jo);
         }
       }
+    fprintf (jo, "]");
+    /* greater-than probabilities (gtint.cpp:128-330), for the pairs print_greater_than_tests computes (:353-373) */
+    fprintf (jo, ",\n\"greater_than\":[");
+    for (first = 1, p = 0; p < numpopsizeparams; p++)
+      for (q = 0; q < numpopsizeparams; q++)
+        if (p != q && itheta[p].pr.max == itheta[q].pr.max)
+        {
+          fprintf (jo, "%s[0,%d,%d,", first ? "" : ",", p, q);
+          jd (harness_greater_than (0, p, q));
+          fputc (']', jo);
+          first = 0;
+        }
+    if (!expo)
+      for (p = 0; p < nummigrateparams; p++)
+        for (q = 0; q < nummigrateparams; q++)
+          if (p != q && imig[p].pr.max > MINPARAMVAL && imig[q].pr.max > MINPARAMVAL && imig[p].pr.max == imig[q].pr.max)
+          {
+            fprintf (jo, "%s[1,%d,%d,", first ? "" : ",", p, q);
+            jd (harness_greater_than (1, p, q));
+            fputc (']', jo);
+            first = 0;
+          }
     fprintf (jo, "]");
   }
   fprintf (jo, "}\n");

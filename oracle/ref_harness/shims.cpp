@@ -81,6 +81,27 @@ double harness_nw_last_mh (void) { return dminarg2; }
 /* output.cpp:14 is file-static */
 double harness_calcx (int ei, int pnum, int mode) { return calcx (ei, pnum, mode); }
 
+#elif defined(SHIM_GTINT)
+#define USETREESMAX_H 20000       /* USETREESMAX gtint.cpp:24 (undefined again at the end of that file) */
+#include "gtint.cpp"
+/* gtint.cpp:19-20 (gtmig, gtpops) are file-static, and so is the row-thinning state print_greater_than_tests sets
+ * (:341-351): the wrapper sets it the same way before calling them */
+double harness_greater_than (int kind, int i, int j)
+{
+  if (genealogiessaved > USETREESMAX_H)
+  {
+    treeinc = (int) genealogiessaved / (int) USETREESMAX_H;
+    numtreesused = USETREESMAX_H;
+    hitreenum = treeinc * USETREESMAX_H;
+  }
+  else
+  {
+    treeinc = 1;
+    hitreenum = numtreesused = genealogiessaved;
+  }
+  return kind == 0 ? gtpops (i, j) : gtmig (i, j);
+}
+
 #else
 #error "select a shim"
 #endif

@@ -219,6 +219,10 @@ def lmode_moments_and_popmig_match_reference(lib, name, rtol=1e-9):
         assert rel_close(lm.marginpopmig(mi, 0, G, x, ti), [_num(t[5]) for t in sel], rtol, 1e-300), (ti, mi)
         assert rel_close(lm.marginpopmig(mi, G // 3, 2 * G // 3, x, ti), [_num(t[6]) for t in sel], rtol, 1e-300), (ti, mi)
         npairs += 1
+    # greater-than probabilities (gtint.cpp): closed forms and the trapezoid quadrature, every pair the reference computes
+    for kind, i, j, v in d["greater_than"]:
+        assert rel_close(lm.greater_than(kind, i, j), _num(v), max(rtol, 1e-8)), (kind, i, j)
+    assert lm.greater_than(0, 0, 0) == -1.0
     lm.close()
     return npairs
 
