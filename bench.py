@@ -64,15 +64,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """Samples from here on count (called when the timed region starts; nvidia-smi is already running)."""
+        self.first = len(self.rows)
+
+    def count(self):
+        return len(self.rows) - getattr(self, "first", 0)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[getattr(self, "first", 0):]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
                     if v.lower().startswith("active"):
@@ -283,15 +290,16 @@ def main():
         if float(flag.item()) == 0.0:
             stepper._graph = None
             graphed = False
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()               # started early: nvidia-smi needs a few hundred ms before its first line
     run_steps(args.burn)          # burn-in: leave the artificial starting genealogies behind (untimed)
     run_steps(W)
     barrier()
     c0 = eng.counters()
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = None
     barrier()
+    sampler.mark()
     e0.record()
     run_steps(args.steps)         # the public path: Engine.run (captured graph, piece-wise overlapped step)
     e1.record()
@@ -302,12 +310,28 @@ def main():
         # (no overlap between kernels): per-kernel durations for the roofline accounting
         kernel_ms = eng.run_timed(args.steps, swaptries, stream)
         torch.cuda.synchronize()
+    c1 = eng.counters()
+    # a short timed region can end before nvidia-smi (100 ms period) has reported three times: the same step keeps running,
+    # untimed, until it has, so that the clocks are always read under this load
+    clocks_extended = False
+    t_ext = time.perf_counter()
+    for _ in range(40):
+        enough = 1.0 if (sampler.proc is None or sampler.count() >= 3 or time.perf_counter() - t_ext > 3.0) else 0.0
+        if world > 1:             # every rank takes the same number of extra steps (they exchange swap sums)
+            f = torch.tensor([enough], dtype=torch.float64, device=dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            enough = float(f.item())
+        if enough:
+            break
+        run_steps(100)
+        torch.cuda.synchronize()
+        clocks_extended = True
     clocks = sampler.stop()
+    clocks["extended_past_timed_region"] = clocks_extended
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    c1 = eng.counters()
     eng.sync()
     updates_all = cpg * world * nloci * args.steps
     value = updates_all / (ms * 1e-3)

@@ -535,3 +535,63 @@ def speculation_depth_does_not_change_the_run(lib, name="state_sim50_hn3", nstep
         assert outs[k][0] == outs[0][0], (k, outs[k][0], outs[0][0])
         assert np.array_equal(outs[k][1], outs[0][1]), k
     return outs[0][0]
+
+
+def full_size_workload_properties(lib, nloci, nchains, nsteps, noracle=48, seed=5):
+    """BASELINE-sized runs (configs[1]: 50 loci x 128 chains; configs[2]'s per-GPU shard: 300 loci x 256 chains), checked through
+    properties that do not need a stored answer: after `nsteps` whole qupdate steps (genealogies, split times, scalars, swaps)
+      * every genealogy still has exactly n - 1 coalescences (integer counts summed over the chain: bit-exact),
+      * the sums the accept sweep maintains incrementally equal a from-scratch evaluation (ints exact, doubles 1e-9),
+      * the temperatures are a permutation of the ladder,
+      * for a random sample of (chain, locus) pairs the oracle's treeweight / infinite-sites likelihood of the genealogy
+        downloaded from the device agree with the device's own values (counts exact, doubles 1e-9)."""
+    from ima2p_b200 import Engine, synth
+    from support import OracleModel, tree_from_engine
+    n0 = n1 = 15
+    loci = synth.make_dataset(nloci, n0, n1, seed=11)
+    eng = Engine(nchains, nloci, mig_capacity=64, seed=seed, lib=lib)
+    eng.set_model(**synth.two_population_model(10.0, 1.0))
+    for li, L in enumerate(loci):
+        eng.set_locus(li, 0, L["n"], L["numsites"], L["samppop"], seq=L["seq"])
+    eng.finalize()
+    eng.set_heating(1, 0.96, 0.9)                     # HEAT_GEOMETRIC (-hfg -ha 0.96 -hb 0.9), as bench.py
+    st = synth.initial_state(loci, nchains, eng.NL, eng.CAP, t0=1.5, seed=100)
+    arrs = [np.ascontiguousarray(st[k]) for k in ["topo", "time", "mseg", "mig_t", "mig_p", "scal_i", "scal_d", "uvals"]]
+    eng.put_state(arrs, st["tvals"])
+    eng.sync()
+    betas0 = sorted(eng.betas())
+    eng.set_update_priors(t_max=[3.0])
+    eng.set_update_schedule(3, 5)
+    eng.run(nsteps)
+    eng.sync()
+    cnt = eng.counters()
+    assert cnt["steps"] == nsteps and cnt["updates"] == nsteps * nchains * nloci and cnt["dropped"] == 0
+    assert 0.15 < cnt["accepted"] / cnt["updates"] < 0.7
+    assert rel_close(sorted(eng.betas()), betas0, 0.0)
+    fm = FlatModel(load_golden("state_sim5_hn4")["model"])        # the same 2-population -q10 -m1 model, as the oracle takes it
+    inc = [eng.chain(c) for c in range(nchains)]
+    ncoal = nloci * (n0 + n1 - 1)
+    for c in range(nchains):
+        assert int(np.sum(inc[c]["wi"][:fm.ncc])) == ncoal, c
+    rng = np.random.default_rng(seed)
+    sample = [(int(rng.integers(nchains)), int(rng.integers(nloci))) for _ in range(noracle)]
+    om = OracleModel(fm)
+    for c, li in sample:
+        t = tree_from_engine(eng.get_genealogy(c, li))
+        r = eng.pair(c, li)
+        loc = dict(samppop=loci[li]["samppop"], hval=1.0, seq=loci[li]["seq"], numsites=loci[li]["numsites"], sumlogk=0.0)
+        w = om.treeweight(inc[c]["tvals"], loc, t)
+        ew = split_weights(fm, r["wi"], r["wd"])
+        assert np.array_equal(ew["cc"], w["cc"]) and np.array_equal(ew["mc"], w["mc"]) and r["mignum"] == w["mignum"]
+        assert rel_close(ew["fc"], w["fc"], 1e-9, 1e-12) and rel_close(ew["fm"], w["fm"], 1e-9, 1e-12)
+        assert rel_close(r["length"], w["length"], 1e-9)
+        u = eng.scalars(c, li)[0][0]
+        assert rel_close(r["pdg"], om.likelihood_is(loc, t, w["length"], u), 1e-9), (c, li)
+    eng.eval()
+    for c in range(nchains):
+        fresh = eng.chain(c)
+        assert np.array_equal(fresh["wi"], inc[c]["wi"])
+        assert rel_close(fresh["wd"], inc[c]["wd"], 1e-9, 1e-9)
+        assert rel_close(fresh["probg"], inc[c]["probg"], 1e-9) and rel_close(fresh["pdg"], inc[c]["pdg"], 1e-9)
+    eng.close()
+    return cnt

@@ -80,6 +80,12 @@ def test_runs_are_reproducible_and_seed_dependent(lib):
     assert np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[0], outs[2])
 
 
+@pytest.mark.parametrize("nloci,nchains,nsteps", [(50, 128, 400), (300, 256, 60)])
+def test_full_size_workload_properties(lib, nloci, nchains, nsteps):
+    # BASELINE configs[1] and the per-GPU shard of configs[2], through size-independent properties
+    ec.full_size_workload_properties(lib, nloci, nchains, nsteps)
+
+
 def test_speculation_depth_does_not_change_the_run(lib):
     ec.speculation_depth_does_not_change_the_run(lib)
 

@@ -41,6 +41,11 @@ def test_lmode(emu, name):
     ec.lmode_matches_reference(emu, name, rtol=1e-12)
 
 
+def test_workload_properties_small(emu):
+    # the GPU suite runs this at BASELINE sizes (50 x 128 and 300 x 256); here a size the one-lane emulation finishes in seconds
+    ec.full_size_workload_properties(emu, 12, 6, 40, noracle=16)
+
+
 def test_speculation_depth_does_not_change_the_run(emu):
     ec.speculation_depth_does_not_change_the_run(emu, nsteps=25)
 
