@@ -9,7 +9,15 @@
 // root population above the last split time; see start_genealogy) -> setheat -> burn-in -> every -d steps the cold chain's
 // row (savegsampinf) is appended to out.ti -> a short report.  Values are arguments attached to the flag ("-q10") or
 // the next word ("-q 10"), as the reference accepts.  Options of the reference outside this path are refused, not ignored.
+//
+//   IMa2p_b200 -r0 -v BASE -i data.u -o out -q QMAX -m MMAX -t TMAX [-j7] [-p6]
+//
+// is L mode (LOAD-GENEALOGY, ima_main_mpi.cpp:3216-3440, 4037-4100): the rows of BASE.ti are loaded onto the device and the
+// report sections that are sums over every sampled genealogy are written in the reference's own layout -- the means /
+// variances / correlations table (output.cpp:687-838), with -p6 the greater-than tables (gtint.cpp:336-447), and the
+// histogram group of the population-size and migration parameters (histograms.cpp:81-99, 146-431, 541-567).
 #include "../../include/ima2p_b200.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -89,11 +97,242 @@ Tree start_genealogy(const Locus &L, int npops, int rootpop, double tbase, unsig
   return T;
 }
 
+
+
+// ---- L mode report ------------------------------------------------------------------------------------------------
+constexpr int kGrid = 1000;                    // GRIDSIZE imamp.hpp
+
+// histformatdouble histograms.cpp:45-78
+std::string histfmt(double v) {
+  char b[64];
+  if (v < -1e9 || v > 1e9) { snprintf(b, sizeof b, "%-9.0lg", v); return b; }
+  const double a = fabs(v);
+  if (a < 1e-4) { snprintf(b, sizeof b, "%-9.8lf", v); if (!strcmp(b, "0.00000000")) return "0.0"; }
+  else if (a < 1e-3) snprintf(b, sizeof b, "%-9.7lf", v);
+  else if (a < 1e-2) snprintf(b, sizeof b, "%-9.6lf", v);
+  else if (a < 1e-1) snprintf(b, sizeof b, "%-9.5lf", v);
+  else if (a < 1e0) snprintf(b, sizeof b, "%-9.4lf", v);
+  else if (a < 1e1) snprintf(b, sizeof b, "%-9.3lf", v);
+  else if (a < 1e2) snprintf(b, sizeof b, "%-9.2lf", v);
+  else if (a < 1e3) snprintf(b, sizeof b, "%-9.1lf", v);
+  else snprintf(b, sizeof b, "%-9.0lf", v);
+  return b;
+}
+
+// print_means_variances_correlations output.cpp:746-838 (the printing half; the sums come from the device)
+void print_moments(FILE *f, const std::vector<std::string> &name, int nq, const std::vector<double> &m_max, const std::vector<double> &mean,
+                   const std::vector<double> &var, const std::vector<double> &corr, int npops) {
+  const int np = (int)name.size();
+  fprintf(f, "\nMEANS, VARIANCES and CORRELATIONS OF PARAMETERS ('$' r > 0.4  '*' r > 0.75)\n");
+  fprintf(f, "=============================================================================\n");
+  fprintf(f, "Param:");
+  for (int p = 0; p < np; p++) if (p < nq || m_max[p - nq] > 0.000001) fprintf(f, "\t%s", name[p].c_str());
+  fprintf(f, "\nMean:");
+  for (int p = 0; p < np; p++) fprintf(f, "\t%-.3lf", mean[p]);
+  fprintf(f, "\nStdv:");
+  for (int p = 0; p < np; p++) fprintf(f, "\t%-.3lf", sqrt(var[p]));
+  if (npops > 1) {
+    fprintf(f, "\n\nCorrelations\n");
+    for (int p = 0; p < np; p++) if (p < nq || m_max[p - nq] > 0.000001) fprintf(f, "\t%s", name[p].c_str());
+    fprintf(f, "\n");
+    for (int p = 0; p < np; p++) {
+      fprintf(f, "%s", name[p].c_str());
+      for (int q = 0; q < np; q++) {
+        if (q == p) { fprintf(f, "\t  - "); continue; }
+        const double c = q > p ? corr[(size_t)p * np + q] : corr[(size_t)q * np + p];
+        if (fabs(c) < 0.4) fprintf(f, "\t%-.3lf", c);
+        else fprintf(f, "\t%-.3lf%s", c, fabs(c) < 0.75 ? "$" : "*");
+      }
+      fprintf(f, "\n");
+    }
+  }
+  fprintf(f, "\n");
+}
+
+// print_greater_than_tests gtint.cpp:336-447
+void print_greater_than(FILE *f, ima2p_lmode *LM, const std::vector<std::string> &name, int nq, int nm, int expo) {
+  bool warn = false;
+  auto table = [&](int kind, int n, int off) {
+    std::vector<double> g((size_t)n * n, -1.0);
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) ck(ima2p_lmode_greater_than(LM, kind, i, j, &g[(size_t)i * n + j]), "greater-than probabilities");
+    for (int i = 0; i < n; i++) fprintf(f, "\t%s", name[off + i].c_str());
+    fprintf(f, "\n");
+    for (int i = 0; i < n; i++) {
+      fprintf(f, "%s", name[off + i].c_str());
+      for (int j = 0; j < n; j++) {
+        if (i == j) fprintf(f, "\t  - ");
+        else if (g[(size_t)i * n + j] < 0.0) fprintf(f, "\tna");
+        else if (fabs(1.0 - (g[(size_t)i * n + j] + g[(size_t)j * n + i])) >= 0.02) { fprintf(f, "\t%.3lf?", g[(size_t)i * n + j]); warn = true; }
+        else fprintf(f, "\t%.3lf", g[(size_t)i * n + j]);
+      }
+      fprintf(f, "\n");
+    }
+  };
+  fprintf(f, "\nPARAMETER COMPARISONS, PROBABILITY THAT ROW PARAMETER IS GREATER THAN COLUMN PARAMETER\n");
+  fprintf(f, "========================================================================================\n");
+  fprintf(f, "Population Sizes\n");
+  table(0, nq, 0);
+  fprintf(f, "\nMigration Rates\n");
+  if (expo) fprintf(f, "  NOT IMPLEMENTED FOR MIGRATION RATES WITH EXPONENTIAL PRIORS \n");
+  else table(1, nm, nq);
+  if (warn) fprintf(f, "  \"?\" indicates that reciprocal values do not sum to approximately 1, possibly due to a small sample of genealogies\n");
+  fprintf(f, "\n\n");
+}
+
+// writehistogram histograms.cpp:146-431 with dosmooth = 0 and unit scale adjustments, as prepare_parameter_histograms sets them
+void write_histograms(FILE *f, const std::vector<std::string> &name, const std::vector<std::vector<double>> &x, const std::vector<std::vector<double>> &y) {
+  const int nh = (int)name.size();
+  std::vector<double> xysum(nh, 0.0), ysum(nh, 0.0), hpdlo(nh, 0.0), hpdhi(nh, 0.0);
+  std::vector<char> c1(nh, ' '), c2(nh, ' ');
+  fprintf(f, " Summaries\n\tValue  ");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t %s", name[j].c_str());
+  fprintf(f, "\n\tMinbin ");
+  for (int j = 0; j < nh; j++) { int i = 0; while (i < kGrid - 1 && y[j][i] <= 0) i++; fprintf(f, "\t%s", histfmt(x[j][i]).c_str()); }
+  fprintf(f, "\n\tMaxbin");
+  for (int j = 0; j < nh; j++) { int i = kGrid - 1; while (i > 0 && y[j][i] <= 0) i--; fprintf(f, "\t%s", histfmt(x[j][i]).c_str()); }
+  fprintf(f, "\n\tHiPt  ");
+  std::vector<int> imax(nh, 0);
+  for (int j = 0; j < nh; j++) {
+    double maxval = -1;
+    for (int i = 0; i < kGrid; i++) {
+      xysum[j] += x[j][i] * y[j][i];
+      ysum[j] += y[j][i];
+      if (maxval < y[j][i]) { maxval = y[j][i]; imax[j] = i; }
+    }
+    fprintf(f, "\t%s", histfmt(x[j][imax[j]]).c_str());
+  }
+  fprintf(f, "\n\tMean  ");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t%s", histfmt(xysum[j] / ysum[j]).c_str());
+  fprintf(f, "\n\t95%%Lo  ");
+  for (int j = 0; j < nh; j++) {
+    int i = 0; double sum = 0;
+    while (i < kGrid && (sum + y[j][i]) / ysum[j] <= 0.025) { sum += y[j][i]; i++; }
+    fprintf(f, "\t%s", histfmt(x[j][i < kGrid ? i : kGrid - 1]).c_str());
+  }
+  fprintf(f, "\n\t95%%Hi  ");
+  for (int j = 0; j < nh; j++) {
+    int i = kGrid - 1; double sum = 0;
+    while ((sum + y[j][i]) / ysum[j] <= 0.025 && i > 0) { sum += y[j][i]; i--; }
+    fprintf(f, "\t%s", histfmt(x[j][i]).c_str());
+  }
+  // highest posterior density interval: smooth over 30 cells, sort by height, accumulate 95% from the top (:296-372)
+  for (int j = 0; j < nh; j++) {
+    std::vector<std::pair<double, double>> h(kGrid);       // (p, v)
+    double tempsum = 0;
+    for (int i = 0; i < kGrid; i++) {
+      int cell = 30 < 2 * i ? 30 : 2 * i;
+      cell = cell < 2 * (kGrid - 1 - i) ? cell : 2 * (kGrid - 1 - i);
+      double den = 0, sm = 0;
+      for (int k = (i - cell / 2 > 0 ? i - cell / 2 : 0); k <= (kGrid - 1 < i + cell / 2 ? kGrid - 1 : i + cell / 2); k++) {
+        const double term = 1.0 / (0.5 + abs(k - i));
+        sm += y[j][k] * term; den += term;
+      }
+      sm /= den;
+      tempsum += sm;
+      h[i] = std::make_pair(sm, x[j][i]);
+    }
+    const double vminhold = h[0].second;
+    std::sort(h.begin(), h.end());                         // by height, ties by value: the order shellhist leaves (utilities.cpp:674-702)
+    double hpdmax = -1, hpdmin = 1e10, sum = h[kGrid - 1].first;
+    int i = kGrid - 1;
+    while (i >= 0 && sum <= 0.95 * tempsum) {
+      if (h[i].second > hpdmax) hpdmax = h[i].second;
+      if (h[i].second < hpdmin) hpdmin = h[i].second;
+      i--;
+      if (i >= 0) sum += h[i].first;
+    }
+    hpdlo[j] = hpdmin <= vminhold ? 0.0 : hpdmin;
+    hpdhi[j] = hpdmax;
+    while (i > 0 && (h[i].second < hpdmin || h[i].second > hpdmax)) i--;
+    if (i > 0) c2[j] = '?';
+    if (0.0 < y[j][0] && 0.0 < y[j][kGrid - 1]) c1[j] = '#';      // smthprobvals is 0 without smoothing (:367)
+  }
+  fprintf(f, "\n\tHPD95Lo");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t%s%c%c", histfmt(hpdlo[j]).c_str(), c1[j], c2[j]);
+  fprintf(f, "\n\tHPD95Hi");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t%s%c%c", histfmt(hpdhi[j]).c_str(), c1[j], c2[j]);
+  fprintf(f, "\n\n\tParameter");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t%s\tP", name[j].c_str());
+  fprintf(f, "\n\tHiPt");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t%s\t%s", histfmt(x[j][imax[j]]).c_str(), histfmt(y[j][imax[j]]).c_str());
+  fprintf(f, "\n\n");
+  for (int i = 0; i < kGrid; i++) {
+    fprintf(f, "\t%4d", i);
+    for (int j = 0; j < nh; j++) fprintf(f, "\t%s\t%s", histfmt(x[j][i]).c_str(), histfmt(y[j][i]).c_str());
+    fprintf(f, "\n");
+  }
+  fprintf(f, " SumP\t");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t\t%s", histfmt(ysum[j]).c_str());
+  fprintf(f, "\n Before\t");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t\t%s", histfmt(0.0).c_str());
+  fprintf(f, "\n After\t");
+  for (int j = 0; j < nh; j++) fprintf(f, "\t\t%s", histfmt(0.0).c_str());
+  fprintf(f, "\n");
+}
+
+int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo) {
+  int md[6];
+  ima2p_modelspec_dims(S, md);
+  const int nsplit = md[1], nq = md[3], nm = md[4], nwp = md[5], np = nq + nm;
+  // parameter names as setup_iparams writes them: q<pop>, m<from>><to> (initialize.cpp:230-232, 466-470)
+  std::vector<int> plist((size_t)npops * npops), addpop(npops + 1), droppops((size_t)(npops + 1) * 2), ptb(2 * npops), pte(2 * npops), ptd(2 * npops),
+      qoff(nq + 1), qp(2 * npops * npops), qr(2 * npops * npops), moff(nm + 1), mp(nwp > 0 ? nwp : 1), mr(nwp > 0 ? nwp : 1), mc(nwp > 0 ? nwp : 1);
+  ck(ima2p_modelspec_tables(S, plist.data(), addpop.data(), droppops.data(), ptb.data(), pte.data(), ptd.data(), qoff.data(), qp.data(), qr.data(), moff.data(),
+                            mp.data(), mr.data(), mc.data()), "model tables");
+  std::vector<std::string> name;
+  for (int i = 0; i < nq; i++) name.push_back("q" + std::to_string(i));
+  for (int i = 0; i < nm; i++) {
+    const int k = moff[i];
+    name.push_back("m" + std::to_string(plist[(size_t)mp[k] * npops + mr[k]]) + ">" + std::to_string(plist[(size_t)mp[k] * npops + mc[k]]));
+  }
+  std::vector<double> qmx(nq, qmax), qmn(nq, 0.0), mmx(nm, expo ? 20.0 * mmax : mmax), mmn(nm, 0.0), mmean(nm, expo ? mmax : 0.0);
+  const int rowlen = 3 * nq + 2 * nm + nq + nm + 2 + nsplit;            // calc_gsampinf_length ginfo.cpp:306-316
+  const std::string ti = opt["v"] + ".ti";
+  long long nrows = 0;
+  const long long maxrows = 1100000;
+  std::vector<float> rows((size_t)maxrows * rowlen);
+  ck(ima2p_ti_load(ti.c_str(), rowlen, rows.data(), maxrows, &nrows), "loading the genealogy file");
+  if (nrows < 1) die("no genealogies in " + ti, 13);
+  ima2p_lmode *LM = nullptr;
+  ck(ima2p_lmode_create(&LM, 0, nq, nm, nsplit, qmx.data(), qmn.data(), mmx.data(), mmn.data(), mmean.data(), expo), "L mode");
+  ck(ima2p_lmode_load(LM, rows.data(), (int)nrows, rowlen, nrows), "uploading the genealogies");
+  FILE *f = fopen(opt["o"].c_str(), "w");
+  if (!f) die("cannot create the output file", 2);
+  fprintf(f, "IMa2p_b200 L mode report\n\nLOAD TREES (L) MODE INFORMATION\n============================================================================\n");
+  fprintf(f, "  Base filename for loading files with sampled genealogies: %s*.ti\n  loaded %lld genealogies from genealogy file  %s\n", opt["v"].c_str(), nrows, ti.c_str());
+  if (opt.count("p") && opt["p"].find('6') != std::string::npos) print_greater_than(f, LM, name, nq, nm, expo);
+  if (!expo) {                                                          // ima_main_mpi.cpp:4086: not done for the exponential prior
+    std::vector<double> mean(np), var(np), corr((size_t)np * np);
+    ck(ima2p_lmode_moments(LM, mean.data(), var.data(), corr.data(), nullptr), "moments");
+    print_moments(f, name, nq, mmx, mean, var, corr, npops);
+  }
+  // fillvec histograms.cpp:81-99: margincalc at the GRIDSIZE mid-bin points of every parameter (initialize.cpp:189-193, 237-242)
+  std::vector<std::vector<double>> xs, ys;
+  std::vector<std::string> hname;
+  for (int p = 0; p < np; p++) {
+    const double mx = p < nq ? qmx[p] : mmx[p - nq], mn = 0.0;
+    if (p >= nq && !(mx > 0.000001)) continue;
+    std::vector<double> x(kGrid), y(kGrid);
+    for (int j = 0; j < kGrid; j++) x[j] = mn + ((j + 0.5) * (mx - mn)) / kGrid;
+    ck(ima2p_lmode_margincalc(LM, p, x.data(), kGrid, 0.0, 0, y.data()), "marginal densities");
+    xs.push_back(x); ys.push_back(y); hname.push_back(name[p]);
+  }
+  fprintf(f, "\n\nHISTOGRAM GROUP 2: MARGINAL DISTRIBUTION VALUES AND HISTOGRAMS OF POPULATION SIZE AND MIGRATION PARAMETERS\n");
+  fprintf(f, "--------------------------------------------------------------------------------------------------------\n");
+  fprintf(f, "       curve height is an estimate of marginal posterior probability\n");
+  write_histograms(f, hname, xs, ys);
+  fprintf(f, "\nEND OF OUTPUT\n");
+  fclose(f);
+  printf("IMa2p_b200: L mode, %lld genealogies from %s, report in %s\n", nrows, ti.c_str(), opt["o"].c_str());
+  ima2p_lmode_destroy(LM);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
   std::map<std::string, std::string> opt;
-  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", nullptr};
+  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", nullptr};
   for (int a = 1; a < argc; a++) {
     if (argv[a][0] != '-') die(std::string("command line: unexpected word ") + argv[a], 5);
     const std::string w = argv[a] + 1;
@@ -106,6 +345,9 @@ int main(int argc, char **argv) {
     if (key == "j" && val != "7") die("model option -j" + val + " is not part of this build", 5);
     opt[key] = val;
   }
+  const bool lmode = opt.count("r") && opt["r"] == "0";
+  if (lmode && !opt.count("v")) die("-r0 invoked without -v information, i.e. no base name for files containing genealogys was given on the command line", 8);
+  if (lmode) { opt.emplace("b", "0"); opt.emplace("l", "1"); }
   for (const char *need : {"i", "o", "q", "t", "b", "l"}) if (!opt.count(need)) die(std::string("command line: -") + need + " is required", 5);
   const double qmax = atof(opt["q"].c_str()), mmax = opt.count("m") ? atof(opt["m"].c_str()) : 0.0, tmax = atof(opt["t"].c_str());
   const int nchains = opt.count("hn") ? atoi(opt["hn"].c_str()) : 1, expo = opt.count("j") ? 1 : 0;
@@ -120,6 +362,12 @@ int main(int argc, char **argv) {
   ck(ima2p_dataset_dims(D, &npops, &nloci, tree, sizeof tree), "data");
   ima2p_modelspec *S = nullptr;
   ck(ima2p_modelspec_create(&S, npops, tree, qmax, expo ? 20.0 * mmax : mmax, expo, expo ? mmax : 0.0, 0, 1.0), "model");   // -j7: -m is the mean, plotted to 20 means
+  if (lmode) {
+    const int rc = run_lmode(opt, S, npops, qmax, mmax, expo);
+    ima2p_modelspec_free(S);
+    ima2p_dataset_free(D);
+    return rc;
+  }
   int md[6];
   ima2p_modelspec_dims(S, md);
   const int nsplit = md[1], rootpop = 2 * npops - 2;

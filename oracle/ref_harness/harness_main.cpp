@@ -16,6 +16,7 @@
  *   lmode    burn=N rows=G every=K       sampled .ti rows (savegsampinf) and marginp/margincalc/jointp values
  *   bench    burn=N iters=K full=0|1     times the updategenealogy() loop (or whole qupdate steps)
  *   lbench   rows=G evals=E              times margincalc / jointp over G synthetic-from-run rows
+ *   stock                                the reference's own main() on the IMa2p command line, unchanged
  */
 #define main ima2p_reference_main
 #include "ima_main_mpi.cpp"
@@ -1383,6 +1384,13 @@ main (int argc, char *argv[])
   av.push_back (argv[0]);
   for (i = split + 1; i < argc; i++)
     av.push_back (argv[i]);
+  if (mode == "stock")           /* the reference's own main(), end to end (M or L mode); OUT receives its exit status */
+  {
+    int rc = ima2p_reference_main ((int) av.size (), av.data ());
+    fprintf (jo, "{\"exit\":%d}\n", rc);
+    fclose (jo);
+    return rc;
+  }
   numprocesses = 1;
   init_IMA ();
   start ((int) av.size (), av.data (), 0);

@@ -53,6 +53,38 @@ def test_run_from_u_file_to_ti_file(exe, tmp_path, name, genes):
     assert len(ti_load(str(tmp_path / "again") + ".ti", rowlen, lib=lib)) == 3
 
 
+def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path):
+    """-r0 -v: the genealogies the reference saved (its own .ti file) go through the device evaluators; the greater-than
+    tables, the means / variances / correlations table and the histogram group of the size and migration parameters must be
+    the reference's text, character for character (fixture: the reference's own L-mode report of the same file)."""
+    import gzip
+    import json
+    import shutil
+    ref = json.load(gzip.open(os.path.join(HERE, "golden", "lmode_report_sim3.json.gz")))
+    with gzip.open(os.path.join(INPUTS, "lmode_report_sim3.ti.gz"), "rb") as f, open(tmp_path / "ref.ti", "wb") as g:
+        shutil.copyfileobj(f, g)
+    u = tmp_path / "Sim3.u"
+    u.write_text(_sim3_u())
+    r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l.out"), "-q10", "-m1", "-t3", "-p6"])
+    assert r.returncode == 0, r.stderr
+    rep = open(tmp_path / "l.out").read()
+    for key in ("greater_than", "moments", "histograms"):
+        assert ref[key].strip("\n") in rep, key
+    r = _run(exe, ["-r0", "-i", str(u), "-o", str(tmp_path / "l2.out"), "-q10", "-m1", "-t3"])
+    assert r.returncode == 8 and "-v" in r.stderr            # IMERR_MISSINGCOMMANDINFO
+
+
+def _sim3_u():
+    """A .u file with the shape of Simulations/Sim3.u (2 populations, 2 infinite-sites loci of 15 + 15 genes): L mode reads the
+    data file only for the population tree and the number of loci."""
+    rows = []
+    for l, ns in enumerate((16, 21)):
+        rows.append("locus%d 15 15 %d I 1" % (l, ns))
+        for g in range(30):
+            rows.append("%-10s%s" % ("g%d" % g, "".join("AC"[(g >> (s % 4)) & 1] if s < 4 else "A" if g else "C" for s in range(ns))))
+    return "synthetic\n2\npop0 pop1\n(0,1):2\n2\n" + "\n".join(rows) + "\n"
+
+
 def test_refuses_what_it_does_not_implement(exe, tmp_path):
     u = os.path.join(INPUTS, "parse_hky.u")
     for bad in (["-a1"], ["-j3"], ["-c0"]):
