@@ -48,6 +48,9 @@ SIGNATURES = {
     "ima2p_engine_run_timed": (_i, [_v, _i, _i, _v, c_flt_p]),
     "ima2p_engine_update_genealogies": (_i, [_v, _v, _v]),
     "ima2p_engine_swap_replay": (_i, [_v, _v, _i, _v]),
+    "ima2p_engine_step_propose": (_i, [_v, _v]),
+    "ima2p_engine_step_decide": (_i, [_v, _v, _v]),
+    "ima2p_engine_swap_replay_late": (_i, [_v, _v, _i, _v]),
     "ima2p_engine_get_proposal": (_i, [_v, _i, _i, c_dbl_p, c_u32_p, c_int_p]),
     "ima2p_debug_gamma": (_i, [_i, c_int_p, c_dbl_p, _i, c_dbl_p]),
     "ima2p_engine_counters": (_i, [_v, c_u64_p]),

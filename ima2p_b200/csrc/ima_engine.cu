@@ -192,11 +192,12 @@ static void launch_update_genealogies(Engine *e, stream_t s) {
   launch_accept(e, s, 0, L);
 }
 
-static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries) {
+static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries, int step_already_advanced = 0) {
   SwapView sv = e->sv;
   sv.S_global = S_global;
   sv.swaptries = swaptries;
-  sv.advance_step = 1;
+  sv.advance_step = step_already_advanced ? 0 : 1;
+  sv.step_bias = step_already_advanced ? 1 : 0;
   const int G = e->d.nchains_global;
   sv.smem_chains = G <= 4000 ? G : 0;                        // 24 bytes per chain, 96 KB opted in at finalize
   IMA_LAUNCH(k_swap, 1, 1, (size_t)sv.smem_chains * 24 + 16, s, e->v, sv);
@@ -804,9 +805,57 @@ int ima2p_engine_update_genealogies(ima2p_engine *h, double *dev_S_local, void *
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, cuda_stream);
   launch_update(&e, s);
-  if (dev_S_local) IMA_LAUNCH(k_copy_swapsum, (e.d.nchains + kWarpsPerBlock * IMA_WARP - 1) / (kWarpsPerBlock * IMA_WARP), kWarpsPerBlock, 0, s, e.v, dev_S_local);
+  if (dev_S_local) IMA_LAUNCH(k_copy_swapsum, (e.d.nchains + kWarpsPerBlock * IMA_WARP - 1) / (kWarpsPerBlock * IMA_WARP), kWarpsPerBlock, 0, s, e.v, dev_S_local, 0);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (update)");
+#endif
+  return IMA2P_OK;
+}
+
+// Split-phase form of the same step.  The proposals of step s+1 do not read the temperatures, so a caller can launch them
+// while the all-gather and the swap replay of step s are still in flight on another stream:
+//   propose (stream A) | wait for the swaps of the previous step | decide (A): accept sweep, split-time and scalar updates,
+//   S to dev_S_local, step counter + 1 | all-gather + swap_replay_late (stream B) ...
+// The swap draws stay keyed by the step they belong to, so the run is the one ima2p_engine_run makes.
+int ima2p_engine_step_propose(ima2p_engine *h, void *cuda_stream) {
+  if (!h) return fail(IMA2P_E_ARG, "null engine");
+  Engine &e = h->eng;
+  int rc = ensure_steppable(e);
+  if (rc) return rc;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, 0, e.d.nloci);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (propose)");
+#endif
+  return IMA2P_OK;
+}
+
+int ima2p_engine_step_decide(ima2p_engine *h, double *dev_S_local, void *cuda_stream) {
+  if (!h || !dev_S_local) return fail(IMA2P_E_ARG, "step_decide: bad argument");
+  Engine &e = h->eng;
+  int rc = ensure_steppable(e);
+  if (rc) return rc;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  launch_accept(&e, s, 0, e.d.nloci);
+  launch_param_updates(&e, s);
+  IMA_LAUNCH(k_copy_swapsum, (e.d.nchains + kWarpsPerBlock * IMA_WARP - 1) / (kWarpsPerBlock * IMA_WARP), kWarpsPerBlock, 0, s, e.v, dev_S_local, 1);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (decide)");
+#endif
+  return IMA2P_OK;
+}
+
+int ima2p_engine_swap_replay_late(ima2p_engine *h, const double *dev_S_global, int swaptries, void *cuda_stream) {
+  if (!h || !h->eng.finalized || !dev_S_global || swaptries < 0) return fail(IMA2P_E_ARG, "swap_replay_late: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  launch_swap(&e, s, dev_S_global, swaptries, 1);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (swap)");
 #endif
   return IMA2P_OK;
 }

@@ -629,6 +629,7 @@ struct SwapView {
   const double *beta_table; // [nchains_global] beta by temperature rank (rank 0 = cold)
   unsigned long long *swap_counts;   // [2] attempts, accepts
   int swaptries, advance_step;
+  int step_bias;            // 1 when the step counter was already advanced (split-phase multi-GPU step): the draws stay keyed by the step they belong to
   int smem_chains;          // chains the launch's shared memory can stage (0: work on global memory)
 };
 
@@ -654,7 +655,10 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
     int *cor = staged ? sC : V.chain_of_rank, *roc = staged ? sR : V.rank_of_chain;
     if (lane == 0) {
       Philox rng;
-      rng_for(rng, E, 0xffffffffu, kRngSwap);
+      {
+        const unsigned long long step = *E.nsteps - (unsigned long long)V.step_bias;
+        rng.init(E.seed, 0xffffffffu, (uint32_t)step, kRngSwap | ((uint32_t)(step >> 32) << 8));
+      }
       unsigned long long nacc = 0;
       for (int x = 0; x < V.swaptries; x++) {
         const int sa = rng.randint(N);
@@ -742,9 +746,10 @@ IMA_KERNEL void k_pack_report(EngineView E, const int *chain_of_rank, int rowlen
   for (int i = 0; i < M.nsplit; i++) row[pdgp + 2 + i] = (float)E.tvals[(size_t)c * kMaxPeriods + i];
 }
 
-IMA_KERNEL void k_copy_swapsum(EngineView E, double *dst) {
+IMA_KERNEL void k_copy_swapsum(EngineView E, double *dst, int advance_step) {
   const int i = ima_block() * kWarpsPerBlock * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
   if (i < E.d.nchains) dst[i] = E.swapsum[i];
+  if (advance_step && i == 0) *E.nsteps += 1;
 }
 
 }  // namespace ima

@@ -222,6 +222,16 @@ class Engine:
     def swap_replay(self, dev_S_global, swaptries, stream=None):
         self._ck(self.lib.ima2p_engine_swap_replay(self._h, dev_S_global, swaptries, stream))
 
+    # split-phase step (multi-GPU): see include/ima2p_b200.h
+    def step_propose(self, stream=None):
+        self._ck(self.lib.ima2p_engine_step_propose(self._h, stream))
+
+    def step_decide(self, dev_S_local, stream=None):
+        self._ck(self.lib.ima2p_engine_step_decide(self._h, dev_S_local, stream))
+
+    def swap_replay_late(self, dev_S_global, swaptries, stream=None):
+        self._ck(self.lib.ima2p_engine_swap_replay_late(self._h, dev_S_global, swaptries, stream))
+
     def sync(self):
         self._ck(self.lib.ima2p_engine_sync(self._h))
 

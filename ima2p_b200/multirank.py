@@ -9,29 +9,77 @@ import torch.distributed as dist
 
 
 class ShardedStepper:
-    def __init__(self, engine, device, stream=None):
+    """Whole qupdate steps over chains sharded by rank.
+
+    On GPUs the step runs in split phases (include/ima2p_b200.h, ima2p_engine_step_*): the all-gather and the swap replay
+    of step s go to a side stream and hide behind the proposals of step s+1, which do not read the temperatures; only the
+    accept sweep of step s+1 waits for them.  The result is the run `Engine.run` makes on one GPU with all the chains
+    (tests/test_multirank_gloo.py), whatever the number of ranks."""
+
+    def __init__(self, engine, device, stream=None, overlap=True, split_phase=True):
         self.eng = engine
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.S_local = torch.zeros(engine.nchains, dtype=torch.float64, device=device)
         self.S_global = torch.zeros(engine.nchains_global, dtype=torch.float64, device=device)
         self.stream = stream
+        self.cuda = torch.cuda.is_available() and self.S_local.device.type == "cuda"
+        self.overlap = bool(overlap) and bool(split_phase) and self.cuda
+        self.split_phase = bool(split_phase)
+        if self.overlap:
+            self.main = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+            self.side = torch.cuda.Stream()
+            self.ev_decided, self.ev_swapped = torch.cuda.Event(), torch.cuda.Event()
+            self._pending = False
         assert engine.nchains * self.world == engine.nchains_global, "chains must shard evenly over ranks"
 
-    def step(self, swaptries):
-        self.eng.update_genealogies(self.S_local.data_ptr(), self.stream)
+    def _gather(self):
         if self.world > 1:
             dist.all_gather_into_tensor(self.S_global, self.S_local)
         else:
             self.S_global.copy_(self.S_local)
+
+    def step(self, swaptries):
+        if self.overlap:
+            return self._step_overlapped(swaptries)
+        if self.split_phase:                                     # the same calls in order (CPU tests, one stream)
+            self.eng.step_propose(self.stream)
+            self.eng.step_decide(self.S_local.data_ptr(), self.stream)
+            self._gather()
+            self.eng.swap_replay_late(self.S_global.data_ptr(), swaptries, self.stream)
+            return
+        self.eng.update_genealogies(self.S_local.data_ptr(), self.stream)
+        self._gather()
         self.eng.swap_replay(self.S_global.data_ptr(), swaptries, self.stream)
+
+    def _step_overlapped(self, swaptries):
+        eng, main, side = self.eng, self.main, self.side
+        eng.step_propose(main.cuda_stream)                       # needs only the genealogies left by the previous decide
+        if self._pending:
+            main.wait_event(self.ev_swapped)                     # the temperatures of this step
+        eng.step_decide(self.S_local.data_ptr(), main.cuda_stream)
+        self.ev_decided.record(main)
+        side.wait_event(self.ev_decided)
+        with torch.cuda.stream(side):
+            self._gather()
+            eng.swap_replay_late(self.S_global.data_ptr(), swaptries, side.cuda_stream)
+            self.ev_swapped.record(side)
+        self._pending = True
+
+    def finish(self):
+        """The launching stream waits for the swaps still in flight (call before reading results or timing)."""
+        if self.overlap and self._pending:
+            self.main.wait_event(self.ev_swapped)
+            self._pending = False
 
     def capture(self, swaptries):
         """One step (kernels + the NCCL all-gather) as a CUDA graph on the current torch stream: the step is a handful
         of short launches, so at 2-8 GPUs the launch gaps between them are what the graph removes.  Returns False and
         keeps the eager path when the capture is not possible (CPU/gloo, or a torch/NCCL that cannot capture)."""
-        if not torch.cuda.is_available() or self.S_local.device.type != "cuda":
+        if not self.cuda:
             return False
         try:
+            self.finish()
+            self.overlap = self.split_phase = False
             for _ in range(3):                      # warm-up outside the capture (NCCL channels, lazy allocations)
                 self.step(swaptries)
             torch.cuda.synchronize()
@@ -55,6 +103,7 @@ class ShardedStepper:
             return
         for _ in range(nsteps):
             self.step(st)
+        self.finish()
 
 
 # ---- L mode: the sampled genealogies (.ti rows) shard by rank; README.md:117 of the reference: "a separate L mode run

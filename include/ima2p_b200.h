@@ -139,6 +139,14 @@ int ima2p_engine_run_timed (ima2p_engine * e, int nsteps, int swaptries, void *c
  * dev_S_global[nchains_global] and every rank replays the same swap attempts. */
 int ima2p_engine_update_genealogies (ima2p_engine * e, double *dev_S_local, void *cuda_stream);
 int ima2p_engine_swap_replay (ima2p_engine * e, const double *dev_S_global, int swaptries, void *cuda_stream);
+/* The same step in split phases, so that the exchange of step s hides behind the proposals of step s+1 (updategenealogy's
+ * proposal half does not read beta): step_propose launches the proposals of every local pair; step_decide the accept sweep,
+ * the split-time / scalar updates, writes S to dev_S_local and advances the step counter; swap_replay_late is swap_replay
+ * for a step whose counter has already been advanced (same draws).  The caller orders them with stream events:
+ * decide(s) -> [all-gather, swap_replay_late](s) -> decide(s+1), while propose(s+1) only follows decide(s). */
+int ima2p_engine_step_propose (ima2p_engine * e, void *cuda_stream);
+int ima2p_engine_step_decide (ima2p_engine * e, double *dev_S_local, void *cuda_stream);
+int ima2p_engine_swap_replay_late (ima2p_engine * e, const double *dev_S_global, int swaptries, void *cuda_stream);
 
 /* last proposal of a pair: out4[5] = {migweight (update_gtree.cpp:663), slideweight (:803-812), slide distance
  * drawn (:783), edge moved, migweight + slideweight + Atermsum (the non-likelihood part of the MH exponent, :919-924)}; flags bit0 infinite-sites reject, bit1 dropped for capacity, bit2 topology changed,
