@@ -70,6 +70,9 @@ SIGNATURES = {
     "ima2p_engine_sync": (_i, [_v]),
     "ima2p_engine_state_bytes": (_i, [_v, c_u64_p]),
     "ima2p_engine_put_state": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v, c_dbl_p, _v]),
+    "ima2p_engine_state_block_layout": (_i, [_v, _ll, c_u64_p]),
+    "ima2p_engine_put_state_block": (_i, [_v, _v, _ll, _v]),
+    "ima2p_engine_put_state_packed": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v, c_dbl_p, _v]),
     "ima2p_engine_fetch_state": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v]),
     "ima2p_engine_fetch_pair_summaries": (_i, [_v, c_dbl_p, c_int_p, c_int_p, _v]),
     "ima2p_engine_fetch_chain_summary": (_i, [_v, c_dbl_p, _v]),

@@ -48,6 +48,11 @@ struct Engine {
   std::vector<void *> allocs;
   double *d_logfact = nullptr;
   int *d_err = nullptr;
+  signed char *d_topo8 = nullptr;        // staging of the packed wire form (ima2p_engine_put_state_packed), made on first use
+  unsigned char *d_mcount = nullptr;
+  unsigned char *d_block = nullptr;      // staging of the one-block wire form (ima2p_engine_put_state_block)
+  int *d_block_moff = nullptr;
+  size_t block_cap = 0;
   DevLocus *d_loci = nullptr;
   double *d_beta_table = nullptr;
   unsigned long long *d_swap_counts = nullptr;
@@ -200,7 +205,7 @@ static void launch_swap(Engine *e, stream_t s, const double *S_global, int swapt
   sv.step_bias = step_already_advanced ? 1 : 0;
   const int G = e->d.nchains_global;
   sv.smem_chains = G <= 4000 ? G : 0;                        // 24 bytes per chain, 96 KB opted in at finalize
-  IMA_LAUNCH(k_swap, 1, 1, (size_t)sv.smem_chains * 24 + 16, s, e->v, sv);
+  IMA_LAUNCH(k_swap, 1, 1, swap_smem_bytes(sv.smem_chains), s, e->v, sv);
 }
 
 }  // namespace ima
@@ -405,7 +410,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
-      !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * 24 + 16)) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem_bytes(4000))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(changeu_smem(&e) * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
   if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");
@@ -1217,6 +1222,80 @@ int ima2p_engine_put_state(ima2p_engine *h, const void *topo, const void *time, 
   memset(e.v.cur, 0, e.d.P);
 #endif
   if (!ok) return fail(IMA2P_E_CUDA, "put_state failed");
+  return launch_eval(&e, s);
+}
+
+// The same state in its narrow wire form: 13 instead of 20 bytes per edge cross PCIe (int8 links and population, uint8
+// migration counts, the pools in edge order so that the segment starts are a prefix sum); widened on the device.
+int ima2p_engine_put_state_packed(ima2p_engine *h, const void *topo8, const void *time, const void *mcount, const void *mig_t, const void *mig_p,
+                                  const void *scal_i, const void *scal_d, const void *uvals, const double *tvals, void *cuda_stream) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "put_state_packed: not finalized");
+  Engine &e = h->eng;
+  if (e.d.NL > 127 || e.d.CAP > 255 || e.model.ntreepops > 127) return fail(IMA2P_E_ARG, "put_state_packed: the sample does not fit the 8-bit wire form; use ima2p_engine_put_state");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  const size_t P = e.d.P, NL = e.d.NL;
+  if (!e.d_topo8) { e.d_topo8 = e.alloc<signed char>(P * NL * 4); e.d_mcount = e.alloc<unsigned char>(P * NL); }
+  if (!e.d_topo8 || !e.d_mcount) return fail(IMA2P_E_CUDA, "device allocation failed");
+  uint64_t b[8];
+  ima2p_engine_state_bytes(h, b);
+  PairBuf &B = e.v.buf[0];
+  bool ok = h2d(e.d_topo8, topo8, P * NL * 4, s) && h2d(B.time, time, b[1], s) && h2d(e.d_mcount, mcount, P * NL, s) &&
+            h2d(B.si, scal_i, b[5], s) && h2d(B.sd, scal_d, b[6], s) && h2d(e.v.uvals, uvals, b[7], s);
+  {
+    const int *si = (const int *)scal_i;
+    int maxmig = 0;
+    for (size_t p = 0; p < P; p++) if (si[2 * p + 1] > maxmig) maxmig = si[2 * p + 1];
+    if (maxmig > e.d.CAP) return fail(IMA2P_E_CAPACITY, "put_state_packed: more migration events than mig_capacity");
+#if IMA_CUDA
+    if (maxmig > 0)
+      ok = ok && IMA_CUDA_OK(cudaMemcpy2DAsync(B.mig_t, (size_t)e.d.CAP * 8, mig_t, (size_t)e.d.CAP * 8, (size_t)maxmig * 8, e.d.P, cudaMemcpyHostToDevice, s)) &&
+           IMA_CUDA_OK(cudaMemcpy2DAsync(B.mig_p, (size_t)e.d.CAP * 2, mig_p, (size_t)e.d.CAP * 2, (size_t)maxmig * 2, e.d.P, cudaMemcpyHostToDevice, s));
+#else
+    ok = ok && h2d(B.mig_t, mig_t, b[3], s) && h2d(B.mig_p, mig_p, b[4], s);
+#endif
+  }
+  if (tvals) {
+    for (int c = 0; c < e.d.nchains; c++) for (int k = 0; k < kMaxPeriods; k++) e.h_tvals[(size_t)c * kMaxPeriods + k] = k < e.model.nsplit ? tvals[(size_t)c * e.model.nsplit + k] : kTimeMax;
+    ok = ok && h2d(e.v.tvals, e.h_tvals.data(), e.h_tvals.size() * sizeof(double), s);
+  }
+#if IMA_CUDA
+  ok = ok && IMA_CUDA_OK(cudaMemsetAsync(e.v.cur, 0, e.d.P, s));
+#else
+  memset(e.v.cur, 0, e.d.P);
+#endif
+  if (!ok) return fail(IMA2P_E_CUDA, "put_state_packed failed");
+  IMA_LAUNCH(k_unpack_state, (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock, 0, s, e.v, e.d_topo8, e.d_mcount);
+  return launch_eval(&e, s);
+}
+
+// One host block, one transfer: sections as state_block_layout (ima_kernels.h), offsets from ima2p_engine_state_block_layout.
+int ima2p_engine_state_block_layout(ima2p_engine *h, long long total_events, uint64_t *out10) {
+  if (!h || !h->eng.finalized || !out10 || total_events < 0) return fail(IMA2P_E_ARG, "state_block_layout: bad argument");
+  const StateBlock b = state_block_layout(h->eng.d, h->eng.model.nsplit, total_events);
+  const size_t v[10] = {b.time, b.sd, b.uvals, b.tvals, b.mig_t, b.si, b.mig_p, b.topo8, b.mcount, b.total};
+  for (int i = 0; i < 10; i++) out10[i] = v[i];
+  return IMA2P_OK;
+}
+
+int ima2p_engine_put_state_block(ima2p_engine *h, const void *block, long long total_events, void *cuda_stream) {
+  if (!h || !h->eng.finalized || !block || total_events < 0) return fail(IMA2P_E_ARG, "put_state_block: bad argument");
+  Engine &e = h->eng;
+  if (e.d.NL > 127 || e.d.CAP > 255 || e.model.ntreepops > 127) return fail(IMA2P_E_ARG, "put_state_block: the sample does not fit the 8-bit wire form; use ima2p_engine_put_state");
+  if (total_events > (long long)e.d.P * e.d.CAP) return fail(IMA2P_E_CAPACITY, "put_state_block: more migration events than mig_capacity");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  const StateBlock L = state_block_layout(e.d, e.model.nsplit, total_events);
+  if (L.total > e.block_cap) {
+    const size_t cap = state_block_layout(e.d, e.model.nsplit, (long long)e.d.P * e.d.CAP).total;
+    e.d_block = e.alloc<unsigned char>(cap);
+    if (!e.d_block_moff) e.d_block_moff = e.alloc<int>(e.d.P);
+    e.block_cap = e.d_block ? cap : 0;
+  }
+  if (!e.d_block || !e.d_block_moff) return fail(IMA2P_E_CUDA, "device allocation failed");
+  if (!h2d(e.d_block, block, L.total, s)) return fail(IMA2P_E_CUDA, "put_state_block failed");
+  IMA_LAUNCH(k_block_offsets, 1, kWarpsPerBlock, kWarpsPerBlock * sizeof(int), s, e.v, e.d_block, L, e.d_block_moff);
+  IMA_LAUNCH(k_unpack_block, (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock, 0, s, e.v, e.d_block, L, e.d_block_moff, e.model.nsplit);
   return launch_eval(&e, s);
 }
 

@@ -633,6 +633,8 @@ struct SwapView {
   int smem_chains;          // chains the launch's shared memory can stage (0: work on global memory)
 };
 
+constexpr int kSwapBatch = 256;           // attempts drawn per pass
+IMA_HD size_t swap_smem_bytes(int staged_chains) { return (size_t)staged_chains * 24 + 16 + (size_t)kSwapBatch * 16; }
 IMA_KERNEL void k_swap(EngineView E, SwapView V) {
   IMA_SMEM_DECL
   if (ima_block() != 0 || ima_warp_in_block() != 0) return;
@@ -653,30 +655,49 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
     }
     const double *Sg = staged ? sS : V.S_global, *Bt = staged ? sB : V.beta_table;
     int *cor = staged ? sC : V.chain_of_rank, *roc = staged ? sR : V.rank_of_chain;
-    if (lane == 0) {
-      Philox rng;
-      {
-        const unsigned long long step = *E.nsteps - (unsigned long long)V.step_bias;
+    // Every attempt has its own counter block of the step's swap stream, so the lanes draw the attempts of a batch in
+    // parallel -- the two temperature ranks (the second uniform over the other ranks of the window, which is what the
+    // reference's redraw-until-different loop samples, swapchains.cpp:224-235) and the uniform of the decision -- and one
+    // lane then only walks the decisions, which depend on each other through the rank tables.
+    double *dU = (double *)(IMA_SMEM + (staged ? (size_t)N * 24 : 0) + 16);
+    int *dA = (int *)(dU + kSwapBatch), *dB = dA + kSwapBatch;
+    const unsigned long long step = *E.nsteps - (unsigned long long)V.step_bias;
+    unsigned long long nacc = 0;
+    for (int x0 = 0; x0 < V.swaptries; x0 += kSwapBatch) {
+      const int nb = V.swaptries - x0 < kSwapBatch ? V.swaptries - x0 : kSwapBatch;
+      for (int i = lane; i < nb; i += IMA_WARP) {
+        Philox rng;
         rng.init(E.seed, 0xffffffffu, (uint32_t)step, kRngSwap | ((uint32_t)(step >> 32) << 8));
-      }
-      unsigned long long nacc = 0;
-      for (int x = 0; x < V.swaptries; x++) {
+        rng.ctr[0] = (uint32_t)(x0 + i);
         const int sa = rng.randint(N);
         int sbmin = 0, sbrange = N;
         if (N >= 2 * kSwapDist + 3) {
           sbmin = sa - kSwapDist > 0 ? sa - kSwapDist : 0;
           sbrange = (N < sa + kSwapDist ? N : sa + kSwapDist) - sbmin;
         }
-        int sb;
-        do { sb = sbmin + rng.randint(sbrange); } while (sb == sa);
-        const int ca = cor[sa], cb = cor[sb];
-        const double w = exp((Bt[sa] - Bt[sb]) * (Sg[cb] - Sg[ca]));
-        if (w >= 1.0 || w > rng.uniform()) {
-          cor[sa] = cb; cor[sb] = ca;
-          roc[ca] = sb; roc[cb] = sa;
-          nacc++;
+        int sb = sbmin + rng.randint(sbrange - 1);
+        if (sb >= sa) sb++;
+        dA[i] = sa; dB[i] = sb; dU[i] = rng.uniform();
+      }
+#if IMA_CUDA
+      __threadfence_block();
+#endif
+      Warp::sync();
+      if (lane == 0) {
+        for (int i = 0; i < nb; i++) {
+          const int sa = dA[i], sb = dB[i];
+          const int ca = cor[sa], cb = cor[sb];
+          const double w = exp((Bt[sa] - Bt[sb]) * (Sg[cb] - Sg[ca]));
+          if (w >= 1.0 || w > dU[i]) {
+            cor[sa] = cb; cor[sb] = ca;
+            roc[ca] = sb; roc[cb] = sa;
+            nacc++;
+          }
         }
       }
+      Warp::sync();
+    }
+    if (lane == 0) {
       V.swap_counts[0] += (unsigned long long)V.swaptries;
       V.swap_counts[1] += nacc;
     }
@@ -744,6 +765,115 @@ IMA_KERNEL void k_pack_report(EngineView E, const int *chain_of_rank, int rowlen
   }
   row[pdgp] = (float)E.pdgsum[c]; row[pdgp + 1] = (float)E.probg[c];
   for (int i = 0; i < M.nsplit; i++) row[pdgp + 2 + i] = (float)E.tvals[(size_t)c * kMaxPeriods + i];
+}
+
+// ima2p_engine_put_state_packed: the narrow wire form of a pair -- int8 (up0, up1, down, pop) and a uint8 migration count per
+// edge, the pools in edge order -- widened to the resident layout (short4 links, (start, count) segments).  One warp per pair.
+IMA_KERNEL void k_unpack_state(EngineView E, const signed char *topo8, const unsigned char *mcount) {
+  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (p >= E.d.P) return;
+  const int lane = Warp::lane(), NL = E.d.NL;
+  const PairBuf &B = E.buf[0];
+  int carry = 0;
+  for (int base = 0; base < NL; base += IMA_WARP) {
+    const int e = base + lane;
+    const int n = e < NL ? (int)mcount[(size_t)p * NL + e] : 0;
+    const int incl = Warp::scan(n);
+    if (e < NL) {
+      const signed char *t = topo8 + ((size_t)p * NL + e) * 4;
+      short4_t o; o.x = t[0]; o.y = t[1]; o.z = t[2]; o.w = t[3];
+      B.topo[(size_t)p * NL + e] = o;
+      ushort2_t m; m.x = (unsigned short)(carry + incl - n); m.y = (unsigned short)n;
+      B.mseg[(size_t)p * NL + e] = m;
+    }
+    carry += Warp::bcast(incl, IMA_WARP - 1);
+  }
+}
+
+// ima2p_engine_put_state_block: the whole state of the GPU's chains as ONE host block (one PCIe transfer), sections in the
+// order of StateBlock, migration events stored ragged (the events of pair 0, then pair 1, ...).  k_block_offsets turns the
+// per-pair event counts into offsets, k_unpack_block widens a pair into the resident layout (one warp per pair).
+struct StateBlock { size_t time, sd, uvals, tvals, mig_t, si, mig_p, topo8, mcount, total; };
+IMA_HD StateBlock state_block_layout(const EngineDims &d, int nsplit, long long events) {
+  StateBlock b; size_t o = 0;
+  const size_t P = (size_t)d.P, NL = (size_t)d.NL;
+  b.time = o; o += P * NL * 8;
+  b.sd = o; o += P * 4 * 8;
+  b.uvals = o; o += P * kMaxLinked * 8;
+  b.tvals = o; o += (size_t)d.nchains * (nsplit > 0 ? nsplit : 1) * 8;
+  b.mig_t = o; o += (size_t)events * 8;
+  b.si = o; o += P * 2 * 4;
+  b.mig_p = o; o += align8((size_t)events * 2);
+  b.topo8 = o; o += align8(P * NL * 4);
+  b.mcount = o; o += align8(P * NL);
+  b.total = o;
+  return b;
+}
+IMA_KERNEL void k_block_offsets(EngineView E, const unsigned char *block, StateBlock L, int *moff) {
+  // exclusive prefix sum of the pairs' event counts (scal_i[p][1]); one block, pairs in chunks of its size
+  IMA_SMEM_DECL
+  const int *si = (const int *)(block + L.si);
+#if IMA_CUDA
+  int *sm = (int *)IMA_SMEM;                               // [warps]
+  const int lane = Warp::lane(), warp = ima_warp_in_block();
+  const int nth = kWarpsPerBlock * IMA_WARP, tid = warp * IMA_WARP + lane;
+  int carry = 0;
+  for (int base = 0; base < E.d.P; base += nth) {
+    const int p = base + tid;
+    const int n = p < E.d.P ? si[2 * p + 1] : 0;
+    const int incl = Warp::scan(n);
+    if (lane == IMA_WARP - 1) sm[warp] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < kWarpsPerBlock; w++) { if (w < warp) woff += sm[w]; tot += sm[w]; }
+    if (p < E.d.P) moff[p] = carry + woff + incl - n;
+    carry += tot;
+    __syncthreads();
+  }
+#else
+  if (ima_warp_in_block() != 0) return;                    // host emulation: one lane walks the pairs
+  int run = 0;
+  for (int p = 0; p < E.d.P; p++) { moff[p] = run; run += si[2 * p + 1]; }
+#endif
+}
+IMA_KERNEL void k_unpack_block(EngineView E, const unsigned char *block, StateBlock L, const int *moff, int nsplit) {
+  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (p >= E.d.P) return;
+  const int lane = Warp::lane(), NL = E.d.NL, CAP = E.d.CAP;
+  const PairBuf &B = E.buf[0];
+  const signed char *topo8 = (const signed char *)(block + L.topo8);
+  const unsigned char *mcount = block + L.mcount;
+  const double *time = (const double *)(block + L.time);
+  int carry = 0;
+  for (int base = 0; base < NL; base += IMA_WARP) {
+    const int e = base + lane;
+    const int n = e < NL ? (int)mcount[(size_t)p * NL + e] : 0;
+    const int incl = Warp::scan(n);
+    if (e < NL) {
+      const signed char *t = topo8 + ((size_t)p * NL + e) * 4;
+      short4_t o; o.x = t[0]; o.y = t[1]; o.z = t[2]; o.w = t[3];
+      B.topo[(size_t)p * NL + e] = o;
+      ushort2_t m; m.x = (unsigned short)(carry + incl - n); m.y = (unsigned short)n;
+      B.mseg[(size_t)p * NL + e] = m;
+      B.time[(size_t)p * NL + e] = time[(size_t)p * NL + e];
+    }
+    carry += Warp::bcast(incl, IMA_WARP - 1);
+  }
+  const int *si = (const int *)(block + L.si);
+  const double *sd = (const double *)(block + L.sd), *uv = (const double *)(block + L.uvals);
+  const int nmig = si[2 * p + 1] < CAP ? si[2 * p + 1] : CAP, m0 = moff[p];
+  const double *mt = (const double *)(block + L.mig_t);
+  const short *mp = (const short *)(block + L.mig_p);
+  for (int i = lane; i < nmig; i += IMA_WARP) { B.mig_t[(size_t)p * CAP + i] = mt[m0 + i]; B.mig_p[(size_t)p * CAP + i] = mp[m0 + i]; }
+  for (int i = lane; i < 2; i += IMA_WARP) B.si[(size_t)p * 2 + i] = si[2 * p + i];
+  for (int i = lane; i < 4; i += IMA_WARP) B.sd[(size_t)p * 4 + i] = sd[(size_t)p * 4 + i];
+  for (int i = lane; i < kMaxLinked; i += IMA_WARP) E.uvals[(size_t)p * kMaxLinked + i] = uv[(size_t)p * kMaxLinked + i];
+  if (lane == 0) E.cur[p] = 0;
+  const int c = p / E.d.nloci;
+  if (p == c * E.d.nloci) {                                   // the first pair of a chain also sets the chain's split times
+    const double *tv = (const double *)(block + L.tvals);
+    for (int k = lane; k < kMaxPeriods; k += IMA_WARP) E.tvals[(size_t)c * kMaxPeriods + k] = k < nsplit ? tv[(size_t)c * nsplit + k] : kTimeMax;
+  }
 }
 
 IMA_KERNEL void k_copy_swapsum(EngineView E, double *dst, int advance_step) {

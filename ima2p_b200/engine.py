@@ -344,6 +344,52 @@ class Engine:
         tv = _f64(tvals)
         self._ck(self.lib.ima2p_engine_put_state(self._h, *ptrs, _dp(tv), stream))
 
+    @staticmethod
+    def pack_state(topo, mseg):
+        """(topo int16 [P][NL][4], mseg uint16 [P][NL][2]) -> (topo8 int8, mcount uint8) of put_state_packed, or None when
+        the state does not fit that form (more than 127 edges, or pools that are not in edge order)."""
+        topo, mseg = np.asarray(topo), np.asarray(mseg)
+        if topo.shape[1] > 127 or topo.min() < -128 or topo.max() > 127 or mseg[..., 1].max() > 255:
+            return None
+        cnt = mseg[..., 1].astype(np.int64)
+        start = np.cumsum(cnt, axis=1) - cnt
+        if not np.array_equal(start[cnt > 0], mseg[..., 0].astype(np.int64)[cnt > 0]):
+            return None
+        return np.ascontiguousarray(topo.astype(np.int8)), np.ascontiguousarray(cnt.astype(np.uint8))
+
+    def pack_state_block(self, arrs, tvals, out=None):
+        """The 8 put_state arrays + split times -> one uint8 block for put_state_block (None when the state does not fit the
+        8-bit wire form).  Returns (block, total_events); `out` may be a preallocated (e.g. pinned) uint8 array."""
+        P, NL, CAP = self.nchains * self.nloci, self.NL, self.CAP
+        topo, time, mseg, mig_t, mig_p, si, sd, uv = [np.asarray(a) for a in arrs]
+        pk = self.pack_state(topo.reshape(P, NL, 4), mseg.reshape(P, NL, 2))
+        if pk is None:
+            return None
+        nm = si.reshape(P, 2)[:, 1].astype(np.int64)
+        keep = np.arange(CAP)[None, :] < nm[:, None]
+        events = int(nm.sum())
+        lay = np.zeros(10, np.uint64)
+        self._ck(self.lib.ima2p_engine_state_block_layout(self._h, events, lay.ctypes.data_as(capi.c_u64_p)))
+        lay = [int(v) for v in lay]
+        blk = np.zeros(lay[9], np.uint8) if out is None else out[:lay[9]]
+        parts = [np.ascontiguousarray(time, np.float64), np.ascontiguousarray(sd, np.float64), np.ascontiguousarray(uv, np.float64),
+                 np.ascontiguousarray(tvals, np.float64), np.ascontiguousarray(mig_t.reshape(P, CAP)[keep], np.float64),
+                 np.ascontiguousarray(si, np.int32), np.ascontiguousarray(mig_p.reshape(P, CAP)[keep], np.int16), pk[0], pk[1]]
+        for off, a in zip(lay[:9], parts):
+            b = a.reshape(-1).view(np.uint8)
+            blk[off:off + b.size] = b
+        return blk, events
+
+    def put_state_block(self, block, events, stream=None):
+        ptr = block if isinstance(block, int) else block.ctypes.data
+        self._ck(self.lib.ima2p_engine_put_state_block(self._h, ptr, events, stream))
+
+    def put_state_packed(self, bufs, tvals, stream=None):
+        """bufs as put_state, with bufs[0] = topo8 and bufs[2] = mcount from pack_state (8-bit wire form)."""
+        ptrs = [b if isinstance(b, int) else b.ctypes.data for b in bufs]
+        tv = _f64(tvals)
+        self._ck(self.lib.ima2p_engine_put_state_packed(self._h, *ptrs, _dp(tv), stream))
+
     def fetch_state(self, bufs, stream=None):
         ptrs = [b if isinstance(b, int) else b.ctypes.data for b in bufs]
         self._ck(self.lib.ima2p_engine_fetch_state(self._h, *ptrs, stream))

@@ -212,6 +212,20 @@ int ima2p_engine_put_state (ima2p_engine * e, const void *topo, const void *time
                             const double *tvals /* [nchains][nsplit] */ , void *cuda_stream);
 int ima2p_engine_fetch_state (ima2p_engine * e, void *topo, void *time, void *mseg, void *mig_t, void *mig_p,
                               void *scal_i, void *scal_d, void *cuda_stream);
+/* put_state in a narrow wire form (13 instead of 20 bytes per edge over PCIe): topo8 = int8 [P][NL][4] (up0, up1, down, pop),
+ * mcount = uint8 [P][NL] migration events per edge, the pools mig_t / mig_p [P][CAP] holding the events of a pair in edge
+ * order (segment starts are the prefix sums of mcount, which is how fetch_state delivers them); the other buffers as in
+ * put_state.  Needs 2n-1 <= 127 edges and mig_capacity <= 255; otherwise IMA2P_E_ARG and put_state is the way. */
+/* The same narrow form as ONE host block, so that a step's state crosses PCIe in a single transfer: sections at the byte
+ * offsets ima2p_engine_state_block_layout returns for `total_events` migration events over all pairs --
+ * out10 = {time f64[P][NL], scal_d f64[P][4], uvals f64[P][IMA2P_MAX_LINKED], tvals f64[nchains][nsplit], mig_t f64[events],
+ * scal_i i32[P][2], mig_p i16[events], topo8 i8[P][NL][4], mcount u8[P][NL], total bytes}; the events of pair 0 first, then
+ * pair 1, ..., each pair's in edge order (scal_i[p][1] of them). */
+int ima2p_engine_state_block_layout (ima2p_engine * e, long long total_events, uint64_t * out10);
+int ima2p_engine_put_state_block (ima2p_engine * e, const void *block, long long total_events, void *cuda_stream);
+int ima2p_engine_put_state_packed (ima2p_engine * e, const void *topo8, const void *time, const void *mcount,
+                                   const void *mig_t, const void *mig_p, const void *scal_i, const void *scal_d,
+                                   const void *uvals, const double *tvals, void *cuda_stream);
 /* per-pair summaries of the current genealogies: sd[P][4] = {roottime, length, tlength, pdg}, si[P][2] = {root, mignum},
  * wi[P][NI] = coalescence | migration counts (struct genealogy fields imamp.hpp:956-987); NULL pointers are skipped */
 int ima2p_engine_fetch_pair_summaries (ima2p_engine * e, double *sd, int *si, int *wi, void *cuda_stream);

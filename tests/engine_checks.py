@@ -595,3 +595,58 @@ def full_size_workload_properties(lib, nloci, nchains, nsteps, noracle=48, seed=
         assert rel_close(fresh["probg"], inc[c]["probg"], 1e-9) and rel_close(fresh["pdg"], inc[c]["pdg"], 1e-9)
     eng.close()
     return cnt
+
+
+def packed_upload_equals_plain_upload(lib, nloci=10, nchains=5, nsteps=60):
+    """ima2p_engine_put_state_packed / put_state_block (8-bit wire forms, widened on the device) load exactly the state put_state loads: the
+    same evaluation, and the same run afterwards.  The state is one with migration events (taken after some steps)."""
+    from ima2p_b200 import Engine, synth
+    keys = ["topo", "time", "mseg", "mig_t", "mig_p", "scal_i", "scal_d", "uvals"]
+
+    def make():
+        loci = synth.make_dataset(nloci, 15, 15, seed=11)
+        eng = Engine(nchains, nloci, mig_capacity=64, seed=9, lib=lib)
+        eng.set_model(**synth.two_population_model(10.0, 1.0))
+        for li, L in enumerate(loci):
+            eng.set_locus(li, 0, L["n"], L["numsites"], L["samppop"], seq=L["seq"])
+        eng.finalize()
+        eng.set_heating(1, 0.96, 0.9)
+        eng.set_update_priors(t_max=[3.0])
+        eng.set_update_schedule(3, 5)
+        return eng, loci
+    eng, loci = make()
+    st = synth.initial_state(loci, nchains, eng.NL, eng.CAP, t0=1.5, seed=100)
+    arrs = [np.ascontiguousarray(st[k]) for k in keys]
+    eng.put_state(arrs, st["tvals"])
+    eng.run(nsteps)
+    eng.sync()
+    eng.fetch_state(arrs[:7])
+    tv, uv, _ = eng.fetch_parameters()
+    arrs[7][...] = uv.reshape(arrs[7].shape)
+    assert arrs[5].reshape(-1, 2)[:, 1].max() > 0                 # there are migration events to carry
+    packed = Engine.pack_state(arrs[0].reshape(nchains * nloci, eng.NL, 4), arrs[2].reshape(nchains * nloci, eng.NL, 2))
+    assert packed is not None
+    outs = []
+    for mode in ("plain", "packed", "block"):
+        e2, _ = make()
+        if mode == "plain":
+            e2.put_state(arrs, tv)
+        elif mode == "packed":
+            e2.put_state_packed([packed[0], arrs[1], packed[1]] + arrs[3:], tv)
+        else:
+            blk, events = e2.pack_state_block(arrs, tv)
+            assert events == int(arrs[5].reshape(-1, 2)[:, 1].sum())
+            e2.put_state_block(blk, events)
+        e2.sync()
+        ev = [e2.chain(c) for c in range(nchains)]
+        e2.run(20)
+        e2.sync()
+        after = [e2.chain(c) for c in range(nchains)]
+        outs.append(np.concatenate([np.r_[c["probg"], c["pdg"], c["wd"], c["wi"]] for c in ev + after]))
+        back = [np.zeros_like(a) for a in arrs[:7]]
+        e2.fetch_state(back)
+        outs.append(np.concatenate([b.reshape(-1).astype(np.float64) for b in back[:3]]))
+        e2.close()
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+    assert np.array_equal(outs[0], outs[4]) and np.array_equal(outs[1], outs[5])
+    eng.close()

@@ -86,6 +86,10 @@ def test_full_size_workload_properties(lib, nloci, nchains, nsteps):
     ec.full_size_workload_properties(lib, nloci, nchains, nsteps)
 
 
+def test_packed_upload_equals_plain_upload(lib):
+    ec.packed_upload_equals_plain_upload(lib)
+
+
 def test_speculation_depth_does_not_change_the_run(lib):
     ec.speculation_depth_does_not_change_the_run(lib)
 

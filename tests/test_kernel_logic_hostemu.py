@@ -46,6 +46,10 @@ def test_workload_properties_small(emu):
     ec.full_size_workload_properties(emu, 12, 6, 40, noracle=16)
 
 
+def test_packed_upload_equals_plain_upload(emu):
+    ec.packed_upload_equals_plain_upload(emu)
+
+
 def test_speculation_depth_does_not_change_the_run(emu):
     ec.speculation_depth_does_not_change_the_run(emu, nsteps=25)
 
