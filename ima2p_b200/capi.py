@@ -100,6 +100,8 @@ SIGNATURES = {
     "ima2p_lmode_marginp": (_i, [_v, _i, _i, _i, c_dbl_p, _i, c_dbl_p]),
     "ima2p_lmode_jointp": (_i, [_v, c_dbl_p, _i, _i, c_dbl_p, c_dbl_p]),
     "ima2p_lmode_moments": (_i, [_v, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]),
+    "ima2p_lmode_moments_finish": (None, [_i, c_dbl_p, _ll, c_dbl_p, c_dbl_p, c_dbl_p]),
+    "ima2p_lmode_popmig_sums": (_i, [_v, _i, _i, c_dbl_p, _i, _i, _i, c_dbl_p]),
     "ima2p_lmode_popmig": (_i, [_v, _i, _i, c_dbl_p, _i, _i, c_dbl_p]),
     "ima2p_lmode_marginpopmig": (_i, [_v, _i, _i, _i, _i, c_dbl_p, _i, c_dbl_p]),
     "ima2p_lmode_greater_than": (_i, [_v, _i, _i, _i, c_dbl_p]),

@@ -759,7 +759,7 @@ struct Lmode {
   JointXs *d_xs = nullptr;
   size_t cap_x = 0, cap_partials = 0;
   struct LmPriors *d_pri = nullptr;            // section 8 (f3) evaluators: priors, logfact table and error word, made on first use
-  double *d_logfact = nullptr;
+  double *d_logfact = nullptr, *d_msums = nullptr;
   int *d_err = nullptr;
   MathCtx mc{};
   std::vector<void *> allocs;
@@ -1072,7 +1072,8 @@ int ima2p_lmode_moments(ima2p_lmode *h, double *means, double *variances, double
   stream_t s = lm_stream(&l, nullptr);
   const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
   if (!lm_grow_partials(l, (size_t)nchunks * nacc)) return lfail(IMA2P_E_CUDA, "device allocation failed");
-  double *d_sums = l.alloc<double>(nacc);
+  if (!l.d_msums) l.d_msums = l.alloc<double>(2 * kMomentsMaxParams + kMomentsMaxParams * (kMomentsMaxParams - 1) / 2);
+  double *d_sums = l.d_msums;
   if (!d_sums) return lfail(IMA2P_E_CUDA, "device allocation failed");
   IMA_LAUNCH(k_moments, nchunks, kLmWarps, (size_t)kLmWarps * nacc * sizeof(double), s, l.v, l.mc, l.d_pri, l.d_partials);
   IMA_LAUNCH(k_reduce_partials, (nacc + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_partials, nchunks, nacc, nacc, d_sums);
@@ -1082,30 +1083,36 @@ int ima2p_lmode_moments(ima2p_lmode *h, double *means, double *variances, double
   std::vector<double> sums(nacc);
   if (!d2h(sums.data(), d_sums, nacc * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
   if ((rc = lm_check_err(l, s, "moments"))) return rc;
-  const double G = (double)l.v.G;
+  std::vector<double> raw((size_t)2 * np + (size_t)np * np, 0.0);
+  for (int p = 0; p < np; p++) { raw[p] = sums[p]; raw[np + p] = sums[np + p]; }
+  {
+    int k = 2 * np;
+    for (int p = 0; p < np - 1; p++) for (int q = p + 1; q < np; q++, k++) raw[2 * np + p * np + q] = sums[k];
+  }
+  if (raw_sums) for (size_t i = 0; i < raw.size(); i++) raw_sums[i] = raw[i];
+  ima2p_lmode_moments_finish(np, raw.data(), l.v.G, means, variances, correlations);
+  return IMA2P_OK;
+}
+
+// the closing arithmetic of print_means_variances_correlations (output.cpp:709-739) on row sums (this GPU's, or the sums
+// over all ranks after an all-reduce): raw = {sum0[np], sum1[np], cross[np][np]}
+void ima2p_lmode_moments_finish(int np, const double *raw, long long nrows_total, double *means, double *variances, double *correlations) {
+  const double G = (double)nrows_total;
   for (int p = 0; p < np; p++) {
-    means[p] = sums[p]; variances[p] = sums[np + p];
+    means[p] = raw[p]; variances[p] = raw[np + p];
     if (means[p] >= 0.0) means[p] /= G;                                          // output.cpp:712-713
     if (variances[p] >= 0.0) { variances[p] /= G; variances[p] -= means[p] * means[p]; }   // :714-718
   }
   if (correlations) {
     for (int i = 0; i < np * np; i++) correlations[i] = 0.0;
-    int k = 2 * np;
     for (int p = 0; p < np - 1; p++)
-      for (int q = p + 1; q < np; q++, k++) {
-        double c = sums[k];
+      for (int q = p + 1; q < np; q++) {
+        double c = raw[2 * np + p * np + q];
         if (c >= 0.0) { c /= G; c -= means[p] * means[q]; c /= sqrt(variances[p] * variances[q]); }   // :731-737
         else c = -1.0;
         correlations[p * np + q] = c;
       }
   }
-  if (raw_sums) {
-    for (int i = 0; i < 2 * np + np * np; i++) raw_sums[i] = 0.0;
-    for (int p = 0; p < np; p++) { raw_sums[p] = sums[p]; raw_sums[np + p] = sums[np + p]; }
-    int k = 2 * np;
-    for (int p = 0; p < np - 1; p++) for (int q = p + 1; q < np; q++, k++) raw_sums[2 * np + p * np + q] = sums[k];
-  }
-  return IMA2P_OK;
 }
 
 // sums over rows [first, last) of the 2NM density terms; uniform prior: one pass; exponential prior: terms, maximum
@@ -1156,6 +1163,14 @@ static int lm_popmig_sums(Lmode &l, int thetai, int mi, const double *x, int nx,
     }
   }
   return lm_check_err(l, s, "popmig");
+}
+
+// row sums of the 2NM density terms over this GPU's rows [first, last) (uniform migration prior): additive over ranks, the
+// caller all-reduces them and divides by the number of rows as calc_popmig / marginpopmig do
+int ima2p_lmode_popmig_sums(ima2p_lmode *h, int thetai, int mi, const double *x, int nx, int first, int last, double *out) {
+  if (!h || !h->lm.d_cols || !x || !out) return lfail(IMA2P_E_ARG, "popmig_sums: bad argument / rows not loaded");
+  if (h->lm.v.expoprior) return lfail(IMA2P_E_ARG, "popmig_sums: with the exponential prior the terms are scaled by their largest exponent and are not additive");
+  return lm_popmig_sums(h->lm, thetai, mi, x, nx, first, last, out);
 }
 
 // calc_popmig popmig.cpp:9-97 / calc_pop_expomig :101-170 (the choice follows the model's migration prior)

@@ -470,6 +470,26 @@ class LMode:
         capi.check(self.lib, self.lib.ima2p_lmode_moments(self._h, _dp(means), _dp(var), _dp(corr), _dp(raw)))
         return means, var, corr, {"sum0": raw[:n].copy(), "sum1": raw[n:2 * n].copy(), "cross": raw[2 * n:].reshape(n, n).copy()}
 
+    def moments_raw(self):
+        """Row sums behind moments() over this handle's rows (additive over ranks), flat: sum0[np], sum1[np], cross[np][np]."""
+        n = self.nq + self.nm
+        means, var, raw = np.zeros(n), np.zeros(n), np.zeros(2 * n + n * n)
+        capi.check(self.lib, self.lib.ima2p_lmode_moments(self._h, _dp(means), _dp(var), None, _dp(raw)))
+        return raw
+
+    def moments_finish(self, raw, nrows_total):
+        n = self.nq + self.nm
+        raw = _f64(raw)
+        means, var, corr = np.zeros(n), np.zeros(n), np.zeros((n, n))
+        self.lib.ima2p_lmode_moments_finish(n, _dp(raw), int(nrows_total), _dp(means), _dp(var), _dp(corr))
+        return means, var, corr
+
+    def popmig_sums(self, thetai, mi, x, first=0, last=None):
+        x = _f64(np.atleast_1d(x))
+        out = np.zeros(len(x))
+        capi.check(self.lib, self.lib.ima2p_lmode_popmig_sums(self._h, thetai, mi, _dp(x), len(x), first, self.nrows if last is None else last, _dp(out)))
+        return out
+
     def popmig(self, thetai, mi, x, prob_or_like=0):
         """calc_popmig / calc_pop_expomig (popmig.cpp:9-170): density of 2NM at x, vectorised over x."""
         x = _f64(np.atleast_1d(x))

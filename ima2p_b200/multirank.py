@@ -154,3 +154,20 @@ def sharded_jointp(lm, x, calc_ess=True, device="cpu"):
         tot[4], tot[5] = allrec[k, v, 4], allrec[k, v, 5]
         q[v], ess[v] = lm.joint_finish(tot, gmax[v], calc_ess)
     return q, ess
+
+
+def sharded_moments(lm, device="cpu"):
+    """print_means_variances_correlations (output.cpp:687-745) over rows sharded across ranks: one all-reduce of the calcx row
+    sums (2 np + np^2 doubles), then the reference's closing arithmetic on the totals."""
+    raw = torch.from_numpy(lm.moments_raw()).to(device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(raw, op=dist.ReduceOp.SUM)
+    return lm.moments_finish(raw.cpu().numpy(), lm.nrows_total)
+
+
+def sharded_popmig(lm, thetai, mi, x, device="cpu"):
+    """calc_popmig with prob_or_like = 0 (popmig.cpp:9-97, uniform migration prior) over rows sharded across ranks."""
+    sums = torch.from_numpy(lm.popmig_sums(thetai, mi, x)).to(device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    return sums.cpu().numpy() / lm.nrows_total

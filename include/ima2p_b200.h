@@ -270,6 +270,13 @@ void ima2p_lmode_joint_finish (const double *rec6, double globalmax, long long n
  * variances[np] (E[x^2] - mean^2), correlations[np][np] (entries p < q; may be NULL); np = nq + nm <= 32.  raw_sums
  * (may be NULL) receives the row sums themselves: [np] of calcx(.,p,0), [np] of calcx(.,p,1), [np][np] of the products. */
 int ima2p_lmode_moments (ima2p_lmode * l, double *means, double *variances, double *correlations, double *raw_sums);
+/* sharded rows: every rank calls moments (raw_sums) / popmig_sums on its rows, the caller all-reduces the sums and finishes:
+ * moments_finish is the closing arithmetic of output.cpp:709-739 on the summed raw_sums; the summed popmig_sums divided by
+ * the total number of rows are calc_popmig's mean (uniform migration prior only) */
+void ima2p_lmode_moments_finish (int np, const double *raw_sums, long long nrows_total, double *means, double *variances,
+                                 double *correlations);
+int ima2p_lmode_popmig_sums (ima2p_lmode * l, int thetai, int mi, const double *x, int nx, int first, int last,
+                             double *out_sums);
 /* density of the product 2NM = theta_thetai * m_mi / 2 at x[nx]: calc_popmig (popmig.cpp:9-97) or, when the handle was
  * created with the exponential migration prior, calc_pop_expomig (:101-170); prob_or_like = 1 divides by the prior density */
 int ima2p_lmode_popmig (ima2p_lmode * l, int thetai, int mi, const double *x, int nx, int prob_or_like, double *out);

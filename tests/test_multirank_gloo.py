@@ -133,3 +133,55 @@ def test_lmode_sharded_over_two_ranks_matches_reference():
     for _, qv, ess, mc in got:          # every rank ends with the same, reference-matching values
         assert rel_close(qv, ref_q, 1e-10) and rel_close(ess, ref_e, 1e-8)
         assert rel_close(mc, ref_mc, 1e-10)
+
+
+def _lmode_extra_worker(rank, world, port, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ima2p_b200 import LMode, capi
+    from ima2p_b200.multirank import sharded_moments, sharded_popmig
+    from support import FlatModel, load_golden
+    d = load_golden("lmode_extra_sim5_hn2")
+    fm = FlatModel(d["model"])
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    G = len(rows)
+    cut = [0, G // 3 + 7, G]
+    lm = LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=capi.bind(EMU))
+    lm.load(rows[cut[rank]:cut[rank + 1]], nrows_total=G, row0=cut[rank])
+    means, var, corr = sharded_moments(lm)
+    sel = [t for t in d["popmig"] if t[0] == 1 and t[1] == 0]
+    pm = sharded_popmig(lm, 1, 0, np.array([t[2] for t in sel]))
+    q.put((rank, means, var, corr, pm))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lmode_moments_and_popmig_sharded_over_two_ranks_match_reference():
+    """section 8 (f3) evaluators with the rows split over two ranks: all-reduced row sums, the reference's values."""
+    from support import _num, load_golden, rel_close
+    subprocess.run([os.path.join(HERE, "hostemu", "build.sh")], check=True)
+    d = load_golden("lmode_extra_sim5_hn2")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_lmode_extra_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    G = len(d["rows"])
+    n = len(d["calcx"]["sum0"])
+    rm = np.array([_num(v) for v in d["calcx"]["sum0"]]) / G
+    rv = np.array([_num(v) for v in d["calcx"]["sum1"]]) / G - rm * rm
+    rc = np.array([_num(v) for v in d["calcx"]["cross"]]).reshape(n, n)
+    ref_pm = [_num(t[3]) for t in d["popmig"] if t[0] == 1 and t[1] == 0]
+    for _, means, var, corr, pm in got:
+        assert rel_close(means, rm, 1e-10) and rel_close(var, rv, 1e-7)
+        for a in range(n - 1):
+            for b in range(a + 1, n):
+                assert abs(corr[a, b] - (rc[a, b] / G - rm[a] * rm[b]) / np.sqrt(rv[a] * rv[b])) < 1e-6
+        assert rel_close(pm, ref_pm, 1e-10, 1e-300)
