@@ -2281,3 +2281,375 @@ ora_nw_migweight (const ora_model * m, const double *tvals, int period, double n
 #undef POPA
 #undef ISDROP
 }
+
+/* ---- section 8 (f3): the other evaluators over the sampled-genealogy rows ---------------------------------- */
+#define MINPARAMVAL 0.0000001   /* imamp.hpp:130 */
+#define SQR(x) ((x)*(x))
+
+/* calcx output.cpp:14-134 */
+double
+ora_calcx (const ora_model * m, const float *rows, int rowlen, int ei, int pnum, int mode)
+{
+  int nq = m->nq, nm = m->nm, cc, mc, p = pnum;
+  int ccp = 0, fcp = nq, hccp = 2 * nq, mcp = 3 * nq, fmp = mcp + nm, qip = fmp + nm, mip = qip + nq;
+  const float *g = rows + (size_t) ei * rowlen;
+  double fc, fm, hval, denom, max, tempval;
+  if (p < nq)
+  {
+    if (m->q_max[p] <= MINPARAMVAL)
+      return -1;
+    cc = (int) g[ccp + p];
+    fc = g[fcp + p];
+    hval = g[hccp + p];
+    denom = g[qip + p];
+    max = m->q_max[p];
+    if (mode == 0)
+    {
+      if (cc == 0 && fc == 0)
+        tempval = (SQR (max) / 2) / exp (denom);
+      else if (cc > 1)
+        tempval = exp (2 * LOG2 - hval + (2 - cc) * log (fc) + ora_uppergamma (cc - 2, 2 * fc / max) - denom);
+      else if (cc == 1)
+        tempval = exp (LOG2 - hval + log (max * exp (-2 * fc / max) - 2 * fc * exp (ora_uppergamma (0, 2 * fc / max))) - denom);
+      else
+        tempval = exp (log ((max / 2) * (max - 2 * fc) * exp (-2 * fc / max) + 2 * SQR (fc) * exp (ora_uppergamma (0, 2 * fc / max))) - denom);
+    }
+    else
+    {
+      if (cc == 0 && fc == 0)
+        tempval = (max * SQR (max) / 3) / exp (denom);
+      else if (cc > 2)
+        tempval = exp (ora_uppergamma (cc - 3, 2 * fc / max) + 3 * LOG2 - hval + (3 - cc) * log (fc) - denom);
+      else if (cc == 2)
+        tempval = exp (2 * LOG2 - hval + log (max * exp (-2 * fc / max) - 2 * fc * exp (ora_uppergamma (0, 2 * fc / max))) - denom);
+      else if (cc == 1)
+        tempval = exp (-hval + log (max * (max - 2 * fc) * exp (-2 * fc / max) + 4 * SQR (fc) * exp (ora_uppergamma (0, 2 * fc / max))) - denom);
+      else
+        tempval = exp (-log (3.0) + log (max * (2 * SQR (fc) - fc * max + SQR (max)) * exp (-2 * fc / max) - 4 * pow ((double) fc, 3.0) * exp (ora_uppergamma (0, 2 * fc / max))) - denom);
+    }
+  }
+  else
+  {
+    p -= nq;
+    if (m->m_max[p] <= MINPARAMVAL)
+      return -1;
+    mc = (int) g[mcp + p];
+    fm = g[fmp + p];
+    denom = g[mip + p];
+    max = m->m_max[p];
+    if (mode == 0)
+    {
+      if (mc == 0 && fm == 0)
+        tempval = (SQR (max) / 2) / exp (denom);
+      else if (mc > 0)
+        tempval = exp (ora_lowergamma (mc + 2, fm * max) - (mc + 2) * log (fm) - denom);
+      else
+        tempval = (1 - (1 + fm * max) * exp (-fm * max)) / SQR (fm) / exp (denom);
+    }
+    else
+    {
+      if (mc == 0 && fm == 0)
+        tempval = (pow (max, 3.0) / 3) / exp (denom);
+      else
+        tempval = exp (ora_lowergamma (mc + 3, fm * max) - (mc + 3) * log (fm) - denom);
+    }
+  }
+  return tempval;
+}
+
+/* the accumulation of print_means_variances_correlations output.cpp:704-728: sums[2 np + np*np] = sum0, sum1, cross (p < q) */
+void
+ora_moment_sums (const ora_model * m, const float *rows, int rowlen, int nrows, double *sums)
+{
+  int np = m->nq + m->nm, i, p, q;
+  for (i = 0; i < 2 * np + np * np; i++)
+    sums[i] = 0;
+  for (i = 0; i < nrows; i++)
+    for (p = 0; p < np; p++)
+    {
+      sums[p] += ora_calcx (m, rows, rowlen, i, p, 0);
+      sums[np + p] += ora_calcx (m, rows, rowlen, i, p, 1);
+    }
+  for (i = 0; i < nrows; i++)
+    for (p = 0; p < np - 1; p++)
+      for (q = p + 1; q < np; q++)
+        sums[2 * np + p * np + q] += ora_calcx (m, rows, rowlen, i, p, 0) * ora_calcx (m, rows, rowlen, i, q, 0);
+}
+
+/* row sum of calc_popmig / marginpopmig popmig.cpp:26-90, 209-263 (uniform migration prior) over rows [first, last) */
+double
+ora_popmig_sum (const ora_model * m, const float *rows, int rowlen, int first, int last, int thetai, int mi, double x)
+{
+  int nq = m->nq, nm = m->nm, ei, cc, mc;
+  int ccp = thetai, fcp = nq + thetai, hcp = 2 * nq + thetai, mcp = 3 * nq + mi, fmp = 3 * nq + nm + mi, qip = 3 * nq + 2 * nm + thetai,
+    mip = 4 * nq + 2 * nm + mi;
+  double sum = 0, temp1, temp2, fc, fm, hc, qintg, mintg, mmax = m->m_max[mi], qmax = m->q_max[thetai], a, b;
+  for (ei = first; ei < last; ei++)
+  {
+    const float *g = rows + (size_t) ei * rowlen;
+    cc = (int) g[ccp];
+    fc = (double) g[fcp];
+    hc = (double) g[hcp];
+    mc = (int) g[mcp];
+    fm = (double) g[fmp];
+    qintg = (double) g[qip];
+    mintg = (double) g[mip];
+    if (fc == 0 && cc == 0 && fm > 0)
+    {
+      temp1 = LOG2 - (mc * log (fm)) - hc - qintg - mintg;
+      temp2 = log (exp (ora_uppergamma (mc, 2 * fm * x / qmax)) - exp (ora_uppergamma (mc, mmax * fm)));
+    }
+    else if (fm == 0 && mc == 0 && fc > 0)
+    {
+      temp1 = LOG2 - (cc * log (fc)) - hc - qintg - mintg;
+      temp2 = log (exp (ora_uppergamma (cc, 2 * fc / qmax)) - exp (ora_uppergamma (cc, fc * mmax / x)));
+    }
+    else if (fc == 0 && cc == 0 && mc == 0 && fm == 0)
+    {
+      temp1 = log (2 * log (mmax * qmax / (2 * x))) - hc - qintg - mintg;
+      temp2 = 0;
+    }
+    else
+    {
+      temp1 = LOG2 + (mc * log (x)) - ((cc + mc) * log (fc + fm * x)) - hc - qintg - mintg;
+      a = ora_uppergamma (cc + mc, 2 * (fc + fm * x) / qmax);
+      b = ora_uppergamma (cc + mc, mmax * (fm + fc / x));
+      if (a == b)
+      {
+        b = ora_lowergamma (cc + mc, 2 * (fc + fm * x) / qmax);
+        a = ora_lowergamma (cc + mc, mmax * (fm + fc / x));
+      }
+      if (a > b)
+        logdiff (&temp2, a, b);
+      else
+        temp1 = temp2 = 0.0;
+    }
+    if ((temp1 + temp2 < 700) && (temp1 + temp2 > -700))
+      sum += exp (temp1 + temp2);
+  }
+  return sum;
+}
+
+/* greater-than probabilities gtint.cpp:26-330.  The integrands read file-static row values there; here they take them in
+ * a struct.  qtrap / trapzd (:83-125) keep the running estimate s between refinements exactly as the static does. */
+struct gtrow
+{
+  int cci, ccj, wi, wj;
+  double fci, fcj, hval, denom, qmax, fmi, fmj, mmax;
+};
+
+static double
+gt_mig_integrand (const struct gtrow *r, double mi)     /* mgt_wj_gt_0 :26-47 */
+{
+  double temp1, temp2, a, b;
+  if (mi < MINPARAMVAL)
+    return 0.0;
+  a = ora_logfact (r->wj);
+  b = ora_uppergamma (r->wj + 1, r->fmj * mi);
+  if (a <= b)
+    return 0.0;
+  if ((a - b) < 1e-15)
+    temp1 = ora_lowergamma (r->wj + 1, r->fmj * mi);
+  else
+    logdiff (&temp1, a, b);
+  temp2 = r->wi * log (mi) - r->fmi * mi - (r->wj + 1) * log (r->fmj) + temp1;
+  temp2 -= r->denom;
+  return exp (temp2);
+}
+
+static double
+gt_pop_integrand (const struct gtrow *r, double qi)     /* pgt_fcj_gt_0 :49-79 */
+{
+  double fcj2, fci2, temp1, temp2, temp3, a, b;
+  if (qi < MINPARAMVAL)
+    return 0.0;
+  fcj2 = 2 * r->fcj;
+  fci2 = 2 * r->fci;
+  if (r->ccj == 0)
+  {
+    a = log (qi) - fcj2 / qi;
+    b = log (fcj2) + ora_uppergamma (0, fcj2 / qi);
+    if (a > b)
+    {
+      logdiff (&temp1, a, b);
+      temp2 = -fci2 / qi + r->cci * log (2 / qi);
+      temp3 = temp1 + temp2 - r->hval - r->denom;
+      return exp (temp3);
+    }
+    return 0.0;
+  }
+  temp1 = ora_uppergamma (r->ccj - 1, fcj2 / qi);
+  temp2 = LOG2 + r->cci * log (2 / qi) + (1 - r->ccj) * log (r->fcj) - fci2 / qi;
+  temp3 = temp2 + temp1 - r->hval - r->denom;
+  return exp (temp3);
+}
+
+static double
+gt_qtrap (double (*func) (const struct gtrow *, double), const struct gtrow *r, double a, double b)
+{
+  int j, k, it;
+  double s = 0, olds = -1.0e100, x, tnm, sum, del;
+  for (j = 1; j <= 20; j++)
+  {
+    if (j == 1)
+      s = 0.5 * (b - a) * (func (r, a) + func (r, b));
+    else
+    {
+      for (it = 1, k = 1; k < j - 1; k++)
+        it <<= 1;
+      tnm = it;
+      del = (b - a) / tnm;
+      x = a + 0.5 * del;
+      for (sum = 0.0, k = 1; k <= it; k++, x += del)
+        sum += func (r, x);
+      s = 0.5 * (s + (b - a) * sum / tnm);
+    }
+    if (j > 5)
+      if (fabs (s - olds) < 1.0e-4 * fabs (olds) || (s == 0.0 && olds == 0.0))
+        return s;
+    olds = s;
+  }
+  return s;
+}
+
+/* gtpops (kind 0, :248-318) / gtmig (kind 1, :128-245) over the rows print_greater_than_tests uses (:341-351) */
+double
+ora_greater_than (const ora_model * m, const float *rows, int rowlen, int nrows, int kind, int pi, int pj)
+{
+  int nq = m->nq, nm = m->nm, ei, treeinc = 1, hitreenum = nrows, numtreesused = nrows;
+  int ccp = 0, fcp = nq, hccp = 2 * nq, mcp = 3 * nq, fmp = mcp + nm, qip = fmp + nm, mip = qip + nq;
+  double sum = 0, temp, temp1, temp2, temp3, temp4, a, b, c;
+  struct gtrow r;
+  if (nrows > 20000)
+  {
+    treeinc = nrows / 20000;
+    numtreesused = 20000;
+    hitreenum = treeinc * 20000;
+  }
+  for (ei = 0; ei < hitreenum; ei += treeinc)
+  {
+    const float *g = rows + (size_t) ei * rowlen;
+    if (kind == 0)
+    {
+      double qmax = r.qmax = m->q_max[pi], fci, hval, denom;
+      int cci;
+      cci = r.cci = (int) g[ccp + pi];
+      r.ccj = (int) g[ccp + pj];
+      fci = r.fci = g[fcp + pi];
+      r.fcj = g[fcp + pj];
+      hval = r.hval = g[hccp + pi] + g[hccp + pj];      /* float sums, as :266-267 */
+      denom = r.denom = g[qip + pi] + g[qip + pj];
+      if (r.ccj == 0 && r.fcj == 0)
+      {
+        if (fci == 0)
+          temp = exp (2.0 * log (qmax) - LOG2 - hval - denom);
+        else if (cci >= 2)
+        {
+          temp1 = 2 * LOG2 + (2 - cci) * log (fci);
+          temp2 = ora_uppergamma (cci - 2, 2 * fci / qmax);
+          temp = exp (temp1 + temp2 - hval - denom);
+        }
+        else if (cci == 1)
+        {
+          temp1 = 4 * fci * exp (ora_uppergamma (0, 2 * fci / qmax));
+          temp2 = 2 * qmax * exp (-2 * fci / qmax) - temp1;
+          temp = exp (log (temp2) - hval - denom);
+        }
+        else
+        {
+          temp1 = exp (ora_uppergamma (0, 2 * fci / qmax));
+          temp2 = (qmax / 2) * (qmax - 2 * fci) * exp (-2 * fci / qmax) + 2 * fci * fci * temp1;
+          temp = exp (log (temp2) - hval - denom);
+        }
+      }
+      else
+        temp = gt_qtrap (gt_pop_integrand, &r, MINPARAMVAL, qmax);
+    }
+    else
+    {
+      double mmax = r.mmax = m->m_max[pi], fmi, fmj, denom;
+      int wi;
+      fmi = r.fmi = g[fmp + pi];
+      fmj = r.fmj = g[fmp + pj];
+      wi = r.wi = (int) g[mcp + pi];
+      r.wj = (int) g[mcp + pj];
+      denom = r.denom = g[mip + pi] + g[mip + pj];      /* float sum, as :144 */
+      if (r.wj == 0)
+      {
+        if (fmj > 0.0)
+        {
+          if (wi > 0)
+          {
+            a = ora_logfact (wi);
+            b = ora_uppergamma (wi + 1, (fmi + fmj) * mmax);
+            c = ora_uppergamma (wi + 1, fmi * mmax);
+            if (a <= b || a <= c)
+              temp = 0.0;
+            else
+            {
+              if ((a - b) < 1e-15)
+                temp1 = ora_lowergamma (wi + 1, (fmi + fmj) * mmax);
+              else
+                logdiff (&temp1, a, b);
+              temp1 += -(wi + 1) * log (fmi + fmj);
+              if ((a - c) < 1e-15)
+                temp2 = ora_lowergamma (wi + 1, fmi * mmax);
+              else
+                logdiff (&temp2, a, c);
+              temp2 += -(wi + 1) * log (fmi);
+              if (temp2 <= temp1)
+                temp = 0.0;
+              else
+              {
+                logdiff (&temp3, temp2, temp1);
+                temp4 = temp3 - log (fmj) - denom;
+                temp = exp (temp4);
+              }
+            }
+          }
+          else if (fmi > 0.0)
+          {
+            temp1 = fmi * (exp (-(fmi + fmj) * mmax) - exp (-fmi * mmax));
+            temp2 = fmj * (1 - exp (-fmi * mmax));
+            temp3 = (temp1 + temp2) / (fmi * fmj * (fmi + fmj));
+            temp = exp (log (temp3) - denom);
+          }
+          else
+          {
+            temp1 = (fmj * mmax - 1.0 + exp (-fmj * mmax)) / (fmj * fmj);
+            temp = exp (log (temp1) - denom);
+          }
+        }
+        else if (wi > 0)
+        {
+          a = ora_logfact (wi + 1);
+          b = ora_uppergamma (wi + 2, fmi * mmax);
+          if (a <= b)
+            temp = 0.0;
+          else
+          {
+            if ((a - b) < 1e-15)
+              temp1 = ora_lowergamma (wi + 2, fmi * mmax);
+            else
+              logdiff (&temp1, a, b);
+            temp2 = -(wi + 2) * log (fmi);
+            temp = exp (temp2 + temp1 - denom);
+          }
+        }
+        else if (fmi > 0.0)
+        {
+          temp1 = (1.0 - exp (-fmi * mmax) * (fmi * mmax + 1.0)) / (fmi * fmi);
+          temp = exp (log (temp1) - denom);
+        }
+        else
+          temp = exp (log (mmax * mmax / 2.0) - denom);
+      }
+      else
+        temp = gt_qtrap (gt_mig_integrand, &r, MINPARAMVAL, mmax);
+    }
+    if (temp > 1.0)
+      temp = 1.0;
+    sum += temp;
+  }
+  return sum / numtreesused;
+}

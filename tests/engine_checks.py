@@ -650,3 +650,33 @@ def packed_upload_equals_plain_upload(lib, nloci=10, nchains=5, nsteps=60):
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
     assert np.array_equal(outs[0], outs[4]) and np.array_equal(outs[1], outs[5])
     eng.close()
+
+
+def lmode_f3_matches_oracle_on_bootstrapped_rows(lib, nrows, name="lmode_extra_sim5_hn2", seed=3, rtol=1e-9):
+    """section 8 (f3) on more rows than the reference fixtures hold: rows drawn with replacement (seeded) from a fixture's
+    rows, the device against the oracle on the same rows -- moment sums, the 2NM density row sums on a grid, and the
+    greater-than probabilities (with more than 20,000 rows that includes the reference's row thinning, gtint.cpp:341-351)."""
+    from ima2p_b200 import LMode
+    from support import OracleModel, oracle, fp, dp
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    src = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    rng = np.random.default_rng(seed)
+    rows = np.ascontiguousarray(src[rng.integers(0, len(src), size=nrows)])
+    G, rl = rows.shape
+    n = fm.nq + fm.nm
+    lm = LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=lib)
+    lm.load(rows)
+    om, ora = OracleModel(fm), oracle()
+    sums = np.zeros(2 * n + n * n)
+    ora.ora_moment_sums(om.h, fp(rows), rl, G, dp(sums))
+    assert rel_close(lm.moments_raw(), sums, rtol)
+    x = fm.q_max[0] * fm.m_max[0] / 2.0 * (np.arange(9) + 0.5) / 9.0
+    for ti, mi in ((0, 0), (fm.nq - 1, fm.nm - 1)):
+        ref = np.array([ora.ora_popmig_sum(om.h, fp(rows), rl, 0, G, ti, mi, float(v)) for v in x])
+        assert rel_close(lm.popmig_sums(ti, mi, x), ref, rtol, 1e-300)
+        half = np.array([ora.ora_popmig_sum(om.h, fp(rows), rl, G // 4, G // 2, ti, mi, float(v)) for v in x])
+        assert rel_close(lm.popmig_sums(ti, mi, x, G // 4, G // 2), half, rtol, 1e-300)
+    for kind, i, j in ((0, 0, 1), (0, 2, 0), (1, 0, 1), (1, 1, 0)):
+        assert rel_close(lm.greater_than(kind, i, j), ora.ora_greater_than(om.h, fp(rows), rl, G, kind, i, j), max(rtol, 1e-8)), (kind, i, j)
+    lm.close()

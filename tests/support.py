@@ -204,6 +204,13 @@ def oracle():
     lib.ora_margincalc.argtypes = [v, c_flt_p, i, i, d, d, i, i]
     lib.ora_jointp.restype = d
     lib.ora_jointp.argtypes = [v, c_flt_p, i, i, c_dbl_p, i, c_dbl_p]
+    lib.ora_calcx.restype = d
+    lib.ora_calcx.argtypes = [v, c_flt_p, i, i, i, i]
+    lib.ora_moment_sums.argtypes = [v, c_flt_p, i, i, c_dbl_p]
+    lib.ora_popmig_sum.restype = d
+    lib.ora_popmig_sum.argtypes = [v, c_flt_p, i, i, i, i, i, d]
+    lib.ora_greater_than.restype = d
+    lib.ora_greater_than.argtypes = [v, c_flt_p, i, i, i, i, i]
     lib.ora_getnewt.restype = d
     lib.ora_getnewt.argtypes = [d, i, i, i, d, d, d]
     lib.ora_ry1_rescale.argtypes = [i, c_int_p, c_dbl_p, i, c_dbl_p, c_dbl_p, i, i, d, d, d, d, c_int_p]

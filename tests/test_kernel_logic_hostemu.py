@@ -50,6 +50,10 @@ def test_packed_upload_equals_plain_upload(emu):
     ec.packed_upload_equals_plain_upload(emu)
 
 
+def test_lmode_f3_matches_oracle_on_bootstrapped_rows(emu):
+    ec.lmode_f3_matches_oracle_on_bootstrapped_rows(emu, 2500)
+
+
 def test_speculation_depth_does_not_change_the_run(emu):
     ec.speculation_depth_does_not_change_the_run(emu, nsteps=25)
 

@@ -173,6 +173,31 @@ def test_lmode_matches_reference(name):
         assert rel_close(ess.value, j["ess"], 1e-10)
 
 
+@pytest.mark.parametrize("name", ["lmode_extra_sim5_hn2", "lmode_extra_sim5_3pop_hn2"])
+def test_moments_popmig_greater_than_match_reference(name):
+    """section 8 (f3) restatements (calcx, the 2NM density, the greater-than probabilities) against the reference's values."""
+    d = load_golden(name)
+    fm = FlatModel(d["model"])
+    om = OracleModel(fm)
+    lib = oracle()
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    G, rl = rows.shape
+    n = fm.nq + fm.nm
+    for g, p, x0, x1 in d["calcx"]["sample"]:
+        assert rel_close(lib.ora_calcx(om.h, fp(rows), rl, g, p, 0), _num(x0), 1e-12)
+        assert rel_close(lib.ora_calcx(om.h, fp(rows), rl, g, p, 1), _num(x1), 1e-12)
+    sums = np.zeros(2 * n + n * n)
+    lib.ora_moment_sums(om.h, fp(rows), rl, G, dp(sums))
+    assert rel_close(sums[:n], [_num(v) for v in d["calcx"]["sum0"]], 1e-12)
+    assert rel_close(sums[n:2 * n], [_num(v) for v in d["calcx"]["sum1"]], 1e-12)
+    assert rel_close(sums[2 * n:], [_num(v) for v in d["calcx"]["cross"]], 1e-12)
+    for ti, mi, x, dens, _post, mp_all, mp_mid in d["popmig"][::3]:
+        assert rel_close(lib.ora_popmig_sum(om.h, fp(rows), rl, 0, G, ti, mi, x) / G, _num(dens), 1e-12, 1e-300)
+        assert rel_close(-lib.ora_popmig_sum(om.h, fp(rows), rl, G // 3, 2 * G // 3, ti, mi, x) / (2 * G // 3 - G // 3), _num(mp_mid), 1e-12, 1e-300)
+    for kind, i, j, v in d["greater_than"]:
+        assert rel_close(lib.ora_greater_than(om.h, fp(rows), rl, G, kind, i, j), _num(v), 1e-12), (kind, i, j)
+
+
 def test_ti_row_packer_matches_reference_rows():
     # savegsampinf (ginfo.cpp:318-377): the fixture's state dump and the row layout must agree on a chain
     d = load_golden("state_sim5_hn4")
