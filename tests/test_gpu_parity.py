@@ -91,7 +91,7 @@ def test_packed_upload_equals_plain_upload(lib):
 
 
 def test_lmode_f3_matches_oracle_on_bootstrapped_rows(lib):
-    ec.lmode_f3_matches_oracle_on_bootstrapped_rows(lib, 30000)
+    ec.lmode_f3_matches_oracle_on_bootstrapped_rows(lib, 200000)
 
 
 def test_speculation_depth_does_not_change_the_run(lib):
