@@ -375,7 +375,7 @@ def main():
         bptr, nev = pinned["block"].data_ptr(), blk[1]
         put, wire = (lambda: eng.put_state_block(bptr, nev, stream)), "put_state_block"
         h2d = int(pinned["block"].numel())
-    for _ in range(3):
+    for _ in range(10):           # the first transfers from a freshly pinned buffer are slow on this (virtualised) PCIe path
         put(); run_steps(1); eng.step_report(stream)
     barrier()
     t0 = time.perf_counter()
@@ -492,6 +492,22 @@ def lmode_bench(eng, dev, G=1000000):
     t2 = time.perf_counter()
     lm.jointp(xs)
     t3 = time.perf_counter()
+    # section 8 (f3) evaluators over the same rows: one unit = one genealogy contributing to one evaluation
+    lm.moments()
+    t4 = time.perf_counter()
+    lm.moments()                                      # calcx of 5 parameters in 2 modes per row + the 10 products
+    t5 = time.perf_counter()
+    xg = (np.arange(100) + 0.5) / 100 * PRIOR_Q * PRIOR_M / 2
+    lm.popmig(0, 0, xg[:8])
+    t6 = time.perf_counter()
+    for ti, mi in ((0, 0), (1, 1)):
+        lm.popmig(ti, mi, xg)                         # the 100-bin scan of marginalopt_popmig, 2NM of both populations
+    t7 = time.perf_counter()
+    lm.greater_than(0, 0, 1)
+    t8 = time.perf_counter()
+    for a, b in ((0, 1), (1, 0), (0, 2), (2, 0)):
+        lm.greater_than(0, a, b)                      # quadrature over 20,000 rows each (USETREESMAX)
+    t9 = time.perf_counter()
     lm.close()
     # the marginal kernel serves 8 evaluation points per pass over the rows (4 columns for a size parameter, 3 for a migration
     # parameter, 4 bytes each): bytes it streams, against the HBM figure; the 84 MB of rows stay in the 126 MB L2 after
@@ -502,7 +518,10 @@ def lmode_bench(eng, dev, G=1000000):
     return {"rows": G, "margincalc_geneval_per_sec": 5 * 1000 * G / (t1 - t0), "jointp_geneval_per_sec": 64 * G / (t3 - t2),
             "unit": "genealogy evals/s", "timing": "host wall clock around the C-ABI calls (includes H2D of x and D2H of results)",
             "margincalc_streamed_GBps": streamed / (t1 - t0) / 1e9, "margincalc_streamed_frac_of_hbm_peak": streamed / (t1 - t0) / 1e9 / pk["hbm_gbs"],
-            "margincalc_algorithmic_GBps_one_pass_per_x": 5 * 1000 * G * 15.2 / (t1 - t0) / 1e9}
+            "margincalc_algorithmic_GBps_one_pass_per_x": 5 * 1000 * G * 15.2 / (t1 - t0) / 1e9,
+            "moments_geneval_per_sec": 10 * G / (t5 - t4), "popmig_geneval_per_sec": 200 * G / (t7 - t6),
+            "greater_than_rows_per_sec": 4 * 20000 / (t9 - t8),
+            "f3_note": "calcx: 2 incomplete gammas per parameter and row; 2NM density: 2-4 per row and point; greater-than: a trapezoid quadrature of incomplete gammas per row -- FP64-bound"}
 
 
 def lmode_bench_sharded(eng, dev, rank, world, step_multi, G=1000000):
