@@ -14,10 +14,12 @@
 //
 // is L mode (LOAD-GENEALOGY, ima_main_mpi.cpp:3216-3440, 4037-4100): the rows of BASE.ti are loaded onto the device and the
 // report sections that are sums over every sampled genealogy are written in the reference's own layout -- the means /
-// variances / correlations table (output.cpp:687-838), with -p6 the greater-than tables (gtint.cpp:336-447), and the
-// histogram group of the population-size and migration parameters (histograms.cpp:81-99, 146-431, 541-567).
+// variances / correlations table (output.cpp:687-838), with -p6 the greater-than tables (gtint.cpp:336-447), the marginal
+// peak table (surface_call_functions.cpp:175-732 over surface_search_functions.cpp:41-187) and the histogram group of the
+// population-size and migration parameters (histograms.cpp:81-99, 146-431, 541-567).
 #include "../../include/ima2p_b200.h"
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -270,6 +272,223 @@ void write_histograms(FILE *f, const std::vector<std::string> &name, const std::
   fprintf(f, "\n");
 }
 
+
+// ---- marginal peak search: surface_search_functions.cpp:41-187 (mnbrakmod, goldenmod), surface_call_functions.cpp:82-104
+// (marginbis), :175-274 (marginalopt), :277-297 (margin95), :316-732 (findmarginpeaks, without the 2NM terms of -p5).
+// The one-dimensional searches are the reference's, statement for statement; every function value is one call of the device
+// evaluator (ima2p_lmode_marginp over the row range of the set, ima2p_lmode_margincalc for the 95% bounds).
+struct PeakCtx { ima2p_lmode *LM; int first, last; };
+double peak_f(const PeakCtx &c, int param, double x) {
+  double v = 0.0;
+  ck(ima2p_lmode_marginp(c.LM, param, c.first, c.last, &x, 1, &v), "marginal density");
+  return v;
+}
+double nr_sign(double a, double b) { return b > 0.0 ? fabs(a) : -fabs(a); }
+
+void mnbrakmod(const PeakCtx &c, int param, double *ax, double *bx, double *cx, double *fa, double *fb, double *fc) {
+  const double gold = 1.618034, glimit = 100.0, tiny = (double)(float)1.0e-20;
+  double ulim, u, rr, q, fu, dum;
+  *fa = peak_f(c, param, *ax);
+  *fb = peak_f(c, param, *bx);
+  if (*fb > *fa) { dum = *ax; *ax = *bx; *bx = dum; dum = *fb; *fb = *fa; *fa = dum; }
+  *cx = fabs(*bx + gold * (*bx - *ax));
+  *fc = peak_f(c, param, *cx);
+  while (*fb >= *fc && *fb > -DBL_MAX && !(*fb == 0 && *fc == 0)) {
+    rr = (*bx - *ax) * (*fb - *fc);
+    q = (*bx - *cx) * (*fb - *fa);
+    const double dq = fabs(q - rr) > tiny ? fabs(q - rr) : tiny;
+    u = *bx - ((*bx - *cx) * q - (*bx - *ax) * rr) / (2.0 * nr_sign(dq, q - rr));
+    ulim = *bx + glimit * (*cx - *bx);
+    if ((*bx - u) * (u - *cx) > 0.0) {
+      fu = peak_f(c, param, u);
+      if (fu < *fc) { *ax = *bx; *fa = *fb; *bx = u; *fb = fu; continue; }
+      if (fu > *fb) { *cx = u; *fc = fu; continue; }
+      u = *cx + gold * (*cx - *bx);
+      fu = peak_f(c, param, u);
+    } else if ((*cx - u) * (u - ulim) > 0.0) {
+      fu = peak_f(c, param, u);
+      if (fu < *fc) {
+        *bx = *cx; *cx = u; u = *cx + gold * (*cx - *bx);
+        *fb = *fc; *fc = fu;
+        fu = peak_f(c, param, u);
+      }
+    } else if ((u - ulim) * (ulim - *cx) >= 0.0) {
+      u = ulim;
+      fu = peak_f(c, param, u);
+    } else {
+      u = *cx + gold * (*cx - *bx);
+      fu = peak_f(c, param, u);
+    }
+    *ax = *bx; *bx = *cx; *cx = u;
+    *fa = *fb; *fb = *fc; *fc = fu;
+  }
+}
+
+double goldenmod(const PeakCtx &c, int param, double ax, double bx, double cx, double tol, double *xmin) {
+  const double r = 0.61803399, cc = 1.0 - r;
+  double f1, f2, x0 = ax, x1, x2, x3 = cx;
+  if (fabs(cx - bx) > fabs(bx - ax)) { x1 = bx; x2 = bx + cc * (cx - bx); }
+  else { x2 = bx; x1 = bx - cc * (bx - ax); }
+  f1 = peak_f(c, param, x1);
+  f2 = peak_f(c, param, x2);
+  while (fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2)) && (x3 > -DBL_MAX)) {
+    if (f2 < f1) { x0 = x1; x1 = x2; x2 = r * x1 + cc * x3; f1 = f2; f2 = peak_f(c, param, x2); continue; }
+    x3 = x2; x2 = x1; x1 = r * x2 + cc * x0; f2 = f1; f1 = peak_f(c, param, x1);
+  }
+  if (f1 < f2) { *xmin = x1; return f1; }
+  *xmin = x2;
+  return f2;
+}
+
+// marginalopt :175-274, with its bracketing-consistency test as written (including the unconditional block of :233-237)
+void marginalopt(const PeakCtx &c, const std::vector<double> &prior_max, double *mlval, double *peakloc) {
+  const double kMinParam = 0.0000001;
+  for (int i = 0; i < (int)prior_max.size(); i++) {
+    const double prior = prior_max[i];
+    double ax = prior, bx = prior / 2, cx = 0, fa, fb, fc;
+    mnbrakmod(c, i, &ax, &bx, &cx, &fa, &fb, &fc);
+    double axt = ax, bxt = bx, cxt = cx;
+    bx = prior / 2;
+    ax = kMinParam;
+    mnbrakmod(c, i, &ax, &bx, &cx, &fa, &fb, &fc);
+    double min0 = 0, max0 = 0, min1 = 0, max1 = 0;
+    if (axt < bxt && axt < cxt) min0 = axt;
+    if (bxt < axt && bxt < cxt) min0 = bxt;
+    if (cxt < axt && cxt < bxt) min0 = cxt;
+    if (axt > bxt && axt > cxt) { if (axt > prior) axt = prior; max0 = axt; }
+    if (bxt > axt && bxt > cxt) { if (bxt > prior) bxt = prior; max0 = bxt; }
+    if (cxt > axt && cxt > bxt) { if (cxt > prior) cxt = prior; max0 = cxt; }
+    if (ax < bx && ax < cx) min1 = ax;
+    if (bx < ax && bx < cx) min1 = bx;
+    if (cx < ax && cx < bx) min1 = cx;
+    if (ax > bx && ax > cx) max1 = ax;
+    { if (ax > prior) ax = prior; max1 = ax; }
+    if (bx > ax && bx > cx) { if (bx > prior) bx = prior; max1 = bx; }
+    if (cx > ax && cx > bx) { if (cx > prior) cx = prior; max1 = cx; }
+    if (max0 <= min1 || max1 <= min0) peakloc[i] = -1;
+    else {
+      double xmax = 0;
+      mlval[i] = -goldenmod(c, i, ax, bx, cx, 1e-7, &xmax);
+      peakloc[i] = xmax;
+    }
+  }
+}
+
+// margin95 :277-297 over marginbis :82-104 (root of log margincalc - yadjust by bisection, BISTOL 1e-4, 40 halvings)
+double margin95(ima2p_lmode *LM, const double *mlval, const double *peakloc, int pi, int upper, double prior) {
+  const double x1 = upper ? peakloc[pi] : 0.0000001, x2 = upper ? prior : peakloc[pi];
+  const double yadjust = log(mlval[pi]) - 1.92;
+  auto f = [&](double x) { double v = 0; ck(ima2p_lmode_margincalc(LM, pi, &x, 1, yadjust, 1, &v), "marginal density"); return v; };
+  double fl = f(x1), fmid = f(x2), dx, rtb, xmid;
+  if (fl * fmid >= 0.0) return DBL_MIN;
+  if (fl < 0.0) { dx = x2 - x1; rtb = x1; } else { dx = x1 - x2; rtb = x2; }
+  for (int j = 1; j <= 40; j++) {
+    fmid = f(xmid = rtb + (dx *= 0.5));
+    if (fmid <= 0.0) rtb = xmid;
+    if (fabs(dx) < 1e-4 || fmid == 0.0) return rtb;
+  }
+  return DBL_MAX;
+}
+
+// findmarginpeaks :316-732
+void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vector<std::string> &name, int nq, int nm, int nsplit,
+                          const std::vector<double> &prior_max, const std::vector<int> &pb, const std::vector<int> &pe) {
+  const int p = nq + nm, NT = 2;                      // NUMTREEINT
+  fprintf(f, "\nMarginal Peak Locations and Probabilities\n=========================================\n");
+  fprintf(f, "  peak locations are estimated using a peak finding algorithm, which may\n");
+  fprintf(f, "  fail if the curve has multiple peaks. All peaks can also be found, and\n");
+  fprintf(f, "  related analyses conducted, by plotting the histograms\n\n");
+  if (G <= 10) { fprintf(f, " TOO FEW TREES SAVED - MARGINAL VALUES NOT FOUND \n\n"); return; }
+  std::vector<std::vector<double>> mlval(NT + 1, std::vector<double>(p, 0.0)), peakloc(NT + 1, std::vector<double>(p, 0.0));
+  int firsttree = 0, lasttree = (int)G / NT;
+  for (int j = 0; j < NT; j++) {
+    PeakCtx c{LM, firsttree, lasttree};
+    marginalopt(c, prior_max, mlval[j].data(), peakloc[j].data());
+    firsttree = lasttree + 1;
+    lasttree += (int)G / NT;
+    if (lasttree > G) lasttree = (int)G;
+  }
+  PeakCtx all{LM, 0, (int)G};
+  marginalopt(all, prior_max, mlval[NT].data(), peakloc[NT].data());
+  std::vector<double> migtest(nm, 0.0);
+  for (int i = 0; i < nm; i++) {
+    const double maxp = -peak_f(all, i + nq, peakloc[NT][i + nq]), max0p = -peak_f(all, i + nq, 0.0000001);
+    migtest[i] = 2 * log(maxp / max0p);
+  }
+  bool errnote = false, signote = false;
+  static const char *sig[4] = {"ns", "*", "**", "***"};
+  for (int k = 0; k <= nsplit; k++) {
+    fprintf(f, "\nPeriod %d\n--------\n", k);
+    const int iihi = k < nsplit ? 2 : 1;
+    for (int ii = 1; ii <= iihi; ii++) {
+      const int ilo = ii == 1 ? 0 : nq, ihi = ii == 1 ? nq : p;
+      int nprint = 0;
+      if (ii == 1) {
+        fprintf(f, "Population Size Parameters\n Param:");
+        for (int i = 0; i < nq; i++) if (pb[i] == k) fprintf(f, "\t %s\tP", name[i].c_str());
+        fprintf(f, "\n");
+      } else {
+        for (int i = 0; i < nm; i++) nprint += pb[nq + i] == k;
+        if (nprint) {
+          fprintf(f, "Migration Rate Parameters\n Param:");
+          for (int i = 0; i < nm; i++) if (prior_max[nq + i] > 0.000001 && pb[nq + i] == k) fprintf(f, "\t %s\tP", name[nq + i].c_str());
+          fprintf(f, "\n");
+        }
+      }
+      if (ii == 2 && nprint == 0) continue;
+      for (int j = 0; j <= NT; j++) {
+        if (j < NT) fprintf(f, " Set%d", j); else fprintf(f, " All");
+        for (int i = ilo; i < ihi; i++)
+          if (pb[i] == k) {
+            if (peakloc[j][i] >= 0) fprintf(f, "\t%7.3lf\t%7.3lf", peakloc[j][i], mlval[j][i]);
+            else { fprintf(f, "\terror*\t"); errnote = true; }
+          }
+        fprintf(f, "\n");
+      }
+      fprintf(f, " LR95%%Lo");
+      for (int i = ilo; i < ihi; i++)
+        if (pb[i] == k) {
+          if (peakloc[NT][i] >= 0) {
+            const double t = margin95(LM, mlval[NT].data(), peakloc[NT].data(), i, 0, prior_max[i]);
+            if (t <= 0) fprintf(f, "\t<min\t");
+            else if (t >= DBL_MAX || t <= DBL_MIN) fprintf(f, "\tna\t");
+            else fprintf(f, "\t%7.3lf\t", t);
+          } else fprintf(f, "\t\t");
+        }
+      fprintf(f, "\n LR95%%Hi");
+      for (int i = ilo; i < ihi; i++)
+        if (pb[i] == k) {
+          if (peakloc[NT][i] >= 0) {
+            const double t = margin95(LM, mlval[NT].data(), peakloc[NT].data(), i, 1, prior_max[i]);
+            if (t >= prior_max[i] || t <= DBL_MIN) fprintf(f, "\t>max\t");
+            else fprintf(f, "\t%7.3lf\t", t);
+          } else fprintf(f, "\t\t");
+        }
+      fprintf(f, "\n");
+      if (ii == 2) {
+        fprintf(f, " LLRtest ");
+        for (int i = 0; i < nm; i++)
+          if (pb[nq + i] == k && prior_max[nq + i] > 0.000001) {
+            if (fabs(migtest[i]) > 1e6) fprintf(f, "bad value\t");
+            else {
+              const int lev = migtest[i] > 9.54954 ? 3 : migtest[i] > 5.41189 ? 2 : migtest[i] > 2.70554 ? 1 : 0;
+              if (lev == 3) signote = true;
+              fprintf(f, "%7.3lf%s\t", migtest[i], sig[lev]);
+            }
+          }
+        fprintf(f, "\n");
+      }
+      fprintf(f, " LastPeriod");
+      for (int i = ilo; i < ihi; i++)
+        if (pb[i] == k && (ii == 1 || prior_max[i] > 0.000001)) fprintf(f, "\t%d\t", pe[i]);
+      fprintf(f, "\n");
+    }
+  }
+  if (errnote) fprintf(f, "*  peak not found possibly due to multiple peaks (check plot of marginal density) \n");
+  if (signote) fprintf(f, " migration rate likelihood ratio test - see Nielsen and Wakeley (2001)\n migration significance levels :  * p < 0.05;   **  p < 0.01,   *** p < 0.001\n");
+  fprintf(f, "\n");
+}
+
 int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo) {
   int md[6];
   ima2p_modelspec_dims(S, md);
@@ -305,6 +524,15 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
     std::vector<double> mean(np), var(np), corr((size_t)np * np);
     ck(ima2p_lmode_moments(LM, mean.data(), var.data(), corr.data(), nullptr), "moments");
     print_moments(f, name, nq, mmx, mean, var, corr, npops);
+  }
+  {
+    // period in which a parameter first appears / ends: a size parameter lives with its population (poptree b, e), a
+    // migration parameter over the periods of its weight positions (initialize.cpp:237-243, 470-520)
+    std::vector<double> pmax;
+    std::vector<int> pb, pe;
+    for (int i = 0; i < nq; i++) { pmax.push_back(qmx[i]); pb.push_back(ptb[i]); pe.push_back(pte[i]); }
+    for (int i = 0; i < nm; i++) { pmax.push_back(mmx[i]); pb.push_back(mp[moff[i]]); pe.push_back(mp[moff[i + 1] - 1]); }
+    print_marginal_peaks(f, LM, nrows, name, nq, nm, nsplit, pmax, pb, pe);
   }
   // fillvec histograms.cpp:81-99: margincalc at the GRIDSIZE mid-bin points of every parameter (initialize.cpp:189-193, 237-242)
   std::vector<std::vector<double>> xs, ys;

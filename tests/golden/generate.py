@@ -278,14 +278,16 @@ def main():
         run("state", "parse_sw_joint", u3, 1, {"burn": 0})
     # L-mode report (section 8 f2/f4): the reference's own main() runs M mode on Sim3.u, then L mode (-r0 -v, -p6) on the .ti it
     # wrote; the .ti file and the report sections that the front end reproduces are kept
-    if not ONLY or "lmode_report_sim3" in ONLY:
-        base = os.path.join(TMP, "lrep_m.out")
-        common = ["-i", s3, "-q10", "-m1", "-t3"]
-        subprocess.run([HARNESS, "stock", os.path.join(TMP, "lrep_m.json"), "--"] + common + ["-o", base, "-b2000", "-l300", "-d10", "-hn2", "-hfl", "-ha0.9"],
-                       check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=600)
-        rep = os.path.join(TMP, "lrep_l.out")
-        subprocess.run([HARNESS, "stock", os.path.join(TMP, "lrep_l.json"), "--"] + common + ["-o", rep, "-r0", "-v", base, "-p6"],
-                       check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=600)
+    for rep_name, rep_u in (("lmode_report_sim3", s3), ("lmode_report_3pop", os.path.join(HERE, "inputs", "parse_is_3pop.u"))):
+        if ONLY and rep_name not in ONLY:
+            continue
+        base = os.path.join(TMP, rep_name + "_m.out")
+        common = ["-i", rep_u, "-q10", "-m1", "-t3"]
+        subprocess.run([HARNESS, "stock", os.path.join(TMP, rep_name + "_m.json"), "--"] + common + ["-o", base, "-b2000", "-l300", "-d10", "-hn2", "-hfl", "-ha0.9"],
+                       check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
+        rep = os.path.join(TMP, rep_name + "_l.out")
+        subprocess.run([HARNESS, "stock", os.path.join(TMP, rep_name + "_l.json"), "--"] + common + ["-o", rep, "-r0", "-v", base, "-p6"],
+                       check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
         text = open(rep).read()
 
         def section(start, end):
@@ -293,13 +295,14 @@ def main():
             return text[a:text.index(end, a)]
         keep = {"greater_than": section("\nPARAMETER COMPARISONS", "\nMEANS, VARIANCES"),
                 "moments": section("\nMEANS, VARIANCES", "\nMarginal Peak Locations"),
+                "peaks": section("\nMarginal Peak Locations", "\nHISTOGRAMS\n"),
                 "histograms": section("HISTOGRAM GROUP 2", " After\t")}
         import json
-        with gzip.GzipFile(os.path.join(HERE, "lmode_report_sim3.json.gz"), "wb", mtime=0) as g:
+        with gzip.GzipFile(os.path.join(HERE, rep_name + ".json.gz"), "wb", mtime=0) as g:
             g.write(json.dumps(keep).encode())
-        with open(base + ".ti", "rb") as f, gzip.GzipFile(os.path.join(HERE, "inputs", "lmode_report_sim3.ti.gz"), "wb", mtime=0) as g:
+        with open(base + ".ti", "rb") as f, gzip.GzipFile(os.path.join(HERE, "inputs", rep_name + ".ti.gz"), "wb", mtime=0) as g:
             shutil.copyfileobj(f, g)
-        print("wrote lmode_report_sim3.json.gz and inputs/lmode_report_sim3.ti.gz")
+        print("wrote %s.json.gz and inputs/%s.ti.gz" % (rep_name, rep_name))
     # the .mcf state file: written by the reference (inputs/*.mcf.gz) and by the engine (inputs/*_ours.mcf.gz), each
     # read back by the reference's readmcf and dumped
     for nm, uf, hn, burn in (("mcf_sim5_hn2", s5, 2, 60), ("mcf_sim3_sw_hn2", sw3, 2, 60), ("mcf_sim5_hky_hn2", hky5, 2, 30),

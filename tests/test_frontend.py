@@ -53,22 +53,27 @@ def test_run_from_u_file_to_ti_file(exe, tmp_path, name, genes):
     assert len(ti_load(str(tmp_path / "again") + ".ti", rowlen, lib=lib)) == 3
 
 
-def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path):
+@pytest.mark.parametrize("name", ["lmode_report_sim3", "lmode_report_3pop"])
+def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path, name):
     """-r0 -v: the genealogies the reference saved (its own .ti file) go through the device evaluators; the greater-than
-    tables, the means / variances / correlations table and the histogram group of the size and migration parameters must be
-    the reference's text, character for character (fixture: the reference's own L-mode report of the same file)."""
+    tables, the means / variances / correlations table, the marginal peak table (peak search, 95% bounds, migration
+    likelihood-ratio tests) and the histogram group of the size and migration parameters must be the reference's text,
+    character for character (fixtures: the reference's own L-mode reports of the same files; 2 and 3 populations)."""
     import gzip
     import json
     import shutil
-    ref = json.load(gzip.open(os.path.join(HERE, "golden", "lmode_report_sim3.json.gz")))
-    with gzip.open(os.path.join(INPUTS, "lmode_report_sim3.ti.gz"), "rb") as f, open(tmp_path / "ref.ti", "wb") as g:
+    ref = json.load(gzip.open(os.path.join(HERE, "golden", name + ".json.gz")))
+    with gzip.open(os.path.join(INPUTS, name + ".ti.gz"), "rb") as f, open(tmp_path / "ref.ti", "wb") as g:
         shutil.copyfileobj(f, g)
-    u = tmp_path / "Sim3.u"
-    u.write_text(_sim3_u())
+    if name == "lmode_report_3pop":
+        u = os.path.join(INPUTS, "parse_is_3pop.u")
+    else:
+        u = tmp_path / "Sim3.u"
+        u.write_text(_sim3_u())
     r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l.out"), "-q10", "-m1", "-t3", "-p6"])
     assert r.returncode == 0, r.stderr
     rep = open(tmp_path / "l.out").read()
-    for key in ("greater_than", "moments", "histograms"):
+    for key in ("greater_than", "moments", "peaks", "histograms"):
         assert ref[key].strip("\n") in rep, key
     r = _run(exe, ["-r0", "-i", str(u), "-o", str(tmp_path / "l2.out"), "-q10", "-m1", "-t3"])
     assert r.returncode == 8 and "-v" in r.stderr            # IMERR_MISSINGCOMMANDINFO
