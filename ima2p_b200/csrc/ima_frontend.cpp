@@ -10,7 +10,7 @@
 // row (savegsampinf) is appended to out.ti -> a short report.  Values are arguments attached to the flag ("-q10") or
 // the next word ("-q 10"), as the reference accepts.  Options of the reference outside this path are refused, not ignored.
 //
-//   IMa2p_b200 -r0 -v BASE -i data.u -o out -q QMAX -m MMAX -t TMAX [-j7] [-p6]
+//   IMa2p_b200 -r0 -v BASE -i data.u -o out -q QMAX -m MMAX -t TMAX [-j7] [-p5] [-p6]
 //
 // is L mode (LOAD-GENEALOGY, ima_main_mpi.cpp:3216-3440, 4037-4100): the rows of BASE.ti are loaded onto the device and the
 // report sections that are sums over every sampled genealogy are written in the reference's own layout -- the means /
@@ -277,10 +277,11 @@ void write_histograms(FILE *f, const std::vector<std::string> &name, const std::
 // (marginbis), :175-274 (marginalopt), :277-297 (margin95), :316-732 (findmarginpeaks, without the 2NM terms of -p5).
 // The one-dimensional searches are the reference's, statement for statement; every function value is one call of the device
 // evaluator (ima2p_lmode_marginp over the row range of the set, ima2p_lmode_margincalc for the 95% bounds).
-struct PeakCtx { ima2p_lmode *LM; int first, last; };
+struct PeakCtx { ima2p_lmode *LM; int first, last; int thetai; };      // thetai >= 0: the 2NM term of (thetai, migration parameter)
 double peak_f(const PeakCtx &c, int param, double x) {
   double v = 0.0;
-  ck(ima2p_lmode_marginp(c.LM, param, c.first, c.last, &x, 1, &v), "marginal density");
+  if (c.thetai >= 0) ck(ima2p_lmode_marginpopmig(c.LM, c.thetai, param, c.first, c.last, &x, 1, &v), "2NM density");
+  else ck(ima2p_lmode_marginp(c.LM, param, c.first, c.last, &x, 1, &v), "marginal density");
   return v;
 }
 double nr_sign(double a, double b) { return b > 0.0 ? fabs(a) : -fabs(a); }
@@ -374,6 +375,31 @@ void marginalopt(const PeakCtx &c, const std::vector<double> &prior_max, double 
   }
 }
 
+// marginalopt_popmig popmig.cpp:366-429: a 100-bin scan for the interval that holds the peak (one device call), then the
+// golden-section search on marginpopmig / marginpop_expomig
+struct PopMigTerm { int thetai, mi; std::string peakname, histname; };
+void marginalopt_popmig(ima2p_lmode *LM, int first, int last, const std::vector<PopMigTerm> &terms, const std::vector<double> &upper,
+                        double *mlval, double *peakloc) {
+  const int bins = 100;
+  const double kMinParam = 0.0000001;
+  for (size_t i = 0; i < terms.size(); i++) {
+    const double ub = upper[i];
+    std::vector<double> x(bins), fa(bins);
+    for (int j = 0; j < bins; j++) x[j] = kMinParam + j * (ub / (double)bins);
+    ck(ima2p_lmode_marginpopmig(LM, terms[i].thetai, terms[i].mi, first, last, x.data(), bins, fa.data()), "2NM density");
+    double maxf = 1e100; int maxj = -1;
+    for (int j = 0; j < bins; j++) if (fa[j] < maxf) { maxf = fa[j]; maxj = j; }
+    double ax, bx, cx;
+    if (maxj == 0) { ax = kMinParam; cx = kMinParam + ub / (double)bins; bx = (ax + cx) / 2.0; }
+    else if (maxj == bins - 1) { ax = kMinParam + ((double)bins - 1) * (ub / (double)bins); bx = kMinParam + ((double)bins - 2) * (ub / (double)bins); cx = ub; }
+    else { bx = kMinParam + ((double)maxj - 1) * (ub / (double)bins); cx = kMinParam + ((double)maxj + 1) * (ub / (double)bins); ax = kMinParam + ((double)maxj) * (ub / (double)bins); }
+    PeakCtx c{LM, first, last, terms[i].thetai};
+    double xmax = 0;
+    mlval[i] = -goldenmod(c, terms[i].mi, ax, bx, cx, 1e-7, &xmax);
+    peakloc[i] = xmax;
+  }
+}
+
 // margin95 :277-297 over marginbis :82-104 (root of log margincalc - yadjust by bisection, BISTOL 1e-4, 40 halvings)
 double margin95(ima2p_lmode *LM, const double *mlval, const double *peakloc, int pi, int upper, double prior) {
   const double x1 = upper ? peakloc[pi] : 0.0000001, x2 = upper ? prior : peakloc[pi];
@@ -392,7 +418,8 @@ double margin95(ima2p_lmode *LM, const double *mlval, const double *peakloc, int
 
 // findmarginpeaks :316-732
 void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vector<std::string> &name, int nq, int nm, int nsplit,
-                          const std::vector<double> &prior_max, const std::vector<int> &pb, const std::vector<int> &pe) {
+                          const std::vector<double> &prior_max, const std::vector<int> &pb, const std::vector<int> &pe,
+                          const std::vector<PopMigTerm> &terms, const std::vector<double> &term_upper) {
   const int p = nq + nm, NT = 2;                      // NUMTREEINT
   fprintf(f, "\nMarginal Peak Locations and Probabilities\n=========================================\n");
   fprintf(f, "  peak locations are estimated using a peak finding algorithm, which may\n");
@@ -400,20 +427,32 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
   fprintf(f, "  related analyses conducted, by plotting the histograms\n\n");
   if (G <= 10) { fprintf(f, " TOO FEW TREES SAVED - MARGINAL VALUES NOT FOUND \n\n"); return; }
   std::vector<std::vector<double>> mlval(NT + 1, std::vector<double>(p, 0.0)), peakloc(NT + 1, std::vector<double>(p, 0.0));
+  const int nt = (int)terms.size();                   // 2NM terms (-p5), in the order of the migration parameters' populations
+  std::vector<std::vector<double>> pmml(NT + 1, std::vector<double>(nt, 0.0)), pmpk(NT + 1, std::vector<double>(nt, 0.0));
   int firsttree = 0, lasttree = (int)G / NT;
   for (int j = 0; j < NT; j++) {
-    PeakCtx c{LM, firsttree, lasttree};
+    PeakCtx c{LM, firsttree, lasttree, -1};
     marginalopt(c, prior_max, mlval[j].data(), peakloc[j].data());
+    if (nt) marginalopt_popmig(LM, firsttree, lasttree, terms, term_upper, pmml[j].data(), pmpk[j].data());
     firsttree = lasttree + 1;
     lasttree += (int)G / NT;
     if (lasttree > G) lasttree = (int)G;
   }
-  PeakCtx all{LM, 0, (int)G};
+  PeakCtx all{LM, 0, (int)G, -1};
   marginalopt(all, prior_max, mlval[NT].data(), peakloc[NT].data());
   std::vector<double> migtest(nm, 0.0);
   for (int i = 0; i < nm; i++) {
     const double maxp = -peak_f(all, i + nq, peakloc[NT][i + nq]), max0p = -peak_f(all, i + nq, 0.0000001);
     migtest[i] = 2 * log(maxp / max0p);
+  }
+  std::vector<double> pmtest(nt, 0.0);
+  if (nt) {
+    marginalopt_popmig(LM, 0, (int)G, terms, term_upper, pmml[NT].data(), pmpk[NT].data());
+    for (int i = 0; i < nt; i++) {
+      PeakCtx c{LM, 0, (int)G, terms[i].thetai};
+      const double maxp = -peak_f(c, terms[i].mi, pmpk[NT][i]), max0p = -peak_f(c, terms[i].mi, 0.0000001);
+      pmtest[i] = 2 * log(maxp / max0p);
+    }
   }
   bool errnote = false, signote = false;
   static const char *sig[4] = {"ns", "*", "**", "***"};
@@ -483,6 +522,38 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
         if (pb[i] == k && (ii == 1 || prior_max[i] > 0.000001)) fprintf(f, "\t%d\t", pe[i]);
       fprintf(f, "\n");
     }
+    if (nt && k < nsplit) {                           // case 3 of the reference's loop: the 2NM terms of this period
+      int nprint = 0;
+      for (int i = 0; i < nm; i++) nprint += pb[nq + i] == k;
+      if (nprint) {
+        fprintf(f, "Population Migration (2NM) Terms\n Term:");
+        for (int i = 0; i < nt; i++) if (prior_max[nq + terms[i].mi] > 0.000001 && pb[nq + terms[i].mi] == k) fprintf(f, "\t %s\tP", terms[i].peakname.c_str());
+        fprintf(f, "\n");
+        for (int j = 0; j <= NT; j++) {
+          if (j < NT) fprintf(f, " Set%d", j); else fprintf(f, " All");
+          for (int i = 0; i < nt; i++)
+            if (pb[nq + terms[i].mi] == k) {
+              if (pmpk[j][i] >= 0) fprintf(f, "\t%7.3lf\t%7.3lf", pmpk[j][i], pmml[j][i]);
+              else { fprintf(f, "\terror*\t"); errnote = true; }
+            }
+          fprintf(f, "\n");
+        }
+        fprintf(f, " LLRtest ");
+        for (int i = 0; i < nt; i++)
+          if (pb[nq + terms[i].mi] == k && prior_max[nq + terms[i].mi] > 0.000001) {
+            if (fabs(pmtest[i]) > 1e6) fprintf(f, "bad value\t");
+            else {
+              const int lev = pmtest[i] > 9.54954 ? 3 : pmtest[i] > 5.41189 ? 2 : pmtest[i] > 2.70554 ? 1 : 0;
+              if (lev == 3) signote = true;
+              fprintf(f, "%7.3lf%s\t", pmtest[i], sig[lev]);
+            }
+          }
+        fprintf(f, "\n LastPeriod");
+        for (int i = 0; i < nt; i++)
+          if (pb[nq + terms[i].mi] == k && prior_max[nq + terms[i].mi] > 0.000001) fprintf(f, "\t%d\t", pe[nq + terms[i].mi]);
+        fprintf(f, "\n");
+      }
+    }
   }
   if (errnote) fprintf(f, "*  peak not found possibly due to multiple peaks (check plot of marginal density) \n");
   if (signote) fprintf(f, " migration rate likelihood ratio test - see Nielsen and Wakeley (2001)\n migration significance levels :  * p < 0.05;   **  p < 0.01,   *** p < 0.001\n");
@@ -525,6 +596,8 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
     ck(ima2p_lmode_moments(LM, mean.data(), var.data(), corr.data(), nullptr), "moments");
     print_moments(f, name, nq, mmx, mean, var, corr, npops);
   }
+  std::vector<PopMigTerm> terms;
+  std::vector<double> term_upper;
   {
     // period in which a parameter first appears / ends: a size parameter lives with its population (poptree b, e), a
     // migration parameter over the periods of its weight positions (initialize.cpp:237-243, 470-520)
@@ -532,7 +605,19 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
     std::vector<int> pb, pe;
     for (int i = 0; i < nq; i++) { pmax.push_back(qmx[i]); pb.push_back(ptb[i]); pe.push_back(pte[i]); }
     for (int i = 0; i < nm; i++) { pmax.push_back(mmx[i]); pb.push_back(mp[moff[i]]); pe.push_back(mp[moff[i + 1] - 1]); }
-    print_marginal_peaks(f, LM, nrows, name, nq, nm, nsplit, pmax, pb, pe);
+    // 2NM terms (-p5): every population of the tree but the root with each migration parameter leaving it
+    // (surface_call_functions.cpp:409-437, histograms.cpp:751-766)
+    if (opt.count("p") && opt["p"].find('5') != std::string::npos && nm > 0)
+      for (int thetai = 0; thetai < 2 * npops - 2; thetai++)
+        for (int mi = 0; mi < nm; mi++)
+          if (atoi(name[nq + mi].c_str() + 1) == thetai) {
+            PopMigTerm t; t.thetai = thetai; t.mi = mi;
+            t.peakname = "2N" + std::to_string(thetai) + "M" + name[nq + mi].substr(1);
+            t.histname = "2N" + std::to_string(thetai) + name[nq + mi];
+            terms.push_back(t);
+            term_upper.push_back(expo ? 20.0 * mmean[mi] : qmx[thetai] * mmx[mi] / 2.0);
+          }
+    print_marginal_peaks(f, LM, nrows, name, nq, nm, nsplit, pmax, pb, pe, terms, term_upper);
   }
   // fillvec histograms.cpp:81-99: margincalc at the GRIDSIZE mid-bin points of every parameter (initialize.cpp:189-193, 237-242)
   std::vector<std::vector<double>> xs, ys;
@@ -549,6 +634,29 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
   fprintf(f, "--------------------------------------------------------------------------------------------------------\n");
   fprintf(f, "       curve height is an estimate of marginal posterior probability\n");
   write_histograms(f, hname, xs, ys);
+  if (!terms.empty()) {
+    // print_populationmigrationrate_histograms histograms.cpp:648-815: the grid ends at the last bin whose density exceeds 1e-9
+    std::vector<std::vector<double>> px, py;
+    std::vector<std::string> pn;
+    for (size_t i = 0; i < terms.size(); i++) {
+      std::vector<double> x(kGrid), y(kGrid);
+      for (int j = 0; j < kGrid; j++) x[j] = (j + 0.5) * term_upper[i] / kGrid;
+      ck(ima2p_lmode_popmig(LM, terms[i].thetai, terms[i].mi, x.data(), kGrid, 0, y.data()), "2NM density");
+      int j = kGrid - 1;
+      while (j >= 0 && !(y[j] > 1e-9)) j--;
+      const double maxx = j < 0 ? term_upper[i] : x[j];
+      for (int q = 0; q < kGrid; q++) x[q] = (q + 0.5) * maxx / kGrid;
+      ck(ima2p_lmode_popmig(LM, terms[i].thetai, terms[i].mi, x.data(), kGrid, 0, y.data()), "2NM density");
+      px.push_back(x); py.push_back(y); pn.push_back(terms[i].histname);
+    }
+    fprintf(f, "\n\nHISTOGRAM GROUP 3: POPULATION MIGRATION (2NM) POSTERIOR PROBABILITY HISTOGRAMS\n");
+    fprintf(f, "-----------------------------------------------------------------------------\n");
+    fprintf(f, "     curve height is an estimate of the posterior probability\n");
+    fprintf(f, "      each term is the product of a population parameter (e.g. q0) and a migration rate (e.g.m0>1) \n");
+    fprintf(f, "      migration rates are in the coalescent (backwards in times), so that a population migration rate of \n");
+    fprintf(f, "        q1m0>1  is the population rate (forward in time) at which population 1 receives migrants from population 0\n");
+    write_histograms(f, pn, px, py);
+  }
   fprintf(f, "\nEND OF OUTPUT\n");
   fclose(f);
   printf("IMa2p_b200: L mode, %lld genealogies from %s, report in %s\n", nrows, ti.c_str(), opt["o"].c_str());

@@ -286,7 +286,7 @@ def main():
         subprocess.run([HARNESS, "stock", os.path.join(TMP, rep_name + "_m.json"), "--"] + common + ["-o", base, "-b2000", "-l300", "-d10", "-hn2", "-hfl", "-ha0.9"],
                        check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
         rep = os.path.join(TMP, rep_name + "_l.out")
-        subprocess.run([HARNESS, "stock", os.path.join(TMP, rep_name + "_l.json"), "--"] + common + ["-o", rep, "-r0", "-v", base, "-p6"],
+        subprocess.run([HARNESS, "stock", os.path.join(TMP, rep_name + "_l.json"), "--"] + common + ["-o", rep, "-r0", "-v", base, "-p56"],
                        check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
         text = open(rep).read()
 
@@ -296,7 +296,8 @@ def main():
         keep = {"greater_than": section("\nPARAMETER COMPARISONS", "\nMEANS, VARIANCES"),
                 "moments": section("\nMEANS, VARIANCES", "\nMarginal Peak Locations"),
                 "peaks": section("\nMarginal Peak Locations", "\nHISTOGRAMS\n"),
-                "histograms": section("HISTOGRAM GROUP 2", " After\t")}
+                "histograms": section("HISTOGRAM GROUP 2", " After\t"),
+                "popmig_histograms": section("HISTOGRAM GROUP 3: POPULATION MIGRATION", " After\t")}
         import json
         with gzip.GzipFile(os.path.join(HERE, rep_name + ".json.gz"), "wb", mtime=0) as g:
             g.write(json.dumps(keep).encode())

@@ -56,8 +56,9 @@ def test_run_from_u_file_to_ti_file(exe, tmp_path, name, genes):
 @pytest.mark.parametrize("name", ["lmode_report_sim3", "lmode_report_3pop"])
 def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path, name):
     """-r0 -v: the genealogies the reference saved (its own .ti file) go through the device evaluators; the greater-than
-    tables, the means / variances / correlations table, the marginal peak table (peak search, 95% bounds, migration
-    likelihood-ratio tests) and the histogram group of the size and migration parameters must be the reference's text,
+    tables (-p6), the means / variances / correlations table, the marginal peak table (peak search, 95% bounds, migration
+    likelihood-ratio tests, with -p5 the 2NM terms), the histogram group of the size and migration parameters and with -p5
+    the histogram group of the 2NM terms must be the reference's text,
     character for character (fixtures: the reference's own L-mode reports of the same files; 2 and 3 populations)."""
     import gzip
     import json
@@ -70,10 +71,10 @@ def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path, name):
     else:
         u = tmp_path / "Sim3.u"
         u.write_text(_sim3_u())
-    r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l.out"), "-q10", "-m1", "-t3", "-p6"])
+    r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l.out"), "-q10", "-m1", "-t3", "-p56"])
     assert r.returncode == 0, r.stderr
     rep = open(tmp_path / "l.out").read()
-    for key in ("greater_than", "moments", "peaks", "histograms"):
+    for key in ("greater_than", "moments", "peaks", "histograms", "popmig_histograms"):
         assert ref[key].strip("\n") in rep, key
     r = _run(exe, ["-r0", "-i", str(u), "-o", str(tmp_path / "l2.out"), "-q10", "-m1", "-t3"])
     assert r.returncode == 8 and "-v" in r.stderr            # IMERR_MISSINGCOMMANDINFO
