@@ -560,7 +560,10 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
   fprintf(f, "\n");
 }
 
-int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo) {
+// The report sections that are sums over the sampled genealogies (printoutput, ima_main_mpi.cpp:4080-4110), written to f from
+// `nrows` rows: used by L mode on the rows of a .ti file and by M mode on the rows the run has just saved.
+void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo,
+                     const float *rowdata, long long nrows) {
   int md[6];
   ima2p_modelspec_dims(S, md);
   const int nsplit = md[1], nq = md[3], nm = md[4], nwp = md[5], np = nq + nm;
@@ -577,19 +580,9 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
   }
   std::vector<double> qmx(nq, qmax), qmn(nq, 0.0), mmx(nm, expo ? 20.0 * mmax : mmax), mmn(nm, 0.0), mmean(nm, expo ? mmax : 0.0);
   const int rowlen = 3 * nq + 2 * nm + nq + nm + 2 + nsplit;            // calc_gsampinf_length ginfo.cpp:306-316
-  const std::string ti = opt["v"] + ".ti";
-  long long nrows = 0;
-  const long long maxrows = 1100000;
-  std::vector<float> rows((size_t)maxrows * rowlen);
-  ck(ima2p_ti_load(ti.c_str(), rowlen, rows.data(), maxrows, &nrows), "loading the genealogy file");
-  if (nrows < 1) die("no genealogies in " + ti, 13);
   ima2p_lmode *LM = nullptr;
   ck(ima2p_lmode_create(&LM, 0, nq, nm, nsplit, qmx.data(), qmn.data(), mmx.data(), mmn.data(), mmean.data(), expo), "L mode");
-  ck(ima2p_lmode_load(LM, rows.data(), (int)nrows, rowlen, nrows), "uploading the genealogies");
-  FILE *f = fopen(opt["o"].c_str(), "w");
-  if (!f) die("cannot create the output file", 2);
-  fprintf(f, "IMa2p_b200 L mode report\n\nLOAD TREES (L) MODE INFORMATION\n============================================================================\n");
-  fprintf(f, "  Base filename for loading files with sampled genealogies: %s*.ti\n  loaded %lld genealogies from genealogy file  %s\n", opt["v"].c_str(), nrows, ti.c_str());
+  ck(ima2p_lmode_load(LM, rowdata, (int)nrows, rowlen, nrows), "uploading the genealogies");
   if (opt.count("p") && opt["p"].find('6') != std::string::npos) print_greater_than(f, LM, name, nq, nm, expo);
   if (!expo) {                                                          // ima_main_mpi.cpp:4086: not done for the exponential prior
     std::vector<double> mean(np), var(np), corr((size_t)np * np);
@@ -658,9 +651,27 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
     write_histograms(f, pn, px, py);
   }
   fprintf(f, "\nEND OF OUTPUT\n");
+  ima2p_lmode_destroy(LM);
+}
+
+int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo) {
+  int md[6];
+  ima2p_modelspec_dims(S, md);
+  const int rowlen = 3 * md[3] + 2 * md[4] + md[3] + md[4] + 2 + md[1];
+  const std::string ti = opt["v"] + ".ti";
+  long long nrows = 0;
+  ck(ima2p_ti_load(ti.c_str(), rowlen, nullptr, 0, &nrows), "loading the genealogy file");
+  if (nrows < 1) die("no genealogies in " + ti, 13);
+  if (nrows > 1100000) nrows = 1100000;
+  std::vector<float> rows((size_t)nrows * rowlen);
+  ck(ima2p_ti_load(ti.c_str(), rowlen, rows.data(), nrows, &nrows), "loading the genealogy file");
+  FILE *f = fopen(opt["o"].c_str(), "w");
+  if (!f) die("cannot create the output file", 2);
+  fprintf(f, "IMa2p_b200 L mode report\n\nLOAD TREES (L) MODE INFORMATION\n============================================================================\n");
+  fprintf(f, "  Base filename for loading files with sampled genealogies: %s*.ti\n  loaded %lld genealogies from genealogy file  %s\n", opt["v"].c_str(), nrows, ti.c_str());
+  report_sections(f, opt, S, npops, qmax, mmax, expo, rows.data(), nrows);
   fclose(f);
   printf("IMa2p_b200: L mode, %lld genealogies from %s, report in %s\n", nrows, ti.c_str(), opt["o"].c_str());
-  ima2p_lmode_destroy(LM);
   return 0;
 }
 
@@ -799,7 +810,7 @@ int main(int argc, char **argv) {
   printf("IMa2p_b200: %d populations %s, %d loci, %d chains, burn %ld steps, %ld genealogies every %ld steps\n", npops, tree, nloci, nchains, burn, nsave, every);
   for (long done = 0; done < burn;) { const int n = burn - done > 1000 ? 1000 : (int)(burn - done); ck(ima2p_engine_run(E, n, swaptries, nullptr), "burn-in"); done += n; }
   std::vector<double> chain4((size_t)nchains * 4);
-  std::vector<float> rows, row(rowlen);
+  std::vector<float> rows, row(rowlen), allrows;
   std::vector<double> tsum(nsplit > 0 ? nsplit : 1, 0.0);
   long saved = 0;
   while (saved < nsave) {
@@ -808,6 +819,7 @@ int main(int argc, char **argv) {
     ck(ima2p_engine_step_report(E, chain4.data(), row.data(), &present, nullptr), "reading the cold chain");
     if (!present) die("the cold chain is not on this device");
     rows.insert(rows.end(), row.begin(), row.end());
+    allrows.insert(allrows.end(), row.begin(), row.end());
     for (int k = 0; k < nsplit; k++) tsum[k] += row[rowlen - nsplit + k];
     saved++;
     if (rows.size() >= (size_t)rowlen * 256 || saved == nsave) { ck(ima2p_ti_append(ti.c_str(), rows.data(), (long long)(rows.size() / rowlen), rowlen), "writing the .ti file"); rows.clear(); }
@@ -824,6 +836,8 @@ int main(int argc, char **argv) {
           (unsigned long long)cnt[5], (unsigned long long)ucnt[1], (unsigned long long)ucnt[0], (unsigned long long)ucnt[3], (unsigned long long)ucnt[2]);
   fprintf(f, "proposals dropped for migration capacity %llu\ngenealogies saved %ld in %s\n", (unsigned long long)cnt[7], saved, ti.c_str());
   for (int k = 0; k < nsplit; k++) fprintf(f, "mean of t%d over the saved genealogies %.6f\n", k, tsum[k] / saved);
+  // the same sections an L-mode run on out.ti would write, from the rows just saved (printoutput at the end of an M-mode run)
+  report_sections(f, opt, S, npops, qmax, mmax, expo, allrows.data(), saved);
   fclose(f);
   if (opt.count("r")) ck(ima2p_engine_write_mcf(E, (outname + ".mcf").c_str()), "writing the state file");
   printf("IMa2p_b200: done, %ld genealogies in %s\n", saved, ti.c_str());

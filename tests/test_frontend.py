@@ -45,6 +45,11 @@ def test_run_from_u_file_to_ti_file(exe, tmp_path, name, genes):
     assert np.all(t > 0) and np.all(t < 3) and np.all(np.diff(t, axis=1) > 0)
     rep = open(out).read()
     assert "genealogies saved 12" in rep and "proposals dropped for migration capacity 0" in rep
+    # the M-mode report ends with the sections computed over the genealogies it saved (as the reference's printoutput does)
+    assert "MEANS, VARIANCES and CORRELATIONS OF PARAMETERS" in rep or npops == 3 and "-j" in rep
+    assert "Marginal Peak Locations and Probabilities" in rep and "HISTOGRAM GROUP 2" in rep and rep.rstrip().endswith("END OF OUTPUT")
+    mean_line = [ln for ln in rep.split("\n") if ln.startswith("Mean:")][0].split("\t")[1:]
+    assert len(mean_line) == nq + nm and all(0.0 < float(v) < 10.0 for v in mean_line[:nq])
     assert os.path.getsize(str(out) + ".mcf") > 1000
     # the state file it wrote restarts a run (-f)
     r2 = _run(exe, ["-i", os.path.join(INPUTS, name + ".u"), "-o", str(tmp_path / "again"), "-q10", "-m1", "-t3", "-b0", "-l3", "-d2", "-hn3", "-hfl",
