@@ -25,12 +25,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
 namespace {
 
+bool g_throw_instead_of_exit = false;      // set around the closing report of an M-mode run: its failure must not lose the run
 [[noreturn]] void die(const std::string &m, int code = 1) {
+  if (g_throw_instead_of_exit) throw std::runtime_error(m);
   fprintf(stderr, "IMa2: %s\n", m.c_str());
   exit(code);
 }
@@ -837,7 +840,13 @@ int main(int argc, char **argv) {
   fprintf(f, "proposals dropped for migration capacity %llu\ngenealogies saved %ld in %s\n", (unsigned long long)cnt[7], saved, ti.c_str());
   for (int k = 0; k < nsplit; k++) fprintf(f, "mean of t%d over the saved genealogies %.6f\n", k, tsum[k] / saved);
   // the same sections an L-mode run on out.ti would write, from the rows just saved (printoutput at the end of an M-mode run)
-  report_sections(f, opt, S, npops, qmax, mmax, expo, allrows.data(), saved);
+  g_throw_instead_of_exit = true;
+  try {
+    report_sections(f, opt, S, npops, qmax, mmax, expo, allrows.data(), saved);
+  } catch (const std::exception &ex) {
+    fprintf(f, "\nthe report sections over the saved genealogies could not be completed: %s\n(the genealogies are in %s; run L mode, -r0 -v, on them)\n", ex.what(), ti.c_str());
+  }
+  g_throw_instead_of_exit = false;
   fclose(f);
   if (opt.count("r")) ck(ima2p_engine_write_mcf(E, (outname + ".mcf").c_str()), "writing the state file");
   printf("IMa2p_b200: done, %ld genealogies in %s\n", saved, ti.c_str());
