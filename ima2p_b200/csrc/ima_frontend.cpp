@@ -185,8 +185,14 @@ void print_greater_than(FILE *f, ima2p_lmode *LM, const std::vector<std::string>
 }
 
 // writehistogram histograms.cpp:146-431 with dosmooth = 0 and unit scale adjustments, as prepare_parameter_histograms sets them
-void write_histograms(FILE *f, const std::vector<std::string> &name, const std::vector<std::vector<double>> &x, const std::vector<std::vector<double>> &y) {
+void write_histograms(FILE *f, const std::vector<std::string> &name, const std::vector<std::vector<double>> &x, const std::vector<std::vector<double>> &yraw,
+                      const std::vector<double> &yscale = std::vector<double>(), bool dosmooth = false,
+                      const std::vector<double> &before = std::vector<double>(), const std::vector<double> &after = std::vector<double>()) {
   const int nh = (int)name.size();
+  // y as printed = yscaleadjust * counts; the smoothing passes of the reference work on the unscaled curve (:253-262, :306-317)
+  std::vector<std::vector<double>> y(yraw);
+  for (int j = 0; j < nh && !yscale.empty(); j++) for (int i = 0; i < kGrid; i++) y[j][i] = yscale[j] * yraw[j][i];
+  std::vector<double> smthprob(nh, 0.0);
   std::vector<double> xysum(nh, 0.0), ysum(nh, 0.0), hpdlo(nh, 0.0), hpdhi(nh, 0.0);
   std::vector<char> c1(nh, ' '), c2(nh, ' ');
   fprintf(f, " Summaries\n\tValue  ");
@@ -205,6 +211,24 @@ void write_histograms(FILE *f, const std::vector<std::string> &name, const std::
       if (maxval < y[j][i]) { maxval = y[j][i]; imax[j] = i; }
     }
     fprintf(f, "\t%s", histfmt(x[j][imax[j]]).c_str());
+  }
+  if (dosmooth) {                                                     // HiSmth :240-270: peak of the curve smoothed over 10 cells
+    fprintf(f, "\n\tHiSmth");
+    for (int j = 0; j < nh; j++) {
+      double maxval = -1; int im = 0;
+      for (int i = 0; i < kGrid; i++) {
+        int cell = 10 < 2 * i ? 10 : 2 * i;
+        cell = cell < 2 * (kGrid - 1 - i) ? cell : 2 * (kGrid - 1 - i);
+        double den = 0, sm = 0;
+        for (int k = (i - cell / 2 > 0 ? i - cell / 2 : 0); k <= (kGrid - 1 < i + cell / 2 ? kGrid - 1 : i + cell / 2); k++) {
+          const double term = 1.0 / (0.5 + abs(k - i));
+          sm += yraw[j][k] * term; den += term;
+        }
+        sm /= den;
+        if (maxval < sm) { maxval = sm; smthprob[j] = maxval; im = i; }
+      }
+      fprintf(f, "\t%s", histfmt(x[j][im]).c_str());
+    }
   }
   fprintf(f, "\n\tMean  ");
   for (int j = 0; j < nh; j++) fprintf(f, "\t%s", histfmt(xysum[j] / ysum[j]).c_str());
@@ -230,7 +254,7 @@ void write_histograms(FILE *f, const std::vector<std::string> &name, const std::
       double den = 0, sm = 0;
       for (int k = (i - cell / 2 > 0 ? i - cell / 2 : 0); k <= (kGrid - 1 < i + cell / 2 ? kGrid - 1 : i + cell / 2); k++) {
         const double term = 1.0 / (0.5 + abs(k - i));
-        sm += y[j][k] * term; den += term;
+        sm += yraw[j][k] * term; den += term;
       }
       sm /= den;
       tempsum += sm;
@@ -250,7 +274,7 @@ void write_histograms(FILE *f, const std::vector<std::string> &name, const std::
     hpdhi[j] = hpdmax;
     while (i > 0 && (h[i].second < hpdmin || h[i].second > hpdmax)) i--;
     if (i > 0) c2[j] = '?';
-    if (0.0 < y[j][0] && 0.0 < y[j][kGrid - 1]) c1[j] = '#';      // smthprobvals is 0 without smoothing (:367)
+    if (smthprob[j] * 0.05 < yraw[j][0] && smthprob[j] * 0.05 < yraw[j][kGrid - 1]) c1[j] = '#';      // smthprobvals is 0 without smoothing (:367)
   }
   fprintf(f, "\n\tHPD95Lo");
   for (int j = 0; j < nh; j++) fprintf(f, "\t%s%c%c", histfmt(hpdlo[j]).c_str(), c1[j], c2[j]);
@@ -269,9 +293,9 @@ void write_histograms(FILE *f, const std::vector<std::string> &name, const std::
   fprintf(f, " SumP\t");
   for (int j = 0; j < nh; j++) fprintf(f, "\t\t%s", histfmt(ysum[j]).c_str());
   fprintf(f, "\n Before\t");
-  for (int j = 0; j < nh; j++) fprintf(f, "\t\t%s", histfmt(0.0).c_str());
+  for (int j = 0; j < nh; j++) fprintf(f, "\t\t%s", histfmt(before.empty() ? 0.0 : before[j] * (yscale.empty() ? 1.0 : yscale[j])).c_str());
   fprintf(f, "\n After\t");
-  for (int j = 0; j < nh; j++) fprintf(f, "\t\t%s", histfmt(0.0).c_str());
+  for (int j = 0; j < nh; j++) fprintf(f, "\t\t%s", histfmt(after.empty() ? 0.0 : after[j] * (yscale.empty() ? 1.0 : yscale[j])).c_str());
   fprintf(f, "\n");
 }
 
@@ -566,7 +590,7 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
 // The report sections that are sums over the sampled genealogies (printoutput, ima_main_mpi.cpp:4080-4110), written to f from
 // `nrows` rows: used by L mode on the rows of a .ti file and by M mode on the rows the run has just saved.
 void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo,
-                     const float *rowdata, long long nrows) {
+                     const float *rowdata, long long nrows, bool loaded_from_ti) {
   int md[6];
   ima2p_modelspec_dims(S, md);
   const int nsplit = md[1], nq = md[3], nm = md[4], nwp = md[5], np = nq + nm;
@@ -626,6 +650,28 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
     ck(ima2p_lmode_margincalc(LM, p, x.data(), kGrid, 0.0, 0, y.data()), "marginal densities");
     xs.push_back(x); ys.push_back(y); hname.push_back(name[p]);
   }
+  if (nsplit > 0) {
+    // histogram group 1 in L mode: the split times of the loaded rows binned as recordval does (ima_main_mpi.cpp:2746-2781,
+    // 3420-3431), scaled to a density (histograms.cpp:496-509); mutation-scalar histograms need an M-mode run
+    const double tmax = atof(opt["t"].c_str());
+    std::vector<std::vector<double>> tx(nsplit, std::vector<double>(kGrid)), ty(nsplit, std::vector<double>(kGrid, 0.0));
+    std::vector<double> tscale(nsplit, (kGrid / tmax) / (double)nrows), tb(nsplit, 0.0), ta(nsplit, 0.0);
+    std::vector<std::string> tn;
+    for (int k = 0; k < nsplit; k++) {
+      tn.push_back("t" + std::to_string(k));
+      for (int j = 0; j < kGrid; j++) tx[k][j] = 0.0 + ((j + 0.5) * (tmax * 1.0 - 0.0)) / kGrid;
+      for (long long r = 0; r < nrows; r++) {
+        const int b = (int)(kGrid * rowdata[(size_t)r * rowlen + (rowlen - nsplit) + k] / tmax);
+        if (b < 0) tb[k] += 1; else if (b >= kGrid) ta[k] += 1; else ty[k][b] += 1;
+      }
+    }
+    fprintf(f, "HISTOGRAM GROUP 1: MARGINAL DISTRIBUTION VALUES AND HISTOGRAMS OF PARAMETERS IN MCMC\n");
+    fprintf(f, "----------------------------------------------------------------------------------\n");
+    fprintf(f, "    curve height is an estimate of marginal posterior probability\n");
+    if (loaded_from_ti) fprintf(f, "  IMa LOAD TREES MODE  - splittime values loaded from *.ti file, mutation rate scalar histograms are not available \n");
+    else fprintf(f, "  split times of the saved genealogies\n");
+    write_histograms(f, tn, tx, ty, tscale, true, tb, ta);
+  }
   fprintf(f, "\n\nHISTOGRAM GROUP 2: MARGINAL DISTRIBUTION VALUES AND HISTOGRAMS OF POPULATION SIZE AND MIGRATION PARAMETERS\n");
   fprintf(f, "--------------------------------------------------------------------------------------------------------\n");
   fprintf(f, "       curve height is an estimate of marginal posterior probability\n");
@@ -672,7 +718,7 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
   if (!f) die("cannot create the output file", 2);
   fprintf(f, "IMa2p_b200 L mode report\n\nLOAD TREES (L) MODE INFORMATION\n============================================================================\n");
   fprintf(f, "  Base filename for loading files with sampled genealogies: %s*.ti\n  loaded %lld genealogies from genealogy file  %s\n", opt["v"].c_str(), nrows, ti.c_str());
-  report_sections(f, opt, S, npops, qmax, mmax, expo, rows.data(), nrows);
+  report_sections(f, opt, S, npops, qmax, mmax, expo, rows.data(), nrows, true);
   fclose(f);
   printf("IMa2p_b200: L mode, %lld genealogies from %s, report in %s\n", nrows, ti.c_str(), opt["o"].c_str());
   return 0;
@@ -842,7 +888,7 @@ int main(int argc, char **argv) {
   // the same sections an L-mode run on out.ti would write, from the rows just saved (printoutput at the end of an M-mode run)
   g_throw_instead_of_exit = true;
   try {
-    report_sections(f, opt, S, npops, qmax, mmax, expo, allrows.data(), saved);
+    report_sections(f, opt, S, npops, qmax, mmax, expo, allrows.data(), saved, false);
   } catch (const std::exception &ex) {
     fprintf(f, "\nthe report sections over the saved genealogies could not be completed: %s\n(the genealogies are in %s; run L mode, -r0 -v, on them)\n", ex.what(), ti.c_str());
   }

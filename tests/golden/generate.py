@@ -296,6 +296,7 @@ def main():
         keep = {"greater_than": section("\nPARAMETER COMPARISONS", "\nMEANS, VARIANCES"),
                 "moments": section("\nMEANS, VARIANCES", "\nMarginal Peak Locations"),
                 "peaks": section("\nMarginal Peak Locations", "\nHISTOGRAMS\n"),
+                "t_histograms": section("HISTOGRAM GROUP 1", " After\t"),
                 "histograms": section("HISTOGRAM GROUP 2", " After\t"),
                 "popmig_histograms": section("HISTOGRAM GROUP 3: POPULATION MIGRATION", " After\t")}
         import json

@@ -79,7 +79,7 @@ def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path, name):
     r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l.out"), "-q10", "-m1", "-t3", "-p56"])
     assert r.returncode == 0, r.stderr
     rep = open(tmp_path / "l.out").read()
-    for key in ("greater_than", "moments", "peaks", "histograms", "popmig_histograms"):
+    for key in ("greater_than", "moments", "peaks", "t_histograms", "histograms", "popmig_histograms"):
         assert ref[key].strip("\n") in rep, key
     r = _run(exe, ["-r0", "-i", str(u), "-o", str(tmp_path / "l2.out"), "-q10", "-m1", "-t3"])
     assert r.returncode == 8 and "-v" in r.stderr            # IMERR_MISSINGCOMMANDINFO
