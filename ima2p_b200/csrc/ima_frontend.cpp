@@ -10,7 +10,7 @@
 // row (savegsampinf) is appended to out.ti -> a short report.  Values are arguments attached to the flag ("-q10") or
 // the next word ("-q 10"), as the reference accepts.  Options of the reference outside this path are refused, not ignored.
 //
-//   IMa2p_b200 -r0 -v BASE -i data.u -o out -q QMAX -m MMAX -t TMAX [-j7] [-p5] [-p6]
+//   IMa2p_b200 -r0 -v BASE -i data.u -o out -q QMAX -m MMAX -t TMAX [-j7] [-p5] [-p6] [-c2]
 //
 // is L mode (LOAD-GENEALOGY, ima_main_mpi.cpp:3216-3440, 4037-4100): the rows of BASE.ti are loaded onto the device and the
 // report sections that are sums over every sampled genealogy are written in the reference's own layout -- the means /
@@ -587,6 +587,92 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
   fprintf(f, "\n");
 }
 
+
+// ---- joint posterior peak: jointfind.cpp:599-812 (differential evolution: startpop, nextgen, difeloop, copybest, modelloop)
+// and :815-879, 1087-1184 (the table).  The reference evaluates jointp for one individual after the other; a generation's
+// trial vectors do not depend on each other (they are all built from the previous population), so the whole generation
+// goes to the device in one ima2p_lmode_jointp call.  Two populations (the FULL model); the random numbers are this
+// program's own, the peak it converges to is the reference's (spread tolerance 1e-7, found twice before stopping).
+std::string logpfmt(double v) {                     // logpstrformat jointfind.cpp:295-318
+  char b[64];
+  const double a = fabs(v);
+  if (a < 1e-2) snprintf(b, sizeof b, "%.6lf", v);
+  else if (a < 1e-1) snprintf(b, sizeof b, "%.5lf", v);
+  else if (a < 1e-0) snprintf(b, sizeof b, "%.4lf", v);
+  else if (a < 1e1) snprintf(b, sizeof b, "%.3lf", v);
+  else if (a < 1e2) snprintf(b, sizeof b, "%.2lf", v);
+  else if (a < 1e3) snprintf(b, sizeof b, "%.1lf", v);
+  else snprintf(b, sizeof b, "%.0lf", v);
+  return b;
+}
+
+void print_joint_peak(FILE *f, ima2p_lmode *LM, long long G, const std::vector<std::string> &name, int nq, int nm, const std::vector<double> &prior_max,
+                      int npops, unsigned long long seed) {
+  fprintf(f, "Joint Peak Locations and Posterior Probabilities\n================================================\n");
+  fprintf(f, "  estimates based on %lld sampled genealogies\n", G);
+  if (npops != 2) { fprintf(f, "  the joint search of this build covers two-population models (the FULL model)\n\n"); return; }
+  fprintf(f, "\nModel#  Model Description\n %d     FULL\n", 1);
+  fprintf(f, "\nModel#\tlog(P)\t#terms\tdf\t2LLR\tESS");
+  const int np = nq + nm;
+  for (int i = 0; i < np; i++) if (i < nq || prior_max[i] > 0.000001) fprintf(f, "\t%s", name[i].c_str());
+  fprintf(f, "\n");
+  const int depop = np * 100;                        // DEFAULTPOPSIZEMULTIPLIER
+  const double recrate = 0.9, fweight = 0.8, lower = 0.0000001;
+  unsigned long long st = seed * 6364136223846793005ull + 1442695040888963407ull;
+  auto uni = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return ((double)(st >> 11) + 0.5) / 9007199254740992.0; };
+  std::vector<double> pop((size_t)depop * np), trial((size_t)depop * np), fpop(depop), ftrial(depop), ess(depop), best(np + 1, 0.0);
+  auto evaluate = [&](std::vector<double> &x, std::vector<double> &fx) { ck(ima2p_lmode_jointp(LM, x.data(), depop, 0, fx.data(), nullptr), "joint density"); };
+  auto startpop = [&]() {
+    for (int i = 0; i < depop; i++) for (int j = 0; j < np; j++) pop[(size_t)i * np + j] = lower + uni() * (prior_max[j] - lower);
+    evaluate(pop, fpop);
+  };
+  double global_pd = 1e200;
+  int newstart = 0, countloop = 0;
+  startpop();
+  for (int i = 0; i < depop; i++) if (fpop[i] < global_pd) global_pd = fpop[i];
+  do {
+    if (newstart > 0) startpop();
+    double lowpd, hipd;
+    do {                                             // difeloop: generations until the population has collapsed on a peak
+      for (int i = 0; i < depop; i++) {
+        const int A = (int)(uni() * depop) % depop, B = (int)(uni() * depop) % depop, Cv = (int)(uni() * depop) % depop;
+        for (int j = 0; j < np; j++) {
+          if (uni() < recrate) {
+            const double c = pop[(size_t)Cv * np + j];
+            double t = c + fweight * (pop[(size_t)A * np + j] - pop[(size_t)B * np + j]);
+            if (t < lower) t = c - uni() * (c - lower);                   // move only part of the way towards the bound
+            if (t > prior_max[j]) t = c + uni() * (prior_max[j] - c);
+            trial[(size_t)i * np + j] = t;
+          } else trial[(size_t)i * np + j] = pop[(size_t)i * np + j];
+        }
+      }
+      evaluate(trial, ftrial);
+      lowpd = 1e200; hipd = -1e200;
+      for (int i = 0; i < depop; i++) {
+        if (ftrial[i] < fpop[i]) { fpop[i] = ftrial[i]; for (int j = 0; j < np; j++) pop[(size_t)i * np + j] = trial[(size_t)i * np + j]; }
+        if (fpop[i] < lowpd) lowpd = fpop[i];
+        if (fpop[i] > hipd) hipd = fpop[i];
+      }
+    } while (hipd - lowpd > 1.0e-7);                 // SPREADTOL
+    const double local_pd = lowpd;
+    if (fabs(local_pd - global_pd) < 1.0e-6) countloop++;               // PLOOPTOL
+    else if (local_pd < global_pd) countloop = 0;
+    if (local_pd < global_pd) {
+      int k = 0;
+      for (int i = 1; i < depop; i++) if (fpop[i] < fpop[k]) k = i;
+      for (int j = 0; j < np; j++) best[j] = pop[(size_t)k * np + j];
+      best[np] = fpop[k];
+      global_pd = local_pd;
+    }
+    newstart++;
+  } while (countloop < 2 && newstart < 10);          // LOOPMATCHCRITERIA, MAXRESTART
+  double q = 0, e = 0;
+  ck(ima2p_lmode_jointp(LM, best.data(), 1, 1, &q, &e), "joint density");
+  fprintf(f, "%d\t%s\t%d\t-\t-\t%s", 1, logpfmt(-best[np]).c_str(), np, logpfmt(e).c_str());
+  for (int i = 0; i < np; i++) fprintf(f, best[i] < 0.001 ? "\t%.5lf" : "\t%.4lf", best[i]);
+  fprintf(f, "\n\n");
+}
+
 // The report sections that are sums over the sampled genealogies (printoutput, ima_main_mpi.cpp:4080-4110), written to f from
 // `nrows` rows: used by L mode on the rows of a .ti file and by M mode on the rows the run has just saved.
 void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo,
@@ -638,6 +724,8 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
             term_upper.push_back(expo ? 20.0 * mmean[mi] : qmx[thetai] * mmx[mi] / 2.0);
           }
     print_marginal_peaks(f, LM, nrows, name, nq, nm, nsplit, pmax, pb, pe, terms, term_upper);
+    if (loaded_from_ti && opt.count("c") && opt["c"].find('2') != std::string::npos)      // -c2 FINDJOINTPOSTERIOR (L mode only, ima_main_mpi.cpp:1466)
+      print_joint_peak(f, LM, nrows, name, nq, nm, pmax, npops, opt.count("s") ? strtoull(opt["s"].c_str(), nullptr, 10) : 1ull);
   }
   // fillvec histograms.cpp:81-99: margincalc at the GRIDSIZE mid-bin points of every parameter (initialize.cpp:189-193, 237-242)
   std::vector<std::vector<double>> xs, ys;
@@ -728,7 +816,7 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
 
 int main(int argc, char **argv) {
   std::map<std::string, std::string> opt;
-  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", nullptr};
+  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", "c", nullptr};
   for (int a = 1; a < argc; a++) {
     if (argv[a][0] != '-') die(std::string("command line: unexpected word ") + argv[a], 5);
     const std::string w = argv[a] + 1;
@@ -736,9 +824,10 @@ int main(int argc, char **argv) {
     for (int k = 0; known[k]; k++) if (w.compare(0, strlen(known[k]), known[k]) == 0) { key = known[k]; break; }
     if (key.empty()) die("command line: option -" + w + " is not part of this build (M-mode hot path only)", 5);
     std::string val = w.substr(key.size());
-    const bool flag_only = key == "hf" || key == "j" || key == "r" || key == "p";
+    const bool flag_only = key == "hf" || key == "j" || key == "r" || key == "p" || key == "c";
     if (val.empty() && !flag_only) { if (a + 1 >= argc) die("command line: -" + key + " needs a value", 5); val = argv[++a]; }
     if (key == "j" && val != "7") die("model option -j" + val + " is not part of this build", 5);
+    if (key == "c" && val != "2") die("calculation option -c" + val + " is not part of this build", 5);
     opt[key] = val;
   }
   const bool lmode = opt.count("r") && opt["r"] == "0";

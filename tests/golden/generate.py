@@ -286,7 +286,8 @@ def main():
         subprocess.run([HARNESS, "stock", os.path.join(TMP, rep_name + "_m.json"), "--"] + common + ["-o", base, "-b2000", "-l300", "-d10", "-hn2", "-hfl", "-ha0.9"],
                        check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
         rep = os.path.join(TMP, rep_name + "_l.out")
-        subprocess.run([HARNESS, "stock", os.path.join(TMP, rep_name + "_l.json"), "--"] + common + ["-o", rep, "-r0", "-v", base, "-p56"],
+        joint = ["-c2"] if rep_name == "lmode_report_sim3" else []          # the joint-posterior search (two populations: the FULL model)
+        subprocess.run([HARNESS, "stock", os.path.join(TMP, rep_name + "_l.json"), "--"] + common + ["-o", rep, "-r0", "-v", base, "-p56"] + joint,
                        check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
         text = open(rep).read()
 
@@ -299,6 +300,8 @@ def main():
                 "t_histograms": section("HISTOGRAM GROUP 1", " After\t"),
                 "histograms": section("HISTOGRAM GROUP 2", " After\t"),
                 "popmig_histograms": section("HISTOGRAM GROUP 3: POPULATION MIGRATION", " After\t")}
+        if joint:
+            keep["joint"] = section("Joint Peak Locations", "\nHISTOGRAMS\n")
         import json
         with gzip.GzipFile(os.path.join(HERE, rep_name + ".json.gz"), "wb", mtime=0) as g:
             g.write(json.dumps(keep).encode())

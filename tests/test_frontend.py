@@ -76,11 +76,25 @@ def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path, name):
     else:
         u = tmp_path / "Sim3.u"
         u.write_text(_sim3_u())
-    r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l.out"), "-q10", "-m1", "-t3", "-p56"])
+    r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l.out"), "-q10", "-m1", "-t3", "-p56", "-c2", "-s", "3"])
     assert r.returncode == 0, r.stderr
     rep = open(tmp_path / "l.out").read()
     for key in ("greater_than", "moments", "peaks", "t_histograms", "histograms", "popmig_histograms"):
         assert ref[key].strip("\n") in rep, key
+    if "joint" in ref:
+        # the joint-posterior peak (-c2): a stochastic search (differential evolution, every generation one batched device
+        # call) with this program's own random numbers, so the comparison is numerical: the peak the reference found
+        def peak_row(text):
+            a = text.index("Joint Peak Locations")
+            lines = text[a:].split("\n")
+            k = [i for i, ln in enumerate(lines) if ln.startswith("Model#\tlog(P)")][0]
+            return lines[k].split("\t"), lines[k + 1].split("\t")
+        (hr, vr), (ho, vo) = peak_row(ref["joint"]), peak_row(rep)
+        assert hr == ho and vr[2:5] == vo[2:5]                            # same columns; #terms, df, 2LLR
+        assert abs(float(vr[1]) - float(vo[1])) <= 2e-3                   # log(P) at the peak
+        assert abs(float(vr[5]) - float(vo[5])) <= 0.02 * float(vr[5])    # effective sample size there
+        for a, b in zip(vr[6:], vo[6:]):
+            assert abs(float(a) - float(b)) <= 2e-3 * max(1.0, abs(float(a))), (vr, vo)
     r = _run(exe, ["-r0", "-i", str(u), "-o", str(tmp_path / "l2.out"), "-q10", "-m1", "-t3"])
     assert r.returncode == 8 and "-v" in r.stderr            # IMERR_MISSINGCOMMANDINFO
 
