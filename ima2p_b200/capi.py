@@ -57,6 +57,7 @@ SIGNATURES = {
     "ima2p_engine_set_update_schedule": (_i, [_v, _i, _i]),
     "ima2p_engine_set_update_priors": (_i, [_v, c_dbl_p, c_dbl_p, _d, _d, _d, _d]),
     "ima2p_engine_update_counters": (_i, [_v, c_u64_p]),
+    "ima2p_engine_cold_counters": (_i, [_v, c_u64_p, c_u64_p, c_u64_p, c_u64_p]),
     "ima2p_engine_get_split_times": (_i, [_v, _i, c_dbl_p]),
     "ima2p_engine_fetch_parameters": (_i, [_v, c_dbl_p, c_dbl_p, c_dbl_p]),
     "ima2p_engine_get_scalars": (_i, [_v, _i, _i, c_dbl_p, c_dbl_p]),
@@ -84,6 +85,7 @@ SIGNATURES = {
     "ima2p_dataset_read": (_i, [C.c_char_p, C.POINTER(_v)]),
     "ima2p_dataset_free": (None, [_v]),
     "ima2p_dataset_dims": (_i, [_v, c_int_p, c_int_p, C.c_char_p, _i]),
+    "ima2p_dataset_text": (_i, [_v, _i, _i, C.c_char_p, _i]),
     "ima2p_dataset_locus": (_i, [_v, _i, c_int_p, c_dbl_p, c_int_p, C.c_char_p, _i]),
     "ima2p_dataset_locus_data": (_i, [_v, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
     "ima2p_engine_step_report": (_i, [_v, c_dbl_p, c_flt_p, c_int_p, _v]),

@@ -454,7 +454,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   v.qint = e.alloc<double>(C * kMaxParams); v.mint = e.alloc<double>(C * kMaxParams);
   v.probg = e.alloc<double>(C); v.pdgsum = e.alloc<double>(C); v.swapsum = e.alloc<double>(C);
   v.prop_extra = e.alloc<double>(P); v.prop_flags = e.alloc<uint32_t>(P); v.prop_dbg = e.alloc<double>(P * 4);
-  v.acc = e.alloc<unsigned int>(P * 3);
+  v.acc = e.alloc<unsigned int>(P * 3); v.cold_acc = e.alloc<unsigned int>((size_t)d.nloci * 3);
   v.nsteps = e.alloc<unsigned long long>(1); v.overflow = e.alloc<unsigned long long>(1);
   v.seed = e.seed;
   v.loci = e.d_loci; v.sitemask = d_sm; v.seq = d_sq; v.mult = d_mu;
@@ -462,6 +462,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   e.sv.rank_of_chain = e.alloc<int>(G); e.sv.chain_of_rank = e.alloc<int>(G);
   e.d_beta_table = e.alloc<double>(G); e.sv.beta_table = e.d_beta_table;
   e.d_swap_counts = e.alloc<unsigned long long>(2); e.sv.swap_counts = e.d_swap_counts;
+  e.sv.adj_counts = e.alloc<unsigned long long>((size_t)G * 2);
   e.d_thermosum = e.alloc<double>(G);
   {
     // mutation-rate scalars in the order of readata.cpp:832-834; update parameters start at the reference's defaults
@@ -471,7 +472,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
     int *ul_l = e.alloc<int>(u.nurates), *ul_a = e.alloc<int>(u.nurates);
     u.ul_l = ul_l; u.ul_a = ul_a;
     u.t_counts = e.alloc<int>(P * 4); u.t_out = e.alloc<double>(C * 4); u.u_out = e.alloc<double>(C * 4);
-    u.stats = e.alloc<unsigned long long>(4);
+    u.stats = e.alloc<unsigned long long>(update_stats_len(u.nurates));
     if (!u.stats || !u.u_out) return fail(IMA2P_E_CUDA, "device allocation failed");
     stream_t s0 = pick_stream(&e, nullptr);
     if (!h2d(ul_l, e.h_ul_l.data(), u.nurates * sizeof(int), s0) || !h2d(ul_a, e.h_ul_a.data(), u.nurates * sizeof(int), s0) || !dev_sync(s0))
@@ -482,7 +483,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
     u.kappa_win = 2.0; u.kappa_max = 100.0;                // initialize.cpp:1499-1501
     u.t_forced = nullptr; u.t_forced_period = 0; u.t_force_accept = -1; u.t_forced_method = 0; u.t_methods = 1; u.u_forced = 0; u.u_every = 5;
   }
-  if (!v.acc || !v.buf[1].gwd || !e.d_swap_counts || !v.overflow) return fail(IMA2P_E_CUDA, "device allocation failed");
+  if (!v.acc || !v.cold_acc || !e.sv.adj_counts || !v.buf[1].gwd || !e.d_swap_counts || !v.overflow) return fail(IMA2P_E_CUDA, "device allocation failed");
   stream_t s = pick_stream(&e, nullptr);
   bool ok = h2d(e.d_logfact, lf.data(), nlf * sizeof(double), s) && h2d(e.d_loci, dl.data(), dl.size() * sizeof(DevLocus), s);
   if (!sm.empty()) ok = ok && h2d(d_sm, sm.data(), sm.size() * sizeof(uint32_t), s);
@@ -1041,6 +1042,26 @@ int ima2p_engine_update_counters(ima2p_engine *h, uint64_t *out4) {
   unsigned long long v[4];
   if (!d2h(v, e.uv.stats, sizeof(v), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   for (int i = 0; i < 4; i++) out4[i] = v[i];
+  return IMA2P_OK;
+}
+
+// The reference's update-rate tables (callprintacceptancerates, ima_main_mpi.cpp:3473-3900) and its swap table
+// (printchaininfo, swapchains.cpp:760-778) count the cold chain / adjacent temperatures only.
+int ima2p_engine_cold_counters(ima2p_engine *h, uint64_t *genealogy, uint64_t *split, uint64_t *scalars, uint64_t *adjacent) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "cold_counters: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const int nur = e.uv.nurates, G = e.d.nchains_global, nsplit = e.model.nsplit;
+  std::vector<unsigned int> g((size_t)e.d.nloci * 3);
+  std::vector<unsigned long long> st(update_stats_len(nur)), adj((size_t)G * 2);
+  if (!d2h(g.data(), e.v.cold_acc, g.size() * sizeof(unsigned int), s) || !d2h(st.data(), e.uv.stats, st.size() * 8, s) ||
+      !d2h(adj.data(), e.sv.adj_counts, adj.size() * 8, s) || !dev_sync(s))
+    return fail(IMA2P_E_CUDA, "download failed");
+  if (genealogy) for (size_t i = 0; i < g.size(); i++) genealogy[i] = g[i];
+  if (split) for (int k = 0; k < nsplit; k++) for (int j = 0; j < 4; j++) split[k * 4 + j] = st[kColdTStat + k * 4 + j];
+  if (scalars) for (int j = 0; j < 2 * nur; j++) scalars[j] = st[kColdUStat + j];
+  if (adjacent) for (int r = 0; r + 1 < G; r++) { adjacent[r * 2] = adj[r * 2]; adjacent[r * 2 + 1] = adj[r * 2 + 1]; }
   return IMA2P_OK;
 }
 

@@ -21,6 +21,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdarg>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -102,6 +104,29 @@ Tree start_genealogy(const Locus &L, int npops, int rootpop, double tbase, unsig
   return T;
 }
 
+// The constant of the infinite-sites likelihood as the reference fixes it (calc_sumlogk, calc_prob_data.cpp:609-719, called
+// once per locus on the genealogy the run starts with): every site is counted at the node whose two daughters carry its two
+// states, and the constant is the sum over nodes of log(count!) -- mutations on two sister branches fall on the same node.
+double sumlogk_of(const Locus &L, const Tree &T) {
+  const int n = L.info[1], ns = L.info[2], nl = 2 * n - 1;
+  std::vector<std::vector<char>> below(nl, std::vector<char>(n, 0));          // tips under every edge
+  for (int j = 0; j < n; j++) for (int e = j; e != -1; e = T.down[e]) below[e][j] = 1;
+  std::vector<int> mutcount(nl, 0);
+  for (int s = 0; s < ns; s++) {
+    int node = -1;
+    for (int e = 0; e < nl && node < 0; e++) {
+      if (T.down[e] == -1) continue;
+      bool same = true, comp = true;
+      for (int j = 0; j < n && (same || comp); j++) { const bool c = L.seq[(size_t)j * ns + s] != 0; same &= c == (below[e][j] != 0); comp &= c != (below[e][j] != 0); }
+      if (same || comp) node = T.down[e];
+    }
+    if (node < 0) die("starting genealogy: data not compatible with the infinite sites model", 36);
+    mutcount[node]++;
+  }
+  double sum = 0.0;
+  for (int k = n; k < nl; k++) sum += lgamma(mutcount[k] + 1.0);
+  return sum;
+}
 
 
 // ---- L mode report ------------------------------------------------------------------------------------------------
@@ -675,6 +700,115 @@ void print_joint_peak(FILE *f, ima2p_lmode *LM, long long G, const std::vector<s
 
 // The report sections that are sums over the sampled genealogies (printoutput, ima_main_mpi.cpp:4080-4110), written to f from
 // `nrows` rows: used by L mode on the rows of a .ti file and by M mode on the rows the run has just saved.
+// ---- the opening sections of the report, in the reference's layout ------------------------------------------------
+// "INPUT AND STARTING INFORMATION": print_outputfile_info_string (ima_main_mpi.cpp:1565-1671) followed by what readdata
+// (readata.cpp:916-1081, locus lines :640-832), reportparamcounts (initialize.cpp:2059-2069) and add_priorinfo_to_output
+// (initialize.cpp:1557-1575) append to the same string while the run is set up.
+struct RunInfo {
+  std::string command_line, heating, calc, model, output;      // scan_commandline's echo strings (ima_main_mpi.cpp:449-487)
+  std::string infile, outfile, ti, mcf_in, mcf_out;
+  unsigned long long seed; long burn, nsave, every; int nchains, heatmode; double ha, hb;
+  bool lmode, expo;
+};
+
+std::string sprintf_s(const char *fmt, ...) {
+  char b[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(b, sizeof b, fmt, ap); va_end(ap);
+  return b;
+}
+
+std::string start_info(const RunInfo &R, ima2p_dataset *D, int npops, int nloci, const char *tree, int nq, int nm, int nsplit, double qmax, double mmax,
+                       double tmax) {
+  std::string s = "IMa2p_b200 - B200 engine for the IMa2p hot path; report sections in the layout of IMa2p version 1.0\n\n";
+  s += "\nINPUT AND STARTING INFORMATION \n================================\n";
+  s += "\nCommand line string : " + R.command_line + " \n";
+  s += "  Input filename : " + R.infile + " \n  Output filename: " + R.outfile + " \n";
+  s += sprintf_s("  Random number seed : %llu \n", R.seed);
+  s += "  Heating terms on command line : " + R.heating + " \n  Calculation options on command line : " + R.calc + " \n";
+  s += "  Model options on command line : " + R.model + " \n  Output options on command line : " + R.output + " \n";
+  if (!R.lmode) {
+    s += "- Run Duration - \n";
+    s += sprintf_s("     Burn period, # steps: %li \n", R.burn);
+    s += sprintf_s("     Record period, #saves: %d  #steps each: %li   total #steps: %li \n", (int)R.nsave, R.every, R.nsave * R.every);
+    s += "- Metropolis Coupling -\n";
+    if (R.nchains > 1) {
+      s += sprintf_s("     Metropolis Coupling implemented using %d chains \n", R.nchains);
+      if (R.heatmode == 0) s += sprintf_s("     Linear Increment Model   term: %.3f\n", R.ha);
+      else if (R.heatmode == 1) s += sprintf_s("     Geometric Increment Model   term1: %.3f  term2: %.3f\n", R.ha, R.hb);
+    } else s += "     None \n";
+  }
+  if (!R.mcf_in.empty()) s += "Initial Markov chain state space loaded from file: " + R.mcf_in + "\n";
+  if (R.expo) s += "Exponential priors used for migration rate parameters\n";
+  if (!R.mcf_out.empty()) s += "State of Markov chain saved to file : " + R.mcf_out + "\n";
+  if (!R.lmode) s += "All genealogy information used for surface estimation printed to file: " + R.ti + "\n";
+  char buf[2048];
+  for (int k = 0; ima2p_dataset_text(D, 0, k, buf, sizeof buf) == IMA2P_OK; k++) s += std::string(k == 0 ? "\n" : "") + "Text from input file: " + buf + "\n";
+  s += sprintf_s("\nNumber of sampled populations given in input file: %d \n- Population Names - \n", npops);
+  for (int i = 0; i < npops; i++) { ck(ima2p_dataset_text(D, 1, i, buf, sizeof buf), "population name"); s += sprintf_s("Population %d : %s \n", i, buf); }
+  s += std::string("\nPopulation Tree : ") + tree + "\n";
+  s += sprintf_s("\nLocus Information\n-----------------\n\nNumber of loci: %d \nLocus#\tLocusname", nloci);
+  for (int i = 0; i < npops; i++) s += sprintf_s("\tPop%d#", i);
+  s += "\tModel\tInheritanceScalar\tMutationRatesPerYear\n";
+  int nurates = 0, nkappas = 0;
+  for (int li = 0; li < nloci; li++) {
+    int info[8]; double hval; std::vector<int> samppop(npops); char name[64];
+    ck(ima2p_dataset_locus(D, li, info, &hval, samppop.data(), name, sizeof name), "locus");
+    s += sprintf_s("%d\t%s", li, name);
+    for (int i = 0; i < npops; i++) s += sprintf_s("\t%3d", samppop[i]);
+    const bool many = (info[7] & 1) != 0;
+    s += info[0] == IMA2P_MODEL_HKY ? "\tHKY" : info[0] == IMA2P_MODEL_SW ? (many ? "\tSW_M" : "\tSW") : info[0] == IMA2P_MODEL_JOINT ? (many ? "\tIS+SW_M" : "\tIS+SW") : "\tIS";
+    s += sprintf_s((info[7] & 2) ? "\t%5.3lf" : "\t%lf", hval);
+    if (info[6] > 0) {
+      std::vector<double> ur(info[6]);
+      const int n = info[1], ns = info[2] > 0 ? info[2] : 1, nl = info[5];
+      std::vector<int> seq((size_t)n * ns), mult(ns), A((size_t)nl * n), mn(nl), mx(nl); double pi[4];
+      ck(ima2p_dataset_locus_data(D, li, seq.data(), mult.data(), A.data(), mn.data(), mx.data(), pi, ur.data()), "locus data");
+      for (double u : ur) s += sprintf_s("\t%lg", u);
+    }
+    s += "\n";
+    nurates += info[5];
+    nkappas += info[0] == IMA2P_MODEL_HKY;
+  }
+  s += sprintf_s("\nParameter Counts\n----------------\n   Population sizes : %d\n   Migration rates  : %d\n   Parameters in the MCMC simulation\n", nq, nm);
+  s += sprintf_s("      Splitting times : %d\n      Mutation scalars: %d\n      HKY Kappa (ti/tv) ratios: %d\n", nsplit, nurates, nkappas);
+  s += sprintf_s("\nParameter Priors\n-----------------\n  Population size parameters maximum value : %.4lf \n", qmax);
+  s += sprintf_s(R.expo ? "  Migration rate parameters exponential distribution mean : %.4lf \n" : "  Migration rate parameters maximum value: %.4lf \n", mmax);
+  s += sprintf_s("  Splitting time : %.4lf\n\n", tmax);
+  return s;
+}
+
+// "%.2e" with the exponent's sign and leading zeros dropped (shorten_e_num, utilities.cpp:1909-1921)
+std::string short_e(double v) {
+  char b[32];
+  snprintf(b, sizeof b, "%.2e", (float)v);
+  std::string s = b;
+  const size_t e = s.find('e');
+  while (e + 1 < s.size() && (s[e + 1] == '0' || s[e + 1] == '+')) s.erase(e + 1, 1);
+  return s;
+}
+
+// printacceptancerates (output.cpp:528-571): one row per record, (#Tries, #Accp, %) per update type
+struct RateRow { std::string name; std::vector<unsigned long long> tries, accp; };
+void print_rates(FILE *f, const char *title, const std::vector<std::string> &types, const std::vector<RateRow> &rows) {
+  fprintf(f, "\n%s\n", title);
+  for (size_t i = 0; i < strlen(title); i++) fprintf(f, "-");
+  fprintf(f, "\nUpdate Type:");
+  for (const auto &t : types) fprintf(f, "\t%s\t", t.c_str());
+  fprintf(f, "\n            ");
+  for (size_t i = 0; i < types.size(); i++) fprintf(f, "\t#Tries\t#Accp\t%%");
+  fprintf(f, "\n");
+  for (const auto &r : rows) {
+    fprintf(f, " %s", r.name.c_str());
+    for (size_t i = r.name.size(); i < 13; i++) fprintf(f, " ");
+    for (size_t i = 0; i < types.size(); i++) {
+      fprintf(f, "\t%s\t%s", short_e((double)r.tries[i]).c_str(), short_e((double)r.accp[i]).c_str());
+      if (r.tries[i] > 0) fprintf(f, "\t%.2f", (float)100 * r.accp[i] / r.tries[i]);
+      else fprintf(f, "\tna");
+    }
+    fprintf(f, "\n");
+  }
+}
+
 void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo,
                      const float *rowdata, long long nrows, bool loaded_from_ti) {
   int md[6];
@@ -791,7 +925,7 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
   ima2p_lmode_destroy(LM);
 }
 
-int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo) {
+int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo, const std::string &info) {
   int md[6];
   ima2p_modelspec_dims(S, md);
   const int rowlen = 3 * md[3] + 2 * md[4] + md[3] + md[4] + 2 + md[1];
@@ -804,7 +938,7 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
   ck(ima2p_ti_load(ti.c_str(), rowlen, rows.data(), nrows, &nrows), "loading the genealogy file");
   FILE *f = fopen(opt["o"].c_str(), "w");
   if (!f) die("cannot create the output file", 2);
-  fprintf(f, "IMa2p_b200 L mode report\n\nLOAD TREES (L) MODE INFORMATION\n============================================================================\n");
+  fprintf(f, "%s\n\nLOAD TREES (L) MODE INFORMATION\n============================================================================\n", info.c_str());
   fprintf(f, "  Base filename for loading files with sampled genealogies: %s*.ti\n  loaded %lld genealogies from genealogy file  %s\n", opt["v"].c_str(), nrows, ti.c_str());
   report_sections(f, opt, S, npops, qmax, mmax, expo, rows.data(), nrows, true);
   fclose(f);
@@ -817,9 +951,15 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
 int main(int argc, char **argv) {
   std::map<std::string, std::string> opt;
   static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", "c", nullptr};
+  RunInfo R{};
   for (int a = 1; a < argc; a++) {
     if (argv[a][0] != '-') die(std::string("command line: unexpected word ") + argv[a], 5);
     const std::string w = argv[a] + 1;
+    const char c1 = (char)toupper((unsigned char)w[0]);
+    if (c1 == 'H') R.heating += std::string(" ") + argv[a];
+    if (c1 == 'J') R.model += std::string(" ") + argv[a];
+    if (c1 == 'C') R.calc += std::string(" ") + argv[a];
+    if (c1 == 'P') R.output += std::string(" ") + argv[a];
     std::string key;
     for (int k = 0; known[k]; k++) if (w.compare(0, strlen(known[k]), known[k]) == 0) { key = known[k]; break; }
     if (key.empty()) die("command line: option -" + w + " is not part of this build (M-mode hot path only)", 5);
@@ -839,6 +979,14 @@ int main(int argc, char **argv) {
   const long burn = atol(opt["b"].c_str()), nsave = atol(opt["l"].c_str()), every = opt.count("d") ? atol(opt["d"].c_str()) : 100;
   const unsigned long long seed = opt.count("s") ? strtoull(opt["s"].c_str(), nullptr, 10) : 1ull;
   if (nchains < 1 || burn < 0 || nsave < 1 || every < 1 || !(tmax > 0)) die("command line: bad value", 5);
+  for (int a = 1; a < argc; a++) R.command_line += std::string(" ") + argv[a];
+  R.infile = opt["i"]; R.outfile = opt["o"]; R.ti = opt["o"] + ".ti"; R.seed = seed; R.burn = burn; R.nsave = nsave; R.every = every; R.nchains = nchains;
+  R.heatmode = opt.count("hf") ? (opt["hf"] == "g" ? 1 : opt["hf"] == "s" ? 2 : 0) : 0;
+  R.ha = opt.count("ha") ? atof(opt["ha"].c_str()) : 0.05; R.hb = opt.count("hb") ? atof(opt["hb"].c_str()) : 0.0;
+  R.lmode = lmode; R.expo = expo != 0;
+  if (opt.count("f")) R.mcf_in = opt["f"];
+  if (opt.count("r") && !lmode) R.mcf_out = opt["o"] + ".mcf";
+  const time_t starttime = time(nullptr);
 
   ima2p_dataset *D = nullptr;
   ck(ima2p_dataset_read(opt["i"].c_str(), &D), "reading data");
@@ -848,7 +996,9 @@ int main(int argc, char **argv) {
   ima2p_modelspec *S = nullptr;
   ck(ima2p_modelspec_create(&S, npops, tree, qmax, expo ? 20.0 * mmax : mmax, expo, expo ? mmax : 0.0, 0, 1.0), "model");   // -j7: -m is the mean, plotted to 20 means
   if (lmode) {
-    const int rc = run_lmode(opt, S, npops, qmax, mmax, expo);
+    int lmd[6];
+    ima2p_modelspec_dims(S, lmd);
+    const int rc = run_lmode(opt, S, npops, qmax, mmax, expo, start_info(R, D, npops, nloci, tree, lmd[3], lmd[4], lmd[1], qmax, mmax, tmax));
     ima2p_modelspec_free(S);
     ima2p_dataset_free(D);
     return rc;
@@ -870,27 +1020,22 @@ int main(int argc, char **argv) {
     if (nlinked > IMA2P_MAX_LINKED) die("more linked stepwise parts than this build keeps on the device", 5);
   }
 
+  // set_tvalues (initialize.cpp:1945-1960): split times evenly spaced inside the prior; the genealogies a run starts with
+  // (with -f they only fix the infinite-sites constant, as the reference's do)
+  std::vector<double> tv(nsplit > 0 ? nsplit : 1);
+  for (int k = 0; k < nsplit; k++) tv[k] = (k + 1.0) / (nsplit + 1.0) * tmax;
+  std::vector<Tree> start(nloci);
+  {
+    unsigned rng = (unsigned)seed * 2654435761u + 12345u;
+    for (int li = 0; li < nloci; li++) start[li] = start_genealogy(loci[li], npops, rootpop, nsplit > 0 ? tv[nsplit - 1] : 0.0, rng);
+  }
   ima2p_engine *E = nullptr;
   ck(ima2p_engine_create(&E, 0, nchains, nchains, 0, nloci, 96, seed), "engine");
   ck(ima2p_engine_set_model_spec(E, S), "model");
   for (int li = 0; li < nloci; li++) {
     Locus &L = loci[li];
     const int model = L.info[0], n = L.info[1], ns = L.info[2], nlinked = L.info[5];
-    // sumlogk (calc_prob_data.cpp:609-719): log k! over the branches carrying k mutations, i.e. over repeated columns
-    double sumlogk = 0.0;
-    if (model == IMA2P_MODEL_IS || model == IMA2P_MODEL_JOINT) {
-      std::vector<char> done(ns, 0);
-      for (int s = 0; s < ns; s++) {
-        if (done[s]) continue;
-        int k = 0;
-        for (int r = s; r < ns; r++) {
-          bool same = true, comp = true;
-          for (int j = 0; j < n && (same || comp); j++) { const int a = L.seq[(size_t)j * ns + s], b = L.seq[(size_t)j * ns + r]; same &= a == b; comp &= a != b; }
-          if (same || comp) { done[r] = 1; k++; }
-        }
-        sumlogk += lgamma(k + 1.0);
-      }
-    }
+    const double sumlogk = (model == IMA2P_MODEL_IS || model == IMA2P_MODEL_JOINT) ? sumlogk_of(L, start[li]) : 0.0;
     std::vector<int> lo(nlinked, 0), hi(nlinked, 0);          // allele range rule of build_gtree.cpp:519-520, 721-722
     for (int a = (model == IMA2P_MODEL_JOINT); a < nlinked && (model == IMA2P_MODEL_SW || model == IMA2P_MODEL_JOINT); a++) {
       const int mn = L.minA[a], mx = L.maxA[a];
@@ -911,14 +1056,10 @@ int main(int argc, char **argv) {
   if (opt.count("f")) {
     ck(ima2p_engine_read_mcf(E, opt["f"].c_str()), "loading the state file");
   } else {
-    // set_tvalues (initialize.cpp:1945-1960): split times evenly spaced inside the prior
-    std::vector<double> tv(nsplit > 0 ? nsplit : 1);
-    for (int k = 0; k < nsplit; k++) tv[k] = (k + 1.0) / (nsplit + 1.0) * tmax;
-    unsigned rng = (unsigned)seed * 2654435761u + 12345u;
     for (int li = 0; li < nloci; li++) {
       const Locus &L = loci[li];
       const int n = L.info[1], nl = 2 * n - 1, nlinked = L.info[5];
-      const Tree T = start_genealogy(L, npops, rootpop, nsplit > 0 ? tv[nsplit - 1] : 0.0, rng);
+      const Tree &T = start[li];
       std::vector<int> moff(nl + 1, 0), mp(1, 0), A((size_t)nlinked * nl, 0);
       std::vector<double> mt(1, 0.0), u(IMA2P_MAX_LINKED, 1.0);
       for (int a = 0; a < nlinked; a++) {                     // internal allele states: those of a descendant tip
@@ -947,6 +1088,15 @@ int main(int argc, char **argv) {
   ck(ima2p_ti_create(ti.c_str(), header.c_str()), "creating the .ti file");
   printf("IMa2p_b200: %d populations %s, %d loci, %d chains, burn %ld steps, %ld genealogies every %ld steps\n", npops, tree, nloci, nchains, burn, nsave, every);
   for (long done = 0; done < burn;) { const int n = burn - done > 1000 ? 1000 : (int)(burn - done); ck(ima2p_engine_run(E, n, swaptries, nullptr), "burn-in"); done += n; }
+  // the reference's update-rate and swap tables start counting after the burn-in (reset_after_burn)
+  uint64_t cnt0[8], ucnt0[4];
+  const int nur = [&] { int k = 0; for (auto &L : loci) k += L.info[5]; return k; }();
+  std::vector<uint64_t> cg0((size_t)nloci * 3), ct0((size_t)(nsplit > 0 ? nsplit : 1) * 4), cu0((size_t)nur * 2), ca0((size_t)nchains * 2, 0), cg(cg0), ct(ct0), cu(cu0), ca(ca0);
+  ck(ima2p_engine_counters(E, cnt0), "counters");
+  ck(ima2p_engine_update_counters(E, ucnt0), "counters");
+  ck(ima2p_engine_cold_counters(E, cg0.data(), ct0.data(), cu0.data(), ca0.data()), "counters");
+  double hilike = -1e20, hiprob = -1e20;                                   // checkhighs (output.cpp:207-240), at the recorded steps
+  std::vector<double> hilocus(nloci, -1e20), pair_sd((size_t)nchains * nloci * 4);
   std::vector<double> chain4((size_t)nchains * 4);
   std::vector<float> rows, row(rowlen), allrows;
   std::vector<double> tsum(nsplit > 0 ? nsplit : 1, 0.0);
@@ -956,6 +1106,13 @@ int main(int argc, char **argv) {
     int present = 0;
     ck(ima2p_engine_step_report(E, chain4.data(), row.data(), &present, nullptr), "reading the cold chain");
     if (!present) die("the cold chain is not on this device");
+    ck(ima2p_engine_fetch_pair_summaries(E, pair_sd.data(), nullptr, nullptr, nullptr), "reading the likelihoods");
+    for (int c = 0; c < nchains; c++) {
+      if (chain4[(size_t)c * 4] != 1.0) continue;
+      if (chain4[(size_t)c * 4 + 1] > hiprob) hiprob = chain4[(size_t)c * 4 + 1];
+      if (chain4[(size_t)c * 4 + 2] > hilike) hilike = chain4[(size_t)c * 4 + 2];
+      for (int li = 0; li < nloci; li++) { const double v = pair_sd[((size_t)c * nloci + li) * 4 + 3]; if (v > hilocus[li]) hilocus[li] = v; }
+    }
     rows.insert(rows.end(), row.begin(), row.end());
     allrows.insert(allrows.end(), row.begin(), row.end());
     for (int k = 0; k < nsplit; k++) tsum[k] += row[rowlen - nsplit + k];
@@ -968,7 +1125,62 @@ int main(int argc, char **argv) {
   const std::string outname = opt["o"];
   FILE *f = fopen(outname.c_str(), "w");
   if (!f) die("cannot create the output file", 2);
-  fprintf(f, "IMa2p_b200 run summary\n%s\n\nsteps %llu  genealogy updates %llu  accepted %.4f  topology changes %.4f\n", header.c_str(), (unsigned long long)cnt[0],
+  ck(ima2p_engine_cold_counters(E, cg.data(), ct.data(), cu.data(), ca.data()), "counters");
+  const unsigned long long poststeps = cnt[0] - cnt0[0];
+  fprintf(f, "%s", start_info(R, D, npops, nloci, tree, md[3], md[4], nsplit, qmax, mmax, tmax).c_str());
+  // printrunbasics (output.cpp:166-206)
+  fprintf(f, "\n\nMCMC INFORMATION\n===========================\n\n");
+  fprintf(f, "Number of steps in burnin: %10d\nNumber of steps in chain following burnin: %10d \n", (int)burn, (int)poststeps);
+  fprintf(f, "Number of steps between recording : %d  Number of record steps: %d \n", (int)every, (int)saved);
+  fprintf(f, "Number of steps between saving genealogy information: %d  Number of genealogies saved per locus: %d \n", (int)every, (int)saved);
+  const int seconds = (int)difftime(time(nullptr), starttime);
+  fprintf(f, "\nTime Elapsed : %d hours, %d minutes, %d seconds \n\n", seconds / 3600, seconds / 60 - 60 * (seconds / 3600), seconds - 60 * (seconds / 60));
+  fprintf(f, "Highest Sampled Joint P(G) (log) : %10.3f \nHighest Joint P(D|G) (log) : %10.3f \n\n\n", hiprob, hilike);
+  fprintf(f, "Highest P(D|G) (log) for each Locus \n\tLocus\tP(D|G)\n");
+  for (int li = 0; li < nloci; li++) fprintf(f, "\t%d\t%.3f\n", li, hilocus[li]);
+  fprintf(f, "\n");
+  // callprintacceptancerates (ima_main_mpi.cpp:3473-3899): the cold chain's tries and accepts since the burn-in
+  if (nsplit > 0) {
+    std::vector<RateRow> tr;
+    for (int k = 0; k < nsplit; k++)
+      tr.push_back({"t" + std::to_string(k), {ct[k * 4 + 2] - ct0[k * 4 + 2], ct[k * 4] - ct0[k * 4]}, {ct[k * 4 + 3] - ct0[k * 4 + 3], ct[k * 4 + 1] - ct0[k * 4 + 1]}});
+    print_rates(f, "Update Rates -- Population Splitting Times", {"NielsenWakeley", "RannalaYang"}, tr);
+  }
+  {
+    std::vector<RateRow> gr;
+    for (int li = 0; li < nloci; li++)
+      gr.push_back({"gtree_" + std::to_string(li), {poststeps, poststeps, poststeps}, {cg[li * 3] - cg0[li * 3], cg[li * 3 + 1] - cg0[li * 3 + 1], cg[li * 3 + 2] - cg0[li * 3 + 2]}});
+    print_rates(f, "Update Rates -- Genealogies", {"branch     ", "topology   ", "tmrca      "}, gr);
+  }
+  if (nur > 1) {
+    std::vector<RateRow> ur;
+    int j = 0;
+    for (int li = 0; li < nloci; li++)
+      for (int a = 0; a < loci[li].info[5]; a++, j++) {
+        const bool sw = loci[li].info[0] == IMA2P_MODEL_SW || (loci[li].info[0] == IMA2P_MODEL_JOINT && a > 0);
+        ur.push_back({sw ? std::to_string(li) + "SW" + std::to_string(a) : std::to_string(li) + "u ", {cu[j * 2] - cu0[j * 2]}, {cu[j * 2 + 1] - cu0[j * 2 + 1]}});     // initialize.cpp:1453-1466
+      }
+    print_rates(f, "Update Rates -- Mutation Rate Scalars", {"scalar update"}, ur);
+  }
+  if (nchains > 1) {
+    // printchaininfo (swapchains.cpp:664-690, 815-823): swaps between adjacent temperatures (only betas move here, so the
+    // per-chain table of the serial build has no counterpart)
+    fprintf(f, "\nCHAIN SWAPPING:");
+    if (R.heatmode == 0) fprintf(f, " Linear Increment  term: %.4f\n", R.ha);
+    else if (R.heatmode == 1) fprintf(f, " Geometric Increment  term1: %.4f term2: %.4f\n", R.ha, R.hb);
+    else fprintf(f, "\n");
+    fprintf(f, "-----------------------------------------------------------------------------\n");
+    std::vector<double> betas(nchains);
+    ck(ima2p_engine_get_betas(E, betas.data()), "betas");
+    std::sort(betas.begin(), betas.end(), [](double a, double b) { return a > b; });
+    fprintf(f, "Temp1    Temp2    #Swaps    #Attempts    Rate\n");
+    for (int r = 0; r + 1 < nchains; r++) {
+      const unsigned long long att = ca[r * 2] - ca0[r * 2], sw = ca[r * 2 + 1] - ca0[r * 2 + 1];
+      if (att > 0) fprintf(f, " %7.4f    %7.4f    %5llu    %5llu    %7.4lf\n", betas[r], betas[r + 1], sw, att, (float)sw / (float)att);
+      else fprintf(f, " %7.4f    %7.4f    %5llu    %5llu    na\n", betas[r], betas[r + 1], sw, att);
+    }
+  }
+  fprintf(f, "\nENGINE INFORMATION (all chains, whole run)\n------------------------------------------\nsteps %llu  genealogy updates %llu  accepted %.4f  topology changes %.4f\n", (unsigned long long)cnt[0],
           (unsigned long long)cnt[1], (double)cnt[2] / (double)(cnt[1] ? cnt[1] : 1), (double)cnt[3] / (double)(cnt[1] ? cnt[1] : 1));
   fprintf(f, "chain swaps %llu of %llu attempts\nsplit-time updates accepted %llu of %llu   mutation-scalar updates accepted %llu of %llu\n", (unsigned long long)cnt[6],
           (unsigned long long)cnt[5], (unsigned long long)ucnt[1], (unsigned long long)ucnt[0], (unsigned long long)ucnt[3], (unsigned long long)ucnt[2]);

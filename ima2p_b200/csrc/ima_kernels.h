@@ -566,10 +566,22 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
               atomicAdd(&E.acc[(size_t)p * 3 + 0], 1u);                 // fire and forget: nothing waits for the old value
               if (flags & kFlagTopol) atomicAdd(&E.acc[(size_t)p * 3 + 1], 1u);
               if (flags & kFlagTmrca) atomicAdd(&E.acc[(size_t)p * 3 + 2], 1u);
+              if (beta == 1.0) {
+                unsigned int *ca = E.cold_acc + (size_t)(li + aoff) * 3;
+                atomicAdd(ca, 1u);
+                if (flags & kFlagTopol) atomicAdd(ca + 1, 1u);
+                if (flags & kFlagTmrca) atomicAdd(ca + 2, 1u);
+              }
 #else
               E.acc[(size_t)p * 3 + 0]++;
               if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
               if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
+              if (beta == 1.0) {
+                unsigned int *ca = E.cold_acc + (size_t)(li + aoff) * 3;
+                ca[0]++;
+                if (flags & kFlagTopol) ca[1]++;
+                if (flags & kFlagTmrca) ca[2]++;
+              }
 #endif
             }
             probg = np;
@@ -628,12 +640,20 @@ struct SwapView {
   int *chain_of_rank;       // [nchains_global]
   const double *beta_table; // [nchains_global] beta by temperature rank (rank 0 = cold)
   unsigned long long *swap_counts;   // [2] attempts, accepts
+  unsigned long long *adj_counts;    // [nchains_global][2] attempts, accepts between temperature ranks r and r + 1 (tempbasedswapcount, swapchains.cpp:760-778)
   int swaptries, advance_step;
   int step_bias;            // 1 when the step counter was already advanced (split-phase multi-GPU step): the draws stay keyed by the step they belong to
   int smem_chains;          // chains the launch's shared memory can stage (0: work on global memory)
 };
 
 constexpr int kSwapBatch = 256;           // attempts drawn per pass
+IMA_DEV void stat_add(unsigned long long *p, unsigned long long v) {
+#if IMA_CUDA
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
 IMA_HD size_t swap_smem_bytes(int staged_chains) { return (size_t)staged_chains * 24 + 16 + (size_t)kSwapBatch * 16; }
 IMA_KERNEL void k_swap(EngineView E, SwapView V) {
   IMA_SMEM_DECL
@@ -688,10 +708,16 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
           const int sa = dA[i], sb = dB[i];
           const int ca = cor[sa], cb = cor[sb];
           const double w = exp((Bt[sa] - Bt[sb]) * (Sg[cb] - Sg[ca]));
-          if (w >= 1.0 || w > dU[i]) {
+          const bool swapped = w >= 1.0 || w > dU[i];
+          if (swapped) {
             cor[sa] = cb; cor[sb] = ca;
             roc[ca] = sb; roc[cb] = sa;
             nacc++;
+          }
+          if (sa - sb == 1 || sb - sa == 1) {                           // fire and forget, off the chain of decisions
+            unsigned long long *ac = V.adj_counts + (size_t)(sa < sb ? sa : sb) * 2;
+            stat_add(ac, 1ull);
+            if (swapped) stat_add(ac + 1, 1ull);
           }
         }
       }

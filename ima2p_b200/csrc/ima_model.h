@@ -103,6 +103,7 @@ struct EngineView {
   double *prop_dbg;         // [P][4] migweight, slideweight, slide distance drawn, edge moved (parity tests)
   // counters
   unsigned int *acc;        // [P][3] accepted: any, topology, tmrca
+  unsigned int *cold_acc;   // [nloci][3] the same, of the chain at beta == 1 only (the reference's update-rate tables count chain 0)
   unsigned long long *nsteps;   // [1] steps done (device-side step counter, feeds the RNG streams)
   unsigned long long *overflow; // [1] proposals dropped because the migration pool was full
   unsigned long long seed;

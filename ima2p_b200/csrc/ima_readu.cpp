@@ -29,6 +29,8 @@ struct ULocus {
   std::string name;
   int model = 0, numgenes = 0, numbases = 0, numsites = 0, totsites = 0, nlinked = 1, nAlinked = 0;
   double hval = 1.0;
+  bool hval_given = false;            // an inheritance scalar stood on the header line (the reference echoes it differently)
+  bool model_digit = false;           // the model letter carried a count (S2, J1): the reference names these SW_M / IS+SW_M
   std::vector<int> samppop;
   std::vector<int> seq;               // [numgenes][numsites]
   std::vector<int> mult;              // [numsites] (HKY)
@@ -63,7 +65,7 @@ bool is_acgt(char c) { return c == 'a' || c == 'c' || c == 'g' || c == 't'; }
 struct ima2p_dataset {
   int npops = 0;
   std::string tree, title;
-  std::vector<std::string> popnames;
+  std::vector<std::string> popnames, comments;      // comments: the '#' lines under the title, without the '#'
   std::vector<ULocus> loci;
 };
 
@@ -248,7 +250,7 @@ int ima2p_dataset_read(const char *path, ima2p_dataset **out) {
   size_t at = 0;
   if (lines.empty()) return bail(IMA2P_E_ARG, "empty data file");
   D->title = lines[at++];
-  while (at < lines.size() && !lines[at].empty() && lines[at][0] == '#') at++;
+  while (at < lines.size() && !lines[at].empty() && lines[at][0] == '#') D->comments.push_back(lines[at++].substr(1));
   // npops, population names, tree string (optional for two populations), number of loci: a token stream (:929-1020)
   std::vector<std::string> tok;
   auto need = [&](size_t k) { while (tok.size() < k && at < lines.size()) { auto t = split_ws(lines[at++]); tok.insert(tok.end(), t.begin(), t.end()); } return tok.size() >= k; };
@@ -282,6 +284,7 @@ int ima2p_dataset_read(const char *path, ima2p_dataset **out) {
     L.numbases = atoi(h[1 + D->npops].c_str());
     const std::string &mt = h[2 + D->npops];
     const int digits = mt.size() > 1 && isdigit((unsigned char)mt[1]) ? atoi(mt.c_str() + 1) : 0;
+    L.model_digit = mt.size() > 1 && isdigit((unsigned char)mt[1]);
     switch (toupper((unsigned char)mt[0])) {
       case 'H': L.model = IMA2P_MODEL_HKY; L.nlinked = 1; break;
       case 'S': L.model = IMA2P_MODEL_SW; L.nAlinked = digits ? digits : 1; L.nlinked = L.nAlinked; break;
@@ -292,7 +295,7 @@ int ima2p_dataset_read(const char *path, ima2p_dataset **out) {
     if (L.numgenes < 2) return bail(IMA2P_E_ARG, "locus " + std::to_string(li) + ": fewer than two genes");
     size_t q = 3 + D->npops;
     if (q < h.size() && h[q][0] == 'A') return bail(IMA2P_E_UNSUPPORTED, "genes of unknown origin (assignment model) are not supported");
-    if (q < h.size()) { L.hval = atof(h[q].c_str()); q++; } else L.hval = 1.0;
+    if (q < h.size()) { L.hval = atof(h[q].c_str()); L.hval_given = true; q++; } else L.hval = 1.0;
     for (; q < h.size() && (int)L.urate.size() < L.nlinked; q++) {
       if (h[q][0] == 'A') return bail(IMA2P_E_UNSUPPORTED, "genes of unknown origin (assignment model) are not supported");
       if (h[q][0] == '(') continue;             // a prior range on the rate: used only with -p options outside this path
@@ -323,12 +326,25 @@ int ima2p_dataset_dims(const ima2p_dataset *d, int *npops, int *nloci, char *tre
   return IMA2P_OK;
 }
 
-// info[8] = model, numgenes, numsites, totsites, numbases, nlinked, number of mutation rates on the header line, 0
+// the text the reference echoes into its report (readata.cpp:916-963): kind 0 = title line (index 0) and the '#' lines
+// under it (index 1..), kind 1 = population names; returns IMA2P_E_ARG past the last one
+int ima2p_dataset_text(const ima2p_dataset *d, int kind, int index, char *buf, int buf_len) {
+  if (!d || !buf || buf_len < 1 || index < 0) return ufail(IMA2P_E_ARG, "dataset_text: bad argument");
+  const std::string *s = nullptr;
+  if (kind == 0) s = index == 0 ? &d->title : index <= (int)d->comments.size() ? &d->comments[index - 1] : nullptr;
+  else if (kind == 1) s = index < (int)d->popnames.size() ? &d->popnames[index] : nullptr;
+  if (!s) return ufail(IMA2P_E_ARG, "dataset_text: no such line");
+  strncpy(buf, s->c_str(), buf_len - 1); buf[buf_len - 1] = '\0';
+  return IMA2P_OK;
+}
+
+// info[8] = model, numgenes, numsites, totsites, numbases, nlinked, number of mutation rates on the header line,
+//           bit 0: the model letter carried a count (S2, J1; readata.cpp:664-692), bit 1: an inheritance scalar was given (:729-734, 826-831)
 int ima2p_dataset_locus(const ima2p_dataset *d, int li, int *info, double *hval, int *samppop, char *name, int name_len) {
   if (!d || li < 0 || li >= (int)d->loci.size() || !info) return ufail(IMA2P_E_ARG, "dataset_locus: bad argument");
   const ULocus &L = d->loci[li];
   info[0] = L.model; info[1] = L.numgenes; info[2] = L.numsites; info[3] = L.totsites; info[4] = L.numbases; info[5] = L.nlinked;
-  info[6] = (int)L.urate.size(); info[7] = 0;
+  info[6] = (int)L.urate.size(); info[7] = (L.model_digit ? 1 : 0) | (L.hval_given ? 2 : 0);
   if (hval) *hval = L.hval;
   if (samppop) for (int i = 0; i < d->npops; i++) samppop[i] = L.samppop[i];
   if (name && name_len > 0) { strncpy(name, L.name.c_str(), name_len - 1); name[name_len - 1] = '\0'; }

@@ -25,7 +25,9 @@ struct UpdateView {
   int *t_counts;                                   // [P][4] edges above / below, migrations above / below the old split time
   double *t_out;                                   // [nchains][4] period, proposed time, MH term, accepted
   double *u_out;                                   // [nchains][4] debug: new pdg of j, new pdg of k, MH term, accepted
-  unsigned long long *stats;                       // [4] t tries, t accepts, u tries, u accepts
+  unsigned long long *stats;                       // [4] t tries, t accepts, u tries, u accepts (all chains); then of the chain
+                                                   // at beta == 1 only: [kMaxPeriods][2 methods: RY, NW][tries, accepts] from
+                                                   // kColdTStat, [nurates][tries, accepts] from kColdUStat
   const double *t_forced;                          // [nchains] tests: proposed time to use instead of the draw (or null)
   int t_forced_period, t_force_accept, t_forced_method;
   int t_methods;                                   // bit 0: Rannala-Yang, bit 1: Nielsen-Wakeley
@@ -34,6 +36,9 @@ struct UpdateView {
   int u_chain, u_j, u_k, u_every;
   double u_d, u_kappa[2];
 };
+
+constexpr int kColdTStat = 4, kColdUStat = 4 + 4 * kMaxPeriods;
+IMA_HD size_t update_stats_len(int nurates) { return (size_t)kColdUStat + 2 * (size_t)nurates; }
 
 IMA_DEV double ry_beforesplit(int tnode, double oldt, double newt, double tau_u, double ptime) {     // update_t_RY.cpp:67-80
   if (tnode == 0) return ptime * newt / oldt;
@@ -488,6 +493,11 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
 #else
     U.stats[0] += 1; if (accept) U.stats[1] += 1;
 #endif
+    if (beta == 1.0 && !U.t_forced) {
+      unsigned long long *cs = U.stats + kColdTStat + ((size_t)t.period * 2 + (t.method == 1 ? 1 : 0)) * 2;
+      stat_add(cs, 1ull);
+      if (accept) stat_add(cs + 1, 1ull);
+    }
   }
 }
 
@@ -589,6 +599,7 @@ IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
           su[j] = newuj; su[k] = newuk; spdg[j] = npj; spdg[k] = npk;
           total += likenewsum;
           nacc++;
+          slacc[j] = 1.0;                                    // its draw has been used: the slot now says "accepted" (a log draw is <= 0)
         }
       }
       E.pdgsum[c] += total; E.swapsum[c] += total;
@@ -607,6 +618,12 @@ IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
       const int p = c * nloci + li;
       E.uvals[(size_t)p * kMaxLinked] = su[li];
       E.buf[E.cur[p]].sd[(size_t)p * 4 + 3] = spdg[li];
+      if (beta == 1.0) {                               // a proposal counts for the scalar and for its partner (ima_main_mpi.cpp:1926-1935)
+        const unsigned long long a = slacc[li] == 1.0 ? 1ull : 0ull;
+        stat_add(U.stats + kColdUStat + 2 * (size_t)li, 1ull);
+        stat_add(U.stats + kColdUStat + 2 * (size_t)sk[li], 1ull);
+        if (a) { stat_add(U.stats + kColdUStat + 2 * (size_t)li + 1, 1ull); stat_add(U.stats + kColdUStat + 2 * (size_t)sk[li] + 1, 1ull); }
+      }
     }
     return;
   }
@@ -699,6 +716,11 @@ IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
 #else
       U.stats[2] += 1; if (accept) U.stats[3] += 1;
 #endif
+      if (beta == 1.0 && !U.u_forced) {                  // counted for the scalar and for its partner (ima_main_mpi.cpp:1926-1935)
+        stat_add(U.stats + kColdUStat + 2 * (size_t)j, 1ull);
+        stat_add(U.stats + kColdUStat + 2 * (size_t)k, 1ull);
+        if (accept) { stat_add(U.stats + kColdUStat + 2 * (size_t)j + 1, 1ull); stat_add(U.stats + kColdUStat + 2 * (size_t)k + 1, 1ull); }
+      }
     }
   }
 }

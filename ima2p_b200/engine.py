@@ -263,6 +263,16 @@ class Engine:
         self._ck(self.lib.ima2p_engine_update_counters(self._h, out))
         return dict(t_tries=out[0], t_accepts=out[1], u_tries=out[2], u_accepts=out[3])
 
+    def cold_counters(self, nsplit, nurates):
+        """Cold-chain update counts as the reference's update-rate tables report them, and adjacent-temperature swaps."""
+        g = np.zeros((self.nloci, 3), dtype=np.uint64)
+        t = np.zeros((max(nsplit, 1), 4), dtype=np.uint64)
+        u = np.zeros((max(nurates, 1), 2), dtype=np.uint64)
+        a = np.zeros((max(self.nchains_global - 1, 1), 2), dtype=np.uint64)
+        p = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint64))
+        self._ck(self.lib.ima2p_engine_cold_counters(self._h, p(g), p(t), p(u), p(a)))
+        return dict(genealogy=g, split=t[:nsplit], scalars=u[:nurates], adjacent=a[:self.nchains_global - 1])
+
     def scalars(self, chain, locus):
         u = np.zeros(capi.MAX_LINKED)
         k = C.c_double()

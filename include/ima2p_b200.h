@@ -171,6 +171,16 @@ int ima2p_engine_set_update_priors (ima2p_engine * e, const double *t_max, const
                                     double u_window, double kappa_window, double kappa_max);
 /* tries / accepts: out4 = split-time tries, accepts, mutation-scalar tries, accepts */
 int ima2p_engine_update_counters (ima2p_engine * e, uint64_t * out4);
+/* What the reference's update-rate tables and swap table report (callprintacceptancerates ima_main_mpi.cpp:3473-3900 over
+ * the cold chain's update_rate_calc records; printchaininfo swapchains.cpp:760-778), counted since the engine was created
+ * for the chain at beta == 1 while it lives on this device; any pointer may be NULL:
+ *   genealogy[nloci][3]  accepted updategenealogy calls: any, topology-changing, tmrca-changing (tries = steps);
+ *   split[nsplit][4]     per split time: Rannala-Yang tries, accepts, Nielsen-Wakeley tries, accepts;
+ *   scalars[nurates][2]  per mutation-rate scalar (readata.cpp:832-834 order): tries, accepts, a proposal counting for
+ *                        both scalars it trades between as in qupdate (ima_main_mpi.cpp:1926-1935);
+ *   adjacent[nchains_global - 1][2]  swap attempts, swaps between temperature ranks r and r + 1 (tempbasedswapcount) */
+int ima2p_engine_cold_counters (ima2p_engine * e, uint64_t * genealogy, uint64_t * split, uint64_t * scalars,
+                                uint64_t * adjacent);
 /* current split times C[ci]->tvals[nsplit] of one chain */
 int ima2p_engine_get_split_times (ima2p_engine * e, int chain, double *tvals);
 /* all of them at once: tvals[nchains][nsplit], uvals[P][IMA2P_MAX_LINKED], kappa[P] (any pointer may be NULL) */
@@ -300,7 +310,12 @@ typedef struct ima2p_dataset ima2p_dataset;
 int ima2p_dataset_read (const char *path, ima2p_dataset ** out);
 void ima2p_dataset_free (ima2p_dataset * d);
 int ima2p_dataset_dims (const ima2p_dataset * d, int *npops, int *nloci, char *tree, int tree_len);
-/* info[8] = model, numgenes, numsites, totsites, numbases, nlinked, mutation rates given on the header line, 0 */
+/* text the reference echoes into its report (readata.cpp:916-963): kind 0 = the title line (index 0) and the '#' lines under
+ * it (index 1.., without the '#'), kind 1 = population names; IMA2P_E_ARG past the last one */
+int ima2p_dataset_text (const ima2p_dataset * d, int kind, int index, char *buf, int buf_len);
+/* info[8] = model, numgenes, numsites, totsites, numbases, nlinked, mutation rates given on the header line,
+ *           flags: bit 0 the model letter carried a count (S2, J1: the reference's SW_M / IS+SW_M, readata.cpp:664-692),
+ *           bit 1 an inheritance scalar stood on the header line (:729-734; echoed "%5.3lf", else "%lf" :826-831) */
 int ima2p_dataset_locus (const ima2p_dataset * d, int locus, int *info, double *hval, int *samppop, char *name,
                          int name_len);
 /* seq[numgenes][numsites]; mult[numsites] (HKY); A[nlinked][numgenes]; minA, maxA[nlinked]; pi[4] (HKY); urate[info[6]] */

@@ -515,6 +515,44 @@ def step_report_matches_separate_reads(lib, name="state_sim5_hn4"):
     eng.close()
 
 
+def cold_chain_counters_are_consistent(lib, nsteps=60):
+    """ima2p_engine_cold_counters (what the reference's update-rate tables and swap table report, ima_main_mpi.cpp:3473-3899,
+    swapchains.cpp:760-778).  With one chain that chain is the cold one, so its counts are the engine's totals exactly (a scalar
+    proposal counting for both scalars it trades between, ima_main_mpi.cpp:1926-1935); with several chains the cold chain tries
+    one split-time update a step and every scalar sweep, and its counts and the adjacent-temperature swaps are part of the totals."""
+    d = load_golden("state_sim300_hn1")
+    eng, fm = engine_from_fixture(d, lib=lib, seed=17)
+    eng.eval()
+    eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+    eng.set_update_schedule(3, 5)
+    eng.run(nsteps)
+    eng.sync()
+    cnt, uc, cc = eng.counters(), eng.update_counters(), eng.cold_counters(fm.nsplit, eng.nloci)
+    g = cc["genealogy"].sum(axis=0)
+    assert (int(g[0]), int(g[1]), int(g[2])) == (cnt["accepted"], cnt["topology"], cnt["tmrca"]) and cnt["accepted"] > 0
+    assert int(cc["split"][:, [0, 2]].sum()) == uc["t_tries"] == nsteps and int(cc["split"][:, [1, 3]].sum()) == uc["t_accepts"]
+    assert cc["split"][:, 0].sum() > 0 and cc["split"][:, 2].sum() > 0                       # both update types were drawn
+    assert int(cc["scalars"][:, 0].sum()) == 2 * uc["u_tries"] > 0 and int(cc["scalars"][:, 1].sum()) == 2 * uc["u_accepts"]
+    assert np.all(cc["scalars"][:, 0] >= nsteps // 5)                                        # every scalar is proposed in every sweep
+    eng.close()
+    d = load_golden("state_sim5_hn4")
+    eng, fm = engine_from_fixture(d, lib=lib, seed=17)
+    eng.eval()
+    eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+    eng.set_update_schedule(3, 5)
+    eng.run(5 * nsteps)
+    eng.sync()
+    cnt, uc, cc = eng.counters(), eng.update_counters(), eng.cold_counters(fm.nsplit, eng.nloci)
+    assert 0 < cc["genealogy"][:, 0].sum() < cnt["accepted"] and np.all(cc["genealogy"][:, 1] <= cc["genealogy"][:, 0])
+    assert np.all(cc["genealogy"][:, 0] <= 5 * nsteps)
+    assert int(cc["split"][:, [0, 2]].sum()) == 5 * nsteps and int(cc["split"][:, [1, 3]].sum()) <= uc["t_accepts"]
+    assert int(cc["scalars"][:, 0].sum()) == 2 * eng.nloci * nsteps and np.all(cc["scalars"][:, 1] <= cc["scalars"][:, 0])
+    adj = cc["adjacent"]
+    assert adj.shape == (3, 2) and np.all(adj[:, 1] <= adj[:, 0]) and 0 < adj[:, 0].sum() <= cnt["swap_attempts"]
+    assert adj[:, 1].sum() <= cnt["swaps"]
+    eng.close()
+
+
 def speculation_depth_does_not_change_the_run(lib, name="state_sim50_hn3", nsteps=60):
     """The accept sweep evaluates several loci of a chain per round speculatively (k_accept<B>); whatever the depth B, the
     run must be the one-locus-at-a-time sweep of update_gtree.cpp:917-927: same acceptances, same sums, same genealogies."""

@@ -308,6 +308,19 @@ def main():
         with open(base + ".ti", "rb") as f, gzip.GzipFile(os.path.join(HERE, "inputs", rep_name + ".ti.gz"), "wb", mtime=0) as g:
             shutil.copyfileobj(f, g)
         print("wrote %s.json.gz and inputs/%s.ti.gz" % (rep_name, rep_name))
+    # opening sections of an M-mode report (section 8 f4): the reference's own main() on a committed input; kept from the top of
+    # the file to the means / variances table -- run information, highest likelihoods, update-rate tables of the cold chain,
+    # swap table
+    if not ONLY or "report_head_3pop" in ONLY:
+        rep = os.path.join(TMP, "report_head_3pop.out")
+        args = ["-i", os.path.join(HERE, "inputs", "parse_is_3pop.u"), "-q10", "-m1", "-t3", "-b5000", "-l6000", "-d10", "-hn4", "-hfg", "-ha0.96", "-hb0.9"]
+        subprocess.run([HARNESS, "stock", os.path.join(TMP, "report_head_3pop.json"), "--"] + args + ["-o", rep], check=True, cwd=TMP,
+                       stdout=subprocess.DEVNULL, timeout=900)
+        text = open(rep).read()
+        import json
+        with gzip.GzipFile(os.path.join(HERE, "report_head_3pop.json.gz"), "wb", mtime=0) as g:
+            g.write(json.dumps({"args": args[2:], "head": text[:text.index("\nMEANS, VARIANCES")]}).encode())
+        print("wrote report_head_3pop.json.gz")
     # the .mcf state file: written by the reference (inputs/*.mcf.gz) and by the engine (inputs/*_ours.mcf.gz), each
     # read back by the reference's readmcf and dumped
     for nm, uf, hn, burn in (("mcf_sim5_hn2", s5, 2, 60), ("mcf_sim3_sw_hn2", sw3, 2, 60), ("mcf_sim5_hky_hn2", hky5, 2, 30),

@@ -144,3 +144,84 @@ def frontend_posterior_matches_reference(exe, lib, tmp_path, nsigma=5.0):
 def test_front_end_samples_the_reference_posterior(exe, tmp_path):
     from ima2p_b200 import capi
     frontend_posterior_matches_reference(exe, capi.bind(os.path.join(HERE, "hostemu", "libima2p_hostemu.so")), tmp_path)
+
+
+def _rate_tables(text):
+    """{table title: {row name: [(tries, accepts, percent), ...]}} of the 'Update Rates -- ...' tables, and the swap table as
+    [(temp1, temp2, swaps, attempts, rate), ...]."""
+    tables, swaps, title, in_swaps = {}, [], None, False
+    for ln in text.split("\n"):
+        if ln.startswith("Update Rates -- "):
+            title, in_swaps = ln[len("Update Rates -- "):], False
+            tables[title] = {}
+        elif ln.startswith("Temp1"):
+            title, in_swaps = None, True
+        elif in_swaps and ln.strip():
+            w = ln.split()
+            if len(w) == 5:
+                swaps.append((float(w[0]), float(w[1]), int(w[2]), int(w[3]), float(w[4])))
+        elif title and ln.startswith(" ") and "\t" in ln and not ln.strip().startswith("#"):
+            w = ln.split("\t")
+            vals = [(float(w[i]), float(w[i + 1]), float(w[i + 2])) for i in range(1, len(w) - 2, 3)]
+            tables[title][w[0].strip()] = vals
+    return tables, swaps
+
+
+def frontend_report_head_matches_reference(exe, tmp_path, lib=None):
+    """The opening sections of an M-mode report: the run information the reference echoes is the
+    reference's text line for line; the update-rate tables of the cold chain (split times by update type, genealogies per
+    locus by branch / topology / tmrca, mutation scalars) and the swap table between adjacent temperatures have the
+    reference's layout, and their rates agree with the reference's own run of the same command (fixture
+    report_head_3pop, written by the reference's unmodified main(); 60,000 steps after the burn-in)."""
+    import gzip
+    import json
+    import re
+    d = json.load(gzip.open(os.path.join(HERE, "golden", "report_head_3pop.json.gz")))
+    out = tmp_path / "head.out"
+    r = _run(exe, ["-i", os.path.join(INPUTS, "parse_is_3pop.u"), "-o", str(out)] + d["args"] + ["-s", "21"])
+    assert r.returncode == 0, r.stderr
+    rep, ref = open(out).read(), d["head"]
+    mine = rep[:rep.index("\nENGINE INFORMATION")]
+
+    def between(text, a, b):
+        i = text.index(a)
+        return text[i:text.index(b, i)]
+    # what readdata / setup echo: identical text (file names and the seed line differ, they are above this block)
+    assert between(mine, "- Run Duration -", "All genealogy information") == between(ref, "- Run Duration -", "All genealogy information")
+    assert between(mine, "\nText from input file", "\n\nMCMC INFORMATION") == between(ref, "\nText from input file", "\n\nMCMC INFORMATION")
+    assert between(mine, "\nMCMC INFORMATION", "\nTime Elapsed") == between(ref, "\nMCMC INFORMATION", "\nTime Elapsed")
+    # same skeleton from the highest likelihoods to the end of the swap table (digits blanked; the serial build's per-chain
+    # swap table has no counterpart when only temperatures move)
+    def skeleton(text):
+        t = between(text + "\n\nEND", "Highest Sampled Joint", "\n\nEND")
+        t = re.sub(r"Chain    #Swaps    Rate\n(?: +\d+ +\d+ +[\d.]+\n)+\n", "", t)
+        return re.sub(r"\s+", " ", re.sub(r"-?\d[\d.e]*", "#", t)).strip()
+    assert skeleton(mine) == skeleton(ref)
+    (tm, sm), (tr, sr) = _rate_tables(mine), _rate_tables(ref)
+    assert list(tm) == list(tr) == ["Population Splitting Times", "Genealogies", "Mutation Rate Scalars"]
+    tol = {"Population Splitting Times": 8.0, "Genealogies": 2.5, "Mutation Rate Scalars": 2.5}      # percentage points
+    for title in tr:
+        assert list(tm[title]) == list(tr[title])
+        for row in tr[title]:
+            for (t1, a1, p1), (t2, a2, p2) in zip(tm[title][row], tr[title][row]):
+                assert abs(t1 - t2) <= 0.06 * t2, (title, row, t1, t2)
+                assert abs(p1 - p2) < tol[title], (title, row, p1, p2)
+    assert [g[0][0] for g in tm["Genealogies"].values()] == [6.0e4] * 4                 # every step tries every locus of the cold chain
+    assert len(sm) == len(sr) == 3
+    for a, b in zip(sm, sr):
+        assert a[:2] == b[:2] and a[3] > 0 and abs(a[4] - b[4]) < 0.06, (a, b)
+    # highest likelihoods: maxima of the recorded cold-chain values, i.e. of the P(D|G) and P(G) columns of the .ti rows.  (The
+    # reference's own figures are not comparable run to run: it looks at the highs at its print intervals only, and its
+    # infinite-sites constant, calc_sumlogk, depends on the random genealogy a run starts with; the front end applies the same
+    # rule to its own starting genealogy.)
+    from ima2p_b200 import capi
+    from ima2p_b200.readu import ti_load
+    rows = ti_load(str(out) + ".ti", 4 * 5 + 3 * 8 + 2 + 2, lib=capi.bind(os.path.join(HERE, "hostemu", "libima2p_hostemu.so")) if lib is None else lib)
+    hm = [float(x) for x in re.findall(r"\(log\) :\s+(-?[\d.]+)", mine)]
+    assert len(hm) == 2 and abs(hm[0] - rows[:, -3].max()) < 2e-3 and abs(hm[1] - rows[:, -4].max()) < 2e-3, (hm, rows[:, -3].max(), rows[:, -4].max())
+    per_locus = [float(x) for x in re.findall(r"\n\t\d+\t(-?[\d.]+)", between(mine, "Highest P(D|G) (log) for each Locus", "Update Rates"))]
+    assert len(per_locus) == 4 and all(v < 0 for v in per_locus) and sum(per_locus) >= hm[1] - 2e-3
+
+
+def test_report_head_matches_reference(exe, tmp_path):
+    frontend_report_head_matches_reference(exe, tmp_path)

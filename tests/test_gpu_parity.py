@@ -171,6 +171,10 @@ def test_step_report(lib):
     ec.step_report_matches_separate_reads(lib)
 
 
+def test_cold_chain_counters(lib):
+    ec.cold_chain_counters_are_consistent(lib)
+
+
 def test_front_end_on_the_device(lib, tmp_path):
     """ima2p_b200/IMa2p_b200 (the product executable) from a .u file: posterior summaries against the reference's."""
     import os
@@ -178,3 +182,13 @@ def test_front_end_on_the_device(lib, tmp_path):
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ima2p_b200", "IMa2p_b200")
     assert os.path.exists(exe), "build the front end with __graft_entry__.build()"
     frontend_posterior_matches_reference(exe, lib, tmp_path)
+
+
+def test_front_end_report_head_on_the_device(lib, tmp_path):
+    """The opening sections of the product executable's report against the reference's own (run information, the cold
+    chain's update-rate tables per locus and update type, swaps between adjacent temperatures)."""
+    import os
+    from test_frontend import frontend_report_head_matches_reference
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ima2p_b200", "IMa2p_b200")
+    assert os.path.exists(exe), "build the front end with __graft_entry__.build()"
+    frontend_report_head_matches_reference(exe, tmp_path, lib=lib)

@@ -131,3 +131,7 @@ def test_nielsen_wakeley_update(emu, name):
 
 def test_step_report(emu):
     ec.step_report_matches_separate_reads(emu)
+
+
+def test_cold_chain_counters(emu):
+    ec.cold_chain_counters_are_consistent(emu)
