@@ -872,6 +872,13 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
     ck(ima2p_lmode_margincalc(LM, p, x.data(), kGrid, 0.0, 0, y.data()), "marginal densities");
     xs.push_back(x); ys.push_back(y); hname.push_back(name[p]);
   }
+  // printhistograms histograms.cpp:895-909
+  fprintf(f, "\nHISTOGRAMS\n==========\n  Each histogram is given as %d pairs of values (i.e. two columns side by side).\n", kGrid);
+  fprintf(f, "  In each case the left column is the value of the parameter or term (i.e. x value)\n  and the right column is the estimated posterior probability (i.e. y value).\n");
+  fprintf(f, "  HPD (Highest Posterior Density) intervals are estimated, and may be incorrect: \n  Possible HPD footnotes: \n");
+  fprintf(f, "       '?' HPD interval may be incorrect due to multiple peaks\n");
+  fprintf(f, "       '#' HPD may not be useful - posterior density does not reach low levels near either the upper or the lower limit of the prior\n");
+  fprintf(f, "\nNUMBER OF GROUPS OF HISTOGRAM TABLES : %d\n\n", 2 + (int)(!terms.empty()));
   if (nsplit > 0) {
     // histogram group 1 in L mode: the split times of the loaded rows binned as recordval does (ima_main_mpi.cpp:2746-2781,
     // 3420-3431), scaled to a density (histograms.cpp:496-509); mutation-scalar histograms need an M-mode run
