@@ -1168,6 +1168,13 @@ int main(int argc, char **argv) {
         ur.push_back({sw ? std::to_string(li) + "SW" + std::to_string(a) : std::to_string(li) + "u ", {cu[j * 2] - cu0[j * 2]}, {cu[j * 2 + 1] - cu0[j * 2 + 1]}});     // initialize.cpp:1453-1466
       }
     print_rates(f, "Update Rates -- Mutation Rate Scalars", {"scalar update"}, ur);
+    // kappa of an HKY locus is proposed and decided together with the locus' scalar (update_mc_params.cpp:258-277, 310-317):
+    // its record counts the same proposals
+    std::vector<RateRow> kr;
+    j = 0;
+    for (int li = 0; li < nloci; j += loci[li].info[5], li++)
+      if (loci[li].info[0] == IMA2P_MODEL_HKY) kr.push_back({std::to_string(li) + "_Ka", {cu[j * 2] - cu0[j * 2]}, {cu[j * 2 + 1] - cu0[j * 2 + 1]}});     // initialize.cpp:1502
+    if (!kr.empty()) print_rates(f, "Update Rates -- HKY Model Kappa parameter", {"kappa update"}, kr);
   }
   if (nchains > 1) {
     // printchaininfo (swapchains.cpp:664-690, 815-823): swaps between adjacent temperatures (only betas move here, so the

@@ -178,7 +178,9 @@ int ima2p_engine_update_counters (ima2p_engine * e, uint64_t * out4);
  *   split[nsplit][4]     per split time: Rannala-Yang tries, accepts, Nielsen-Wakeley tries, accepts;
  *   scalars[nurates][2]  per mutation-rate scalar (readata.cpp:832-834 order): tries, accepts, a proposal counting for
  *                        both scalars it trades between as in qupdate (ima_main_mpi.cpp:1926-1935);
- *   adjacent[nchains_global - 1][2]  swap attempts, swaps between temperature ranks r and r + 1 (tempbasedswapcount) */
+ *   adjacent[nchains_global - 1][2]  swap attempts, swaps between temperature ranks r and r + 1 (tempbasedswapcount).
+ * With several GPUs the first three are this rank's share (sum them over ranks); `adjacent` is the same on every rank, the
+ * swap replay being replicated. */
 int ima2p_engine_cold_counters (ima2p_engine * e, uint64_t * genealogy, uint64_t * split, uint64_t * scalars,
                                 uint64_t * adjacent);
 /* current split times C[ci]->tvals[nsplit] of one chain */
