@@ -809,6 +809,44 @@ void print_rates(FILE *f, const char *title, const std::vector<std::string> &typ
   }
 }
 
+// asciicurve (output.cpp:428-524): a 75 x 50 character plot of a histogram's 1,000 points, y scaled to its maximum
+void ascii_curve(FILE *f, const std::vector<double> &x, const std::vector<double> &y, const std::string &label, bool logscale, double recordstep) {
+  constexpr int kLeft = 10, kPlotX = 75, kMaxX = kLeft + kPlotX, kPlotY = 50, kMaxY = kPlotY + 3;
+  std::vector<std::string> g(kMaxY);
+  double ymax = -1e10;
+  const double ymin = 0.0;                               // "don't shift plot on y axis"
+  for (int i = 0; i < kGrid; i++) if (ymax < y[i]) ymax = y[i];
+  ymax /= recordstep;
+  int xmax = kGrid - 1;
+  if (!logscale) {
+    xmax = -1;
+    for (int i = kGrid - 1; i >= 0 && xmax == -1; i--) if (fabs(y[i]) > 1e-6) xmax = i;     // ASCIICURVEMINVAL
+    if (xmax < 0) xmax = kGrid - 1;
+  }
+  auto pad = [&](std::string &s, size_t n, char c = ' ') { while (s.size() < n) s.push_back(c); };
+  char tc[32];
+  g[0] = label + " curve"; pad(g[0], kMaxX);
+  snprintf(tc, sizeof tc, "%8.4g", ymax); g[1] = tc; pad(g[1], kMaxX);
+  snprintf(tc, sizeof tc, "%8.4f", ymin); g[kPlotY] = tc; pad(g[kPlotY], kMaxX);
+  g[kPlotY + 1] = std::string(kLeft, ' '); pad(g[kPlotY + 1], kMaxX, '-');
+  g[kPlotY + 2] = std::string(kLeft, ' ');
+  snprintf(tc, sizeof tc, "%8.4f", x[0]); g[kPlotY + 2] += tc;
+  snprintf(tc, sizeof tc, "%8.4f", x[xmax]);
+  if (logscale) g[kPlotY + 2] += "           Log Scale";
+  pad(g[kPlotY + 2], kMaxX - strlen(tc) - 1);
+  g[kPlotY + 2] += tc; pad(g[kPlotY + 2], kMaxX);
+  for (int i = 2; i < kPlotY; i++) pad(g[i], kMaxX);
+  for (int i = 1; i < kPlotY + 1; i++) g[i][kLeft] = '|';
+  for (int i = 0; i <= xmax; i++) {
+    const int yspot = (int)1 + kPlotY - (int)(kPlotY * (y[i] / recordstep - ymin) / (ymax - ymin));
+    const int xspot = logscale ? (int)kLeft + 1 + (int)((kPlotX - 2) * (log(x[i]) - log(x[0])) / (2 * log(x[xmax])))
+                               : (int)kLeft + 1 + (int)((kPlotX - 2) * (x[i] - x[0]) / (x[xmax] - x[0]));
+    if (xspot < kMaxX && xspot >= kLeft + 1 && yspot < kMaxY && yspot >= 1 && xspot < (int)g[yspot].size()) g[yspot][xspot] = '*';
+  }
+  for (int i = 0; i < kMaxY; i++) fprintf(f, "%s \n", g[i].c_str());
+  fprintf(f, "\n");
+}
+
 void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_modelspec *S, int npops, double qmax, double mmax, int expo,
                      const float *rowdata, long long nrows, bool loaded_from_ti) {
   int md[6];
@@ -879,6 +917,8 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
   fprintf(f, "       '?' HPD interval may be incorrect due to multiple peaks\n");
   fprintf(f, "       '#' HPD may not be useful - posterior density does not reach low levels near either the upper or the lower limit of the prior\n");
   fprintf(f, "\nNUMBER OF GROUPS OF HISTOGRAM TABLES : %d\n\n", 2 + (int)(!terms.empty()));
+  std::vector<std::vector<double>> acx, acy;          // the split-time histograms, kept for the ASCII curves
+  std::vector<std::string> acn;
   if (nsplit > 0) {
     // histogram group 1 in L mode: the split times of the loaded rows binned as recordval does (ima_main_mpi.cpp:2746-2781,
     // 3420-3431), scaled to a density (histograms.cpp:496-509); mutation-scalar histograms need an M-mode run
@@ -900,6 +940,7 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
     if (loaded_from_ti) fprintf(f, "  IMa LOAD TREES MODE  - splittime values loaded from *.ti file, mutation rate scalar histograms are not available \n");
     else fprintf(f, "  split times of the saved genealogies\n");
     write_histograms(f, tn, tx, ty, tscale, true, tb, ta);
+    acn = tn; acx = tx; acy = ty;
   }
   fprintf(f, "\n\nHISTOGRAM GROUP 2: MARGINAL DISTRIBUTION VALUES AND HISTOGRAMS OF POPULATION SIZE AND MIGRATION PARAMETERS\n");
   fprintf(f, "--------------------------------------------------------------------------------------------------------\n");
@@ -928,6 +969,11 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
     fprintf(f, "        q1m0>1  is the population rate (forward in time) at which population 1 receives migrants from population 0\n");
     write_histograms(f, pn, px, py);
   }
+  // callasciicurves ima_main_mpi.cpp:3905-4000: population sizes, migration rates with a prior above MPRIORMIN, split times
+  // (their counts over the recorded steps)
+  fprintf(f, "\n\nASCII Curves - Approximate Posterior Densities \n===================================================\n");
+  for (size_t i = 0; i < hname.size(); i++) ascii_curve(f, xs[i], ys[i], hname[i], false, 1.0);
+  for (size_t i = 0; i < acn.size(); i++) ascii_curve(f, acx[i], acy[i], acn[i], false, (double)nrows);
   fprintf(f, "\nEND OF OUTPUT\n");
   ima2p_lmode_destroy(LM);
 }

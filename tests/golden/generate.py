@@ -308,6 +308,20 @@ def main():
         with open(base + ".ti", "rb") as f, gzip.GzipFile(os.path.join(HERE, "inputs", rep_name + ".ti.gz"), "wb", mtime=0) as g:
             shutil.copyfileobj(f, g)
         print("wrote %s.json.gz and inputs/%s.ti.gz" % (rep_name, rep_name))
+    # ASCII curves of an L-mode report (section 8 f4): the reference's L mode on the committed .ti file of lmode_report_sim3
+    if not ONLY or "lmode_ascii_sim3" in ONLY:
+        base = os.path.join(TMP, "ascii_ref")
+        with gzip.open(os.path.join(HERE, "inputs", "lmode_report_sim3.ti.gz"), "rb") as f, open(base + ".ti", "wb") as g:
+            shutil.copyfileobj(f, g)
+        rep = os.path.join(TMP, "lmode_ascii_sim3.out")
+        subprocess.run([HARNESS, "stock", os.path.join(TMP, "lmode_ascii_sim3.json"), "--", "-i", s3, "-q10", "-m1", "-t3", "-o", rep, "-r0", "-v", base],
+                       check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
+        text = open(rep).read()
+        a = text.index("ASCII Curves - Approximate Posterior Densities")
+        import json
+        with gzip.GzipFile(os.path.join(HERE, "lmode_ascii_sim3.json.gz"), "wb", mtime=0) as g:
+            g.write(json.dumps({"curves": text[a:text.index("ASCII Plots of Parameter Trends", a)]}).encode())
+        print("wrote lmode_ascii_sim3.json.gz")
     # opening sections of an M-mode report (section 8 f4): the reference's own main() on a committed input; kept from the top of
     # the file to the means / variances table -- run information, highest likelihoods, update-rate tables of the cold chain,
     # swap table
