@@ -57,6 +57,7 @@ SIGNATURES = {
     "ima2p_engine_set_update_schedule": (_i, [_v, _i, _i]),
     "ima2p_engine_set_update_priors": (_i, [_v, c_dbl_p, c_dbl_p, _d, _d, _d, _d]),
     "ima2p_engine_update_counters": (_i, [_v, c_u64_p]),
+    "ima2p_engine_fetch_chain_pdg": (_i, [_v, _i, c_dbl_p]),
     "ima2p_engine_cold_counters": (_i, [_v, c_u64_p, c_u64_p, c_u64_p, c_u64_p]),
     "ima2p_engine_get_split_times": (_i, [_v, _i, c_dbl_p]),
     "ima2p_engine_fetch_parameters": (_i, [_v, c_dbl_p, c_dbl_p, c_dbl_p]),

@@ -1372,6 +1372,23 @@ int ima2p_engine_fetch_pair_summaries(ima2p_engine *h, double *sd, int *si, int 
   return IMA2P_OK;
 }
 
+// P(D|G) of every locus of one chain (C[ci]->G[li].pdg): three small copies and one synchronisation whatever the number of
+// chains -- what checkhighs (output.cpp:207-240) looks at for the cold chain at a recorded step
+int ima2p_engine_fetch_chain_pdg(ima2p_engine *h, int ci, double *pdg) {
+  if (!h || !h->eng.finalized || !pdg || ci < 0 || ci >= h->eng.d.nchains) return fail(IMA2P_E_ARG, "fetch_chain_pdg: bad argument");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+  const size_t L = e.d.nloci, p0 = (size_t)ci * L;
+  std::vector<unsigned char> cur(L);
+  std::vector<double> sd0(L * 4), sd1(L * 4);
+  if (!d2h(cur.data(), e.v.cur + p0, L, s) || !d2h(sd0.data(), e.v.buf[0].sd + p0 * 4, L * 4 * sizeof(double), s) ||
+      !d2h(sd1.data(), e.v.buf[1].sd + p0 * 4, L * 4 * sizeof(double), s) || !dev_sync(s))
+    return fail(IMA2P_E_CUDA, "download failed");
+  for (size_t li = 0; li < L; li++) pdg[li] = (cur[li] ? sd1 : sd0)[li * 4 + 3];
+  return IMA2P_OK;
+}
+
 // The per-step read-back in one kernel, one copy and one synchronisation: chain4[nchains][4] = beta, probg, pdg, S;
 // row[rowlen] = the cold chain's .ti row when it lives on this rank (*present), as ima2p_engine_cold_row
 int ima2p_engine_step_report(ima2p_engine *h, double *chain4, float *row, int *present, void *cuda_stream) {

@@ -1149,7 +1149,7 @@ int main(int argc, char **argv) {
   ck(ima2p_engine_update_counters(E, ucnt0), "counters");
   ck(ima2p_engine_cold_counters(E, cg0.data(), ct0.data(), cu0.data(), ca0.data()), "counters");
   double hilike = -1e20, hiprob = -1e20;                                   // checkhighs (output.cpp:207-240), at the recorded steps
-  std::vector<double> hilocus(nloci, -1e20), pair_sd((size_t)nchains * nloci * 4);
+  std::vector<double> hilocus(nloci, -1e20), locus_pdg(nloci);
   std::vector<double> chain4((size_t)nchains * 4);
   std::vector<float> rows, row(rowlen), allrows;
   std::vector<double> tsum(nsplit > 0 ? nsplit : 1, 0.0);
@@ -1159,12 +1159,12 @@ int main(int argc, char **argv) {
     int present = 0;
     ck(ima2p_engine_step_report(E, chain4.data(), row.data(), &present, nullptr), "reading the cold chain");
     if (!present) die("the cold chain is not on this device");
-    ck(ima2p_engine_fetch_pair_summaries(E, pair_sd.data(), nullptr, nullptr, nullptr), "reading the likelihoods");
     for (int c = 0; c < nchains; c++) {
       if (chain4[(size_t)c * 4] != 1.0) continue;
       if (chain4[(size_t)c * 4 + 1] > hiprob) hiprob = chain4[(size_t)c * 4 + 1];
       if (chain4[(size_t)c * 4 + 2] > hilike) hilike = chain4[(size_t)c * 4 + 2];
-      for (int li = 0; li < nloci; li++) { const double v = pair_sd[((size_t)c * nloci + li) * 4 + 3]; if (v > hilocus[li]) hilocus[li] = v; }
+      ck(ima2p_engine_fetch_chain_pdg(E, c, locus_pdg.data()), "reading the likelihoods");
+      for (int li = 0; li < nloci; li++) if (locus_pdg[li] > hilocus[li]) hilocus[li] = locus_pdg[li];
     }
     rows.insert(rows.end(), row.begin(), row.end());
     allrows.insert(allrows.end(), row.begin(), row.end());

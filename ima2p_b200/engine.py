@@ -263,6 +263,11 @@ class Engine:
         self._ck(self.lib.ima2p_engine_update_counters(self._h, out))
         return dict(t_tries=out[0], t_accepts=out[1], u_tries=out[2], u_accepts=out[3])
 
+    def fetch_chain_pdg(self, chain):
+        out = np.zeros(self.nloci)
+        self._ck(self.lib.ima2p_engine_fetch_chain_pdg(self._h, chain, _dp(out)))
+        return out
+
     def cold_counters(self, nsplit, nurates):
         """Cold-chain update counts as the reference's update-rate tables report them, and adjacent-temperature swaps."""
         g = np.zeros((self.nloci, 3), dtype=np.uint64)

@@ -241,6 +241,8 @@ int ima2p_engine_put_state_packed (ima2p_engine * e, const void *topo8, const vo
 /* per-pair summaries of the current genealogies: sd[P][4] = {roottime, length, tlength, pdg}, si[P][2] = {root, mignum},
  * wi[P][NI] = coalescence | migration counts (struct genealogy fields imamp.hpp:956-987); NULL pointers are skipped */
 int ima2p_engine_fetch_pair_summaries (ima2p_engine * e, double *sd, int *si, int *wi, void *cuda_stream);
+/* P(D|G) of every locus of one local chain, pdg[nloci] (C[ci]->G[li].pdg; what checkhighs output.cpp:207-240 reads) */
+int ima2p_engine_fetch_chain_pdg (ima2p_engine * e, int ci, double *pdg);
 /* per-chain summary after a run: out[ci] = {beta, probg, pdg, S} */
 int ima2p_engine_fetch_chain_summary (ima2p_engine * e, double *out4 /* [nchains_local][4] */ , void *cuda_stream);
 

@@ -547,6 +547,9 @@ def cold_chain_counters_are_consistent(lib, nsteps=60):
     assert np.all(cc["genealogy"][:, 0] <= 5 * nsteps)
     assert int(cc["split"][:, [0, 2]].sum()) == 5 * nsteps and int(cc["split"][:, [1, 3]].sum()) <= uc["t_accepts"]
     assert int(cc["scalars"][:, 0].sum()) == 2 * eng.nloci * nsteps and np.all(cc["scalars"][:, 1] <= cc["scalars"][:, 0])
+    sd = eng.fetch_pair_summaries()[0].reshape(eng.nchains, eng.nloci, 4)
+    for c in range(eng.nchains):
+        assert np.array_equal(eng.fetch_chain_pdg(c), sd[c, :, 3])
     adj = cc["adjacent"]
     assert adj.shape == (3, 2) and np.all(adj[:, 1] <= adj[:, 0]) and 0 < adj[:, 0].sum() <= cnt["swap_attempts"]
     assert adj[:, 1].sum() <= cnt["swaps"]
