@@ -99,3 +99,36 @@ def test_ti_file_round_trip_matches_reference_text(lib, tmp_path):
         ti_load(src, rows.shape[1] + 1, lib=lib)                  # too few values per genealogy
     with pytest.raises(Ima2pError):
         ti_load(src, rows.shape[1] - 1, lib=lib)                  # too many
+
+
+def test_reader_keeps_the_text_the_report_echoes(lib):
+    """ima2p_dataset_text and the header-line flags: what readdata echoes into the report (readata.cpp:916-963, 640-832) --
+    the title and '#' lines, the population names, whether the model letter carried a count (SW_M / IS+SW_M) and whether an
+    inheritance scalar stood on the line ("%5.3lf" against "%lf")."""
+    import ctypes as C
+
+    def texts(d, kind):
+        out, buf, k = [], C.create_string_buffer(512), 0
+        while lib.ima2p_dataset_text(d, kind, k, buf, 512) == 0:
+            out.append(buf.value.decode())
+            k += 1
+        return out
+
+    def flags(d, nloci):
+        info = (C.c_int * 8)()
+        res = []
+        for li in range(nloci):
+            assert lib.ima2p_dataset_locus(d, li, info, None, None, None, 0) == 0
+            res.append(info[7])
+        return res
+    d = C.c_void_p()
+    assert lib.ima2p_dataset_read(os.path.join(HERE, "golden", "inputs", "parse_is_3pop.u").encode(), C.byref(d)) == 0
+    assert texts(d, 0) == ["parser corner cases, infinite sites", " a comment line", "another"]
+    assert texts(d, 1) == ["popA", "popB", "popC"]
+    assert flags(d, 4) == [0, 2, 2, 2]                      # loc0 has no inheritance scalar on its line
+    lib.ima2p_dataset_free(d)
+    d = C.c_void_p()
+    assert lib.ima2p_dataset_read(os.path.join(HERE, "golden", "inputs", "parse_sw_joint.u").encode(), C.byref(d)) == 0
+    assert flags(d, 3) == [3, 3, 2]                         # S2, J1, I -- all with a scalar
+    assert len(texts(d, 1)) == 2 and texts(d, 0)[0]
+    lib.ima2p_dataset_free(d)
