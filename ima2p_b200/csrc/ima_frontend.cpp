@@ -33,6 +33,7 @@
 
 namespace {
 
+time_t g_starttime = 0;                    // set when main starts: the report's "Time Elapsed" lines
 bool g_throw_instead_of_exit = false;      // set around the closing report of an M-mode run: its failure must not lose the run
 [[noreturn]] void die(const std::string &m, int code = 1) {
   if (g_throw_instead_of_exit) throw std::runtime_error(m);
@@ -974,6 +975,10 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
   fprintf(f, "\n\nASCII Curves - Approximate Posterior Densities \n===================================================\n");
   for (size_t i = 0; i < hname.size(); i++) ascii_curve(f, xs[i], ys[i], hname[i], false, 1.0);
   for (size_t i = 0; i < acn.size(); i++) ascii_curve(f, acx[i], acy[i], acn[i], false, (double)nrows);
+  {
+    const int seconds = (int)difftime(time(nullptr), g_starttime);          // ima_main_mpi.cpp:4149-4155
+    fprintf(f, "Time Elapsed : %d hours, %d minutes, %d seconds \n\n", seconds / 3600, seconds / 60 - 60 * (seconds / 3600), seconds - 60 * (seconds / 60));
+  }
   fprintf(f, "\nEND OF OUTPUT\n");
   ima2p_lmode_destroy(LM);
 }
@@ -1002,6 +1007,7 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
 }  // namespace
 
 int main(int argc, char **argv) {
+  g_starttime = time(nullptr);
   std::map<std::string, std::string> opt;
   static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", "c", nullptr};
   RunInfo R{};
@@ -1039,7 +1045,7 @@ int main(int argc, char **argv) {
   R.lmode = lmode; R.expo = expo != 0;
   if (opt.count("f")) R.mcf_in = opt["f"];
   if (opt.count("r") && !lmode) R.mcf_out = opt["o"] + ".mcf";
-  const time_t starttime = time(nullptr);
+  const time_t starttime = g_starttime;
 
   ima2p_dataset *D = nullptr;
   ck(ima2p_dataset_read(opt["i"].c_str(), &D), "reading data");

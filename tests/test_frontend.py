@@ -253,7 +253,8 @@ def test_l_mode_ascii_curves_equal_the_reference_text(exe, tmp_path):
     assert r.returncode == 0, r.stderr
     rep = open(tmp_path / "l.out").read()
     a = rep.index("ASCII Curves - Approximate Posterior Densities")
-    mine = rep[a:rep.index("\nEND OF OUTPUT", a)].rstrip("\n").split("\n")
+    mine = rep[a:rep.index("\nTime Elapsed", a)].rstrip("\n").split("\n")
+    assert rep.rstrip().endswith("END OF OUTPUT")
     want = ref.rstrip("\n").split("\n")
     assert len(mine) == len(want) == 2 + 6 * 54 - 1
     differing = [i for i, (x, y) in enumerate(zip(mine, want)) if x != y]
