@@ -198,7 +198,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sim50x128", choices=sorted(WORKLOADS))
     ap.add_argument("--burn", type=int, default=3000, help="untimed burn-in steps before warm-up (migration counts need ~3000 steps to settle)")
-    ap.add_argument("--pieces", type=int, default=0, help="locus ranges per step (0 = engine default)")
+    ap.add_argument("--pipeline", default="", help="groups,depth[,decisions_first] of Engine.set_pipeline (default: the engine's)")
     ap.add_argument("--schedule", default="full", choices=["full", "genealogy"],
                     help="full: qupdate's schedule (genealogies, split time every step, mutation scalars every 5th, swaps); "
                          "genealogy: updategenealogy + swaps only")
@@ -244,8 +244,8 @@ def main():
     eng.set_update_priors(t_max=[PRIOR_T])
     if full:
         eng.set_update_schedule(3, 5)
-    if args.pieces > 0:
-        eng.set_pieces(args.pieces)
+    if args.pipeline:
+        eng.set_pipeline(*[int(x) for x in args.pipeline.split(",")])
     if os.environ.get("IMA_SPEC"):
         eng.set_speculation(int(os.environ["IMA_SPEC"]))
     work_stream = torch.cuda.Stream()              # a real (non-default) stream: kernels, NCCL and the timing events all go here

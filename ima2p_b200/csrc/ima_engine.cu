@@ -28,6 +28,8 @@ struct HostLocus {
   bool set = false;
 };
 
+constexpr int kMaxGroups = 16;
+
 struct Engine {
   int device = 0;
   EngineDims d{};
@@ -62,13 +64,13 @@ struct Engine {
   int t_updates = 0, u_every = 0;
   std::vector<int> h_ul_l, h_ul_a;
 #if IMA_CUDA
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  cudaStream_t own_stream = nullptr, aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_piece[16] = {};
+  cudaGraphExec_t graph_exec = nullptr, graph_exec_deep = nullptr;   // one step; `depth` steps
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t group_stream[kMaxGroups][2] = {};    // per chain group: proposals (low priority), decisions (high priority)
+  std::vector<cudaEvent_t> pipe_events;
 #endif
-  int pieces = 1;      // measured on B200: overlapping the sweep with proposals does not pay
-  size_t pair_smem = 0, chain_smem = 0, overlap_smem = 0, accept_smem = 0;
+  int groups = 1, depth = 1, pipe_prio = 0;          // see capture_steps
+  size_t pair_smem = 0, chain_smem = 0, accept_smem = 0;
   int spec = 3;        // speculative depth of the accept sweep (see k_accept)
 
   template <class T> T *alloc(size_t n) {
@@ -79,11 +81,10 @@ struct Engine {
   ~Engine() {
 #if IMA_CUDA
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
-    if (graph) cudaGraphDestroy(graph);
+    if (graph_exec_deep) cudaGraphExecDestroy(graph_exec_deep);
     if (own_stream) cudaStreamDestroy(own_stream);
-    if (aux_stream) cudaStreamDestroy(aux_stream);
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    for (auto &x : ev_piece) if (x) cudaEventDestroy(x);
+    for (auto &g : group_stream) for (auto &x : g) if (x) cudaStreamDestroy(x);
+    for (auto &x : pipe_events) if (x) cudaEventDestroy(x);
 #endif
     for (void *p : allocs) dev_free(p);
   }
@@ -129,84 +130,143 @@ static int launch_eval(Engine *e, stream_t s) {
 }
 
 static int accept_block_warps(int spec) { return IMA_CUDA ? spec * kTermWarps : 1; }
-static void launch_accept(Engine *e, stream_t s, int l0, int l1) {
-  const int nw = accept_block_warps(e->spec);
-  if (e->spec >= 4) IMA_LAUNCH(k_accept<4>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
-  else if (e->spec == 3) IMA_LAUNCH(k_accept<3>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
-  else if (e->spec == 2) IMA_LAUNCH(k_accept<2>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
-  else IMA_LAUNCH(k_accept<1>, e->d.nchains, nw, e->accept_smem, s, e->v, l0, l1);
+
+// the view a launch gets: which chains it covers and which step (relative to the device counter) it belongs to
+static EngineView view_of(const Engine *e, int c_lo, int c_n, int step_off) {
+  EngineView v = e->v;
+  v.c_lo = c_lo; v.c_n = c_n; v.step_off = step_off;
+  return v;
 }
-// One step's genealogy updates.  The accept sweep is a dependent chain over the loci of a chain, the
-// proposals are independent per pair, and a proposal only needs its own pair's state -- so the loci are cut
-// into `pieces` ranges and the sweep of range q (stream s) overlaps the proposals of range q+1 (aux stream):
-//     P0 -> [A0 | P1] -> [A1 | P2] -> ... -> A(Q-1)          step time ~ P/Q + A instead of P + A.
-// Works under stream capture too (the event record/wait pairs become graph edges).
+static int pair_grid(const Engine *e, const EngineView &v) { return (v.c_n * e->d.nloci + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+
+static void launch_propose(Engine *e, stream_t s, const EngineView &v) {
+  IMA_LAUNCH(k_propose, pair_grid(e, v), kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v);
+}
+static void launch_accept(Engine *e, stream_t s, const EngineView &v) {
+  const int nw = accept_block_warps(e->spec);
+  if (e->spec >= 4) IMA_LAUNCH(k_accept<4>, v.c_n, nw, e->accept_smem, s, v);
+  else if (e->spec == 3) IMA_LAUNCH(k_accept<3>, v.c_n, nw, e->accept_smem, s, v);
+  else if (e->spec == 2) IMA_LAUNCH(k_accept<2>, v.c_n, nw, e->accept_smem, s, v);
+  else IMA_LAUNCH(k_accept<1>, v.c_n, nw, e->accept_smem, s, v);
+}
 static size_t changeu_smem(const Engine *e) {
   const size_t need = changeu_smem_doubles(e->d.nloci) * sizeof(double);
   return need > e->pair_smem ? need : e->pair_smem;
 }
-
+static bool does_split_t(const Engine *e) { return e->t_updates && e->model.nsplit > 0; }
+static bool does_changeu(const Engine *e) { return e->u_every > 0 && (e->uv.nurates > 1 || e->loci[0].d.model == kHKY); }
 // the rest of qupdate's schedule (ima_main_mpi.cpp:1867-1945): a split-time update of every chain each step
-// (TUPDATEINC 0), the mutation scalars every u_every-th step (UUPDATEINC 4); both are local to a chain
-static void launch_param_updates(Engine *e, stream_t s) {
-  const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  if (e->t_updates && e->model.nsplit > 0) {
-    // every chain picks one of the two split-time updates (t_proposal); a warp whose chain picked the other one returns at once
-    IMA_LAUNCH(k_split_t, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, e->uv);
-    IMA_LAUNCH(k_accept_t, e->d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e->d), s, e->v, e->uv);
-  }
-  if (e->u_every > 0 && (e->uv.nurates > 1 || e->loci[0].d.model == kHKY)) {
-    UpdateView u = e->uv;
-    u.u_every = e->u_every;
-    IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, changeu_smem(e) * kWarpsPerBlock, s, e->v, u);
-  }
+// (TUPDATEINC 0), the mutation scalars every u_every-th step (UUPDATEINC 4); both are local to a chain.
+// Every chain picks one of the two split-time updates (t_proposal); a warp whose chain picked the other one returns at once.
+static void launch_split_t(Engine *e, stream_t s, const EngineView &v) {
+  IMA_LAUNCH(k_split_t, pair_grid(e, v), kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v, e->uv);
 }
-
-static void launch_update_genealogies(Engine *e, stream_t s);
-static void launch_update(Engine *e, stream_t s) {
-  launch_update_genealogies(e, s);
-  launch_param_updates(e, s);
+static void launch_accept_t(Engine *e, stream_t s, const EngineView &v) {
+  IMA_LAUNCH(k_accept_t, v.c_n, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e->d), s, v, e->uv);
 }
-
-static void launch_update_genealogies(Engine *e, stream_t s) {
-  const int gc = (e->d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock, L = e->d.nloci;
-  int Q = e->pieces < 1 ? 1 : e->pieces;
-  if (Q > L) Q = L;
-#if IMA_CUDA
-  if (Q > 1) {
-    cudaEventRecord(e->ev_fork, s);
-    cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0);
-    for (int q = 0; q < Q; q++) {
-      const int l0 = (int)((long long)L * q / Q), l1 = (int)((long long)L * (q + 1) / Q);
-      const int gp = (e->d.nchains * (l1 - l0) + kWarpsPerBlock - 1) / kWarpsPerBlock;
-      // padded dynamic shared memory caps the proposal kernel at 4 blocks per SM, which leaves registers for one
-      // accept block (256 threads) on every SM: the two kernels then really run side by side
-      IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e->overlap_smem, e->aux_stream, e->v, l0, l1);
-      cudaEventRecord(e->ev_piece[q], e->aux_stream);
-    }
-    for (int q = 0; q < Q; q++) {
-      const int l0 = (int)((long long)L * q / Q), l1 = (int)((long long)L * (q + 1) / Q);
-      cudaStreamWaitEvent(s, e->ev_piece[q], 0);
-      launch_accept(e, s, l0, l1);
-    }
-    return;
-  }
-#endif
-  const int gp = (e->d.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, e->v, 0, L);
-  launch_accept(e, s, 0, L);
+static void launch_changeu(Engine *e, stream_t s, const EngineView &v) {
+  UpdateView u = e->uv;
+  u.u_every = e->u_every;
+  IMA_LAUNCH(k_changeu, (v.c_n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock, changeu_smem(e) * kWarpsPerBlock, s, v, u);
 }
+static void launch_param_updates(Engine *e, stream_t s, const EngineView &v) {
+  if (does_split_t(e)) { launch_split_t(e, s, v); launch_accept_t(e, s, v); }
+  if (does_changeu(e)) launch_changeu(e, s, v);
+}
+// one step of chains [c_lo, c_lo + c_n) up to, not including, the swaps
+static void launch_update(Engine *e, stream_t s, const EngineView &v) {
+  launch_propose(e, s, v);
+  launch_accept(e, s, v);
+  launch_param_updates(e, s, v);
+}
+static void launch_update(Engine *e, stream_t s) { launch_update(e, s, view_of(e, 0, e->d.nchains, 0)); }
 
-static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries, int step_already_advanced = 0) {
+// advance: what the launch adds to the device step counter (1 for a plain step, the number of steps at the end of a
+// multi-step graph, 0 otherwise); step_off: the step it belongs to, relative to the counter
+static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries, int step_already_advanced = 0, int advance = 1, int step_off = 0) {
   SwapView sv = e->sv;
   sv.S_global = S_global;
   sv.swaptries = swaptries;
-  sv.advance_step = step_already_advanced ? 0 : 1;
+  sv.advance_step = step_already_advanced ? 0 : advance;
   sv.step_bias = step_already_advanced ? 1 : 0;
   const int G = e->d.nchains_global;
   sv.smem_chains = G <= 4000 ? G : 0;                        // 24 bytes per chain, 96 KB opted in at finalize
-  IMA_LAUNCH(k_swap, 1, 1, swap_smem_bytes(sv.smem_chains), s, e->v, sv);
+  IMA_LAUNCH(k_swap, 1, 1, swap_smem_bytes(sv.smem_chains), s, view_of(e, 0, e->d.nchains, step_off), sv);
 }
+
+#if IMA_CUDA
+// ---- the step as a CUDA graph --------------------------------------------------------------------------------------
+// Chains only meet at the swaps, and the proposal half of a step does not read the temperatures.  The accept sweep is a
+// long dependent chain per chain (loci in order) that leaves most of the GPU idle, so the chains are cut into `groups`
+// groups, each on its own stream: the sweep of one group overlaps the proposals / split-time proposals of the others.
+// A graph holds `depth` consecutive steps: group g's proposals of step j+1 start as soon as ITS step j is done (they
+// need neither the other groups nor the swaps of step j); only its accept sweep waits for the swaps.  Every random
+// stream is keyed by (chain, locus, step, purpose), so the run is bit for bit the plain one-stream run.
+static cudaEvent_t pipe_event(Engine &e, size_t &next) {
+  if (next == e.pipe_events.size()) {
+    cudaEvent_t ev = nullptr;
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    e.pipe_events.push_back(ev);
+  }
+  return e.pipe_events[next++];
+}
+static bool capture_steps(Engine &e, int swaptries, int depth, cudaGraphExec_t *out) {
+  int G = e.groups < 1 ? 1 : e.groups;
+  if (G > e.d.nchains) G = e.d.nchains;
+  if (G > kMaxGroups) G = kMaxGroups;
+  for (int g = 0; g < G; g++)
+    for (int k = 0; k < 2; k++)
+      if (!e.group_stream[g][k]) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (!IMA_CUDA_OK(cudaStreamCreateWithPriority(&e.group_stream[g][k], cudaStreamNonBlocking, k ? hi : lo))) return false;
+      }
+  cudaStream_t s = e.own_stream;
+  size_t nev = 0;
+  cudaGraph_t graph = nullptr;
+  if (!IMA_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal))) return false;
+  cudaEvent_t fork = pipe_event(e, nev);
+  cudaEventRecord(fork, s);
+  std::vector<cudaEvent_t> prev_swap(1, nullptr);
+  cudaEvent_t swap_done = nullptr;
+  for (int g = 0; g < G; g++) cudaStreamWaitEvent(e.group_stream[g][0], fork, 0);
+  for (int j = 0; j < depth; j++) {
+    std::vector<cudaEvent_t> done(G);
+    for (int g = 0; g < G; g++) {
+      const int c_lo = (int)((long long)e.d.nchains * g / G), c_hi = (int)((long long)e.d.nchains * (g + 1) / G);
+      const EngineView v = view_of(&e, c_lo, c_hi - c_lo, j);
+      cudaStream_t sp = e.group_stream[g][0], sa = e.pipe_prio ? e.group_stream[g][1] : sp;   // proposals / decisions
+      auto hop = [&](cudaStream_t from, cudaStream_t to) {
+        if (from == to) return;
+        cudaEvent_t ev = pipe_event(e, nev);
+        cudaEventRecord(ev, from);
+        cudaStreamWaitEvent(to, ev, 0);
+      };
+      launch_propose(&e, sp, v);
+      hop(sp, sa);
+      if (swap_done) cudaStreamWaitEvent(sa, swap_done, 0);          // the temperatures of this step
+      launch_accept(&e, sa, v);
+      if (does_split_t(&e)) {
+        hop(sa, sp);
+        launch_split_t(&e, sp, v);
+        hop(sp, sa);
+        launch_accept_t(&e, sa, v);
+      }
+      if (does_changeu(&e)) launch_changeu(&e, sa, v);
+      done[g] = pipe_event(e, nev);
+      cudaEventRecord(done[g], sa);
+      if (sa != sp) cudaStreamWaitEvent(sp, done[g], 0);             // the group's next proposals follow its own step
+    }
+    for (int g = 0; g < G; g++) cudaStreamWaitEvent(s, done[g], 0);
+    launch_swap(&e, s, e.v.swapsum, swaptries, 0, j == depth - 1 ? depth : 0, j);
+    if (j + 1 < depth) { swap_done = pipe_event(e, nev); cudaEventRecord(swap_done, s); }
+  }
+  if (!IMA_CUDA_OK(cudaStreamEndCapture(s, &graph))) return false;
+  const bool ok = IMA_CUDA_OK(cudaGraphInstantiate(out, graph, 0));
+  cudaGraphDestroy(graph);
+  return ok;
+}
+#endif
 
 }  // namespace ima
 
@@ -245,14 +305,9 @@ int ima2p_engine_create(ima2p_engine **out, int device, int nchains_local, int n
   e.loci.resize(nloci);
   if (!use_device(&e)) { delete h; return fail(IMA2P_E_CUDA, "cudaSetDevice failed"); }
 #if IMA_CUDA
-  // the accept sweep is the latency-critical chain: its stream gets the highest priority so that its blocks are
-  // placed ahead of the (throughput-oriented) proposal blocks of the aux stream whenever an SM frees resources
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  if (!IMA_CUDA_OK(cudaStreamCreateWithPriority(&e.own_stream, cudaStreamNonBlocking, prio_hi)) ||
-      !IMA_CUDA_OK(cudaStreamCreateWithPriority(&e.aux_stream, cudaStreamNonBlocking, prio_lo)) ||
-      !IMA_CUDA_OK(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming))) { delete h; return fail(IMA2P_E_CUDA, "stream create failed"); }
-  for (auto &x : e.ev_piece) if (!IMA_CUDA_OK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming))) { delete h; return fail(IMA2P_E_CUDA, "event create failed"); }
+  if (!IMA_CUDA_OK(cudaStreamCreateWithPriority(&e.own_stream, cudaStreamNonBlocking, prio_hi))) { delete h; return fail(IMA2P_E_CUDA, "stream create failed"); }
 #endif
   *out = h;
   return IMA2P_OK;
@@ -402,12 +457,11 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   e.spec = d.nchains <= 148 ? 3 : 2;
 #if IMA_CUDA
   if (e.pair_smem * kWarpsPerBlock > 227 * 1024) return fail(IMA2P_E_ARG, "finalize: pair does not fit in shared memory; lower mig_capacity");
-  e.overlap_smem = e.pair_smem * kWarpsPerBlock;
   if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
-      !IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.overlap_smem)) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem_bytes(4000))) ||
@@ -457,6 +511,7 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   v.acc = e.alloc<unsigned int>(P * 3); v.cold_acc = e.alloc<unsigned int>((size_t)d.nloci * 3);
   v.nsteps = e.alloc<unsigned long long>(1); v.overflow = e.alloc<unsigned long long>(1);
   v.seed = e.seed;
+  v.c_lo = 0; v.c_n = d.nchains; v.step_off = 0;
   v.loci = e.d_loci; v.sitemask = d_sm; v.seq = d_sq; v.mult = d_mu;
   v.mc.logfact = e.d_logfact; v.mc.logfact_n = nlf; v.mc.err = e.d_err;
   e.sv.rank_of_chain = e.alloc<int>(G); e.sv.chain_of_rank = e.alloc<int>(G);
@@ -737,15 +792,16 @@ int ima2p_engine_run(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stre
 #if IMA_CUDA
   if (!e.graph_ready || e.graph_swaptries != swaptries) {
     if (e.graph_exec) { cudaGraphExecDestroy(e.graph_exec); e.graph_exec = nullptr; }
-    if (e.graph) { cudaGraphDestroy(e.graph); e.graph = nullptr; }
-    if (!IMA_CUDA_OK(cudaStreamBeginCapture(e.own_stream, cudaStreamCaptureModeThreadLocal))) return fail(IMA2P_E_CUDA, "graph capture failed");
-    launch_update(&e, e.own_stream);
-    launch_swap(&e, e.own_stream, e.v.swapsum, swaptries);
-    if (!IMA_CUDA_OK(cudaStreamEndCapture(e.own_stream, &e.graph)) || !IMA_CUDA_OK(cudaGraphInstantiate(&e.graph_exec, e.graph, 0)))
-      return fail(IMA2P_E_CUDA, "graph instantiate failed");
+    if (e.graph_exec_deep) { cudaGraphExecDestroy(e.graph_exec_deep); e.graph_exec_deep = nullptr; }
+    if (!capture_steps(e, swaptries, 1, &e.graph_exec)) return fail(IMA2P_E_CUDA, "graph capture failed");
+    if (e.depth > 1 && !capture_steps(e, swaptries, e.depth, &e.graph_exec_deep)) return fail(IMA2P_E_CUDA, "graph capture failed (deep)");
     e.graph_ready = true; e.graph_swaptries = swaptries;
   }
-  for (int i = 0; i < nsteps; i++)
+  int i = 0;
+  if (e.graph_exec_deep)
+    for (; i + e.depth <= nsteps; i += e.depth)
+      if (!IMA_CUDA_OK(cudaGraphLaunch(e.graph_exec_deep, s))) return fail(IMA2P_E_CUDA, "graph launch failed");
+  for (; i < nsteps; i++)
     if (!IMA_CUDA_OK(cudaGraphLaunch(e.graph_exec, s))) return fail(IMA2P_E_CUDA, "graph launch failed");
 #else
   for (int i = 0; i < nsteps; i++) { launch_update(&e, s); launch_swap(&e, s, e.v.swapsum, swaptries); }
@@ -766,27 +822,25 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
   stream_t s = pick_stream(&e, cuda_stream);
   for (int k = 0; k < 7; k++) kernel_ms[k] = 0.f;
 #if IMA_CUDA
-  const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int chunk = 256;
   std::vector<cudaEvent_t> ev((size_t)chunk * 8);
-  const bool do_t = e.t_updates && e.model.nsplit > 0, do_u = e.u_every > 0 && (e.uv.nurates > 1 || e.loci[0].d.model == kHKY);
-  UpdateView uvu = e.uv;
-  uvu.u_every = e.u_every > 0 ? e.u_every : 1;
+  const bool do_t = does_split_t(&e), do_u = does_changeu(&e);
+  const EngineView all = view_of(&e, 0, e.d.nchains, 0);
   for (auto &x : ev) if (!IMA_CUDA_OK(cudaEventCreate(&x))) return fail(IMA2P_E_CUDA, "event create failed");
   for (int s0 = 0; s0 < nsteps; s0 += chunk) {
     const int n = nsteps - s0 < chunk ? nsteps - s0 : chunk;
     for (int i = 0; i < n; i++) {
       cudaEventRecord(ev[i * 8 + 0], s);
-      IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, 0, e.d.nloci);
+      launch_propose(&e, s, all);
       cudaEventRecord(ev[i * 8 + 1], s);
-      launch_accept(&e, s, 0, e.d.nloci);
+      launch_accept(&e, s, all);
       cudaEventRecord(ev[i * 8 + 2], s);
       cudaEventRecord(ev[i * 8 + 3], s);
-      if (do_t) IMA_LAUNCH(k_split_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, e.uv);
+      if (do_t) launch_split_t(&e, s, all);
       cudaEventRecord(ev[i * 8 + 4], s);
-      if (do_t) IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e.d), s, e.v, e.uv);
+      if (do_t) launch_accept_t(&e, s, all);
       cudaEventRecord(ev[i * 8 + 5], s);
-      if (do_u) IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, changeu_smem(&e) * kWarpsPerBlock, s, e.v, uvu);
+      if (do_u) launch_changeu(&e, s, all);
       cudaEventRecord(ev[i * 8 + 6], s);
       launch_swap(&e, s, e.v.swapsum, swaptries);
       cudaEventRecord(ev[i * 8 + 7], s);
@@ -830,8 +884,7 @@ int ima2p_engine_step_propose(ima2p_engine *h, void *cuda_stream) {
   if (rc) return rc;
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, cuda_stream);
-  const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  IMA_LAUNCH(k_propose, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, 0, e.d.nloci);
+  launch_propose(&e, s, view_of(&e, 0, e.d.nchains, 0));
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (propose)");
 #endif
@@ -845,8 +898,8 @@ int ima2p_engine_step_decide(ima2p_engine *h, double *dev_S_local, void *cuda_st
   if (rc) return rc;
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, cuda_stream);
-  launch_accept(&e, s, 0, e.d.nloci);
-  launch_param_updates(&e, s);
+  launch_accept(&e, s, view_of(&e, 0, e.d.nchains, 0));
+  launch_param_updates(&e, s, view_of(&e, 0, e.d.nchains, 0));
   IMA_LAUNCH(k_copy_swapsum, (e.d.nchains + kWarpsPerBlock * IMA_WARP - 1) / (kWarpsPerBlock * IMA_WARP), kWarpsPerBlock, 0, s, e.v, dev_S_local, 1);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (decide)");
@@ -929,9 +982,11 @@ int ima2p_engine_set_speculation(ima2p_engine *h, int depth) {
   return IMA2P_OK;
 }
 
-int ima2p_engine_set_pieces(ima2p_engine *h, int pieces) {
-  if (!h || pieces < 1 || pieces > 16) return fail(IMA2P_E_ARG, "set_pieces: 1..16");
-  h->eng.pieces = pieces;
+// how ima2p_engine_run issues its steps (capture_steps): chain groups on their own streams, steps per graph, and whether a
+// group's decision kernels go to a high-priority stream of their own.  The chains a run visits do not depend on it.
+int ima2p_engine_set_pipeline(ima2p_engine *h, int groups, int depth, int decisions_first) {
+  if (!h || groups < 1 || groups > kMaxGroups || depth < 1 || depth > 64) return fail(IMA2P_E_ARG, "set_pipeline: groups 1..16, depth 1..64");
+  h->eng.groups = groups; h->eng.depth = depth; h->eng.pipe_prio = decisions_first ? 1 : 0;
   h->eng.graph_ready = false;
   return IMA2P_OK;
 }
@@ -1006,9 +1061,9 @@ int ima2p_engine_debug_split_time(ima2p_engine *h, int method, int period, const
     if (!d_newt || !h2d(d_newt, newt, C * sizeof(double), s)) return fail(IMA2P_E_CUDA, "upload failed");
     u.t_forced = d_newt; u.t_forced_period = period; u.t_force_accept = force_accept; u.t_forced_method = method;
   } else u.t_methods = method ? 2 : 1;
-  const int gp = (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  IMA_LAUNCH(k_split_t, gp, kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, e.v, u);
-  IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e.d), s, e.v, u);
+  const EngineView all = view_of(&e, 0, e.d.nchains, 0);
+  IMA_LAUNCH(k_split_t, pair_grid(&e, all), kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, all, u);
+  IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e.d), s, all, u);
   if (!d2h(out, e.uv.t_out, C * 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   return check_device_error(&e, s);
 }
@@ -1028,7 +1083,7 @@ int ima2p_engine_debug_changeu(ima2p_engine *h, int chain, int j, int k, double 
   UpdateView u = e.uv;
   u.u_forced = 1; u.u_chain = chain; u.u_j = j; u.u_k = k; u.u_d = d; u.u_kappa[0] = kappa_j; u.u_kappa[1] = kappa_k; u.u_every = 1;
   const int gc = (e.d.nchains + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, changeu_smem(&e) * kWarpsPerBlock, s, e.v, u);
+  IMA_LAUNCH(k_changeu, gc, kWarpsPerBlock, changeu_smem(&e) * kWarpsPerBlock, s, view_of(&e, 0, e.d.nchains, 0), u);
   if (!d2h(out, e.uv.u_out + (size_t)chain * 4, 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   return check_device_error(&e, s);
 }

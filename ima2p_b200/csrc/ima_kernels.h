@@ -22,7 +22,7 @@ IMA_CONSTANT DevModel c_model;
 constexpr int kWarpsPerBlock = 4;
 
 IMA_DEV void rng_for(Philox &rng, const EngineView &E, uint32_t stream_id, uint32_t purpose) {
-  const unsigned long long step = *E.nsteps;
+  const unsigned long long step = current_step(E);
   rng.init(E.seed, stream_id, (uint32_t)step, purpose | ((uint32_t)(step >> 32) << 8));
 }
 
@@ -194,14 +194,13 @@ IMA_KERNEL void k_eval_chains(EngineView E) {
 #else
 #define IMA_PROPOSE_BOUNDS
 #endif
-// loci [l0, l1) of every chain (one warp per pair); see launch_update for why a step is cut into pieces
-IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E, int l0, int l1) {
+// every locus of chains [c_lo, c_lo + c_n) (one warp per pair)
+IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E) {
   IMA_SMEM_DECL
   const int idx = ima_block() * kWarpsPerBlock + ima_warp_in_block();
-  const int nsub = l1 - l0;
-  if (idx >= E.d.nchains * nsub) return;
+  if (idx >= E.c_n * E.d.nloci) return;
   const DevModel &M = IMA_MODEL;
-  const int c = idx / nsub, li = l0 + (idx - c * nsub);
+  const int c = E.c_lo + idx / E.d.nloci, li = idx % E.d.nloci;
   const int p = c * E.d.nloci + li;
   const DevLocus &L = E.loci[li];
   PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
@@ -379,10 +378,11 @@ IMA_DEV AcceptSm carve_accept_smem(unsigned char *base, const EngineDims &d, int
 #define IMA_ACCEPT_BOUNDS(B)
 #endif
 template <int B>
-IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E, int l0, int l1) {
+IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E) {
   IMA_SMEM_DECL
-  const int c = ima_block();
-  if (c >= E.d.nchains) return;
+  if (ima_block() >= E.c_n) return;
+  const int c = E.c_lo + ima_block();
+  const int l0 = 0, l1 = E.d.nloci;
   const DevModel &M = IMA_MODEL;
   const int NW = B * kTermWarps;                                     // warps in the block
   const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
@@ -641,7 +641,7 @@ struct SwapView {
   const double *beta_table; // [nchains_global] beta by temperature rank (rank 0 = cold)
   unsigned long long *swap_counts;   // [2] attempts, accepts
   unsigned long long *adj_counts;    // [nchains_global][2] attempts, accepts between temperature ranks r and r + 1 (tempbasedswapcount, swapchains.cpp:760-778)
-  int swaptries, advance_step;
+  int swaptries, advance_step;   // advance_step: what the launch adds to the device step counter afterwards (0, 1, or the steps of a graph)
   int step_bias;            // 1 when the step counter was already advanced (split-phase multi-GPU step): the draws stay keyed by the step they belong to
   int smem_chains;          // chains the launch's shared memory can stage (0: work on global memory)
 };
@@ -681,7 +681,7 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
     // lane then only walks the decisions, which depend on each other through the rank tables.
     double *dU = (double *)(IMA_SMEM + (staged ? (size_t)N * 24 : 0) + 16);
     int *dA = (int *)(dU + kSwapBatch), *dB = dA + kSwapBatch;
-    const unsigned long long step = *E.nsteps - (unsigned long long)V.step_bias;
+    const unsigned long long step = current_step(E) - (unsigned long long)V.step_bias;
     unsigned long long nacc = 0;
     for (int x0 = 0; x0 < V.swaptries; x0 += kSwapBatch) {
       const int nb = V.swaptries - x0 < kSwapBatch ? V.swaptries - x0 : kSwapBatch;
@@ -734,7 +734,7 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
     if (staged) for (int i = lane; i < N; i += IMA_WARP) { V.chain_of_rank[i] = sC[i]; V.rank_of_chain[i] = sR[i]; }
     for (int c = lane; c < E.d.nchains; c += IMA_WARP) E.beta[c] = Bt[roc[E.d.chain0 + c]];
   }
-  if (V.advance_step && lane == 0) *E.nsteps += 1;
+  if (V.advance_step && lane == 0) *E.nsteps += (unsigned long long)V.advance_step;
 }
 
 // parity hook: one warp per (a, x) pair

@@ -107,6 +107,12 @@ struct EngineView {
   unsigned long long *nsteps;   // [1] steps done (device-side step counter, feeds the RNG streams)
   unsigned long long *overflow; // [1] proposals dropped because the migration pool was full
   unsigned long long seed;
+  // what this launch covers: chains [c_lo, c_lo + c_n) of the GPU's chains (chain groups run on their own streams and
+  // overlap each other's accept sweeps), and the step the launch belongs to relative to the device counter (a graph of
+  // several steps advances the counter once, at its end)
+  int c_lo, c_n, step_off;
 };
+
+IMA_HD unsigned long long current_step(const EngineView &E) { return *E.nsteps + (unsigned long long)E.step_off; }
 
 }  // namespace ima

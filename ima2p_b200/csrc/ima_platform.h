@@ -169,6 +169,6 @@ struct Philox {
   }
 };
 
-enum RngPurpose : uint32_t { kRngPropose = 1, kRngAccept = 2, kRngSwap = 3, kRngAlleles = 4, kRngSplitTime = 5, kRngScalars = 6, kRngSplitMig = 7 };
+enum RngPurpose : uint32_t { kRngPropose = 1, kRngAccept = 2, kRngSwap = 3, kRngAlleles = 4, kRngSplitTime = 5, kRngScalars = 6, kRngSplitMig = 7, kRngSplitMigSim = 8 };
 
 }  // namespace ima

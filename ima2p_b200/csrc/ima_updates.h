@@ -120,9 +120,10 @@ IMA_DEV double nw_getmprob(const DevModel &M, int period, double mrate, double m
 // walk couples two edges except (i) an edge whose upper node lies inside the interval takes its upper populations from
 // its daughters' record and (ii) the random draws, so here lanes take edges: a first pass decides the lower end of every
 // stretch (one draw stream per edge), a second pass re-simulates every stretch against those decisions.
-IMA_DEV void nw_edge_rng(Philox &rng, const EngineView &E, int pair_global, int nl_max, int edge) {
-  const unsigned long long step = *E.nsteps;
-  rng.init(E.seed, (uint32_t)(pair_global * nl_max + edge), (uint32_t)step, kRngSplitMig | ((uint32_t)(step >> 32) << 8));
+// One stream per (pair, edge, pass): the first pass (lower-end populations) and the second (re-simulated paths) use
+// different purpose tags, so no draw of one edge is ever the draw of another edge or pair.
+IMA_DEV void nw_edge_rng(Philox &rng, const EngineView &E, int pair_global, int nl_max, int edge, uint32_t purpose) {
+  rng_for(rng, E, (uint32_t)(pair_global * nl_max + edge), purpose);
 }
 
 IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const double *tv, int period, double oldt, double newt,
@@ -150,7 +151,7 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
       if (up) {
         if (db == addp) {
           const int c0 = nw_nowpop(M, tv, S, i, tu);
-          nw_edge_rng(rng, E, pair_global, E.d.NL, i);
+          nw_edge_rng(rng, E, pair_global, E.d.NL, i, kRngSplitMig);
           if (uptime < tu && (c0 == d0 || c0 == d1)) {
             if (rng.uniform() < 0.999) { da = c0; cf = 1; } else { da = c0 == d0 ? d1 : d0; cf = 2; }
           } else { cf = 3; da = rng.bit() ? d1 : d0; }
@@ -171,7 +172,7 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
       if (up) {
         if (db == addp) {
           const int c0 = nw_nowpop(M, tv, S, i, tu), c1 = nw_nowpop(M, tv, S, sis, tu);
-          nw_edge_rng(rng, E, pair_global, E.d.NL, i);
+          nw_edge_rng(rng, E, pair_global, E.d.NL, i, kRngSplitMig);
           if (uptime < tu && uptime1 < tu && c0 == c1 && (c0 == d0 || c0 == d1)) {
             if (rng.uniform() < 0.999) { da = c0; cf = 4; } else { da = c0 == d0 ? d1 : d0; cf = 5; }
           } else { cf = 6; da = rng.bit() ? d1 : d0; }
@@ -220,7 +221,7 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
     const int mcount = mi, npopsa = M.npops - period_a, npopsb = M.npops - period_b;
     const double mrate = period_a < M.nsplit ? calcmrate(mcount, mtime) * mtime : 0.0;
     Philox rng;
-    nw_edge_rng(rng, E, pair_global, E.d.NL, E.d.NL + ei);          // second block of streams: the simulation draws
+    nw_edge_rng(rng, E, pair_global, E.d.NL, ei, kRngSplitMigSim);       // its own purpose tag: the simulation draws
     int mnew;
     if (npopsa == 1) mnew = 0;
     else if (npopsa == 2) mnew = poisson_cond(rng, mrate, upa == da ? 0 : 1);
@@ -370,10 +371,10 @@ IMA_DEV void rescale_t_pair(const EngineView &E, const UpdateView &U, const DevM
 // One launch for both split-time updates: every chain drew its update type (t_proposal), every warp follows its chain.
 IMA_KERNEL void IMA_PROPOSE_BOUNDS k_split_t(EngineView E, UpdateView U) {
   IMA_SMEM_DECL
-  const int p = ima_block() * kWarpsPerBlock + ima_warp_in_block();
-  if (p >= E.d.P) return;
+  const int idx = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (idx >= E.c_n * E.d.nloci) return;
   const DevModel &M = IMA_MODEL;
-  const int c = p / E.d.nloci, li = p - c * E.d.nloci;
+  const int c = E.c_lo + idx / E.d.nloci, li = idx % E.d.nloci, p = c * E.d.nloci + li;
   PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
   const TProposal t = t_proposal(E, U, M, c);
   if (t.method == 1) nw_t_pair(E, U, M, t, p, c, li, S);
@@ -384,8 +385,8 @@ constexpr int kTWarps = 8;            // warps of a k_accept_t block (one block 
 
 IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   IMA_SMEM_DECL
-  const int c = ima_block();
-  if (c >= E.d.nchains) return;
+  if (ima_block() >= E.c_n) return;
+  const int c = E.c_lo + ima_block();
   const DevModel &M = IMA_MODEL;
   const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, nloci = E.d.nloci;
   ChainSm S = carve_chain_smem(IMA_SMEM, E.d);
@@ -543,9 +544,9 @@ IMA_HD size_t changeu_smem_doubles(int nloci) { return (size_t)5 * nloci + (nloc
 
 IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
   IMA_SMEM_DECL
-  const int c = ima_block() * kWarpsPerBlock + ima_warp_in_block();
-  if (c >= E.d.nchains) return;
-  if (U.u_forced ? c != U.u_chain : ((*E.nsteps + 1) % (unsigned long long)U.u_every) != 0) return;   // every UUPDATEINC+1 steps
+  if (ima_block() * kWarpsPerBlock + ima_warp_in_block() >= E.c_n) return;
+  const int c = E.c_lo + ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (U.u_forced ? c != U.u_chain : ((current_step(E) + 1) % (unsigned long long)U.u_every) != 0) return;   // every UUPDATEINC+1 steps
   const DevModel &M = IMA_MODEL;
   const int lane = Warp::lane(), nloci = E.d.nloci, nur = U.nurates;
   PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
@@ -568,7 +569,7 @@ IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
       spdg[li] = B.sd[(size_t)p * 4 + 3];
       slen[li] = B.sd[(size_t)p * 4 + 1];
       Philox r2;
-      const unsigned long long step = *E.nsteps;
+      const unsigned long long step = current_step(E);
       r2.init(E.seed, (uint32_t)((E.d.chain0 + c) * nloci + li), (uint32_t)step, kRngScalars | ((uint32_t)(step >> 32) << 8));
       int k;
       do { k = (int)(r2.uniform() * nur); } while (k == li || k < 0 || k >= nur);          // :78-90

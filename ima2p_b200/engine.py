@@ -198,9 +198,9 @@ class Engine:
             swaptries = max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0    # ima_main_mpi.cpp:1378
         self._ck(self.lib.ima2p_engine_run(self._h, nsteps, swaptries, stream))
 
-    def set_pieces(self, pieces):
-        """Cut a step into `pieces` locus ranges (accept sweep of one range overlaps the proposals of the next)."""
-        self._ck(self.lib.ima2p_engine_set_pieces(self._h, pieces))
+    def set_pipeline(self, groups=1, depth=1, decisions_first=False):
+        """Chain groups on their own streams and steps per CUDA graph of `run` (the chains a run visits do not depend on it)."""
+        self._ck(self.lib.ima2p_engine_set_pipeline(self._h, groups, depth, 1 if decisions_first else 0))
 
     def set_speculation(self, depth):
         """Loci evaluated per round of the accept sweep (1..4); the results do not depend on it."""

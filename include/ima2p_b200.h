@@ -124,9 +124,13 @@ int ima2p_engine_dims (ima2p_engine * e, int *out /* {NI, ND, NL, CAP, rowlen} *
  * update_gtree.cpp:723-966) followed by swaptries MC3 temperature swaps (swapchains.cpp:526-653;
  * temperature-rank form of swapchains_bwprocesses :192-523).  Single-GPU form: */
 int ima2p_engine_run (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream);
-/* number of locus ranges a step is cut into so that the accept sweep of one range overlaps the proposals of the
- * next (default 4; 1 = propose everything, then sweep) */
-int ima2p_engine_set_pieces (ima2p_engine * e, int pieces);
+/* How ima2p_engine_run issues its steps.  Chains only meet at the swaps (swapchains.cpp:526-653) and a chain's loci are
+ * decided in order (qupdate's loop over li, ima_main_mpi.cpp:1821-1841), so the GPU's chains are cut into `groups`
+ * groups on their own streams -- the accept sweep of one group overlaps the proposals of the others -- and `depth`
+ * consecutive steps form one CUDA graph in which a group starts its next proposals without waiting for the other
+ * groups' swaps.  decisions_first != 0 puts every group's decision kernels on a high-priority stream of their own.
+ * The run is bit for bit the same for every setting. */
+int ima2p_engine_set_pipeline (ima2p_engine * e, int groups, int depth, int decisions_first);
 /* speculative depth of the accept sweep (1..3): how many consecutive loci of a chain are evaluated per round against
  * the same all-locus sums; results are identical for every depth (see csrc/ima_kernels.h k_accept) */
 int ima2p_engine_set_speculation (ima2p_engine * e, int depth);

@@ -578,6 +578,34 @@ def speculation_depth_does_not_change_the_run(lib, name="state_sim50_hn3", nstep
     return outs[0][0]
 
 
+def pipeline_does_not_change_the_run(lib, name="state_sim50_hn3", nsteps=37):
+    """ima2p_engine_set_pipeline only changes how the step is issued (chain groups on their own streams, several steps per
+    graph, cross-step overlap): with the whole qupdate schedule running, every setting must visit exactly the same chain."""
+    from support import engine_from_fixture, load_golden
+    d = load_golden(name)
+    outs = []
+    settings = [(1, 1, 0), (2, 1, 0), (3, 4, 0), (3, 5, 1), (16, 8, 1)]
+    for groups, depth, first in settings:
+        eng, fm = engine_from_fixture(d, lib=lib, seed=77)
+        eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+        eng.set_update_schedule(3, 5)
+        eng.set_pipeline(groups, depth, first)
+        eng.eval()
+        eng.run(nsteps)
+        eng.run(3)                                   # a second call: the step counter carried over correctly
+        eng.sync()
+        ch = [eng.chain(c) for c in range(eng.nchains)]
+        outs.append((eng.counters(), eng.update_counters(),
+                     np.concatenate([np.r_[c["probg"], c["pdg"], c["beta"], c["tvals"], c["wd"], c["wi"]] for c in ch])))
+        eng.close()
+    assert outs[0][0]["accepted"] > 0 and outs[0][0]["steps"] == nsteps + 3
+    for k in range(1, len(settings)):
+        assert outs[k][0] == outs[0][0], (settings[k], outs[k][0], outs[0][0])
+        assert outs[k][1] == outs[0][1], (settings[k], outs[k][1], outs[0][1])
+        assert np.array_equal(outs[k][2], outs[0][2]), settings[k]
+    return outs[0][0]
+
+
 def full_size_workload_properties(lib, nloci, nchains, nsteps, noracle=48, seed=5):
     """BASELINE-sized runs (configs[1]: 50 loci x 128 chains; configs[2]'s per-GPU shard: 300 loci x 256 chains), checked through
     properties that do not need a stored answer: after `nsteps` whole qupdate steps (genealogies, split times, scalars, swaps)

@@ -98,6 +98,10 @@ def test_speculation_depth_does_not_change_the_run(lib):
     ec.speculation_depth_does_not_change_the_run(lib)
 
 
+def test_pipeline_does_not_change_the_run(lib):
+    ec.pipeline_does_not_change_the_run(lib)
+
+
 # ---- section 8 (f1): the rest of the step on the device ------------------------------------------------------------
 @pytest.mark.parametrize("name", ["tupdates_sim5_hn2", "tupdates_sim5_3pop_hn2", "tupdates_sim3_sw_hn2", "tupdates_sim3_joint_hn2"])
 def test_split_time_update_matches_reference(lib, name):

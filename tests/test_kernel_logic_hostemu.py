@@ -58,6 +58,10 @@ def test_speculation_depth_does_not_change_the_run(emu):
     ec.speculation_depth_does_not_change_the_run(emu, nsteps=25)
 
 
+def test_pipeline_setting_is_accepted_and_does_not_change_the_run(emu):
+    ec.pipeline_does_not_change_the_run(emu, nsteps=9)
+
+
 @pytest.mark.parametrize("name", ["lmode_extra_sim5_hn2", "lmode_extra_sim5_expo_hn2", "lmode_extra_sim5_3pop_hn2"])
 def test_lmode_moments_and_popmig(emu, name):
     assert ec.lmode_moments_and_popmig_match_reference(emu, name) >= 6
