@@ -16,11 +16,17 @@
  *   lmode    burn=N rows=G every=K       sampled .ti rows (savegsampinf) and marginp/margincalc/jointp values
  *   bench    burn=N iters=K full=0|1     times the updategenealogy() loop (or whole qupdate steps)
  *   lbench   rows=G evals=E              times margincalc / jointp over G synthetic-from-run rows
- *   stock                                the reference's own main() on the IMa2p command line, unchanged
+ *   stock    [seed=K]                    the reference's own main() on the IMa2p command line, unchanged (the serial build
+ *                                        always seeds its generator with seed * currentid = 0; seed=K makes replicates possible)
  */
 #define main ima2p_reference_main
+#define setseeds harness_seed_hook      /* start()'s call (ima_main_mpi.cpp:1721) goes through the hook below */
 #include "ima_main_mpi.cpp"
+#undef setseeds
 #undef main
+void setseeds (int seed);
+static long g_stock_seed = -1;
+void harness_seed_hook (int seed) { setseeds (g_stock_seed >= 0 ? (int) g_stock_seed : seed); }
 #include "update_gtree_common.hpp"      /* getmprob :850, calcmrate :462 */
 
 #include <chrono>
@@ -1150,17 +1156,28 @@ mode_thermo (void)
  * with batch-means standard errors (nbatch batches).  Used for the statistical parity fixture. */
 /* diagnostic schedules built from the reference's own update functions: full=2 the engine's schedule (RY1 every
  * step, changeu every 5th), full=3 NW only, full=4 RY1 only without changeu */
+/* tries / accepts of the split-time updates per period: [period][RY tries, RY accepts, NW tries, NW accepts], all chains */
+static std::vector<double> g_trate;
+
 static void
 ry_only_rest (long it, long full)
 {
   int k;
+  if (g_trate.empty ())
+    g_trate.assign ((size_t) 4 * (numsplittimes > 0 ? numsplittimes : 1), 0.0);
   for (int ci = 0; ci < numchains; ci++)
   {
     int period = randposint (numsplittimes);
     if (full == 3)
-      changet_NW (ci, period);
+    {
+      g_trate[4 * period + 2] += 1;
+      g_trate[4 * period + 3] += changet_NW (ci, period) ? 1 : 0;
+    }
     else
-      changet_RY1 (ci, period);
+    {
+      g_trate[4 * period + 0] += 1;
+      g_trate[4 * period + 1] += changet_RY1 (ci, period) ? 1 : 0;
+    }
   }
   if ((it + 1) % 5 == 0 && nurates > 1 && full != 4)
     for (int ci = 0; ci < numchains; ci++)
@@ -1176,6 +1193,10 @@ mode_trace (long gburn, long sweeps, long nbatch, long full)
   /* full=1: whole qupdate() steps (genealogies, split times by RY1 or NW, mutation scalars); the split times and
    * the log scalars are then summarised too */
   std::vector<double> t0v, u0v;
+  /* the genealogies the run starts from (they belong to the split times in "tvals") */
+  fprintf (jo, "{\"start\":");
+  dump_tree_all ();
+  fputc (',', jo);
   for (k = 0; k < numsplittimes; k++)
     t0v.push_back (C[0]->tvals[k]);
   for (li = 0; li < nloci; li++)
@@ -1194,6 +1215,18 @@ mode_trace (long gburn, long sweeps, long nbatch, long full)
     if (full >= 2)
       ry_only_rest (it, full);
   }
+  /* split-time update counts start after the burn-in: qupdate() counts the cold chain in T[].upinf, the diagnostic
+   * schedules count every chain in g_trate */
+  std::vector<double> trate0 ((size_t) 4 * (numsplittimes > 0 ? numsplittimes : 1), 0.0);
+  for (k = 0; k < numsplittimes; k++)
+    if (full == 1)
+    {
+      trate0[4 * k + 0] = T[k].upinf[IM_UPDATE_TIME_RY1].tries; trate0[4 * k + 1] = T[k].upinf[IM_UPDATE_TIME_RY1].accp;
+      trate0[4 * k + 2] = T[k].upinf[IM_UPDATE_TIME_NW].tries; trate0[4 * k + 3] = T[k].upinf[IM_UPDATE_TIME_NW].accp;
+    }
+    else if (!g_trate.empty ())
+      for (a = 0; a < 4; a++)
+        trate0[4 * k + a] = g_trate[4 * k + a];
   const int NS = 6;             /* length, roottime, mignum, cc0, cc1, cc2(+) */
   std::vector<double> bsum ((size_t) nbatch * nloci * NS, 0.0);
   std::vector<double> tsum ((size_t) nbatch * (numsplittimes + 1), 0.0), usum ((size_t) nbatch * nloci, 0.0);
@@ -1237,7 +1270,6 @@ mode_trace (long gburn, long sweeps, long nbatch, long full)
         }
       }
     }
-  fprintf (jo, "{");
   dump_model ();
   fprintf (jo, "\"sweeps\":%ld,\"chains\":%d,\"nbatch\":%ld,\"full\":%ld,\"accept\":%.6f,\"tvals\":[", per * nbatch, numchains, nbatch, full,
            tries ? (double) acc / tries : -1.0);
@@ -1260,6 +1292,21 @@ mode_trace (long gburn, long sweeps, long nbatch, long full)
     if (k)
       fputc (',', jo);
     jd (T[k].pr.max);
+  }
+  fprintf (jo, "],\"t_rates\":[");
+  for (k = 0; k < numsplittimes; k++)
+  {
+    double now[4] = { 0, 0, 0, 0 };
+    if (full == 1)
+    {
+      now[0] = T[k].upinf[IM_UPDATE_TIME_RY1].tries; now[1] = T[k].upinf[IM_UPDATE_TIME_RY1].accp;
+      now[2] = T[k].upinf[IM_UPDATE_TIME_NW].tries; now[3] = T[k].upinf[IM_UPDATE_TIME_NW].accp;
+    }
+    else if (!g_trate.empty ())
+      for (a = 0; a < 4; a++)
+        now[a] = g_trate[4 * k + a];
+    fprintf (jo, "%s[%.0f,%.0f,%.0f,%.0f]", k ? "," : "", now[0] - trate0[4 * k], now[1] - trate0[4 * k + 1], now[2] - trate0[4 * k + 2],
+             now[3] - trate0[4 * k + 3]);
   }
   fprintf (jo, "],\"t_batch_means\":[");
   for (bi = 0; bi < nbatch; bi++)
@@ -1302,9 +1349,7 @@ mode_trace (long gburn, long sweeps, long nbatch, long full)
     }
     fputc (']', jo);
   }
-  fprintf (jo, "],\"start\":");
-  dump_tree_all ();
-  fprintf (jo, "}\n");
+  fprintf (jo, "]}\n");
 }
 
 static void
@@ -1386,6 +1431,7 @@ main (int argc, char *argv[])
     av.push_back (argv[i]);
   if (mode == "stock")           /* the reference's own main(), end to end (M or L mode); OUT receives its exit status */
   {
+    g_stock_seed = kv.count ("seed") ? atol (kv["seed"].c_str ()) : -1;
     int rc = ima2p_reference_main ((int) av.size (), av.data ());
     fprintf (jo, "{\"exit\":%d}\n", rc);
     fclose (jo);

@@ -335,6 +335,30 @@ def main():
         with gzip.GzipFile(os.path.join(HERE, "report_head_3pop.json.gz"), "wb", mtime=0) as g:
             g.write(json.dumps({"args": args[2:], "head": text[:text.index("\nMEANS, VARIANCES")]}).encode())
         print("wrote report_head_3pop.json.gz")
+    # the same command from 8 seeds (ref_harness stock seed=K; the serial build itself always seeds with 0): the update-rate and
+    # swap tables of every run, so that a single run of the engine can be held against the reference's run-to-run spread
+    if not ONLY or "report_rates_3pop" in ONLY:
+        import json
+        from concurrent.futures import ThreadPoolExecutor
+        sys.path.insert(0, os.path.dirname(HERE))
+        from test_frontend import _rate_tables
+        args = ["-i", os.path.join(HERE, "inputs", "parse_is_3pop.u"), "-q10", "-m1", "-t3", "-b5000", "-l6000", "-d10", "-hn4", "-hfg", "-ha0.96", "-hb0.9"]
+
+        def one(seed):
+            rep = os.path.join(TMP, "report_rates_3pop_%d.out" % seed)
+            try:
+                subprocess.run([HARNESS, "stock", rep + ".json", "seed=%d" % seed, "--"] + args + ["-o", rep], check=True, cwd=TMP,
+                               stdout=subprocess.DEVNULL, timeout=600)
+            except subprocess.TimeoutExpired:       # the reference occasionally spins forever for some seeds
+                return None
+            text = open(rep).read()
+            tables, swaps = _rate_tables(text[:text.index("\nMEANS, VARIANCES")])
+            return {"seed": seed, "tables": tables, "swaps": swaps}
+        with ThreadPoolExecutor(8) as ex:
+            runs = [r for r in ex.map(one, range(101, 111)) if r is not None][:8]
+        with gzip.GzipFile(os.path.join(HERE, "report_rates_3pop.json.gz"), "wb", mtime=0) as g:
+            g.write(json.dumps({"args": args[2:], "runs": runs}).encode())
+        print("wrote report_rates_3pop.json.gz", len(runs), "runs")
     # the .mcf state file: written by the reference (inputs/*.mcf.gz) and by the engine (inputs/*_ours.mcf.gz), each
     # read back by the reference's readmcf and dumped
     for nm, uf, hn, burn in (("mcf_sim5_hn2", s5, 2, 60), ("mcf_sim3_sw_hn2", sw3, 2, 60), ("mcf_sim5_hky_hn2", hky5, 2, 30),

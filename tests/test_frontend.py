@@ -176,14 +176,47 @@ def frontend_report_head_matches_reference(exe, tmp_path, lib=None):
     import gzip
     import json
     d = json.load(gzip.open(os.path.join(HERE, "golden", "report_head_3pop.json.gz")))
-    out = tmp_path / "head.out"
-    r = _run(exe, ["-i", os.path.join(INPUTS, "parse_is_3pop.u"), "-o", str(out)] + d["args"] + ["-s", "21"])
-    assert r.returncode == 0, r.stderr
-    check_report_head(str(out), d["head"], lib)
+    outs = []
+    for seed in (21, 22, 23):            # three runs: the rates are compared as means over runs (see check_report_rates)
+        out = tmp_path / ("head%d.out" % seed)
+        r = _run(exe, ["-i", os.path.join(INPUTS, "parse_is_3pop.u"), "-o", str(out)] + d["args"] + ["-s", str(seed)])
+        assert r.returncode == 0, r.stderr
+        outs.append(str(out))
+    check_report_head(outs[0], d["head"], lib)
+    check_report_rates(outs)
+
+
+def check_report_rates(outs):
+    """Update-rate tables and swap table of several runs of the front end against the reference's own runs of the same command
+    from eight seeds (fixture report_rates_3pop: `ref_harness stock seed=K`).  Every cell is compared as mean over our runs
+    against mean over the reference's runs.  Tolerances in percentage points: genealogies 2.5 and mutation scalars 1.0 (the
+    reference's run-to-run standard deviation is at most 1.04 and 0.25 there, so the difference of the means has a standard
+    deviation of 0.7 and 0.17); split times, which mix slowly (run-to-run standard deviation 1.2 to 3.4 points), four standard
+    deviations of the difference of the means.  profiles/r2_split_time_replicates.md holds the 12-seed study behind this."""
+    import gzip
+    import json
+    runs = json.load(gzip.open(os.path.join(HERE, "golden", "report_rates_3pop.json.gz")))["runs"]
+    mine = [_rate_tables(open(o).read()[:open(o).read().index("\nENGINE INFORMATION")]) for o in outs]
+    nr, nm = len(runs), len(mine)
+    for title in ("Population Splitting Times", "Genealogies", "Mutation Rate Scalars"):
+        assert list(mine[0][0][title]) == list(runs[0]["tables"][title])
+        for row in runs[0]["tables"][title]:
+            ref = np.array([[c[2] for c in r["tables"][title][row]] for r in runs])          # [run][update type] percent
+            got = np.array([[c[2] for c in m[0][title][row]] for m in mine])
+            sd = ref.std(axis=0, ddof=1) * np.sqrt(1.0 / nr + 1.0 / nm)
+            tol = {"Genealogies": np.full(ref.shape[1], 2.5), "Mutation Rate Scalars": np.full(ref.shape[1], 1.0),
+                   "Population Splitting Times": np.maximum(2.5, 4.0 * sd)}[title]
+            dev = np.abs(got.mean(axis=0) - ref.mean(axis=0))
+            assert np.all(dev < tol), (title, row, got.mean(axis=0), ref.mean(axis=0), tol)
+    ref_sw = np.array([[s[4] for s in r["swaps"]] for r in runs])
+    got_sw = np.array([[s[4] for s in m[1]] for m in mine])
+    assert got_sw.shape[1] == ref_sw.shape[1] == 3
+    assert np.all(np.abs(got_sw.mean(axis=0) - ref_sw.mean(axis=0)) < 0.05), (got_sw.mean(axis=0), ref_sw.mean(axis=0))
 
 
 def check_report_head(out, ref, lib=None):
-    """The checks of frontend_report_head_matches_reference on a report file `out` (and its .ti file) already written."""
+    """The text checks of frontend_report_head_matches_reference on a report file `out` (and its .ti file) already written;
+    the rates are compared by check_report_rates."""
     import re
     rep = open(out).read()
     mine = rep[:rep.index("\nENGINE INFORMATION")]
@@ -204,16 +237,12 @@ def check_report_head(out, ref, lib=None):
     assert skeleton(mine) == skeleton(ref)
     (tm, sm), (tr, sr) = _rate_tables(mine), _rate_tables(ref)
     assert list(tm) == list(tr) == ["Population Splitting Times", "Genealogies", "Mutation Rate Scalars"]
-    # percentage points; the split times mix slowly (runs of 10,000 steps differ by 10 points between seeds of either program,
-    # runs of 60,000 by about 3 to 9), and the genealogy rates follow the split times (a B200 run of this command with t0
-    # averaging 0.75 instead of 0.95 had every branch rate 2 to 3 points under the reference's); the scalars are tight
-    tol = {"Population Splitting Times": 12.0, "Genealogies": 5.0, "Mutation Rate Scalars": 2.5}
+    # same rows, same numbers of tries (the rates themselves: check_report_rates, means over several runs of both programs)
     for title in tr:
         assert list(tm[title]) == list(tr[title])
         for row in tr[title]:
             for (t1, a1, p1), (t2, a2, p2) in zip(tm[title][row], tr[title][row]):
                 assert abs(t1 - t2) <= 0.06 * t2, (title, row, t1, t2)
-                assert abs(p1 - p2) < tol[title], (title, row, p1, p2)
     assert [g[0][0] for g in tm["Genealogies"].values()] == [6.0e4] * 4                 # every step tries every locus of the cold chain
     assert len(sm) == len(sr) == 3
     for a, b in zip(sm, sr):
