@@ -416,8 +416,9 @@ def main():
     roof = None
     if kernel_ms is not None:
         per = np.asarray(kernel_ms, dtype=np.float64) / args.steps                       # ms per launch
-        names = ["k_propose", "k_accept", "k_swap", "k_split_t", "k_accept_t", "k_changeu"]
-        dom = int(np.argmax(per))
+        names = ["k_propose", "k_accept", "k_swap", "k_split_t", "k_accept_t", "k_changeu", "k_move", "k_weigh", "k_propose_redo"]
+        per = per[:len(names)]
+        dom = int(np.argmax(per[:6]))
         P = cpg * nloci
         b_update = algorithmic_bytes_per_update(n0 + n1, mig_mean, p_acc, eng.NI, eng.ND)
         W_g = 4 * eng.NI + 8 * eng.ND

@@ -44,6 +44,8 @@ SIGNATURES = {
     "ima2p_engine_dims": (_i, [_v, c_int_p]),
     "ima2p_engine_run": (_i, [_v, _i, _i, _v]),
     "ima2p_engine_set_pipeline": (_i, [_v, _i, _i, _i]),
+    "ima2p_engine_set_proposal_path": (_i, [_v, _i, _i]),
+    "ima2p_engine_set_debug_records": (_i, [_v, _i]),
     "ima2p_engine_set_speculation": (_i, [_v, _i]),
     "ima2p_engine_run_timed": (_i, [_v, _i, _i, _v, c_flt_p]),
     "ima2p_engine_update_genealogies": (_i, [_v, _v, _v]),

@@ -5,6 +5,7 @@
 // replayed; the step counter that feeds the counter-based RNG lives on the device so the graph needs no
 // parameter updates.
 #include "ima_kernels.h"
+#include "ima_fastpath.h"
 #include "ima_updates.h"
 #include "../../include/ima2p_b200.h"
 #include <string>
@@ -57,6 +58,7 @@ struct Engine {
   size_t block_cap = 0;
   DevLocus *d_loci = nullptr;
   double *d_beta_table = nullptr;
+  double *d_prop_dbg = nullptr;
   unsigned long long *d_swap_counts = nullptr;
   double *d_thermosum = nullptr;
   double *d_report = nullptr, *h_report = nullptr;      // step_report: device staging and its pinned host mirror
@@ -70,6 +72,9 @@ struct Engine {
   std::vector<cudaEvent_t> pipe_events;
 #endif
   int groups = 1, depth = 1, pipe_prio = 0;          // see capture_steps
+  bool fast_ok = false, fast = false;                // the two-kernel proposal path (ima_fastpath.h): possible / in use
+  int ppw = 0;                                       // pairs per warp of k_move (0: chosen from the number of pairs)
+  int redo_grid = 64;
   size_t pair_smem = 0, chain_smem = 0, accept_smem = 0;
   int spec = 3;        // speculative depth of the accept sweep (see k_accept)
 
@@ -132,15 +137,41 @@ static int launch_eval(Engine *e, stream_t s) {
 static int accept_block_warps(int spec) { return IMA_CUDA ? spec * kTermWarps : 1; }
 
 // the view a launch gets: which chains it covers and which step (relative to the device counter) it belongs to
-static EngineView view_of(const Engine *e, int c_lo, int c_n, int step_off) {
+static EngineView view_of(const Engine *e, int c_lo, int c_n, int step_off, int grp = 0) {
   EngineView v = e->v;
-  v.c_lo = c_lo; v.c_n = c_n; v.step_off = step_off;
+  v.c_lo = c_lo; v.c_n = c_n; v.step_off = step_off; v.grp = grp; v.redo_grid = e->redo_grid;
   return v;
 }
 static int pair_grid(const Engine *e, const EngineView &v) { return (v.c_n * e->d.nloci + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
+// pairs per warp of k_move: few pairs -> few per warp (more warps in flight, less divergence); many -> fuller warps
+static int move_ppw(const Engine *e, int npairs) {
+#if IMA_CUDA
+  if (e->ppw == 4 || e->ppw == 8 || e->ppw == 16 || e->ppw == 32) return e->ppw;
+  return npairs <= 148 * 96 ? 4 : 8;
+#else
+  (void)e; (void)npairs;
+  return 1;
+#endif
+}
 static void launch_propose(Engine *e, stream_t s, const EngineView &v) {
-  IMA_LAUNCH(k_propose, pair_grid(e, v), kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v);
+  if (!e->fast) {
+    IMA_LAUNCH(k_propose, pair_grid(e, v), kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v);
+    return;
+  }
+  const int npairs = v.c_n * e->d.nloci, ppw = move_ppw(e, npairs);
+  const int gm = (npairs + ppw * kMoveWarps - 1) / (ppw * kMoveWarps);
+  const size_t sm = move_smem_bytes_per_pair(e->d) * ppw * kMoveWarps;
+#if IMA_CUDA
+  if (ppw == 4) IMA_LAUNCH(k_move<4>, gm, kMoveWarps, sm, s, v);
+  else if (ppw == 8) IMA_LAUNCH(k_move<8>, gm, kMoveWarps, sm, s, v);
+  else if (ppw == 16) IMA_LAUNCH(k_move<16>, gm, kMoveWarps, sm, s, v);
+  else IMA_LAUNCH(k_move<32>, gm, kMoveWarps, sm, s, v);
+#else
+  IMA_LAUNCH(k_move<1>, gm, kMoveWarps, sm, s, v);
+#endif
+  IMA_LAUNCH(k_weigh, pair_grid(e, v), kWarpsPerBlock, weigh_smem_bytes(e->d) * kWarpsPerBlock, s, v);
+  IMA_LAUNCH(k_propose_redo, e->redo_grid, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v);
 }
 static void launch_accept(Engine *e, stream_t s, const EngineView &v) {
   const int nw = accept_block_warps(e->spec);
@@ -234,7 +265,7 @@ static bool capture_steps(Engine &e, int swaptries, int depth, cudaGraphExec_t *
     std::vector<cudaEvent_t> done(G);
     for (int g = 0; g < G; g++) {
       const int c_lo = (int)((long long)e.d.nchains * g / G), c_hi = (int)((long long)e.d.nchains * (g + 1) / G);
-      const EngineView v = view_of(&e, c_lo, c_hi - c_lo, j);
+      const EngineView v = view_of(&e, c_lo, c_hi - c_lo, j, g);
       cudaStream_t sp = e.group_stream[g][0], sa = e.pipe_prio ? e.group_stream[g][1] : sp;   // proposals / decisions
       auto hop = [&](cudaStream_t from, cudaStream_t to) {
         if (from == to) return;
@@ -450,6 +481,15 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   int ev = (maxng - 1) + d.CAP + e.model.nsplit;
   d.EVP = 1; while (d.EVP < ev) d.EVP <<= 1;
   d.W64 = (e.model.ntreepops + 3) / 4;
+  // the two-kernel proposal path: tables for FC migration events per genealogy (every shipped input stays far below; a pair
+  // that does not fit takes the general path, whose tables hold CAP)
+  d.FC = d.CAP < 64 ? d.CAP : 64;
+  d.FP = 64;
+  if (const char *x = getenv("IMA2P_FAST_EVENTS")) { const int v = atoi(x); if (v >= 8 && v <= d.CAP) d.FC = v; }
+  if (const char *x = getenv("IMA2P_FAST_POOL")) { const int v = atoi(x); if (v >= 8 && v <= 4096) d.FP = v; }
+  d.FEV = (maxng - 1) + d.FC + e.model.nsplit;
+  e.fast_ok = !d.any_sw && d.NL <= 4096 && move_smem_bytes_per_pair(d) * 4 * kMoveWarps <= 200 * 1024 && weigh_smem_bytes(d) * kWarpsPerBlock <= 200 * 1024;
+  e.fast = e.fast_ok && !getenv("IMA2P_GENERAL_PATH");
   e.pair_smem = pair_smem_bytes(d);
   e.chain_smem = chain_smem_bytes(d);
   e.accept_smem = accept_smem_bytes(d);
@@ -462,11 +502,22 @@ int ima2p_engine_finalize(ima2p_engine *h) {
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.accept_smem)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_propose_redo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem_bytes(4000))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(changeu_smem(&e) * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
+  if (e.fast_ok) {
+    const int per = (int)(move_smem_bytes_per_pair(d) * kMoveWarps);
+    const int cap = 227 * 1024;
+    if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_move<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 4 < cap ? per * 4 : cap)) ||
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 8 < cap ? per * 8 : cap)) ||
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 16 < cap ? per * 16 : cap)) ||
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 32 < cap ? per * 32 : cap)) ||
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_weigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(weigh_smem_bytes(d) * kWarpsPerBlock))))
+      return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed (fast path)");
+  }
   if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");
 #else
   c_model = e.model;
@@ -507,11 +558,13 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   v.all_i = e.alloc<int>(C * d.NI); v.all_d = e.alloc<double>(C * d.ND);
   v.qint = e.alloc<double>(C * kMaxParams); v.mint = e.alloc<double>(C * kMaxParams);
   v.probg = e.alloc<double>(C); v.pdgsum = e.alloc<double>(C); v.swapsum = e.alloc<double>(C);
-  v.prop_extra = e.alloc<double>(P); v.prop_flags = e.alloc<uint32_t>(P); v.prop_dbg = e.alloc<double>(P * 4);
+  v.prop_extra = e.alloc<double>(P); v.prop_flags = e.alloc<uint32_t>(P); v.prop_dbg = nullptr;   // see ima2p_engine_set_debug_records
+  v.redo_count = e.alloc<int>(kMaxGroups * 4); v.redo_list = e.alloc<int>(2 * P);
+  if (!v.redo_count || !v.redo_list) return fail(IMA2P_E_CUDA, "device allocation failed");
   v.acc = e.alloc<unsigned int>(P * 3); v.cold_acc = e.alloc<unsigned int>((size_t)d.nloci * 3);
   v.nsteps = e.alloc<unsigned long long>(1); v.overflow = e.alloc<unsigned long long>(1);
   v.seed = e.seed;
-  v.c_lo = 0; v.c_n = d.nchains; v.step_off = 0;
+  v.c_lo = 0; v.c_n = d.nchains; v.step_off = 0; v.grp = 0; v.redo_grid = e.redo_grid;
   v.loci = e.d_loci; v.sitemask = d_sm; v.seq = d_sq; v.mult = d_mu;
   v.mc.logfact = e.d_logfact; v.mc.logfact_n = nlf; v.mc.err = e.d_err;
   e.sv.rank_of_chain = e.alloc<int>(G); e.sv.chain_of_rank = e.alloc<int>(G);
@@ -809,9 +862,10 @@ int ima2p_engine_run(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stre
   return IMA2P_OK;
 }
 
-// Same work as ima2p_engine_run, launched kernel by kernel with CUDA events recorded on the launching
-// stream around each kernel of every step; kernel_ms[7] receives the summed device time of
-// {propose, accept, swap, split_t, accept_t, changeu, 0} over the nsteps (bench.py's roofline numerator comes from here).
+// Same work as ima2p_engine_run, launched kernel by kernel with CUDA events recorded on the launching stream around each
+// kernel of every step (no overlap between kernels); kernel_ms[IMA2P_TIMED_SLOTS] receives the summed device time over the
+// nsteps of {0 proposal kernels together, 1 accept, 2 swap, 3 split-time proposals, 4 accept_t, 5 changeu, 6 k_move, 7 k_weigh,
+// 8 k_propose_redo (6-8 are zero on the general path), 9-11 unused}.  bench.py's roofline numerators come from here.
 int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms) {
   if (!h || nsteps < 0 || swaptries < 0 || !kernel_ms) return fail(IMA2P_E_ARG, "run_timed: bad argument");
   Engine &e = h->eng;
@@ -820,36 +874,51 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
   if (e.d.nchains != e.d.nchains_global) return fail(IMA2P_E_ARG, "run_timed: engine holds a shard");
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, cuda_stream);
-  for (int k = 0; k < 7; k++) kernel_ms[k] = 0.f;
+  for (int k = 0; k < IMA2P_TIMED_SLOTS; k++) kernel_ms[k] = 0.f;
 #if IMA_CUDA
-  const int chunk = 256;
-  std::vector<cudaEvent_t> ev((size_t)chunk * 8);
+  const int chunk = 128, per = 12;                       // events per step
+  std::vector<cudaEvent_t> ev((size_t)chunk * per);
+  std::vector<int> slot_of((size_t)chunk * per, -1);     // interval ending at event i belongs to this slot
   const bool do_t = does_split_t(&e), do_u = does_changeu(&e);
   const EngineView all = view_of(&e, 0, e.d.nchains, 0);
   for (auto &x : ev) if (!IMA_CUDA_OK(cudaEventCreate(&x))) return fail(IMA2P_E_CUDA, "event create failed");
   for (int s0 = 0; s0 < nsteps; s0 += chunk) {
     const int n = nsteps - s0 < chunk ? nsteps - s0 : chunk;
+    size_t ne = 0;
+    auto mark = [&](int slot) { slot_of[ne] = slot; cudaEventRecord(ev[ne++], s); };
     for (int i = 0; i < n; i++) {
-      cudaEventRecord(ev[i * 8 + 0], s);
-      launch_propose(&e, s, all);
-      cudaEventRecord(ev[i * 8 + 1], s);
+      mark(-1);
+      if (e.fast) {
+        // the three launches of launch_propose one by one
+        Engine &ee = e;
+        const int npairs = all.c_n * ee.d.nloci, ppw = move_ppw(&ee, npairs);
+        const int gm = (npairs + ppw * kMoveWarps - 1) / (ppw * kMoveWarps);
+        const size_t sm = move_smem_bytes_per_pair(ee.d) * ppw * kMoveWarps;
+        if (ppw == 4) IMA_LAUNCH(k_move<4>, gm, kMoveWarps, sm, s, all);
+        else if (ppw == 8) IMA_LAUNCH(k_move<8>, gm, kMoveWarps, sm, s, all);
+        else if (ppw == 16) IMA_LAUNCH(k_move<16>, gm, kMoveWarps, sm, s, all);
+        else IMA_LAUNCH(k_move<32>, gm, kMoveWarps, sm, s, all);
+        mark(6);
+        IMA_LAUNCH(k_weigh, pair_grid(&ee, all), kWarpsPerBlock, weigh_smem_bytes(ee.d) * kWarpsPerBlock, s, all);
+        mark(7);
+        IMA_LAUNCH(k_propose_redo, ee.redo_grid, kWarpsPerBlock, ee.pair_smem * kWarpsPerBlock, s, all);
+        mark(8);
+      } else {
+        launch_propose(&e, s, all);
+        mark(0);
+      }
       launch_accept(&e, s, all);
-      cudaEventRecord(ev[i * 8 + 2], s);
-      cudaEventRecord(ev[i * 8 + 3], s);
-      if (do_t) launch_split_t(&e, s, all);
-      cudaEventRecord(ev[i * 8 + 4], s);
-      if (do_t) launch_accept_t(&e, s, all);
-      cudaEventRecord(ev[i * 8 + 5], s);
-      if (do_u) launch_changeu(&e, s, all);
-      cudaEventRecord(ev[i * 8 + 6], s);
+      mark(1);
+      if (do_t) { launch_split_t(&e, s, all); mark(3); launch_accept_t(&e, s, all); mark(4); }
+      if (do_u) { launch_changeu(&e, s, all); mark(5); }
       launch_swap(&e, s, e.v.swapsum, swaptries);
-      cudaEventRecord(ev[i * 8 + 7], s);
+      mark(2);
     }
     if (!IMA_CUDA_OK(cudaStreamSynchronize(s))) return fail(IMA2P_E_CUDA, "sync failed (run_timed)");
-    static const int slot[7] = {0, 1, 6, 3, 4, 5, 2};      // event interval -> kernel_ms index
-    for (int i = 0; i < n; i++)
-      for (int k = 0; k < 7; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i * 8 + k], ev[i * 8 + k + 1]); kernel_ms[slot[k]] += ms; }
+    for (size_t i = 1; i < ne; i++)
+      if (slot_of[i] >= 0) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); kernel_ms[slot_of[i]] += ms; }
   }
+  kernel_ms[0] += kernel_ms[6] + kernel_ms[7] + kernel_ms[8];
   for (auto &x : ev) cudaEventDestroy(x);
 #else
   for (int i = 0; i < nsteps; i++) { launch_update(&e, s); launch_swap(&e, s, e.v.swapsum, swaptries); }
@@ -940,6 +1009,7 @@ int ima2p_engine_get_proposal(ima2p_engine *h, int ci, int li, double *out4, uns
   const size_t p = (size_t)ci * e.d.nloci + li;
   unsigned char cur = 0;
   uint32_t fl = 0;
+  if (!e.v.prop_dbg) return fail(IMA2P_E_ARG, "get_proposal: call ima2p_engine_set_debug_records(e, 1) before the step");
   bool ok = d2h(out4, e.v.prop_dbg + p * 4, 4 * sizeof(double), s) && d2h(out4 + 4, e.v.prop_extra + p, sizeof(double), s) &&
             d2h(&fl, e.v.prop_flags + p, sizeof fl, s) && d2h(&cur, e.v.cur + p, 1, s);
   if (!ok || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
@@ -988,6 +1058,37 @@ int ima2p_engine_set_pipeline(ima2p_engine *h, int groups, int depth, int decisi
   if (!h || groups < 1 || groups > kMaxGroups || depth < 1 || depth > 64) return fail(IMA2P_E_ARG, "set_pipeline: groups 1..16, depth 1..64");
   h->eng.groups = groups; h->eng.depth = depth; h->eng.pipe_prio = decisions_first ? 1 : 0;
   h->eng.graph_ready = false;
+  return IMA2P_OK;
+}
+
+// which proposal path ima2p_engine_run uses: fast != 0 the two kernels of ima_fastpath.h (with pairs_per_warp lanes of a
+// k_move warp at work: 4, 8, 16, 32, or 0 = chosen from the number of pairs), fast == 0 the general one-warp-per-pair kernel
+// for every pair.  The chain does not depend on it.
+int ima2p_engine_set_proposal_path(ima2p_engine *h, int fast, int pairs_per_warp) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "set_proposal_path: not finalized");
+  Engine &e = h->eng;
+  if (pairs_per_warp != 0 && pairs_per_warp != 4 && pairs_per_warp != 8 && pairs_per_warp != 16 && pairs_per_warp != 32)
+    return fail(IMA2P_E_ARG, "set_proposal_path: pairs_per_warp must be 0, 4, 8, 16 or 32");
+  if (fast && !e.fast_ok) return fail(IMA2P_E_UNSUPPORTED, "set_proposal_path: this data set takes the general path (stepwise loci or very large samples)");
+#if IMA_CUDA
+  if (fast && pairs_per_warp && move_smem_bytes_per_pair(e.d) * pairs_per_warp * kMoveWarps > 227 * 1024)
+    return fail(IMA2P_E_ARG, "set_proposal_path: that many pairs per warp do not fit in shared memory");
+#endif
+  e.fast = fast != 0; e.ppw = pairs_per_warp;
+  e.graph_ready = false;
+  return IMA2P_OK;
+}
+
+// parity tests: keep the per-proposal record ima2p_engine_get_proposal reads (migration weight, slide weight, slide distance,
+// edge moved); off by default -- it is 32 bytes written per pair and step that nothing else reads
+int ima2p_engine_set_debug_records(ima2p_engine *h, int on) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "set_debug_records: not finalized");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  if (on && !e.d_prop_dbg) e.d_prop_dbg = e.alloc<double>((size_t)e.d.P * 4);
+  if (on && !e.d_prop_dbg) return fail(IMA2P_E_CUDA, "device allocation failed");
+  e.v.prop_dbg = on ? e.d_prop_dbg : nullptr;
+  e.graph_ready = false;
   return IMA2P_OK;
 }
 

@@ -15,13 +15,22 @@
 
 namespace ima {
 
+// Array view of one pair's data in shared memory.  ST == 1: the pair has the arrays to itself (one warp works on the pair).
+// ST > 1: ST pairs are interleaved element by element (element i of this pair lives at base[i * ST]) and one LANE works on
+// each pair -- whatever elements the lanes of a warp touch, they fall into different shared-memory banks.
+template <class T, int ST> struct Arr {
+  T *p;
+  IMA_DEV T &operator[](int i) const { return p[i * ST]; }
+};
+
 // shared-memory view of one pair (pointers into the warp's slice of dynamic shared memory)
-struct PairSm {
-  double *time;            // [NL]
-  short *up0, *up1, *down, *pop;   // [NL]
-  unsigned short *ms, *mcn;        // [NL] migration segment start / count (into pt/pp)
-  double *pt;              // [4*CAP] pool: [0,CAP) current lists, [CAP,2CAP) join scratch, [2CAP,3CAP) new edge, [3CAP,4CAP) new sister
-  short *pp;               // [4*CAP]
+template <int ST> struct PairSmT {
+  Arr<double, ST> time;            // [NL]
+  Arr<short, ST> up0, up1, down, pop;   // [NL]
+  Arr<unsigned short, ST> ms, mcn;      // [NL] migration segment start / count (into pt/pp)
+  Arr<double, ST> pt;              // pool.  warp-per-pair kernels: [4*CAP], [0,CAP) current lists, [CAP,2CAP) join scratch, [2CAP,3CAP)
+                                   // new edge, [3CAP,4CAP) new sister; the lane-per-pair move kernel carves its smaller pool itself
+  Arr<short, ST> pp;
   double *evt;             // [EVP] event times (sort keys)
   int *evi;                // [EVP] packed event info
   int *evk;                // [EVP] period of the event | lineages before it << 8
@@ -30,9 +39,20 @@ struct PairSm {
   int *moff;               // [NL+1] exclusive prefix of mcn
   int *gwi;                // [NI]
   double *gwd;             // [ND]
-  double *ctl_d;           // [8]  roottime, length, tlength, migweight, slideweight, pdg, Aterm, slide distance
-  int *ctl_i;              // [12] root, mignum, flags, nev, edge, freed, oldsis, newsis, parent of freed before the move
+  Arr<double, ST> ctl_d;   // [8]  roottime, length, tlength, migweight, slideweight, pdg, Aterm, slide distance
+  Arr<int, ST> ctl_i;      // [12] root, mignum, flags, nev, edge, freed, oldsis, newsis, parent of freed before the move
+  int pool_free, pool_end;         // pool entries [pool_free, pool_end) are scratch: propose_move builds its lists there
+#if defined(IMA_PROF)
+  long long *prof; int nprof;      // tuning builds: clock marks inside eval_weights / likelihood_is
+#endif
 };
+typedef PairSmT<1> PairSm;
+
+#if defined(IMA_PROF) && IMA_CUDA
+#define IMA_SPROF(S) { if ((S).prof) (S).prof[(S).nprof++] = clock64(); }
+#else
+#define IMA_SPROF(S)
+#endif
 
 enum { kCdRoottime = 0, kCdLength, kCdTlength, kCdMigw, kCdSlidew, kCdPdg, kCdAterm, kCdSlideDist };
 enum { kCiRoot = 0, kCiMignum, kCiFlags, kCiNev, kCiEdge, kCiFreed, kCiOldsis, kCiNewsis, kCiOldDownDown };
@@ -63,25 +83,29 @@ IMA_DEV PairSm carve_pair_smem(unsigned char *base, const EngineDims &d) {
   PairSm s;
   unsigned char *p = base;
   auto take = [&](size_t bytes) { unsigned char *q = p; p += align8(bytes); return q; };
-  s.time = (double *)take(sizeof(double) * d.NL);
-  s.pt = (double *)take(sizeof(double) * 4 * d.CAP);
+  s.time.p = (double *)take(sizeof(double) * d.NL);
+  s.pt.p = (double *)take(sizeof(double) * 4 * d.CAP);
   s.evt = (double *)take(sizeof(double) * d.EVP);
   s.pre = (unsigned long long *)take(sizeof(unsigned long long) * d.EVP * d.W64);
   s.gwd = (double *)take(sizeof(double) * d.ND);
-  s.ctl_d = (double *)take(sizeof(double) * 8);
-  s.up0 = (short *)take(sizeof(short) * d.NL);
-  s.up1 = (short *)take(sizeof(short) * d.NL);
-  s.down = (short *)take(sizeof(short) * d.NL);
-  s.pop = (short *)take(sizeof(short) * d.NL);
-  s.ms = (unsigned short *)take(sizeof(unsigned short) * d.NL);
-  s.mcn = (unsigned short *)take(sizeof(unsigned short) * d.NL);
-  s.pp = (short *)take(sizeof(short) * 4 * d.CAP);
+  s.ctl_d.p = (double *)take(sizeof(double) * 8);
+  s.up0.p = (short *)take(sizeof(short) * d.NL);
+  s.up1.p = (short *)take(sizeof(short) * d.NL);
+  s.down.p = (short *)take(sizeof(short) * d.NL);
+  s.pop.p = (short *)take(sizeof(short) * d.NL);
+  s.ms.p = (unsigned short *)take(sizeof(unsigned short) * d.NL);
+  s.mcn.p = (unsigned short *)take(sizeof(unsigned short) * d.NL);
+  s.pp.p = (short *)take(sizeof(short) * 4 * d.CAP);
   s.evi = (int *)take(sizeof(int) * d.EVP);
   s.evk = (int *)take(sizeof(int) * d.EVP);
   s.mask = (uint32_t *)take(sizeof(uint32_t) * d.NL * d.W);
   s.moff = (int *)take(sizeof(int) * (d.NL + 1));
   s.gwi = (int *)take(sizeof(int) * d.NI);
-  s.ctl_i = (int *)take(sizeof(int) * 12);
+  s.ctl_i.p = (int *)take(sizeof(int) * 12);
+  s.pool_free = d.CAP; s.pool_end = 4 * d.CAP;
+#if defined(IMA_PROF)
+  s.prof = nullptr; s.nprof = 0;
+#endif
   return s;
 }
 
@@ -172,7 +196,7 @@ IMA_DEV int pop_in_period(const DevModel &M, int pop, int period) {
   while (M.pt_e[pop] <= period && M.pt_e[pop] != -1) pop = M.pt_down[pop];
   return pop;
 }
-IMA_DEV double edge_top_time(const PairSm &S, int ng, int e) { return e < ng ? 0.0 : S.time[S.up0[e]]; }
+template <class PS> IMA_DEV double edge_top_time(const PS &S, int ng, int e) { return e < ng ? 0.0 : S.time[S.up0[e]]; }
 
 // ------------------------------------------------------------------------------------------------
 // migration-path proposal: struct edgemiginfo (imamp.hpp:627-647) with the list held in the pool
@@ -211,7 +235,7 @@ IMA_DEV void emi_periods(const DevModel &M, const double *tv, Emi &em) {
 }
 
 // fillmiginfo for one edge, update_gtree_common.cpp:1169-1246
-IMA_DEV void emi_fill_old(const DevModel &M, const double *tv, const PairSm &S, int ng, int edge, Emi &em) {
+template <class PS> IMA_DEV void emi_fill_old(const DevModel &M, const double *tv, const PS &S, int ng, int edge, Emi &em) {
   emi_reset(em);
   em.edgeid = edge;
   em.upt = edge_top_time(S, ng, edge);
@@ -284,7 +308,7 @@ IMA_DEV int picktopop(const DevModel &M, Philox &rng, int nowpop, int period, in
 // simmpath update_gtree_common.cpp:329-398: numm migration times uniform on the period's stretch of
 // the edge, sorted, re-drawn on an exact tie; destinations random, the last two constrained when the
 // edge must end in `constrainpop`.  Appends to the list of `em` in the pool; false on pool overflow.
-IMA_DEV bool simmpath(const DevModel &M, Philox &rng, PairSm &S, Emi &em, int cap_end, int period, int numm,
+template <class PS> IMA_DEV bool simmpath(const DevModel &M, Philox &rng, PS &S, Emi &em, int cap_end, int period, int numm,
                       double timein, double upt, int pop, int constrainpop) {
   const int start = em.seg + em.nmig;
   if (start + numm > cap_end) return false;
@@ -314,7 +338,7 @@ IMA_DEV bool simmpath(const DevModel &M, Philox &rng, PairSm &S, Emi &em, int ca
 
 // one period of one edge, shared by mwork_single_edge (:1353-1427) and mwork_two_edges (:1430-1575)
 // mode: 0 = free period (any count), 1 = last period of the edge (count conditioned on ending in fpop)
-IMA_DEV bool mwork_period(const DevModel &M, Philox &rng, PairSm &S, Emi &em, const Emi &oldem, int cap_end, int periodi,
+template <class PS> IMA_DEV bool mwork_period(const DevModel &M, Philox &rng, PS &S, Emi &em, const Emi &oldem, int cap_end, int periodi,
                           int mode, double timestart) {
   const double r = calcmrate(oldem.mp[periodi], oldem.mtimeavail[periodi]) * em.mtimeavail[periodi];
   int cond = -1, constrain = -1;
@@ -333,7 +357,7 @@ IMA_DEV bool mwork_period(const DevModel &M, Philox &rng, PairSm &S, Emi &em, co
 }
 
 // mwork_single_edge update_gtree_common.cpp:1353-1427
-IMA_DEV bool mwork_single_edge(const DevModel &M, const double *tv, Philox &rng, PairSm &S, Emi &em, const Emi &oldem,
+template <class PS> IMA_DEV bool mwork_single_edge(const DevModel &M, const double *tv, Philox &rng, PS &S, Emi &em, const Emi &oldem,
                                int cap_end, int lastmigperiod) {
   if (lastmigperiod < em.b) return true;
   double timestart = em.upt;
@@ -348,7 +372,7 @@ IMA_DEV bool mwork_single_edge(const DevModel &M, const double *tv, Philox &rng,
 }
 
 // mwork_two_edges update_gtree_common.cpp:1430-1575
-IMA_DEV bool mwork_two_edges(const DevModel &M, const double *tv, Philox &rng, PairSm &S, Emi &ee, Emi &se, const Emi &oe,
+template <class PS> IMA_DEV bool mwork_two_edges(const DevModel &M, const double *tv, Philox &rng, PS &S, Emi &ee, Emi &se, const Emi &oe,
                              const Emi &os, int cap_e, int cap_s, int lastmigperiod) {
   double tstart[2] = { ee.upt, se.upt };
   const int b = ee.b < se.b ? ee.b : se.b;
@@ -392,7 +416,7 @@ IMA_DEV bool mwork_two_edges(const DevModel &M, const double *tv, Philox &rng, P
 }
 
 // last-period term of getmprob (update_gtree_common.cpp:879-939 and :1007-1065)
-IMA_DEV double getmprob_last(const DevModel &M, const PairSm &S, const Emi &mm, const Emi &oldmm, int cm) {
+template <class PS> IMA_DEV double getmprob_last(const DevModel &M, const PS &S, const Emi &mm, const Emi &oldmm, int cm) {
   const int e = mm.e;
   const double r = calcmrate(oldmm.mp[e], oldmm.mtimeavail[e]) * mm.mtimeavail[e];
   const int k = mm.mp[e];
@@ -415,7 +439,7 @@ IMA_DEV double getmprob_last(const DevModel &M, const PairSm &S, const Emi &mm, 
 
 // getmprob update_gtree_common.cpp:850-1071: log probability of having simulated the lists of
 // (edgem, sisem) given the migration counts of (oldedgem, oldsisem)
-IMA_DEV double getmprob(const DevModel &M, const double *tv, const PairSm &S, const Emi &edgem, const Emi &sisem,
+template <class PS> IMA_DEV double getmprob(const DevModel &M, const double *tv, const PS &S, const Emi &edgem, const Emi &sisem,
                         const Emi &oldedgem, const Emi &oldsisem) {
   double tempp = 0.0;
   const int last = M.nsplit, npops = M.npops;
@@ -499,8 +523,7 @@ IMA_DEV double findjointime(const DevModel &M, const double *tv, int slidepop, i
   return edgeperiod == 0 ? 0.0 : tv[edgeperiod - 1];
 }
 
-IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *tv, int ng, int nl, Philox &rng, PairSm &S) {
-  const int CAP = d.CAP;
+template <class PS> IMA_DEV void propose_move(const DevModel &M, const double *tv, int ng, int nl, Philox &rng, PS &S) {
   int root = S.ctl_i[kCiRoot];
   double roottime = S.ctl_d[kCdRoottime];
   uint32_t flags = 0;
@@ -517,15 +540,18 @@ IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *
   double slidedist = holdslidedist;
 
   // joinsisdown :374-454 -- sister swallows the freed edge (lists concatenated in the join scratch)
-  int rootmove, tmrca = 0;
+  // the scratch part of the pool is handed out as needed: the joined list first, the rest in halves to the two new lists
+  int rootmove, tmrca = 0, pool_edge = S.pool_free;
   {
     const int n1 = S.mcn[oldsis], n2 = S.mcn[freed];
     if (n1 > 0 && n2 > 0) {
-      if (n1 + n2 > CAP) flags |= kFlagOverflow;
+      const int J = S.pool_free;
+      if (J + n1 + n2 > S.pool_end) flags |= kFlagOverflow;
       else {
-        for (int i = 0; i < n1; i++) { S.pt[CAP + i] = S.pt[S.ms[oldsis] + i]; S.pp[CAP + i] = S.pp[S.ms[oldsis] + i]; }
-        for (int i = 0; i < n2; i++) { S.pt[CAP + n1 + i] = S.pt[S.ms[freed] + i]; S.pp[CAP + n1 + i] = S.pp[S.ms[freed] + i]; }
-        S.ms[oldsis] = (unsigned short)CAP;
+        pool_edge = J + n1 + n2;
+        for (int i = 0; i < n1; i++) { S.pt[J + i] = S.pt[S.ms[oldsis] + i]; S.pp[J + i] = S.pp[S.ms[oldsis] + i]; }
+        for (int i = 0; i < n2; i++) { S.pt[J + n1 + i] = S.pt[S.ms[freed] + i]; S.pp[J + n1 + i] = S.pp[S.ms[freed] + i]; }
+        S.ms[oldsis] = (unsigned short)J;
         S.mcn[oldsis] = (unsigned short)(n1 + n2);
       }
     } else if (n2 > 0) { S.ms[oldsis] = S.ms[freed]; S.mcn[oldsis] = (unsigned short)n2; }
@@ -635,7 +661,8 @@ IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *
     ne.fpop = S.pop[freed];
     ne.pop = ne.temppop = S.pop[edge];
     ne.dnt = S.time[edge];
-    ne.seg = 2 * CAP; ne.nmig = 0;
+    const int pool_sis = pool_edge + (S.pool_end - pool_edge) / 2;
+    ne.seg = pool_edge; ne.nmig = 0;
     emi_periods(M, tv, ne);
     bool ok = true;
     const int lastmigperiod = ne.e < M.nsplit - 1 ? ne.e : M.nsplit - 1;
@@ -646,14 +673,14 @@ IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *
       ns.fpop = -1;
       ns.pop = ns.temppop = S.pop[newsis];
       ns.dnt = S.time[newsis];
-      ns.seg = 3 * CAP; ns.nmig = 0;
+      ns.seg = pool_sis; ns.nmig = 0;
       emi_periods(M, tv, ns);
       // getm :536-568
-      if (ne.mtall <= 0) ok = mwork_single_edge(M, tv, rng, S, ns, os, 4 * CAP, lastmigperiod);
-      else ok = mwork_two_edges(M, tv, rng, S, ne, ns, oe, os, 3 * CAP, 4 * CAP, lastmigperiod);
+      if (ne.mtall <= 0) ok = mwork_single_edge(M, tv, rng, S, ns, os, S.pool_end, lastmigperiod);
+      else ok = mwork_two_edges(M, tv, rng, S, ne, ns, oe, os, pool_sis, S.pool_end, lastmigperiod);
     } else {
-      ns.seg = 3 * CAP;
-      ok = mwork_single_edge(M, tv, rng, S, ne, oe, 3 * CAP, lastmigperiod);
+      ns.seg = pool_sis;
+      ok = mwork_single_edge(M, tv, rng, S, ne, oe, pool_sis, lastmigperiod);
     }
     if (!ok) flags |= kFlagOverflow;
     else {
@@ -685,56 +712,93 @@ IMA_DEV void propose_move(const DevModel &M, const EngineDims &d, const double *
 // treeweight: update_gtree_common.cpp:1679-1931
 // ------------------------------------------------------------------------------------------------
 // packed event: bits 0-1 kind (0 coalescence, 1 migration, 2 population split), 2-6 pop, 7-11 topop, 12.. node
+constexpr int kRankSortMax = 128;
 IMA_DEV int pack_event(int kind, int pop, int topop, int node) { return kind | (pop << 2) | (topop << 7) | (node << 12); }
 
 // returns false when the event table does not fit (flagged as overflow by the caller)
-IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus &L, const double *tv, PairSm &S) {
+IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus &L, const double *tv, PairSm &S, int evcap = -1) {
   const int lane = Warp::lane();
   const int ng = L.ng, nl = L.nl, W = L.nwords;
   const int mignum = scan_mig_counts(nl, S);
   const double roottime = S.ctl_d[kCdRoottime];
   const int nsplitev = findperiod(M, tv, roottime);
   const int nev = (ng - 1) + mignum + nsplitev;
-  if (nev > d.EVP) return false;
+  if (nev > (evcap < 0 ? d.EVP : evcap)) return false;
+  // Events sorted by (time, info) -- the reference: indexx quicksort, utilities.cpp:709-793.  Up to kRankSortMax events (every
+  // genealogy of the shipped inputs) by counting: the events are built into scratch (the prefix table and the period table are
+  // not in use yet), every lane counts, for its own events, the events that sort before them -- independent broadcast reads,
+  // no barrier -- and writes them to their places.  Larger tables by a bitonic network in place.
+  IMA_SPROF(S)
+  const bool small = nev <= kRankSortMax;
+  double *bt = small ? (double *)S.pre : S.evt;
+  int *bi = small ? S.evk : S.evi;
   // event build (:1741-1799): lane per edge
   for (int i = lane; i < nl; i += IMA_WARP) {
     int nowpop = S.pop[i];
     if (i >= ng) {
-      S.evt[i - ng] = S.time[S.up0[i]];
-      S.evi[i - ng] = pack_event(0, nowpop, 0, i);
+      bt[i - ng] = S.time[S.up0[i]];
+      bi[i - ng] = pack_event(0, nowpop, 0, i);
     }
     const int n = S.mcn[i], s0 = S.ms[i], o = (ng - 1) + S.moff[i];
     for (int j = 0; j < n; j++) {
       const double t = S.pt[s0 + j];
       nowpop = pop_in_period(M, nowpop, findperiod(M, tv, t));
       const int topop = S.pp[s0 + j];
-      S.evt[o + j] = t;
-      S.evi[o + j] = pack_event(1, nowpop, topop, 0);
+      bt[o + j] = t;
+      bi[o + j] = pack_event(1, nowpop, topop, 0);
       nowpop = topop;
     }
   }
   for (int i = lane; i < nsplitev; i += IMA_WARP) {
-    S.evt[(ng - 1) + mignum + i] = tv[i];
-    S.evi[(ng - 1) + mignum + i] = pack_event(2, 0, 0, i);
+    bt[(ng - 1) + mignum + i] = tv[i];
+    bi[(ng - 1) + mignum + i] = pack_event(2, 0, 0, i);
   }
-  int np2 = 1;
-  while (np2 < nev) np2 <<= 1;
-  for (int i = nev + lane; i < np2; i += IMA_WARP) { S.evt[i] = DBL_MAX; S.evi[i] = 0x7fffffff; }
-  Warp::sync();
-  // bitonic sort by (time, info) in shared memory (the reference: indexx quicksort, utilities.cpp:709-793)
-  for (int k = 2; k <= np2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = lane; i < np2; i += IMA_WARP) {
-        const int x = i ^ j;
-        if (x > i) {
-          const double a = S.evt[i], b = S.evt[x];
-          const int ia = S.evi[i], ib = S.evi[x];
-          const bool gt = (a > b) || (a == b && ia > ib);
-          if (gt == ((i & k) == 0)) { S.evt[i] = b; S.evt[x] = a; S.evi[i] = ib; S.evi[x] = ia; }
-        }
+  IMA_SPROF(S)
+  if (small) {
+#if IMA_CUDA
+    __threadfence_block();
+#endif
+    Warp::sync();
+    for (int j0 = lane; j0 < nev; j0 += 4 * IMA_WARP) {            // four events of the lane share every read of the table
+      double t[4]; int inf[4], r[4], jj[4];
+      for (int q = 0; q < 4; q++) {
+        jj[q] = j0 + q * IMA_WARP;
+        const bool v = jj[q] < nev;
+        t[q] = v ? bt[jj[q]] : 0.0; inf[q] = v ? bi[jj[q]] : 0; r[q] = 0;
       }
-      Warp::sync();
+      for (int k = 0; k < nev; k++) {
+        const double tk = bt[k];
+        const int ik = bi[k];
+        for (int q = 0; q < 4; q++)
+          r[q] += (tk < t[q] || (tk == t[q] && (ik < inf[q] || (ik == inf[q] && k < jj[q])))) ? 1 : 0;
+      }
+      for (int q = 0; q < 4; q++)
+        if (jj[q] < nev) { S.evt[r[q]] = t[q]; S.evi[r[q]] = inf[q]; }
     }
+#if IMA_CUDA
+    __threadfence_block();
+#endif
+    Warp::sync();
+  } else {
+    int np2 = 1;
+    while (np2 < nev) np2 <<= 1;
+    for (int i = nev + lane; i < np2; i += IMA_WARP) { S.evt[i] = DBL_MAX; S.evi[i] = 0x7fffffff; }
+    Warp::sync();
+    for (int k = 2; k <= np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < np2; i += IMA_WARP) {
+          const int x = i ^ j;
+          if (x > i) {
+            const double a = S.evt[i], b = S.evt[x];
+            const int ia = S.evi[i], ib = S.evi[x];
+            const bool gt = (a > b) || (a == b && ia > ib);
+            if (gt == ((i & k) == 0)) { S.evt[i] = b; S.evt[x] = a; S.evi[i] = ib; S.evi[x] = ia; }
+          }
+        }
+        Warp::sync();
+      }
+  }
+  IMA_SPROF(S)
   for (int i = lane; i < d.NI; i += IMA_WARP) S.gwi[i] = 0;
   for (int i = lane; i < d.ND; i += IMA_WARP) S.gwd[i] = 0.0;
   Warp::sync();
@@ -789,6 +853,7 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
     }
   }
   Warp::sync();
+  IMA_SPROF(S)
   // number of lineages in tree population `pop` just before event j
   auto lineages = [&](int pop, int j) {
     int n = 0;
@@ -863,6 +928,7 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
       }
     }
   Warp::sync();
+  IMA_SPROF(S)
   const double hlog = log(L.hval);
   if (hlog != 0.0)
     for (int i = lane; i < M.ncc; i += IMA_WARP) S.gwd[M.ncc + i] += hlog * S.gwi[i];
@@ -918,7 +984,9 @@ IMA_DEV void build_tip_keys(const DevLocus &L, PairSm &S) {
 IMA_DEV double likelihood_is(const EngineView &E, const DevLocus &L, PairSm &S, double mutrate) {
   const int lane = Warp::lane();
   const int ng = L.ng, nl = L.nl, W = L.nwords, root = S.ctl_i[kCiRoot];
+  IMA_SPROF(S)
   build_tip_keys(L, S);
+  IMA_SPROF(S)
   const uint32_t *sm = E.sitemask + L.sitemask_off;     // canonical site keys (set_locus)
   double acc = 0.0;
   bool reject = false;

@@ -194,16 +194,13 @@ IMA_KERNEL void k_eval_chains(EngineView E) {
 #else
 #define IMA_PROPOSE_BOUNDS
 #endif
-// every locus of chains [c_lo, c_lo + c_n) (one warp per pair)
-IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E) {
-  IMA_SMEM_DECL
-  const int idx = ima_block() * kWarpsPerBlock + ima_warp_in_block();
-  if (idx >= E.c_n * E.d.nloci) return;
-  const DevModel &M = IMA_MODEL;
-  const int c = E.c_lo + idx / E.d.nloci, li = idx % E.d.nloci;
+// updategenealogy's proposal half for one pair by one warp, any model, any migration load up to the pool capacity: the
+// general path.  (The shipped workloads go through the two kernels of ima_fastpath.h and come here only when a pair does not
+// fit their smaller tables.)
+IMA_DEV void propose_pair_general(const EngineView &E, const DevModel &M, int c, int li, PairSm &S) {
   const int p = c * E.d.nloci + li;
+  const int idx = p;
   const DevLocus &L = E.loci[li];
-  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
   const int cb = E.cur[p];
   const PairBuf &B = E.buf[cb];
   const PairBuf &Bn = E.buf[cb ^ 1];
@@ -215,7 +212,7 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E) {
   if (lane == 0) {
     Philox rng;
     rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + li), kRngPropose);
-    propose_move(M, E.d, tv, L.ng, L.nl, rng, S);
+    propose_move(M, tv, L.ng, L.nl, rng, S);
   }
   Warp::sync();
   IMA_PROF_MARK()
@@ -284,9 +281,20 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E) {
   if (lane == 0) {
     E.prop_flags[p] = flags;
     E.prop_extra[p] = S.ctl_d[kCdMigw] + S.ctl_d[kCdSlidew] + S.ctl_d[kCdAterm];
-    E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw]; E.prop_dbg[(size_t)p * 4 + 1] = S.ctl_d[kCdSlidew];
-    E.prop_dbg[(size_t)p * 4 + 2] = S.ctl_d[kCdSlideDist]; E.prop_dbg[(size_t)p * 4 + 3] = (double)S.ctl_i[kCiEdge];
+    if (E.prop_dbg) {                                     // parity tests only (ima2p_engine_set_debug_records)
+      E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw]; E.prop_dbg[(size_t)p * 4 + 1] = S.ctl_d[kCdSlidew];
+      E.prop_dbg[(size_t)p * 4 + 2] = S.ctl_d[kCdSlideDist]; E.prop_dbg[(size_t)p * 4 + 3] = (double)S.ctl_i[kCiEdge];
+    }
   }
+}
+
+// every locus of chains [c_lo, c_lo + c_n) (one warp per pair)
+IMA_KERNEL void IMA_PROPOSE_BOUNDS k_propose(EngineView E) {
+  IMA_SMEM_DECL
+  const int idx = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (idx >= E.c_n * E.d.nloci) return;
+  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
+  propose_pair_general(E, IMA_MODEL, E.c_lo + idx / E.d.nloci, idx % E.d.nloci, S);
 }
 
 // what the accept sweep needs from one pair: per-lane slice of the weight records plus the scalars

@@ -69,6 +69,8 @@ struct EngineDims {
   int chain0;           // global index of local chain 0
   int nloci, P;
   int NL, CAP, NI, ND, EVP, W, S, W64;     // maxima over loci: numlines, pool capacity, record sizes, event slots, mask words, sites
+  int FP, FC, FEV;      // the small tables of the two-kernel proposal path (ima_fastpath.h): pool entries per pair in k_move,
+                        // migration events per genealogy and event slots in k_weigh; a pair that needs more takes the general path
   int any_sw, any_hky;
   long long hky_stride; // doubles of HKY scratch per pair: (max genes - 1) * (max patterns) * 5
 };
@@ -111,6 +113,9 @@ struct EngineView {
   // overlap each other's accept sweeps), and the step the launch belongs to relative to the device counter (a graph of
   // several steps advances the counter once, at its end)
   int c_lo, c_n, step_off;
+  int grp, redo_grid;           // chain group of the launch (its redo counters), blocks of the redo kernels
+  int *redo_count;              // [groups][2 kinds][2 step parities]
+  int *redo_list;               // [2 kinds][P]
 };
 
 IMA_HD unsigned long long current_step(const EngineView &E) { return *E.nsteps + (unsigned long long)E.step_off; }

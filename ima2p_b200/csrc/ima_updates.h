@@ -298,7 +298,7 @@ IMA_DEV void nw_t_pair(const EngineView &E, const UpdateView &U, const DevModel 
   if (lane == 0) {
     E.prop_flags[p] = ok ? 0u : (uint32_t)kFlagOverflow;
     E.prop_extra[p] = S.ctl_d[kCdMigw];
-    E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw];
+    if (E.prop_dbg) E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw];
     int *o = U.t_counts + (size_t)p * 4;
     o[0] = o[1] = o[2] = o[3] = 0;
   }

@@ -202,6 +202,14 @@ class Engine:
         """Chain groups on their own streams and steps per CUDA graph of `run` (the chains a run visits do not depend on it)."""
         self._ck(self.lib.ima2p_engine_set_pipeline(self._h, groups, depth, 1 if decisions_first else 0))
 
+    def set_proposal_path(self, fast=True, pairs_per_warp=0):
+        """Two-kernel proposal path (lane-per-pair move + warp-per-pair weights) or the general kernel for every pair."""
+        self._ck(self.lib.ima2p_engine_set_proposal_path(self._h, 1 if fast else 0, pairs_per_warp))
+
+    def set_debug_records(self, on=True):
+        """Keep the per-proposal record `proposal()` reads (parity tests)."""
+        self._ck(self.lib.ima2p_engine_set_debug_records(self._h, 1 if on else 0))
+
     def set_speculation(self, depth):
         """Loci evaluated per round of the accept sweep (1..4); the results do not depend on it."""
         self._ck(self.lib.ima2p_engine_set_speculation(self._h, depth))
@@ -210,8 +218,9 @@ class Engine:
         return max(1, self.nchains_global // 10) if self.nchains_global > 1 else 0             # ima_main_mpi.cpp:1378
 
     def run_timed(self, nsteps, swaptries=None, stream=None):
-        """run() launched kernel by kernel; returns summed device ms of (propose, accept, swap, split_t, accept_t, changeu, unused)."""
-        ms = np.zeros(7, np.float32)
+        """run() launched kernel by kernel; returns summed device ms of (proposal kernels together, accept, swap, split_t,
+        accept_t, changeu, k_move, k_weigh, k_propose_redo, 3 unused)."""
+        ms = np.zeros(12, np.float32)
         self._ck(self.lib.ima2p_engine_run_timed(self._h, nsteps, self.default_swaptries() if swaptries is None else swaptries,
                                                  stream, ms.ctypes.data_as(capi.c_flt_p)))
         return ms

@@ -131,11 +131,20 @@ int ima2p_engine_run (ima2p_engine * e, int nsteps, int swaptries, void *cuda_st
  * groups' swaps.  decisions_first != 0 puts every group's decision kernels on a high-priority stream of their own.
  * The run is bit for bit the same for every setting. */
 int ima2p_engine_set_pipeline (ima2p_engine * e, int groups, int depth, int decisions_first);
+/* Which kernels make updategenealogy's proposal (update_gtree.cpp:723-827): fast != 0 (the default where it applies) a
+ * lane-per-pair move kernel followed by a warp-per-pair weights / likelihood kernel, with pairs_per_warp lanes of a move warp at
+ * work (4, 8, 16, 32, or 0 = chosen from the number of pairs); fast == 0 the general one-warp-per-pair kernel for every pair.
+ * Pairs that do not fit the fast kernels' tables take the general path either way; the chain does not depend on the choice. */
+int ima2p_engine_set_proposal_path (ima2p_engine * e, int fast, int pairs_per_warp);
+/* parity tests: keep the per-proposal record that ima2p_engine_get_proposal reads (off by default) */
+int ima2p_engine_set_debug_records (ima2p_engine * e, int on);
 /* speculative depth of the accept sweep (1..3): how many consecutive loci of a chain are evaluated per round against
  * the same all-locus sums; results are identical for every depth (see csrc/ima_kernels.h k_accept) */
 int ima2p_engine_set_speculation (ima2p_engine * e, int depth);
 /* same steps, launched kernel by kernel with CUDA events on the launching stream around each kernel;
- * kernel_ms[7] = summed device time of {propose, accept, swap, split_t, accept_t, changeu, (unused)} (roofline accounting) */
+ * kernel_ms[IMA2P_TIMED_SLOTS] = summed device time of {0 the proposal kernels together, 1 accept, 2 swap, 3 split-time proposals,
+ * 4 accept_t, 5 changeu, 6 k_move, 7 k_weigh, 8 k_propose_redo, 9-11 unused} (roofline accounting) */
+#define IMA2P_TIMED_SLOTS 12
 int ima2p_engine_run_timed (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream, float *kernel_ms);
 /* Multi-GPU form (one process per GPU): genealogy updates of the local chains, then the per-chain
  * S = sum_li pdg + probg (swapweight, swapchains.cpp:12-34) is written to dev_S_local[nchains_local]

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Step time of Engine.run for a list of set_pipeline settings (one GPU).  Prints one JSON line per setting.
-usage: python profiles/tools/pipe_sweep.py WORKLOAD STEPS "g,d,f g,d,f ..." """
+"""Step time of Engine.run for a list of settings (one GPU).  Prints one JSON line per setting.
+usage: python profiles/tools/pipe_sweep.py WORKLOAD STEPS "g,d,f[,fast,ppw] ..."   (set_pipeline groups, depth, decisions_first;
+set_proposal_path fast, pairs_per_warp).  IMA_TIMED=1 adds the per-kernel times of run_timed for every setting."""
 import json
 import os
 import sys
@@ -30,8 +31,11 @@ def main():
     eng.run(burn, sw, stream)
     torch.cuda.synchronize()
     nloci, _, _, cpg, _ = bench.WORKLOADS[wl]
+    names = ["proposal", "k_accept", "k_swap", "k_split_t", "k_accept_t", "k_changeu", "k_move", "k_weigh", "k_propose_redo"]
     for s in settings:
-        eng.set_pipeline(*s)
+        eng.set_pipeline(*s[:3])
+        if len(s) >= 5:
+            eng.set_proposal_path(s[3], s[4])
         eng.run(2 * max(1, s[1]) + 8, sw, stream)
         torch.cuda.synchronize()
         best = None
@@ -43,7 +47,12 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
             best = ms if best is None else min(best, ms)
-        print(json.dumps({"workload": wl, "pipeline": s, "ms_per_step": best, "updates_per_s": cpg * nloci / (best * 1e-3)}), flush=True)
+        rec = {"workload": wl, "setting": s, "ms_per_step": best, "updates_per_s": cpg * nloci / (best * 1e-3)}
+        if os.environ.get("IMA_TIMED"):
+            km = eng.run_timed(steps, sw, stream)
+            torch.cuda.synchronize()
+            rec["kernel_us"] = {n: round(float(v) / steps * 1e3, 2) for n, v in zip(names, km)}
+        print(json.dumps(rec), flush=True)
     c = eng.counters()
     print(json.dumps({"counters": {k: int(v) for k, v in c.items()}}), flush=True)
 

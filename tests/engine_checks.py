@@ -606,6 +606,42 @@ def pipeline_does_not_change_the_run(lib, name="state_sim50_hn3", nsteps=37):
     return outs[0][0]
 
 
+def fast_path_equals_general_path(lib, name="state_sim50_hn3", nsteps=40, ppws=(0,)):
+    """The two-kernel proposal path (lane-per-pair k_move + warp-per-pair k_weigh, ima_fastpath.h) and the general
+    one-warp-per-pair kernel make the same moves from the same random streams: whichever path the pairs take -- all fast,
+    all general, or a mixture because the fast kernels' tables are too small for some pairs -- the run is the same chain."""
+    import os
+    from support import engine_from_fixture, load_golden
+    d = load_golden(name)
+    outs = []
+    # (fast, pairs per warp, environment): tiny tables send most pairs through the redo list
+    settings = [(0, 0, {})] + [(1, w, {}) for w in ppws] + [(1, ppws[-1], {"IMA2P_FAST_POOL": "12", "IMA2P_FAST_EVENTS": "8"})]
+    for fast, ppw, env in settings:
+        os.environ.update(env)
+        try:
+            eng, fm = engine_from_fixture(d, lib=lib, seed=123)
+        finally:
+            for k in env:
+                del os.environ[k]
+        eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+        eng.set_update_schedule(3, 5)
+        eng.set_proposal_path(fast, ppw)
+        eng.eval()
+        eng.run(nsteps)
+        eng.sync()
+        ch = [eng.chain(c) for c in range(eng.nchains)]
+        trees = [eng.get_genealogy(c, l) for c in range(eng.nchains) for l in range(eng.nloci)]
+        outs.append((eng.counters(), np.concatenate([np.r_[c["probg"], c["pdg"], c["beta"], c["tvals"], c["wd"], c["wi"]] for c in ch]),
+                     np.concatenate([np.r_[t["time"], t["mig_t"], t["up0"], t["pop"], t["mig_p"]] for t in trees])))
+        eng.close()
+    assert outs[0][0]["accepted"] > 0
+    for k in range(1, len(settings)):
+        assert outs[k][0] == outs[0][0], (settings[k], outs[k][0], outs[0][0])
+        assert np.array_equal(outs[k][1], outs[0][1]), settings[k]
+        assert np.array_equal(outs[k][2], outs[0][2]), settings[k]
+    return outs[0][0]
+
+
 def full_size_workload_properties(lib, nloci, nchains, nsteps, noracle=48, seed=5):
     """BASELINE-sized runs (configs[1]: 50 loci x 128 chains; configs[2]'s per-GPU shard: 300 loci x 256 chains), checked through
     properties that do not need a stored answer: after `nsteps` whole qupdate steps (genealogies, split times, scalars, swaps)

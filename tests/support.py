@@ -324,6 +324,7 @@ def engine_from_fixture(d, lib=None, chains=None, mig_capacity=64, seed=1234, be
                       totsites=loc["totsites"], nlinked=loc["nlinked"], minA=loc["minA"], maxA=loc["maxA"],
                       sumlogk=loc["sumlogk"])
     eng.finalize()
+    eng.set_debug_records(True)                 # the checks read the per-proposal record (Engine.proposal)
     eng.set_betas(betas if betas is not None else [d["chains"][c]["beta"] for c in chains])
     for k, c in enumerate(chains):
         ch = d["chains"][c]

@@ -58,6 +58,11 @@ def test_speculation_depth_does_not_change_the_run(emu):
     ec.speculation_depth_does_not_change_the_run(emu, nsteps=25)
 
 
+@pytest.mark.parametrize("name", ["state_sim50_hn3", "state_sim5_3pop_hn2", "state_sim5_hky_hn2", "state_sim5_4popA_hn2"])
+def test_fast_path_equals_general_path(emu, name):
+    ec.fast_path_equals_general_path(emu, name, nsteps=25)
+
+
 def test_pipeline_setting_is_accepted_and_does_not_change_the_run(emu):
     ec.pipeline_does_not_change_the_run(emu, nsteps=9)
 
