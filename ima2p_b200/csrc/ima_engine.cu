@@ -74,7 +74,7 @@ struct Engine {
   int groups = 1, depth = 1, pipe_prio = 0;          // see capture_steps
   bool fast_ok = false, fast = false;                // the two-kernel proposal path (ima_fastpath.h): possible / in use
   int ppw = 0;                                       // pairs per warp of k_move (0: chosen from the number of pairs)
-  int redo_grid = 64;
+  int redo_grid = 16;
   size_t pair_smem = 0, chain_smem = 0, accept_smem = 0;
   int spec = 3;        // speculative depth of the accept sweep (see k_accept)
 
@@ -190,7 +190,12 @@ static bool does_changeu(const Engine *e) { return e->u_every > 0 && (e->uv.nura
 // (TUPDATEINC 0), the mutation scalars every u_every-th step (UUPDATEINC 4); both are local to a chain.
 // Every chain picks one of the two split-time updates (t_proposal); a warp whose chain picked the other one returns at once.
 static void launch_split_t(Engine *e, stream_t s, const EngineView &v) {
-  IMA_LAUNCH(k_split_t, pair_grid(e, v), kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v, e->uv);
+  if (!e->fast) {
+    IMA_LAUNCH(k_split_t, pair_grid(e, v), kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v, e->uv);
+    return;
+  }
+  IMA_LAUNCH(k_split_t_fast, pair_grid(e, v), kWarpsPerBlock, split_smem_bytes(e->d) * kWarpsPerBlock, s, v, e->uv);
+  IMA_LAUNCH(k_split_t_redo, e->redo_grid, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v, e->uv);
 }
 static void launch_accept_t(Engine *e, stream_t s, const EngineView &v) {
   IMA_LAUNCH(k_accept_t, v.c_n, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e->d), s, v, e->uv);
@@ -420,6 +425,7 @@ int ima2p_engine_set_locus(ima2p_engine *h, int li, int model, int numgenes, int
   memset(&L.d, 0, sizeof L.d);
   L.d.model = model; L.d.ng = numgenes; L.d.nl = 2 * numgenes - 1; L.d.nsites = numsites; L.d.totsites = totsites;
   L.d.nwords = (numgenes + 31) / 32; L.d.nlinked = nlinked; L.d.hval = hval; L.d.sumlogk = sumlogk;
+  L.d.hlog = log(hval); L.d.h2term = 1 / (2 * hval);
   int tot = 0;
   for (int i = 0; i < e.model.npops; i++) { L.d.samppop[i] = samppop[i]; tot += samppop[i]; }
   if (tot != numgenes) return fail(IMA2P_E_ARG, "set_locus: samppop does not sum to numgenes");
@@ -487,8 +493,9 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   d.FP = 64;
   if (const char *x = getenv("IMA2P_FAST_EVENTS")) { const int v = atoi(x); if (v >= 8 && v <= d.CAP) d.FC = v; }
   if (const char *x = getenv("IMA2P_FAST_POOL")) { const int v = atoi(x); if (v >= 8 && v <= 4096) d.FP = v; }
+  d.FS = d.FC;
   d.FEV = (maxng - 1) + d.FC + e.model.nsplit;
-  e.fast_ok = !d.any_sw && d.NL <= 4096 && move_smem_bytes_per_pair(d) * 4 * kMoveWarps <= 200 * 1024 && weigh_smem_bytes(d) * kWarpsPerBlock <= 200 * 1024;
+  e.fast_ok = !d.any_sw && d.NL <= 4096 && move_smem_bytes_per_pair(d) * 4 * kMoveWarps <= 200 * 1024 && weigh_smem_bytes(d) * kWarpsPerBlock <= 200 * 1024 && split_smem_bytes(d) * kWarpsPerBlock <= 200 * 1024;
   e.fast = e.fast_ok && !getenv("IMA2P_GENERAL_PATH");
   e.pair_smem = pair_smem_bytes(d);
   e.chain_smem = chain_smem_bytes(d);
@@ -515,7 +522,9 @@ int ima2p_engine_finalize(ima2p_engine *h) {
         !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 8 < cap ? per * 8 : cap)) ||
         !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 16 < cap ? per * 16 : cap)) ||
         !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 32 < cap ? per * 32 : cap)) ||
-        !IMA_CUDA_OK(cudaFuncSetAttribute(k_weigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(weigh_smem_bytes(d) * kWarpsPerBlock))))
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_weigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(weigh_smem_bytes(d) * kWarpsPerBlock))) ||
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(split_smem_bytes(d) * kWarpsPerBlock))) ||
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t_redo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))))
       return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed (fast path)");
   }
   if (!IMA_CUDA_OK(cudaMemcpyToSymbol(c_model, &e.model, sizeof(DevModel)))) return fail(IMA2P_E_CUDA, "model upload failed");
@@ -534,6 +543,18 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   uint32_t *d_sm = e.alloc<uint32_t>(sm.size() + 1);
   unsigned char *d_sq = e.alloc<unsigned char>(sq.size() + 1);
   int *d_mu = e.alloc<int>(mu.size() + 1);
+  {
+    // the tables the event sweep indexes per lane (EngineDims::tab)
+    std::vector<int> tab(kTabInts, 0);
+    const DevModel &M = e.model;
+    for (int i = 0; i < M.ntreepops; i++) tab[kTabDesc + i] = M.desc_mask[i];
+    for (int k = 0; k <= M.nsplit + 1 && k < kMaxPeriods + 1; k++) { tab[kTabCcOff + k] = M.cc_off[k]; tab[kTabMcOff + k] = M.mc_off[k]; }
+    for (int k = 0; k < M.npops; k++) for (int i = 0; i < M.npops; i++) tab[kTabPlist + k * kMaxPops + i] = M.plist[k][i];
+    int *d_tab = e.alloc<int>(kTabInts);
+    if (!d_tab || !h2d(d_tab, tab.data(), kTabInts * sizeof(int), pick_stream(&e, nullptr)) || !dev_sync(pick_stream(&e, nullptr)))
+      return fail(IMA2P_E_CUDA, "table upload failed");
+    d.tab = d_tab;
+  }
   EngineView &v = e.v;
   v.d = d;
   for (int b = 0; b < 2; b++) {

@@ -89,36 +89,55 @@ IMA_KERNEL void IMA_MOVE_BOUNDS k_move(EngineView E) {
 #if defined(IMA_PROF) && IMA_CUDA
   long long pm_[4]; pm_[0] = clock64();
 #endif
-  // ---- stage: the warp copies pair after pair (coalesced reads) into the interleaved layout ------------------------
-  for (int t = 0; t < nmine; t++) {
-    const int p = p0 + t;
-    const int li = p % E.d.nloci, nl = E.loci[li].nl;
-    const PairBuf &B = E.buf[E.cur[p]];
-    const PairSmT<PPW> S = move_slot(S0, t);
-    const short4_t *topo = B.topo + (size_t)p * NL;
-    const double *time = B.time + (size_t)p * NL;
-    const ushort2_t *mseg = B.mseg + (size_t)p * NL;
-    for (int i = lane; i < nl; i += IMA_WARP) {
-      const short4_t q = topo[i];
+  // ---- stage: the warp copies its pairs (coalesced reads) into the interleaved layout.  Lane t first fetches what says where
+  // pair t lives (current buffer, edges, scalars); the copies of all pairs are then issued without waiting for each other.
+  int my_cb = 0, my_nl = 0, my_mig = 0, my_root = 0;
+  double my_roottime = 0.0;
+  if (lane < nmine) {
+    const int p = p0 + lane;
+    my_cb = E.cur[p];
+    my_nl = E.loci[p % E.d.nloci].nl;
+    const int *si = my_cb ? E.buf[1].si : E.buf[0].si;
+    my_mig = si[(size_t)p * 2 + 1];
+    my_root = si[(size_t)p * 2];
+    my_roottime = (my_cb ? E.buf[1].sd : E.buf[0].sd)[(size_t)p * 4];
+  }
+  const int total = nmine * NL;
+#if IMA_CUDA
+#pragma unroll 4
+#endif
+  for (int base = 0; base < total; base += IMA_WARP) {     // every lane makes every trip (the shuffles need all of them)
+    const int idx = base + lane;
+    const bool valid = idx < total;
+    const int t = valid ? idx / NL : 0, i = idx - t * NL;
+    const int cb = Warp::bcast(my_cb, t);
+    if (valid) {
+      const size_t g = (size_t)(p0 + t) * NL + i;
+      const short4_t q = (cb ? E.buf[1].topo : E.buf[0].topo)[g];
+      const double tm = (cb ? E.buf[1].time : E.buf[0].time)[g];
+      const ushort2_t m = (cb ? E.buf[1].mseg : E.buf[0].mseg)[g];
+      const PairSmT<PPW> S = move_slot(S0, t);
       S.up0[i] = q.x; S.up1[i] = q.y; S.down[i] = q.z; S.pop[i] = q.w;
-      S.time[i] = time[i];
-      const ushort2_t m = mseg[i];
+      S.time[i] = tm;
       S.ms[i] = m.x; S.mcn[i] = m.y;
     }
-    const int mignum = B.si[(size_t)p * 2 + 1];
-    if (mignum <= FP) {
-      const double *mt = B.mig_t + (size_t)p * CAP;
-      const short *mp = B.mig_p + (size_t)p * CAP;
+  }
+  for (int t = 0; t < nmine; t++) {                       // migration events: the first IMA_WARP of every pair at once
+    const int cb = Warp::bcast(my_cb, t), mignum = Warp::bcast(my_mig, t);
+    const double *mt = (cb ? E.buf[1].mig_t : E.buf[0].mig_t) + (size_t)(p0 + t) * CAP;
+    const short *mp = (cb ? E.buf[1].mig_p : E.buf[0].mig_p) + (size_t)(p0 + t) * CAP;
+    const PairSmT<PPW> S = move_slot(S0, t);
+    if (mignum <= FP)
       for (int i = lane; i < mignum; i += IMA_WARP) { S.pt[i] = mt[i]; S.pp[i] = mp[i]; }
-    }
-    if (lane == 0) {
-      S.ctl_i[kCiRoot] = B.si[(size_t)p * 2];
-      S.ctl_i[kCiMignum] = mignum;
-      S.ctl_i[kCiFlags] = mignum <= FP ? 0 : (int)kFlagOverflow;
-      S.ctl_d[kCdRoottime] = B.sd[(size_t)p * 4];
-      S.ctl_d[kCdMigw] = 0.0; S.ctl_d[kCdSlidew] = 0.0; S.ctl_d[kCdAterm] = 0.0; S.ctl_d[kCdSlideDist] = 0.0;
-      S.ctl_i[kCiEdge] = -1;
-    }
+  }
+  if (lane < nmine) {
+    const PairSmT<PPW> S = move_slot(S0, lane);
+    S.ctl_i[kCiRoot] = my_root;
+    S.ctl_i[kCiMignum] = my_mig;
+    S.ctl_i[kCiFlags] = my_mig <= FP ? 0 : (int)kFlagOverflow;
+    S.ctl_d[kCdRoottime] = my_roottime;
+    S.ctl_d[kCdMigw] = 0.0; S.ctl_d[kCdSlidew] = 0.0; S.ctl_d[kCdAterm] = 0.0; S.ctl_d[kCdSlideDist] = 0.0;
+    S.ctl_i[kCiEdge] = -1;
   }
 #if IMA_CUDA
   __threadfence_block();
@@ -150,8 +169,8 @@ IMA_KERNEL void IMA_MOVE_BOUNDS k_move(EngineView E) {
   // ---- store: the warp writes pair after pair, migration lists compacted in edge order, to the pair's other buffer ---
   for (int t = 0; t < nmine; t++) {
     const int p = p0 + t;
-    const int li = p % E.d.nloci, nl = E.loci[li].nl;
-    const PairBuf &Bn = E.buf[E.cur[p] ^ 1];
+    const int nl = Warp::bcast(my_nl, t);
+    const PairBuf &Bn = E.buf[Warp::bcast(my_cb, t) ^ 1];
     const PairSmT<PPW> S = move_slot(S0, t);
     uint32_t flags = (uint32_t)S.ctl_i[kCiFlags];
     int total = 0;
@@ -210,20 +229,22 @@ IMA_KERNEL void IMA_MOVE_BOUNDS k_move(EngineView E) {
 // ---- shared memory of k_weigh: one pair per warp, tables sized for FC migration events -------------------------------
 // the prefix table doubles as the 2 x 16 transition probabilities of the HKY likelihood: never under 32 doubles
 IMA_HD size_t weigh_pre_bytes(const EngineDims &d) { const size_t b = sizeof(unsigned long long) * d.FEV * d.W64; return b < 256 ? 256 : b; }
-IMA_HD size_t weigh_smem_bytes(const EngineDims &d) {
+IMA_HD size_t weigh_smem_bytes(const EngineDims &d, int pool = -1) {
   size_t b = 0;
-  b += align8(sizeof(double) * d.NL) + align8(sizeof(double) * d.FC) + align8(sizeof(double) * d.FEV);
+  if (pool < 0) pool = d.FC;
+  b += align8(sizeof(double) * d.NL) + align8(sizeof(double) * pool) + align8(sizeof(double) * d.FEV);
   b += align8(weigh_pre_bytes(d)) + align8(sizeof(double) * d.ND) + 64;
-  b += 4 * align8(sizeof(short) * d.NL) + 2 * align8(sizeof(unsigned short) * d.NL) + align8(sizeof(short) * d.FC);
+  b += 4 * align8(sizeof(short) * d.NL) + 2 * align8(sizeof(unsigned short) * d.NL) + align8(sizeof(short) * pool);
   b += 2 * align8(sizeof(int) * d.FEV) + align8(sizeof(uint32_t) * d.NL * d.W) + align8(sizeof(int) * (d.NL + 1)) + align8(sizeof(int) * d.NI) + 48;
   return b;
 }
-IMA_DEV PairSm carve_weigh_smem(unsigned char *base, const EngineDims &d) {
+IMA_DEV PairSm carve_weigh_smem(unsigned char *base, const EngineDims &d, int pool = -1) {
   PairSm s;
   unsigned char *p = base;
+  if (pool < 0) pool = d.FC;
   auto take = [&](size_t bytes) { unsigned char *q = p; p += align8(bytes); return q; };
   s.time.p = (double *)take(sizeof(double) * d.NL);
-  s.pt.p = (double *)take(sizeof(double) * d.FC);
+  s.pt.p = (double *)take(sizeof(double) * pool);
   s.evt = (double *)take(sizeof(double) * d.FEV);
   s.pre = (unsigned long long *)take(weigh_pre_bytes(d));
   s.gwd = (double *)take(sizeof(double) * d.ND);
@@ -234,14 +255,14 @@ IMA_DEV PairSm carve_weigh_smem(unsigned char *base, const EngineDims &d) {
   s.pop.p = (short *)take(sizeof(short) * d.NL);
   s.ms.p = (unsigned short *)take(sizeof(unsigned short) * d.NL);
   s.mcn.p = (unsigned short *)take(sizeof(unsigned short) * d.NL);
-  s.pp.p = (short *)take(sizeof(short) * d.FC);
+  s.pp.p = (short *)take(sizeof(short) * pool);
   s.evi = (int *)take(sizeof(int) * d.FEV);
   s.evk = (int *)take(sizeof(int) * d.FEV);
   s.mask = (uint32_t *)take(sizeof(uint32_t) * d.NL * d.W);
   s.moff = (int *)take(sizeof(int) * (d.NL + 1));
   s.gwi = (int *)take(sizeof(int) * d.NI);
   s.ctl_i.p = (int *)take(48);
-  s.pool_free = d.FC; s.pool_end = d.FC;
+  s.pool_free = d.FC; s.pool_end = pool;
 #if defined(IMA_PROF)
   s.prof = nullptr; s.nprof = 0;
 #endif

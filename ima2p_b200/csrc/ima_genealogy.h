@@ -117,6 +117,15 @@ IMA_DEV void stage_pair(const EngineView &E, const PairBuf &B, int p, int nl, Pa
   const short4_t *topo = B.topo + (size_t)p * E.d.NL;
   const double *time = B.time + (size_t)p * E.d.NL;
   const ushort2_t *mseg = B.mseg + (size_t)p * E.d.NL;
+  // every global load is issued before anything waits for one: the scalars, the first IMA_WARP migration events (read
+  // whether or not the genealogy has that many: the pool row exists) and the edges; only a genealogy with more events than
+  // lanes makes a second, dependent trip
+  const double *mt = B.mig_t + (size_t)p * E.d.CAP;
+  const short *mp = B.mig_p + (size_t)p * E.d.CAP;
+  const int mignum = B.si[(size_t)p * 2 + 1], root = B.si[(size_t)p * 2];
+  const double roottime = B.sd[(size_t)p * 4];
+  const double mt0 = lane < E.d.CAP ? mt[lane] : 0.0;
+  const short mp0 = lane < E.d.CAP ? mp[lane] : (short)0;
   for (int i = lane; i < nl; i += IMA_WARP) {
     short4_t t = topo[i];
     S.up0[i] = t.x; S.up1[i] = t.y; S.down[i] = t.z; S.pop[i] = t.w;
@@ -124,15 +133,13 @@ IMA_DEV void stage_pair(const EngineView &E, const PairBuf &B, int p, int nl, Pa
     ushort2_t m = mseg[i];
     S.ms[i] = m.x; S.mcn[i] = m.y;
   }
-  const int mignum = B.si[(size_t)p * 2 + 1];
-  const double *mt = B.mig_t + (size_t)p * E.d.CAP;
-  const short *mp = B.mig_p + (size_t)p * E.d.CAP;
-  for (int i = lane; i < mignum; i += IMA_WARP) { S.pt[i] = mt[i]; S.pp[i] = mp[i]; }
+  if (lane < mignum) { S.pt[lane] = mt0; S.pp[lane] = mp0; }
+  for (int i = lane + IMA_WARP; i < mignum; i += IMA_WARP) { S.pt[i] = mt[i]; S.pp[i] = mp[i]; }
   if (lane == 0) {
-    S.ctl_i[kCiRoot] = B.si[(size_t)p * 2];
+    S.ctl_i[kCiRoot] = root;
     S.ctl_i[kCiMignum] = mignum;
     S.ctl_i[kCiFlags] = 0;
-    S.ctl_d[kCdRoottime] = B.sd[(size_t)p * 4];
+    S.ctl_d[kCdRoottime] = roottime;
     S.ctl_d[kCdMigw] = 0.0; S.ctl_d[kCdSlidew] = 0.0; S.ctl_d[kCdAterm] = 0.0;
   }
   Warp::sync();
@@ -713,6 +720,13 @@ template <class PS> IMA_DEV void propose_move(const DevModel &M, const double *t
 // ------------------------------------------------------------------------------------------------
 // packed event: bits 0-1 kind (0 coalescence, 1 migration, 2 population split), 2-6 pop, 7-11 topop, 12.. node
 constexpr int kRankSortMax = 128;
+IMA_DEV long long dbl_bits(double x) {
+#if IMA_CUDA
+  return __double_as_longlong(x);
+#else
+  long long v; memcpy(&v, &x, sizeof v); return v;
+#endif
+}
 IMA_DEV int pack_event(int kind, int pop, int topop, int node) { return kind | (pop << 2) | (topop << 7) | (node << 12); }
 
 // returns false when the event table does not fit (flagged as overflow by the caller)
@@ -759,21 +773,21 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
     __threadfence_block();
 #endif
     Warp::sync();
-    for (int j0 = lane; j0 < nev; j0 += 4 * IMA_WARP) {            // four events of the lane share every read of the table
-      double t[4]; int inf[4], r[4], jj[4];
-      for (int q = 0; q < 4; q++) {
-        jj[q] = j0 + q * IMA_WARP;
-        const bool v = jj[q] < nev;
-        t[q] = v ? bt[jj[q]] : 0.0; inf[q] = v ? bi[jj[q]] : 0; r[q] = 0;
-      }
+    // times are not negative, so their bit patterns order like the times: integer compares (the FP64 pipe is narrow)
+    for (int j0 = lane; j0 < nev; j0 += 2 * IMA_WARP) {            // two events of the lane share every read of the table
+      const int j1 = j0 + IMA_WARP;
+      const bool two = j1 < nev;
+      const long long k0 = dbl_bits(bt[j0]), k1 = two ? dbl_bits(bt[j1]) : 0;
+      const int i0 = bi[j0], i1 = two ? bi[j1] : 0;
+      int r0 = 0, r1 = 0;
       for (int k = 0; k < nev; k++) {
-        const double tk = bt[k];
+        const long long kk = dbl_bits(bt[k]);
         const int ik = bi[k];
-        for (int q = 0; q < 4; q++)
-          r[q] += (tk < t[q] || (tk == t[q] && (ik < inf[q] || (ik == inf[q] && k < jj[q])))) ? 1 : 0;
+        r0 += (kk < k0 || (kk == k0 && (ik < i0 || (ik == i0 && k < j0)))) ? 1 : 0;
+        r1 += (kk < k1 || (kk == k1 && (ik < i1 || (ik == i1 && k < j1)))) ? 1 : 0;
       }
-      for (int q = 0; q < 4; q++)
-        if (jj[q] < nev) { S.evt[r[q]] = t[q]; S.evi[r[q]] = inf[q]; }
+      S.evt[r0] = bt[j0]; S.evi[r0] = i0;
+      if (two) { S.evt[r1] = bt[j1]; S.evi[r1] = i1; }
     }
 #if IMA_CUDA
     __threadfence_block();
@@ -815,7 +829,11 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
   {
     int carry_k = 0, carry_c = 0;
     unsigned long long carry_w[(kMaxTreePops + 3) / 4];
-    for (int w = 0; w < W64; w++) carry_w[w] = 0ull;
+    for (int w = 0; w < W64; w++) {                      // the scan starts from the samples (sampled populations only)
+      unsigned long long c0 = 0ull;
+      for (int f = 0; f < 4; f++) { const int q = w * 4 + f; if (q < M.npops) c0 |= (unsigned long long)L.samppop[q] << (16 * f); }
+      carry_w[w] = c0;
+    }
     for (int base = 0; base < nev; base += IMA_WARP) {
       const int j = base + lane;
       const bool valid = j < nev;
@@ -854,52 +872,52 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
   }
   Warp::sync();
   IMA_SPROF(S)
-  // number of lineages in tree population `pop` just before event j
+  // number of lineages in tree population `pop` just before event j (the samples are in the scan's starting value)
+  const int *tab = d.tab;
+  const int ntp = M.ntreepops, npops = M.npops, nsplit = M.nsplit, ncc = M.ncc;
   auto lineages = [&](int pop, int j) {
     int n = 0;
-    const unsigned dm = (unsigned)M.desc_mask[pop];
-    for (int q = 0; q < M.ntreepops; q++)
-      if (dm & (1u << q)) {
-        const int dq = (int)((S.pre[(size_t)j * W64 + (q >> 2)] >> (16 * (q & 3))) & 0xffffull) - j;   // remove the +1 bias
-        n += dq + (q < M.npops ? L.samppop[q] : 0);
-      }
+    const unsigned dm = (unsigned)tab[kTabDesc + pop];
+    for (int q = 0; q < ntp; q++)
+      if (dm & (1u << q)) n += (int)((S.pre[(size_t)j * W64 + (q >> 2)] >> (16 * (q & 3))) & 0xffffull) - j;   // remove the +1 bias
     return n;
   };
-  const double h2term = 1 / (2 * L.hval);
-  const double lastsplitt = M.nsplit > 0 ? tv[M.nsplit - 1] : kTimeMax;
+  const double h2term = L.h2term;
+  const double lastsplitt = nsplit > 0 ? tv[nsplit - 1] : kTimeMax;
   double length = 0.0, tlength = 0.0;
   int bad = 0;
   for (int j = lane; j < nev; j += IMA_WARP) {
     const double t = S.evt[j], lasttime = j > 0 ? S.evt[j - 1] : 0.0;
     const double dt = t - lasttime;
-    const int kj = S.evk[j] & 0xff, nsum = S.evk[j] >> 8;
+    const int ek = S.evk[j], kj = ek & 0xff, nsum = ek >> 8;
     const double timeadd = nsum * dt;
     length += timeadd;
     if (t < lastsplitt) tlength += timeadd;
     else if (lasttime < lastsplitt) tlength += nsum * (lastsplitt - lasttime);
     const int info = S.evi[j], kind = info & 3, ip = (info >> 2) & 31, jp = (info >> 7) & 31;
-    const int np = M.npops - kj;
+    const int np = npops - kj;
+    const int *pl = tab + kTabPlist + kj * kMaxPops;
     if (kind == 0) {
       int ii = 0;
-      while (ii < np && M.plist[kj][ii] != ip) ii++;
+      while (ii < np && pl[ii] != ip) ii++;
       if (ii >= np || lineages(ip, j) < 2) bad = 1;
       else {
 #if IMA_CUDA
-        atomicAdd(&S.gwi[wi_cc(M, kj, ii)], 1);
+        atomicAdd(&S.gwi[tab[kTabCcOff + kj] + ii], 1);
 #else
-        S.gwi[wi_cc(M, kj, ii)]++;
+        S.gwi[tab[kTabCcOff + kj] + ii]++;
 #endif
       }
     } else if (kind == 1) {
       int ii = 0, jj = 0;
-      while (ii < np && M.plist[kj][ii] != ip) ii++;
-      while (jj < np && M.plist[kj][jj] != jp) jj++;
-      if (ii >= np || jj >= np || kj >= M.nsplit || lineages(ip, j) < 1) bad = 1;
+      while (ii < np && pl[ii] != ip) ii++;
+      while (jj < np && pl[jj] != jp) jj++;
+      if (ii >= np || jj >= np || kj >= nsplit || lineages(ip, j) < 1) bad = 1;
       else {
 #if IMA_CUDA
-        atomicAdd(&S.gwi[wi_mc(M, kj, ii, jj)], 1);
+        atomicAdd(&S.gwi[ncc + tab[kTabMcOff + kj] + ii * np + jj], 1);
 #else
-        S.gwi[wi_mc(M, kj, ii, jj)]++;
+        S.gwi[ncc + tab[kTabMcOff + kj] + ii * np + jj]++;
 #endif
       }
     }
@@ -908,9 +926,9 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
   tlength = Warp::sum(tlength);
   bad = Warp::any(bad != 0) ? 1 : 0;
   // fc[k][ii] += n(n-1) dt / (2h) and fm[k][ii][*] += n dt: one target (k, ii) at a time
-  for (int k = 0; k <= M.nsplit; k++)
-    for (int ii = 0; ii < M.npops - k; ii++) {
-      const int ip = M.plist[k][ii];
+  for (int k = 0; k <= nsplit; k++)
+    for (int ii = 0; ii < npops - k; ii++) {
+      const int ip = tab[kTabPlist + k * kMaxPops + ii];
       double fcacc = 0.0, fmacc = 0.0;
       for (int j = lane; j < nev; j += IMA_WARP)
         if ((S.evk[j] & 0xff) == k) {
@@ -923,13 +941,13 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
       fmacc = Warp::sum(fmacc);
       if (lane == 0) {
         S.gwd[wd_fc(M, k, ii)] = fcacc;
-        if (!M.nomigration && k < M.nsplit)
-          for (int jj = 0; jj < M.npops - k; jj++) if (jj != ii) S.gwd[wd_fm(M, k, ii, jj)] = fmacc;
+        if (!M.nomigration && k < nsplit)
+          for (int jj = 0; jj < npops - k; jj++) if (jj != ii) S.gwd[wd_fm(M, k, ii, jj)] = fmacc;
       }
     }
   Warp::sync();
   IMA_SPROF(S)
-  const double hlog = log(L.hval);
+  const double hlog = L.hlog;
   if (hlog != 0.0)
     for (int i = lane; i < M.ncc; i += IMA_WARP) S.gwd[M.ncc + i] += hlog * S.gwi[i];
   if (lane == 0) {

@@ -26,6 +26,9 @@ struct DevModel {
   short nomig_idx[kMaxParams];
 };
 
+// layout of EngineDims::tab
+constexpr int kTabDesc = 0, kTabCcOff = 20, kTabMcOff = 32, kTabPlist = 44, kTabInts = 44 + kMaxPops * kMaxPops;
+
 // weight record layout: ints  [cc(ncc) | mc(nmc)],  doubles [fc(ncc) | hcc(ncc) | fm(nmc)]
 IMA_HD int wi_cc(const DevModel &M, int k, int i) { return M.cc_off[k] + i; }
 IMA_HD int wi_mc(const DevModel &M, int k, int i, int j) { return M.ncc + M.mc_off[k] + i * (M.npops - k) + j; }
@@ -39,6 +42,7 @@ struct DevLocus {
   int samppop[kMaxPops];
   int minA[kMaxLinked], maxA[kMaxLinked];
   double hval, sumlogk;
+  double hlog, h2term;      // log(hval) and 1 / (2 hval), made once by set_locus
   long long sitemask_off;   // uint32 [nsites][nwords]: carrier-tip bit masks of the segregating sites (IS)
   long long seq_off;        // uint8  [ng][nsites]: bases 0..3 of the compressed site patterns (HKY)
   long long mult_off;       // int    [nsites]: pattern multiplicities (HKY)
@@ -69,10 +73,13 @@ struct EngineDims {
   int chain0;           // global index of local chain 0
   int nloci, P;
   int NL, CAP, NI, ND, EVP, W, S, W64;     // maxima over loci: numlines, pool capacity, record sizes, event slots, mask words, sites
-  int FP, FC, FEV;      // the small tables of the two-kernel proposal path (ima_fastpath.h): pool entries per pair in k_move,
-                        // migration events per genealogy and event slots in k_weigh; a pair that needs more takes the general path
+  int FP, FC, FEV, FS;  // the small tables of the two-kernel proposal path (ima_fastpath.h): pool entries per pair in k_move,
+                        // migration events per genealogy and event slots in k_weigh, scratch entries of the fast split-time kernel;
+                        // a pair that needs more takes the general path
   int any_sw, any_hky;
   long long hky_stride; // doubles of HKY scratch per pair: (max genes - 1) * (max patterns) * 5
+  const int *tab;       // model tables the event sweep indexes with lane-dependent subscripts, in global memory (constant
+                        // memory serialises such reads): see kTab* below
 };
 
 // Everything a kernel needs, passed by value.

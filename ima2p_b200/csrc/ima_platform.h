@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <float.h>
+#include <string.h>
 
 #if defined(__CUDACC__) && !defined(IMA_HOSTEMU)
 #define IMA_CUDA 1

@@ -13,6 +13,7 @@
 // independent.  Random streams are keyed by (global chain, step, purpose) like everything else.
 #pragma once
 #include "ima_kernels.h"
+#include "ima_fastpath.h"
 
 namespace ima {
 
@@ -128,14 +129,14 @@ IMA_DEV void nw_edge_rng(Philox &rng, const EngineView &E, int pair_global, int 
 
 IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const double *tv, int period, double oldt, double newt,
                               int ng, int nl, int pair_global, PairSm &S) {
-  const int CAP = E.d.CAP, root = S.ctl_i[kCiRoot], lane = Warp::lane();
+  const int root = S.ctl_i[kCiRoot], lane = Warp::lane();
   const bool up = newt > oldt;                        // the split moves back in time
   const double tu = up ? oldt : newt, td = up ? newt : oldt;
   const int period_a = up ? period : period + 1, period_b = up ? period + 1 : period, p1 = period + 1;
   const int addp = M.addpop[p1], d0 = M.droppops[p1][0], d1 = M.droppops[p1][1];
   int *rec = S.moff;                                  // per edge: db | da << 5 | codef << 10 | coder << 13 | set << 18
   for (int i = lane; i < nl; i += IMA_WARP) rec[i] = 0;
-  if (lane == 0) S.ctl_i[kCiNev] = CAP;               // rewritten lists are appended to the scratch part of the pool
+  if (lane == 0) S.ctl_i[kCiNev] = S.pool_free;       // rewritten lists are appended to the scratch part of the pool
 #if IMA_CUDA
   __threadfence_block();
 #endif
@@ -243,11 +244,11 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
       const int at = S.ctl_i[kCiNev];
       S.ctl_i[kCiNev] += total;
 #endif
-      if (at + total > 4 * CAP) { overflow = true; continue; }
+      if (at + total > S.pool_end) { overflow = true; continue; }
       for (int j = 0; j < above; j++) { S.pt[at + j] = S.pt[s0 + j]; S.pp[at + j] = S.pp[s0 + j]; }
       if (mnew > 0) {
         Emi em; em.seg = at + above; em.nmig = 0;
-        simmpath(M, rng, S, em, 4 * CAP, period_a, mnew, mtime, top, upa, da);
+        simmpath(M, rng, S, em, S.pool_end, period_a, mnew, mtime, top, upa, da);
         if (mnew >= 2) cm2_a = mnew == 2 ? upa : (int)S.pp[at + above + mnew - 3];
       }
       for (int j = 0; j < numheld; j++) { S.pt[at + above + mnew + j] = S.pt[s0 + below + j]; S.pp[at + above + mnew + j] = S.pp[s0 + below + j]; }
@@ -260,7 +261,9 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
   return Warp::sum(num - denom);
 }
 
-IMA_DEV void nw_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S) {
+// evcap / migcap: what the caller's tables hold (the general kernel: EVP events, CAP migration events; the fast one: FEV, FC).
+// Returns false when the pair did not fit: the caller decides whether that is a dropped proposal or a pair for the general path.
+IMA_DEV bool nw_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S, int evcap, int migcap) {
   const DevLocus &L = E.loci[li];
   const int cb = E.cur[p];
   const PairBuf &B = E.buf[cb];
@@ -281,9 +284,9 @@ IMA_DEV void nw_t_pair(const EngineView &E, const UpdateView &U, const DevModel 
 #endif
   Warp::sync();
   bool ok = !(S.ctl_i[kCiFlags] & kFlagOverflow);
-  if (ok) ok = eval_weights(M, E.d, L, tvn, S);
+  if (ok) ok = eval_weights(M, E.d, L, tvn, S, evcap);
   const int total_mig = ok ? S.ctl_i[kCiMignum] : 0;
-  if (ok && total_mig > E.d.CAP) ok = false;
+  if (ok && total_mig > migcap) ok = false;
   if (ok) {
     // branch lengths do not change: P(D|G) and everything it is built from are carried over (:908)
     if (has_stepwise(L.model)) {
@@ -302,9 +305,10 @@ IMA_DEV void nw_t_pair(const EngineView &E, const UpdateView &U, const DevModel 
     int *o = U.t_counts + (size_t)p * 4;
     o[0] = o[1] = o[2] = o[3] = 0;
   }
+  return ok;
 }
 
-IMA_DEV void rescale_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S) {
+IMA_DEV bool rescale_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S, int evcap, int migcap) {
   const DevLocus &L = E.loci[li];
   const int cb = E.cur[p];
   const PairBuf &B = E.buf[cb];
@@ -338,9 +342,9 @@ IMA_DEV void rescale_t_pair(const EngineView &E, const UpdateView &U, const DevM
   __threadfence_block();
 #endif
   Warp::sync();
-  bool ok = eval_weights(M, E.d, L, tvn, S);
+  bool ok = eval_weights(M, E.d, L, tvn, S, evcap);
   const int total_mig = ok ? S.ctl_i[kCiMignum] : 0;
-  if (ok && total_mig > E.d.CAP) ok = false;
+  if (ok && total_mig > migcap) ok = false;
   uint32_t flags = ok ? (uint32_t)S.ctl_i[kCiFlags] : (uint32_t)kFlagOverflow;
   if (ok) {
     if (has_stepwise(L.model)) {           // the allele states do not move; the branch terms are recomputed below
@@ -366,6 +370,7 @@ IMA_DEV void rescale_t_pair(const EngineView &E, const UpdateView &U, const DevM
     int *o = U.t_counts + (size_t)p * 4;
     o[0] = n_eu; o[1] = n_ed; o[2] = n_mu; o[3] = n_md;
   }
+  return ok;
 }
 
 // One launch for both split-time updates: every chain drew its update type (t_proposal), every warp follows its chain.
@@ -377,8 +382,49 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_split_t(EngineView E, UpdateView U) {
   const int c = E.c_lo + idx / E.d.nloci, li = idx % E.d.nloci, p = c * E.d.nloci + li;
   PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
   const TProposal t = t_proposal(E, U, M, c);
-  if (t.method == 1) nw_t_pair(E, U, M, t, p, c, li, S);
-  else rescale_t_pair(E, U, M, t, p, c, li, S);
+  if (t.method == 1) nw_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
+  else rescale_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
+}
+
+// ---- the same proposals with the small tables of the fast path (ima_fastpath.h): FC migration events per genealogy plus FS
+// entries of scratch for the lists Nielsen-Wakeley rewrites.  A pair that does not fit goes to the redo list and k_split_t_redo
+// makes its proposal with the general tables, from the same random streams.
+IMA_HD size_t split_smem_bytes(const EngineDims &d) { return weigh_smem_bytes(d, d.FC + d.FS); }
+IMA_DEV PairSm carve_split_smem(unsigned char *base, const EngineDims &d) { return carve_weigh_smem(base, d, d.FC + d.FS); }
+#ifndef IMA_SPLIT_MINBLOCKS
+#define IMA_SPLIT_MINBLOCKS 6
+#endif
+#if IMA_CUDA
+#define IMA_SPLIT_BOUNDS __launch_bounds__(kWarpsPerBlock * 32, IMA_SPLIT_MINBLOCKS)
+#else
+#define IMA_SPLIT_BOUNDS
+#endif
+IMA_KERNEL void IMA_SPLIT_BOUNDS k_split_t_fast(EngineView E, UpdateView U) {
+  IMA_SMEM_DECL
+  const int idx = ima_block() * kWarpsPerBlock + ima_warp_in_block();
+  if (idx == 0 && Warp::lane() == 0) *redo_counter(E, 1, (int)((current_step(E) + 1) & 1ull)) = 0;
+  if (idx >= E.c_n * E.d.nloci) return;
+  const DevModel &M = IMA_MODEL;
+  const int c = E.c_lo + idx / E.d.nloci, li = idx % E.d.nloci, p = c * E.d.nloci + li;
+  PairSm S = carve_split_smem(IMA_SMEM + (size_t)ima_warp_in_block() * split_smem_bytes(E.d), E.d);
+  const TProposal t = t_proposal(E, U, M, c);
+  bool ok = E.buf[E.cur[p]].si[(size_t)p * 2 + 1] <= E.d.FC;
+  if (ok) ok = t.method == 1 ? nw_t_pair(E, U, M, t, p, c, li, S, E.d.FEV, E.d.FC) : rescale_t_pair(E, U, M, t, p, c, li, S, E.d.FEV, E.d.FC);
+  if (!ok && Warp::lane() == 0) { E.prop_flags[p] = kFlagRedo; redo_push(E, 1, p); }
+}
+IMA_KERNEL void IMA_PROPOSE_BOUNDS k_split_t_redo(EngineView E, UpdateView U) {
+  IMA_SMEM_DECL
+  const DevModel &M = IMA_MODEL;
+  const int n = *redo_counter(E, 1, (int)(current_step(E) & 1ull));
+  const int *list = redo_list(E, 1);
+  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
+  for (int k = ima_block() * kWarpsPerBlock + ima_warp_in_block(); k < n; k += E.redo_grid * kWarpsPerBlock) {
+    const int p = list[k], c = p / E.d.nloci, li = p - c * E.d.nloci;
+    const TProposal t = t_proposal(E, U, M, c);
+    if (t.method == 1) nw_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
+    else rescale_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
+    Warp::sync();
+  }
 }
 
 constexpr int kTWarps = 8;            // warps of a k_accept_t block (one block per chain)

@@ -100,7 +100,7 @@ def test_speculation_depth_does_not_change_the_run(lib):
 
 @pytest.mark.parametrize("name", ["state_sim50_hn3", "state_sim5_3pop_hn2", "state_sim5_hky_hn2", "state_sim5_4popA_hn2"])
 def test_fast_path_equals_general_path(lib, name):
-    ec.fast_path_equals_general_path(lib, name, ppws=(4, 8, 16, 32))
+    ec.fast_path_equals_general_path(lib, name, ppws=(4, 8, 16))
 
 
 def test_pipeline_does_not_change_the_run(lib):
