@@ -147,11 +147,23 @@ static int pair_grid(const Engine *e, const EngineView &v) { return (v.c_n * e->
 // pairs per warp of k_move: few pairs -> few per warp (more warps in flight, less divergence); many -> fuller warps
 static int move_ppw(const Engine *e, int npairs) {
 #if IMA_CUDA
-  if (e->ppw == 4 || e->ppw == 8 || e->ppw == 16 || e->ppw == 32) return e->ppw;
+  if (e->ppw == 1 || e->ppw == 2 || e->ppw == 4 || e->ppw == 8 || e->ppw == 16) return e->ppw;
   return npairs <= 148 * 96 ? 4 : 8;
 #else
   (void)e; (void)npairs;
   return 1;
+#endif
+}
+static void launch_move(int ppw, int gm, size_t sm, stream_t s, const EngineView &v) {
+#if IMA_CUDA
+  if (ppw == 1) IMA_LAUNCH(k_move<1>, gm, kMoveWarps, sm, s, v);
+  else if (ppw == 2) IMA_LAUNCH(k_move<2>, gm, kMoveWarps, sm, s, v);
+  else if (ppw == 4) IMA_LAUNCH(k_move<4>, gm, kMoveWarps, sm, s, v);
+  else if (ppw == 8) IMA_LAUNCH(k_move<8>, gm, kMoveWarps, sm, s, v);
+  else IMA_LAUNCH(k_move<16>, gm, kMoveWarps, sm, s, v);
+#else
+  (void)ppw;
+  IMA_LAUNCH(k_move<1>, gm, kMoveWarps, sm, s, v);
 #endif
 }
 static void launch_propose(Engine *e, stream_t s, const EngineView &v) {
@@ -162,14 +174,7 @@ static void launch_propose(Engine *e, stream_t s, const EngineView &v) {
   const int npairs = v.c_n * e->d.nloci, ppw = move_ppw(e, npairs);
   const int gm = (npairs + ppw * kMoveWarps - 1) / (ppw * kMoveWarps);
   const size_t sm = move_smem_bytes_per_pair(e->d) * ppw * kMoveWarps;
-#if IMA_CUDA
-  if (ppw == 4) IMA_LAUNCH(k_move<4>, gm, kMoveWarps, sm, s, v);
-  else if (ppw == 8) IMA_LAUNCH(k_move<8>, gm, kMoveWarps, sm, s, v);
-  else if (ppw == 16) IMA_LAUNCH(k_move<16>, gm, kMoveWarps, sm, s, v);
-  else IMA_LAUNCH(k_move<32>, gm, kMoveWarps, sm, s, v);
-#else
-  IMA_LAUNCH(k_move<1>, gm, kMoveWarps, sm, s, v);
-#endif
+  launch_move(ppw, gm, sm, s, v);
   IMA_LAUNCH(k_weigh, pair_grid(e, v), kWarpsPerBlock, weigh_smem_bytes(e->d) * kWarpsPerBlock, s, v);
   IMA_LAUNCH(k_propose_redo, e->redo_grid, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v);
 }
@@ -198,7 +203,7 @@ static void launch_split_t(Engine *e, stream_t s, const EngineView &v) {
   IMA_LAUNCH(k_split_t_redo, e->redo_grid, kWarpsPerBlock, e->pair_smem * kWarpsPerBlock, s, v, e->uv);
 }
 static void launch_accept_t(Engine *e, stream_t s, const EngineView &v) {
-  IMA_LAUNCH(k_accept_t, v.c_n, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e->d), s, v, e->uv);
+  IMA_LAUNCH(k_accept_t, v.c_n, IMA_CUDA ? kTWarps : 1, accept_t_smem_bytes(e->d), s, v, e->uv);
 }
 static void launch_changeu(Engine *e, stream_t s, const EngineView &v) {
   UpdateView u = e->uv;
@@ -407,6 +412,7 @@ int ima2p_engine_set_model(ima2p_engine *h, int npops, int nsplit, const int *pl
   for (int i = 0; i < nomig_n; i++) M.nomig_idx[i] = (short)(M.mc_off[nomig_p[i]] + nomig_r[i] * (npops - nomig_p[i]) + nomig_c[i]);
   e.d.NI = M.ncc + M.nmc;
   e.d.ND = 2 * M.ncc + M.nmc;
+  e.d.NT = nq + nm;
   e.model_set = true;
   return IMA2P_OK;
 }
@@ -497,6 +503,9 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   d.FEV = (maxng - 1) + d.FC + e.model.nsplit;
   e.fast_ok = !d.any_sw && d.NL <= 4096 && move_smem_bytes_per_pair(d) * 4 * kMoveWarps <= 200 * 1024 && weigh_smem_bytes(d) * kWarpsPerBlock <= 200 * 1024 && split_smem_bytes(d) * kWarpsPerBlock <= 200 * 1024;
   e.fast = e.fast_ok && !getenv("IMA2P_GENERAL_PATH");
+  // measured on B200 (profiles/r2s1_pipeline_*.jsonl, r2s2_*): two chain groups and four steps per graph
+  e.groups = d.nchains >= 16 ? 2 : 1;
+  e.depth = 4;
   e.pair_smem = pair_smem_bytes(d);
   e.chain_smem = chain_smem_bytes(d);
   e.accept_smem = accept_smem_bytes(d);
@@ -513,15 +522,17 @@ int ima2p_engine_finalize(ima2p_engine *h) {
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_eval_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem_bytes(4000))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)accept_t_smem_bytes(d))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(changeu_smem(&e) * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
   if (e.fast_ok) {
     const int per = (int)(move_smem_bytes_per_pair(d) * kMoveWarps);
     const int cap = 227 * 1024;
-    if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_move<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 4 < cap ? per * 4 : cap)) ||
+    if (!IMA_CUDA_OK(cudaFuncSetAttribute(k_move<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, per < cap ? per : cap)) ||
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 2 < cap ? per * 2 : cap)) ||
+        !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 4 < cap ? per * 4 : cap)) ||
         !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 8 < cap ? per * 8 : cap)) ||
         !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 16 < cap ? per * 16 : cap)) ||
-        !IMA_CUDA_OK(cudaFuncSetAttribute(k_move<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, per * 32 < cap ? per * 32 : cap)) ||
         !IMA_CUDA_OK(cudaFuncSetAttribute(k_weigh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(weigh_smem_bytes(d) * kWarpsPerBlock))) ||
         !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(split_smem_bytes(d) * kWarpsPerBlock))) ||
         !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t_redo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))))
@@ -915,10 +926,7 @@ int ima2p_engine_run_timed(ima2p_engine *h, int nsteps, int swaptries, void *cud
         const int npairs = all.c_n * ee.d.nloci, ppw = move_ppw(&ee, npairs);
         const int gm = (npairs + ppw * kMoveWarps - 1) / (ppw * kMoveWarps);
         const size_t sm = move_smem_bytes_per_pair(ee.d) * ppw * kMoveWarps;
-        if (ppw == 4) IMA_LAUNCH(k_move<4>, gm, kMoveWarps, sm, s, all);
-        else if (ppw == 8) IMA_LAUNCH(k_move<8>, gm, kMoveWarps, sm, s, all);
-        else if (ppw == 16) IMA_LAUNCH(k_move<16>, gm, kMoveWarps, sm, s, all);
-        else IMA_LAUNCH(k_move<32>, gm, kMoveWarps, sm, s, all);
+        launch_move(ppw, gm, sm, s, all);
         mark(6);
         IMA_LAUNCH(k_weigh, pair_grid(&ee, all), kWarpsPerBlock, weigh_smem_bytes(ee.d) * kWarpsPerBlock, s, all);
         mark(7);
@@ -1088,8 +1096,8 @@ int ima2p_engine_set_pipeline(ima2p_engine *h, int groups, int depth, int decisi
 int ima2p_engine_set_proposal_path(ima2p_engine *h, int fast, int pairs_per_warp) {
   if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "set_proposal_path: not finalized");
   Engine &e = h->eng;
-  if (pairs_per_warp != 0 && pairs_per_warp != 4 && pairs_per_warp != 8 && pairs_per_warp != 16 && pairs_per_warp != 32)
-    return fail(IMA2P_E_ARG, "set_proposal_path: pairs_per_warp must be 0, 4, 8, 16 or 32");
+  if (pairs_per_warp != 0 && pairs_per_warp != 1 && pairs_per_warp != 2 && pairs_per_warp != 4 && pairs_per_warp != 8 && pairs_per_warp != 16)
+    return fail(IMA2P_E_ARG, "set_proposal_path: pairs_per_warp must be 0, 1, 2, 4, 8 or 16");
   if (fast && !e.fast_ok) return fail(IMA2P_E_UNSUPPORTED, "set_proposal_path: this data set takes the general path (stepwise loci or very large samples)");
 #if IMA_CUDA
   if (fast && pairs_per_warp && move_smem_bytes_per_pair(e.d) * pairs_per_warp * kMoveWarps > 227 * 1024)
@@ -1185,7 +1193,7 @@ int ima2p_engine_debug_split_time(ima2p_engine *h, int method, int period, const
   } else u.t_methods = method ? 2 : 1;
   const EngineView all = view_of(&e, 0, e.d.nchains, 0);
   IMA_LAUNCH(k_split_t, pair_grid(&e, all), kWarpsPerBlock, e.pair_smem * kWarpsPerBlock, s, all, u);
-  IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, chain_smem_bytes(e.d), s, all, u);
+  IMA_LAUNCH(k_accept_t, e.d.nchains, IMA_CUDA ? kTWarps : 1, accept_t_smem_bytes(e.d), s, all, u);
   if (!d2h(out, e.uv.t_out, C * 4 * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   return check_device_error(&e, s);
 }

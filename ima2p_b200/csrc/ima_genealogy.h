@@ -729,6 +729,55 @@ IMA_DEV long long dbl_bits(double x) {
 }
 IMA_DEV int pack_event(int kind, int pop, int topop, int node) { return kind | (pop << 2) | (topop << 7) | (node << 12); }
 
+#if IMA_CUDA
+// sorts the nev <= 32 E events (time bits, info) of the scratch table by (time, info) into (evt, evi): see eval_weights
+template <int E> IMA_DEV void warp_sort_events(const double *bt, const int *bi, int nev, double *evt, int *evi) {
+  const int lane = Warp::lane();
+  long long key[E];
+  int val[E];
+#pragma unroll
+  for (int q = 0; q < E; q++) {
+    const int g = q * 32 + lane;
+    key[q] = g < nev ? __double_as_longlong(bt[g]) : 0x7fffffffffffffffll;
+    val[q] = g < nev ? bi[g] : 0x7fffffff;
+  }
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int dq = j >> 5;
+#pragma unroll
+        for (int q = 0; q < E; q++) {
+          if ((q & dq) == 0) {                               // q is the lower register of the pair (q, q ^ dq)
+            const int r = q ^ dq;
+            const bool asc = (((q * 32 + lane) & k) == 0);
+            const bool gt = key[q] > key[r] || (key[q] == key[r] && val[q] > val[r]);
+            if (gt == asc) { const long long tk = key[q]; key[q] = key[r]; key[r] = tk; const int tv = val[q]; val[q] = val[r]; val[r] = tv; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < E; q++) {
+          const long long ok = __shfl_xor_sync(0xffffffffu, key[q], j);
+          const int ov = __shfl_xor_sync(0xffffffffu, val[q], j);
+          const int g = q * 32 + lane;
+          const bool asc = ((g & k) == 0), lower = ((lane & j) == 0);
+          const bool mine_gt = key[q] > ok || (key[q] == ok && val[q] > ov);
+          // the lower index of an ascending pair keeps the smaller element
+          if (mine_gt == (lower == asc)) { key[q] = ok; val[q] = ov; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < E; q++) {
+    const int g = q * 32 + lane;
+    if (g < nev) { evt[g] = __longlong_as_double(key[q]); evi[g] = val[q]; }
+  }
+}
+#endif
+
 // returns false when the event table does not fit (flagged as overflow by the caller)
 IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus &L, const double *tv, PairSm &S, int evcap = -1) {
   const int lane = Warp::lane();
@@ -774,6 +823,13 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
 #endif
     Warp::sync();
     // times are not negative, so their bit patterns order like the times: integer compares (the FP64 pipe is narrow)
+#if IMA_CUDA
+    // a bitonic network over registers: element q * 32 + lane sits in register q of the lane; partners closer than 32 are
+    // exchanged by shuffles, the others are registers of the same lane
+    if (nev <= 32) warp_sort_events<1>(bt, bi, nev, S.evt, S.evi);
+    else if (nev <= 64) warp_sort_events<2>(bt, bi, nev, S.evt, S.evi);
+    else warp_sort_events<4>(bt, bi, nev, S.evt, S.evi);
+#else
     for (int j0 = lane; j0 < nev; j0 += 2 * IMA_WARP) {            // two events of the lane share every read of the table
       const int j1 = j0 + IMA_WARP;
       const bool two = j1 < nev;
@@ -789,6 +845,7 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
       S.evt[r0] = bt[j0]; S.evi[r0] = i0;
       if (two) { S.evt[r1] = bt[j1]; S.evi[r1] = i1; }
     }
+#endif
 #if IMA_CUDA
     __threadfence_block();
 #endif

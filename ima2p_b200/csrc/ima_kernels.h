@@ -313,8 +313,8 @@ IMA_DEV void fetch_accept_record(const EngineView &E, int p, int lane, int NI, i
 
 // ---- accept sweep ---------------------------------------------------------------------------------------
 // One block per chain.  The loci of a chain must be decided in order: they are coupled through the integrated
-// prior, so locus li sees the sums left by every accepted update before it.  Three things
-// shorten that dependent chain without changing its result:
+// prior, so locus li sees the sums left by every accepted update before it.  What shortens that
+// dependent chain without changing its result:
 //   * inside a locus the nq + nm prior terms are independent: each goes to its own warp, which runs the term's
 //     series / continued fraction 32 terms per round (ima_math.h *_coop);
 //   * the next B-1 loci are evaluated SPECULATIVELY in the same round, against the same sums.  Decisions are then
@@ -324,9 +324,12 @@ IMA_DEV void fetch_accept_record(const EngineView &E, int p, int lane, int NI, i
 //     (chain, locus, step), so the outcome is identical to the one-locus-at-a-time sweep;
 //   * nothing on the per-round path touches global memory: the weight records of a whole run of loci (all of them
 //     when they fit, else chunks of accept_chunk()) are brought into shared memory by every thread of the block at
-//     once, with the uniforms drawn one locus per thread, before the rounds start.  A round is then
-//     terms -> barrier -> warp 0 decides and commits -> barrier.
-// Loci [l0, l1): the sums travel through global memory between launches.
+//     once, with the uniforms drawn one locus per thread, before the rounds start;
+//   * ONE barrier per round.  Every warp keeps its own copy of the chain's sums and prior terms; after the barrier that
+//     publishes the round's candidate terms every warp takes the round's decisions itself (the same arithmetic on the same
+//     numbers: the same outcome in every warp) and commits the accepted locus to its own copy.  No warp waits for another
+//     one's commit, and the candidate terms are double-buffered by round so the next round's terms can be written while a
+//     slower warp still reads this round's.  Warp 0 alone performs the global side effects (buffer flip, counters).
 #if IMA_CUDA
 constexpr int kSpecMax = 4;          // speculative depth B
 constexpr int kTermWarps = 5;        // warps per speculative locus (terms are strided over them)
@@ -339,20 +342,20 @@ IMA_DEV void block_sync() {}
 #define IMA_FOR_WARPS(wv, nw) for (int wv = 0; wv < (nw); wv++)      // host emulation: one thread plays every warp in turn
 #endif
 constexpr int kAcceptSmemBudget = 100 * 1024;   // two blocks per SM stay possible
+constexpr int kAcceptWarpsMax = kSpecMax * kTermWarps;
 
 struct AcceptSm {
-  int *ai; double *ad, *q;                                   // all-locus sums and current prior terms
-  double *cq;                                                // [kSpecMax][2*kMaxParams] candidate terms per speculative locus
-  int *cflag;                                                // [kSpecMax] candidate would put migration where the model forbids it
-  int *r_dI; double *r_oD, *r_nD, *r_sc; int *r_ic;          // [chunk] records
-  int *ctl;                                                  // [2]: loci consumed by the round
+  unsigned char *priv;                                       // [warps] private copies: ad[ND], q[NT], ai[NI]
+  double *cq;                                                // [2][kSpecMax][NT] candidate terms per speculative locus, by round parity
+  int *cflag;                                                // [2][kSpecMax] candidate would put migration where the model forbids it
+  int *r_dI; double *r_oD, *r_nD, *r_sc; int *r_ic;          // [chunk] records; r_ic: flags, current buffer, next locus to decide
 };
+IMA_HD size_t accept_priv_bytes(const EngineDims &d) { return align8(sizeof(double) * d.ND) + align8(sizeof(double) * d.NT) + align8(sizeof(int) * d.NI); }
 IMA_HD size_t accept_fixed_bytes(const EngineDims &d) {
-  return align8(sizeof(int) * d.NI) + align8(sizeof(double) * d.ND) + align8(sizeof(double) * 2 * kMaxParams) +
-         align8(sizeof(double) * kSpecMax * 2 * kMaxParams) + align8(sizeof(int) * kSpecMax) + 16;
+  return kAcceptWarpsMax * accept_priv_bytes(d) + align8(sizeof(double) * 2 * kSpecMax * d.NT) + align8(sizeof(int) * 2 * kSpecMax);
 }
 IMA_HD size_t accept_record_bytes(const EngineDims &d) {
-  return align8(sizeof(int) * d.NI) + 2 * align8(sizeof(double) * d.ND) + 4 * 8 + 8;
+  return align8(sizeof(int) * d.NI) + 2 * align8(sizeof(double) * d.ND) + 4 * 8 + 16;
 }
 // loci whose records are resident at a time
 IMA_HD int accept_chunk(const EngineDims &d) {
@@ -364,17 +367,14 @@ IMA_HD int accept_chunk(const EngineDims &d) {
 IMA_HD size_t accept_smem_bytes(const EngineDims &d) { return accept_fixed_bytes(d) + (size_t)accept_chunk(d) * accept_record_bytes(d); }
 IMA_DEV AcceptSm carve_accept_smem(unsigned char *base, const EngineDims &d, int K) {
   AcceptSm s; unsigned char *p = base;
-  s.ad = (double *)p; p += align8(sizeof(double) * d.ND);
-  s.q = (double *)p; p += align8(sizeof(double) * 2 * kMaxParams);
-  s.cq = (double *)p; p += align8(sizeof(double) * kSpecMax * 2 * kMaxParams);
+  s.priv = p; p += kAcceptWarpsMax * accept_priv_bytes(d);
+  s.cq = (double *)p; p += align8(sizeof(double) * 2 * kSpecMax * d.NT);
   s.r_oD = (double *)p; p += (size_t)K * align8(sizeof(double) * d.ND);
   s.r_nD = (double *)p; p += (size_t)K * align8(sizeof(double) * d.ND);
   s.r_sc = (double *)p; p += (size_t)K * 4 * 8;              // oldpdg, newpdg, extra, uniform
-  s.ai = (int *)p; p += align8(sizeof(int) * d.NI);
   s.r_dI = (int *)p; p += (size_t)K * align8(sizeof(int) * d.NI);
-  s.r_ic = (int *)p; p += (size_t)K * 8;                     // flags, cb
-  s.cflag = (int *)p; p += align8(sizeof(int) * kSpecMax);
-  s.ctl = (int *)p;
+  s.r_ic = (int *)p; p += (size_t)K * 16;                    // flags, cb, next undecided-and-decidable slot, unused
+  s.cflag = (int *)p;
   return s;
 }
 
@@ -393,22 +393,27 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E) {
   const int l0 = 0, l1 = E.d.nloci;
   const DevModel &M = IMA_MODEL;
   const int NW = B * kTermWarps;                                     // warps in the block
-  const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, ncc = M.ncc;
+  const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, NT = E.d.NT, ncc = M.ncc;
   const int sI = (int)(align8(sizeof(int) * NI) / sizeof(int)), sD = (int)(align8(sizeof(double) * ND) / sizeof(double));
   const int K = accept_chunk(E.d);
   AcceptSm S = carve_accept_smem(IMA_SMEM, E.d, K);
-  const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
+  const int nq = M.nq, nmt = M.nomigration ? 0 : M.nm, nterms = nq + nmt;
+  // every warp's own copy of the chain's sums and prior terms (term t of the size parameters at [t], of the migration
+  // parameters at [nq + t])
+  const size_t pb = accept_priv_bytes(E.d);
   IMA_FOR_WARPS(w, NW) {
-    const int tid = w * IMA_WARP + lane, nth = NW * IMA_WARP;
-    for (int i = tid; i < NI; i += nth) S.ai[i] = E.all_i[(size_t)c * NI + i];
-    for (int i = tid; i < ND; i += nth) S.ad[i] = E.all_d[(size_t)c * ND + i];
-    for (int i = tid; i < M.nq; i += nth) S.q[i] = E.qint[(size_t)c * kMaxParams + i];
-    for (int i = tid; i < M.nm; i += nth) S.q[kMaxParams + i] = E.mint[(size_t)c * kMaxParams + i];
+    double *ad = (double *)(S.priv + (size_t)w * pb), *q = ad + sD;
+    int *ai = (int *)(q + (align8(sizeof(double) * NT) / sizeof(double)));
+    for (int i = lane; i < NI; i += IMA_WARP) ai[i] = E.all_i[(size_t)c * NI + i];
+    for (int i = lane; i < ND; i += IMA_WARP) ad[i] = E.all_d[(size_t)c * ND + i];
+    for (int i = lane; i < nq; i += IMA_WARP) q[i] = E.qint[(size_t)c * kMaxParams + i];
+    for (int i = lane; i < nmt; i += IMA_WARP) q[nq + i] = E.mint[(size_t)c * kMaxParams + i];
   }
   const double beta = E.beta[c];
-  double probg = E.probg[c], pdgsum = E.pdgsum[c];                    // kept by warp 0
-  unsigned long long dropped = 0;
+  double probg = E.probg[c], pdgsum = E.pdgsum[c];                    // kept by every warp
+  unsigned long long ndropped = 0;                                   // proposals that arrived flagged as dropped (per thread)
   constexpr uint32_t kNoGo = kFlagRejectIS | kFlagOverflow | kFlagBadTree;
+  int round = 0;
 #if defined(IMA_PROF) && IMA_CUDA
   auto pclk_ = []() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; };
   long long pf_[6] = {0, 0, 0, 0, 0, 0}, pt_ = pclk_(), pt0_ = pt_; int prounds_ = 0;
@@ -426,11 +431,14 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E) {
         const int p = c * E.d.nloci + l, slot = l - ch0;
         const int cb = E.cur[p];
         const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
-        S.r_ic[slot * 2 + 0] = (int)E.prop_flags[p]; S.r_ic[slot * 2 + 1] = cb;
+        const uint32_t fl = E.prop_flags[p];
+        S.r_ic[slot * 4 + 0] = (int)fl; S.r_ic[slot * 4 + 1] = cb; S.r_ic[slot * 4 + 3] = 0;
+        if (fl & kFlagOverflow) ndropped++;
         S.r_sc[slot * 4 + 0] = O.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 4 + 1] = N.sd[(size_t)p * 4 + 3]; S.r_sc[slot * 4 + 2] = E.prop_extra[p];
         Philox rng;
         rng_for(rng, E, (uint32_t)((E.d.chain0 + c) * E.d.nloci + l), kRngAccept);
-        S.r_sc[slot * 4 + 3] = rng.uniform();
+        // U < min(1, e^x) is taken as log U < min(0, x): the logarithm is off the chain of decisions, the exponential was on it
+        S.r_sc[slot * 4 + 3] = log(rng.uniform());
       }
       const int nl = ch1 - ch0, per = NI + 2 * ND;
       for (int k = tid; k < nl * per; k += nth) {
@@ -444,21 +452,47 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E) {
       }
     }
     block_sync();
+    // A proposal that arrives flagged (the data rule it out, or it was dropped) is rejected whatever the prior says: such
+    // loci are passed over without spending a speculative slot on them.  r_ic[slot][2] = the first slot >= slot that needs a
+    // decision (the chunk's length when there is none).
+    IMA_FOR_WARPS(w, NW) {
+      const int tid = w * IMA_WARP + lane, nth = NW * IMA_WARP, nl = ch1 - ch0;
+      for (int sl = tid; sl < nl; sl += nth) {
+        int k = sl;
+        while (k < nl && ((uint32_t)S.r_ic[k * 4] & kNoGo)) k++;
+        S.r_ic[sl * 4 + 2] = k;
+      }
+    }
+    block_sync();
+    if (ndropped) {                                                  // every locus is consumed exactly once: counted where it is loaded
+#if IMA_CUDA
+      atomicAdd(E.overflow, ndropped);
+#else
+      *E.overflow += ndropped;
+#endif
+      ndropped = 0;
+    }
     IMA_PF(3)
     for (int li = ch0; li < ch1;) {
-      // A proposal that arrives flagged (the data rule it out, or it was dropped) is rejected whatever the prior says: such
-      // loci are passed over without spending a speculative slot on them.  cand[g] = offset from li of the g-th locus that
-      // needs a decision, span = loci consumed when none of them is accepted.
+      // cand[g] = offset from li of the g-th locus that needs a decision, span = loci consumed when none of them is accepted
       int cand[B], nb = 0;
       const int visible = ch1 - li;
-      int k = 0;
-      for (; k < visible && nb < B; k++)
-        if (!((uint32_t)S.r_ic[(li - ch0 + k) * 2] & kNoGo)) cand[nb++] = k;
-      for (int g = nb; g < B; g++) cand[g] = 0;
-      const int span = k;                    // nb == B: up to and including the last candidate; else everything left in the chunk
+      {
+        int sl = li - ch0;
+        for (int g = 0; g < B; g++) {
+          const int k = sl < ch1 - ch0 ? S.r_ic[sl * 4 + 2] : ch1 - ch0;
+          if (k < ch1 - ch0) { cand[nb++] = k - (li - ch0); sl = k + 1; } else sl = ch1 - ch0;
+        }
+        for (int g = nb; g < B; g++) cand[g] = 0;
+      }
+      const int span = nb == B ? cand[B - 1] + 1 : visible;   // nb == B: up to and including the last candidate; else everything left in the chunk
+      double *cq = S.cq + (size_t)(round & 1) * kSpecMax * NT;
+      int *cflag = S.cflag + (round & 1) * kSpecMax;
       // ---- phase 1: term t of speculative candidate g on warp g*kTermWarps + (t % kTermWarps) ------------------
       IMA_FOR_WARPS(w, NW) {
         const int g = w / kTermWarps, t0 = w - g * kTermWarps;
+        const double *ad = (const double *)(S.priv + (size_t)w * pb), *q = ad + sD;
+        const int *ai = (const int *)(q + (align8(sizeof(double) * NT) / sizeof(double)));
         if (g < nb) {
           const int slot = li - ch0 + cand[g];
           const int *dI = S.r_dI + slot * sI;
@@ -467,158 +501,168 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E) {
             int bad = 0;
             if (M.nomigration == 0)
               for (int i = 0; i < M.nomig_n; i++)
-                if (S.ai[ncc + M.nomig_idx[i]] + dI[ncc + M.nomig_idx[i]] != 0) bad = 1;
-            S.cflag[g] = bad;
+                if (ai[ncc + M.nomig_idx[i]] + dI[ncc + M.nomig_idx[i]] != 0) bad = 1;
+            cflag[g] = bad;
           }
           // candidate sums = sum_subtract_treeinfo (ginfo.cpp:248-285) on the entries this term reads: subtract old, add
           // new, clamp fc and fm at 0; then integrate_tree_prob's reuse rule (:1997-2000, :2031-2034) or the integral
           for (int t = t0; t < nterms; t += kTermWarps) {
             double v;
-            if (t < M.nq) {
+            if (t < nq) {
               int cn = 0, co = 0; double fn = 0.0, fo = 0.0, hn = 0.0;
               for (int j = 0; j < M.q_n[t]; j++) {
                 const int x = M.q_idx[t][j];
-                co += S.ai[x]; cn += S.ai[x] + dI[x];
-                fo += S.ad[x];
-                double f = S.ad[x]; f -= oD[x]; f += nD[x]; if (0.0 > f) f = 0.0;
+                co += ai[x]; cn += ai[x] + dI[x];
+                fo += ad[x];
+                double f = ad[x]; f -= oD[x]; f += nD[x]; if (0.0 > f) f = 0.0;
                 fn += f;
-                double hh = S.ad[ncc + x]; hh -= oD[ncc + x]; hh += nD[ncc + x];
+                double hh = ad[ncc + x]; hh -= oD[ncc + x]; hh += nD[ncc + x];
                 hn += hh;
               }
-              v = (cn == co && fn == fo) ? S.q[t] : integrate_coalescent_term_coop(E.mc, cn, fn, hn, M.q_max[t], M.q_min[t]);
-              if (lane == 0) S.cq[g * 2 * kMaxParams + t] = v;
+              v = (cn == co && fn == fo) ? q[t] : integrate_coalescent_term_coop(E.mc, cn, fn, hn, M.q_max[t], M.q_min[t]);
             } else {
-              const int tm = t - M.nq;
+              const int tm = t - nq;
               int cn = 0, co = 0; double fn = 0.0, fo = 0.0;
               for (int j = 0; j < M.m_n[tm]; j++) {
                 const int x = M.m_idx[tm][j];
-                co += S.ai[ncc + x]; cn += S.ai[ncc + x] + dI[ncc + x];
-                fo += S.ad[2 * ncc + x];
-                double f = S.ad[2 * ncc + x]; f -= oD[2 * ncc + x]; f += nD[2 * ncc + x]; if (0.0 > f) f = 0.0;
+                co += ai[ncc + x]; cn += ai[ncc + x] + dI[ncc + x];
+                fo += ad[2 * ncc + x];
+                double f = ad[2 * ncc + x]; f -= oD[2 * ncc + x]; f += nD[2 * ncc + x]; if (0.0 > f) f = 0.0;
                 fn += f;
               }
-              v = (cn == co && fn == fo) ? S.q[kMaxParams + tm]
+              v = (cn == co && fn == fo) ? q[t]
                   : (M.expoprior ? integrate_migration_term_expo(E.mc, cn, fn, M.m_mean[tm])
                                  : integrate_migration_term_coop(E.mc, cn, fn, M.m_max[tm], M.m_min[tm]));
-              if (lane == 0) S.cq[g * 2 * kMaxParams + kMaxParams + tm] = v;
             }
+            if (lane == 0) cq[g * NT + t] = v;
           }
         }
       }
       IMA_PF(0)
       block_sync();
       IMA_PF(1)
-      // ---- phase 2: warp 0 decides in locus order (update_gtree.cpp:917-927) and commits the accepted locus ------
+      // ---- phase 2: every warp decides in locus order (update_gtree.cpp:917-927) and commits the accepted locus to its copy
+      int accepted = -1;
+      double np = 0.0;
       IMA_FOR_WARPS(w, NW) {
-        if (w == 0) {
-          int accepted = -1;
-          double np = 0.0;
 #if IMA_CUDA
-          {
-            // lane g evaluates the MH ratio of speculative candidate g (all against the same sums); the first accepting
-            // lane in locus order wins
-            bool acc = false;
-            double newprobg = 0.0;
-            if (lane < nb) {
-              const int g = lane, slot = li - ch0 + cand[lane];
-              for (int t = 0; t < M.nq; t++) newprobg += S.cq[g * 2 * kMaxParams + t];
-              if (!M.nomigration) for (int t = 0; t < M.nm; t++) newprobg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
-              if (S.cflag[g]) newprobg = -kMyDblMax;
-              const double tpw = newprobg - probg, dpdg = S.r_sc[slot * 4 + 1] - S.r_sc[slot * 4 + 0], extra = S.r_sc[slot * 4 + 2];
-              double mh;
-              if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
-              else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
-              acc = S.r_sc[slot * 4 + 3] < fmin(1.0, mh);
-            }
-            accepted = Warp::first(acc);
-            np = Warp::bcast(newprobg, accepted < 0 ? 0 : accepted);
-            IMA_PF(4)
-          }
-#else
-          for (int g = 0; g < nb && accepted < 0; g++) {       // one lane: walk the speculative loci in order
-            const int slot = li - ch0 + cand[g];
-            double npg = 0.0;
-            for (int t = 0; t < M.nq; t++) npg += S.cq[g * 2 * kMaxParams + t];
-            if (!M.nomigration) for (int t = 0; t < M.nm; t++) npg += S.cq[g * 2 * kMaxParams + kMaxParams + t];
-            if (S.cflag[g]) npg = -kMyDblMax;
-            const double tpw = npg - probg, dpdg = S.r_sc[slot * 4 + 1] - S.r_sc[slot * 4 + 0], extra = S.r_sc[slot * 4 + 2];
+        {
+          // lane g evaluates the MH ratio of speculative candidate g (all against the same sums); the first accepting
+          // lane in locus order wins
+          bool acc = false;
+          double newprobg = 0.0;
+          if (lane < nb) {
+            const int g = lane, slot = li - ch0 + cand[lane];
+            for (int t = 0; t < nterms; t++) newprobg += cq[g * NT + t];
+            if (cflag[g]) newprobg = -kMyDblMax;
+            const double tpw = newprobg - probg, dpdg = S.r_sc[slot * 4 + 1] - S.r_sc[slot * 4 + 0], extra = S.r_sc[slot * 4 + 2];
             double mh;
-            if (M.thermo) mh = exp(beta * M.gbeta * dpdg + tpw + extra);
-            else mh = exp(beta * (tpw + M.gbeta * dpdg) + extra);
-            if (S.r_sc[slot * 4 + 3] < fmin(1.0, mh)) { accepted = g; np = npg; }
+            if (M.thermo) mh = beta * M.gbeta * dpdg + tpw + extra;
+            else mh = beta * (tpw + M.gbeta * dpdg) + extra;
+            acc = S.r_sc[slot * 4 + 3] < fmin(0.0, mh);
           }
-#endif
-          const int aoff = accepted < 0 ? 0 : cand[accepted];
-          const int adv = accepted < 0 ? span : aoff + 1;
-          if (lane == 0) S.ctl[0] = adv;
-          for (int g = 0; g < adv; g++) if ((uint32_t)S.r_ic[(li - ch0 + g) * 2] & kFlagOverflow) dropped++;
-          if (accepted >= 0) {
-            const int slot = li - ch0 + aoff;
-            const int *dI = S.r_dI + slot * sI;
-            const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
-            for (int i = lane; i < NI; i += IMA_WARP) S.ai[i] += dI[i];
-            for (int i = lane; i < ND; i += IMA_WARP) {
-              double x = S.ad[i];
-              x -= oD[i];
-              x += nD[i];
-              if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
-              S.ad[i] = x;
-            }
-            for (int i = lane; i < M.nq; i += IMA_WARP) S.q[i] = S.cq[accepted * 2 * kMaxParams + i];
-            for (int i = lane; i < M.nm; i += IMA_WARP) S.q[kMaxParams + i] = S.cq[accepted * 2 * kMaxParams + kMaxParams + i];
-            if (lane == 0) {
-              const int p = c * E.d.nloci + li + aoff;
-              const uint32_t flags = (uint32_t)S.r_ic[slot * 2];
-              E.cur[p] = (unsigned char)(S.r_ic[slot * 2 + 1] ^ 1);
-#if IMA_CUDA
-              atomicAdd(&E.acc[(size_t)p * 3 + 0], 1u);                 // fire and forget: nothing waits for the old value
-              if (flags & kFlagTopol) atomicAdd(&E.acc[(size_t)p * 3 + 1], 1u);
-              if (flags & kFlagTmrca) atomicAdd(&E.acc[(size_t)p * 3 + 2], 1u);
-              if (beta == 1.0) {
-                unsigned int *ca = E.cold_acc + (size_t)(li + aoff) * 3;
-                atomicAdd(ca, 1u);
-                if (flags & kFlagTopol) atomicAdd(ca + 1, 1u);
-                if (flags & kFlagTmrca) atomicAdd(ca + 2, 1u);
-              }
+          accepted = Warp::first(acc);
+          np = Warp::bcast(newprobg, accepted < 0 ? 0 : accepted);
+        }
 #else
-              E.acc[(size_t)p * 3 + 0]++;
-              if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
-              if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
-              if (beta == 1.0) {
-                unsigned int *ca = E.cold_acc + (size_t)(li + aoff) * 3;
-                ca[0]++;
-                if (flags & kFlagTopol) ca[1]++;
-                if (flags & kFlagTmrca) ca[2]++;
-              }
+        accepted = -1;
+        for (int g = 0; g < nb && accepted < 0; g++) {       // one lane: walk the speculative loci in order
+          const int slot = li - ch0 + cand[g];
+          double npg = 0.0;
+          for (int t = 0; t < nterms; t++) npg += cq[g * NT + t];
+          if (cflag[g]) npg = -kMyDblMax;
+          const double tpw = npg - probg, dpdg = S.r_sc[slot * 4 + 1] - S.r_sc[slot * 4 + 0], extra = S.r_sc[slot * 4 + 2];
+          double mh;
+          if (M.thermo) mh = beta * M.gbeta * dpdg + tpw + extra;
+          else mh = beta * (tpw + M.gbeta * dpdg) + extra;
+          if (S.r_sc[slot * 4 + 3] < fmin(0.0, mh)) { accepted = g; np = npg; }
+        }
 #endif
-            }
-            probg = np;
-            pdgsum -= S.r_sc[slot * 4 + 0];
-            pdgsum += S.r_sc[slot * 4 + 1];
+        if (accepted >= 0) {
+          const int slot = li - ch0 + cand[accepted];
+          const int *dI = S.r_dI + slot * sI;
+          const double *oD = S.r_oD + slot * sD, *nD = S.r_nD + slot * sD;
+          double *ad = (double *)(S.priv + (size_t)w * pb), *q = ad + sD;
+          int *ai = (int *)(q + (align8(sizeof(double) * NT) / sizeof(double)));
+          for (int i = lane; i < NI; i += IMA_WARP) ai[i] += dI[i];
+          for (int i = lane; i < ND; i += IMA_WARP) {
+            double x = ad[i];
+            x -= oD[i];
+            x += nD[i];
+            if ((i < ncc || i >= 2 * ncc) && 0.0 > x) x = 0.0;
+            ad[i] = x;
           }
+          for (int i = lane; i < nterms; i += IMA_WARP) q[i] = cq[accepted * NT + i];
+#if IMA_CUDA
+          __syncwarp();
+#endif
+          if (w == 0 && lane == 0) S.r_ic[slot * 4 + 3] = 1;          // accepted: the global side effects follow the chunk's rounds
         }
       }
+      // what every warp keeps in registers (after the loop: the host emulation plays all warps with one set of variables)
+      const int aoff = accepted < 0 ? 0 : cand[accepted];
+      const int adv = accepted < 0 ? span : aoff + 1;
+      if (accepted >= 0) {
+        const int slot = li - ch0 + aoff;
+        probg = np;
+        pdgsum -= S.r_sc[slot * 4 + 0];
+        pdgsum += S.r_sc[slot * 4 + 1];
+      }
       IMA_PF(2)
-      block_sync();
-      IMA_PF(3)
-      li += S.ctl[0];
+      li += adv;
+      round++;
 #if defined(IMA_PROF) && IMA_CUDA
       prounds_++;
 #endif
     }
+    // the chunk's accepted loci: flip their buffers, count them (the whole block, off the chain of decisions)
+    block_sync();
+    IMA_FOR_WARPS(w, NW) {
+      const int tid = w * IMA_WARP + lane, nth = NW * IMA_WARP;
+      for (int sl = tid; sl < ch1 - ch0; sl += nth) {
+        if (!S.r_ic[sl * 4 + 3]) continue;
+        const int p = c * E.d.nloci + ch0 + sl;
+        const uint32_t flags = (uint32_t)S.r_ic[sl * 4];
+        E.cur[p] = (unsigned char)(S.r_ic[sl * 4 + 1] ^ 1);
+#if IMA_CUDA
+        atomicAdd(&E.acc[(size_t)p * 3 + 0], 1u);
+        if (flags & kFlagTopol) atomicAdd(&E.acc[(size_t)p * 3 + 1], 1u);
+        if (flags & kFlagTmrca) atomicAdd(&E.acc[(size_t)p * 3 + 2], 1u);
+        if (beta == 1.0) {
+          unsigned int *ca = E.cold_acc + (size_t)(ch0 + sl) * 3;
+          atomicAdd(ca, 1u);
+          if (flags & kFlagTopol) atomicAdd(ca + 1, 1u);
+          if (flags & kFlagTmrca) atomicAdd(ca + 2, 1u);
+        }
+#else
+        E.acc[(size_t)p * 3 + 0]++;
+        if (flags & kFlagTopol) E.acc[(size_t)p * 3 + 1]++;
+        if (flags & kFlagTmrca) E.acc[(size_t)p * 3 + 2]++;
+        if (beta == 1.0) {
+          unsigned int *ca = E.cold_acc + (size_t)(ch0 + sl) * 3;
+          ca[0]++;
+          if (flags & kFlagTopol) ca[1]++;
+          if (flags & kFlagTmrca) ca[2]++;
+        }
+#endif
+      }
+    }
   }
 #if defined(IMA_PROF) && IMA_CUDA
-  if ((c == 0 || c == 77) && lane == 0)
-    printf("PROFA chain %d warp %d rounds %d phase1 %lld wait1 %lld decide %lld commit %lld wait2 %lld total %lld\n", c, ima_warp_in_block(), prounds_, pf_[0], pf_[1],
-           pf_[4], pf_[2], pf_[3], pclk_() - pt0_);
+  if (c == 3 && lane == 0)
+    printf("PROFA chain %d warp %d rounds %d terms %lld barrier %lld decide+commit %lld load %lld total %lld\n", c, ima_warp_in_block(), prounds_, pf_[0], pf_[1],
+           pf_[2], pf_[3], pclk_() - pt0_);
 #endif
-  // warp 0 wrote the sums last and holds probg / pdgsum: it writes the chain's state back
+  block_sync();                                                      // the flips above are read by chain_swapsum below
+  // warp 0 writes the chain's state back from its copy
   IMA_FOR_WARPS(w, NW) {
     if (w == 0) {
-      for (int i = lane; i < NI; i += IMA_WARP) E.all_i[(size_t)c * NI + i] = S.ai[i];
-      for (int i = lane; i < ND; i += IMA_WARP) E.all_d[(size_t)c * ND + i] = S.ad[i];
-      for (int i = lane; i < M.nq; i += IMA_WARP) E.qint[(size_t)c * kMaxParams + i] = S.q[i];
-      for (int i = lane; i < M.nm; i += IMA_WARP) E.mint[(size_t)c * kMaxParams + i] = S.q[kMaxParams + i];
+      const double *ad = (const double *)(S.priv), *q = ad + sD;
+      const int *ai = (const int *)(q + (align8(sizeof(double) * NT) / sizeof(double)));
+      for (int i = lane; i < NI; i += IMA_WARP) E.all_i[(size_t)c * NI + i] = ai[i];
+      for (int i = lane; i < ND; i += IMA_WARP) E.all_d[(size_t)c * ND + i] = ad[i];
+      for (int i = lane; i < nq; i += IMA_WARP) E.qint[(size_t)c * kMaxParams + i] = q[i];
+      for (int i = lane; i < nmt; i += IMA_WARP) E.mint[(size_t)c * kMaxParams + i] = q[nq + i];
 #if IMA_CUDA
       __threadfence_block();
       __syncwarp();
@@ -627,13 +671,6 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E) {
       if (lane == 0) {
         E.probg[c] = probg; E.pdgsum[c] = pdgsum;
         if (l1 == E.d.nloci) E.swapsum[c] = ssum;
-        if (dropped) {
-#if IMA_CUDA
-          atomicAdd(E.overflow, dropped);
-#else
-          *E.overflow += dropped;
-#endif
-        }
       }
     }
   }

@@ -383,6 +383,70 @@ IMA_DEV double lower_of(const GammaCore &g, double x) {
   return p;
 }
 
+// Several independent logarithms / exponentials in the time of one: lane k evaluates the k-th argument, the results are
+// broadcast.  (The value of log(x) does not depend on the lane that computes it, so nothing changes numerically.)
+IMA_DEV void log3_coop(double a, double b, double c, double &la, double &lb, double &lc) {
+#if IMA_CUDA
+  const int lane = Warp::lane();
+  const double r = log(lane == 1 ? b : (lane == 2 ? c : a));
+  la = Warp::bcast(r, 0); lb = Warp::bcast(r, 1); lc = Warp::bcast(r, 2);
+#else
+  la = log(a); lb = log(b); lc = log(c);
+#endif
+}
+IMA_DEV void log2_coop(double a, double b, double &la, double &lb) {
+#if IMA_CUDA
+  const double r = log(Warp::lane() == 1 ? b : a);
+  la = Warp::bcast(r, 0); lb = Warp::bcast(r, 1);
+#else
+  la = log(a); lb = log(b);
+#endif
+}
+IMA_DEV void exp2_coop(double a, double b, double &ea, double &eb) {
+#if IMA_CUDA
+  const double r = exp(Warp::lane() == 1 ? b : a);
+  ea = Warp::bcast(r, 0); eb = Warp::bcast(r, 1);
+#else
+  ea = exp(a); eb = exp(b);
+#endif
+}
+
+// The incomplete gamma of the integrated prior with the reference's fallback to the complementary function
+// (update_gtree_common.cpp:128-141 for the upper one of a coalescent term, :222-237 for the lower one of a migration term), a >= 1,
+// x > 0, and log(extra) on the side.  Same series / continued fraction, same arithmetic per value as upper_of / lower_of /
+// logdiff; the dependent chain is three transcendental evaluations long instead of seven: {log x, log v, log extra}, then
+// {exp t, exp(full - direct)}, then {log(1 - v exp t), log(exp(full - direct) - 1)}, where `direct` is whichever of the two
+// functions needs no exponential (the lower one from the series, the upper one from the continued fraction) -- the second
+// member of each pair is what the fallback needs, computed whether or not the fallback is taken.
+IMA_DEV double gamma_with_fallback_coop(const MathCtx &mc, int a, double x, bool want_upper, double tol, double extra, double &lextra) {
+  const double gln = lfact(mc, a - 1);
+  const bool series = x < a + 1.0;
+  const double v = series ? gamma_series_coop(mc, a, x) : gamma_cf_coop(mc, (double)a, x);
+  double lx, lv;
+  log3_coop(x, v, extra, lx, lv, lextra);
+  const double t = -x + a * lx - gln;
+  double direct = gln + (lv + t);                         // lower (series) / upper (continued fraction)
+  if (direct < -1e200) direct = -1e200;
+  const double fullg = gln;
+  double e1, e2, l1, l2;
+  exp2_coop(t, fullg - direct, e1, e2);
+  log2_coop(1.0 - v * e1, e2 - 1.0, l1, l2);
+  double indirect = gln + l1;                             // upper (series) / lower (continued fraction)
+  if (indirect < -1e200) indirect = -1e200;
+  const bool primary_is_indirect = (want_upper == series);
+  double p = primary_is_indirect ? indirect : direct;
+  if (fullg - p < 1e-15 || fullg - p > kLogDblMax) {
+    const double other = primary_is_indirect ? direct : indirect;
+    if (fullg > other) {
+      double alt;
+      if (primary_is_indirect) alt = (fullg - other < kLogDblMax) ? other + l2 : fullg;     // LogDiff(fullg, other) from the pieces at hand
+      else logdiff(mc, alt, fullg, other);
+      if (fabs(alt - p) > tol) p = alt;
+    }
+  }
+  return p;
+}
+
 // integrate_coalescent_term / integrate_migration_term with the cooperative gamma functions
 IMA_DEV double integrate_coalescent_term_coop(const MathCtx &mc, int cc, double fc, double hcc, double max, double min) {
   double p, a, b, c, d;
@@ -390,7 +454,11 @@ IMA_DEV double integrate_coalescent_term_coop(const MathCtx &mc, int cc, double 
     if (min == 0) {
       const double x = 2 * fc / max;
       double ug;
-      if (cc > 1 && x >= 0.0) {
+      if (cc > 1 && x > 0.0) {
+        double lfc;
+        ug = gamma_with_fallback_coop(mc, cc - 1, x, true, 1e-10, fc, lfc);
+        return ug + kLog2 - hcc + (1 - cc) * lfc;
+      } else if (cc > 1 && x >= 0.0) {
         const GammaCore g = gamma_core_coop(mc, cc - 1, x);
         ug = upper_of(g, x);
         const double fullg = g.gln;                        // lfact(cc - 2)
@@ -439,6 +507,11 @@ IMA_DEV double integrate_migration_term_coop(const MathCtx &mc, int cm, double f
     if (min == 0) {
       const double x = fm * max;
       if (x < 0.0) { raise(mc, kErrGamma); return 0.0; }
+      if (x > 0.0) {
+        double lfm;
+        const double lgf = gamma_with_fallback_coop(mc, cm + 1, x, false, 1e-12, fm, lfm);
+        return (-1 - cm) * lfm + lgf;
+      }
       const GammaCore g = gamma_core_coop(mc, cm + 1, x);
       double lg = lower_of(g, x);
       const double fullg = g.gln;                          // lfact(cm)

@@ -72,6 +72,7 @@ struct EngineDims {
   int nchains_global;   // chains over all ranks
   int chain0;           // global index of local chain 0
   int nloci, P;
+  int NT;               // prior terms: size parameters + migration parameters
   int NL, CAP, NI, ND, EVP, W, S, W64;     // maxima over loci: numlines, pool capacity, record sizes, event slots, mask words, sites
   int FP, FC, FEV, FS;  // the small tables of the two-kernel proposal path (ima_fastpath.h): pool entries per pair in k_move,
                         // migration events per genealogy and event slots in k_weigh, scratch entries of the fast split-time kernel;

@@ -428,6 +428,14 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_split_t_redo(EngineView E, UpdateView U) {
 }
 
 constexpr int kTWarps = 8;            // warps of a k_accept_t block (one block per chain)
+constexpr int kAcceptTStageBudget = 96 * 1024;
+// staging of the chain's proposed weight records and per-locus scalars: [nloci] other-buffer index, [ND][nloci] doubles,
+// [NI][nloci] ints, [nloci] new pdg, [nloci] migration term, [nloci][4] counts, [nloci] flags
+IMA_HD size_t accept_t_stage_bytes(const EngineDims &d) {
+  return align8((size_t)d.nloci * 4) + (size_t)d.nloci * (8 * (size_t)d.ND + 4 * (size_t)d.NI + 8 + 8 + 16 + 4) + 64;
+}
+IMA_HD bool accept_t_staged(const EngineDims &d) { return accept_t_stage_bytes(d) <= (size_t)kAcceptTStageBudget; }
+IMA_HD size_t accept_t_smem_bytes(const EngineDims &d) { return chain_smem_bytes(d) + (accept_t_staged(d) ? accept_t_stage_bytes(d) : 0); }
 
 IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   IMA_SMEM_DECL
@@ -438,18 +446,55 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   ChainSm S = carve_chain_smem(IMA_SMEM, E.d);
   const TProposal t = t_proposal(E, U, M, c);
   const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
+  // When the chain's records fit, everything this kernel reads from global memory is brought into shared memory in two
+  // trips (which buffer every locus proposes into; then every weight and scalar, all loads independent of each other).
+  const bool staged = accept_t_staged(E.d);
+  unsigned char *sp = IMA_SMEM + chain_smem_bytes(E.d);
+  int *s_ob = (int *)sp; sp += align8((size_t)nloci * 4);
+  double *s_wd = (double *)sp; sp += (size_t)nloci * 8 * ND;
+  double *s_pdg = (double *)sp; sp += (size_t)nloci * 8;
+  double *s_mw = (double *)sp; sp += (size_t)nloci * 8;
+  int *s_wi = (int *)sp; sp += (size_t)nloci * 4 * NI;
+  int *s_cnt = (int *)sp; sp += (size_t)nloci * 16;
+  int *s_fl = (int *)sp;
+  if (staged) {
+    IMA_FOR_WARPS(w, kTWarps) {
+      const int tid = w * IMA_WARP + lane, nth = kTWarps * IMA_WARP;
+      for (int li = tid; li < nloci; li += nth) s_ob[li] = E.cur[c * nloci + li] ^ 1;
+    }
+    block_sync();
+    IMA_FOR_WARPS(w, kTWarps) {
+      const int tid = w * IMA_WARP + lane, nth = kTWarps * IMA_WARP, per = NI + ND + 1;
+      for (int k = tid; k < nloci * per; k += nth) {
+        const int li = k / per, i = k - li * per, p = c * nloci + li;
+        const PairBuf &N = E.buf[s_ob[li]];
+        if (i < NI) s_wi[i * nloci + li] = N.gwi[(size_t)p * NI + i];
+        else if (i < NI + ND) s_wd[(i - NI) * nloci + li] = N.gwd[(size_t)p * ND + i - NI];
+        else {
+          s_pdg[li] = N.sd[(size_t)p * 4 + 3];
+          s_mw[li] = E.prop_extra[p];
+          const int *o = U.t_counts + (size_t)p * 4;
+          s_cnt[li * 4] = o[0]; s_cnt[li * 4 + 1] = o[1]; s_cnt[li * 4 + 2] = o[2]; s_cnt[li * 4 + 3] = o[3];
+          s_fl[li] = (int)(E.prop_flags[p] & (kFlagOverflow | kFlagRejectIS | kFlagBadTree));
+        }
+      }
+    }
+    block_sync();
+  }
   // setzero + sum_treeinfo over the loci (:256, 331), from the proposed (other) buffers: warps take weights, lanes take
   // loci, one warp reduction per weight (the loads of one weight do not wait for each other)
   IMA_FOR_WARPS(w, kTWarps) {
     for (int i = w; i < NI + ND; i += kTWarps) {
       if (i < NI) {
         int a = 0;
-        for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwi[(size_t)p * NI + i]; }
+        if (staged) for (int li = lane; li < nloci; li += IMA_WARP) a += s_wi[i * nloci + li];
+        else for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwi[(size_t)p * NI + i]; }
         a = Warp::sum(a);
         if (lane == 0) S.ai[i] = a;
       } else {
         double a = 0.0;
-        for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwd[(size_t)p * ND + i - NI]; }
+        if (staged) for (int li = lane; li < nloci; li += IMA_WARP) a += s_wd[(i - NI) * nloci + li];
+        else for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwd[(size_t)p * ND + i - NI]; }
         a = Warp::sum(a);
         if (lane == 0) S.ad[i - NI] = a;
       }
@@ -482,12 +527,19 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   int n_eu = 0, n_ed = 0, n_mu = 0, n_md = 0;
   uint32_t bad = 0;
   for (int li = lane; li < nloci; li += IMA_WARP) {
-    const int p = c * nloci + li;
-    pdgnew += E.buf[E.cur[p] ^ 1].sd[(size_t)p * 4 + 3];
-    if (t.method == 1) migw += E.prop_extra[p];
-    const int *o = U.t_counts + (size_t)p * 4;
-    n_eu += o[0]; n_ed += o[1]; n_mu += o[2]; n_md += o[3];
-    bad |= E.prop_flags[p] & (kFlagOverflow | kFlagRejectIS | kFlagBadTree);
+    if (staged) {
+      pdgnew += s_pdg[li];
+      if (t.method == 1) migw += s_mw[li];
+      n_eu += s_cnt[li * 4]; n_ed += s_cnt[li * 4 + 1]; n_mu += s_cnt[li * 4 + 2]; n_md += s_cnt[li * 4 + 3];
+      bad |= (uint32_t)s_fl[li];
+    } else {
+      const int p = c * nloci + li;
+      pdgnew += E.buf[E.cur[p] ^ 1].sd[(size_t)p * 4 + 3];
+      if (t.method == 1) migw += E.prop_extra[p];
+      const int *o = U.t_counts + (size_t)p * 4;
+      n_eu += o[0]; n_ed += o[1]; n_mu += o[2]; n_md += o[3];
+      bad |= E.prop_flags[p] & (kFlagOverflow | kFlagRejectIS | kFlagBadTree);
+    }
   }
   pdgnew = Warp::sum(pdgnew);
   migw = Warp::sum(migw);

@@ -133,7 +133,7 @@ int ima2p_engine_run (ima2p_engine * e, int nsteps, int swaptries, void *cuda_st
 int ima2p_engine_set_pipeline (ima2p_engine * e, int groups, int depth, int decisions_first);
 /* Which kernels make updategenealogy's proposal (update_gtree.cpp:723-827): fast != 0 (the default where it applies) a
  * lane-per-pair move kernel followed by a warp-per-pair weights / likelihood kernel, with pairs_per_warp lanes of a move warp at
- * work (4, 8, 16, 32, or 0 = chosen from the number of pairs); fast == 0 the general one-warp-per-pair kernel for every pair.
+ * work (1, 2, 4, 8, 16, or 0 = chosen from the number of pairs); fast == 0 the general one-warp-per-pair kernel for every pair.
  * Pairs that do not fit the fast kernels' tables take the general path either way; the chain does not depend on the choice. */
 int ima2p_engine_set_proposal_path (ima2p_engine * e, int fast, int pairs_per_warp);
 /* parity tests: keep the per-proposal record that ima2p_engine_get_proposal reads (off by default) */

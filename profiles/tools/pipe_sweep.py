@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Step time of Engine.run for a list of settings (one GPU).  Prints one JSON line per setting.
-usage: python profiles/tools/pipe_sweep.py WORKLOAD STEPS "g,d,f[,fast,ppw] ..."   (set_pipeline groups, depth, decisions_first;
+usage: python profiles/tools/pipe_sweep.py WORKLOAD STEPS "g,d,f[,fast,ppw[,spec]] ..."   (set_pipeline groups, depth, decisions_first;
 set_proposal_path fast, pairs_per_warp).  IMA_TIMED=1 adds the per-kernel times of run_timed for every setting."""
 import json
 import os
@@ -36,6 +36,8 @@ def main():
         eng.set_pipeline(*s[:3])
         if len(s) >= 5:
             eng.set_proposal_path(s[3], s[4])
+        if len(s) >= 6:
+            eng.set_speculation(s[5])
         eng.run(2 * max(1, s[1]) + 8, sw, stream)
         torch.cuda.synchronize()
         best = None
