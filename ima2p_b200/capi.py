@@ -46,6 +46,13 @@ SIGNATURES = {
     "ima2p_engine_set_pipeline": (_i, [_v, _i, _i, _i]),
     "ima2p_engine_set_proposal_path": (_i, [_v, _i, _i]),
     "ima2p_engine_set_debug_records": (_i, [_v, _i]),
+    "ima2p_engine_exchange_create": (_i, [_v, C.POINTER(_v), c_u64_p]),
+    "ima2p_engine_exchange_attach": (_i, [_v, C.POINTER(_v)]),
+    "ima2p_ipc_export": (_i, [_v, C.c_char_p]),
+    "ima2p_ipc_import": (_i, [_i, C.c_char_p, C.POINTER(_v)]),
+    "ima2p_engine_run_sharded": (_i, [_v, _i, _i, _v]),
+    "ima2p_engine_sharded_update": (_i, [_v, _v]),
+    "ima2p_engine_sharded_swap": (_i, [_v, _i, _v]),
     "ima2p_engine_set_speculation": (_i, [_v, _i]),
     "ima2p_engine_run_timed": (_i, [_v, _i, _i, _v, c_flt_p]),
     "ima2p_engine_update_genealogies": (_i, [_v, _v, _v]),

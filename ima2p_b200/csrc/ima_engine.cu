@@ -67,6 +67,8 @@ struct Engine {
   std::vector<int> h_ul_l, h_ul_a;
 #if IMA_CUDA
   cudaGraphExec_t graph_exec = nullptr, graph_exec_deep = nullptr;   // one step; `depth` steps
+  cudaGraphExec_t graph_exec_sh = nullptr, graph_exec_sh_deep = nullptr;   // the same for a shard (exchange of swap sums inside)
+  int graph_sh_swaptries = -1;
   cudaStream_t own_stream = nullptr;
   cudaStream_t group_stream[kMaxGroups][2] = {};    // per chain group: proposals (low priority), decisions (high priority)
   std::vector<cudaEvent_t> pipe_events;
@@ -75,6 +77,10 @@ struct Engine {
   bool fast_ok = false, fast = false;                // the two-kernel proposal path (ima_fastpath.h): possible / in use
   int ppw = 0;                                       // pairs per warp of k_move (0: chosen from the number of pairs)
   int redo_grid = 16;
+  // multi-GPU exchange (struct Exchange): this rank's table, and whether peers are attached
+  unsigned char *d_xch = nullptr;
+  size_t xch_bytes = 0;
+  bool xch_attached = false;
   size_t pair_smem = 0, chain_smem = 0, accept_smem = 0;
   int spec = 3;        // speculative depth of the accept sweep (see k_accept)
 
@@ -87,6 +93,8 @@ struct Engine {
 #if IMA_CUDA
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (graph_exec_deep) cudaGraphExecDestroy(graph_exec_deep);
+    if (graph_exec_sh) cudaGraphExecDestroy(graph_exec_sh);
+    if (graph_exec_sh_deep) cudaGraphExecDestroy(graph_exec_sh_deep);
     if (own_stream) cudaStreamDestroy(own_stream);
     for (auto &g : group_stream) for (auto &x : g) if (x) cudaStreamDestroy(x);
     for (auto &x : pipe_events) if (x) cudaEventDestroy(x);
@@ -140,6 +148,7 @@ static int accept_block_warps(int spec) { return IMA_CUDA ? spec * kTermWarps : 
 static EngineView view_of(const Engine *e, int c_lo, int c_n, int step_off, int grp = 0) {
   EngineView v = e->v;
   v.c_lo = c_lo; v.c_n = c_n; v.step_off = step_off; v.grp = grp; v.redo_grid = e->redo_grid;
+  v.xch.publisher = 0;
   return v;
 }
 static int pair_grid(const Engine *e, const EngineView &v) { return (v.c_n * e->d.nloci + kWarpsPerBlock - 1) / kWarpsPerBlock; }
@@ -227,6 +236,7 @@ static void launch_update(Engine *e, stream_t s) { launch_update(e, s, view_of(e
 static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries, int step_already_advanced = 0, int advance = 1, int step_off = 0) {
   SwapView sv = e->sv;
   sv.S_global = S_global;
+  sv.use_exchange = S_global == nullptr ? 1 : 0;             // a shard: the sums of all ranks come through the exchange tables
   sv.swaptries = swaptries;
   sv.advance_step = step_already_advanced ? 0 : advance;
   sv.step_bias = step_already_advanced ? 1 : 0;
@@ -234,6 +244,9 @@ static void launch_swap(Engine *e, stream_t s, const double *S_global, int swapt
   sv.smem_chains = G <= 4000 ? G : 0;                        // 24 bytes per chain, 96 KB opted in at finalize
   IMA_LAUNCH(k_swap, 1, 1, swap_smem_bytes(sv.smem_chains), s, view_of(e, 0, e->d.nchains, step_off), sv);
 }
+
+// which kernel ends a chain's step (and publishes its swap sum when the engine holds a shard)
+static int last_kernel_of_step(const Engine *e) { return does_changeu(e) ? 3 : (does_split_t(e) ? 2 : 1); }
 
 #if IMA_CUDA
 // ---- the step as a CUDA graph --------------------------------------------------------------------------------------
@@ -251,7 +264,7 @@ static cudaEvent_t pipe_event(Engine &e, size_t &next) {
   }
   return e.pipe_events[next++];
 }
-static bool capture_steps(Engine &e, int swaptries, int depth, cudaGraphExec_t *out) {
+static bool capture_steps(Engine &e, int swaptries, int depth, cudaGraphExec_t *out, bool sharded = false) {
   int G = e.groups < 1 ? 1 : e.groups;
   if (G > e.d.nchains) G = e.d.nchains;
   if (G > kMaxGroups) G = kMaxGroups;
@@ -275,7 +288,8 @@ static bool capture_steps(Engine &e, int swaptries, int depth, cudaGraphExec_t *
     std::vector<cudaEvent_t> done(G);
     for (int g = 0; g < G; g++) {
       const int c_lo = (int)((long long)e.d.nchains * g / G), c_hi = (int)((long long)e.d.nchains * (g + 1) / G);
-      const EngineView v = view_of(&e, c_lo, c_hi - c_lo, j, g);
+      EngineView v = view_of(&e, c_lo, c_hi - c_lo, j, g);
+      if (sharded) v.xch.publisher = last_kernel_of_step(&e);
       cudaStream_t sp = e.group_stream[g][0], sa = e.pipe_prio ? e.group_stream[g][1] : sp;   // proposals / decisions
       auto hop = [&](cudaStream_t from, cudaStream_t to) {
         if (from == to) return;
@@ -299,7 +313,7 @@ static bool capture_steps(Engine &e, int swaptries, int depth, cudaGraphExec_t *
       if (sa != sp) cudaStreamWaitEvent(sp, done[g], 0);             // the group's next proposals follow its own step
     }
     for (int g = 0; g < G; g++) cudaStreamWaitEvent(s, done[g], 0);
-    launch_swap(&e, s, e.v.swapsum, swaptries, 0, j == depth - 1 ? depth : 0, j);
+    launch_swap(&e, s, sharded ? nullptr : e.v.swapsum, swaptries, 0, j == depth - 1 ? depth : 0, j);
     if (j + 1 < depth) { swap_done = pipe_event(e, nev); cudaEventRecord(swap_done, s); }
   }
   if (!IMA_CUDA_OK(cudaStreamEndCapture(s, &graph))) return false;
@@ -878,6 +892,8 @@ int ima2p_engine_run(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stre
   if (!e.graph_ready || e.graph_swaptries != swaptries) {
     if (e.graph_exec) { cudaGraphExecDestroy(e.graph_exec); e.graph_exec = nullptr; }
     if (e.graph_exec_deep) { cudaGraphExecDestroy(e.graph_exec_deep); e.graph_exec_deep = nullptr; }
+    if (e.graph_exec_sh) { cudaGraphExecDestroy(e.graph_exec_sh); e.graph_exec_sh = nullptr; }
+    if (e.graph_exec_sh_deep) { cudaGraphExecDestroy(e.graph_exec_sh_deep); e.graph_exec_sh_deep = nullptr; }
     if (!capture_steps(e, swaptries, 1, &e.graph_exec)) return fail(IMA2P_E_CUDA, "graph capture failed");
     if (e.depth > 1 && !capture_steps(e, swaptries, e.depth, &e.graph_exec_deep)) return fail(IMA2P_E_CUDA, "graph capture failed (deep)");
     e.graph_ready = true; e.graph_swaptries = swaptries;
@@ -1025,6 +1041,153 @@ int ima2p_engine_swap_replay(ima2p_engine *h, const double *dev_S_global, int sw
   launch_swap(&e, s, dev_S_global, swaptries);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (swap)");
+#endif
+  return IMA2P_OK;
+}
+
+// ---- multi-GPU: chains sharded over ranks, swap sums exchanged through peer memory (struct Exchange, ima_model.h) ----------
+// Replaces swapchains_bwprocesses' MPI messages (swapchains.cpp:192-523).  Set-up, once per run and on every rank:
+//   exchange_create -> (this rank's table) -> hand it to the peers (same process: the pointer itself after
+//   cudaDeviceEnablePeerAccess; other processes: ima2p_ipc_export / ima2p_ipc_import) -> exchange_attach(all tables).
+// Every rank must attach before any rank steps, and all ranks step in lockstep (same nsteps, same swaptries).
+int ima2p_engine_exchange_create(ima2p_engine *h, void **table, uint64_t *bytes) {
+  if (!h || !h->eng.finalized || !table || !bytes) return fail(IMA2P_E_ARG, "exchange_create: bad argument");
+  Engine &e = h->eng;
+  if (e.d.nchains_global % e.d.nchains != 0 || e.d.chain0 % e.d.nchains != 0 || e.d.nchains_global / e.d.nchains > kMaxRanks)
+    return fail(IMA2P_E_ARG, "exchange_create: chains must shard evenly over at most 16 ranks");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  if (!e.d_xch) {
+    e.xch_bytes = (size_t)2 * e.d.nchains_global * sizeof(double) + 64;
+#if IMA_CUDA
+    // its own allocation (not a slice of a pool): cudaIpcGetMemHandle exports whole allocations
+    void *p = nullptr;
+    if (!IMA_CUDA_OK(cudaMalloc(&p, e.xch_bytes)) || !IMA_CUDA_OK(cudaMemset(p, 0, e.xch_bytes)) || !IMA_CUDA_OK(cudaDeviceSynchronize()))
+      return fail(IMA2P_E_CUDA, "exchange_create: allocation failed");
+    e.d_xch = (unsigned char *)p;
+    e.allocs.push_back(p);
+#else
+    e.d_xch = e.alloc<unsigned char>(e.xch_bytes);
+#endif
+    if (!e.d_xch) return fail(IMA2P_E_CUDA, "exchange_create: allocation failed");
+  }
+  *table = e.d_xch; *bytes = e.xch_bytes;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_exchange_attach(ima2p_engine *h, void *const *tables) {
+  if (!h || !h->eng.finalized || !tables || !h->eng.d_xch) return fail(IMA2P_E_ARG, "exchange_attach: call exchange_create first");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  Exchange &X = e.v.xch;
+  X.world = e.d.nchains_global / e.d.nchains;
+  X.rank = e.d.chain0 / e.d.nchains;
+  X.publisher = 0;
+  for (int r = 0; r < X.world; r++) {
+    unsigned char *t = r == X.rank ? e.d_xch : (unsigned char *)tables[r];
+    if (!t) return fail(IMA2P_E_ARG, "exchange_attach: a peer's table is missing");
+    X.peer_S[r] = (double *)t;
+    X.peer_arrived[r] = (unsigned long long *)(t + (size_t)2 * e.d.nchains_global * sizeof(double));
+  }
+  stream_t s = pick_stream(&e, nullptr);
+  unsigned long long st = 0;
+  if (!d2h(&st, e.v.nsteps, sizeof st, s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+  X.step0 = st;
+  e.xch_attached = true;
+  e.graph_ready = false;
+#if IMA_CUDA
+  if (e.graph_exec_sh) { cudaGraphExecDestroy(e.graph_exec_sh); e.graph_exec_sh = nullptr; }
+  if (e.graph_exec_sh_deep) { cudaGraphExecDestroy(e.graph_exec_sh_deep); e.graph_exec_sh_deep = nullptr; }
+#endif
+  return IMA2P_OK;
+}
+
+// a device allocation of this process as 64 opaque bytes another process of the same node can open
+int ima2p_ipc_export(const void *dev_ptr, unsigned char *handle64) {
+  if (!dev_ptr || !handle64) return fail(IMA2P_E_ARG, "ipc_export: bad argument");
+#if IMA_CUDA
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t hd;
+  if (!IMA_CUDA_OK(cudaIpcGetMemHandle(&hd, (void *)dev_ptr))) return fail(IMA2P_E_CUDA, "cudaIpcGetMemHandle failed");
+  memcpy(handle64, &hd, 64);
+  return IMA2P_OK;
+#else
+  memset(handle64, 0, 64);
+  memcpy(handle64, &dev_ptr, sizeof dev_ptr);                 // host emulation: one process, the pointer is the handle
+  return IMA2P_OK;
+#endif
+}
+int ima2p_ipc_import(int device, const unsigned char *handle64, void **dev_ptr) {
+  if (!handle64 || !dev_ptr) return fail(IMA2P_E_ARG, "ipc_import: bad argument");
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaSetDevice(device))) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  if (!IMA_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess))) return fail(IMA2P_E_CUDA, "cudaIpcOpenMemHandle failed");
+  return IMA2P_OK;
+#else
+  (void)device;
+  memcpy(dev_ptr, handle64, sizeof *dev_ptr);
+  return IMA2P_OK;
+#endif
+}
+
+// The two halves of a shard's step, for callers that keep the ranks in lockstep themselves (one process driving several GPUs
+// or the host emulation: every rank's update, then every rank's swap).  ima2p_engine_run_sharded issues both, as one graph.
+int ima2p_engine_sharded_update(ima2p_engine *h, void *cuda_stream) {
+  if (!h || !h->eng.xch_attached) return fail(IMA2P_E_ARG, "sharded_update: attach the exchange first");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  EngineView v = view_of(&e, 0, e.d.nchains, 0);
+  v.xch.publisher = last_kernel_of_step(&e);
+  launch_update(&e, s, v);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (sharded update)");
+#endif
+  return IMA2P_OK;
+}
+int ima2p_engine_sharded_swap(ima2p_engine *h, int swaptries, void *cuda_stream) {
+  if (!h || !h->eng.xch_attached || swaptries < 0) return fail(IMA2P_E_ARG, "sharded_swap: attach the exchange first");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  launch_swap(&e, s, nullptr, swaptries);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return fail(IMA2P_E_CUDA, "kernel launch failed (sharded swap)");
+#endif
+  return IMA2P_OK;
+}
+
+// nsteps whole steps of this rank's chains; the swap sums travel through the exchange tables inside the kernels, so there is
+// nothing for the host to do between steps: the step is one CUDA graph (ima2p_engine_set_pipeline applies), replayed nsteps times
+int ima2p_engine_run_sharded(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stream) {
+  if (!h || nsteps < 0 || swaptries < 0) return fail(IMA2P_E_ARG, "run_sharded: bad argument");
+  Engine &e = h->eng;
+  if (!e.xch_attached) return fail(IMA2P_E_ARG, "run_sharded: attach the exchange first");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+#if IMA_CUDA
+  if (!e.graph_exec_sh || e.graph_sh_swaptries != swaptries || !e.graph_ready) {
+    if (e.graph_exec_sh) { cudaGraphExecDestroy(e.graph_exec_sh); e.graph_exec_sh = nullptr; }
+    if (e.graph_exec_sh_deep) { cudaGraphExecDestroy(e.graph_exec_sh_deep); e.graph_exec_sh_deep = nullptr; }
+    if (!capture_steps(e, swaptries, 1, &e.graph_exec_sh, true)) return fail(IMA2P_E_CUDA, "graph capture failed (sharded)");
+    if (e.depth > 1 && !capture_steps(e, swaptries, e.depth, &e.graph_exec_sh_deep, true)) return fail(IMA2P_E_CUDA, "graph capture failed (sharded, deep)");
+    e.graph_sh_swaptries = swaptries;
+    // the single-rank graphs are rebuilt by ima2p_engine_run when it is next called
+    if (e.graph_exec) { cudaGraphExecDestroy(e.graph_exec); e.graph_exec = nullptr; }
+    if (e.graph_exec_deep) { cudaGraphExecDestroy(e.graph_exec_deep); e.graph_exec_deep = nullptr; }
+    e.graph_swaptries = -1;
+    e.graph_ready = true;
+  }
+  int i = 0;
+  if (e.graph_exec_sh_deep)
+    for (; i + e.depth <= nsteps; i += e.depth)
+      if (!IMA_CUDA_OK(cudaGraphLaunch(e.graph_exec_sh_deep, s))) return fail(IMA2P_E_CUDA, "graph launch failed");
+  for (; i < nsteps; i++)
+    if (!IMA_CUDA_OK(cudaGraphLaunch(e.graph_exec_sh, s))) return fail(IMA2P_E_CUDA, "graph launch failed");
+#else
+  (void)s;
+  return fail(IMA2P_E_UNSUPPORTED, "run_sharded: the host emulation steps ranks with sharded_update / sharded_swap");
 #endif
   return IMA2P_OK;
 }

@@ -85,6 +85,44 @@ IMA_KERNEL void k_eval_pairs(EngineView E) {
   }
 }
 
+// ---- the exchange of swap sums between GPUs (struct Exchange) ------------------------------------------------------------
+// called by one whole warp when chain c's S for this step is final
+IMA_DEV void publish_chain(const EngineView &E, int c, double S) {
+  const Exchange &X = E.xch;
+  const unsigned long long ep = current_step(E) - X.step0;
+  const size_t at = (size_t)(ep & 1ull) * E.d.nchains_global + (size_t)(E.d.chain0 + c);
+  for (int r = Warp::lane(); r < X.world; r += IMA_WARP) {
+#if IMA_CUDA
+    *(volatile double *)(X.peer_S[r] + at) = S;                   // a store into rank r's memory (its own when r == rank)
+    __threadfence_system();                                       // the value is visible before the count that announces it
+    atomicAdd_system(X.peer_arrived[r] + (ep & 1ull), 1ull);
+#else
+    X.peer_S[r][at] = S;
+    X.peer_arrived[r][ep & 1ull] += 1ull;
+#endif
+  }
+}
+// the swap kernel's side: wait until every chain of the job has arrived for this step; returns this rank's table of the step
+IMA_DEV const double *await_swap_sums(const EngineView &E, int step_bias) {
+  const Exchange &X = E.xch;
+  const unsigned long long ep = current_step(E) - (unsigned long long)step_bias - X.step0;
+  const unsigned long long target = (ep / 2ull + 1ull) * (unsigned long long)E.d.nchains_global;
+#if IMA_CUDA
+  if (Warp::lane() == 0) {
+    volatile unsigned long long *cnt = X.peer_arrived[X.rank] + (ep & 1ull);
+    const long long t0 = clock64();
+    while (*cnt < target) {
+      if (clock64() - t0 > 8000000000ll) { raise(E.mc, kErrExchange); break; }      // a peer never arrived (about four seconds)
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+#else
+  if (X.peer_arrived[X.rank][ep & 1ull] < target) raise(E.mc, kErrExchange);
+#endif
+  return X.peer_S[X.rank] + (size_t)(ep & 1ull) * E.d.nchains_global;
+}
+
 // gather (c, f, hc) of one parameter from a weight record (update_gtree_common.cpp:1985-1994, 2018-2030)
 IMA_DEV void gather_q(const DevModel &M, int t, const int *wi, const double *wd, int &c, double &f, double &hc) {
   c = 0; f = 0.0; hc = 0.0;
@@ -672,6 +710,7 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E) {
         E.probg[c] = probg; E.pdgsum[c] = pdgsum;
         if (l1 == E.d.nloci) E.swapsum[c] = ssum;
       }
+      if (E.xch.publisher == 1) publish_chain(E, c, ssum);
     }
   }
 }
@@ -689,6 +728,7 @@ struct SwapView {
   int swaptries, advance_step;   // advance_step: what the launch adds to the device step counter afterwards (0, 1, or the steps of a graph)
   int step_bias;            // 1 when the step counter was already advanced (split-phase multi-GPU step): the draws stay keyed by the step they belong to
   int smem_chains;          // chains the launch's shared memory can stage (0: work on global memory)
+  int use_exchange;         // S of all chains comes from the exchange tables (struct Exchange), after waiting for them
 };
 
 constexpr int kSwapBatch = 256;           // attempts drawn per pass
@@ -705,6 +745,7 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
   if (ima_block() != 0 || ima_warp_in_block() != 0) return;
   const int N = E.d.nchains_global;
   const int lane = Warp::lane();
+  if (V.use_exchange) V.S_global = await_swap_sums(E, V.step_bias);
   if (N > 1 && V.swaptries > 0) {
     // the attempts are a dependent chain of small decisions over (beta, S, rank): the warp stages those in shared memory
     // (when they fit) so that one lane walks the attempts without waiting on global memory, and writes the ranks back
@@ -712,7 +753,7 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
     double *sS = (double *)IMA_SMEM, *sB = sS + (staged ? N : 0);
     int *sC = (int *)(sB + (staged ? N : 0)), *sR = sC + (staged ? N : 0);
     if (staged) {
-      for (int i = lane; i < N; i += IMA_WARP) { sS[i] = V.S_global[i]; sB[i] = V.beta_table[i]; sC[i] = V.chain_of_rank[i]; sR[i] = V.rank_of_chain[i]; }
+      for (int i = lane; i < N; i += IMA_WARP) { sS[i] = *(const volatile double *)(V.S_global + i); sB[i] = V.beta_table[i]; sC[i] = V.chain_of_rank[i]; sR[i] = V.rank_of_chain[i]; }
 #if IMA_CUDA
       __threadfence_block();
 #endif

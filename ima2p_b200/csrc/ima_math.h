@@ -17,7 +17,7 @@ struct MathCtx {
   int *err;                // device error word (first error wins); 0 = none
 };
 
-enum DevErr { kErrNone = 0, kErrLogDiff = 14, kErrGamma = 15, kErrRange = 16 };
+enum DevErr { kErrNone = 0, kErrLogDiff = 14, kErrGamma = 15, kErrRange = 16, kErrExchange = 17 };
 
 IMA_DEV void raise(const MathCtx &mc, int code) {
 #if IMA_CUDA

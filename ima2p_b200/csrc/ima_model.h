@@ -83,6 +83,20 @@ struct EngineDims {
                         // memory serialises such reads): see kTab* below
 };
 
+// Multi-GPU exchange of the swap sums (swapchains_bwprocesses, swapchains.cpp:192-523, exchanges them by MPI messages): every
+// rank holds S[2 step parities][all chains] and two arrival counters in its own memory, mapped into every peer (NVLink peer
+// access, cudaIpc between processes).  The kernel that finishes a chain's step stores the chain's S into EVERY rank's table and
+// then bumps that rank's counter; the swap kernel of a rank waits until its counter says all chains have arrived.  No host
+// round trip, no collective call: the exchange is the epilogue of the compute kernel and the prologue of the swap kernel.
+constexpr int kMaxRanks = 16;
+struct Exchange {
+  double *peer_S[kMaxRanks];                      // rank r's table, as this GPU addresses it
+  unsigned long long *peer_arrived[kMaxRanks];    // rank r's counters [2]
+  unsigned long long step0;                       // device step counter when the exchange was attached (same on every rank)
+  int world, rank;
+  int publisher;                                  // which kernel of the step publishes: 1 k_accept, 2 k_accept_t, 3 k_changeu (0: nobody)
+};
+
 // Everything a kernel needs, passed by value.
 struct EngineView {
   EngineDims d;
@@ -124,6 +138,7 @@ struct EngineView {
   int grp, redo_grid;           // chain group of the launch (its redo counters), blocks of the redo kernels
   int *redo_count;              // [groups][2 kinds][2 step parities]
   int *redo_list;               // [2 kinds][P]
+  Exchange xch;
 };
 
 IMA_HD unsigned long long current_step(const EngineView &E) { return *E.nsteps + (unsigned long long)E.step_off; }

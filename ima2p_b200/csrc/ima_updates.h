@@ -569,6 +569,7 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
     accept = !anybad && log(uacc) < (mh < 1.0 ? mh : 1.0);                        // update_t_RY.cpp:424-425
   }
   if (U.t_forced && U.t_force_accept >= 0) accept = !anybad && U.t_force_accept != 0;
+  if (E.xch.publisher == 2) publish_chain(E, c, accept ? (M.thermo ? pdgnew : pdgnew + probg) : E.swapsum[c]);
   if (accept) {
     for (int i = lane; i < NI; i += IMA_WARP) E.all_i[(size_t)c * NI + i] = S.ai[i];
     for (int i = lane; i < ND; i += IMA_WARP) E.all_d[(size_t)c * ND + i] = S.ad[i];
@@ -640,14 +641,27 @@ IMA_DEV double reflect_kappa(double u, double kappa, double win, double kmax) { 
 // (doubles) and the partner (int) of every locus
 IMA_HD size_t changeu_smem_doubles(int nloci) { return (size_t)5 * nloci + (nloci + 1) / 2 + 1; }
 
+IMA_DEV void changeu_chain(const EngineView &E, const UpdateView &U, int c, PairSm &S);
 IMA_KERNEL void k_changeu(EngineView E, UpdateView U) {
   IMA_SMEM_DECL
   if (ima_block() * kWarpsPerBlock + ima_warp_in_block() >= E.c_n) return;
   const int c = E.c_lo + ima_block() * kWarpsPerBlock + ima_warp_in_block();
-  if (U.u_forced ? c != U.u_chain : ((current_step(E) + 1) % (unsigned long long)U.u_every) != 0) return;   // every UUPDATEINC+1 steps
+  if (U.u_forced ? c == U.u_chain : ((current_step(E) + 1) % (unsigned long long)U.u_every) == 0) {         // every UUPDATEINC+1 steps
+    PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
+    changeu_chain(E, U, c, S);
+  }
+  if (E.xch.publisher == 3) {                          // the chain's step ends here, whether or not it was the scalars' turn
+#if IMA_CUDA
+    __threadfence_block();
+    __syncwarp();
+#endif
+    publish_chain(E, c, *(volatile double *)(E.swapsum + c));
+  }
+}
+IMA_DEV void changeu_chain(const EngineView &E, const UpdateView &U, int c, PairSm &S) {
+  IMA_SMEM_DECL
   const DevModel &M = IMA_MODEL;
   const int lane = Warp::lane(), nloci = E.d.nloci, nur = U.nurates;
-  PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
   Philox rng;
   rng_for(rng, E, (uint32_t)(E.d.chain0 + c), kRngScalars);
   const double beta = E.beta[c];

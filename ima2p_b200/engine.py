@@ -202,6 +202,39 @@ class Engine:
         """Chain groups on their own streams and steps per CUDA graph of `run` (the chains a run visits do not depend on it)."""
         self._ck(self.lib.ima2p_engine_set_pipeline(self._h, groups, depth, 1 if decisions_first else 0))
 
+    # ---- chains sharded over GPUs: swap sums exchanged through peer memory by the kernels themselves ------------------
+    def exchange_create(self):
+        """This rank's exchange table: (device pointer, bytes)."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.ima2p_engine_exchange_create(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def exchange_handle(self):
+        """64 bytes another process of this node can open with exchange_open."""
+        ptr, _ = self.exchange_create()
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.ima2p_ipc_export(C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def exchange_open(self, handle64, device=0):
+        p = C.c_void_p()
+        self._ck(self.lib.ima2p_ipc_import(device, C.c_char_p(handle64), C.byref(p)))
+        return p.value
+
+    def exchange_attach(self, tables):
+        """tables[r] = rank r's table as this GPU addresses it (None for this rank)."""
+        arr = (C.c_void_p * len(tables))(*[C.c_void_p(t) if t else None for t in tables])
+        self._ck(self.lib.ima2p_engine_exchange_attach(self._h, arr))
+
+    def run_sharded(self, nsteps, swaptries=None, stream=None):
+        self._ck(self.lib.ima2p_engine_run_sharded(self._h, nsteps, self.default_swaptries() if swaptries is None else swaptries, stream))
+
+    def sharded_update(self, stream=None):
+        self._ck(self.lib.ima2p_engine_sharded_update(self._h, stream))
+
+    def sharded_swap(self, swaptries=None, stream=None):
+        self._ck(self.lib.ima2p_engine_sharded_swap(self._h, self.default_swaptries() if swaptries is None else swaptries, stream))
+
     def set_proposal_path(self, fast=True, pairs_per_warp=0):
         """Two-kernel proposal path (lane-per-pair move + warp-per-pair weights) or the general kernel for every pair."""
         self._ck(self.lib.ima2p_engine_set_proposal_path(self._h, 1 if fast else 0, pairs_per_warp))

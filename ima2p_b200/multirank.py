@@ -8,6 +8,20 @@ import torch
 import torch.distributed as dist
 
 
+def attach_exchange(engine, device_index=0):
+    """One rank per process: hand every rank's exchange table to every other rank (cudaIpc handles through
+    torch.distributed's object all-gather, once) and attach them.  After this the ranks only call
+    ``engine.run_sharded(nsteps)`` in lockstep: the swap sums cross NVLink inside the kernels
+    (include/ima2p_b200.h, ima2p_engine_exchange_*), no collective is called per step."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = engine.exchange_handle()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    tables = [None if r == rank else engine.exchange_open(handles[r], device_index) for r in range(world)]
+    engine.exchange_attach(tables)
+    dist.barrier()                      # nobody steps before everybody is attached
+
+
 class ShardedStepper:
     """Whole qupdate steps over chains sharded by rank.
 

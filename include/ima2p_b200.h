@@ -136,6 +136,23 @@ int ima2p_engine_set_pipeline (ima2p_engine * e, int groups, int depth, int deci
  * work (1, 2, 4, 8, 16, or 0 = chosen from the number of pairs); fast == 0 the general one-warp-per-pair kernel for every pair.
  * Pairs that do not fit the fast kernels' tables take the general path either way; the chain does not depend on the choice. */
 int ima2p_engine_set_proposal_path (ima2p_engine * e, int fast, int pairs_per_warp);
+/* ---- chains sharded over several GPUs: the reference's `mpirun -np P IMa2p -hn ...` (ima_main_mpi.cpp:4317-4560), whose
+ * processes exchange swap sums by MPI messages (swapchains_bwprocesses, swapchains.cpp:192-523).  Here every rank keeps a
+ * small table (S of every chain of the job, two step parities, and arrival counters) that its peers map -- NVLink peer
+ * access inside one process, cudaIpc handles between processes -- and the kernels do the exchange themselves: the kernel that
+ * finishes a chain's step stores its S into every rank's table, the swap kernel waits for all chains to arrive.  Set-up on
+ * every rank: exchange_create, pass the table to the peers (ipc_export -> any channel -> ipc_import), exchange_attach with
+ * all ranks' tables (tables[own rank] may be NULL); every rank attaches before any rank steps, and all ranks make the same
+ * calls.  ima2p_engine_run_sharded = ima2p_engine_run for a shard: the whole step, exchange included, is one CUDA graph. */
+int ima2p_engine_exchange_create (ima2p_engine * e, void **table, uint64_t * bytes);
+int ima2p_engine_exchange_attach (ima2p_engine * e, void *const *tables);
+int ima2p_ipc_export (const void *device_pointer, unsigned char *handle64);
+int ima2p_ipc_import (int device, const unsigned char *handle64, void **device_pointer);
+int ima2p_engine_run_sharded (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream);
+/* the two halves of a shard's step for callers that keep the ranks in lockstep themselves (every rank's update, then every
+ * rank's swap): one process driving several GPUs, and the tests */
+int ima2p_engine_sharded_update (ima2p_engine * e, void *cuda_stream);
+int ima2p_engine_sharded_swap (ima2p_engine * e, int swaptries, void *cuda_stream);
 /* parity tests: keep the per-proposal record that ima2p_engine_get_proposal reads (off by default) */
 int ima2p_engine_set_debug_records (ima2p_engine * e, int on);
 /* speculative depth of the accept sweep (1..3): how many consecutive loci of a chain are evaluated per round against

@@ -185,3 +185,66 @@ def test_lmode_moments_and_popmig_sharded_over_two_ranks_match_reference():
             for b in range(a + 1, n):
                 assert abs(corr[a, b] - (rc[a, b] / G - rm[a] * rm[b]) / np.sqrt(rv[a] * rv[b])) < 1e-6
         assert rel_close(pm, ref_pm, 1e-10, 1e-300)
+
+
+def _shard_engine(d, fm, lib, rank, world, seed=99):
+    from ima2p_b200 import Engine
+    from support import FlatTree
+    nglob = len(d["chains"])
+    per = nglob // world
+    eng = Engine(per, len(d["loci"]), seed=seed, lib=lib, nchains_global=nglob, chain0=per * rank)
+    eng.set_model_flat(*fm.create_args())
+    for li, loc in enumerate(d["loci"]):
+        eng.set_locus(li, loc["model"], loc["numgenes"], loc["numsites"], loc["samppop"], seq=loc["seq"], hval=loc["hval"],
+                      sumlogk=loc["sumlogk"])
+    eng.finalize()
+    eng.set_betas([ch["beta"] for ch in d["chains"]])
+    for k in range(per):
+        ch = d["chains"][per * rank + k]
+        eng.set_chain(k, ch["tvals"])
+        for li, g in enumerate(ch["G"]):
+            t = FlatTree(g["tree"])
+            eng.set_genealogy(k, li, t.up0, t.up1, t.down, t.pop, t.time, t.mig_off, t.mig_t[:-1], t.mig_p[:-1], t.root,
+                              t.roottime, uvals=g["uvals"])
+    eng.upload()
+    eng.eval()
+    eng.set_update_priors(t_max=[3.0])
+    eng.set_update_schedule(3, 5)
+    return eng
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_memory_exchange_reproduces_the_single_process_run(world):
+    """The exchange the product uses between GPUs (include/ima2p_b200.h, ima2p_engine_exchange_*): every rank's kernels store
+    their chains' swap sums into every rank's table and the swap kernel reads its own table -- here `world` shard engines of one
+    process, attached to each other's tables through the export / import calls and stepped in lockstep (every rank's update,
+    then every rank's swap).  The chains must be the single-engine run's, bit for bit."""
+    from ima2p_b200 import capi
+    from support import FlatModel, load_golden
+    subprocess.run([os.path.join(HERE, "hostemu", "build.sh")], check=True)
+    single, betas1, cnt1 = _run_single()
+    lib = capi.bind(EMU)
+    d = load_golden(FIXTURE)
+    fm = FlatModel(d["model"])
+    engs = [_shard_engine(d, fm, lib, r, world) for r in range(world)]
+    handles = [e.exchange_handle() for e in engs]
+    for r, e in enumerate(engs):
+        e.exchange_attach([None if k == r else e.exchange_open(handles[k]) for k in range(world)])
+    for _ in range(NSTEPS):
+        for e in engs:
+            e.sharded_update()
+        for e in engs:
+            e.sharded_swap(SWAPTRIES)
+    for e in engs:
+        e.sync()                                           # raises if a swap kernel did not find every chain's sum
+    both = np.concatenate([np.array([[e.chain(c)["probg"], e.chain(c)["pdg"], e.chain(c)["tvals"][0]] for c in range(e.nchains)]) for e in engs])
+    assert np.array_equal(both, single)
+    for e in engs:
+        assert np.array_equal(e.betas(), betas1)
+        assert e.counters()["swaps"] == cnt1["swaps"]
+    assert sum(e.counters()["accepted"] for e in engs) == cnt1["accepted"]
+    # a rank that steps alone finds the others' sums missing: the device error word says so (no hang, no silent garbage)
+    engs[0].sharded_update()
+    engs[0].sharded_swap(SWAPTRIES)
+    with pytest.raises(capi.Ima2pError):
+        engs[0].sync()
