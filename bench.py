@@ -4,13 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (rank 0 prints ONE JSON line)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU code
 
-Metric (BASELINE.json): chain x locus genealogy updates/sec.  One "step" = one M-mode step of the whole job:
-updategenealogy for every chain x locus followed by the step's MC3 swap attempts.  Workload at N = 1:
-BASELINE configs[1] -- Sim1_50loci-shaped synthetic loci (50 infinite-sites loci, 15+15 genes) with 128
-Metropolis-coupled chains; with N GPUs every GPU holds 128 chains (weak scaling, chains shard by rank and only
-(beta, S) scalars cross GPUs).
+Metric (BASELINE.json): chain x locus genealogy updates/sec.  One "step" = one M-mode step of the whole job (qupdate,
+ima_main_mpi.cpp:1788-2047): updategenealogy for every chain x locus, a split-time update of every chain, the mutation
+scalars every 5th step, the step's MC3 swap attempts.  Workload at N = 1: BASELINE configs[1] -- Sim1_50loci-shaped loci (50
+infinite-sites loci, 15+15 genes) with 128 Metropolis-coupled chains; with N GPUs every GPU holds 128 chains (weak scaling,
+chains shard by rank and only the chains' swap sums cross GPUs, through peer memory inside the kernels).  With N >= 2 the line
+also carries `config3`: BASELINE configs[2]'s shape, 300 loci x 256 chains per GPU (2,048 chains at N = 8), with the
+reference's own figure on the same 300-locus input from all host cores of the same run.
 """
 import argparse
+import gzip
 import json
 import os
 import subprocess
@@ -26,15 +29,17 @@ sys.path.insert(0, ROOT)
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 WORKLOADS = {
-    # name: (loci, genes pop0, genes pop1, chains per GPU, description)
-    "sim50x128": (50, 15, 15, 128, "Sim1_50loci-shaped synthetic: 50 IS loci, 15+15 genes, 128 coupled chains per GPU"),
-    "sim300x256": (300, 15, 15, 256, "Sim1_300loci-shaped synthetic: 300 IS loci, 15+15 genes, 256 coupled chains per GPU"),
-    "sim5x4": (5, 10, 10, 4, "Sim1_5loci-shaped synthetic: 5 IS loci, 10+10 genes, 4 coupled chains"),
+    # name: (loci, genes pop0, genes pop1, chains per GPU, description, golden fixture holding the reference's own input)
+    "sim50x128": (50, 15, 15, 128, "Sim1_50loci-shaped: 50 IS loci, 15+15 genes, 128 coupled chains per GPU", "state_sim50_hn3"),
+    "sim300x256": (300, 15, 15, 256, "Sim1_300loci-shaped: 300 IS loci, 15+15 genes, 256 coupled chains per GPU", "state_sim300_hn1"),
+    "sim5x4": (5, 10, 10, 4, "Sim1_5loci-shaped: 5 IS loci, 10+10 genes, 4 coupled chains", "state_sim5_hn4"),
 }
 PRIOR_Q, PRIOR_M, PRIOR_T = 10.0, 1.0, 3.0
-T0 = 0.5 * PRIOR_T           # the reference starts every chain at (i+1)/(nsplit+1) of the -t prior (initialize.cpp:1959);
-                             # neither arm updates split times (updategenealogy-only comparison)
-HEAT = (1, 0.96, 0.9)          # -hfg -ha 0.96 -hb 0.9
+T0 = 0.5 * PRIOR_T           # the reference starts every chain at (i+1)/(nsplit+1) of the -t prior (initialize.cpp:1959); both
+                             # arms then run the whole qupdate step, split-time updates included, from there
+HEAT = (1, 0.96, 0.9)        # -hfg -ha 0.96 -hb 0.9
+BURN = 1000                  # whole steps before anything is timed, in BOTH arms (the migration load per genealogy settles)
+L2_MB = 126.0
 
 
 def peaks():
@@ -88,10 +93,66 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_engine(wl, rank, world, seed=2026, mig_capacity=64):
+# ---- workloads ------------------------------------------------------------------------------------------------------------
+def fixture(wl):
+    return json.load(gzip.open(os.path.join(ROOT, "tests", "golden", WORKLOADS[wl][5] + ".json.gz")))
+
+
+def dataset(wl, data):
+    """Loci in the form synth.make_dataset returns.  data == "real": the reference's own Simulations/*.u input as the golden
+    fixture of the workload holds it (the fixtures were written by the reference after it read the file: same 0/1 columns in the
+    same order; /root/reference does not exist on the GPU box)."""
+    from ima2p_b200 import synth
+    nloci, n0, n1 = WORKLOADS[wl][:3]
+    if data == "synthetic":
+        return synth.make_dataset(nloci, n0, n1, seed=11)
+    d = fixture(wl)
+    loci = []
+    for li, L in enumerate(d["loci"]):
+        seq = np.asarray(L["seq"], np.int32).reshape(L["numgenes"], L["numsites"])
+        loci.append(dict(name="Locus%d" % (li + 1), n=L["numgenes"], samppop=list(L["samppop"]), numsites=L["numsites"], seq=seq))
+    return loci
+
+
+def state_from_fixture(d, nchains, NL, CAP):
+    """put_state buffers for nchains chains from the genealogies of a fixture (its chains used in turn: valid genealogies of
+    the reference's own run on the real input, with the split times they belong to)."""
+    nloci = len(d["loci"])
+    P = nchains * nloci
+    topo = -np.ones((P, NL, 4), np.int16); time_ = np.zeros((P, NL)); mseg = np.zeros((P, NL, 2), np.uint16)
+    mig_t = np.zeros((P, CAP)); mig_p = np.zeros((P, CAP), np.int16); si = np.zeros((P, 2), np.int32); sd = np.zeros((P, 4))
+    uv = np.ones((P, 4)); tvals = np.zeros((nchains, 1))
+    for c in range(nchains):
+        ch = d["chains"][c % len(d["chains"])]
+        tvals[c, 0] = ch["tvals"][0]
+        for li, g in enumerate(ch["G"]):
+            t, p = g["tree"], c * nloci + li
+            nl = len(t["up0"])
+            topo[p, :nl, 0], topo[p, :nl, 1], topo[p, :nl, 2], topo[p, :nl, 3] = t["up0"], t["up1"], t["down"], t["pop"]
+            time_[p, :nl] = t["time"]
+            o = 0
+            for e, lst in enumerate(t["mig"]):
+                k = len(lst) // 2
+                mseg[p, e] = (o, k)
+                mig_t[p, o:o + k], mig_p[p, o:o + k] = lst[0::2], lst[1::2]
+                o += k
+            si[p] = (t["root"], o)
+            sd[p, 0] = t["roottime"]
+            uv[p, 0] = g["uvals"][0]
+    return dict(topo=topo, time=time_, mseg=mseg, mig_t=mig_t, mig_p=mig_p, scal_i=si, scal_d=sd, uvals=uv, tvals=tvals)
+
+
+def build_engine(wl, rank, world, seed=2026, mig_capacity=64, data="synthetic"):
     from ima2p_b200 import Engine, synth
-    nloci, n0, n1, cpg, _ = WORKLOADS[wl]
-    loci = synth.make_dataset(nloci, n0, n1, seed=11)
+    nloci, n0, n1, cpg = WORKLOADS[wl][:4]
+    loci = dataset(wl, data)
+    if data == "real":
+        # the product's own reader on the file, as a user's run would: write the input in the reference's .u format, read it back
+        from ima2p_b200.readu import read_u
+        tmp = tempfile.mkdtemp(prefix="ima2p_u_")
+        synth.write_u(os.path.join(tmp, "real.u"), loci)
+        rd = read_u(os.path.join(tmp, "real.u"))["loci"]
+        assert len(rd) == nloci and all(np.array_equal(a["seq"], b["seq"]) for a, b in zip(rd, loci)), "the .u reader changed the data"
     model = synth.two_population_model(PRIOR_Q, PRIOR_M)
     eng = Engine(cpg, nloci, mig_capacity=mig_capacity, seed=seed, device=0 if world == 1 else int(os.environ.get("LOCAL_RANK", 0)),
                  nchains_global=cpg * world, chain0=cpg * rank)
@@ -103,7 +164,10 @@ def build_engine(wl, rank, world, seed=2026, mig_capacity=64):
         eng.set_heating(*HEAT)
     elif cpg * world > 1:
         eng.set_heating(0, 0.05, 0.0)
-    st = synth.initial_state(loci, cpg, eng.NL, eng.CAP, t0=T0, seed=100 + rank)
+    if data == "real":
+        st = state_from_fixture(fixture(wl), cpg, eng.NL, eng.CAP)
+    else:
+        st = synth.initial_state(loci, cpg, eng.NL, eng.CAP, t0=T0, seed=100 + rank)
     return eng, loci, st
 
 
@@ -118,7 +182,29 @@ def algorithmic_bytes_per_update(n, mig_per_genealogy, p_acc, NI, ND):
     return 24.0 * (2 * n - 1) + 12.0 * M + W_g + 24.0 + p_acc * (72.0 + 12.0 * M_e + W_g + 16.0)
 
 
-def run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn, full, tmp, budget_s=20.0, gburn=1000):
+def state_mb_per_gpu(wl, cap=64):
+    """Both state buffers of one GPU's chains: topo 8 + time 8 + mseg 4 bytes per edge, 10 per pool entry,
+    40 + 108 of scalars and weights per pair."""
+    nloci, n0, n1, cpg = WORKLOADS[wl][:4]
+    nl = 2 * (n0 + n1) - 1
+    return 2.0 * cpg * nloci * (20.0 * nl + 10.0 * cap + 148.0) / 1e6
+
+
+def make_config(wl, world, schedule, data):
+    """The same dictionary in both arms (the driver compares them)."""
+    nloci, n0, n1, cpg, desc = WORKLOADS[wl][:5]
+    mb = state_mb_per_gpu(wl)
+    return {"workload": desc, "chains_total": cpg * max(world, 1), "loci": nloci, "genes_per_locus": n0 + n1,
+            "priors": "-q %g -m %g -t %g" % (PRIOR_Q, PRIOR_M, PRIOR_T), "heating": "-hfg -ha 0.96 -hb 0.9",
+            "parallelism": "chains sharded by rank x%d" % world, "input": data, "burn_in_steps": BURN,
+            "l2": "no flush between steps: the resident state (%.0f MB per GPU, both buffers) is what every step re-reads by design; %s"
+                  % (mb, "it fits the 126 MB L2" if mb < L2_MB else "it is larger than the 126 MB L2, every step streams it from HBM"),
+            "schedule": ("qupdate: updategenealogy for every chain x locus, split-time update of every chain, mutation scalars every 5th step, swaps")
+            if schedule == "full" else "updategenealogy for every chain x locus + swaps"}
+
+
+# ---- the reference's own CPU code ---------------------------------------------------------------------------------------------
+def run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn, full, tmp, budget_s=20.0, gburn=0):
     """The reference's own updategenealogy()/qupdate() loop (oracle/_ref/ref_harness `bench` mode) in nproc
     independent serial processes, each holding total_chains/nproc chains (no MPI in this image: no cross-process
     swaps, which makes this an upper bound on the reference's MPI build)."""
@@ -138,7 +224,7 @@ def run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn, ful
     # A process that is still running long after most of the others have finished is taken to be in that state: it is
     # killed and started again with another seed (twice at most), so that every host core contributes to the figure.
     t_start = time.time()
-    deadline = t_start + max(90.0, 6.0 * budget_s)
+    deadline = t_start + max(120.0, 8.0 * budget_s)
     live = {i: launch(i, c, 1000 + 17 * i) + (0, time.time()) for i, c in enumerate(per)}
     res, durations = [], []
     while live and time.time() < deadline:
@@ -160,76 +246,139 @@ def run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn, ful
     return res, len(res)
 
 
-def reference_throughput(wl, world, steps, warmup, budget_s, full=1):
+def reference_throughput(wl, world, steps, warmup, budget_s, full=1, data="synthetic", burn=BURN):
     """(value updates/s over all host cores, ms per step, cores, sample description); each step is one chunk."""
     from ima2p_b200 import synth
     if not os.path.exists(HARNESS):
         return None
-    nloci, n0, n1, cpg, _ = WORKLOADS[wl]
+    nloci, n0, n1, cpg = WORKLOADS[wl][:4]
     total_chains = cpg * world
     ncores = os.cpu_count() or 1
     nproc = max(1, min(ncores, total_chains))
     tmp = tempfile.mkdtemp(prefix="ima2p_ref_")
-    ufile = os.path.join(tmp, "synthetic.u")
-    synth.write_u(ufile, synth.make_dataset(nloci, n0, n1, seed=11))
+    ufile = os.path.join(tmp, "input.u")
+    synth.write_u(ufile, dataset(wl, data))
     chains_pp = -(-total_chains // nproc)
     est = 30000.0 if not full else 17000.0                 # updates/s/core, survey probe (BASELINE.md section 2)
+    # the untimed burn-in is bounded too: what a core does in about 20 s (whole steps, as in our arm)
+    burn = int(max(5, min(burn, 20.0 * est / (chains_pp * nloci))))
     chunks = steps + warmup
     iters = max(1, int(budget_s * est / (chunks * chains_pp * nloci)))
-    res, used = run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn=0, full=full, tmp=tmp, budget_s=budget_s)
+    res, used = run_reference_processes(ufile, total_chains, nproc, iters, chunks, burn=burn, full=full, tmp=tmp, budget_s=budget_s + 20.0)
     if not res:
         return None
     chunk_s = np.array([r["chunk_seconds"] for r in res])            # [proc][chunk]
     upd = sum(r["updates_per_chunk"] for r in res)
     timed = chunk_s[:, warmup:]
     step_s = timed.max(axis=0).mean()
-    sample = "%d serial reference processes x %d chains, %d loci; %d %s per step" % (
-        used, chains_pp, nloci, iters, "whole qupdate() steps" if full else "updategenealogy sweeps")
+    sample = "%d serial reference processes x %d chains, %d loci (%s input); %d %s per step after %d whole steps of burn-in" % (
+        used, chains_pp, nloci, data, iters, "whole qupdate() steps" if full else "updategenealogy sweeps", burn)
     return dict(value=upd / step_s, ms_per_step=step_s * 1e3, cores=used, sample=sample,
                 accept=sum(r["accepted"] for r in res) / max(1, sum(r["updates"] for r in res)))
 
 
+# ---- our arm ----------------------------------------------------------------------------------------------------------------
+class Job:
+    """One workload on this rank's GPU: engine, streams, stepping (one GPU: Engine.run; several: Engine.run_sharded after the
+    ranks attached each other's exchange tables)."""
+
+    def __init__(self, wl, args, rank, world, dev):
+        import torch
+        self.torch, self.wl, self.rank, self.world, self.dev = torch, wl, rank, world, dev
+        self.nloci, self.n0, self.n1, self.cpg = WORKLOADS[wl][:4]
+        self.eng, self.loci, self.st = build_engine(wl, rank, world, data=args.data)
+        eng = self.eng
+        eng.set_update_priors(t_max=[PRIOR_T])
+        self.full = 1 if args.schedule == "full" else 0
+        if self.full:
+            eng.set_update_schedule(3, 5)
+        if args.pipeline:
+            eng.set_pipeline(*[int(x) for x in args.pipeline.split(",")])
+        if args.proposal:
+            eng.set_proposal_path(*[int(x) for x in args.proposal.split(",")])
+        if os.environ.get("IMA_SPEC"):
+            eng.set_speculation(int(os.environ["IMA_SPEC"]))
+        self.work_stream = torch.cuda.Stream()         # a real (non-default) stream: kernels and the timing events all go here
+        torch.cuda.set_stream(self.work_stream)
+        self.stream = self.work_stream.cuda_stream
+        self.swaptries = eng.default_swaptries()
+        self.pinned = {k: torch.from_numpy(np.ascontiguousarray(self.st[k])).pin_memory() for k in STATE_KEYS}
+        self.bufs = [self.pinned[k].data_ptr() for k in STATE_KEYS]
+        eng.put_state(self.bufs, self.st["tvals"], self.stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            from ima2p_b200.multirank import attach_exchange
+            attach_exchange(eng, torch.cuda.current_device())
+
+    def run_steps(self, n):
+        if self.world == 1:
+            self.eng.run(n, self.swaptries, self.stream)
+        else:
+            self.eng.run_sharded(n, self.swaptries, self.stream)
+
+    def barrier(self):
+        import torch.distributed as dist
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def timed(self, steps):
+        """ms for `steps` steps, device events on the launching stream, max over ranks."""
+        import torch.distributed as dist
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        self.run_steps(steps)
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+
 def main():
-    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keeps NCCL's version banner off stdout (one JSON line only)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sim50x128", choices=sorted(WORKLOADS))
-    ap.add_argument("--burn", type=int, default=3000, help="untimed burn-in steps before warm-up (migration counts need ~3000 steps to settle)")
+    ap.add_argument("--data", default="real", choices=["synthetic", "real"],
+                    help="synthetic: Simulations-shaped loci drawn by ima2p_b200.synth; real: the reference's own Simulations/*.u loci "
+                         "(as held by the golden fixtures), written as a .u file and read by the product's reader")
+    ap.add_argument("--burn", type=int, default=BURN, help="untimed whole steps before warm-up (the same in both arms)")
     ap.add_argument("--pipeline", default="", help="groups,depth[,decisions_first] of Engine.set_pipeline (default: the engine's)")
+    ap.add_argument("--proposal", default="", help="fast,pairs_per_warp of Engine.set_proposal_path (default: the engine's)")
     ap.add_argument("--schedule", default="full", choices=["full", "genealogy"],
                     help="full: qupdate's schedule (genealogies, split time every step, mutation scalars every 5th, swaps); "
                          "genealogy: updategenealogy + swaps only")
-    ap.add_argument("--graph-multi", action="store_true",
-                    help="N > 1: replay the step (kernels + NCCL all-gather) as a CUDA graph; measured gain 1.3 %% at N = 2, and "
-                         "torch 2.11 / NCCL 2.28 then hangs tearing the process group down, so the default is eager launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lmode", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     wl = args.workload
-    nloci, n0, n1, cpg, desc = WORKLOADS[wl]
+    nloci, n0, n1, cpg = WORKLOADS[wl][:4]
     W = max(3, args.warmup)
     metric, unit = "chain_x_locus_genealogy_updates_per_sec", "updates/s"
-    config = {"workload": desc, "chains_total": cpg * max(world, 1), "loci": nloci, "genes_per_locus": n0 + n1,
-              "priors": "-q %g -m %g" % (PRIOR_Q, PRIOR_M), "heating": "-hfg -ha 0.96 -hb 0.9", "parallelism": "chains sharded by rank x%d" % world,
-              "l2": "inputs %s L2: state of all pairs is re-read every step; see l2_note" % "vs",
-              "schedule": ("qupdate: updategenealogy for every chain x locus, split-time update of every chain (-t %g), mutation scalars "
-                           "every 5th step, swaps" % PRIOR_T) if args.schedule == "full" else "updategenealogy for every chain x locus + swaps"}
+    config = make_config(wl, world, args.schedule, args.data)
     full = 1 if args.schedule == "full" else 0
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = reference_throughput(wl, world, args.steps, W, budget_s=100.0, full=full)
+        r = reference_throughput(wl, world, args.steps, W, budget_s=100.0, full=full, data=args.data, burn=args.burn)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness was not built (needs /root/reference at build time)"}))
             return
         print(json.dumps({"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f64", "data": "synthetic", "config": config,
+                          "dtype": "f64", "data": args.data, "config": config,
                           "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
                           "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -240,71 +389,17 @@ def main():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
     dev = torch.device("cuda", torch.cuda.current_device())
-    eng, loci, st = build_engine(wl, rank, world)
-    eng.set_update_priors(t_max=[PRIOR_T])
-    if full:
-        eng.set_update_schedule(3, 5)
-    if args.pipeline:
-        eng.set_pipeline(*[int(x) for x in args.pipeline.split(",")])
-    if os.environ.get("IMA_SPEC"):
-        eng.set_speculation(int(os.environ["IMA_SPEC"]))
-    work_stream = torch.cuda.Stream()              # a real (non-default) stream: kernels, NCCL and the timing events all go here
-    torch.cuda.set_stream(work_stream)
-    stream = work_stream.cuda_stream
-    swaptries = eng.default_swaptries()
-    pinned = {k: torch.from_numpy(np.ascontiguousarray(st[k])).pin_memory() for k in STATE_KEYS}
-    bufs = [pinned[k].data_ptr() for k in STATE_KEYS]
-    eng.put_state(bufs, st["tvals"], stream)
-    torch.cuda.synchronize()
-    S_local = torch.zeros(cpg, dtype=torch.float64, device=dev)
-    S_global = torch.zeros(cpg * world, dtype=torch.float64, device=dev)
-
-    def step_multi():
-        eng.update_genealogies(S_local.data_ptr(), stream)
-        dist.all_gather_into_tensor(S_global, S_local)
-        eng.swap_replay(S_global.data_ptr(), swaptries, stream)
-
-    stepper = None
-    if world > 1:
-        from ima2p_b200.multirank import ShardedStepper
-        stepper = ShardedStepper(eng, dev, stream)
-
-    def run_steps(n):
-        if world == 1:
-            eng.run(n, swaptries, stream)
-        else:
-            stepper.run(n, swaptries)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    graphed = False
-    if world > 1 and args.graph_multi:
-        with torch.cuda.stream(work_stream):
-            graphed = stepper.capture(swaptries)      # kernels + the NCCL all-gather of one step as one CUDA graph
-        flag = torch.tensor([1.0 if graphed else 0.0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # all ranks replay a graph, or none does
-        if float(flag.item()) == 0.0:
-            stepper._graph = None
-            graphed = False
+    job = Job(wl, args, rank, world, dev)
+    eng, stream, swaptries, pinned = job.eng, job.stream, job.swaptries, job.pinned
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()               # started early: nvidia-smi needs a few hundred ms before its first line
-    run_steps(args.burn)          # burn-in: leave the artificial starting genealogies behind (untimed)
-    run_steps(W)
-    barrier()
+    job.run_steps(args.burn)      # burn-in: leave the artificial starting genealogies behind (untimed)
+    job.run_steps(W)
+    job.barrier()
     c0 = eng.counters()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = None
-    barrier()
     sampler.mark()
-    e0.record()
-    run_steps(args.steps)         # the public path: Engine.run (captured graph, piece-wise overlapped step)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = job.timed(args.steps)    # the public path: Engine.run / Engine.run_sharded (captured graphs)
+    kernel_ms = None
     if world == 1:
         # same K steps again, kernel by kernel with CUDA events on the launching stream around each kernel
         # (no overlap between kernels): per-kernel durations for the roofline accounting
@@ -323,15 +418,11 @@ def main():
             enough = float(f.item())
         if enough:
             break
-        run_steps(100)
+        job.run_steps(100)
         torch.cuda.synchronize()
         clocks_extended = True
     clocks = sampler.stop()
     clocks["extended_past_timed_region"] = clocks_extended
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     eng.sync()
     updates_all = cpg * world * nloci * args.steps
     value = updates_all / (ms * 1e-3)
@@ -342,7 +433,7 @@ def main():
     if world == 1 and full:
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.set_update_schedule(False, 0)
-        eng.run(3, swaptries, stream)
+        eng.run(8, swaptries, stream)
         torch.cuda.synchronize()
         g0.record(); eng.run(args.steps, swaptries, stream); g1.record()
         torch.cuda.synchronize()
@@ -368,7 +459,7 @@ def main():
     # one-block wire form (ima2p_engine_put_state_block) when the sample fits it: the same genealogies with 8-bit links and
     # migration counts (13 instead of 20 bytes per edge) and the migration events stored ragged, as ONE pinned host block ->
     # one PCIe transfer per step; packed once here (untimed), uploaded from pinned memory every step
-    put, wire = (lambda: eng.put_state(bufs, tv_now, stream)), "put_state"
+    put, wire = (lambda: eng.put_state(job.bufs, tv_now, stream)), "put_state"
     blk = None if os.environ.get("IMA_PLAIN_UPLOAD") else eng.pack_state_block([pinned[k].numpy() for k in STATE_KEYS], tv_now)
     if blk is not None:
         pinned["block"] = torch.from_numpy(blk[0]).pin_memory()
@@ -376,26 +467,30 @@ def main():
         put, wire = (lambda: eng.put_state_block(bptr, nev, stream)), "put_state_block"
         h2d = int(pinned["block"].numel())
     for _ in range(10):           # the first transfers from a freshly pinned buffer are slow on this (virtualised) PCIe path
-        put(); run_steps(1); eng.step_report(stream)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        put()
-        run_steps(1)
-        summ, _row = eng.step_report(stream)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = cpg * world * nloci * ke / e2e_s
+        put(); job.run_steps(1); eng.step_report(stream)
+    # the figure moves with the state of the (virtualised) PCIe path: median of five repetitions of the ke-step loop
+    reps = []
+    for _ in range(5):
+        job.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            put()
+            job.run_steps(1)
+            summ, _row = eng.step_report(stream)
+        job.barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        reps.append(e2e_s)
+    e2e_value = cpg * world * nloci * ke / float(np.median(reps))
     assert np.isfinite(summ).all()
     # where an end-to-end step goes (each part synchronised on its own; untimed for the metric)
     parts = {"upload_and_evaluate": 0.0, "step": 0.0, "read_back": 0.0}
     for _ in range(10):
         t0 = time.perf_counter(); put(); torch.cuda.synchronize()
-        t1 = time.perf_counter(); run_steps(1); torch.cuda.synchronize()
+        t1 = time.perf_counter(); job.run_steps(1); torch.cuda.synchronize()
         t2 = time.perf_counter(); eng.step_report(stream); torch.cuda.synchronize()
         t3 = time.perf_counter()
         parts["upload_and_evaluate"] += (t1 - t0) * 100; parts["step"] += (t2 - t1) * 100; parts["read_back"] += (t3 - t2) * 100
@@ -403,41 +498,78 @@ def main():
     lmode_multi = None
     if world > 1 and not args.no_lmode:
         try:
-            lmode_multi = lmode_bench_sharded(eng, dev, rank, world, step_multi)
+            lmode_multi = lmode_bench_sharded(eng, dev, rank, world, job)
         except Exception as ex:
             lmode_multi = {"error": str(ex)}
+    upd_counters = {k: int(v) for k, v in eng.update_counters().items()}
+
+    # ---- BASELINE configs[2]'s shape on the same GPUs: 300 loci x 256 chains per GPU ------------------------------------------
+    config3 = None
+    if world > 1 and not args.no_config3 and wl != "sim300x256":
+        try:
+            job.barrier()
+            eng.close()
+            torch.cuda.empty_cache()
+            job3 = Job("sim300x256", args, rank, world, dev)
+            job3.run_steps(min(args.burn, 600))
+            job3.run_steps(W)
+            k3 = max(10, args.steps // 4)
+            ms3 = job3.timed(k3)
+            l3, _, _, c3 = WORKLOADS["sim300x256"][:4]
+            v3 = c3 * world * l3 * k3 / (ms3 * 1e-3)
+            cnt3 = job3.eng.counters()
+            config3 = {"config": make_config("sim300x256", world, args.schedule, args.data), "value": v3, "unit": unit, "ms_per_step": ms3 / k3,
+                       "steps": k3, "accept_rate": cnt3["accepted"] / max(1, cnt3["updates"]), "dropped_for_capacity": cnt3["dropped"]}
+            if rank == 0 and not args.no_cpu_baseline:
+                r3 = reference_throughput("sim300x256", world, 2, 1, budget_s=15.0, full=full, data=args.data)
+                if r3 is not None:
+                    config3["cpu_baseline"] = {"value": r3["value"], "unit": unit, "cores": r3["cores"], "kind": "reference", "sample": r3["sample"]}
+                    config3["ratio_to_cpu_baseline"] = v3 / r3["value"]
+            job3.barrier()
+            job3.eng.close()
+        except Exception as ex:
+            config3 = {"error": repr(ex)}
     if rank != 0:
         if world > 1:
-            if graphed:
-                os._exit(0)         # see --graph-multi
             dist.destroy_process_group()
         return
     pk, pk_kind = peaks()
     roof = None
     if kernel_ms is not None:
-        per = np.asarray(kernel_ms, dtype=np.float64) / args.steps                       # ms per launch
-        names = ["k_propose", "k_accept", "k_swap", "k_split_t", "k_accept_t", "k_changeu", "k_move", "k_weigh", "k_propose_redo"]
-        per = per[:len(names)]
-        dom = int(np.argmax(per[:6]))
+        names = ["proposal_kernels", "k_accept", "k_swap", "k_split_t", "k_accept_t", "k_changeu", "k_move", "k_weigh", "k_propose_redo"]
+        per = np.asarray(kernel_ms, dtype=np.float64)[:len(names)] / args.steps              # ms per launch
         P = cpg * nloci
-        b_update = algorithmic_bytes_per_update(n0 + n1, mig_mean, p_acc, eng.NI, eng.ND)
+        b_update = algorithmic_bytes_per_update(n0 + n1, mig_mean, p_acc, eng.NI, eng.ND)      # B_IS of SURVEY.md section 8(d)
         W_g = 4 * eng.NI + 8 * eng.ND
-        b_accept = 2 * W_g + 16 + 12 + 1 + (W_g + 8 * (eng.nq + eng.nm) + 40) / nloci
         b_pair = 24.0 * (2 * (n0 + n1) - 1) + 12.0 * mig_mean + W_g + 24.0                # one genealogy with its weights
-        alg = {"k_propose": b_update * P, "k_accept": b_accept * P, "k_swap": 16.0 * cpg, "k_split_t": 2.0 * b_pair * P,
-               "k_accept_t": (W_g + 8 + 16 + 1) * P, "k_changeu": 48.0 * P}[names[dom]]
-        achieved = alg / (per[dom] * 1e-3) / 1e9
+        # algorithmic bytes per launch of every kernel: what it must read and write of the pairs' records
+        alg = {"proposal_kernels": b_update * P, "k_move": 2.0 * (b_pair - W_g) * P, "k_weigh": (b_pair + W_g + 24.0) * P,
+               "k_propose_redo": 0.0, "k_accept": (2 * W_g + 16 + 12 + 1) * P + (W_g + 8 * (eng.nq + eng.nm) + 40) * cpg,
+               "k_swap": 16.0 * cpg, "k_split_t": 2.0 * b_pair * P, "k_accept_t": (W_g + 8 + 16 + 1) * P, "k_changeu": 48.0 * P}
+        timed_names = [n for n in names if n != "proposal_kernels"] if per[6] > 0 else names[:6]
+        dom = max(timed_names, key=lambda n: per[names.index(n)])
+        dom_ms = per[names.index(dom)]
+        # the roofline line of the contract: SURVEY 8(d)'s per-update figure x the updates of one launch over the dominant
+        # kernel's launch time; the same bytes over the whole step, and every kernel against its own bytes, beside it
+        achieved = b_update * P / (dom_ms * 1e-3) / 1e9
         traffic = None
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
-            traffic = json.load(open(tf)).get(names[dom])
-        roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_launch": alg,
+            traffic = json.load(open(tf)).get(dom)
+        step_gbps = b_update * P / (ms / args.steps * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes_per_update": b_update,
+                "algorithmic_bytes_per_launch": b_update * P,
+                "whole_step": {"achieved": step_gbps, "frac": step_gbps / pk["hbm_gbs"]},
                 "kernel_ms_per_launch": {n: float(v) for n, v in zip(names, per)},
+                "per_kernel": {n: {"algorithmic_bytes_per_launch": alg[n],
+                                   "GBps": (alg[n] / (per[names.index(n)] * 1e-3) / 1e9) if per[names.index(n)] > 0 else None,
+                                   "frac": (alg[n] / (per[names.index(n)] * 1e-3) / 1e9 / pk["hbm_gbs"]) if per[names.index(n)] > 0 else None}
+                               for n in names},
                 "note": "latency/dependency-bound path: small FP64/integer work per pair, see DESIGN.md"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r = reference_throughput(wl, 1, 3, 1, budget_s=12.0, full=full)
+        r = reference_throughput(wl, 1, 3, 1, budget_s=12.0, full=full, data=args.data, burn=args.burn)
         if r is not None:
             cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference", "sample": r["sample"], "accept_rate": r["accept"]}
     lmode = lmode_multi
@@ -446,22 +578,22 @@ def main():
             lmode = lmode_bench(eng, dev)
         except Exception as ex:       # the L-mode line is supplementary; the M-mode metric must still be reported
             lmode = {"error": str(ex)}
-    config["l2"] = "working set %.1f MB per GPU (both state buffers) vs 126 MB L2: L2-resident; no flush (state is reused every step by design)" % (2 * sum(sb) / 1e6)
+    # k_move, k_weigh, k_propose_redo, k_accept, k_split_t_fast, k_split_t_redo, k_accept_t, k_changeu, k_swap
+    launches_per_step = 9 if full else 5
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-           "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke, "parts_ms": parts, "upload": wire},
-           "gpu_launches": (6 if full else 3) * args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": args.data, "config": config,
+           "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke, "parts_ms": parts,
+                                     "upload": wire, "repetitions_s": reps, "statistic": "median of 5 repetitions"},
+           "gpu_launches": launches_per_step * args.steps,
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
            "genealogy_updates_only": ({"ms_per_step": graph_ms / args.steps, "value": updates_all / (graph_ms * 1e-3), "unit": unit}
-                                      if graph_ms else None), "lmode": lmode,
-           "multi_gpu_step": (("cuda graph (kernels + NCCL all-gather)" if graphed else "eager launches") if world > 1 else None),
-           "dropped_for_capacity": c1["dropped"], "split_time_mean": split_time_mean,
-           "update_counters": {k: int(v) for k, v in eng.update_counters().items()}, "swap_rate": (c1["swaps"] - c0["swaps"]) / max(1, c1["swap_attempts"] - c0["swap_attempts"])}
+                                      if graph_ms else None), "lmode": lmode, "config3": config3,
+           "multi_gpu_step": ("one CUDA graph per step on every rank; swap sums exchanged through peer memory inside the kernels "
+                              "(ima2p_engine_run_sharded)" if world > 1 else None),
+           "dropped_for_capacity": c1["dropped"], "split_time_mean": split_time_mean, "update_counters": upd_counters,
+           "swap_rate": (c1["swaps"] - c0["swaps"]) / max(1, c1["swap_attempts"] - c0["swap_attempts"])}
     print(json.dumps(out, default=float))
     if world > 1:
-        if graphed:
-            sys.stdout.flush()
-            os._exit(0)             # see --graph-multi
         dist.destroy_process_group()
 
 
@@ -525,7 +657,7 @@ def lmode_bench(eng, dev, G=1000000):
             "f3_note": "calcx: 2 incomplete gammas per parameter and row; 2NM density: 2-4 per row and point; greater-than: a trapezoid quadrature of incomplete gammas per row -- FP64-bound"}
 
 
-def lmode_bench_sharded(eng, dev, rank, world, step_multi, G=1000000):
+def lmode_bench_sharded(eng, dev, rank, world, job, G=1000000):
     """The same L-mode evaluations with the G rows sharded over the ranks (BASELINE config 4): every evaluation is local
     partial sums plus one small collective (ima2p_b200/multirank.py).  Whole-job evals/s, slowest rank."""
     import torch
@@ -534,7 +666,7 @@ def lmode_bench_sharded(eng, dev, rank, world, step_multi, G=1000000):
     from ima2p_b200.multirank import sharded_jointp, sharded_margincalc
     mine = []
     for _ in range(200):                              # cold-chain rows of this run, wherever the cold chain lives
-        step_multi(); step_multi()
+        job.run_steps(2)
         r = eng.cold_row()
         if r is not None:
             mine.append(r.copy())

@@ -112,7 +112,7 @@ IMA_DEV const double *await_swap_sums(const EngineView &E, int step_bias) {
     volatile unsigned long long *cnt = X.peer_arrived[X.rank] + (ep & 1ull);
     const long long t0 = clock64();
     while (*cnt < target) {
-      if (clock64() - t0 > 8000000000ll) { raise(E.mc, kErrExchange); break; }      // a peer never arrived (about four seconds)
+      if (clock64() - t0 > 30000000000ll) { raise(E.mc, kErrExchange); break; }     // a peer never arrived (about fifteen seconds)
     }
     __threadfence_system();
   }
