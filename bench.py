@@ -597,6 +597,16 @@ def main():
         dist.destroy_process_group()
 
 
+def fp64_peaks(device=0):
+    """(FP64 fused multiply-adds per second, FP64 exp evaluations per second) measured on this GPU by the library's own
+    micro-kernels (ima2p_debug_fp64_peaks): what the FP64-bound L-mode kernels are quoted against."""
+    import ctypes as C
+    from ima2p_b200 import capi
+    out = (C.c_double * 2)()
+    capi.check(capi.lib(), capi.lib().ima2p_debug_fp64_peaks(device, out))
+    return float(out[0]), float(out[1])
+
+
 def lmode_bench(eng, dev, G=1000000):
     """L-mode evals/sec (BASELINE config 4 shape: 1e6 sampled genealogies, 21 floats each): margincalc on the
     1000-point grids of all parameters (histograms.cpp:81-99) and jointp for a differential-evolution population."""
@@ -648,7 +658,11 @@ def lmode_bench(eng, dev, G=1000000):
     passes = -(-1000 // 8)
     streamed = G * 4.0 * passes * (3 * 4 + 2 * 3)
     pk, _ = peaks()
+    fma_s, exp_s = fp64_peaks(torch.cuda.current_device())
     return {"rows": G, "margincalc_geneval_per_sec": 5 * 1000 * G / (t1 - t0), "jointp_geneval_per_sec": 64 * G / (t3 - t2),
+            "fp64_fma_per_sec_measured": fma_s, "fp64_exp_per_sec_measured": exp_s,
+            # one exp per genealogy-evaluation in margincalc; one exp (eexp) + 2 (3 nq + 2 nm) multiply-adds in jointp
+            "fp64_frac": {"margincalc_vs_exp_peak": 5 * 1000 * G / (t1 - t0) / exp_s, "jointp_vs_exp_peak": 64 * G / (t3 - t2) / exp_s},
             "unit": "genealogy evals/s", "timing": "host wall clock around the C-ABI calls (includes H2D of x and D2H of results)",
             "margincalc_streamed_GBps": streamed / (t1 - t0) / 1e9, "margincalc_streamed_frac_of_hbm_peak": streamed / (t1 - t0) / 1e9 / pk["hbm_gbs"],
             "margincalc_algorithmic_GBps_one_pass_per_x": 5 * 1000 * G * 15.2 / (t1 - t0) / 1e9,
@@ -663,7 +677,7 @@ def lmode_bench_sharded(eng, dev, rank, world, job, G=1000000):
     import torch
     import torch.distributed as dist
     from ima2p_b200 import LMode
-    from ima2p_b200.multirank import sharded_jointp, sharded_margincalc
+    from ima2p_b200.multirank import sharded_jointp_device, sharded_margincalc
     mine = []
     for _ in range(200):                              # cold-chain rows of this run, wherever the cold chain lives
         job.run_steps(2)
@@ -686,19 +700,24 @@ def lmode_bench_sharded(eng, dev, rank, world, job, G=1000000):
         sharded_margincalc(lm, grid[p], 0.0, p, 0, device=dev)
     torch.cuda.synchronize(); dist.barrier()
     t1 = time.perf_counter()
-    xs = np.column_stack([rng.uniform(0.05, 0.9, 64) * (PRIOR_Q if p < 3 else PRIOR_M) for p in range(5)])
-    sharded_jointp(lm, xs[:32], device=dev)
+    # a differential-evolution generation of the joint search: 500 trial vectors (100 x the 5 parameters, jointfind.cpp:599-812),
+    # in batches of 32 queued on one stream with two device all-gathers each and one copy back at the end
+    NV = 512
+    xs = np.column_stack([rng.uniform(0.05, 0.9, NV) * (PRIOR_Q if p < 3 else PRIOR_M) for p in range(5)])
+    sharded_jointp_device(lm, xs[:64], device=dev)
     torch.cuda.synchronize(); dist.barrier()
     t2 = time.perf_counter()
-    q1, _ = sharded_jointp(lm, xs[:32], device=dev)
-    q2, _ = sharded_jointp(lm, xs[32:], device=dev)
+    q1, _ = sharded_jointp_device(lm, xs, device=dev)
     torch.cuda.synchronize(); dist.barrier()
     t3 = time.perf_counter()
     lm.close()
     t = torch.tensor([t1 - t0, t3 - t2], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {"rows": G, "rows_per_rank": hi - lo, "margincalc_geneval_per_sec": 5 * 1000 * G / float(t[0]), "jointp_geneval_per_sec": 64 * G / float(t[1]),
-            "unit": "genealogy evals/s", "checksum": float(np.sum(q1) + np.sum(q2)),
+    fma_s, exp_s = fp64_peaks(torch.cuda.current_device())
+    return {"rows": G, "rows_per_rank": hi - lo, "margincalc_geneval_per_sec": 5 * 1000 * G / float(t[0]), "jointp_geneval_per_sec": NV * G / float(t[1]),
+            "jointp_vectors": NV, "fp64_exp_per_sec_measured_per_gpu": exp_s,
+            "fp64_frac": {"margincalc_vs_exp_peak_all_gpus": 5 * 1000 * G / float(t[0]) / (exp_s * world), "jointp_vs_exp_peak_all_gpus": NV * G / float(t[1]) / (exp_s * world)},
+            "unit": "genealogy evals/s", "checksum": float(np.sum(q1)),
             "timing": "host wall clock around the sharded calls incl. the collectives, max over ranks"}
 
 

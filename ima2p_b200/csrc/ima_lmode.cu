@@ -261,6 +261,27 @@ IMA_KERNEL void k_joint_fold(const double *partials, int nchunks, int nvec, doub
   r[0] = ins; r[1] = kept; r[2] = sum; r[3] = sq; r[4] = minp; r[5] = minterm;
 }
 
+// device-resident exchange of the sharded jointp (ima2p_lmode_joint_begin / _middle): from the local maxima of all ranks, the
+// maximum over the rows held by lower ranks (the seed of this rank's running maximum) and the maximum over all rows
+IMA_KERNEL void k_joint_seed(const double *allmax, int world, int rank, int nvec, double *seed, double *gmax) {
+  const int v = ima_block() * kLmWarps * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
+  if (v >= nvec) return;
+  double s = -DBL_MAX, g = -DBL_MAX;
+  for (int r = 0; r < world; r++) {
+    const double m = allmax[(size_t)r * nvec + v];
+    if (r < rank && m > s) s = m;
+    if (m > g) g = m;
+  }
+  seed[v] = s; gmax[v] = g;
+}
+// records of this rank with the global maximum beside them: [nvec][8] = the six of k_joint_fold, the global maximum, 0
+IMA_KERNEL void k_joint_pack(const double *rec6, const double *gmax, int nvec, double *out8) {
+  const int v = ima_block() * kLmWarps * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
+  if (v >= nvec) return;
+  for (int k = 0; k < kJP; k++) out8[(size_t)v * 8 + k] = rec6[(size_t)v * kJP + k];
+  out8[(size_t)v * 8 + 6] = gmax[v]; out8[(size_t)v * 8 + 7] = 0.0;
+}
+
 
 // ---- section 8 (f3): the other evaluators that stream over the rows -------------------------------------------------
 // calcx moments (output.cpp:14-134, 687-745) and the densities of the product 2NM (popmig.cpp:9-357).  Same shape as
@@ -755,7 +776,7 @@ struct Lmode {
   double q_max[kMaxParams], q_min[kMaxParams], m_max[kMaxParams], m_min[kMaxParams], m_mean[kMaxParams];
   float *d_cols = nullptr;
   double *d_x = nullptr, *d_partials = nullptr, *d_out = nullptr, *d_pbuf = nullptr, *d_chunkmax = nullptr, *d_prefix = nullptr,
-         *d_lmax = nullptr, *d_jpart = nullptr, *d_jout = nullptr;
+         *d_lmax = nullptr, *d_jpart = nullptr, *d_jout = nullptr, *d_seed = nullptr, *d_gmax = nullptr, *d_ltmp = nullptr;
   JointXs *d_xs = nullptr;
   size_t cap_x = 0, cap_partials = 0;
   struct LmPriors *d_pri = nullptr;            // section 8 (f3) evaluators: priors, logfact table and error word, made on first use
@@ -928,6 +949,56 @@ int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const do
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint terms)");
 #endif
   if (!d2h(localmax_out, l.d_lmax, nvec * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+  return IMA2P_OK;
+}
+
+// The same two phases with everything left on the device, for callers that exchange between ranks with device collectives
+// (NCCL all-gather of the local maxima, then of the records): nothing crosses PCIe and nothing synchronises between the phases,
+// so batch after batch can be queued on one stream.
+//   begin : terms of nvec (<= 32) vectors over the local rows; dev_localmax_out[nvec] (device) = maximum over the local rows
+//   middle: dev_allmax[world][nvec] (device, the gathered local maxima) -> seed and global maximum on the device, prefixes,
+//           scan, fold; dev_records_out[nvec][8] (device) = the six record fields, the global maximum, 0
+// The caller gathers the records of all ranks and closes every vector with ima2p_lmode_joint_finish on their sums.
+int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *dev_localmax_out, void *cuda_stream) {
+  if (!h || !h->lm.d_cols || !x || nvec < 1 || nvec > kJointVecMax || !dev_localmax_out) return lfail(IMA2P_E_ARG, "joint_begin: bad argument");
+  Lmode &l = h->lm;
+  if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = lm_stream(&l, cuda_stream);
+  const int np = l.v.nq + l.v.nm, nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
+  std::vector<JointXs> xs(nvec);
+  for (int v = 0; v < nvec; v++)
+    for (int i = 0; i < np; i++) {                     // jointfind.cpp:955-970
+      const double xv = x[(size_t)v * np + i];
+      xs[v].x[i] = xv; xs[v].logx[i] = log(xv); xs[v].divx[i] = 1.0 / xv;
+      if (i < l.v.nq) xs[v].log2diffx[i] = kLog2 - log(xv);
+    }
+  if (!h2d(l.d_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
+  IMA_LAUNCH(k_joint_terms, nchunks, kLmWarps, kLmWarps * kJointVecMax * sizeof(double), s, l.v, l.d_xs, nvec, l.d_pbuf, l.d_chunkmax);
+  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, (const double *)nullptr, l.d_prefix, dev_localmax_out);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint begin)");
+#endif
+  return IMA2P_OK;
+}
+
+int ima2p_lmode_joint_middle(ima2p_lmode *h, int nvec, const double *dev_allmax, int world, int rank, long long global_row0,
+                             double *dev_records_out, void *cuda_stream) {
+  if (!h || !h->lm.d_cols || nvec < 1 || nvec > kJointVecMax || !dev_allmax || !dev_records_out || world < 1 || rank < 0 || rank >= world)
+    return lfail(IMA2P_E_ARG, "joint_middle: bad argument");
+  Lmode &l = h->lm;
+  if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = lm_stream(&l, cuda_stream);
+  const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock), gv = (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP);
+  if (!l.d_seed) { l.d_seed = l.alloc<double>(kJointVecMax); l.d_gmax = l.alloc<double>(kJointVecMax); l.d_ltmp = l.alloc<double>(kJointVecMax); }
+  if (!l.d_seed || !l.d_gmax || !l.d_ltmp) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  IMA_LAUNCH(k_joint_seed, gv, kLmWarps, 0, s, dev_allmax, world, rank, nvec, l.d_seed, l.d_gmax);
+  IMA_LAUNCH(k_joint_prefix, gv, kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, (const double *)l.d_seed, l.d_prefix, l.d_ltmp);
+  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, l.d_pbuf, nvec, l.d_prefix, l.d_gmax, global_row0, l.d_jpart);
+  IMA_LAUNCH(k_joint_fold, gv, kLmWarps, 0, s, l.d_jpart, nchunks, nvec, l.d_jout);
+  IMA_LAUNCH(k_joint_pack, gv, kLmWarps, 0, s, l.d_jout, l.d_gmax, nvec, dev_records_out);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint middle)");
+#endif
   return IMA2P_OK;
 }
 
@@ -1250,5 +1321,69 @@ int ima2p_lmode_greater_than(ima2p_lmode *h, int kind, int i, int j, double *out
   if ((rc = lm_check_err(l, s, "greater_than"))) return rc;
   *out = sum / (double)nused;
   return IMA2P_OK;
+}
+// ---- measured FP64 peaks of the device (the L-mode evaluators and the prior sweep are bound by FP64
+// arithmetic and by exp, not by HBM; their fractions are quoted against what this GPU does, measured here) ---------------
+}  // extern "C"
+namespace ima {
+// 8 independent fused multiply-add chains per thread (fma() is exempt from --fmad=false: it is asked for)
+IMA_KERNEL void k_peak_fma(double *out, int iters) {
+  double a[8];
+  const double x = 1.0 + 1e-9 * (ima_block() + 1), y = 1e-12 * (Warp::lane() + 1);
+  for (int k = 0; k < 8; k++) a[k] = 1.0 + k;
+  for (int i = 0; i < iters; i++)
+    for (int k = 0; k < 8; k++) a[k] = fma(a[k], x, y);
+  double s = 0.0;
+  for (int k = 0; k < 8; k++) s += a[k];
+  if (s == 123.456) out[0] = s;                      // never true: keeps the loop alive
+}
+// 4 independent exp evaluations per thread and iteration
+IMA_KERNEL void k_peak_exp(double *out, int iters) {
+  double a[4];
+  for (int k = 0; k < 4; k++) a[k] = -1e-3 * (k + 1 + Warp::lane());
+  for (int i = 0; i < iters; i++)
+    for (int k = 0; k < 4; k++) a[k] = exp(a[k]) - 1.0001;
+  double s = 0.0;
+  for (int k = 0; k < 4; k++) s += a[k];
+  if (s == 123.456) out[0] = s;
+}
+}  // namespace ima
+extern "C" {
+// out[0] = FP64 fused multiply-adds per second (x 2 = flop/s), out[1] = FP64 exp evaluations per second, whole device
+int ima2p_debug_fp64_peaks(int device, double *out2) {
+  if (!out2) return lfail(IMA2P_E_ARG, "fp64_peaks: bad argument");
+  out2[0] = out2[1] = 0.0;
+#if IMA_CUDA
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return lfail(IMA2P_E_CUDA, "no CUDA device: ima2p_b200 has no CPU path");
+  if (!IMA_CUDA_OK(cudaSetDevice(device))) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  if (!IMA_CUDA_OK(cudaGetDeviceProperties(&prop, device))) return lfail(IMA2P_E_CUDA, "cudaGetDeviceProperties failed");
+  double *d = (double *)dev_alloc(8);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = prop.multiProcessorCount * 8, warps = 8, it_fma = 20000, it_exp = 2000;
+  float ms = 0.f;
+  IMA_LAUNCH(k_peak_fma, blocks, warps, 0, 0, d, 100);
+  cudaEventRecord(e0, 0);
+  IMA_LAUNCH(k_peak_fma, blocks, warps, 0, 0, d, it_fma);
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&ms, e0, e1);
+  out2[0] = (double)blocks * warps * 32 * 8.0 * it_fma / (ms * 1e-3);
+  IMA_LAUNCH(k_peak_exp, blocks, warps, 0, 0, d, 100);
+  cudaEventRecord(e0, 0);
+  IMA_LAUNCH(k_peak_exp, blocks, warps, 0, 0, d, it_exp);
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&ms, e0, e1);
+  out2[1] = (double)blocks * warps * 32 * 4.0 * it_exp / (ms * 1e-3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  dev_free(d);
+  return IMA2P_OK;
+#else
+  (void)device;
+  return lfail(IMA2P_E_UNSUPPORTED, "fp64_peaks: needs the device");
+#endif
 }
 }  // extern "C"

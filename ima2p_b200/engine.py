@@ -594,6 +594,14 @@ class LMode:
         capi.check(self.lib, self.lib.ima2p_lmode_joint_phase2(self._h, nvec, _dp(_f64(globalmax)), self.row0, _dp(rec)))
         return rec
 
+    def joint_begin(self, x, dev_localmax, stream=None):
+        """Device-resident phase 1: dev_localmax = device pointer to len(x) doubles (see ima2p_lmode_joint_begin)."""
+        x = _f64(np.atleast_2d(x))
+        capi.check(self.lib, self.lib.ima2p_lmode_joint_begin(self._h, _dp(x), len(x), dev_localmax, stream))
+
+    def joint_middle(self, nvec, dev_allmax, world, rank, dev_records, stream=None):
+        capi.check(self.lib, self.lib.ima2p_lmode_joint_middle(self._h, nvec, dev_allmax, world, rank, self.row0, dev_records, stream))
+
     def joint_finish(self, rec, globalmax, calc_ess=True):
         q, ess = C.c_double(), C.c_double()
         self.lib.ima2p_lmode_joint_finish(_dp(_f64(rec)), float(globalmax), self.nrows_total, int(calc_ess), C.byref(q),

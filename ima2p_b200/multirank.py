@@ -170,6 +170,48 @@ def sharded_jointp(lm, x, calc_ess=True, device="cpu"):
     return q, ess
 
 
+def sharded_jointp_device(lm, x, calc_ess=True, device="cuda", batch=32):
+    """sharded_jointp with nothing but device collectives between the phases: per batch of <= 32 vectors two NCCL all-gathers
+    on device buffers (local maxima; records), every batch queued behind the previous one on the current stream, ONE
+    device-to-host copy of all records at the end.  Any number of vectors per call."""
+    import numpy as np
+    x = np.atleast_2d(x)
+    nv_all = len(x)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    stream = torch.cuda.current_stream().cuda_stream
+    recs = []
+    for b0 in range(0, nv_all, batch):
+        xb = x[b0:b0 + batch]
+        nv = len(xb)
+        local = torch.empty(nv, dtype=torch.float64, device=device)
+        lm.joint_begin(xb, local.data_ptr(), stream)
+        allmax = torch.empty(world * nv, dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_gather_into_tensor(allmax, local)
+        else:
+            allmax.copy_(local)
+        rec = torch.empty(nv * 8, dtype=torch.float64, device=device)
+        lm.joint_middle(nv, allmax.data_ptr(), world, rank, rec.data_ptr(), stream)
+        allrec = torch.empty(world * nv * 8, dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_gather_into_tensor(allrec, rec)
+        else:
+            allrec.copy_(rec)
+        recs.append((nv, allrec, local, allmax, rec))           # the tensors stay alive until the stream has used them
+    q, ess = np.zeros(nv_all), np.zeros(nv_all)
+    o = 0
+    for nv, allrec, _, _, _ in recs:
+        a = allrec.cpu().numpy().reshape(world, nv, 8)
+        for v in range(nv):
+            tot = a[:, v, :6].sum(axis=0)
+            k = int(np.argmin(a[:, v, 4]))
+            tot[4], tot[5] = a[k, v, 4], a[k, v, 5]
+            q[o + v], ess[o + v] = lm.joint_finish(tot, a[0, v, 6], calc_ess)
+        o += nv
+    return q, ess
+
+
 def sharded_moments(lm, device="cpu"):
     """print_means_variances_correlations (output.cpp:687-745) over rows sharded across ranks: one all-reduce of the calcx row
     sums (2 np + np^2 doubles), then the reference's closing arithmetic on the totals."""

@@ -308,6 +308,19 @@ int ima2p_lmode_joint_phase2 (ima2p_lmode * l, int nvec, const double *globalmax
                               double *records_out);
 void ima2p_lmode_joint_finish (const double *rec6, double globalmax, long long nrows_total, int calc_ess, double *q,
                                double *ess);
+/* The same phases with every intermediate left on the device, for ranks that exchange with device collectives (an NCCL
+ * all-gather of the local maxima, then one of the records): nothing crosses PCIe between the phases and nothing
+ * synchronises, so batch after batch queues on one stream.
+ *   begin : nvec (<= 32) vectors over the local rows; dev_localmax_out[nvec] (device memory) = maxima over the local rows
+ *   middle: dev_allmax[world][nvec] (device, the gathered maxima) -> dev_records_out[nvec][8] (device) = the six record
+ *           fields of phase 2, the global maximum, 0.  Sum the first four fields over ranks, take fields 4-5 from the rank with
+ *           the smallest field 4, and close with ima2p_lmode_joint_finish. */
+/* measured FP64 peaks of the device the roofline fractions of the FP64-bound kernels are quoted against (SURVEY.md section
+ * 8d): out2[0] = fused multiply-adds per second (x 2 = flop/s), out2[1] = exp evaluations per second */
+int ima2p_debug_fp64_peaks (int device, double *out2);
+int ima2p_lmode_joint_begin (ima2p_lmode * l, const double *x, int nvec, double *dev_localmax_out, void *cuda_stream);
+int ima2p_lmode_joint_middle (ima2p_lmode * l, int nvec, const double *dev_allmax, int world, int rank, long long global_row0,
+                              double *dev_records_out, void *cuda_stream);
 
 /* ---- L mode, the other evaluators that stream over the rows ------------------------------
  * moments = print_means_variances_correlations (output.cpp:687-745) over calcx (output.cpp:14-134): means[np],

@@ -248,3 +248,53 @@ def test_peer_memory_exchange_reproduces_the_single_process_run(world):
     engs[0].sharded_swap(SWAPTRIES)
     with pytest.raises(capi.Ima2pError):
         engs[0].sync()
+
+
+def test_device_resident_sharded_jointp_equals_the_single_rank_jointp():
+    """ima2p_lmode_joint_begin / _middle (the phases of the sharded jointp with every intermediate left in device memory, as the
+    NCCL path of ima2p_b200.multirank.sharded_jointp_device uses them): three uneven shards held by three LMode objects of one
+    process, the all-gathers played by concatenation, against jointp over all rows on one object (jointfind.cpp:885-1047)."""
+    from ima2p_b200 import LMode, capi
+    from support import FlatModel, load_golden
+    subprocess.run([os.path.join(HERE, "hostemu", "build.sh")], check=True)
+    lib = capi.bind(EMU)
+    d = load_golden("lmode_sim5_hn2")
+    fm = FlatModel(d["model"])
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    G = len(rows)
+    mk = lambda: LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=lib)
+    whole = mk()
+    whole.load(rows)
+    xs = np.array([j["x"] for j in d["jointp"]])[:40]
+    q1, e1 = whole.jointp(xs[:32])
+    q1b, e1b = whole.jointp(xs[32:])
+    want_q, want_e = np.r_[q1, q1b], np.r_[e1, e1b]
+    cut = [0, G // 4 + 7, G // 2 + 3, G]
+    world = 3
+    lms = []
+    for r in range(world):
+        lm = mk()
+        lm.load(rows[cut[r]:cut[r + 1]], nrows_total=G, row0=cut[r])
+        lms.append(lm)
+    got_q, got_e = [], []
+    for b0 in range(0, len(xs), 32):
+        xb = xs[b0:b0 + 32]
+        nv = len(xb)
+        local = [np.zeros(nv) for _ in range(world)]
+        for r, lm in enumerate(lms):
+            lm.joint_begin(xb, local[r].ctypes.data)
+        allmax = np.ascontiguousarray(np.concatenate(local))
+        rec = [np.zeros(nv * 8) for _ in range(world)]
+        for r, lm in enumerate(lms):
+            lm.joint_middle(nv, allmax.ctypes.data, world, r, rec[r].ctypes.data)
+        a = np.stack(rec).reshape(world, nv, 8)
+        for v in range(nv):
+            tot = a[:, v, :6].sum(axis=0)
+            k = int(np.argmin(a[:, v, 4]))
+            tot[4], tot[5] = a[k, v, 4], a[k, v, 5]
+            q, e = lms[0].joint_finish(tot, a[0, v, 6], True)
+            got_q.append(q); got_e.append(e)
+    assert np.allclose(got_q, want_q, rtol=1e-12, atol=0) and np.allclose(got_e, want_e, rtol=1e-9, atol=0), (got_q[:3], want_q[:3])
+    # against the reference's own values of the fixture
+    ref = np.array([j["q"] for j in d["jointp"]])[:40]
+    assert np.allclose(got_q, ref, rtol=1e-9, atol=0)
