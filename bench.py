@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lmode", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--no-models", action="store_true", help="skip the HKY / stepwise / joint per-model throughput section (N = 1)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     wl = args.workload
@@ -572,6 +573,12 @@ def main():
         r = reference_throughput(wl, 1, 3, 1, budget_s=12.0, full=full, data=args.data, burn=args.burn)
         if r is not None:
             cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "reference", "sample": r["sample"], "accept_rate": r["accept"]}
+    models = None
+    if world == 1 and not args.no_models:
+        try:
+            models = models_bench(stream)
+        except Exception as ex:
+            models = {"error": repr(ex)}
     lmode = lmode_multi
     if not args.no_lmode and world == 1:
         try:
@@ -587,7 +594,7 @@ def main():
            "gpu_launches": launches_per_step * args.steps,
            "roofline": roof, "cpu_baseline": cpu, "accept_rate": p_acc, "mig_events_per_genealogy": mig_mean, "mig_events_max": mig_max,
            "genealogy_updates_only": ({"ms_per_step": graph_ms / args.steps, "value": updates_all / (graph_ms * 1e-3), "unit": unit}
-                                      if graph_ms else None), "lmode": lmode, "config3": config3,
+                                      if graph_ms else None), "lmode": lmode, "config3": config3, "models": models,
            "multi_gpu_step": ("one CUDA graph per step on every rank; swap sums exchanged through peer memory inside the kernels "
                               "(ima2p_engine_run_sharded)" if world > 1 else None),
            "dropped_for_capacity": c1["dropped"], "split_time_mean": split_time_mean, "update_counters": upd_counters,
@@ -595,6 +602,80 @@ def main():
     print(json.dumps(out, default=float))
     if world > 1:
         dist.destroy_process_group()
+
+
+MODEL_FIXTURES = {
+    # mutation model -> golden fixture written by the reference (tests/golden/generate.py): HKY = Sim1_5loci relabelled H,
+    # stepwise / joint = the synthetic S1 / J1 inputs of SURVEY.md section 8(d) (BASELINE configs[4])
+    "hky": "state_sim5_hky_hn2", "stepwise": "state_sim3_sw_hn2", "joint_is_sw": "state_sim3_joint_hn2",
+}
+
+
+def models_bench(stream, nloci=50, nchains=128, burn=300, steps=100):
+    """updates/s of the whole step on loci of the other mutation models (BASELINE configs[4]): the loci and
+    the genealogies of a reference-written fixture, repeated to nloci loci x nchains chains.  Per model: value, step time,
+    per-kernel times, the algorithmic bytes of an update (B_HKY = B_IS + 120 S R for HKY, R = internal nodes recomputed per
+    proposal) and the HBM fraction they amount to."""
+    import torch
+    from ima2p_b200 import Engine, synth
+    pk, _ = peaks()
+    out = {}
+    for name, fx in MODEL_FIXTURES.items():
+        d = json.load(gzip.open(os.path.join(ROOT, "tests", "golden", fx + ".json.gz")))
+        fl, fc = d["loci"], d["chains"]
+        eng = Engine(nchains, nloci, mig_capacity=64, seed=77)
+        eng.set_model(**synth.two_population_model(PRIOR_Q, PRIOR_M))
+        for li in range(nloci):
+            L = fl[li % len(fl)]
+            eng.set_locus(li, L["model"], L["numgenes"], L["numsites"], L["samppop"], seq=L["seq"] if L["seq"] else None, mult=L.get("mult"),
+                          hval=L["hval"], totsites=L["totsites"], nlinked=L["nlinked"], minA=L["minA"], maxA=L["maxA"], sumlogk=L["sumlogk"])
+        eng.finalize()
+        eng.set_heating(*HEAT)
+        for c in range(nchains):
+            ch = fc[c % len(fc)]
+            eng.set_chain(c, ch["tvals"])
+            for li in range(nloci):
+                g = ch["G"][li % len(fl)]
+                t = g["tree"]
+                off, mt, mp = [0], [], []
+                for lst in t["mig"]:
+                    mt += lst[0::2]; mp += lst[1::2]; off.append(len(mt))
+                A = np.stack([np.asarray(a, np.int32) for a in t["A"]]) if t.get("A") else None
+                eng.set_genealogy(c, li, t["up0"], t["up1"], t["down"], t["pop"], t["time"], off, mt, mp, t["root"], t["roottime"],
+                                  uvals=g["uvals"], kappa=g["kappa"], pi=g["pi"], A=A)
+        eng.upload()
+        eng.eval()
+        eng.set_update_priors(t_max=[PRIOR_T])
+        eng.set_update_schedule(3, 5)
+        sw = eng.default_swaptries()
+        eng.run(burn, sw, stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = eng.counters()
+        e0.record(); eng.run(steps, sw, stream); e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        km = np.asarray(eng.run_timed(steps, sw, stream), np.float64) / steps
+        torch.cuda.synchronize()
+        c1 = eng.counters()
+        eng.sync()
+        p_acc = (c1["accepted"] - c0["accepted"]) / max(1, c1["updates"] - c0["updates"])
+        n = fl[0]["numgenes"]
+        b_is = algorithmic_bytes_per_update(n, 2.0, p_acc, eng.NI, eng.ND)
+        S = float(np.mean([L["numsites"] for L in fl]))
+        # internal nodes on the union of the root paths of the touched edges: about twice the expected depth of a node
+        R = 2.0 * np.log2(n) if name == "hky" else 0.0
+        extra = 120.0 * S * R if name == "hky" else 12.0 * (2 * n - 1) * max(1, fl[0]["nlinked"] - (1 if name == "joint_is_sw" else 0))
+        b_upd = b_is + extra
+        P = nloci * nchains
+        names = ["proposal_kernels", "k_accept", "k_swap", "k_split_t", "k_accept_t", "k_changeu", "k_move", "k_weigh", "k_propose_redo"]
+        out[name] = {"fixture": fx, "loci": nloci, "chains": nchains, "genes_per_locus": n, "value": P / (ms * 1e-3), "unit": "updates/s", "ms_per_step": ms,
+                     "accept_rate": p_acc, "kernel_ms_per_launch": {k: float(v) for k, v in zip(names, km)},
+                     "algorithmic_bytes_per_update": b_upd, "formula": ("B_IS + 120 S R, S = %.1f patterns, R = %.1f nodes" % (S, R)) if name == "hky" else "B_IS + 12 bytes per edge and linked stepwise part",
+                     "roofline": {"bound": "hbm", "achieved": b_upd * P / (ms * 1e-3) / 1e9, "frac": b_upd * P / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "unit": "GB/s"},
+                     "proposal_path": "two kernels (k_move + k_weigh)" if km[6] > 0 else "general one-warp-per-pair kernel", "dropped_for_capacity": c1["dropped"]}
+        eng.close()
+    return out
 
 
 def fp64_peaks(device=0):

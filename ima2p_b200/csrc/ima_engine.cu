@@ -590,13 +590,18 @@ int ima2p_engine_finalize(ima2p_engine *h) {
     B.gwi = e.alloc<int>(P * d.NI); B.gwd = e.alloc<double>(P * d.ND);
     if (d.any_sw) { B.A = e.alloc<short>(P * kMaxLinked * NL); B.dlikeA = e.alloc<double>(P * kMaxLinked * NL); B.pdg_a = e.alloc<double>(P * kMaxLinked); }
     else { B.A = nullptr; B.dlikeA = nullptr; B.pdg_a = nullptr; }
+    B.hky_mask = nullptr;
   }
   if (d.any_hky) {
     int hs = 0, hg = 0;
     for (int li = 0; li < d.nloci; li++) if (e.loci[li].d.model == kHKY) { if (e.loci[li].d.nsites > hs) hs = e.loci[li].d.nsites; if (e.loci[li].d.ng > hg) hg = e.loci[li].d.ng; }
-    v.d.hky_stride = d.hky_stride = (long long)(hg - 1) * hs * 5;
-    v.hky_scratch = e.alloc<double>((size_t)P * d.hky_stride);
-    if (!v.hky_scratch) return fail(IMA2P_E_CUDA, "device allocation failed (HKY scratch)");
+    v.d.hky_sites = d.hky_sites = hs;
+    v.d.hky_mask_words = d.hky_mask_words = (hg - 1 + 31) / 32;
+    v.d.hky_stride = d.hky_stride = (long long)(hg - 1) * 2 * 5 * hs;
+    v.hky_frac = e.alloc<double>((size_t)P * d.hky_stride);
+    v.prop_ids = e.alloc<short>((size_t)P * 2);
+    for (int b = 0; b < 2; b++) v.buf[b].hky_mask = e.alloc<uint32_t>((size_t)P * d.hky_mask_words);
+    if (!v.hky_frac || !v.prop_ids || !v.buf[1].hky_mask) return fail(IMA2P_E_CUDA, "device allocation failed (HKY partial likelihoods)");
   }
   v.cur = e.alloc<unsigned char>(P);
   v.uvals = e.alloc<double>(P * kMaxLinked); v.kappa = e.alloc<double>(P); v.pi = e.alloc<double>(P * 4);

@@ -213,6 +213,7 @@ IMA_KERNEL void IMA_MOVE_BOUNDS k_move(EngineView E) {
         Bn.sd[(size_t)p * 4] = S.ctl_d[kCdRoottime];
         E.prop_flags[p] = flags;
         E.prop_extra[p] = S.ctl_d[kCdMigw] + S.ctl_d[kCdSlidew];
+        if (E.prop_ids) { E.prop_ids[(size_t)p * 2] = (short)S.ctl_i[kCiFreed]; E.prop_ids[(size_t)p * 2 + 1] = (short)S.ctl_i[kCiOldDownDown]; }
         if (E.prop_dbg) {
           E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw]; E.prop_dbg[(size_t)p * 4 + 1] = S.ctl_d[kCdSlidew];
           E.prop_dbg[(size_t)p * 4 + 2] = S.ctl_d[kCdSlideDist]; E.prop_dbg[(size_t)p * 4 + 3] = (double)S.ctl_i[kCiEdge];
@@ -302,7 +303,12 @@ IMA_KERNEL void IMA_WEIGH_BOUNDS k_weigh(EngineView E) {
   double pdg = 0.0;
   if (ok) {
     double pdga[kMaxLinked];
-    pdg = pair_likelihood(E, L, Bn, p, S, pdga);
+    const PairBuf &Bc = E.buf[E.cur[p]];
+    HkyCall hk; hk.mode = kHkyPartial; hk.freed = hk.olddd = -1;
+    if (L.model == kHKY) { hk.freed = E.prop_ids[(size_t)p * 2]; hk.olddd = E.prop_ids[(size_t)p * 2 + 1]; }
+    hk.mask_cur = Bc.hky_mask ? Bc.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+    hk.mask_new = Bn.hky_mask ? Bn.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+    pdg = pair_likelihood(E, L, Bn, p, S, pdga, hk);
     flags |= (uint32_t)S.ctl_i[kCiFlags];
     if (pdg == kRejectIS) flags |= kFlagRejectIS;
     if (!(flags & (kFlagRejectIS | kFlagBadTree))) {

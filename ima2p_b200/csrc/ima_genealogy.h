@@ -1094,12 +1094,17 @@ IMA_DEV double likelihood_is(const EngineView &E, const DevLocus &L, PairSm &S, 
 
 // ------------------------------------------------------------------------------------------------
 // HKY: calc_prob_data.cpp:26-41 (pijt), 118-471 (makefrac), 473-493 (getstandfactor), 583-607.
-// The reference keeps frac/newfrac per internal node and recomputes only the nodes above the touched
-// edges (a CPU economy).  Here every call prunes the whole genealogy: nodes are visited in coalescence
-// order (children first -- the order eval_weights' sorted event list already gives), the 32 lanes first
-// compute the 2 x 16 transition probabilities of the node's two child branches (one entry each), then take
-// one compressed site pattern each.  Partial likelihoods of a pair live in an L2-resident scratch slab;
-// nothing HKY-specific has to be kept between calls, so accept/reject stays a buffer flip.
+// Like the reference, every internal node keeps its partial likelihoods (frac) and scale factors, and a proposal recomputes
+// only the nodes above the edges it touched (makefrac's e1..e4 rule, :137-164): the new parent of the moved edge, the old
+// parent of its old sister, and everything between them and the root.  The reference keeps frac / newfrac per node and
+// copies newfrac -> frac on acceptance (copyfraclike, update_gtree_common.cpp:2139-2154); here every node has TWO slots in a
+// per-pair slab and every genealogy buffer carries a bit mask saying which slot is the node's current one.  A proposal writes
+// the recomputed nodes into their other slots and hands the proposed buffer the mask with those bits flipped: acceptance is the
+// buffer flip it always was, rejection leaves the current slots untouched, nothing is ever copied.
+// Slab of a pair: [node][slot][5][patterns] doubles (4 partials and the scale of every compressed site pattern; lanes take
+// patterns, so every load and store is a coalesced row).  Nodes are visited in coalescence order (children first -- the order
+// eval_weights' sorted event list already gives); the 32 lanes first compute the 2 x 16 transition probabilities of the
+// node's two child branches (one entry each), then take one compressed site pattern each.
 // ------------------------------------------------------------------------------------------------
 IMA_DEV double hky_pijt(const double *pi, double mutrate, double t, double kappa, int from, int to) {
   const double PIj = (to == 0 || to == 2) ? pi[0] + pi[2] : pi[1] + pi[3];
@@ -1109,10 +1114,17 @@ IMA_DEV double hky_pijt(const double *pi, double mutrate, double t, double kappa
   return pi[to] * (1.0 - exp(-mutrate * t));
 }
 
-IMA_DEV double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S, int p, double u, double kappa, const double *pi) {
+// how a call treats the slots: kHkyInit -- every node into slot 0, mask 0 (a state that was just loaded); kHkyFull -- every
+// node into its other slot (a rescaled genealogy, new mutation scalar or kappa); kHkyPartial -- the nodes above `freed` and
+// `olddd` (the junction node after the move; the parent of the freed node before it, -1 when that was the root)
+enum { kHkyInit = 0, kHkyFull = 1, kHkyPartial = 2 };
+struct HkyCall { int mode, freed, olddd; const uint32_t *mask_cur; uint32_t *mask_new; };
+
+IMA_DEV double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S, int p, double u, double kappa, const double *pi, const HkyCall &hk) {
   const int lane = Warp::lane();
-  const int ng = L.ng, ns = L.nsites, nev = S.ctl_i[kCiNev], root = S.ctl_i[kCiRoot];
-  double *slab = E.hky_scratch + (size_t)p * E.d.hky_stride;      // [internal node][pattern][4 partials + scale]
+  const int ng = L.ng, nl = L.nl, ns = L.nsites, nev = S.ctl_i[kCiNev], root = S.ctl_i[kCiRoot];
+  const size_t hs = (size_t)E.d.hky_sites;
+  double *slab = E.hky_frac + (size_t)p * E.d.hky_stride;          // [internal node][slot][5][hky_sites]
   const unsigned char *seq = E.seq + L.seq_off;
   const int *mult = E.mult + L.mult_off;
   double sf = 0.0;                                                 // getstandfactor :473-493
@@ -1120,41 +1132,71 @@ IMA_DEV double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S,
     for (int j = 0; j < 4; j++)
       if (i != j) sf += (i + j == 2 || i + j == 4) ? pi[i] * pi[j] * kappa : pi[i] * pi[j];
   const double mu = u / (L.totsites * sf);                         // :593
+  // which nodes are recomputed (the tip-mask table of the infinite-sites likelihood is free on an HKY locus): dirty[e] for
+  // every internal edge e; then newslot[e] = the slot that holds e's partials in the proposed genealogy
+  uint32_t *dirty = S.mask;
+  for (int e = lane; e < nl; e += IMA_WARP) dirty[e] = (hk.mode != kHkyPartial && e >= ng) ? 1u : 0u;
+#if IMA_CUDA
+  __threadfence_block();
+#endif
+  Warp::sync();
+  if (hk.mode == kHkyPartial && lane == 0) {
+    for (int e = hk.freed, guard = 0; e >= ng && guard < nl && !dirty[e]; e = S.down[e], guard++) dirty[e] = 1u;
+    for (int e = hk.olddd, guard = 0; e >= ng && guard < nl && !dirty[e]; e = S.down[e], guard++) dirty[e] = 1u;
+  }
+#if IMA_CUDA
+  __threadfence_block();
+#endif
+  Warp::sync();
+  auto cur_slot = [&](int e) { return hk.mode == kHkyInit ? 1 : (int)((hk.mask_cur[(e - ng) >> 5] >> ((e - ng) & 31)) & 1u); };
+  auto new_slot = [&](int e) { return cur_slot(e) ^ (int)dirty[e]; };
   double *P = (double *)S.pre;                                     // 32 doubles; the prefix table is free after the sweep
   for (int j = 0; j < nev; j++) {
     const int info = S.evi[j];
     if ((info & 3) != 0) continue;
-    const int node = info >> 12, a = S.up0[node], b = S.up1[node];
+    const int node = info >> 12;
+    if (!dirty[node]) continue;
+    const int a = S.up0[node], b = S.up1[node];
     const double ta = S.time[a] - edge_top_time(S, ng, a), tb = S.time[b] - edge_top_time(S, ng, b);
     for (int e = lane; e < 32; e += IMA_WARP) P[e] = hky_pijt(pi, mu, (e >> 4) ? tb : ta, kappa, (e >> 2) & 3, e & 3);
     Warp::sync();
-    double *out = slab + (size_t)(node - ng) * ns * 5;
-    const double *fa = slab + (size_t)(a - ng) * ns * 5, *fb = slab + (size_t)(b - ng) * ns * 5;
+    double *out = slab + ((size_t)(node - ng) * 2 + new_slot(node)) * 5 * hs;
+    const double *fa = a < ng ? nullptr : slab + ((size_t)(a - ng) * 2 + new_slot(a)) * 5 * hs;
+    const double *fb = b < ng ? nullptr : slab + ((size_t)(b - ng) * 2 + new_slot(b)) * 5 * hs;
     for (int s = lane; s < ns; s += IMA_WARP) {
-      double v[4], mx = 0.0;
+      double v[4], mx = 0.0, ca[4], cb[4];
+      if (fa) for (int k = 0; k < 4; k++) ca[k] = fa[k * hs + s];
+      if (fb) for (int k = 0; k < 4; k++) cb[k] = fb[k * hs + s];
       for (int from = 0; from < 4; from++) {
         double sa, sb;
-        if (a < ng) sa = P[from * 4 + seq[(size_t)a * ns + s]];
-        else { sa = 0.0; for (int k = 0; k < 4; k++) sa += P[from * 4 + k] * fa[s * 5 + k]; }
-        if (b < ng) sb = P[16 + from * 4 + seq[(size_t)b * ns + s]];
-        else { sb = 0.0; for (int k = 0; k < 4; k++) sb += P[16 + from * 4 + k] * fb[s * 5 + k]; }
+        if (!fa) sa = P[from * 4 + seq[(size_t)a * ns + s]];
+        else { sa = 0.0; for (int k = 0; k < 4; k++) sa += P[from * 4 + k] * ca[k]; }
+        if (!fb) sb = P[16 + from * 4 + seq[(size_t)b * ns + s]];
+        else { sb = 0.0; for (int k = 0; k < 4; k++) sb += P[16 + from * 4 + k] * cb[k]; }
         v[from] = sa * sb;
         if (v[from] > mx) mx = v[from];
       }
-      for (int k = 0; k < 4; k++) out[s * 5 + k] = v[k] / mx;
-      out[s * 5 + 4] = (a < ng ? 0.0 : fa[s * 5 + 4]) + (b < ng ? 0.0 : fb[s * 5 + 4]) + log(mx);
+      for (int k = 0; k < 4; k++) out[k * hs + s] = v[k] / mx;
+      out[4 * hs + s] = (fa ? fa[4 * hs + s] : 0.0) + (fb ? fb[4 * hs + s] : 0.0) + log(mx);
     }
 #if IMA_CUDA
     __threadfence_block();
 #endif
     Warp::sync();
   }
-  const double *fr = slab + (size_t)(root - ng) * ns * 5;
+  const double *fr = slab + ((size_t)(root - ng) * 2 + new_slot(root)) * 5 * hs;
   double acc = 0.0;
   for (int s = lane; s < ns; s += IMA_WARP) {
     double fracp = 0.0;
-    for (int k = 0; k < 4; k++) fracp += pi[k] * fr[s * 5 + k];
-    acc += mult[s] * (log(fracp) + fr[s * 5 + 4]);
+    for (int k = 0; k < 4; k++) fracp += pi[k] * fr[k * hs + s];
+    acc += mult[s] * (log(fracp) + fr[4 * hs + s]);
+  }
+  // the proposed genealogy's slot mask
+  const int MW = E.d.hky_mask_words;
+  for (int w = lane; w < MW; w += IMA_WARP) {
+    uint32_t m = 0u;
+    for (int k = 0; k < 32; k++) { const int e = ng + w * 32 + k; if (e < nl && new_slot(e)) m |= 1u << k; }
+    hk.mask_new[w] = m;
   }
   return Warp::sum(acc);
 }

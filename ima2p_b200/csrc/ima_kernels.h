@@ -27,7 +27,8 @@ IMA_DEV void rng_for(Philox &rng, const EngineView &E, uint32_t stream_id, uint3
 }
 
 // P(D|G) of the staged genealogy for the locus's mutation model; every lane returns the value
-IMA_DEV double pair_likelihood(const EngineView &E, const DevLocus &L, const PairBuf &B, int p, PairSm &S, double *pdg_a_out) {
+// hk: how an HKY locus treats its stored partials (likelihood_hky); ignored by the other models
+IMA_DEV double pair_likelihood(const EngineView &E, const DevLocus &L, const PairBuf &B, int p, PairSm &S, double *pdg_a_out, const HkyCall &hk) {
   const double *u = E.uvals + (size_t)p * kMaxLinked;
   if (L.model == kInfiniteSites) {
     const double v = likelihood_is(E, L, S, u[0]);
@@ -51,7 +52,7 @@ IMA_DEV double pair_likelihood(const EngineView &E, const DevLocus &L, const Pai
     return tot;
   }
   if (L.model == kHKY) {
-    const double v = likelihood_hky(E, L, S, p, u[0], E.kappa[p], E.pi + (size_t)p * 4);
+    const double v = likelihood_hky(E, L, S, p, u[0], E.kappa[p], E.pi + (size_t)p * 4, hk);
     pdg_a_out[0] = v;
     return v;
   }
@@ -72,7 +73,9 @@ IMA_KERNEL void k_eval_pairs(EngineView E) {
   stage_pair(E, B, p, L.nl, S);
   const bool ok = eval_weights(M, E.d, L, tv, S);
   double pdga[kMaxLinked];
-  const double pdg = ok ? pair_likelihood(E, L, B, p, S, pdga) : 0.0;
+  HkyCall hk; hk.mode = kHkyInit; hk.freed = hk.olddd = -1; hk.mask_cur = nullptr;
+  hk.mask_new = B.hky_mask ? B.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+  const double pdg = ok ? pair_likelihood(E, L, B, p, S, pdga, hk) : 0.0;
   const int lane = Warp::lane();
   for (int i = lane; i < E.d.NI; i += IMA_WARP) B.gwi[(size_t)p * E.d.NI + i] = S.gwi[i];
   for (int i = lane; i < E.d.ND; i += IMA_WARP) B.gwd[(size_t)p * E.d.ND + i] = S.gwd[i];
@@ -300,7 +303,10 @@ IMA_DEV void propose_pair_general(const EngineView &E, const DevModel &M, int c,
     if (!(pdg > -DBL_MAX)) flags |= kFlagRejectIS;       // a branch term of -inf (bessi == 0): the move cannot be accepted
     if (!(flags & (kFlagRejectIS | kFlagBadTree))) store_pair(E, Bn, p, L.nl, S, total_mig);
   } else if (ok) {
-    pdg = pair_likelihood(E, L, Bn, p, S, pdga);
+    HkyCall hk; hk.mode = kHkyPartial; hk.freed = S.ctl_i[kCiFreed]; hk.olddd = S.ctl_i[kCiOldDownDown];
+    hk.mask_cur = B.hky_mask ? B.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+    hk.mask_new = Bn.hky_mask ? Bn.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+    pdg = pair_likelihood(E, L, Bn, p, S, pdga, hk);
     IMA_PROF_MARK()
     flags = (uint32_t)S.ctl_i[kCiFlags];
     if (pdg == kRejectIS) flags |= kFlagRejectIS;

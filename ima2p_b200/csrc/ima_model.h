@@ -65,6 +65,7 @@ struct PairBuf {
   short *A;             // [P][kMaxLinked][NL]   stepwise allele states (only when some locus is stepwise)
   double *dlikeA;       // [P][kMaxLinked][NL]
   double *pdg_a;        // [P][kMaxLinked]
+  uint32_t *hky_mask;   // [P][hky_mask_words] which of its two slots holds every internal node's HKY partials in THIS buffer's genealogy
 };
 
 struct EngineDims {
@@ -78,7 +79,8 @@ struct EngineDims {
                         // migration events per genealogy and event slots in k_weigh, scratch entries of the fast split-time kernel;
                         // a pair that needs more takes the general path
   int any_sw, any_hky;
-  long long hky_stride; // doubles of HKY scratch per pair: (max genes - 1) * (max patterns) * 5
+  long long hky_stride; // doubles of HKY partials per pair: (max genes - 1) nodes * 2 slots * 5 * hky_sites
+  int hky_sites, hky_mask_words;   // largest number of compressed site patterns of an HKY locus; 32-bit words of a pair's slot mask
   const int *tab;       // model tables the event sweep indexes with lane-dependent subscripts, in global memory (constant
                         // memory serialises such reads): see kTab* below
 };
@@ -110,7 +112,7 @@ struct EngineView {
   double *uvals;            // [P][kMaxLinked] mutation-rate scalars
   double *kappa;            // [P]
   double *pi;               // [P][4]
-  double *hky_scratch;      // [P][hky_stride] partial likelihoods (scratch, recomputed by every call)
+  double *hky_frac;         // [P][hky_stride] partial likelihoods and scale factors of every internal node, two slots each (likelihood_hky)
   // per chain
   double *tvals;            // [nchains][kMaxPeriods] split times, TIMEMAX sentinel at [nsplit]
   double *beta;             // [nchains]
@@ -124,6 +126,7 @@ struct EngineView {
   // proposal hand-off (propose kernel -> accept kernel)
   double *prop_extra;       // [P] migweight + slideweight + Aterm
   uint32_t *prop_flags;     // [P]
+  short *prop_ids;          // [P][2] HKY loci: junction node after the move, parent of the freed node before it (what k_weigh needs of the move)
   double *prop_dbg;         // [P][4] migweight, slideweight, slide distance drawn, edge moved (parity tests)
   // counters
   unsigned int *acc;        // [P][3] accepted: any, topology, tmrca

@@ -294,6 +294,8 @@ IMA_DEV bool nw_t_pair(const EngineView &E, const UpdateView &U, const DevModel 
       for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) { Bn.A[ao + i] = B.A[ao + i]; Bn.dlikeA[ao + i] = B.dlikeA[ao + i]; }
       for (int ai = lane; ai < L.nlinked; ai += IMA_WARP) Bn.pdg_a[(size_t)p * kMaxLinked + ai] = B.pdg_a[(size_t)p * kMaxLinked + ai];
     }
+    if (L.model == kHKY)                                  // and so are the stored partials: the same slots stay current
+      for (int w = lane; w < E.d.hky_mask_words; w += IMA_WARP) Bn.hky_mask[(size_t)p * E.d.hky_mask_words + w] = B.hky_mask[(size_t)p * E.d.hky_mask_words + w];
     if (lane == 0) S.ctl_d[kCdPdg] = B.sd[(size_t)p * 4 + 3];
     Warp::sync();
     store_pair(E, Bn, p, L.nl, S, total_mig);
@@ -356,7 +358,10 @@ IMA_DEV bool rescale_t_pair(const EngineView &E, const UpdateView &U, const DevM
       Warp::sync();
     }
     double pdga[kMaxLinked];
-    const double pdg = pair_likelihood(E, L, Bn, p, S, pdga);
+    HkyCall hk; hk.mode = kHkyFull; hk.freed = hk.olddd = -1;       // every time moved: every node is recomputed
+    hk.mask_cur = B.hky_mask ? B.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+    hk.mask_new = Bn.hky_mask ? Bn.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+    const double pdg = pair_likelihood(E, L, Bn, p, S, pdga, hk);
     if (pdg == kRejectIS) flags |= kFlagRejectIS;
     if (lane == 0) {
       S.ctl_d[kCdPdg] = pdg;
@@ -627,7 +632,10 @@ IMA_DEV double scalar_likelihood(const EngineView &E, const DevModel &M, int c, 
     return likelihood_sw(L, S, B.A + ao, Bscratch.dlikeA + ao, unew);          // new branch terms go to the other buffer
   }
   if (!eval_weights(M, E.d, L, E.tvals + (size_t)c * kMaxPeriods, S)) return kRejectIS;
-  return likelihood_hky(E, L, S, p, unew, kappa_new, E.pi + (size_t)p * 4);
+  // the trial's partials go to the other slots, its slot mask to the other buffer's mask: k_changeu adopts it on acceptance
+  HkyCall hk; hk.mode = kHkyFull; hk.freed = hk.olddd = -1;
+  hk.mask_cur = B.hky_mask + (size_t)p * E.d.hky_mask_words; hk.mask_new = Bscratch.hky_mask + (size_t)p * E.d.hky_mask_words;
+  return likelihood_hky(E, L, S, p, unew, kappa_new, E.pi + (size_t)p * 4, hk);
 }
 
 IMA_DEV double reflect_kappa(double u, double kappa, double win, double kmax) {       // update_mc_params.cpp:258-272
@@ -756,6 +764,8 @@ IMA_DEV void changeu_chain(const EngineView &E, const UpdateView &U, int c, Pair
         E.pdgsum[c] += dl; E.swapsum[c] += dl;
         B.sd[(size_t)p * 4 + 3] = newpdg;
         E.kappa[p] = nk;
+        for (int w = 0; w < E.d.hky_mask_words; w++)        // the trial's partials become the current ones
+          B.hky_mask[(size_t)p * E.d.hky_mask_words + w] = E.buf[E.cur[p] ^ 1].hky_mask[(size_t)p * E.d.hky_mask_words + w];
       }
       double *o = U.u_out + (size_t)c * 4;
       o[0] = newpdg; o[1] = 0.0; o[2] = mh; o[3] = accept ? 1.0 : 0.0;
@@ -811,7 +821,10 @@ IMA_DEV void changeu_chain(const EngineView &E, const UpdateView &U, int c, Pair
         if (lane == 0) {
           E.uvals[(size_t)p * kMaxLinked + ai] = i ? newuk : newuj;
           set_part_pdg(L, B, p, ai, newpdg[i]);
-          if (L.model == kHKY) E.kappa[p] = newkappa[i];
+          if (L.model == kHKY) {
+            E.kappa[p] = newkappa[i];
+            for (int w = 0; w < E.d.hky_mask_words; w++) B.hky_mask[(size_t)p * E.d.hky_mask_words + w] = Bo.hky_mask[(size_t)p * E.d.hky_mask_words + w];
+          }
         }
       }
       if (lane == 0) { E.pdgsum[c] += likenewsum; E.swapsum[c] += likenewsum; }

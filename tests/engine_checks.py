@@ -642,6 +642,37 @@ def fast_path_equals_general_path(lib, name="state_sim50_hn3", nsteps=40, ppws=(
     return outs[0][0]
 
 
+def hky_partials_stay_consistent(lib, name="state_sim5_hky_hn2", nsteps=400):
+    """HKY loci keep the partial likelihoods of every internal node between steps (two slots per node, a slot mask per
+    genealogy buffer) and a proposal recomputes only the nodes above the edges it touched (makefrac's rule,
+    calc_prob_data.cpp:137-164).  After many whole steps -- genealogy proposals accepted and rejected, Rannala-Yang and
+    Nielsen-Wakeley split-time updates, mutation-scalar and kappa updates -- the likelihood carried along must equal a
+    from-scratch pruning of the same genealogies, on both the fast and the general proposal path."""
+    from support import engine_from_fixture, load_golden, rel_close
+    d = load_golden(name)
+    out = {}
+    for fast in (1, 0):
+        eng, fm = engine_from_fixture(d, lib=lib, seed=4711)
+        eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+        eng.set_update_schedule(3, 5)
+        eng.set_proposal_path(fast, 0)
+        eng.eval()
+        for _ in range(4):
+            eng.run(nsteps // 4)
+            eng.sync()
+            kept = [(eng.chain(c)["pdg"], [eng.pair(c, l)["pdg"] for l in range(eng.nloci)]) for c in range(eng.nchains)]
+            eng.eval()                                  # prunes every genealogy from the tips again
+            for c in range(eng.nchains):
+                assert rel_close(eng.chain(c)["pdg"], kept[c][0], 1e-9), (fast, c, eng.chain(c)["pdg"], kept[c][0])
+                for l in range(eng.nloci):
+                    assert rel_close(eng.pair(c, l)["pdg"], kept[c][1][l], 1e-9), (fast, c, l)
+        cnt, uc = eng.counters(), eng.update_counters()
+        assert cnt["accepted"] > nsteps and uc["t_accepts"] > 0 and uc["u_accepts"] > 0, (cnt, uc)
+        out[fast] = (cnt, uc)
+        eng.close()
+    return out
+
+
 def full_size_workload_properties(lib, nloci, nchains, nsteps, noracle=48, seed=5):
     """BASELINE-sized runs (configs[1]: 50 loci x 128 chains; configs[2]'s per-GPU shard: 300 loci x 256 chains), checked through
     properties that do not need a stored answer: after `nsteps` whole qupdate steps (genealogies, split times, scalars, swaps)

@@ -103,6 +103,10 @@ def test_fast_path_equals_general_path(lib, name):
     ec.fast_path_equals_general_path(lib, name, ppws=(4, 8, 16))
 
 
+def test_hky_partials_stay_consistent(lib):
+    ec.hky_partials_stay_consistent(lib)
+
+
 def test_pipeline_does_not_change_the_run(lib):
     ec.pipeline_does_not_change_the_run(lib)
 

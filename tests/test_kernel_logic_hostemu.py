@@ -63,6 +63,10 @@ def test_fast_path_equals_general_path(emu, name):
     ec.fast_path_equals_general_path(emu, name, nsteps=25)
 
 
+def test_hky_partials_stay_consistent(emu):
+    ec.hky_partials_stay_consistent(emu, nsteps=200)
+
+
 def test_pipeline_setting_is_accepted_and_does_not_change_the_run(emu):
     ec.pipeline_does_not_change_the_run(emu, nsteps=9)
 
