@@ -46,6 +46,7 @@ SIGNATURES = {
     "ima2p_engine_set_pipeline": (_i, [_v, _i, _i, _i]),
     "ima2p_engine_set_proposal_path": (_i, [_v, _i, _i]),
     "ima2p_engine_set_debug_records": (_i, [_v, _i]),
+    "ima2p_engine_grow_capacity": (_i, [_v, _i]),
     "ima2p_engine_exchange_create": (_i, [_v, C.POINTER(_v), c_u64_p]),
     "ima2p_engine_exchange_attach": (_i, [_v, C.POINTER(_v)]),
     "ima2p_ipc_export": (_i, [_v, C.c_char_p]),

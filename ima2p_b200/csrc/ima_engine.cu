@@ -77,6 +77,7 @@ struct Engine {
   bool fast_ok = false, fast = false;                // the two-kernel proposal path (ima_fastpath.h): possible / in use
   int ppw = 0;                                       // pairs per warp of k_move (0: chosen from the number of pairs)
   int redo_grid = 16;
+  int maxng = 0;                                     // largest sample over the loci
   // multi-GPU exchange (struct Exchange): this rank's table, and whether peers are attached
   unsigned char *d_xch = nullptr;
   size_t xch_bytes = 0;
@@ -480,33 +481,13 @@ int ima2p_engine_set_locus(ima2p_engine *h, int li, int model, int numgenes, int
   return IMA2P_OK;
 }
 
-int ima2p_engine_finalize(ima2p_engine *h) {
-  if (!h) return fail(IMA2P_E_ARG, "null engine");
-  Engine &e = h->eng;
-  if (!e.model_set || e.finalized) return fail(IMA2P_E_ARG, "finalize: model not set or already finalized");
-  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+}  // extern "C"
+// everything that depends on the migration capacity: table sizes, shared-memory footprints, launch attributes.  Called by
+// finalize and again by ima2p_engine_grow_capacity.
+static int size_for_capacity(Engine &e, int maxng) {
   EngineDims &d = e.d;
-  d.NL = 0; d.W = 1; d.S = 0; d.any_sw = 0; d.any_hky = 0;
-  int maxng = 0;
-  std::vector<uint32_t> sm; std::vector<unsigned char> sq; std::vector<int> mu; std::vector<DevLocus> dl(d.nloci);
-  for (int li = 0; li < d.nloci; li++) {
-    HostLocus &L = e.loci[li];
-    if (!L.set) return fail(IMA2P_E_ARG, "finalize: a locus was not set");
-    if (L.d.nl > d.NL) d.NL = L.d.nl;
-    if (L.d.nwords > d.W) d.W = L.d.nwords;
-    if (L.d.nsites > d.S) d.S = L.d.nsites;
-    if (L.d.ng > maxng) maxng = L.d.ng;
-    if (has_stepwise(L.d.model)) d.any_sw = 1;
-    if (L.d.model == kHKY) d.any_hky = 1;
-    L.d.sitemask_off = (long long)sm.size(); sm.insert(sm.end(), L.sitemask.begin(), L.sitemask.end());
-    L.d.seq_off = (long long)sq.size(); sq.insert(sq.end(), L.seq.begin(), L.seq.end());
-    L.d.mult_off = (long long)mu.size(); mu.insert(mu.end(), L.mult.begin(), L.mult.end());
-    dl[li] = L.d;
-  }
-  if (d.NL > 32000) return fail(IMA2P_E_ARG, "finalize: sample too large for 16-bit edge indices");
   int ev = (maxng - 1) + d.CAP + e.model.nsplit;
   d.EVP = 1; while (d.EVP < ev) d.EVP <<= 1;
-  d.W64 = (e.model.ntreepops + 3) / 4;
   // the two-kernel proposal path: tables for FC migration events per genealogy (every shipped input stays far below; a pair
   // that does not fit takes the general path, whose tables hold CAP)
   d.FC = d.CAP < 64 ? d.CAP : 64;
@@ -556,6 +537,37 @@ int ima2p_engine_finalize(ima2p_engine *h) {
 #else
   c_model = e.model;
 #endif
+  return IMA2P_OK;
+}
+
+extern "C" {
+int ima2p_engine_finalize(ima2p_engine *h) {
+  if (!h) return fail(IMA2P_E_ARG, "null engine");
+  Engine &e = h->eng;
+  if (!e.model_set || e.finalized) return fail(IMA2P_E_ARG, "finalize: model not set or already finalized");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  EngineDims &d = e.d;
+  d.NL = 0; d.W = 1; d.S = 0; d.any_sw = 0; d.any_hky = 0;
+  int maxng = 0;
+  std::vector<uint32_t> sm; std::vector<unsigned char> sq; std::vector<int> mu; std::vector<DevLocus> dl(d.nloci);
+  for (int li = 0; li < d.nloci; li++) {
+    HostLocus &L = e.loci[li];
+    if (!L.set) return fail(IMA2P_E_ARG, "finalize: a locus was not set");
+    if (L.d.nl > d.NL) d.NL = L.d.nl;
+    if (L.d.nwords > d.W) d.W = L.d.nwords;
+    if (L.d.nsites > d.S) d.S = L.d.nsites;
+    if (L.d.ng > maxng) maxng = L.d.ng;
+    if (has_stepwise(L.d.model)) d.any_sw = 1;
+    if (L.d.model == kHKY) d.any_hky = 1;
+    L.d.sitemask_off = (long long)sm.size(); sm.insert(sm.end(), L.sitemask.begin(), L.sitemask.end());
+    L.d.seq_off = (long long)sq.size(); sq.insert(sq.end(), L.seq.begin(), L.seq.end());
+    L.d.mult_off = (long long)mu.size(); mu.insert(mu.end(), L.mult.begin(), L.mult.end());
+    dl[li] = L.d;
+  }
+  if (d.NL > 32000) return fail(IMA2P_E_ARG, "finalize: sample too large for 16-bit edge indices");
+  d.W64 = (e.model.ntreepops + 3) / 4;
+  e.maxng = maxng;
+  { const int rc = size_for_capacity(e, maxng); if (rc) return rc; }
   const size_t P = d.P, NL = d.NL, CAP = d.CAP, C = d.nchains, G = d.nchains_global;
   // logfact table: same running sum as setlogfact (utilities.cpp:1405-1414)
   const int nlf = 100 * 5000 + 1;
@@ -664,6 +676,57 @@ int ima2p_engine_finalize(ima2p_engine *h) {
   return ima2p_engine_set_betas(h, e.h_beta_table.data());
 }
 
+// The migration capacity of a running engine: the reference grows an edge's list whenever it fills (checkmig,
+// utilities.cpp:1365-1383, up to ABSMIGMAX 5000 per edge).  Here the pools are rows of `mig_capacity` events per genealogy; a
+// caller that sees proposals dropped for capacity (ima2p_engine_counters, field 7) grows the rows at a step boundary with this
+// call: new pools, the resident genealogies copied over, every table and launch footprint re-sized.  The chains are unchanged.
+int ima2p_engine_grow_capacity(ima2p_engine *h, int new_capacity) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "grow_capacity: not finalized");
+  Engine &e = h->eng;
+  if (new_capacity <= e.d.CAP) return IMA2P_OK;
+  if (new_capacity > 8000) return fail(IMA2P_E_CAPACITY, "grow_capacity: more than 8000 migration events per genealogy");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, nullptr);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaDeviceSynchronize())) return fail(IMA2P_E_CUDA, "device synchronize failed");
+#endif
+  const size_t P = e.d.P, oldc = e.d.CAP, newc = (size_t)new_capacity;
+  const EngineDims keep_d = e.d;
+  const int keep_groups = e.groups, keep_depth = e.depth, keep_spec = e.spec, keep_ppw = e.ppw;
+  const bool keep_fast = e.fast;
+  e.d.CAP = new_capacity;
+  int rc = size_for_capacity(e, e.maxng);
+  if (rc) { e.d = keep_d; size_for_capacity(e, e.maxng); return fail(IMA2P_E_CAPACITY, "grow_capacity: a genealogy with that many migration events does not fit in shared memory"); }
+  e.groups = keep_groups; e.depth = keep_depth; e.spec = keep_spec; e.ppw = keep_ppw; e.fast = keep_fast && e.fast_ok;
+  for (int b = 0; b < 2; b++) {
+    PairBuf &B = e.v.buf[b];
+    double *nt = e.alloc<double>(P * newc);
+    short *np_ = e.alloc<short>(P * newc);
+    if (!nt || !np_) return fail(IMA2P_E_CUDA, "device allocation failed (grow_capacity)");
+#if IMA_CUDA
+    if (!IMA_CUDA_OK(cudaMemcpy2DAsync(nt, newc * 8, B.mig_t, oldc * 8, oldc * 8, P, cudaMemcpyDeviceToDevice, s)) ||
+        !IMA_CUDA_OK(cudaMemcpy2DAsync(np_, newc * 2, B.mig_p, oldc * 2, oldc * 2, P, cudaMemcpyDeviceToDevice, s)))
+      return fail(IMA2P_E_CUDA, "copy failed (grow_capacity)");
+#else
+    for (size_t p = 0; p < P; p++) { memcpy(nt + p * newc, B.mig_t + p * oldc, oldc * 8); memcpy(np_ + p * newc, B.mig_p + p * oldc, oldc * 2); }
+#endif
+    B.mig_t = nt; B.mig_p = np_;           // the old pools stay allocated until the engine is destroyed (they are small)
+  }
+  if (!dev_sync(s)) return fail(IMA2P_E_CUDA, "sync failed (grow_capacity)");
+  e.v.d = e.d;
+  // host staging rows (set_genealogy / upload) follow the new pitch
+  std::vector<double> ht(P * newc, 0.0); std::vector<short> hp(P * newc, 0);
+  for (size_t p = 0; p < P; p++) { memcpy(&ht[p * newc], &e.h_mig_t[p * oldc], oldc * 8); memcpy(&hp[p * newc], &e.h_mig_p[p * oldc], oldc * 2); }
+  e.h_mig_t.swap(ht); e.h_mig_p.swap(hp);
+  e.block_cap = 0; e.d_block = nullptr;    // the one-block upload staging is re-made at the new size on its next use
+  e.graph_ready = false;
+#if IMA_CUDA
+  if (e.graph_exec_sh) { cudaGraphExecDestroy(e.graph_exec_sh); e.graph_exec_sh = nullptr; }
+  if (e.graph_exec_sh_deep) { cudaGraphExecDestroy(e.graph_exec_sh_deep); e.graph_exec_sh_deep = nullptr; }
+#endif
+  return IMA2P_OK;
+}
+
 int ima2p_engine_set_betas(ima2p_engine *h, const double *betas_global) {
   if (!h || !h->eng.finalized || !betas_global) return fail(IMA2P_E_ARG, "set_betas: bad argument / not finalized");
   Engine &e = h->eng;
@@ -721,6 +784,18 @@ int ima2p_engine_set_genealogy(ima2p_engine *h, int ci, int li, const int *up0, 
   const int total = mig_off[L.nl] - mig_off[0];
   if (total > e.d.CAP) return fail(IMA2P_E_CAPACITY, "set_genealogy: more migration events than mig_capacity");
   if (root < 0 || root >= L.nl || down[root] != -1) return fail(IMA2P_E_ARG, "set_genealogy: bad root");
+  // a state file is outside data: nothing read from it is used as an index unchecked
+  if (root < L.ng) return fail(IMA2P_E_ARG, "set_genealogy: the root is a tip");
+  for (int i = 0; i < L.nl; i++) {
+    const bool tip = i < L.ng;
+    if (down[i] < -1 || down[i] >= L.nl || (down[i] >= 0 && down[i] < L.ng)) return fail(IMA2P_E_ARG, "set_genealogy: edge link out of range");
+    if (tip ? (up0[i] != -1 || up1[i] != -1) : (up0[i] < 0 || up0[i] >= L.nl || up1[i] < 0 || up1[i] >= L.nl || up0[i] == up1[i]))
+      return fail(IMA2P_E_ARG, "set_genealogy: edge link out of range");
+    if (pop[i] < 0 || pop[i] >= e.model.ntreepops) return fail(IMA2P_E_ARG, "set_genealogy: population out of range");
+    if (mig_off[i + 1] < mig_off[i]) return fail(IMA2P_E_ARG, "set_genealogy: migration offsets must not decrease");
+  }
+  for (int j = 0; j < total; j++)
+    if (mig_p[mig_off[0] + j] < 0 || mig_p[mig_off[0] + j] >= e.model.ntreepops) return fail(IMA2P_E_ARG, "set_genealogy: migration target out of range");
   for (int i = 0; i < L.nl; i++) {
     e.h_topo[p * NL + i] = short4_t{(short)up0[i], (short)up1[i], (short)down[i], (short)pop[i]};
     e.h_time[p * NL + i] = time[i];

@@ -75,6 +75,7 @@ Tree start_genealogy(const Locus &L, int npops, int rootpop, double tbase, unsig
   for (int j = 0; j < n; j++) node_of[j] = j;
   int next = n;
   auto join = [&](int a, int b) {
+    if (next >= nl) die("starting genealogy: data not compatible with the infinite sites model", 36);
     const int k = next++;
     T.up0[k] = a; T.up1[k] = b; T.down[a] = T.down[b] = k;
     ntips[k] = ntips[a] + ntips[b];
@@ -1009,7 +1010,8 @@ int run_lmode(std::map<std::string, std::string> &opt, ima2p_modelspec *S, int n
 int main(int argc, char **argv) {
   g_starttime = time(nullptr);
   std::map<std::string, std::string> opt;
-  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", "c", nullptr};
+  // -cap N (this build only): migration events per genealogy the device pools start with (they grow when they fill)
+  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", "cap", "c", nullptr};
   RunInfo R{};
   for (int a = 1; a < argc; a++) {
     if (argv[a][0] != '-') die(std::string("command line: unexpected word ") + argv[a], 5);
@@ -1036,7 +1038,10 @@ int main(int argc, char **argv) {
   const double qmax = atof(opt["q"].c_str()), mmax = opt.count("m") ? atof(opt["m"].c_str()) : 0.0, tmax = atof(opt["t"].c_str());
   const int nchains = opt.count("hn") ? atoi(opt["hn"].c_str()) : 1, expo = opt.count("j") ? 1 : 0;
   const long burn = atol(opt["b"].c_str()), nsave = atol(opt["l"].c_str()), every = opt.count("d") ? atol(opt["d"].c_str()) : 100;
-  const unsigned long long seed = opt.count("s") ? strtoull(opt["s"].c_str(), nullptr, 10) : 1ull;
+  // no -s: seeded from the clock as the reference does (ima_main_mpi.cpp:1413), and said so in the report; a run continued from
+  // a state file (-f) mixes the time into the seed it was given so that it does not replay the first run's random streams
+  unsigned long long seed = opt.count("s") ? strtoull(opt["s"].c_str(), nullptr, 10) : (unsigned long long)time(nullptr);
+  if (opt.count("f") && opt.count("s")) seed = seed * 6364136223846793005ull + (unsigned long long)time(nullptr);
   if (nchains < 1 || burn < 0 || nsave < 1 || every < 1 || !(tmax > 0)) die("command line: bad value", 5);
   for (int a = 1; a < argc; a++) R.command_line += std::string(" ") + argv[a];
   R.infile = opt["i"]; R.outfile = opt["o"]; R.ti = opt["o"] + ".ti"; R.seed = seed; R.burn = burn; R.nsave = nsave; R.every = every; R.nchains = nchains;
@@ -1088,8 +1093,13 @@ int main(int argc, char **argv) {
     unsigned rng = (unsigned)seed * 2654435761u + 12345u;
     for (int li = 0; li < nloci; li++) start[li] = start_genealogy(loci[li], npops, rootpop, nsplit > 0 ? tv[nsplit - 1] : 0.0, rng);
   }
+  // Migration capacity: the reference grows an edge's list whenever it fills (checkmig, utilities.cpp:1365-1383).  Here the
+  // pools start with `capacity` events per genealogy (-cap, default 96) and double when a proposal did not fit; a proposal
+  // that did not fit was rejected unseen, which is reported on stderr with the count, never silently.
+  int capacity = opt.count("cap") ? atoi(opt["cap"].c_str()) : 96;
+  if (capacity < 8 || capacity > 8000) die("command line: -cap must be between 8 and 8000", 5);
   ima2p_engine *E = nullptr;
-  ck(ima2p_engine_create(&E, 0, nchains, nchains, 0, nloci, 96, seed), "engine");
+  ck(ima2p_engine_create(&E, 0, nchains, nchains, 0, nloci, capacity, seed), "engine");
   ck(ima2p_engine_set_model_spec(E, S), "model");
   for (int li = 0; li < nloci; li++) {
     Locus &L = loci[li];
@@ -1146,7 +1156,25 @@ int main(int argc, char **argv) {
   for (int a = 0; a < argc; a++) header += std::string(argv[a]) + " ";
   ck(ima2p_ti_create(ti.c_str(), header.c_str()), "creating the .ti file");
   printf("IMa2p_b200: %d populations %s, %d loci, %d chains, burn %ld steps, %ld genealogies every %ld steps\n", npops, tree, nloci, nchains, burn, nsave, every);
-  for (long done = 0; done < burn;) { const int n = burn - done > 1000 ? 1000 : (int)(burn - done); ck(ima2p_engine_run(E, n, swaptries, nullptr), "burn-in"); done += n; }
+  // after every stretch of steps: did a proposal fail to fit the migration pools?  Then the pools double (or the run ends with
+  // the reference's own error when a genealogy of that size cannot be held at all: IMERR_MIGARRAYTOOBIG, utilities.hpp:43)
+  unsigned long long dropped_seen = 0;
+  auto check_capacity = [&](const char *phase) {
+    uint64_t c8[8];
+    ck(ima2p_engine_counters(E, c8), "counters");
+    if (c8[7] == dropped_seen) return;
+    const unsigned long long lost = c8[7] - dropped_seen;
+    dropped_seen = c8[7];
+    const int bigger = capacity * 2;
+    if (ima2p_engine_grow_capacity(E, bigger) != IMA2P_OK) {
+      fprintf(stderr, "IMa2: %llu genealogy proposals needed more than %d migration events (%s)\n", lost, capacity, phase);
+      die(" too many migrations in array " + std::to_string(capacity), 22);
+    }
+    fprintf(stderr, "IMa2: %llu genealogy proposals needed more than %d migration events and were rejected unseen (%s); the pools now hold %d -- "
+            "start with -cap %d to avoid this\n", lost, capacity, phase, bigger, bigger);
+    capacity = bigger;
+  };
+  for (long done = 0; done < burn;) { const int n = burn - done > 1000 ? 1000 : (int)(burn - done); ck(ima2p_engine_run(E, n, swaptries, nullptr), "burn-in"); done += n; check_capacity("burn-in"); }
   // the reference's update-rate and swap tables start counting after the burn-in (reset_after_burn)
   uint64_t cnt0[8], ucnt0[4];
   const int nur = [&] { int k = 0; for (auto &L : loci) k += L.info[5]; return k; }();
@@ -1162,6 +1190,7 @@ int main(int argc, char **argv) {
   long saved = 0;
   while (saved < nsave) {
     ck(ima2p_engine_run(E, (int)every, swaptries, nullptr), "run");
+    check_capacity("sampling");
     int present = 0;
     ck(ima2p_engine_step_report(E, chain4.data(), row.data(), &present, nullptr), "reading the cold chain");
     if (!present) die("the cold chain is not on this device");

@@ -161,6 +161,7 @@ int ima2p_engine_read_mcf(ima2p_engine *h, const char *path) {
       if (!ok || root < 0) { rc = fail(IMA2P_E_ARG, R.err.empty() ? "mcf file: genealogy without a root" : R.err.c_str()); break; }
       moff[L.nl] = (int)mt.size();
       mt.push_back(0.0); mp.push_back(0);
+      if (up0[root] < 0 || up0[root] >= L.nl) { rc = fail(IMA2P_E_ARG, "mcf file: the root of a genealogy is a tip"); break; }
       const double roottime = time[up0[root]];                                    // :413
       rc = ima2p_engine_set_genealogy(h, ci, li, up0.data(), up1.data(), down.data(), pop.data(), time.data(), moff.data(), mt.data(),
                                       mp.data(), root, roottime, u, kappa, pi, has_stepwise(L.model) ? A.data() : nullptr);

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -197,6 +198,7 @@ int read_hky_locus(ULocus &L, const std::vector<std::string> &lines, size_t firs
   for (int i = 0; i < n; i++)
     for (int q = 0; q < L.numsites; q++) L.seq[(size_t)i * L.numsites + q] = seq[(size_t)i * ns + pat[q]];
   double tot = L.pi[0] + L.pi[1] + L.pi[2] + L.pi[3];
+  if (!(tot > 0)) return ufail(IMA2P_E_ARG, "locus " + std::to_string(li) + ": no base left after the columns with gaps were removed");
   for (int b = 0; b < 4; b++) L.pi[b] = L.pi[b] / tot;
   return 0;
 }
@@ -230,7 +232,18 @@ int read_sw_locus(ULocus &L, const std::vector<std::string> &lines, size_t first
 
 extern "C" {
 
+static int dataset_read_impl(const char *path, ima2p_dataset **out);
+// no exception crosses the C boundary: a malformed file is an error code, whatever it breaks on the way
 int ima2p_dataset_read(const char *path, ima2p_dataset **out) {
+  try {
+    return dataset_read_impl(path, out);
+  } catch (const std::exception &ex) {
+    return ufail(IMA2P_E_ARG, std::string("malformed data file: ") + ex.what());
+  } catch (...) {
+    return ufail(IMA2P_E_ARG, "malformed data file");
+  }
+}
+static int dataset_read_impl(const char *path, ima2p_dataset **out) {
   if (!path || !out) return ufail(IMA2P_E_ARG, "dataset_read: bad argument");
   FILE *f = fopen(path, "r");
   if (!f) return ufail(IMA2P_E_ARG, std::string("data file not found or can't be opened: ") + path);
@@ -280,8 +293,13 @@ int ima2p_dataset_read(const char *path, ima2p_dataset **out) {
     const std::vector<std::string> h = split_ws(lines[at++]);
     if ((int)h.size() < D->npops + 3) return bail(IMA2P_E_ARG, "locus " + std::to_string(li) + ": header line too short");
     L.name = h[0];
-    for (int i = 0; i < D->npops; i++) { L.samppop.push_back(atoi(h[1 + i].c_str())); L.numgenes += L.samppop.back(); }
+    for (int i = 0; i < D->npops; i++) {
+      L.samppop.push_back(atoi(h[1 + i].c_str()));
+      if (L.samppop.back() < 0) return bail(IMA2P_E_ARG, "locus " + std::to_string(li) + ": negative sample size");
+      L.numgenes += L.samppop.back();
+    }
     L.numbases = atoi(h[1 + D->npops].c_str());
+    if (L.numbases < 0) return bail(IMA2P_E_ARG, "locus " + std::to_string(li) + ": negative sequence length");
     const std::string &mt = h[2 + D->npops];
     const int digits = mt.size() > 1 && isdigit((unsigned char)mt[1]) ? atoi(mt.c_str() + 1) : 0;
     L.model_digit = mt.size() > 1 && isdigit((unsigned char)mt[1]);

@@ -239,6 +239,11 @@ class Engine:
         """Two-kernel proposal path (lane-per-pair move + warp-per-pair weights) or the general kernel for every pair."""
         self._ck(self.lib.ima2p_engine_set_proposal_path(self._h, 1 if fast else 0, pairs_per_warp))
 
+    def grow_capacity(self, new_capacity):
+        """More room for migration events per genealogy, between two steps (checkmig, utilities.cpp:1365-1383)."""
+        self._ck(self.lib.ima2p_engine_grow_capacity(self._h, new_capacity))
+        self.CAP = max(self.CAP, new_capacity)
+
     def set_debug_records(self, on=True):
         """Keep the per-proposal record `proposal()` reads (parity tests)."""
         self._ck(self.lib.ima2p_engine_set_debug_records(self._h, 1 if on else 0))

@@ -153,6 +153,12 @@ int ima2p_engine_run_sharded (ima2p_engine * e, int nsteps, int swaptries, void 
  * rank's swap): one process driving several GPUs, and the tests */
 int ima2p_engine_sharded_update (ima2p_engine * e, void *cuda_stream);
 int ima2p_engine_sharded_swap (ima2p_engine * e, int swaptries, void *cuda_stream);
+/* Migration capacity while the engine runs.  The reference grows an edge's migration list whenever it fills (checkmig,
+ * utilities.cpp:1365-1383; IMERR_MIGARRAYTOOBIG beyond ABSMIGMAX 5000).  Here a proposal whose genealogy would hold more than
+ * mig_capacity events is dropped and counted (ima2p_engine_counters field 7); a caller that sees the count move calls this at a
+ * step boundary: the pools are re-made with the new capacity, the resident genealogies copied over, nothing else changes.
+ * IMA2P_E_CAPACITY when a genealogy of that size no longer fits the kernels' shared-memory tables. */
+int ima2p_engine_grow_capacity (ima2p_engine * e, int new_capacity);
 /* parity tests: keep the per-proposal record that ima2p_engine_get_proposal reads (off by default) */
 int ima2p_engine_set_debug_records (ima2p_engine * e, int on);
 /* speculative depth of the accept sweep (1..3): how many consecutive loci of a chain are evaluated per round against

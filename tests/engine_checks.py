@@ -673,6 +673,38 @@ def hky_partials_stay_consistent(lib, name="state_sim5_hky_hn2", nsteps=400):
     return out
 
 
+def capacity_grows_without_changing_the_chain(lib, name="state_sim3_hn3", nsteps=60):
+    """ima2p_engine_grow_capacity (checkmig, utilities.cpp:1365-1383): growing the migration pools between two steps re-houses
+    the resident genealogies and nothing else -- a run that grows half way is the run that had the room from the start.  With a
+    capacity the genealogies outgrow, proposals are dropped and COUNTED (never silently): the count is what a caller reacts to."""
+    from support import engine_from_fixture, load_golden
+    d = load_golden(name)
+
+    def run(cap0, grow_to):
+        eng, fm = engine_from_fixture(d, lib=lib, seed=9, mig_capacity=cap0)
+        eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+        eng.set_update_schedule(3, 5)
+        eng.eval()
+        eng.run(nsteps // 2)
+        if grow_to:
+            eng.grow_capacity(grow_to)
+        eng.run(nsteps - nsteps // 2)
+        eng.sync()
+        ch = [eng.chain(c) for c in range(eng.nchains)]
+        trees = [eng.get_genealogy(c, l) for c in range(eng.nchains) for l in range(eng.nloci)]
+        out = (eng.counters(), np.concatenate([np.r_[c["probg"], c["pdg"], c["tvals"], c["wd"], c["wi"]] for c in ch]),
+               np.concatenate([np.r_[t["time"], t["mig_t"], t["mig_p"]] for t in trees]))
+        eng.close()
+        return out
+    a, b = run(64, 160), run(160, 0)
+    assert a[0] == b[0] and a[0]["dropped"] == 0 and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    # a capacity below what the start state holds is refused outright; one the run outgrows is counted
+    mx = max(len(sum(g["tree"]["mig"], [])) // 2 for ch in d["chains"] for g in ch["G"])
+    tight = run(max(8, mx + 1), 0)
+    assert tight[0]["dropped"] >= 0
+    return a[0], tight[0]["dropped"]
+
+
 def full_size_workload_properties(lib, nloci, nchains, nsteps, noracle=48, seed=5):
     """BASELINE-sized runs (configs[1]: 50 loci x 128 chains; configs[2]'s per-GPU shard: 300 loci x 256 chains), checked through
     properties that do not need a stored answer: after `nsteps` whole qupdate steps (genealogies, split times, scalars, swaps)

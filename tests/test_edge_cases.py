@@ -144,3 +144,45 @@ def test_engine_argument_errors(emu):
     with pytest.raises(Ima2pError):
         eng.pair(0, 2)
     eng.close()
+
+
+def test_malformed_inputs_are_error_codes_not_crashes(tmp_path):
+    """The .u reader and the state loader are fed by files: a negative sequence length, a negative sample size, an HKY locus
+    whose columns are all gaps, a genealogy whose links point outside the tree -- every one of them is an error code with a
+    message, never an exception through the C boundary or an out-of-range index on the device."""
+    import os
+    import numpy as np
+    from ima2p_b200 import Engine, capi, synth
+    from ima2p_b200.readu import read_u
+    here = os.path.dirname(os.path.abspath(__file__))
+    lib = capi.bind(os.path.join(here, "hostemu", "libima2p_hostemu.so"))
+    head = "bad input\n2\npop1 pop2\n(0,1):2\n1\n"
+    cases = {"neglen": "loc 2 2 -5 H 1\n", "negsamp": "loc -1 5 4 I 1\n" + "".join("g%-9dACGT\n" % i for i in range(4)),
+             "allgaps": "loc 2 2 3 H 1\n" + "".join("g%-9d---\n" % i for i in range(4))}
+    for name, body in cases.items():
+        p = tmp_path / (name + ".u")
+        p.write_text(head + body)
+        with pytest.raises(capi.Ima2pError):
+            read_u(str(p), lib=lib)
+    # a genealogy with a link outside the tree / a tip as root / a migration into a population that does not exist
+    loci = synth.make_dataset(1, 3, 3, seed=2)
+    eng = Engine(1, 1, lib=lib)
+    eng.set_model(**synth.two_population_model())
+    eng.set_locus(0, 0, loci[0]["n"], loci[0]["numsites"], loci[0]["samppop"], seq=loci[0]["seq"])
+    eng.finalize()
+    L = loci[0]
+    nl = 2 * L["n"] - 1
+    pop = np.r_[np.zeros(3, int), np.ones(3, int), np.full(nl - 6, 2)]
+    time = np.where(L["down"] >= 0, 2.0 + L["height"][np.maximum(L["down"], 0)], 1e6)
+    good = dict(up0=L["up0"].copy(), up1=L["up1"].copy(), down=L["down"].copy(), pop=pop.copy(), time=time, mig_off=np.zeros(nl + 1, int),
+                mig_t=[], mig_p=[], root=nl - 1, roottime=2.0 + L["height"][nl - 1])
+    eng.set_genealogy(0, 0, **good)
+    for field, idx, val in (("up0", nl - 1, nl + 3), ("down", 0, -7), ("pop", 2, 9)):
+        bad = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in good.items()}
+        bad[field][idx] = val
+        with pytest.raises(capi.Ima2pError):
+            eng.set_genealogy(0, 0, **bad)
+    bad = dict(good, root=0)
+    with pytest.raises(capi.Ima2pError):
+        eng.set_genealogy(0, 0, **bad)
+    eng.close()

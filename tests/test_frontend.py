@@ -1,6 +1,7 @@
 """The command-line front end (csrc/ima_frontend.cpp) over the C ABI, built here against the host-emulation library:
 host logic only -- option scan, .u -> model -> starting genealogies -> schedule -> .ti / .mcf / report files."""
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -293,3 +294,27 @@ def test_l_mode_ascii_curves_equal_the_reference_text(exe, tmp_path):
         assert (i - 2) % 54 == 1, (i, mine[i], want[i])
         assert mine[i][:11] == want[i][:11] and sorted((mine[i][11:].count("*"), want[i][11:].count("*"))) == [0, 1], (mine[i], want[i])
     assert len(differing) <= 3
+
+
+def test_migration_pools_grow_and_nothing_is_lost_silently(exe, tmp_path):
+    """A wide migration prior (-m 10) on Sim3-shaped data with pools that start far too small (-cap 8): the front end must notice
+    every proposal that did not fit, say so on stderr, double the pools (ima2p_engine_grow_capacity; the reference's checkmig grows
+    an edge's list the same way, utilities.cpp:1365-1383) and finish; started with room to spare (-cap 512) the same command
+    reports no proposal lost."""
+    from ima2p_b200 import synth
+    u = tmp_path / "Sim3.u"
+    synth.write_u(str(u), synth.make_dataset(2, 15, 15, seed=3))       # two infinite-sites loci of 15 + 15 genes, like Simulations/Sim3.u
+    common = ["-i", str(u), "-q10", "-m10", "-t3", "-b3000", "-l60", "-d20", "-hn2", "-hfl", "-ha0.3", "-s7"]
+    r = _run(exe, common + ["-o", str(tmp_path / "tight.out"), "-cap", "8"])
+    assert r.returncode == 0, r.stderr
+    assert "rejected unseen" in r.stderr and "the pools now hold" in r.stderr, r.stderr[-600:]
+    lost = int(re.search(r"proposals dropped for migration capacity (\d+)", open(tmp_path / "tight.out").read()).group(1))
+    assert lost > 0
+    r = _run(exe, common + ["-o", str(tmp_path / "roomy.out"), "-cap", "512"])
+    assert r.returncode == 0 and "rejected unseen" not in r.stderr, r.stderr[-600:]
+    assert int(re.search(r"proposals dropped for migration capacity (\d+)", open(tmp_path / "roomy.out").read()).group(1)) == 0
+    # many migration events were indeed sampled: the .ti rows' migration counts (columns mc0, mc1 of 21)
+    from ima2p_b200 import capi
+    from ima2p_b200.readu import ti_load
+    rows = ti_load(str(tmp_path / "roomy.out") + ".ti", 21, lib=capi.bind(os.path.join(HERE, "hostemu", "libima2p_hostemu.so")))
+    assert rows[:, 9:11].sum(axis=1).mean() > 8

@@ -103,6 +103,10 @@ def test_fast_path_equals_general_path(lib, name):
     ec.fast_path_equals_general_path(lib, name, ppws=(4, 8, 16))
 
 
+def test_capacity_grows_without_changing_the_chain(lib):
+    ec.capacity_grows_without_changing_the_chain(lib)
+
+
 def test_hky_partials_stay_consistent(lib):
     ec.hky_partials_stay_consistent(lib)
 

@@ -63,6 +63,10 @@ def test_fast_path_equals_general_path(emu, name):
     ec.fast_path_equals_general_path(emu, name, nsteps=25)
 
 
+def test_capacity_grows_without_changing_the_chain(emu):
+    ec.capacity_grows_without_changing_the_chain(emu)
+
+
 def test_hky_partials_stay_consistent(emu):
     ec.hky_partials_stay_consistent(emu, nsteps=200)
 
