@@ -52,6 +52,7 @@ SIGNATURES = {
     "ima2p_ipc_export": (_i, [_v, C.c_char_p]),
     "ima2p_ipc_import": (_i, [_i, C.c_char_p, C.POINTER(_v)]),
     "ima2p_engine_run_sharded": (_i, [_v, _i, _i, _v]),
+    "ima2p_engine_cold_message": (_i, [_v, c_dbl_p, _v]),
     "ima2p_engine_sharded_update": (_i, [_v, _v]),
     "ima2p_engine_sharded_swap": (_i, [_v, _i, _v]),
     "ima2p_engine_set_speculation": (_i, [_v, _i]),

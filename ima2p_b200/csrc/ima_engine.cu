@@ -11,6 +11,12 @@
 #include <string>
 #include <vector>
 #include <new>
+#if !IMA_CUDA
+#include <map>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#endif
 
 namespace ima {
 
@@ -18,6 +24,9 @@ namespace ima {
 thread_local EmuCtx g_emu;
 #endif
 
+#if !IMA_CUDA
+static std::map<const void *, std::pair<std::string, size_t>> g_emu_tables;     // exchange tables of this process (host emulation)
+#endif
 static thread_local std::string g_last_error;
 static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
 
@@ -82,6 +91,10 @@ struct Engine {
   unsigned char *d_xch = nullptr;
   size_t xch_bytes = 0;
   bool xch_attached = false;
+  int cold_len = 0;
+  unsigned long long cold_seq = 0;                  // requests for the cold chain's record so far (the same on every rank)
+  double *d_cold = nullptr, *h_cold = nullptr;
+  char xch_shm[64] = {0};                           // host emulation: name of the shared-memory object of the table
   size_t pair_smem = 0, chain_smem = 0, accept_smem = 0;
   int spec = 3;        // speculative depth of the accept sweep (see k_accept)
 
@@ -101,6 +114,9 @@ struct Engine {
     for (auto &x : pipe_events) if (x) cudaEventDestroy(x);
 #endif
     for (void *p : allocs) dev_free(p);
+#if !IMA_CUDA
+    if (xch_shm[0]) { if (d_xch) munmap(d_xch, xch_bytes); shm_unlink(xch_shm); }
+#endif
   }
 };
 
@@ -1137,7 +1153,10 @@ int ima2p_engine_exchange_create(ima2p_engine *h, void **table, uint64_t *bytes)
     return fail(IMA2P_E_ARG, "exchange_create: chains must shard evenly over at most 16 ranks");
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   if (!e.d_xch) {
-    e.xch_bytes = (size_t)2 * e.d.nchains_global * sizeof(double) + 64;
+    int dm[5];
+    ima2p_engine_dims(h, dm);
+    e.cold_len = dm[4] + 2 + e.d.nloci;
+    e.xch_bytes = (size_t)2 * e.d.nchains_global * sizeof(double) + 64 + 64 + (size_t)e.cold_len * sizeof(double);
 #if IMA_CUDA
     // its own allocation (not a slice of a pool): cudaIpcGetMemHandle exports whole allocations
     void *p = nullptr;
@@ -1146,10 +1165,20 @@ int ima2p_engine_exchange_create(ima2p_engine *h, void **table, uint64_t *bytes)
     e.d_xch = (unsigned char *)p;
     e.allocs.push_back(p);
 #else
-    e.d_xch = e.alloc<unsigned char>(e.xch_bytes);
+    // host emulation (tests): the table lives in POSIX shared memory so that ranks can be separate processes here too
+    snprintf(e.xch_shm, sizeof e.xch_shm, "/ima2p_xch_%d_%p", (int)getpid(), (void *)&e);
+    const int fd = shm_open(e.xch_shm, O_CREAT | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)e.xch_bytes) != 0) return fail(IMA2P_E_CUDA, "exchange_create: shared memory failed");
+    e.d_xch = (unsigned char *)mmap(nullptr, e.xch_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (e.d_xch == (unsigned char *)MAP_FAILED) { e.d_xch = nullptr; return fail(IMA2P_E_CUDA, "exchange_create: mmap failed"); }
+    memset(e.d_xch, 0, e.xch_bytes);
 #endif
     if (!e.d_xch) return fail(IMA2P_E_CUDA, "exchange_create: allocation failed");
   }
+#if !IMA_CUDA
+  g_emu_tables[e.d_xch] = std::make_pair(std::string(e.xch_shm), e.xch_bytes);
+#endif
   *table = e.d_xch; *bytes = e.xch_bytes;
   return IMA2P_OK;
 }
@@ -1167,6 +1196,11 @@ int ima2p_engine_exchange_attach(ima2p_engine *h, void *const *tables) {
     if (!t) return fail(IMA2P_E_ARG, "exchange_attach: a peer's table is missing");
     X.peer_S[r] = (double *)t;
     X.peer_arrived[r] = (unsigned long long *)(t + (size_t)2 * e.d.nchains_global * sizeof(double));
+    if (r == 0) {
+      X.cold_seq0 = (unsigned long long *)(t + (size_t)2 * e.d.nchains_global * sizeof(double) + 64);
+      X.cold_msg0 = (double *)(t + (size_t)2 * e.d.nchains_global * sizeof(double) + 128);
+      X.cold_len = e.cold_len;
+    }
   }
   stream_t s = pick_stream(&e, nullptr);
   unsigned long long st = 0;
@@ -1191,9 +1225,10 @@ int ima2p_ipc_export(const void *dev_ptr, unsigned char *handle64) {
   memcpy(handle64, &hd, 64);
   return IMA2P_OK;
 #else
+  // host emulation: the handle is the name of the shared-memory object the table lives in (exchange_create), looked up by address
   memset(handle64, 0, 64);
-  memcpy(handle64, &dev_ptr, sizeof dev_ptr);                 // host emulation: one process, the pointer is the handle
-  return IMA2P_OK;
+  for (auto &kv : g_emu_tables) if (kv.first == dev_ptr) { snprintf((char *)handle64, 64, "%s %zu", kv.second.first.c_str(), kv.second.second); return IMA2P_OK; }
+  return fail(IMA2P_E_ARG, "ipc_export: not an exchange table");
 #endif
 }
 int ima2p_ipc_import(int device, const unsigned char *handle64, void **dev_ptr) {
@@ -1206,7 +1241,14 @@ int ima2p_ipc_import(int device, const unsigned char *handle64, void **dev_ptr) 
   return IMA2P_OK;
 #else
   (void)device;
-  memcpy(dev_ptr, handle64, sizeof *dev_ptr);
+  char name[64]; size_t bytes = 0;
+  if (sscanf((const char *)handle64, "%63s %zu", name, &bytes) != 2) return fail(IMA2P_E_ARG, "ipc_import: bad handle");
+  const int fd = shm_open(name, O_RDWR, 0600);
+  if (fd < 0) return fail(IMA2P_E_CUDA, "ipc_import: shared memory object not found");
+  void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return fail(IMA2P_E_CUDA, "ipc_import: mmap failed");
+  *dev_ptr = p;
   return IMA2P_OK;
 #endif
 }
@@ -1238,6 +1280,36 @@ int ima2p_engine_sharded_swap(ima2p_engine *h, int swaptries, void *cuda_stream)
   return IMA2P_OK;
 }
 
+// The cold chain's record of a sharded job (all ranks call this at the same step boundary): on rank 0 out_msg[rowlen + 2 + nloci]
+// = the .ti row (floats, as doubles), probg, P(D|G), P(D|G) of every locus -- whichever rank holds the chain at beta = 1 stored it
+// into rank 0's table; on the other ranks nothing is returned.  savegsampinf ginfo.cpp:318-377 for the row.
+int ima2p_engine_cold_message(ima2p_engine *h, double *out_msg, void *cuda_stream) {
+  if (!h || !h->eng.xch_attached) return fail(IMA2P_E_ARG, "cold_message: attach the exchange first");
+  Engine &e = h->eng;
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  int dm[5];
+  ima2p_engine_dims(h, dm);
+  if (!e.d_cold) {
+    e.d_cold = e.alloc<double>(e.cold_len);
+#if IMA_CUDA
+    if (!IMA_CUDA_OK(cudaMallocHost((void **)&e.h_cold, e.cold_len * sizeof(double)))) return fail(IMA2P_E_CUDA, "pinned allocation failed");
+#else
+    e.h_cold = (double *)malloc(e.cold_len * sizeof(double));
+#endif
+    if (!e.d_cold || !e.h_cold) return fail(IMA2P_E_CUDA, "allocation failed (cold message)");
+  }
+  e.cold_seq++;
+  IMA_LAUNCH(k_cold_message, 1, 1, 0, s, view_of(&e, 0, e.d.nchains, 0), (const int *)e.sv.chain_of_rank, dm[4], e.cold_seq, e.d_cold);
+  if (e.v.xch.rank == 0) {
+    if (!out_msg) return fail(IMA2P_E_ARG, "cold_message: rank 0 needs the output buffer");
+    if (!d2h(e.h_cold, e.d_cold, e.cold_len * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
+    memcpy(out_msg, e.h_cold, e.cold_len * sizeof(double));
+    return check_device_error(&e, s);
+  }
+  return dev_sync(s) ? IMA2P_OK : fail(IMA2P_E_CUDA, "sync failed");
+}
+
 // nsteps whole steps of this rank's chains; the swap sums travel through the exchange tables inside the kernels, so there is
 // nothing for the host to do between steps: the step is one CUDA graph (ima2p_engine_set_pipeline applies), replayed nsteps times
 int ima2p_engine_run_sharded(ima2p_engine *h, int nsteps, int swaptries, void *cuda_stream) {
@@ -1266,8 +1338,13 @@ int ima2p_engine_run_sharded(ima2p_engine *h, int nsteps, int swaptries, void *c
   for (; i < nsteps; i++)
     if (!IMA_CUDA_OK(cudaGraphLaunch(e.graph_exec_sh, s))) return fail(IMA2P_E_CUDA, "graph launch failed");
 #else
-  (void)s;
-  return fail(IMA2P_E_UNSUPPORTED, "run_sharded: the host emulation steps ranks with sharded_update / sharded_swap");
+  // host emulation: ranks are separate processes sharing their tables (the swap kernel polls, IMA2P_EMU_WAIT_MS)
+  for (int i = 0; i < nsteps; i++) {
+    EngineView v = view_of(&e, 0, e.d.nchains, 0);
+    v.xch.publisher = last_kernel_of_step(&e);
+    launch_update(&e, s, v);
+    launch_swap(&e, s, nullptr, swaptries);
+  }
 #endif
   return IMA2P_OK;
 }

@@ -30,6 +30,8 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <time.h>
+#include <unistd.h>
 
 namespace {
 
@@ -45,6 +47,61 @@ void ck(int rc, const char *what) {
 }
 
 struct Locus { int info[8]; double hval; std::vector<int> samppop, seq, mult, A, minA, maxA; double pi[4]; };
+
+// ---- several ranks, one GPU each (the reference: mpirun -np P IMa2p -hn N, ima_main_mpi.cpp:4317-4560) -----------------------
+// Started once per GPU by any launcher that sets RANK / WORLD_SIZE / LOCAL_RANK (torchrun, mpirun wrappers, a shell loop).  -hn
+// is the number of chains PER RANK, as in the reference.  The ranks find each other through small files in a directory all of
+// them see (IMA2P_RENDEZVOUS_DIR, default /dev/shm): each publishes the 64-byte handle of its exchange table, opens the others'
+// and from then on the kernels exchange the swap sums and the cold chain's record themselves (include/ima2p_b200.h).
+struct Ranks {
+  int world = 1, rank = 0, local = 0;
+  std::string key;
+  void init() {
+    if (const char *w = getenv("WORLD_SIZE")) world = atoi(w) > 1 ? atoi(w) : 1;
+    if (world == 1) return;
+    rank = getenv("RANK") ? atoi(getenv("RANK")) : 0;
+    local = getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : rank;
+    if (rank < 0 || rank >= world) die("RANK must be in [0, WORLD_SIZE)", 5);
+    const char *dir = getenv("IMA2P_RENDEZVOUS_DIR");
+    const char *job = getenv("TORCHELASTIC_RUN_ID");
+    const char *port = getenv("MASTER_PORT");
+    // the launcher's process id tells one launch from the next when the launcher gives the job no name
+    key = std::string(dir ? dir : "/dev/shm") + "/ima2p_" + (job && strcmp(job, "none") ? job : "job") + "_" + std::to_string((long)getppid()) + "_" + (port ? port : "0");
+  }
+  std::string file(const std::string &what, int r) const { return key + "." + what + "." + std::to_string(r); }
+  void put(const std::string &what, const void *data, size_t n) const {
+    const std::string tmp = file(what, rank) + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f || fwrite(data, 1, n, f) != n) die("rendezvous: cannot write " + tmp, 2);
+    fclose(f);
+    if (rename(tmp.c_str(), file(what, rank).c_str()) != 0) die("rendezvous: cannot publish " + file(what, rank), 2);
+  }
+  std::vector<unsigned char> get(const std::string &what, int r, size_t n) const {
+    std::vector<unsigned char> buf(n);
+    for (int tries = 0; tries < 240000; tries++) {              // up to about two minutes
+      FILE *f = fopen(file(what, r).c_str(), "rb");
+      if (f) { const size_t k = fread(buf.data(), 1, n, f); fclose(f); if (k == n) return buf; }
+      struct timespec ts = {0, 500000};
+      nanosleep(&ts, nullptr);
+    }
+    die("rendezvous: rank " + std::to_string(r) + " did not show up (" + file(what, r) + ")", 2);
+  }
+  void barrier(const std::string &name) const {
+    if (world == 1) return;
+    const char one = 1;
+    put("bar_" + name, &one, 1);
+    for (int r = 0; r < world; r++) get("bar_" + name, r, 1);
+  }
+  // the end of a run: every other rank says it is done and leaves; rank 0 waits for all of them and removes every file
+  void finish() const {
+    if (world == 1) return;
+    const char one = 1;
+    if (rank != 0) { put("bar_done", &one, 1); return; }
+    for (int r = 1; r < world; r++) get("bar_done", r, 1);
+    for (int r = 0; r < world; r++)
+      for (const char *w : {"xch", "cnt", "bar_attached", "bar_done"}) remove(file(w, r).c_str());
+  }
+};
 
 // One valid genealogy for a locus, every coalescence above `tbase` (so every lineage has reached the root population
 // by the population tree alone and no migration event is needed).  Infinite-sites columns (0 = the first gene's base)
@@ -1036,7 +1093,9 @@ int main(int argc, char **argv) {
   if (lmode) { opt.emplace("b", "0"); opt.emplace("l", "1"); }
   for (const char *need : {"i", "o", "q", "t", "b", "l"}) if (!opt.count(need)) die(std::string("command line: -") + need + " is required", 5);
   const double qmax = atof(opt["q"].c_str()), mmax = opt.count("m") ? atof(opt["m"].c_str()) : 0.0, tmax = atof(opt["t"].c_str());
-  const int nchains = opt.count("hn") ? atoi(opt["hn"].c_str()) : 1, expo = opt.count("j") ? 1 : 0;
+  Ranks ranks;
+  ranks.init();
+  const int nlocal = opt.count("hn") ? atoi(opt["hn"].c_str()) : 1, nchains = nlocal * ranks.world, expo = opt.count("j") ? 1 : 0;      // -hn: chains per rank
   const long burn = atol(opt["b"].c_str()), nsave = atol(opt["l"].c_str()), every = opt.count("d") ? atol(opt["d"].c_str()) : 100;
   // no -s: seeded from the clock as the reference does (ima_main_mpi.cpp:1413), and said so in the report; a run continued from
   // a state file (-f) mixes the time into the seed it was given so that it does not replay the first run's random streams
@@ -1099,7 +1158,7 @@ int main(int argc, char **argv) {
   int capacity = opt.count("cap") ? atoi(opt["cap"].c_str()) : 96;
   if (capacity < 8 || capacity > 8000) die("command line: -cap must be between 8 and 8000", 5);
   ima2p_engine *E = nullptr;
-  ck(ima2p_engine_create(&E, 0, nchains, nchains, 0, nloci, capacity, seed), "engine");
+  ck(ima2p_engine_create(&E, ranks.local, nlocal, nchains, ranks.rank * nlocal, nloci, capacity, seed), "engine");
   ck(ima2p_engine_set_model_spec(E, S), "model");
   for (int li = 0; li < nloci; li++) {
     Locus &L = loci[li];
@@ -1123,7 +1182,7 @@ int main(int argc, char **argv) {
   ck(ima2p_engine_set_update_priors(E, tmaxv.data(), tminv.data(), 0.0, 0.0, 0.0, 0.0), "priors");
 
   if (opt.count("f")) {
-    ck(ima2p_engine_read_mcf(E, opt["f"].c_str()), "loading the state file");
+    ck(ima2p_engine_read_mcf(E, (ranks.world > 1 ? opt["f"] + "." + std::to_string(ranks.rank) : opt["f"]).c_str()), "loading the state file");
   } else {
     for (int li = 0; li < nloci; li++) {
       const Locus &L = loci[li];
@@ -1135,7 +1194,7 @@ int main(int argc, char **argv) {
         for (int i = 0; i < n; i++) A[(size_t)a * nl + i] = L.A[(size_t)a * n + i];
         for (int k = n; k < nl; k++) A[(size_t)a * nl + k] = A[(size_t)a * nl + T.up0[k]];
       }
-      for (int c = 0; c < nchains; c++) {
+      for (int c = 0; c < nlocal; c++) {
         if (li == 0) ck(ima2p_engine_set_chain(E, c, tv.data()), "chain");
         ck(ima2p_engine_set_genealogy(E, c, li, T.up0.data(), T.up1.data(), T.down.data(), T.pop.data(), T.time.data(), moff.data(), mt.data(),
                                       mp.data(), T.root, T.roottime, u.data(), 2.0, L.pi, nlinked > 0 && (L.info[0] == IMA2P_MODEL_SW || L.info[0] == IMA2P_MODEL_JOINT) ? A.data() : nullptr),
@@ -1148,14 +1207,34 @@ int main(int argc, char **argv) {
   ck(ima2p_engine_set_update_schedule(E, nsplit > 0 ? 3 : 0, 5), "schedule");
 
   const int swaptries = nchains > 1 ? (nchains / 10 > 1 ? nchains / 10 : 1) : 0;                 // ima_main_mpi.cpp:1378
+  if (ranks.world > 1) {
+    // exchange tables: publish mine, open the others', attach; nobody steps before everybody is attached
+    void *table = nullptr; uint64_t tbytes = 0;
+    ck(ima2p_engine_exchange_create(E, &table, &tbytes), "exchange table");
+    unsigned char hd[64];
+    ck(ima2p_ipc_export(table, hd), "exchange handle");
+    ranks.put("xch", hd, 64);
+    std::vector<void *> tables(ranks.world, nullptr);
+    for (int r = 0; r < ranks.world; r++) {
+      if (r == ranks.rank) continue;
+      const std::vector<unsigned char> h = ranks.get("xch", r, 64);
+      ck(ima2p_ipc_import(ranks.local, h.data(), &tables[r]), "opening a peer's exchange table");
+    }
+    ck(ima2p_engine_exchange_attach(E, tables.data()), "attaching the exchange");
+    ranks.barrier("attached");
+  }
+  auto run_steps = [&](int n, const char *what) {
+    if (ranks.world > 1) ck(ima2p_engine_run_sharded(E, n, swaptries, nullptr), what);
+    else ck(ima2p_engine_run(E, n, swaptries, nullptr), what);
+  };
   int dims[5];
   ima2p_engine_dims(E, dims);
   const int rowlen = dims[4];
   const std::string ti = opt["o"] + ".ti";
   std::string header = "Command line string : ";
   for (int a = 0; a < argc; a++) header += std::string(argv[a]) + " ";
-  ck(ima2p_ti_create(ti.c_str(), header.c_str()), "creating the .ti file");
-  printf("IMa2p_b200: %d populations %s, %d loci, %d chains, burn %ld steps, %ld genealogies every %ld steps\n", npops, tree, nloci, nchains, burn, nsave, every);
+  if (ranks.rank == 0) ck(ima2p_ti_create(ti.c_str(), header.c_str()), "creating the .ti file");
+  if (ranks.rank == 0) printf("IMa2p_b200: %d populations %s, %d loci, %d chains, burn %ld steps, %ld genealogies every %ld steps\n", npops, tree, nloci, nchains, burn, nsave, every);
   // after every stretch of steps: did a proposal fail to fit the migration pools?  Then the pools double (or the run ends with
   // the reference's own error when a genealogy of that size cannot be held at all: IMERR_MIGARRAYTOOBIG, utilities.hpp:43)
   unsigned long long dropped_seen = 0;
@@ -1174,7 +1253,7 @@ int main(int argc, char **argv) {
             "start with -cap %d to avoid this\n", lost, capacity, phase, bigger, bigger);
     capacity = bigger;
   };
-  for (long done = 0; done < burn;) { const int n = burn - done > 1000 ? 1000 : (int)(burn - done); ck(ima2p_engine_run(E, n, swaptries, nullptr), "burn-in"); done += n; check_capacity("burn-in"); }
+  for (long done = 0; done < burn;) { const int n = burn - done > 1000 ? 1000 : (int)(burn - done); run_steps(n, "burn-in"); done += n; check_capacity("burn-in"); }
   // the reference's update-rate and swap tables start counting after the burn-in (reset_after_burn)
   uint64_t cnt0[8], ucnt0[4];
   const int nur = [&] { int k = 0; for (auto &L : loci) k += L.info[5]; return k; }();
@@ -1189,17 +1268,30 @@ int main(int argc, char **argv) {
   std::vector<double> tsum(nsplit > 0 ? nsplit : 1, 0.0);
   long saved = 0;
   while (saved < nsave) {
-    ck(ima2p_engine_run(E, (int)every, swaptries, nullptr), "run");
+    run_steps((int)every, "run");
     check_capacity("sampling");
-    int present = 0;
-    ck(ima2p_engine_step_report(E, chain4.data(), row.data(), &present, nullptr), "reading the cold chain");
-    if (!present) die("the cold chain is not on this device");
-    for (int c = 0; c < nchains; c++) {
-      if (chain4[(size_t)c * 4] != 1.0) continue;
-      if (chain4[(size_t)c * 4 + 1] > hiprob) hiprob = chain4[(size_t)c * 4 + 1];
-      if (chain4[(size_t)c * 4 + 2] > hilike) hilike = chain4[(size_t)c * 4 + 2];
-      ck(ima2p_engine_fetch_chain_pdg(E, c, locus_pdg.data()), "reading the likelihoods");
-      for (int li = 0; li < nloci; li++) if (locus_pdg[li] > hilocus[li]) hilocus[li] = locus_pdg[li];
+    if (ranks.world > 1) {
+      // the cold chain may live on any rank: its record comes to rank 0 through the exchange (ima2p_engine_cold_message)
+      std::vector<double> msg((size_t)rowlen + 2 + nloci);
+      ck(ima2p_engine_cold_message(E, msg.data(), nullptr), "reading the cold chain");
+      saved++;
+      if (ranks.rank != 0) continue;
+      saved--;
+      for (int i = 0; i < rowlen; i++) row[i] = (float)msg[i];
+      if (msg[rowlen] > hiprob) hiprob = msg[rowlen];
+      if (msg[rowlen + 1] > hilike) hilike = msg[rowlen + 1];
+      for (int li = 0; li < nloci; li++) if (msg[rowlen + 2 + li] > hilocus[li]) hilocus[li] = msg[rowlen + 2 + li];
+    } else {
+      int present = 0;
+      ck(ima2p_engine_step_report(E, chain4.data(), row.data(), &present, nullptr), "reading the cold chain");
+      if (!present) die("the cold chain is not on this device");
+      for (int c = 0; c < nchains; c++) {
+        if (chain4[(size_t)c * 4] != 1.0) continue;
+        if (chain4[(size_t)c * 4 + 1] > hiprob) hiprob = chain4[(size_t)c * 4 + 1];
+        if (chain4[(size_t)c * 4 + 2] > hilike) hilike = chain4[(size_t)c * 4 + 2];
+        ck(ima2p_engine_fetch_chain_pdg(E, c, locus_pdg.data()), "reading the likelihoods");
+        for (int li = 0; li < nloci; li++) if (locus_pdg[li] > hilocus[li]) hilocus[li] = locus_pdg[li];
+      }
     }
     rows.insert(rows.end(), row.begin(), row.end());
     allrows.insert(allrows.end(), row.begin(), row.end());
@@ -1211,9 +1303,39 @@ int main(int argc, char **argv) {
   ck(ima2p_engine_counters(E, cnt), "counters");
   ck(ima2p_engine_update_counters(E, ucnt), "counters");
   const std::string outname = opt["o"];
+  ck(ima2p_engine_cold_counters(E, cg.data(), ct.data(), cu.data(), ca.data()), "counters");
+  if (opt.count("r") && ranks.world > 1) ck(ima2p_engine_write_mcf(E, (outname + ".mcf." + std::to_string(ranks.rank)).c_str()), "writing the state file");
+  if (ranks.world > 1) {
+    // Update counts are kept where the updates were made (the cold chain moves between ranks): every rank publishes what it
+    // counted since the burn-in, rank 0 adds them up.  Steps and swaps are replayed identically on every rank: not added.
+    std::vector<uint64_t> mine;
+    for (int i = 0; i < 8; i++) mine.push_back(cnt[i]);
+    for (int i = 0; i < 4; i++) mine.push_back(ucnt[i]);
+    for (size_t i = 0; i < cg.size(); i++) mine.push_back(cg[i] - cg0[i]);
+    for (size_t i = 0; i < ct.size(); i++) mine.push_back(ct[i] - ct0[i]);
+    for (size_t i = 0; i < cu.size(); i++) mine.push_back(cu[i] - cu0[i]);
+    ranks.put("cnt", mine.data(), mine.size() * 8);
+    if (ranks.rank != 0) {
+      ranks.finish();
+      ima2p_engine_destroy(E); ima2p_modelspec_free(S); ima2p_dataset_free(D);
+      return 0;
+    }
+    for (size_t i = 0; i < cg.size(); i++) { cg[i] -= cg0[i]; cg0[i] = 0; }
+    for (size_t i = 0; i < ct.size(); i++) { ct[i] -= ct0[i]; ct0[i] = 0; }
+    for (size_t i = 0; i < cu.size(); i++) { cu[i] -= cu0[i]; cu0[i] = 0; }
+    for (int r = 1; r < ranks.world; r++) {
+      const std::vector<unsigned char> raw = ranks.get("cnt", r, mine.size() * 8);
+      const uint64_t *o = (const uint64_t *)raw.data();
+      for (int i : {1, 2, 3, 4, 7}) cnt[i] += o[i];
+      for (int i = 0; i < 4; i++) ucnt[i] += o[8 + i];
+      size_t at = 12;
+      for (size_t i = 0; i < cg.size(); i++) cg[i] += o[at++];
+      for (size_t i = 0; i < ct.size(); i++) ct[i] += o[at++];
+      for (size_t i = 0; i < cu.size(); i++) cu[i] += o[at++];
+    }
+  }
   FILE *f = fopen(outname.c_str(), "w");
   if (!f) die("cannot create the output file", 2);
-  ck(ima2p_engine_cold_counters(E, cg.data(), ct.data(), cu.data(), ca.data()), "counters");
   const unsigned long long poststeps = cnt[0] - cnt0[0];
   fprintf(f, "%s", start_info(R, D, npops, nloci, tree, md[3], md[4], nsplit, qmax, mmax, tmax).c_str());
   // printrunbasics (output.cpp:166-206)
@@ -1290,7 +1412,8 @@ int main(int argc, char **argv) {
   }
   g_throw_instead_of_exit = false;
   fclose(f);
-  if (opt.count("r")) ck(ima2p_engine_write_mcf(E, (outname + ".mcf").c_str()), "writing the state file");
+  if (opt.count("r") && ranks.world == 1) ck(ima2p_engine_write_mcf(E, (outname + ".mcf").c_str()), "writing the state file");
+  ranks.finish();
   printf("IMa2p_b200: done, %ld genealogies in %s\n", saved, ti.c_str());
   ima2p_engine_destroy(E);
   ima2p_modelspec_free(S);

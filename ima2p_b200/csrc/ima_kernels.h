@@ -89,6 +89,21 @@ IMA_KERNEL void k_eval_pairs(EngineView E) {
 }
 
 // ---- the exchange of swap sums between GPUs (struct Exchange) ------------------------------------------------------------
+#if !IMA_CUDA
+// host emulation (tests): ranks in separate processes share their tables through POSIX shared memory; a waiting rank polls for
+// IMA2P_EMU_WAIT_MS milliseconds (default 0: ranks stepped in lockstep by one process never have to wait)
+inline bool emu_wait_for(volatile unsigned long long *word, unsigned long long target) {
+  const char *w = getenv("IMA2P_EMU_WAIT_MS");
+  const long budget_ms = w ? atol(w) : 0;
+  for (long waited_us = 0; *word < target; waited_us += 50) {
+    if (waited_us / 1000 >= budget_ms) return false;
+    struct timespec ts = {0, 50000};
+    nanosleep(&ts, nullptr);
+  }
+  __sync_synchronize();
+  return true;
+}
+#endif
 // called by one whole warp when chain c's S for this step is final
 IMA_DEV void publish_chain(const EngineView &E, int c, double S) {
   const Exchange &X = E.xch;
@@ -101,7 +116,7 @@ IMA_DEV void publish_chain(const EngineView &E, int c, double S) {
     atomicAdd_system(X.peer_arrived[r] + (ep & 1ull), 1ull);
 #else
     X.peer_S[r][at] = S;
-    X.peer_arrived[r][ep & 1ull] += 1ull;
+    __sync_fetch_and_add(X.peer_arrived[r] + (ep & 1ull), 1ull);          // ranks may be separate processes on shared memory
 #endif
   }
 }
@@ -121,7 +136,7 @@ IMA_DEV const double *await_swap_sums(const EngineView &E, int step_bias) {
   }
   __syncwarp();
 #else
-  if (X.peer_arrived[X.rank][ep & 1ull] < target) raise(E.mc, kErrExchange);
+  if (!emu_wait_for(X.peer_arrived[X.rank] + (ep & 1ull), target)) raise(E.mc, kErrExchange);
 #endif
   return X.peer_S[X.rank] + (size_t)(ep & 1ull) * E.d.nchains_global;
 }
@@ -991,6 +1006,65 @@ IMA_KERNEL void k_unpack_block(EngineView E, const unsigned char *block, StateBl
   if (p == c * E.d.nloci) {                                   // the first pair of a chain also sets the chain's split times
     const double *tv = (const double *)(block + L.tvals);
     for (int k = lane; k < kMaxPeriods; k += IMA_WARP) E.tvals[(size_t)c * kMaxPeriods + k] = k < nsplit ? tv[(size_t)c * nsplit + k] : kTimeMax;
+  }
+}
+
+// The cold chain's record of a sharded job, wherever the chain lives: msg = [rowlen floats of the .ti row (as doubles) | probg |
+// pdg | pdg of every locus].  The rank that holds the chain at beta = 1 writes it into rank 0's table and then the request's
+// sequence number; rank 0 waits for that number and copies the message out for its host.  Every rank launches this kernel.
+IMA_KERNEL void k_cold_message(EngineView E, const int *chain_of_rank, int rowlen, unsigned long long seq, double *out_rank0) {
+  if (ima_block() != 0 || ima_warp_in_block() != 0) return;
+  const DevModel &M = IMA_MODEL;
+  const Exchange &X = E.xch;
+  const int lane = Warp::lane(), nloci = E.d.nloci;
+  const int c = chain_of_rank[0] - E.d.chain0;
+  if (c >= 0 && c < E.d.nchains) {
+    volatile double *msg = X.cold_msg0;
+    if (lane == 0) {
+      const int *wi = E.all_i + (size_t)c * E.d.NI;
+      const double *wd = E.all_d + (size_t)c * E.d.ND;
+      const int nq = M.nq, nm = M.nomigration ? 0 : M.nm;
+      const int fcp = nq, hccp = 2 * nq, mcp = 3 * nq, fmp = mcp + nm, qip = fmp + nm, mip = qip + nq, pdgp = mip + nm;
+      for (int i = 0; i < nq; i++) {                       // savegsampinf ginfo.cpp:318-377 (sums accumulated in float, as there)
+        int cc = 0; float f = 0.f, hc = 0.f;
+        for (int j = 0; j < M.q_n[i]; j++) { const int x = M.q_idx[i][j]; cc += wi[x]; f += (float)wd[x]; hc += (float)wd[M.ncc + x]; }
+        msg[i] = (float)cc; msg[fcp + i] = f; msg[hccp + i] = hc; msg[qip + i] = (float)E.qint[(size_t)c * kMaxParams + i];
+      }
+      for (int i = 0; i < nm; i++) {
+        int cm = 0; float f = 0.f;
+        for (int j = 0; j < M.m_n[i]; j++) { const int x = M.m_idx[i][j]; cm += wi[M.ncc + x]; f += (float)wd[2 * M.ncc + x]; }
+        msg[mcp + i] = (float)cm; msg[fmp + i] = f; msg[mip + i] = (float)E.mint[(size_t)c * kMaxParams + i];
+      }
+      msg[pdgp] = (float)E.pdgsum[c]; msg[pdgp + 1] = (float)E.probg[c];
+      for (int i = 0; i < M.nsplit; i++) msg[pdgp + 2 + i] = (float)E.tvals[(size_t)c * kMaxPeriods + i];
+      msg[rowlen] = E.probg[c]; msg[rowlen + 1] = E.pdgsum[c];
+    }
+    for (int li = lane; li < nloci; li += IMA_WARP) {
+      const int p = c * nloci + li;
+      msg[rowlen + 2 + li] = E.buf[E.cur[p]].sd[(size_t)p * 4 + 3];
+    }
+#if IMA_CUDA
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) { *(volatile unsigned long long *)X.cold_seq0 = seq; __threadfence_system(); }
+#else
+    __sync_synchronize();
+    *X.cold_seq0 = seq;
+#endif
+  }
+  if (X.rank == 0) {
+#if IMA_CUDA
+    if (lane == 0) {
+      volatile unsigned long long *sq = X.cold_seq0;
+      const long long t0 = clock64();
+      while (*sq < seq) { if (clock64() - t0 > 30000000000ll) { raise(E.mc, kErrExchange); break; } }
+      __threadfence_system();
+    }
+    __syncwarp();
+#else
+    if (!emu_wait_for(X.cold_seq0, seq)) raise(E.mc, kErrExchange);
+#endif
+    for (int i = lane; i < X.cold_len; i += IMA_WARP) out_rank0[i] = ((volatile double *)X.cold_msg0)[i];
   }
 }
 

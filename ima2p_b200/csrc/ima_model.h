@@ -97,6 +97,11 @@ struct Exchange {
   unsigned long long step0;                       // device step counter when the exchange was attached (same on every rank)
   int world, rank;
   int publisher;                                  // which kernel of the step publishes: 1 k_accept, 2 k_accept_t, 3 k_changeu (0: nobody)
+  // the cold chain's record (what rank 0 writes to the .ti file and the report) travels the same way: the rank that holds the
+  // chain at beta = 1 stores it into rank 0's table and then the sequence number of the request
+  double *cold_msg0;                              // rank 0's message area [cold_len], as this GPU addresses it
+  unsigned long long *cold_seq0;                  // rank 0's sequence word
+  int cold_len;
 };
 
 // Everything a kernel needs, passed by value.

@@ -149,6 +149,10 @@ int ima2p_engine_exchange_attach (ima2p_engine * e, void *const *tables);
 int ima2p_ipc_export (const void *device_pointer, unsigned char *handle64);
 int ima2p_ipc_import (int device, const unsigned char *handle64, void **device_pointer);
 int ima2p_engine_run_sharded (ima2p_engine * e, int nsteps, int swaptries, void *cuda_stream);
+/* the cold chain's record of a sharded job, called by every rank at the same step boundary: on rank 0 out_msg[rowlen + 2 + nloci] =
+ * the .ti row (savegsampinf ginfo.cpp:318-377), probg, P(D|G), P(D|G) per locus -- stored into rank 0's table by whichever rank
+ * holds the chain at beta = 1; on the other ranks out_msg is not touched */
+int ima2p_engine_cold_message (ima2p_engine * e, double *out_msg, void *cuda_stream);
 /* the two halves of a shard's step for callers that keep the ranks in lockstep themselves (every rank's update, then every
  * rank's swap): one process driving several GPUs, and the tests */
 int ima2p_engine_sharded_update (ima2p_engine * e, void *cuda_stream);

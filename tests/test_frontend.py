@@ -318,3 +318,26 @@ def test_migration_pools_grow_and_nothing_is_lost_silently(exe, tmp_path):
     from ima2p_b200.readu import ti_load
     rows = ti_load(str(tmp_path / "roomy.out") + ".ti", 21, lib=capi.bind(os.path.join(HERE, "hostemu", "libima2p_hostemu.so")))
     assert rows[:, 9:11].sum(axis=1).mean() > 8
+
+
+def test_two_ranks_write_the_single_rank_ti_file(exe, tmp_path):
+    """The front end started once per rank (RANK / WORLD_SIZE in the environment, -hn chains per rank, as `mpirun -np 2 IMa2p -hn 2`
+    starts the reference, ima_main_mpi.cpp:4317-4560): the ranks find each other through the rendezvous files, exchange swap sums
+    and the cold chain's record through each other's tables, and rank 0 writes the .ti file -- the file one rank with all four
+    chains writes from the same seed, byte for byte; the update-rate tables add up to the same counts."""
+    from ima2p_b200 import synth
+    u = tmp_path / "two.u"
+    synth.write_u(str(u), synth.make_dataset(3, 6, 6, seed=5))
+    common = ["-i", str(u), "-q10", "-m1", "-t3", "-b400", "-l40", "-d10", "-hfg", "-ha0.9", "-hb0.8", "-s11"]
+    r1 = _run(exe, common + ["-hn4", "-o", str(tmp_path / "one.out")])
+    assert r1.returncode == 0, r1.stderr
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_PORT="29999", IMA2P_RENDEZVOUS_DIR=str(tmp_path), IMA2P_EMU_WAIT_MS="60000")
+    procs = [subprocess.Popen([exe] + common + ["-hn2", "-o", str(tmp_path / "two.out")], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-400:] for o in outs]
+    body = lambda path: open(path).read().split("VALUESSTART", 1)[1]
+    assert body(tmp_path / "one.out.ti") == body(tmp_path / "two.out.ti")
+    (t1, s1), (t2, s2) = _rate_tables(open(tmp_path / "one.out").read().split("\nENGINE INFORMATION")[0]), _rate_tables(open(tmp_path / "two.out").read().split("\nENGINE INFORMATION")[0])
+    assert t1 == t2 and s1 == s2
+    assert not [f for f in os.listdir(tmp_path) if f.startswith("ima2p_")]         # the rendezvous files are gone

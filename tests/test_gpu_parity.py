@@ -209,3 +209,28 @@ def test_front_end_report_head_on_the_device(lib, tmp_path):
     exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ima2p_b200", "IMa2p_b200")
     assert os.path.exists(exe), "build the front end with __graft_entry__.build()"
     frontend_report_head_matches_reference(exe, tmp_path, lib=lib)
+
+
+def test_two_gpus_front_end_writes_the_single_gpu_ti_file(lib, tmp_path):
+    """The product executable started once per GPU (RANK / WORLD_SIZE / LOCAL_RANK): the ranks exchange swap sums and the cold
+    chain's record through peer memory (cudaIpc handles over the rendezvous files) and rank 0 writes the .ti file the one-GPU
+    run of the same seed writes.  Needs two GPUs."""
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from ima2p_b200 import synth
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ima2p_b200", "IMa2p_b200")
+    u = tmp_path / "two.u"
+    synth.write_u(str(u), synth.make_dataset(6, 10, 10, seed=5))
+    common = ["-i", str(u), "-q10", "-m1", "-t3", "-b2000", "-l100", "-d10", "-hfg", "-ha0.96", "-hb0.9", "-s11"]
+    r1 = subprocess.run([exe] + common + ["-hn16", "-o", str(tmp_path / "one.out")], capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stderr
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_PORT="29998", IMA2P_RENDEZVOUS_DIR=str(tmp_path))
+    procs = [subprocess.Popen([exe] + common + ["-hn8", "-o", str(tmp_path / "two.out")], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-400:] for o in outs]
+    body = lambda path: open(path).read().split("VALUESSTART", 1)[1]
+    assert body(tmp_path / "one.out.ti") == body(tmp_path / "two.out.ti")
