@@ -776,7 +776,9 @@ struct Lmode {
   double q_max[kMaxParams], q_min[kMaxParams], m_max[kMaxParams], m_min[kMaxParams], m_mean[kMaxParams];
   float *d_cols = nullptr;
   double *d_x = nullptr, *d_partials = nullptr, *d_out = nullptr, *d_pbuf = nullptr, *d_chunkmax = nullptr, *d_prefix = nullptr,
-         *d_lmax = nullptr, *d_jpart = nullptr, *d_jout = nullptr, *d_seed = nullptr, *d_gmax = nullptr, *d_ltmp = nullptr;
+         *d_lmax = nullptr, *d_jpart = nullptr, *d_jout = nullptr, *d_seed = nullptr, *d_gmax = nullptr, *d_ltmp = nullptr,
+         *w_pbuf = nullptr, *w_chunkmax = nullptr, *w_prefix = nullptr, *w_jpart = nullptr, *w_jout = nullptr;   // wide batches (joint_begin / _middle)
+  JointXs *w_xs = nullptr;
   JointXs *d_xs = nullptr;
   size_t cap_x = 0, cap_partials = 0;
   struct LmPriors *d_pri = nullptr;            // section 8 (f3) evaluators: priors, logfact table and error word, made on first use
@@ -959,11 +961,29 @@ int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const do
 //   middle: dev_allmax[world][nvec] (device, the gathered local maxima) -> seed and global maximum on the device, prefixes,
 //           scan, fold; dev_records_out[nvec][8] (device) = the six record fields, the global maximum, 0
 // The caller gathers the records of all ranks and closes every vector with ima2p_lmode_joint_finish on their sums.
+// up to kJointCallMax vectors per call, in sub-batches of kJointVecMax queued back to back on their own buffers
+constexpr int kJointCallMax = 256;
+static int joint_wide_buffers(Lmode &l) {
+  if (l.w_pbuf) return IMA2P_OK;
+  const size_t G = (size_t)l.v.G, nchunks = (G + kRowsPerBlock - 1) / kRowsPerBlock;
+  l.w_pbuf = l.alloc<double>((size_t)kJointCallMax * G);
+  l.w_chunkmax = l.alloc<double>((size_t)kJointCallMax * nchunks);
+  l.w_prefix = l.alloc<double>((size_t)kJointCallMax * nchunks);
+  l.w_jpart = l.alloc<double>((size_t)kJointCallMax * nchunks * kJP);
+  l.w_jout = l.alloc<double>((size_t)kJointCallMax * kJP);
+  l.w_xs = l.alloc<JointXs>(kJointCallMax);
+  l.d_seed = l.alloc<double>(kJointCallMax); l.d_gmax = l.alloc<double>(kJointCallMax); l.d_ltmp = l.alloc<double>(kJointCallMax);
+  if (!l.w_pbuf || !l.w_chunkmax || !l.w_prefix || !l.w_jpart || !l.w_jout || !l.w_xs || !l.d_seed || !l.d_gmax || !l.d_ltmp)
+    return lfail(IMA2P_E_CUDA, "device allocation failed (jointp, wide batch)");
+  return IMA2P_OK;
+}
 int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *dev_localmax_out, void *cuda_stream) {
-  if (!h || !h->lm.d_cols || !x || nvec < 1 || nvec > kJointVecMax || !dev_localmax_out) return lfail(IMA2P_E_ARG, "joint_begin: bad argument");
+  if (!h || !h->lm.d_cols || !x || nvec < 1 || nvec > kJointCallMax || !dev_localmax_out) return lfail(IMA2P_E_ARG, "joint_begin: bad argument (at most 256 vectors per call)");
   Lmode &l = h->lm;
   if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = lm_stream(&l, cuda_stream);
+  int rc = joint_wide_buffers(l);
+  if (rc) return rc;
   const int np = l.v.nq + l.v.nm, nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
   std::vector<JointXs> xs(nvec);
   for (int v = 0; v < nvec; v++)
@@ -972,9 +992,13 @@ int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *d
       xs[v].x[i] = xv; xs[v].logx[i] = log(xv); xs[v].divx[i] = 1.0 / xv;
       if (i < l.v.nq) xs[v].log2diffx[i] = kLog2 - log(xv);
     }
-  if (!h2d(l.d_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
-  IMA_LAUNCH(k_joint_terms, nchunks, kLmWarps, kLmWarps * kJointVecMax * sizeof(double), s, l.v, l.d_xs, nvec, l.d_pbuf, l.d_chunkmax);
-  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, (const double *)nullptr, l.d_prefix, dev_localmax_out);
+  if (!h2d(l.w_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
+  for (int b0 = 0; b0 < nvec; b0 += kJointVecMax) {
+    const int nb = nvec - b0 < kJointVecMax ? nvec - b0 : kJointVecMax;
+    IMA_LAUNCH(k_joint_terms, nchunks, kLmWarps, kLmWarps * kJointVecMax * sizeof(double), s, l.v, (const JointXs *)(l.w_xs + b0), nb, l.w_pbuf + (size_t)b0 * l.v.G, l.w_chunkmax + (size_t)b0 * nchunks);
+    IMA_LAUNCH(k_joint_prefix, (nb + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, (const double *)(l.w_chunkmax + (size_t)b0 * nchunks), nchunks, nb, (const double *)nullptr,
+               l.w_prefix + (size_t)b0 * nchunks, dev_localmax_out + b0);
+  }
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint begin)");
 #endif
@@ -983,19 +1007,25 @@ int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *d
 
 int ima2p_lmode_joint_middle(ima2p_lmode *h, int nvec, const double *dev_allmax, int world, int rank, long long global_row0,
                              double *dev_records_out, void *cuda_stream) {
-  if (!h || !h->lm.d_cols || nvec < 1 || nvec > kJointVecMax || !dev_allmax || !dev_records_out || world < 1 || rank < 0 || rank >= world)
+  if (!h || !h->lm.d_cols || nvec < 1 || nvec > kJointCallMax || !dev_allmax || !dev_records_out || world < 1 || rank < 0 || rank >= world)
     return lfail(IMA2P_E_ARG, "joint_middle: bad argument");
   Lmode &l = h->lm;
   if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = lm_stream(&l, cuda_stream);
-  const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock), gv = (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP);
-  if (!l.d_seed) { l.d_seed = l.alloc<double>(kJointVecMax); l.d_gmax = l.alloc<double>(kJointVecMax); l.d_ltmp = l.alloc<double>(kJointVecMax); }
-  if (!l.d_seed || !l.d_gmax || !l.d_ltmp) return lfail(IMA2P_E_CUDA, "device allocation failed");
-  IMA_LAUNCH(k_joint_seed, gv, kLmWarps, 0, s, dev_allmax, world, rank, nvec, l.d_seed, l.d_gmax);
-  IMA_LAUNCH(k_joint_prefix, gv, kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, (const double *)l.d_seed, l.d_prefix, l.d_ltmp);
-  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, l.d_pbuf, nvec, l.d_prefix, l.d_gmax, global_row0, l.d_jpart);
-  IMA_LAUNCH(k_joint_fold, gv, kLmWarps, 0, s, l.d_jpart, nchunks, nvec, l.d_jout);
-  IMA_LAUNCH(k_joint_pack, gv, kLmWarps, 0, s, l.d_jout, l.d_gmax, nvec, dev_records_out);
+  int rc = joint_wide_buffers(l);
+  if (rc) return rc;
+  const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
+  const int gall = (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP);
+  IMA_LAUNCH(k_joint_seed, gall, kLmWarps, 0, s, dev_allmax, world, rank, nvec, l.d_seed, l.d_gmax);
+  for (int b0 = 0; b0 < nvec; b0 += kJointVecMax) {
+    const int nb = nvec - b0 < kJointVecMax ? nvec - b0 : kJointVecMax, gv = (nb + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP);
+    const size_t oc = (size_t)b0 * nchunks;
+    IMA_LAUNCH(k_joint_prefix, gv, kLmWarps, 0, s, (const double *)(l.w_chunkmax + oc), nchunks, nb, (const double *)(l.d_seed + b0), l.w_prefix + oc, l.d_ltmp + b0);
+    IMA_LAUNCH(k_joint_scan, (nchunks * nb + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, (const double *)(l.w_pbuf + (size_t)b0 * l.v.G), nb, (const double *)(l.w_prefix + oc),
+               (const double *)(l.d_gmax + b0), global_row0, l.w_jpart + oc * kJP);
+    IMA_LAUNCH(k_joint_fold, gv, kLmWarps, 0, s, (const double *)(l.w_jpart + oc * kJP), nchunks, nb, l.w_jout + (size_t)b0 * kJP);
+  }
+  IMA_LAUNCH(k_joint_pack, gall, kLmWarps, 0, s, (const double *)l.w_jout, (const double *)l.d_gmax, nvec, dev_records_out);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint middle)");
 #endif
