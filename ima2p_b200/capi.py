@@ -124,6 +124,7 @@ SIGNATURES = {
     "ima2p_lmode_joint_phase2": (_i, [_v, _i, c_dbl_p, _ll, c_dbl_p]),
     "ima2p_lmode_joint_finish": (None, [c_dbl_p, _d, _ll, _i, c_dbl_p, c_dbl_p]),
     "ima2p_lmode_joint_begin": (_i, [_v, c_dbl_p, _i, _v, _v]),
+    "ima2p_lmode_joint_finish_gathered": (None, [c_dbl_p, _i, _i, _ll, _i, c_dbl_p, c_dbl_p]),
     "ima2p_debug_fp64_peaks": (_i, [_i, c_dbl_p]),
     "ima2p_lmode_joint_middle": (_i, [_v, _i, _v, _i, _i, _ll, _v, _v]),
 }

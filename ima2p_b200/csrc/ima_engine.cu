@@ -253,6 +253,7 @@ static void launch_update(Engine *e, stream_t s) { launch_update(e, s, view_of(e
 static void launch_swap(Engine *e, stream_t s, const double *S_global, int swaptries, int step_already_advanced = 0, int advance = 1, int step_off = 0) {
   SwapView sv = e->sv;
   sv.S_global = S_global;
+  sv.sequential = getenv("IMA2P_SWAP_SEQUENTIAL") ? 1 : 0;
   sv.use_exchange = S_global == nullptr ? 1 : 0;             // a shard: the sums of all ranks come through the exchange tables
   sv.swaptries = swaptries;
   sv.advance_step = step_already_advanced ? 0 : advance;

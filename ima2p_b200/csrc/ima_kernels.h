@@ -749,6 +749,7 @@ struct SwapView {
   int swaptries, advance_step;   // advance_step: what the launch adds to the device step counter afterwards (0, 1, or the steps of a graph)
   int step_bias;            // 1 when the step counter was already advanced (split-phase multi-GPU step): the draws stay keyed by the step they belong to
   int smem_chains;          // chains the launch's shared memory can stage (0: work on global memory)
+  int sequential;           // tests: one lane walks the attempts in order (what the level-wise walk must reproduce)
   int use_exchange;         // S of all chains comes from the exchange tables (struct Exchange), after waiting for them
 };
 
@@ -760,7 +761,7 @@ IMA_DEV void stat_add(unsigned long long *p, unsigned long long v) {
   *p += v;
 #endif
 }
-IMA_HD size_t swap_smem_bytes(int staged_chains) { return (size_t)staged_chains * 24 + 16 + (size_t)kSwapBatch * 16; }
+IMA_HD size_t swap_smem_bytes(int staged_chains) { return (size_t)staged_chains * 28 + 16 + (size_t)kSwapBatch * 20; }
 IMA_KERNEL void k_swap(EngineView E, SwapView V) {
   IMA_SMEM_DECL
   if (ima_block() != 0 || ima_warp_in_block() != 0) return;
@@ -785,9 +786,12 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
     // Every attempt has its own counter block of the step's swap stream, so the lanes draw the attempts of a batch in
     // parallel -- the two temperature ranks (the second uniform over the other ranks of the window, which is what the
     // reference's redraw-until-different loop samples, swapchains.cpp:224-235) and the uniform of the decision -- and one
-    // lane then only walks the decisions, which depend on each other through the rank tables.
+    // decisions that share no temperature rank commute.  One lane gives every attempt its level (one more than the last earlier
+    // attempt that touched either of its ranks: four shared-memory operations per attempt, no arithmetic), then the attempts
+    // of a level are decided by the lanes together -- an exponential each -- and the levels follow one another.
     double *dU = (double *)(IMA_SMEM + (staged ? (size_t)N * 24 : 0) + 16);
-    int *dA = (int *)(dU + kSwapBatch), *dB = dA + kSwapBatch;
+    int *dA = (int *)(dU + kSwapBatch), *dB = dA + kSwapBatch, *dL = dB + kSwapBatch;
+    int *last = dL + kSwapBatch;                              // [N] level of the last attempt that touched a rank (staged tables only)
     const unsigned long long step = current_step(E) - (unsigned long long)V.step_bias;
     unsigned long long nacc = 0;
     for (int x0 = 0; x0 < V.swaptries; x0 += kSwapBatch) {
@@ -810,7 +814,50 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
       __threadfence_block();
 #endif
       Warp::sync();
-      if (lane == 0) {
+      if (staged && IMA_WARP > 1 && !V.sequential) {
+        int nlevels = 0;
+        for (int i = lane; i < N; i += IMA_WARP) last[i] = 0;
+#if IMA_CUDA
+        __threadfence_block();
+#endif
+        Warp::sync();
+        if (lane == 0) {
+          for (int i = 0; i < nb; i++) {
+            const int sa = dA[i], sb = dB[i];
+            const int la = last[sa], lb = last[sb], lv = (la > lb ? la : lb) + 1;
+            dL[i] = lv; last[sa] = lv; last[sb] = lv;
+            if (lv > nlevels) nlevels = lv;
+          }
+        }
+#if IMA_CUDA
+        __threadfence_block();
+#endif
+        Warp::sync();
+        nlevels = Warp::bcast(nlevels, 0);
+        for (int lv = 1; lv <= nlevels; lv++) {
+          for (int i = lane; i < nb; i += IMA_WARP) {
+            if (dL[i] != lv) continue;
+            const int sa = dA[i], sb = dB[i];
+            const int ca = cor[sa], cb = cor[sb];
+            const double w = exp((Bt[sa] - Bt[sb]) * (Sg[cb] - Sg[ca]));
+            const bool swapped = w >= 1.0 || w > dU[i];
+            if (swapped) {
+              cor[sa] = cb; cor[sb] = ca;
+              roc[ca] = sb; roc[cb] = sa;
+              nacc++;
+            }
+            if (sa - sb == 1 || sb - sa == 1) {
+              unsigned long long *ac = V.adj_counts + (size_t)(sa < sb ? sa : sb) * 2;
+              stat_add(ac, 1ull);
+              if (swapped) stat_add(ac + 1, 1ull);
+            }
+          }
+#if IMA_CUDA
+          __threadfence_block();
+#endif
+          Warp::sync();
+        }
+      } else if (lane == 0) {
         for (int i = 0; i < nb; i++) {
           const int sa = dA[i], sb = dB[i];
           const int ca = cor[sa], cb = cor[sb];
@@ -830,9 +877,10 @@ IMA_KERNEL void k_swap(EngineView E, SwapView V) {
       }
       Warp::sync();
     }
+    const int nacc_all = Warp::sum((int)nacc);                // the lanes of the level-wise walk counted their own
     if (lane == 0) {
       V.swap_counts[0] += (unsigned long long)V.swaptries;
-      V.swap_counts[1] += nacc;
+      V.swap_counts[1] += (unsigned long long)nacc_all;
     }
 #if IMA_CUDA
     __threadfence_block();

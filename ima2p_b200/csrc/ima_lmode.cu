@@ -1086,6 +1086,22 @@ void ima2p_lmode_joint_finish(const double *rec6, double globalmax, long long nr
   *q = log((double)nrows_total) - (log(sum) + maxz * 2.3025850929940456840);
 }
 
+// the records of joint_middle gathered from every rank, [world][nvec][8]: sums over ranks, the smallest kept term from the rank
+// that holds it, then joint_finish per vector (host arithmetic on world x nvec small records)
+void ima2p_lmode_joint_finish_gathered(const double *rec8, int world, int nvec, long long nrows_total, int calc_ess, double *q, double *ess) {
+  for (int v = 0; v < nvec; v++) {
+    double tot[6] = {0, 0, 0, 0, DBL_MAX, 0};
+    for (int r = 0; r < world; r++) {
+      const double *o = rec8 + ((size_t)r * nvec + v) * 8;
+      tot[0] += o[0]; tot[1] += o[1]; tot[2] += o[2]; tot[3] += o[3];
+      if (o[4] < tot[4]) { tot[4] = o[4]; tot[5] = o[5]; }
+    }
+    double e = 0.0;
+    ima2p_lmode_joint_finish(tot, rec8[(size_t)v * 8 + 6], nrows_total, calc_ess, q + v, &e);
+    if (ess) ess[v] = e;
+  }
+}
+
 int ima2p_lmode_jointp(ima2p_lmode *h, const double *x, int nvec, int calc_ess, double *out_q, double *out_ess) {
   if (!h || !x || nvec < 1 || !out_q) return lfail(IMA2P_E_ARG, "jointp: bad argument");
   Lmode &l = h->lm;

@@ -201,13 +201,13 @@ def sharded_jointp_device(lm, x, calc_ess=True, device="cuda", batch=256):
         recs.append((nv, allrec, local, allmax, rec))           # the tensors stay alive until the stream has used them
     q, ess = np.zeros(nv_all), np.zeros(nv_all)
     o = 0
+    import ctypes as C
     for nv, allrec, _, _, _ in recs:
-        a = allrec.cpu().numpy().reshape(world, nv, 8)
-        for v in range(nv):
-            tot = a[:, v, :6].sum(axis=0)
-            k = int(np.argmin(a[:, v, 4]))
-            tot[4], tot[5] = a[k, v, 4], a[k, v, 5]
-            q[o + v], ess[o + v] = lm.joint_finish(tot, a[0, v, 6], calc_ess)
+        a = np.ascontiguousarray(allrec.cpu().numpy())
+        qb, eb = np.zeros(nv), np.zeros(nv)
+        dp = lambda z: z.ctypes.data_as(C.POINTER(C.c_double))
+        lm.lib.ima2p_lmode_joint_finish_gathered(dp(a), world, nv, lm.nrows_total, int(calc_ess), dp(qb), dp(eb))
+        q[o:o + nv], ess[o:o + nv] = qb, eb
         o += nv
     return q, ess
 

@@ -328,6 +328,8 @@ void ima2p_lmode_joint_finish (const double *rec6, double globalmax, long long n
 /* measured FP64 peaks of the device the roofline fractions of the FP64-bound kernels are quoted against (SURVEY.md section
  * 8d): out2[0] = fused multiply-adds per second (x 2 = flop/s), out2[1] = exp evaluations per second */
 int ima2p_debug_fp64_peaks (int device, double *out2);
+void ima2p_lmode_joint_finish_gathered (const double *records8 /* [world][nvec][8] */, int world, int nvec, long long nrows_total,
+                                        int calc_ess, double *q, double *ess);
 int ima2p_lmode_joint_begin (ima2p_lmode * l, const double *x, int nvec, double *dev_localmax_out, void *cuda_stream);
 int ima2p_lmode_joint_middle (ima2p_lmode * l, int nvec, const double *dev_allmax, int world, int rank, long long global_row0,
                               double *dev_records_out, void *cuda_stream);

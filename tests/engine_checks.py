@@ -705,6 +705,39 @@ def capacity_grows_without_changing_the_chain(lib, name="state_sim3_hn3", nsteps
     return a[0], tight[0]["dropped"]
 
 
+def swap_walk_by_levels_equals_the_walk_in_order(lib, nchains=320, nloci=3, nsteps=40):
+    """k_swap decides the attempts of a step level by level (attempts that share no temperature rank commute and are decided
+    by the lanes together); with many chains and many attempts a step (swaptries = chains / 10) the temperatures, the swap
+    counts and the chains must be those of the one-lane walk in attempt order (swapchains.cpp:192-523)."""
+    import os
+    from ima2p_b200 import Engine, synth
+    loci = synth.make_dataset(nloci, 6, 6, seed=3)
+    outs = []
+    for seq in (True, False):
+        if seq:
+            os.environ["IMA2P_SWAP_SEQUENTIAL"] = "1"
+        else:
+            os.environ.pop("IMA2P_SWAP_SEQUENTIAL", None)
+        try:
+            eng = Engine(nchains, nloci, seed=12, lib=lib)
+            eng.set_model(**synth.two_population_model(10.0, 1.0))
+            for li, L in enumerate(loci):
+                eng.set_locus(li, 0, L["n"], L["numsites"], L["samppop"], seq=L["seq"])
+            eng.finalize()
+            eng.set_heating(1, 0.99, 0.3)
+            st = synth.initial_state(loci, nchains, eng.NL, eng.CAP, t0=1.5, seed=100)
+            eng.put_state([st[k] for k in ("topo", "time", "mseg", "mig_t", "mig_p", "scal_i", "scal_d", "uvals")], st["tvals"])
+            eng.run(nsteps)
+            eng.sync()
+            outs.append((eng.counters(), eng.betas().copy(), np.array([eng.chain(c)["pdg"] for c in range(nchains)])))
+            eng.close()
+        finally:
+            os.environ.pop("IMA2P_SWAP_SEQUENTIAL", None)
+    assert outs[0][0] == outs[1][0] and outs[0][0]["swaps"] > 10 * nsteps, outs[0][0]
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    return outs[0][0]
+
+
 def full_size_workload_properties(lib, nloci, nchains, nsteps, noracle=48, seed=5):
     """BASELINE-sized runs (configs[1]: 50 loci x 128 chains; configs[2]'s per-GPU shard: 300 loci x 256 chains), checked through
     properties that do not need a stored answer: after `nsteps` whole qupdate steps (genealogies, split times, scalars, swaps)

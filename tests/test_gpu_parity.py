@@ -107,6 +107,10 @@ def test_capacity_grows_without_changing_the_chain(lib):
     ec.capacity_grows_without_changing_the_chain(lib)
 
 
+def test_swap_walk_by_levels_equals_the_walk_in_order(lib):
+    ec.swap_walk_by_levels_equals_the_walk_in_order(lib)
+
+
 def test_hky_partials_stay_consistent(lib):
     ec.hky_partials_stay_consistent(lib)
 
