@@ -274,7 +274,7 @@ def reference_throughput(wl, world, steps, warmup, budget_s, full=1, data="synth
     sample = "%d serial reference processes x %d chains, %d loci (%s input); %d %s per step after %d whole steps of burn-in" % (
         used, chains_pp, nloci, data, iters, "whole qupdate() steps" if full else "updategenealogy sweeps", burn)
     return dict(value=upd / step_s, ms_per_step=step_s * 1e3, cores=used, sample=sample,
-                accept=sum(r["accepted"] for r in res) / max(1, sum(r["updates"] for r in res)))
+                accept=sum(r["accepted"] for r in res) / max(1, sum(r.get("accept_base", r["updates"]) for r in res)))
 
 
 # ---- our arm ----------------------------------------------------------------------------------------------------------------

@@ -103,32 +103,71 @@ IMA_KERNEL void IMA_MOVE_BOUNDS k_move(EngineView E) {
     my_roottime = (my_cb ? E.buf[1].sd : E.buf[0].sd)[(size_t)p * 4];
   }
   const int total = nmine * NL;
+  // kStageTrips trips of loads are in flight before the first value is stored (the stores to shared memory may alias the
+  // next loads as far as the compiler knows: trip by trip every trip waited a whole memory latency)
+  constexpr int kStageTrips = 8;
+  for (int base0 = 0; base0 < total; base0 += kStageTrips * IMA_WARP) {     // every lane makes every trip (the shuffles need all of them)
+    short4_t q[kStageTrips]; double tm[kStageTrips]; ushort2_t m[kStageTrips];
 #if IMA_CUDA
-#pragma unroll 4
+#pragma unroll
 #endif
-  for (int base = 0; base < total; base += IMA_WARP) {     // every lane makes every trip (the shuffles need all of them)
-    const int idx = base + lane;
-    const bool valid = idx < total;
-    const int t = valid ? idx / NL : 0, i = idx - t * NL;
-    const int cb = Warp::bcast(my_cb, t);
-    if (valid) {
-      const size_t g = (size_t)(p0 + t) * NL + i;
-      const short4_t q = (cb ? E.buf[1].topo : E.buf[0].topo)[g];
-      const double tm = (cb ? E.buf[1].time : E.buf[0].time)[g];
-      const ushort2_t m = (cb ? E.buf[1].mseg : E.buf[0].mseg)[g];
-      const PairSmT<PPW> S = move_slot(S0, t);
-      S.up0[i] = q.x; S.up1[i] = q.y; S.down[i] = q.z; S.pop[i] = q.w;
-      S.time[i] = tm;
-      S.ms[i] = m.x; S.mcn[i] = m.y;
+    for (int u = 0; u < kStageTrips; u++) {
+      const int idx = base0 + u * IMA_WARP + lane;
+      const bool valid = idx < total;
+      const int t = valid ? idx / NL : 0;
+      const int cb = Warp::bcast(my_cb, t);
+      if (valid) {
+        const size_t g = (size_t)p0 * NL + idx;                        // pair p0 + t, edge idx - t NL
+        q[u] = (cb ? E.buf[1].topo : E.buf[0].topo)[g];
+        tm[u] = (cb ? E.buf[1].time : E.buf[0].time)[g];
+        m[u] = (cb ? E.buf[1].mseg : E.buf[0].mseg)[g];
+      }
+    }
+#if IMA_CUDA
+#pragma unroll
+#endif
+    for (int u = 0; u < kStageTrips; u++) {
+      const int idx = base0 + u * IMA_WARP + lane;
+      if (idx < total) {
+        const int t = idx / NL, i = idx - t * NL;
+        const PairSmT<PPW> S = move_slot(S0, t);
+        S.up0[i] = q[u].x; S.up1[i] = q[u].y; S.down[i] = q[u].z; S.pop[i] = q[u].w;
+        S.time[i] = tm[u];
+        S.ms[i] = m[u].x; S.mcn[i] = m[u].y;
+      }
     }
   }
-  for (int t = 0; t < nmine; t++) {                       // migration events: the first IMA_WARP of every pair at once
-    const int cb = Warp::bcast(my_cb, t), mignum = Warp::bcast(my_mig, t);
-    const double *mt = (cb ? E.buf[1].mig_t : E.buf[0].mig_t) + (size_t)(p0 + t) * CAP;
-    const short *mp = (cb ? E.buf[1].mig_p : E.buf[0].mig_p) + (size_t)(p0 + t) * CAP;
-    const PairSmT<PPW> S = move_slot(S0, t);
-    if (mignum <= FP)
-      for (int i = lane; i < mignum; i += IMA_WARP) { S.pt[i] = mt[i]; S.pp[i] = mp[i]; }
+  // migration events: the first IMA_WARP of every pair in flight together, the rest (rare) pair by pair
+  {
+    constexpr int kMigPairs = PPW < 8 ? PPW : 8;
+    for (int t0 = 0; t0 < nmine; t0 += kMigPairs) {
+      double mt0[kMigPairs]; short mp0[kMigPairs];
+#if IMA_CUDA
+#pragma unroll
+#endif
+      for (int u = 0; u < kMigPairs; u++) {
+        const int t = t0 + u < nmine ? t0 + u : nmine - 1;
+        const int cb = Warp::bcast(my_cb, t), mignum = Warp::bcast(my_mig, t);
+        if (t0 + u < nmine && mignum <= FP && lane < mignum) {
+          mt0[u] = ((cb ? E.buf[1].mig_t : E.buf[0].mig_t) + (size_t)(p0 + t) * CAP)[lane];
+          mp0[u] = ((cb ? E.buf[1].mig_p : E.buf[0].mig_p) + (size_t)(p0 + t) * CAP)[lane];
+        }
+      }
+#if IMA_CUDA
+#pragma unroll
+#endif
+      for (int u = 0; u < kMigPairs; u++) {
+        const int t = t0 + u < nmine ? t0 + u : nmine - 1;
+        const int cb = Warp::bcast(my_cb, t), mignum = Warp::bcast(my_mig, t);
+        if (t0 + u < nmine && mignum <= FP) {
+          const PairSmT<PPW> S = move_slot(S0, t);
+          if (lane < mignum) { S.pt[lane] = mt0[u]; S.pp[lane] = mp0[u]; }
+          const double *mt = (cb ? E.buf[1].mig_t : E.buf[0].mig_t) + (size_t)(p0 + t) * CAP;
+          const short *mp = (cb ? E.buf[1].mig_p : E.buf[0].mig_p) + (size_t)(p0 + t) * CAP;
+          for (int i = lane + IMA_WARP; i < mignum; i += IMA_WARP) { S.pt[i] = mt[i]; S.pp[i] = mp[i]; }
+        }
+      }
+    }
   }
   if (lane < nmine) {
     const PairSmT<PPW> S = move_slot(S0, lane);

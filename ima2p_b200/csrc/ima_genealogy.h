@@ -126,7 +126,28 @@ IMA_DEV void stage_pair(const EngineView &E, const PairBuf &B, int p, int nl, Pa
   const double roottime = B.sd[(size_t)p * 4];
   const double mt0 = lane < E.d.CAP ? mt[lane] : 0.0;
   const short mp0 = lane < E.d.CAP ? mp[lane] : (short)0;
-  for (int i = lane; i < nl; i += IMA_WARP) {
+  // the first two trips over the edges (64 edges: every locus of the shipped inputs) are in flight together
+  constexpr int kTrips = 2;
+  short4_t q[kTrips]; double tm[kTrips]; ushort2_t ms[kTrips];
+#if IMA_CUDA
+#pragma unroll
+#endif
+  for (int u = 0; u < kTrips; u++) {
+    const int i = lane + u * IMA_WARP;
+    if (i < nl) { q[u] = topo[i]; tm[u] = time[i]; ms[u] = mseg[i]; }
+  }
+#if IMA_CUDA
+#pragma unroll
+#endif
+  for (int u = 0; u < kTrips; u++) {
+    const int i = lane + u * IMA_WARP;
+    if (i < nl) {
+      S.up0[i] = q[u].x; S.up1[i] = q[u].y; S.down[i] = q[u].z; S.pop[i] = q[u].w;
+      S.time[i] = tm[u];
+      S.ms[i] = ms[u].x; S.mcn[i] = ms[u].y;
+    }
+  }
+  for (int i = lane + kTrips * IMA_WARP; i < nl; i += IMA_WARP) {
     short4_t t = topo[i];
     S.up0[i] = t.x; S.up1[i] = t.y; S.down[i] = t.z; S.pop[i] = t.w;
     S.time[i] = time[i];
@@ -727,12 +748,28 @@ IMA_DEV long long dbl_bits(double x) {
   long long v; memcpy(&v, &x, sizeof v); return v;
 #endif
 }
+IMA_DEV double bits_dbl(long long v) {
+#if IMA_CUDA
+  return __longlong_as_double(v);
+#else
+  double x; memcpy(&x, &v, sizeof x); return x;
+#endif
+}
 IMA_DEV int pack_event(int kind, int pop, int topop, int node) { return kind | (pop << 2) | (topop << 7) | (node << 12); }
 
 #if IMA_CUDA
-// sorts the nev <= 32 E events (time bits, info) of the scratch table by (time, info) into (evt, evi): see eval_weights
-template <int E> IMA_DEV void warp_sort_events(const double *bt, const int *bi, int nev, double *evt, int *evi) {
+// Sorts the nev <= 128 events (time bits, info) of the scratch table by (time, info) into (evt, evi): see eval_weights.
+// A bitonic network over registers: element q * 32 + lane sits in register q of the lane; partners closer than 32 are
+// exchanged by shuffles, the others are registers of the same lane.  The stages are a ROLLED loop and only the stages the table
+// needs are run (np2 = the power of two that holds nev): unrolled per table size the network was half of the code of every
+// kernel that weighs a genealogy, and those kernels run their code once per warp -- instruction fetch led their stall reasons.
+IMA_DEV void warp_sort_events(const double *bt, const int *bi, int nev, double *evt, int *evi) {
+  constexpr int E = kRankSortMax / 32;
+  static_assert(E == 4, "the in-lane stages below are written for four registers per lane");
   const int lane = Warp::lane();
+  int np2 = 32;
+  while (np2 < nev) np2 <<= 1;
+  const int nq = np2 >> 5;                                   // registers in use: 1, 2 or 4
   long long key[E];
   int val[E];
 #pragma unroll
@@ -741,31 +778,29 @@ template <int E> IMA_DEV void warp_sort_events(const double *bt, const int *bi, 
     key[q] = g < nev ? __double_as_longlong(bt[g]) : 0x7fffffffffffffffll;
     val[q] = g < nev ? bi[g] : 0x7fffffff;
   }
-#pragma unroll
-  for (int k = 2; k <= 32 * E; k <<= 1) {
-#pragma unroll
+  // registers q < r of one lane: the lower index of an ascending pair keeps the smaller element
+  auto in_lane = [&](int q, int r, int k) {
+    const bool asc = (((q * 32 + lane) & k) == 0);
+    const bool gt = key[q] > key[r] || (key[q] == key[r] && val[q] > val[r]);
+    if (gt == asc) { const long long tk = key[q]; key[q] = key[r]; key[r] = tk; const int tv = val[q]; val[q] = val[r]; val[r] = tv; }
+  };
+#pragma unroll 1
+  for (int k = 2; k <= np2; k <<= 1) {
+#pragma unroll 1
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {
-        const int dq = j >> 5;
+      if (j == 64) { in_lane(0, 2, k); in_lane(1, 3, k); }                  // only a 128-element table gets here
+      else if (j == 32) { in_lane(0, 1, k); if (nq > 2) in_lane(2, 3, k); }
+      else {
 #pragma unroll
         for (int q = 0; q < E; q++) {
-          if ((q & dq) == 0) {                               // q is the lower register of the pair (q, q ^ dq)
-            const int r = q ^ dq;
-            const bool asc = (((q * 32 + lane) & k) == 0);
-            const bool gt = key[q] > key[r] || (key[q] == key[r] && val[q] > val[r]);
-            if (gt == asc) { const long long tk = key[q]; key[q] = key[r]; key[r] = tk; const int tv = val[q]; val[q] = val[r]; val[r] = tv; }
+          if (q < nq) {                                                     // warp-uniform
+            const long long ok = __shfl_xor_sync(0xffffffffu, key[q], j);
+            const int ov = __shfl_xor_sync(0xffffffffu, val[q], j);
+            const int g = q * 32 + lane;
+            const bool asc = ((g & k) == 0), lower = ((lane & j) == 0);
+            const bool mine_gt = key[q] > ok || (key[q] == ok && val[q] > ov);
+            if (mine_gt == (lower == asc)) { key[q] = ok; val[q] = ov; }
           }
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < E; q++) {
-          const long long ok = __shfl_xor_sync(0xffffffffu, key[q], j);
-          const int ov = __shfl_xor_sync(0xffffffffu, val[q], j);
-          const int g = q * 32 + lane;
-          const bool asc = ((g & k) == 0), lower = ((lane & j) == 0);
-          const bool mine_gt = key[q] > ok || (key[q] == ok && val[q] > ov);
-          // the lower index of an ascending pair keeps the smaller element
-          if (mine_gt == (lower == asc)) { key[q] = ok; val[q] = ov; }
         }
       }
     }
@@ -824,11 +859,7 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
     Warp::sync();
     // times are not negative, so their bit patterns order like the times: integer compares (the FP64 pipe is narrow)
 #if IMA_CUDA
-    // a bitonic network over registers: element q * 32 + lane sits in register q of the lane; partners closer than 32 are
-    // exchanged by shuffles, the others are registers of the same lane
-    if (nev <= 32) warp_sort_events<1>(bt, bi, nev, S.evt, S.evi);
-    else if (nev <= 64) warp_sort_events<2>(bt, bi, nev, S.evt, S.evi);
-    else warp_sort_events<4>(bt, bi, nev, S.evt, S.evi);
+    warp_sort_events(bt, bi, nev, S.evt, S.evi);
 #else
     for (int j0 = lane; j0 < nev; j0 += 2 * IMA_WARP) {            // two events of the lane share every read of the table
       const int j1 = j0 + IMA_WARP;
@@ -979,27 +1010,42 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
       }
     }
   }
-  length = Warp::sum(length);
-  tlength = Warp::sum(tlength);
   bad = Warp::any(bad != 0) ? 1 : 0;
-  // fc[k][ii] += n(n-1) dt / (2h) and fm[k][ii][*] += n dt: one target (k, ii) at a time
+  // fc[k][ii] += n(n-1) dt / (2h) and fm[k][ii][*] += n dt.  Two targets (k, ii), (k, ii + 1) per pass over the events, and
+  // the reductions of a pass issued together: independent shuffle chains overlap, one after another they were a quarter of
+  // the sweep.  Every sum adds the same numbers in the same order as the one-target-at-a-time loop.
+  bool first_pass = true;
   for (int k = 0; k <= nsplit; k++)
-    for (int ii = 0; ii < npops - k; ii++) {
-      const int ip = tab[kTabPlist + k * kMaxPops + ii];
-      double fcacc = 0.0, fmacc = 0.0;
+    for (int ii = 0; ii < npops - k; ii += 2) {
+      const bool two = ii + 1 < npops - k;
+      const int ip0 = tab[kTabPlist + k * kMaxPops + ii], ip1 = two ? tab[kTabPlist + k * kMaxPops + ii + 1] : ip0;
+      double fc0 = 0.0, fm0 = 0.0, fc1 = 0.0, fm1 = 0.0;
       for (int j = lane; j < nev; j += IMA_WARP)
         if ((S.evk[j] & 0xff) == k) {
           const double dt = S.evt[j] - (j > 0 ? S.evt[j - 1] : 0.0);
-          const int n = lineages(ip, j);
-          fcacc += ((double)n * ((double)n - 1)) * dt * h2term;
-          fmacc += n * dt;
+          const int n0 = lineages(ip0, j);
+          fc0 += ((double)n0 * ((double)n0 - 1)) * dt * h2term;
+          fm0 += n0 * dt;
+          if (two) {
+            const int n1 = lineages(ip1, j);
+            fc1 += ((double)n1 * ((double)n1 - 1)) * dt * h2term;
+            fm1 += n1 * dt;
+          }
         }
-      fcacc = Warp::sum(fcacc);
-      fmacc = Warp::sum(fmacc);
+      if (first_pass) {                                   // the two lengths ride along with the first pass
+        Warp::sum4(fc0, fm0, length, tlength);
+        if (two) Warp::sum2(fc1, fm1);
+        first_pass = false;
+      } else if (two) Warp::sum4(fc0, fm0, fc1, fm1);
+      else Warp::sum2(fc0, fm0);
       if (lane == 0) {
-        S.gwd[wd_fc(M, k, ii)] = fcacc;
+        S.gwd[wd_fc(M, k, ii)] = fc0;
+        if (two) S.gwd[wd_fc(M, k, ii + 1)] = fc1;
         if (!M.nomigration && k < nsplit)
-          for (int jj = 0; jj < npops - k; jj++) if (jj != ii) S.gwd[wd_fm(M, k, ii, jj)] = fmacc;
+          for (int jj = 0; jj < npops - k; jj++) {
+            if (jj != ii) S.gwd[wd_fm(M, k, ii, jj)] = fm0;
+            if (two && jj != ii + 1) S.gwd[wd_fm(M, k, ii + 1, jj)] = fm1;
+          }
       }
     }
   Warp::sync();

@@ -499,15 +499,45 @@ IMA_KERNEL void IMA_ACCEPT_BOUNDS(B) k_accept(EngineView E) {
         // U < min(1, e^x) is taken as log U < min(0, x): the logarithm is off the chain of decisions, the exponential was on it
         S.r_sc[slot * 4 + 3] = log(rng.uniform());
       }
-      const int nl = ch1 - ch0, per = NI + 2 * ND;
-      for (int k = tid; k < nl * per; k += nth) {
-        const int slot = k / per, i = k - slot * per;
-        const int p = c * E.d.nloci + ch0 + slot;
-        const int cb = E.cur[p];
-        const PairBuf &O = E.buf[cb], &N = E.buf[cb ^ 1];
-        if (i < NI) S.r_dI[slot * sI + i] = N.gwi[(size_t)p * NI + i] - O.gwi[(size_t)p * NI + i];
-        else if (i < NI + ND) S.r_oD[slot * sD + (i - NI)] = O.gwd[(size_t)p * ND + (i - NI)];
-        else S.r_nD[slot * sD + (i - NI - ND)] = N.gwd[(size_t)p * ND + (i - NI - ND)];
+      // kLoadTrips trips per thread in flight: first which buffer is current for each, then the values
+      const int nl = ch1 - ch0, per = NI + 2 * ND, nrec = nl * per;
+      constexpr int kLoadTrips = 3;
+      for (int k0 = tid; k0 < nrec; k0 += kLoadTrips * nth) {
+        int cbv[kLoadTrips];
+        long long raw[kLoadTrips];
+#if IMA_CUDA
+#pragma unroll
+#endif
+        for (int u = 0; u < kLoadTrips; u++) {
+          const int k = k0 + u * nth;
+          cbv[u] = k < nrec ? (int)E.cur[c * E.d.nloci + ch0 + k / per] : 0;
+        }
+#if IMA_CUDA
+#pragma unroll
+#endif
+        for (int u = 0; u < kLoadTrips; u++) {
+          const int k = k0 + u * nth;
+          if (k < nrec) {
+            const int slot = k / per, i = k - slot * per;
+            const int p = c * E.d.nloci + ch0 + slot;
+            const PairBuf &O = E.buf[cbv[u]], &N = E.buf[cbv[u] ^ 1];
+            if (i < NI) raw[u] = (long long)(N.gwi[(size_t)p * NI + i] - O.gwi[(size_t)p * NI + i]);
+            else if (i < NI + ND) raw[u] = dbl_bits(O.gwd[(size_t)p * ND + (i - NI)]);
+            else raw[u] = dbl_bits(N.gwd[(size_t)p * ND + (i - NI - ND)]);
+          }
+        }
+#if IMA_CUDA
+#pragma unroll
+#endif
+        for (int u = 0; u < kLoadTrips; u++) {
+          const int k = k0 + u * nth;
+          if (k < nrec) {
+            const int slot = k / per, i = k - slot * per;
+            if (i < NI) S.r_dI[slot * sI + i] = (int)raw[u];
+            else if (i < NI + ND) S.r_oD[slot * sD + (i - NI)] = bits_dbl(raw[u]);
+            else S.r_nD[slot * sD + (i - NI - ND)] = bits_dbl(raw[u]);
+          }
+        }
       }
     }
     block_sync();

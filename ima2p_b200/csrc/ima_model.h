@@ -48,8 +48,8 @@ struct DevLocus {
   long long mult_off;       // int    [nsites]: pattern multiplicities (HKY)
 };
 
-struct short4_t { short x, y, z, w; };       // up0, up1, down, pop
-struct ushort2_t { unsigned short x, y; };   // migration segment (start, count) in the pair's pool
+struct alignas(8) short4_t { short x, y, z, w; };       // up0, up1, down, pop (one 64-bit load)
+struct alignas(4) ushort2_t { unsigned short x, y; };   // migration segment (start, count) in the pair's pool
 
 // One of the two state buffers.  Pair-major arrays: pair p = local_chain * nloci + locus.
 struct PairBuf {

@@ -74,6 +74,24 @@ struct Warp {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   }
+  // several sums at once: the shuffle chains are independent and overlap
+  IMA_DEV static void sum2(double &a, double &b) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+      a += ta; b += tb;
+    }
+  }
+  IMA_DEV static void sum4(double &a, double &b, double &c, double &d) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+      const double tc = __shfl_xor_sync(0xffffffffu, c, o), td = __shfl_xor_sync(0xffffffffu, d, o);
+      a += ta; b += tb; c += tc; d += td;
+    }
+  }
+  IMA_DEV static unsigned long long sum(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
   IMA_DEV static int max(int v) {
     for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
     return v;
@@ -81,6 +99,8 @@ struct Warp {
   IMA_DEV static int bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
   IMA_DEV static double bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
   IMA_DEV static bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+  IMA_DEV static unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+  IMA_DEV static int popc(unsigned m) { return __popc(m); }
   // inclusive prefix sum over the 32 lanes
   IMA_DEV static int scan(int v) {
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane() >= o) v += t; }
@@ -102,10 +122,15 @@ struct Warp {
   static void sync() {}
   static double sum(double v) { return v; }
   static int sum(int v) { return v; }
+  static unsigned long long sum(unsigned long long v) { return v; }
+  static void sum2(double &, double &) {}
+  static void sum4(double &, double &, double &, double &) {}
   static int max(int v) { return v; }
   static int bcast(int v, int) { return v; }
   static double bcast(double v, int) { return v; }
   static bool any(bool p) { return p; }
+  static unsigned ballot(bool p) { return p ? 1u : 0u; }
+  static int popc(unsigned m) { int n = 0; while (m) { n += (int)(m & 1u); m >>= 1; } return n; }
   static int scan(int v) { return v; }
   static double scan_add(double v) { return v; }
   static double scan_mul(double v) { return v; }

@@ -93,12 +93,12 @@ IMA_DEV int nw_nowpop(const DevModel &M, const double *tv, const PairSm &S, int 
 }
 
 IMA_DEV double nw_logpf(int code) {            // the seven values logpfpop / logpfpop_r take (:372-583, MIGSIMFRAC 0.999)
-  switch (code) {
-    case 1: return log(0.999);
-    case 2: return log(1.0 - 0.999);
+  switch (code) {                                 // written out: a logarithm in the code is ~100 instructions per call site
+    case 1: return -0.0010005003335835344;          // log(0.999)
+    case 2: return -6.907755278982136;              // log(1.0 - 0.999)
     case 3: return -kLog2;
-    case 4: return log(0.999) / 2.0;
-    case 5: return log(1.0 - 0.999) / 2.0;
+    case 4: return -0.0005002501667917672;          // log(0.999) / 2
+    case 5: return -3.453877639491068;              // log(1.0 - 0.999) / 2
     case 6: return -0.34657359027997265470861606073;      // LOG2HALF, imamp.hpp:189
     default: return 0.0;
   }
@@ -141,10 +141,26 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
   __threadfence_block();
 #endif
   Warp::sync();
-  // which edges have a stretch inside the interval, and where their lower ends are before (db) and after (da) the update
-  for (int i = lane; i < nl; i += IMA_WARP) {
+  // The edges with a stretch inside the interval, compacted (ballot + prefix count) so that the lanes of one trip all have
+  // work: a trip of the two passes below is a few thousand dependent instructions whatever the number of lanes in it.
+  int *list = (int *)S.mask;                          // NL words, not in use before the likelihood
+  int nset = 0;
+  for (int base = 0; base < nl; base += IMA_WARP) {
+    const int i = base + lane;
+    bool in = false;
+    if (i < nl) { const double uptime = edge_top_time(S, ng, i); in = S.time[i] > tu && uptime <= td; }
+    const unsigned m = Warp::ballot(in);
+    if (in) list[nset + Warp::popc(m & ((1u << lane) - 1u))] = i;
+    nset += Warp::popc(m);
+  }
+#if IMA_CUDA
+  __threadfence_block();
+#endif
+  Warp::sync();
+  // where their lower ends are before (db) and after (da) the update
+  for (int k = lane; k < nset; k += IMA_WARP) {
+    const int i = list[k];
     const double uptime = edge_top_time(S, ng, i);
-    if (!(S.time[i] > tu && uptime <= td)) continue;
     int db, da, cf = 0, cr = 0, sis = -1;
     Philox rng;
     if (S.time[i] > td) {                             // the edge leaves the interval at its lower end: on its own
@@ -197,7 +213,8 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
   // per stretch: population at the upper end before / after, migration counts and rates, the new path, Hastings terms
   double num = 0.0, denom = 0.0;
   bool overflow = false;
-  for (int ei = lane; ei < nl; ei += IMA_WARP) {
+  for (int k = lane; k < nset; k += IMA_WARP) {
+    const int ei = list[k];
     if (!(rec[ei] >> 18)) continue;
     const int db = rec[ei] & 31, da = (rec[ei] >> 5) & 31;
     const double logpf = nw_logpf((rec[ei] >> 10) & 7), logpf_r = nw_logpf((rec[ei] >> 13) & 7);
@@ -263,115 +280,111 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
 
 // evcap / migcap: what the caller's tables hold (the general kernel: EVP events, CAP migration events; the fast one: FEV, FC).
 // Returns false when the pair did not fit: the caller decides whether that is a dropped proposal or a pair for the general path.
-IMA_DEV bool nw_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S, int evcap, int migcap) {
+// One body for both update types, so that the staging, the weights and the store exist once in a kernel's code (the kernels
+// that call this run their code once per warp: instruction fetch is what they wait for most).
+IMA_DEV bool split_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S, int evcap, int migcap) {
   const DevLocus &L = E.loci[li];
   const int cb = E.cur[p];
   const PairBuf &B = E.buf[cb];
   const PairBuf &Bn = E.buf[cb ^ 1];
   const int lane = Warp::lane();
-  double tvo[kMaxPeriods], tvn[kMaxPeriods];
-  for (int k = 0; k < kMaxPeriods; k++) tvo[k] = tvn[k] = E.tvals[(size_t)c * kMaxPeriods + k];
-  tvn[t.period] = t.newt;
-  stage_pair(E, B, p, L.nl, S);
-  const double roottime = S.ctl_d[kCdRoottime];
-  // :967-969: a genealogy whose root is younger than both split times is not touched
-  const bool touched = (t.newt > t.oldt && roottime > t.oldt) || (t.newt < t.oldt && roottime > t.newt);
-  double mw = 0.0;
-  if (touched) mw = nw_update_pair(E, M, tvo, t.period, t.oldt, t.newt, L.ng, L.nl, (E.d.chain0 + c) * E.d.nloci + li, S);
-  if (lane == 0) S.ctl_d[kCdMigw] = mw;
-#if IMA_CUDA
-  __threadfence_block();
-#endif
-  Warp::sync();
-  bool ok = !(S.ctl_i[kCiFlags] & kFlagOverflow);
-  if (ok) ok = eval_weights(M, E.d, L, tvn, S, evcap);
-  const int total_mig = ok ? S.ctl_i[kCiMignum] : 0;
-  if (ok && total_mig > migcap) ok = false;
-  if (ok) {
-    // branch lengths do not change: P(D|G) and everything it is built from are carried over (:908)
-    if (has_stepwise(L.model)) {
-      const size_t ao = (size_t)p * kMaxLinked * E.d.NL;
-      for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) { Bn.A[ao + i] = B.A[ao + i]; Bn.dlikeA[ao + i] = B.dlikeA[ao + i]; }
-      for (int ai = lane; ai < L.nlinked; ai += IMA_WARP) Bn.pdg_a[(size_t)p * kMaxLinked + ai] = B.pdg_a[(size_t)p * kMaxLinked + ai];
-    }
-    if (L.model == kHKY)                                  // and so are the stored partials: the same slots stay current
-      for (int w = lane; w < E.d.hky_mask_words; w += IMA_WARP) Bn.hky_mask[(size_t)p * E.d.hky_mask_words + w] = B.hky_mask[(size_t)p * E.d.hky_mask_words + w];
-    if (lane == 0) S.ctl_d[kCdPdg] = B.sd[(size_t)p * 4 + 3];
-    Warp::sync();
-    store_pair(E, Bn, p, L.nl, S, total_mig);
-  }
-  if (lane == 0) {
-    E.prop_flags[p] = ok ? 0u : (uint32_t)kFlagOverflow;
-    E.prop_extra[p] = S.ctl_d[kCdMigw];
-    if (E.prop_dbg) E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw];
-    int *o = U.t_counts + (size_t)p * 4;
-    o[0] = o[1] = o[2] = o[3] = 0;
-  }
-  return ok;
-}
-
-IMA_DEV bool rescale_t_pair(const EngineView &E, const UpdateView &U, const DevModel &M, const TProposal &t, int p, int c, int li, PairSm &S, int evcap, int migcap) {
-  const DevLocus &L = E.loci[li];
-  const int cb = E.cur[p];
-  const PairBuf &B = E.buf[cb];
-  const PairBuf &Bn = E.buf[cb ^ 1];
-  const int lane = Warp::lane();
+  const bool nw = t.method == 1;
   double tvn[kMaxPeriods];
   for (int k = 0; k < kMaxPeriods; k++) tvn[k] = E.tvals[(size_t)c * kMaxPeriods + k];
-  tvn[t.period] = t.newt;
+  IMA_PROF_DECL(8)
   stage_pair(E, B, p, L.nl, S);
-  // :268-328: every time between the neighbouring split times moves with the split time
+  IMA_PROF_MARK()
   int n_eu = 0, n_ed = 0, n_mu = 0, n_md = 0;
-  for (int i = lane; i < L.nl; i += IMA_WARP) {
-    if (S.down[i] == -1) continue;
-    const double x = S.time[i];
-    if (x <= t.oldt && x > t.t_u) { S.time[i] = ry_beforesplit(t.period, t.oldt, t.newt, t.t_u, x); n_eu++; }
-    else if (x > t.oldt && x < t.t_d) { S.time[i] = ry_aftersplit(t.period, M.nsplit, t.oldt, t.newt, t.t_d, x); n_ed++; }
+  if (nw) {
+    const double roottime = S.ctl_d[kCdRoottime];
+    // update_t_NW.cpp:967-969: a genealogy whose root is younger than both split times is not touched
+    const bool touched = (t.newt > t.oldt && roottime > t.oldt) || (t.newt < t.oldt && roottime > t.newt);
+    double mw = 0.0;
+    if (touched) mw = nw_update_pair(E, M, tvn, t.period, t.oldt, t.newt, L.ng, L.nl, (E.d.chain0 + c) * E.d.nloci + li, S);   // tvn: still the old times
+    if (lane == 0) S.ctl_d[kCdMigw] = mw;
+  } else {
+    // update_t_RY.cpp:268-328: every time between the neighbouring split times moves with the split time
+    for (int i = lane; i < L.nl; i += IMA_WARP) {
+      if (S.down[i] == -1) continue;
+      const double x = S.time[i];
+      if (x <= t.oldt && x > t.t_u) { S.time[i] = ry_beforesplit(t.period, t.oldt, t.newt, t.t_u, x); n_eu++; }
+      else if (x > t.oldt && x < t.t_d) { S.time[i] = ry_aftersplit(t.period, M.nsplit, t.oldt, t.newt, t.t_d, x); n_ed++; }
+    }
+    const int mignum = S.ctl_i[kCiMignum];
+    for (int i = lane; i < mignum; i += IMA_WARP) {
+      const double x = S.pt[i];
+      if (x <= t.oldt && x > t.t_u) { S.pt[i] = ry_beforesplit(t.period, t.oldt, t.newt, t.t_u, x); n_mu++; }
+      else if (x > t.oldt && x < t.t_d) { S.pt[i] = ry_aftersplit(t.period, M.nsplit, t.oldt, t.newt, t.t_d, x); n_md++; }
+    }
+    if (lane == 0) {
+      const double x = S.ctl_d[kCdRoottime];
+      if (x <= t.oldt && x > t.t_u) S.ctl_d[kCdRoottime] = ry_beforesplit(t.period, t.oldt, t.newt, t.t_u, x);
+      else if (x > t.oldt && x < t.t_d) S.ctl_d[kCdRoottime] = ry_aftersplit(t.period, M.nsplit, t.oldt, t.newt, t.t_d, x);
+    }
+    // the four counts in one reduction (each is at most 2 NL + CAP: 16 bits apiece)
+    unsigned long long packed = (unsigned long long)n_eu | ((unsigned long long)n_ed << 16) | ((unsigned long long)n_mu << 32) | ((unsigned long long)n_md << 48);
+    packed = Warp::sum(packed);
+    n_eu = (int)(packed & 0xffffull); n_ed = (int)((packed >> 16) & 0xffffull); n_mu = (int)((packed >> 32) & 0xffffull); n_md = (int)(packed >> 48);
   }
-  const int mignum = S.ctl_i[kCiMignum];
-  for (int i = lane; i < mignum; i += IMA_WARP) {
-    const double x = S.pt[i];
-    if (x <= t.oldt && x > t.t_u) { S.pt[i] = ry_beforesplit(t.period, t.oldt, t.newt, t.t_u, x); n_mu++; }
-    else if (x > t.oldt && x < t.t_d) { S.pt[i] = ry_aftersplit(t.period, M.nsplit, t.oldt, t.newt, t.t_d, x); n_md++; }
-  }
-  if (lane == 0) {
-    const double x = S.ctl_d[kCdRoottime];
-    if (x <= t.oldt && x > t.t_u) S.ctl_d[kCdRoottime] = ry_beforesplit(t.period, t.oldt, t.newt, t.t_u, x);
-    else if (x > t.oldt && x < t.t_d) S.ctl_d[kCdRoottime] = ry_aftersplit(t.period, M.nsplit, t.oldt, t.newt, t.t_d, x);
-  }
-  n_eu = Warp::sum(n_eu); n_ed = Warp::sum(n_ed); n_mu = Warp::sum(n_mu); n_md = Warp::sum(n_md);
+  tvn[t.period] = t.newt;
 #if IMA_CUDA
   __threadfence_block();
 #endif
   Warp::sync();
-  bool ok = eval_weights(M, E.d, L, tvn, S, evcap);
+  IMA_PROF_MARK()
+  bool ok = !(S.ctl_i[kCiFlags] & kFlagOverflow);
+  if (ok) ok = eval_weights(M, E.d, L, tvn, S, evcap);
+  IMA_PROF_MARK()
   const int total_mig = ok ? S.ctl_i[kCiMignum] : 0;
   if (ok && total_mig > migcap) ok = false;
-  uint32_t flags = ok ? (uint32_t)S.ctl_i[kCiFlags] : (uint32_t)kFlagOverflow;
+  uint32_t flags = ok ? (nw ? 0u : (uint32_t)S.ctl_i[kCiFlags]) : (uint32_t)kFlagOverflow;
   if (ok) {
-    if (has_stepwise(L.model)) {           // the allele states do not move; the branch terms are recomputed below
-      const size_t ao = (size_t)p * kMaxLinked * E.d.NL;
-      for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) Bn.A[ao + i] = B.A[ao + i];
+    if (nw) {
+      // branch lengths do not change: P(D|G) and everything it is built from are carried over (update_t_NW.cpp:908)
+      if (has_stepwise(L.model)) {
+        const size_t ao = (size_t)p * kMaxLinked * E.d.NL;
+        for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) { Bn.A[ao + i] = B.A[ao + i]; Bn.dlikeA[ao + i] = B.dlikeA[ao + i]; }
+        for (int ai = lane; ai < L.nlinked; ai += IMA_WARP) Bn.pdg_a[(size_t)p * kMaxLinked + ai] = B.pdg_a[(size_t)p * kMaxLinked + ai];
+      }
+      if (L.model == kHKY)                                  // and so are the stored partials: the same slots stay current
+        for (int w = lane; w < E.d.hky_mask_words; w += IMA_WARP) Bn.hky_mask[(size_t)p * E.d.hky_mask_words + w] = B.hky_mask[(size_t)p * E.d.hky_mask_words + w];
+      if (lane == 0) S.ctl_d[kCdPdg] = B.sd[(size_t)p * 4 + 3];
+    } else {
+      if (has_stepwise(L.model)) {           // the allele states do not move; the branch terms are recomputed below
+        const size_t ao = (size_t)p * kMaxLinked * E.d.NL;
+        for (int i = lane; i < L.nlinked * E.d.NL; i += IMA_WARP) Bn.A[ao + i] = B.A[ao + i];
 #if IMA_CUDA
-      __threadfence_block();
+        __threadfence_block();
 #endif
-      Warp::sync();
-    }
-    double pdga[kMaxLinked];
-    HkyCall hk; hk.mode = kHkyFull; hk.freed = hk.olddd = -1;       // every time moved: every node is recomputed
-    hk.mask_cur = B.hky_mask ? B.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
-    hk.mask_new = Bn.hky_mask ? Bn.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
-    const double pdg = pair_likelihood(E, L, Bn, p, S, pdga, hk);
-    if (pdg == kRejectIS) flags |= kFlagRejectIS;
-    if (lane == 0) {
-      S.ctl_d[kCdPdg] = pdg;
-      if (Bn.pdg_a) for (int ai = 0; ai < L.nlinked; ai++) Bn.pdg_a[(size_t)p * kMaxLinked + ai] = pdga[ai];
+        Warp::sync();
+      }
+      double pdga[kMaxLinked];
+      HkyCall hk; hk.mode = kHkyFull; hk.freed = hk.olddd = -1;       // every time moved: every node is recomputed
+      hk.mask_cur = B.hky_mask ? B.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+      hk.mask_new = Bn.hky_mask ? Bn.hky_mask + (size_t)p * E.d.hky_mask_words : nullptr;
+      const double pdg = pair_likelihood(E, L, Bn, p, S, pdga, hk);
+      if (pdg == kRejectIS) flags |= kFlagRejectIS;
+      if (lane == 0) {
+        S.ctl_d[kCdPdg] = pdg;
+        if (Bn.pdg_a) for (int ai = 0; ai < L.nlinked; ai++) Bn.pdg_a[(size_t)p * kMaxLinked + ai] = pdga[ai];
+      }
     }
     Warp::sync();
+    IMA_PROF_MARK()
     store_pair(E, Bn, p, L.nl, S, total_mig);
+    IMA_PROF_MARK()
+#if defined(IMA_PROF) && IMA_CUDA
+    if (lane == 0 && p % 641 == 0 && (current_step(E) % 64) == 0)
+      printf("PROFS %s p %d stage %lld update %lld weights %lld like %lld store %lld\n", nw ? "nw" : "ry", p, prof_t_[1] - prof_t_[0], prof_t_[2] - prof_t_[1],
+             prof_t_[3] - prof_t_[2], prof_t_[4] - prof_t_[3], prof_t_[5] - prof_t_[4]);
+#endif
   }
   if (lane == 0) {
     E.prop_flags[p] = flags;
+    if (nw) {
+      E.prop_extra[p] = S.ctl_d[kCdMigw];
+      if (E.prop_dbg) E.prop_dbg[(size_t)p * 4 + 0] = S.ctl_d[kCdMigw];
+    }
     int *o = U.t_counts + (size_t)p * 4;
     o[0] = n_eu; o[1] = n_ed; o[2] = n_mu; o[3] = n_md;
   }
@@ -387,8 +400,7 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_split_t(EngineView E, UpdateView U) {
   const int c = E.c_lo + idx / E.d.nloci, li = idx % E.d.nloci, p = c * E.d.nloci + li;
   PairSm S = carve_pair_smem(IMA_SMEM + (size_t)ima_warp_in_block() * pair_smem_bytes(E.d), E.d);
   const TProposal t = t_proposal(E, U, M, c);
-  if (t.method == 1) nw_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
-  else rescale_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
+  split_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
 }
 
 // ---- the same proposals with the small tables of the fast path (ima_fastpath.h): FC migration events per genealogy plus FS
@@ -414,7 +426,7 @@ IMA_KERNEL void IMA_SPLIT_BOUNDS k_split_t_fast(EngineView E, UpdateView U) {
   PairSm S = carve_split_smem(IMA_SMEM + (size_t)ima_warp_in_block() * split_smem_bytes(E.d), E.d);
   const TProposal t = t_proposal(E, U, M, c);
   bool ok = E.buf[E.cur[p]].si[(size_t)p * 2 + 1] <= E.d.FC;
-  if (ok) ok = t.method == 1 ? nw_t_pair(E, U, M, t, p, c, li, S, E.d.FEV, E.d.FC) : rescale_t_pair(E, U, M, t, p, c, li, S, E.d.FEV, E.d.FC);
+  if (ok) ok = split_t_pair(E, U, M, t, p, c, li, S, E.d.FEV, E.d.FC);
   if (!ok && Warp::lane() == 0) { E.prop_flags[p] = kFlagRedo; redo_push(E, 1, p); }
 }
 IMA_KERNEL void IMA_PROPOSE_BOUNDS k_split_t_redo(EngineView E, UpdateView U) {
@@ -426,8 +438,7 @@ IMA_KERNEL void IMA_PROPOSE_BOUNDS k_split_t_redo(EngineView E, UpdateView U) {
   for (int k = ima_block() * kWarpsPerBlock + ima_warp_in_block(); k < n; k += E.redo_grid * kWarpsPerBlock) {
     const int p = list[k], c = p / E.d.nloci, li = p - c * E.d.nloci;
     const TProposal t = t_proposal(E, U, M, c);
-    if (t.method == 1) nw_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
-    else rescale_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
+    split_t_pair(E, U, M, t, p, c, li, S, E.d.EVP, E.d.CAP);
     Warp::sync();
   }
 }
@@ -449,10 +460,17 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
   const DevModel &M = IMA_MODEL;
   const int lane = Warp::lane(), NI = E.d.NI, ND = E.d.ND, nloci = E.d.nloci;
   ChainSm S = carve_chain_smem(IMA_SMEM, E.d);
-  const TProposal t = t_proposal(E, U, M, c);
+#if defined(IMA_PROF) && IMA_CUDA
+  auto pclk_ = []() { long long x; asm volatile("mov.u64 %0, %%clock64;" : "=l"(x) :: "memory"); return x; };
+  long long pq_[8]; int pn_ = 0; pq_[pn_++] = pclk_();
+#define IMA_PT() pq_[pn_++] = pclk_();
+#else
+#define IMA_PT()
+#endif
   const int nterms = M.nq + (M.nomigration ? 0 : M.nm);
-  // When the chain's records fit, everything this kernel reads from global memory is brought into shared memory in two
-  // trips (which buffer every locus proposes into; then every weight and scalar, all loads independent of each other).
+  // When the chain's records fit, everything this kernel reads from global memory is brought into shared memory: which buffer
+  // every locus proposes into first, then every weight and scalar with kLoadTrips independent loads in flight per thread.  The
+  // chain's scalars, the proposal and the uniform -- nothing of which depends on the records -- are computed while they travel.
   const bool staged = accept_t_staged(E.d);
   unsigned char *sp = IMA_SMEM + chain_smem_bytes(E.d);
   int *s_ob = (int *)sp; sp += align8((size_t)nloci * 4);
@@ -467,45 +485,111 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
       const int tid = w * IMA_WARP + lane, nth = kTWarps * IMA_WARP;
       for (int li = tid; li < nloci; li += nth) s_ob[li] = E.cur[c * nloci + li] ^ 1;
     }
+  }
+  const double beta = E.beta[c], pdgsum_old = E.pdgsum[c], probg_old = E.probg[c], swapsum_old = E.swapsum[c];
+  const TProposal t = t_proposal(E, U, M, c);
+  Philox rng;
+  rng_for(rng, E, (uint32_t)(E.d.nchains_global + E.d.chain0 + c), kRngSplitTime);
+  const double uacc = rng.uniform();
+  const double t_u_hterm = (t.newt - t.t_u) / (t.oldt - t.t_u);
+  const double t_d_hterm = t.period == M.nsplit - 1 ? 1.0 : (t.t_d - t.newt) / (t.t_d - t.oldt);
+  double log_u_h, log_d_h, log_uacc;
+  log3_coop(t_u_hterm, t_d_hterm, uacc, log_u_h, log_d_h, log_uacc);
+  IMA_PT()
+  if (staged) {
     block_sync();
+    constexpr int kLoadTrips = 4;
     IMA_FOR_WARPS(w, kTWarps) {
-      const int tid = w * IMA_WARP + lane, nth = kTWarps * IMA_WARP, per = NI + ND + 1;
-      for (int k = tid; k < nloci * per; k += nth) {
-        const int li = k / per, i = k - li * per, p = c * nloci + li;
-        const PairBuf &N = E.buf[s_ob[li]];
-        if (i < NI) s_wi[i * nloci + li] = N.gwi[(size_t)p * NI + i];
-        else if (i < NI + ND) s_wd[(i - NI) * nloci + li] = N.gwd[(size_t)p * ND + i - NI];
-        else {
-          s_pdg[li] = N.sd[(size_t)p * 4 + 3];
-          s_mw[li] = E.prop_extra[p];
-          const int *o = U.t_counts + (size_t)p * 4;
-          s_cnt[li * 4] = o[0]; s_cnt[li * 4 + 1] = o[1]; s_cnt[li * 4 + 2] = o[2]; s_cnt[li * 4 + 3] = o[3];
-          s_fl[li] = (int)(E.prop_flags[p] & (kFlagOverflow | kFlagRejectIS | kFlagBadTree));
+      const int tid = w * IMA_WARP + lane, nth = kTWarps * IMA_WARP, per = NI + ND, n = nloci * per;
+      for (int k0 = tid; k0 < n; k0 += kLoadTrips * nth) {
+        long long raw[kLoadTrips];
+#if IMA_CUDA
+#pragma unroll
+#endif
+        for (int u = 0; u < kLoadTrips; u++) {
+          const int k = k0 + u * nth;
+          if (k < n) {
+            const int li = k / per, i = k - li * per, p = c * nloci + li;
+            const PairBuf &N = E.buf[s_ob[li]];
+            raw[u] = i < NI ? (long long)N.gwi[(size_t)p * NI + i] : dbl_bits(N.gwd[(size_t)p * ND + i - NI]);
+          }
         }
+#if IMA_CUDA
+#pragma unroll
+#endif
+        for (int u = 0; u < kLoadTrips; u++) {
+          const int k = k0 + u * nth;
+          if (k < n) {
+            const int li = k / per, i = k - li * per;
+            if (i < NI) s_wi[i * nloci + li] = (int)raw[u];
+            else s_wd[(i - NI) * nloci + li] = bits_dbl(raw[u]);
+          }
+        }
+      }
+      for (int li = tid; li < nloci; li += nth) {
+        const int p = c * nloci + li;
+        const PairBuf &N = E.buf[s_ob[li]];
+        const double pdg = N.sd[(size_t)p * 4 + 3], mw = E.prop_extra[p];
+        const int *o = U.t_counts + (size_t)p * 4;
+        const int o0 = o[0], o1 = o[1], o2 = o[2], o3 = o[3];
+        const int fl = (int)(E.prop_flags[p] & (kFlagOverflow | kFlagRejectIS | kFlagBadTree));
+        s_pdg[li] = pdg; s_mw[li] = mw;
+        s_cnt[li * 4] = o0; s_cnt[li * 4 + 1] = o1; s_cnt[li * 4 + 2] = o2; s_cnt[li * 4 + 3] = o3;
+        s_fl[li] = fl;
       }
     }
     block_sync();
   }
+  IMA_PT()
   // setzero + sum_treeinfo over the loci (:256, 331), from the proposed (other) buffers: warps take weights, lanes take
-  // loci, one warp reduction per weight (the loads of one weight do not wait for each other)
+  // loci, one warp reduction per weight (the loads of one weight do not wait for each other).  The per-locus scalars the
+  // decision needs (new P(D|G), migration term, counts, flags) are three more "weights": S.dc[0..2], S.ic[0..4]
   IMA_FOR_WARPS(w, kTWarps) {
-    for (int i = w; i < NI + ND; i += kTWarps) {
+    for (int i = w; i < NI + ND + 3; i += kTWarps) {
       if (i < NI) {
         int a = 0;
         if (staged) for (int li = lane; li < nloci; li += IMA_WARP) a += s_wi[i * nloci + li];
         else for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwi[(size_t)p * NI + i]; }
         a = Warp::sum(a);
         if (lane == 0) S.ai[i] = a;
-      } else {
+      } else if (i < NI + ND) {
         double a = 0.0;
         if (staged) for (int li = lane; li < nloci; li += IMA_WARP) a += s_wd[(i - NI) * nloci + li];
         else for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; a += E.buf[E.cur[p] ^ 1].gwd[(size_t)p * ND + i - NI]; }
         a = Warp::sum(a);
         if (lane == 0) S.ad[i - NI] = a;
+      } else if (i == NI + ND) {                                  // new P(D|G) and the migration term
+        double pdgnew = 0.0, migw = 0.0;
+        for (int li = lane; li < nloci; li += IMA_WARP) {
+          if (staged) { pdgnew += s_pdg[li]; if (t.method == 1) migw += s_mw[li]; }
+          else {
+            const int p = c * nloci + li;
+            pdgnew += E.buf[E.cur[p] ^ 1].sd[(size_t)p * 4 + 3];
+            if (t.method == 1) migw += E.prop_extra[p];
+          }
+        }
+        Warp::sum2(pdgnew, migw);
+        if (lane == 0) { S.dc[0] = pdgnew; S.dc[1] = migw; }
+      } else if (i == NI + ND + 1) {                              // the four counts (each at most NL or CAP per locus)
+        long long a01 = 0, a23 = 0;
+        for (int li = lane; li < nloci; li += IMA_WARP) {
+          const int *o = staged ? s_cnt + li * 4 : U.t_counts + (size_t)(c * nloci + li) * 4;
+          a01 += (long long)o[0] | ((long long)o[1] << 32);
+          a23 += (long long)o[2] | ((long long)o[3] << 32);
+        }
+        a01 = (long long)Warp::sum((unsigned long long)a01); a23 = (long long)Warp::sum((unsigned long long)a23);
+        if (lane == 0) { S.ic[0] = (int)(a01 & 0xffffffffll); S.ic[1] = (int)(a01 >> 32); S.ic[2] = (int)(a23 & 0xffffffffll); S.ic[3] = (int)(a23 >> 32); }
+      } else {
+        uint32_t bad = 0;
+        for (int li = lane; li < nloci; li += IMA_WARP)
+          bad |= staged ? (uint32_t)s_fl[li] : (E.prop_flags[c * nloci + li] & (kFlagOverflow | kFlagRejectIS | kFlagBadTree));
+        const bool anyb = Warp::any(bad != 0);
+        if (lane == 0) S.ic[4] = anyb ? 1 : 0;
       }
     }
   }
   block_sync();
+  IMA_PT()
   // integrate_tree_prob (:410): a term whose (c, f) did not change evaluates to the value it had, so the reuse rule
   // of update_gtree_common.cpp:1997-2000 and a fresh evaluation agree.  One warp per term.
   IMA_FOR_WARPS(w, kTWarps) {
@@ -524,57 +608,34 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
     }
   }
   block_sync();
+  IMA_PT()
   if (ima_warp_in_block() != 0) return;              // the decision and the commit are one warp's work
   double probg = 0.0;
   for (int k = 0; k < nterms; k++) probg += S.q[k];
   if (!migration_allowed(M, S.ai)) probg = -kMyDblMax;
-  double pdgnew = 0.0, migw = 0.0;
-  int n_eu = 0, n_ed = 0, n_mu = 0, n_md = 0;
-  uint32_t bad = 0;
-  for (int li = lane; li < nloci; li += IMA_WARP) {
-    if (staged) {
-      pdgnew += s_pdg[li];
-      if (t.method == 1) migw += s_mw[li];
-      n_eu += s_cnt[li * 4]; n_ed += s_cnt[li * 4 + 1]; n_mu += s_cnt[li * 4 + 2]; n_md += s_cnt[li * 4 + 3];
-      bad |= (uint32_t)s_fl[li];
-    } else {
-      const int p = c * nloci + li;
-      pdgnew += E.buf[E.cur[p] ^ 1].sd[(size_t)p * 4 + 3];
-      if (t.method == 1) migw += E.prop_extra[p];
-      const int *o = U.t_counts + (size_t)p * 4;
-      n_eu += o[0]; n_ed += o[1]; n_mu += o[2]; n_md += o[3];
-      bad |= E.prop_flags[p] & (kFlagOverflow | kFlagRejectIS | kFlagBadTree);
-    }
-  }
-  pdgnew = Warp::sum(pdgnew);
-  migw = Warp::sum(migw);
-  n_eu = Warp::sum(n_eu); n_ed = Warp::sum(n_ed); n_mu = Warp::sum(n_mu); n_md = Warp::sum(n_md);
-  const bool anybad = Warp::any(bad != 0);
+  double pdgnew = S.dc[0];
+  const double migw = S.dc[1];
+  const int n_eu = S.ic[0], n_ed = S.ic[1], n_mu = S.ic[2], n_md = S.ic[3];
+  const bool anybad = S.ic[4] != 0;
   // every coalescent node was met on both of its daughter edges (:405-408)
   const int ecu = n_eu / 2, ecd = n_ed / 2;
-  const double t_u_hterm = (t.newt - t.t_u) / (t.oldt - t.t_u);
-  const double t_d_hterm = t.period == M.nsplit - 1 ? 1.0 : (t.t_d - t.newt) / (t.t_d - t.oldt);
-  const double beta = E.beta[c];
-  double tpw = M.gbeta * (pdgnew - E.pdgsum[c]), mh;
-  const double hast = (ecd + n_md) * log(t_d_hterm) + (ecu + n_mu) * log(t_u_hterm);
-  if (M.thermo) mh = beta * tpw + (probg - E.probg[c]) + hast;                    // :413-416
-  else { tpw += probg - E.probg[c]; mh = beta * tpw + hast; }                     // :419-421
-  Philox rng;
-  rng_for(rng, E, (uint32_t)(E.d.nchains_global + E.d.chain0 + c), kRngSplitTime);
-  const double uacc = rng.uniform();
+  double tpw = M.gbeta * (pdgnew - pdgsum_old), mh;
+  const double hast = (ecd + n_md) * log_d_h + (ecu + n_mu) * log_u_h;
+  if (M.thermo) mh = beta * tpw + (probg - probg_old) + hast;                    // :413-416
+  else { tpw += probg - probg_old; mh = beta * tpw + hast; }                     // :419-421
   bool accept;
   if (t.method == 1) {
     // changet_NW update_t_NW.cpp:993-1005: no likelihood term (branch lengths are unchanged), the migration events'
     // Hastings ratio instead; the decision is taken on the natural scale
-    const double dprobg = probg - E.probg[c];
+    const double dprobg = probg - probg_old;
     mh = exp((M.thermo ? dprobg : beta * dprobg) + migw);
-    pdgnew = E.pdgsum[c];
+    pdgnew = pdgsum_old;
     accept = !anybad && uacc < (mh < 1.0 ? mh : 1.0);
   } else {
-    accept = !anybad && log(uacc) < (mh < 1.0 ? mh : 1.0);                        // update_t_RY.cpp:424-425
+    accept = !anybad && log_uacc < (mh < 1.0 ? mh : 1.0);                        // update_t_RY.cpp:424-425
   }
   if (U.t_forced && U.t_force_accept >= 0) accept = !anybad && U.t_force_accept != 0;
-  if (E.xch.publisher == 2) publish_chain(E, c, accept ? (M.thermo ? pdgnew : pdgnew + probg) : E.swapsum[c]);
+  if (E.xch.publisher == 2) publish_chain(E, c, accept ? (M.thermo ? pdgnew : pdgnew + probg) : swapsum_old);
   if (accept) {
     for (int i = lane; i < NI; i += IMA_WARP) E.all_i[(size_t)c * NI + i] = S.ai[i];
     for (int i = lane; i < ND; i += IMA_WARP) E.all_d[(size_t)c * ND + i] = S.ad[i];
@@ -587,8 +648,16 @@ IMA_KERNEL void k_accept_t(EngineView E, UpdateView U) {
       E.swapsum[c] = M.thermo ? pdgnew : pdgnew + probg;
       E.tvals[(size_t)c * kMaxPeriods + t.period] = t.newt;
     }
-    for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; E.cur[p] ^= 1; }
+    // the flip: the other buffer's index is at hand for a staged chain (no read-modify-write of global memory)
+    if (staged) for (int li = lane; li < nloci; li += IMA_WARP) E.cur[c * nloci + li] = (unsigned char)s_ob[li];
+    else for (int li = lane; li < nloci; li += IMA_WARP) { const int p = c * nloci + li; E.cur[p] ^= 1; }
   }
+  IMA_PT()
+#if defined(IMA_PROF) && IMA_CUDA
+  if (lane == 0 && (c == 3 || c == 77) && (current_step(E) % 64) == 0)
+    printf("PROFT chain %d method %d early %lld load %lld sums %lld terms %lld decide+commit %lld\n", c, t.method, pq_[1] - pq_[0], pq_[2] - pq_[1],
+           pq_[3] - pq_[2], pq_[4] - pq_[3], pq_[5] - pq_[4]);
+#endif
   if (lane == 0) {
     double *o = U.t_out + (size_t)c * 4;
     o[0] = t.period; o[1] = t.newt; o[2] = mh; o[3] = accept ? 1.0 : 0.0;

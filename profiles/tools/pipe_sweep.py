@@ -30,7 +30,7 @@ def main():
     torch.cuda.synchronize()
     eng.run(burn, sw, stream)
     torch.cuda.synchronize()
-    nloci, _, _, cpg, _ = bench.WORKLOADS[wl]
+    nloci, _, _, cpg = bench.WORKLOADS[wl][:4]
     names = ["proposal", "k_accept", "k_swap", "k_split_t", "k_accept_t", "k_changeu", "k_move", "k_weigh", "k_propose_redo"]
     for s in settings:
         eng.set_pipeline(*s[:3])

@@ -50,3 +50,47 @@ def test_multi_gpu_records(name, n):
     per_step = d["config"]["chains_total"] * d["config"]["loci"]
     assert abs(d["value"] - per_step / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
     assert d["e2e"]["value"] > 0 and d["clocks"]["sm_mhz"]
+
+
+# ---- round 2 records (profiles/r2s*): real input by default, nine launches a step, the target configuration at N >= 2 ----------
+def test_round2_single_gpu_record():
+    d = _line("r2s5_bench_n1.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "models", "dropped_for_capacity"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["data"] == "real" and d["config"]["input"] == "real" and d["dtype"] == "f64" and d["warmup"] >= 3
+    assert "L2" in d["config"]["l2"] and d["dropped_for_capacity"] == 0
+    assert abs(d["value"] - 128 * 50 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    # k_move, k_weigh, k_propose_redo, k_accept, k_split_t_fast, k_split_t_redo, k_accept_t, k_changeu, k_swap
+    assert d["gpu_launches"] == d["steps"] * 9
+    e = d["e2e"]
+    assert e["statistic"].startswith("median") and len(e["repetitions_s"]) >= 3 and 0 < e["value"] < d["value"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["peak_kind"] in ("measured", "fallback") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms_per_launch"][r["kernel"]] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert set(r["per_kernel"]) >= {"k_move", "k_weigh", "k_accept", "k_split_t", "k_accept_t", "k_changeu", "k_swap"} and r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] > 0 and "real input" in c["sample"]
+    for m in ("hky", "stepwise", "joint_is_sw"):
+        assert d["models"][m]["value"] > 0 and d["models"][m]["dropped_for_capacity"] == 0
+    assert d["lmode"]["fp64_fma_per_sec_measured"] > 0 and d["lmode"]["fp64_exp_per_sec_measured"] > 0
+
+
+@pytest.mark.parametrize("name,n", [("r2s4_bench_n2.json", 2), ("r2s4_bench_n8.json", 8)])
+def test_round2_multi_gpu_records_carry_the_target_configuration(name, n):
+    d = _line(name)
+    assert d["n_gpus"] == n and d["scaling"] == "weak" and d["data"] == "real" and d["config"]["chains_total"] == 128 * n
+    assert abs(d["value"] - d["config"]["chains_total"] * d["config"]["loci"] / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    assert "peer memory" in d["multi_gpu_step"] and d["gpu_launches"] == d["steps"] * 9
+    c3 = d["config3"]
+    assert c3["config"]["loci"] == 300 and c3["config"]["chains_total"] == 256 * n and "larger than" in c3["config"]["l2"]
+    assert abs(c3["value"] - c3["config"]["chains_total"] * 300 / (c3["ms_per_step"] * 1e-3)) <= 1e-6 * c3["value"]
+    assert c3["cpu_baseline"]["kind"] == "reference" and "300 loci" in c3["cpu_baseline"]["sample"] and c3["dropped_for_capacity"] == 0
+    assert abs(c3["ratio_to_cpu_baseline"] - c3["value"] / c3["cpu_baseline"]["value"]) < 1e-9 * c3["ratio_to_cpu_baseline"]
+
+
+def test_round2_reference_arm_record():
+    d = _line("r2s3_bench_ref.json")
+    assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"] and "qupdate" in d["cpu_baseline"]["sample"]
