@@ -44,6 +44,7 @@ SIGNATURES = {
     "ima2p_engine_dims": (_i, [_v, c_int_p]),
     "ima2p_engine_run": (_i, [_v, _i, _i, _v]),
     "ima2p_engine_set_pipeline": (_i, [_v, _i, _i, _i]),
+    "ima2p_engine_launches_per_step": (_i, [_v, _i]),
     "ima2p_engine_set_proposal_path": (_i, [_v, _i, _i]),
     "ima2p_engine_set_debug_records": (_i, [_v, _i]),
     "ima2p_engine_grow_capacity": (_i, [_v, _i]),
@@ -85,6 +86,8 @@ SIGNATURES = {
     "ima2p_engine_put_state": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v, c_dbl_p, _v]),
     "ima2p_engine_state_block_layout": (_i, [_v, _ll, c_u64_p]),
     "ima2p_engine_put_state_block": (_i, [_v, _v, _ll, _v]),
+    "ima2p_engine_upload_block": (_i, [_v, _v, _ll, _v]),
+    "ima2p_engine_adopt_block": (_i, [_v, _v]),
     "ima2p_engine_put_state_packed": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v, c_dbl_p, _v]),
     "ima2p_engine_fetch_state": (_i, [_v, _v, _v, _v, _v, _v, _v, _v, _v]),
     "ima2p_engine_fetch_pair_summaries": (_i, [_v, c_dbl_p, c_int_p, c_int_p, _v]),

@@ -36,9 +36,24 @@ inline bool d2h(void *h, const void *d, size_t n, stream_t s) { return IMA_CUDA_
 inline bool dev_sync(stream_t s) { return IMA_CUDA_OK(cudaStreamSynchronize(s)); }
 IMA_DEV int ima_block() { return blockIdx.x; }
 IMA_DEV int ima_warp_in_block() { return threadIdx.x >> 5; }
-#define IMA_SMEM_DECL extern __shared__ __align__(16) unsigned char ima_dyn_smem[];
+// Every kernel opens with this line.  griddepcontrol.wait returns at once for a kernel launched the plain way; for one
+// launched with programmatic stream serialisation (the step graph, see launch_kernel) it is where the kernel waits for the
+// kernel before it on the stream to have finished and flushed its writes -- everything above it (block scheduling, parameter
+// loads) overlaps that kernel's tail.
+#define IMA_SMEM_DECL extern __shared__ __align__(16) unsigned char ima_dyn_smem[]; asm volatile("griddepcontrol.wait;" ::: "memory");
 #define IMA_SMEM ima_dyn_smem
-#define IMA_LAUNCH(kern, grid, warps, smem_bytes_, stream, ...) kern<<<(grid), (warps) * 32, (smem_bytes_), (stream)>>>(__VA_ARGS__)
+extern bool g_programmatic_launch;       // set by capture_steps around the launches of a step graph (ima_engine.cu)
+template <class K, class... A> inline void launch_kernel(K kern, int grid, int threads, size_t smem, cudaStream_t s, A... args) {
+  if (!g_programmatic_launch) { kern<<<grid, threads, smem, s>>>(args...); return; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#define IMA_LAUNCH(kern, grid, warps, smem_bytes_, stream, ...) ::ima::launch_kernel(kern, (int)(grid), (int)(warps) * 32, (size_t)(smem_bytes_), (stream), __VA_ARGS__)
 }  // namespace ima
 #else
 namespace ima {

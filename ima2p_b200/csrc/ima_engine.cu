@@ -27,6 +27,9 @@ thread_local EmuCtx g_emu;
 #if !IMA_CUDA
 static std::map<const void *, std::pair<std::string, size_t>> g_emu_tables;     // exchange tables of this process (host emulation)
 #endif
+#if IMA_CUDA
+bool g_programmatic_launch = false;
+#endif
 static thread_local std::string g_last_error;
 static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
 
@@ -62,9 +65,17 @@ struct Engine {
   int *d_err = nullptr;
   signed char *d_topo8 = nullptr;        // staging of the packed wire form (ima2p_engine_put_state_packed), made on first use
   unsigned char *d_mcount = nullptr;
-  unsigned char *d_block = nullptr;      // staging of the one-block wire form (ima2p_engine_put_state_block)
+  // staging of the one-block wire form (ima2p_engine_put_state_block / upload_block + adopt_block): two slots, so that the
+  // block of the next step can travel while the kernels of this one run
+  unsigned char *d_block[2] = {nullptr, nullptr};
+  long long block_events[2] = {0, 0};
+  int block_pending = 0, block_next_up = 0, block_next_adopt = 0;
   int *d_block_moff = nullptr;
   size_t block_cap = 0;
+#if IMA_CUDA
+  cudaEvent_t block_up_ev[2] = {nullptr, nullptr}, block_done_ev[2] = {nullptr, nullptr};
+  bool block_done_set[2] = {false, false};
+#endif
   DevLocus *d_loci = nullptr;
   double *d_beta_table = nullptr;
   double *d_prop_dbg = nullptr;
@@ -83,6 +94,9 @@ struct Engine {
   std::vector<cudaEvent_t> pipe_events;
 #endif
   int groups = 1, depth = 1, pipe_prio = 0;          // see capture_steps
+  // programmatic dependent launch inside the step graph: a kernel is scheduled while the one before it on its stream drains
+  // (measured 1.5 % of the step, same run; IMA2P_PDL=0 turns it off)
+  int pdl = getenv("IMA2P_PDL") ? atoi(getenv("IMA2P_PDL")) : 1;
   bool fast_ok = false, fast = false;                // the two-kernel proposal path (ima_fastpath.h): possible / in use
   int ppw = 0;                                       // pairs per warp of k_move (0: chosen from the number of pairs)
   int redo_grid = 16;
@@ -112,6 +126,7 @@ struct Engine {
     if (own_stream) cudaStreamDestroy(own_stream);
     for (auto &g : group_stream) for (auto &x : g) if (x) cudaStreamDestroy(x);
     for (auto &x : pipe_events) if (x) cudaEventDestroy(x);
+    for (int k = 0; k < 2; k++) { if (block_up_ev[k]) cudaEventDestroy(block_up_ev[k]); if (block_done_ev[k]) cudaEventDestroy(block_done_ev[k]); }
 #endif
     for (void *p : allocs) dev_free(p);
 #if !IMA_CUDA
@@ -231,9 +246,18 @@ static void launch_split_t(Engine *e, stream_t s, const EngineView &v) {
 static void launch_accept_t(Engine *e, stream_t s, const EngineView &v) {
   IMA_LAUNCH(k_accept_t, v.c_n, IMA_CUDA ? kTWarps : 1, accept_t_smem_bytes(e->d), s, v, e->uv);
 }
+// data whose likelihood is recomputed under a new scalar (HKY, stepwise, joint loci) and more than two scalars: the levelled walk
+static bool changeu_by_levels(const Engine *e) {
+  return (e->d.any_hky || e->d.any_sw) && e->uv.nurates > 2 && !e->uv.u_forced && !getenv("IMA2P_CHANGEU_IN_ORDER") &&
+         changeu_levels_smem_bytes(e->d, e->uv.nurates) <= 200 * 1024;
+}
 static void launch_changeu(Engine *e, stream_t s, const EngineView &v) {
   UpdateView u = e->uv;
   u.u_every = e->u_every;
+  if (changeu_by_levels(e)) {
+    IMA_LAUNCH(k_changeu_levels, v.c_n, IMA_CUDA ? kUWarps : 1, changeu_levels_smem_bytes(e->d, u.nurates), s, v, u);
+    return;
+  }
   IMA_LAUNCH(k_changeu, (v.c_n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock, changeu_smem(e) * kWarpsPerBlock, s, v, u);
 }
 static void launch_param_updates(Engine *e, stream_t s, const EngineView &v) {
@@ -283,6 +307,7 @@ static cudaEvent_t pipe_event(Engine &e, size_t &next) {
   return e.pipe_events[next++];
 }
 static bool capture_steps(Engine &e, int swaptries, int depth, cudaGraphExec_t *out, bool sharded = false) {
+  struct Pdl { Pdl(bool on) { g_programmatic_launch = on; } ~Pdl() { g_programmatic_launch = false; } } pdl_scope(e.pdl != 0);
   int G = e.groups < 1 ? 1 : e.groups;
   if (G > e.d.nchains) G = e.d.nchains;
   if (G > kMaxGroups) G = kMaxGroups;
@@ -515,9 +540,11 @@ static int size_for_capacity(Engine &e, int maxng) {
   d.FEV = (maxng - 1) + d.FC + e.model.nsplit;
   e.fast_ok = !d.any_sw && d.NL <= 4096 && move_smem_bytes_per_pair(d) * 4 * kMoveWarps <= 200 * 1024 && weigh_smem_bytes(d) * kWarpsPerBlock <= 200 * 1024 && split_smem_bytes(d) * kWarpsPerBlock <= 200 * 1024;
   e.fast = e.fast_ok && !getenv("IMA2P_GENERAL_PATH");
-  // measured on B200 (profiles/r2s1_pipeline_*.jsonl, r2s2_*): two chain groups and four steps per graph
-  e.groups = d.nchains >= 16 ? 2 : 1;
-  e.depth = 4;
+  // measured on B200 (profiles/r2s1_pipeline_*.jsonl, r2s2_*, r2s6_paths.jsonl): two chain groups and four steps per graph; four groups
+  // and two steps where the per-pair kernels run many waves (76,800 pairs: 2.065 against 2.109 ms a step)
+  const bool many_waves = (long long)d.nchains * d.nloci >= 20000 && d.nchains >= 64;
+  e.groups = many_waves ? 4 : (d.nchains >= 16 ? 2 : 1);
+  e.depth = many_waves ? 2 : 4;
   e.pair_smem = pair_smem_bytes(d);
   e.chain_smem = chain_smem_bytes(d);
   e.accept_smem = accept_smem_bytes(d);
@@ -535,6 +562,7 @@ static int size_for_capacity(Engine &e, int maxng) {
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_split_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e.pair_smem * kWarpsPerBlock))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)swap_smem_bytes(4000))) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_accept_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)accept_t_smem_bytes(d))) ||
+      !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) ||
       !IMA_CUDA_OK(cudaFuncSetAttribute(k_changeu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(changeu_smem(&e) * kWarpsPerBlock))))
     return fail(IMA2P_E_CUDA, "cudaFuncSetAttribute failed");
   if (e.fast_ok) {
@@ -735,7 +763,8 @@ int ima2p_engine_grow_capacity(ima2p_engine *h, int new_capacity) {
   std::vector<double> ht(P * newc, 0.0); std::vector<short> hp(P * newc, 0);
   for (size_t p = 0; p < P; p++) { memcpy(&ht[p * newc], &e.h_mig_t[p * oldc], oldc * 8); memcpy(&hp[p * newc], &e.h_mig_p[p * oldc], oldc * 2); }
   e.h_mig_t.swap(ht); e.h_mig_p.swap(hp);
-  e.block_cap = 0; e.d_block = nullptr;    // the one-block upload staging is re-made at the new size on its next use
+  // the one-block upload staging is re-made at the new size on its next use (a block uploaded for the old size is dropped)
+  e.block_cap = 0; e.d_block[0] = e.d_block[1] = nullptr; e.block_pending = 0; e.block_next_up = e.block_next_adopt = 0;
   e.graph_ready = false;
 #if IMA_CUDA
   if (e.graph_exec_sh) { cudaGraphExecDestroy(e.graph_exec_sh); e.graph_exec_sh = nullptr; }
@@ -1411,6 +1440,21 @@ int ima2p_engine_set_pipeline(ima2p_engine *h, int groups, int depth, int decisi
   return IMA2P_OK;
 }
 
+int ima2p_engine_launches_per_step(ima2p_engine *h, int swaptries) {
+  if (!h || !h->eng.finalized) return 0;
+  Engine &e = h->eng;
+  int G = e.groups < 1 ? 1 : e.groups;
+  if (G > e.d.nchains) G = e.d.nchains;
+#if !IMA_CUDA
+  G = 1;
+#endif
+  int per_group = (e.fast ? 3 : 1) + 1;                                    // proposals, accept sweep
+  if (does_split_t(&e)) per_group += (e.fast ? 2 : 1) + 1;                 // split-time proposals, their decision
+  if (does_changeu(&e)) per_group += 1;
+  (void)swaptries;
+  return G * per_group + 1;                                                // k_swap is launched every step: it also advances the step counter
+}
+
 // which proposal path ima2p_engine_run uses: fast != 0 the two kernels of ima_fastpath.h (with pairs_per_warp lanes of a
 // k_move warp at work: 4, 8, 16, 32, or 0 = chosen from the number of pairs), fast == 0 the general one-warp-per-pair kernel
 // for every pair.  The chain does not depend on it.
@@ -1805,25 +1849,71 @@ int ima2p_engine_state_block_layout(ima2p_engine *h, long long total_events, uin
   return IMA2P_OK;
 }
 
-int ima2p_engine_put_state_block(ima2p_engine *h, const void *block, long long total_events, void *cuda_stream) {
-  if (!h || !h->eng.finalized || !block || total_events < 0) return fail(IMA2P_E_ARG, "put_state_block: bad argument");
+// The one-block upload in two halves, so that a caller that steps a stream of uploaded states can keep the copy engine and the SMs
+// busy at the same time: upload_block starts the transfer of a block into one of two staging slots on `copy_stream` and returns;
+// adopt_block makes `cuda_stream` wait for the oldest transfer, widens the block into the resident state and re-evaluates it.
+int ima2p_engine_upload_block(ima2p_engine *h, const void *block, long long total_events, void *copy_stream) {
+  if (!h || !h->eng.finalized || !block || total_events < 0) return fail(IMA2P_E_ARG, "upload_block: bad argument");
   Engine &e = h->eng;
-  if (e.d.NL > 127 || e.d.CAP > 255 || e.model.ntreepops > 127) return fail(IMA2P_E_ARG, "put_state_block: the sample does not fit the 8-bit wire form; use ima2p_engine_put_state");
-  if (total_events > (long long)e.d.P * e.d.CAP) return fail(IMA2P_E_CAPACITY, "put_state_block: more migration events than mig_capacity");
+  if (e.d.NL > 127 || e.d.CAP > 255 || e.model.ntreepops > 127) return fail(IMA2P_E_ARG, "upload_block: the sample does not fit the 8-bit wire form; use ima2p_engine_put_state");
+  if (total_events > (long long)e.d.P * e.d.CAP) return fail(IMA2P_E_CAPACITY, "upload_block: more migration events than mig_capacity");
+  if (e.block_pending >= 2) return fail(IMA2P_E_ARG, "upload_block: both staging slots hold a block that has not been adopted");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, copy_stream);
+  const StateBlock L = state_block_layout(e.d, e.model.nsplit, total_events);
+  if (L.total > e.block_cap || !e.d_block[0] || !e.d_block[1]) {
+    if (e.block_pending) return fail(IMA2P_E_ARG, "upload_block: staging must grow while a block is pending");
+    const size_t cap = state_block_layout(e.d, e.model.nsplit, (long long)e.d.P * e.d.CAP).total;
+    e.d_block[0] = e.alloc<unsigned char>(cap);
+    e.d_block[1] = e.alloc<unsigned char>(cap);
+    if (!e.d_block_moff) e.d_block_moff = e.alloc<int>(e.d.P);
+    e.block_cap = (e.d_block[0] && e.d_block[1]) ? cap : 0;
+  }
+  if (!e.d_block[0] || !e.d_block[1] || !e.d_block_moff) return fail(IMA2P_E_CUDA, "device allocation failed");
+  const int k = e.block_next_up;
+#if IMA_CUDA
+  if (!e.block_up_ev[k]) {
+    cudaEventCreateWithFlags(&e.block_up_ev[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e.block_done_ev[k], cudaEventDisableTiming);
+  }
+  if (e.block_done_set[k]) cudaStreamWaitEvent(s, e.block_done_ev[k], 0);       // the slot's previous block has been widened
+#endif
+  if (!h2d(e.d_block[k], block, L.total, s)) return fail(IMA2P_E_CUDA, "upload_block failed");
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaEventRecord(e.block_up_ev[k], s))) return fail(IMA2P_E_CUDA, "upload_block failed");
+#endif
+  e.block_events[k] = total_events;
+  e.block_next_up = k ^ 1;
+  e.block_pending++;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_adopt_block(ima2p_engine *h, void *cuda_stream) {
+  if (!h || !h->eng.finalized) return fail(IMA2P_E_ARG, "adopt_block: not finalized");
+  Engine &e = h->eng;
+  if (e.block_pending < 1) return fail(IMA2P_E_ARG, "adopt_block: no uploaded block is waiting");
   if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = pick_stream(&e, cuda_stream);
-  const StateBlock L = state_block_layout(e.d, e.model.nsplit, total_events);
-  if (L.total > e.block_cap) {
-    const size_t cap = state_block_layout(e.d, e.model.nsplit, (long long)e.d.P * e.d.CAP).total;
-    e.d_block = e.alloc<unsigned char>(cap);
-    if (!e.d_block_moff) e.d_block_moff = e.alloc<int>(e.d.P);
-    e.block_cap = e.d_block ? cap : 0;
-  }
-  if (!e.d_block || !e.d_block_moff) return fail(IMA2P_E_CUDA, "device allocation failed");
-  if (!h2d(e.d_block, block, L.total, s)) return fail(IMA2P_E_CUDA, "put_state_block failed");
-  IMA_LAUNCH(k_block_offsets, 1, kWarpsPerBlock, kWarpsPerBlock * sizeof(int), s, e.v, e.d_block, L, e.d_block_moff);
-  IMA_LAUNCH(k_unpack_block, (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock, 0, s, e.v, e.d_block, L, e.d_block_moff, e.model.nsplit);
+  const int k = e.block_next_adopt;
+  const StateBlock L = state_block_layout(e.d, e.model.nsplit, e.block_events[k]);
+#if IMA_CUDA
+  cudaStreamWaitEvent(s, e.block_up_ev[k], 0);
+#endif
+  IMA_LAUNCH(k_block_offsets, 1, kWarpsPerBlock, kWarpsPerBlock * sizeof(int), s, e.v, e.d_block[k], L, e.d_block_moff);
+  IMA_LAUNCH(k_unpack_block, (e.d.P + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock, 0, s, e.v, e.d_block[k], L, e.d_block_moff, e.model.nsplit);
+#if IMA_CUDA
+  cudaEventRecord(e.block_done_ev[k], s);
+  e.block_done_set[k] = true;
+#endif
+  e.block_next_adopt = k ^ 1;
+  e.block_pending--;
   return launch_eval(&e, s);
+}
+
+int ima2p_engine_put_state_block(ima2p_engine *h, const void *block, long long total_events, void *cuda_stream) {
+  if (h && h->eng.block_pending) return fail(IMA2P_E_ARG, "put_state_block: an uploaded block is waiting to be adopted");
+  const int rc = ima2p_engine_upload_block(h, block, total_events, cuda_stream);
+  return rc != IMA2P_OK ? rc : ima2p_engine_adopt_block(h, cuda_stream);
 }
 
 // gathers the CURRENT buffer of every pair (pairs flip independently) into host memory

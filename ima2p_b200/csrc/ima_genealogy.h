@@ -758,57 +758,38 @@ IMA_DEV double bits_dbl(long long v) {
 IMA_DEV int pack_event(int kind, int pop, int topop, int node) { return kind | (pop << 2) | (topop << 7) | (node << 12); }
 
 #if IMA_CUDA
-// Sorts the nev <= 128 events (time bits, info) of the scratch table by (time, info) into (evt, evi): see eval_weights.
-// A bitonic network over registers: element q * 32 + lane sits in register q of the lane; partners closer than 32 are
-// exchanged by shuffles, the others are registers of the same lane.  The stages are a ROLLED loop and only the stages the table
-// needs are run (np2 = the power of two that holds nev): unrolled per table size the network was half of the code of every
-// kernel that weighs a genealogy, and those kernels run their code once per warp -- instruction fetch led their stall reasons.
-IMA_DEV void warp_sort_events(const double *bt, const int *bi, int nev, double *evt, int *evi) {
-  constexpr int E = kRankSortMax / 32;
-  static_assert(E == 4, "the in-lane stages below are written for four registers per lane");
+// Sorts the nev <= 32 NQ events (time bits, info) of the scratch table by (time, info) into (evt, evi): see eval_weights.
+// By counting: element q * 32 + lane sits in register q of the lane; every lane reads every event of the table (a broadcast
+// read of shared memory: the reads do not depend on each other, so they pipeline) and counts the events that sort before its
+// own.  A bitonic network over the same registers takes 15 to 28 DEPENDENT stages of shuffles and measured six times this;
+// unrolled it was also half of the code of every kernel that weighs a genealogy.
+template <int NQ> IMA_DEV void warp_sort_events(const double *bt, const int *bi, int nev, double *evt, int *evi) {
   const int lane = Warp::lane();
-  int np2 = 32;
-  while (np2 < nev) np2 <<= 1;
-  const int nq = np2 >> 5;                                   // registers in use: 1, 2 or 4
-  long long key[E];
-  int val[E];
+  const long long *kb = (const long long *)bt;             // times are not negative: their bit patterns order like the times
+  long long key[NQ];
+  int val[NQ], rank[NQ];
 #pragma unroll
-  for (int q = 0; q < E; q++) {
+  for (int q = 0; q < NQ; q++) {
     const int g = q * 32 + lane;
-    key[q] = g < nev ? __double_as_longlong(bt[g]) : 0x7fffffffffffffffll;
+    key[q] = g < nev ? kb[g] : 0x7fffffffffffffffll;
     val[q] = g < nev ? bi[g] : 0x7fffffff;
+    rank[q] = 0;
   }
-  // registers q < r of one lane: the lower index of an ascending pair keeps the smaller element
-  auto in_lane = [&](int q, int r, int k) {
-    const bool asc = (((q * 32 + lane) & k) == 0);
-    const bool gt = key[q] > key[r] || (key[q] == key[r] && val[q] > val[r]);
-    if (gt == asc) { const long long tk = key[q]; key[q] = key[r]; key[r] = tk; const int tv = val[q]; val[q] = val[r]; val[r] = tv; }
-  };
-#pragma unroll 1
-  for (int k = 2; k <= np2; k <<= 1) {
-#pragma unroll 1
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j == 64) { in_lane(0, 2, k); in_lane(1, 3, k); }                  // only a 128-element table gets here
-      else if (j == 32) { in_lane(0, 1, k); if (nq > 2) in_lane(2, 3, k); }
-      else {
+#pragma unroll 4
+  for (int s = 0; s < nev; s++) {
+    const long long ok = kb[s];
+    const int ov = bi[s];
 #pragma unroll
-        for (int q = 0; q < E; q++) {
-          if (q < nq) {                                                     // warp-uniform
-            const long long ok = __shfl_xor_sync(0xffffffffu, key[q], j);
-            const int ov = __shfl_xor_sync(0xffffffffu, val[q], j);
-            const int g = q * 32 + lane;
-            const bool asc = ((g & k) == 0), lower = ((lane & j) == 0);
-            const bool mine_gt = key[q] > ok || (key[q] == ok && val[q] > ov);
-            if (mine_gt == (lower == asc)) { key[q] = ok; val[q] = ov; }
-          }
-        }
-      }
+    for (int q = 0; q < NQ; q++) {
+      const int g = q * 32 + lane;
+      // no short-circuit: the lanes disagree on every one of these, a branch each would serialise them
+      rank[q] += (int)((ok < key[q]) | ((ok == key[q]) & ((ov < val[q]) | ((ov == val[q]) & (s < g)))));
     }
   }
 #pragma unroll
-  for (int q = 0; q < E; q++) {
+  for (int q = 0; q < NQ; q++) {
     const int g = q * 32 + lane;
-    if (g < nev) { evt[g] = __longlong_as_double(key[q]); evi[g] = val[q]; }
+    if (g < nev) { evt[rank[q]] = __longlong_as_double(key[q]); evi[rank[q]] = val[q]; }
   }
 }
 #endif
@@ -859,7 +840,9 @@ IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus
     Warp::sync();
     // times are not negative, so their bit patterns order like the times: integer compares (the FP64 pipe is narrow)
 #if IMA_CUDA
-    warp_sort_events(bt, bi, nev, S.evt, S.evi);
+    if (nev <= 32) warp_sort_events<1>(bt, bi, nev, S.evt, S.evi);
+    else if (nev <= 64) warp_sort_events<2>(bt, bi, nev, S.evt, S.evi);
+    else warp_sort_events<4>(bt, bi, nev, S.evt, S.evi);
 #else
     for (int j0 = lane; j0 < nev; j0 += 2 * IMA_WARP) {            // two events of the lane share every read of the table
       const int j1 = j0 + IMA_WARP;
@@ -1166,7 +1149,9 @@ IMA_DEV double hky_pijt(const double *pi, double mutrate, double t, double kappa
 enum { kHkyInit = 0, kHkyFull = 1, kHkyPartial = 2 };
 struct HkyCall { int mode, freed, olddd; const uint32_t *mask_cur; uint32_t *mask_new; };
 
-IMA_DEV double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S, int p, double u, double kappa, const double *pi, const HkyCall &hk) {
+// (out of line, like likelihood_sw: a kernel's code is fetched once per warp, and the warps of an infinite-sites run should not
+// have to step over the pruning and the Bessel functions)
+IMA_DEV_NOINLINE double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S, int p, double u, double kappa, const double *pi, const HkyCall &hk) {
   const int lane = Warp::lane();
   const int ng = L.ng, nl = L.nl, ns = L.nsites, nev = S.ctl_i[kCiNev], root = S.ctl_i[kCiRoot];
   const size_t hs = (size_t)E.d.hky_sites;
@@ -1305,7 +1290,7 @@ IMA_DEV double sw_update_alleles(const DevLocus &L, const PairSm &S, int ai, Phi
 }
 
 // stepwise: calc_prob_data.cpp:841-909 (full evaluation of one linked portion); A/dlikeA in global memory
-IMA_DEV double likelihood_sw(const DevLocus &L, const PairSm &S, const short *A, double *dlikeA, double u) {
+IMA_DEV_NOINLINE double likelihood_sw(const DevLocus &L, const PairSm &S, const short *A, double *dlikeA, double u) {
   const int lane = Warp::lane();
   double like = 0.0;
   bool zero = false;

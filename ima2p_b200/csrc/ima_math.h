@@ -309,6 +309,27 @@ IMA_DEV double gamma_cf_coop(const MathCtx &mc, double a, double x) {
   return h0;
 }
 
+// The same continued fraction by its convergents A_i / B_i (A_i = b_i A_{i-1} + an_i A_{i-2}, the same for B): Lentz's
+// c_i = A_i / A_{i-1}, d_i = B_{i-1} / B_i and h_i = A_i / B_i, so the walk needs no division until it stops, and the stopping
+// rule |c d - 1| < EPS is |A_i B_{i-1} - A_{i-1} B_i| < EPS |A_{i-1} B_i|.  Where the integrated prior calls it (x well above a:
+// the all-locus sums) the fraction stops after 3 to 6 terms, which one lane's dependent chain reaches sooner than a 32-wide
+// matrix scan does; a call that is still running after kCfSeq terms is handed to the scan, one where the reference's FPMIN
+// clamps could matter to the reference's own walk.
+constexpr int kCfSeq = 40;
+IMA_DEV double gamma_cf_fast(const MathCtx &mc, double a, double x) {
+  double Am = kFpMin, A = 1.0, Bm = 1.0, B = x + 1.0 - a, b = B;      // c_0 = 1 / FPMIN, d_0 = h_0 = 1 / b_0
+  for (int i = 1; i <= kCfSeq; i++) {
+    const double an = -i * (i - a);
+    b += 2.0;
+    const double An = b * A + an * Am, Bn = b * B + an * Bm;
+    if (fabs(Bn) < kFpMin * fabs(B) || fabs(An) < kFpMin * fabs(A) || !(fabs(An) < 1e250) || !(fabs(Bn) < 1e250)) return gamma_cf(mc, a, x);
+    const double num = An * B, den = A * Bn;
+    Am = A; A = An; Bm = B; B = Bn;
+    if (fabs(num - den) < kEps * fabs(den)) return A / B;
+  }
+  return gamma_cf_coop(mc, a, x);
+}
+
 IMA_DEV double uppergamma_coop(const MathCtx &mc, int a, double x) {
   double p;
   if (x < 0.0 || a < 0) { raise(mc, kErrGamma); return 0.0; }
@@ -321,7 +342,7 @@ IMA_DEV double uppergamma_coop(const MathCtx &mc, int a, double x) {
       const double gamser = (x <= 0.0) ? 0.0 : s * exp(-x + a * log(x) - gln);
       p = gln + log(1.0 - gamser);
     } else {
-      const double h = gamma_cf_coop(mc, (double)a, x);
+      const double h = gamma_cf_fast(mc, (double)a, x);
       p = gln + ((-x + a * log(x) - gln) + log(h));
     }
   }
@@ -338,7 +359,7 @@ IMA_DEV double lowergamma_coop(const MathCtx &mc, int a, double x) {
     const double gamserlog = (x <= 0.0) ? 0.0 : log(s) + (-x + a * log(x) - gln);
     p = gln + gamserlog;
   } else {
-    const double h = gamma_cf_coop(mc, (double)a, x);
+    const double h = gamma_cf_fast(mc, (double)a, x);
     const double gammcf = exp(-x + a * log(x) - gln) * h;
     p = gln + log(1 - gammcf);
   }
@@ -355,7 +376,7 @@ IMA_DEV GammaCore gamma_core_coop(const MathCtx &mc, int a, double x) {      // 
   GammaCore g;
   g.gln = lfact(mc, a - 1);
   g.series = x < a + 1.0;
-  g.v = g.series ? gamma_series_coop(mc, a, x) : gamma_cf_coop(mc, (double)a, x);
+  g.v = g.series ? gamma_series_coop(mc, a, x) : gamma_cf_fast(mc, (double)a, x);
   g.t = -x + a * log(x) - g.gln;
   return g;
 }
@@ -421,19 +442,22 @@ IMA_DEV void exp2_coop(double a, double b, double &ea, double &eb) {
 IMA_DEV double gamma_with_fallback_coop(const MathCtx &mc, int a, double x, bool want_upper, double tol, double extra, double &lextra) {
   const double gln = lfact(mc, a - 1);
   const bool series = x < a + 1.0;
-  const double v = series ? gamma_series_coop(mc, a, x) : gamma_cf_coop(mc, (double)a, x);
+  const double v = series ? gamma_series_coop(mc, a, x) : gamma_cf_fast(mc, (double)a, x);
   double lx, lv;
   log3_coop(x, v, extra, lx, lv, lextra);
   const double t = -x + a * lx - gln;
   double direct = gln + (lv + t);                         // lower (series) / upper (continued fraction)
   if (direct < -1e200) direct = -1e200;
   const double fullg = gln;
+  const bool primary_is_indirect = (want_upper == series);
+  // the wanted function is the direct one and it is neither indistinguishable from the complete gamma nor out of range (the
+  // upper function of a coalescent term with x above a, the usual case of the all-locus sums): no exponential is needed at all
+  if (!primary_is_indirect && !(fullg - direct < 1e-15 || fullg - direct > kLogDblMax)) return direct;
   double e1, e2, l1, l2;
   exp2_coop(t, fullg - direct, e1, e2);
   log2_coop(1.0 - v * e1, e2 - 1.0, l1, l2);
   double indirect = gln + l1;                             // upper (series) / lower (continued fraction)
   if (indirect < -1e200) indirect = -1e200;
-  const bool primary_is_indirect = (want_upper == series);
   double p = primary_is_indirect ? indirect : direct;
   if (fullg - p < 1e-15 || fullg - p > kLogDblMax) {
     const double other = primary_is_indirect ? direct : indirect;

@@ -22,7 +22,7 @@
 #define IMA_CUDA 0
 #define IMA_HD inline
 #define IMA_DEV inline
-#define IMA_DEV_NOINLINE
+#define IMA_DEV_NOINLINE inline
 #define IMA_WARP 1
 #endif
 

@@ -271,8 +271,17 @@ IMA_DEV double nw_update_pair(const EngineView &E, const DevModel &M, const doub
       for (int j = 0; j < numheld; j++) { S.pt[at + above + mnew + j] = S.pt[s0 + below + j]; S.pp[at + above + mnew + j] = S.pp[s0 + below + j]; }
       S.ms[ei] = (unsigned short)at; S.mcn[ei] = (unsigned short)total;
     }
-    if (mrate > 0) denom += logpf + nw_getmprob(M, period_a, mrate, mtime, mnew, upa, da, cm2_a, npopsa);
-    if (mrate_r > 0) num += logpf_r + nw_getmprob(M, period_b, mrate_r, mtime, mcount, upb, db, cm2_b, npopsb);
+    // forward then reverse, one copy of getmprob_NW's code (a rolled loop of two)
+#if IMA_CUDA
+#pragma unroll 1
+#endif
+    for (int h = 0; h < 2; h++) {
+      const double mr = h ? mrate_r : mrate;
+      if (mr > 0) {
+        const double v = (h ? logpf_r : logpf) + nw_getmprob(M, h ? period_b : period_a, mr, mtime, h ? mcount : mnew, h ? upb : upa, h ? db : da, h ? cm2_b : cm2_a, h ? npopsb : npopsa);
+        if (h) num += v; else denom += v;
+      }
+    }
   }
   if (Warp::any(overflow) && lane == 0) S.ctl_i[kCiFlags] |= (int)kFlagOverflow;
   return Warp::sum(num - denom);
@@ -915,6 +924,166 @@ IMA_DEV void changeu_chain(const EngineView &E, const UpdateView &U, int c, Pair
         stat_add(U.stats + kColdUStat + 2 * (size_t)j, 1ull);
         stat_add(U.stats + kColdUStat + 2 * (size_t)k, 1ull);
         if (accept) { stat_add(U.stats + kColdUStat + 2 * (size_t)j + 1, 1ull); stat_add(U.stats + kColdUStat + 2 * (size_t)k + 1, 1ull); }
+      }
+    }
+  }
+}
+
+
+// ---- the mutation-scalar walk for data whose likelihood must be recomputed (HKY, stepwise, joint loci) ------------------------
+// changeu (update_mc_params.cpp:23-431) walks the scalars in order; a proposal trades scalar j against a partner k and needs
+// the likelihood of their two loci under the new scalars -- a whole pruning for an HKY locus.  One warp per chain took a
+// millisecond per launch on 50 HKY loci.  Two proposals can only influence each other through a locus they share, so the
+// proposals are LEVELLED (level = 1 + the latest earlier proposal touching either of its loci, as k_swap levels its attempts)
+// and one level is evaluated by the warps of a block in parallel -- every proposal with its own draws (one stream per chain
+// and scalar), the accepted likelihood changes added to the chain's sum in proposal order at the end: the chain is the one
+// the walk in order would visit with those draws.
+constexpr int kUWarps = 8;
+IMA_HD size_t changeu_levels_smem_bytes(const EngineDims &d, int nur) {
+  return pair_smem_bytes(d) * kUWarps + (size_t)nur * (5 * sizeof(double) + 2 * sizeof(int)) + align8(sizeof(int) * (size_t)d.nloci) + 64;
+}
+IMA_KERNEL void k_changeu_levels(EngineView E, UpdateView U) {
+  IMA_SMEM_DECL
+  if (ima_block() >= E.c_n) return;
+  const int c = E.c_lo + ima_block();
+  const DevModel &M = IMA_MODEL;
+  const int lane = Warp::lane(), nloci = E.d.nloci, nur = U.nurates;
+  if (((current_step(E) + 1) % (unsigned long long)U.u_every) == 0) {         // every UUPDATEINC+1 steps
+    unsigned char *sp = IMA_SMEM + pair_smem_bytes(E.d) * kUWarps;
+    double *s_u = (double *)sp; sp += sizeof(double) * nur;                   // the step draw
+    double *s_k0 = (double *)sp; sp += sizeof(double) * nur;                  // kappa draws of the two loci
+    double *s_k1 = (double *)sp; sp += sizeof(double) * nur;
+    double *s_acc = (double *)sp; sp += sizeof(double) * nur;                 // the accept draw
+    double *s_delta = (double *)sp; sp += sizeof(double) * nur;               // accepted change of the likelihood sum
+    int *s_k = (int *)sp; sp += sizeof(int) * nur;                            // partner
+    int *s_lv = (int *)sp; sp += sizeof(int) * nur;                           // level
+    int *s_last = (int *)sp; sp += align8(sizeof(int) * nloci);               // per locus: level of the latest proposal touching it
+    int *s_ctl = (int *)sp;                                                   // [0] number of levels
+    const double beta = E.beta[c];
+    IMA_FOR_WARPS(w, kUWarps) {
+      const int tid = w * IMA_WARP + lane, nth = kUWarps * IMA_WARP;
+      for (int j = tid; j < nur; j += nth) {
+        Philox r2;
+        const unsigned long long step = current_step(E);
+        r2.init(E.seed, (uint32_t)((E.d.chain0 + c) * nur + j), (uint32_t)step, kRngScalars | ((uint32_t)(step >> 32) << 8));
+        int k;
+        do { k = (int)(r2.uniform() * nur); } while (k == j || k < 0 || k >= nur);          // :78-90
+        s_k[j] = k;
+        s_u[j] = r2.uniform(); s_k0[j] = r2.uniform(); s_k1[j] = r2.uniform(); s_acc[j] = r2.uniform();
+        s_delta[j] = 0.0;
+      }
+      for (int l = tid; l < nloci; l += nth) s_last[l] = 0;
+    }
+    block_sync();
+    IMA_FOR_WARPS(w, kUWarps) {
+      if (w == 0 && lane == 0) {
+        int top = 0;
+        for (int j = 0; j < nur; j++) {
+          const int lj = U.ul_l[j], lk = U.ul_l[s_k[j]];
+          const int lv = 1 + (s_last[lj] > s_last[lk] ? s_last[lj] : s_last[lk]);
+          s_lv[j] = lv; s_last[lj] = lv; s_last[lk] = lv;
+          if (lv > top) top = lv;
+        }
+        s_ctl[0] = top;
+      }
+    }
+    block_sync();
+    const int nlevels = s_ctl[0];
+    for (int lv = 1; lv <= nlevels; lv++) {
+      IMA_FOR_WARPS(w, kUWarps) {
+        PairSm S = carve_pair_smem(IMA_SMEM + (size_t)w * pair_smem_bytes(E.d), E.d);
+        for (int j = 0, n = 0; j < nur; j++) {
+          if (s_lv[j] != lv) continue;
+          if ((n++ % kUWarps) != w) continue;
+          const int k = s_k[j];
+          const int lj = U.ul_l[j], aj = U.ul_a[j], lk = U.ul_l[k], ak = U.ul_a[k];
+          const int pj = c * nloci + lj, pk = c * nloci + lk;
+          const double olduj = E.uvals[(size_t)pj * kMaxLinked + aj], olduk = E.uvals[(size_t)pk * kMaxLinked + ak];
+          // :201-212: uniform step on the log ratio, reflected at +-maxratio; the two scalars move in opposite directions
+          const double r = log(olduj / olduk), u = s_u[j];
+          double newr = u > 0.5 ? r + (2.0 * u - 1.0) * U.u_win : r - U.u_win * u * 2.0;
+          if (newr > U.u_maxratio) newr = 2.0 * U.u_maxratio - newr;
+          else if (newr < -U.u_maxratio) newr = 2.0 * (-U.u_maxratio) - newr;
+          const double logd = (newr - r) / 2, d = exp(logd);
+          const double newuj = olduj * d, newuk = olduk / d;
+          double newpdg[2], newkappa[2] = {0.0, 0.0}, likenewsum = 0.0;
+          bool bad = false;
+          for (int i = 0; i < 2; i++) {
+            const int li = i ? lk : lj, ai = i ? ak : aj, p = i ? pk : pj;
+            const PairBuf &B = E.buf[E.cur[p]];
+            if (E.loci[li].model == kHKY) newkappa[i] = reflect_kappa(i ? s_k1[j] : s_k0[j], E.kappa[p], U.kappa_win, U.kappa_max);
+            newpdg[i] = scalar_likelihood(E, M, c, li, ai, i ? newuk : newuj, i ? -logd : logd, newkappa[i], S, B, E.buf[E.cur[p] ^ 1]);
+            if (newpdg[i] == kRejectIS || !(newpdg[i] > -DBL_MAX)) bad = true;
+            likenewsum += newpdg[i] - part_pdg(E.loci[li], B, p, ai);
+            Warp::sync();
+          }
+          const double mh = exp(beta * M.gbeta * likenewsum);                               // :291
+          const bool accept = !bad && s_acc[j] < (mh < 1.0 ? mh : 1.0);                     // :294
+          if (accept) {
+            for (int i = 0; i < 2; i++) {
+              const int li = i ? lk : lj, ai = i ? ak : aj, p = i ? pk : pj;
+              const DevLocus &L = E.loci[li];
+              const PairBuf &B = E.buf[E.cur[p]], &Bo = E.buf[E.cur[p] ^ 1];
+              if (has_stepwise(L.model) && ai >= sw_first(L.model)) {
+                const size_t ao = ((size_t)p * kMaxLinked + ai) * E.d.NL;
+                for (int e = lane; e < L.nl; e += IMA_WARP) B.dlikeA[ao + e] = Bo.dlikeA[ao + e];
+              }
+              if (lane == 0) {
+                E.uvals[(size_t)p * kMaxLinked + ai] = i ? newuk : newuj;
+                set_part_pdg(L, B, p, ai, newpdg[i]);
+                if (L.model == kHKY) {
+                  E.kappa[p] = newkappa[i];
+                  for (int x = 0; x < E.d.hky_mask_words; x++) B.hky_mask[(size_t)p * E.d.hky_mask_words + x] = Bo.hky_mask[(size_t)p * E.d.hky_mask_words + x];
+                }
+              }
+            }
+            if (lane == 0) s_delta[j] = likenewsum;
+          }
+#if IMA_CUDA
+          __threadfence_block();
+#endif
+          Warp::sync();
+          if (lane == 0) {
+            if (j == nur - 1) {
+              double *o = U.u_out + (size_t)c * 4;
+              o[0] = newpdg[0]; o[1] = newpdg[1]; o[2] = mh; o[3] = accept ? 1.0 : 0.0;
+            }
+#if IMA_CUDA
+            atomicAdd(U.stats + 2, 1ull);
+            if (accept) atomicAdd(U.stats + 3, 1ull);
+#else
+            U.stats[2] += 1; if (accept) U.stats[3] += 1;
+#endif
+            if (beta == 1.0) {                                 // counted for the scalar and for its partner (ima_main_mpi.cpp:1926-1935)
+              stat_add(U.stats + kColdUStat + 2 * (size_t)j, 1ull);
+              stat_add(U.stats + kColdUStat + 2 * (size_t)k, 1ull);
+              if (accept) { stat_add(U.stats + kColdUStat + 2 * (size_t)j + 1, 1ull); stat_add(U.stats + kColdUStat + 2 * (size_t)k + 1, 1ull); }
+            }
+          }
+        }
+      }
+#if IMA_CUDA
+      __threadfence();                                       // a level reads what the level before it wrote to global memory
+#endif
+      block_sync();
+    }
+    IMA_FOR_WARPS(w, kUWarps) {
+      if (w == 0 && lane == 0) {
+        double pd = E.pdgsum[c], ss = E.swapsum[c];
+        for (int j = 0; j < nur; j++) if (s_delta[j] != 0.0) { pd += s_delta[j]; ss += s_delta[j]; }
+        E.pdgsum[c] = pd; E.swapsum[c] = ss;
+      }
+    }
+    block_sync();
+  }
+  if (E.xch.publisher == 3) {                          // the chain's step ends here, whether or not it was the scalars' turn
+    IMA_FOR_WARPS(w, kUWarps) {
+      if (w == 0) {
+#if IMA_CUDA
+        __threadfence_block();
+        __syncwarp();
+#endif
+        publish_chain(E, c, *(volatile double *)(E.swapsum + c));
       }
     }
   }

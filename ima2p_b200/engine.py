@@ -202,6 +202,12 @@ class Engine:
         """Chain groups on their own streams and steps per CUDA graph of `run` (the chains a run visits do not depend on it)."""
         self._ck(self.lib.ima2p_engine_set_pipeline(self._h, groups, depth, 1 if decisions_first else 0))
 
+    def launches_per_step(self, swaptries=None):
+        """Kernel launches one step of `run` makes with the current settings."""
+        if swaptries is None:
+            swaptries = self.default_swaptries()
+        return int(self.lib.ima2p_engine_launches_per_step(self._h, swaptries))
+
     # ---- chains sharded over GPUs: swap sums exchanged through peer memory by the kernels themselves ------------------
     def exchange_create(self):
         """This rank's exchange table: (device pointer, bytes)."""
@@ -445,6 +451,15 @@ class Engine:
     def put_state_block(self, block, events, stream=None):
         ptr = block if isinstance(block, int) else block.ctypes.data
         self._ck(self.lib.ima2p_engine_put_state_block(self._h, ptr, events, stream))
+
+    def upload_block(self, block, events, copy_stream=None):
+        """First half of put_state_block: the transfer only, into one of two staging slots (on copy_stream)."""
+        ptr = block if isinstance(block, int) else block.ctypes.data
+        self._ck(self.lib.ima2p_engine_upload_block(self._h, ptr, events, copy_stream))
+
+    def adopt_block(self, stream=None):
+        """Second half: `stream` waits for the oldest uploaded block, widens it into the resident state, re-evaluates it."""
+        self._ck(self.lib.ima2p_engine_adopt_block(self._h, stream))
 
     def put_state_packed(self, bufs, tvals, stream=None):
         """bufs as put_state, with bufs[0] = topo8 and bufs[2] = mcount from pack_state (8-bit wire form)."""

@@ -131,6 +131,10 @@ int ima2p_engine_run (ima2p_engine * e, int nsteps, int swaptries, void *cuda_st
  * groups' swaps.  decisions_first != 0 puts every group's decision kernels on a high-priority stream of their own.
  * The run is bit for bit the same for every setting. */
 int ima2p_engine_set_pipeline (ima2p_engine * e, int groups, int depth, int decisions_first);
+/* Kernel launches one step of ima2p_engine_run makes with the current settings (per chain group: the proposal kernels, the
+ * accept sweep, the split-time proposals and their decision, the mutation scalars; plus the swaps once), for a caller that
+ * reports them.  The calls it replaces are the body of qupdate(), ima_main_mpi.cpp:1808-1945. */
+int ima2p_engine_launches_per_step (ima2p_engine * e, int swaptries);
 /* Which kernels make updategenealogy's proposal (update_gtree.cpp:723-827): fast != 0 (the default where it applies) a
  * lane-per-pair move kernel followed by a warp-per-pair weights / likelihood kernel, with pairs_per_warp lanes of a move warp at
  * work (1, 2, 4, 8, 16, or 0 = chosen from the number of pairs); fast == 0 the general one-warp-per-pair kernel for every pair.
@@ -275,6 +279,12 @@ int ima2p_engine_fetch_state (ima2p_engine * e, void *topo, void *time, void *ms
  * pair 1, ..., each pair's in edge order (scal_i[p][1] of them). */
 int ima2p_engine_state_block_layout (ima2p_engine * e, long long total_events, uint64_t * out10);
 int ima2p_engine_put_state_block (ima2p_engine * e, const void *block, long long total_events, void *cuda_stream);
+/* put_state_block in two halves for a caller that steps a stream of uploaded states: upload_block starts the transfer of a
+ * block into one of two device staging slots on `copy_stream` and returns (IMA2P_E_ARG when both slots are taken);
+ * adopt_block makes `cuda_stream` wait for the oldest transfer, widens that block into the resident state and re-evaluates
+ * it.  With the next block uploaded before this step's results are read, the copy overlaps the step's kernels. */
+int ima2p_engine_upload_block (ima2p_engine * e, const void *block, long long total_events, void *copy_stream);
+int ima2p_engine_adopt_block (ima2p_engine * e, void *cuda_stream);
 int ima2p_engine_put_state_packed (ima2p_engine * e, const void *topo8, const void *time, const void *mcount,
                                    const void *mig_t, const void *mig_p, const void *scal_i, const void *scal_d,
                                    const void *uvals, const double *tvals, void *cuda_stream);

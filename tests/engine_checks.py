@@ -828,16 +828,38 @@ def packed_upload_equals_plain_upload(lib, nloci=10, nchains=5, nsteps=60):
     packed = Engine.pack_state(arrs[0].reshape(nchains * nloci, eng.NL, 4), arrs[2].reshape(nchains * nloci, eng.NL, 2))
     assert packed is not None
     outs = []
-    for mode in ("plain", "packed", "block"):
+    for mode in ("plain", "packed", "block", "two halves"):
         e2, _ = make()
         if mode == "plain":
             e2.put_state(arrs, tv)
         elif mode == "packed":
             e2.put_state_packed([packed[0], arrs[1], packed[1]] + arrs[3:], tv)
-        else:
+        elif mode == "block":
             blk, events = e2.pack_state_block(arrs, tv)
             assert events == int(arrs[5].reshape(-1, 2)[:, 1].sum())
             e2.put_state_block(blk, events)
+        else:
+            # upload_block + adopt_block with both staging slots in use: a block of another state first (the start state), adopted
+            # and stepped; the wanted block travels meanwhile and is adopted after it.  A third upload before anything is adopted
+            # is refused.
+            blk0, ev0 = e2.pack_state_block([np.ascontiguousarray(st[k]) for k in keys], st["tvals"])
+            blk, events = e2.pack_state_block(arrs, tv)
+            e2.upload_block(blk0, ev0)
+            e2.upload_block(blk, events)
+            try:
+                e2.upload_block(blk, events)
+                raise AssertionError("a third pending upload was accepted")
+            except Exception as ex:
+                assert "staging" in str(ex)
+            e2.adopt_block()
+            e2.run(3)
+            e2.adopt_block()
+            try:
+                e2.adopt_block()
+                raise AssertionError("adopt_block without a pending upload was accepted")
+            except Exception as ex:
+                assert "no uploaded block" in str(ex)
+
         e2.sync()
         ev = [e2.chain(c) for c in range(nchains)]
         e2.run(20)
@@ -850,6 +872,10 @@ def packed_upload_equals_plain_upload(lib, nloci=10, nchains=5, nsteps=60):
         e2.close()
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
     assert np.array_equal(outs[0], outs[4]) and np.array_equal(outs[1], outs[5])
+    # the two-halves engine ran three steps before the wanted state arrived: its step counter (which keys the draws) differs,
+    # so only the evaluation on arrival is comparable
+    n_ev = len(outs[0]) // 2
+    assert np.array_equal(outs[0][:n_ev], outs[6][:n_ev]) and not np.array_equal(outs[0][n_ev:], outs[6][n_ev:])
     eng.close()
 
 
