@@ -523,6 +523,8 @@ def main():
         except Exception as ex:
             lmode_multi = {"error": str(ex)}
     upd_counters = {k: int(v) for k, v in eng.update_counters().items()}
+    # per chain group: k_move, k_weigh, k_propose_redo, k_accept, k_split_t_fast, k_split_t_redo, k_accept_t, k_changeu; k_swap once
+    launches_per_step = eng.launches_per_step()
 
     # ---- BASELINE configs[2]'s shape on the same GPUs: 300 loci x 256 chains per GPU ------------------------------------------
     config3 = None
@@ -540,7 +542,8 @@ def main():
             v3 = c3 * world * l3 * k3 / (ms3 * 1e-3)
             cnt3 = job3.eng.counters()
             config3 = {"config": make_config("sim300x256", world, args.schedule, args.data), "value": v3, "unit": unit, "ms_per_step": ms3 / k3,
-                       "steps": k3, "accept_rate": cnt3["accepted"] / max(1, cnt3["updates"]), "dropped_for_capacity": cnt3["dropped"]}
+                       "steps": k3, "accept_rate": cnt3["accepted"] / max(1, cnt3["updates"]), "dropped_for_capacity": cnt3["dropped"],
+                       "gpu_launches": job3.eng.launches_per_step() * k3}
             if rank == 0 and not args.no_cpu_baseline:
                 r3 = reference_throughput("sim300x256", world, 2, 1, budget_s=15.0, full=full, data=args.data)
                 if r3 is not None:
@@ -605,8 +608,6 @@ def main():
             lmode = lmode_bench(eng, dev)
         except Exception as ex:       # the L-mode line is supplementary; the M-mode metric must still be reported
             lmode = {"error": str(ex)}
-    # per chain group: k_move, k_weigh, k_propose_redo, k_accept, k_split_t_fast, k_split_t_redo, k_accept_t, k_changeu; k_swap once
-    launches_per_step = eng.launches_per_step()
     out = {"metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": args.data, "config": config,
            "clocks": clocks, "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke, "parts_ms": parts,

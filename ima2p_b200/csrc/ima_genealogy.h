@@ -1149,9 +1149,7 @@ IMA_DEV double hky_pijt(const double *pi, double mutrate, double t, double kappa
 enum { kHkyInit = 0, kHkyFull = 1, kHkyPartial = 2 };
 struct HkyCall { int mode, freed, olddd; const uint32_t *mask_cur; uint32_t *mask_new; };
 
-// (out of line, like likelihood_sw: a kernel's code is fetched once per warp, and the warps of an infinite-sites run should not
-// have to step over the pruning and the Bessel functions)
-IMA_DEV_NOINLINE double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S, int p, double u, double kappa, const double *pi, const HkyCall &hk) {
+IMA_DEV double likelihood_hky(const EngineView &E, const DevLocus &L, PairSm &S, int p, double u, double kappa, const double *pi, const HkyCall &hk) {
   const int lane = Warp::lane();
   const int ng = L.ng, nl = L.nl, ns = L.nsites, nev = S.ctl_i[kCiNev], root = S.ctl_i[kCiRoot];
   const size_t hs = (size_t)E.d.hky_sites;
@@ -1290,7 +1288,7 @@ IMA_DEV double sw_update_alleles(const DevLocus &L, const PairSm &S, int ai, Phi
 }
 
 // stepwise: calc_prob_data.cpp:841-909 (full evaluation of one linked portion); A/dlikeA in global memory
-IMA_DEV_NOINLINE double likelihood_sw(const DevLocus &L, const PairSm &S, const short *A, double *dlikeA, double u) {
+IMA_DEV double likelihood_sw(const DevLocus &L, const PairSm &S, const short *A, double *dlikeA, double u) {
   const int lane = Warp::lane();
   double like = 0.0;
   bool zero = false;
