@@ -255,6 +255,7 @@ static void launch_changeu(Engine *e, stream_t s, const EngineView &v) {
   UpdateView u = e->uv;
   u.u_every = e->u_every;
   if (changeu_by_levels(e)) {
+    u.u_levels_in_order = getenv("IMA2P_CHANGEU_LEVELS_IN_ORDER") ? 1 : 0;
     IMA_LAUNCH(k_changeu_levels, v.c_n, IMA_CUDA ? kUWarps : 1, changeu_levels_smem_bytes(e->d, u.nurates), s, v, u);
     return;
   }

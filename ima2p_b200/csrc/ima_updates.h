@@ -35,6 +35,7 @@ struct UpdateView {
   // tests: one forced changeu proposal per launch
   int u_forced;                                    // 0: production sweep; 1: evaluate (u_j, u_k, d, kappas) below on u_chain only
   int u_chain, u_j, u_k, u_every;
+  int u_levels_in_order;                           // tests: k_changeu_levels gives every proposal a level of its own (the walk in order)
   double u_d, u_kappa[2];
 };
 
@@ -980,7 +981,7 @@ IMA_KERNEL void k_changeu_levels(EngineView E, UpdateView U) {
         int top = 0;
         for (int j = 0; j < nur; j++) {
           const int lj = U.ul_l[j], lk = U.ul_l[s_k[j]];
-          const int lv = 1 + (s_last[lj] > s_last[lk] ? s_last[lj] : s_last[lk]);
+          const int lv = U.u_levels_in_order ? j + 1 : 1 + (s_last[lj] > s_last[lk] ? s_last[lj] : s_last[lk]);
           s_lv[j] = lv; s_last[lj] = lv; s_last[lk] = lv;
           if (lv > top) top = lv;
         }

@@ -673,6 +673,55 @@ def hky_partials_stay_consistent(lib, name="state_sim5_hky_hn2", nsteps=400):
     return out
 
 
+def run_summary(lib, name="state_sim50_hn3", nsteps=120, seed=5):
+    """Per-chain P(G), P(D|G), split times and the counters after nsteps whole steps from a fixture's state (one flat array)."""
+    from support import engine_from_fixture, load_golden
+    d = load_golden(name)
+    eng, fm = engine_from_fixture(d, lib=lib, seed=seed)
+    eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+    eng.set_update_schedule(3, 5)
+    eng.eval()
+    eng.run(nsteps)
+    eng.sync()
+    tv, uv, _ = eng.fetch_parameters()
+    cnt = eng.counters()
+    out = np.concatenate([np.concatenate([np.r_[eng.chain(c)["probg"], eng.chain(c)["pdg"]] for c in range(eng.nchains)]), tv.reshape(-1), uv.reshape(-1),
+                          np.array([cnt["accepted"], cnt["swaps"]], dtype=np.float64)])
+    eng.close()
+    return out
+
+
+def scalar_walk_by_levels_equals_the_walk_in_order(lib, names=("state_sim5_hky_hn2", "state_sim3_sw_hn2"), nsteps=60):
+    """k_changeu_levels evaluates the proposals of a mutation-scalar sweep that share no locus in parallel (levels).  With every
+    proposal given a level of its own (IMA2P_CHANGEU_LEVELS_IN_ORDER: the reference's walk in order, same draws) the chains must
+    be the same to the last bit -- likelihoods, scalars, kappas, counters."""
+    import os
+    from support import engine_from_fixture, load_golden
+    for name in names:
+        d = load_golden(name)
+        got = []
+        for in_order in (False, True):
+            if in_order:
+                os.environ["IMA2P_CHANGEU_LEVELS_IN_ORDER"] = "1"
+            try:
+                eng, fm = engine_from_fixture(d, lib=lib, seed=77)
+                eng.set_update_priors(t_max=[3.0] * fm.nsplit)
+                eng.set_update_schedule(3, 2)                        # the scalars every second step
+                eng.eval()
+                eng.run(nsteps)
+                eng.sync()
+                tv, uv, kp = eng.fetch_parameters()
+                uc = eng.update_counters()
+                got.append((np.concatenate([np.r_[eng.chain(c)["probg"], eng.chain(c)["pdg"]] for c in range(eng.nchains)]), uv.copy(), np.asarray(kp).copy(),
+                            uc["u_tries"], uc["u_accepts"]))
+                eng.close()
+            finally:
+                os.environ.pop("IMA2P_CHANGEU_LEVELS_IN_ORDER", None)
+        a, b = got
+        assert a[3] == b[3] > 0 and a[4] == b[4] > 0, (name, a[3:], b[3:])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), name
+
+
 def capacity_grows_without_changing_the_chain(lib, name="state_sim3_hn3", nsteps=60):
     """ima2p_engine_grow_capacity (checkmig, utilities.cpp:1365-1383): growing the migration pools between two steps re-houses
     the resident genealogies and nothing else -- a run that grows half way is the run that had the room from the start.  With a

@@ -94,3 +94,31 @@ def test_round2_reference_arm_record():
     d = _line("r2s3_bench_ref.json")
     assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"] and "qupdate" in d["cpu_baseline"]["sample"]
+
+
+# ---- the round's final records (profiles/r2s6_*, r2s7_*): launches counted from the engine's settings, uploads overlapping the steps ----
+def test_final_single_gpu_record():
+    d = _line("r2s7_bench_n1.json")
+    assert d["n_gpus"] == 1 and d["data"] == "real" and d["dtype"] == "f64" and d["warmup"] >= 3 and d["dropped_for_capacity"] == 0
+    assert abs(d["value"] - 128 * 50 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    assert d["gpu_launches"] == d["steps"] * 17          # two chain groups x eight kernels + k_swap (ima2p_engine_launches_per_step)
+    e = d["e2e"]
+    assert "upload_block" in e["upload"] and e["statistic"].startswith("median") and 0 < e["value"] < d["value"]
+    r = d["roofline"]
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms_per_launch"][r["kernel"]] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert r["traffic"] > 0 and r["peak_kind"] in ("measured", "fallback")
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and 0.2 < c["accept_rate"] < 0.5 and abs(c["accept_rate"] - d["accept_rate"]) < 0.05
+    ref = _line("r2s7_bench_ref.json")
+    assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["config"]["workload"] == d["config"]["workload"]
+    assert ref["e2e"]["value"] == ref["value"] and ref["e2e"]["h2d_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("name,n", [("r2s6_bench_n2.json", 2), ("r2s6_bench_n8.json", 8)])
+def test_final_multi_gpu_records(name, n):
+    d = _line(name)
+    assert d["n_gpus"] == n and d["scaling"] == "weak" and d["config"]["chains_total"] == 128 * n and d["gpu_launches"] == d["steps"] * 17
+    assert abs(d["value"] - d["config"]["chains_total"] * d["config"]["loci"] / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    c3 = d["config3"]
+    assert c3["config"]["chains_total"] == 256 * n and c3["gpu_launches"] == c3["steps"] * 33      # four groups where the kernels run many waves
+    assert abs(c3["ratio_to_cpu_baseline"] - c3["value"] / c3["cpu_baseline"]["value"]) < 1e-9 * c3["ratio_to_cpu_baseline"]

@@ -115,6 +115,24 @@ def test_hky_partials_stay_consistent(lib):
     ec.hky_partials_stay_consistent(lib)
 
 
+def test_scalar_walk_by_levels_equals_the_walk_in_order(lib):
+    ec.scalar_walk_by_levels_equals_the_walk_in_order(lib)
+
+
+def test_programmatic_launches_do_not_change_the_run(lib):
+    """Inside the step graph kernels are launched with programmatic stream serialisation and open with griddepcontrol.wait
+    (IMA2P_PDL, on by default): the chains must be those of plainly launched kernels."""
+    import os
+    got = []
+    for pdl in ("1", "0"):
+        os.environ["IMA2P_PDL"] = pdl
+        try:
+            got.append(ec.run_summary(lib, nsteps=120))
+        finally:
+            os.environ.pop("IMA2P_PDL", None)
+    assert got[0] is not None and np.array_equal(got[0], got[1])
+
+
 def test_pipeline_does_not_change_the_run(lib):
     ec.pipeline_does_not_change_the_run(lib)
 

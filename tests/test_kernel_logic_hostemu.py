@@ -71,6 +71,10 @@ def test_hky_partials_stay_consistent(emu):
     ec.hky_partials_stay_consistent(emu, nsteps=200)
 
 
+def test_scalar_walk_by_levels_equals_the_walk_in_order(emu):
+    ec.scalar_walk_by_levels_equals_the_walk_in_order(emu, nsteps=30)
+
+
 def test_pipeline_setting_is_accepted_and_does_not_change_the_run(emu):
     ec.pipeline_does_not_change_the_run(emu, nsteps=9)
 
