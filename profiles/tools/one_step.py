@@ -19,6 +19,8 @@ def main():
     eng.set_update_schedule(3, 5)
     if len(sys.argv) > 5:
         eng.set_proposal_path(int(sys.argv[4]), int(sys.argv[5]))
+    if os.environ.get("IMA_SPEC"):
+        eng.set_speculation(int(os.environ["IMA_SPEC"]))
     ws = torch.cuda.Stream()
     torch.cuda.set_stream(ws)
     stream = ws.cuda_stream
