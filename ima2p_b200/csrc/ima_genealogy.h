@@ -797,7 +797,7 @@ template <int NQ> IMA_DEV void warp_sort_events(const double *bt, const int *bi,
 // returns false when the event table does not fit (flagged as overflow by the caller)
 IMA_DEV bool eval_weights(const DevModel &M, const EngineDims &d, const DevLocus &L, const double *tv, PairSm &S, int evcap = -1) {
   const int lane = Warp::lane();
-  const int ng = L.ng, nl = L.nl, W = L.nwords;
+  const int ng = L.ng, nl = L.nl;
   const int mignum = scan_mig_counts(nl, S);
   const double roottime = S.ctl_d[kCdRoottime];
   const int nsplitev = findperiod(M, tv, roottime);

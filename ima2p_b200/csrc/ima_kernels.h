@@ -255,7 +255,8 @@ IMA_KERNEL void k_eval_chains(EngineView E) {
 // fit their smaller tables.)
 IMA_DEV void propose_pair_general(const EngineView &E, const DevModel &M, int c, int li, PairSm &S) {
   const int p = c * E.d.nloci + li;
-  const int idx = p;
+  const int idx = p;                                     // named in the tuning build's cycle stamps
+  (void)idx;
   const DevLocus &L = E.loci[li];
   const int cb = E.cur[p];
   const PairBuf &B = E.buf[cb];
