@@ -115,6 +115,7 @@ SIGNATURES = {
     "ima2p_lmode_marginal_sums": (_i, [_v, _i, c_dbl_p, _i, _i, _i, _i, c_dbl_p, _v, _v]),
     "ima2p_lmode_margincalc": (_i, [_v, _i, c_dbl_p, _i, _d, _i, c_dbl_p]),
     "ima2p_lmode_marginp": (_i, [_v, _i, _i, _i, c_dbl_p, _i, c_dbl_p]),
+    "ima2p_lmode_marginal_many": (_i, [_v, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     "ima2p_lmode_jointp": (_i, [_v, c_dbl_p, _i, _i, c_dbl_p, c_dbl_p]),
     "ima2p_lmode_moments": (_i, [_v, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     "ima2p_lmode_moments_finish": (None, [_i, c_dbl_p, _ll, c_dbl_p, c_dbl_p, c_dbl_p]),

@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -384,147 +385,235 @@ void write_histograms(FILE *f, const std::vector<std::string> &name, const std::
 }
 
 
-// ---- marginal peak search: surface_search_functions.cpp:41-187 (mnbrakmod, goldenmod), surface_call_functions.cpp:82-104
-// (marginbis), :175-274 (marginalopt), :277-297 (margin95), :316-732 (findmarginpeaks, without the 2NM terms of -p5).
-// The one-dimensional searches are the reference's, statement for statement; every function value is one call of the device
-// evaluator (ima2p_lmode_marginp over the row range of the set, ima2p_lmode_margincalc for the 95% bounds).
-struct PeakCtx { ima2p_lmode *LM; int first, last; int thetai; };      // thetai >= 0: the 2NM term of (thetai, migration parameter)
-double peak_f(const PeakCtx &c, int param, double x) {
-  double v = 0.0;
-  if (c.thetai >= 0) ck(ima2p_lmode_marginpopmig(c.LM, c.thetai, param, c.first, c.last, &x, 1, &v), "2NM density");
-  else ck(ima2p_lmode_marginp(c.LM, param, c.first, c.last, &x, 1, &v), "marginal density");
-  return v;
-}
-double nr_sign(double a, double b) { return b > 0.0 ? fabs(a) : -fabs(a); }
+// ---- marginal peak search, in lock step.  The reference finds the peak of one marginal curve at a time and calls marginp once
+// per iterate (surface_search_functions.cpp:41-187 mnbrakmod / goldenmod under surface_call_functions.cpp:175-274 marginalopt;
+// :277-297 margin95 over :82-104 marginbis; popmig.cpp:366-429 for the 2NM terms).  Every such search only ever asks "the curve's
+// value at my next abscissa", and the searches of different parameters, row sets and brackets do not depend on one another.  So each
+// search is a small resumable object (`want()` = the abscissa it needs, `take(f)` = here is the value, advance to the next one), and
+// SearchPool::run advances all of them together: one round = one device pass (ima2p_lmode_marginal_many) over the current abscissa
+// of every search still running.  A search sees the same sequence of values the reference's serial loop would have produced, so
+// iterates, peaks and bounds are the reference's to the last bit; the number of device passes is the longest search's length instead
+// of the sum of all lengths.
+struct Curve {                       // which function a search evaluates
+  int kind;                          // 0 marginp over [first, last); 1 log margincalc - yadjust (all rows); 2 marginpopmig (2NM term)
+  int param, first, last, thetai;
+  double yadjust;
+};
 
-void mnbrakmod(const PeakCtx &c, int param, double *ax, double *bx, double *cx, double *fa, double *fb, double *fc) {
-  const double gold = 1.618034, glimit = 100.0, tiny = (double)(float)1.0e-20;
-  double ulim, u, rr, q, fu, dum;
-  *fa = peak_f(c, param, *ax);
-  *fb = peak_f(c, param, *bx);
-  if (*fb > *fa) { dum = *ax; *ax = *bx; *bx = dum; dum = *fb; *fb = *fa; *fa = dum; }
-  *cx = fabs(*bx + gold * (*bx - *ax));
-  *fc = peak_f(c, param, *cx);
-  while (*fb >= *fc && *fb > -DBL_MAX && !(*fb == 0 && *fc == 0)) {
-    rr = (*bx - *ax) * (*fb - *fc);
-    q = (*bx - *cx) * (*fb - *fa);
+// Downhill bracketing with parabolic extrapolation (the rule of mnbrakmod :41-131): from two abscissae, walk downhill until the
+// middle point lies below both ends.  at = which evaluation is outstanding.
+struct Bracketing {
+  enum At { kFirst, kSecond, kThird, kInside, kBeyond, kShift, kDone } at = kDone;
+  double a = 0, b = 0, c = 0, fa = 0, fb = 0, fc = 0, u = 0;
+  void start(double a0, double b0) { a = a0; b = b0; at = kFirst; }
+  bool done() const { return at == kDone; }
+  double want() const { return at == kFirst ? a : at == kSecond ? b : at == kThird ? c : u; }
+  void take(double f) {
+    const double gold = 1.618034;
+    switch (at) {
+    case kFirst: fa = f; at = kSecond; return;
+    case kSecond:
+      fb = f;
+      if (fb > fa) { std::swap(a, b); std::swap(fa, fb); }
+      c = fabs(b + gold * (b - a));
+      at = kThird;
+      return;
+    case kThird: fc = f; break;
+    case kInside:                                        // the parabola's minimum lay between b and c
+      if (f < fc) { a = b; fa = fb; b = u; fb = f; break; }
+      if (f > fb) { c = u; fc = f; break; }
+      u = c + gold * (c - b);                            // no use: default magnification
+      at = kShift;
+      return;
+    case kBeyond:                                        // it lay between c and the allowed limit
+      if (f < fc) { b = c; c = u; u = c + gold * (c - b); fb = fc; fc = f; at = kShift; return; }
+      shift(f);
+      break;
+    case kShift: shift(f); break;
+    case kDone: return;
+    }
+    next_trial();
+  }
+ private:
+  void shift(double fu) { a = b; b = c; c = u; fa = fb; fb = fc; fc = fu; }
+  void next_trial() {
+    const double gold = 1.618034, glimit = 100.0, tiny = (double)(float)1.0e-20;
+    if (!(fb >= fc && fb > -DBL_MAX && !(fb == 0 && fc == 0))) { at = kDone; return; }
+    const double rr = (b - a) * (fb - fc), q = (b - c) * (fb - fa);
     const double dq = fabs(q - rr) > tiny ? fabs(q - rr) : tiny;
-    u = *bx - ((*bx - *cx) * q - (*bx - *ax) * rr) / (2.0 * nr_sign(dq, q - rr));
-    ulim = *bx + glimit * (*cx - *bx);
-    if ((*bx - u) * (u - *cx) > 0.0) {
-      fu = peak_f(c, param, u);
-      if (fu < *fc) { *ax = *bx; *fa = *fb; *bx = u; *fb = fu; continue; }
-      if (fu > *fb) { *cx = u; *fc = fu; continue; }
-      u = *cx + gold * (*cx - *bx);
-      fu = peak_f(c, param, u);
-    } else if ((*cx - u) * (u - ulim) > 0.0) {
-      fu = peak_f(c, param, u);
-      if (fu < *fc) {
-        *bx = *cx; *cx = u; u = *cx + gold * (*cx - *bx);
-        *fb = *fc; *fc = fu;
-        fu = peak_f(c, param, u);
+    u = b - ((b - c) * q - (b - a) * rr) / (2.0 * (q - rr > 0.0 ? fabs(dq) : -fabs(dq)));
+    const double ulim = b + glimit * (c - b);
+    if ((b - u) * (u - c) > 0.0) at = kInside;
+    else if ((c - u) * (u - ulim) > 0.0) at = kBeyond;
+    else { if ((u - ulim) * (ulim - c) >= 0.0) u = ulim; else u = c + gold * (c - b); at = kShift; }
+  }
+};
+
+// Golden-section descent inside a bracket (the rule of goldenmod :133-187)
+struct GoldenSection {
+  enum At { kInner1, kInner2, kLeft, kRight, kDone } at = kDone;
+  double x0 = 0, x1 = 0, x2 = 0, x3 = 0, f1 = 0, f2 = 0, tol = 1e-7;
+  void start(double ax, double bx, double cx, double tolerance) {
+    const double cc = 1.0 - 0.61803399;
+    tol = tolerance; x0 = ax; x3 = cx;
+    if (fabs(cx - bx) > fabs(bx - ax)) { x1 = bx; x2 = bx + cc * (cx - bx); }
+    else { x2 = bx; x1 = bx - cc * (bx - ax); }
+    at = kInner1;
+  }
+  bool done() const { return at == kDone; }
+  double want() const { return (at == kInner1 || at == kLeft) ? x1 : x2; }
+  void take(double f) {
+    const double r = 0.61803399, cc = 1.0 - r;
+    if (at == kInner1) { f1 = f; at = kInner2; return; }
+    if (at == kInner2 || at == kRight) f2 = f; else f1 = f;
+    if (!(fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2)) && x3 > -DBL_MAX)) { at = kDone; return; }
+    if (f2 < f1) { x0 = x1; x1 = x2; x2 = r * x1 + cc * x3; f1 = f2; at = kRight; }
+    else { x3 = x2; x2 = x1; x1 = r * x2 + cc * x0; f2 = f1; at = kLeft; }
+  }
+  double xmin() const { return f1 < f2 ? x1 : x2; }
+  double fmin() const { return f1 < f2 ? f1 : f2; }
+};
+
+// Root by halving (the rule of marginbis :82-104: BISTOL 1e-4, at most 40 halvings)
+struct Bisection {
+  enum At { kLow, kHigh, kMid, kDone } at = kDone;
+  double x1 = 0, x2 = 0, fl = 0, dx = 0, rtb = 0, xmid = 0, root = DBL_MAX;
+  int j = 0;
+  void start(double lo, double hi) { x1 = lo; x2 = hi; at = kLow; }
+  bool done() const { return at == kDone; }
+  double want() const { return at == kLow ? x1 : at == kHigh ? x2 : xmid; }
+  void take(double f) {
+    if (at == kLow) { fl = f; at = kHigh; return; }
+    if (at == kHigh) {
+      if (fl * f >= 0.0) { root = DBL_MIN; at = kDone; return; }
+      if (fl < 0.0) { dx = x2 - x1; rtb = x1; } else { dx = x1 - x2; rtb = x2; }
+      j = 1; xmid = rtb + (dx *= 0.5); at = kMid;
+      return;
+    }
+    if (f <= 0.0) rtb = xmid;
+    if (fabs(dx) < 1e-4 || f == 0.0) { root = rtb; at = kDone; return; }
+    if (++j > 40) { root = DBL_MAX; at = kDone; return; }
+    xmid = rtb + (dx *= 0.5);
+  }
+};
+
+// One peak of one curve: the two bracketings of marginalopt (from the prior's upper end and from its lower end, :192-201; they
+// run side by side), its test that both found the same valley (:203-262, as written, with the unconditional clamp of :233-237),
+// then the golden section.  With `bracket` given (2NM terms: the bin of a 100-point scan), only the golden section.
+struct PeakSearch {
+  Curve curve;
+  double prior = 0, mlval = 0, peakloc = 0;
+  Bracketing down, up;
+  GoldenSection gs;
+  int stage = 0;                      // 0 bracketing, 1 golden section, 2 finished
+  void start(const Curve &c, double prior_max) {
+    curve = c; prior = prior_max;
+    down.start(prior, prior / 2);
+    up.start(0.0000001, prior / 2);
+    stage = 0;
+  }
+  void start_in(const Curve &c, double ax, double bx, double cx) { curve = c; gs.start(ax, bx, cx, 1e-7); stage = 1; }
+  bool done() const { return stage == 2; }
+  // the abscissae wanted this round (the two bracketings are independent: up to two)
+  int wants(double *x) const {
+    int n = 0;
+    if (stage == 0) { if (!down.done()) x[n++] = down.want(); if (!up.done()) x[n++] = up.want(); }
+    else if (stage == 1) x[n++] = gs.want();
+    return n;
+  }
+  void take(const double *f) {
+    int n = 0;
+    if (stage == 0) {
+      if (!down.done()) down.take(f[n++]);
+      if (!up.done()) up.take(f[n++]);
+      if (down.done() && up.done()) same_valley();
+    } else if (stage == 1) {
+      gs.take(f[n++]);
+      if (gs.done()) { mlval = -gs.fmin(); peakloc = gs.xmin(); stage = 2; }
+    }
+  }
+ private:
+  static double lowest(double a, double b, double c) { double v = 0; if (a < b && a < c) v = a; if (b < a && b < c) v = b; if (c < a && c < b) v = c; return v; }
+  void same_valley() {
+    double axt = down.a, bxt = down.b, cxt = down.c, ax = up.a, bx = up.b, cx = up.c;
+    const double min0 = lowest(axt, bxt, cxt), min1 = lowest(ax, bx, cx);
+    double max0 = 0, max1 = 0;
+    if (axt > bxt && axt > cxt) max0 = axt = std::min(axt, prior);
+    if (bxt > axt && bxt > cxt) max0 = bxt = std::min(bxt, prior);
+    if (cxt > axt && cxt > bxt) max0 = cxt = std::min(cxt, prior);
+    max1 = ax = std::min(ax, prior);                       // :233-237: clamps ax and takes it whatever the order
+    if (bx > ax && bx > cx) max1 = bx = std::min(bx, prior);
+    if (cx > ax && cx > bx) max1 = cx = std::min(cx, prior);
+    if (max0 <= min1 || max1 <= min0) { peakloc = -1; stage = 2; return; }
+    gs.start(ax, bx, cx, 1e-7);
+    stage = 1;
+  }
+};
+
+// Advances any number of searches together: every round, one device pass for the marginal curves of all of them
+// (ima2p_lmode_marginal_many) and one marginpopmig call per 2NM curve.
+struct SearchPool {
+  ima2p_lmode *LM;
+  int passes = 0;
+  long long points = 0;
+  struct Slot { Curve c; std::function<int(double *)> wants; std::function<void(const double *)> take; };
+  std::vector<Slot> slots;
+  template <class S> void add(S *s, const Curve &c) {
+    slots.push_back(Slot{c, [s](double *x) { if (s->done()) return 0; x[0] = s->want(); return 1; }, [s](const double *f) { s->take(f[0]); }});
+  }
+  void add(PeakSearch *s) { slots.push_back(Slot{s->curve, [s](double *x) { return s->wants(x); }, [s](const double *f) { s->take(f); }}); }
+  void run() {
+    std::vector<int> kind, param, first, last, owner, nwant(slots.size());
+    std::vector<double> x, yadj, f;
+    for (;;) {
+      kind.clear(); param.clear(); first.clear(); last.clear(); x.clear(); yadj.clear(); owner.clear();
+      for (size_t i = 0; i < slots.size(); i++) {
+        double w[2];
+        nwant[i] = slots[i].wants(w);
+        for (int k = 0; k < nwant[i]; k++) {
+          const Curve &c = slots[i].c;
+          kind.push_back(c.kind); param.push_back(c.param); first.push_back(c.first); last.push_back(c.last);
+          x.push_back(w[k]); yadj.push_back(c.yadjust); owner.push_back((int)i);
+        }
       }
-    } else if ((u - ulim) * (ulim - *cx) >= 0.0) {
-      u = ulim;
-      fu = peak_f(c, param, u);
-    } else {
-      u = *cx + gold * (*cx - *bx);
-      fu = peak_f(c, param, u);
+      const int n = (int)x.size();
+      if (!n) break;
+      f.assign(n, 0.0);
+      // the marginal curves of this round in one pass; 2NM curves (their own kernels) one call each
+      std::vector<int> mk, mp, mf, ml, at;
+      std::vector<double> mx, my, mo;
+      for (int q = 0; q < n; q++) {
+        if (kind[q] == 2) {
+          const Curve &c = slots[owner[q]].c;
+          ck(ima2p_lmode_marginpopmig(LM, c.thetai, c.param, c.first, c.last, &x[q], 1, &f[q]), "2NM density");
+        } else { mk.push_back(kind[q]); mp.push_back(param[q]); mf.push_back(first[q]); ml.push_back(last[q]); mx.push_back(x[q]); my.push_back(yadj[q]); at.push_back(q); }
+      }
+      if (!mx.empty()) {
+        mo.assign(mx.size(), 0.0);
+        ck(ima2p_lmode_marginal_many(LM, (int)mx.size(), mk.data(), mp.data(), mf.data(), ml.data(), mx.data(), my.data(), mo.data()), "marginal density");
+        for (size_t k = 0; k < at.size(); k++) f[at[k]] = mo[k];
+        passes++; points += (long long)mx.size();
+      }
+      int q = 0;
+      for (size_t i = 0; i < slots.size(); i++) if (nwant[i]) { slots[i].take(&f[q]); q += nwant[i]; }
     }
-    *ax = *bx; *bx = *cx; *cx = u;
-    *fa = *fb; *fb = *fc; *fc = fu;
+    slots.clear();
   }
-}
+};
 
-double goldenmod(const PeakCtx &c, int param, double ax, double bx, double cx, double tol, double *xmin) {
-  const double r = 0.61803399, cc = 1.0 - r;
-  double f1, f2, x0 = ax, x1, x2, x3 = cx;
-  if (fabs(cx - bx) > fabs(bx - ax)) { x1 = bx; x2 = bx + cc * (cx - bx); }
-  else { x2 = bx; x1 = bx - cc * (bx - ax); }
-  f1 = peak_f(c, param, x1);
-  f2 = peak_f(c, param, x2);
-  while (fabs(x3 - x0) > tol * (fabs(x1) + fabs(x2)) && (x3 > -DBL_MAX)) {
-    if (f2 < f1) { x0 = x1; x1 = x2; x2 = r * x1 + cc * x3; f1 = f2; f2 = peak_f(c, param, x2); continue; }
-    x3 = x2; x2 = x1; x1 = r * x2 + cc * x0; f2 = f1; f1 = peak_f(c, param, x1);
-  }
-  if (f1 < f2) { *xmin = x1; return f1; }
-  *xmin = x2;
-  return f2;
-}
-
-// marginalopt :175-274, with its bracketing-consistency test as written (including the unconditional block of :233-237)
-void marginalopt(const PeakCtx &c, const std::vector<double> &prior_max, double *mlval, double *peakloc) {
-  const double kMinParam = 0.0000001;
-  for (int i = 0; i < (int)prior_max.size(); i++) {
-    const double prior = prior_max[i];
-    double ax = prior, bx = prior / 2, cx = 0, fa, fb, fc;
-    mnbrakmod(c, i, &ax, &bx, &cx, &fa, &fb, &fc);
-    double axt = ax, bxt = bx, cxt = cx;
-    bx = prior / 2;
-    ax = kMinParam;
-    mnbrakmod(c, i, &ax, &bx, &cx, &fa, &fb, &fc);
-    double min0 = 0, max0 = 0, min1 = 0, max1 = 0;
-    if (axt < bxt && axt < cxt) min0 = axt;
-    if (bxt < axt && bxt < cxt) min0 = bxt;
-    if (cxt < axt && cxt < bxt) min0 = cxt;
-    if (axt > bxt && axt > cxt) { if (axt > prior) axt = prior; max0 = axt; }
-    if (bxt > axt && bxt > cxt) { if (bxt > prior) bxt = prior; max0 = bxt; }
-    if (cxt > axt && cxt > bxt) { if (cxt > prior) cxt = prior; max0 = cxt; }
-    if (ax < bx && ax < cx) min1 = ax;
-    if (bx < ax && bx < cx) min1 = bx;
-    if (cx < ax && cx < bx) min1 = cx;
-    if (ax > bx && ax > cx) max1 = ax;
-    { if (ax > prior) ax = prior; max1 = ax; }
-    if (bx > ax && bx > cx) { if (bx > prior) bx = prior; max1 = bx; }
-    if (cx > ax && cx > bx) { if (cx > prior) cx = prior; max1 = cx; }
-    if (max0 <= min1 || max1 <= min0) peakloc[i] = -1;
-    else {
-      double xmax = 0;
-      mlval[i] = -goldenmod(c, i, ax, bx, cx, 1e-7, &xmax);
-      peakloc[i] = xmax;
-    }
-  }
-}
-
-// marginalopt_popmig popmig.cpp:366-429: a 100-bin scan for the interval that holds the peak (one device call), then the
-// golden-section search on marginpopmig / marginpop_expomig
 struct PopMigTerm { int thetai, mi; std::string peakname, histname; };
-void marginalopt_popmig(ima2p_lmode *LM, int first, int last, const std::vector<PopMigTerm> &terms, const std::vector<double> &upper,
-                        double *mlval, double *peakloc) {
+// the bin of a 100-point scan that holds the lowest value of a 2NM curve (popmig.cpp:384-417): the bracket its golden section starts in
+void popmig_bracket(ima2p_lmode *LM, const PopMigTerm &t, int first, int last, double ub, double *ax, double *bx, double *cx) {
   const int bins = 100;
-  const double kMinParam = 0.0000001;
-  for (size_t i = 0; i < terms.size(); i++) {
-    const double ub = upper[i];
-    std::vector<double> x(bins), fa(bins);
-    for (int j = 0; j < bins; j++) x[j] = kMinParam + j * (ub / (double)bins);
-    ck(ima2p_lmode_marginpopmig(LM, terms[i].thetai, terms[i].mi, first, last, x.data(), bins, fa.data()), "2NM density");
-    double maxf = 1e100; int maxj = -1;
-    for (int j = 0; j < bins; j++) if (fa[j] < maxf) { maxf = fa[j]; maxj = j; }
-    double ax, bx, cx;
-    if (maxj == 0) { ax = kMinParam; cx = kMinParam + ub / (double)bins; bx = (ax + cx) / 2.0; }
-    else if (maxj == bins - 1) { ax = kMinParam + ((double)bins - 1) * (ub / (double)bins); bx = kMinParam + ((double)bins - 2) * (ub / (double)bins); cx = ub; }
-    else { bx = kMinParam + ((double)maxj - 1) * (ub / (double)bins); cx = kMinParam + ((double)maxj + 1) * (ub / (double)bins); ax = kMinParam + ((double)maxj) * (ub / (double)bins); }
-    PeakCtx c{LM, first, last, terms[i].thetai};
-    double xmax = 0;
-    mlval[i] = -goldenmod(c, terms[i].mi, ax, bx, cx, 1e-7, &xmax);
-    peakloc[i] = xmax;
-  }
-}
-
-// margin95 :277-297 over marginbis :82-104 (root of log margincalc - yadjust by bisection, BISTOL 1e-4, 40 halvings)
-double margin95(ima2p_lmode *LM, const double *mlval, const double *peakloc, int pi, int upper, double prior) {
-  const double x1 = upper ? peakloc[pi] : 0.0000001, x2 = upper ? prior : peakloc[pi];
-  const double yadjust = log(mlval[pi]) - 1.92;
-  auto f = [&](double x) { double v = 0; ck(ima2p_lmode_margincalc(LM, pi, &x, 1, yadjust, 1, &v), "marginal density"); return v; };
-  double fl = f(x1), fmid = f(x2), dx, rtb, xmid;
-  if (fl * fmid >= 0.0) return DBL_MIN;
-  if (fl < 0.0) { dx = x2 - x1; rtb = x1; } else { dx = x1 - x2; rtb = x2; }
-  for (int j = 1; j <= 40; j++) {
-    fmid = f(xmid = rtb + (dx *= 0.5));
-    if (fmid <= 0.0) rtb = xmid;
-    if (fabs(dx) < 1e-4 || fmid == 0.0) return rtb;
-  }
-  return DBL_MAX;
+  const double kMinParam = 0.0000001, w = ub / (double)bins;
+  std::vector<double> x(bins), fa(bins);
+  for (int j = 0; j < bins; j++) x[j] = kMinParam + j * w;
+  ck(ima2p_lmode_marginpopmig(LM, t.thetai, t.mi, first, last, x.data(), bins, fa.data()), "2NM density");
+  double maxf = 1e100; int maxj = -1;
+  for (int j = 0; j < bins; j++) if (fa[j] < maxf) { maxf = fa[j]; maxj = j; }
+  if (maxj == 0) { *ax = kMinParam; *cx = kMinParam + w; *bx = (*ax + *cx) / 2.0; }
+  else if (maxj == bins - 1) { *ax = kMinParam + ((double)bins - 1) * w; *bx = kMinParam + ((double)bins - 2) * w; *cx = ub; }
+  else { *bx = kMinParam + ((double)maxj - 1) * w; *cx = kMinParam + ((double)maxj + 1) * w; *ax = kMinParam + ((double)maxj) * w; }
 }
 
 // findmarginpeaks :316-732
@@ -540,31 +629,65 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
   std::vector<std::vector<double>> mlval(NT + 1, std::vector<double>(p, 0.0)), peakloc(NT + 1, std::vector<double>(p, 0.0));
   const int nt = (int)terms.size();                   // 2NM terms (-p5), in the order of the migration parameters' populations
   std::vector<std::vector<double>> pmml(NT + 1, std::vector<double>(nt, 0.0)), pmpk(NT + 1, std::vector<double>(nt, 0.0));
-  int firsttree = 0, lasttree = (int)G / NT;
-  for (int j = 0; j < NT; j++) {
-    PeakCtx c{LM, firsttree, lasttree, -1};
-    marginalopt(c, prior_max, mlval[j].data(), peakloc[j].data());
-    if (nt) marginalopt_popmig(LM, firsttree, lasttree, terms, term_upper, pmml[j].data(), pmpk[j].data());
-    firsttree = lasttree + 1;
-    lasttree += (int)G / NT;
-    if (lasttree > G) lasttree = (int)G;
+  // row sets: the two halves of the run and all rows (:352-372)
+  int set_first[NT + 1], set_last[NT + 1];
+  {
+    int firsttree = 0, lasttree = (int)G / NT;
+    for (int j = 0; j < NT; j++) {
+      set_first[j] = firsttree; set_last[j] = lasttree;
+      firsttree = lasttree + 1;
+      lasttree += (int)G / NT;
+      if (lasttree > G) lasttree = (int)G;
+    }
+    set_first[NT] = 0; set_last[NT] = (int)G;
   }
-  PeakCtx all{LM, 0, (int)G, -1};
-  marginalopt(all, prior_max, mlval[NT].data(), peakloc[NT].data());
-  std::vector<double> migtest(nm, 0.0);
-  for (int i = 0; i < nm; i++) {
-    const double maxp = -peak_f(all, i + nq, peakloc[NT][i + nq]), max0p = -peak_f(all, i + nq, 0.0000001);
-    migtest[i] = 2 * log(maxp / max0p);
-  }
-  std::vector<double> pmtest(nt, 0.0);
-  if (nt) {
-    marginalopt_popmig(LM, 0, (int)G, terms, term_upper, pmml[NT].data(), pmpk[NT].data());
+  // every peak search of the table -- (NT + 1) row sets x (p parameters + nt 2NM terms) -- advances in one pool
+  SearchPool pool{LM};
+  std::vector<PeakSearch> ps((size_t)(NT + 1) * p), pms((size_t)(NT + 1) * nt);
+  for (int j = 0; j <= NT; j++) {
+    for (int i = 0; i < p; i++) {
+      ps[(size_t)j * p + i].start(Curve{0, i, set_first[j], set_last[j], -1, 0.0}, prior_max[i]);
+      pool.add(&ps[(size_t)j * p + i]);
+    }
     for (int i = 0; i < nt; i++) {
-      PeakCtx c{LM, 0, (int)G, terms[i].thetai};
-      const double maxp = -peak_f(c, terms[i].mi, pmpk[NT][i]), max0p = -peak_f(c, terms[i].mi, 0.0000001);
-      pmtest[i] = 2 * log(maxp / max0p);
+      double ax, bx, cx;
+      popmig_bracket(LM, terms[i], set_first[j], set_last[j], term_upper[i], &ax, &bx, &cx);
+      pms[(size_t)j * nt + i].start_in(Curve{2, terms[i].mi, set_first[j], set_last[j], terms[i].thetai, 0.0}, ax, bx, cx);
+      pool.add(&pms[(size_t)j * nt + i]);
     }
   }
+  pool.run();
+  for (int j = 0; j <= NT; j++) {
+    for (int i = 0; i < p; i++) { mlval[j][i] = ps[(size_t)j * p + i].mlval; peakloc[j][i] = ps[(size_t)j * p + i].peakloc; }
+    for (int i = 0; i < nt; i++) { pmml[j][i] = pms[(size_t)j * nt + i].mlval; pmpk[j][i] = pms[(size_t)j * nt + i].peakloc; }
+  }
+  // likelihood-ratio tests of the migration rates and 2NM terms: the curve at its peak and at zero (:380-399), one pass for all
+  std::vector<double> migtest(nm, 0.0), pmtest(nt, 0.0);
+  {
+    std::vector<int> kind(2 * nm, 0), par(2 * nm), fi(2 * nm, 0), la(2 * nm, (int)G);
+    std::vector<double> x(2 * nm), v(2 * nm, 0.0);
+    for (int i = 0; i < nm; i++) { par[2 * i] = par[2 * i + 1] = i + nq; x[2 * i] = peakloc[NT][i + nq]; x[2 * i + 1] = 0.0000001; }
+    if (nm) ck(ima2p_lmode_marginal_many(LM, 2 * nm, kind.data(), par.data(), fi.data(), la.data(), x.data(), nullptr, v.data()), "marginal density");
+    for (int i = 0; i < nm; i++) migtest[i] = 2 * log((-v[2 * i]) / (-v[2 * i + 1]));
+    for (int i = 0; i < nt; i++) {
+      const double xs[2] = {pmpk[NT][i], 0.0000001};
+      double f2[2];
+      ck(ima2p_lmode_marginpopmig(LM, terms[i].thetai, terms[i].mi, 0, (int)G, xs, 2, f2), "2NM density");
+      pmtest[i] = 2 * log((-f2[0]) / (-f2[1]));
+    }
+  }
+  // the 95% bounds (:277-297): for every parameter with a peak, two roots of log margincalc - (log peak height - 1.92), by
+  // halving, all 2 p of them in lock step
+  std::vector<Bisection> lo95(p), hi95(p);
+  for (int i = 0; i < p; i++) {
+    if (peakloc[NT][i] < 0) continue;
+    const Curve c{1, i, 0, (int)G, -1, log(mlval[NT][i]) - 1.92};
+    lo95[i].start(0.0000001, peakloc[NT][i]);
+    hi95[i].start(peakloc[NT][i], prior_max[i]);
+    pool.add(&lo95[i], c);
+    pool.add(&hi95[i], c);
+  }
+  pool.run();
   bool errnote = false, signote = false;
   static const char *sig[4] = {"ns", "*", "**", "***"};
   for (int k = 0; k <= nsplit; k++) {
@@ -599,7 +722,7 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
       for (int i = ilo; i < ihi; i++)
         if (pb[i] == k) {
           if (peakloc[NT][i] >= 0) {
-            const double t = margin95(LM, mlval[NT].data(), peakloc[NT].data(), i, 0, prior_max[i]);
+            const double t = lo95[i].root;
             if (t <= 0) fprintf(f, "\t<min\t");
             else if (t >= DBL_MAX || t <= DBL_MIN) fprintf(f, "\tna\t");
             else fprintf(f, "\t%7.3lf\t", t);
@@ -609,7 +732,7 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
       for (int i = ilo; i < ihi; i++)
         if (pb[i] == k) {
           if (peakloc[NT][i] >= 0) {
-            const double t = margin95(LM, mlval[NT].data(), peakloc[NT].data(), i, 1, prior_max[i]);
+            const double t = hi95[i].root;
             if (t >= prior_max[i] || t <= DBL_MIN) fprintf(f, "\t>max\t");
             else fprintf(f, "\t%7.3lf\t", t);
           } else fprintf(f, "\t\t");

@@ -111,6 +111,69 @@ IMA_KERNEL void k_reduce_partials(const double *partials, int nchunks, int width
   out[i] = s;
 }
 
+// Many independent one-point marginal evaluations in one launch: the lock-step peak and bound searches of the front end (one
+// search per parameter and row set, each wanting its next abscissa) hand all their current points to one pass.  Request q owns
+// the blocks [block0[q], block0[q+1]): one block per chunk of its row range, one evaluation point per block.  Lane, warp and chunk
+// order of the additions are k_marginal's with nx = 1, so a value is bit for bit the one the single-request call gives.
+struct MargReq { long long first, last; double x; int param, round_counts, block0, pad; };
+
+IMA_KERNEL void k_marginal_many(LmView V, const MargReq *req, int nreq, double *partials) {
+  IMA_SMEM_DECL
+  const int lane = Warp::lane(), warp = ima_warp_in_block();
+  int lo = 0, hi = nreq - 1;                   // the request this block belongs to (block0 ascending)
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (req[mid].block0 <= (int)ima_block()) lo = mid; else hi = mid - 1; }
+  const MargReq R = req[lo];
+  const int chunk = ima_block() - R.block0;
+  const long long r0 = R.first + (long long)chunk * kRowsPerBlock;
+  long long r1 = r0 + kRowsPerBlock;
+  if (r1 > R.last) r1 = R.last;
+  const bool theta = R.param < V.nq;
+  const int p = theta ? R.param : R.param - V.nq;
+  const double xs = R.x;
+  const double a1 = theta ? (kLog2 - log(xs)) : log(xs);
+  const double a2 = (!theta && V.expoprior) ? (log(V.m_meaninv[p]) - xs * V.m_meaninv[p]) : 0.0;
+  const float *c0 = V.cols + (size_t)((theta ? V.ccp : V.mcp) + p) * V.G;
+  const float *c1 = V.cols + (size_t)((theta ? V.fcp : V.fmp) + p) * V.G;
+  const float *c2 = V.cols + (size_t)((theta ? V.qip : V.mip) + p) * V.G;
+  const float *c3 = V.cols + (size_t)(V.hccp + (theta ? p : 0)) * V.G;
+  double acc = 0.0;
+  for (long long r = r0 + warp * IMA_WARP + lane; r < r1; r += kLmWarps * IMA_WARP) {
+    double cnt = c0[r];
+    const double f = c1[r], integ = c2[r];
+    if (R.round_counts) cnt = integerround(cnt);
+    if (theta) acc += exp(-integ + cnt * a1 - (double)c3[r] - 2 * f / xs);
+    else if (V.expoprior) acc += exp(-integ + (a2 + cnt * a1) - f * xs);
+    else acc += exp(-integ + cnt * a1 - f * xs);
+  }
+  double *sm = (double *)IMA_SMEM;     // [kLmWarps]
+  const double s = Warp::sum(acc);
+  if (lane == 0) sm[warp] = s;
+#if IMA_CUDA
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kLmWarps; w++) t += sm[w];
+    partials[ima_block()] = t;
+  }
+#else
+  if (warp == kLmWarps - 1) {
+    double t = 0.0;
+    for (int w = 0; w < kLmWarps; w++) t += sm[w];
+    partials[ima_block()] = t;
+  }
+#endif
+}
+
+// out[q] = the chunk partials of request q added in chunk order
+IMA_KERNEL void k_reduce_many(const MargReq *req, int nreq, int nblocks, const double *partials, double *out) {
+  const int q = ima_block() * kLmWarps * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
+  if (q >= nreq) return;
+  const int b1 = q + 1 < nreq ? req[q + 1].block0 : nblocks;
+  double s = 0.0;
+  for (int b = req[q].block0; b < b1; b++) s += partials[b];
+  out[q] = s;
+}
+
 struct JointXs { double log2diffx[kMaxParams], logx[kMaxParams], divx[kMaxParams], x[kMaxParams]; };
 
 // p_g of jointp (jointfind.cpp:971-996, two populations / full model): one thread per row, all vectors of the batch
@@ -781,6 +844,8 @@ struct Lmode {
   JointXs *w_xs = nullptr;
   JointXs *d_xs = nullptr;
   size_t cap_x = 0, cap_partials = 0;
+  MargReq *d_req = nullptr; double *d_mpart = nullptr, *d_mout = nullptr;      // marginal_many: requests, per-block partials, sums
+  size_t cap_req = 0, cap_mpart = 0;
   struct LmPriors *d_pri = nullptr;            // section 8 (f3) evaluators: priors, logfact table and error word, made on first use
   double *d_logfact = nullptr, *d_msums = nullptr;
   int *d_err = nullptr;
@@ -922,6 +987,56 @@ int ima2p_lmode_marginp(ima2p_lmode *h, int param, int firsttree, int lasttree, 
   for (int i = 0; i < nx; i++) {
     if (x[i] < mn || x[i] > mx) out[i] = 1;          // OFFSCALEVAL :45-46
     else out[i] = -(out[i] / (lasttree - firsttree + (firsttree == 0)));
+  }
+  return IMA2P_OK;
+}
+
+// The current points of many independent one-dimensional searches in one device pass (k_marginal_many): request q evaluates
+// parameter param[q] at x[q]; kind[q] = 0: marginp over rows [first[q], last[q]) (:25-80), kind[q] = 1: log margincalc over all rows
+// minus yadjust[q] (:119-173, the function margin95 finds the root of).  One upload, two launches, one download for the batch.
+int ima2p_lmode_marginal_many(ima2p_lmode *h, int n, const int *kind, const int *param, const int *first, const int *last, const double *x,
+                              const double *yadjust, double *out) {
+  if (!h || !h->lm.d_cols || n < 0 || (n && (!kind || !param || !x || !out))) return lfail(IMA2P_E_ARG, "marginal_many: bad argument / rows not loaded");
+  if (n == 0) return IMA2P_OK;
+  Lmode &l = h->lm;
+  std::vector<MargReq> req(n);
+  int nblocks = 0;
+  for (int q = 0; q < n; q++) {
+    MargReq &R = req[q];
+    if (param[q] < 0 || param[q] >= l.v.nq + l.v.nm) return lfail(IMA2P_E_ARG, "marginal_many: bad parameter index");
+    if (kind[q] == 0) {
+      if (!first || !last || first[q] < 0 || last[q] > l.v.G || first[q] >= last[q]) return lfail(IMA2P_E_ARG, "marginal_many: bad range");
+      R.first = first[q]; R.last = last[q]; R.round_counts = param[q] < l.v.nq ? 0 : 1;
+    } else if (kind[q] == 1) {
+      if (!yadjust) return lfail(IMA2P_E_ARG, "marginal_many: kind 1 needs yadjust");
+      R.first = 0; R.last = l.v.G; R.round_counts = 1;
+    } else return lfail(IMA2P_E_ARG, "marginal_many: kind is 0 (marginp) or 1 (log margincalc)");
+    R.x = x[q]; R.param = param[q]; R.block0 = nblocks; R.pad = 0;
+    nblocks += (int)((R.last - R.first + kRowsPerBlock - 1) / kRowsPerBlock);
+  }
+  if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = lm_stream(&l, nullptr);
+  if ((size_t)n > l.cap_req) { l.d_req = l.alloc<MargReq>(n); l.d_mout = l.alloc<double>(n); l.cap_req = n; }
+  if ((size_t)nblocks > l.cap_mpart) { l.d_mpart = l.alloc<double>(nblocks); l.cap_mpart = nblocks; }
+  if (!l.d_req || !l.d_mout || !l.d_mpart) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  if (!h2d(l.d_req, req.data(), n * sizeof(MargReq), s)) return lfail(IMA2P_E_CUDA, "upload failed");
+  IMA_LAUNCH(k_marginal_many, nblocks, kLmWarps, kLmWarps * sizeof(double), s, l.v, l.d_req, n, l.d_mpart);
+  IMA_LAUNCH(k_reduce_many, (n + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_req, n, nblocks, l.d_mpart, l.d_mout);
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (marginal_many)");
+#endif
+  if (!d2h(out, l.d_mout, n * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
+  for (int q = 0; q < n; q++) {
+    const int pi = param[q];
+    if (kind[q] == 0) {
+      const double mx = pi < l.v.nq ? l.q_max[pi] : l.m_max[pi - l.v.nq], mn = pi < l.v.nq ? l.q_min[pi] : l.m_min[pi - l.v.nq];
+      if (x[q] < mn || x[q] > mx) out[q] = 1;          // OFFSCALEVAL :45-46
+      else out[q] = -(out[q] / (last[q] - first[q] + (first[q] == 0)));
+    } else {
+      double v = out[q] / (double)l.v.G;
+      v = v <= 0 ? -1e200 : log(v);
+      out[q] = v - yadjust[q];
+    }
   }
   return IMA2P_OK;
 }

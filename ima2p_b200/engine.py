@@ -539,6 +539,20 @@ class LMode:
         capi.check(self.lib, self.lib.ima2p_lmode_marginp(self._h, param, firsttree, lasttree, _dp(x), len(x), _dp(out)))
         return out
 
+    def marginal_many(self, kind, param, first, last, x, yadjust=None):
+        """The current points of many independent searches in one device pass (ima2p_lmode_marginal_many): request q is
+        marginp(param[q], first[q], last[q], x[q]) for kind[q] = 0 and log margincalc(x[q]) - yadjust[q] for kind[q] = 1; the
+        lock-step form of the calls marginalopt / margin95 make one at a time (surface_call_functions.cpp:175-297)."""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        kind, param, first, last = i32(kind), i32(param), i32(first), i32(last)
+        x = _f64(np.atleast_1d(x))
+        ya = _f64(np.zeros(len(x)) if yadjust is None else yadjust)
+        out = np.zeros(len(x))
+        ip = lambda a: a.ctypes.data_as(capi.c_int_p)
+        capi.check(self.lib, self.lib.ima2p_lmode_marginal_many(self._h, len(x), ip(kind), ip(param), ip(first), ip(last), _dp(x),
+                                                                _dp(ya), _dp(out)))
+        return out
+
     def moments(self):
         """print_means_variances_correlations (output.cpp:687-745): means, variances, correlations (p < q entries) of the
         parameters from the calcx sums over every row, plus the raw sums (sum0[np], sum1[np], cross[np][np])."""

@@ -312,6 +312,12 @@ int ima2p_lmode_marginal_sums (ima2p_lmode * l, int param, const double *x, int 
 /* margincalc (:119-173) / marginp (:25-80) on a single GPU holding all rows */
 int ima2p_lmode_margincalc (ima2p_lmode * l, int param, const double *x, int nx, double yadjust, int logi, double *out);
 int ima2p_lmode_marginp (ima2p_lmode * l, int param, int firsttree, int lasttree, const double *x, int nx, double *out);
+/* n independent one-point evaluations in one device pass, for searches that advance in lock step (the marginal peak searches
+ * and the 95% bounds of findmarginpeaks, surface_call_functions.cpp:175-297, each of which calls marginp / margincalc once per
+ * iterate in the reference): kind[q] = 0 -> marginp(param[q], first[q], last[q], x[q]); kind[q] = 1 -> log margincalc(x[q])
+ * of param[q] over all rows minus yadjust[q].  Values are bit for bit those of the single calls. */
+int ima2p_lmode_marginal_many (ima2p_lmode * l, int n, const int *kind, const int *param, const int *first, const int *last,
+                               const double *x, const double *yadjust, double *out);
 /* jointp for nvec parameter vectors x[nvec][nq+nm]; out_q[nvec] = -log joint density, out_ess[nvec] */
 int ima2p_lmode_jointp (ima2p_lmode * l, const double *x, int nvec, int calc_ess, double *out_q, double *out_ess);
 

@@ -2,6 +2,7 @@
 kernel sources through the tests-only host-emulation build (tests/hostemu).  The checker is always the
 CPU oracle (pinned against the reference's own values) or the golden fixtures themselves."""
 import numpy as np
+import pytest
 
 from support import (FlatModel, FlatTree, OracleModel, check_static_eval, engine_from_fixture, f64, fp, dp, i32, load_golden, oracle,
                      rel_close, split_weights, tree_from_engine, _num)
@@ -145,6 +146,25 @@ def lmode_matches_reference(lib, name, rtol=1e-9):
         assert rel_close(lm.margincalc(x, 0.25, p, 1), [_num(t[3]) for t in sel], rtol)
         assert rel_close(lm.marginp(p, 0, G, x), [_num(t[4]) for t in sel], rtol, 1e-300)
         assert rel_close(lm.marginp(p, G // 3, 2 * G // 3, x), [_num(t[5]) for t in sel], rtol, 1e-300)
+    # the lock-step form (one pass for the current points of many searches) gives the single calls' values bit for bit
+    P = sorted(set(t[0] for t in tab))
+    rng = np.random.default_rng(5)
+    n = 64
+    par = rng.choice(P, n)
+    kind = rng.integers(0, 2, n)
+    first = np.where(rng.random(n) < 0.5, 0, rng.integers(0, G // 2, n))
+    last = np.where(rng.random(n) < 0.5, G, first + 1 + rng.integers(0, G // 2, n))
+    hi = np.array([(fm.q_max[p] if p < fm.nq else fm.m_max[p - fm.nq]) for p in par])
+    x = rng.random(n) * hi * 1.05 + 1e-7                # a few beyond the prior (OFFSCALEVAL)
+    ya = rng.random(n)
+    many = lm.marginal_many(kind, par, first, last, x, ya)
+    for k in range(n):
+        one = lm.marginp(int(par[k]), int(first[k]), int(last[k]), x[k:k + 1]) if kind[k] == 0 else \
+            lm.margincalc(x[k:k + 1], ya[k], int(par[k]), 1)
+        assert many[k] == one[0], (k, kind[k], many[k], one[0])
+    assert len(lm.marginal_many([], [], [], [], [])) == 0
+    with pytest.raises(Exception):
+        lm.marginal_many([0], [P[0]], [5], [5], [1.0])       # empty row range
     xs = np.array([j["x"] for j in d["jointp"]])
     q, ess = lm.jointp(xs, True)
     assert rel_close(q, [j["q"] for j in d["jointp"]], rtol), (q[:4], [j["q"] for j in d["jointp"]][:4])
