@@ -176,55 +176,87 @@ IMA_KERNEL void k_reduce_many(const MargReq *req, int nreq, int nblocks, const d
 
 struct JointXs { double log2diffx[kMaxParams], logx[kMaxParams], divx[kMaxParams], x[kMaxParams]; };
 
-// p_g of jointp (jointfind.cpp:971-996, two populations / full model): one thread per row, all vectors of the batch
-IMA_KERNEL void k_joint_terms(LmView V, const JointXs *xs, int nvec, double *pbuf, double *chunkmax) {
+// p_g of jointp (jointfind.cpp:971-996, two populations / full model).  One block = a chunk of rows x a tile of kVT parameter
+// vectors; any number of vectors per launch (grid = chunks x tiles).  The tile's accumulators and running maxima live in registers
+// (loops over the tile fully unrolled); the per-vector coefficients of parameter i (log(2/x), 1/x for a size, log x, x for a
+// migration rate) are staged once per block in shared memory and read as broadcasts; a row's columns are read once per tile,
+// parameter by parameter, so nothing is indexed dynamically and nothing spills.  Every p is the same sequence of additions as
+// the reference's loop over the parameters (:974-992).
+constexpr int kVT = 16;              // parameter vectors per block of k_joint_terms
+IMA_HD size_t joint_terms_smem(int np) { return (size_t)(2 * kVT * np + kLmWarps * kVT) * sizeof(double); }
+
+IMA_KERNEL void k_joint_terms(LmView V, const JointXs *xs, int nvec, int nchunks, double *pbuf, double *chunkmax) {
   IMA_SMEM_DECL
   const int lane = Warp::lane(), warp = ima_warp_in_block();
-  const int chunk = ima_block();
+  const int tile = ima_block() / nchunks, chunk = ima_block() - tile * nchunks;
+  const int v0 = tile * kVT, nt = nvec - v0 < kVT ? nvec - v0 : kVT;
   const long long r0 = (long long)chunk * kRowsPerBlock;
   long long r1 = r0 + kRowsPerBlock;
   if (r1 > V.G) r1 = V.G;
-  double *sm = (double *)IMA_SMEM;     // [kLmWarps][kJointVecMax]
-  double vmax[kJointVecMax];
-  for (int v = 0; v < nvec; v++) vmax[v] = -DBL_MAX;
   const int np = V.nq + V.nm;
-  for (long long r = r0 + warp * IMA_WARP + lane; r < r1; r += kLmWarps * IMA_WARP) {
-    float g[2 * kMaxParams];
-    // columns are read once per row and reused for every vector of the batch
-    const double probg = V.cols[(size_t)V.probgp * V.G + r];
-    for (int i = 0; i < V.nq; i++) { g[3 * i] = V.cols[(size_t)(V.ccp + i) * V.G + r]; g[3 * i + 1] = V.cols[(size_t)(V.hccp + i) * V.G + r]; g[3 * i + 2] = V.cols[(size_t)(V.fcp + i) * V.G + r]; }
-    for (int i = 0; i < V.nm; i++) { g[3 * V.nq + 2 * i] = V.cols[(size_t)(V.mcp + i) * V.G + r]; g[3 * V.nq + 2 * i + 1] = V.cols[(size_t)(V.fmp + i) * V.G + r]; }
-    for (int v = 0; v < nvec; v++) {
-      const JointXs &X = xs[v];
-      double p = -probg;
-      for (int i = 0; i < np; i++) {
-        if (i < V.nq) p += g[3 * i] * X.log2diffx[i] - g[3 * i + 1] - (2.0 * g[3 * i + 2]) * X.divx[i];
-        else { const int i1 = i - V.nq; p += g[3 * V.nq + 2 * i1] * X.logx[i] - g[3 * V.nq + 2 * i1 + 1] * X.x[i]; }
-      }
-      pbuf[(size_t)v * V.G + r] = p;
-      if (p > vmax[v]) vmax[v] = p;
-    }
-  }
-  for (int v = 0; v < nvec; v++) {
-    double m = vmax[v];
+  double *ca = (double *)IMA_SMEM, *cb = ca + kVT * np, *sm = cb + kVT * np;     // [np][kVT], [np][kVT], [kLmWarps][kVT]
 #if IMA_CUDA
-    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+  for (int k = threadIdx.x; k < kVT * np; k += blockDim.x) {
+#else
+  for (int k = 0; k < kVT * np; k++) {                   // the emulation runs a block's warps one after the other
 #endif
-    if (lane == 0) sm[warp * kJointVecMax + v] = m;
+    const int i = k / kVT, j = k - i * kVT;
+    const JointXs &X = xs[v0 + (j < nt ? j : 0)];
+    ca[k] = i < V.nq ? X.log2diffx[i] : X.logx[i];
+    cb[k] = i < V.nq ? X.divx[i] : X.x[i];
   }
 #if IMA_CUDA
   __syncthreads();
-  if ((int)threadIdx.x < nvec) {
+#endif
+  double vmax[kVT];
+#pragma unroll
+  for (int j = 0; j < kVT; j++) vmax[j] = -DBL_MAX;
+  for (long long r = r0 + warp * IMA_WARP + lane; r < r1; r += kLmWarps * IMA_WARP) {
+    const double probg = V.cols[(size_t)V.probgp * V.G + r];
+    double p[kVT];
+#pragma unroll
+    for (int j = 0; j < kVT; j++) p[j] = -probg;
+    for (int i = 0; i < V.nq; i++) {
+      const double cc = V.cols[(size_t)(V.ccp + i) * V.G + r], hc = V.cols[(size_t)(V.hccp + i) * V.G + r];
+      const double fc2 = 2.0 * V.cols[(size_t)(V.fcp + i) * V.G + r];
+      const double *a = ca + i * kVT, *b = cb + i * kVT;
+#pragma unroll
+      for (int j = 0; j < kVT; j++) p[j] += cc * a[j] - hc - fc2 * b[j];
+    }
+    for (int i = 0; i < V.nm; i++) {
+      const double mc = V.cols[(size_t)(V.mcp + i) * V.G + r], fm = V.cols[(size_t)(V.fmp + i) * V.G + r];
+      const double *a = ca + (V.nq + i) * kVT, *b = cb + (V.nq + i) * kVT;
+#pragma unroll
+      for (int j = 0; j < kVT; j++) p[j] += mc * a[j] - fm * b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < kVT; j++)
+      if (j < nt) {
+        pbuf[(size_t)(v0 + j) * V.G + r] = p[j];
+        if (p[j] > vmax[j]) vmax[j] = p[j];
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < kVT; j++) {
+    double m = vmax[j];
+#if IMA_CUDA
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+#endif
+    if (lane == 0) sm[warp * kVT + j] = m;
+  }
+#if IMA_CUDA
+  __syncthreads();
+  if ((int)threadIdx.x < nt) {
     double m = -DBL_MAX;
-    for (int w = 0; w < kLmWarps; w++) m = sm[w * kJointVecMax + threadIdx.x] > m ? sm[w * kJointVecMax + threadIdx.x] : m;
-    chunkmax[(size_t)threadIdx.x * gridDim.x + chunk] = m;
+    for (int w = 0; w < kLmWarps; w++) m = sm[w * kVT + threadIdx.x] > m ? sm[w * kVT + threadIdx.x] : m;
+    chunkmax[(size_t)(v0 + threadIdx.x) * nchunks + chunk] = m;
   }
 #else
   if (warp == kLmWarps - 1)
-    for (int v = 0; v < nvec; v++) {
+    for (int j = 0; j < nt; j++) {
       double m = -DBL_MAX;
-      for (int w = 0; w < kLmWarps; w++) m = sm[w * kJointVecMax + v] > m ? sm[w * kJointVecMax + v] : m;
-      chunkmax[(size_t)v * ((V.G + kRowsPerBlock - 1) / kRowsPerBlock) + chunk] = m;
+      for (int w = 0; w < kLmWarps; w++) m = sm[w * kVT + j] > m ? sm[w * kVT + j] : m;
+      chunkmax[(size_t)(v0 + j) * nchunks + chunk] = m;
     }
 #endif
 }
@@ -839,7 +871,7 @@ struct Lmode {
   double q_max[kMaxParams], q_min[kMaxParams], m_max[kMaxParams], m_min[kMaxParams], m_mean[kMaxParams];
   float *d_cols = nullptr;
   double *d_x = nullptr, *d_partials = nullptr, *d_out = nullptr, *d_pbuf = nullptr, *d_chunkmax = nullptr, *d_prefix = nullptr,
-         *d_lmax = nullptr, *d_jpart = nullptr, *d_jout = nullptr, *d_seed = nullptr, *d_gmax = nullptr, *d_ltmp = nullptr,
+         *d_lmax = nullptr, *d_jpart = nullptr, *d_jout = nullptr, *d_seed = nullptr, *d_gmax = nullptr, *d_ltmp = nullptr, *d_wlmax = nullptr, *d_wrec = nullptr,
          *w_pbuf = nullptr, *w_chunkmax = nullptr, *w_prefix = nullptr, *w_jpart = nullptr, *w_jout = nullptr;   // wide batches (joint_begin / _middle)
   JointXs *w_xs = nullptr;
   JointXs *d_xs = nullptr;
@@ -1060,7 +1092,7 @@ int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const do
   double *d_seed = nullptr;
   if (seed_before) { d_seed = l.d_jout; if (!h2d(d_seed, seed_before, nvec * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed"); }
   if (!h2d(l.d_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
-  IMA_LAUNCH(k_joint_terms, nchunks, kLmWarps, kLmWarps * kJointVecMax * sizeof(double), s, l.v, l.d_xs, nvec, l.d_pbuf, l.d_chunkmax);
+  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.d_xs, nvec, nchunks, l.d_pbuf, l.d_chunkmax);
   IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, d_seed, l.d_prefix, l.d_lmax);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint terms)");
@@ -1076,7 +1108,7 @@ int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const do
 //   middle: dev_allmax[world][nvec] (device, the gathered local maxima) -> seed and global maximum on the device, prefixes,
 //           scan, fold; dev_records_out[nvec][8] (device) = the six record fields, the global maximum, 0
 // The caller gathers the records of all ranks and closes every vector with ima2p_lmode_joint_finish on their sums.
-// up to kJointCallMax vectors per call, in sub-batches of kJointVecMax queued back to back on their own buffers
+// up to kJointCallMax vectors per call; every kernel is launched once for all of them
 constexpr int kJointCallMax = 256;
 static int joint_wide_buffers(Lmode &l) {
   if (l.w_pbuf) return IMA2P_OK;
@@ -1088,7 +1120,8 @@ static int joint_wide_buffers(Lmode &l) {
   l.w_jout = l.alloc<double>((size_t)kJointCallMax * kJP);
   l.w_xs = l.alloc<JointXs>(kJointCallMax);
   l.d_seed = l.alloc<double>(kJointCallMax); l.d_gmax = l.alloc<double>(kJointCallMax); l.d_ltmp = l.alloc<double>(kJointCallMax);
-  if (!l.w_pbuf || !l.w_chunkmax || !l.w_prefix || !l.w_jpart || !l.w_jout || !l.w_xs || !l.d_seed || !l.d_gmax || !l.d_ltmp)
+  l.d_wlmax = l.alloc<double>(kJointCallMax); l.d_wrec = l.alloc<double>((size_t)kJointCallMax * 8);
+  if (!l.w_pbuf || !l.w_chunkmax || !l.w_prefix || !l.w_jpart || !l.w_jout || !l.w_xs || !l.d_seed || !l.d_gmax || !l.d_ltmp || !l.d_wlmax || !l.d_wrec)
     return lfail(IMA2P_E_CUDA, "device allocation failed (jointp, wide batch)");
   return IMA2P_OK;
 }
@@ -1108,12 +1141,10 @@ int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *d
       if (i < l.v.nq) xs[v].log2diffx[i] = kLog2 - log(xv);
     }
   if (!h2d(l.w_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
-  for (int b0 = 0; b0 < nvec; b0 += kJointVecMax) {
-    const int nb = nvec - b0 < kJointVecMax ? nvec - b0 : kJointVecMax;
-    IMA_LAUNCH(k_joint_terms, nchunks, kLmWarps, kLmWarps * kJointVecMax * sizeof(double), s, l.v, (const JointXs *)(l.w_xs + b0), nb, l.w_pbuf + (size_t)b0 * l.v.G, l.w_chunkmax + (size_t)b0 * nchunks);
-    IMA_LAUNCH(k_joint_prefix, (nb + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, (const double *)(l.w_chunkmax + (size_t)b0 * nchunks), nchunks, nb, (const double *)nullptr,
-               l.w_prefix + (size_t)b0 * nchunks, dev_localmax_out + b0);
-  }
+  // every buffer is [vector][...]: one launch of each kernel serves all vectors of the call
+  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.w_xs, nvec, nchunks, l.w_pbuf, l.w_chunkmax);
+  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)nullptr,
+             l.w_prefix, dev_localmax_out);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint begin)");
 #endif
@@ -1132,14 +1163,10 @@ int ima2p_lmode_joint_middle(ima2p_lmode *h, int nvec, const double *dev_allmax,
   const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
   const int gall = (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP);
   IMA_LAUNCH(k_joint_seed, gall, kLmWarps, 0, s, dev_allmax, world, rank, nvec, l.d_seed, l.d_gmax);
-  for (int b0 = 0; b0 < nvec; b0 += kJointVecMax) {
-    const int nb = nvec - b0 < kJointVecMax ? nvec - b0 : kJointVecMax, gv = (nb + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP);
-    const size_t oc = (size_t)b0 * nchunks;
-    IMA_LAUNCH(k_joint_prefix, gv, kLmWarps, 0, s, (const double *)(l.w_chunkmax + oc), nchunks, nb, (const double *)(l.d_seed + b0), l.w_prefix + oc, l.d_ltmp + b0);
-    IMA_LAUNCH(k_joint_scan, (nchunks * nb + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, (const double *)(l.w_pbuf + (size_t)b0 * l.v.G), nb, (const double *)(l.w_prefix + oc),
-               (const double *)(l.d_gmax + b0), global_row0, l.w_jpart + oc * kJP);
-    IMA_LAUNCH(k_joint_fold, gv, kLmWarps, 0, s, (const double *)(l.w_jpart + oc * kJP), nchunks, nb, l.w_jout + (size_t)b0 * kJP);
-  }
+  IMA_LAUNCH(k_joint_prefix, gall, kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)l.d_seed, l.w_prefix, l.d_ltmp);
+  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, (const double *)l.w_pbuf, nvec, (const double *)l.w_prefix,
+             (const double *)l.d_gmax, global_row0, l.w_jpart);
+  IMA_LAUNCH(k_joint_fold, gall, kLmWarps, 0, s, (const double *)l.w_jpart, nchunks, nvec, l.w_jout);
   IMA_LAUNCH(k_joint_pack, gall, kLmWarps, 0, s, (const double *)l.w_jout, (const double *)l.d_gmax, nvec, dev_records_out);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint middle)");
@@ -1222,16 +1249,19 @@ int ima2p_lmode_jointp(ima2p_lmode *h, const double *x, int nvec, int calc_ess, 
   Lmode &l = h->lm;
   if (l.v.G != l.v.G_total) return lfail(IMA2P_E_ARG, "jointp: this handle holds a shard; use the two-phase form");
   const int np = l.v.nq + l.v.nm;
-  for (int v0 = 0; v0 < nvec; v0 += kJointVecMax) {
-    const int nb = nvec - v0 < kJointVecMax ? nvec - v0 : kJointVecMax;
-    double lmax[kJointVecMax], rec[kJointVecMax * kJP];
-    int rc = ima2p_lmode_joint_phase1(h, x + (size_t)v0 * np, nb, nullptr, lmax);
-    if (rc) return rc;
-    rc = ima2p_lmode_joint_phase2(h, nb, lmax, 0, rec);
-    if (rc) return rc;
+  // the device-resident form with a world of one: up to 256 vectors per pass, seven launches and one copy back per pass
+  int rc = joint_wide_buffers(l);
+  if (rc) return rc;
+  stream_t s = lm_stream(&l, nullptr);
+  std::vector<double> rec((size_t)kJointCallMax * 8);
+  for (int v0 = 0; v0 < nvec; v0 += kJointCallMax) {
+    const int nb = nvec - v0 < kJointCallMax ? nvec - v0 : kJointCallMax;
+    if ((rc = ima2p_lmode_joint_begin(h, x + (size_t)v0 * np, nb, l.d_wlmax, nullptr))) return rc;
+    if ((rc = ima2p_lmode_joint_middle(h, nb, l.d_wlmax, 1, 0, 0, l.d_wrec, nullptr))) return rc;
+    if (!d2h(rec.data(), l.d_wrec, (size_t)nb * 8 * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
     for (int v = 0; v < nb; v++) {
       double e = 0.0;
-      ima2p_lmode_joint_finish(rec + (size_t)v * kJP, lmax[v], l.v.G_total, calc_ess, &out_q[v0 + v], &e);
+      ima2p_lmode_joint_finish(rec.data() + (size_t)v * 8, rec[(size_t)v * 8 + 6], l.v.G_total, calc_ess, &out_q[v0 + v], &e);
       if (out_ess) out_ess[v0 + v] = e;
     }
   }
