@@ -104,6 +104,8 @@ SIGNATURES = {
     "ima2p_dataset_locus": (_i, [_v, _i, c_int_p, c_dbl_p, c_int_p, C.c_char_p, _i]),
     "ima2p_dataset_locus_data": (_i, [_v, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p]),
     "ima2p_engine_step_report": (_i, [_v, c_dbl_p, c_flt_p, c_int_p, _v]),
+    "ima2p_engine_step_report_begin": (_i, [_v, _i, _v]),
+    "ima2p_engine_step_report_end": (_i, [_v, _i, c_dbl_p, c_flt_p, c_int_p]),
     "ima2p_engine_write_mcf": (_i, [_v, C.c_char_p]),
     "ima2p_engine_read_mcf": (_i, [_v, C.c_char_p]),
     "ima2p_ti_create": (_i, [C.c_char_p, C.c_char_p]),
@@ -115,6 +117,7 @@ SIGNATURES = {
     "ima2p_lmode_marginal_sums": (_i, [_v, _i, c_dbl_p, _i, _i, _i, _i, c_dbl_p, _v, _v]),
     "ima2p_lmode_margincalc": (_i, [_v, _i, c_dbl_p, _i, _d, _i, c_dbl_p]),
     "ima2p_lmode_marginp": (_i, [_v, _i, _i, _i, c_dbl_p, _i, c_dbl_p]),
+    "ima2p_lmode_set_joint_model": (_i, [_v, _i]),
     "ima2p_lmode_marginal_many": (_i, [_v, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     "ima2p_lmode_jointp": (_i, [_v, c_dbl_p, _i, _i, c_dbl_p, c_dbl_p]),
     "ima2p_lmode_moments": (_i, [_v, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]),

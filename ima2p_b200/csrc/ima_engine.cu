@@ -82,6 +82,11 @@ struct Engine {
   unsigned long long *d_swap_counts = nullptr;
   double *d_thermosum = nullptr;
   double *d_report = nullptr, *h_report = nullptr;      // step_report: device staging and its pinned host mirror
+  double *d_report2[2] = {nullptr, nullptr}, *h_report2[2] = {nullptr, nullptr};    // step_report_begin / _end: two slots in flight
+#if IMA_CUDA
+  cudaEvent_t report_ev[2] = {nullptr, nullptr};
+#endif
+  bool report_pending[2] = {false, false};
   UpdateView uv{};              // split-time / mutation-scalar updates
   int t_updates = 0, u_every = 0;
   std::vector<int> h_ul_l, h_ul_a;
@@ -2010,6 +2015,61 @@ int ima2p_engine_step_report(ima2p_engine *h, double *chain4, float *row, int *p
   if (!d2h(e.h_report, e.d_report, n * sizeof(double), s) || !dev_sync(s)) return fail(IMA2P_E_CUDA, "download failed");
   memcpy(chain4, e.h_report, 4 * (size_t)C * sizeof(double));
   const double *r = e.h_report + 4 * (size_t)C;
+  *present = r[rowlen] != 0.0;
+  if (*present) for (int i = 0; i < rowlen; i++) row[i] = (float)r[i];
+  if (r[rowlen + 1] != 0.0) {
+    char buf[120];
+    snprintf(buf, sizeof buf, "device error word %d raised by a kernel", (int)r[rowlen + 1]);
+    return fail(IMA2P_E_DEVICE, buf);
+  }
+  return IMA2P_OK;
+}
+
+// The same report in two halves, so that the host can queue step s+1 before it waits for the results of step s: _begin packs
+// and starts the copy into slot (0 or 1) and returns at once; _end waits for that slot's copy only and hands the results out.
+// The device never idles between steps while the host wakes up and reads: the two slots alternate.
+int ima2p_engine_step_report_begin(ima2p_engine *h, int slot, void *cuda_stream) {
+  if (!h || !h->eng.finalized || slot < 0 || slot > 1) return fail(IMA2P_E_ARG, "step_report_begin: bad argument");
+  Engine &e = h->eng;
+  if (e.report_pending[slot]) return fail(IMA2P_E_ARG, "step_report_begin: the slot holds a report that has not been read");
+  if (!use_device(&e)) return fail(IMA2P_E_CUDA, "cudaSetDevice failed");
+  stream_t s = pick_stream(&e, cuda_stream);
+  int dims[5];
+  ima2p_engine_dims(h, dims);
+  const int rowlen = dims[4], C = e.d.nchains;
+  const size_t n = 4 * (size_t)C + rowlen + 2;
+  if (!e.d_report2[slot]) {
+    e.d_report2[slot] = e.alloc<double>(n);
+#if IMA_CUDA
+    if (!IMA_CUDA_OK(cudaMallocHost((void **)&e.h_report2[slot], n * sizeof(double)))) return fail(IMA2P_E_CUDA, "pinned allocation failed");
+    if (!IMA_CUDA_OK(cudaEventCreateWithFlags(&e.report_ev[slot], cudaEventDisableTiming))) return fail(IMA2P_E_CUDA, "event creation failed");
+#else
+    e.h_report2[slot] = (double *)malloc(n * sizeof(double));
+#endif
+    if (!e.d_report2[slot] || !e.h_report2[slot]) return fail(IMA2P_E_CUDA, "allocation failed (step report)");
+  }
+  IMA_LAUNCH(k_pack_report, 1, 1, 0, s, e.v, (const int *)e.sv.chain_of_rank, rowlen, e.d_report2[slot]);
+  if (!d2h(e.h_report2[slot], e.d_report2[slot], n * sizeof(double), s)) return fail(IMA2P_E_CUDA, "download failed");
+#if IMA_CUDA
+  if (!IMA_CUDA_OK(cudaEventRecord(e.report_ev[slot], s))) return fail(IMA2P_E_CUDA, "event record failed");
+#endif
+  e.report_pending[slot] = true;
+  return IMA2P_OK;
+}
+
+int ima2p_engine_step_report_end(ima2p_engine *h, int slot, double *chain4, float *row, int *present) {
+  if (!h || !h->eng.finalized || slot < 0 || slot > 1 || !chain4 || !row || !present) return fail(IMA2P_E_ARG, "step_report_end: bad argument");
+  Engine &e = h->eng;
+  if (!e.report_pending[slot]) return fail(IMA2P_E_ARG, "step_report_end: no report was begun in this slot");
+#if IMA_CUDA
+  if (!use_device(&e) || !IMA_CUDA_OK(cudaEventSynchronize(e.report_ev[slot]))) return fail(IMA2P_E_CUDA, "waiting for the report failed");
+#endif
+  e.report_pending[slot] = false;
+  int dims[5];
+  ima2p_engine_dims(h, dims);
+  const int rowlen = dims[4], C = e.d.nchains;
+  memcpy(chain4, e.h_report2[slot], 4 * (size_t)C * sizeof(double));
+  const double *r = e.h_report2[slot] + 4 * (size_t)C;
   *present = r[rowlen] != 0.0;
   if (*present) for (int i = 0; i < rowlen; i++) row[i] = (float)r[i];
   if (r[rowlen + 1] != 0.0) {

@@ -798,7 +798,7 @@ void print_marginal_peaks(FILE *f, ima2p_lmode *LM, long long G, const std::vect
 // ---- joint posterior peak: jointfind.cpp:599-812 (differential evolution: startpop, nextgen, difeloop, copybest, modelloop)
 // and :815-879, 1087-1184 (the table).  The reference evaluates jointp for one individual after the other; a generation's
 // trial vectors do not depend on each other (they are all built from the previous population), so the whole generation
-// goes to the device in one ima2p_lmode_jointp call.  Two populations (the FULL model); the random numbers are this
+// goes to the device in one ima2p_lmode_jointp call.  The random numbers are this
 // program's own, the peak it converges to is the reference's (spread tolerance 1e-7, found twice before stopping).
 std::string logpfmt(double v) {                     // logpstrformat jointfind.cpp:295-318
   char b[64];
@@ -813,24 +813,18 @@ std::string logpfmt(double v) {                     // logpstrformat jointfind.c
   return b;
 }
 
-void print_joint_peak(FILE *f, ima2p_lmode *LM, long long G, const std::vector<std::string> &name, int nq, int nm, const std::vector<double> &prior_max,
-                      int npops, unsigned long long seed) {
-  fprintf(f, "Joint Peak Locations and Posterior Probabilities\n================================================\n");
-  fprintf(f, "  estimates based on %lld sampled genealogies\n", G);
-  if (npops != 2) { fprintf(f, "  the joint search of this build covers two-population models (the FULL model)\n\n"); return; }
-  fprintf(f, "\nModel#  Model Description\n %d     FULL\n", 1);
-  fprintf(f, "\nModel#\tlog(P)\t#terms\tdf\t2LLR\tESS");
-  const int np = nq + nm;
-  for (int i = 0; i < np; i++) if (i < nq || prior_max[i] > 0.000001) fprintf(f, "\t%s", name[i].c_str());
-  fprintf(f, "\n");
-  const int depop = np * 100;                        // DEFAULTPOPSIZEMULTIPLIER
+// One search of the differential evolution over the parameters [lo, hi) of a model type (modelloop jointfind.cpp:744-812 with
+// difeloop :702-716, nextgen :599-684, startpop :686-699); best[np] = -log joint density at the peak best[0..np)
+void joint_model_search(ima2p_lmode *LM, int np, int lo, int hi, const std::vector<double> &prior_max, unsigned long long &st, std::vector<double> &best) {
+  const int depop = np * 100;                        // DEFAULTPOPSIZEMULTIPLIER x the number of parameters of the analysis (:1091)
   const double recrate = 0.9, fweight = 0.8, lower = 0.0000001;
-  unsigned long long st = seed * 6364136223846793005ull + 1442695040888963407ull;
   auto uni = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return ((double)(st >> 11) + 0.5) / 9007199254740992.0; };
-  std::vector<double> pop((size_t)depop * np), trial((size_t)depop * np), fpop(depop), ftrial(depop), ess(depop), best(np + 1, 0.0);
+  // entries outside [lo, hi) are not part of the model: the device does not read them, they stay at 1
+  std::vector<double> pop((size_t)depop * np, 1.0), trial((size_t)depop * np, 1.0), fpop(depop), ftrial(depop);
+  best.assign(np + 1, 0.0);
   auto evaluate = [&](std::vector<double> &x, std::vector<double> &fx) { ck(ima2p_lmode_jointp(LM, x.data(), depop, 0, fx.data(), nullptr), "joint density"); };
   auto startpop = [&]() {
-    for (int i = 0; i < depop; i++) for (int j = 0; j < np; j++) pop[(size_t)i * np + j] = lower + uni() * (prior_max[j] - lower);
+    for (int i = 0; i < depop; i++) for (int j = lo; j < hi; j++) pop[(size_t)i * np + j] = lower + uni() * (prior_max[j] - lower);
     evaluate(pop, fpop);
   };
   double global_pd = 1e200;
@@ -843,7 +837,7 @@ void print_joint_peak(FILE *f, ima2p_lmode *LM, long long G, const std::vector<s
     do {                                             // difeloop: generations until the population has collapsed on a peak
       for (int i = 0; i < depop; i++) {
         const int A = (int)(uni() * depop) % depop, B = (int)(uni() * depop) % depop, Cv = (int)(uni() * depop) % depop;
-        for (int j = 0; j < np; j++) {
+        for (int j = lo; j < hi; j++) {
           if (uni() < recrate) {
             const double c = pop[(size_t)Cv * np + j];
             double t = c + fweight * (pop[(size_t)A * np + j] - pop[(size_t)B * np + j]);
@@ -856,7 +850,7 @@ void print_joint_peak(FILE *f, ima2p_lmode *LM, long long G, const std::vector<s
       evaluate(trial, ftrial);
       lowpd = 1e200; hipd = -1e200;
       for (int i = 0; i < depop; i++) {
-        if (ftrial[i] < fpop[i]) { fpop[i] = ftrial[i]; for (int j = 0; j < np; j++) pop[(size_t)i * np + j] = trial[(size_t)i * np + j]; }
+        if (ftrial[i] < fpop[i]) { fpop[i] = ftrial[i]; for (int j = lo; j < hi; j++) pop[(size_t)i * np + j] = trial[(size_t)i * np + j]; }
         if (fpop[i] < lowpd) lowpd = fpop[i];
         if (fpop[i] > hipd) hipd = fpop[i];
       }
@@ -873,11 +867,41 @@ void print_joint_peak(FILE *f, ima2p_lmode *LM, long long G, const std::vector<s
     }
     newstart++;
   } while (countloop < 2 && newstart < 10);          // LOOPMATCHCRITERIA, MAXRESTART
-  double q = 0, e = 0;
-  ck(ima2p_lmode_jointp(LM, best.data(), 1, 1, &q, &e), "joint density");
-  fprintf(f, "%d\t%s\t%d\t-\t-\t%s", 1, logpfmt(-best[np]).c_str(), np, logpfmt(e).c_str());
-  for (int i = 0; i < np; i++) fprintf(f, best[i] < 0.001 ? "\t%.5lf" : "\t%.4lf", best[i]);
-  fprintf(f, "\n\n");
+}
+
+// findjointpeaks jointfind.cpp:1087-1170 without a nested-model file: the FULL model of a two-population analysis, or the two
+// searches of a three-population analysis -- all population sizes (nowmodeltype 1), then all migration rates (2); jointp is a
+// function of that family only (ima2p_lmode_set_joint_model).  More populations: the reference refuses too (:1076-1081).
+void print_joint_peak(FILE *f, ima2p_lmode *LM, long long G, const std::vector<std::string> &name, int nq, int nm, const std::vector<double> &prior_max,
+                      int npops, unsigned long long seed) {
+  fprintf(f, "Joint Peak Locations and Posterior Probabilities\n================================================\n");
+  fprintf(f, "  estimates based on %lld sampled genealogies\n", G);
+  if (npops != 2 && npops != 3) { fprintf(f, "  the joint search is defined for two- and three-population models\n\n"); return; }
+  static const char *modelstart[3] = {"FULL", "ALL POPULATION SIZE PARAMETERS", "ALL MIGRATION PARAMETERS"};     // modelstartstr :163
+  const int type0 = npops == 2 ? 0 : 1, type1 = npops == 2 ? 0 : 2;
+  fprintf(f, "\nModel#  Model Description\n");
+  for (int t = type0, j = 1; t <= type1; t++, j++) fprintf(f, "%2d     %s\n", j, modelstart[t]);
+  fprintf(f, "\nModel#\tlog(P)\t#terms\tdf\t2LLR\tESS");
+  const int np = nq + nm;
+  for (int i = 0; i < np; i++) if (i < nq || prior_max[i] > 0.000001) fprintf(f, "\t%s", name[i].c_str());
+  fprintf(f, "\n");
+  unsigned long long st = seed * 6364136223846793005ull + 1442695040888963407ull;
+  for (int t = type0, j = 1; t <= type1; t++, j++) {
+    const int lo = t == 2 ? nq : 0, hi = t == 1 ? nq : np;
+    ck(ima2p_lmode_set_joint_model(LM, t), "joint model");
+    std::vector<double> best;
+    joint_model_search(LM, np, lo, hi, prior_max, st, best);
+    double q = 0, e = 0;
+    ck(ima2p_lmode_jointp(LM, best.data(), 1, 1, &q, &e), "joint density");
+    fprintf(f, "%d\t%s\t%d\t-\t-\t%s", j, logpfmt(-best[np]).c_str(), hi - lo, logpfmt(e).c_str());
+    for (int i = 0; i < np; i++) {                   // printjointpeakvals :814-840
+      if (i < lo || i >= hi) fprintf(f, "\t-");
+      else fprintf(f, best[i] < 0.001 ? "\t%.5lf" : "\t%.4lf", best[i]);
+    }
+    fprintf(f, "\n");
+  }
+  ck(ima2p_lmode_set_joint_model(LM, 0), "joint model");
+  fprintf(f, "\n");
 }
 
 // The report sections that are sums over the sampled genealogies (printoutput, ima_main_mpi.cpp:4080-4110), written to f from

@@ -185,7 +185,7 @@ struct JointXs { double log2diffx[kMaxParams], logx[kMaxParams], divx[kMaxParams
 constexpr int kVT = 16;              // parameter vectors per block of k_joint_terms
 IMA_HD size_t joint_terms_smem(int np) { return (size_t)(2 * kVT * np + kLmWarps * kVT) * sizeof(double); }
 
-IMA_KERNEL void k_joint_terms(LmView V, const JointXs *xs, int nvec, int nchunks, double *pbuf, double *chunkmax) {
+IMA_KERNEL void k_joint_terms(LmView V, const JointXs *xs, int nvec, int nchunks, int modeltype, double *pbuf, double *chunkmax) {
   IMA_SMEM_DECL
   const int lane = Warp::lane(), warp = ima_warp_in_block();
   const int tile = ima_block() / nchunks, chunk = ima_block() - tile * nchunks;
@@ -212,18 +212,24 @@ IMA_KERNEL void k_joint_terms(LmView V, const JointXs *xs, int nvec, int nchunks
 #pragma unroll
   for (int j = 0; j < kVT; j++) vmax[j] = -DBL_MAX;
   for (long long r = r0 + warp * IMA_WARP + lane; r < r1; r += kLmWarps * IMA_WARP) {
-    const double probg = V.cols[(size_t)V.probgp * V.G + r];
+    // modeltype 0: two populations, all parameters, p starts at -probg (:973); 1 / 2: the size-only and migration-only models
+    // of a three-population search, p starts at minus the sum of that family's integrals (:949-952, :976-978)
+    double probg = 0.0;
+    if (modeltype == 0) probg = V.cols[(size_t)V.probgp * V.G + r];
+    else if (modeltype == 1) for (int i = 0; i < V.nq; i++) probg += V.cols[(size_t)(V.qip + i) * V.G + r];
+    else for (int i = 0; i < V.nm; i++) probg += V.cols[(size_t)(V.mip + i) * V.G + r];
     double p[kVT];
 #pragma unroll
     for (int j = 0; j < kVT; j++) p[j] = -probg;
-    for (int i = 0; i < V.nq; i++) {
+    const int nq_used = modeltype == 2 ? 0 : V.nq, nm_used = modeltype == 1 ? 0 : V.nm;
+    for (int i = 0; i < nq_used; i++) {
       const double cc = V.cols[(size_t)(V.ccp + i) * V.G + r], hc = V.cols[(size_t)(V.hccp + i) * V.G + r];
       const double fc2 = 2.0 * V.cols[(size_t)(V.fcp + i) * V.G + r];
       const double *a = ca + i * kVT, *b = cb + i * kVT;
 #pragma unroll
       for (int j = 0; j < kVT; j++) p[j] += cc * a[j] - hc - fc2 * b[j];
     }
-    for (int i = 0; i < V.nm; i++) {
+    for (int i = 0; i < nm_used; i++) {
       const double mc = V.cols[(size_t)(V.mcp + i) * V.G + r], fm = V.cols[(size_t)(V.fmp + i) * V.G + r];
       const double *a = ca + (V.nq + i) * kVT, *b = cb + (V.nq + i) * kVT;
 #pragma unroll
@@ -876,6 +882,7 @@ struct Lmode {
   JointXs *w_xs = nullptr;
   JointXs *d_xs = nullptr;
   size_t cap_x = 0, cap_partials = 0;
+  int joint_model = 0;                         // which parameters jointp is a function of (ima2p_lmode_set_joint_model)
   MargReq *d_req = nullptr; double *d_mpart = nullptr, *d_mout = nullptr;      // marginal_many: requests, per-block partials, sums
   size_t cap_req = 0, cap_mpart = 0;
   struct LmPriors *d_pri = nullptr;            // section 8 (f3) evaluators: priors, logfact table and error word, made on first use
@@ -1092,7 +1099,7 @@ int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const do
   double *d_seed = nullptr;
   if (seed_before) { d_seed = l.d_jout; if (!h2d(d_seed, seed_before, nvec * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed"); }
   if (!h2d(l.d_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
-  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.d_xs, nvec, nchunks, l.d_pbuf, l.d_chunkmax);
+  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.d_xs, nvec, nchunks, l.joint_model, l.d_pbuf, l.d_chunkmax);
   IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, d_seed, l.d_prefix, l.d_lmax);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint terms)");
@@ -1142,7 +1149,7 @@ int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *d
     }
   if (!h2d(l.w_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
   // every buffer is [vector][...]: one launch of each kernel serves all vectors of the call
-  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.w_xs, nvec, nchunks, l.w_pbuf, l.w_chunkmax);
+  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.w_xs, nvec, nchunks, l.joint_model, l.w_pbuf, l.w_chunkmax);
   IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)nullptr,
              l.w_prefix, dev_localmax_out);
 #if IMA_CUDA
@@ -1242,6 +1249,15 @@ void ima2p_lmode_joint_finish_gathered(const double *rec8, int world, int nvec, 
     ima2p_lmode_joint_finish(tot, rec8[(size_t)v * 8 + 6], nrows_total, calc_ess, q + v, &e);
     if (ess) ess[v] = e;
   }
+}
+
+// nowmodeltype of findjointpeaks (jointfind.cpp:1104-1133): 0 = all parameters (two populations), 1 = the population sizes only,
+// 2 = the migration rates only (the two searches of a three-population analysis); applies to every joint evaluation that follows.
+// The entries of x outside the model's parameter range are not read.
+int ima2p_lmode_set_joint_model(ima2p_lmode *h, int modeltype) {
+  if (!h || modeltype < 0 || modeltype > 2) return lfail(IMA2P_E_ARG, "set_joint_model: model type is 0, 1 or 2");
+  h->lm.joint_model = modeltype;
+  return IMA2P_OK;
 }
 
 int ima2p_lmode_jointp(ima2p_lmode *h, const double *x, int nvec, int calc_ess, double *out_q, double *out_ess) {

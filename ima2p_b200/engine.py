@@ -365,6 +365,18 @@ class Engine:
         self._ck(self.lib.ima2p_engine_step_report(self._h, _dp(out), row.ctypes.data_as(capi.c_flt_p), C.byref(present), stream))
         return out, (row if present.value else None)
 
+    def step_report_begin(self, slot, stream=None):
+        """First half of step_report: queue the packing kernel and the copy into slot 0 / 1, return at once."""
+        self._ck(self.lib.ima2p_engine_step_report_begin(self._h, int(slot), stream))
+
+    def step_report_end(self, slot):
+        """Second half: wait for that slot's copy and return what step_report returns."""
+        out = np.zeros((self.nchains, 4))
+        row = np.zeros(self.rowlen, np.float32)
+        present = C.c_int()
+        self._ck(self.lib.ima2p_engine_step_report_end(self._h, int(slot), _dp(out), row.ctypes.data_as(capi.c_flt_p), C.byref(present)))
+        return out, (row if present.value else None)
+
     def write_mcf(self, path):
         """writemcf (mcmcfile.cpp:203-296): the state of the local chains in the reference's .mcf format."""
         self._ck(self.lib.ima2p_engine_write_mcf(self._h, str(path).encode()))
@@ -607,6 +619,11 @@ class LMode:
         q, ess = np.zeros(len(x)), np.zeros(len(x))
         capi.check(self.lib, self.lib.ima2p_lmode_jointp(self._h, _dp(x), len(x), int(calc_ess), _dp(q), _dp(ess)))
         return q, ess
+
+    def set_joint_model(self, modeltype):
+        """nowmodeltype of findjointpeaks (jointfind.cpp:1104-1133): 0 all parameters (two populations), 1 the population sizes,
+        2 the migration rates (the two searches of a three-population analysis); applies to the joint evaluations that follow."""
+        capi.check(self.lib, self.lib.ima2p_lmode_set_joint_model(self._h, int(modeltype)))
 
     # sharded form: see ima2p_lmode_joint_phase1/2 in include/ima2p_b200.h
     def joint_phase1(self, x, seed_before=None):

@@ -320,6 +320,9 @@ int ima2p_lmode_marginal_many (ima2p_lmode * l, int n, const int *kind, const in
                                const double *x, const double *yadjust, double *out);
 /* jointp for nvec parameter vectors x[nvec][nq+nm]; out_q[nvec] = -log joint density, out_ess[nvec] */
 int ima2p_lmode_jointp (ima2p_lmode * l, const double *x, int nvec, int calc_ess, double *out_q, double *out_ess);
+/* nowmodeltype (jointfind.cpp:1104-1133): 0 all parameters (two populations, the default), 1 population sizes only, 2 migration
+ * rates only -- the two full models of a three-population search (:949-952, :973-980) */
+int ima2p_lmode_set_joint_model (ima2p_lmode * l, int modeltype);
 
 /* Sharded form (rows split over GPUs; the caller exchanges a few doubles per vector over NCCL):
  *   phase 1: p_g of every local row for nvec (<= 32) vectors; seed_before[v] = max of p over the rows held by
@@ -401,6 +404,11 @@ int ima2p_dataset_locus_data (const ima2p_dataset * d, int locus, int *seq, int 
  * synchronisation: chain4[nchains][4] = beta, probg, P(D|G), swap sum of every local chain; row = the cold chain's .ti
  * row (ima2p_engine_cold_row) when it lives on this rank (*present). */
 int ima2p_engine_step_report (ima2p_engine * e, double *chain4, float *row, int *present, void *cuda_stream);
+/* The same in two halves with two slots (0, 1): _begin queues the packing kernel and the copy and returns; _end waits for
+ * that slot's copy only.  A host that queues step s+1 before it reads the results of step s (the recording of :2891 does not
+ * feed back into the step) keeps the device busy while it reads. */
+int ima2p_engine_step_report_begin (ima2p_engine * e, int slot, void *cuda_stream);
+int ima2p_engine_step_report_end (ima2p_engine * e, int slot, double *chain4, float *row, int *present);
 
 /* ---- the MCMC state file (.mcf): writemcf / readmcf, mcmcfile.cpp:203-442 --------------------------------------
  * write_mcf: the chains this engine holds, in the reference's record stream ("name type count values", doubles as

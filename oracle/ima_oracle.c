@@ -1825,8 +1825,10 @@ ora_margincalc (const ora_model * m, const float *rows, int rowlen, int nrows, d
   return sum;
 }
 
-/* jointp jointfind.cpp:885-1047 for the full model (nowmodeltype 0, npops == 2 uses -probg; more
- * populations: the p-only model, nowmodeltype 1 is NOT restated).  The sorted linked list of
+/* jointp jointfind.cpp:885-1047.  modeltype 0: the full model of a two-population analysis (p starts at -probg, all
+ * parameters, :973, :1110-1113); 1 / 2: the two "full" models of a three-population analysis -- all population sizes
+ * (p starts at minus the sum of the size integrals, :949-950, :976; parameters [0, nq)) and all migration rates (minus the
+ * sum of the migration integrals, :951-952, :978; parameters [nq, nq + nm)), findjointpeaks :1118-1133.  The sorted linked list of
  * :191-270 is replaced by its observable behaviour: a term is *inserted* iff it lies within
  * PRANGELOG of the running maximum at the time it is met (:1005); the summation walks the inserted
  * terms downwards from the maximum while they lie within PRANGELOG of it, but visits at most
@@ -1842,8 +1844,16 @@ double
 ora_jointp (const ora_model * m, const float *rows, int rowlen, int nrows, const double *x, int calc_ess,
             double *effective_n)
 {
+  return ora_jointp_model (m, rows, rowlen, nrows, x, 0, calc_ess, effective_n);
+}
+
+double
+ora_jointp_model (const ora_model * m, const float *rows, int rowlen, int nrows, const double *x, int modeltype,
+                  int calc_ess, double *effective_n)
+{
   int gi, i, i1, nq = m->nq, nm = m->nm, np = nq + nm;
-  int ccp = 0, fcp = nq, hccp = 2 * nq, mcp = 3 * nq, fmp = mcp + nm, probgp = fmp + nm + nq + nm + 1;
+  int ccp = 0, fcp = nq, hccp = 2 * nq, mcp = 3 * nq, fmp = mcp + nm, qip = fmp + nm, mip = qip + nq, probgp = fmp + nm + nq + nm + 1;
+  int lo = modeltype == 2 ? nq : 0, hi = modeltype == 1 ? nq : np;
   double logx[ORA_MAXPARAMS], divx[ORA_MAXPARAMS], log2diffx[ORA_MAXPARAMS];
   double p, last = 0, acumm = 0, acumm_sqr = 0, sum;
   double *kept = (double *) malloc ((size_t) nrows * sizeof (double));
@@ -1860,8 +1870,20 @@ ora_jointp (const ora_model * m, const float *rows, int rowlen, int nrows, const
   for (gi = 0; gi < nrows; gi++)
   {
     const float *g = rows + (size_t) gi * rowlen;
-    p = -g[probgp];
-    for (i = 0; i < np; i++)
+    if (modeltype == 0)
+      p = -g[probgp];
+    else
+    {
+      double acc = 0;
+      if (modeltype == 1)
+        for (i = 0; i < nq; i++)
+          acc += g[qip + i];
+      else
+        for (i = 0; i < nm; i++)
+          acc += g[mip + i];
+      p = -acc;
+    }
+    for (i = lo; i < hi; i++)
     {
       if (i < nq)
         p += g[ccp + i] * log2diffx[i] - g[hccp + i] - (2.0 * g[fcp + i]) * divx[i];

@@ -42,6 +42,7 @@ double harness_swapweight (int ci, int cj);
 double harness_swapweight_bwprocesses (double sumi, double sumj, double betai, double betaj);
 double harness_marginp (int param, int firsttree, int lasttree, double x);
 void harness_jointp_setup (void);
+void harness_jointp_set_type (int type);
 double harness_calcx (int ei, int pnum, int mode);
 double harness_greater_than (int kind, int i, int j);
 void print_greater_than_tests (FILE * outfile);
@@ -823,6 +824,39 @@ mode_lmode (long burn, long rows, long every)
     }
   }
   fprintf (jo, "]");
+  if (npops > 2)
+  {
+    /* the two full models of a three-population joint search: the same kind of points under nowmodeltype 1 and 2 */
+    for (int type = 1; type <= 2; type++)
+    {
+      unsigned long long lcg = 88172645463325252ULL + (unsigned long long) type;
+      harness_jointp_set_type (type);
+      fprintf (jo, ",\n\"jointp_type%d\":[", type);
+      for (i = 0; i < 32; i++)
+      {
+        double xv[64], ess = 0;
+        for (p = 0; p < np; p++)
+        {
+          double mx = p < numpopsizeparams ? itheta[p].pr.max : imig[p - numpopsizeparams].pr.max;
+          lcg ^= lcg << 13;
+          lcg ^= lcg >> 7;
+          lcg ^= lcg << 17;
+          double u = (double) (lcg >> 11) / 9007199254740992.0;
+          xv[p] = (i & 1) ? mx * (0.02 + 0.3 * u) : mx * (1e-3 + 0.998 * u);
+        }
+        double q = jointp (xv, 1, &ess);
+        fprintf (jo, "%s{", i ? ",\n" : "");
+        jdarr ("x", xv, np, ",");
+        fprintf (jo, "\"q\":");
+        jd (q);
+        fprintf (jo, ",\"ess\":");
+        jd (ess);
+        fputc ('}', jo);
+      }
+      fprintf (jo, "]");
+    }
+    harness_jointp_set_type (0);
+  }
   if (kv.count ("extra"))
   {
     /* section 8 (f3): the other evaluators that stream over the rows.  calcx sums in row order exactly as

@@ -43,6 +43,14 @@ void harness_jointp_setup (void)
   nowmodeltype = 0;
   eexpsum = (struct extendnum *) malloc ((genealogiessaved + 1) * sizeof (struct extendnum));
 }
+/* the two "full" models of a three-population analysis (findjointpeaks :1118-1133): 1 = all population sizes,
+ * 2 = all migration rates; 0 = the two-population full model */
+void harness_jointp_set_type (int type)
+{
+  nowmodeltype = type;
+  nparamrange[0] = type == 2 ? numpopsizeparams : 0;
+  nparamrange[1] = type == 1 ? numpopsizeparams : numpopsizeparams + nummigrateparams;
+}
 
 #elif defined(SHIM_CALC_PROB_DATA)
 #include "calc_prob_data.cpp"

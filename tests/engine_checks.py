@@ -129,6 +129,56 @@ def incremental_sums_match_fresh_evaluation(lib, name, nsteps, rtol=1e-9, full_s
     return cnt
 
 
+def lmode_joint_models_match_reference(lib, rtol=1e-9):
+    """jointp as a function of the population sizes only / the migration rates only (nowmodeltype 1 / 2, the two searches of a
+    three-population analysis, jointfind.cpp:949-952, 973-980, 1118-1133) against the reference's own values; single call,
+    wide batches and the two-rank sharded form."""
+    from ima2p_b200 import LMode
+    d = load_golden("lmode_extra_sim5_3pop_hn2")
+    fm = FlatModel(d["model"])
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    G = len(rows)
+    mk = lambda: LMode(fm.nq, fm.nm, fm.nsplit, fm.q_max, fm.q_min, fm.m_max, fm.m_min, fm.m_mean, fm.expoprior, lib=lib)
+    lm = mk()
+    lm.load(rows)
+    for mt in (1, 2):
+        tab = d["jointp_type%d" % mt]
+        xs = np.array([j["x"] for j in tab])
+        lm.set_joint_model(mt)
+        q, ess = lm.jointp(xs, True)
+        assert rel_close(q, [j["q"] for j in tab], rtol), (mt, q[:3])
+        assert rel_close(ess, [j["ess"] for j in tab], 1e-8)
+        # the entries outside the model's range are not read
+        xo = xs.copy()
+        if mt == 1:
+            xo[:, fm.nq:] = 1.0
+        else:
+            xo[:, :fm.nq] = 1.0
+        assert np.array_equal(lm.jointp(xo, True)[0], q)
+        # rows split over two handles
+        half = G // 2 + 11
+        a, b = mk(), mk()
+        a.load(rows[:half], nrows_total=G, row0=0)
+        b.load(rows[half:], nrows_total=G, row0=half)
+        a.set_joint_model(mt); b.set_joint_model(mt)
+        nv = len(xs)
+        ma = a.joint_phase1(xs)
+        mb = b.joint_phase1(xs, seed_before=ma)
+        gmax = np.maximum(ma, mb)
+        ra, rb = a.joint_phase2(nv, gmax), b.joint_phase2(nv, gmax)
+        for v in range(nv):
+            rec = ra[v] + rb[v]
+            lo = ra[v] if ra[v][4] <= rb[v][4] else rb[v]
+            rec[4], rec[5] = lo[4], lo[5]
+            qv, ev = a.joint_finish(rec, gmax[v])
+            assert rel_close(qv, q[v], 1e-12) and rel_close(ev, ess[v], 1e-9)
+        a.close(); b.close()
+    lm.set_joint_model(0)
+    with pytest.raises(Exception):
+        lm.set_joint_model(3)
+    lm.close()
+
+
 def lmode_matches_reference(lib, name, rtol=1e-9):
     """a14 + a15: margincalc / marginp / jointp against the reference's own values on the same rows."""
     from ima2p_b200 import LMode
@@ -532,6 +582,20 @@ def step_report_matches_separate_reads(lib, name="state_sim5_hn4"):
     assert np.array_equal(summ, eng.fetch_chain_summary())
     ref_row = eng.cold_row()
     assert (row is None) == (ref_row is None) and (row is None or np.array_equal(row, ref_row))
+    # the two-slot form: step s+1 is queued before the report of step s is read; every report is that step's
+    eng.step_report_begin(0)
+    with pytest.raises(Exception):
+        eng.step_report_begin(0)                       # the slot holds an unread report
+    eng.run(1)
+    want1 = eng.fetch_chain_summary()
+    eng.step_report_begin(1)
+    eng.run(1)
+    s0, r0 = eng.step_report_end(0)
+    s1, _ = eng.step_report_end(1)
+    assert np.array_equal(s0, summ) and (r0 is None) == (row is None) and (row is None or np.array_equal(r0, row))
+    assert np.array_equal(s1, want1) and not np.array_equal(s1, s0)
+    with pytest.raises(Exception):
+        eng.step_report_end(1)                         # nothing was begun
     eng.close()
 
 

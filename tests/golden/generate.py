@@ -308,6 +308,25 @@ def main():
         with open(base + ".ti", "rb") as f, gzip.GzipFile(os.path.join(HERE, "inputs", rep_name + ".ti.gz"), "wb", mtime=0) as g:
             shutil.copyfileobj(f, g)
         print("wrote %s.json.gz and inputs/%s.ti.gz" % (rep_name, rep_name))
+    # the joint-posterior search of a three-population analysis (-c2: all population sizes, then all migration rates,
+    # jointfind.cpp:1118-1133): the reference's L mode on the committed .ti file of lmode_report_3pop; the table is added to
+    # that fixture under "joint"
+    if not ONLY or "lmode_report_3pop_joint" in ONLY:
+        import json
+        base = os.path.join(TMP, "j3pop")
+        with gzip.open(os.path.join(HERE, "inputs", "lmode_report_3pop.ti.gz"), "rb") as f, open(base + ".ti", "wb") as g:
+            shutil.copyfileobj(f, g)
+        rep = os.path.join(TMP, "j3pop_l.out")
+        subprocess.run([HARNESS, "stock", os.path.join(TMP, "j3pop_l.json"), "--", "-i", os.path.join(HERE, "inputs", "parse_is_3pop.u"), "-q10", "-m1", "-t3",
+                        "-o", rep, "-r0", "-v", base, "-p56", "-c2"], check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
+        text = open(rep).read()
+        a = text.index("Joint Peak Locations")
+        fx = os.path.join(HERE, "lmode_report_3pop.json.gz")
+        keep = json.load(gzip.open(fx))
+        keep["joint"] = text[a:text.index("\nHISTOGRAMS\n", a)]
+        with gzip.GzipFile(fx, "wb", mtime=0) as g:
+            g.write(json.dumps(keep).encode())
+        print("added the joint table to lmode_report_3pop.json.gz")
     # ASCII curves of an L-mode report (section 8 f4): the reference's L mode on the committed .ti file of lmode_report_sim3
     if not ONLY or "lmode_ascii_sim3" in ONLY:
         base = os.path.join(TMP, "ascii_ref")

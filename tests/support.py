@@ -204,6 +204,8 @@ def oracle():
     lib.ora_margincalc.argtypes = [v, c_flt_p, i, i, d, d, i, i]
     lib.ora_jointp.restype = d
     lib.ora_jointp.argtypes = [v, c_flt_p, i, i, c_dbl_p, i, c_dbl_p]
+    lib.ora_jointp_model.restype = d
+    lib.ora_jointp_model.argtypes = [v, c_flt_p, i, i, c_dbl_p, i, i, c_dbl_p]
     lib.ora_calcx.restype = d
     lib.ora_calcx.argtypes = [v, c_flt_p, i, i, i, i]
     lib.ora_moment_sums.argtypes = [v, c_flt_p, i, i, c_dbl_p]

@@ -85,17 +85,27 @@ def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path, name):
     if "joint" in ref:
         # the joint-posterior peak (-c2): a stochastic search (differential evolution, every generation one batched device
         # call) with this program's own random numbers, so the comparison is numerical: the peak the reference found
-        def peak_row(text):
+        # (two populations: the FULL model; three: all population sizes, then all migration rates, jointfind.cpp:1118-1133)
+        def peak_rows(text):
             a = text.index("Joint Peak Locations")
             lines = text[a:].split("\n")
             k = [i for i, ln in enumerate(lines) if ln.startswith("Model#\tlog(P)")][0]
-            return lines[k].split("\t"), lines[k + 1].split("\t")
-        (hr, vr), (ho, vo) = peak_row(ref["joint"]), peak_row(rep)
-        assert hr == ho and vr[2:5] == vo[2:5]                            # same columns; #terms, df, 2LLR
-        assert abs(float(vr[1]) - float(vo[1])) <= 2e-3                   # log(P) at the peak
-        assert abs(float(vr[5]) - float(vo[5])) <= 0.02 * float(vr[5])    # effective sample size there
-        for a, b in zip(vr[6:], vo[6:]):
-            assert abs(float(a) - float(b)) <= 2e-3 * max(1.0, abs(float(a))), (vr, vo)
+            rows = []
+            for ln in lines[k + 1:]:
+                if not ln.strip():
+                    break
+                rows.append(ln.split("\t"))
+            return text[a:a + text[a:].index("Model#\tlog(P)")], lines[k].split("\t"), rows
+        (dr, hr, rr), (do, ho, ro) = peak_rows(ref["joint"]), peak_rows(rep)
+        assert dr == do and hr == ho and len(rr) == len(ro) == (1 if name == "lmode_report_sim3" else 2)     # the model list, the columns
+        for vr, vo in zip(rr, ro):
+            assert vr[0] == vo[0] and vr[2:5] == vo[2:5]                      # model number; #terms, df, 2LLR
+            assert abs(float(vr[1]) - float(vo[1])) <= 2e-3                   # log(P) at the peak
+            assert abs(float(vr[5]) - float(vo[5])) <= 0.02 * float(vr[5])    # effective sample size there
+            for a, b in zip(vr[6:], vo[6:]):
+                assert (a == "-") == (b == "-"), (vr, vo)                     # parameters outside the model
+                if a != "-":
+                    assert abs(float(a) - float(b)) <= 2e-3 * max(1.0, abs(float(a))), (vr, vo)
     r = _run(exe, ["-r0", "-i", str(u), "-o", str(tmp_path / "l2.out"), "-q10", "-m1", "-t3"])
     assert r.returncode == 8 and "-v" in r.stderr            # IMERR_MISSINGCOMMANDINFO
 

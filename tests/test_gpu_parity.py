@@ -40,6 +40,10 @@ def test_incremental_sums_match_fresh_evaluation(lib, name, nsteps):
     assert cnt["steps"] == nsteps and cnt["dropped"] == 0
 
 
+def test_lmode_joint_models_of_three_populations(lib):
+    ec.lmode_joint_models_match_reference(lib)
+
+
 @pytest.mark.parametrize("name", ["lmode_sim5_hn2", "lmode_sim5_expo_hn2"])
 def test_lmode_matches_reference(lib, name):
     ec.lmode_matches_reference(lib, name, rtol=RTOL)

@@ -79,6 +79,10 @@ def test_pipeline_setting_is_accepted_and_does_not_change_the_run(emu):
     ec.pipeline_does_not_change_the_run(emu, nsteps=9)
 
 
+def test_lmode_joint_models_of_three_populations(emu):
+    ec.lmode_joint_models_match_reference(emu, rtol=1e-12)
+
+
 @pytest.mark.parametrize("name", ["lmode_extra_sim5_hn2", "lmode_extra_sim5_expo_hn2", "lmode_extra_sim5_3pop_hn2"])
 def test_lmode_moments_and_popmig(emu, name):
     assert ec.lmode_moments_and_popmig_match_reference(emu, name) >= 6

@@ -173,6 +173,25 @@ def test_lmode_matches_reference(name):
         assert rel_close(ess.value, j["ess"], 1e-10)
 
 
+def test_three_population_jointp_models_match_reference():
+    """jointp under nowmodeltype 1 (all population sizes) and 2 (all migration rates), the two full models of a
+    three-population joint search (jointfind.cpp:949-952, 973-980, 1118-1133): the reference's own values."""
+    import ctypes as C
+    d = load_golden("lmode_extra_sim5_3pop_hn2")
+    fm = FlatModel(d["model"])
+    om = OracleModel(fm)
+    lib = om.lib
+    rows = np.ascontiguousarray(d["rows"], dtype=np.float32)
+    G, rl = rows.shape
+    for mt in (1, 2):
+        assert len(d["jointp_type%d" % mt]) == 32
+        for j in d["jointp_type%d" % mt]:
+            ess = C.c_double()
+            q = lib.ora_jointp_model(om.h, fp(rows), rl, G, dp(f64(j["x"])), mt, 1, C.byref(ess))
+            assert rel_close(q, j["q"], 1e-12), (mt, q, j["q"])
+            assert rel_close(ess.value, j["ess"], 1e-10)
+
+
 @pytest.mark.parametrize("name", ["lmode_extra_sim5_hn2", "lmode_extra_sim5_3pop_hn2"])
 def test_moments_popmig_greater_than_match_reference(name):
     """section 8 (f3) restatements (calcx, the 2NM density, the greater-than probabilities) against the reference's values."""
