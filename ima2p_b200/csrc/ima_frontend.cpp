@@ -813,18 +813,131 @@ std::string logpfmt(double v) {                     // logpstrformat jointfind.c
   return b;
 }
 
-// One search of the differential evolution over the parameters [lo, hi) of a model type (modelloop jointfind.cpp:744-812 with
-// difeloop :702-716, nextgen :599-684, startpop :686-699); best[np] = -log joint density at the peak best[0..np)
-void joint_model_search(ima2p_lmode *LM, int np, int lo, int hi, const std::vector<double> &prior_max, unsigned long long &st, std::vector<double> &best) {
-  const int depop = np * 100;                        // DEFAULTPOPSIZEMULTIPLIER x the number of parameters of the analysis (:1091)
-  const double recrate = 0.9, fweight = 0.8, lower = 0.0000001;
+// A nested model (-w file, jointfind.cpp:40-135): some parameters of the full model are tied to another one ("equal") or fixed
+// ("constant"); the search runs over the parameters that are left.  map[i] says where full parameter i comes from: a position in
+// the vector of free parameters (>= 0) or minus a constant (< 0) -- the reference's xmap.
+struct NestedModel {
+  std::string name;
+  int type = -1;                     // 0: sizes and migration rates (two populations); 1: sizes only; 2: migration rates only
+  std::vector<double> map;
+  std::vector<int> listed;           // parameters named on an equal / constant line (printed in brackets)
+  int nfree = 0;                     // free parameters within the model type's family (#terms)
+  bool boundary = false;             // a constant sits on a bound of the prior: the 2LLR distribution is a mixture
+  void expand(const double *freevals, double *full) const {            // mapvals :563-574
+    for (size_t i = 0; i < map.size(); i++) full[i] = map[i] < 0 ? -map[i] : freevals[(int)map[i]];
+  }
+  void reduce(const double *full, double *freevals) const {            // reversemapvals :547-560
+    int to = 0;
+    for (size_t i = 0; i < map.size(); i++) if (to == (int)map[i]) freevals[to++] = full[i];
+  }
+};
+
+// setup_mapping :380-543.  File: a line with the number of models, then per model a line "model <name>" followed by lines
+// "equal p|m i j k ..." (j, k, ... always take the value of i) and "constant p|m value i j ..." (fixed at value, clamped into the
+// prior); p indices are population numbers, m indices count the migration parameters; anything after the numbers is comment.
+std::vector<NestedModel> read_nested_models(const std::string &fname, int npops, int nq, int nm, double thetaprior, double mprior) {
+  FILE *f = fopen(fname.c_str(), "r");
+  if (!f) die("Error opening nested model file: " + fname, 1);        // IMERR_READFILEOPENFAIL
+  const int np = nq + nm;
+  std::vector<NestedModel> models;
+  struct Tie { bool constant; double head; std::vector<int> members; };
+  std::vector<Tie> ties;
+  std::vector<char> removed;
+  auto finish = [&]() {
+    if (models.empty()) return;
+    NestedModel &M = models.back();
+    const int k = (int)models.size() - 1;
+    if (ties.empty()) die("nested model " + std::to_string(k) + " does not include any 'constant' or 'equal' specifications", 16);
+    if (npops == 2 && M.type != 0) die("nested model " + std::to_string(k) + " has m or p type but should be both when there are only two sampled populations", 16);
+    if (npops > 2 && M.type <= 0) die("nested model " + std::to_string(k) + " has type 0 but should be m or p type", 16);
+    int rank = 0;
+    for (int i = 0; i < np; i++) if (!removed[i]) M.map[i] = rank++;           // the free parameters keep their order
+    for (const Tie &t : ties)
+      for (int i : t.members) M.map[i] = t.constant ? -t.head : (double)(int)M.map[(int)t.head];
+    const int family = M.type == 1 ? nq : M.type == 2 ? nm : np;
+    int gone = 0;
+    for (int i = 0; i < np; i++) gone += removed[i];
+    M.nfree = family - gone;
+  };
+  char line[1024];
+  bool counted = false;
+  while (fgets(line, sizeof line, f)) {
+    if (!counted) { counted = isdigit((unsigned char)line[0]) != 0; continue; }          // the count itself is implied by the model lines
+    if (!isalpha((unsigned char)line[0])) continue;
+    std::string word;
+    char *c = line;
+    while (*c && !isspace((unsigned char)*c)) word += (char)tolower((unsigned char)*c++);
+    while (*c && isspace((unsigned char)*c)) c++;
+    if (word == "model") {
+      finish();
+      NestedModel M;
+      M.name = c;
+      while (!M.name.empty() && (M.name.back() == '\n' || M.name.back() == '\r')) M.name.pop_back();
+      M.type = npops == 2 ? 0 : -1;
+      M.map.assign(np, -1.0); M.listed.assign(np, 0);
+      models.push_back(M);
+      ties.clear(); removed.assign(np, 0);
+    } else if ((word == "equal" || word == "constant") && !models.empty()) {
+      NestedModel &M = models.back();
+      const char family = *c;
+      if (family != 'm' && family != 'p') continue;
+      if (M.type == -1) M.type = family == 'm' ? 2 : 1;
+      else if ((family == 'm' && M.type == 1) || (family == 'p' && M.type == 2)) die("nested model " + std::to_string(models.size() - 1) + " specified as both p and m types", 16);
+      const int base = family == 'm' ? nq : 0;
+      c++;
+      char *end = c;
+      Tie t;
+      t.constant = word == "constant";
+      t.head = strtod(c, &end);
+      if (end == c) continue;
+      c = end;
+      if (!t.constant) t.head += base;
+      else if (t.head <= 0.0000001) { t.head = 0.0000001; M.boundary = true; }           // MINPARAMVAL
+      else if (family == 'm' && t.head >= mprior) { t.head = mprior; M.boundary = true; }
+      else if (family == 'p' && t.head >= thetaprior) { t.head = thetaprior; M.boundary = true; }
+      for (;;) {
+        const long v = strtol(c, &end, 10);
+        if (end == c) break;
+        c = end;
+        const int i = (int)v + base;
+        if (i < 0 || i >= np) die("nested model file: parameter number out of range", 16);
+        t.members.push_back(i);
+        M.listed[i] = 1;
+        removed[i] = 1;
+      }
+      ties.push_back(t);
+    }
+  }
+  finish();
+  fclose(f);
+  return models;
+}
+
+// One search of the differential evolution (modelloop jointfind.cpp:744-812 with difeloop :702-716, nextgen :599-684, startpop
+// :686-699) over nvar free parameters that sit at positions [lo, lo + nvar) of the vectors; under a nested model a vector is
+// expanded to the full parameter list before it goes to the device.  best[0..np) = the peak (as searched), best[np] = -log joint
+// density there.  A whole generation is one device call.
+void joint_model_search(ima2p_lmode *LM, int np, int lo, int nvar, const std::vector<double> &upper_full, const NestedModel *nested,
+                        unsigned long long &st, std::vector<double> &best) {
+  const int depop = nvar * 100, hi = lo + nvar;      // DEFAULTPOPSIZEMULTIPLIER (:765)
+  const double recrate = 0.9, fweight = 0.8;
   auto uni = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return ((double)(st >> 11) + 0.5) / 9007199254740992.0; };
-  // entries outside [lo, hi) are not part of the model: the device does not read them, they stay at 1
-  std::vector<double> pop((size_t)depop * np, 1.0), trial((size_t)depop * np, 1.0), fpop(depop), ftrial(depop);
+  std::vector<double> lowerb(np, 0.0000001), upperb(upper_full);
+  if (nested) {                                      // bounds of the free parameters (:691-692)
+    std::vector<double> lf(np, 0.0000001);
+    nested->reduce(lf.data(), lowerb.data());
+    nested->reduce(upper_full.data(), upperb.data());
+  }
+  // entries outside [lo, hi) are not part of the search: the device does not read what they map to, they stay at 1
+  std::vector<double> pop((size_t)depop * np, 1.0), trial((size_t)depop * np, 1.0), full, fpop(depop), ftrial(depop);
+  if (nested) full.assign((size_t)depop * np, 1.0);
   best.assign(np + 1, 0.0);
-  auto evaluate = [&](std::vector<double> &x, std::vector<double> &fx) { ck(ima2p_lmode_jointp(LM, x.data(), depop, 0, fx.data(), nullptr), "joint density"); };
+  auto evaluate = [&](std::vector<double> &x, std::vector<double> &fx) {
+    if (nested) for (int i = 0; i < depop; i++) nested->expand(&x[(size_t)i * np], &full[(size_t)i * np]);
+    ck(ima2p_lmode_jointp(LM, nested ? full.data() : x.data(), depop, 0, fx.data(), nullptr), "joint density");
+  };
   auto startpop = [&]() {
-    for (int i = 0; i < depop; i++) for (int j = lo; j < hi; j++) pop[(size_t)i * np + j] = lower + uni() * (prior_max[j] - lower);
+    for (int i = 0; i < depop; i++) for (int j = lo; j < hi; j++) pop[(size_t)i * np + j] = lowerb[j] + uni() * (upperb[j] - lowerb[j]);
     evaluate(pop, fpop);
   };
   double global_pd = 1e200;
@@ -841,8 +954,8 @@ void joint_model_search(ima2p_lmode *LM, int np, int lo, int hi, const std::vect
           if (uni() < recrate) {
             const double c = pop[(size_t)Cv * np + j];
             double t = c + fweight * (pop[(size_t)A * np + j] - pop[(size_t)B * np + j]);
-            if (t < lower) t = c - uni() * (c - lower);                   // move only part of the way towards the bound
-            if (t > prior_max[j]) t = c + uni() * (prior_max[j] - c);
+            if (t < lowerb[j]) t = c - uni() * (c - lowerb[j]);           // move only part of the way towards the bound
+            if (t > upperb[j]) t = c + uni() * (upperb[j] - c);
             trial[(size_t)i * np + j] = t;
           } else trial[(size_t)i * np + j] = pop[(size_t)i * np + j];
         }
@@ -869,38 +982,63 @@ void joint_model_search(ima2p_lmode *LM, int np, int lo, int hi, const std::vect
   } while (countloop < 2 && newstart < 10);          // LOOPMATCHCRITERIA, MAXRESTART
 }
 
-// findjointpeaks jointfind.cpp:1087-1170 without a nested-model file: the FULL model of a two-population analysis, or the two
-// searches of a three-population analysis -- all population sizes (nowmodeltype 1), then all migration rates (2); jointp is a
-// function of that family only (ima2p_lmode_set_joint_model).  More populations: the reference refuses too (:1076-1081).
+// findjointpeaks jointfind.cpp:1087-1170: the FULL model of a two-population analysis, or the two searches of a three-population
+// analysis -- all population sizes (nowmodeltype 1), then all migration rates (2); jointp is a function of that family only
+// (ima2p_lmode_set_joint_model).  After each full model, the nested models of its type (-w file) with their likelihood-ratio
+// statistics against it.  More populations: the reference refuses too (:1076-1081).
 void print_joint_peak(FILE *f, ima2p_lmode *LM, long long G, const std::vector<std::string> &name, int nq, int nm, const std::vector<double> &prior_max,
-                      int npops, unsigned long long seed) {
+                      int npops, unsigned long long seed, const std::string &nestfname, double thetaprior, double mprior) {
   fprintf(f, "Joint Peak Locations and Posterior Probabilities\n================================================\n");
   fprintf(f, "  estimates based on %lld sampled genealogies\n", G);
   if (npops != 2 && npops != 3) { fprintf(f, "  the joint search is defined for two- and three-population models\n\n"); return; }
+  std::vector<NestedModel> nested;
+  if (!nestfname.empty()) {
+    nested = read_nested_models(nestfname, npops, nq, nm, thetaprior, mprior);
+    fprintf(f, "  nested model filename:%s\n", nestfname.c_str());
+  }
   static const char *modelstart[3] = {"FULL", "ALL POPULATION SIZE PARAMETERS", "ALL MIGRATION PARAMETERS"};     // modelstartstr :163
   const int type0 = npops == 2 ? 0 : 1, type1 = npops == 2 ? 0 : 2;
   fprintf(f, "\nModel#  Model Description\n");
-  for (int t = type0, j = 1; t <= type1; t++, j++) fprintf(f, "%2d     %s\n", j, modelstart[t]);
+  for (int t = type0, j = 0; t <= type1; t++) {
+    fprintf(f, "%2d     %s\n", ++j, modelstart[t]);
+    for (const NestedModel &M : nested) if (M.type == t) fprintf(f, "%2d   %s\n", ++j, M.name.c_str());
+  }
   fprintf(f, "\nModel#\tlog(P)\t#terms\tdf\t2LLR\tESS");
   const int np = nq + nm;
   for (int i = 0; i < np; i++) if (i < nq || prior_max[i] > 0.000001) fprintf(f, "\t%s", name[i].c_str());
   fprintf(f, "\n");
   unsigned long long st = seed * 6364136223846793005ull + 1442695040888963407ull;
-  for (int t = type0, j = 1; t <= type1; t++, j++) {
-    const int lo = t == 2 ? nq : 0, hi = t == 1 ? nq : np;
-    ck(ima2p_lmode_set_joint_model(LM, t), "joint model");
-    std::vector<double> best;
-    joint_model_search(LM, np, lo, hi, prior_max, st, best);
-    double q = 0, e = 0;
-    ck(ima2p_lmode_jointp(LM, best.data(), 1, 1, &q, &e), "joint density");
-    fprintf(f, "%d\t%s\t%d\t-\t-\t%s", j, logpfmt(-best[np]).c_str(), hi - lo, logpfmt(e).c_str());
-    for (int i = 0; i < np; i++) {                   // printjointpeakvals :814-840
-      if (i < lo || i >= hi) fprintf(f, "\t-");
-      else fprintf(f, best[i] < 0.001 ? "\t%.5lf" : "\t%.4lf", best[i]);
+  bool any_boundary = false;
+  auto print_vals = [&](const double *v, int lo, int hi, const std::vector<int> *listed) {      // printjointpeakvals :814-840
+    for (int i = 0; i < np; i++) {
+      if (i < lo || i >= hi) { fprintf(f, "\t-"); continue; }
+      const bool br = listed && (*listed)[i];
+      fprintf(f, v[i] < 0.001 ? (br ? "\t[%.5lf]" : "\t%.5lf") : (br ? "\t[%.4lf]" : "\t%.4lf"), v[i]);
     }
     fprintf(f, "\n");
+  };
+  for (int t = type0, j = 0; t <= type1; t++) {
+    const int lo = t == 2 ? nq : 0, hi = t == 1 ? nq : np;
+    ck(ima2p_lmode_set_joint_model(LM, t), "joint model");
+    std::vector<double> best, full(np);
+    joint_model_search(LM, np, lo, hi - lo, prior_max, nullptr, st, best);
+    double q = 0, e = 0;
+    ck(ima2p_lmode_jointp(LM, best.data(), 1, 1, &q, &e), "joint density");
+    const double holdml = best[np];
+    fprintf(f, "%d\t%s\t%d\t-\t-\t%s", ++j, logpfmt(-best[np]).c_str(), hi - lo, logpfmt(e).c_str());
+    print_vals(best.data(), lo, hi, nullptr);
+    for (const NestedModel &M : nested) if (M.type == t) {
+      joint_model_search(LM, np, lo, M.nfree, prior_max, &M, st, best);
+      M.expand(best.data(), full.data());
+      ck(ima2p_lmode_jointp(LM, full.data(), 1, 1, &q, &e), "joint density");
+      fprintf(f, "%d\t%s\t%d\t%d%s\t%s\t%s", ++j, logpfmt(-best[np]).c_str(), M.nfree, (hi - lo) - M.nfree, M.boundary ? "*" : "",
+              logpfmt(2 * (best[np] - holdml)).c_str(), logpfmt(e).c_str());
+      print_vals(full.data(), lo, hi, &M.listed);
+      any_boundary |= M.boundary;
+    }
   }
   ck(ima2p_lmode_set_joint_model(LM, 0), "joint model");
+  if (any_boundary) fprintf(f, "    * test distribution of 2LLR is a mixture\n");
   fprintf(f, "\n");
 }
 
@@ -1102,8 +1240,10 @@ void report_sections(FILE *f, std::map<std::string, std::string> &opt, ima2p_mod
             term_upper.push_back(expo ? 20.0 * mmean[mi] : qmx[thetai] * mmx[mi] / 2.0);
           }
     print_marginal_peaks(f, LM, nrows, name, nq, nm, nsplit, pmax, pb, pe, terms, term_upper);
-    if (loaded_from_ti && opt.count("c") && opt["c"].find('2') != std::string::npos)      // -c2 FINDJOINTPOSTERIOR (L mode only, ima_main_mpi.cpp:1466)
-      print_joint_peak(f, LM, nrows, name, nq, nm, pmax, npops, opt.count("s") ? strtoull(opt["s"].c_str(), nullptr, 10) : 1ull);
+    // -c2 FINDJOINTPOSTERIOR (L mode only, ima_main_mpi.cpp:1466); -w <nested model file> implies it (:934-937)
+    if (loaded_from_ti && ((opt.count("c") && opt["c"].find('2') != std::string::npos) || opt.count("w")))
+      print_joint_peak(f, LM, nrows, name, nq, nm, pmax, npops, opt.count("s") ? strtoull(opt["s"].c_str(), nullptr, 10) : 1ull,
+                       opt.count("w") ? opt["w"] : std::string(), atof(opt["q"].c_str()), opt.count("m") ? atof(opt["m"].c_str()) : 0.0);
   }
   // fillvec histograms.cpp:81-99: margincalc at the GRIDSIZE mid-bin points of every parameter (initialize.cpp:189-193, 237-242)
   std::vector<std::vector<double>> xs, ys;
@@ -1215,11 +1355,12 @@ int main(int argc, char **argv) {
   g_starttime = time(nullptr);
   std::map<std::string, std::string> opt;
   // -cap N (this build only): migration events per genealogy the device pools start with (they grow when they fill)
-  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", "cap", "c", nullptr};
+  static const char *known[] = {"hn", "hf", "ha", "hb", "i", "o", "q", "m", "t", "b", "l", "d", "s", "j", "r", "f", "p", "z", "v", "cap", "c", "w", nullptr};
   RunInfo R{};
   for (int a = 1; a < argc; a++) {
     if (argv[a][0] != '-') die(std::string("command line: unexpected word ") + argv[a], 5);
-    const std::string w = argv[a] + 1;
+    std::string w = argv[a] + 1;
+    if (w[0] == 'W') w[0] = 'w';                    // the reference's options are case-blind (ima_main_mpi.cpp:640)
     const char c1 = (char)toupper((unsigned char)w[0]);
     if (c1 == 'H') R.heating += std::string(" ") + argv[a];
     if (c1 == 'J') R.model += std::string(" ") + argv[a];

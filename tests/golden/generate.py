@@ -327,6 +327,28 @@ def main():
         with gzip.GzipFile(fx, "wb", mtime=0) as g:
             g.write(json.dumps(keep).encode())
         print("added the joint table to lmode_report_3pop.json.gz")
+    # nested models (-w file, jointfind.cpp:40-135, 380-543): the reference's L mode on the committed .ti files with the committed
+    # nested-model files; its joint table is added to the report fixtures under "joint_nested"
+    if not ONLY or "lmode_nested_joint" in ONLY:
+        import json
+        for rep_name, rep_u, nest in (("lmode_report_sim3", s3, "nested_models_2pop.txt"),
+                                      ("lmode_report_3pop", os.path.join(HERE, "inputs", "parse_is_3pop.u"), "nested_models_3pop.txt")):
+            base = os.path.join(TMP, "nest_" + rep_name)
+            with gzip.open(os.path.join(HERE, "inputs", rep_name + ".ti.gz"), "rb") as f, open(base + ".ti", "wb") as g:
+                shutil.copyfileobj(f, g)
+            rep = base + "_l.out"
+            nestf = os.path.join(TMP, nest)                      # a short path: the report echoes the file name
+            shutil.copy(os.path.join(HERE, "inputs", nest), nestf)
+            subprocess.run([HARNESS, "stock", base + "_l.json", "--", "-i", rep_u, "-q10", "-m1", "-t3", "-o", rep, "-r0", "-v", base, "-w", nestf],
+                           check=True, cwd=TMP, stdout=subprocess.DEVNULL, timeout=900)
+            text = open(rep).read()
+            a = text.index("Joint Peak Locations")
+            fx = os.path.join(HERE, rep_name + ".json.gz")
+            keep = json.load(gzip.open(fx))
+            keep["joint_nested"] = text[a:text.index("\nHISTOGRAMS\n", a)].replace(nestf, "NESTEDFILE")
+            with gzip.GzipFile(fx, "wb", mtime=0) as g:
+                g.write(json.dumps(keep).encode())
+            print("added the nested-model joint table to %s.json.gz" % rep_name)
     # ASCII curves of an L-mode report (section 8 f4): the reference's L mode on the committed .ti file of lmode_report_sim3
     if not ONLY or "lmode_ascii_sim3" in ONLY:
         base = os.path.join(TMP, "ascii_ref")

@@ -83,31 +83,67 @@ def test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path, name):
     for key in ("greater_than", "moments", "peaks", "t_histograms", "histograms", "popmig_histograms"):
         assert ref[key].strip("\n") in rep, key
     if "joint" in ref:
-        # the joint-posterior peak (-c2): a stochastic search (differential evolution, every generation one batched device
-        # call) with this program's own random numbers, so the comparison is numerical: the peak the reference found
-        # (two populations: the FULL model; three: all population sizes, then all migration rates, jointfind.cpp:1118-1133)
-        def peak_rows(text):
-            a = text.index("Joint Peak Locations")
-            lines = text[a:].split("\n")
-            k = [i for i, ln in enumerate(lines) if ln.startswith("Model#\tlog(P)")][0]
-            rows = []
-            for ln in lines[k + 1:]:
-                if not ln.strip():
-                    break
-                rows.append(ln.split("\t"))
-            return text[a:a + text[a:].index("Model#\tlog(P)")], lines[k].split("\t"), rows
-        (dr, hr, rr), (do, ho, ro) = peak_rows(ref["joint"]), peak_rows(rep)
-        assert dr == do and hr == ho and len(rr) == len(ro) == (1 if name == "lmode_report_sim3" else 2)     # the model list, the columns
-        for vr, vo in zip(rr, ro):
-            assert vr[0] == vo[0] and vr[2:5] == vo[2:5]                      # model number; #terms, df, 2LLR
-            assert abs(float(vr[1]) - float(vo[1])) <= 2e-3                   # log(P) at the peak
-            assert abs(float(vr[5]) - float(vo[5])) <= 0.02 * float(vr[5])    # effective sample size there
-            for a, b in zip(vr[6:], vo[6:]):
-                assert (a == "-") == (b == "-"), (vr, vo)                     # parameters outside the model
-                if a != "-":
-                    assert abs(float(a) - float(b)) <= 2e-3 * max(1.0, abs(float(a))), (vr, vo)
+        _same_joint_table(ref["joint"], rep, 1 if name == "lmode_report_sim3" else 2)
     r = _run(exe, ["-r0", "-i", str(u), "-o", str(tmp_path / "l2.out"), "-q10", "-m1", "-t3"])
     assert r.returncode == 8 and "-v" in r.stderr            # IMERR_MISSINGCOMMANDINFO
+
+
+def _same_joint_table(ref_text, rep, nrows):
+    """The joint-posterior peak table (-c2 / -w): a stochastic search (differential evolution, every generation one batched
+    device call) with this program's own random numbers, so the comparison is numerical: the peaks the reference found
+    (two populations: the FULL model; three: all population sizes, then all migration rates, jointfind.cpp:1118-1133; each
+    followed by the nested models of its type).  Model list, columns, #terms, df and brackets must be the reference's text."""
+    def peak_rows(text):
+        a = text.index("Joint Peak Locations")
+        lines = text[a:].split("\n")
+        k = [i for i, ln in enumerate(lines) if ln.startswith("Model#\tlog(P)")][0]
+        rows = []
+        for ln in lines[k + 1:]:
+            if not ln.strip() or ln.startswith("    *"):
+                break
+            rows.append(ln.split("\t"))
+        return text[a:a + text[a:].index("Model#\tlog(P)")], lines[k].split("\t"), rows, lines[k + 1 + len(rows)]
+    (dr, hr, rr, tr), (do, ho, ro, to) = peak_rows(ref_text), peak_rows(rep)
+    assert dr == do and hr == ho and len(rr) == len(ro) == nrows and tr == to     # the model list, the columns, the footnote
+    num = lambda t: float(t.strip("[]"))
+    for vr, vo in zip(rr, ro):
+        assert vr[0] == vo[0] and vr[2:4] == vo[2:4]                      # model number; #terms, df
+        assert abs(float(vr[1]) - float(vo[1])) <= 2e-3 * max(1.0, abs(float(vr[1])))      # log(P) at the peak (4 digits printed)
+        if vr[4] != "-":
+            assert abs(float(vr[4]) - float(vo[4])) <= 5e-3 * max(1.0, abs(float(vr[4])))  # 2LLR against the full model
+        else:
+            assert vo[4] == "-"
+        assert abs(float(vr[5]) - float(vo[5])) <= 0.02 * float(vr[5])    # effective sample size there
+        for a, b in zip(vr[6:], vo[6:]):
+            assert (a == "-") == (b == "-") and a.startswith("[") == b.startswith("["), (vr, vo)     # outside the model; tied / fixed
+            if a != "-":
+                assert abs(num(a) - num(b)) <= 2e-3 * max(1.0, abs(num(a))), (vr, vo)
+
+
+@pytest.mark.parametrize("name", ["lmode_report_sim3", "lmode_report_3pop"])
+def test_nested_models_of_the_joint_search(exe, tmp_path, name):
+    """-w <nested model file> (jointfind.cpp:40-135, setup_mapping :380-543): parameters tied together ('equal') or fixed
+    ('constant', clamped into the prior, boundary footnote); every nested model is searched over its free parameters and
+    compared with the full model of its type.  Fixtures: the reference's own tables for the committed .ti and model files."""
+    import gzip
+    import json
+    import shutil
+    ref = json.load(gzip.open(os.path.join(HERE, "golden", name + ".json.gz")))
+    with gzip.open(os.path.join(INPUTS, name + ".ti.gz"), "rb") as f, open(tmp_path / "ref.ti", "wb") as g:
+        shutil.copyfileobj(f, g)
+    if name == "lmode_report_3pop":
+        u, nest, nrows = os.path.join(INPUTS, "parse_is_3pop.u"), os.path.join(INPUTS, "nested_models_3pop.txt"), 4
+    else:
+        u, nest, nrows = tmp_path / "Sim3.u", os.path.join(INPUTS, "nested_models_2pop.txt"), 3
+        u.write_text(_sim3_u())
+    r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l.out"), "-q10", "-m1", "-t3", "-W", nest, "-s", "3"])
+    assert r.returncode == 0, r.stderr
+    rep = open(tmp_path / "l.out").read().replace(nest, "NESTEDFILE")
+    _same_joint_table(ref["joint_nested"], rep, nrows)
+    bad = tmp_path / "bad.txt"
+    bad.write_text("1\nmodel nothing tied\n")
+    r = _run(exe, ["-r0", "-v", str(tmp_path / "ref"), "-i", str(u), "-o", str(tmp_path / "l2.out"), "-q10", "-m1", "-t3", "-w", str(bad)])
+    assert r.returncode == 16 and "does not include any" in r.stderr          # IMERR_NESTEDMODELLSPECIFYLFAIL
 
 
 def _sim3_u():
