@@ -1116,7 +1116,7 @@ int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const do
 //           scan, fold; dev_records_out[nvec][8] (device) = the six record fields, the global maximum, 0
 // The caller gathers the records of all ranks and closes every vector with ima2p_lmode_joint_finish on their sums.
 // up to kJointCallMax vectors per call; every kernel is launched once for all of them
-constexpr int kJointCallMax = 256;
+constexpr int kJointCallMax = 512;
 static int joint_wide_buffers(Lmode &l) {
   if (l.w_pbuf) return IMA2P_OK;
   const size_t G = (size_t)l.v.G, nchunks = (G + kRowsPerBlock - 1) / kRowsPerBlock;
@@ -1133,7 +1133,7 @@ static int joint_wide_buffers(Lmode &l) {
   return IMA2P_OK;
 }
 int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *dev_localmax_out, void *cuda_stream) {
-  if (!h || !h->lm.d_cols || !x || nvec < 1 || nvec > kJointCallMax || !dev_localmax_out) return lfail(IMA2P_E_ARG, "joint_begin: bad argument (at most 256 vectors per call)");
+  if (!h || !h->lm.d_cols || !x || nvec < 1 || nvec > kJointCallMax || !dev_localmax_out) return lfail(IMA2P_E_ARG, "joint_begin: bad argument (at most 512 vectors per call)");
   Lmode &l = h->lm;
   if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = lm_stream(&l, cuda_stream);
@@ -1265,7 +1265,7 @@ int ima2p_lmode_jointp(ima2p_lmode *h, const double *x, int nvec, int calc_ess, 
   Lmode &l = h->lm;
   if (l.v.G != l.v.G_total) return lfail(IMA2P_E_ARG, "jointp: this handle holds a shard; use the two-phase form");
   const int np = l.v.nq + l.v.nm;
-  // the device-resident form with a world of one: up to 256 vectors per pass, seven launches and one copy back per pass
+  // the device-resident form with a world of one: up to 512 vectors per pass, seven launches and one copy back per pass
   int rc = joint_wide_buffers(l);
   if (rc) return rc;
   stream_t s = lm_stream(&l, nullptr);

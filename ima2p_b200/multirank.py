@@ -170,8 +170,8 @@ def sharded_jointp(lm, x, calc_ess=True, device="cpu"):
     return q, ess
 
 
-def sharded_jointp_device(lm, x, calc_ess=True, device="cuda", batch=256):
-    """sharded_jointp with nothing but device collectives between the phases: per batch of <= 256 vectors two NCCL all-gathers
+def sharded_jointp_device(lm, x, calc_ess=True, device="cuda", batch=512):
+    """sharded_jointp with nothing but device collectives between the phases: per batch of <= 512 vectors two NCCL all-gathers
     on device buffers (local maxima; records), every batch queued behind the previous one on the current stream, ONE
     device-to-host copy of all records at the end.  Any number of vectors per call."""
     import numpy as np

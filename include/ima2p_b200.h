@@ -340,7 +340,7 @@ void ima2p_lmode_joint_finish (const double *rec6, double globalmax, long long n
 /* The same phases with every intermediate left on the device, for ranks that exchange with device collectives (an NCCL
  * all-gather of the local maxima, then one of the records): nothing crosses PCIe between the phases and nothing
  * synchronises, so batch after batch queues on one stream.
- *   begin : nvec (<= 256) vectors over the local rows; dev_localmax_out[nvec] (device memory) = maxima over the local rows
+ *   begin : nvec (<= 512) vectors over the local rows; dev_localmax_out[nvec] (device memory) = maxima over the local rows
  *   middle: dev_allmax[world][nvec] (device, the gathered maxima) -> dev_records_out[nvec][8] (device) = the six record
  *           fields of phase 2, the global maximum, 0.  Sum the first four fields over ranks, take fields 4-5 from the rank with
  *           the smallest field 4, and close with ima2p_lmode_joint_finish. */

@@ -277,7 +277,7 @@ def test_device_resident_sharded_jointp_equals_the_single_rank_jointp():
         lm.load(rows[cut[r]:cut[r + 1]], nrows_total=G, row0=cut[r])
         lms.append(lm)
     got_q, got_e = [], []
-    for b0 in range(0, len(xs), 256):                          # one call: two sub-batches of up to 32 vectors inside
+    for b0 in range(0, len(xs), 256):                          # one call for all vectors (up to 512)
         xb = xs[b0:b0 + 256]
         nv = len(xb)
         local = [np.zeros(nv) for _ in range(world)]
