@@ -267,25 +267,31 @@ IMA_KERNEL void k_joint_terms(LmView V, const JointXs *xs, int nvec, int nchunks
 #endif
 }
 
-// per vector: exclusive prefix maxima of the chunks (seeded with the maximum of the rows held by earlier ranks)
-// and the maximum over this rank's rows; one thread per vector (a few hundred chunks)
+// per vector: exclusive prefix maxima of the chunks (seeded with the maximum of the rows held by earlier ranks) and the maximum
+// over this rank's rows.  One warp per vector, 32 chunks a trip (a prefix maximum is exact: the serial walk's values)
 IMA_KERNEL void k_joint_prefix(const double *chunkmax, int nchunks, int nvec, const double *seed_before, double *chunkprefix, double *localmax) {
-  const int v = ima_block() * kLmWarps * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
+  const int v = ima_block() * kLmWarps + ima_warp_in_block(), lane = Warp::lane();
   if (v >= nvec) return;
   double run = seed_before ? seed_before[v] : -DBL_MAX;
-  for (int c = 0; c < nchunks; c++) {
-    chunkprefix[(size_t)v * nchunks + c] = run;
-    const double m = chunkmax[(size_t)v * nchunks + c];
-    if (m > run) run = m;
+  for (int base = 0; base < nchunks; base += IMA_WARP) {
+    const int c = base + lane;
+    double pre = c < nchunks ? chunkmax[(size_t)v * nchunks + c] : -DBL_MAX;
+    for (int o = 1; o < IMA_WARP; o <<= 1) { const double t = Warp::shfl_up(pre, o); if (lane >= o && t > pre) pre = t; }
+    double before = Warp::shfl_up(pre, 1);
+    if (lane == 0) before = -DBL_MAX;
+    if (run > before) before = run;
+    if (c < nchunks) chunkprefix[(size_t)v * nchunks + c] = before;
+    const double groupmax = Warp::bcast(pre, IMA_WARP - 1);
+    if (groupmax > run) run = groupmax;
   }
-  localmax[v] = run;      // includes the seed
+  if (lane == 0) localmax[v] = run;      // includes the seed
 }
 
 // partial record of one chunk: inserted count, kept count, sum, sum of squares, smallest kept p, its scaled term
 constexpr int kJP = 6;
 
 IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const double *chunkprefix, const double *globalmax,
-                             long long global_row0, double *partials) {
+                             long long global_row0, const double *pow10, double *partials) {
   IMA_SMEM_DECL
   // one warp per (chunk, vector): rows of the chunk are walked in order, 32 at a time, with a running maximum
   const int nchunks = (int)((V.G + kRowsPerBlock - 1) / kRowsPerBlock);
@@ -307,6 +313,9 @@ IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const doubl
     const long long r = base + lane;
     const bool valid = r < r1;
     const double p = valid ? pb[r] : -DBL_MAX;
+    // a row at least 10 below the carried maximum is neither inserted (its own running maximum is no smaller) nor a new maximum:
+    // when that holds for the whole group there is nothing to do -- the common case away from the bulk of the posterior
+    if (!Warp::any(valid && (run - p < 10 || global_row0 + r == 0))) continue;
     // running maximum of the rows before r: prefix max within the group of 32, then the carried maximum
     double pre = p;
 #if IMA_CUDA
@@ -327,7 +336,7 @@ IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const doubl
           double m; int z;
           eexp(p, m, z);
           const int zadj = z - maxz;
-          double term = (zadj > -308 && zadj < 308) ? m * pow(10.0, (double)zadj) : (zadj <= -308 ? 0.0 : DBL_MAX);
+          double term = (zadj > -308 && zadj < 308) ? m * pow10[zadj + 308] : (zadj <= -308 ? 0.0 : DBL_MAX);      // the table of :907-908
           kept += 1.0; sum += term; sumsq += term * term;
           if (p < minp) { minp = p; minterm = term; }
         }
@@ -348,18 +357,27 @@ IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const doubl
   }
 }
 
-// fold the chunk records of each vector in chunk order
+// fold the chunk records of each vector: one warp per vector, lanes over the chunks, then a fixed butterfly (deterministic)
 IMA_KERNEL void k_joint_fold(const double *partials, int nchunks, int nvec, double *out) {
-  const int v = ima_block() * kLmWarps * IMA_WARP + ima_warp_in_block() * IMA_WARP + Warp::lane();
+  const int v = ima_block() * kLmWarps + ima_warp_in_block(), lane = Warp::lane();
   if (v >= nvec) return;
   double ins = 0, kept = 0, sum = 0, sq = 0, minp = DBL_MAX, minterm = 0;
-  for (int c = 0; c < nchunks; c++) {
+  for (int c = lane; c < nchunks; c += IMA_WARP) {
     const double *o = partials + ((size_t)v * nchunks + c) * kJP;
     ins += o[0]; kept += o[1]; sum += o[2]; sq += o[3];
     if (o[4] < minp) { minp = o[4]; minterm = o[5]; }
   }
-  double *r = out + (size_t)v * kJP;
-  r[0] = ins; r[1] = kept; r[2] = sum; r[3] = sq; r[4] = minp; r[5] = minterm;
+  Warp::sum4(ins, kept, sum, sq);
+#if IMA_CUDA
+  for (int o = 16; o > 0; o >>= 1) {
+    const double op = __shfl_xor_sync(0xffffffffu, minp, o), ot = __shfl_xor_sync(0xffffffffu, minterm, o);
+    if (op < minp) { minp = op; minterm = ot; }
+  }
+#endif
+  if (lane == 0) {
+    double *r = out + (size_t)v * kJP;
+    r[0] = ins; r[1] = kept; r[2] = sum; r[3] = sq; r[4] = minp; r[5] = minterm;
+  }
 }
 
 // device-resident exchange of the sharded jointp (ima2p_lmode_joint_begin / _middle): from the local maxima of all ranks, the
@@ -882,6 +900,7 @@ struct Lmode {
   JointXs *w_xs = nullptr;
   JointXs *d_xs = nullptr;
   size_t cap_x = 0, cap_partials = 0;
+  double *d_pow10 = nullptr;                   // 10^i, i = -308..308, from the host's pow as the reference's table (jointfind.cpp:907-908)
   int joint_model = 0;                         // which parameters jointp is a function of (ima2p_lmode_set_joint_model)
   MargReq *d_req = nullptr; double *d_mpart = nullptr, *d_mout = nullptr;      // marginal_many: requests, per-block partials, sums
   size_t cap_req = 0, cap_mpart = 0;
@@ -971,8 +990,12 @@ int ima2p_lmode_load(ima2p_lmode *h, const float *rows, int nrows, int rowlen, l
   l.d_jpart = l.alloc<double>((size_t)kJointVecMax * nchunks * kJP);
   l.d_jout = l.alloc<double>((size_t)kJointVecMax * kJP);
   l.d_xs = l.alloc<JointXs>(kJointVecMax);
-  if (!l.d_cols || !l.d_pbuf || !l.d_xs) return lfail(IMA2P_E_CUDA, "device allocation failed");
+  l.d_pow10 = l.alloc<double>(617);
+  if (!l.d_cols || !l.d_pbuf || !l.d_xs || !l.d_pow10) return lfail(IMA2P_E_CUDA, "device allocation failed");
   stream_t s = lm_stream(&l, nullptr);
+  double p10[617];
+  for (int i = -308; i <= 308; i++) p10[i + 308] = pow(10.0, (double)i);
+  if (!h2d(l.d_pow10, p10, sizeof p10, s)) return lfail(IMA2P_E_CUDA, "table upload failed");
   if (!h2d(l.d_cols, cols.data(), cols.size() * sizeof(float), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "row upload failed");
   l.v.cols = l.d_cols; l.v.G = nrows; l.v.G_total = nrows_total;
   return IMA2P_OK;
@@ -1100,7 +1123,7 @@ int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const do
   if (seed_before) { d_seed = l.d_jout; if (!h2d(d_seed, seed_before, nvec * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed"); }
   if (!h2d(l.d_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
   IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.d_xs, nvec, nchunks, l.joint_model, l.d_pbuf, l.d_chunkmax);
-  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, d_seed, l.d_prefix, l.d_lmax);
+  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, d_seed, l.d_prefix, l.d_lmax);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint terms)");
 #endif
@@ -1150,7 +1173,7 @@ int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *d
   if (!h2d(l.w_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
   // every buffer is [vector][...]: one launch of each kernel serves all vectors of the call
   IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.w_xs, nvec, nchunks, l.joint_model, l.w_pbuf, l.w_chunkmax);
-  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)nullptr,
+  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)nullptr,
              l.w_prefix, dev_localmax_out);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint begin)");
@@ -1170,10 +1193,10 @@ int ima2p_lmode_joint_middle(ima2p_lmode *h, int nvec, const double *dev_allmax,
   const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
   const int gall = (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP);
   IMA_LAUNCH(k_joint_seed, gall, kLmWarps, 0, s, dev_allmax, world, rank, nvec, l.d_seed, l.d_gmax);
-  IMA_LAUNCH(k_joint_prefix, gall, kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)l.d_seed, l.w_prefix, l.d_ltmp);
+  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)l.d_seed, l.w_prefix, l.d_ltmp);
   IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, (const double *)l.w_pbuf, nvec, (const double *)l.w_prefix,
-             (const double *)l.d_gmax, global_row0, l.w_jpart);
-  IMA_LAUNCH(k_joint_fold, gall, kLmWarps, 0, s, (const double *)l.w_jpart, nchunks, nvec, l.w_jout);
+             (const double *)l.d_gmax, global_row0, (const double *)l.d_pow10, l.w_jpart);
+  IMA_LAUNCH(k_joint_fold, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, (const double *)l.w_jpart, nchunks, nvec, l.w_jout);
   IMA_LAUNCH(k_joint_pack, gall, kLmWarps, 0, s, (const double *)l.w_jout, (const double *)l.d_gmax, nvec, dev_records_out);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint middle)");
@@ -1191,7 +1214,7 @@ int ima2p_lmode_joint_reseed(ima2p_lmode *h, int nvec, const double *seed_before
   const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
   double *d_seed = nullptr;
   if (seed_before) { d_seed = l.d_jout; if (!h2d(d_seed, seed_before, nvec * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed"); }
-  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, d_seed, l.d_prefix, l.d_lmax);
+  IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, d_seed, l.d_prefix, l.d_lmax);
   if (!d2h(localmax_out, l.d_lmax, nvec * sizeof(double), s) || !dev_sync(s)) return lfail(IMA2P_E_CUDA, "download failed");
   return IMA2P_OK;
 }
@@ -1203,8 +1226,8 @@ int ima2p_lmode_joint_phase2(ima2p_lmode *h, int nvec, const double *globalmax, 
   stream_t s = lm_stream(&l, nullptr);
   const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
   if (!h2d(l.d_lmax, globalmax, nvec * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed");
-  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, l.d_pbuf, nvec, l.d_prefix, l.d_lmax, global_row0, l.d_jpart);
-  IMA_LAUNCH(k_joint_fold, (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP), kLmWarps, 0, s, l.d_jpart, nchunks, nvec, l.d_jout);
+  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, l.d_pbuf, nvec, l.d_prefix, l.d_lmax, global_row0, (const double *)l.d_pow10, l.d_jpart);
+  IMA_LAUNCH(k_joint_fold, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.d_jpart, nchunks, nvec, l.d_jout);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint scan)");
 #endif
