@@ -174,7 +174,8 @@ IMA_KERNEL void k_reduce_many(const MargReq *req, int nreq, int nblocks, const d
   out[q] = s;
 }
 
-struct JointXs { double log2diffx[kMaxParams], logx[kMaxParams], divx[kMaxParams], x[kMaxParams]; };
+// what jointp precomputes per parameter vector (jointfind.cpp:955-970), two numbers per parameter: log(2/x) and 1/x for a
+// population size, log x and x for a migration rate; layout [vector][2][np]
 
 // p_g of jointp (jointfind.cpp:971-996, two populations / full model).  One block = a chunk of rows x a tile of kVT parameter
 // vectors; any number of vectors per launch (grid = chunks x tiles).  The tile's accumulators and running maxima live in registers
@@ -185,7 +186,7 @@ struct JointXs { double log2diffx[kMaxParams], logx[kMaxParams], divx[kMaxParams
 constexpr int kVT = 16;              // parameter vectors per block of k_joint_terms
 IMA_HD size_t joint_terms_smem(int np) { return (size_t)(2 * kVT * np + kLmWarps * kVT) * sizeof(double); }
 
-IMA_KERNEL void k_joint_terms(LmView V, const JointXs *xs, int nvec, int nchunks, int modeltype, double *pbuf, double *chunkmax) {
+IMA_KERNEL void k_joint_terms(LmView V, const double *coef, int nvec, int nchunks, int modeltype, double *pbuf, double *chunkmax) {
   IMA_SMEM_DECL
   const int lane = Warp::lane(), warp = ima_warp_in_block();
   const int tile = ima_block() / nchunks, chunk = ima_block() - tile * nchunks;
@@ -201,9 +202,9 @@ IMA_KERNEL void k_joint_terms(LmView V, const JointXs *xs, int nvec, int nchunks
   for (int k = 0; k < kVT * np; k++) {                   // the emulation runs a block's warps one after the other
 #endif
     const int i = k / kVT, j = k - i * kVT;
-    const JointXs &X = xs[v0 + (j < nt ? j : 0)];
-    ca[k] = i < V.nq ? X.log2diffx[i] : X.logx[i];
-    cb[k] = i < V.nq ? X.divx[i] : X.x[i];
+    const double *X = coef + (size_t)(v0 + (j < nt ? j : 0)) * 2 * np;
+    ca[k] = X[i];
+    cb[k] = X[np + i];
   }
 #if IMA_CUDA
   __syncthreads();
@@ -897,8 +898,7 @@ struct Lmode {
   double *d_x = nullptr, *d_partials = nullptr, *d_out = nullptr, *d_pbuf = nullptr, *d_chunkmax = nullptr, *d_prefix = nullptr,
          *d_lmax = nullptr, *d_jpart = nullptr, *d_jout = nullptr, *d_seed = nullptr, *d_gmax = nullptr, *d_ltmp = nullptr, *d_wlmax = nullptr, *d_wrec = nullptr,
          *w_pbuf = nullptr, *w_chunkmax = nullptr, *w_prefix = nullptr, *w_jpart = nullptr, *w_jout = nullptr;   // wide batches (joint_begin / _middle)
-  JointXs *w_xs = nullptr;
-  JointXs *d_xs = nullptr;
+  double *w_xs = nullptr, *d_xs = nullptr;      // coefficient tables of the vectors of a call
   size_t cap_x = 0, cap_partials = 0;
   double *d_pow10 = nullptr;                   // 10^i, i = -308..308, from the host's pow as the reference's table (jointfind.cpp:907-908)
   int joint_model = 0;                         // which parameters jointp is a function of (ima2p_lmode_set_joint_model)
@@ -989,7 +989,7 @@ int ima2p_lmode_load(ima2p_lmode *h, const float *rows, int nrows, int rowlen, l
   l.d_lmax = l.alloc<double>(kJointVecMax);
   l.d_jpart = l.alloc<double>((size_t)kJointVecMax * nchunks * kJP);
   l.d_jout = l.alloc<double>((size_t)kJointVecMax * kJP);
-  l.d_xs = l.alloc<JointXs>(kJointVecMax);
+  l.d_xs = l.alloc<double>((size_t)kJointVecMax * 2 * kMaxParams);
   l.d_pow10 = l.alloc<double>(617);
   if (!l.d_cols || !l.d_pbuf || !l.d_xs || !l.d_pow10) return lfail(IMA2P_E_CUDA, "device allocation failed");
   stream_t s = lm_stream(&l, nullptr);
@@ -1106,23 +1106,28 @@ int ima2p_lmode_marginal_many(ima2p_lmode *h, int n, const int *kind, const int 
 // two-phase joint evaluation, also the building block of the multi-GPU form:
 //   phase 1: terms + this rank's maximum per vector (seeded with the maximum of the rows of earlier ranks)
 //   phase 2: keep-set records given the global maximum
+static std::vector<double> joint_coefficients(const Lmode &l, const double *x, int nvec) {
+  const int nq = l.v.nq, np = nq + l.v.nm;
+  std::vector<double> c((size_t)nvec * 2 * np);
+  for (int v = 0; v < nvec; v++)
+    for (int i = 0; i < np; i++) {                     // jointfind.cpp:955-970
+      const double xv = x[(size_t)v * np + i];
+      c[((size_t)v * 2) * np + i] = i < nq ? kLog2 - log(xv) : log(xv);
+      c[((size_t)v * 2 + 1) * np + i] = i < nq ? 1.0 / xv : xv;
+    }
+  return c;
+}
 int ima2p_lmode_joint_phase1(ima2p_lmode *h, const double *x, int nvec, const double *seed_before, double *localmax_out) {
   if (!h || !h->lm.d_cols || !x || nvec < 1 || nvec > kJointVecMax) return lfail(IMA2P_E_ARG, "joint_phase1: bad argument");
   Lmode &l = h->lm;
   if (!lm_use(&l)) return lfail(IMA2P_E_CUDA, "cudaSetDevice failed");
   stream_t s = lm_stream(&l, nullptr);
   const int np = l.v.nq + l.v.nm, nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
-  std::vector<JointXs> xs(nvec);
-  for (int v = 0; v < nvec; v++)
-    for (int i = 0; i < np; i++) {                     // jointfind.cpp:955-970
-      const double xv = x[(size_t)v * np + i];
-      xs[v].x[i] = xv; xs[v].logx[i] = log(xv); xs[v].divx[i] = 1.0 / xv;
-      if (i < l.v.nq) xs[v].log2diffx[i] = kLog2 - log(xv);
-    }
+  const std::vector<double> xs = joint_coefficients(l, x, nvec);
   double *d_seed = nullptr;
   if (seed_before) { d_seed = l.d_jout; if (!h2d(d_seed, seed_before, nvec * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed"); }
-  if (!h2d(l.d_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
-  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.d_xs, nvec, nchunks, l.joint_model, l.d_pbuf, l.d_chunkmax);
+  if (!h2d(l.d_xs, xs.data(), xs.size() * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed");
+  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const double *)l.d_xs, nvec, nchunks, l.joint_model, l.d_pbuf, l.d_chunkmax);
   IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.d_chunkmax, nchunks, nvec, d_seed, l.d_prefix, l.d_lmax);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint terms)");
@@ -1148,7 +1153,7 @@ static int joint_wide_buffers(Lmode &l) {
   l.w_prefix = l.alloc<double>((size_t)kJointCallMax * nchunks);
   l.w_jpart = l.alloc<double>((size_t)kJointCallMax * nchunks * kJP);
   l.w_jout = l.alloc<double>((size_t)kJointCallMax * kJP);
-  l.w_xs = l.alloc<JointXs>(kJointCallMax);
+  l.w_xs = l.alloc<double>((size_t)kJointCallMax * 2 * kMaxParams);
   l.d_seed = l.alloc<double>(kJointCallMax); l.d_gmax = l.alloc<double>(kJointCallMax); l.d_ltmp = l.alloc<double>(kJointCallMax);
   l.d_wlmax = l.alloc<double>(kJointCallMax); l.d_wrec = l.alloc<double>((size_t)kJointCallMax * 8);
   if (!l.w_pbuf || !l.w_chunkmax || !l.w_prefix || !l.w_jpart || !l.w_jout || !l.w_xs || !l.d_seed || !l.d_gmax || !l.d_ltmp || !l.d_wlmax || !l.d_wrec)
@@ -1163,16 +1168,10 @@ int ima2p_lmode_joint_begin(ima2p_lmode *h, const double *x, int nvec, double *d
   int rc = joint_wide_buffers(l);
   if (rc) return rc;
   const int np = l.v.nq + l.v.nm, nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
-  std::vector<JointXs> xs(nvec);
-  for (int v = 0; v < nvec; v++)
-    for (int i = 0; i < np; i++) {                     // jointfind.cpp:955-970
-      const double xv = x[(size_t)v * np + i];
-      xs[v].x[i] = xv; xs[v].logx[i] = log(xv); xs[v].divx[i] = 1.0 / xv;
-      if (i < l.v.nq) xs[v].log2diffx[i] = kLog2 - log(xv);
-    }
-  if (!h2d(l.w_xs, xs.data(), nvec * sizeof(JointXs), s)) return lfail(IMA2P_E_CUDA, "upload failed");
+  const std::vector<double> xs = joint_coefficients(l, x, nvec);
+  if (!h2d(l.w_xs, xs.data(), xs.size() * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed");
   // every buffer is [vector][...]: one launch of each kernel serves all vectors of the call
-  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const JointXs *)l.w_xs, nvec, nchunks, l.joint_model, l.w_pbuf, l.w_chunkmax);
+  IMA_LAUNCH(k_joint_terms, nchunks * ((nvec + kVT - 1) / kVT), kLmWarps, joint_terms_smem(np), s, l.v, (const double *)l.w_xs, nvec, nchunks, l.joint_model, l.w_pbuf, l.w_chunkmax);
   IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)nullptr,
              l.w_prefix, dev_localmax_out);
 #if IMA_CUDA
