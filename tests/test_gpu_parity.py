@@ -237,6 +237,21 @@ def test_front_end_report_head_on_the_device(lib, tmp_path):
     frontend_report_head_matches_reference(exe, tmp_path, lib=lib)
 
 
+@pytest.mark.parametrize("name", ["lmode_report_sim3", "lmode_report_3pop"])
+def test_front_end_l_mode_report_on_the_device(lib, tmp_path, name):
+    """The product executable's L mode on the device: the report sections of the reference's own L-mode run on the same .ti file
+    character for character (greater-than tables, moments, the marginal peak table found by the lock-step searches, histogram
+    groups), the joint-posterior peaks (-c2; three populations: the size-only and migration-only models) and the nested models
+    of -w, all against the reference's tables."""
+    import os
+    import test_frontend as tf
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ima2p_b200", "IMa2p_b200")
+    assert os.path.exists(exe), "build the front end with __graft_entry__.build()"
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    tf.test_l_mode_report_sections_equal_the_reference_text(exe, tmp_path / "a", name)
+    tf.test_nested_models_of_the_joint_search(exe, tmp_path / "b", name)
+
+
 def test_two_gpus_front_end_writes_the_single_gpu_ti_file(lib, tmp_path):
     """The product executable started once per GPU (RANK / WORLD_SIZE / LOCAL_RANK): the ranks exchange swap sums and the cold
     chain's record through peer memory (cudaIpc handles over the rendezvous files) and rank 0 writes the .ti file the one-GPU
