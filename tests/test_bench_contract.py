@@ -122,3 +122,19 @@ def test_final_multi_gpu_records(name, n):
     c3 = d["config3"]
     assert c3["config"]["chains_total"] == 256 * n and c3["gpu_launches"] == c3["steps"] * 33      # four groups where the kernels run many waves
     assert abs(c3["ratio_to_cpu_baseline"] - c3["value"] / c3["cpu_baseline"]["value"]) < 1e-9 * c3["ratio_to_cpu_baseline"]
+
+
+# ---- session 8 (profiles/r2s8_*): results read through the two-slot report, jointp in one pass of 512 vectors ----
+def test_session8_records():
+    d, old = _line("r2s8_bench_n1.json"), _line("r2s7_bench_n1.json")
+    assert d["n_gpus"] == 1 and d["data"] == "real" and d["config"] == old["config"] and d["gpu_launches"] == d["steps"] * 17
+    assert abs(d["value"] - 128 * 50 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    e = d["e2e"]
+    assert "step_report_begin" in e["read_back"] and e["h2d_bytes_per_step"] > 5e6 and e["d2h_bytes_per_step"] == 4280
+    assert old["e2e"]["value"] < e["value"] < d["value"]
+    lm = d["lmode"]
+    assert lm["jointp_vectors"] == 512 and lm["jointp_geneval_per_sec"] > 3 * old["lmode"]["jointp_geneval_per_sec"]
+    assert abs(lm["margincalc_geneval_per_sec"] / old["lmode"]["margincalc_geneval_per_sec"] - 1) < 0.05      # untouched kernel, same figure
+    d2 = _line("r2s8_bench_n2.json")
+    assert d2["n_gpus"] == 2 and d2["config"]["chains_total"] == 256 and d2["value"] > 1.9 * d["value"]
+    assert d2["lmode"]["jointp_geneval_per_sec"] > 1.8 * lm["jointp_geneval_per_sec"]                       # rows sharded over the two GPUs
