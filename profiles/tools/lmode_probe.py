@@ -1,7 +1,7 @@
 """L-mode probe for ncu / timing (round 2, session 8): G bootstrapped .ti rows of the two-population model of bench.py's
 L-mode section, then jointp for NV vectors in one device pass and one lock-step round of the peak searches
 (ima2p_lmode_marginal_many: 3 row sets x 5 parameters x 2 brackets = 30 points).
-usage: python profiles/tools/lmode_probe.py [G] [NV]"""
+usage: python profiles/tools/lmode_probe.py [G] [NV] [all-model-types]"""
 import os
 import sys
 import time
@@ -29,6 +29,10 @@ rows = base[rng.integers(0, 400, G)]
 lm = LMode(nq, nm, nsplit, [10.0] * nq, [0.0] * nq, [1.0] * nm, [0.0] * nm)
 lm.load(rows)
 xs = np.column_stack([rng.uniform(0.05, 0.9, NV) * (10.0 if p < nq else 1.0) for p in range(nq + nm)])
+if len(sys.argv) > 3:                                  # every model type once (compute-sanitizer runs)
+    for mt in (1, 2, 0):
+        lm.set_joint_model(mt)
+        lm.jointp(xs)
 lm.jointp(xs[:64])
 t0 = time.perf_counter()
 for _ in range(3):
