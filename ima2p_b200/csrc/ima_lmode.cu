@@ -310,6 +310,19 @@ IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const doubl
   double run = chunkprefix[(size_t)v * nchunks + chunk];
   double inserted = 0.0, kept = 0.0, sum = 0.0, sumsq = 0.0, minp = DBL_MAX, minterm = 0.0;
   const double *pb = pbuf + (size_t)v * V.G;
+  // Rows that go into the sum are few and scattered, and their term (eexp: a division, a polynomial, a fractional power of ten)
+  // is by far the longest code of the loop: taken where it is found, a group with one such row pays for it in full.  So the
+  // rows are queued (per warp, in shared memory) and their terms are taken 32 at a time, one per lane.
+  double *queue = (double *)IMA_SMEM + (size_t)ima_warp_in_block() * 2 * IMA_WARP;
+  int qn = 0;
+  auto take_term = [&](double pk) {
+    double m; int z;
+    eexp(pk, m, z);
+    const int zadj = z - maxz;
+    const double term = (zadj > -308 && zadj < 308) ? m * pow10[zadj + 308] : (zadj <= -308 ? 0.0 : DBL_MAX);      // the table of :907-908
+    kept += 1.0; sum += term; sumsq += term * term;
+    if (pk < minp) { minp = pk; minterm = term; }
+  };
   for (long long base = r0; base < r1; base += IMA_WARP) {
     const long long r = base + lane;
     const bool valid = r < r1;
@@ -329,22 +342,32 @@ IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const doubl
     const double groupmax = pre;
 #endif
     if (run > before) before = run;
+    bool keep = false;
     if (valid) {
       const bool first_row = (global_row0 + r == 0);
       if (first_row || before - p < 10) {            // :1005 (row 0 is always the list head :998-1003)
         inserted += 1.0;
-        if (gmax - p < 10) {                         // :1022
-          double m; int z;
-          eexp(p, m, z);
-          const int zadj = z - maxz;
-          double term = (zadj > -308 && zadj < 308) ? m * pow10[zadj + 308] : (zadj <= -308 ? 0.0 : DBL_MAX);      // the table of :907-908
-          kept += 1.0; sum += term; sumsq += term * term;
-          if (p < minp) { minp = p; minterm = term; }
-        }
+        keep = gmax - p < 10;                        // :1022
       }
     }
     if (groupmax > run) run = groupmax;
+    const unsigned km = Warp::ballot(keep);
+    if (km) {
+      if (keep) queue[qn + Warp::popc(km & ((1u << lane) - 1u))] = p;
+      qn += Warp::popc(km);
+      Warp::sync();
+      if (qn >= IMA_WARP) {                          // a full set: one term per lane
+        take_term(queue[lane]);
+        const int left = qn - IMA_WARP;
+        const double carry = lane < left ? queue[IMA_WARP + lane] : 0.0;
+        Warp::sync();
+        if (lane < left) queue[lane] = carry;
+        qn = left;
+        Warp::sync();
+      }
+    }
   }
+  if (lane < qn) take_term(queue[lane]);
   inserted = Warp::sum(inserted); kept = Warp::sum(kept); sum = Warp::sum(sum); sumsq = Warp::sum(sumsq);
 #if IMA_CUDA
   for (int o = 16; o > 0; o >>= 1) {
@@ -1193,7 +1216,7 @@ int ima2p_lmode_joint_middle(ima2p_lmode *h, int nvec, const double *dev_allmax,
   const int gall = (nvec + kLmWarps * IMA_WARP - 1) / (kLmWarps * IMA_WARP);
   IMA_LAUNCH(k_joint_seed, gall, kLmWarps, 0, s, dev_allmax, world, rank, nvec, l.d_seed, l.d_gmax);
   IMA_LAUNCH(k_joint_prefix, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, (const double *)l.w_chunkmax, nchunks, nvec, (const double *)l.d_seed, l.w_prefix, l.d_ltmp);
-  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, (const double *)l.w_pbuf, nvec, (const double *)l.w_prefix,
+  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, kLmWarps * 2 * IMA_WARP * sizeof(double), s, l.v, (const double *)l.w_pbuf, nvec, (const double *)l.w_prefix,
              (const double *)l.d_gmax, global_row0, (const double *)l.d_pow10, l.w_jpart);
   IMA_LAUNCH(k_joint_fold, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, (const double *)l.w_jpart, nchunks, nvec, l.w_jout);
   IMA_LAUNCH(k_joint_pack, gall, kLmWarps, 0, s, (const double *)l.w_jout, (const double *)l.d_gmax, nvec, dev_records_out);
@@ -1225,7 +1248,7 @@ int ima2p_lmode_joint_phase2(ima2p_lmode *h, int nvec, const double *globalmax, 
   stream_t s = lm_stream(&l, nullptr);
   const int nchunks = (int)((l.v.G + kRowsPerBlock - 1) / kRowsPerBlock);
   if (!h2d(l.d_lmax, globalmax, nvec * sizeof(double), s)) return lfail(IMA2P_E_CUDA, "upload failed");
-  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.v, l.d_pbuf, nvec, l.d_prefix, l.d_lmax, global_row0, (const double *)l.d_pow10, l.d_jpart);
+  IMA_LAUNCH(k_joint_scan, (nchunks * nvec + kLmWarps - 1) / kLmWarps, kLmWarps, kLmWarps * 2 * IMA_WARP * sizeof(double), s, l.v, l.d_pbuf, nvec, l.d_prefix, l.d_lmax, global_row0, (const double *)l.d_pow10, l.d_jpart);
   IMA_LAUNCH(k_joint_fold, (nvec + kLmWarps - 1) / kLmWarps, kLmWarps, 0, s, l.d_jpart, nchunks, nvec, l.d_jout);
 #if IMA_CUDA
   if (!IMA_CUDA_OK(cudaGetLastError())) return lfail(IMA2P_E_CUDA, "kernel launch failed (joint scan)");
