@@ -143,3 +143,7 @@ def test_session8_records():
     # the VERDICT's "jointp flat at 2.4e10 for every N": now 4.6 x N = 1 on eight GPUs, 7.5 x the figure the round began with
     assert d8["lmode"]["jointp_geneval_per_sec"] > 4.5 * lm["jointp_geneval_per_sec"] > 4.5 * 3 * old["lmode"]["jointp_geneval_per_sec"]
     assert d8["lmode"]["margincalc_geneval_per_sec"] > 5.5 * lm["margincalc_geneval_per_sec"]
+    # the session's last build (the scan queues the rows that enter the sum): same step, jointp past 1e11 on one GPU
+    f = _line("r2s8_bench_n1_final.json")
+    assert f["config"] == d["config"] and abs(f["value"] / d["value"] - 1) < 0.01 and f["e2e"]["value"] > 15.5e6
+    assert f["lmode"]["jointp_geneval_per_sec"] > 1e11 > lm["jointp_geneval_per_sec"]
