@@ -291,6 +291,16 @@ IMA_KERNEL void k_joint_prefix(const double *chunkmax, int nchunks, int nvec, co
 // partial record of one chunk: inserted count, kept count, sum, sum of squares, smallest kept p, its scaled term
 constexpr int kJP = 6;
 
+IMA_DEV int lowest_bit(unsigned m) {
+#if IMA_CUDA
+  return __ffs((int)m) - 1;
+#else
+  int i = 0;
+  while (!(m & 1u)) { m >>= 1; i++; }
+  return i;
+#endif
+}
+
 IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const double *chunkprefix, const double *globalmax,
                              long long global_row0, const double *pow10, double *partials) {
   IMA_SMEM_DECL
@@ -328,20 +338,27 @@ IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const doubl
     const bool valid = r < r1;
     const double p = valid ? pb[r] : -DBL_MAX;
     // a row at least 10 below the carried maximum is neither inserted (its own running maximum is no smaller) nor a new maximum:
-    // when that holds for the whole group there is nothing to do -- the common case away from the bulk of the posterior
-    if (!Warp::any(valid && (run - p < 10 || global_row0 + r == 0))) continue;
-    // running maximum of the rows before r: prefix max within the group of 32, then the carried maximum
-    double pre = p;
-#if IMA_CUDA
-    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o && t > pre) pre = t; }
-    double before = __shfl_up_sync(0xffffffffu, pre, 1);
-    if (lane == 0) before = -DBL_MAX;
-    const double groupmax = __shfl_sync(0xffffffffu, pre, 31);
-#else
-    double before = -DBL_MAX;
-    const double groupmax = pre;
-#endif
-    if (run > before) before = run;
+    // only the other rows -- the candidates -- matter, to themselves and to the rows after them.  No candidate in the group:
+    // nothing to do, the common case away from the bulk of the posterior.
+    const unsigned cm = Warp::ballot(valid && (run - p < 10 || global_row0 + r == 0));
+    if (!cm) continue;
+    // running maximum of the rows before r (`before`) and of the whole group
+    double before = run, groupmax = run;
+    if (Warp::popc(cm) <= 4) {                       // few candidates: each tells the lanes after it its value
+      for (unsigned m = cm; m; m &= m - 1u) {
+        const int c = lowest_bit(m);
+        const double pc = Warp::bcast(p, c);
+        if (lane > c && pc > before) before = pc;
+        if (pc > groupmax) groupmax = pc;
+      }
+    } else {                                         // many: prefix maximum over the 32 lanes by shuffles
+      double pre = p;
+      for (int o = 1; o < IMA_WARP; o <<= 1) { const double t = Warp::shfl_up(pre, o); if (lane >= o && t > pre) pre = t; }
+      const double prev = Warp::shfl_up(pre, 1);
+      if (lane > 0 && prev > before) before = prev;
+      const double gm = Warp::bcast(pre, IMA_WARP - 1);
+      if (gm > groupmax) groupmax = gm;
+    }
     bool keep = false;
     if (valid) {
       const bool first_row = (global_row0 + r == 0);
