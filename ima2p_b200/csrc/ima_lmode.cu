@@ -333,15 +333,12 @@ IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const doubl
     kept += 1.0; sum += term; sumsq += term * term;
     if (pk < minp) { minp = pk; minterm = term; }
   };
-  for (long long base = r0; base < r1; base += IMA_WARP) {
-    const long long r = base + lane;
-    const bool valid = r < r1;
-    const double p = valid ? pb[r] : -DBL_MAX;
+  auto group = [&](long long r, bool valid, double p) {
     // a row at least 10 below the carried maximum is neither inserted (its own running maximum is no smaller) nor a new maximum:
     // only the other rows -- the candidates -- matter, to themselves and to the rows after them.  No candidate in the group:
     // nothing to do, the common case away from the bulk of the posterior.
     const unsigned cm = Warp::ballot(valid && (run - p < 10 || global_row0 + r == 0));
-    if (!cm) continue;
+    if (!cm) return;
     // running maximum of the rows before r (`before`) and of the whole group
     double before = run, groupmax = run;
     if (Warp::popc(cm) <= 4) {                       // few candidates: each tells the lanes after it its value
@@ -382,6 +379,22 @@ IMA_KERNEL void k_joint_scan(LmView V, const double *pbuf, int nvec, const doubl
         qn = left;
         Warp::sync();
       }
+    }
+    };
+  // four groups of rows are loaded before the first of them is processed: the scan is one dependent walk per warp, and with a
+  // single 256-byte load in flight per warp it ran at the memory latency, not the bandwidth (ncu: long_scoreboard 15 of 19)
+  constexpr int kAhead = 4;
+  for (long long base = r0; base < r1; base += kAhead * IMA_WARP) {
+    double pa[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; k++) {
+      const long long r = base + k * IMA_WARP + lane;
+      pa[k] = r < r1 ? pb[r] : -DBL_MAX;
+    }
+#pragma unroll
+    for (int k = 0; k < kAhead; k++) {
+      const long long r = base + k * IMA_WARP + lane;
+      if (base + k * IMA_WARP < r1) group(r, r < r1, pa[k]);
     }
   }
   if (lane < qn) take_term(queue[lane]);
